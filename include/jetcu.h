@@ -1,0 +1,261 @@
+/*
+ * jetcu.h — C ABI of the B200-native hybrid-liquid hot path (drop-in for Jet's CPU path).
+ *
+ * Everything here is plain C: opaque handles, plain pointers and sizes, `int` status returns
+ * (0 = JETCU_OK; never throws, never aborts).  All array arguments are HOST pointers owned by
+ * the caller unless the name ends in `_dev`; the context owns all device scratch.  Arrays use
+ * Jet's Array3 layout: x-fastest, contiguous (reference: include/jet/detail/array3-inl.h:144).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the Jet tree,
+ * doyubkim/fluid-engine-dev).  INTEGRATION.md shows the C++ adapters that bind them.
+ *
+ * One ctx per GPU; calls on one ctx must be serialised by the caller (Jet's solvers are not
+ * re-entrant either: SURVEY.md §8b).  There is NO CPU fallback: every call fails with
+ * JETCU_ERR_CUDA if no sm_100-class device is usable.
+ */
+#ifndef JETCU_H_
+#define JETCU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ status */
+enum {
+    JETCU_OK = 0,
+    JETCU_ERR_INVALID_ARG = 1, /* mirrors std::invalid_argument from JET_THROW_INVALID_ARG_IF (include/jet/macros.h:37-41) */
+    JETCU_ERR_CUDA = 2,        /* CUDA runtime error; text in jetcu_last_error() */
+    JETCU_ERR_UNSUPPORTED = 3, /* e.g. lexicographic Gauss-Seidel (inherently serial) */
+    JETCU_ERR_OOM = 4,
+    JETCU_ERR_NCCL = 5
+};
+
+typedef struct jetcu_ctx jetcu_ctx;
+
+/* Creates a context bound to CUDA device `device`. */
+int jetcu_ctx_create(int device, jetcu_ctx** out);
+int jetcu_ctx_destroy(jetcu_ctx* ctx);
+/* Last error text for ctx (or for the calling thread's last failed create when ctx == NULL). */
+const char* jetcu_last_error(const jetcu_ctx* ctx);
+/* Library / build identification ("jetcu <ver> sm_100a"). */
+const char* jetcu_version(void);
+/* Number of kernel launches issued by this ctx since creation (bench.py's gpu_launches). */
+uint64_t jetcu_launch_count(const jetcu_ctx* ctx);
+/* cudaStream_t the ctx launches on (as void*), so callers can record CUDA events on it. */
+void* jetcu_stream(const jetcu_ctx* ctx);
+int jetcu_synchronize(jetcu_ctx* ctx);
+
+/* ------------------------------------------------------------------ types */
+
+/* == jet::FdmMatrixRow3 (include/jet/fdm_linear_system3.h:18-30): 32-byte AoS row. */
+typedef struct jetcu_matrix_row {
+    double center, right, up, front;
+} jetcu_matrix_row;
+
+/* == ctor arguments of jet::FdmMgpcgSolver3 (include/jet/fdm_mgpcg_solver3.h:35-41). */
+typedef struct jetcu_mgpcg_params {
+    uint32_t max_iterations;    /* numberOfCgIter */
+    uint32_t max_levels;        /* maxNumberOfLevels */
+    uint32_t n_restriction;     /* numberOfRestrictionIter (pre-smoothing sweeps) */
+    uint32_t n_correction;      /* numberOfCorrectionIter (post-smoothing sweeps, levels > 0) */
+    uint32_t n_coarsest;        /* numberOfCoarsestIter */
+    uint32_t n_final;           /* numberOfFinalIter (post-smoothing sweeps on level 0) */
+    double tolerance;           /* maxTolerance */
+    double sor_factor;          /* sorFactor */
+    int32_t use_red_black;      /* useRedBlackOrdering; 0 -> JETCU_ERR_UNSUPPORTED */
+    int32_t reserved;
+} jetcu_mgpcg_params;
+
+typedef struct jetcu_mgpcg_result {
+    uint32_t iterations;        /* FdmMgpcgSolver3::lastNumberOfIterations() */
+    int32_t returned;           /* what FdmMgpcgSolver3::solve() returns (src/jet/fdm_mgpcg_solver3.cpp:78-79) */
+    double last_residual;       /* FdmMgpcgSolver3::lastResidual() = sqrt(|r.M^-1 r|) */
+    double true_residual_l2;    /* ||b - A x||_2 recomputed at exit (not in the reference) */
+    double b_l2;                /* ||b||_2 */
+    double solve_ms;            /* device time of the solve (CUDA events) */
+} jetcu_mgpcg_result;
+
+/* Uniform grid descriptor == jet::Grid3 (resolution, gridSpacing, origin; src/jet/grid3.cpp:30-75). */
+typedef struct jetcu_grid {
+    uint64_t nx, ny, nz;
+    double hx, hy, hz;
+    double ox, oy, oz;
+} jetcu_grid;
+
+/* ------------------------------------------------ seam 1: linear-system level
+ * FdmBlas3 / FdmGaussSeidelSolver3 / FdmMgUtils3 building blocks, exposed so that every kernel
+ * can be checked bit-for-bit against the reference on the same inputs.  Sizes are the size of
+ * the (finer) array; vectors are nx*ny*nz doubles.                                            */
+
+/* FdmBlas3::mvm (src/jet/fdm_linear_system3.cpp:79-96). */
+int jetcu_fdm_mvm(jetcu_ctx*, uint64_t nx, uint64_t ny, uint64_t nz,
+                  const jetcu_matrix_row* A, const double* v, double* result);
+/* FdmBlas3::residual (src/jet/fdm_linear_system3.cpp:98-116): result = b - A x. */
+int jetcu_fdm_residual(jetcu_ctx*, uint64_t nx, uint64_t ny, uint64_t nz,
+                       const jetcu_matrix_row* A, const double* x, const double* b, double* result);
+/* `iterations` x FdmGaussSeidelSolver3::relaxRedBlack (src/jet/fdm_gauss_seidel_solver3.cpp:150-221), in place on x. */
+int jetcu_fdm_relax_red_black(jetcu_ctx*, uint64_t nx, uint64_t ny, uint64_t nz,
+                              const jetcu_matrix_row* A, const double* b, double sor_factor,
+                              uint32_t iterations, double* x);
+/* FdmMgUtils3::restrict (src/jet/fdm_mg_linear_system3.cpp:43-98); (nx,ny,nz) = finer size, all even. */
+int jetcu_fdm_restrict(jetcu_ctx*, uint64_t nx, uint64_t ny, uint64_t nz,
+                       const double* finer, double* coarser);
+/* FdmMgUtils3::correct (src/jet/fdm_mg_linear_system3.cpp:100-179): finer += P coarser.
+ * The reference's k-clamp tests n.y instead of n.z (:159); we implement the intended n.z test, which is
+ * identical whenever ny == nz (the only case in which the reference does not read out of bounds). */
+int jetcu_fdm_correct(jetcu_ctx*, uint64_t nx, uint64_t ny, uint64_t nz,
+                      const double* coarser, double* finer);
+/* FdmBlas3::dot (src/jet/fdm_linear_system3.cpp:49-65). Deterministic two-stage tree (not the serial order). */
+int jetcu_fdm_dot(jetcu_ctx*, uint64_t n, const double* a, const double* b, double* result);
+/* FdmBlas3::axpy (src/jet/fdm_linear_system3.cpp:67-77): result = a*x + y. */
+int jetcu_fdm_axpy(jetcu_ctx*, uint64_t n, double a, const double* x, const double* y, double* result);
+
+/* One MG V-cycle == FdmMgSolver3::solve(FdmMgLinearSystem3*) (src/jet/fdm_mg_solver3.cpp:69-74,
+ * include/jet/detail/mg-inl.h:16-68) on x (in/out, finest level) with rhs b.  A[l] is level l's matrix
+ * (level 0 = finest = nx*ny*nz, each next level halves every axis). */
+int jetcu_fdm_vcycle(jetcu_ctx*, uint64_t nx, uint64_t ny, uint64_t nz, uint32_t levels,
+                     const jetcu_matrix_row* const* A, const double* b, double* x,
+                     const jetcu_mgpcg_params* params);
+
+/* FdmMgpcgSolver3::solve(FdmMgLinearSystem3*) (src/jet/fdm_mgpcg_solver3.cpp:54-80 +
+ * include/jet/detail/cg-inl.h:18-94).  x is output only (the reference zeroes it, :61). */
+int jetcu_mgpcg_solve(jetcu_ctx*, uint64_t nx, uint64_t ny, uint64_t nz, uint32_t levels,
+                      const jetcu_matrix_row* const* A, const double* b, double* x,
+                      const jetcu_mgpcg_params* params, jetcu_mgpcg_result* result);
+
+/* Number of MG levels Jet builds for a finest resolution (FdmMgUtils3::resizeArrayWithFinest,
+ * include/jet/detail/fdm_mg_linear_system3-inl.h:34-50). */
+uint32_t jetcu_mg_num_levels(uint64_t nx, uint64_t ny, uint64_t nz, uint32_t max_levels);
+
+/* ------------------------------------------------ seam 2: pressure projection
+ * GridFractionalSinglePhasePressureSolver3::solve (src/jet/grid_fractional_single_phase_pressure_solver3.cpp:456-484)
+ * with an FdmMgpcgSolver3 installed through setLinearSystemSolver (:497-510), i.e. buildWeights (:520-636),
+ * buildSystem (:651-713, uncompressed MG path), MGPCG, applyPressureGradient (:715-765).
+ *
+ *  u_in/v_in/w_in    face-centred input velocity, sizes (nx+1,ny,nz) / (nx,ny+1,nz) / (nx,ny,nz+1)
+ *  collider_sdf      cell-centred boundary SDF (a CellCenteredScalarGrid3's data()); NULL => +kMaxD (no collider)
+ *  bnd_u/bnd_v/bnd_w boundaryVelocity sampled at the u/v/w face positions (x/y/z component resp.); NULL => 0
+ *  fluid_sdf         cell-centred fluid SDF; NULL => -kMaxD (all liquid, GridFluidSolver3::fluidSdf, src/jet/grid_fluid_solver3.cpp:313-315)
+ *  u_out/v_out/w_out in/out: faces the reference does not touch keep their incoming value (may alias the inputs)
+ *  pressure_out      nullable; == GridFractionalSinglePhasePressureSolver3::pressure()
+ */
+int jetcu_pressure_solve(jetcu_ctx*, const jetcu_grid* grid,
+                         const double* u_in, const double* v_in, const double* w_in,
+                         const double* collider_sdf,
+                         const double* bnd_u, const double* bnd_v, const double* bnd_w,
+                         const double* fluid_sdf,
+                         const jetcu_mgpcg_params* params,
+                         double* u_out, double* v_out, double* w_out,
+                         double* pressure_out, jetcu_mgpcg_result* result);
+
+/* Test/inspection hook: copies out what buildWeights/buildSystem produced in the last jetcu_pressure_solve
+ * on this ctx.  Any pointer may be NULL.  level < number of levels built. */
+int jetcu_pressure_get_system(jetcu_ctx*, uint32_t level, jetcu_matrix_row* A, double* b,
+                              float* fluid_sdf, float* u_weights, float* v_weights, float* w_weights);
+
+/* ------------------------------------------------ particle binning
+ * PointParallelHashGridSearcher3::build (src/jet/point_parallel_hash_grid_searcher3.cpp:52-146) with the
+ * key arithmetic of getHashKeyFromPosition (:232-269).  positions are AoS xyz doubles (Vector3D).
+ * The sort is STABLE, so inside a bucket points are in ascending original index, i.e. exactly the order of
+ * PointHashGridSearcher3::buckets() (src/jet/point_hash_grid_searcher3.cpp:50-69).  Empty buckets hold
+ * JETCU_EMPTY_BUCKET (== jet::kMaxSize) in both tables.  Any output may be NULL. */
+#define JETCU_EMPTY_BUCKET UINT64_MAX
+int jetcu_bin_points(jetcu_ctx*, uint64_t n, const double* positions,
+                     uint64_t res_x, uint64_t res_y, uint64_t res_z, double grid_spacing,
+                     uint64_t* keys_unsorted,   /* n: getHashKeyFromPosition(points[i]) */
+                     uint64_t* sorted_indices,  /* n: PointParallelHashGridSearcher3::sortedIndices() */
+                     uint64_t* keys_sorted,     /* n: ::keys() */
+                     uint64_t* start_table,     /* res_x*res_y*res_z: ::startIndexTable() */
+                     uint64_t* end_table);      /* ::endIndexTable() */
+
+/* ------------------------------------------------ seam 3: device-resident PIC / FLIP / APIC solver
+ * Mirrors PicSolver3 / FlipSolver3 / ApicSolver3 (src/jet/{pic,flip,apic}_solver3.cpp) driven by
+ * GridFluidSolver3::onAdvanceTimeStep (src/jet/grid_fluid_solver3.cpp:179-210).  Particles and grids stay
+ * in HBM between calls; host copies happen only in the set_* / get_* calls. */
+typedef struct jetcu_hybrid jetcu_hybrid;
+
+enum { JETCU_PIC = 0, JETCU_FLIP = 1, JETCU_APIC = 2 };
+
+/* == jet::kDirection* (include/jet/constants.h). */
+enum {
+    JETCU_DIR_LEFT = 1, JETCU_DIR_RIGHT = 2, JETCU_DIR_DOWN = 4, JETCU_DIR_UP = 8,
+    JETCU_DIR_BACK = 16, JETCU_DIR_FRONT = 32, JETCU_DIR_ALL = 63
+};
+
+typedef struct jetcu_hybrid_params {
+    jetcu_grid grid;
+    int32_t mode;                        /* JETCU_PIC / FLIP / APIC */
+    int32_t closed_domain_boundary_flag; /* GridFluidSolver3::closedDomainBoundaryFlag (default JETCU_DIR_ALL) */
+    double pic_blending_factor;          /* FlipSolver3::picBlendingFactor (default 0) */
+    double gravity[3];                   /* default (0,-9.8,0) */
+    double max_cfl;                      /* default 5 */
+    jetcu_mgpcg_params mgpcg;            /* pressure solver = fractional + MGPCG */
+} jetcu_hybrid_params;
+
+typedef struct jetcu_step_stats {
+    uint32_t pcg_iterations;
+    double pcg_last_residual;
+    double pcg_true_residual_l2;
+    double pcg_b_l2;
+    double ms_total, ms_bin, ms_p2g, ms_sdf, ms_extrapolate, ms_bc, ms_pressure, ms_g2p, ms_move;
+} jetcu_step_stats;
+
+void jetcu_hybrid_default_params(jetcu_hybrid_params* p);
+int jetcu_hybrid_create(jetcu_ctx*, const jetcu_hybrid_params* params, jetcu_hybrid** out);
+int jetcu_hybrid_destroy(jetcu_hybrid*);
+
+/* ParticleSystemData3::positions()/velocities() (AoS xyz doubles). set replaces all particles. */
+int jetcu_hybrid_set_particles(jetcu_hybrid*, uint64_t n, const double* positions, const double* velocities);
+/* Emits the lattice VolumeParticleEmitter3 + GridPointGenerator3 produce for an axis-aligned box
+ * (src/jet/volume_particle_emitter3.cpp:65-140, src/jet/grid_point_generator3.cpp:12-37; jitter 0, one shot),
+ * directly on the device, in the reference's k,j,i order.  Appends; returns the count via n_emitted. */
+int jetcu_hybrid_emit_box(jetcu_hybrid*, const double lower[3], const double upper[3], double spacing,
+                          const double initial_velocity[3], uint64_t* n_emitted);
+uint64_t jetcu_hybrid_num_particles(const jetcu_hybrid*);
+/* Returned in the caller's ORIGINAL particle order (the device keeps particles cell-sorted). */
+int jetcu_hybrid_get_particles(jetcu_hybrid*, double* positions, double* velocities);
+/* APIC affine vectors _cX,_cY,_cZ (src/jet/apic_solver3.h), original order; NULL entries skipped. */
+int jetcu_hybrid_get_affine(jetcu_hybrid*, double* cx, double* cy, double* cz);
+
+/* Collider as the grid solver sees it: cell-centred SDF (GridFractionalBoundaryConditionSolver3::onColliderUpdated,
+ * src/jet/grid_fractional_boundary_condition_solver3.cpp:244-280) + rigid-body velocity
+ * (RigidBodyCollider3::velocityAt, src/jet/rigid_body_collider3.cpp:25-28) + friction.  sdf == NULL => no collider. */
+int jetcu_hybrid_set_collider(jetcu_hybrid*, const double* collider_sdf, const double linear_velocity[3],
+                              const double angular_velocity[3], const double rotation_origin[3],
+                              double friction_coefficient);
+
+int jetcu_hybrid_set_velocity(jetcu_hybrid*, const double* u, const double* v, const double* w);
+int jetcu_hybrid_get_velocity(jetcu_hybrid*, double* u, double* v, double* w);
+int jetcu_hybrid_get_sdf(jetcu_hybrid*, double* sdf);              /* PicSolver3::signedDistanceField() */
+int jetcu_hybrid_get_pressure(jetcu_hybrid*, double* pressure);
+int jetcu_hybrid_get_markers(jetcu_hybrid*, char* um, char* vm, char* wm); /* PicSolver3::_uMarkers.. */
+
+/* GridFluidSolver3::cfl (src/jet/grid_fluid_solver3.cpp:57-72; note: no abs) and numberOfSubTimeSteps (:212-217). */
+int jetcu_hybrid_cfl(jetcu_hybrid*, double dt, double* cfl);
+int jetcu_hybrid_num_sub_steps(jetcu_hybrid*, double dt, uint32_t* n);
+
+/* One GridFluidSolver3::onAdvanceTimeStep(dt) (src/jet/grid_fluid_solver3.cpp:179-210). stats may be NULL. */
+int jetcu_hybrid_step(jetcu_hybrid*, double dt, jetcu_step_stats* stats);
+/* PhysicsAnimation::advanceTimeStep adaptive sub-stepping over one frame (src/jet/physics_animation.cpp:75-123). */
+int jetcu_hybrid_advance_frame(jetcu_hybrid*, double frame_dt, uint32_t* n_sub_steps, jetcu_step_stats* last_stats);
+
+/* Stage-level entry points == the virtuals an adapter overrides (include/jet/pic_solver3.h:75-81,
+ * include/jet/grid_fluid_solver3.h:208-240); also what the parity tests drive one by one. */
+int jetcu_hybrid_apply_boundary_condition(jetcu_hybrid*);            /* GridFluidSolver3::applyBoundaryCondition */
+int jetcu_hybrid_transfer_particles_to_grids(jetcu_hybrid*);         /* transferFromParticlesToGrids (PIC/FLIP/APIC) */
+int jetcu_hybrid_build_signed_distance_field(jetcu_hybrid*);         /* PicSolver3::buildSignedDistanceField */
+int jetcu_hybrid_extrapolate_velocity_to_air(jetcu_hybrid*);         /* PicSolver3::extrapolateVelocityToAir */
+int jetcu_hybrid_begin_advance_time_step(jetcu_hybrid*, double dt);  /* beginAdvanceTimeStep incl. PicSolver3::onBeginAdvanceTimeStep */
+int jetcu_hybrid_compute_external_forces(jetcu_hybrid*, double dt);  /* computeGravity + BC */
+int jetcu_hybrid_compute_pressure(jetcu_hybrid*, double dt, jetcu_mgpcg_result* result); /* computePressure + BC */
+int jetcu_hybrid_transfer_grids_to_particles(jetcu_hybrid*);         /* transferFromGridsToParticles */
+int jetcu_hybrid_move_particles(jetcu_hybrid*, double dt);           /* PicSolver3::moveParticles */
+int jetcu_hybrid_compute_advection(jetcu_hybrid*, double dt);        /* PicSolver3::computeAdvection */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JETCU_H_ */

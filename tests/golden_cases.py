@@ -1,0 +1,152 @@
+"""Golden-vector cases shared by the CPU (port) and GPU (jetcu) parity tests.  The .npz files under
+tests/golden/ were produced by the UNMODIFIED reference (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+
+import scenes
+from oracle_api import APIC, FLIP, PIC, Grid, HybridParams, MgpcgParams
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def close(a, b, rtol, what):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = max(float(np.abs(b).max()), 1e-300)
+    err = float(np.abs(a - b).max()) / scale
+    assert err <= rtol, "%s: relative L-inf error %.3e > %.1e" % (what, err, rtol)
+
+
+def exact(a, b, what):
+    assert np.array_equal(a, b), "%s: not bit-identical (max abs diff %g)" % (
+        what, float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max()))
+
+
+def linear_ops(api, dot_rtol=0.0):
+    g = load("linear_ops.npz")
+    A, x, b = scenes.random_system(10, 8, 8, seed=11)
+    f = np.random.default_rng(12).uniform(-1, 1, (8, 8, 12))
+    c = np.random.default_rng(13).uniform(-1, 1, (4, 4, 6))
+    exact(api.mvm(A, x), g["mvm"], "mvm")
+    exact(api.residual(A, x, b), g["residual"], "residual")
+    exact(api.relax_red_black(A, b, x, 1.5, 2), g["relax2"], "relaxRedBlack x2")
+    exact(api.restrict(f), g["restrict"], "restrict")
+    exact(api.correct(c, f), g["correct"], "correct")
+    exact(api.axpy(-0.7, x, b), g["axpy"], "axpy")
+    d = api.dot(x, b)
+    if dot_rtol == 0.0:
+        assert d == float(g["dot"])
+    else:
+        assert abs(d - float(g["dot"])) <= dot_rtol * np.abs(x * b).sum()
+
+
+def mgpcg_poisson(api, exact_bits):
+    g = load("mgpcg_poisson16.npz")
+    n, levels = 16, 3
+    Al = scenes.poisson_levels(n, levels)
+    rng = np.random.default_rng(3)
+    bb = rng.uniform(-1, 1, (n, n, n)); bb -= bb.mean()
+    x0 = rng.uniform(-1, 1, (n, n, n))
+    p = MgpcgParams.make(max_iterations=25, max_levels=levels)
+    exact(api.vcycle(Al, bb, x0, p), g["vcycle"], "V-cycle")  # no reductions inside a V-cycle: bit-exact everywhere
+    x, res = api.mgpcg_solve(Al, bb, p)
+    if exact_bits:
+        exact(x, g["x"], "mgpcg x")
+        assert res.iterations == int(g["iterations"]) and res.last_residual == float(g["last_residual"])
+    else:
+        # singular Neumann system stopped at 25 iterations (not converged): compare loosely, same iteration count
+        assert res.iterations == int(g["iterations"])
+        close(x, g["x"], 1e-6, "mgpcg x")
+
+
+def pressure_column_box(api, n, exact_bits):
+    g = load("pressure_column_box_%d.npz" % n)
+    levels = {16: 3, 32: 5}[n]
+    sc = scenes.projection_scene(n, "column", True)
+    p = MgpcgParams.make(max_iterations=200, max_levels=levels)
+    u, v, w, pr, res = api.pressure_solve(sc["grid"], sc["u"], sc["v"], sc["w"], p, collider_sdf=sc["collider_sdf"],
+                                          fluid_sdf=sc["fluid_sdf"])
+    s0 = api.pressure_get_system(sc["grid"], 0)
+    sl = api.pressure_get_system(sc["grid"], levels - 1)
+    # system build has no reductions: bit-exact for every implementation
+    exact(s0["fluid_sdf"], g["sdf0"], "fluidSdf[0]")
+    exact(s0["u_weights"], g["uw0"], "uWeights[0]")
+    exact(s0["v_weights"], g["vw0"], "vWeights[0]")
+    exact(s0["w_weights"], g["ww0"], "wWeights[0]")
+    exact(sl["fluid_sdf"], g["sdf_last"], "fluidSdf[last]")
+    exact(sl["u_weights"], g["uw_last"], "uWeights[last]")
+    for fld in ("center", "right", "up", "front"):
+        exact(s0["A"][fld], g["A0"][fld], "A[0]." + fld)
+        exact(sl["A"][fld], g["A_last"][fld], "A[last]." + fld)
+    exact(s0["b"], g["b0"], "b[0]")
+    if exact_bits:
+        for name, a in (("u", u), ("v", v), ("w", w), ("p", pr)):
+            exact(a, g[name], name)
+        assert res.iterations == int(g["iterations"])
+    else:
+        # north_star tolerance: pressure within 1e-6 relative L-inf at equal solver tolerance
+        assert float(g["true_residual"]) <= 1e-8 * float(g["b_l2"]) * 10  # the oracle itself converged
+        close(pr, g["p"], 1e-6, "pressure")
+        for name, a in (("u", u), ("v", v), ("w", w)):
+            close(a, g[name], 1e-6, name)
+        assert abs(int(res.iterations) - int(g["iterations"])) <= 1
+    return res
+
+
+def bin_points(api):
+    g = load("bin_points.npz")
+    pts = np.random.default_rng(0).uniform(-0.3, 1.3, (3000, 3))
+    r = api.bin_points(pts, (8, 8, 8), 0.11)
+    for k in ("keys_unsorted", "keys_sorted", "start_table", "end_table"):
+        exact(r[k], g[k], k)
+    si, ks, st = r["sorted_indices"], r["keys_sorted"], r["start_table"]
+    exact(g["serial_rank"][si], np.arange(len(si), dtype=np.uint64) - st[ks], "stable order == serial buckets")
+
+
+def hybrid(make_hybrid, mode, exact_bits, tol_pos=1e-5, tol_grid=1e-9):
+    name = {PIC: "pic", FLIP: "flip", APIC: "apic"}[mode]
+    g = load("hybrid_%s_8.npz" % name)
+    n = 8
+    prm = HybridParams.make(Grid.cube(n), mode=mode, mgpcg=MgpcgParams.make(max_iterations=100, max_levels=2))
+    h = make_hybrid(prm)
+    h.set_particles(scenes.dam_particles(n))
+    dt = 1 / 60.0
+    cmp_grid = (lambda a, b, w: exact(a, b, w)) if exact_bits else (lambda a, b, w: close(a, b, tol_grid, w))
+    h.begin_advance_time_step(dt)
+    for nm, a in zip(("u_begin", "v_begin", "w_begin"), h.get_velocity()):
+        cmp_grid(a, g[nm], nm)
+    exact(h.get_sdf(), g["sdf"], "particle SDF")  # exact min over the same distances: bit-exact everywhere
+    for nm, a in zip(("um", "vm", "wm"), h.get_markers()):
+        exact(a, g[nm], nm)
+    h.compute_external_forces(dt)
+    r0 = h.compute_pressure(dt)
+    if exact_bits:
+        assert r0.iterations == int(g["iterations0"])
+        exact(h.get_pressure(), g["pressure"], "pressure")
+    else:
+        close(h.get_pressure(), g["pressure"], 1e-6, "pressure")
+    for nm, a in zip(("u_press", "v_press", "w_press"), h.get_velocity()):
+        (exact if exact_bits else (lambda a, b, w: close(a, b, 1e-6, w)))(a, g[nm], nm)
+    h.compute_advection(dt)
+    pos, vel = h.get_particles()
+    domain = 1.0
+    if exact_bits:
+        exact(pos, g["pos1"], "pos after 1 step"); exact(vel, g["vel1"], "vel after 1 step")
+    else:
+        assert np.abs(pos - g["pos1"]).max() <= tol_pos * domain
+    for _ in range(4):
+        h.step(dt)
+    pos, vel = h.get_particles()
+    if exact_bits:
+        exact(pos, g["pos5"], "pos after 5 steps"); exact(vel, g["vel5"], "vel after 5 steps")
+        if mode == APIC:
+            for nm, a in zip(("cx5", "cy5", "cz5"), h.get_affine()):
+                exact(a, g[nm], nm)
+    else:
+        assert np.abs(pos - g["pos5"]).max() <= tol_pos * domain
+    h.close()

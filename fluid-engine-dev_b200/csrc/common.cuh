@@ -1,0 +1,126 @@
+// common.cuh — context, error plumbing and small device helpers shared by all jetcu translation units.
+// Target: sm_100a only (B200). Built with -fmad=false: the reference is compiled without FMA contraction and
+// every stencil here is HBM-bound, so exact IEEE replay of Jet's expressions costs nothing.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/jetcu.h"
+
+struct jetcu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    std::string error;
+    int sm_count = 148;
+    // last pressure system (kept for jetcu_pressure_get_system and reused between solves)
+    struct PressureSystem* psys = nullptr;
+    // reusable PCG workspace
+    struct MgWorkspace* mgws = nullptr;
+    // pinned staging for scalar read-backs
+    double* h_scalars = nullptr;
+    double* d_scalars = nullptr;
+    double* d_partials = nullptr;  // dot-product partial sums
+    size_t partials_cap = 0;
+};
+
+int jetcu_fail(jetcu_ctx* ctx, int code, const char* fmt, ...);
+
+#define JC_CUDA(ctx, expr)                                                                          \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return jetcu_fail((ctx), JETCU_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                \
+                              cudaGetErrorString(_e), __FILE__, __LINE__);                          \
+    } while (0)
+
+#define JC_TRY(expr)                 \
+    do {                             \
+        int _rc = (expr);            \
+        if (_rc != JETCU_OK) return _rc; \
+    } while (0)
+
+#define JC_ARG(ctx, cond)                                                                           \
+    do {                                                                                            \
+        if (!(cond)) return jetcu_fail((ctx), JETCU_ERR_INVALID_ARG, "invalid argument: %s", #cond); \
+    } while (0)
+
+// Every kernel launch goes through this so that jetcu_launch_count() is an honest count.
+#define JC_LAUNCH(ctx, kernel, grid, block, smem, ...)                                              \
+    do {                                                                                            \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                            \
+        (ctx)->launches++;                                                                          \
+        cudaError_t _e = cudaPeekAtLastError();                                                     \
+        if (_e != cudaSuccess)                                                                      \
+            return jetcu_fail((ctx), JETCU_ERR_CUDA, "launch of %s failed: %s (%s:%d)", #kernel,    \
+                              cudaGetErrorString(_e), __FILE__, __LINE__);                          \
+    } while (0)
+
+// Stream-ordered device allocation (cudaMallocAsync pool of the ctx's device).
+template <typename T>
+static inline int jc_alloc(jetcu_ctx* ctx, T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMallocAsync((void**)p, count * sizeof(T), ctx->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return jetcu_fail(ctx, e == cudaErrorMemoryAllocation ? JETCU_ERR_OOM : JETCU_ERR_CUDA,
+                          "cudaMallocAsync(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    }
+    return JETCU_OK;
+}
+
+template <typename T>
+static inline void jc_free(jetcu_ctx* ctx, T*& p) {
+    if (p) cudaFreeAsync((void*)p, ctx->stream);
+    p = nullptr;
+}
+
+template <typename T>
+static inline int jc_h2d(jetcu_ctx* ctx, T* dst, const T* src, size_t count) {
+    JC_CUDA(ctx, cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return JETCU_OK;
+}
+
+template <typename T>
+static inline int jc_d2h(jetcu_ctx* ctx, T* dst, const T* src, size_t count) {
+    JC_CUDA(ctx, cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    return JETCU_OK;
+}
+
+template <typename T>
+static inline int jc_d2d(jetcu_ctx* ctx, T* dst, const T* src, size_t count) {
+    JC_CUDA(ctx, cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+    return JETCU_OK;
+}
+
+template <typename T>
+static inline int jc_zero(jetcu_ctx* ctx, T* dst, size_t count) {
+    JC_CUDA(ctx, cudaMemsetAsync(dst, 0, count * sizeof(T), ctx->stream));
+    return JETCU_OK;
+}
+
+static inline int jc_sync(jetcu_ctx* ctx) {
+    JC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return JETCU_OK;
+}
+
+static inline unsigned jc_blocks(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+// Matrix in structure-of-arrays form: the device layout of Jet's FdmMatrix3 (AoS 32-byte rows on the host).
+// Four contiguous nx*ny*nz double planes => every stencil load is a coalesced 8-byte access.
+struct MatSoA {
+    double* center = nullptr;
+    double* right = nullptr;
+    double* up = nullptr;
+    double* front = nullptr;
+};
+
+struct Dim3i {
+    int nx, ny, nz;
+    __host__ __device__ size_t n() const { return (size_t)nx * ny * nz; }
+};

@@ -1,0 +1,400 @@
+// fdm.cu — sm_100a kernels for Jet's FDM linear-system chain and the MGPCG driver.
+//
+// Every kernel replays the reference's floating-point expression order (cited per kernel) and the TU is built
+// with -fmad=false, so mvm / residual / red-black SOR / restrict / correct are BIT-IDENTICAL to the CPU path.
+// Only the dot product differs (tree instead of a 16M-long serial chain) — deterministic, fixed shape.
+//
+// Device layout: matrix as 4 SoA planes (MatSoA), vectors as plain nx*ny*nz doubles, x fastest.
+#include "fdm.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+
+// ------------------------------------------------------------------------------------------------ AoS <-> SoA
+__global__ void k_aos_to_soa(const jetcu_matrix_row* __restrict__ aos, double* __restrict__ c, double* __restrict__ r,
+                             double* __restrict__ u, double* __restrict__ f, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double2* p = reinterpret_cast<const double2*>(aos + i);
+    double2 a = p[0], b = p[1];
+    c[i] = a.x; r[i] = a.y; u[i] = b.x; f[i] = b.y;
+}
+
+__global__ void k_soa_to_aos(const double* __restrict__ c, const double* __restrict__ r, const double* __restrict__ u,
+                             const double* __restrict__ f, jetcu_matrix_row* __restrict__ aos, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double2* p = reinterpret_cast<double2*>(aos + i);
+    p[0] = make_double2(c[i], r[i]);
+    p[1] = make_double2(u[i], f[i]);
+}
+
+int fdm_alloc_mat(jetcu_ctx* ctx, MatSoA* A, size_t n) {
+    double* base;
+    JC_TRY(jc_alloc(ctx, &base, 4 * n));
+    A->center = base; A->right = base + n; A->up = base + 2 * n; A->front = base + 3 * n;
+    return JETCU_OK;
+}
+
+void fdm_free_mat(jetcu_ctx* ctx, MatSoA* A) {
+    jc_free(ctx, A->center);
+    A->right = A->up = A->front = nullptr;
+}
+
+int fdm_aos_to_soa(jetcu_ctx* ctx, const jetcu_matrix_row* d_aos, MatSoA A, size_t n) {
+    JC_LAUNCH(ctx, k_aos_to_soa, jc_blocks(n, 256), 256, 0, d_aos, A.center, A.right, A.up, A.front, n);
+    return JETCU_OK;
+}
+
+int fdm_soa_to_aos(jetcu_ctx* ctx, MatSoA A, jetcu_matrix_row* d_aos, size_t n) {
+    JC_LAUNCH(ctx, k_soa_to_aos, jc_blocks(n, 256), 256, 0, A.center, A.right, A.up, A.front, d_aos, n);
+    return JETCU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ stencils
+#define BX 64
+#define BY 4
+
+static inline dim3 grid3(Dim3i d) { return dim3((d.nx + BX - 1) / BX, (d.ny + BY - 1) / BY, d.nz); }
+
+// The six off-diagonal products in the reference's order -i,+i,-j,+j,-k,+k
+// (FdmBlas3::mvm, src/jet/fdm_linear_system3.cpp:79-96; out-of-range terms are literal 0.0).
+struct Offdiag {
+    double t[6];
+};
+
+__device__ __forceinline__ Offdiag offdiag_terms(const MatSoA& A, const double* __restrict__ v, int i, int j, int k,
+                                                 int nx, int ny, int nz, size_t c) {
+    const size_t sy = (size_t)nx, sz = (size_t)nx * ny;
+    Offdiag o;
+    o.t[0] = (i > 0) ? A.right[c - 1] * v[c - 1] : 0.0;
+    o.t[1] = (i + 1 < nx) ? A.right[c] * v[c + 1] : 0.0;
+    o.t[2] = (j > 0) ? A.up[c - sy] * v[c - sy] : 0.0;
+    o.t[3] = (j + 1 < ny) ? A.up[c] * v[c + sy] : 0.0;
+    o.t[4] = (k > 0) ? A.front[c - sz] * v[c - sz] : 0.0;
+    o.t[5] = (k + 1 < nz) ? A.front[c] * v[c + sz] : 0.0;
+    return o;
+}
+
+__global__ void __launch_bounds__(BX* BY) k_mvm(MatSoA A, const double* __restrict__ v, double* __restrict__ out,
+                                                int nx, int ny, int nz) {
+    int i = blockIdx.x * BX + threadIdx.x, j = blockIdx.y * BY + threadIdx.y, k = blockIdx.z;
+    if (i >= nx || j >= ny) return;
+    size_t c = ((size_t)k * ny + j) * nx + i;
+    Offdiag o = offdiag_terms(A, v, i, j, k, nx, ny, nz, c);
+    out[c] = A.center[c] * v[c] + o.t[0] + o.t[1] + o.t[2] + o.t[3] + o.t[4] + o.t[5];
+}
+
+// FdmBlas3::residual, src/jet/fdm_linear_system3.cpp:98-116.
+__global__ void __launch_bounds__(BX* BY) k_residual(MatSoA A, const double* __restrict__ x,
+                                                     const double* __restrict__ b, double* __restrict__ out, int nx,
+                                                     int ny, int nz) {
+    int i = blockIdx.x * BX + threadIdx.x, j = blockIdx.y * BY + threadIdx.y, k = blockIdx.z;
+    if (i >= nx || j >= ny) return;
+    size_t c = ((size_t)k * ny + j) * nx + i;
+    Offdiag o = offdiag_terms(A, x, i, j, k, nx, ny, nz, c);
+    out[c] = b[c] - A.center[c] * x[c] - o.t[0] - o.t[1] - o.t[2] - o.t[3] - o.t[4] - o.t[5];
+}
+
+// One colour of FdmGaussSeidelSolver3::relaxRedBlack, src/jet/fdm_gauss_seidel_solver3.cpp:150-221.
+// Each thread owns the cell of the requested colour inside the x-pair (2t, 2t+1).
+__global__ void __launch_bounds__(BX* BY) k_relax_colour(MatSoA A, const double* __restrict__ b, double* __restrict__ x,
+                                                         double w, int colour, int nx, int ny, int nz) {
+    int j = blockIdx.y * BY + threadIdx.y, k = blockIdx.z;
+    int i = 2 * (blockIdx.x * BX + threadIdx.x) + ((j + k + colour) & 1);
+    if (i >= nx || j >= ny) return;
+    size_t c = ((size_t)k * ny + j) * nx + i;
+    Offdiag o = offdiag_terms(A, x, i, j, k, nx, ny, nz, c);
+    double r = o.t[0] + o.t[1] + o.t[2] + o.t[3] + o.t[4] + o.t[5];
+    x[c] = (1.0 - w) * x[c] + w * (b[c] - r) / A.center[c];
+}
+
+int fdm_mvm(jetcu_ctx* ctx, Dim3i d, MatSoA A, const double* v, double* out) {
+    JC_LAUNCH(ctx, k_mvm, grid3(d), dim3(BX, BY), 0, A, v, out, d.nx, d.ny, d.nz);
+    return JETCU_OK;
+}
+
+int fdm_residual(jetcu_ctx* ctx, Dim3i d, MatSoA A, const double* x, const double* b, double* out) {
+    JC_LAUNCH(ctx, k_residual, grid3(d), dim3(BX, BY), 0, A, x, b, out, d.nx, d.ny, d.nz);
+    return JETCU_OK;
+}
+
+int fdm_relax_rb(jetcu_ctx* ctx, Dim3i d, MatSoA A, const double* b, double sor, unsigned iterations, double* x) {
+    dim3 grid(((d.nx + 1) / 2 + BX - 1) / BX, (d.ny + BY - 1) / BY, d.nz);
+    for (unsigned it = 0; it < iterations; ++it) {
+        JC_LAUNCH(ctx, k_relax_colour, grid, dim3(BX, BY), 0, A, b, x, sor, 0, d.nx, d.ny, d.nz);
+        JC_LAUNCH(ctx, k_relax_colour, grid, dim3(BX, BY), 0, A, b, x, sor, 1, d.nx, d.ny, d.nz);
+    }
+    return JETCU_OK;
+}
+
+// FdmMgUtils3::restrict, src/jet/fdm_mg_linear_system3.cpp:43-98: 4x4x4 (1,3,3,1)/8 tensor filter with edge clamp;
+// accumulation z-outer, y, x-inner; w = (kx*ky)*kz.
+__global__ void __launch_bounds__(BX* BY) k_restrict(const double* __restrict__ finer, double* __restrict__ coarser,
+                                                     int cnx, int cny, int cnz) {
+    int i = blockIdx.x * BX + threadIdx.x, j = blockIdx.y * BY + threadIdx.y, k = blockIdx.z;
+    if (i >= cnx || j >= cny) return;
+    const double kern[4] = {0.125, 0.375, 0.375, 0.125};
+    int iI[4] = {(i > 0) ? 2 * i - 1 : 2 * i, 2 * i, 2 * i + 1, (i + 1 < cnx) ? 2 * i + 2 : 2 * i + 1};
+    int jI[4] = {(j > 0) ? 2 * j - 1 : 2 * j, 2 * j, 2 * j + 1, (j + 1 < cny) ? 2 * j + 2 : 2 * j + 1};
+    int kI[4] = {(k > 0) ? 2 * k - 1 : 2 * k, 2 * k, 2 * k + 1, (k + 1 < cnz) ? 2 * k + 2 : 2 * k + 1};
+    const size_t fnx = 2 * (size_t)cnx, fny = 2 * (size_t)cny;
+    double sum = 0.0;
+#pragma unroll
+    for (int z = 0; z < 4; ++z)
+#pragma unroll
+        for (int y = 0; y < 4; ++y)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                double w = kern[x] * kern[y] * kern[z];
+                sum += w * finer[((size_t)kI[z] * fny + jI[y]) * fnx + iI[x]];
+            }
+    coarser[((size_t)k * cny + j) * cnx + i] = sum;
+}
+
+// FdmMgUtils3::correct, src/jet/fdm_mg_linear_system3.cpp:100-179: finer += sum_{z,y,x} ((wx*wy)*wz)*coarse.
+// The k-clamp uses nz (the reference tests n.y, :159 — identical for ny == nz, out of bounds otherwise).
+__global__ void __launch_bounds__(BX* BY) k_correct(const double* __restrict__ coarser, double* __restrict__ finer,
+                                                    int nx, int ny, int nz) {
+    int i = blockIdx.x * BX + threadIdx.x, j = blockIdx.y * BY + threadIdx.y, k = blockIdx.z;
+    if (i >= nx || j >= ny) return;
+    int iI[2], jI[2], kI[2];
+    double iW[2], jW[2], kW[2];
+    int ci = i / 2, cj = j / 2, ck = k / 2;
+    if ((i & 1) == 0) { iI[0] = (i > 1) ? ci - 1 : ci; iI[1] = ci; iW[0] = 0.25; iW[1] = 0.75; }
+    else { iI[0] = ci; iI[1] = (i + 1 < nx) ? ci + 1 : ci; iW[0] = 0.75; iW[1] = 0.25; }
+    if ((j & 1) == 0) { jI[0] = (j > 1) ? cj - 1 : cj; jI[1] = cj; jW[0] = 0.25; jW[1] = 0.75; }
+    else { jI[0] = cj; jI[1] = (j + 1 < ny) ? cj + 1 : cj; jW[0] = 0.75; jW[1] = 0.25; }
+    if ((k & 1) == 0) { kI[0] = (k > 1) ? ck - 1 : ck; kI[1] = ck; kW[0] = 0.25; kW[1] = 0.75; }
+    else { kI[0] = ck; kI[1] = (k + 1 < nz) ? ck + 1 : ck; kW[0] = 0.75; kW[1] = 0.25; }
+    const size_t cnx = (size_t)nx / 2, cny = (size_t)ny / 2;
+    size_t f = ((size_t)k * ny + j) * nx + i;
+    double acc = finer[f];
+#pragma unroll
+    for (int z = 0; z < 2; ++z)
+#pragma unroll
+        for (int y = 0; y < 2; ++y)
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+                double w = iW[x] * jW[y] * kW[z] * coarser[((size_t)kI[z] * cny + jI[y]) * cnx + iI[x]];
+                acc += w;
+            }
+    finer[f] = acc;
+}
+
+int fdm_restrict(jetcu_ctx* ctx, Dim3i fine, const double* finer, double* coarser) {
+    Dim3i c{fine.nx / 2, fine.ny / 2, fine.nz / 2};
+    JC_LAUNCH(ctx, k_restrict, grid3(c), dim3(BX, BY), 0, finer, coarser, c.nx, c.ny, c.nz);
+    return JETCU_OK;
+}
+
+int fdm_residual_restrict(jetcu_ctx* ctx, Dim3i fine, MatSoA A, const double* x, const double* b, double* buf,
+                          double* coarser) {
+    JC_TRY(fdm_residual(ctx, fine, A, x, b, buf));
+    return fdm_restrict(ctx, fine, buf, coarser);
+}
+
+int fdm_correct(jetcu_ctx* ctx, Dim3i fine, const double* coarser, double* finer) {
+    JC_LAUNCH(ctx, k_correct, grid3(fine), dim3(BX, BY), 0, coarser, finer, fine.nx, fine.ny, fine.nz);
+    return JETCU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ BLAS-1
+#define DOT_BLOCK 256
+#define DOT_GRID 592  // 4 CTAs per SM x 148 SMs; fixed so the reduction tree (and the result bits) never change
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double s[DOT_BLOCK / 32];
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x < 32) {
+        r = (threadIdx.x < DOT_BLOCK / 32) ? s[threadIdx.x] : 0.0;
+        r = warp_sum(r);
+    }
+    return r;  // valid in thread 0
+}
+
+__global__ void __launch_bounds__(DOT_BLOCK) k_dot_partial(const double* __restrict__ a, const double* __restrict__ b,
+                                                           double* __restrict__ partials, size_t n) {
+    double acc = 0.0;
+    for (size_t i = (size_t)blockIdx.x * DOT_BLOCK + threadIdx.x; i < n; i += (size_t)DOT_GRID * DOT_BLOCK)
+        acc += a[i] * b[i];
+    double r = block_sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = r;
+}
+
+__global__ void __launch_bounds__(DOT_BLOCK) k_dot_final(const double* __restrict__ partials, double* __restrict__ out) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < DOT_GRID; i += DOT_BLOCK) acc += partials[i];
+    double r = block_sum(acc);
+    if (threadIdx.x == 0) out[0] = r;
+}
+
+int fdm_dot(jetcu_ctx* ctx, size_t n, const double* a, const double* b, double* d_result) {
+    JC_LAUNCH(ctx, k_dot_partial, DOT_GRID, DOT_BLOCK, 0, a, b, ctx->d_partials, n);
+    JC_LAUNCH(ctx, k_dot_final, 1, DOT_BLOCK, 0, ctx->d_partials, d_result);
+    return JETCU_OK;
+}
+
+// FdmBlas3::axpy, src/jet/fdm_linear_system3.cpp:67-77.
+__global__ void k_axpy(double a, const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ out,
+                       size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a * x[i] + y[i];
+}
+
+__global__ void k_pcg_update(double alpha, const double* __restrict__ d, const double* __restrict__ q,
+                             double* __restrict__ x, double* __restrict__ r, int update_r, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    x[i] = alpha * d[i] + x[i];
+    if (update_r) r[i] = -alpha * q[i] + r[i];
+}
+
+int fdm_axpy(jetcu_ctx* ctx, size_t n, double a, const double* x, const double* y, double* out) {
+    JC_LAUNCH(ctx, k_axpy, jc_blocks(n, 256), 256, 0, a, x, y, out, n);
+    return JETCU_OK;
+}
+
+int fdm_pcg_update(jetcu_ctx* ctx, size_t n, double alpha, const double* d, const double* q, double* x, double* r,
+                   bool update_r) {
+    JC_LAUNCH(ctx, k_pcg_update, jc_blocks(n, 256), 256, 0, alpha, d, q, x, r, update_r ? 1 : 0, n);
+    return JETCU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ MG + PCG
+int mg_alloc_vectors(jetcu_ctx* ctx, MgLevels* mg) {
+    for (int l = 0; l < mg->levels; ++l) {
+        size_t n = mg->dims[l].n();
+        JC_TRY(jc_alloc(ctx, &mg->x[l], n));
+        JC_TRY(jc_alloc(ctx, &mg->b[l], n));
+        JC_TRY(jc_alloc(ctx, &mg->buf[l], n));
+    }
+    return JETCU_OK;
+}
+
+void mg_free(jetcu_ctx* ctx, MgLevels* mg) {
+    for (int l = 0; l < mg->levels; ++l) {
+        jc_free(ctx, mg->x[l]); jc_free(ctx, mg->b[l]); jc_free(ctx, mg->buf[l]);
+        if (mg->owns_A) fdm_free_mat(ctx, &mg->A[l]);
+    }
+    mg->levels = 0;
+}
+
+// internal::mgVCycle, include/jet/detail/mg-inl.h:16-68, with FdmMgSolver3's relax lambdas
+// (src/jet/fdm_mg_solver3.cpp:26-49).  The residual + l2Norm the reference evaluates on the way up only feed
+// MgResult.lastResidualNorm, which FdmMgpcgSolver3::Preconditioner discards; they never touch x and are skipped.
+int mg_vcycle(jetcu_ctx* ctx, MgLevels* mg, const jetcu_mgpcg_params* p, int l) {
+    Dim3i d = mg->dims[l];
+    JC_TRY(fdm_relax_rb(ctx, d, mg->A[l], mg->b[l], p->sor_factor, p->n_restriction, mg->x[l]));
+    if (l + 1 < mg->levels) {
+        JC_TRY(fdm_residual_restrict(ctx, d, mg->A[l], mg->x[l], mg->b[l], mg->buf[l], mg->b[l + 1]));
+        JC_TRY(jc_zero(ctx, mg->x[l + 1], mg->dims[l + 1].n()));
+        JC_TRY(mg_vcycle(ctx, mg, p, l + 1));
+        JC_TRY(fdm_correct(ctx, d, mg->x[l + 1], mg->x[l]));
+        JC_TRY(fdm_relax_rb(ctx, d, mg->A[l], mg->b[l], p->sor_factor, l > 0 ? p->n_correction : p->n_final, mg->x[l]));
+    } else {
+        JC_TRY(fdm_relax_rb(ctx, d, mg->A[l], mg->b[l], p->sor_factor, p->n_coarsest, mg->x[l]));
+    }
+    return JETCU_OK;
+}
+
+// FdmMgpcgSolver3::Preconditioner::solve, src/jet/fdm_mgpcg_solver3.cpp:21-36: the V-cycle's initial guess is the
+// CURRENT content of the output vector.  We run the cycle directly on (b_in, x_inout) as level 0's b and x.
+static int precondition(jetcu_ctx* ctx, MgLevels* mg, const jetcu_mgpcg_params* p, double* b_in, double* x_inout) {
+    double* saved_x = mg->x[0];
+    double* saved_b = mg->b[0];
+    mg->x[0] = x_inout;
+    mg->b[0] = b_in;
+    int rc = mg_vcycle(ctx, mg, p, 0);
+    mg->x[0] = saved_x;
+    mg->b[0] = saved_b;
+    return rc;
+}
+
+static int read_scalar(jetcu_ctx* ctx, const double* d, double* out) {
+    JC_TRY(jc_d2h(ctx, ctx->h_scalars, d, 1));
+    JC_TRY(jc_sync(ctx));
+    *out = ctx->h_scalars[0];
+    return JETCU_OK;
+}
+
+// pcg<FdmBlas3, Preconditioner>, include/jet/detail/cg-inl.h:18-94, as called by FdmMgpcgSolver3::solve
+// (src/jet/fdm_mgpcg_solver3.cpp:54-80): x = 0 first; exit test sigma > tol^2 (also leaves on sigma <= 0);
+// residual recomputed when iter % 50 == 0 (iter > 0) or after sigma rose.
+int mgpcg_solve_device(jetcu_ctx* ctx, MgLevels* mg, const double* b, double* x, const jetcu_mgpcg_params* p,
+                       jetcu_mgpcg_result* result) {
+    if (!p->use_red_black)
+        return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED,
+                          "lexicographic Gauss-Seidel is inherently serial; use useRedBlackOrdering = true");
+    const Dim3i d = mg->dims[0];
+    const size_t n = d.n();
+    double *r, *dd, *q, *s;
+    JC_TRY(jc_alloc(ctx, &r, n)); JC_TRY(jc_alloc(ctx, &dd, n)); JC_TRY(jc_alloc(ctx, &q, n)); JC_TRY(jc_alloc(ctx, &s, n));
+    cudaEvent_t e0, e1;
+    JC_CUDA(ctx, cudaEventCreate(&e0)); JC_CUDA(ctx, cudaEventCreate(&e1));
+    JC_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+
+    JC_TRY(jc_zero(ctx, x, n)); JC_TRY(jc_zero(ctx, dd, n)); JC_TRY(jc_zero(ctx, q, n)); JC_TRY(jc_zero(ctx, s, n));
+    JC_TRY(fdm_residual(ctx, d, mg->A[0], x, b, r));
+    JC_TRY(precondition(ctx, mg, p, r, dd));
+    double sigmaNew;
+    JC_TRY(fdm_dot(ctx, n, r, dd, ctx->d_scalars));
+    JC_TRY(read_scalar(ctx, ctx->d_scalars, &sigmaNew));
+
+    unsigned iter = 0;
+    bool trigger = false;
+    while (sigmaNew > p->tolerance * p->tolerance && iter < p->max_iterations) {
+        JC_TRY(fdm_mvm(ctx, d, mg->A[0], dd, q));
+        double dq;
+        JC_TRY(fdm_dot(ctx, n, dd, q, ctx->d_scalars));
+        JC_TRY(read_scalar(ctx, ctx->d_scalars, &dq));
+        double alpha = sigmaNew / dq;
+        bool recompute = trigger || (iter % 50 == 0 && iter > 0);
+        JC_TRY(fdm_pcg_update(ctx, n, alpha, dd, q, x, r, !recompute));
+        if (recompute) {
+            JC_TRY(fdm_residual(ctx, d, mg->A[0], x, b, r));
+            trigger = false;
+        }
+        JC_TRY(precondition(ctx, mg, p, r, s));
+        double sigmaOld = sigmaNew;
+        JC_TRY(fdm_dot(ctx, n, r, s, ctx->d_scalars));
+        JC_TRY(read_scalar(ctx, ctx->d_scalars, &sigmaNew));
+        if (sigmaNew > sigmaOld) trigger = true;
+        double beta = sigmaNew / sigmaOld;
+        JC_TRY(fdm_axpy(ctx, n, beta, dd, s, dd));
+        ++iter;
+    }
+    JC_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+
+    if (result) {
+        result->iterations = iter;
+        result->last_residual = sqrt(fabs(sigmaNew));
+        result->returned = (result->last_residual <= p->tolerance || iter < p->max_iterations) ? 1 : 0;
+        double rr, bb;
+        JC_TRY(fdm_residual(ctx, d, mg->A[0], x, b, r));
+        JC_TRY(fdm_dot(ctx, n, r, r, ctx->d_scalars));
+        JC_TRY(fdm_dot(ctx, n, b, b, ctx->d_scalars + 1));
+        JC_TRY(jc_d2h(ctx, ctx->h_scalars, ctx->d_scalars, 2));
+        JC_TRY(jc_sync(ctx));
+        rr = ctx->h_scalars[0]; bb = ctx->h_scalars[1];
+        result->true_residual_l2 = sqrt(rr);
+        result->b_l2 = sqrt(bb);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        result->solve_ms = ms;
+    } else {
+        JC_TRY(jc_sync(ctx));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    jc_free(ctx, r); jc_free(ctx, dd); jc_free(ctx, q); jc_free(ctx, s);
+    return JETCU_OK;
+}

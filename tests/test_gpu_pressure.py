@@ -1,0 +1,93 @@
+"""GPU parity, seam 2: GridFractionalSinglePhasePressureSolver3 + MGPCG through jetcu_pressure_solve.
+System build (sdf, weights, A, b on every level) must be BIT-EXACT; pressure within 1e-6 relative L-inf
+(BASELINE.json north_star) on inputs where the oracle's true residual is small."""
+import numpy as np
+import pytest
+
+import golden_cases as gc
+import scenes
+from gpu_common import checker, jetcu_or_fail
+from oracle_api import MgpcgParams
+from test_oracle_known_answers import check_free_surface, check_relax_decreases, check_vcycle_reduces, check_bucket_counts
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def jc():
+    return jetcu_or_fail()
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return checker()
+
+
+def test_reference_known_answers(jc):
+    check_free_surface(jc)       # pressure = 1.5 - j, velocity -> 0
+    check_relax_decreases(jc)
+    check_vcycle_reduces(jc)
+    check_bucket_counts(jc)
+
+
+@pytest.mark.parametrize("n", [16, 32])
+def test_golden_pressure_column_box(jc, n):
+    gc.pressure_column_box(jc, n, exact_bits=False)
+
+
+@pytest.mark.parametrize("n,kind,collider,levels", [(16, "slab", False, 3), (24, "column", False, 9),
+                                                     (32, "slab", True, 4), (64, "column", True, 5),
+                                                     (64, "slab", False, 5), (96, "column", True, 5)])
+def test_pressure_vs_oracle(jc, oracle, n, kind, collider, levels):
+    sc = scenes.projection_scene(n, kind, collider)
+    p = MgpcgParams.make(max_iterations=200, max_levels=levels)
+    kw = dict(collider_sdf=sc["collider_sdf"], fluid_sdf=sc["fluid_sdf"])
+    u0, v0, w0, p0, r0 = jc.pressure_solve(sc["grid"], sc["u"], sc["v"], sc["w"], p, **kw)
+    u1, v1, w1, p1, r1 = oracle.pressure_solve(sc["grid"], sc["u"], sc["v"], sc["w"], p, **kw)
+    nl = jc.mg_num_levels(n, n, n, levels)
+    assert nl == oracle.mg_num_levels(n, n, n, levels)
+    for l in range(nl):
+        s0, s1 = jc.pressure_get_system(sc["grid"], l), oracle.pressure_get_system(sc["grid"], l)
+        for key in ("fluid_sdf", "u_weights", "v_weights", "w_weights"):
+            assert np.array_equal(s0[key], s1[key]), (l, key)
+        for fld in ("center", "right", "up", "front"):
+            assert np.array_equal(s0["A"][fld], s1["A"][fld]), (l, fld)
+        if l == 0:
+            assert np.array_equal(s0["b"], s1["b"])
+    if r1.true_residual_l2 <= 1e-8 * r1.b_l2 * 10:  # oracle converged: the 1e-6 pressure bar applies
+        assert np.abs(p0 - p1).max() <= 1e-6 * np.abs(p1).max()
+        assert np.abs(v0 - v1).max() <= 1e-6 * max(np.abs(v1).max(), 1.0)
+        assert abs(int(r0.iterations) - int(r1.iterations)) <= 1
+    else:  # early exit quirk (sigma <= 0): both must leave at the same iteration with the same sigma to 1e-6
+        assert int(r0.iterations) == int(r1.iterations)
+
+
+def test_pressure_moving_boundary_and_defaults(jc, oracle):
+    n = 16
+    sc = scenes.projection_scene(n, "slab", True)
+    g = sc["grid"]
+    rng = np.random.default_rng(5)
+    u = rng.uniform(-1, 1, sc["u"].shape); v = rng.uniform(-1, 1, sc["v"].shape); w = rng.uniform(-1, 1, sc["w"].shape)
+    bnd = (np.full(sc["u"].shape, 0.25), np.full(sc["v"].shape, -0.5), np.full(sc["w"].shape, 0.125))
+    p = MgpcgParams.make(max_iterations=20, max_levels=3)
+    for kw in (dict(), dict(collider_sdf=sc["collider_sdf"], bnd=bnd, fluid_sdf=sc["fluid_sdf"]),
+               dict(collider_sdf=sc["collider_sdf"], bnd=bnd)):
+        r0 = jc.pressure_solve(g, u, v, w, p, **kw)
+        r1 = oracle.pressure_solve(g, u, v, w, p, **kw)
+        assert np.array_equal(jc.pressure_get_system(g, 0)["b"], oracle.pressure_get_system(g, 0)["b"])
+        assert int(r0[4].iterations) == int(r1[4].iterations)
+        assert np.abs(r0[3] - r1[3]).max() <= 1e-6 * max(np.abs(r1[3]).max(), 1e-30)
+
+
+def test_pressure_output_keeps_untouched_faces(jc, oracle):
+    """Faces the reference does not update keep the OUTPUT grid's incoming values (input != output)."""
+    n = 16
+    sc = scenes.projection_scene(n, "column", True)
+    p = MgpcgParams.make(max_iterations=50, max_levels=3)
+    out = tuple(np.full(a.shape, 7.0) for a in (sc["u"], sc["v"], sc["w"]))
+    kw = dict(collider_sdf=sc["collider_sdf"], fluid_sdf=sc["fluid_sdf"], out=out)
+    r0 = jc.pressure_solve(sc["grid"], sc["u"], sc["v"], sc["w"], p, **kw)
+    r1 = oracle.pressure_solve(sc["grid"], sc["u"], sc["v"], sc["w"], p, **kw)
+    for a, b in zip(r0[:3], r1[:3]):
+        assert np.array_equal(a == 7.0, b == 7.0)
+        assert np.abs(a - b).max() <= 1e-6

@@ -1,0 +1,1069 @@
+// hybrid.cu — device-resident PIC / FLIP / APIC solver (seam 3 of include/jetcu.h).
+//
+// Mirrors GridFluidSolver3::onAdvanceTimeStep (src/jet/grid_fluid_solver3.cpp:179-210) with the PicSolver3 /
+// FlipSolver3 / ApicSolver3 stage overrides (src/jet/{pic,flip,apic}_solver3.cpp).  B200-first design:
+//   * particles live in HBM as SoA doubles, CELL-SORTED every step by a one-pass counting sort (histogram ->
+//     scan -> scatter -> per-cell order fix-up by original index), so that
+//   * P2G is a deterministic GATHER per face over the 18 neighbouring cells' contiguous particle ranges
+//     (no atomics on FP64 data; fixed summation order: cells z,y,x then ascending original index),
+//   * the particle SDF is a pruned per-cell gather over the same ranges (exact min => bit-exact),
+//   * G2P / advection read the grids with cell-coherent (L2-resident) access.
+// Parity notes: everything except the P2G summation order (reference: global particle index order) replays
+// the reference's expressions; P2G agrees to rounding (documented tolerance 1e-12 relative in the tests).
+#include <math.h>
+#include <string.h>
+
+#include "particles.cuh"
+#include "pressure.cuh"
+#include "sampling.cuh"
+
+#define NATTR 15  // px,py,pz, vx,vy,vz, cX(3), cY(3), cZ(3)
+
+struct jetcu_hybrid {
+    jetcu_ctx* ctx = nullptr;
+    jetcu_hybrid_params P{};
+    int nx = 0, ny = 0, nz = 0;
+    size_t nu = 0, nv = 0, nw = 0, nc = 0;
+    double *u = nullptr, *v = nullptr, *w = nullptr;
+    char *um = nullptr, *vm = nullptr, *wm = nullptr;
+    char *valid0 = nullptr, *valid1 = nullptr;
+    double* sdf = nullptr;
+    float *ud = nullptr, *vd = nullptr, *wd = nullptr;
+    // particles
+    uint64_t np = 0, cap = 0;
+    int nattr = 6;
+    double* attr[2][NATTR] = {};
+    uint32_t* orig[2] = {};
+    int cur = 0;
+    uint32_t *cell_of = nullptr, *rank = nullptr, *perm = nullptr;
+    uint32_t* cell_start = nullptr;  // nc + 1
+    bool binned = false;
+    PressureSystem ps;
+    jetcu_mgpcg_result last{};
+    cudaEvent_t ev[12] = {};
+};
+
+struct GridD {
+    int nx, ny, nz;
+    double hx, hy, hz, ox, oy, oz;
+};
+
+static GridD gridd(const jetcu_hybrid* h) {
+    const jetcu_grid& g = h->P.grid;
+    return GridD{h->nx, h->ny, h->nz, g.hx, g.hy, g.hz, g.ox, g.oy, g.oz};
+}
+
+// Component grid (AXIS = 0/1/2 -> u/v/w): size and data origin (src/jet/face_centered_grid3.cpp:430-444).
+template <int AXIS>
+__device__ __forceinline__ void comp_grid(const GridD& g, int* sx, int* sy, int* sz, double* ox, double* oy, double* oz) {
+    *sx = g.nx + (AXIS == 0); *sy = g.ny + (AXIS == 1); *sz = g.nz + (AXIS == 2);
+    *ox = g.ox + 0.5 * (AXIS == 0 ? 0.0 : g.hx);
+    *oy = g.oy + 0.5 * (AXIS == 1 ? 0.0 : g.hy);
+    *oz = g.oz + 0.5 * (AXIS == 2 ? 0.0 : g.hz);
+}
+
+__device__ __forceinline__ GridView comp_view(const GridD& g, int axis, const double* data) {
+    GridView v;
+    v.data = data;
+    v.nx = g.nx + (axis == 0); v.ny = g.ny + (axis == 1); v.nz = g.nz + (axis == 2);
+    v.hx = g.hx; v.hy = g.hy; v.hz = g.hz;
+    v.ox = g.ox + 0.5 * (axis == 0 ? 0.0 : g.hx);
+    v.oy = g.oy + 0.5 * (axis == 1 ? 0.0 : g.hy);
+    v.oz = g.oz + 0.5 * (axis == 2 ? 0.0 : g.hz);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------ cell sort
+// Owning cell of a particle (our own binning for locality, NOT the reference's hash grid): clamped floor.
+__device__ __forceinline__ int cell_coord(double x, double o, double ih, int n) {
+    double s = floor((x - o) * ih);
+    int c = (s < 0.0) ? 0 : ((s > (double)(n - 1)) ? n - 1 : (int)s);
+    return c;
+}
+
+__global__ void k_cell_count(const double* __restrict__ px, const double* __restrict__ py, const double* __restrict__ pz,
+                             size_t np, GridD g, uint32_t* __restrict__ cell_of, uint32_t* __restrict__ rank,
+                             uint32_t* __restrict__ count) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    int ci = cell_coord(px[p], g.ox, 1.0 / g.hx, g.nx);
+    int cj = cell_coord(py[p], g.oy, 1.0 / g.hy, g.ny);
+    int ck = cell_coord(pz[p], g.oz, 1.0 / g.hz, g.nz);
+    uint32_t cell = (uint32_t)(((size_t)ck * g.ny + cj) * g.nx + ci);
+    cell_of[p] = cell;
+    rank[p] = atomicAdd(&count[cell], 1u);  // slot inside the cell; order fixed up by k_sort_cells
+}
+
+__global__ void k_scatter_perm(const uint32_t* __restrict__ cell_of, const uint32_t* __restrict__ rank,
+                               const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ perm, size_t np) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    perm[cell_start[cell_of[p]] + rank[p]] = (uint32_t)p;
+}
+
+// Make the order inside every cell deterministic: ascending ORIGINAL particle index (insertion sort; ~8 items).
+__global__ void k_sort_cells(const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ orig,
+                             uint32_t* __restrict__ perm, size_t nc) {
+    size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    uint32_t s = cell_start[c], e = cell_start[c + 1];
+    for (uint32_t a = s + 1; a < e; ++a) {
+        uint32_t pa = perm[a];
+        uint32_t ka = orig[pa];
+        uint32_t b = a;
+        while (b > s) {
+            uint32_t pb = perm[b - 1];
+            if (orig[pb] <= ka) break;
+            perm[b] = pb;
+            --b;
+        }
+        perm[b] = pa;
+    }
+}
+
+struct AttrPtrs {
+    double* p[NATTR];
+};
+
+__global__ void k_gather_attrs(AttrPtrs src, AttrPtrs dst, const uint32_t* __restrict__ orig_src,
+                               uint32_t* __restrict__ orig_dst, const uint32_t* __restrict__ perm, int nattr, size_t np) {
+    size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= np) return;
+    uint32_t from = perm[s];
+    for (int a = 0; a < nattr; ++a) dst.p[a][s] = src.p[a][from];
+    orig_dst[s] = orig_src[from];
+}
+
+// ------------------------------------------------------------------------------------------------ P2G
+// transferFromParticlesToGrids: PIC src/jet/pic_solver3.cpp:118-193, APIC src/jet/apic_solver3.cpp:26-146.
+// One thread per face; gathers from the 2x3x3 cells whose particles can list this face among their 8 sampler
+// corners (getCoordinatesAndWeights, array_samplers3-inl.h:151-193), in the fixed order cells (z,y,x) then slot.
+template <int AXIS, bool APIC>
+__global__ void __launch_bounds__(128)
+    k_p2g(GridD g, const uint32_t* __restrict__ cell_start, AttrPtrs a, double* __restrict__ out, char* __restrict__ marker) {
+    int sx, sy, sz;
+    double ox, oy, oz;
+    comp_grid<AXIS>(g, &sx, &sy, &sz, &ox, &oy, &oz);
+    int i = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+    if (i >= sx || j >= sy || k >= sz) return;
+    const double ihx = 1.0 / g.hx, ihy = 1.0 / g.hy, ihz = 1.0 / g.hz;
+    // cell ranges: along the face's own axis cells {f-1, f}; along the tangential axes {f-1, f, f+1}
+    int ci0 = max(i - 1, 0), ci1 = min(AXIS == 0 ? i : i + 1, g.nx - 1);
+    int cj0 = max(j - 1, 0), cj1 = min(AXIS == 1 ? j : j + 1, g.ny - 1);
+    int ck0 = max(k - 1, 0), ck1 = min(AXIS == 2 ? k : k + 1, g.nz - 1);
+    const double* __restrict__ vel = a.p[3 + AXIS];
+    const double* __restrict__ c0 = a.p[6 + 3 * AXIS];
+    const double* __restrict__ c1 = a.p[7 + 3 * AXIS];
+    const double* __restrict__ c2 = a.p[8 + 3 * AXIS];
+    // APIC clamps the two tangential coordinates to [lo + h/2, hi - h/2] (apic_solver3.cpp:76-84,94-102,112-120)
+    const double lox = g.ox + g.hx / 2.0, hix = (g.ox + g.hx * (double)g.nx) - g.hx / 2.0;
+    const double loy = g.oy + g.hy / 2.0, hiy = (g.oy + g.hy * (double)g.ny) - g.hy / 2.0;
+    const double loz = g.oz + g.hz / 2.0, hiz = (g.oz + g.hz * (double)g.nz) - g.hz / 2.0;
+    double sum = 0.0, wsum = 0.0;
+    int mark = 0;
+    for (int ck = ck0; ck <= ck1; ++ck)
+        for (int cj = cj0; cj <= cj1; ++cj) {
+            size_t row = ((size_t)ck * g.ny + cj) * g.nx;
+            uint32_t s = cell_start[row + ci0], e = cell_start[row + ci1 + 1];  // x-adjacent cells are contiguous
+            for (uint32_t q = s; q < e; ++q) {
+                double px = a.p[0][q], py = a.p[1][q], pz = a.p[2][q];
+                if (APIC) {
+                    if (AXIS != 0) px = jc_clamp(px, lox, hix);
+                    if (AXIS != 1) py = jc_clamp(py, loy, hiy);
+                    if (AXIS != 2) pz = jc_clamp(pz, loz, hiz);
+                }
+                BaseFrac b = jc_base_mul(sx, sy, sz, ihx, ihy, ihz, ox, oy, oz, px, py, pz);
+                bool mx0 = (b.i == i), mx1 = (b.ip1 == i), my0 = (b.j == j), my1 = (b.jp1 == j), mz0 = (b.k == k),
+                     mz1 = (b.kp1 == k);
+                if (!((mx0 | mx1) & (my0 | my1) & (mz0 | mz1))) continue;
+                double pv = vel[q];
+                if (APIC) {
+                    // apicTerm = c . (facePosition - clampedPosition); facePosition = faceOrigin + h*(i,j,k)
+                    double gx = ox + g.hx * (double)i, gy = oy + g.hy * (double)j, gz = oz + g.hz * (double)k;
+                    double term = c0[q] * (gx - px) + c1[q] * (gy - py) + c2[q] * (gz - pz);
+                    pv = pv + term;
+                }
+#pragma unroll
+                for (int cnr = 0; cnr < 8; ++cnr) {  // the reference's corner order; duplicates only on size-1 axes
+                    bool hit = ((cnr & 1) ? mx1 : mx0) && ((cnr & 2) ? my1 : my0) && ((cnr & 4) ? mz1 : mz0);
+                    if (hit) {
+                        double wgt = jc_corner_weight(b, cnr);
+                        sum += APIC ? wgt * pv : pv * wgt;
+                        wsum += wgt;
+                        mark = 1;
+                    }
+                }
+            }
+        }
+    size_t f = ((size_t)k * sy + j) * sx + i;
+    out[f] = (wsum > 0.0) ? sum / wsum : sum;  // pic_solver3.cpp:178-192
+    marker[f] = (char)mark;
+}
+
+__global__ void k_to_float(const double* __restrict__ in, float* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];  // FlipSolver3 snapshot, src/jet/flip_solver3.cpp:39-47
+}
+
+__global__ void k_flip_delta(const double* __restrict__ in, float* __restrict__ d, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = (float)in[i] - d[i];  // src/jet/flip_solver3.cpp:57-70
+}
+
+// ------------------------------------------------------------------------------------------------ particle SDF
+// PicSolver3::buildSignedDistanceField, src/jet/pic_solver3.cpp:296-317: phi(cell) = min(2r, min |x_c - x_p|) - r
+// over particles with |x_p - x_c|^2 <= (2r)^2.  The reference finds them through a 64^3 hash grid of spacing 4r
+// (8 buckets around the query); any superset of "all particles within 2r" yields the same exact min, so we walk
+// the cell-sorted ranges within `reach` cells and prune by box distance.
+__global__ void __launch_bounds__(128)
+    k_build_sdf(GridD g, const uint32_t* __restrict__ cell_start, const double* __restrict__ ppx,
+                const double* __restrict__ ppy, const double* __restrict__ ppz, double radius, double band, int rx, int ry,
+                int rz, double* __restrict__ sdf) {
+    int i = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+    if (i >= g.nx || j >= g.ny) return;
+    // data position = (origin + 0.5 h) + h*(i,j,k)  (src/jet/scalar_grid3.cpp:127-132)
+    const double ptx = (g.ox + 0.5 * g.hx) + g.hx * (double)i;
+    const double pty = (g.oy + 0.5 * g.hy) + g.hy * (double)j;
+    const double ptz = (g.oz + 0.5 * g.hz) + g.hz * (double)k;
+    const double r2 = band * band;
+    double minDist = band;
+    double best2 = r2;  // pruning bound on squared distance (only ever shrinks)
+    // visit order: own cell first (tightens the bound fastest), then the rest; the min is order-independent
+    for (int pass = 0; pass < 2; ++pass) {
+        int k0 = pass == 0 ? k : max(k - rz, 0), k1 = pass == 0 ? k : min(k + rz, g.nz - 1);
+        int j0 = pass == 0 ? j : max(j - ry, 0), j1 = pass == 0 ? j : min(j + ry, g.ny - 1);
+        int i0 = pass == 0 ? i : max(i - rx, 0), i1 = pass == 0 ? i : min(i + rx, g.nx - 1);
+        for (int ck = k0; ck <= k1; ++ck) {
+            // conservative distance from pt to the slab of cells ck (open towards the domain exterior)
+            double dz = 0.0;
+            if (ck > k) dz = (g.oz + g.hz * (double)ck) - ptz; else if (ck < k) dz = ptz - (g.oz + g.hz * (double)(ck + 1));
+            dz = fmax(dz, 0.0) * 0.999999;
+            for (int cj = j0; cj <= j1; ++cj) {
+                double dy = 0.0;
+                if (cj > j) dy = (g.oy + g.hy * (double)cj) - pty; else if (cj < j) dy = pty - (g.oy + g.hy * (double)(cj + 1));
+                dy = fmax(dy, 0.0) * 0.999999;
+                if (dz * dz + dy * dy > best2) continue;
+                size_t row = ((size_t)ck * g.ny + cj) * g.nx;
+                for (int ci = i0; ci <= i1; ++ci) {
+                    if (pass == 1 && ci == i && cj == j && ck == k) continue;
+                    double dx = 0.0;
+                    if (ci > i) dx = (g.ox + g.hx * (double)ci) - ptx; else if (ci < i) dx = ptx - (g.ox + g.hx * (double)(ci + 1));
+                    dx = fmax(dx, 0.0) * 0.999999;
+                    if (dz * dz + dy * dy + dx * dx > best2) continue;
+                    uint32_t s = cell_start[row + ci], e = cell_start[row + ci + 1];
+                    for (uint32_t q = s; q < e; ++q) {
+                        double ex = ppx[q] - ptx, ey = ppy[q] - pty, ez = ppz[q] - ptz;
+                        double d2 = ex * ex + ey * ey + ez * ez;
+                        if (d2 <= r2) {
+                            double fx = ptx - ppx[q], fy = pty - ppy[q], fz = ptz - ppz[q];
+                            double dist = sqrt(fx * fx + fy * fy + fz * fz);
+                            if (dist < minDist) { minDist = dist; best2 = fmin(best2, d2 * 1.000001); }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    sdf[((size_t)k * g.ny + j) * g.nx + i] = minDist - radius;
+}
+
+// ------------------------------------------------------------------------------------------------ extrapolation
+// One sweep of extrapolateToRegion, include/jet/detail/array_utils-inl.h:191-239: reads only cells valid at sweep
+// start, writes only invalid ones (so it is safe in place); neighbour order +i,-i,+j,-j,+k,-k; divide by count.
+__global__ void __launch_bounds__(256) k_extrapolate_sweep(double* data, const char* __restrict__ v0, char* __restrict__ v1,
+                                                           int nx, int ny, int nz) {
+    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+    if (i >= nx || j >= ny) return;
+    const size_t sy = (size_t)nx, sz = (size_t)nx * ny;
+    size_t c = (size_t)k * sz + (size_t)j * sy + i;
+    if (v0[c]) { v1[c] = 1; return; }
+    double sum = 0.0;
+    unsigned count = 0;
+    if (i + 1 < nx && v0[c + 1]) { sum += data[c + 1]; ++count; }
+    if (i > 0 && v0[c - 1]) { sum += data[c - 1]; ++count; }
+    if (j + 1 < ny && v0[c + sy]) { sum += data[c + sy]; ++count; }
+    if (j > 0 && v0[c - sy]) { sum += data[c - sy]; ++count; }
+    if (k + 1 < nz && v0[c + sz]) { sum += data[c + sz]; ++count; }
+    if (k > 0 && v0[c - sz]) { sum += data[c - sz]; ++count; }
+    if (count > 0) { data[c] = sum / (double)count; v1[c] = 1; }
+    else v1[c] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ grid ops
+// Closed-wall part of GridFractionalBoundaryConditionSolver3::constrainVelocity
+// (src/jet/grid_fractional_boundary_condition_solver3.cpp:190-232).  Without a collider the rest of
+// constrainVelocity is the identity (all face markers 1, no cell inside the collider SDF = kMaxD).
+__global__ void k_zero_walls(GridD g, int flag, double* __restrict__ u, double* __restrict__ v, double* __restrict__ w) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t nyz = (size_t)g.ny * g.nz, nxz = (size_t)g.nx * g.nz, nxy = (size_t)g.nx * g.ny;
+    if (t < nyz) {
+        int j = (int)(t % g.ny), k = (int)(t / g.ny);
+        size_t rowu = ((size_t)k * g.ny + j) * (g.nx + 1);
+        if (flag & JETCU_DIR_LEFT) u[rowu] = 0;
+        if (flag & JETCU_DIR_RIGHT) u[rowu + g.nx] = 0;
+    }
+    if (t < nxz) {
+        int i = (int)(t % g.nx), k = (int)(t / g.nx);
+        size_t base = (size_t)k * (g.ny + 1) * g.nx + i;
+        if (flag & JETCU_DIR_DOWN) v[base] = 0;
+        if (flag & JETCU_DIR_UP) v[base + (size_t)g.ny * g.nx] = 0;
+    }
+    if (t < nxy) {
+        if (flag & JETCU_DIR_BACK) w[t] = 0;
+        if (flag & JETCU_DIR_FRONT) w[(size_t)g.nz * nxy + t] = 0;
+    }
+}
+
+__global__ void k_add_scalar(double* __restrict__ a, double s, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] += s;  // computeGravity: u += dt * g  (src/jet/grid_fluid_solver3.cpp:317-344)
+}
+
+// GridFluidSolver3::cfl, src/jet/grid_fluid_solver3.cpp:57-72: max over cells of the SIGNED components of
+// valueAtCellCenter + dt*g, starting from 0 (max is exact, so any reduction order gives the same bits).
+#define CFL_BLOCK 256
+#define CFL_GRID 592
+__global__ void __launch_bounds__(CFL_BLOCK) k_cfl_partial(GridD g, const double* __restrict__ u, const double* __restrict__ v,
+                                                           const double* __restrict__ w, double dtgx, double dtgy, double dtgz,
+                                                           double* __restrict__ partials) {
+    __shared__ double sm[CFL_BLOCK];
+    double m = 0.0;
+    size_t nc = (size_t)g.nx * g.ny * g.nz;
+    for (size_t c = (size_t)blockIdx.x * CFL_BLOCK + threadIdx.x; c < nc; c += (size_t)CFL_GRID * CFL_BLOCK) {
+        int i = (int)(c % g.nx);
+        size_t t = c / g.nx;
+        int j = (int)(t % g.ny), k = (int)(t / g.ny);
+        size_t iu = ((size_t)k * g.ny + j) * (g.nx + 1) + i;
+        size_t iv = ((size_t)k * (g.ny + 1) + j) * g.nx + i;
+        double vx = 0.5 * (u[iu] + u[iu + 1]) + dtgx;
+        double vy = 0.5 * (v[iv] + v[iv + g.nx]) + dtgy;
+        double vz = 0.5 * (w[c] + w[c + (size_t)g.nx * g.ny]) + dtgz;
+        m = fmax(m, vx); m = fmax(m, vy); m = fmax(m, vz);
+    }
+    sm[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = CFL_BLOCK / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = sm[0];
+}
+
+__global__ void __launch_bounds__(CFL_BLOCK) k_max_final(const double* __restrict__ partials, int n, double* out) {
+    __shared__ double sm[CFL_BLOCK];
+    double m = 0.0;
+    for (int i = threadIdx.x; i < n; i += CFL_BLOCK) m = fmax(m, partials[i]);
+    sm[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = CFL_BLOCK / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sm[0];
+}
+
+// ------------------------------------------------------------------------------------------------ G2P + advection
+__device__ __forceinline__ void sample_velocity(const GridD& g, const double* u, const double* v, const double* w,
+                                                double px, double py, double pz, double* ou, double* ov, double* ow) {
+    // FaceCenteredGrid3::sample: three LinearArraySampler3::operator() calls (face_centered_grid3.cpp:447-467)
+    *ou = jc_sample(comp_view(g, 0, u), px, py, pz);
+    *ov = jc_sample(comp_view(g, 1, v), px, py, pz);
+    *ow = jc_sample(comp_view(g, 2, w), px, py, pz);
+}
+
+// PicSolver3::transferFromGridsToParticles, src/jet/pic_solver3.cpp:195-204.
+__global__ void k_g2p_pic(GridD g, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
+                          AttrPtrs a, size_t np) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    double ou, ov, ow;
+    sample_velocity(g, u, v, w, a.p[0][p], a.p[1][p], a.p[2][p], &ou, &ov, &ow);
+    a.p[3][p] = ou; a.p[4][p] = ov; a.p[5][p] = ow;
+}
+
+// FlipSolver3::transferFromGridsToParticles, src/jet/flip_solver3.cpp:50-99: v += sampleF32(delta)(float(x)),
+// optional lerp towards the PIC sample.
+__global__ void k_g2p_flip(GridD g, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
+                           const float* __restrict__ ud, const float* __restrict__ vd, const float* __restrict__ wd,
+                           double blend, AttrPtrs a, size_t np) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    double px = a.p[0][p], py = a.p[1][p], pz = a.p[2][p];
+    float xf = (float)px, yf = (float)py, zf = (float)pz;
+    float fhx = (float)g.hx, fhy = (float)g.hy, fhz = (float)g.hz;
+    GridView vu = comp_view(g, 0, u), vv = comp_view(g, 1, v), vw = comp_view(g, 2, w);
+    double du = jc_samplef(ud, vu.nx, vu.ny, vu.nz, fhx, fhy, fhz, (float)vu.ox, (float)vu.oy, (float)vu.oz, xf, yf, zf);
+    double dv = jc_samplef(vd, vv.nx, vv.ny, vv.nz, fhx, fhy, fhz, (float)vv.ox, (float)vv.oy, (float)vv.oz, xf, yf, zf);
+    double dw = jc_samplef(wd, vw.nx, vw.ny, vw.nz, fhx, fhy, fhz, (float)vw.ox, (float)vw.oy, (float)vw.oz, xf, yf, zf);
+    double f0 = a.p[3][p] + du, f1 = a.p[4][p] + dv, f2 = a.p[5][p] + dw;
+    if (blend > 0.0) {
+        double pu = jc_sample(vu, px, py, pz), pv = jc_sample(vv, px, py, pz), pw = jc_sample(vw, px, py, pz);
+        f0 = (1 - blend) * f0 + blend * pu;
+        f1 = (1 - blend) * f1 + blend * pv;
+        f2 = (1 - blend) * f2 + blend * pw;
+    }
+    a.p[3][p] = f0; a.p[4][p] = f1; a.p[5][p] = f2;
+}
+
+// ApicSolver3::transferFromGridsToParticles, src/jet/apic_solver3.cpp:148-229: PIC sample + c = sum gradW * value
+// with getCoordinatesAndGradientWeights (array_samplers3-inl.h:195-261) at the tangentially clamped position.
+template <int AXIS>
+__device__ __forceinline__ void apic_affine(const GridD& g, const double* __restrict__ data, double px, double py,
+                                            double pz, double* c0, double* c1, double* c2) {
+    int sx, sy, sz;
+    double ox, oy, oz;
+    comp_grid<AXIS>(g, &sx, &sy, &sz, &ox, &oy, &oz);
+    const double hix = g.ox + g.hx * (double)g.nx, hiy = g.oy + g.hy * (double)g.ny, hiz = g.oz + g.hz * (double)g.nz;
+    if (AXIS != 0) px = jc_clamp(px, g.ox + g.hx / 2.0, hix - g.hx / 2.0);
+    if (AXIS != 1) py = jc_clamp(py, g.oy + g.hy / 2.0, hiy - g.hy / 2.0);
+    if (AXIS != 2) pz = jc_clamp(pz, g.oz + g.hz / 2.0, hiz - g.hz / 2.0);
+    BaseFrac b = jc_base_div(sx, sy, sz, g.hx, g.hy, g.hz, ox, oy, oz, px, py, pz);
+    const double ix = 1.0 / g.hx, iy = 1.0 / g.hy, iz = 1.0 / g.hz;
+    const double fx = b.fx, fy = b.fy, fz = b.fz, ax = 1 - b.fx, ay = 1 - b.fy, az = 1 - b.fz;
+    double gw[8][3];
+    gw[0][0] = -ix * ay * az;    gw[0][1] = -iy * ax * az;    gw[0][2] = -iz * ax * ay;
+    gw[1][0] = ix * ay * az;     gw[1][1] = fx * (-iy) * az;  gw[1][2] = fx * ay * (-iz);
+    gw[2][0] = (-ix) * fy * az;  gw[2][1] = ax * iy * az;     gw[2][2] = ax * fy * (-iz);
+    gw[3][0] = ix * fy * az;     gw[3][1] = fx * iy * az;     gw[3][2] = fx * fy * (-iz);
+    gw[4][0] = (-ix) * ay * fz;  gw[4][1] = ax * (-iy) * fz;  gw[4][2] = ax * ay * iz;
+    gw[5][0] = ix * ay * fz;     gw[5][1] = fx * (-iy) * fz;  gw[5][2] = fx * ay * iz;
+    gw[6][0] = (-ix) * fy * fz;  gw[6][1] = ax * iy * fz;     gw[6][2] = ax * fy * iz;
+    gw[7][0] = ix * fy * fz;     gw[7][1] = fx * iy * fz;     gw[7][2] = fx * fy * iz;
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        int ii = (q & 1) ? b.ip1 : b.i, jj = (q & 2) ? b.jp1 : b.j, kk = (q & 4) ? b.kp1 : b.k;
+        double val = data[((size_t)kk * sy + jj) * sx + ii];
+        r0 += gw[q][0] * val; r1 += gw[q][1] * val; r2 += gw[q][2] * val;
+    }
+    *c0 = r0; *c1 = r1; *c2 = r2;
+}
+
+__global__ void k_g2p_apic(GridD g, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
+                           AttrPtrs a, size_t np) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    double px = a.p[0][p], py = a.p[1][p], pz = a.p[2][p];
+    double ou, ov, ow;
+    sample_velocity(g, u, v, w, px, py, pz, &ou, &ov, &ow);
+    a.p[3][p] = ou; a.p[4][p] = ov; a.p[5][p] = ow;
+    double c0, c1, c2;
+    apic_affine<0>(g, u, px, py, pz, &c0, &c1, &c2); a.p[6][p] = c0; a.p[7][p] = c1; a.p[8][p] = c2;
+    apic_affine<1>(g, v, px, py, pz, &c0, &c1, &c2); a.p[9][p] = c0; a.p[10][p] = c1; a.p[11][p] = c2;
+    apic_affine<2>(g, w, px, py, pz, &c0, &c1, &c2); a.p[12][p] = c0; a.p[13][p] = c1; a.p[14][p] = c2;
+}
+
+// PicSolver3::moveParticles, src/jet/pic_solver3.cpp:206-282: uint(max(maxCfl,1)) midpoint-rule sub-steps, then
+// clamp to the domain box and zero the velocity component on closed walls (<= / >= tests).
+__global__ void k_move(GridD g, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
+                       double dt, unsigned nsub, int flag, AttrPtrs a, size_t np) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    double p0x = a.p[0][p], p0y = a.p[1][p], p0z = a.p[2][p];
+    double p1x = p0x, p1y = p0y, p1z = p0z;
+    for (unsigned t = 0; t < nsub; ++t) {
+        double v0x, v0y, v0z, mvx, mvy, mvz;
+        sample_velocity(g, u, v, w, p0x, p0y, p0z, &v0x, &v0y, &v0z);
+        double mx = p0x + 0.5 * dt * v0x, my = p0y + 0.5 * dt * v0y, mz = p0z + 0.5 * dt * v0z;
+        sample_velocity(g, u, v, w, mx, my, mz, &mvx, &mvy, &mvz);
+        p1x = p0x + dt * mvx; p1y = p0y + dt * mvy; p1z = p0z + dt * mvz;
+        p0x = p1x; p0y = p1y; p0z = p1z;
+    }
+    const double hix = g.ox + g.hx * (double)g.nx, hiy = g.oy + g.hy * (double)g.ny, hiz = g.oz + g.hz * (double)g.nz;
+    double vx = a.p[3][p], vy = a.p[4][p], vz = a.p[5][p];
+    if ((flag & JETCU_DIR_LEFT) && p1x <= g.ox) { p1x = g.ox; vx = 0.0; }
+    if ((flag & JETCU_DIR_RIGHT) && p1x >= hix) { p1x = hix; vx = 0.0; }
+    if ((flag & JETCU_DIR_DOWN) && p1y <= g.oy) { p1y = g.oy; vy = 0.0; }
+    if ((flag & JETCU_DIR_UP) && p1y >= hiy) { p1y = hiy; vy = 0.0; }
+    if ((flag & JETCU_DIR_BACK) && p1z <= g.oz) { p1z = g.oz; vz = 0.0; }
+    if ((flag & JETCU_DIR_FRONT) && p1z >= hiz) { p1z = hiz; vz = 0.0; }
+    a.p[0][p] = p1x; a.p[1][p] = p1y; a.p[2][p] = p1z;
+    a.p[3][p] = vx; a.p[4][p] = vy; a.p[5][p] = vz;
+}
+
+// ------------------------------------------------------------------------------------------------ particle I/O
+__global__ void k_aos_to_soa3(const double* __restrict__ aos, double* __restrict__ x, double* __restrict__ y,
+                              double* __restrict__ z, size_t n, size_t offset) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    x[offset + i] = aos[3 * i]; y[offset + i] = aos[3 * i + 1]; z[offset + i] = aos[3 * i + 2];
+}
+
+// sorted SoA -> caller's AoS in ORIGINAL particle order
+__global__ void k_soa_to_aos3_orig(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                                   const uint32_t* __restrict__ orig, double* __restrict__ aos, size_t n) {
+    size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    size_t o = orig[s];
+    aos[3 * o] = x[s]; aos[3 * o + 1] = y[s]; aos[3 * o + 2] = z[s];
+}
+
+__global__ void k_iota_u32(uint32_t* p, uint32_t start, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = start + (uint32_t)i;
+}
+
+__global__ void k_fill_f64(double* p, double v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// GridPointGenerator3::forEachPoint lattice, src/jet/grid_point_generator3.cpp:12-37: position = idx*spacing + lower,
+// emitted k-outer, j, i-inner.
+__global__ void k_emit_lattice(double* __restrict__ x, double* __restrict__ y, double* __restrict__ z, double* __restrict__ vx,
+                               double* __restrict__ vy, double* __restrict__ vz, uint32_t* __restrict__ orig, size_t offset,
+                               unsigned cx, unsigned cy, unsigned cz, double spacing, double lx, double ly, double lz,
+                               double v0x, double v0y, double v0z) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)cx * cy * cz;
+    if (t >= total) return;
+    int i = (int)(t % cx), j = (int)((t / cx) % cy), k = (int)(t / ((size_t)cx * cy));
+    size_t o = offset + t;
+    x[o] = i * spacing + lx; y[o] = j * spacing + ly; z[o] = k * spacing + lz;
+    vx[o] = v0x; vy[o] = v0y; vz[o] = v0z;
+    orig[o] = (uint32_t)o;
+}
+
+// ================================================================================================ host side
+static AttrPtrs attr_ptrs(jetcu_hybrid* h, int which) {
+    AttrPtrs a;
+    for (int q = 0; q < NATTR; ++q) a.p[q] = h->attr[which][q];
+    return a;
+}
+
+static int hyb_reserve(jetcu_hybrid* h, uint64_t n) {
+    jetcu_ctx* ctx = h->ctx;
+    if (n <= h->cap) return JETCU_OK;
+    uint64_t cap = n + n / 16 + 1024;
+    for (int b = 0; b < 2; ++b) {
+        for (int q = 0; q < h->nattr; ++q) {
+            double* np_ = nullptr;
+            JC_TRY(jc_alloc(ctx, &np_, cap));
+            if (b == h->cur && h->np > 0) JC_TRY(jc_d2d(ctx, np_, h->attr[b][q], h->np));
+            if (q >= 6) JC_TRY(jc_zero(ctx, np_ + h->np, cap - h->np));
+            jc_free(ctx, h->attr[b][q]);
+            h->attr[b][q] = np_;
+        }
+        uint32_t* no = nullptr;
+        JC_TRY(jc_alloc(ctx, &no, cap));
+        if (b == h->cur && h->np > 0) JC_TRY(jc_d2d(ctx, no, h->orig[b], h->np));
+        jc_free(ctx, h->orig[b]);
+        h->orig[b] = no;
+    }
+    uint32_t* t;
+    jc_free(ctx, h->cell_of); jc_free(ctx, h->rank); jc_free(ctx, h->perm);
+    JC_TRY(jc_alloc(ctx, &t, cap)); h->cell_of = t;
+    JC_TRY(jc_alloc(ctx, &t, cap)); h->rank = t;
+    JC_TRY(jc_alloc(ctx, &t, cap)); h->perm = t;
+    h->cap = cap;
+    return JETCU_OK;
+}
+
+// Counting sort of the particles by owning cell; afterwards cell_start[c]..cell_start[c+1] is cell c's range.
+static int hyb_bin(jetcu_hybrid* h) {
+    jetcu_ctx* ctx = h->ctx;
+    if (h->binned) return JETCU_OK;
+    GridD g = gridd(h);
+    size_t np = h->np;
+    JC_TRY(jc_zero(ctx, h->cell_start, h->nc + 1));
+    if (np > 0) {
+        JC_LAUNCH(ctx, k_cell_count, jc_blocks(np, 256), 256, 0, h->attr[h->cur][0], h->attr[h->cur][1], h->attr[h->cur][2],
+                  np, g, h->cell_of, h->rank, h->cell_start);
+    }
+    JC_TRY(scan_exclusive_u32(ctx, h->cell_start, h->cell_start, h->nc + 1));
+    if (np > 0) {
+        JC_LAUNCH(ctx, k_scatter_perm, jc_blocks(np, 256), 256, 0, h->cell_of, h->rank, h->cell_start, h->perm, np);
+        JC_LAUNCH(ctx, k_sort_cells, jc_blocks(h->nc, 128), 128, 0, h->cell_start, h->orig[h->cur], h->perm, h->nc);
+        JC_LAUNCH(ctx, k_gather_attrs, jc_blocks(np, 256), 256, 0, attr_ptrs(h, h->cur), attr_ptrs(h, 1 - h->cur),
+                  h->orig[h->cur], h->orig[1 - h->cur], h->perm, h->nattr, np);
+        h->cur = 1 - h->cur;
+    }
+    h->binned = true;
+    return JETCU_OK;
+}
+
+static int hyb_zero_walls(jetcu_hybrid* h) {
+    jetcu_ctx* ctx = h->ctx;
+    GridD g = gridd(h);
+    size_t m = (size_t)g.ny * g.nz;
+    if ((size_t)g.nx * g.nz > m) m = (size_t)g.nx * g.nz;
+    if ((size_t)g.nx * g.ny > m) m = (size_t)g.nx * g.ny;
+    JC_LAUNCH(ctx, k_zero_walls, jc_blocks(m, 256), 256, 0, g, h->P.closed_domain_boundary_flag, h->u, h->v, h->w);
+    return JETCU_OK;
+}
+
+static int hyb_extrapolate_one(jetcu_hybrid* h, double* data, const char* marker, int sx, int sy, int sz, unsigned depth) {
+    jetcu_ctx* ctx = h->ctx;
+    size_t n = (size_t)sx * sy * sz;
+    JC_TRY(jc_d2d(ctx, h->valid0, marker, n));
+    char *v0 = h->valid0, *v1 = h->valid1;
+    dim3 grid((sx + 63) / 64, (sy + 3) / 4, sz);
+    for (unsigned it = 0; it < depth; ++it) {
+        JC_LAUNCH(ctx, k_extrapolate_sweep, grid, dim3(64, 4), 0, data, v0, v1, sx, sy, sz);
+        char* t = v0; v0 = v1; v1 = t;
+    }
+    return JETCU_OK;
+}
+
+#define HYB_ENTER(h)                                                      \
+    if (!(h)) return JETCU_ERR_INVALID_ARG;                               \
+    jetcu_ctx* ctx = (h)->ctx;                                            \
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return jetcu_fail(ctx, JETCU_ERR_CUDA, "cudaSetDevice failed");
+
+extern "C" {
+
+void jetcu_hybrid_default_params(jetcu_hybrid_params* p) {
+    memset(p, 0, sizeof(*p));
+    p->grid.nx = p->grid.ny = p->grid.nz = 1;
+    p->grid.hx = p->grid.hy = p->grid.hz = 1.0;
+    p->mode = JETCU_FLIP;
+    p->closed_domain_boundary_flag = JETCU_DIR_ALL;
+    p->gravity[1] = -9.8;
+    p->max_cfl = 5.0;
+    p->mgpcg.max_iterations = 100; p->mgpcg.max_levels = 5; p->mgpcg.n_restriction = 5; p->mgpcg.n_correction = 5;
+    p->mgpcg.n_coarsest = 20; p->mgpcg.n_final = 20; p->mgpcg.tolerance = 1e-9; p->mgpcg.sor_factor = 1.5;
+    p->mgpcg.use_red_black = 1;
+}
+
+int jetcu_hybrid_create(jetcu_ctx* ctx, const jetcu_hybrid_params* p, jetcu_hybrid** out) {
+    if (!ctx) return JETCU_ERR_INVALID_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return jetcu_fail(ctx, JETCU_ERR_CUDA, "cudaSetDevice failed");
+    JC_ARG(ctx, p && out);
+    JC_ARG(ctx, p->grid.nx > 0 && p->grid.ny > 0 && p->grid.nz > 0 && p->grid.nx < 32768 && p->grid.ny < 32768 && p->grid.nz < 32768);
+    JC_ARG(ctx, p->grid.hx > 0 && p->grid.hy > 0 && p->grid.hz > 0);
+    JC_ARG(ctx, p->mode >= JETCU_PIC && p->mode <= JETCU_APIC);
+    JC_ARG(ctx, (uint64_t)p->grid.nx * p->grid.ny * p->grid.nz < (1ull << 32) - 2);
+    if (!p->mgpcg.use_red_black)
+        return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED, "lexicographic Gauss-Seidel is not available on the GPU path");
+    if (jetcu_mg_num_levels(p->grid.nx, p->grid.ny, p->grid.nz, p->mgpcg.max_levels) > 1) JC_ARG(ctx, p->grid.ny == p->grid.nz);
+    jetcu_hybrid* h = new jetcu_hybrid();
+    h->ctx = ctx;
+    h->P = *p;
+    h->nx = (int)p->grid.nx; h->ny = (int)p->grid.ny; h->nz = (int)p->grid.nz;
+    h->nu = (size_t)(h->nx + 1) * h->ny * h->nz;
+    h->nv = (size_t)h->nx * (h->ny + 1) * h->nz;
+    h->nw = (size_t)h->nx * h->ny * (h->nz + 1);
+    h->nc = (size_t)h->nx * h->ny * h->nz;
+    h->nattr = (p->mode == JETCU_APIC) ? NATTR : 6;
+    size_t nmax = h->nu > h->nv ? h->nu : h->nv;
+    if (h->nw > nmax) nmax = h->nw;
+    int rc = JETCU_OK;
+#define STEP(x) if (rc == JETCU_OK) rc = (x)
+    STEP(jc_alloc(ctx, &h->u, h->nu)); STEP(jc_alloc(ctx, &h->v, h->nv)); STEP(jc_alloc(ctx, &h->w, h->nw));
+    STEP(jc_zero(ctx, h->u, h->nu)); STEP(jc_zero(ctx, h->v, h->nv)); STEP(jc_zero(ctx, h->w, h->nw));
+    STEP(jc_alloc(ctx, &h->um, h->nu)); STEP(jc_alloc(ctx, &h->vm, h->nv)); STEP(jc_alloc(ctx, &h->wm, h->nw));
+    STEP(jc_zero(ctx, h->um, h->nu)); STEP(jc_zero(ctx, h->vm, h->nv)); STEP(jc_zero(ctx, h->wm, h->nw));
+    STEP(jc_alloc(ctx, &h->valid0, nmax)); STEP(jc_alloc(ctx, &h->valid1, nmax));
+    STEP(jc_alloc(ctx, &h->sdf, h->nc));
+    if (p->mode == JETCU_FLIP) {
+        STEP(jc_alloc(ctx, &h->ud, h->nu)); STEP(jc_alloc(ctx, &h->vd, h->nv)); STEP(jc_alloc(ctx, &h->wd, h->nw));
+        STEP(jc_zero(ctx, h->ud, h->nu)); STEP(jc_zero(ctx, h->vd, h->nv)); STEP(jc_zero(ctx, h->wd, h->nw));
+    }
+    STEP(jc_alloc(ctx, &h->cell_start, h->nc + 1));
+    STEP(jc_zero(ctx, h->cell_start, h->nc + 1));
+    if (rc == JETCU_OK) {
+        // signedDistanceField is created with kMaxD (src/jet/pic_solver3.cpp:29-30)
+        k_fill_f64<<<jc_blocks(h->nc, 256), 256, 0, ctx->stream>>>(h->sdf, DBL_MAX, h->nc);
+        ctx->launches++;
+    }
+    STEP(pressure_prepare(ctx, &h->ps, &p->grid, p->mgpcg.max_levels));
+    STEP(jc_zero(ctx, h->ps.x0, h->nc));
+    for (int e = 0; e < 12 && rc == JETCU_OK; ++e)
+        if (cudaEventCreate(&h->ev[e]) != cudaSuccess) rc = jetcu_fail(ctx, JETCU_ERR_CUDA, "cudaEventCreate failed");
+    STEP(jc_sync(ctx));
+#undef STEP
+    if (rc != JETCU_OK) { jetcu_hybrid_destroy(h); return rc; }
+    *out = h;
+    return JETCU_OK;
+}
+
+int jetcu_hybrid_destroy(jetcu_hybrid* h) {
+    if (!h) return JETCU_OK;
+    jetcu_ctx* ctx = h->ctx;
+    cudaSetDevice(ctx->device);
+    jc_free(ctx, h->u); jc_free(ctx, h->v); jc_free(ctx, h->w);
+    jc_free(ctx, h->um); jc_free(ctx, h->vm); jc_free(ctx, h->wm);
+    jc_free(ctx, h->valid0); jc_free(ctx, h->valid1); jc_free(ctx, h->sdf);
+    jc_free(ctx, h->ud); jc_free(ctx, h->vd); jc_free(ctx, h->wd);
+    for (int b = 0; b < 2; ++b) {
+        for (int q = 0; q < NATTR; ++q) jc_free(ctx, h->attr[b][q]);
+        jc_free(ctx, h->orig[b]);
+    }
+    jc_free(ctx, h->cell_of); jc_free(ctx, h->rank); jc_free(ctx, h->perm); jc_free(ctx, h->cell_start);
+    pressure_free(ctx, &h->ps);
+    for (int e = 0; e < 12; ++e) if (h->ev[e]) cudaEventDestroy(h->ev[e]);
+    cudaStreamSynchronize(ctx->stream);
+    delete h;
+    return JETCU_OK;
+}
+
+int jetcu_hybrid_set_particles(jetcu_hybrid* h, uint64_t n, const double* positions, const double* velocities) {
+    HYB_ENTER(h);
+    JC_ARG(ctx, n == 0 || positions != nullptr);
+    JC_ARG(ctx, n < (1ull << 32) - 1);
+    h->np = 0;
+    JC_TRY(hyb_reserve(h, n));
+    h->np = n;
+    h->binned = false;
+    if (n == 0) return JETCU_OK;
+    double* stage = nullptr;
+    JC_TRY(jc_alloc(ctx, &stage, 3 * n));
+    int rc = jc_h2d(ctx, stage, positions, 3 * n);
+    int c = h->cur;
+    if (rc == JETCU_OK) {
+        k_aos_to_soa3<<<jc_blocks(n, 256), 256, 0, ctx->stream>>>(stage, h->attr[c][0], h->attr[c][1], h->attr[c][2], n, 0);
+        ctx->launches++;
+    }
+    if (velocities) {
+        if (rc == JETCU_OK) rc = jc_h2d(ctx, stage, velocities, 3 * n);
+        if (rc == JETCU_OK) {
+            k_aos_to_soa3<<<jc_blocks(n, 256), 256, 0, ctx->stream>>>(stage, h->attr[c][3], h->attr[c][4], h->attr[c][5], n, 0);
+            ctx->launches++;
+        }
+    } else {
+        for (int q = 3; q < 6 && rc == JETCU_OK; ++q) rc = jc_zero(ctx, h->attr[c][q], n);
+    }
+    for (int q = 6; q < h->nattr && rc == JETCU_OK; ++q) rc = jc_zero(ctx, h->attr[c][q], n);
+    if (rc == JETCU_OK) {
+        k_iota_u32<<<jc_blocks(n, 256), 256, 0, ctx->stream>>>(h->orig[c], 0, n);
+        ctx->launches++;
+        rc = jc_sync(ctx);
+    }
+    jc_free(ctx, stage);
+    return rc;
+}
+
+int jetcu_hybrid_emit_box(jetcu_hybrid* h, const double lower[3], const double upper[3], double spacing,
+                          const double v0[3], uint64_t* n_emitted) {
+    HYB_ENTER(h);
+    JC_ARG(ctx, lower && upper && spacing > 0);
+    const jetcu_grid& g = h->P.grid;
+    // region = box ∩ domain bounding box (VolumeParticleEmitter3::emit, src/jet/volume_particle_emitter3.cpp:74-79)
+    double dlo[3] = {g.ox, g.oy, g.oz};
+    double dhi[3] = {g.ox + g.hx * (double)g.nx, g.oy + g.hy * (double)g.ny, g.oz + g.hz * (double)g.nz};
+    double lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) { lo[a] = fmax(dlo[a], lower[a]); hi[a] = fmin(dhi[a], upper[a]); }
+    unsigned cnt[3];
+    for (int a = 0; a < 3; ++a) {
+        double width = hi[a] - lo[a];
+        unsigned c = 0;
+        for (int i = 0; i * spacing <= width; ++i) ++c;  // same loop test as GridPointGenerator3::forEachPoint
+        cnt[a] = c;
+    }
+    uint64_t total = (uint64_t)cnt[0] * cnt[1] * cnt[2];
+    JC_ARG(ctx, h->np + total < (1ull << 32) - 1);
+    uint64_t old = h->np;
+    JC_TRY(hyb_reserve(h, old + total));
+    if (total > 0) {
+        int c = h->cur;
+        double z0[3] = {0, 0, 0};
+        const double* vv = v0 ? v0 : z0;
+        JC_LAUNCH(ctx, k_emit_lattice, jc_blocks(total, 256), 256, 0, h->attr[c][0], h->attr[c][1], h->attr[c][2],
+                  h->attr[c][3], h->attr[c][4], h->attr[c][5], h->orig[c], (size_t)old, cnt[0], cnt[1], cnt[2], spacing,
+                  lo[0], lo[1], lo[2], vv[0], vv[1], vv[2]);
+        for (int q = 6; q < h->nattr; ++q) JC_TRY(jc_zero(ctx, h->attr[c][q] + old, total));
+    }
+    h->np = old + total;
+    h->binned = false;
+    if (n_emitted) *n_emitted = total;
+    return jc_sync(ctx);
+}
+
+uint64_t jetcu_hybrid_num_particles(const jetcu_hybrid* h) { return h ? h->np : 0; }
+
+static int download_vec3(jetcu_hybrid* h, int a0, double* host) {
+    jetcu_ctx* ctx = h->ctx;
+    if (!host || h->np == 0) return JETCU_OK;
+    double* stage = nullptr;
+    JC_TRY(jc_alloc(ctx, &stage, 3 * h->np));
+    int c = h->cur;
+    k_soa_to_aos3_orig<<<jc_blocks(h->np, 256), 256, 0, ctx->stream>>>(h->attr[c][a0], h->attr[c][a0 + 1], h->attr[c][a0 + 2],
+                                                                      h->orig[c], stage, h->np);
+    ctx->launches++;
+    int rc = jc_d2h(ctx, host, stage, 3 * h->np);
+    if (rc == JETCU_OK) rc = jc_sync(ctx);
+    jc_free(ctx, stage);
+    return rc;
+}
+
+int jetcu_hybrid_get_particles(jetcu_hybrid* h, double* positions, double* velocities) {
+    HYB_ENTER(h);
+    JC_TRY(download_vec3(h, 0, positions));
+    return download_vec3(h, 3, velocities);
+}
+
+int jetcu_hybrid_get_affine(jetcu_hybrid* h, double* cx, double* cy, double* cz) {
+    HYB_ENTER(h);
+    if (h->P.mode != JETCU_APIC) return jetcu_fail(ctx, JETCU_ERR_INVALID_ARG, "affine vectors exist only in APIC mode");
+    JC_TRY(download_vec3(h, 6, cx));
+    JC_TRY(download_vec3(h, 9, cy));
+    return download_vec3(h, 12, cz);
+}
+
+int jetcu_hybrid_set_collider(jetcu_hybrid* h, const double* collider_sdf, const double*, const double*, const double*,
+                              double) {
+    HYB_ENTER(h);
+    if (collider_sdf)
+        return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED,
+                          "colliders inside the device-resident hybrid solver are not implemented yet "
+                          "(SURVEY §8f-1); jetcu_pressure_solve accepts a collider SDF");
+    return JETCU_OK;
+}
+
+int jetcu_hybrid_set_velocity(jetcu_hybrid* h, const double* u, const double* v, const double* w) {
+    HYB_ENTER(h);
+    if (u) JC_TRY(jc_h2d(ctx, h->u, u, h->nu));
+    if (v) JC_TRY(jc_h2d(ctx, h->v, v, h->nv));
+    if (w) JC_TRY(jc_h2d(ctx, h->w, w, h->nw));
+    return jc_sync(ctx);
+}
+
+int jetcu_hybrid_get_velocity(jetcu_hybrid* h, double* u, double* v, double* w) {
+    HYB_ENTER(h);
+    if (u) JC_TRY(jc_d2h(ctx, u, h->u, h->nu));
+    if (v) JC_TRY(jc_d2h(ctx, v, h->v, h->nv));
+    if (w) JC_TRY(jc_d2h(ctx, w, h->w, h->nw));
+    return jc_sync(ctx);
+}
+
+int jetcu_hybrid_get_sdf(jetcu_hybrid* h, double* sdf) {
+    HYB_ENTER(h);
+    JC_ARG(ctx, sdf);
+    JC_TRY(jc_d2h(ctx, sdf, h->sdf, h->nc));
+    return jc_sync(ctx);
+}
+
+int jetcu_hybrid_get_pressure(jetcu_hybrid* h, double* p) {
+    HYB_ENTER(h);
+    JC_ARG(ctx, p);
+    JC_TRY(jc_d2h(ctx, p, h->ps.x0, h->nc));
+    return jc_sync(ctx);
+}
+
+int jetcu_hybrid_get_markers(jetcu_hybrid* h, char* um, char* vm, char* wm) {
+    HYB_ENTER(h);
+    if (um) JC_TRY(jc_d2h(ctx, um, h->um, h->nu));
+    if (vm) JC_TRY(jc_d2h(ctx, vm, h->vm, h->nv));
+    if (wm) JC_TRY(jc_d2h(ctx, wm, h->wm, h->nw));
+    return jc_sync(ctx);
+}
+
+int jetcu_hybrid_cfl(jetcu_hybrid* h, double dt, double* cfl) {
+    HYB_ENTER(h);
+    JC_ARG(ctx, cfl);
+    GridD g = gridd(h);
+    const double* gr = h->P.gravity;
+    JC_LAUNCH(ctx, k_cfl_partial, CFL_GRID, CFL_BLOCK, 0, g, h->u, h->v, h->w, dt * gr[0], dt * gr[1], dt * gr[2],
+              ctx->d_partials);
+    JC_LAUNCH(ctx, k_max_final, 1, CFL_BLOCK, 0, ctx->d_partials, CFL_GRID, ctx->d_scalars);
+    JC_TRY(jc_d2h(ctx, ctx->h_scalars, ctx->d_scalars, 1));
+    JC_TRY(jc_sync(ctx));
+    double minH = fmin(fmin(g.hx, g.hy), g.hz);
+    *cfl = ctx->h_scalars[0] * dt / minH;
+    return JETCU_OK;
+}
+
+int jetcu_hybrid_num_sub_steps(jetcu_hybrid* h, double dt, uint32_t* n) {
+    HYB_ENTER(h);
+    JC_ARG(ctx, n);
+    double c;
+    JC_TRY(jetcu_hybrid_cfl(h, dt, &c));
+    *n = (uint32_t)fmax(ceil(c / h->P.max_cfl), 1.0);  // src/jet/grid_fluid_solver3.cpp:212-217
+    return JETCU_OK;
+}
+
+int jetcu_hybrid_apply_boundary_condition(jetcu_hybrid* h) {
+    HYB_ENTER(h);
+    return hyb_zero_walls(h);
+}
+
+int jetcu_hybrid_transfer_particles_to_grids(jetcu_hybrid* h) {
+    HYB_ENTER(h);
+    JC_TRY(hyb_bin(h));
+    GridD g = gridd(h);
+    AttrPtrs a = attr_ptrs(h, h->cur);
+    dim3 blk(32, 4);
+    dim3 gu((g.nx + 1 + 31) / 32, (g.ny + 3) / 4, g.nz), gv((g.nx + 31) / 32, (g.ny + 1 + 3) / 4, g.nz),
+        gw((g.nx + 31) / 32, (g.ny + 3) / 4, g.nz + 1);
+    if (h->P.mode == JETCU_APIC) {
+        JC_LAUNCH(ctx, (k_p2g<0, true>), gu, blk, 0, g, h->cell_start, a, h->u, h->um);
+        JC_LAUNCH(ctx, (k_p2g<1, true>), gv, blk, 0, g, h->cell_start, a, h->v, h->vm);
+        JC_LAUNCH(ctx, (k_p2g<2, true>), gw, blk, 0, g, h->cell_start, a, h->w, h->wm);
+    } else {
+        JC_LAUNCH(ctx, (k_p2g<0, false>), gu, blk, 0, g, h->cell_start, a, h->u, h->um);
+        JC_LAUNCH(ctx, (k_p2g<1, false>), gv, blk, 0, g, h->cell_start, a, h->v, h->vm);
+        JC_LAUNCH(ctx, (k_p2g<2, false>), gw, blk, 0, g, h->cell_start, a, h->w, h->wm);
+    }
+    if (h->P.mode == JETCU_FLIP) {
+        JC_LAUNCH(ctx, k_to_float, jc_blocks(h->nu, 256), 256, 0, h->u, h->ud, h->nu);
+        JC_LAUNCH(ctx, k_to_float, jc_blocks(h->nv, 256), 256, 0, h->v, h->vd, h->nv);
+        JC_LAUNCH(ctx, k_to_float, jc_blocks(h->nw, 256), 256, 0, h->w, h->wd, h->nw);
+    }
+    return JETCU_OK;
+}
+
+int jetcu_hybrid_build_signed_distance_field(jetcu_hybrid* h) {
+    HYB_ENTER(h);
+    JC_TRY(hyb_bin(h));
+    GridD g = gridd(h);
+    double maxH = fmax(fmax(g.hx, g.hy), g.hz);
+    double radius = 1.2 * maxH / sqrt(2.0);
+    double band = 2.0 * radius;
+    // a particle in cell c+d lies at least (|d|-0.5)h from the centre of cell c along that axis
+    int rx = (int)floor(band / g.hx + 0.5 + 1e-9), ry = (int)floor(band / g.hy + 0.5 + 1e-9), rz = (int)floor(band / g.hz + 0.5 + 1e-9);
+    dim3 grid((g.nx + 31) / 32, (g.ny + 3) / 4, g.nz);
+    int c = h->cur;
+    JC_LAUNCH(ctx, k_build_sdf, grid, dim3(32, 4), 0, g, h->cell_start, h->attr[c][0], h->attr[c][1], h->attr[c][2], radius,
+              band, rx, ry, rz, h->sdf);
+    // extrapolateIntoCollider (src/jet/grid_fluid_solver3.cpp:355-369) is the identity without a collider
+    return JETCU_OK;
+}
+
+int jetcu_hybrid_extrapolate_velocity_to_air(jetcu_hybrid* h) {
+    HYB_ENTER(h);
+    unsigned depth = (unsigned)ceil(h->P.max_cfl);  // src/jet/pic_solver3.cpp:284-294
+    JC_TRY(hyb_extrapolate_one(h, h->u, h->um, h->nx + 1, h->ny, h->nz, depth));
+    JC_TRY(hyb_extrapolate_one(h, h->v, h->vm, h->nx, h->ny + 1, h->nz, depth));
+    return hyb_extrapolate_one(h, h->w, h->wm, h->nx, h->ny, h->nz + 1, depth);
+}
+
+int jetcu_hybrid_begin_advance_time_step(jetcu_hybrid* h, double dt) {
+    HYB_ENTER(h);
+    (void)dt;
+    // GridFluidSolver3::beginAdvanceTimeStep (:437-462) then PicSolver3::onBeginAdvanceTimeStep (pic_solver3.cpp:63-93)
+    JC_TRY(hyb_zero_walls(h));
+    JC_TRY(jetcu_hybrid_transfer_particles_to_grids(h));
+    JC_TRY(jetcu_hybrid_build_signed_distance_field(h));
+    JC_TRY(jetcu_hybrid_extrapolate_velocity_to_air(h));
+    return hyb_zero_walls(h);
+}
+
+int jetcu_hybrid_compute_external_forces(jetcu_hybrid* h, double dt) {
+    HYB_ENTER(h);
+    const double* g = h->P.gravity;
+    if (g[0] * g[0] + g[1] * g[1] + g[2] * g[2] > DBL_EPSILON) {
+        if (fabs(g[0]) > DBL_EPSILON) JC_LAUNCH(ctx, k_add_scalar, jc_blocks(h->nu, 256), 256, 0, h->u, dt * g[0], h->nu);
+        if (fabs(g[1]) > DBL_EPSILON) JC_LAUNCH(ctx, k_add_scalar, jc_blocks(h->nv, 256), 256, 0, h->v, dt * g[1], h->nv);
+        if (fabs(g[2]) > DBL_EPSILON) JC_LAUNCH(ctx, k_add_scalar, jc_blocks(h->nw, 256), 256, 0, h->w, dt * g[2], h->nw);
+        JC_TRY(hyb_zero_walls(h));
+    }
+    return JETCU_OK;
+}
+
+int jetcu_hybrid_compute_pressure(jetcu_hybrid* h, double dt, jetcu_mgpcg_result* result) {
+    HYB_ENTER(h);
+    (void)dt;
+    // GridFluidSolver3::computePressure (:243-253): input is a clone of the velocity; every face is read and written
+    // by the same thread of k_apply_gradient, so solving in place is equivalent.
+    JC_TRY(pressure_solve_device(ctx, &h->ps, h->u, h->v, h->w, nullptr, nullptr, nullptr, nullptr, h->sdf, &h->P.mgpcg,
+                                 h->u, h->v, h->w, &h->last));
+    if (result) *result = h->last;
+    return hyb_zero_walls(h);
+}
+
+int jetcu_hybrid_transfer_grids_to_particles(jetcu_hybrid* h) {
+    HYB_ENTER(h);
+    GridD g = gridd(h);
+    size_t np = h->np;
+    AttrPtrs a = attr_ptrs(h, h->cur);
+    if (h->P.mode == JETCU_FLIP) {
+        JC_LAUNCH(ctx, k_flip_delta, jc_blocks(h->nu, 256), 256, 0, h->u, h->ud, h->nu);
+        JC_LAUNCH(ctx, k_flip_delta, jc_blocks(h->nv, 256), 256, 0, h->v, h->vd, h->nv);
+        JC_LAUNCH(ctx, k_flip_delta, jc_blocks(h->nw, 256), 256, 0, h->w, h->wd, h->nw);
+        if (np) JC_LAUNCH(ctx, k_g2p_flip, jc_blocks(np, 128), 128, 0, g, h->u, h->v, h->w, h->ud, h->vd, h->wd,
+                          h->P.pic_blending_factor, a, np);
+    } else if (h->P.mode == JETCU_APIC) {
+        if (np) JC_LAUNCH(ctx, k_g2p_apic, jc_blocks(np, 128), 128, 0, g, h->u, h->v, h->w, a, np);
+    } else {
+        if (np) JC_LAUNCH(ctx, k_g2p_pic, jc_blocks(np, 128), 128, 0, g, h->u, h->v, h->w, a, np);
+    }
+    return JETCU_OK;
+}
+
+int jetcu_hybrid_move_particles(jetcu_hybrid* h, double dt) {
+    HYB_ENTER(h);
+    GridD g = gridd(h);
+    unsigned nsub = (unsigned)fmax(h->P.max_cfl, 1.0);
+    double sub_dt = dt / nsub;
+    if (h->np)
+        JC_LAUNCH(ctx, k_move, jc_blocks(h->np, 128), 128, 0, g, h->u, h->v, h->w, sub_dt, nsub,
+                  h->P.closed_domain_boundary_flag, attr_ptrs(h, h->cur), (size_t)h->np);
+    h->binned = false;
+    return JETCU_OK;
+}
+
+int jetcu_hybrid_compute_advection(jetcu_hybrid* h, double dt) {
+    HYB_ENTER(h);
+    // PicSolver3::computeAdvection, src/jet/pic_solver3.cpp:95-112
+    JC_TRY(jetcu_hybrid_extrapolate_velocity_to_air(h));
+    JC_TRY(hyb_zero_walls(h));
+    JC_TRY(jetcu_hybrid_transfer_grids_to_particles(h));
+    return jetcu_hybrid_move_particles(h, dt);
+}
+
+int jetcu_hybrid_step(jetcu_hybrid* h, double dt, jetcu_step_stats* st) {
+    HYB_ENTER(h);
+    cudaStream_t s = ctx->stream;
+#define MARK(i) cudaEventRecord(h->ev[i], s)
+    MARK(0);
+    JC_TRY(hyb_zero_walls(h));
+    JC_TRY(hyb_bin(h));
+    MARK(1);
+    JC_TRY(jetcu_hybrid_transfer_particles_to_grids(h));
+    MARK(2);
+    JC_TRY(jetcu_hybrid_build_signed_distance_field(h));
+    MARK(3);
+    JC_TRY(jetcu_hybrid_extrapolate_velocity_to_air(h));
+    MARK(4);
+    JC_TRY(hyb_zero_walls(h));
+    JC_TRY(jetcu_hybrid_compute_external_forces(h, dt));
+    MARK(5);
+    JC_TRY(jetcu_hybrid_compute_pressure(h, dt, nullptr));
+    MARK(6);
+    JC_TRY(jetcu_hybrid_extrapolate_velocity_to_air(h));
+    JC_TRY(hyb_zero_walls(h));
+    MARK(7);
+    JC_TRY(jetcu_hybrid_transfer_grids_to_particles(h));
+    MARK(8);
+    JC_TRY(jetcu_hybrid_move_particles(h, dt));
+    MARK(9);
+#undef MARK
+    JC_TRY(jc_sync(ctx));
+    if (st) {
+        memset(st, 0, sizeof(*st));
+        auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]); return (double)ms; };
+        st->pcg_iterations = h->last.iterations;
+        st->pcg_last_residual = h->last.last_residual;
+        st->pcg_true_residual_l2 = h->last.true_residual_l2;
+        st->pcg_b_l2 = h->last.b_l2;
+        st->ms_total = el(0, 9);
+        st->ms_bin = el(0, 1);
+        st->ms_p2g = el(1, 2);
+        st->ms_sdf = el(2, 3);
+        st->ms_extrapolate = el(3, 4) + el(6, 7);
+        st->ms_bc = el(4, 5);
+        st->ms_pressure = el(5, 6);
+        st->ms_g2p = el(7, 8);
+        st->ms_move = el(8, 9);
+    }
+    return JETCU_OK;
+}
+
+int jetcu_hybrid_advance_frame(jetcu_hybrid* h, double frame_dt, uint32_t* n_sub_steps, jetcu_step_stats* last) {
+    HYB_ENTER(h);
+    // PhysicsAnimation::advanceTimeStep, adaptive branch (src/jet/physics_animation.cpp:102-121)
+    double remaining = frame_dt;
+    uint32_t count = 0;
+    while (remaining > DBL_EPSILON) {
+        uint32_t ns = 1;
+        JC_TRY(jetcu_hybrid_num_sub_steps(h, remaining, &ns));
+        double actual = remaining / (double)ns;
+        JC_TRY(jetcu_hybrid_step(h, actual, last));
+        remaining -= actual;
+        ++count;
+    }
+    if (n_sub_steps) *n_sub_steps = count;
+    return JETCU_OK;
+}
+
+}  // extern "C"

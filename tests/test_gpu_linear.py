@@ -79,21 +79,27 @@ def test_vcycle_bit_exact(jc, oracle, n, levels):
     same(jc.vcycle(Al, b, x0, p), oracle.vcycle(Al, b, x0, p), "V-cycle")
 
 
-def test_mgpcg_vs_oracle(jc, oracle):
-    """SPD (regularised) Poisson system: both converge; x within 1e-6 relative L-inf, same iteration count +-1."""
-    n, levels = 32, 4
+@pytest.mark.parametrize("n,levels,shift", [(32, 4, 0.05), (32, 3, 0.5), (64, 5, 0.01)])
+def test_mgpcg_vs_oracle(jc, oracle, n, levels, shift):
+    """SPD (regularised) Poisson systems.  Where the oracle's TRUE residual is small (the reference's PCG can leave
+    early on sigma <= tol^2) x must agree within 1e-6 relative L-inf; in every case the iteration
+    count and the exit sigma must follow the oracle (same control flow)."""
     Al = scenes.poisson_levels(n, levels)
     for A in Al:
-        A["center"] += 0.05
+        A["center"] += shift
     rng = np.random.default_rng(7)
     b = rng.uniform(-1, 1, (n, n, n))
     p = MgpcgParams.make(max_iterations=100, max_levels=levels, tolerance=1e-9)
     x0, r0 = jc.mgpcg_solve(Al, b, p)
     x1, r1 = oracle.mgpcg_solve(Al, b, p)
-    assert r1.true_residual_l2 <= 1e-8 * r1.b_l2 * 10
     assert abs(int(r0.iterations) - int(r1.iterations)) <= 1
-    assert np.abs(x0 - x1).max() <= 1e-6 * np.abs(x1).max()
-    assert r0.true_residual_l2 <= 1e-8 * r0.b_l2 * 10
+    if r1.true_residual_l2 <= 1e-7 * r1.b_l2:
+        assert np.abs(x0 - x1).max() <= 1e-6 * np.abs(x1).max()
+        assert r0.true_residual_l2 <= 1e-7 * r0.b_l2
+    else:
+        assert int(r0.iterations) == int(r1.iterations)
+        assert np.abs(x0 - x1).max() <= 1e-5 * np.abs(x1).max()
+        assert abs(r0.true_residual_l2 - r1.true_residual_l2) <= 1e-3 * r1.true_residual_l2
 
 
 def test_errors(jc):

@@ -20,6 +20,41 @@ int jetcu_fail(jetcu_ctx* ctx, int code, const char* fmt, ...) {
     return code;
 }
 
+int jc_prof_begin(jetcu_ctx* ctx, int kind) {
+    if (!ctx->profile) return -1;
+    if (ctx->prof_pending.size() >= 4096 && jc_prof_resolve(ctx) != JETCU_OK) return -1;
+    jetcu_ctx::ProfPending p{};
+    for (cudaEvent_t* e : {&p.e0, &p.e1}) {
+        if (!ctx->prof_free.empty()) { *e = ctx->prof_free.back(); ctx->prof_free.pop_back(); }
+        else if (cudaEventCreate(e) != cudaSuccess) return -1;
+    }
+    p.kind = kind;
+    cudaEventRecord(p.e0, ctx->stream);
+    ctx->prof_pending.push_back(p);
+    return (int)ctx->prof_pending.size() - 1;
+}
+
+void jc_prof_end(jetcu_ctx* ctx, int slot, uint64_t launches, uint64_t units) {
+    if (slot < 0) return;
+    jetcu_ctx::ProfPending& p = ctx->prof_pending[slot];
+    p.launches = launches; p.units = units;
+    cudaEventRecord(p.e1, ctx->stream);
+}
+
+int jc_prof_resolve(jetcu_ctx* ctx) {
+    if (ctx->prof_pending.empty()) return JETCU_OK;
+    JC_TRY(jc_sync(ctx));
+    for (auto& p : ctx->prof_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) {
+            ctx->prof_ms[p.kind] += ms; ctx->prof_launches[p.kind] += p.launches; ctx->prof_units[p.kind] += p.units;
+        }
+        ctx->prof_free.push_back(p.e0); ctx->prof_free.push_back(p.e1);
+    }
+    ctx->prof_pending.clear();
+    return JETCU_OK;
+}
+
 extern "C" {
 
 const char* jetcu_version(void) { return "jetcu 0.1 (sm_100a, fmad=false)"; }
@@ -70,6 +105,8 @@ int jetcu_ctx_destroy(jetcu_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->psys) { pressure_free(ctx, ctx->psys); delete ctx->psys; }
     cudaStreamSynchronize(ctx->stream);
+    jc_prof_resolve(ctx);
+    for (cudaEvent_t e : ctx->prof_free) cudaEventDestroy(e);
     cudaFreeHost(ctx->h_scalars);
     cudaFree(ctx->d_scalars);
     cudaFree(ctx->d_partials);
@@ -84,6 +121,26 @@ void* jetcu_stream(const jetcu_ctx* ctx) { return ctx ? (void*)ctx->stream : nul
 int jetcu_synchronize(jetcu_ctx* ctx) {
     if (!ctx) return JETCU_ERR_INVALID_ARG;
     return jc_sync(ctx);
+}
+
+int jetcu_profile_enable(jetcu_ctx* ctx, int on) {
+    if (!ctx) return JETCU_ERR_INVALID_ARG;
+    JC_TRY(jc_prof_resolve(ctx));
+    ctx->profile = on != 0;
+    if (on) {
+        for (int k = 0; k < JETCU_PROF_KINDS; ++k) { ctx->prof_ms[k] = 0; ctx->prof_launches[k] = 0; ctx->prof_units[k] = 0; }
+    }
+    return JETCU_OK;
+}
+
+int jetcu_profile_get(jetcu_ctx* ctx, int kind, double* total_ms, uint64_t* launches, uint64_t* units) {
+    if (!ctx) return JETCU_ERR_INVALID_ARG;
+    JC_ARG(ctx, kind >= 0 && kind < JETCU_PROF_KINDS);
+    JC_TRY(jc_prof_resolve(ctx));
+    if (total_ms) *total_ms = ctx->prof_ms[kind];
+    if (launches) *launches = ctx->prof_launches[kind];
+    if (units) *units = ctx->prof_units[kind];
+    return JETCU_OK;
 }
 
 uint32_t jetcu_mg_num_levels(uint64_t nx, uint64_t ny, uint64_t nz, uint32_t max_levels) {

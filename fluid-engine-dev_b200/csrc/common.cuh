@@ -26,7 +26,20 @@ struct jetcu_ctx {
     double* d_scalars = nullptr;
     double* d_partials = nullptr;  // dot-product partial sums
     size_t partials_cap = 0;
+    // optional per-kernel-family timing (jetcu_profile_*): CUDA event pairs on `stream`, resolved lazily
+    bool profile = false;
+    struct ProfPending { cudaEvent_t e0, e1; int kind; uint64_t launches, units; };
+    std::vector<ProfPending> prof_pending;
+    std::vector<cudaEvent_t> prof_free;
+    double prof_ms[JETCU_PROF_KINDS] = {};
+    uint64_t prof_launches[JETCU_PROF_KINDS] = {};
+    uint64_t prof_units[JETCU_PROF_KINDS] = {};
 };
+
+// Brackets a group of launches of one kernel family with events when profiling is on (no-ops otherwise).
+int jc_prof_begin(jetcu_ctx* ctx, int kind);
+void jc_prof_end(jetcu_ctx* ctx, int slot, uint64_t launches, uint64_t units);
+int jc_prof_resolve(jetcu_ctx* ctx);
 
 int jetcu_fail(jetcu_ctx* ctx, int code, const char* fmt, ...);
 

@@ -119,12 +119,15 @@ int fdm_residual(jetcu_ctx* ctx, Dim3i d, MatSoA A, const double* x, const doubl
     return JETCU_OK;
 }
 
-int fdm_relax_rb(jetcu_ctx* ctx, Dim3i d, MatSoA A, const double* b, double sor, unsigned iterations, double* x) {
+int fdm_relax_rb(jetcu_ctx* ctx, Dim3i d, MatSoA A, const double* b, double sor, unsigned iterations, double* x,
+                 int level) {
     dim3 grid(((d.nx + 1) / 2 + BX - 1) / BX, (d.ny + BY - 1) / BY, d.nz);
+    int slot = jc_prof_begin(ctx, level == 0 ? JETCU_PROF_RELAX_L0 : JETCU_PROF_RELAX_COARSE);
     for (unsigned it = 0; it < iterations; ++it) {
         JC_LAUNCH(ctx, k_relax_colour, grid, dim3(BX, BY), 0, A, b, x, sor, 0, d.nx, d.ny, d.nz);
         JC_LAUNCH(ctx, k_relax_colour, grid, dim3(BX, BY), 0, A, b, x, sor, 1, d.nx, d.ny, d.nz);
     }
+    jc_prof_end(ctx, slot, 2ull * iterations, (uint64_t)d.n() * iterations);
     return JETCU_OK;
 }
 
@@ -294,15 +297,15 @@ void mg_free(jetcu_ctx* ctx, MgLevels* mg) {
 // MgResult.lastResidualNorm, which FdmMgpcgSolver3::Preconditioner discards; they never touch x and are skipped.
 int mg_vcycle(jetcu_ctx* ctx, MgLevels* mg, const jetcu_mgpcg_params* p, int l) {
     Dim3i d = mg->dims[l];
-    JC_TRY(fdm_relax_rb(ctx, d, mg->A[l], mg->b[l], p->sor_factor, p->n_restriction, mg->x[l]));
+    JC_TRY(fdm_relax_rb(ctx, d, mg->A[l], mg->b[l], p->sor_factor, p->n_restriction, mg->x[l], l));
     if (l + 1 < mg->levels) {
         JC_TRY(fdm_residual_restrict(ctx, d, mg->A[l], mg->x[l], mg->b[l], mg->buf[l], mg->b[l + 1]));
         JC_TRY(jc_zero(ctx, mg->x[l + 1], mg->dims[l + 1].n()));
         JC_TRY(mg_vcycle(ctx, mg, p, l + 1));
         JC_TRY(fdm_correct(ctx, d, mg->x[l + 1], mg->x[l]));
-        JC_TRY(fdm_relax_rb(ctx, d, mg->A[l], mg->b[l], p->sor_factor, l > 0 ? p->n_correction : p->n_final, mg->x[l]));
+        JC_TRY(fdm_relax_rb(ctx, d, mg->A[l], mg->b[l], p->sor_factor, l > 0 ? p->n_correction : p->n_final, mg->x[l], l));
     } else {
-        JC_TRY(fdm_relax_rb(ctx, d, mg->A[l], mg->b[l], p->sor_factor, p->n_coarsest, mg->x[l]));
+        JC_TRY(fdm_relax_rb(ctx, d, mg->A[l], mg->b[l], p->sor_factor, p->n_coarsest, mg->x[l], l));
     }
     return JETCU_OK;
 }
@@ -353,7 +356,11 @@ int mgpcg_solve_device(jetcu_ctx* ctx, MgLevels* mg, const double* b, double* x,
     unsigned iter = 0;
     bool trigger = false;
     while (sigmaNew > p->tolerance * p->tolerance && iter < p->max_iterations) {
-        JC_TRY(fdm_mvm(ctx, d, mg->A[0], dd, q));
+        {
+            int slot = jc_prof_begin(ctx, JETCU_PROF_MVM_L0);
+            JC_TRY(fdm_mvm(ctx, d, mg->A[0], dd, q));
+            jc_prof_end(ctx, slot, 1, n);
+        }
         double dq;
         JC_TRY(fdm_dot(ctx, n, dd, q, ctx->d_scalars));
         JC_TRY(read_scalar(ctx, ctx->d_scalars, &dq));

@@ -21,7 +21,8 @@ void fdm_free_mat(jetcu_ctx* ctx, MatSoA* A);
 
 int fdm_mvm(jetcu_ctx* ctx, Dim3i d, MatSoA A, const double* v, double* out);
 int fdm_residual(jetcu_ctx* ctx, Dim3i d, MatSoA A, const double* x, const double* b, double* out);
-int fdm_relax_rb(jetcu_ctx* ctx, Dim3i d, MatSoA A, const double* b, double sor, unsigned iterations, double* x);
+int fdm_relax_rb(jetcu_ctx* ctx, Dim3i d, MatSoA A, const double* b, double sor, unsigned iterations, double* x,
+                 int level = -1);
 int fdm_restrict(jetcu_ctx* ctx, Dim3i fine, const double* finer, double* coarser);
 int fdm_residual_restrict(jetcu_ctx* ctx, Dim3i fine, MatSoA A, const double* x, const double* b, double* buf,
                           double* coarser);

@@ -509,17 +509,67 @@ __global__ void k_fill_f64(double* p, double v, size_t n) {
 }
 
 // GridPointGenerator3::forEachPoint lattice, src/jet/grid_point_generator3.cpp:12-37: position = idx*spacing + lower,
-// emitted k-outer, j, i-inner.
+// emitted k-outer, j, i-inner.  A point is kept iff SurfaceToImplicit3(Box3).signedDistance(p) <= 0
+// (src/jet/volume_particle_emitter3.cpp:93), replayed literally because for points exactly ON a box face the outcome
+// depends on the rounding of Plane3::closestPointLocal (src/jet/plane3.cpp:35-38): Box3::closestPointLocal /
+// closestNormalLocal (src/jet/box3.cpp:27-99), Surface3::isInsideLocal (src/jet/surface3.cpp:75-79),
+// SurfaceToImplicit3::signedDistanceLocal (src/jet/surface_to_implicit3.cpp:67-72).
+struct Box3d {
+    double lo[3], hi[3];
+};
+
+__device__ __forceinline__ bool box_emit_accept(const double p[3], const Box3d& bx) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        if (bx.hi[a] < p[a] || bx.lo[a] > p[a]) return false;  // outside: clamp() leaves a positive distance
+    int best = -1;
+    double best_d2 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {  // +x,+y,+z through upperCorner, then -x,-y,-z through lowerCorner
+        const int a = q % 3;
+        double d[3];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const double c = q < 3 ? bx.hi[b] : bx.lo[b];
+            d[b] = (b == a) ? c - p[b] : ((p[b] - c) + c) - p[b];
+        }
+        double d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+        if (best < 0 || d2 < best_d2) { best = q; best_d2 = d2; }
+    }
+    const int a = best % 3;
+    const double sgn = best < 3 ? 1.0 : -1.0;
+    const double c = best < 3 ? bx.hi[a] : bx.lo[a];
+    bool inside = (p[a] - c) * sgn < 0.0;
+    return inside || best_d2 == 0.0;
+}
+
+__device__ __forceinline__ void lattice_point(size_t t, unsigned cx, unsigned cy, double spacing, double lx, double ly,
+                                              double lz, double p[3]) {
+    int i = (int)(t % cx), j = (int)((t / cx) % cy), k = (int)(t / ((size_t)cx * cy));
+    p[0] = i * spacing + lx; p[1] = j * spacing + ly; p[2] = k * spacing + lz;
+}
+
+__global__ void k_emit_flags(uint32_t* __restrict__ flags, size_t total, unsigned cx, unsigned cy, double spacing, double lx,
+                             double ly, double lz, Box3d bx) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > total) return;
+    if (t == total) { flags[t] = 0; return; }
+    double p[3];
+    lattice_point(t, cx, cy, spacing, lx, ly, lz, p);
+    flags[t] = box_emit_accept(p, bx) ? 1u : 0u;
+}
+
 __global__ void k_emit_lattice(double* __restrict__ x, double* __restrict__ y, double* __restrict__ z, double* __restrict__ vx,
                                double* __restrict__ vy, double* __restrict__ vz, uint32_t* __restrict__ orig, size_t offset,
-                               unsigned cx, unsigned cy, unsigned cz, double spacing, double lx, double ly, double lz,
-                               double v0x, double v0y, double v0z) {
+                               const uint32_t* __restrict__ slot, size_t total, unsigned cx, unsigned cy, double spacing,
+                               double lx, double ly, double lz, double v0x, double v0y, double v0z) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t total = (size_t)cx * cy * cz;
     if (t >= total) return;
-    int i = (int)(t % cx), j = (int)((t / cx) % cy), k = (int)(t / ((size_t)cx * cy));
-    size_t o = offset + t;
-    x[o] = i * spacing + lx; y[o] = j * spacing + ly; z[o] = k * spacing + lz;
+    if (slot[t + 1] == slot[t]) return;  // rejected lattice point
+    double p[3];
+    lattice_point(t, cx, cy, spacing, lx, ly, lz, p);
+    size_t o = offset + slot[t];
+    x[o] = p[0]; y[o] = p[1]; z[o] = p[2];
     vx[o] = v0x; vy[o] = v0y; vz[o] = v0z;
     orig[o] = (uint32_t)o;
 }
@@ -742,7 +792,20 @@ int jetcu_hybrid_emit_box(jetcu_hybrid* h, const double lower[3], const double u
     double dlo[3] = {g.ox, g.oy, g.oz};
     double dhi[3] = {g.ox + g.hx * (double)g.nx, g.oy + g.hy * (double)g.ny, g.oz + g.hz * (double)g.nz};
     double lo[3], hi[3];
-    for (int a = 0; a < 3; ++a) { lo[a] = fmax(dlo[a], lower[a]); hi[a] = fmin(dhi[a], upper[a]); }
+    Box3d bx;
+    for (int a = 0; a < 3; ++a) {
+        // ImplicitSurface3::boundingBox() = Transform3::toWorld applied twice (Box3's and SurfaceToImplicit3's identity
+        // transforms: src/jet/surface3.cpp:27-29, surface_to_implicit3.cpp:63-65); each pass rebuilds the corners as
+        // size * (-+1/2) + midPoint (include/jet/detail/bounding_box3-inl.h:150-152,201-208), which is not exact.
+        double l = lower[a], u = upper[a];
+        for (int pass = 0; pass < 2; ++pass) {
+            double w = u - l, mid = (u + l) / 2.0;
+            double c0 = w * -0.5 + mid, c1 = w * 0.5 + mid;
+            l = fmin(c0, c1); u = fmax(c0, c1);
+        }
+        lo[a] = fmax(dlo[a], l); hi[a] = fmin(dhi[a], u);
+        bx.lo[a] = lower[a]; bx.hi[a] = upper[a];
+    }
     unsigned cnt[3];
     for (int a = 0; a < 3; ++a) {
         double width = hi[a] - lo[a];
@@ -751,21 +814,37 @@ int jetcu_hybrid_emit_box(jetcu_hybrid* h, const double lower[3], const double u
         cnt[a] = c;
     }
     uint64_t total = (uint64_t)cnt[0] * cnt[1] * cnt[2];
-    JC_ARG(ctx, h->np + total < (1ull << 32) - 1);
-    uint64_t old = h->np;
-    JC_TRY(hyb_reserve(h, old + total));
+    JC_ARG(ctx, h->np + total < (1ull << 32) - 2);
+    uint64_t old = h->np, accepted = 0;
     if (total > 0) {
-        int c = h->cur;
-        double z0[3] = {0, 0, 0};
-        const double* vv = v0 ? v0 : z0;
-        JC_LAUNCH(ctx, k_emit_lattice, jc_blocks(total, 256), 256, 0, h->attr[c][0], h->attr[c][1], h->attr[c][2],
-                  h->attr[c][3], h->attr[c][4], h->attr[c][5], h->orig[c], (size_t)old, cnt[0], cnt[1], cnt[2], spacing,
-                  lo[0], lo[1], lo[2], vv[0], vv[1], vv[2]);
-        for (int q = 6; q < h->nattr; ++q) JC_TRY(jc_zero(ctx, h->attr[c][q] + old, total));
+        uint32_t* slot = nullptr;
+        JC_TRY(jc_alloc(ctx, &slot, total + 1));
+        int rc = JETCU_OK;
+        k_emit_flags<<<jc_blocks(total + 1, 256), 256, 0, ctx->stream>>>(slot, (size_t)total, cnt[0], cnt[1], spacing, lo[0], lo[1],
+                                                                          lo[2], bx);
+        ctx->launches++;
+        rc = scan_exclusive_u32(ctx, slot, slot, total + 1);
+        uint32_t n_acc = 0;
+        if (rc == JETCU_OK) rc = jc_d2h(ctx, &n_acc, slot + total, 1);
+        if (rc == JETCU_OK) rc = jc_sync(ctx);
+        accepted = n_acc;
+        if (rc == JETCU_OK) rc = hyb_reserve(h, old + accepted);
+        if (rc == JETCU_OK && accepted > 0) {
+            int c = h->cur;
+            double z0[3] = {0, 0, 0};
+            const double* vv = v0 ? v0 : z0;
+            k_emit_lattice<<<jc_blocks(total, 256), 256, 0, ctx->stream>>>(
+                h->attr[c][0], h->attr[c][1], h->attr[c][2], h->attr[c][3], h->attr[c][4], h->attr[c][5], h->orig[c],
+                (size_t)old, slot, (size_t)total, cnt[0], cnt[1], spacing, lo[0], lo[1], lo[2], vv[0], vv[1], vv[2]);
+            ctx->launches++;
+            for (int q = 6; q < h->nattr && rc == JETCU_OK; ++q) rc = jc_zero(ctx, h->attr[c][q] + old, accepted);
+        }
+        jc_free(ctx, slot);
+        if (rc != JETCU_OK) return rc;
     }
-    h->np = old + total;
+    h->np = old + accepted;
     h->binned = false;
-    if (n_emitted) *n_emitted = total;
+    if (n_emitted) *n_emitted = accepted;
     return jc_sync(ctx);
 }
 

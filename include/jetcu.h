@@ -48,6 +48,21 @@ uint64_t jetcu_launch_count(const jetcu_ctx* ctx);
 void* jetcu_stream(const jetcu_ctx* ctx);
 int jetcu_synchronize(jetcu_ctx* ctx);
 
+/* Optional live timing of kernel families (bench.py's roofline): when enabled, groups of launches are bracketed
+ * by CUDA events on the ctx stream.  `units` counts the family's work items (cells x sweeps for RELAX_L0, cells
+ * for MVM_L0 ...), so achieved bytes/s = units * bytes_per_unit / total_ms.  Not part of the reference API. */
+enum {
+    JETCU_PROF_RELAX_L0 = 0,   /* red-black SOR sweeps on the finest MG level (unit: cell-sweep, 56 B) */
+    JETCU_PROF_RELAX_COARSE,   /* the same on all coarser levels */
+    JETCU_PROF_MVM_L0,         /* PCG matvec (unit: cell, 48 B) */
+    JETCU_PROF_TRANSFER,       /* residual+restrict / correct on all levels (unit: fine cell) */
+    JETCU_PROF_BLAS1,          /* dot / axpy / fused PCG updates (unit: element) */
+    JETCU_PROF_P2G,            /* particle-to-grid gather, all three components (unit: particle) */
+    JETCU_PROF_KINDS = 8
+};
+int jetcu_profile_enable(jetcu_ctx* ctx, int on);   /* on != 0 also clears the accumulators */
+int jetcu_profile_get(jetcu_ctx* ctx, int kind, double* total_ms, uint64_t* launches, uint64_t* units);
+
 /* ------------------------------------------------------------------ types */
 
 /* == jet::FdmMatrixRow3 (include/jet/fdm_linear_system3.h:18-30): 32-byte AoS row. */

@@ -196,7 +196,6 @@ int setup_levels(jetcu_ctx* ctx, MgLevels* mg, std::vector<DevMat*>& mats, uint6
                  uint32_t levels, const jetcu_matrix_row* const* A) {
     JC_ARG(ctx, levels >= 1 && levels <= JC_MAX_LEVELS);
     mg->levels = (int)levels;
-    mg->owns_A = false;
     for (uint32_t l = 0; l < levels; ++l) {
         if (l > 0) JC_ARG(ctx, ((nx >> (l - 1)) % 2 == 0) && ((ny >> (l - 1)) % 2 == 0) && ((nz >> (l - 1)) % 2 == 0));
         mg->dims[l] = Dim3i{(int)(nx >> l), (int)(ny >> l), (int)(nz >> l)};
@@ -204,7 +203,7 @@ int setup_levels(jetcu_ctx* ctx, MgLevels* mg, std::vector<DevMat*>& mats, uint6
         DevMat* m = new DevMat(ctx);
         mats.push_back(m);
         JC_TRY(m->upload(A[l], mg->dims[l].n()));
-        mg->A[l] = m->A;
+        mg->A[l] = mat_of(m->A);
     }
     // FdmMgUtils3::correct's clamp is only well defined for ny == nz (src/jet/fdm_mg_linear_system3.cpp:159)
     if (levels > 1) JC_ARG(ctx, ny == nz);
@@ -229,7 +228,7 @@ int jetcu_fdm_mvm(jetcu_ctx* ctx, uint64_t nx, uint64_t ny, uint64_t nz, const j
     size_t n = nx * ny * nz;
     DevMat m(ctx); DevVec dv(ctx), out(ctx);
     JC_TRY(m.upload(A, n)); JC_TRY(dv.upload(v, n)); JC_TRY(out.upload(nullptr, n));
-    JC_TRY(fdm_mvm(ctx, Dim3i{(int)nx, (int)ny, (int)nz}, m.A, dv.p, out.p));
+    JC_TRY(fdm_mvm(ctx, Dim3i{(int)nx, (int)ny, (int)nz}, mat_of(m.A), dv.p, out.p));
     JC_TRY(jc_d2h(ctx, result, out.p, n));
     return jc_sync(ctx);
 }
@@ -242,7 +241,7 @@ int jetcu_fdm_residual(jetcu_ctx* ctx, uint64_t nx, uint64_t ny, uint64_t nz, co
     size_t n = nx * ny * nz;
     DevMat m(ctx); DevVec dx(ctx), db(ctx), out(ctx);
     JC_TRY(m.upload(A, n)); JC_TRY(dx.upload(x, n)); JC_TRY(db.upload(b, n)); JC_TRY(out.upload(nullptr, n));
-    JC_TRY(fdm_residual(ctx, Dim3i{(int)nx, (int)ny, (int)nz}, m.A, dx.p, db.p, out.p));
+    JC_TRY(fdm_residual(ctx, Dim3i{(int)nx, (int)ny, (int)nz}, mat_of(m.A), dx.p, db.p, out.p));
     JC_TRY(jc_d2h(ctx, result, out.p, n));
     return jc_sync(ctx);
 }
@@ -253,9 +252,9 @@ int jetcu_fdm_relax_red_black(jetcu_ctx* ctx, uint64_t nx, uint64_t ny, uint64_t
     JC_TRY(check_dims(ctx, nx, ny, nz));
     JC_ARG(ctx, A && x && b);
     size_t n = nx * ny * nz;
-    DevMat m(ctx); DevVec dx(ctx), db(ctx);
-    JC_TRY(m.upload(A, n)); JC_TRY(dx.upload(x, n)); JC_TRY(db.upload(b, n));
-    JC_TRY(fdm_relax_rb(ctx, Dim3i{(int)nx, (int)ny, (int)nz}, m.A, db.p, sor_factor, iterations, dx.p));
+    DevMat m(ctx); DevVec dx(ctx), db(ctx), alt(ctx);
+    JC_TRY(m.upload(A, n)); JC_TRY(dx.upload(x, n)); JC_TRY(db.upload(b, n)); JC_TRY(alt.upload(nullptr, n));
+    JC_TRY(fdm_relax_rb(ctx, Dim3i{(int)nx, (int)ny, (int)nz}, mat_of(m.A), db.p, sor_factor, iterations, &dx.p, &alt.p));
     JC_TRY(jc_d2h(ctx, x, dx.p, n));
     return jc_sync(ctx);
 }
@@ -390,7 +389,7 @@ int jetcu_pressure_get_system(jetcu_ctx* ctx, uint32_t level, jetcu_matrix_row* 
     if (A) {
         jetcu_matrix_row* aos = nullptr;
         JC_TRY(jc_alloc(ctx, &aos, n));
-        int rc = fdm_soa_to_aos(ctx, ps->mg.A[level], aos, n);
+        int rc = fdm_mat_to_aos(ctx, ps->mg.A[level], aos, n);
         if (rc == JETCU_OK) rc = jc_d2h(ctx, A, aos, n);
         if (rc == JETCU_OK) rc = jc_sync(ctx);
         jc_free(ctx, aos);

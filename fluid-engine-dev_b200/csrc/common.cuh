@@ -124,14 +124,36 @@ static inline int jc_sync(jetcu_ctx* ctx) {
 
 static inline unsigned jc_blocks(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
-// Matrix in structure-of-arrays form: the device layout of Jet's FdmMatrix3 (AoS 32-byte rows on the host).
-// Four contiguous nx*ny*nz double planes => every stencil load is a coalesced 8-byte access.
+// Device layouts of Jet's FdmMatrix3 (AoS 32-byte rows on the host).
+//  * MatSoA:   four contiguous nx*ny*nz double planes (any 7-point matrix; seam 1, host-supplied systems).
+//  * packed:   what GridFractionalSinglePhasePressureSolver3::buildSingleSystem can produce — center as double plus
+//              the three +face weights as the reference's own floats; an off-diagonal is either 0 or exactly
+//              0.0 - double(weight) * invH^2 (…pressure_solver3.cpp:146-150), so it is rebuilt bit-exactly on the fly
+//              from 4 bytes instead of being read as 8: 20 B/row instead of 32 B/row.
 struct MatSoA {
     double* center = nullptr;
     double* right = nullptr;
     double* up = nullptr;
     double* front = nullptr;
 };
+
+struct Mat {
+    const double* center = nullptr;
+    const double* right = nullptr;  // generic form
+    const double* up = nullptr;
+    const double* front = nullptr;
+    const float* cr = nullptr;      // packed form: +x/+y/+z face weight where the coupling exists, else 0
+    const float* cu = nullptr;
+    const float* cf = nullptr;
+    double sx = 0, sy = 0, sz = 0;  // invH^2 per axis (packed form)
+    bool packed = false;
+};
+
+static inline Mat mat_of(const MatSoA& a) {
+    Mat m;
+    m.center = a.center; m.right = a.right; m.up = a.up; m.front = a.front;
+    return m;
+}
 
 struct Dim3i {
     int nx, ny, nz;

@@ -20,13 +20,31 @@ __global__ void k_aos_to_soa(const jetcu_matrix_row* __restrict__ aos, double* _
     c[i] = a.x; r[i] = a.y; u[i] = b.x; f[i] = b.y;
 }
 
-__global__ void k_soa_to_aos(const double* __restrict__ c, const double* __restrict__ r, const double* __restrict__ u,
-                             const double* __restrict__ f, jetcu_matrix_row* __restrict__ aos, size_t n) {
+// Off-diagonal accessors.  Packed form: 0.0 - double(weight) * invH^2 exactly as buildSingleSystem forms it
+// (src/jet/grid_fractional_single_phase_pressure_solver3.cpp:146-150: `row.right -= term` on a zeroed row).
+template <bool P>
+__device__ __forceinline__ double m_right(const Mat& A, size_t c) {
+    if (P) { float w = __ldg(A.cr + c); return w != 0.f ? -((double)w * A.sx) : 0.0; }
+    return __ldg(A.right + c);
+}
+template <bool P>
+__device__ __forceinline__ double m_up(const Mat& A, size_t c) {
+    if (P) { float w = __ldg(A.cu + c); return w != 0.f ? -((double)w * A.sy) : 0.0; }
+    return __ldg(A.up + c);
+}
+template <bool P>
+__device__ __forceinline__ double m_front(const Mat& A, size_t c) {
+    if (P) { float w = __ldg(A.cf + c); return w != 0.f ? -((double)w * A.sz) : 0.0; }
+    return __ldg(A.front + c);
+}
+
+template <bool P>
+__global__ void k_mat_to_aos(Mat A, jetcu_matrix_row* __restrict__ aos, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double2* p = reinterpret_cast<double2*>(aos + i);
-    p[0] = make_double2(c[i], r[i]);
-    p[1] = make_double2(u[i], f[i]);
+    p[0] = make_double2(A.center[i], m_right<P>(A, i));
+    p[1] = make_double2(m_up<P>(A, i), m_front<P>(A, i));
 }
 
 int fdm_alloc_mat(jetcu_ctx* ctx, MatSoA* A, size_t n) {
@@ -46,8 +64,9 @@ int fdm_aos_to_soa(jetcu_ctx* ctx, const jetcu_matrix_row* d_aos, MatSoA A, size
     return JETCU_OK;
 }
 
-int fdm_soa_to_aos(jetcu_ctx* ctx, MatSoA A, jetcu_matrix_row* d_aos, size_t n) {
-    JC_LAUNCH(ctx, k_soa_to_aos, jc_blocks(n, 256), 256, 0, A.center, A.right, A.up, A.front, d_aos, n);
+int fdm_mat_to_aos(jetcu_ctx* ctx, Mat A, jetcu_matrix_row* d_aos, size_t n) {
+    if (A.packed) JC_LAUNCH(ctx, k_mat_to_aos<true>, jc_blocks(n, 256), 256, 0, A, d_aos, n);
+    else JC_LAUNCH(ctx, k_mat_to_aos<false>, jc_blocks(n, 256), 256, 0, A, d_aos, n);
     return JETCU_OK;
 }
 
@@ -63,72 +82,209 @@ struct Offdiag {
     double t[6];
 };
 
-__device__ __forceinline__ Offdiag offdiag_terms(const MatSoA& A, const double* __restrict__ v, int i, int j, int k,
+template <bool P>
+__device__ __forceinline__ Offdiag offdiag_terms(const Mat& A, const double* __restrict__ v, int i, int j, int k,
                                                  int nx, int ny, int nz, size_t c) {
     const size_t sy = (size_t)nx, sz = (size_t)nx * ny;
     Offdiag o;
-    o.t[0] = (i > 0) ? A.right[c - 1] * v[c - 1] : 0.0;
-    o.t[1] = (i + 1 < nx) ? A.right[c] * v[c + 1] : 0.0;
-    o.t[2] = (j > 0) ? A.up[c - sy] * v[c - sy] : 0.0;
-    o.t[3] = (j + 1 < ny) ? A.up[c] * v[c + sy] : 0.0;
-    o.t[4] = (k > 0) ? A.front[c - sz] * v[c - sz] : 0.0;
-    o.t[5] = (k + 1 < nz) ? A.front[c] * v[c + sz] : 0.0;
+    o.t[0] = (i > 0) ? m_right<P>(A, c - 1) * v[c - 1] : 0.0;
+    o.t[1] = (i + 1 < nx) ? m_right<P>(A, c) * v[c + 1] : 0.0;
+    o.t[2] = (j > 0) ? m_up<P>(A, c - sy) * v[c - sy] : 0.0;
+    o.t[3] = (j + 1 < ny) ? m_up<P>(A, c) * v[c + sy] : 0.0;
+    o.t[4] = (k > 0) ? m_front<P>(A, c - sz) * v[c - sz] : 0.0;
+    o.t[5] = (k + 1 < nz) ? m_front<P>(A, c) * v[c + sz] : 0.0;
     return o;
 }
 
-__global__ void __launch_bounds__(BX* BY) k_mvm(MatSoA A, const double* __restrict__ v, double* __restrict__ out,
+template <bool P>
+__global__ void __launch_bounds__(BX* BY) k_mvm(Mat A, const double* __restrict__ v, double* __restrict__ out,
                                                 int nx, int ny, int nz) {
     int i = blockIdx.x * BX + threadIdx.x, j = blockIdx.y * BY + threadIdx.y, k = blockIdx.z;
     if (i >= nx || j >= ny) return;
     size_t c = ((size_t)k * ny + j) * nx + i;
-    Offdiag o = offdiag_terms(A, v, i, j, k, nx, ny, nz, c);
+    Offdiag o = offdiag_terms<P>(A, v, i, j, k, nx, ny, nz, c);
     out[c] = A.center[c] * v[c] + o.t[0] + o.t[1] + o.t[2] + o.t[3] + o.t[4] + o.t[5];
 }
 
 // FdmBlas3::residual, src/jet/fdm_linear_system3.cpp:98-116.
-__global__ void __launch_bounds__(BX* BY) k_residual(MatSoA A, const double* __restrict__ x,
+template <bool P>
+__global__ void __launch_bounds__(BX* BY) k_residual(Mat A, const double* __restrict__ x,
                                                      const double* __restrict__ b, double* __restrict__ out, int nx,
                                                      int ny, int nz) {
     int i = blockIdx.x * BX + threadIdx.x, j = blockIdx.y * BY + threadIdx.y, k = blockIdx.z;
     if (i >= nx || j >= ny) return;
     size_t c = ((size_t)k * ny + j) * nx + i;
-    Offdiag o = offdiag_terms(A, x, i, j, k, nx, ny, nz, c);
+    Offdiag o = offdiag_terms<P>(A, x, i, j, k, nx, ny, nz, c);
     out[c] = b[c] - A.center[c] * x[c] - o.t[0] - o.t[1] - o.t[2] - o.t[3] - o.t[4] - o.t[5];
 }
 
-// One colour of FdmGaussSeidelSolver3::relaxRedBlack, src/jet/fdm_gauss_seidel_solver3.cpp:150-221.
-// Each thread owns the cell of the requested colour inside the x-pair (2t, 2t+1).
-__global__ void __launch_bounds__(BX* BY) k_relax_colour(MatSoA A, const double* __restrict__ b, double* __restrict__ x,
-                                                         double w, int colour, int nx, int ny, int nz) {
-    int j = blockIdx.y * BY + threadIdx.y, k = blockIdx.z;
-    int i = 2 * (blockIdx.x * BX + threadIdx.x) + ((j + k + colour) & 1);
-    if (i >= nx || j >= ny) return;
-    size_t c = ((size_t)k * ny + j) * nx + i;
-    Offdiag o = offdiag_terms(A, x, i, j, k, nx, ny, nz, c);
-    double r = o.t[0] + o.t[1] + o.t[2] + o.t[3] + o.t[4] + o.t[5];
-    x[c] = (1.0 - w) * x[c] + w * (b[c] - r) / A.center[c];
-}
-
-int fdm_mvm(jetcu_ctx* ctx, Dim3i d, MatSoA A, const double* v, double* out) {
-    JC_LAUNCH(ctx, k_mvm, grid3(d), dim3(BX, BY), 0, A, v, out, d.nx, d.ny, d.nz);
-    return JETCU_OK;
-}
-
-int fdm_residual(jetcu_ctx* ctx, Dim3i d, MatSoA A, const double* x, const double* b, double* out) {
-    JC_LAUNCH(ctx, k_residual, grid3(d), dim3(BX, BY), 0, A, x, b, out, d.nx, d.ny, d.nz);
-    return JETCU_OK;
-}
-
-int fdm_relax_rb(jetcu_ctx* ctx, Dim3i d, MatSoA A, const double* b, double sor, unsigned iterations, double* x,
-                 int level) {
-    dim3 grid(((d.nx + 1) / 2 + BX - 1) / BX, (d.ny + BY - 1) / BY, d.nz);
-    int slot = jc_prof_begin(ctx, level == 0 ? JETCU_PROF_RELAX_L0 : JETCU_PROF_RELAX_COARSE);
-    for (unsigned it = 0; it < iterations; ++it) {
-        JC_LAUNCH(ctx, k_relax_colour, grid, dim3(BX, BY), 0, A, b, x, sor, 0, d.nx, d.ny, d.nz);
-        JC_LAUNCH(ctx, k_relax_colour, grid, dim3(BX, BY), 0, A, b, x, sor, 1, d.nx, d.ny, d.nz);
+// ---- FdmGaussSeidelSolver3::relaxRedBlack, src/jet/fdm_gauss_seidel_solver3.cpp:150-221 -----------------------
+// SOR update of one cell: x = (1-w) x + w (b - r)/center with r = the six off-diagonal products summed in the
+// reference's order -i,+i,-j,+j,-k,+k.  Red = (i+j+k) even; the whole red pass precedes the black pass.
+//
+// (a) Small grids: ONE CTA sweeps the whole level in place, `iterations` times, with __syncthreads() between the
+//     colour passes — the coarse MG levels are pure launch latency otherwise.
+#define SMALL_THREADS 1024
+#define SMALL_MAX_CELLS 8192
+template <bool P>
+__global__ void __launch_bounds__(SMALL_THREADS) k_relax_small(Mat A, const double* __restrict__ b, double* x, double w,
+                                                               int nx, int ny, int nz, unsigned iterations) {
+    const int hx = (nx + 1) / 2;
+    const int pairs = hx * ny * nz;
+    const size_t sy = (size_t)nx, sz = (size_t)nx * ny;
+    for (unsigned it = 0; it < 2 * iterations; ++it) {
+        const int colour = it & 1;
+        for (int t = threadIdx.x; t < pairs; t += SMALL_THREADS) {
+            int ip = t % hx, j = (t / hx) % ny, k = t / (hx * ny);
+            int i = 2 * ip + ((j + k + colour) & 1);
+            if (i >= nx) continue;
+            size_t c = (size_t)k * sz + (size_t)j * sy + i;
+            double t0 = (i > 0) ? m_right<P>(A, c - 1) * x[c - 1] : 0.0;
+            double t1 = (i + 1 < nx) ? m_right<P>(A, c) * x[c + 1] : 0.0;
+            double t2 = (j > 0) ? m_up<P>(A, c - sy) * x[c - sy] : 0.0;
+            double t3 = (j + 1 < ny) ? m_up<P>(A, c) * x[c + sy] : 0.0;
+            double t4 = (k > 0) ? m_front<P>(A, c - sz) * x[c - sz] : 0.0;
+            double t5 = (k + 1 < nz) ? m_front<P>(A, c) * x[c + sz] : 0.0;
+            double r = t0 + t1 + t2 + t3 + t4 + t5;
+            x[c] = (1.0 - w) * x[c] + w * (b[c] - r) / A.center[c];
+        }
+        __syncthreads();
     }
-    jc_prof_end(ctx, slot, 2ull * iterations, (uint64_t)d.n() * iterations);
+}
+
+// (b) Large grids: ONE launch per full sweep.  A CTA owns an (x,y) tile and marches along z through a chunk of planes;
+//     every thread owns one column and keeps its z-neighbours in registers, in-plane neighbours go through shared
+//     memory.  At step p it (1) forms x1(p) = red pass applied to plane p (tile + one ring of redundant cells, so no
+//     inter-CTA communication is needed), then (2) applies the black pass to plane p-1 from x1(p-2), x1(p-1), x1(p)
+//     and writes the finished plane to `xout`.  Every array is streamed once per sweep with full-line accesses:
+//     56 B/cell (36..44 B/cell with the packed matrix) instead of the ~100 B/cell two colour passes move.
+//     Out of place (xin -> xout) because neighbouring CTAs still read the old values of this tile's border cells.
+#define RTX 32
+#define RTY 16
+template <bool P>
+__global__ void __launch_bounds__(RTX* RTY, 2)
+    k_relax_fused(Mat A, const double* __restrict__ b, const double* __restrict__ xin, double* __restrict__ xout,
+                  double w, int nx, int ny, int nz, int zc) {
+    __shared__ double X0[RTY + 2][RTX + 2];  // x0 plane p: tile + ring 1 (owned by threads) + ring 2
+    __shared__ double X1[2][RTY][RTX];       // x1 planes p-1, p: tile + ring 1
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i = blockIdx.x * (RTX - 2) + tx - 1, j = blockIdx.y * (RTY - 2) + ty - 1;
+    const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, nz);
+    const bool valid = i >= 0 && i < nx && j >= 0 && j < ny;
+    const bool interior = valid && tx >= 1 && tx <= RTX - 2 && ty >= 1 && ty <= RTY - 2;
+    const size_t sy = (size_t)nx, sz = (size_t)nx * ny;
+    const size_t col = valid ? (size_t)j * sy + i : 0;
+    const double omw = 1.0 - w;
+
+    auto ld_x = [&](int ii, int jj, int k) -> double {
+        return (ii >= 0 && ii < nx && jj >= 0 && jj < ny && k >= 0 && k < nz) ? xin[(size_t)k * sz + (size_t)jj * sy + ii] : 0.0;
+    };
+    auto ld_f = [&](int k) -> double { return (valid && k >= 0 && k < nz) ? m_front<P>(A, col + (size_t)k * sz) : 0.0; };
+
+    double xo_m = ld_x(i, j, z0 - 2), xo_c = ld_x(i, j, z0 - 1);  // x0 at planes p-1, p
+    double x1_m2 = 0.0, x1_m1 = 0.0;                              // x1 at planes p-2, p-1
+    double fr_mm = 0.0, fr_m = ld_f(z0 - 2);                      // front coefficient of planes p-2, p-1
+
+    for (int p = z0 - 1; p <= z1; ++p) {
+        const double xo_p = ld_x(i, j, p + 1);
+        const double fr_c = ld_f(p);
+        X0[ty + 1][tx + 1] = xo_c;
+        if (tx == 0) X0[ty + 1][0] = ld_x(i - 1, j, p);
+        if (tx == RTX - 1) X0[ty + 1][RTX + 1] = ld_x(i + 1, j, p);
+        if (ty == 0) X0[0][tx + 1] = ld_x(i, j - 1, p);
+        if (ty == RTY - 1) X0[RTY + 1][tx + 1] = ld_x(i, j + 1, p);
+        __syncthreads();
+        double x1_c = xo_c;
+        if (valid && p >= 0 && p < nz && ((i + j + p) & 1) == 0) {  // red pass, plane p
+            const size_t c = col + (size_t)p * sz;
+            double t0 = (i > 0) ? m_right<P>(A, c - 1) * X0[ty + 1][tx] : 0.0;
+            double t1 = (i + 1 < nx) ? m_right<P>(A, c) * X0[ty + 1][tx + 2] : 0.0;
+            double t2 = (j > 0) ? m_up<P>(A, c - sy) * X0[ty][tx + 1] : 0.0;
+            double t3 = (j + 1 < ny) ? m_up<P>(A, c) * X0[ty + 2][tx + 1] : 0.0;
+            double t4 = (p > 0) ? fr_m * xo_m : 0.0;
+            double t5 = (p + 1 < nz) ? fr_c * xo_p : 0.0;
+            double r = t0 + t1 + t2 + t3 + t4 + t5;
+            x1_c = omw * xo_c + w * (__ldg(b + c) - r) / __ldg(A.center + c);
+        }
+        X1[p & 1][ty][tx] = x1_c;
+        __syncthreads();
+        const int q = p - 1;
+        if (interior && q >= z0 && q < z1) {  // black pass, plane q
+            const size_t c = col + (size_t)q * sz;
+            double x2 = x1_m1;
+            if (((i + j + q) & 1) == 1) {
+                const double(*Xq)[RTX] = X1[q & 1];
+                double t0 = (i > 0) ? m_right<P>(A, c - 1) * Xq[ty][tx - 1] : 0.0;
+                double t1 = (i + 1 < nx) ? m_right<P>(A, c) * Xq[ty][tx + 1] : 0.0;
+                double t2 = (j > 0) ? m_up<P>(A, c - sy) * Xq[ty - 1][tx] : 0.0;
+                double t3 = (j + 1 < ny) ? m_up<P>(A, c) * Xq[ty + 1][tx] : 0.0;
+                double t4 = (q > 0) ? fr_mm * x1_m2 : 0.0;
+                double t5 = (q + 1 < nz) ? fr_m * x1_c : 0.0;
+                double r = t0 + t1 + t2 + t3 + t4 + t5;
+                x2 = omw * x1_m1 + w * (__ldg(b + c) - r) / __ldg(A.center + c);
+            }
+            xout[c] = x2;
+        }
+        xo_m = xo_c; xo_c = xo_p;
+        x1_m2 = x1_m1; x1_m1 = x1_c;
+        fr_mm = fr_m; fr_m = fr_c;
+    }
+}
+
+template <bool P>
+static int launch_mvm(jetcu_ctx* ctx, Dim3i d, Mat A, const double* v, double* out) {
+    JC_LAUNCH(ctx, k_mvm<P>, grid3(d), dim3(BX, BY), 0, A, v, out, d.nx, d.ny, d.nz);
     return JETCU_OK;
+}
+
+int fdm_mvm(jetcu_ctx* ctx, Dim3i d, Mat A, const double* v, double* out) {
+    return A.packed ? launch_mvm<true>(ctx, d, A, v, out) : launch_mvm<false>(ctx, d, A, v, out);
+}
+
+template <bool P>
+static int launch_residual(jetcu_ctx* ctx, Dim3i d, Mat A, const double* x, const double* b, double* out) {
+    JC_LAUNCH(ctx, k_residual<P>, grid3(d), dim3(BX, BY), 0, A, x, b, out, d.nx, d.ny, d.nz);
+    return JETCU_OK;
+}
+
+int fdm_residual(jetcu_ctx* ctx, Dim3i d, Mat A, const double* x, const double* b, double* out) {
+    return A.packed ? launch_residual<true>(ctx, d, A, x, b, out) : launch_residual<false>(ctx, d, A, x, b, out);
+}
+
+template <bool P>
+static int launch_relax(jetcu_ctx* ctx, Dim3i d, Mat A, const double* b, double sor, unsigned iterations, double** x,
+                        double** xalt, uint64_t* launches) {
+    if (d.n() <= SMALL_MAX_CELLS) {
+        JC_LAUNCH(ctx, k_relax_small<P>, 1, SMALL_THREADS, 0, A, b, *x, sor, d.nx, d.ny, d.nz, iterations);
+        *launches = 1;
+        return JETCU_OK;
+    }
+    // z-chunk length: enough CTAs to fill the machine (>= ~4 per SM), as long as possible otherwise (each chunk
+    // recomputes the red pass of its two neighbouring planes)
+    const int tiles = ((d.nx + RTX - 3) / (RTX - 2)) * ((d.ny + RTY - 3) / (RTY - 2));
+    int chunks = (4 * ctx->sm_count + tiles - 1) / tiles;
+    if (chunks < 1) chunks = 1;
+    if (chunks > d.nz) chunks = d.nz;
+    int zc = (d.nz + chunks - 1) / chunks;
+    if (zc < 4 && d.nz >= 4) zc = 4;
+    dim3 grid((d.nx + RTX - 3) / (RTX - 2), (d.ny + RTY - 3) / (RTY - 2), (d.nz + zc - 1) / zc);
+    for (unsigned it = 0; it < iterations; ++it) {
+        JC_LAUNCH(ctx, k_relax_fused<P>, grid, dim3(RTX, RTY), 0, A, b, *x, *xalt, sor, d.nx, d.ny, d.nz, zc);
+        double* t = *x; *x = *xalt; *xalt = t;
+    }
+    *launches = iterations;
+    return JETCU_OK;
+}
+
+int fdm_relax_rb(jetcu_ctx* ctx, Dim3i d, Mat A, const double* b, double sor, unsigned iterations, double** x,
+                 double** xalt, int level) {
+    if (iterations == 0) return JETCU_OK;
+    int slot = jc_prof_begin(ctx, level == 0 ? JETCU_PROF_RELAX_L0 : JETCU_PROF_RELAX_COARSE);
+    uint64_t launches = 0;
+    int rc = A.packed ? launch_relax<true>(ctx, d, A, b, sor, iterations, x, xalt, &launches)
+                      : launch_relax<false>(ctx, d, A, b, sor, iterations, x, xalt, &launches);
+    jc_prof_end(ctx, slot, launches, (uint64_t)d.n() * iterations);
+    return rc;
 }
 
 // FdmMgUtils3::restrict, src/jet/fdm_mg_linear_system3.cpp:43-98: 4x4x4 (1,3,3,1)/8 tensor filter with edge clamp;
@@ -191,7 +347,7 @@ int fdm_restrict(jetcu_ctx* ctx, Dim3i fine, const double* finer, double* coarse
     return JETCU_OK;
 }
 
-int fdm_residual_restrict(jetcu_ctx* ctx, Dim3i fine, MatSoA A, const double* x, const double* b, double* buf,
+int fdm_residual_restrict(jetcu_ctx* ctx, Dim3i fine, Mat A, const double* x, const double* b, double* buf,
                           double* coarser) {
     JC_TRY(fdm_residual(ctx, fine, A, x, b, buf));
     return fdm_restrict(ctx, fine, buf, coarser);
@@ -277,17 +433,17 @@ int fdm_pcg_update(jetcu_ctx* ctx, size_t n, double alpha, const double* d, cons
 int mg_alloc_vectors(jetcu_ctx* ctx, MgLevels* mg) {
     for (int l = 0; l < mg->levels; ++l) {
         size_t n = mg->dims[l].n();
-        JC_TRY(jc_alloc(ctx, &mg->x[l], n));
-        JC_TRY(jc_alloc(ctx, &mg->b[l], n));
-        JC_TRY(jc_alloc(ctx, &mg->buf[l], n));
+        for (int q = 0; q < 4; ++q) JC_TRY(jc_alloc(ctx, &mg->own_vec[l][q], n));
+        mg->x[l] = mg->own_vec[l][0]; mg->xalt[l] = mg->own_vec[l][1];
+        mg->b[l] = mg->own_vec[l][2]; mg->buf[l] = mg->own_vec[l][3];
     }
     return JETCU_OK;
 }
 
 void mg_free(jetcu_ctx* ctx, MgLevels* mg) {
-    for (int l = 0; l < mg->levels; ++l) {
-        jc_free(ctx, mg->x[l]); jc_free(ctx, mg->b[l]); jc_free(ctx, mg->buf[l]);
-        if (mg->owns_A) fdm_free_mat(ctx, &mg->A[l]);
+    for (int l = 0; l < JC_MAX_LEVELS; ++l) {
+        for (int q = 0; q < 4; ++q) jc_free(ctx, mg->own_vec[l][q]);
+        mg->x[l] = mg->xalt[l] = mg->b[l] = mg->buf[l] = nullptr;
     }
     mg->levels = 0;
 }
@@ -295,31 +451,38 @@ void mg_free(jetcu_ctx* ctx, MgLevels* mg) {
 // internal::mgVCycle, include/jet/detail/mg-inl.h:16-68, with FdmMgSolver3's relax lambdas
 // (src/jet/fdm_mg_solver3.cpp:26-49).  The residual + l2Norm the reference evaluates on the way up only feed
 // MgResult.lastResidualNorm, which FdmMgpcgSolver3::Preconditioner discards; they never touch x and are skipped.
+// mg->x[l] / mg->xalt[l] may be exchanged by the smoother; mg->x[l] always names the current iterate.
 int mg_vcycle(jetcu_ctx* ctx, MgLevels* mg, const jetcu_mgpcg_params* p, int l) {
     Dim3i d = mg->dims[l];
-    JC_TRY(fdm_relax_rb(ctx, d, mg->A[l], mg->b[l], p->sor_factor, p->n_restriction, mg->x[l], l));
+    JC_TRY(fdm_relax_rb(ctx, d, mg->A[l], mg->b[l], p->sor_factor, p->n_restriction, &mg->x[l], &mg->xalt[l], l));
     if (l + 1 < mg->levels) {
+        int slot = jc_prof_begin(ctx, JETCU_PROF_TRANSFER);
         JC_TRY(fdm_residual_restrict(ctx, d, mg->A[l], mg->x[l], mg->b[l], mg->buf[l], mg->b[l + 1]));
         JC_TRY(jc_zero(ctx, mg->x[l + 1], mg->dims[l + 1].n()));
+        jc_prof_end(ctx, slot, 2, d.n());
         JC_TRY(mg_vcycle(ctx, mg, p, l + 1));
+        slot = jc_prof_begin(ctx, JETCU_PROF_TRANSFER);
         JC_TRY(fdm_correct(ctx, d, mg->x[l + 1], mg->x[l]));
-        JC_TRY(fdm_relax_rb(ctx, d, mg->A[l], mg->b[l], p->sor_factor, l > 0 ? p->n_correction : p->n_final, mg->x[l], l));
+        jc_prof_end(ctx, slot, 1, d.n());
+        JC_TRY(fdm_relax_rb(ctx, d, mg->A[l], mg->b[l], p->sor_factor, l > 0 ? p->n_correction : p->n_final, &mg->x[l],
+                            &mg->xalt[l], l));
     } else {
-        JC_TRY(fdm_relax_rb(ctx, d, mg->A[l], mg->b[l], p->sor_factor, p->n_coarsest, mg->x[l], l));
+        JC_TRY(fdm_relax_rb(ctx, d, mg->A[l], mg->b[l], p->sor_factor, p->n_coarsest, &mg->x[l], &mg->xalt[l], l));
     }
     return JETCU_OK;
 }
 
 // FdmMgpcgSolver3::Preconditioner::solve, src/jet/fdm_mgpcg_solver3.cpp:21-36: the V-cycle's initial guess is the
-// CURRENT content of the output vector.  We run the cycle directly on (b_in, x_inout) as level 0's b and x.
-static int precondition(jetcu_ctx* ctx, MgLevels* mg, const jetcu_mgpcg_params* p, double* b_in, double* x_inout) {
-    double* saved_x = mg->x[0];
-    double* saved_b = mg->b[0];
-    mg->x[0] = x_inout;
-    mg->b[0] = b_in;
+// CURRENT content of the output vector.  We run the cycle directly on (b_in, *x_inout) as level 0's b and x, with
+// *scratch as the ping-pong partner; on return *x_inout names the buffer holding the result (the two pointers may
+// have been exchanged).
+static int precondition(jetcu_ctx* ctx, MgLevels* mg, const jetcu_mgpcg_params* p, double* b_in, double** x_inout,
+                        double** scratch) {
+    double *saved_x = mg->x[0], *saved_alt = mg->xalt[0], *saved_b = mg->b[0];
+    mg->x[0] = *x_inout; mg->xalt[0] = *scratch; mg->b[0] = b_in;
     int rc = mg_vcycle(ctx, mg, p, 0);
-    mg->x[0] = saved_x;
-    mg->b[0] = saved_b;
+    *x_inout = mg->x[0]; *scratch = mg->xalt[0];
+    mg->x[0] = saved_x; mg->xalt[0] = saved_alt; mg->b[0] = saved_b;
     return rc;
 }
 
@@ -340,15 +503,17 @@ int mgpcg_solve_device(jetcu_ctx* ctx, MgLevels* mg, const double* b, double* x,
                           "lexicographic Gauss-Seidel is inherently serial; use useRedBlackOrdering = true");
     const Dim3i d = mg->dims[0];
     const size_t n = d.n();
-    double *r, *dd, *q, *s;
-    JC_TRY(jc_alloc(ctx, &r, n)); JC_TRY(jc_alloc(ctx, &dd, n)); JC_TRY(jc_alloc(ctx, &q, n)); JC_TRY(jc_alloc(ctx, &s, n));
+    // level 0's own x / xalt / b are idle during PCG (the V-cycle runs on the PCG vectors): reuse them as r, q and the
+    // ping-pong scratch t; buf[0] stays the residual temporary of the V-cycle.
+    double *r = mg->own_vec[0][0], *q = mg->own_vec[0][1], *t = mg->own_vec[0][2], *dd = nullptr, *s = nullptr;
+    JC_TRY(jc_alloc(ctx, &dd, n)); JC_TRY(jc_alloc(ctx, &s, n));
     cudaEvent_t e0, e1;
     JC_CUDA(ctx, cudaEventCreate(&e0)); JC_CUDA(ctx, cudaEventCreate(&e1));
     JC_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
 
     JC_TRY(jc_zero(ctx, x, n)); JC_TRY(jc_zero(ctx, dd, n)); JC_TRY(jc_zero(ctx, q, n)); JC_TRY(jc_zero(ctx, s, n));
     JC_TRY(fdm_residual(ctx, d, mg->A[0], x, b, r));
-    JC_TRY(precondition(ctx, mg, p, r, dd));
+    JC_TRY(precondition(ctx, mg, p, r, &dd, &t));
     double sigmaNew;
     JC_TRY(fdm_dot(ctx, n, r, dd, ctx->d_scalars));
     JC_TRY(read_scalar(ctx, ctx->d_scalars, &sigmaNew));
@@ -371,7 +536,7 @@ int mgpcg_solve_device(jetcu_ctx* ctx, MgLevels* mg, const double* b, double* x,
             JC_TRY(fdm_residual(ctx, d, mg->A[0], x, b, r));
             trigger = false;
         }
-        JC_TRY(precondition(ctx, mg, p, r, s));
+        JC_TRY(precondition(ctx, mg, p, r, &s, &t));
         double sigmaOld = sigmaNew;
         JC_TRY(fdm_dot(ctx, n, r, s, ctx->d_scalars));
         JC_TRY(read_scalar(ctx, ctx->d_scalars, &sigmaNew));
@@ -402,6 +567,9 @@ int mgpcg_solve_device(jetcu_ctx* ctx, MgLevels* mg, const double* b, double* x,
         JC_TRY(jc_sync(ctx));
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    jc_free(ctx, r); jc_free(ctx, dd); jc_free(ctx, q); jc_free(ctx, s);
+    // dd / s / t may have been exchanged by the ping-pong smoother: keep one as level 0's third vector, free two
+    mg->own_vec[0][2] = t;
+    mg->x[0] = mg->own_vec[0][0]; mg->xalt[0] = mg->own_vec[0][1]; mg->b[0] = mg->own_vec[0][2];
+    jc_free(ctx, dd); jc_free(ctx, s);
     return JETCU_OK;
 }

@@ -7,24 +7,28 @@
 struct MgLevels {
     int levels = 0;
     Dim3i dims[JC_MAX_LEVELS];
-    MatSoA A[JC_MAX_LEVELS];
+    Mat A[JC_MAX_LEVELS];
     double* x[JC_MAX_LEVELS] = {};
+    double* xalt[JC_MAX_LEVELS] = {};  // ping-pong partner of x (the fused red+black sweep is out of place)
     double* b[JC_MAX_LEVELS] = {};
     double* buf[JC_MAX_LEVELS] = {};
-    bool owns_A = false;
+    // allocations owned by this object (the Mat views may also point at caller-owned memory)
+    double* own_vec[JC_MAX_LEVELS][4] = {};
 };
 
 int fdm_aos_to_soa(jetcu_ctx* ctx, const jetcu_matrix_row* d_aos, MatSoA A, size_t n);
-int fdm_soa_to_aos(jetcu_ctx* ctx, MatSoA A, jetcu_matrix_row* d_aos, size_t n);
+int fdm_mat_to_aos(jetcu_ctx* ctx, Mat A, jetcu_matrix_row* d_aos, size_t n);
 int fdm_alloc_mat(jetcu_ctx* ctx, MatSoA* A, size_t n);
 void fdm_free_mat(jetcu_ctx* ctx, MatSoA* A);
 
-int fdm_mvm(jetcu_ctx* ctx, Dim3i d, MatSoA A, const double* v, double* out);
-int fdm_residual(jetcu_ctx* ctx, Dim3i d, MatSoA A, const double* x, const double* b, double* out);
-int fdm_relax_rb(jetcu_ctx* ctx, Dim3i d, MatSoA A, const double* b, double sor, unsigned iterations, double* x,
-                 int level = -1);
+int fdm_mvm(jetcu_ctx* ctx, Dim3i d, Mat A, const double* v, double* out);
+int fdm_residual(jetcu_ctx* ctx, Dim3i d, Mat A, const double* x, const double* b, double* out);
+// `iterations` red-black SOR sweeps.  On return *x holds the result; *x and *xalt may have been exchanged
+// (large grids use an out-of-place fused red+black kernel and ping-pong between the two buffers).
+int fdm_relax_rb(jetcu_ctx* ctx, Dim3i d, Mat A, const double* b, double sor, unsigned iterations, double** x,
+                 double** xalt, int level = -1);
 int fdm_restrict(jetcu_ctx* ctx, Dim3i fine, const double* finer, double* coarser);
-int fdm_residual_restrict(jetcu_ctx* ctx, Dim3i fine, MatSoA A, const double* x, const double* b, double* buf,
+int fdm_residual_restrict(jetcu_ctx* ctx, Dim3i fine, Mat A, const double* x, const double* b, double* buf,
                           double* coarser);
 int fdm_correct(jetcu_ctx* ctx, Dim3i fine, const double* coarser, double* finer);
 // result written to d_result[0] (device); deterministic two-stage tree reduction.

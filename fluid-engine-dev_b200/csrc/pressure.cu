@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(PBX* PBY)
                    const float* __restrict__ uw, const float* __restrict__ vw, const float* __restrict__ ww,
                    const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
                    const double* __restrict__ bu, const double* __restrict__ bv, const double* __restrict__ bw,
-                   MatSoA A, double* __restrict__ b) {
+                   double* __restrict__ Acenter, float* __restrict__ Acr, float* __restrict__ Acu, float* __restrict__ Acf,
+                   double* __restrict__ b) {
     int i = blockIdx.x * PBX + threadIdx.x, j = blockIdx.y * PBY + threadIdx.y, k = blockIdx.z;
     if (i >= nx || j >= ny) return;
     const double ihx = 1.0 / hx, ihy = 1.0 / hy, ihz = 1.0 / hz;
@@ -121,14 +122,15 @@ __global__ void __launch_bounds__(PBX* PBY)
     size_t u0 = ((size_t)k * ny + j) * (nx + 1) + i, u1 = u0 + 1;
     size_t v0 = ((size_t)k * (ny + 1) + j) * nx + i, v1 = v0 + nx;
     size_t w0 = c, w1 = c + sz;
-    double center = 0.0, right = 0.0, up = 0.0, front = 0.0, bb = 0.0;
+    double center = 0.0, bb = 0.0;
+    float right = 0.f, up = 0.f, front = 0.f;  // packed off-diagonals: the face weight where `row.right -= term` applies
     double cphi = sdf[c];
     if (cphi < 0) {
         double term, theta;
         if (i + 1 < nx) {
             term = uw[u1] * ihx2;
             double nphi = sdf[c + 1];
-            if (nphi < 0) { center += term; right -= term; }
+            if (nphi < 0) { center += term; right = uw[u1]; }
             else { theta = fmax(jc_frac_inside_sdf(cphi, nphi), 0.01); center += term / theta; }
             if (b) bb += uw[u1] * u[u1] * ihx;
         } else if (b) { bb += u[u1] * ihx; }
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(PBX* PBY)
         if (j + 1 < ny) {
             term = vw[v1] * ihy2;
             double nphi = sdf[c + sy];
-            if (nphi < 0) { center += term; up -= term; }
+            if (nphi < 0) { center += term; up = vw[v1]; }
             else { theta = fmax(jc_frac_inside_sdf(cphi, nphi), 0.01); center += term / theta; }
             if (b) bb += vw[v1] * v[v1] * ihy;
         } else if (b) { bb += v[v1] * ihy; }
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(PBX* PBY)
         if (k + 1 < nz) {
             term = ww[w1] * ihz2;
             double nphi = sdf[c + sz];
-            if (nphi < 0) { center += term; front -= term; }
+            if (nphi < 0) { center += term; front = ww[w1]; }
             else { theta = fmax(jc_frac_inside_sdf(cphi, nphi), 0.01); center += term / theta; }
             if (b) bb += ww[w1] * w[w1] * ihz;
         } else if (b) { bb += w[w1] * ihz; }
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(PBX* PBY)
     } else {
         center = 1.0;
     }
-    A.center[c] = center; A.right[c] = right; A.up[c] = up; A.front[c] = front;
+    Acenter[c] = center; Acr[c] = right; Acu[c] = up; Acf[c] = front;
     if (b) b[c] = bb;
 }
 
@@ -224,8 +226,8 @@ __global__ void __launch_bounds__(PBX* PBY)
 void pressure_free(jetcu_ctx* ctx, PressureSystem* ps) {
     for (int l = 0; l < ps->levels; ++l) {
         jc_free(ctx, ps->sdf[l]); jc_free(ctx, ps->uw[l]); jc_free(ctx, ps->vw[l]); jc_free(ctx, ps->ww[l]);
+        jc_free(ctx, ps->center[l]); jc_free(ctx, ps->codes[l]);
     }
-    ps->mg.owns_A = true;
     mg_free(ctx, &ps->mg);
     jc_free(ctx, ps->b0); jc_free(ctx, ps->x0);
     ps->levels = 0;
@@ -244,7 +246,6 @@ int pressure_prepare(jetcu_ctx* ctx, PressureSystem* ps, const jetcu_grid* g, ui
     if (levels > JC_MAX_LEVELS) return jetcu_fail(ctx, JETCU_ERR_INVALID_ARG, "too many MG levels (%d)", levels);
     ps->levels = levels;
     ps->mg.levels = levels;
-    ps->mg.owns_A = true;
     for (int l = 0; l < levels; ++l) {
         Dim3i d{(int)(g->nx >> l), (int)(g->ny >> l), (int)(g->nz >> l)};
         ps->dims[l] = d;
@@ -253,7 +254,8 @@ int pressure_prepare(jetcu_ctx* ctx, PressureSystem* ps, const jetcu_grid* g, ui
         JC_TRY(jc_alloc(ctx, &ps->uw[l], (size_t)(d.nx + 1) * d.ny * d.nz));
         JC_TRY(jc_alloc(ctx, &ps->vw[l], (size_t)d.nx * (d.ny + 1) * d.nz));
         JC_TRY(jc_alloc(ctx, &ps->ww[l], (size_t)d.nx * d.ny * (d.nz + 1)));
-        JC_TRY(fdm_alloc_mat(ctx, &ps->mg.A[l], d.n()));
+        JC_TRY(jc_alloc(ctx, &ps->center[l], d.n()));
+        JC_TRY(jc_alloc(ctx, &ps->codes[l], 3 * d.n()));
     }
     JC_TRY(mg_alloc_vectors(ctx, &ps->mg));
     JC_TRY(jc_alloc(ctx, &ps->b0, ps->dims[0].n()));
@@ -286,8 +288,15 @@ int pressure_solve_device(jetcu_ctx* ctx, PressureSystem* ps, const double* u_in
         Dim3i d = ps->dims[l];
         JC_LAUNCH(ctx, k_build_system, pgrid(d.nx, d.ny, d.nz), blk, 0, d.nx, d.ny, d.nz, hx, hy, hz, ps->sdf[l], ps->uw[l],
                   ps->vw[l], ps->ww[l], l == 0 ? u_in : nullptr, l == 0 ? v_in : nullptr, l == 0 ? w_in : nullptr,
-                  l == 0 ? bnd_u : nullptr, l == 0 ? bnd_v : nullptr, l == 0 ? bnd_w : nullptr, ps->mg.A[l],
-                  l == 0 ? ps->b0 : nullptr);
+                  l == 0 ? bnd_u : nullptr, l == 0 ? bnd_v : nullptr, l == 0 ? bnd_w : nullptr, ps->center[l],
+                  ps->codes[l], ps->codes[l] + d.n(), ps->codes[l] + 2 * d.n(), l == 0 ? ps->b0 : nullptr);
+        Mat m;
+        m.packed = true;
+        m.center = ps->center[l];
+        m.cr = ps->codes[l]; m.cu = ps->codes[l] + d.n(); m.cf = ps->codes[l] + 2 * d.n();
+        // term = weight * invHSqr with invHSqr = invH * invH (…pressure_solver3.cpp:127-128)
+        m.sx = (1.0 / hx) * (1.0 / hx); m.sy = (1.0 / hy) * (1.0 / hy); m.sz = (1.0 / hz) * (1.0 / hz);
+        ps->mg.A[l] = m;
         hx *= 2.0; hy *= 2.0; hz *= 2.0;
     }
     JC_TRY(mgpcg_solve_device(ctx, &ps->mg, ps->b0, ps->x0, p, result));

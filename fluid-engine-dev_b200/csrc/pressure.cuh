@@ -10,7 +10,9 @@ struct PressureSystem {
     float* uw[JC_MAX_LEVELS] = {};   // _uWeights[l]  (nx+1, ny, nz)
     float* vw[JC_MAX_LEVELS] = {};
     float* ww[JC_MAX_LEVELS] = {};
-    MgLevels mg;                     // A[l] (SoA), x/b/buf per level
+    double* center[JC_MAX_LEVELS] = {};  // packed matrix: diagonal ...
+    float* codes[JC_MAX_LEVELS] = {};    // ... and the three +face weights (3 planes of n floats)
+    MgLevels mg;                     // A[l] (views of center/codes), x/b/buf per level
     double* b0 = nullptr;            // finest-level right-hand side
     double* x0 = nullptr;            // finest-level solution == pressure()
     uint32_t built_max_levels = 0;

@@ -405,4 +405,19 @@ int jetcu_pressure_get_system(jetcu_ctx* ctx, uint32_t level, jetcu_matrix_row* 
     return jc_sync(ctx);
 }
 
+int jetcu_pressure_vcycle(jetcu_ctx* ctx, const double* b, double* x, const jetcu_mgpcg_params* p) {
+    JC_ENTER(ctx);
+    PressureSystem* ps = ctx->psys;
+    JC_ARG(ctx, ps && ps->levels > 0 && b && x && p);
+    if (!p->use_red_black)
+        return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED, "lexicographic Gauss-Seidel is not available on the GPU path");
+    MgLevels* mg = &ps->mg;
+    size_t n = ps->dims[0].n();
+    JC_TRY(jc_h2d(ctx, mg->x[0], x, n));
+    JC_TRY(jc_h2d(ctx, mg->b[0], b, n));
+    JC_TRY(mg_vcycle(ctx, mg, p, 0));
+    JC_TRY(jc_d2h(ctx, x, mg->x[0], n));
+    return jc_sync(ctx);
+}
+
 }  // extern "C"

@@ -145,6 +145,8 @@ struct Mat {
     const float* cr = nullptr;      // packed form: +x/+y/+z face weight where the coupling exists, else 0
     const float* cu = nullptr;
     const float* cf = nullptr;
+    const uint8_t* code = nullptr;  // packed form: per cell, 2 bits per +face (right | up << 2 | front << 4):
+                                    // 0 no coupling, 1 weight == 1.0f, 2 fractional weight (read cr/cu/cf)
     double sx = 0, sy = 0, sz = 0;  // invH^2 per axis (packed form)
     bool packed = false;
 };

@@ -10,6 +10,8 @@
 #include <math.h>
 #include <stdarg.h>
 
+#include <type_traits>
+
 // ------------------------------------------------------------------------------------------------ AoS <-> SoA
 __global__ void k_aos_to_soa(const jetcu_matrix_row* __restrict__ aos, double* __restrict__ c, double* __restrict__ r,
                              double* __restrict__ u, double* __restrict__ f, size_t n) {
@@ -152,84 +154,193 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_relax_small(Mat A, const doub
     }
 }
 
-// (b) Large grids: ONE launch per full sweep.  A CTA owns an (x,y) tile and marches along z through a chunk of planes;
-//     every thread owns one column and keeps its z-neighbours in registers, in-plane neighbours go through shared
-//     memory.  At step p it (1) forms x1(p) = red pass applied to plane p (tile + one ring of redundant cells, so no
-//     inter-CTA communication is needed), then (2) applies the black pass to plane p-1 from x1(p-2), x1(p-1), x1(p)
-//     and writes the finished plane to `xout`.  Every array is streamed once per sweep with full-line accesses:
-//     56 B/cell (36..44 B/cell with the packed matrix) instead of the ~100 B/cell two colour passes move.
-//     Out of place (xin -> xout) because neighbouring CTAs still read the old values of this tile's border cells.
-#define RTX 32
-#define RTY 16
+// (b) Any grid, any matrix form: one launch per colour, one thread per cell of that colour (x-pairs).  Fallback for
+//     host-supplied (generic) matrices and odd nx; moves ~110 B/cell per sweep because every 32-byte sector is
+//     fetched in both passes with half of it unused (ncu: profiles/r01_baseline_relax_colour_full.txt).
 template <bool P>
+__global__ void __launch_bounds__(BX* BY) k_relax_colour(Mat A, const double* __restrict__ b, double* __restrict__ x,
+                                                         double w, int colour, int nx, int ny, int nz) {
+    int j = blockIdx.y * BY + threadIdx.y, k = blockIdx.z;
+    int i = 2 * (blockIdx.x * BX + threadIdx.x) + ((j + k + colour) & 1);
+    if (i >= nx || j >= ny) return;
+    size_t c = ((size_t)k * ny + j) * nx + i;
+    Offdiag o = offdiag_terms<P>(A, x, i, j, k, nx, ny, nz, c);
+    double r = o.t[0] + o.t[1] + o.t[2] + o.t[3] + o.t[4] + o.t[5];
+    x[c] = (1.0 - w) * x[c] + w * (b[c] - r) / A.center[c];
+}
+
+// (c) Packed matrix, even nx (every level the pressure solver builds except possibly the coarsest): ONE launch per
+//     full sweep.  A CTA owns an (x,y) tile and marches along z through a chunk of planes; a thread owns the cell
+//     pair (i0, i0+1) of one row, so in every plane exactly one of its two cells is red and one is black and the
+//     choice is uniform across the warp (a warp is one row): all 32 lanes do useful FP64 work in both passes — the
+//     FP64 pipe (16 lanes/SM/clk on this part) is as scarce as HBM bandwidth here.
+//     x planes are staged in shared memory by an RS-deep cp.async ring (16-byte copies, zero fill outside the
+//     domain) issued two planes ahead, so HBM latency hides behind whole march steps.  At step p the CTA
+//       (1) forms x1(p) = red pass applied to plane p on tile + one ring of redundant cells (no inter-CTA traffic),
+//       (2) applies the black pass to plane p-1 from x1(p-2), x1(p-1), x1(p) and writes the finished plane to xout.
+//     Matrix rows are read once per sweep as vectors (double2 center, double2 b, one code byte per cell) and kept
+//     in registers for the one extra step the black cell needs them.  Traffic: x 8 r + 8 w, b 8, center 8, code 1
+//     = 33 B/cell/sweep (ideal) against ~110 B/cell for the two-pass kernel.
+//     Out of place (xin -> xout): neighbouring CTAs still read the old values of this tile's border cells.
+#define RTX 32   // threads per row; each owns two cells
+#define RCX 64   // cells per tile row, including two ring cells on either side
+#define RTY 16   // rows per tile, including one ring row on either side
+#define RS 5     // ring depth: planes p-1, p, p+1 live, p+2 and p+3 in flight
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool ok) {
+    unsigned dst = (unsigned)__cvta_generic_to_shared(smem);
+    int src_bytes = ok ? 16 : 0;  // src-size 0 => destination is zero-filled, nothing is read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gmem), "r"(src_bytes) : "memory");
+}
+
+// Off-diagonal coefficient from the 2-bit code of a face: 0 -> 0.0 (no coupling), 1 -> -(1.0f * invH^2) (open face,
+// the overwhelmingly common case: no FP64 work), 2 -> -(double(weight) * invH^2) with the weight fetched on demand.
+__device__ __forceinline__ double code_coef(unsigned bits, double neg_s, double s, const float* __restrict__ wts, size_t c) {
+    if (bits == 0) return 0.0;
+    if (bits == 1) return neg_s;
+    return -((double)__ldg(wts + c) * s);
+}
+
+__device__ __forceinline__ double sor_update(double xc, double xl, double xr, double xd, double xu, double xb, double xf,
+                                             double cl, double cr, double cd, double cu, double cb, double cf, double bb,
+                                             double ce, double w, double omw) {
+    // out-of-range neighbours arrive with coefficient 0.0 and value 0.0: the product is the literal 0.0 of the reference
+    double r = cl * xl + cr * xr + cd * xd + cu * xu + cb * xb + cf * xf;
+    return omw * xc + w * (bb - r) / ce;
+}
+
 __global__ void __launch_bounds__(RTX* RTY, 2)
     k_relax_fused(Mat A, const double* __restrict__ b, const double* __restrict__ xin, double* __restrict__ xout,
                   double w, int nx, int ny, int nz, int zc) {
-    __shared__ double X0[RTY + 2][RTX + 2];  // x0 plane p: tile + ring 1 (owned by threads) + ring 2
-    __shared__ double X1[2][RTY][RTX];       // x1 planes p-1, p: tile + ring 1
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double(*XS)[RTY + 2][RCX] = reinterpret_cast<double(*)[RTY + 2][RCX]>(smem_raw);  // [RS] x0 planes, rows j-1..j+RTY
+    double(*X1)[RTY][RCX] =
+        reinterpret_cast<double(*)[RTY][RCX]>(smem_raw + (size_t)RS * (RTY + 2) * RCX * sizeof(double));  // [2] x1 planes
+
     const int tx = threadIdx.x, ty = threadIdx.y;
-    const int i = blockIdx.x * (RTX - 2) + tx - 1, j = blockIdx.y * (RTY - 2) + ty - 1;
+    const int i0 = blockIdx.x * (RCX - 4) - 2 + 2 * tx;  // even; the pair is (i0, i0+1)
+    const int j = blockIdx.y * (RTY - 2) - 1 + ty;
     const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, nz);
-    const bool valid = i >= 0 && i < nx && j >= 0 && j < ny;
+    const bool valid = i0 >= 0 && i0 < nx && j >= 0 && j < ny;  // nx even => both cells of the pair or neither
     const bool interior = valid && tx >= 1 && tx <= RTX - 2 && ty >= 1 && ty <= RTY - 2;
     const size_t sy = (size_t)nx, sz = (size_t)nx * ny;
-    const size_t col = valid ? (size_t)j * sy + i : 0;
+    const size_t col = valid ? (size_t)j * sy + i0 : 0;
     const double omw = 1.0 - w;
+    const double nsx = -A.sx, nsy = -A.sy, nsz = -A.sz;
+    const bool has_l = valid && i0 > 0, has_r = valid && i0 + 2 < nx, has_d = valid && j > 0, has_u = valid && j + 1 < ny;
 
-    auto ld_x = [&](int ii, int jj, int k) -> double {
-        return (ii >= 0 && ii < nx && jj >= 0 && jj < ny && k >= 0 && k < nz) ? xin[(size_t)k * sz + (size_t)jj * sy + ii] : 0.0;
+    auto slot_of = [](int k) { return ((k % RS) + RS) % RS; };
+    // Issues the copies of x plane k into its ring slot and commits them as one group.
+    auto stage_plane = [&](int k) {
+        double(*S)[RCX] = XS[slot_of(k)];
+        const bool kin = k >= 0 && k < nz;
+        const bool icol = i0 >= 0 && i0 < nx;
+        const size_t base = (size_t)(kin ? k : 0) * sz + (size_t)(icol ? i0 : 0);
+        const bool ok = kin && icol;
+        cp_async16(&S[ty + 1][2 * tx], xin + base + (size_t)(valid ? j : 0) * sy, ok && j >= 0 && j < ny);
+        if (ty == 0) cp_async16(&S[0][2 * tx], xin + base + (size_t)(j - 1 >= 0 && j - 1 < ny ? j - 1 : 0) * sy, ok && j - 1 >= 0 && j - 1 < ny);
+        if (ty == RTY - 1) cp_async16(&S[RTY + 1][2 * tx], xin + base + (size_t)(j + 1 >= 0 && j + 1 < ny ? j + 1 : 0) * sy, ok && j + 1 >= 0 && j + 1 < ny);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
-    auto ld_f = [&](int k) -> double { return (valid && k >= 0 && k < nz) ? m_front<P>(A, col + (size_t)k * sz) : 0.0; };
+    struct Row {  // matrix row data of the cell pair in one plane
+        double2 ce, b;
+        unsigned code;  // byte 0: cell A, byte 1: cell B, byte 2: cell left of A (right bits), byte 3: unused
+        unsigned coded; // byte 0/1: cells below A/B (row j-1; up bits)
+    };
+    auto load_row = [&](int k) -> Row {
+        Row r;
+        r.ce = make_double2(1.0, 1.0); r.b = make_double2(0.0, 0.0); r.code = 0; r.coded = 0;
+        if (valid && k >= 0 && k < nz) {
+            const size_t c = col + (size_t)k * sz;
+            r.ce = __ldg(reinterpret_cast<const double2*>(A.center + c));
+            r.b = __ldg(reinterpret_cast<const double2*>(b + c));
+            unsigned own = __ldg(reinterpret_cast<const unsigned short*>(A.code + c));
+            unsigned left = has_l ? __ldg(A.code + c - 1) : 0u;
+            r.code = own | (left << 16);
+            r.coded = has_d ? __ldg(reinterpret_cast<const unsigned short*>(A.code + c - sy)) : 0u;
+        }
+        return r;
+    };
 
-    double xo_m = ld_x(i, j, z0 - 2), xo_c = ld_x(i, j, z0 - 1);  // x0 at planes p-1, p
-    double x1_m2 = 0.0, x1_m1 = 0.0;                              // x1 at planes p-2, p-1
-    double fr_mm = 0.0, fr_m = ld_f(z0 - 2);                      // front coefficient of planes p-2, p-1
+    for (int k = z0 - 2; k <= z0 + 1; ++k) stage_plane(k);  // step p needs p-1, p, p+1; p+2, p+3 are issued in the loop
 
+    double2 x1_m2 = make_double2(0.0, 0.0), x1_m1 = make_double2(0.0, 0.0);  // x1 of the pair at planes p-2, p-1
+    Row row_m = load_row(z0 - 2);  // becomes plane p-1's row below
+    unsigned fcode_mm = 0;         // front bits of plane p-2 (A: bits 0-1, B: bits 2-3)
     for (int p = z0 - 1; p <= z1; ++p) {
-        const double xo_p = ld_x(i, j, p + 1);
-        const double fr_c = ld_f(p);
-        X0[ty + 1][tx + 1] = xo_c;
-        if (tx == 0) X0[ty + 1][0] = ld_x(i - 1, j, p);
-        if (tx == RTX - 1) X0[ty + 1][RTX + 1] = ld_x(i + 1, j, p);
-        if (ty == 0) X0[0][tx + 1] = ld_x(i, j - 1, p);
-        if (ty == RTY - 1) X0[RTY + 1][tx + 1] = ld_x(i, j + 1, p);
-        __syncthreads();
-        double x1_c = xo_c;
-        if (valid && p >= 0 && p < nz && ((i + j + p) & 1) == 0) {  // red pass, plane p
+        const Row row_c = load_row(p);
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");  // x planes up to p+1 have landed (p+2 may fly)
+        __syncthreads();                                          // ... for all threads; step p-1 is finished by all
+        stage_plane(p + 3);                                       // into the slot of plane p-2, last read in step p-1
+        const double(*Sm)[RCX] = XS[slot_of(p - 1)];
+        const double(*Sc)[RCX] = XS[slot_of(p)];
+        const double(*Sp)[RCX] = XS[slot_of(p + 1)];
+        const int r = ty + 1, cA = 2 * tx;
+        const double2 xo = *reinterpret_cast<const double2*>(&Sc[r][cA]);
+        double2 x1_c = xo;
+        if (valid && p >= 0 && p < nz) {  // red pass, plane p: cell A if (j+p) is even (i0 is even), else cell B
             const size_t c = col + (size_t)p * sz;
-            double t0 = (i > 0) ? m_right<P>(A, c - 1) * X0[ty + 1][tx] : 0.0;
-            double t1 = (i + 1 < nx) ? m_right<P>(A, c) * X0[ty + 1][tx + 2] : 0.0;
-            double t2 = (j > 0) ? m_up<P>(A, c - sy) * X0[ty][tx + 1] : 0.0;
-            double t3 = (j + 1 < ny) ? m_up<P>(A, c) * X0[ty + 2][tx + 1] : 0.0;
-            double t4 = (p > 0) ? fr_m * xo_m : 0.0;
-            double t5 = (p + 1 < nz) ? fr_c * xo_p : 0.0;
-            double r = t0 + t1 + t2 + t3 + t4 + t5;
-            x1_c = omw * xo_c + w * (__ldg(b + c) - r) / __ldg(A.center + c);
-        }
-        X1[p & 1][ty][tx] = x1_c;
-        __syncthreads();
-        const int q = p - 1;
-        if (interior && q >= z0 && q < z1) {  // black pass, plane q
-            const size_t c = col + (size_t)q * sz;
-            double x2 = x1_m1;
-            if (((i + j + q) & 1) == 1) {
-                const double(*Xq)[RTX] = X1[q & 1];
-                double t0 = (i > 0) ? m_right<P>(A, c - 1) * Xq[ty][tx - 1] : 0.0;
-                double t1 = (i + 1 < nx) ? m_right<P>(A, c) * Xq[ty][tx + 1] : 0.0;
-                double t2 = (j > 0) ? m_up<P>(A, c - sy) * Xq[ty - 1][tx] : 0.0;
-                double t3 = (j + 1 < ny) ? m_up<P>(A, c) * Xq[ty + 1][tx] : 0.0;
-                double t4 = (q > 0) ? fr_mm * x1_m2 : 0.0;
-                double t5 = (q + 1 < nz) ? fr_m * x1_c : 0.0;
-                double r = t0 + t1 + t2 + t3 + t4 + t5;
-                x2 = omw * x1_m1 + w * (__ldg(b + c) - r) / __ldg(A.center + c);
+            const unsigned fm_a = (row_m.code >> 4) & 3, fm_b = (row_m.code >> 12) & 3;  // front bits of plane p-1
+            if (((j + p) & 1) == 0) {
+                if (tx > 0) {
+                    const unsigned cd = row_c.code & 0xff, cl = (row_c.code >> 16) & 0xff, cdn = row_c.coded & 0xff;
+                    x1_c.x = sor_update(xo.x, Sc[r][cA - 1], xo.y, Sc[r - 1][cA], Sc[r + 1][cA], Sm[r][cA], Sp[r][cA],
+                                        has_l ? code_coef(cl & 3, nsx, A.sx, A.cr, c - 1) : 0.0,
+                                        code_coef(cd & 3, nsx, A.sx, A.cr, c),
+                                        code_coef((cdn >> 2) & 3, nsy, A.sy, A.cu, c - sy),
+                                        has_u ? code_coef((cd >> 2) & 3, nsy, A.sy, A.cu, c) : 0.0,
+                                        p > 0 ? code_coef(fm_a, nsz, A.sz, A.cf, c - sz) : 0.0,
+                                        p + 1 < nz ? code_coef((cd >> 4) & 3, nsz, A.sz, A.cf, c) : 0.0, row_c.b.x, row_c.ce.x,
+                                        w, omw);
+                }
+            } else if (tx < RTX - 1) {
+                const unsigned ca = row_c.code & 0xff, cd = (row_c.code >> 8) & 0xff, cdn = (row_c.coded >> 8) & 0xff;
+                x1_c.y = sor_update(xo.y, xo.x, Sc[r][cA + 2], Sc[r - 1][cA + 1], Sc[r + 1][cA + 1], Sm[r][cA + 1],
+                                    Sp[r][cA + 1], code_coef(ca & 3, nsx, A.sx, A.cr, c),
+                                    has_r ? code_coef(cd & 3, nsx, A.sx, A.cr, c + 1) : 0.0,
+                                    code_coef((cdn >> 2) & 3, nsy, A.sy, A.cu, c + 1 - sy),
+                                    has_u ? code_coef((cd >> 2) & 3, nsy, A.sy, A.cu, c + 1) : 0.0,
+                                    p > 0 ? code_coef(fm_b, nsz, A.sz, A.cf, c + 1 - sz) : 0.0,
+                                    p + 1 < nz ? code_coef((cd >> 4) & 3, nsz, A.sz, A.cf, c + 1) : 0.0, row_c.b.y,
+                                    row_c.ce.y, w, omw);
             }
-            xout[c] = x2;
         }
-        xo_m = xo_c; xo_c = xo_p;
+        *reinterpret_cast<double2*>(&X1[p & 1][ty][cA]) = x1_c;
+        const int q = p - 1;
+        if (interior && q >= z0 && q < z1) {  // black pass, plane q (its in-plane x1 was published one step ago)
+            const size_t c = col + (size_t)q * sz;
+            const double(*Xq)[RCX] = X1[q & 1];
+            double2 x2 = x1_m1;
+            if (((j + q) & 1) == 1) {  // cell A is black
+                const unsigned cd = row_m.code & 0xff, cl = (row_m.code >> 16) & 0xff, cdn = row_m.coded & 0xff;
+                x2.x = sor_update(x1_m1.x, Xq[ty][cA - 1], x1_m1.y, Xq[ty - 1][cA], Xq[ty + 1][cA], x1_m2.x, x1_c.x,
+                                  has_l ? code_coef(cl & 3, nsx, A.sx, A.cr, c - 1) : 0.0,
+                                  code_coef(cd & 3, nsx, A.sx, A.cr, c),
+                                  code_coef((cdn >> 2) & 3, nsy, A.sy, A.cu, c - sy),
+                                  has_u ? code_coef((cd >> 2) & 3, nsy, A.sy, A.cu, c) : 0.0,
+                                  q > 0 ? code_coef(fcode_mm & 3, nsz, A.sz, A.cf, c - sz) : 0.0,
+                                  q + 1 < nz ? code_coef((cd >> 4) & 3, nsz, A.sz, A.cf, c) : 0.0, row_m.b.x, row_m.ce.x, w,
+                                  omw);
+            } else {  // cell B is black
+                const unsigned ca = row_m.code & 0xff, cd = (row_m.code >> 8) & 0xff, cdn = (row_m.coded >> 8) & 0xff;
+                x2.y = sor_update(x1_m1.y, x1_m1.x, Xq[ty][cA + 2], Xq[ty - 1][cA + 1], Xq[ty + 1][cA + 1], x1_m2.y, x1_c.y,
+                                  code_coef(ca & 3, nsx, A.sx, A.cr, c), has_r ? code_coef(cd & 3, nsx, A.sx, A.cr, c + 1) : 0.0,
+                                  code_coef((cdn >> 2) & 3, nsy, A.sy, A.cu, c + 1 - sy),
+                                  has_u ? code_coef((cd >> 2) & 3, nsy, A.sy, A.cu, c + 1) : 0.0,
+                                  q > 0 ? code_coef((fcode_mm >> 2) & 3, nsz, A.sz, A.cf, c + 1 - sz) : 0.0,
+                                  q + 1 < nz ? code_coef((cd >> 4) & 3, nsz, A.sz, A.cf, c + 1) : 0.0, row_m.b.y, row_m.ce.y,
+                                  w, omw);
+            }
+            *reinterpret_cast<double2*>(xout + c) = x2;
+        }
         x1_m2 = x1_m1; x1_m1 = x1_c;
-        fr_mm = fr_m; fr_m = fr_c;
+        fcode_mm = ((row_m.code >> 4) & 3) | (((row_m.code >> 12) & 3) << 2);
+        row_m = row_c;
     }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
+
+static size_t relax_smem_bytes() { return ((size_t)RS * (RTY + 2) + 2 * RTY) * RCX * sizeof(double); }
 
 template <bool P>
 static int launch_mvm(jetcu_ctx* ctx, Dim3i d, Mat A, const double* v, double* out) {
@@ -259,17 +370,31 @@ static int launch_relax(jetcu_ctx* ctx, Dim3i d, Mat A, const double* b, double 
         *launches = 1;
         return JETCU_OK;
     }
-    // z-chunk length: enough CTAs to fill the machine (>= ~4 per SM), as long as possible otherwise (each chunk
+    if (!P || (d.nx & 1) || A.code == nullptr) {
+        dim3 grid(((d.nx + 1) / 2 + BX - 1) / BX, (d.ny + BY - 1) / BY, d.nz);
+        for (unsigned it = 0; it < iterations; ++it) {
+            JC_LAUNCH(ctx, k_relax_colour<P>, grid, dim3(BX, BY), 0, A, b, *x, sor, 0, d.nx, d.ny, d.nz);
+            JC_LAUNCH(ctx, k_relax_colour<P>, grid, dim3(BX, BY), 0, A, b, *x, sor, 1, d.nx, d.ny, d.nz);
+        }
+        *launches = 2ull * iterations;
+        return JETCU_OK;
+    }
+    // z-chunk length: enough CTAs to fill the machine twice over, as long as possible otherwise (each chunk
     // recomputes the red pass of its two neighbouring planes)
-    const int tiles = ((d.nx + RTX - 3) / (RTX - 2)) * ((d.ny + RTY - 3) / (RTY - 2));
+    const int tiles = ((d.nx + RCX - 5) / (RCX - 4)) * ((d.ny + RTY - 3) / (RTY - 2));
     int chunks = (4 * ctx->sm_count + tiles - 1) / tiles;
     if (chunks < 1) chunks = 1;
     if (chunks > d.nz) chunks = d.nz;
     int zc = (d.nz + chunks - 1) / chunks;
-    if (zc < 4 && d.nz >= 4) zc = 4;
-    dim3 grid((d.nx + RTX - 3) / (RTX - 2), (d.ny + RTY - 3) / (RTY - 2), (d.nz + zc - 1) / zc);
+    if (zc < 8 && d.nz >= 8) zc = 8;
+    dim3 grid((d.nx + RCX - 5) / (RCX - 4), (d.ny + RTY - 3) / (RTY - 2), (d.nz + zc - 1) / zc);
+    static bool attr_set = false;
+    if (!attr_set) {
+        JC_CUDA(ctx, cudaFuncSetAttribute(k_relax_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)relax_smem_bytes()));
+        attr_set = true;
+    }
     for (unsigned it = 0; it < iterations; ++it) {
-        JC_LAUNCH(ctx, k_relax_fused<P>, grid, dim3(RTX, RTY), 0, A, b, *x, *xalt, sor, d.nx, d.ny, d.nz, zc);
+        JC_LAUNCH(ctx, k_relax_fused, grid, dim3(RTX, RTY), relax_smem_bytes(), A, b, *x, *xalt, sor, d.nx, d.ny, d.nz, zc);
         double* t = *x; *x = *xalt; *xalt = t;
     }
     *launches = iterations;

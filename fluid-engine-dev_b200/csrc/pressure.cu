@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(PBX* PBY)
                    const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
                    const double* __restrict__ bu, const double* __restrict__ bv, const double* __restrict__ bw,
                    double* __restrict__ Acenter, float* __restrict__ Acr, float* __restrict__ Acu, float* __restrict__ Acf,
-                   double* __restrict__ b) {
+                   uint8_t* __restrict__ Acode, double* __restrict__ b) {
     int i = blockIdx.x * PBX + threadIdx.x, j = blockIdx.y * PBY + threadIdx.y, k = blockIdx.z;
     if (i >= nx || j >= ny) return;
     const double ihx = 1.0 / hx, ihy = 1.0 / hy, ihz = 1.0 / hz;
@@ -181,6 +181,8 @@ __global__ void __launch_bounds__(PBX* PBY)
         center = 1.0;
     }
     Acenter[c] = center; Acr[c] = right; Acu[c] = up; Acf[c] = front;
+    auto bits = [](float wgt) -> unsigned { return wgt == 0.f ? 0u : (wgt == 1.0f ? 1u : 2u); };
+    Acode[c] = (uint8_t)(bits(right) | (bits(up) << 2) | (bits(front) << 4));
     if (b) b[c] = bb;
 }
 
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(PBX* PBY)
 void pressure_free(jetcu_ctx* ctx, PressureSystem* ps) {
     for (int l = 0; l < ps->levels; ++l) {
         jc_free(ctx, ps->sdf[l]); jc_free(ctx, ps->uw[l]); jc_free(ctx, ps->vw[l]); jc_free(ctx, ps->ww[l]);
-        jc_free(ctx, ps->center[l]); jc_free(ctx, ps->codes[l]);
+        jc_free(ctx, ps->center[l]); jc_free(ctx, ps->codes[l]); jc_free(ctx, ps->code8[l]);
     }
     mg_free(ctx, &ps->mg);
     jc_free(ctx, ps->b0); jc_free(ctx, ps->x0);
@@ -256,6 +258,7 @@ int pressure_prepare(jetcu_ctx* ctx, PressureSystem* ps, const jetcu_grid* g, ui
         JC_TRY(jc_alloc(ctx, &ps->ww[l], (size_t)d.nx * d.ny * (d.nz + 1)));
         JC_TRY(jc_alloc(ctx, &ps->center[l], d.n()));
         JC_TRY(jc_alloc(ctx, &ps->codes[l], 3 * d.n()));
+        JC_TRY(jc_alloc(ctx, &ps->code8[l], d.n() + 16));
     }
     JC_TRY(mg_alloc_vectors(ctx, &ps->mg));
     JC_TRY(jc_alloc(ctx, &ps->b0, ps->dims[0].n()));
@@ -289,11 +292,12 @@ int pressure_solve_device(jetcu_ctx* ctx, PressureSystem* ps, const double* u_in
         JC_LAUNCH(ctx, k_build_system, pgrid(d.nx, d.ny, d.nz), blk, 0, d.nx, d.ny, d.nz, hx, hy, hz, ps->sdf[l], ps->uw[l],
                   ps->vw[l], ps->ww[l], l == 0 ? u_in : nullptr, l == 0 ? v_in : nullptr, l == 0 ? w_in : nullptr,
                   l == 0 ? bnd_u : nullptr, l == 0 ? bnd_v : nullptr, l == 0 ? bnd_w : nullptr, ps->center[l],
-                  ps->codes[l], ps->codes[l] + d.n(), ps->codes[l] + 2 * d.n(), l == 0 ? ps->b0 : nullptr);
+                  ps->codes[l], ps->codes[l] + d.n(), ps->codes[l] + 2 * d.n(), ps->code8[l], l == 0 ? ps->b0 : nullptr);
         Mat m;
         m.packed = true;
         m.center = ps->center[l];
         m.cr = ps->codes[l]; m.cu = ps->codes[l] + d.n(); m.cf = ps->codes[l] + 2 * d.n();
+        m.code = ps->code8[l];
         // term = weight * invHSqr with invHSqr = invH * invH (…pressure_solver3.cpp:127-128)
         m.sx = (1.0 / hx) * (1.0 / hx); m.sy = (1.0 / hy) * (1.0 / hy); m.sz = (1.0 / hz) * (1.0 / hz);
         ps->mg.A[l] = m;

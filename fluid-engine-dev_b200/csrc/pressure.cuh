@@ -12,6 +12,7 @@ struct PressureSystem {
     float* ww[JC_MAX_LEVELS] = {};
     double* center[JC_MAX_LEVELS] = {};  // packed matrix: diagonal ...
     float* codes[JC_MAX_LEVELS] = {};    // ... and the three +face weights (3 planes of n floats)
+    uint8_t* code8[JC_MAX_LEVELS] = {};  // ... and their 2-bit classes, one byte per cell
     MgLevels mg;                     // A[l] (views of center/codes), x/b/buf per level
     double* b0 = nullptr;            // finest-level right-hand side
     double* x0 = nullptr;            // finest-level solution == pressure()

@@ -219,6 +219,12 @@ class LinearApi:
                    _p(vw, PF), _p(ww, PF))
         return dict(A=A, b=b, fluid_sdf=sdf, u_weights=uw, v_weights=vw, w_weights=ww)
 
+    def pressure_vcycle(self, b, x, params):
+        """One V-cycle on the system built by the last pressure_solve (jetcu only; test hook)."""
+        out = np.array(x, dtype=np.float64, order="C", copy=True)
+        self._call("pressure_vcycle", _p(c64(b)), _p(out), C.byref(params))
+        return out
+
     def bin_points(self, positions, res, spacing):
         n = positions.shape[0]
         nb = res[0] * res[1] * res[2]

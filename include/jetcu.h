@@ -171,6 +171,11 @@ int jetcu_pressure_solve(jetcu_ctx*, const jetcu_grid* grid,
 int jetcu_pressure_get_system(jetcu_ctx*, uint32_t level, jetcu_matrix_row* A, double* b,
                               float* fluid_sdf, float* u_weights, float* v_weights, float* w_weights);
 
+/* Test/inspection hook: one MG V-cycle (as jetcu_fdm_vcycle) on the device-resident system the last
+ * jetcu_pressure_solve on this ctx built, i.e. through the packed-matrix kernels the solver itself uses.
+ * b, x: finest-level host vectors; x is in/out. */
+int jetcu_pressure_vcycle(jetcu_ctx*, const double* b, double* x, const jetcu_mgpcg_params* params);
+
 /* ------------------------------------------------ particle binning
  * PointParallelHashGridSearcher3::build (src/jet/point_parallel_hash_grid_searcher3.cpp:52-146) with the
  * key arithmetic of getHashKeyFromPosition (:232-269).  positions are AoS xyz doubles (Vector3D).

@@ -148,6 +148,7 @@ struct Mat {
     const uint8_t* code = nullptr;  // packed form: per cell, 2 bits per +face (right | up << 2 | front << 4):
                                     // 0 no coupling, 1 weight == 1.0f, 2 fractional weight (read cr/cu/cf)
     double sx = 0, sy = 0, sz = 0;  // invH^2 per axis (packed form)
+    size_t stride_y = 0, stride_z = 0;  // nx, nx*ny (packed form; used on the rare fractional-weight path)
     bool packed = false;
 };
 

@@ -9,8 +9,8 @@
 
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
-#include <type_traits>
 
 // ------------------------------------------------------------------------------------------------ AoS <-> SoA
 __global__ void k_aos_to_soa(const jetcu_matrix_row* __restrict__ aos, double* __restrict__ c, double* __restrict__ r,
@@ -154,9 +154,9 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_relax_small(Mat A, const doub
     }
 }
 
-// (b) Any grid, any matrix form: one launch per colour, one thread per cell of that colour (x-pairs).  Fallback for
-//     host-supplied (generic) matrices and odd nx; moves ~110 B/cell per sweep because every 32-byte sector is
-//     fetched in both passes with half of it unused (ncu: profiles/r01_baseline_relax_colour_full.txt).
+// (b) Any grid, any matrix form: one launch per colour, one thread per cell of that colour (x-pairs).  With 8-byte
+//     off-diagonal planes (host-supplied matrices) a sweep moves ~110 B/cell, because every 32-byte sector of every
+//     plane is fetched in both passes with half of it unused (ncu: profiles/r01_baseline_relax_colour_full.txt).
 template <bool P>
 __global__ void __launch_bounds__(BX* BY) k_relax_colour(Mat A, const double* __restrict__ b, double* __restrict__ x,
                                                          double w, int colour, int nx, int ny, int nz) {
@@ -169,178 +169,52 @@ __global__ void __launch_bounds__(BX* BY) k_relax_colour(Mat A, const double* __
     x[c] = (1.0 - w) * x[c] + w * (b[c] - r) / A.center[c];
 }
 
-// (c) Packed matrix, even nx (every level the pressure solver builds except possibly the coarsest): ONE launch per
-//     full sweep.  A CTA owns an (x,y) tile and marches along z through a chunk of planes; a thread owns the cell
-//     pair (i0, i0+1) of one row, so in every plane exactly one of its two cells is red and one is black and the
-//     choice is uniform across the warp (a warp is one row): all 32 lanes do useful FP64 work in both passes — the
-//     FP64 pipe (16 lanes/SM/clk on this part) is as scarce as HBM bandwidth here.
-//     x planes are staged in shared memory by an RS-deep cp.async ring (16-byte copies, zero fill outside the
-//     domain) issued two planes ahead, so HBM latency hides behind whole march steps.  At step p the CTA
-//       (1) forms x1(p) = red pass applied to plane p on tile + one ring of redundant cells (no inter-CTA traffic),
-//       (2) applies the black pass to plane p-1 from x1(p-2), x1(p-1), x1(p) and writes the finished plane to xout.
-//     Matrix rows are read once per sweep as vectors (double2 center, double2 b, one code byte per cell) and kept
-//     in registers for the one extra step the black cell needs them.  Traffic: x 8 r + 8 w, b 8, center 8, code 1
-//     = 33 B/cell/sweep (ideal) against ~110 B/cell for the two-pass kernel.
-//     Out of place (xin -> xout): neighbouring CTAs still read the old values of this tile's border cells.
-#define RTX 32   // threads per row; each owns two cells
-#define RCX 64   // cells per tile row, including two ring cells on either side
-#define RTY 16   // rows per tile, including one ring row on either side
-#define RS 5     // ring depth: planes p-1, p, p+1 live, p+2 and p+3 in flight
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool ok) {
-    unsigned dst = (unsigned)__cvta_generic_to_shared(smem);
-    int src_bytes = ok ? 16 : 0;  // src-size 0 => destination is zero-filled, nothing is read
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gmem), "r"(src_bytes) : "memory");
-}
-
-// Off-diagonal coefficient from the 2-bit code of a face: 0 -> 0.0 (no coupling), 1 -> -(1.0f * invH^2) (open face,
-// the overwhelmingly common case: no FP64 work), 2 -> -(double(weight) * invH^2) with the weight fetched on demand.
-__device__ __forceinline__ double code_coef(unsigned bits, double neg_s, double s, const float* __restrict__ wts, size_t c) {
+// (b') Packed matrix with face codes: the same two colour passes, but the three 8-byte off-diagonal planes are
+//     replaced by one code byte per cell (2 bits per +face: 0 closed, 1 fully open => -invH^2 with no FP64 work,
+//     2 fractional => weight fetched on demand), so a pass streams center 8 + b 8 + x 8 r + ~8 w + code 1 = 33 B/cell.
+__device__ __forceinline__ double face_coef(unsigned bits, double s, const float* __restrict__ wts, size_t c) {
     if (bits == 0) return 0.0;
-    if (bits == 1) return neg_s;
+    if (bits == 1) return -s;
     return -((double)__ldg(wts + c) * s);
 }
 
-__device__ __forceinline__ double sor_update(double xc, double xl, double xr, double xd, double xu, double xb, double xf,
-                                             double cl, double cr, double cd, double cu, double cb, double cf, double bb,
-                                             double ce, double w, double omw) {
-    // out-of-range neighbours arrive with coefficient 0.0 and value 0.0: the product is the literal 0.0 of the reference
-    double r = cl * xl + cr * xr + cd * xd + cu * xu + cb * xb + cf * xf;
-    return omw * xc + w * (bb - r) / ce;
+__device__ __forceinline__ double mask_coef(unsigned bit, double neg_s) {
+    return __longlong_as_double(__double_as_longlong(neg_s) & -(long long)(bit & 1u));
 }
 
-__global__ void __launch_bounds__(RTX* RTY, 2)
-    k_relax_fused(Mat A, const double* __restrict__ b, const double* __restrict__ xin, double* __restrict__ xout,
-                  double w, int nx, int ny, int nz, int zc) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double(*XS)[RTY + 2][RCX] = reinterpret_cast<double(*)[RTY + 2][RCX]>(smem_raw);  // [RS] x0 planes, rows j-1..j+RTY
-    double(*X1)[RTY][RCX] =
-        reinterpret_cast<double(*)[RTY][RCX]>(smem_raw + (size_t)RS * (RTY + 2) * RCX * sizeof(double));  // [2] x1 planes
-
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int i0 = blockIdx.x * (RCX - 4) - 2 + 2 * tx;  // even; the pair is (i0, i0+1)
-    const int j = blockIdx.y * (RTY - 2) - 1 + ty;
-    const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, nz);
-    const bool valid = i0 >= 0 && i0 < nx && j >= 0 && j < ny;  // nx even => both cells of the pair or neither
-    const bool interior = valid && tx >= 1 && tx <= RTX - 2 && ty >= 1 && ty <= RTY - 2;
+__global__ void __launch_bounds__(BX* BY) k_relax_colour_code(Mat A, const double* __restrict__ b, double* __restrict__ x,
+                                                              double w, int colour, int nx, int ny, int nz) {
+    const int j = blockIdx.y * BY + threadIdx.y, k = blockIdx.z;
+    const int i = 2 * (blockIdx.x * BX + threadIdx.x) + ((j + k + colour) & 1);
+    if (i >= nx || j >= ny) return;
     const size_t sy = (size_t)nx, sz = (size_t)nx * ny;
-    const size_t col = valid ? (size_t)j * sy + i0 : 0;
-    const double omw = 1.0 - w;
-    const double nsx = -A.sx, nsy = -A.sy, nsz = -A.sz;
-    const bool has_l = valid && i0 > 0, has_r = valid && i0 + 2 < nx, has_d = valid && j > 0, has_u = valid && j + 1 < ny;
-
-    auto slot_of = [](int k) { return ((k % RS) + RS) % RS; };
-    // Issues the copies of x plane k into its ring slot and commits them as one group.
-    auto stage_plane = [&](int k) {
-        double(*S)[RCX] = XS[slot_of(k)];
-        const bool kin = k >= 0 && k < nz;
-        const bool icol = i0 >= 0 && i0 < nx;
-        const size_t base = (size_t)(kin ? k : 0) * sz + (size_t)(icol ? i0 : 0);
-        const bool ok = kin && icol;
-        cp_async16(&S[ty + 1][2 * tx], xin + base + (size_t)(valid ? j : 0) * sy, ok && j >= 0 && j < ny);
-        if (ty == 0) cp_async16(&S[0][2 * tx], xin + base + (size_t)(j - 1 >= 0 && j - 1 < ny ? j - 1 : 0) * sy, ok && j - 1 >= 0 && j - 1 < ny);
-        if (ty == RTY - 1) cp_async16(&S[RTY + 1][2 * tx], xin + base + (size_t)(j + 1 >= 0 && j + 1 < ny ? j + 1 : 0) * sy, ok && j + 1 >= 0 && j + 1 < ny);
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
-    };
-    struct Row {  // matrix row data of the cell pair in one plane
-        double2 ce, b;
-        unsigned code;  // byte 0: cell A, byte 1: cell B, byte 2: cell left of A (right bits), byte 3: unused
-        unsigned coded; // byte 0/1: cells below A/B (row j-1; up bits)
-    };
-    auto load_row = [&](int k) -> Row {
-        Row r;
-        r.ce = make_double2(1.0, 1.0); r.b = make_double2(0.0, 0.0); r.code = 0; r.coded = 0;
-        if (valid && k >= 0 && k < nz) {
-            const size_t c = col + (size_t)k * sz;
-            r.ce = __ldg(reinterpret_cast<const double2*>(A.center + c));
-            r.b = __ldg(reinterpret_cast<const double2*>(b + c));
-            unsigned own = __ldg(reinterpret_cast<const unsigned short*>(A.code + c));
-            unsigned left = has_l ? __ldg(A.code + c - 1) : 0u;
-            r.code = own | (left << 16);
-            r.coded = has_d ? __ldg(reinterpret_cast<const unsigned short*>(A.code + c - sy)) : 0u;
-        }
-        return r;
-    };
-
-    for (int k = z0 - 2; k <= z0 + 1; ++k) stage_plane(k);  // step p needs p-1, p, p+1; p+2, p+3 are issued in the loop
-
-    double2 x1_m2 = make_double2(0.0, 0.0), x1_m1 = make_double2(0.0, 0.0);  // x1 of the pair at planes p-2, p-1
-    Row row_m = load_row(z0 - 2);  // becomes plane p-1's row below
-    unsigned fcode_mm = 0;         // front bits of plane p-2 (A: bits 0-1, B: bits 2-3)
-    for (int p = z0 - 1; p <= z1; ++p) {
-        const Row row_c = load_row(p);
-        asm volatile("cp.async.wait_group 1;\n" ::: "memory");  // x planes up to p+1 have landed (p+2 may fly)
-        __syncthreads();                                          // ... for all threads; step p-1 is finished by all
-        stage_plane(p + 3);                                       // into the slot of plane p-2, last read in step p-1
-        const double(*Sm)[RCX] = XS[slot_of(p - 1)];
-        const double(*Sc)[RCX] = XS[slot_of(p)];
-        const double(*Sp)[RCX] = XS[slot_of(p + 1)];
-        const int r = ty + 1, cA = 2 * tx;
-        const double2 xo = *reinterpret_cast<const double2*>(&Sc[r][cA]);
-        double2 x1_c = xo;
-        if (valid && p >= 0 && p < nz) {  // red pass, plane p: cell A if (j+p) is even (i0 is even), else cell B
-            const size_t c = col + (size_t)p * sz;
-            const unsigned fm_a = (row_m.code >> 4) & 3, fm_b = (row_m.code >> 12) & 3;  // front bits of plane p-1
-            if (((j + p) & 1) == 0) {
-                if (tx > 0) {
-                    const unsigned cd = row_c.code & 0xff, cl = (row_c.code >> 16) & 0xff, cdn = row_c.coded & 0xff;
-                    x1_c.x = sor_update(xo.x, Sc[r][cA - 1], xo.y, Sc[r - 1][cA], Sc[r + 1][cA], Sm[r][cA], Sp[r][cA],
-                                        has_l ? code_coef(cl & 3, nsx, A.sx, A.cr, c - 1) : 0.0,
-                                        code_coef(cd & 3, nsx, A.sx, A.cr, c),
-                                        code_coef((cdn >> 2) & 3, nsy, A.sy, A.cu, c - sy),
-                                        has_u ? code_coef((cd >> 2) & 3, nsy, A.sy, A.cu, c) : 0.0,
-                                        p > 0 ? code_coef(fm_a, nsz, A.sz, A.cf, c - sz) : 0.0,
-                                        p + 1 < nz ? code_coef((cd >> 4) & 3, nsz, A.sz, A.cf, c) : 0.0, row_c.b.x, row_c.ce.x,
-                                        w, omw);
-                }
-            } else if (tx < RTX - 1) {
-                const unsigned ca = row_c.code & 0xff, cd = (row_c.code >> 8) & 0xff, cdn = (row_c.coded >> 8) & 0xff;
-                x1_c.y = sor_update(xo.y, xo.x, Sc[r][cA + 2], Sc[r - 1][cA + 1], Sc[r + 1][cA + 1], Sm[r][cA + 1],
-                                    Sp[r][cA + 1], code_coef(ca & 3, nsx, A.sx, A.cr, c),
-                                    has_r ? code_coef(cd & 3, nsx, A.sx, A.cr, c + 1) : 0.0,
-                                    code_coef((cdn >> 2) & 3, nsy, A.sy, A.cu, c + 1 - sy),
-                                    has_u ? code_coef((cd >> 2) & 3, nsy, A.sy, A.cu, c + 1) : 0.0,
-                                    p > 0 ? code_coef(fm_b, nsz, A.sz, A.cf, c + 1 - sz) : 0.0,
-                                    p + 1 < nz ? code_coef((cd >> 4) & 3, nsz, A.sz, A.cf, c + 1) : 0.0, row_c.b.y,
-                                    row_c.ce.y, w, omw);
-            }
-        }
-        *reinterpret_cast<double2*>(&X1[p & 1][ty][cA]) = x1_c;
-        const int q = p - 1;
-        if (interior && q >= z0 && q < z1) {  // black pass, plane q (its in-plane x1 was published one step ago)
-            const size_t c = col + (size_t)q * sz;
-            const double(*Xq)[RCX] = X1[q & 1];
-            double2 x2 = x1_m1;
-            if (((j + q) & 1) == 1) {  // cell A is black
-                const unsigned cd = row_m.code & 0xff, cl = (row_m.code >> 16) & 0xff, cdn = row_m.coded & 0xff;
-                x2.x = sor_update(x1_m1.x, Xq[ty][cA - 1], x1_m1.y, Xq[ty - 1][cA], Xq[ty + 1][cA], x1_m2.x, x1_c.x,
-                                  has_l ? code_coef(cl & 3, nsx, A.sx, A.cr, c - 1) : 0.0,
-                                  code_coef(cd & 3, nsx, A.sx, A.cr, c),
-                                  code_coef((cdn >> 2) & 3, nsy, A.sy, A.cu, c - sy),
-                                  has_u ? code_coef((cd >> 2) & 3, nsy, A.sy, A.cu, c) : 0.0,
-                                  q > 0 ? code_coef(fcode_mm & 3, nsz, A.sz, A.cf, c - sz) : 0.0,
-                                  q + 1 < nz ? code_coef((cd >> 4) & 3, nsz, A.sz, A.cf, c) : 0.0, row_m.b.x, row_m.ce.x, w,
-                                  omw);
-            } else {  // cell B is black
-                const unsigned ca = row_m.code & 0xff, cd = (row_m.code >> 8) & 0xff, cdn = (row_m.coded >> 8) & 0xff;
-                x2.y = sor_update(x1_m1.y, x1_m1.x, Xq[ty][cA + 2], Xq[ty - 1][cA + 1], Xq[ty + 1][cA + 1], x1_m2.y, x1_c.y,
-                                  code_coef(ca & 3, nsx, A.sx, A.cr, c), has_r ? code_coef(cd & 3, nsx, A.sx, A.cr, c + 1) : 0.0,
-                                  code_coef((cdn >> 2) & 3, nsy, A.sy, A.cu, c + 1 - sy),
-                                  has_u ? code_coef((cd >> 2) & 3, nsy, A.sy, A.cu, c + 1) : 0.0,
-                                  q > 0 ? code_coef((fcode_mm >> 2) & 3, nsz, A.sz, A.cf, c + 1 - sz) : 0.0,
-                                  q + 1 < nz ? code_coef((cd >> 4) & 3, nsz, A.sz, A.cf, c + 1) : 0.0, row_m.b.y, row_m.ce.y,
-                                  w, omw);
-            }
-            *reinterpret_cast<double2*>(xout + c) = x2;
-        }
-        x1_m2 = x1_m1; x1_m1 = x1_c;
-        fcode_mm = ((row_m.code >> 4) & 3) | (((row_m.code >> 12) & 3) << 2);
-        row_m = row_c;
+    const size_t c = ((size_t)k * ny + j) * nx + i;
+    const unsigned own = __ldg(A.code + c);
+    const unsigned lft = i > 0 ? __ldg(A.code + c - 1) : 0u;
+    const unsigned dwn = j > 0 ? __ldg(A.code + c - sy) : 0u;
+    const unsigned bck = k > 0 ? __ldg(A.code + c - sz) : 0u;
+    // the six 2-bit face classes in the sum order -i,+i,-j,+j,-k,+k (the +face codes are 0 on the domain boundary)
+    const unsigned six = (lft & 3u) | ((own & 3u) << 2) | (((dwn >> 2) & 3u) << 4) | (((own >> 2) & 3u) << 6) |
+                         (((bck >> 4) & 3u) << 8) | (((own >> 4) & 3u) << 10);
+    const double xl = i > 0 ? x[c - 1] : 0.0, xr = i + 1 < nx ? x[c + 1] : 0.0;
+    const double xd = j > 0 ? x[c - sy] : 0.0, xu = j + 1 < ny ? x[c + sy] : 0.0;
+    const double xb = k > 0 ? x[c - sz] : 0.0, xf = k + 1 < nz ? x[c + sz] : 0.0;
+    double cl, cr, cd, cu, cb, cf;
+    if (six == 0x555u) {  // all six faces fully open: the bulk of the liquid
+        cl = cr = -A.sx; cd = cu = -A.sy; cb = cf = -A.sz;
+    } else if ((six & 0xaaau) == 0) {  // open / closed faces only
+        cl = mask_coef(six, -A.sx); cr = mask_coef(six >> 2, -A.sx);
+        cd = mask_coef(six >> 4, -A.sy); cu = mask_coef(six >> 6, -A.sy);
+        cb = mask_coef(six >> 8, -A.sz); cf = mask_coef(six >> 10, -A.sz);
+    } else {  // fractional weights (next to colliders)
+        cl = face_coef(six & 3u, A.sx, A.cr, c - 1); cr = face_coef((six >> 2) & 3u, A.sx, A.cr, c);
+        cd = face_coef((six >> 4) & 3u, A.sy, A.cu, c - sy); cu = face_coef((six >> 6) & 3u, A.sy, A.cu, c);
+        cb = face_coef((six >> 8) & 3u, A.sz, A.cf, c - sz); cf = face_coef((six >> 10) & 3u, A.sz, A.cf, c);
     }
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    // absent neighbours carry coefficient 0.0 and value 0.0: the literal 0.0 terms of the reference
+    const double r = cl * xl + cr * xr + cd * xd + cu * xu + cb * xb + cf * xf;
+    x[c] = (1.0 - w) * x[c] + w * (b[c] - r) / A.center[c];
 }
-
-static size_t relax_smem_bytes() { return ((size_t)RS * (RTY + 2) + 2 * RTY) * RCX * sizeof(double); }
 
 template <bool P>
 static int launch_mvm(jetcu_ctx* ctx, Dim3i d, Mat A, const double* v, double* out) {
@@ -365,39 +239,23 @@ int fdm_residual(jetcu_ctx* ctx, Dim3i d, Mat A, const double* x, const double* 
 template <bool P>
 static int launch_relax(jetcu_ctx* ctx, Dim3i d, Mat A, const double* b, double sor, unsigned iterations, double** x,
                         double** xalt, uint64_t* launches) {
+    (void)xalt;
     if (d.n() <= SMALL_MAX_CELLS) {
         JC_LAUNCH(ctx, k_relax_small<P>, 1, SMALL_THREADS, 0, A, b, *x, sor, d.nx, d.ny, d.nz, iterations);
         *launches = 1;
         return JETCU_OK;
     }
-    if (!P || (d.nx & 1) || A.code == nullptr) {
-        dim3 grid(((d.nx + 1) / 2 + BX - 1) / BX, (d.ny + BY - 1) / BY, d.nz);
-        for (unsigned it = 0; it < iterations; ++it) {
+    dim3 grid(((d.nx + 1) / 2 + BX - 1) / BX, (d.ny + BY - 1) / BY, d.nz);
+    for (unsigned it = 0; it < iterations; ++it) {
+        if (P && A.code != nullptr) {
+            JC_LAUNCH(ctx, k_relax_colour_code, grid, dim3(BX, BY), 0, A, b, *x, sor, 0, d.nx, d.ny, d.nz);
+            JC_LAUNCH(ctx, k_relax_colour_code, grid, dim3(BX, BY), 0, A, b, *x, sor, 1, d.nx, d.ny, d.nz);
+        } else {
             JC_LAUNCH(ctx, k_relax_colour<P>, grid, dim3(BX, BY), 0, A, b, *x, sor, 0, d.nx, d.ny, d.nz);
             JC_LAUNCH(ctx, k_relax_colour<P>, grid, dim3(BX, BY), 0, A, b, *x, sor, 1, d.nx, d.ny, d.nz);
         }
-        *launches = 2ull * iterations;
-        return JETCU_OK;
     }
-    // z-chunk length: enough CTAs to fill the machine twice over, as long as possible otherwise (each chunk
-    // recomputes the red pass of its two neighbouring planes)
-    const int tiles = ((d.nx + RCX - 5) / (RCX - 4)) * ((d.ny + RTY - 3) / (RTY - 2));
-    int chunks = (4 * ctx->sm_count + tiles - 1) / tiles;
-    if (chunks < 1) chunks = 1;
-    if (chunks > d.nz) chunks = d.nz;
-    int zc = (d.nz + chunks - 1) / chunks;
-    if (zc < 8 && d.nz >= 8) zc = 8;
-    dim3 grid((d.nx + RCX - 5) / (RCX - 4), (d.ny + RTY - 3) / (RTY - 2), (d.nz + zc - 1) / zc);
-    static bool attr_set = false;
-    if (!attr_set) {
-        JC_CUDA(ctx, cudaFuncSetAttribute(k_relax_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)relax_smem_bytes()));
-        attr_set = true;
-    }
-    for (unsigned it = 0; it < iterations; ++it) {
-        JC_LAUNCH(ctx, k_relax_fused, grid, dim3(RTX, RTY), relax_smem_bytes(), A, b, *x, *xalt, sor, d.nx, d.ny, d.nz, zc);
-        double* t = *x; *x = *xalt; *xalt = t;
-    }
-    *launches = iterations;
+    *launches = 2ull * iterations;
     return JETCU_OK;
 }
 

@@ -298,6 +298,7 @@ int pressure_solve_device(jetcu_ctx* ctx, PressureSystem* ps, const double* u_in
         m.center = ps->center[l];
         m.cr = ps->codes[l]; m.cu = ps->codes[l] + d.n(); m.cf = ps->codes[l] + 2 * d.n();
         m.code = ps->code8[l];
+        m.stride_y = (size_t)d.nx; m.stride_z = (size_t)d.nx * d.ny;
         // term = weight * invHSqr with invHSqr = invH * invH (…pressure_solver3.cpp:127-128)
         m.sx = (1.0 / hx) * (1.0 / hx); m.sy = (1.0 / hy) * (1.0 / hy); m.sz = (1.0 / hz) * (1.0 / hz);
         ps->mg.A[l] = m;

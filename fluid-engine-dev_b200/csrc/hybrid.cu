@@ -29,6 +29,11 @@ struct jetcu_hybrid {
     char *valid0 = nullptr, *valid1 = nullptr;
     double* sdf = nullptr;
     float *ud = nullptr, *vd = nullptr, *wd = nullptr;
+    unsigned long long* wsum[3] = {};      // P2G fixed-point weight sums (u, v, w faces), high words
+    unsigned long long* wsum_lo[3] = {};   // ... low words
+    unsigned long long* sum_lo[3] = {};    // low words of the value sums (high words live in u, v, w)
+    struct P2GScale* p2g_scale = nullptr;  // device: 2^k / 2^-k of the current step's value accumulators
+    int* p2g_err = nullptr;                // device flag: fixed-point headroom exceeded
     // particles
     uint64_t np = 0, cap = 0;
     int nattr = 6;
@@ -136,73 +141,250 @@ __global__ void k_gather_attrs(AttrPtrs src, AttrPtrs dst, const uint32_t* __res
 
 // ------------------------------------------------------------------------------------------------ P2G
 // transferFromParticlesToGrids: PIC src/jet/pic_solver3.cpp:118-193, APIC src/jet/apic_solver3.cpp:26-146.
-// One thread per face; gathers from the 2x3x3 cells whose particles can list this face among their 8 sampler
-// corners (getCoordinatesAndWeights, array_samplers3-inl.h:151-193), in the fixed order cells (z,y,x) then slot.
-template <int AXIS, bool APIC>
-__global__ void __launch_bounds__(128)
-    k_p2g(GridD g, const uint32_t* __restrict__ cell_start, AttrPtrs a, double* __restrict__ out, char* __restrict__ marker) {
-    int sx, sy, sz;
-    double ox, oy, oz;
-    comp_grid<AXIS>(g, &sx, &sy, &sz, &ox, &oy, &oz);
-    int i = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
-    if (i >= sx || j >= sy || k >= sz) return;
+//
+// The reference accumulates `u += v*w; wsum += w` over particles in a serial loop, so any parallel version has to
+// choose its own summation order.  Here the sums are carried in 128-bit FIXED POINT (two 64-bit words, carry
+// propagated by hand): every contribution is converted once to a multiple of 2^-(k+64) (k chosen per step from
+// max|value| so that nothing can overflow) and added as an integer.  Integer addition is associative, so the result
+// does not depend on the order of the particles, of the tiles, or — on several GPUs — of the slabs: bit-reproducible
+// by construction.  With 114 fractional bits a contribution keeps all 53 bits of its double down to 2^-61 of
+// max|value| (weights down to 2^-61), so faces at the liquid fringe that only see tiny weights are as accurate as
+// in the reference's double sum.
+//
+// Structure: particles are cell-sorted; a CTA owns a tile of TC^3 cells, walks the particles of its 64 cell rows
+// (contiguous ranges, coalesced SoA reads), accumulates into shared-memory tiles of the u/v/w faces the tile can
+// reach (tile + one ring), and finally adds the tile into the global accumulators.  Markers are plain stores of 1.
+#define TC 8
+#define P2G_THREADS 256
+#define P2G_KW 50          // weight sums: fixed point with 50 fractional bits (sum of weights per face < 4096)
+#define P2G_HEADROOM 12    // value sums: max|value| * 2^HEADROOM * 2^k < 2^62
+
+struct P2GScale {
+    double scale, inv_scale;  // 2^k, 2^-k
+};
+
+// max over particles of the largest value a particle can deposit: |v_a| (+ h * (|c_a0|+|c_a1|+|c_a2|) for APIC)
+__global__ void __launch_bounds__(256) k_p2g_vmax_partial(AttrPtrs a, size_t np, int apic, double hx, double hy, double hz,
+                                                          double* __restrict__ partials) {
+    __shared__ double sm[256];
+    double m = 0.0;
+    for (size_t p = (size_t)blockIdx.x * 256 + threadIdx.x; p < np; p += (size_t)gridDim.x * 256) {
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) {
+            double v = fabs(a.p[3 + ax][p]);
+            if (apic) v += hx * fabs(a.p[6 + 3 * ax][p]) + hy * fabs(a.p[7 + 3 * ax][p]) + hz * fabs(a.p[8 + 3 * ax][p]);
+            m = fmax(m, v);
+        }
+    }
+    sm[threadIdx.x] = m;
+    __syncthreads();
+    for (int s2 = 128; s2 > 0; s2 >>= 1) {
+        if (threadIdx.x < s2) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + s2]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = sm[0];
+}
+
+__global__ void __launch_bounds__(256) k_p2g_scale_final(const double* __restrict__ partials, int n, P2GScale* out) {
+    __shared__ double sm[256];
+    double m = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) m = fmax(m, partials[i]);
+    sm[threadIdx.x] = m;
+    __syncthreads();
+    for (int s2 = 128; s2 > 0; s2 >>= 1) {
+        if (threadIdx.x < s2) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + s2]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double vmax = sm[0];
+        int e = (vmax > 0.0 && isfinite(vmax)) ? ilogb(vmax) + 1 : 0;  // vmax < 2^e
+        int k = 62 - P2G_HEADROOM - e;
+        out->scale = ldexp(1.0, k);
+        out->inv_scale = ldexp(1.0, -k);
+    }
+}
+
+struct P2GAcc {  // global accumulators; the high words of the value sums live in the velocity arrays themselves
+    unsigned long long* sum[3];     // value sum, high word
+    unsigned long long* sum_lo[3];  // value sum, low word
+    unsigned long long* wsum[3];    // weight sum, high word
+    unsigned long long* wsum_lo[3]; // weight sum, low word
+    char* marker[3];
+};
+
+// |t| < 2^63 -> signed 128-bit fixed point with 64 fractional bits (two's complement in hi:lo)
+__device__ __forceinline__ void to_fixed128(double t, unsigned long long* hi, unsigned long long* lo) {
+    const double a = fabs(t), fl = floor(a);
+    unsigned long long h = (unsigned long long)fl;
+    unsigned long long l = __double2ull_rd((a - fl) * 18446744073709551616.0);  // exact difference, < 2^64
+    if (t < 0.0) { l = 0ull - l; h = ~h + (l == 0ull ? 1ull : 0ull); }
+    *hi = h; *lo = l;
+}
+
+// (HI:LO) += (hi:lo) with two 64-bit atomics; the number of carries out of LO is fixed by the final sum, so the
+// result is independent of the order in which contributions arrive.
+__device__ __forceinline__ void acc128(unsigned long long* HI, unsigned long long* LO, unsigned long long hi,
+                                       unsigned long long lo) {
+    if (lo) {
+        const unsigned long long old = atomicAdd(LO, lo);
+        hi += (old > ~lo) ? 1ull : 0ull;
+    }
+    if (hi) atomicAdd(HI, hi);
+}
+
+// The same on a shared-memory accumulator stored as four 32-bit limbs `stride` words apart (non-negative addend).
+__device__ __forceinline__ void acc_limbs(unsigned* L, int stride, unsigned long long hi, unsigned long long lo) {
+    const unsigned x[4] = {(unsigned)lo, (unsigned)(lo >> 32), (unsigned)hi, (unsigned)(hi >> 32)};
+    unsigned carry = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const unsigned long long add = (unsigned long long)x[j] + carry;
+        const unsigned a32 = (unsigned)add;
+        carry = (unsigned)(add >> 32);
+        if (a32) {
+            const unsigned old = atomicAdd(L + j * stride, a32);
+            carry += (old > ~a32) ? 1u : 0u;
+        }
+    }
+}
+
+__device__ __forceinline__ double from_fixed128(unsigned long long hi, unsigned long long lo) {  // value * 2^64
+    const bool neg = (long long)hi < 0;
+    if (neg) { lo = 0ull - lo; hi = ~hi + (lo == 0ull ? 1ull : 0ull); }
+    const double v = (double)hi * 18446744073709551616.0 + (double)lo;
+    return neg ? -v : v;
+}
+
+template <bool APIC>
+__global__ void __launch_bounds__(P2G_THREADS)
+    k_p2g_scatter(GridD g, const uint32_t* __restrict__ cell_start, AttrPtrs a, const P2GScale* __restrict__ sc, P2GAcc acc) {
+    // per component: tile of faces reachable from the TC^3 cells: the component's own axis spans TC+1, the others TC+2
+    constexpr int NF = (TC + 1) * (TC + 2) * (TC + 2);
+    // Shared accumulators: 128-bit integers as four 32-bit limbs (32-bit shared atomics are native; 64-bit ones
+    // compile to compare-and-swap spin loops).  The value accumulator holds value + 2^e * weight, which is never
+    // negative (|value| < 2^e * weight), so small contributions leave the high limbs untouched; the bias equals the
+    // weight accumulator bit for bit and is removed exactly when the tile is flushed.
+    extern __shared__ __align__(16) unsigned p2g_smem[];
+    unsigned(*sV)[4][NF] = reinterpret_cast<unsigned(*)[4][NF]>(p2g_smem);             // [3][limb] value + bias
+    unsigned(*sW)[4][NF] = reinterpret_cast<unsigned(*)[4][NF]>(p2g_smem + 12 * NF);   // [3][limb] weight
+    unsigned char(*sM)[NF] = reinterpret_cast<unsigned char(*)[NF]>(p2g_smem + 24 * NF);  // [3] markers
+    __shared__ int any;
+    const int I0 = blockIdx.x * TC, J0 = blockIdx.y * TC, K0 = blockIdx.z * TC;
+    if (threadIdx.x == 0) any = 0;
+    for (int t = threadIdx.x; t < 24 * NF; t += P2G_THREADS) p2g_smem[t] = 0u;
+    for (int t = threadIdx.x; t < 3 * NF; t += P2G_THREADS) (&sM[0][0])[t] = 0;
+    __syncthreads();
+    const double scale = sc->scale;
+    const double wscale = 1125899906842624.0;  // 2^50
     const double ihx = 1.0 / g.hx, ihy = 1.0 / g.hy, ihz = 1.0 / g.hz;
-    // cell ranges: along the face's own axis cells {f-1, f}; along the tangential axes {f-1, f, f+1}
-    int ci0 = max(i - 1, 0), ci1 = min(AXIS == 0 ? i : i + 1, g.nx - 1);
-    int cj0 = max(j - 1, 0), cj1 = min(AXIS == 1 ? j : j + 1, g.ny - 1);
-    int ck0 = max(k - 1, 0), ck1 = min(AXIS == 2 ? k : k + 1, g.nz - 1);
-    const double* __restrict__ vel = a.p[3 + AXIS];
-    const double* __restrict__ c0 = a.p[6 + 3 * AXIS];
-    const double* __restrict__ c1 = a.p[7 + 3 * AXIS];
-    const double* __restrict__ c2 = a.p[8 + 3 * AXIS];
-    // APIC clamps the two tangential coordinates to [lo + h/2, hi - h/2] (apic_solver3.cpp:76-84,94-102,112-120)
     const double lox = g.ox + g.hx / 2.0, hix = (g.ox + g.hx * (double)g.nx) - g.hx / 2.0;
     const double loy = g.oy + g.hy / 2.0, hiy = (g.oy + g.hy * (double)g.ny) - g.hy / 2.0;
     const double loz = g.oz + g.hz / 2.0, hiz = (g.oz + g.hz * (double)g.nz) - g.hz / 2.0;
-    double sum = 0.0, wsum = 0.0;
-    int mark = 0;
-    for (int ck = ck0; ck <= ck1; ++ck)
-        for (int cj = cj0; cj <= cj1; ++cj) {
-            size_t row = ((size_t)ck * g.ny + cj) * g.nx;
-            uint32_t s = cell_start[row + ci0], e = cell_start[row + ci1 + 1];  // x-adjacent cells are contiguous
-            for (uint32_t q = s; q < e; ++q) {
-                double px = a.p[0][q], py = a.p[1][q], pz = a.p[2][q];
-                if (APIC) {
-                    if (AXIS != 0) px = jc_clamp(px, lox, hix);
-                    if (AXIS != 1) py = jc_clamp(py, loy, hiy);
-                    if (AXIS != 2) pz = jc_clamp(pz, loz, hiz);
-                }
-                BaseFrac b = jc_base_mul(sx, sy, sz, ihx, ihy, ihz, ox, oy, oz, px, py, pz);
-                bool mx0 = (b.i == i), mx1 = (b.ip1 == i), my0 = (b.j == j), my1 = (b.jp1 == j), mz0 = (b.k == k),
-                     mz1 = (b.kp1 == k);
-                if (!((mx0 | mx1) & (my0 | my1) & (mz0 | mz1))) continue;
-                double pv = vel[q];
-                if (APIC) {
-                    // apicTerm = c . (facePosition - clampedPosition); facePosition = faceOrigin + h*(i,j,k)
-                    double gx = ox + g.hx * (double)i, gy = oy + g.hy * (double)j, gz = oz + g.hz * (double)k;
-                    double term = c0[q] * (gx - px) + c1[q] * (gy - py) + c2[q] * (gz - pz);
-                    pv = pv + term;
-                }
+    int touched = 0;
+    // one thread per cell, walking the cell's particles: the lanes of a warp then work on 32 DIFFERENT cells, so that
+    // concurrent atomics rarely hit the same face (the particles of one cell all hit the same few faces)
+    for (int cl = threadIdx.x; cl < TC * TC * TC; cl += P2G_THREADS) {
+        const int ci = I0 + (cl % TC), cj = J0 + ((cl / TC) % TC), ck = K0 + (cl / (TC * TC));
+        if (ci >= g.nx || cj >= g.ny || ck >= g.nz) continue;
+        const size_t cell = ((size_t)ck * g.ny + cj) * g.nx + ci;
+        const uint32_t s0 = cell_start[cell], e0 = cell_start[cell + 1];
+        for (uint32_t q = s0; q < e0; ++q) {
+            touched = 1;
+            const double px0 = a.p[0][q], py0 = a.p[1][q], pz0 = a.p[2][q];
 #pragma unroll
-                for (int cnr = 0; cnr < 8; ++cnr) {  // the reference's corner order; duplicates only on size-1 axes
-                    bool hit = ((cnr & 1) ? mx1 : mx0) && ((cnr & 2) ? my1 : my0) && ((cnr & 4) ? mz1 : mz0);
-                    if (hit) {
-                        double wgt = jc_corner_weight(b, cnr);
-                        sum += APIC ? wgt * pv : pv * wgt;
-                        wsum += wgt;
-                        mark = 1;
+            for (int ax = 0; ax < 3; ++ax) {
+                const int sx = g.nx + (ax == 0), sy = g.ny + (ax == 1), sz = g.nz + (ax == 2);
+                const double ox = g.ox + 0.5 * (ax == 0 ? 0.0 : g.hx), oy = g.oy + 0.5 * (ax == 1 ? 0.0 : g.hy),
+                             oz = g.oz + 0.5 * (ax == 2 ? 0.0 : g.hz);
+                double px = px0, py = py0, pz = pz0;
+                if (APIC) {  // tangential clamp to [lo + h/2, hi - h/2] (apic_solver3.cpp:76-84,94-102,112-120)
+                    if (ax != 0) px = jc_clamp(px, lox, hix);
+                    if (ax != 1) py = jc_clamp(py, loy, hiy);
+                    if (ax != 2) pz = jc_clamp(pz, loz, hiz);
+                }
+                const BaseFrac bf = jc_base_mul(sx, sy, sz, ihx, ihy, ihz, ox, oy, oz, px, py, pz);
+                const double pv = a.p[3 + ax][q];
+                double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+                if (APIC) { c0 = a.p[6 + 3 * ax][q]; c1 = a.p[7 + 3 * ax][q]; c2 = a.p[8 + 3 * ax][q]; }
+                // local tile frame of this component
+                const int lx0 = I0 - (ax == 0 ? 0 : 1), ly0 = J0 - (ax == 1 ? 0 : 1), lz0 = K0 - (ax == 2 ? 0 : 1);
+                const int dx = TC + (ax == 0 ? 1 : 2), dy = TC + (ax == 1 ? 1 : 2), dz = TC + (ax == 2 ? 1 : 2);
+#pragma unroll
+                for (int cnr = 0; cnr < 8; ++cnr) {  // the reference's corner order
+                    const int fi = (cnr & 1) ? bf.ip1 : bf.i, fj = (cnr & 2) ? bf.jp1 : bf.j, fk = (cnr & 4) ? bf.kp1 : bf.k;
+                    const double wgt = jc_corner_weight(bf, cnr);
+                    double val;
+                    if (APIC) {
+                        // apicTerm = c . (facePosition - clampedPosition); facePosition = faceOrigin + h*(i,j,k)
+                        const double gx = ox + g.hx * (double)fi, gy = oy + g.hy * (double)fj, gz = oz + g.hz * (double)fk;
+                        const double term = c0 * (gx - px) + c1 * (gy - py) + c2 * (gz - pz);
+                        val = wgt * (pv + term);
+                    } else {
+                        val = pv * wgt;
+                    }
+                    unsigned long long vh, vl, wh, wl;
+                    to_fixed128(val * scale, &vh, &vl);
+                    to_fixed128(wgt * wscale, &wh, &wl);
+                    const int lx = fi - lx0, ly = fj - ly0, lz = fk - lz0;
+                    if ((unsigned)lx < (unsigned)dx && (unsigned)ly < (unsigned)dy && (unsigned)lz < (unsigned)dz) {
+                        const int t = (lz * dy + ly) * dx + lx;
+                        unsigned long long bl = vl + wl, bh = vh + wh + (bl < vl ? 1ull : 0ull);  // value + bias >= 0
+                        acc_limbs(&sV[ax][0][t], NF, bh, bl);
+                        acc_limbs(&sW[ax][0][t], NF, wh, wl);
+                        sM[ax][t] = 1;
+                    } else {  // cannot happen for in-domain particles; kept so that a wild position is still summed
+                        const size_t f = ((size_t)fk * sy + fj) * sx + fi;
+                        acc128(acc.sum[ax] + f, acc.sum_lo[ax] + f, vh, vl);
+                        acc128(acc.wsum[ax] + f, acc.wsum_lo[ax] + f, wh, wl);
+                        acc.marker[ax][f] = 1;
                     }
                 }
             }
         }
-    size_t f = ((size_t)k * sy + j) * sx + i;
-    out[f] = (wsum > 0.0) ? sum / wsum : sum;  // pic_solver3.cpp:178-192
-    marker[f] = (char)mark;
+    }
+    if (touched) any = 1;
+    __syncthreads();
+    if (!any) return;
+    // add the tile into the global accumulators (integer adds: order-independent)
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        const int sx = g.nx + (ax == 0), sy = g.ny + (ax == 1);
+        const int lx0 = I0 - (ax == 0 ? 0 : 1), ly0 = J0 - (ax == 1 ? 0 : 1), lz0 = K0 - (ax == 2 ? 0 : 1);
+        const int dx = TC + (ax == 0 ? 1 : 2), dy = TC + (ax == 1 ? 1 : 2), dz = TC + (ax == 2 ? 1 : 2);
+        for (int t = threadIdx.x; t < dx * dy * dz; t += P2G_THREADS) {
+            if (!sM[ax][t]) continue;
+            const int lx = t % dx, ly = (t / dx) % dy, lz = t / (dx * dy);
+            const size_t f = ((size_t)(lz0 + lz) * sy + (ly0 + ly)) * sx + (lx0 + lx);
+            const unsigned long long wl = (unsigned long long)sW[ax][0][t] | ((unsigned long long)sW[ax][1][t] << 32);
+            const unsigned long long wh = (unsigned long long)sW[ax][2][t] | ((unsigned long long)sW[ax][3][t] << 32);
+            unsigned long long vl = (unsigned long long)sV[ax][0][t] | ((unsigned long long)sV[ax][1][t] << 32);
+            unsigned long long vh = (unsigned long long)sV[ax][2][t] | ((unsigned long long)sV[ax][3][t] << 32);
+            vh = vh - wh - (vl < wl ? 1ull : 0ull); vl = vl - wl;  // remove the bias: exact 128-bit subtraction
+            acc128(acc.sum[ax] + f, acc.sum_lo[ax] + f, vh, vl);
+            acc128(acc.wsum[ax] + f, acc.wsum_lo[ax] + f, wh, wl);
+            acc.marker[ax][f] = 1;
+        }
+    }
 }
 
-__global__ void k_to_float(const double* __restrict__ in, float* __restrict__ out, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (float)in[i];  // FlipSolver3 snapshot, src/jet/flip_solver3.cpp:39-47
+// u = sum / wsum where wsum > 0 (pic_solver3.cpp:178-192), back in double; FLIP's float snapshot
+// (src/jet/flip_solver3.cpp:39-47) is taken in the same pass.  err[0] is raised if a weight sum left the
+// fixed-point headroom (more than 2^HEADROOM particles' worth of weight on one face).
+__global__ void k_p2g_normalise(double* __restrict__ u, const unsigned long long* __restrict__ sum_lo,
+                                const unsigned long long* __restrict__ wsum, const unsigned long long* __restrict__ wsum_lo,
+                                const P2GScale* __restrict__ sc, float* __restrict__ snapshot, int* __restrict__ err, size_t n) {
+    size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    const double S = from_fixed128(reinterpret_cast<const unsigned long long*>(u)[f], sum_lo[f]);  // value * 2^(k+64)
+    const unsigned long long Wh = wsum[f], Wl = wsum_lo[f];
+    double val = S * 5.421010862427522e-20 * sc->inv_scale;  // * 2^-64 * 2^-k (exact scalings)
+    if (Wh | Wl) {
+        const double wd = from_fixed128(Wh, Wl) * 5.421010862427522e-20 * 8.8817841970012523e-16;  // * 2^-64 * 2^-50
+        val = val / wd;
+        if (wd > (double)(1 << P2G_HEADROOM)) err[0] = 1;
+    }
+    u[f] = val;
+    if (snapshot) snapshot[f] = (float)val;
 }
 
 __global__ void k_flip_delta(const double* __restrict__ in, float* __restrict__ d, size_t n) {
@@ -704,6 +886,13 @@ int jetcu_hybrid_create(jetcu_ctx* ctx, const jetcu_hybrid_params* p, jetcu_hybr
     STEP(jc_alloc(ctx, &h->um, h->nu)); STEP(jc_alloc(ctx, &h->vm, h->nv)); STEP(jc_alloc(ctx, &h->wm, h->nw));
     STEP(jc_zero(ctx, h->um, h->nu)); STEP(jc_zero(ctx, h->vm, h->nv)); STEP(jc_zero(ctx, h->wm, h->nw));
     STEP(jc_alloc(ctx, &h->valid0, nmax)); STEP(jc_alloc(ctx, &h->valid1, nmax));
+    {
+        const size_t nf[3] = {h->nu, h->nv, h->nw};
+        for (int q = 0; q < 3; ++q) {
+            STEP(jc_alloc(ctx, &h->wsum[q], nf[q])); STEP(jc_alloc(ctx, &h->wsum_lo[q], nf[q])); STEP(jc_alloc(ctx, &h->sum_lo[q], nf[q]));
+        }
+    }
+    STEP(jc_alloc(ctx, &h->p2g_scale, 1)); STEP(jc_alloc(ctx, &h->p2g_err, 1)); STEP(jc_zero(ctx, h->p2g_err, 1));
     STEP(jc_alloc(ctx, &h->sdf, h->nc));
     if (p->mode == JETCU_FLIP) {
         STEP(jc_alloc(ctx, &h->ud, h->nu)); STEP(jc_alloc(ctx, &h->vd, h->nv)); STEP(jc_alloc(ctx, &h->wd, h->nw));
@@ -735,6 +924,8 @@ int jetcu_hybrid_destroy(jetcu_hybrid* h) {
     jc_free(ctx, h->um); jc_free(ctx, h->vm); jc_free(ctx, h->wm);
     jc_free(ctx, h->valid0); jc_free(ctx, h->valid1); jc_free(ctx, h->sdf);
     jc_free(ctx, h->ud); jc_free(ctx, h->vd); jc_free(ctx, h->wd);
+    for (int q = 0; q < 3; ++q) { jc_free(ctx, h->wsum[q]); jc_free(ctx, h->wsum_lo[q]); jc_free(ctx, h->sum_lo[q]); }
+    jc_free(ctx, h->p2g_scale); jc_free(ctx, h->p2g_err);
     for (int b = 0; b < 2; ++b) {
         for (int q = 0; q < NATTR; ++q) jc_free(ctx, h->attr[b][q]);
         jc_free(ctx, h->orig[b]);
@@ -961,23 +1152,40 @@ int jetcu_hybrid_transfer_particles_to_grids(jetcu_hybrid* h) {
     JC_TRY(hyb_bin(h));
     GridD g = gridd(h);
     AttrPtrs a = attr_ptrs(h, h->cur);
-    dim3 blk(32, 4);
-    dim3 gu((g.nx + 1 + 31) / 32, (g.ny + 3) / 4, g.nz), gv((g.nx + 31) / 32, (g.ny + 1 + 3) / 4, g.nz),
-        gw((g.nx + 31) / 32, (g.ny + 3) / 4, g.nz + 1);
-    if (h->P.mode == JETCU_APIC) {
-        JC_LAUNCH(ctx, (k_p2g<0, true>), gu, blk, 0, g, h->cell_start, a, h->u, h->um);
-        JC_LAUNCH(ctx, (k_p2g<1, true>), gv, blk, 0, g, h->cell_start, a, h->v, h->vm);
-        JC_LAUNCH(ctx, (k_p2g<2, true>), gw, blk, 0, g, h->cell_start, a, h->w, h->wm);
-    } else {
-        JC_LAUNCH(ctx, (k_p2g<0, false>), gu, blk, 0, g, h->cell_start, a, h->u, h->um);
-        JC_LAUNCH(ctx, (k_p2g<1, false>), gv, blk, 0, g, h->cell_start, a, h->v, h->vm);
-        JC_LAUNCH(ctx, (k_p2g<2, false>), gw, blk, 0, g, h->cell_start, a, h->w, h->wm);
+    const bool apic = h->P.mode == JETCU_APIC;
+    int slot = jc_prof_begin(ctx, JETCU_PROF_P2G);
+    // u, v, w double as the fixed-point value accumulators; weight sums and markers start from zero as well
+    JC_TRY(jc_zero(ctx, h->u, h->nu)); JC_TRY(jc_zero(ctx, h->v, h->nv)); JC_TRY(jc_zero(ctx, h->w, h->nw));
+    const size_t nf[3] = {h->nu, h->nv, h->nw};
+    for (int q = 0; q < 3; ++q) {
+        JC_TRY(jc_zero(ctx, h->wsum[q], nf[q])); JC_TRY(jc_zero(ctx, h->wsum_lo[q], nf[q])); JC_TRY(jc_zero(ctx, h->sum_lo[q], nf[q]));
     }
-    if (h->P.mode == JETCU_FLIP) {
-        JC_LAUNCH(ctx, k_to_float, jc_blocks(h->nu, 256), 256, 0, h->u, h->ud, h->nu);
-        JC_LAUNCH(ctx, k_to_float, jc_blocks(h->nv, 256), 256, 0, h->v, h->vd, h->nv);
-        JC_LAUNCH(ctx, k_to_float, jc_blocks(h->nw, 256), 256, 0, h->w, h->wd, h->nw);
+    JC_TRY(jc_zero(ctx, h->um, h->nu)); JC_TRY(jc_zero(ctx, h->vm, h->nv)); JC_TRY(jc_zero(ctx, h->wm, h->nw));
+    if (h->np > 0) {
+        JC_LAUNCH(ctx, k_p2g_vmax_partial, 592, 256, 0, a, (size_t)h->np, apic ? 1 : 0, g.hx, g.hy, g.hz, ctx->d_partials);
+        JC_LAUNCH(ctx, k_p2g_scale_final, 1, 256, 0, ctx->d_partials, 592, h->p2g_scale);
+        P2GAcc acc;
+        acc.sum[0] = (unsigned long long*)h->u; acc.sum[1] = (unsigned long long*)h->v; acc.sum[2] = (unsigned long long*)h->w;
+        for (int q = 0; q < 3; ++q) { acc.wsum[q] = h->wsum[q]; acc.wsum_lo[q] = h->wsum_lo[q]; acc.sum_lo[q] = h->sum_lo[q]; }
+        acc.marker[0] = h->um; acc.marker[1] = h->vm; acc.marker[2] = h->wm;
+        dim3 grid((g.nx + TC - 1) / TC, (g.ny + TC - 1) / TC, (g.nz + TC - 1) / TC);
+        const size_t smem = (size_t)(TC + 1) * (TC + 2) * (TC + 2) * (24 * 4 + 3);
+        static bool attr_set = false;
+        if (!attr_set) {
+            JC_CUDA(ctx, cudaFuncSetAttribute(k_p2g_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            JC_CUDA(ctx, cudaFuncSetAttribute(k_p2g_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        if (apic) JC_LAUNCH(ctx, (k_p2g_scatter<true>), grid, P2G_THREADS, smem, g, h->cell_start, a, h->p2g_scale, acc);
+        else JC_LAUNCH(ctx, (k_p2g_scatter<false>), grid, P2G_THREADS, smem, g, h->cell_start, a, h->p2g_scale, acc);
+        const bool flip = h->P.mode == JETCU_FLIP;
+        JC_LAUNCH(ctx, k_p2g_normalise, jc_blocks(h->nu, 256), 256, 0, h->u, h->sum_lo[0], h->wsum[0], h->wsum_lo[0], h->p2g_scale, flip ? h->ud : nullptr, h->p2g_err, h->nu);
+        JC_LAUNCH(ctx, k_p2g_normalise, jc_blocks(h->nv, 256), 256, 0, h->v, h->sum_lo[1], h->wsum[1], h->wsum_lo[1], h->p2g_scale, flip ? h->vd : nullptr, h->p2g_err, h->nv);
+        JC_LAUNCH(ctx, k_p2g_normalise, jc_blocks(h->nw, 256), 256, 0, h->w, h->sum_lo[2], h->wsum[2], h->wsum_lo[2], h->p2g_scale, flip ? h->wd : nullptr, h->p2g_err, h->nw);
+    } else if (h->P.mode == JETCU_FLIP) {
+        JC_TRY(jc_zero(ctx, h->ud, h->nu)); JC_TRY(jc_zero(ctx, h->vd, h->nv)); JC_TRY(jc_zero(ctx, h->wd, h->nw));
     }
+    jc_prof_end(ctx, slot, 6, h->np);
     return JETCU_OK;
 }
 
@@ -1107,7 +1315,14 @@ int jetcu_hybrid_step(jetcu_hybrid* h, double dt, jetcu_step_stats* st) {
     JC_TRY(jetcu_hybrid_move_particles(h, dt));
     MARK(9);
 #undef MARK
+    int p2g_err = 0;
+    JC_TRY(jc_d2h(ctx, &p2g_err, h->p2g_err, 1));
     JC_TRY(jc_sync(ctx));
+    if (p2g_err) {
+        jc_zero(ctx, h->p2g_err, 1);
+        return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED,
+                          "P2G fixed-point headroom exceeded: more than 4096 particles' worth of weight on one face");
+    }
     if (st) {
         memset(st, 0, sizeof(*st));
         auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]); return (double)ms; };

@@ -1,0 +1,424 @@
+// jetcu_jet_adapters.h — header-only C++11 adapters that put the jetcu C ABI (include/jetcu.h) behind Jet's own
+// virtual interfaces, so UNMODIFIED Jet host code (doyubkim/fluid-engine-dev) runs the hybrid-liquid hot path on a
+// B200.  Compile this header inside a Jet application: it includes <jet/jet.h> from the Jet tree and links
+// libjetcu.so.  Nothing of Jet is copied here; the adapters only subclass / call its public API.
+//
+//   seam 1  jetcu::CudaFdmMgpcgSolver3 : jet::FdmMgSolver3            (include/jet/fdm_mg_solver3.h:45)
+//           install with  pressureSolver->setLinearSystemSolver(std::make_shared<jetcu::CudaFdmMgpcgSolver3>(...))
+//           — Jet builds the multigrid system on the host, the GPU solves it (jetcu_mgpcg_solve).
+//   seam 2  jetcu::CudaGridFractionalSinglePhasePressureSolver3 : jet::GridPressureSolver3
+//           (include/jet/grid_pressure_solver3.h:58-74); install with  solver->setPressureSolver(...)
+//           — weights, system build, MGPCG and the pressure gradient all run on the GPU (jetcu_pressure_solve).
+//   seam 3  jetcu::CudaPicSolver3 / CudaFlipSolver3 / CudaApicSolver3 : jet::PicSolver3 / FlipSolver3 / ApicSolver3
+//           — the whole sub-step (GridFluidSolver3::onAdvanceTimeStep, src/jet/grid_fluid_solver3.cpp:179-210)
+//           runs device-resident (jetcu_hybrid_step); particles and grids are mirrored back into Jet's
+//           ParticleSystemData3 / FaceCenteredGrid3 / signedDistanceField() objects.
+//
+// Error convention: the C ABI returns int codes; the adapters rethrow JETCU_ERR_INVALID_ARG as
+// std::invalid_argument (what JET_THROW_INVALID_ARG_IF raises, include/jet/macros.h:37-41) and everything else as
+// std::runtime_error.  There is no CPU fallback: without a usable B200 every call throws.
+#ifndef JETCU_JET_ADAPTERS_H_
+#define JETCU_JET_ADAPTERS_H_
+
+#include <jet/jet.h>
+
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../include/jetcu.h"
+
+namespace jetcu {
+
+// ------------------------------------------------------------------------------------------------ context
+class Context {
+ public:
+    explicit Context(int device = 0) {
+        int rc = jetcu_ctx_create(device, &_ctx);
+        if (rc != JETCU_OK) {
+            const char* msg = jetcu_last_error(nullptr);
+            throw std::runtime_error(std::string("jetcu_ctx_create failed: ") + (msg ? msg : "?"));
+        }
+    }
+    ~Context() { jetcu_ctx_destroy(_ctx); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    jetcu_ctx* get() const { return _ctx; }
+
+    void check(int rc) const {
+        if (rc == JETCU_OK) return;
+        const char* msg = jetcu_last_error(_ctx);
+        std::string text = std::string("jetcu: ") + (msg ? msg : "error");
+        if (rc == JETCU_ERR_INVALID_ARG) throw std::invalid_argument(text);
+        throw std::runtime_error(text);
+    }
+
+    //! One lazily created context per process for device 0 (Jet's solvers are single-threaded per object).
+    static std::shared_ptr<Context> shared(int device = 0) {
+        static std::shared_ptr<Context> inst[16];
+        if (device < 0 || device >= 16) throw std::invalid_argument("jetcu: device index out of range");
+        if (!inst[device]) inst[device] = std::make_shared<Context>(device);
+        return inst[device];
+    }
+
+ private:
+    jetcu_ctx* _ctx = nullptr;
+};
+typedef std::shared_ptr<Context> ContextPtr;
+
+inline jetcu_mgpcg_params makeMgpcgParams(unsigned int numberOfCgIter, size_t maxNumberOfLevels,
+                                          unsigned int numberOfRestrictionIter, unsigned int numberOfCorrectionIter,
+                                          unsigned int numberOfCoarsestIter, unsigned int numberOfFinalIter,
+                                          double maxTolerance, double sorFactor, bool useRedBlackOrdering) {
+    jetcu_mgpcg_params p;
+    std::memset(&p, 0, sizeof(p));
+    p.max_iterations = numberOfCgIter;
+    p.max_levels = static_cast<uint32_t>(maxNumberOfLevels);
+    p.n_restriction = numberOfRestrictionIter;
+    p.n_correction = numberOfCorrectionIter;
+    p.n_coarsest = numberOfCoarsestIter;
+    p.n_final = numberOfFinalIter;
+    p.tolerance = maxTolerance;
+    p.sor_factor = sorFactor;
+    p.use_red_black = useRedBlackOrdering ? 1 : 0;
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------------ seam 1
+//! Drop-in for jet::FdmMgpcgSolver3 (which is `final`, include/jet/fdm_mgpcg_solver3.h:23): same constructor
+//! arguments, same accessors; GridFractionalSinglePhasePressureSolver3 routes to solve(FdmMgLinearSystem3*) for any
+//! FdmMgSolver3 subclass (src/jet/grid_fractional_single_phase_pressure_solver3.cpp:477-478,497-510).
+class CudaFdmMgpcgSolver3 final : public jet::FdmMgSolver3 {
+ public:
+    CudaFdmMgpcgSolver3(unsigned int numberOfCgIter, size_t maxNumberOfLevels,
+                        unsigned int numberOfRestrictionIter = 5, unsigned int numberOfCorrectionIter = 5,
+                        unsigned int numberOfCoarsestIter = 20, unsigned int numberOfFinalIter = 20,
+                        double maxTolerance = 1e-9, double sorFactor = 1.5, bool useRedBlackOrdering = false,
+                        ContextPtr ctx = ContextPtr())
+        : jet::FdmMgSolver3(maxNumberOfLevels, numberOfRestrictionIter, numberOfCorrectionIter, numberOfCoarsestIter,
+                            numberOfFinalIter, maxTolerance, sorFactor, useRedBlackOrdering),
+          _ctx(ctx ? ctx : Context::shared()),
+          _p(makeMgpcgParams(numberOfCgIter, maxNumberOfLevels, numberOfRestrictionIter, numberOfCorrectionIter,
+                             numberOfCoarsestIter, numberOfFinalIter, maxTolerance, sorFactor, useRedBlackOrdering)) {
+        std::memset(&_last, 0, sizeof(_last));
+    }
+
+    bool solve(jet::FdmMgLinearSystem3* system) override {
+        const size_t levels = system->numberOfLevels();
+        if (levels == 0) return true;
+        static_assert(sizeof(jet::FdmMatrixRow3) == sizeof(jetcu_matrix_row), "FdmMatrixRow3 must be 4 doubles");
+        std::vector<const jetcu_matrix_row*> A(levels);
+        for (size_t l = 0; l < levels; ++l)
+            A[l] = reinterpret_cast<const jetcu_matrix_row*>(system->A.levels[l].data());
+        const jet::Size3 n = system->A.levels[0].size();
+        JET_THROW_INVALID_ARG_IF(system->b.levels[0].size() != n);
+        JET_THROW_INVALID_ARG_IF(system->x.levels[0].size() != n);
+        _ctx->check(jetcu_mgpcg_solve(_ctx->get(), n.x, n.y, n.z, static_cast<uint32_t>(levels), A.data(),
+                                      system->b.levels[0].data(), system->x.levels[0].data(), &_p, &_last));
+        return _last.returned != 0;
+    }
+
+    unsigned int maxNumberOfIterations() const { return _p.max_iterations; }
+    unsigned int lastNumberOfIterations() const { return _last.iterations; }
+    double tolerance() const { return _p.tolerance; }
+    double lastResidual() const { return _last.last_residual; }
+    //! ||b - A x||_2 recomputed at exit and ||b||_2 (not available in Jet).
+    double lastTrueResidual() const { return _last.true_residual_l2; }
+    double lastRhsNorm() const { return _last.b_l2; }
+    //! Device time of the last solve in milliseconds (CUDA events).
+    double lastSolveMilliseconds() const { return _last.solve_ms; }
+    const jetcu_mgpcg_params& cudaParams() const { return _p; }
+
+ private:
+    ContextPtr _ctx;
+    jetcu_mgpcg_params _p;
+    jetcu_mgpcg_result _last;
+};
+typedef std::shared_ptr<CudaFdmMgpcgSolver3> CudaFdmMgpcgSolver3Ptr;
+
+namespace detail {
+
+//! MGPCG parameters of whatever linear solver a Jet pressure solver carries (FdmMgpcgSolver3 or our seam-1 class).
+inline bool mgpcgParamsOf(const jet::FdmLinearSystemSolver3Ptr& lin, jetcu_mgpcg_params* out) {
+    if (auto s = std::dynamic_pointer_cast<jet::FdmMgpcgSolver3>(lin)) {
+        const auto& mp = s->params();
+        *out = makeMgpcgParams(s->maxNumberOfIterations(), mp.maxNumberOfLevels, mp.numberOfRestrictionIter,
+                               mp.numberOfCorrectionIter, mp.numberOfCoarsestIter, mp.numberOfFinalIter,
+                               s->tolerance(), s->sorFactor(), s->useRedBlackOrdering());
+        return true;
+    }
+    if (auto s = std::dynamic_pointer_cast<CudaFdmMgpcgSolver3>(lin)) {
+        *out = s->cudaParams();
+        return true;
+    }
+    return false;
+}
+
+//! Cell-centred samples of a ScalarField3 for grid (res, h, origin): the raw array when the field already is a
+//! matching CellCenteredScalarGrid3 (what Jet's solvers pass: SURVEY §8b), nullptr for the +-kMaxD constants the
+//! interface defaults to, otherwise host sampling at the cell centres into `scratch`.
+inline const double* cellSamples(const jet::ScalarField3& f, const jet::Size3& res, const jet::Vector3D& h,
+                                 const jet::Vector3D& origin, bool nullWhenPositiveConstant,
+                                 std::vector<double>* scratch) {
+    if (auto g = dynamic_cast<const jet::CellCenteredScalarGrid3*>(&f)) {
+        if (g->resolution() == res && g->gridSpacing().isSimilar(h, 0.0) && g->origin().isSimilar(origin, 0.0))
+            return g->constDataAccessor().data();
+    }
+    if (auto c = dynamic_cast<const jet::ConstantScalarField3*>(&f)) {
+        const double v = c->sample(jet::Vector3D());
+        if (nullWhenPositiveConstant ? (v >= jet::kMaxD) : (v <= -jet::kMaxD)) return nullptr;
+    }
+    scratch->resize(res.x * res.y * res.z);
+    double* out = scratch->data();
+    jet::parallelFor(jet::kZeroSize, res.x, jet::kZeroSize, res.y, jet::kZeroSize, res.z,
+                     [&](size_t i, size_t j, size_t k) {
+                         jet::Vector3D x = origin + jet::Vector3D((i + 0.5) * h.x, (j + 0.5) * h.y, (k + 0.5) * h.z);
+                         out[(k * res.y + j) * res.x + i] = f.sample(x);
+                     });
+    return out;
+}
+
+}  // namespace detail
+
+// ------------------------------------------------------------------------------------------------ seam 2
+//! Drop-in for jet::GridFractionalSinglePhasePressureSolver3 with an MGPCG linear solver.
+class CudaGridFractionalSinglePhasePressureSolver3 final : public jet::GridPressureSolver3 {
+ public:
+    explicit CudaGridFractionalSinglePhasePressureSolver3(
+        const jetcu_mgpcg_params& params = makeMgpcgParams(100, 6, 5, 5, 20, 20, 1e-9, 1.5, true),
+        ContextPtr ctx = ContextPtr())
+        : _ctx(ctx ? ctx : Context::shared()), _p(params) {
+        std::memset(&_last, 0, sizeof(_last));
+    }
+
+    void solve(const jet::FaceCenteredGrid3& input, double timeIntervalInSeconds, jet::FaceCenteredGrid3* output,
+               const jet::ScalarField3& boundarySdf = jet::ConstantScalarField3(jet::kMaxD),
+               const jet::VectorField3& boundaryVelocity = jet::ConstantVectorField3({0, 0, 0}),
+               const jet::ScalarField3& fluidSdf = jet::ConstantScalarField3(-jet::kMaxD),
+               bool useCompressed = false) override {
+        (void)timeIntervalInSeconds;
+        if (useCompressed)
+            throw std::runtime_error("jetcu: the compressed linear system is not on the GPU path (SURVEY §8f-4)");
+        const jet::Size3 res = input.resolution();
+        JET_THROW_INVALID_ARG_IF(output->resolution() != res);
+        const jet::Vector3D h = input.gridSpacing(), o = input.origin();
+        jetcu_grid g;
+        g.nx = res.x; g.ny = res.y; g.nz = res.z;
+        g.hx = h.x; g.hy = h.y; g.hz = h.z;
+        g.ox = o.x; g.oy = o.y; g.oz = o.z;
+
+        const double* csdf = detail::cellSamples(boundarySdf, res, h, o, true, &_colliderScratch);
+        const double* fsdf = detail::cellSamples(fluidSdf, res, h, o, false, &_fluidScratch);
+
+        // boundaryVelocity is sampled at face positions, one component per face family
+        // (src/jet/grid_fractional_single_phase_pressure_solver3.cpp:242-255); only needed next to a collider.
+        const double *bu = nullptr, *bv = nullptr, *bw = nullptr;
+        bool zeroVel = false;
+        if (auto c = dynamic_cast<const jet::ConstantVectorField3*>(&boundaryVelocity))
+            zeroVel = c->sample(jet::Vector3D()).lengthSquared() == 0.0;
+        if (csdf != nullptr && !zeroVel) {
+            _bu.resize((res.x + 1) * res.y * res.z);
+            _bv.resize(res.x * (res.y + 1) * res.z);
+            _bw.resize(res.x * res.y * (res.z + 1));
+            auto uPos = input.uPosition();
+            auto vPos = input.vPosition();
+            auto wPos = input.wPosition();
+            double *pu = _bu.data(), *pv = _bv.data(), *pw = _bw.data();
+            jet::parallelFor(jet::kZeroSize, res.x + 1, jet::kZeroSize, res.y, jet::kZeroSize, res.z,
+                             [&](size_t i, size_t j, size_t k) {
+                                 pu[(k * res.y + j) * (res.x + 1) + i] = boundaryVelocity.sample(uPos(i, j, k)).x;
+                             });
+            jet::parallelFor(jet::kZeroSize, res.x, jet::kZeroSize, res.y + 1, jet::kZeroSize, res.z,
+                             [&](size_t i, size_t j, size_t k) {
+                                 pv[(k * (res.y + 1) + j) * res.x + i] = boundaryVelocity.sample(vPos(i, j, k)).y;
+                             });
+            jet::parallelFor(jet::kZeroSize, res.x, jet::kZeroSize, res.y, jet::kZeroSize, res.z + 1,
+                             [&](size_t i, size_t j, size_t k) {
+                                 pw[(k * res.y + j) * res.x + i] = boundaryVelocity.sample(wPos(i, j, k)).z;
+                             });
+            bu = pu; bv = pv; bw = pw;
+        }
+
+        _pressure.resize(res);
+        _ctx->check(jetcu_pressure_solve(_ctx->get(), &g, input.uConstAccessor().data(), input.vConstAccessor().data(),
+                                         input.wConstAccessor().data(), csdf, bu, bv, bw, fsdf, &_p,
+                                         output->uAccessor().data(), output->vAccessor().data(),
+                                         output->wAccessor().data(), _pressure.data(), &_last));
+    }
+
+    jet::GridBoundaryConditionSolver3Ptr suggestedBoundaryConditionSolver() const override {
+        return std::make_shared<jet::GridFractionalBoundaryConditionSolver3>();
+    }
+
+    //! == GridFractionalSinglePhasePressureSolver3::pressure().
+    const jet::FdmVector3& pressure() const { return _pressure; }
+    const jetcu_mgpcg_result& lastResult() const { return _last; }
+    const jetcu_mgpcg_params& cudaParams() const { return _p; }
+    void setCudaParams(const jetcu_mgpcg_params& p) { _p = p; }
+
+ private:
+    ContextPtr _ctx;
+    jetcu_mgpcg_params _p;
+    jetcu_mgpcg_result _last;
+    jet::FdmVector3 _pressure;
+    std::vector<double> _colliderScratch, _fluidScratch, _bu, _bv, _bw;
+};
+typedef std::shared_ptr<CudaGridFractionalSinglePhasePressureSolver3> CudaGridFractionalSinglePhasePressureSolver3Ptr;
+
+// ------------------------------------------------------------------------------------------------ seam 3
+//! When the host-side Jet objects (ParticleSystemData3 positions/velocities, velocity grid, SDF grid) are refreshed
+//! from the device.
+enum class HostMirror {
+    kEveryStep,  //!< after every sub-step: strict drop-in (any Jet code reading the solver's state sees it)
+    kOnDemand    //!< only in syncToHost(): device-resident stepping without PCIe traffic per step
+};
+
+//! Device-resident PIC/FLIP/APIC solver behind Jet's class hierarchy.  Base = jet::PicSolver3 / FlipSolver3 /
+//! ApicSolver3.  Overrides PhysicsAnimation::onAdvanceTimeStep / numberOfSubTimeSteps (include/jet/physics_animation.h:
+//! 109,124), i.e. the whole of GridFluidSolver3::onAdvanceTimeStep; the particle emitter still runs on the host
+//! (VolumeParticleEmitter3 etc.), newly emitted particles are appended to the device set.
+template <class Base, int Mode>
+class CudaHybridSolver3 : public Base {
+ public:
+    CudaHybridSolver3(const jet::Size3& resolution, const jet::Vector3D& gridSpacing, const jet::Vector3D& gridOrigin,
+                      const jetcu_mgpcg_params& mgpcg = makeMgpcgParams(100, 6, 5, 5, 20, 20, 1e-9, 1.5, true),
+                      ContextPtr ctx = ContextPtr())
+        : Base(resolution, gridSpacing, gridOrigin), _ctx(ctx ? ctx : Context::shared()), _mgpcg(mgpcg) {}
+
+    ~CudaHybridSolver3() override {
+        if (_h) jetcu_hybrid_destroy(_h);
+    }
+
+    void setHostMirror(HostMirror m) { _mirror = m; }
+    HostMirror hostMirror() const { return _mirror; }
+    void setCudaMgpcgParams(const jetcu_mgpcg_params& p) { _mgpcg = p; releaseDevice(); }
+
+    //! Tell the adapter that host-side particles or the velocity grid were edited by the caller since the last step.
+    void markHostDirty() { _hostDirty = true; }
+
+    //! Copies particles, velocity grid and SDF from the device into Jet's objects (kOnDemand mode).
+    void syncToHost() {
+        if (!_h) return;
+        auto particles = this->particleSystemData();
+        const size_t n = jetcu_hybrid_num_particles(_h);
+        particles->resize(n);
+        if (n > 0)
+            _ctx->check(jetcu_hybrid_get_particles(_h, reinterpret_cast<double*>(particles->positions().data()),
+                                                   reinterpret_cast<double*>(particles->velocities().data())));
+        auto vel = this->velocity();
+        _ctx->check(jetcu_hybrid_get_velocity(_h, vel->uAccessor().data(), vel->vAccessor().data(),
+                                              vel->wAccessor().data()));
+        auto sdf = this->signedDistanceField();
+        _ctx->check(jetcu_hybrid_get_sdf(_h, sdf->dataAccessor().data()));
+        _deviceCount = n;
+    }
+
+    const jetcu_step_stats& lastStepStats() const { return _stats; }
+
+ protected:
+    void onAdvanceTimeStep(double timeIntervalInSeconds) override {
+        auto grids = this->gridSystemData();
+        if (grids->resolution().x == 0 || grids->resolution().y == 0 || grids->resolution().z == 0) return;
+        if (this->collider() != nullptr)
+            throw std::runtime_error("jetcu: colliders inside the device-resident hybrid solver are not supported yet; "
+                                     "use seam 2 (CudaGridFractionalSinglePhasePressureSolver3) with the stock solver");
+        ensureDevice();
+        // PicSolver3::onBeginAdvanceTimeStep -> updateParticleEmitter (src/jet/pic_solver3.cpp:63-75)
+        auto particles = this->particleSystemData();
+        if (this->particleEmitter() != nullptr)
+            this->particleEmitter()->update(this->currentTimeInSeconds(), timeIntervalInSeconds);
+        uploadIfNeeded();
+        _ctx->check(jetcu_hybrid_step(_h, timeIntervalInSeconds, &_stats));
+        if (_mirror == HostMirror::kEveryStep) syncToHost();
+    }
+
+    unsigned int numberOfSubTimeSteps(double timeIntervalInSeconds) const override {
+        if (!_h || _hostDirty) return Base::numberOfSubTimeSteps(timeIntervalInSeconds);
+        uint32_t n = 1;
+        _ctx->check(jetcu_hybrid_num_sub_steps(_h, timeIntervalInSeconds, &n));
+        return n;
+    }
+
+ private:
+    void releaseDevice() {
+        if (_h) jetcu_hybrid_destroy(_h);
+        _h = nullptr;
+        _deviceCount = 0;
+        _hostDirty = true;
+    }
+
+    void ensureDevice() {
+        if (_h) return;
+        jetcu_hybrid_params p;
+        jetcu_hybrid_default_params(&p);
+        auto grids = this->gridSystemData();
+        const jet::Size3 res = grids->resolution();
+        const jet::Vector3D h = grids->gridSpacing(), o = grids->origin();
+        p.grid.nx = res.x; p.grid.ny = res.y; p.grid.nz = res.z;
+        p.grid.hx = h.x; p.grid.hy = h.y; p.grid.hz = h.z;
+        p.grid.ox = o.x; p.grid.oy = o.y; p.grid.oz = o.z;
+        p.mode = Mode;
+        p.closed_domain_boundary_flag = this->closedDomainBoundaryFlag();
+        p.pic_blending_factor = picBlend(static_cast<Base*>(this));
+        const jet::Vector3D g = this->gravity();
+        p.gravity[0] = g.x; p.gravity[1] = g.y; p.gravity[2] = g.z;
+        p.max_cfl = this->maxCfl();
+        // honour an MGPCG configured on the Jet pressure solver; otherwise the ctor's parameters
+        jetcu_mgpcg_params fromJet;
+        auto frac = std::dynamic_pointer_cast<jet::GridFractionalSinglePhasePressureSolver3>(this->pressureSolver());
+        if (frac && detail::mgpcgParamsOf(frac->linearSystemSolver(), &fromJet)) _mgpcg = fromJet;
+        auto cu = std::dynamic_pointer_cast<CudaGridFractionalSinglePhasePressureSolver3>(this->pressureSolver());
+        if (cu) _mgpcg = cu->cudaParams();
+        p.mgpcg = _mgpcg;
+        _ctx->check(jetcu_hybrid_create(_ctx->get(), &p, &_h));
+        _hostDirty = true;
+    }
+
+    void uploadIfNeeded() {
+        auto particles = this->particleSystemData();
+        const size_t n = particles->numberOfParticles();
+        if (_hostDirty || n != _deviceCount) {
+            // host state is authoritative: (re)upload everything, including the velocity grid
+            if (_mirror == HostMirror::kOnDemand && !_hostDirty && n > _deviceCount && _deviceCount > 0) {
+                // emitter appended particles while the device holds the live copy of the old ones: fetch those first
+                std::vector<jet::Vector3D> newPos(particles->positions().data() + _deviceCount,
+                                                  particles->positions().data() + n);
+                std::vector<jet::Vector3D> newVel(particles->velocities().data() + _deviceCount,
+                                                  particles->velocities().data() + n);
+                const size_t old = _deviceCount;
+                syncToHost();
+                particles->resize(n);
+                std::copy(newPos.begin(), newPos.end(), particles->positions().data() + old);
+                std::copy(newVel.begin(), newVel.end(), particles->velocities().data() + old);
+            }
+            _ctx->check(jetcu_hybrid_set_particles(_h, n, reinterpret_cast<const double*>(particles->positions().data()),
+                                                   reinterpret_cast<const double*>(particles->velocities().data())));
+            auto vel = this->velocity();
+            _ctx->check(jetcu_hybrid_set_velocity(_h, vel->uConstAccessor().data(), vel->vConstAccessor().data(),
+                                                  vel->wConstAccessor().data()));
+            _deviceCount = n;
+            _hostDirty = false;
+        }
+    }
+
+    static double picBlend(jet::FlipSolver3* s) { return s->picBlendingFactor(); }
+    static double picBlend(jet::PicSolver3*) { return 0.0; }
+
+    ContextPtr _ctx;
+    jetcu_mgpcg_params _mgpcg;
+    jetcu_hybrid* _h = nullptr;
+    size_t _deviceCount = 0;
+    bool _hostDirty = true;
+    HostMirror _mirror = HostMirror::kEveryStep;
+    jetcu_step_stats _stats = jetcu_step_stats();
+};
+
+typedef CudaHybridSolver3<jet::PicSolver3, JETCU_PIC> CudaPicSolver3;
+typedef CudaHybridSolver3<jet::FlipSolver3, JETCU_FLIP> CudaFlipSolver3;
+typedef CudaHybridSolver3<jet::ApicSolver3, JETCU_APIC> CudaApicSolver3;
+
+}  // namespace jetcu
+
+#endif  // JETCU_JET_ADAPTERS_H_

@@ -196,6 +196,37 @@ def workload_config(args, npart):
     return c
 
 
+def run_projection(jc, n, peak):
+    """BASELINE config 2: standalone GridFractionalSinglePhasePressureSolver3 + MGPCG projection at n^3 on the flat-slab
+    input with the box collider (the variant on which the reference's own solver converges), through
+    jetcu_pressure_solve with host arrays.  solve_ms = device time of the MGPCG solve (CUDA events inside the library);
+    bytes = SURVEY §8d's model: N * [(56 + 1647 + 16) + iterations * 1799]."""
+    import scenes
+    from fluid_engine_dev_b200.jetcu import MgpcgParams
+    sc = scenes.projection_scene(n, "slab", True)
+    levels = mg_levels(n, 7)
+    prm = MgpcgParams.make(max_iterations=100, max_levels=levels)
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        _, _, _, _, res = jc.pressure_solve(sc["grid"], sc["u"], sc["v"], sc["w"], prm, collider_sdf=sc["collider_sdf"],
+                                            fluid_sdf=sc["fluid_sdf"], want_pressure=True)
+        call_ms = 1e3 * (time.perf_counter() - t0)
+        if best is None or res.solve_ms < best[0].solve_ms:
+            best = (res, call_ms)
+    res, call_ms = best
+    ncell = float(n) ** 3
+    model_bytes = ncell * ((56 + 1647 + 16) + res.iterations * 1799.0)
+    gbs = model_bytes / (res.solve_ms * 1e-3) / 1e9 if res.solve_ms > 0 else None
+    return {"workload": "config 2: projection %d^3, fluidSdf = y - 0.5, v = +1, box collider, MGPCG(100, %d levels, "
+                        "5/5/20/20, 1e-9, omega 1.5, red-black)" % (n, levels),
+            "mgpcg_solve_ms": res.solve_ms, "iterations": int(res.iterations),
+            "ms_per_iteration": res.solve_ms / max(int(res.iterations), 1),
+            "last_residual": res.last_residual, "true_rel_residual": res.true_residual_l2 / max(res.b_l2, 1e-300),
+            "call_ms_host_buffers": call_ms, "model_bytes": model_bytes, "achieved_gbs": gbs,
+            "frac_of_hbm_peak": (gbs / peak) if gbs else None}
+
+
 def run_jetcu(args):
     import numpy as np
     import torch
@@ -325,6 +356,8 @@ def run_jetcu(args):
                                         "jetcu_hybrid_get_particles(host), wall clock with synchronize on both sides"},
         "roofline": roof,
     }
+    if world == 1 and not args.no_projection:
+        line["projection"] = run_projection(jc, args.n, peak)
     if world == 1 and not args.no_cpu_baseline:
         oracle = load_oracle(True)
         oracle.set_num_threads(0)
@@ -353,6 +386,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--sample-n", type=int, default=0, help="grid size of the CPU sample (0 = automatic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-projection", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

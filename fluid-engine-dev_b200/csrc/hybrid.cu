@@ -51,11 +51,13 @@ struct jetcu_hybrid {
 struct GridD {
     int nx, ny, nz;
     double hx, hy, hz, ox, oy, oz;
+    double ihx, ihy, ihz;  // exact 1/h for power-of-two spacings, else 0 (jc_norm)
 };
 
 static GridD gridd(const jetcu_hybrid* h) {
     const jetcu_grid& g = h->P.grid;
-    return GridD{h->nx, h->ny, h->nz, g.hx, g.hy, g.hz, g.ox, g.oy, g.oz};
+    return GridD{h->nx, h->ny, h->nz, g.hx, g.hy, g.hz, g.ox, g.oy, g.oz,
+                 jc_pow2_inverse(g.hx), jc_pow2_inverse(g.hy), jc_pow2_inverse(g.hz)};
 }
 
 // Component grid (AXIS = 0/1/2 -> u/v/w): size and data origin (src/jet/face_centered_grid3.cpp:430-444).
@@ -75,6 +77,7 @@ __device__ __forceinline__ GridView comp_view(const GridD& g, int axis, const do
     v.ox = g.ox + 0.5 * (axis == 0 ? 0.0 : g.hx);
     v.oy = g.oy + 0.5 * (axis == 1 ? 0.0 : g.hy);
     v.oz = g.oz + 0.5 * (axis == 2 ? 0.0 : g.hz);
+    v.ihx = g.ihx; v.ihy = g.ihy; v.ihz = g.ihz;
     return v;
 }
 
@@ -547,10 +550,42 @@ __global__ void __launch_bounds__(CFL_BLOCK) k_max_final(const double* __restric
 // ------------------------------------------------------------------------------------------------ G2P + advection
 __device__ __forceinline__ void sample_velocity(const GridD& g, const double* u, const double* v, const double* w,
                                                 double px, double py, double pz, double* ou, double* ov, double* ow) {
-    // FaceCenteredGrid3::sample: three LinearArraySampler3::operator() calls (face_centered_grid3.cpp:447-467)
-    *ou = jc_sample(comp_view(g, 0, u), px, py, pz);
-    *ov = jc_sample(comp_view(g, 1, v), px, py, pz);
-    *ow = jc_sample(comp_view(g, 2, w), px, py, pz);
+    // FaceCenteredGrid3::sample: three LinearArraySampler3::operator() calls (face_centered_grid3.cpp:447-467).
+    // The three component grids share their per-axis normalisations pairwise (node-aligned along the component's own
+    // axis, cell-centred along the other two), so 6 barycentric evaluations serve all 3 samplers instead of 9; each is
+    // the same expression the per-grid sampler evaluates, so the results are bit-identical to three jc_sample calls.
+    int inx, icx, jny, jcy, knz, kcz;
+    double fnx, fcx, fny, fcy, fnz, fcz;
+    jc_barycentric(jc_norm(px, g.ox + 0.5 * 0.0, g.hx, g.ihx), g.nx, &inx, &fnx);            // u grid: nx + 1 nodes
+    jc_barycentric(jc_norm(px, g.ox + 0.5 * g.hx, g.hx, g.ihx), g.nx - 1, &icx, &fcx);      // v, w grids
+    jc_barycentric(jc_norm(py, g.oy + 0.5 * 0.0, g.hy, g.ihy), g.ny, &jny, &fny);            // v grid
+    jc_barycentric(jc_norm(py, g.oy + 0.5 * g.hy, g.hy, g.ihy), g.ny - 1, &jcy, &fcy);      // u, w grids
+    jc_barycentric(jc_norm(pz, g.oz + 0.5 * 0.0, g.hz, g.ihz), g.nz, &knz, &fnz);            // w grid
+    jc_barycentric(jc_norm(pz, g.oz + 0.5 * g.hz, g.hz, g.ihz), g.nz - 1, &kcz, &fcz);      // u, v grids
+    const int inx1 = min(inx + 1, g.nx), icx1 = min(icx + 1, g.nx - 1);
+    const int jny1 = min(jny + 1, g.ny), jcy1 = min(jcy + 1, g.ny - 1);
+    const int knz1 = min(knz + 1, g.nz), kcz1 = min(kcz + 1, g.nz - 1);
+    {
+        const size_t sy = (size_t)(g.nx + 1), sz = sy * g.ny;
+        const size_t r00 = kcz * sz + jcy * sy, r10 = kcz * sz + jcy1 * sy, r01 = kcz1 * sz + jcy * sy, r11 = kcz1 * sz + jcy1 * sy;
+        const double a = jc_lerp(jc_lerp(u[r00 + inx], u[r00 + inx1], fnx), jc_lerp(u[r10 + inx], u[r10 + inx1], fnx), fcy);
+        const double b = jc_lerp(jc_lerp(u[r01 + inx], u[r01 + inx1], fnx), jc_lerp(u[r11 + inx], u[r11 + inx1], fnx), fcy);
+        *ou = jc_lerp(a, b, fcz);
+    }
+    {
+        const size_t sy = (size_t)g.nx, sz = sy * (g.ny + 1);
+        const size_t r00 = kcz * sz + jny * sy, r10 = kcz * sz + jny1 * sy, r01 = kcz1 * sz + jny * sy, r11 = kcz1 * sz + jny1 * sy;
+        const double a = jc_lerp(jc_lerp(v[r00 + icx], v[r00 + icx1], fcx), jc_lerp(v[r10 + icx], v[r10 + icx1], fcx), fny);
+        const double b = jc_lerp(jc_lerp(v[r01 + icx], v[r01 + icx1], fcx), jc_lerp(v[r11 + icx], v[r11 + icx1], fcx), fny);
+        *ov = jc_lerp(a, b, fcz);
+    }
+    {
+        const size_t sy = (size_t)g.nx, sz = sy * g.ny;
+        const size_t r00 = knz * sz + jcy * sy, r10 = knz * sz + jcy1 * sy, r01 = knz1 * sz + jcy * sy, r11 = knz1 * sz + jcy1 * sy;
+        const double a = jc_lerp(jc_lerp(w[r00 + icx], w[r00 + icx1], fcx), jc_lerp(w[r10 + icx], w[r10 + icx1], fcx), fcy);
+        const double b = jc_lerp(jc_lerp(w[r01 + icx], w[r01 + icx1], fcx), jc_lerp(w[r11 + icx], w[r11 + icx1], fcx), fcy);
+        *ow = jc_lerp(a, b, fnz);
+    }
 }
 
 // PicSolver3::transferFromGridsToParticles, src/jet/pic_solver3.cpp:195-204.
@@ -574,9 +609,11 @@ __global__ void k_g2p_flip(GridD g, const double* __restrict__ u, const double* 
     float xf = (float)px, yf = (float)py, zf = (float)pz;
     float fhx = (float)g.hx, fhy = (float)g.hy, fhz = (float)g.hz;
     GridView vu = comp_view(g, 0, u), vv = comp_view(g, 1, v), vw = comp_view(g, 2, w);
-    double du = jc_samplef(ud, vu.nx, vu.ny, vu.nz, fhx, fhy, fhz, (float)vu.ox, (float)vu.oy, (float)vu.oz, xf, yf, zf);
-    double dv = jc_samplef(vd, vv.nx, vv.ny, vv.nz, fhx, fhy, fhz, (float)vv.ox, (float)vv.oy, (float)vv.oz, xf, yf, zf);
-    double dw = jc_samplef(wd, vw.nx, vw.ny, vw.nz, fhx, fhy, fhz, (float)vw.ox, (float)vw.oy, (float)vw.oz, xf, yf, zf);
+    // float(h) of a power-of-two h is the same power of two, so the exact-reciprocal shortcut carries over
+    const float fix = (float)g.ihx, fiy = (float)g.ihy, fiz = (float)g.ihz;
+    double du = jc_samplef(ud, vu.nx, vu.ny, vu.nz, fhx, fhy, fhz, (float)vu.ox, (float)vu.oy, (float)vu.oz, xf, yf, zf, fix, fiy, fiz);
+    double dv = jc_samplef(vd, vv.nx, vv.ny, vv.nz, fhx, fhy, fhz, (float)vv.ox, (float)vv.oy, (float)vv.oz, xf, yf, zf, fix, fiy, fiz);
+    double dw = jc_samplef(wd, vw.nx, vw.ny, vw.nz, fhx, fhy, fhz, (float)vw.ox, (float)vw.oy, (float)vw.oz, xf, yf, zf, fix, fiy, fiz);
     double f0 = a.p[3][p] + du, f1 = a.p[4][p] + dv, f2 = a.p[5][p] + dw;
     if (blend > 0.0) {
         double pu = jc_sample(vu, px, py, pz), pv = jc_sample(vv, px, py, pz), pw = jc_sample(vw, px, py, pz);
@@ -599,7 +636,7 @@ __device__ __forceinline__ void apic_affine(const GridD& g, const double* __rest
     if (AXIS != 0) px = jc_clamp(px, g.ox + g.hx / 2.0, hix - g.hx / 2.0);
     if (AXIS != 1) py = jc_clamp(py, g.oy + g.hy / 2.0, hiy - g.hy / 2.0);
     if (AXIS != 2) pz = jc_clamp(pz, g.oz + g.hz / 2.0, hiz - g.hz / 2.0);
-    BaseFrac b = jc_base_div(sx, sy, sz, g.hx, g.hy, g.hz, ox, oy, oz, px, py, pz);
+    BaseFrac b = jc_base_div(sx, sy, sz, g.hx, g.hy, g.hz, ox, oy, oz, px, py, pz, g.ihx, g.ihy, g.ihz);
     const double ix = 1.0 / g.hx, iy = 1.0 / g.hy, iz = 1.0 / g.hz;
     const double fx = b.fx, fy = b.fy, fz = b.fz, ax = 1 - b.fx, ay = 1 - b.fy, az = 1 - b.fz;
     double gw[8][3];

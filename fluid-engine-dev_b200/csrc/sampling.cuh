@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <float.h>
+#include <math.h>
 
 // View of one scalar array with Jet's sampler parameters (spacing + data origin).
 struct GridView {
@@ -10,7 +11,25 @@ struct GridView {
     int nx, ny, nz;
     double hx, hy, hz;
     double ox, oy, oz;
+    double ihx = 0.0, ihy = 0.0, ihz = 0.0;  // 1/h where h is an exact power of two, else 0 (see jc_norm)
 };
+
+// (x - o) / h as the reference's samplers normalise positions (array_samplers3-inl.h:123,206).  An IEEE division by a
+// power of two is an exact scaling, so it equals the multiplication by the (exact) reciprocal bit for bit; the host
+// passes ih = 1/h only when h is a power of two (ih == 0 selects the literal division).  FP64 division costs ~30
+// instructions and the advection kernel needs 90 of them per particle, so this matters on 2^-k grids.
+__device__ __forceinline__ double jc_norm(double x, double o, double h, double ih) {
+    return ih != 0.0 ? (x - o) * ih : (x - o) / h;
+}
+__device__ __forceinline__ float jc_normf(float x, float o, float h, float ih) {
+    return ih != 0.0f ? (x - o) * ih : (x - o) / h;
+}
+
+// Host: 1/h if h is a power of two (then the reciprocal is exact), else 0.
+static inline double jc_pow2_inverse(double h) {
+    int e = 0;
+    return (h > 0.0 && frexp(h, &e) == 0.5) ? 1.0 / h : 0.0;
+}
 
 // getBarycentric, include/jet/detail/math_utils-inl.h:146-174 (iLow == 0 on this path).
 __device__ __forceinline__ void jc_barycentric(double x, int iHigh, int* i, double* f) {
@@ -40,9 +59,9 @@ __device__ __forceinline__ float jc_lerpf(float a, float b, float f) { return (1
 __device__ __forceinline__ double jc_sample(const GridView& g, double px, double py, double pz) {
     int i, j, k;
     double fx, fy, fz;
-    jc_barycentric((px - g.ox) / g.hx, g.nx - 1, &i, &fx);
-    jc_barycentric((py - g.oy) / g.hy, g.ny - 1, &j, &fy);
-    jc_barycentric((pz - g.oz) / g.hz, g.nz - 1, &k, &fz);
+    jc_barycentric(jc_norm(px, g.ox, g.hx, g.ihx), g.nx - 1, &i, &fx);
+    jc_barycentric(jc_norm(py, g.oy, g.hy, g.ihy), g.ny - 1, &j, &fy);
+    jc_barycentric(jc_norm(pz, g.oz, g.hz, g.ihz), g.nz - 1, &k, &fz);
     int ip1 = min(i + 1, g.nx - 1), jp1 = min(j + 1, g.ny - 1), kp1 = min(k + 1, g.nz - 1);
     const size_t sy = (size_t)g.nx, sz = (size_t)g.nx * g.ny;
     const double* d = g.data;
@@ -55,12 +74,13 @@ __device__ __forceinline__ double jc_sample(const GridView& g, double px, double
 
 // LinearArraySampler3<float,float>::operator() as FlipSolver3's delta sampler uses it (src/jet/flip_solver3.cpp:72-88).
 __device__ __forceinline__ float jc_samplef(const float* d, int nx, int ny, int nz, float hx, float hy, float hz,
-                                            float ox, float oy, float oz, float px, float py, float pz) {
+                                            float ox, float oy, float oz, float px, float py, float pz,
+                                            float ihx = 0.f, float ihy = 0.f, float ihz = 0.f) {
     int i, j, k;
     float fx, fy, fz;
-    jc_barycentricf((px - ox) / hx, nx - 1, &i, &fx);
-    jc_barycentricf((py - oy) / hy, ny - 1, &j, &fy);
-    jc_barycentricf((pz - oz) / hz, nz - 1, &k, &fz);
+    jc_barycentricf(jc_normf(px, ox, hx, ihx), nx - 1, &i, &fx);
+    jc_barycentricf(jc_normf(py, oy, hy, ihy), ny - 1, &j, &fy);
+    jc_barycentricf(jc_normf(pz, oz, hz, ihz), nz - 1, &k, &fz);
     int ip1 = min(i + 1, nx - 1), jp1 = min(j + 1, ny - 1), kp1 = min(k + 1, nz - 1);
     const size_t sy = (size_t)nx, sz = (size_t)nx * ny;
     size_t r00 = (size_t)k * sz + (size_t)j * sy, r10 = (size_t)k * sz + (size_t)jp1 * sy;
@@ -89,11 +109,12 @@ __device__ __forceinline__ BaseFrac jc_base_mul(int nx, int ny, int nz, double i
 
 // Same with the division form used by operator() and getCoordinatesAndGradientWeights (:195-261).
 __device__ __forceinline__ BaseFrac jc_base_div(int nx, int ny, int nz, double hx, double hy, double hz, double ox,
-                                                double oy, double oz, double px, double py, double pz) {
+                                                double oy, double oz, double px, double py, double pz,
+                                                double ihx = 0.0, double ihy = 0.0, double ihz = 0.0) {
     BaseFrac b;
-    jc_barycentric((px - ox) / hx, nx - 1, &b.i, &b.fx);
-    jc_barycentric((py - oy) / hy, ny - 1, &b.j, &b.fy);
-    jc_barycentric((pz - oz) / hz, nz - 1, &b.k, &b.fz);
+    jc_barycentric(jc_norm(px, ox, hx, ihx), nx - 1, &b.i, &b.fx);
+    jc_barycentric(jc_norm(py, oy, hy, ihy), ny - 1, &b.j, &b.fy);
+    jc_barycentric(jc_norm(pz, oz, hz, ihz), nz - 1, &b.k, &b.fz);
     b.ip1 = min(b.i + 1, nx - 1); b.jp1 = min(b.j + 1, ny - 1); b.kp1 = min(b.k + 1, nz - 1);
     return b;
 }

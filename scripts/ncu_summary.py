@@ -27,7 +27,9 @@ def rep(path):
         print()
 
 
-def launches(path):
+def launches(path, segment=None):
+    """segment = "kernel:k" keeps the launches from the k-th occurrence (1-based) of `kernel` up to the next one
+    (e.g. k_cell_count:2 = the second sub-step of a bench run: every step starts with one k_cell_count)."""
     rows = [r for r in csv.reader(open(path, errors="replace")) if len(r) > 5]
     hdr = None
     for idx, r in enumerate(rows):
@@ -36,6 +38,14 @@ def launches(path):
             rows = rows[idx + 1:]
             break
     kn, mv, mu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    if segment:
+        name, k = segment.split(":")
+        hits = [i for i, r in enumerate(rows) if r[kn].split("(")[0] == name]
+        lo = hits[int(k) - 1]
+        hi = hits[int(k)] if int(k) < len(hits) else len(rows)
+        # a step begins two launches earlier (k_zero_walls precedes the binning) — immaterial for the shares
+        rows = rows[lo:hi]
+        print("# segment %s: launches %d..%d of the capture" % (segment, lo, hi))
     agg = OrderedDict()
     total = 0.0
     for r in rows:
@@ -56,4 +66,4 @@ def launches(path):
 
 
 if __name__ == "__main__":
-    {"rep": rep, "launches": launches}[sys.argv[1]](sys.argv[2])
+    {"rep": rep, "launches": launches}[sys.argv[1]](*sys.argv[2:])

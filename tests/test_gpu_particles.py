@@ -89,7 +89,10 @@ def test_emit_box_face_rounding_bit_exact(jc, oracle, lower, upper, spacing):
         assert np.array_equal(x, y)
 
 
-@pytest.mark.parametrize("mode,n,levels", [(PIC, 16, 3), (FLIP, 16, 3), (APIC, 16, 3), (FLIP, 32, 4), (APIC, 32, 4)])
+# n = 16, 32: h is a power of two (samplers take the exact-reciprocal shortcut, sampling.cuh jc_norm);
+# n = 24, 20: h is not, so the literal FP64 / FP32 divisions of the reference run.
+@pytest.mark.parametrize("mode,n,levels", [(PIC, 16, 3), (FLIP, 16, 3), (APIC, 16, 3), (FLIP, 32, 4), (APIC, 32, 4),
+                                           (FLIP, 24, 3), (APIC, 24, 3), (PIC, 20, 2)])
 def test_hybrid_stages_vs_oracle(jc, oracle, mode, n, levels):
     prm = HybridParams.make(Grid.cube(n), mode=mode, mgpcg=MgpcgParams.make(max_iterations=100, max_levels=levels),
                             pic_blending_factor=(0.1 if mode == FLIP and n == 16 else 0.0))

@@ -190,7 +190,10 @@ def workload_config(args, npart):
                      "omega 1.5, red-black)" % (args.n, "sloshing tank" if args.workload == "tank" else "dam break",
                                                 sc["lower"], sc["upper"], sc["v0"], args.dt, mg_levels(args.n)),
          "grid": [args.n] * 3, "cache": "inputs larger than L2 (particle + grid state >> 126 MB)",
-         "parallelism": "1 GPU" if args.gpus == 1 else "%d independent replicas" % args.gpus}
+         "parallelism": "1 GPU" if args.gpus == 1 else
+         "%d GPUs, z-slabs of %d planes per rank (one domain, strong scaling): NCCL halo-plane exchange per smoother colour "
+         "pass / matvec / transfer, slab-invariant PCG dot products, coarse MG levels replicated, particle migration + "
+         "2 ghost planes per step" % (args.gpus, args.n // args.gpus)}
     if npart is not None:
         c["particles"] = int(npart)
     return c
@@ -259,6 +262,8 @@ def run_jetcu(args):
         return float(t.item())
 
     jc = Jetcu(local)
+    if world > 1:
+        jc.comm_init_torch()   # z-slab communicator (NCCL) next to torch's own process group
     stream = torch.cuda.ExternalStream(jc.stream(), device=dev)
     n = args.n
     sc = scene(args.workload, n)
@@ -283,6 +288,7 @@ def run_jetcu(args):
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier(); torch.cuda.synchronize()
     l0 = jc.launch_count()
+    m0, b0 = jc.comm_stats()
     t0 = time.perf_counter()
     e0.record(stream)
     stats = []
@@ -292,34 +298,62 @@ def run_jetcu(args):
     torch.cuda.synchronize(); barrier()
     wall = time.perf_counter() - t0
     launches = jc.launch_count() - l0
+    m1, b1 = jc.comm_stats()
     dev_s = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
     relax_ms, relax_launches, relax_units = prof(0)
     mvm_ms, mvm_launches, mvm_units = prof(2)
     jc._call("profile_enable", C.c_int(0))
     clk = clocks.stop() if clocks else None
-    steps_per_s = world * args.steps / dev_s
+    steps_per_s = args.steps / dev_s   # one domain split over the ranks: the job advances `steps` sub-steps
 
     # ---------------------------------------------------------------- e2e: host buffers in and out every step
-    pos, vel = h.get_particles()
-    ppos = torch.empty(pos.shape, dtype=torch.float64).pin_memory().numpy(); ppos[...] = pos
-    pvel = torch.empty(vel.shape, dtype=torch.float64).pin_memory().numpy(); pvel[...] = vel
-    opos = torch.empty(pos.shape, dtype=torch.float64).pin_memory().numpy()
-    ovel = torch.empty(vel.shape, dtype=torch.float64).pin_memory().numpy()
-    del pos, vel
-    from fluid_engine_dev_b200.jetcu import _p, u64
+    from fluid_engine_dev_b200.jetcu import _p, u64, PU64
     k_e2e = max(1, min(args.steps, args.e2e_steps))
-    barrier(); torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(k_e2e):
-        jc._call_raw("hybrid_set_particles", h.h, u64(npart), _p(ppos), _p(pvel))
-        h.step(dt)
-        jc._call_raw("hybrid_get_particles", h.h, _p(opos), _p(ovel))
-        ppos, opos = opos, ppos
-        pvel, ovel = ovel, pvel
-    torch.cuda.synchronize(); barrier()
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+    if world == 1:
+        pos, vel = h.get_particles()
+        nloc = int(npart)
+        ppos = pin(pos.shape, torch.float64); ppos[...] = pos
+        pvel = pin(vel.shape, torch.float64); pvel[...] = vel
+        opos, ovel = pin(pos.shape, torch.float64), pin(vel.shape, torch.float64)
+        del pos, vel
+        barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            jc._call_raw("hybrid_set_particles", h.h, u64(npart), _p(ppos), _p(pvel))
+            h.step(dt)
+            jc._call_raw("hybrid_get_particles", h.h, _p(opos), _p(ovel))
+            ppos, opos = opos, ppos
+            pvel, ovel = ovel, pvel
+        torch.cuda.synchronize(); barrier()
+        bytes_in = bytes_out = nloc * 48
+        e2e_note = ("jetcu_hybrid_set_particles(pinned host) -> jetcu_hybrid_step -> jetcu_hybrid_get_particles(host), "
+                    "wall clock with synchronize on both sides")
+    else:
+        # every rank round-trips ITS OWN particles (ids + positions + velocities) through pinned host memory
+        capn = int(npart // world * 1.5) + 1024
+        ids = pin((capn,), torch.int64).view(np.uint64)
+        ppos, pvel = pin((capn, 3), torch.float64), pin((capn, 3), torch.float64)
+        nloc = h.num_local_particles()
+        assert nloc <= capn
+        jc._call_raw("hybrid_get_local_particles", h.h, _p(ids, PU64), _p(ppos), _p(pvel))
+        barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        moved = 0
+        for _ in range(k_e2e):
+            jc._call_raw("hybrid_set_local_particles", h.h, u64(nloc), _p(ids, PU64), _p(ppos), _p(pvel), u64(npart))
+            h.step(dt)
+            moved += nloc
+            nloc = h.num_local_particles()
+            assert nloc <= capn
+            jc._call_raw("hybrid_get_local_particles", h.h, _p(ids, PU64), _p(ppos), _p(pvel))
+            moved += nloc
+        torch.cuda.synchronize(); barrier()
+        bytes_in = bytes_out = int(moved // (2 * k_e2e)) * 56
+        e2e_note = ("per rank: jetcu_hybrid_set_local_particles(pinned host) -> jetcu_hybrid_step -> "
+                    "jetcu_hybrid_get_local_particles(host); bytes are rank 0's, wall clock max over ranks")
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_rate = world * k_e2e / e2e_s
-    bytes_io = int(npart) * 48
+    e2e_rate = k_e2e / e2e_s
     h.close()
 
     if rank != 0:
@@ -346,16 +380,18 @@ def run_jetcu(args):
     line = {
         "metric": METRIC, "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
-        "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, npart),
         "mcell_per_s": steps_per_s * ncell / 1e6, "particles_per_s": steps_per_s * npart,
         "mgpcg_solve_ms": stages["ms_pressure"], "stages_ms": stages, "wall_s_timed_region": wall,
         "gpu_launches": int(launches), "clocks": clk,
-        "e2e": {"value": e2e_rate, "unit": "steps/s", "h2d_bytes_per_step": bytes_io, "d2h_bytes_per_step": bytes_io,
-                "steps": k_e2e, "note": "jetcu_hybrid_set_particles(pinned host) -> jetcu_hybrid_step -> "
-                                        "jetcu_hybrid_get_particles(host), wall clock with synchronize on both sides"},
+        "e2e": {"value": e2e_rate, "unit": "steps/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out,
+                "steps": k_e2e, "note": e2e_note},
         "roofline": roof,
     }
+    if world > 1:
+        line["comm"] = {"rank0_messages_per_step": (m1 - m0) / args.steps, "rank0_bytes_sent_per_step": (b1 - b0) / args.steps,
+                        "backend": "NCCL send/recv + all-gather on the solver stream"}
     if world == 1 and not args.no_projection:
         line["projection"] = run_projection(jc, args.n, peak)
     if world == 1 and not args.no_cpu_baseline:

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjetcu.so")
-SOURCES = ["abi.cu", "fdm.cu", "pressure.cu", "particles.cu", "hybrid.cu", "multigpu.cu"]
+SOURCES = ["abi.cu", "fdm.cu", "pressure.cu", "particles.cu", "hybrid.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",   # B200 only
     "-lineinfo", "-O3", "-std=c++17",
@@ -60,19 +60,13 @@ def build(force=False, verbose=False):
             sys.stderr.write(" ".join(cmd) + "\n" + out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed for " + cmd[-3])
-    libs = ["-lcudart"]
-    if os.path.exists(os.path.join(CSRC, "multigpu.cu")):
-        libs += nccl_link_flags()
+    libs = ["-lcudart", "-ldl"]   # NCCL is resolved with dlopen at run time (csrc/comm.cu): no link-time dependency
     cmd = [nvcc_path(), "-shared", "-o", LIB] + objs + libs
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(" ".join(cmd) + "\n" + r.stdout)
         raise RuntimeError("link failed")
     return LIB
-
-
-def nccl_link_flags():
-    return []
 
 
 if __name__ == "__main__":

@@ -103,6 +103,7 @@ int jetcu_ctx_create(int device, jetcu_ctx** out) {
 int jetcu_ctx_destroy(jetcu_ctx* ctx) {
     if (!ctx) return JETCU_OK;
     cudaSetDevice(ctx->device);
+    comm_free(ctx);
     if (ctx->psys) { pressure_free(ctx, ctx->psys); delete ctx->psys; }
     cudaStreamSynchronize(ctx->stream);
     jc_prof_resolve(ctx);
@@ -185,6 +186,14 @@ struct DevMat {
         return rc;
     }
 };
+
+// slab mode: every rank ends up with the whole level-0 vector
+int gather_level0(jetcu_ctx* ctx, MgLevels* mg, double* v) {
+    const SlabPlan& pl = mg->plan;
+    if (pl.dist_levels == 0) return JETCU_OK;
+    const Dim3i d = mg->dims[0];
+    return comm_allgather_inplace(ctx, v, (size_t)(pl.z1[0] - pl.z0[0]) * d.nx * d.ny * sizeof(double));
+}
 
 int check_dims(jetcu_ctx* ctx, uint64_t nx, uint64_t ny, uint64_t nz) {
     JC_ARG(ctx, nx > 0 && ny > 0 && nz > 0);
@@ -322,6 +331,7 @@ int jetcu_fdm_vcycle(jetcu_ctx* ctx, uint64_t nx, uint64_t ny, uint64_t nz, uint
     if (rc == JETCU_OK) rc = jc_h2d(ctx, mg.x[0], x, n);
     if (rc == JETCU_OK) rc = jc_h2d(ctx, mg.b[0], b, n);
     if (rc == JETCU_OK) rc = mg_vcycle(ctx, &mg, p, 0);
+    if (rc == JETCU_OK) rc = gather_level0(ctx, &mg, mg.x[0]);
     if (rc == JETCU_OK) rc = jc_d2h(ctx, x, mg.x[0], n);
     if (rc == JETCU_OK) rc = jc_sync(ctx);
     mg_free(ctx, &mg);
@@ -415,7 +425,9 @@ int jetcu_pressure_vcycle(jetcu_ctx* ctx, const double* b, double* x, const jetc
     size_t n = ps->dims[0].n();
     JC_TRY(jc_h2d(ctx, mg->x[0], x, n));
     JC_TRY(jc_h2d(ctx, mg->b[0], b, n));
+    JC_TRY(mg_make_plan(ctx, mg));
     JC_TRY(mg_vcycle(ctx, mg, p, 0));
+    JC_TRY(gather_level0(ctx, mg, mg->x[0]));
     JC_TRY(jc_d2h(ctx, x, mg->x[0], n));
     return jc_sync(ctx);
 }

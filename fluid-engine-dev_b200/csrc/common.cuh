@@ -24,8 +24,9 @@ struct jetcu_ctx {
     // pinned staging for scalar read-backs
     double* h_scalars = nullptr;
     double* d_scalars = nullptr;
-    double* d_partials = nullptr;  // dot-product partial sums
-    size_t partials_cap = 0;
+    double* d_partials = nullptr;  // dot-product partial sums (JC_PARTIALS_CAP doubles)
+    // z-slab communicator (comm.cu); null = single GPU
+    struct JcComm* comm = nullptr;
     // optional per-kernel-family timing (jetcu_profile_*): CUDA event pairs on `stream`, resolved lazily
     bool profile = false;
     struct ProfPending { cudaEvent_t e0, e1; int kind; uint64_t launches, units; };
@@ -35,6 +36,40 @@ struct jetcu_ctx {
     uint64_t prof_launches[JETCU_PROF_KINDS] = {};
     uint64_t prof_units[JETCU_PROF_KINDS] = {};
 };
+
+#define JC_PARTIALS_CAP 4096
+
+// ---- multi-GPU plumbing (comm.cu): NCCL over NVLink, one rank per GPU; all calls enqueue on ctx->stream ------------
+int jc_comm_world(const jetcu_ctx* ctx);
+int jc_comm_rank(const jetcu_ctx* ctx);
+// Arrays are full-size and globally indexed on every rank; this rank owns planes [k0, k1) of nz.  Sends plane k0 down /
+// plane k1-1 up and receives plane k0-1 / k1 from the neighbouring ranks (no-op at the domain ends).
+int comm_halo_planes(jetcu_ctx* ctx, void* base, size_t plane_bytes, int k0, int k1, int nz);
+// In-place all-gather: rank r contributes bytes [r*bytes_per_rank, (r+1)*bytes_per_rank) of `base`.
+int comm_allgather_inplace(jetcu_ctx* ctx, void* base, size_t bytes_per_rank);
+int comm_allreduce_max_f64(jetcu_ctx* ctx, double* d_values, size_t n);
+int comm_bcast(jetcu_ctx* ctx, void* d_ptr, size_t bytes, int root);
+// all-gather of small per-rank records through the device: out[r*count .. ] = rank r's `count` u64 values (host result)
+int comm_allgather_u64_host(jetcu_ctx* ctx, const uint64_t* mine, size_t count, uint64_t* all);
+// one message per peer: send_ptr[q]/send_bytes[q] to rank q, recv_ptr[q]/recv_bytes[q] from rank q (zero = skip)
+int comm_exchange(jetcu_ctx* ctx, void* const* send_ptr, const size_t* send_bytes, void* const* recv_ptr,
+                  const size_t* recv_bytes);
+void comm_free(jetcu_ctx* ctx);
+
+// Slab routing rule shared by the device kernel (k_slab_route) and the host-side test hook (jetcu_slab_route_mask):
+// bit q is set for every rank q != me whose extended slab [q*T - ghost, (q+1)*T + ghost) contains cell plane ck.
+// With T >= 2*ghost only the owner and its two neighbours can qualify.
+__host__ __device__ inline unsigned long long jc_slab_dest_mask(int ck, int T, int world, int me, int ghost) {
+    unsigned long long m = 0ull;
+    const int owner = ck / T;
+    for (int dq = -1; dq <= 1; ++dq) {
+        const int q = owner + dq;
+        if (q < 0 || q >= world || q == me) continue;
+        if (ck < q * T - ghost || ck >= (q + 1) * T + ghost) continue;
+        m |= 1ull << q;
+    }
+    return m;
+}
 
 // Brackets a group of launches of one kernel family with events when profiling is on (no-ops otherwise).
 int jc_prof_begin(jetcu_ctx* ctx, int kind);

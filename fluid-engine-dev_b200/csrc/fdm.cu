@@ -76,8 +76,6 @@ int fdm_mat_to_aos(jetcu_ctx* ctx, Mat A, jetcu_matrix_row* d_aos, size_t n) {
 #define BX 64
 #define BY 4
 
-static inline dim3 grid3(Dim3i d) { return dim3((d.nx + BX - 1) / BX, (d.ny + BY - 1) / BY, d.nz); }
-
 // The six off-diagonal products in the reference's order -i,+i,-j,+j,-k,+k
 // (FdmBlas3::mvm, src/jet/fdm_linear_system3.cpp:79-96; out-of-range terms are literal 0.0).
 struct Offdiag {
@@ -100,8 +98,8 @@ __device__ __forceinline__ Offdiag offdiag_terms(const Mat& A, const double* __r
 
 template <bool P>
 __global__ void __launch_bounds__(BX* BY) k_mvm(Mat A, const double* __restrict__ v, double* __restrict__ out,
-                                                int nx, int ny, int nz) {
-    int i = blockIdx.x * BX + threadIdx.x, j = blockIdx.y * BY + threadIdx.y, k = blockIdx.z;
+                                                int nx, int ny, int nz, int k0) {
+    int i = blockIdx.x * BX + threadIdx.x, j = blockIdx.y * BY + threadIdx.y, k = k0 + blockIdx.z;
     if (i >= nx || j >= ny) return;
     size_t c = ((size_t)k * ny + j) * nx + i;
     Offdiag o = offdiag_terms<P>(A, v, i, j, k, nx, ny, nz, c);
@@ -112,8 +110,8 @@ __global__ void __launch_bounds__(BX* BY) k_mvm(Mat A, const double* __restrict_
 template <bool P>
 __global__ void __launch_bounds__(BX* BY) k_residual(Mat A, const double* __restrict__ x,
                                                      const double* __restrict__ b, double* __restrict__ out, int nx,
-                                                     int ny, int nz) {
-    int i = blockIdx.x * BX + threadIdx.x, j = blockIdx.y * BY + threadIdx.y, k = blockIdx.z;
+                                                     int ny, int nz, int k0) {
+    int i = blockIdx.x * BX + threadIdx.x, j = blockIdx.y * BY + threadIdx.y, k = k0 + blockIdx.z;
     if (i >= nx || j >= ny) return;
     size_t c = ((size_t)k * ny + j) * nx + i;
     Offdiag o = offdiag_terms<P>(A, x, i, j, k, nx, ny, nz, c);
@@ -159,8 +157,8 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_relax_small(Mat A, const doub
 //     plane is fetched in both passes with half of it unused (ncu: profiles/r01_baseline_relax_colour_full.txt).
 template <bool P>
 __global__ void __launch_bounds__(BX* BY) k_relax_colour(Mat A, const double* __restrict__ b, double* __restrict__ x,
-                                                         double w, int colour, int nx, int ny, int nz) {
-    int j = blockIdx.y * BY + threadIdx.y, k = blockIdx.z;
+                                                         double w, int colour, int nx, int ny, int nz, int k0) {
+    int j = blockIdx.y * BY + threadIdx.y, k = k0 + blockIdx.z;
     int i = 2 * (blockIdx.x * BX + threadIdx.x) + ((j + k + colour) & 1);
     if (i >= nx || j >= ny) return;
     size_t c = ((size_t)k * ny + j) * nx + i;
@@ -183,8 +181,8 @@ __device__ __forceinline__ double mask_coef(unsigned bit, double neg_s) {
 }
 
 __global__ void __launch_bounds__(BX* BY) k_relax_colour_code(Mat A, const double* __restrict__ b, double* __restrict__ x,
-                                                              double w, int colour, int nx, int ny, int nz) {
-    const int j = blockIdx.y * BY + threadIdx.y, k = blockIdx.z;
+                                                              double w, int colour, int nx, int ny, int nz, int k0) {
+    const int j = blockIdx.y * BY + threadIdx.y, k = k0 + blockIdx.z;
     const int i = 2 * (blockIdx.x * BX + threadIdx.x) + ((j + k + colour) & 1);
     if (i >= nx || j >= ny) return;
     const size_t sy = (size_t)nx, sz = (size_t)nx * ny;
@@ -216,65 +214,87 @@ __global__ void __launch_bounds__(BX* BY) k_relax_colour_code(Mat A, const doubl
     x[c] = (1.0 - w) * x[c] + w * (b[c] - r) / A.center[c];
 }
 
+static inline dim3 grid3z(Dim3i d, ZRange z) { return dim3((d.nx + BX - 1) / BX, (d.ny + BY - 1) / BY, z.k1 - z.k0); }
+static inline ZRange zfull(Dim3i d) { return ZRange{0, d.nz}; }
+
 template <bool P>
-static int launch_mvm(jetcu_ctx* ctx, Dim3i d, Mat A, const double* v, double* out) {
-    JC_LAUNCH(ctx, k_mvm<P>, grid3(d), dim3(BX, BY), 0, A, v, out, d.nx, d.ny, d.nz);
+static int launch_mvm(jetcu_ctx* ctx, Dim3i d, ZRange z, Mat A, const double* v, double* out) {
+    JC_LAUNCH(ctx, k_mvm<P>, grid3z(d, z), dim3(BX, BY), 0, A, v, out, d.nx, d.ny, d.nz, z.k0);
     return JETCU_OK;
 }
 
-int fdm_mvm(jetcu_ctx* ctx, Dim3i d, Mat A, const double* v, double* out) {
-    return A.packed ? launch_mvm<true>(ctx, d, A, v, out) : launch_mvm<false>(ctx, d, A, v, out);
+int fdm_mvm(jetcu_ctx* ctx, Dim3i d, ZRange z, Mat A, const double* v, double* out) {
+    if (z.k1 <= z.k0) return JETCU_OK;
+    return A.packed ? launch_mvm<true>(ctx, d, z, A, v, out) : launch_mvm<false>(ctx, d, z, A, v, out);
 }
+int fdm_mvm(jetcu_ctx* ctx, Dim3i d, Mat A, const double* v, double* out) { return fdm_mvm(ctx, d, zfull(d), A, v, out); }
 
 template <bool P>
-static int launch_residual(jetcu_ctx* ctx, Dim3i d, Mat A, const double* x, const double* b, double* out) {
-    JC_LAUNCH(ctx, k_residual<P>, grid3(d), dim3(BX, BY), 0, A, x, b, out, d.nx, d.ny, d.nz);
+static int launch_residual(jetcu_ctx* ctx, Dim3i d, ZRange z, Mat A, const double* x, const double* b, double* out) {
+    JC_LAUNCH(ctx, k_residual<P>, grid3z(d, z), dim3(BX, BY), 0, A, x, b, out, d.nx, d.ny, d.nz, z.k0);
     return JETCU_OK;
 }
 
+int fdm_residual(jetcu_ctx* ctx, Dim3i d, ZRange z, Mat A, const double* x, const double* b, double* out) {
+    if (z.k1 <= z.k0) return JETCU_OK;
+    return A.packed ? launch_residual<true>(ctx, d, z, A, x, b, out) : launch_residual<false>(ctx, d, z, A, x, b, out);
+}
 int fdm_residual(jetcu_ctx* ctx, Dim3i d, Mat A, const double* x, const double* b, double* out) {
-    return A.packed ? launch_residual<true>(ctx, d, A, x, b, out) : launch_residual<false>(ctx, d, A, x, b, out);
+    return fdm_residual(ctx, d, zfull(d), A, x, b, out);
 }
 
+// One colour pass over the planes of `z` (colour 0 = red = (i+j+k) even with GLOBAL k).
 template <bool P>
-static int launch_relax(jetcu_ctx* ctx, Dim3i d, Mat A, const double* b, double sor, unsigned iterations, double** x,
-                        double** xalt, uint64_t* launches) {
+static int launch_colour(jetcu_ctx* ctx, Dim3i d, ZRange z, Mat A, const double* b, double sor, int colour, double* x) {
+    dim3 grid(((d.nx + 1) / 2 + BX - 1) / BX, (d.ny + BY - 1) / BY, z.k1 - z.k0);
+    if (P && A.code != nullptr) JC_LAUNCH(ctx, k_relax_colour_code, grid, dim3(BX, BY), 0, A, b, x, sor, colour, d.nx, d.ny, d.nz, z.k0);
+    else JC_LAUNCH(ctx, k_relax_colour<P>, grid, dim3(BX, BY), 0, A, b, x, sor, colour, d.nx, d.ny, d.nz, z.k0);
+    return JETCU_OK;
+}
+
+// `halo` = slab-distributed level: the planes just outside `z` are refreshed from the neighbouring ranks before each
+// colour pass (a red cell reads black neighbours only and vice versa, so one exchange per pass keeps the sweep
+// bit-identical to the undivided one).
+template <bool P>
+static int launch_relax(jetcu_ctx* ctx, Dim3i d, ZRange z, bool halo, Mat A, const double* b, double sor,
+                        unsigned iterations, double** x, double** xalt, uint64_t* launches) {
     (void)xalt;
-    if (d.n() <= SMALL_MAX_CELLS) {
+    if (!halo && d.n() <= SMALL_MAX_CELLS) {
         JC_LAUNCH(ctx, k_relax_small<P>, 1, SMALL_THREADS, 0, A, b, *x, sor, d.nx, d.ny, d.nz, iterations);
         *launches = 1;
         return JETCU_OK;
     }
-    dim3 grid(((d.nx + 1) / 2 + BX - 1) / BX, (d.ny + BY - 1) / BY, d.nz);
+    const size_t plane = (size_t)d.nx * d.ny * sizeof(double);
     for (unsigned it = 0; it < iterations; ++it) {
-        if (P && A.code != nullptr) {
-            JC_LAUNCH(ctx, k_relax_colour_code, grid, dim3(BX, BY), 0, A, b, *x, sor, 0, d.nx, d.ny, d.nz);
-            JC_LAUNCH(ctx, k_relax_colour_code, grid, dim3(BX, BY), 0, A, b, *x, sor, 1, d.nx, d.ny, d.nz);
-        } else {
-            JC_LAUNCH(ctx, k_relax_colour<P>, grid, dim3(BX, BY), 0, A, b, *x, sor, 0, d.nx, d.ny, d.nz);
-            JC_LAUNCH(ctx, k_relax_colour<P>, grid, dim3(BX, BY), 0, A, b, *x, sor, 1, d.nx, d.ny, d.nz);
+        for (int colour = 0; colour < 2; ++colour) {
+            if (halo) JC_TRY(comm_halo_planes(ctx, *x, plane, z.k0, z.k1, d.nz));
+            JC_TRY(launch_colour<P>(ctx, d, z, A, b, sor, colour, *x));
         }
     }
     *launches = 2ull * iterations;
     return JETCU_OK;
 }
 
-int fdm_relax_rb(jetcu_ctx* ctx, Dim3i d, Mat A, const double* b, double sor, unsigned iterations, double** x,
-                 double** xalt, int level) {
-    if (iterations == 0) return JETCU_OK;
+int fdm_relax_rb(jetcu_ctx* ctx, Dim3i d, ZRange z, bool halo, Mat A, const double* b, double sor, unsigned iterations,
+                 double** x, double** xalt, int level) {
+    if (iterations == 0 || z.k1 <= z.k0) return JETCU_OK;
     int slot = jc_prof_begin(ctx, level == 0 ? JETCU_PROF_RELAX_L0 : JETCU_PROF_RELAX_COARSE);
     uint64_t launches = 0;
-    int rc = A.packed ? launch_relax<true>(ctx, d, A, b, sor, iterations, x, xalt, &launches)
-                      : launch_relax<false>(ctx, d, A, b, sor, iterations, x, xalt, &launches);
-    jc_prof_end(ctx, slot, launches, (uint64_t)d.n() * iterations);
+    int rc = A.packed ? launch_relax<true>(ctx, d, z, halo, A, b, sor, iterations, x, xalt, &launches)
+                      : launch_relax<false>(ctx, d, z, halo, A, b, sor, iterations, x, xalt, &launches);
+    jc_prof_end(ctx, slot, launches, (uint64_t)d.nx * d.ny * (z.k1 - z.k0) * iterations);
     return rc;
+}
+int fdm_relax_rb(jetcu_ctx* ctx, Dim3i d, Mat A, const double* b, double sor, unsigned iterations, double** x,
+                 double** xalt, int level) {
+    return fdm_relax_rb(ctx, d, zfull(d), false, A, b, sor, iterations, x, xalt, level);
 }
 
 // FdmMgUtils3::restrict, src/jet/fdm_mg_linear_system3.cpp:43-98: 4x4x4 (1,3,3,1)/8 tensor filter with edge clamp;
 // accumulation z-outer, y, x-inner; w = (kx*ky)*kz.
 __global__ void __launch_bounds__(BX* BY) k_restrict(const double* __restrict__ finer, double* __restrict__ coarser,
-                                                     int cnx, int cny, int cnz) {
-    int i = blockIdx.x * BX + threadIdx.x, j = blockIdx.y * BY + threadIdx.y, k = blockIdx.z;
+                                                     int cnx, int cny, int cnz, int k0) {
+    int i = blockIdx.x * BX + threadIdx.x, j = blockIdx.y * BY + threadIdx.y, k = k0 + blockIdx.z;
     if (i >= cnx || j >= cny) return;
     const double kern[4] = {0.125, 0.375, 0.375, 0.125};
     int iI[4] = {(i > 0) ? 2 * i - 1 : 2 * i, 2 * i, 2 * i + 1, (i + 1 < cnx) ? 2 * i + 2 : 2 * i + 1};
@@ -297,8 +317,8 @@ __global__ void __launch_bounds__(BX* BY) k_restrict(const double* __restrict__ 
 // FdmMgUtils3::correct, src/jet/fdm_mg_linear_system3.cpp:100-179: finer += sum_{z,y,x} ((wx*wy)*wz)*coarse.
 // The k-clamp uses nz (the reference tests n.y, :159 — identical for ny == nz, out of bounds otherwise).
 __global__ void __launch_bounds__(BX* BY) k_correct(const double* __restrict__ coarser, double* __restrict__ finer,
-                                                    int nx, int ny, int nz) {
-    int i = blockIdx.x * BX + threadIdx.x, j = blockIdx.y * BY + threadIdx.y, k = blockIdx.z;
+                                                    int nx, int ny, int nz, int k0) {
+    int i = blockIdx.x * BX + threadIdx.x, j = blockIdx.y * BY + threadIdx.y, k = k0 + blockIdx.z;
     if (i >= nx || j >= ny) return;
     int iI[2], jI[2], kI[2];
     double iW[2], jW[2], kW[2];
@@ -324,21 +344,25 @@ __global__ void __launch_bounds__(BX* BY) k_correct(const double* __restrict__ c
     finer[f] = acc;
 }
 
-int fdm_restrict(jetcu_ctx* ctx, Dim3i fine, const double* finer, double* coarser) {
+// `cz` = the COARSE planes to produce; reads fine planes 2*k0-1 .. 2*k1 (clamped to the level).
+int fdm_restrict(jetcu_ctx* ctx, Dim3i fine, ZRange cz, const double* finer, double* coarser) {
     Dim3i c{fine.nx / 2, fine.ny / 2, fine.nz / 2};
-    JC_LAUNCH(ctx, k_restrict, grid3(c), dim3(BX, BY), 0, finer, coarser, c.nx, c.ny, c.nz);
+    if (cz.k1 <= cz.k0) return JETCU_OK;
+    JC_LAUNCH(ctx, k_restrict, grid3z(c, cz), dim3(BX, BY), 0, finer, coarser, c.nx, c.ny, c.nz, cz.k0);
     return JETCU_OK;
 }
-
-int fdm_residual_restrict(jetcu_ctx* ctx, Dim3i fine, Mat A, const double* x, const double* b, double* buf,
-                          double* coarser) {
-    JC_TRY(fdm_residual(ctx, fine, A, x, b, buf));
-    return fdm_restrict(ctx, fine, buf, coarser);
+int fdm_restrict(jetcu_ctx* ctx, Dim3i fine, const double* finer, double* coarser) {
+    return fdm_restrict(ctx, fine, ZRange{0, fine.nz / 2}, finer, coarser);
 }
 
+// `z` = the FINE planes to correct; reads coarse planes k0/2-1 .. (k1-1)/2+1 (clamped).
+int fdm_correct(jetcu_ctx* ctx, Dim3i fine, ZRange z, const double* coarser, double* finer) {
+    if (z.k1 <= z.k0) return JETCU_OK;
+    JC_LAUNCH(ctx, k_correct, grid3z(fine, z), dim3(BX, BY), 0, coarser, finer, fine.nx, fine.ny, fine.nz, z.k0);
+    return JETCU_OK;
+}
 int fdm_correct(jetcu_ctx* ctx, Dim3i fine, const double* coarser, double* finer) {
-    JC_LAUNCH(ctx, k_correct, grid3(fine), dim3(BX, BY), 0, coarser, finer, fine.nx, fine.ny, fine.nz);
-    return JETCU_OK;
+    return fdm_correct(ctx, fine, zfull(fine), coarser, finer);
 }
 
 // ------------------------------------------------------------------------------------------------ BLAS-1
@@ -373,16 +397,49 @@ __global__ void __launch_bounds__(DOT_BLOCK) k_dot_partial(const double* __restr
     if (threadIdx.x == 0) partials[blockIdx.x] = r;
 }
 
-__global__ void __launch_bounds__(DOT_BLOCK) k_dot_final(const double* __restrict__ partials, double* __restrict__ out) {
+__global__ void __launch_bounds__(DOT_BLOCK) k_dot_final(const double* __restrict__ partials, int count,
+                                                         double* __restrict__ out) {
     double acc = 0.0;
-    for (int i = threadIdx.x; i < DOT_GRID; i += DOT_BLOCK) acc += partials[i];
+    for (int i = threadIdx.x; i < count; i += DOT_BLOCK) acc += partials[i];
     double r = block_sum(acc);
     if (threadIdx.x == 0) out[0] = r;
 }
 
 int fdm_dot(jetcu_ctx* ctx, size_t n, const double* a, const double* b, double* d_result) {
     JC_LAUNCH(ctx, k_dot_partial, DOT_GRID, DOT_BLOCK, 0, a, b, ctx->d_partials, n);
-    JC_LAUNCH(ctx, k_dot_final, 1, DOT_BLOCK, 0, ctx->d_partials, d_result);
+    JC_LAUNCH(ctx, k_dot_final, 1, DOT_BLOCK, 0, ctx->d_partials, DOT_GRID, d_result);
+    return JETCU_OK;
+}
+
+// Dot product whose bits do not depend on how the grid is split into z-slabs: one partial per (z-plane, segment),
+// each summed by one CTA in a fixed order; the partials of all planes (all ranks) are then reduced by one CTA in a
+// fixed tree.  Used by PCG, so that an N-GPU solve takes exactly the iterations of the 1-GPU solve.
+__global__ void __launch_bounds__(DOT_BLOCK) k_dot_plane_partial(const double* __restrict__ a, const double* __restrict__ b,
+                                                                 double* __restrict__ partials, size_t plane, int seg,
+                                                                 int k0) {
+    const int k = k0 + blockIdx.y, s = blockIdx.x;
+    const size_t chunk = (plane + seg - 1) / seg;
+    const size_t lo = (size_t)s * chunk, hi = (lo + chunk < plane) ? lo + chunk : plane;
+    const size_t base = (size_t)k * plane;
+    double acc = 0.0;
+    for (size_t i = lo + threadIdx.x; i < hi; i += DOT_BLOCK) acc += a[base + i] * b[base + i];
+    double r = block_sum(acc);
+    if (threadIdx.x == 0) partials[(size_t)k * seg + s] = r;
+}
+
+static inline int dot_segments(Dim3i d) {
+    int seg = JC_PARTIALS_CAP / d.nz;
+    return seg > 4 ? 4 : seg;
+}
+
+int fdm_dot_planes(jetcu_ctx* ctx, Dim3i d, ZRange z, bool dist, const double* a, const double* b, double* d_result) {
+    const int seg = dot_segments(d);
+    if (seg < 1) return jetcu_fail(ctx, JETCU_ERR_INVALID_ARG, "nz = %d exceeds the dot-product partial buffer", d.nz);
+    const size_t plane = (size_t)d.nx * d.ny;
+    if (z.k1 > z.k0)
+        JC_LAUNCH(ctx, k_dot_plane_partial, dim3(seg, z.k1 - z.k0), DOT_BLOCK, 0, a, b, ctx->d_partials, plane, seg, z.k0);
+    if (dist) JC_TRY(comm_allgather_inplace(ctx, ctx->d_partials, (size_t)(z.k1 - z.k0) * seg * sizeof(double)));
+    JC_LAUNCH(ctx, k_dot_final, 1, DOT_BLOCK, 0, ctx->d_partials, d.nz * seg, d_result);
     return JETCU_OK;
 }
 
@@ -420,7 +477,7 @@ int mg_alloc_vectors(jetcu_ctx* ctx, MgLevels* mg) {
         mg->x[l] = mg->own_vec[l][0]; mg->xalt[l] = mg->own_vec[l][1];
         mg->b[l] = mg->own_vec[l][2]; mg->buf[l] = mg->own_vec[l][3];
     }
-    return JETCU_OK;
+    return mg_make_plan(ctx, mg);
 }
 
 void mg_free(jetcu_ctx* ctx, MgLevels* mg) {
@@ -431,26 +488,83 @@ void mg_free(jetcu_ctx* ctx, MgLevels* mg) {
     mg->levels = 0;
 }
 
+// z-slab plan of an MG hierarchy over the ctx's communicator.  Level l is slab-distributed while every
+// rank keeps an even number (>= 4) of planes and the level is too big for the single-CTA smoother; all coarser levels
+// are REPLICATED: their right-hand side is all-gathered once on the way down and every rank relaxes the whole (tiny)
+// level redundantly, which costs no further messages and keeps the arithmetic identical to one GPU.
+int slab_plan_compute(const Dim3i* dims, int levels, int world, int rank, SlabPlan* out) {
+    SlabPlan& pl = *out;
+    pl = SlabPlan();
+    pl.world = world; pl.rank = rank;
+    for (int l = 0; l < JC_MAX_LEVELS; ++l) { pl.z0[l] = 0; pl.z1[l] = l < levels ? dims[l].nz : 0; }
+    if (world <= 1) return 0;
+    int l = 0;
+    for (; l < levels; ++l) {
+        const int nz = dims[l].nz;
+        if (nz % (2 * world) != 0 || nz / world < 4 || dims[l].n() <= SMALL_MAX_CELLS) break;
+        pl.z0[l] = rank * (nz / world); pl.z1[l] = (rank + 1) * (nz / world);
+    }
+    pl.dist_levels = l;
+    return l == 0 ? -1 : 0;
+}
+
+int mg_make_plan(jetcu_ctx* ctx, MgLevels* mg) {
+    if (slab_plan_compute(mg->dims, mg->levels, jc_comm_world(ctx), jc_comm_rank(ctx), &mg->plan) != 0)
+        return jetcu_fail(ctx, JETCU_ERR_INVALID_ARG, "z-slab decomposition needs nz (%d) to be a multiple of 2 x %d ranks "
+                          "with at least 4 planes per rank", mg->dims[0].nz, jc_comm_world(ctx));
+    return JETCU_OK;
+}
+
+extern "C" int jetcu_slab_plan(uint64_t nx, uint64_t ny, uint64_t nz, uint32_t levels, int world, int rank,
+                               uint32_t* dist_levels, uint64_t* z0, uint64_t* z1) {
+    if (levels < 1 || levels > JC_MAX_LEVELS || world < 1 || rank < 0 || rank >= world) return JETCU_ERR_INVALID_ARG;
+    Dim3i dims[JC_MAX_LEVELS];
+    for (uint32_t l = 0; l < levels; ++l) dims[l] = Dim3i{(int)(nx >> l), (int)(ny >> l), (int)(nz >> l)};
+    SlabPlan pl;
+    if (slab_plan_compute(dims, (int)levels, world, rank, &pl) != 0) return JETCU_ERR_INVALID_ARG;
+    if (dist_levels) *dist_levels = (uint32_t)pl.dist_levels;
+    for (uint32_t l = 0; l < levels; ++l) {
+        if (z0) z0[l] = (uint64_t)pl.z0[l];
+        if (z1) z1[l] = (uint64_t)pl.z1[l];
+    }
+    return JETCU_OK;
+}
+
 // internal::mgVCycle, include/jet/detail/mg-inl.h:16-68, with FdmMgSolver3's relax lambdas
 // (src/jet/fdm_mg_solver3.cpp:26-49).  The residual + l2Norm the reference evaluates on the way up only feed
 // MgResult.lastResidualNorm, which FdmMgpcgSolver3::Preconditioner discards; they never touch x and are skipped.
 // mg->x[l] / mg->xalt[l] may be exchanged by the smoother; mg->x[l] always names the current iterate.
+// On a slab-distributed level every rank works on its planes [z0, z1) of the full-size (globally indexed) arrays and
+// refreshes the two planes around them from its neighbours before each stencil application.
 int mg_vcycle(jetcu_ctx* ctx, MgLevels* mg, const jetcu_mgpcg_params* p, int l) {
-    Dim3i d = mg->dims[l];
-    JC_TRY(fdm_relax_rb(ctx, d, mg->A[l], mg->b[l], p->sor_factor, p->n_restriction, &mg->x[l], &mg->xalt[l], l));
+    const Dim3i d = mg->dims[l];
+    const SlabPlan& pl = mg->plan;
+    const bool dist = l < pl.dist_levels;
+    const ZRange z{pl.z0[l], pl.z1[l]};
+    const size_t plane = (size_t)d.nx * d.ny * sizeof(double);
+    JC_TRY(fdm_relax_rb(ctx, d, z, dist, mg->A[l], mg->b[l], p->sor_factor, p->n_restriction, &mg->x[l], &mg->xalt[l], l));
     if (l + 1 < mg->levels) {
+        const Dim3i dc = mg->dims[l + 1];
+        const ZRange cz{z.k0 / 2, z.k1 / 2};
         int slot = jc_prof_begin(ctx, JETCU_PROF_TRANSFER);
-        JC_TRY(fdm_residual_restrict(ctx, d, mg->A[l], mg->x[l], mg->b[l], mg->buf[l], mg->b[l + 1]));
-        JC_TRY(jc_zero(ctx, mg->x[l + 1], mg->dims[l + 1].n()));
-        jc_prof_end(ctx, slot, 2, d.n());
+        if (dist) JC_TRY(comm_halo_planes(ctx, mg->x[l], plane, z.k0, z.k1, d.nz));
+        JC_TRY(fdm_residual(ctx, d, z, mg->A[l], mg->x[l], mg->b[l], mg->buf[l]));
+        if (dist) JC_TRY(comm_halo_planes(ctx, mg->buf[l], plane, z.k0, z.k1, d.nz));
+        JC_TRY(fdm_restrict(ctx, d, cz, mg->buf[l], mg->b[l + 1]));
+        if (dist && l + 1 >= pl.dist_levels)  // first replicated level: every rank needs the whole right-hand side
+            JC_TRY(comm_allgather_inplace(ctx, mg->b[l + 1], (size_t)(cz.k1 - cz.k0) * dc.nx * dc.ny * sizeof(double)));
+        JC_TRY(jc_zero(ctx, mg->x[l + 1], dc.n()));
+        jc_prof_end(ctx, slot, 2, (uint64_t)d.nx * d.ny * (z.k1 - z.k0));
         JC_TRY(mg_vcycle(ctx, mg, p, l + 1));
         slot = jc_prof_begin(ctx, JETCU_PROF_TRANSFER);
-        JC_TRY(fdm_correct(ctx, d, mg->x[l + 1], mg->x[l]));
-        jc_prof_end(ctx, slot, 1, d.n());
-        JC_TRY(fdm_relax_rb(ctx, d, mg->A[l], mg->b[l], p->sor_factor, l > 0 ? p->n_correction : p->n_final, &mg->x[l],
-                            &mg->xalt[l], l));
+        if (l + 1 < pl.dist_levels)
+            JC_TRY(comm_halo_planes(ctx, mg->x[l + 1], (size_t)dc.nx * dc.ny * sizeof(double), pl.z0[l + 1], pl.z1[l + 1], dc.nz));
+        JC_TRY(fdm_correct(ctx, d, z, mg->x[l + 1], mg->x[l]));
+        jc_prof_end(ctx, slot, 1, (uint64_t)d.nx * d.ny * (z.k1 - z.k0));
+        JC_TRY(fdm_relax_rb(ctx, d, z, dist, mg->A[l], mg->b[l], p->sor_factor, l > 0 ? p->n_correction : p->n_final,
+                            &mg->x[l], &mg->xalt[l], l));
     } else {
-        JC_TRY(fdm_relax_rb(ctx, d, mg->A[l], mg->b[l], p->sor_factor, p->n_coarsest, &mg->x[l], &mg->xalt[l], l));
+        JC_TRY(fdm_relax_rb(ctx, d, z, dist, mg->A[l], mg->b[l], p->sor_factor, p->n_coarsest, &mg->x[l], &mg->xalt[l], l));
     }
     return JETCU_OK;
 }
@@ -479,13 +593,22 @@ static int read_scalar(jetcu_ctx* ctx, const double* d, double* out) {
 // pcg<FdmBlas3, Preconditioner>, include/jet/detail/cg-inl.h:18-94, as called by FdmMgpcgSolver3::solve
 // (src/jet/fdm_mgpcg_solver3.cpp:54-80): x = 0 first; exit test sigma > tol^2 (also leaves on sigma <= 0);
 // residual recomputed when iter % 50 == 0 (iter > 0) or after sigma rose.
+// With a multi-rank communicator on the ctx the solve is z-slab distributed (mg->plan): b must be valid on this rank's
+// planes, x is complete (all-gathered) on return, and — thanks to fdm_dot_planes — every rank sees the same scalars,
+// takes the same branches and produces the bits of the single-GPU solve.
 int mgpcg_solve_device(jetcu_ctx* ctx, MgLevels* mg, const double* b, double* x, const jetcu_mgpcg_params* p,
                        jetcu_mgpcg_result* result) {
     if (!p->use_red_black)
         return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED,
                           "lexicographic Gauss-Seidel is inherently serial; use useRedBlackOrdering = true");
+    JC_TRY(mg_make_plan(ctx, mg));
     const Dim3i d = mg->dims[0];
     const size_t n = d.n();
+    const SlabPlan& pl = mg->plan;
+    const bool dist = pl.dist_levels > 0;
+    const ZRange z{pl.z0[0], pl.z1[0]};
+    const size_t nxy = (size_t)d.nx * d.ny, off = (size_t)z.k0 * nxy, cnt = (size_t)(z.k1 - z.k0) * nxy;
+    const size_t plane = nxy * sizeof(double);
     // level 0's own x / xalt / b are idle during PCG (the V-cycle runs on the PCG vectors): reuse them as r, q and the
     // ping-pong scratch t; buf[0] stays the residual temporary of the V-cycle.
     double *r = mg->own_vec[0][0], *q = mg->own_vec[0][1], *t = mg->own_vec[0][2], *dd = nullptr, *s = nullptr;
@@ -495,10 +618,10 @@ int mgpcg_solve_device(jetcu_ctx* ctx, MgLevels* mg, const double* b, double* x,
     JC_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
 
     JC_TRY(jc_zero(ctx, x, n)); JC_TRY(jc_zero(ctx, dd, n)); JC_TRY(jc_zero(ctx, q, n)); JC_TRY(jc_zero(ctx, s, n));
-    JC_TRY(fdm_residual(ctx, d, mg->A[0], x, b, r));
+    JC_TRY(fdm_residual(ctx, d, z, mg->A[0], x, b, r));  // x = 0 everywhere: no halo needed
     JC_TRY(precondition(ctx, mg, p, r, &dd, &t));
     double sigmaNew;
-    JC_TRY(fdm_dot(ctx, n, r, dd, ctx->d_scalars));
+    JC_TRY(fdm_dot_planes(ctx, d, z, dist, r, dd, ctx->d_scalars));
     JC_TRY(read_scalar(ctx, ctx->d_scalars, &sigmaNew));
 
     unsigned iter = 0;
@@ -506,28 +629,31 @@ int mgpcg_solve_device(jetcu_ctx* ctx, MgLevels* mg, const double* b, double* x,
     while (sigmaNew > p->tolerance * p->tolerance && iter < p->max_iterations) {
         {
             int slot = jc_prof_begin(ctx, JETCU_PROF_MVM_L0);
-            JC_TRY(fdm_mvm(ctx, d, mg->A[0], dd, q));
-            jc_prof_end(ctx, slot, 1, n);
+            if (dist) JC_TRY(comm_halo_planes(ctx, dd, plane, z.k0, z.k1, d.nz));
+            JC_TRY(fdm_mvm(ctx, d, z, mg->A[0], dd, q));
+            jc_prof_end(ctx, slot, 1, cnt);
         }
         double dq;
-        JC_TRY(fdm_dot(ctx, n, dd, q, ctx->d_scalars));
+        JC_TRY(fdm_dot_planes(ctx, d, z, dist, dd, q, ctx->d_scalars));
         JC_TRY(read_scalar(ctx, ctx->d_scalars, &dq));
         double alpha = sigmaNew / dq;
         bool recompute = trigger || (iter % 50 == 0 && iter > 0);
-        JC_TRY(fdm_pcg_update(ctx, n, alpha, dd, q, x, r, !recompute));
+        JC_TRY(fdm_pcg_update(ctx, cnt, alpha, dd + off, q + off, x + off, r + off, !recompute));
         if (recompute) {
-            JC_TRY(fdm_residual(ctx, d, mg->A[0], x, b, r));
+            if (dist) JC_TRY(comm_halo_planes(ctx, x, plane, z.k0, z.k1, d.nz));
+            JC_TRY(fdm_residual(ctx, d, z, mg->A[0], x, b, r));
             trigger = false;
         }
         JC_TRY(precondition(ctx, mg, p, r, &s, &t));
         double sigmaOld = sigmaNew;
-        JC_TRY(fdm_dot(ctx, n, r, s, ctx->d_scalars));
+        JC_TRY(fdm_dot_planes(ctx, d, z, dist, r, s, ctx->d_scalars));
         JC_TRY(read_scalar(ctx, ctx->d_scalars, &sigmaNew));
         if (sigmaNew > sigmaOld) trigger = true;
         double beta = sigmaNew / sigmaOld;
-        JC_TRY(fdm_axpy(ctx, n, beta, dd, s, dd));
+        JC_TRY(fdm_axpy(ctx, cnt, beta, dd + off, s + off, dd + off));
         ++iter;
     }
+    if (dist) JC_TRY(comm_allgather_inplace(ctx, x, cnt * sizeof(double)));  // pressure complete on every rank
     JC_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
 
     if (result) {
@@ -535,9 +661,9 @@ int mgpcg_solve_device(jetcu_ctx* ctx, MgLevels* mg, const double* b, double* x,
         result->last_residual = sqrt(fabs(sigmaNew));
         result->returned = (result->last_residual <= p->tolerance || iter < p->max_iterations) ? 1 : 0;
         double rr, bb;
-        JC_TRY(fdm_residual(ctx, d, mg->A[0], x, b, r));
-        JC_TRY(fdm_dot(ctx, n, r, r, ctx->d_scalars));
-        JC_TRY(fdm_dot(ctx, n, b, b, ctx->d_scalars + 1));
+        JC_TRY(fdm_residual(ctx, d, z, mg->A[0], x, b, r));  // x complete after the all-gather: halos valid
+        JC_TRY(fdm_dot_planes(ctx, d, z, dist, r, r, ctx->d_scalars));
+        JC_TRY(fdm_dot_planes(ctx, d, z, dist, b, b, ctx->d_scalars + 1));
         JC_TRY(jc_d2h(ctx, ctx->h_scalars, ctx->d_scalars, 2));
         JC_TRY(jc_sync(ctx));
         rr = ctx->h_scalars[0]; bb = ctx->h_scalars[1];

@@ -43,6 +43,12 @@ struct jetcu_hybrid {
     uint32_t *cell_of = nullptr, *rank = nullptr, *perm = nullptr;
     uint32_t* cell_start = nullptr;  // nc + 1
     bool binned = false;
+    // z-slab mode (the ctx had a multi-rank communicator when the solver was created): this rank owns the cell planes
+    // [z0, z1); after binning attr[cur] holds [ghost-lo | owned | ghost-hi | dead], the owned block starts at `base`.
+    int world = 1, me = 0, z0 = 0, z1 = 0;
+    uint64_t base = 0;     // first owned particle inside attr[cur]
+    uint64_t nsorted = 0;  // ghost-lo + owned + ghost-hi (the cell-sorted live range starts at 0)
+    uint64_t nglobal = 0;  // particles on all ranks (== np on a single GPU)
     PressureSystem ps;
     jetcu_mgpcg_result last{};
     cudaEvent_t ev[12] = {};
@@ -89,15 +95,18 @@ __device__ __forceinline__ int cell_coord(double x, double o, double ih, int n) 
     return c;
 }
 
+// Particles whose cell plane lies outside [e0, e1) (slab mode: this rank's slab + ghost planes) go to the trash bin,
+// cell id nx*ny*nz, which sorts behind every real cell and is dropped.
 __global__ void k_cell_count(const double* __restrict__ px, const double* __restrict__ py, const double* __restrict__ pz,
-                             size_t np, GridD g, uint32_t* __restrict__ cell_of, uint32_t* __restrict__ rank,
-                             uint32_t* __restrict__ count) {
+                             size_t np, GridD g, int e0, int e1, uint32_t* __restrict__ cell_of,
+                             uint32_t* __restrict__ rank, uint32_t* __restrict__ count) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= np) return;
     int ci = cell_coord(px[p], g.ox, 1.0 / g.hx, g.nx);
     int cj = cell_coord(py[p], g.oy, 1.0 / g.hy, g.ny);
     int ck = cell_coord(pz[p], g.oz, 1.0 / g.hz, g.nz);
     uint32_t cell = (uint32_t)(((size_t)ck * g.ny + cj) * g.nx + ci);
+    if (ck < e0 || ck >= e1) cell = (uint32_t)((size_t)g.nx * g.ny * g.nz);
     cell_of[p] = cell;
     rank[p] = atomicAdd(&count[cell], 1u);  // slot inside the cell; order fixed up by k_sort_cells
 }
@@ -140,6 +149,47 @@ __global__ void k_gather_attrs(AttrPtrs src, AttrPtrs dst, const uint32_t* __res
     uint32_t from = perm[s];
     for (int a = 0; a < nattr; ++a) dst.p[a][s] = src.p[a][from];
     orig_dst[s] = orig_src[from];
+}
+
+// ------------------------------------------------------------------------------------------------ z-slab routing
+// Slab mode: rank q owns the cell planes [q*T, (q+1)*T) and additionally needs read-only GHOST copies
+// of the particles within SLAB_GHOST planes of its slab (P2G reaches 1 plane, the particle SDF 2r = 1.7 h -> 2).
+// After moveParticles every rank holds owned particles only; each one is copied to every OTHER rank whose extended
+// slab contains its new plane (its new owner when it migrated, the neighbour when it sits near a slab face), and kept
+// locally iff it lies in this rank's extended slab.  The cell sort that follows puts [ghost-lo | owned | ghost-hi] in
+// order, so "owned" stays one contiguous range.  FILL = false only counts, FILL = true writes the index lists.
+#define SLAB_GHOST JETCU_SLAB_GHOST_PLANES
+template <bool FILL>
+__global__ void k_slab_route(const double* __restrict__ pz, size_t np, double oz, double ihz, int nz, int T, int world, int me,
+                             uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets, uint32_t* __restrict__ lists) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    const int ck = cell_coord(pz[p], oz, ihz, nz);
+    unsigned long long m = jc_slab_dest_mask(ck, T, world, me, SLAB_GHOST);
+    while (m) {
+        const int q = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const uint32_t slot = atomicAdd(&counts[q], 1u);
+        if (FILL) lists[offsets[q] + slot] = (uint32_t)p;
+    }
+}
+
+// message to one rank: (nattr + 1) blocks of `cnt` doubles (attributes, then the original index as a double)
+__global__ void k_slab_pack(AttrPtrs src, const uint32_t* __restrict__ orig, const uint32_t* __restrict__ list, int nattr,
+                            size_t cnt, double* __restrict__ msg) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    const uint32_t p = list[i];
+    for (int a = 0; a < nattr; ++a) msg[(size_t)a * cnt + i] = src.p[a][p];
+    msg[(size_t)nattr * cnt + i] = (double)orig[p];
+}
+
+__global__ void k_slab_unpack(const double* __restrict__ msg, int nattr, size_t cnt, AttrPtrs dst, uint32_t* __restrict__ orig,
+                              size_t at) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    for (int a = 0; a < nattr; ++a) dst.p[a][at + i] = msg[(size_t)a * cnt + i];
+    orig[at + i] = (uint32_t)msg[(size_t)nattr * cnt + i];
 }
 
 // ------------------------------------------------------------------------------------------------ P2G
@@ -260,7 +310,8 @@ __device__ __forceinline__ double from_fixed128(unsigned long long hi, unsigned 
 
 template <bool APIC>
 __global__ void __launch_bounds__(P2G_THREADS)
-    k_p2g_scatter(GridD g, const uint32_t* __restrict__ cell_start, AttrPtrs a, const P2GScale* __restrict__ sc, P2GAcc acc) {
+    k_p2g_scatter(GridD g, int kbase, int kend, const uint32_t* __restrict__ cell_start, AttrPtrs a,
+                  const P2GScale* __restrict__ sc, P2GAcc acc) {
     // per component: tile of faces reachable from the TC^3 cells: the component's own axis spans TC+1, the others TC+2
     constexpr int NF = (TC + 1) * (TC + 2) * (TC + 2);
     // Shared accumulators: 128-bit integers as four 32-bit limbs (32-bit shared atomics are native; 64-bit ones
@@ -272,7 +323,8 @@ __global__ void __launch_bounds__(P2G_THREADS)
     unsigned(*sW)[4][NF] = reinterpret_cast<unsigned(*)[4][NF]>(p2g_smem + 12 * NF);   // [3][limb] weight
     unsigned char(*sM)[NF] = reinterpret_cast<unsigned char(*)[NF]>(p2g_smem + 24 * NF);  // [3] markers
     __shared__ int any;
-    const int I0 = blockIdx.x * TC, J0 = blockIdx.y * TC, K0 = blockIdx.z * TC;
+    // cell planes [kbase, kend): the whole grid, or (slab mode) this rank's slab plus its ghost planes
+    const int I0 = blockIdx.x * TC, J0 = blockIdx.y * TC, K0 = kbase + blockIdx.z * TC;
     if (threadIdx.x == 0) any = 0;
     for (int t = threadIdx.x; t < 24 * NF; t += P2G_THREADS) p2g_smem[t] = 0u;
     for (int t = threadIdx.x; t < 3 * NF; t += P2G_THREADS) (&sM[0][0])[t] = 0;
@@ -288,7 +340,7 @@ __global__ void __launch_bounds__(P2G_THREADS)
     // concurrent atomics rarely hit the same face (the particles of one cell all hit the same few faces)
     for (int cl = threadIdx.x; cl < TC * TC * TC; cl += P2G_THREADS) {
         const int ci = I0 + (cl % TC), cj = J0 + ((cl / TC) % TC), ck = K0 + (cl / (TC * TC));
-        if (ci >= g.nx || cj >= g.ny || ck >= g.nz) continue;
+        if (ci >= g.nx || cj >= g.ny || ck >= kend) continue;
         const size_t cell = ((size_t)ck * g.ny + cj) * g.nx + ci;
         const uint32_t s0 = cell_start[cell], e0 = cell_start[cell + 1];
         for (uint32_t q = s0; q < e0; ++q) {
@@ -403,8 +455,8 @@ __global__ void k_flip_delta(const double* __restrict__ in, float* __restrict__ 
 __global__ void __launch_bounds__(128)
     k_build_sdf(GridD g, const uint32_t* __restrict__ cell_start, const double* __restrict__ ppx,
                 const double* __restrict__ ppy, const double* __restrict__ ppz, double radius, double band, int rx, int ry,
-                int rz, double* __restrict__ sdf) {
-    int i = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+                int rz, int kfirst, double* __restrict__ sdf) {
+    int i = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = kfirst + blockIdx.z;
     if (i >= g.nx || j >= g.ny) return;
     // data position = (origin + 0.5 h) + h*(i,j,k)  (src/jet/scalar_grid3.cpp:127-132)
     const double ptx = (g.ox + 0.5 * g.hx) + g.hx * (double)i;
@@ -768,54 +820,106 @@ __device__ __forceinline__ void lattice_point(size_t t, unsigned cx, unsigned cy
     p[0] = i * spacing + lx; p[1] = j * spacing + ly; p[2] = k * spacing + lz;
 }
 
-__global__ void k_emit_flags(uint32_t* __restrict__ flags, size_t total, unsigned cx, unsigned cy, double spacing, double lx,
-                             double ly, double lz, Box3d bx) {
+// flags[t] = lattice point t is emitted; mine[t] (slab mode, else null) = ... and its cell plane belongs to this rank
+__global__ void k_emit_flags(uint32_t* __restrict__ flags, uint32_t* __restrict__ mine, size_t total, unsigned cx, unsigned cy,
+                             double spacing, double lx, double ly, double lz, Box3d bx, double oz, double ihz, int nz, int z0,
+                             int z1) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t > total) return;
-    if (t == total) { flags[t] = 0; return; }
+    if (t == total) { flags[t] = 0; if (mine) mine[t] = 0; return; }
     double p[3];
     lattice_point(t, cx, cy, spacing, lx, ly, lz, p);
-    flags[t] = box_emit_accept(p, bx) ? 1u : 0u;
+    const bool acc = box_emit_accept(p, bx);
+    flags[t] = acc ? 1u : 0u;
+    if (mine) {
+        const int ck = cell_coord(p[2], oz, ihz, nz);
+        mine[t] = (acc && ck >= z0 && ck < z1) ? 1u : 0u;
+    }
 }
 
+// slot = exclusive scan of flags (position in the reference's emission order = the particle's original index),
+// local = exclusive scan of mine (position among this rank's particles; == slot on a single GPU)
 __global__ void k_emit_lattice(double* __restrict__ x, double* __restrict__ y, double* __restrict__ z, double* __restrict__ vx,
                                double* __restrict__ vy, double* __restrict__ vz, uint32_t* __restrict__ orig, size_t offset,
-                               const uint32_t* __restrict__ slot, size_t total, unsigned cx, unsigned cy, double spacing,
-                               double lx, double ly, double lz, double v0x, double v0y, double v0z) {
+                               size_t orig_base, const uint32_t* __restrict__ slot, const uint32_t* __restrict__ local,
+                               size_t total, unsigned cx, unsigned cy, double spacing, double lx, double ly, double lz,
+                               double v0x, double v0y, double v0z) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
-    if (slot[t + 1] == slot[t]) return;  // rejected lattice point
+    if (local[t + 1] == local[t]) return;  // rejected lattice point (or another rank's)
     double p[3];
     lattice_point(t, cx, cy, spacing, lx, ly, lz, p);
-    size_t o = offset + slot[t];
+    size_t o = offset + local[t];
     x[o] = p[0]; y[o] = p[1]; z[o] = p[2];
     vx[o] = v0x; vy[o] = v0y; vz[o] = v0z;
-    orig[o] = (uint32_t)o;
+    orig[o] = (uint32_t)(orig_base + slot[t]);
+}
+
+// slab mode set_particles: keep the caller's particles whose cell plane this rank owns
+__global__ void k_own_flags(const double* __restrict__ aos_pos, size_t n, double oz, double ihz, int nz, int z0, int z1,
+                            uint32_t* __restrict__ mine) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) { mine[i] = 0; return; }
+    const int ck = cell_coord(aos_pos[3 * i + 2], oz, ihz, nz);
+    mine[i] = (ck >= z0 && ck < z1) ? 1u : 0u;
+}
+
+__global__ void k_compact_aos3(const double* __restrict__ aos, const uint32_t* __restrict__ local, size_t n,
+                               double* __restrict__ x, double* __restrict__ y, double* __restrict__ z,
+                               uint32_t* __restrict__ orig, size_t id_base) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || local[i + 1] == local[i]) return;
+    const size_t o = local[i];
+    x[o] = aos[3 * i]; y[o] = aos[3 * i + 1]; z[o] = aos[3 * i + 2];
+    if (orig) orig[o] = (uint32_t)(id_base + i);
+}
+
+// local (compact) download: positions/velocities in the sorted order plus their original indices
+__global__ void k_soa_to_aos3(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                              double* __restrict__ aos, size_t n) {
+    size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    aos[3 * s] = x[s]; aos[3 * s + 1] = y[s]; aos[3 * s + 2] = z[s];
+}
+
+__global__ void k_u32_to_u64(const uint32_t* __restrict__ in, uint64_t* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+
+__global__ void k_u64_to_u32(const uint64_t* __restrict__ in, uint32_t* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)in[i];
 }
 
 // ================================================================================================ host side
-static AttrPtrs attr_ptrs(jetcu_hybrid* h, int which) {
+static AttrPtrs attr_ptrs(jetcu_hybrid* h, int which, size_t offset = 0) {
     AttrPtrs a;
-    for (int q = 0; q < NATTR; ++q) a.p[q] = h->attr[which][q];
+    for (int q = 0; q < NATTR; ++q) a.p[q] = h->attr[which][q] ? h->attr[which][q] + offset : nullptr;
     return a;
 }
+// the owned particles (everything on a single GPU; the middle block of the sorted array in slab mode)
+static AttrPtrs owned_ptrs(jetcu_hybrid* h) { return attr_ptrs(h, h->cur, h->base); }
 
-static int hyb_reserve(jetcu_hybrid* h, uint64_t n) {
+// Makes room for `need` particles per buffer; the owned block [base, base + np) of the current buffer survives and
+// moves to offset 0.
+static int hyb_reserve(jetcu_hybrid* h, uint64_t need) {
     jetcu_ctx* ctx = h->ctx;
-    if (n <= h->cap) return JETCU_OK;
-    uint64_t cap = n + n / 16 + 1024;
+    if (need <= h->cap) return JETCU_OK;
+    uint64_t cap = need + need / 8 + 1024;
     for (int b = 0; b < 2; ++b) {
         for (int q = 0; q < h->nattr; ++q) {
             double* np_ = nullptr;
             JC_TRY(jc_alloc(ctx, &np_, cap));
-            if (b == h->cur && h->np > 0) JC_TRY(jc_d2d(ctx, np_, h->attr[b][q], h->np));
+            if (b == h->cur && h->np > 0) JC_TRY(jc_d2d(ctx, np_, h->attr[b][q] + h->base, h->np));
             if (q >= 6) JC_TRY(jc_zero(ctx, np_ + h->np, cap - h->np));
             jc_free(ctx, h->attr[b][q]);
             h->attr[b][q] = np_;
         }
         uint32_t* no = nullptr;
         JC_TRY(jc_alloc(ctx, &no, cap));
-        if (b == h->cur && h->np > 0) JC_TRY(jc_d2d(ctx, no, h->orig[b], h->np));
+        if (b == h->cur && h->np > 0) JC_TRY(jc_d2d(ctx, no, h->orig[b] + h->base, h->np));
         jc_free(ctx, h->orig[b]);
         h->orig[b] = no;
     }
@@ -825,27 +929,120 @@ static int hyb_reserve(jetcu_hybrid* h, uint64_t n) {
     JC_TRY(jc_alloc(ctx, &t, cap)); h->rank = t;
     JC_TRY(jc_alloc(ctx, &t, cap)); h->perm = t;
     h->cap = cap;
+    h->base = 0;
+    h->nsorted = h->np;
+    h->binned = false;
     return JETCU_OK;
 }
 
+// Slab mode, first half of the binning: copies every owned particle to the other ranks whose extended slab holds its
+// (new) cell plane — migration and ghost refresh in one exchange — and appends what the other ranks sent to the owned
+// block.  *ntot = owned + received.
+static int hyb_slab_exchange(jetcu_hybrid* h, uint64_t* ntot) {
+    jetcu_ctx* ctx = h->ctx;
+    const int G = h->world, T = h->nz / G;
+    const jetcu_grid& gg = h->P.grid;
+    const size_t np = h->np;
+    uint32_t* d_cnt = nullptr;   // [G] counts, [G] offsets, [G] fill cursors
+    JC_TRY(jc_alloc(ctx, &d_cnt, 3 * (size_t)G));
+    JC_TRY(jc_zero(ctx, d_cnt, 3 * (size_t)G));
+    AttrPtrs own = owned_ptrs(h);
+    uint32_t* orig = h->orig[h->cur] + h->base;
+    if (np) JC_LAUNCH(ctx, k_slab_route<false>, jc_blocks(np, 256), 256, 0, own.p[2], np, gg.oz, 1.0 / gg.hz, h->nz, T, G, h->me,
+                      d_cnt, nullptr, nullptr);
+    uint32_t cnt32[64] = {};
+    JC_TRY(jc_d2h(ctx, cnt32, d_cnt, (size_t)G));
+    JC_TRY(jc_sync(ctx));
+    uint64_t mine[64] = {}, all[64 * 64];
+    for (int q = 0; q < G; ++q) mine[q] = cnt32[q];
+    JC_TRY(comm_allgather_u64_host(ctx, mine, (size_t)G, all));
+    size_t send_off[65] = {}, recv_off[65] = {};
+    uint32_t off32[64] = {};
+    for (int q = 0; q < G; ++q) {
+        send_off[q + 1] = send_off[q] + mine[q];
+        recv_off[q + 1] = recv_off[q] + all[(size_t)q * G + h->me];
+        off32[q] = (uint32_t)send_off[q];
+    }
+    const size_t nsend = send_off[G], nrecv = recv_off[G];
+    const size_t rec = (size_t)h->nattr + 1;  // doubles per particle in a message
+    uint32_t* d_list = nullptr;
+    double *sendbuf = nullptr, *recvbuf = nullptr;
+    int rc = JETCU_OK;
+#define STEP(x) if (rc == JETCU_OK) rc = (x)
+    STEP(jc_alloc(ctx, &d_list, nsend)); STEP(jc_alloc(ctx, &sendbuf, nsend * rec)); STEP(jc_alloc(ctx, &recvbuf, nrecv * rec));
+    if (rc == JETCU_OK && nsend) {
+        STEP(jc_h2d(ctx, d_cnt + G, off32, (size_t)G));
+        if (rc == JETCU_OK) {
+            k_slab_route<true><<<jc_blocks(np, 256), 256, 0, ctx->stream>>>(own.p[2], np, gg.oz, 1.0 / gg.hz, h->nz, T, G, h->me,
+                                                                           d_cnt + 2 * G, d_cnt + G, d_list);
+            ctx->launches++;
+        }
+        for (int q = 0; q < G && rc == JETCU_OK; ++q) {
+            if (!mine[q]) continue;
+            k_slab_pack<<<jc_blocks(mine[q], 256), 256, 0, ctx->stream>>>(own, orig, d_list + send_off[q], h->nattr, (size_t)mine[q],
+                                                                         sendbuf + send_off[q] * rec);
+            ctx->launches++;
+        }
+    }
+    void *sp[64], *rp[64];
+    size_t sb[64], rb[64];
+    for (int q = 0; q < G; ++q) {
+        sp[q] = sendbuf + send_off[q] * rec; sb[q] = (size_t)mine[q] * rec * sizeof(double);
+        rp[q] = recvbuf + recv_off[q] * rec; rb[q] = (size_t)(recv_off[q + 1] - recv_off[q]) * rec * sizeof(double);
+    }
+    STEP(comm_exchange(ctx, sp, sb, rp, rb));
+    STEP(hyb_reserve(h, h->base + np + nrecv));  // may move the owned block to offset 0
+    if (rc == JETCU_OK) {
+        AttrPtrs dst = owned_ptrs(h);
+        uint32_t* dorig = h->orig[h->cur] + h->base;
+        for (int q = 0; q < G; ++q) {
+            const size_t c = recv_off[q + 1] - recv_off[q];
+            if (!c) continue;
+            k_slab_unpack<<<jc_blocks(c, 256), 256, 0, ctx->stream>>>(recvbuf + recv_off[q] * rec, h->nattr, c, dst, dorig,
+                                                                     np + recv_off[q]);
+            ctx->launches++;
+        }
+    }
+#undef STEP
+    jc_free(ctx, d_list); jc_free(ctx, sendbuf); jc_free(ctx, recvbuf); jc_free(ctx, d_cnt);
+    *ntot = np + nrecv;
+    return rc;
+}
+
 // Counting sort of the particles by owning cell; afterwards cell_start[c]..cell_start[c+1] is cell c's range.
+// Slab mode: preceded by the migration / ghost exchange; the sorted array is [ghost-lo | owned | ghost-hi | dead].
 static int hyb_bin(jetcu_hybrid* h) {
     jetcu_ctx* ctx = h->ctx;
     if (h->binned) return JETCU_OK;
     GridD g = gridd(h);
-    size_t np = h->np;
-    JC_TRY(jc_zero(ctx, h->cell_start, h->nc + 1));
-    if (np > 0) {
-        JC_LAUNCH(ctx, k_cell_count, jc_blocks(np, 256), 256, 0, h->attr[h->cur][0], h->attr[h->cur][1], h->attr[h->cur][2],
-                  np, g, h->cell_of, h->rank, h->cell_start);
+    const bool slab = h->world > 1;
+    uint64_t ntot = h->np;
+    if (slab) JC_TRY(hyb_slab_exchange(h, &ntot));
+    const int e0 = slab ? max(h->z0 - SLAB_GHOST, 0) : 0, e1 = slab ? min(h->z1 + SLAB_GHOST, h->nz) : h->nz;
+    JC_TRY(jc_zero(ctx, h->cell_start, h->nc + 2));
+    if (ntot > 0) {
+        AttrPtrs src = owned_ptrs(h);
+        JC_LAUNCH(ctx, k_cell_count, jc_blocks(ntot, 256), 256, 0, src.p[0], src.p[1], src.p[2], (size_t)ntot, g, e0, e1,
+                  h->cell_of, h->rank, h->cell_start);
     }
-    JC_TRY(scan_exclusive_u32(ctx, h->cell_start, h->cell_start, h->nc + 1));
-    if (np > 0) {
-        JC_LAUNCH(ctx, k_scatter_perm, jc_blocks(np, 256), 256, 0, h->cell_of, h->rank, h->cell_start, h->perm, np);
-        JC_LAUNCH(ctx, k_sort_cells, jc_blocks(h->nc, 128), 128, 0, h->cell_start, h->orig[h->cur], h->perm, h->nc);
-        JC_LAUNCH(ctx, k_gather_attrs, jc_blocks(np, 256), 256, 0, attr_ptrs(h, h->cur), attr_ptrs(h, 1 - h->cur),
-                  h->orig[h->cur], h->orig[1 - h->cur], h->perm, h->nattr, np);
+    JC_TRY(scan_exclusive_u32(ctx, h->cell_start, h->cell_start, h->nc + 2));
+    if (ntot > 0) {
+        JC_LAUNCH(ctx, k_scatter_perm, jc_blocks(ntot, 256), 256, 0, h->cell_of, h->rank, h->cell_start, h->perm, (size_t)ntot);
+        JC_LAUNCH(ctx, k_sort_cells, jc_blocks(h->nc, 128), 128, 0, h->cell_start, h->orig[h->cur] + h->base, h->perm, h->nc);
+        JC_LAUNCH(ctx, k_gather_attrs, jc_blocks(ntot, 256), 256, 0, owned_ptrs(h), attr_ptrs(h, 1 - h->cur),
+                  h->orig[h->cur] + h->base, h->orig[1 - h->cur], h->perm, h->nattr, (size_t)ntot);
         h->cur = 1 - h->cur;
+    }
+    if (slab) {
+        const size_t nxy = (size_t)h->nx * h->ny;
+        uint32_t marks[3] = {0, 0, 0};
+        JC_TRY(jc_d2h(ctx, &marks[0], h->cell_start + (size_t)h->z0 * nxy, 1));
+        JC_TRY(jc_d2h(ctx, &marks[1], h->cell_start + (size_t)h->z1 * nxy, 1));
+        JC_TRY(jc_d2h(ctx, &marks[2], h->cell_start + h->nc, 1));
+        JC_TRY(jc_sync(ctx));
+        h->base = marks[0]; h->np = marks[1] - marks[0]; h->nsorted = marks[2];
+    } else {
+        h->base = 0; h->nsorted = h->np;
     }
     h->binned = true;
     return JETCU_OK;
@@ -914,6 +1111,17 @@ int jetcu_hybrid_create(jetcu_ctx* ctx, const jetcu_hybrid_params* p, jetcu_hybr
     h->nw = (size_t)h->nx * h->ny * (h->nz + 1);
     h->nc = (size_t)h->nx * h->ny * h->nz;
     h->nattr = (p->mode == JETCU_APIC) ? NATTR : 6;
+    h->world = jc_comm_world(ctx); h->me = jc_comm_rank(ctx);
+    h->z0 = 0; h->z1 = h->nz;
+    if (h->world > 1) {
+        if (h->world > 64 || h->nz % (2 * h->world) != 0 || h->nz / h->world < 2 * SLAB_GHOST) {
+            int rc0 = jetcu_fail(ctx, JETCU_ERR_INVALID_ARG, "z-slab mode needs nz (%d) to be a multiple of 2 x %d ranks with "
+                                 "at least %d planes per rank", h->nz, h->world, 2 * SLAB_GHOST);
+            delete h;
+            return rc0;
+        }
+        h->z0 = h->me * (h->nz / h->world); h->z1 = (h->me + 1) * (h->nz / h->world);
+    }
     size_t nmax = h->nu > h->nv ? h->nu : h->nv;
     if (h->nw > nmax) nmax = h->nw;
     int rc = JETCU_OK;
@@ -935,8 +1143,8 @@ int jetcu_hybrid_create(jetcu_ctx* ctx, const jetcu_hybrid_params* p, jetcu_hybr
         STEP(jc_alloc(ctx, &h->ud, h->nu)); STEP(jc_alloc(ctx, &h->vd, h->nv)); STEP(jc_alloc(ctx, &h->wd, h->nw));
         STEP(jc_zero(ctx, h->ud, h->nu)); STEP(jc_zero(ctx, h->vd, h->nv)); STEP(jc_zero(ctx, h->wd, h->nw));
     }
-    STEP(jc_alloc(ctx, &h->cell_start, h->nc + 1));
-    STEP(jc_zero(ctx, h->cell_start, h->nc + 1));
+    STEP(jc_alloc(ctx, &h->cell_start, h->nc + 2));  // + the trash bin of slab mode + the end marker
+    STEP(jc_zero(ctx, h->cell_start, h->nc + 2));
     if (rc == JETCU_OK) {
         // signedDistanceField is created with kMaxD (src/jet/pic_solver3.cpp:29-30)
         k_fill_f64<<<jc_blocks(h->nc, 256), 256, 0, ctx->stream>>>(h->sdf, DBL_MAX, h->nc);
@@ -975,40 +1183,83 @@ int jetcu_hybrid_destroy(jetcu_hybrid* h) {
     return JETCU_OK;
 }
 
+// Uploads n AoS particles; on a single GPU all of them, in slab mode (own_only) those whose cell plane this rank owns.
+// ids == nullptr: original index = position in the caller's array (+ id_base).
+static int hyb_upload(jetcu_hybrid* h, uint64_t n, const double* positions, const double* velocities, const uint64_t* ids,
+                      bool own_only) {
+    jetcu_ctx* ctx = h->ctx;
+    const jetcu_grid& gg = h->P.grid;
+    h->np = 0; h->base = 0; h->nsorted = 0;
+    h->binned = false;
+    if (n == 0) return JETCU_OK;
+    double* stage = nullptr;
+    uint32_t* local = nullptr;
+    uint64_t* dids = nullptr;
+    int rc = jc_alloc(ctx, &stage, 3 * n);
+#define STEP(x) if (rc == JETCU_OK) rc = (x)
+    STEP(jc_alloc(ctx, &local, n + 1));
+    STEP(jc_h2d(ctx, stage, positions, 3 * n));
+    uint64_t keep = n;
+    if (rc == JETCU_OK) {
+        // own_only: flag by cell plane; otherwise every particle is kept (flag 1 for i < n)
+        const int z0 = own_only ? h->z0 : 0, z1 = own_only ? h->z1 : h->nz;
+        k_own_flags<<<jc_blocks(n + 1, 256), 256, 0, ctx->stream>>>(stage, (size_t)n, gg.oz, 1.0 / gg.hz, h->nz, z0, z1, local);
+        ctx->launches++;
+        rc = scan_exclusive_u32(ctx, local, local, n + 1);
+        uint32_t k32 = 0;
+        STEP(jc_d2h(ctx, &k32, local + n, 1));
+        STEP(jc_sync(ctx));
+        keep = k32;
+    }
+    STEP(hyb_reserve(h, keep));
+    const int c = h->cur;
+    if (rc == JETCU_OK && keep > 0) {
+        k_compact_aos3<<<jc_blocks(n, 256), 256, 0, ctx->stream>>>(stage, local, (size_t)n, h->attr[c][0], h->attr[c][1],
+                                                                  h->attr[c][2], ids ? nullptr : h->orig[c], 0);
+        ctx->launches++;
+        if (velocities) {
+            STEP(jc_h2d(ctx, stage, velocities, 3 * n));
+            if (rc == JETCU_OK) {
+                k_compact_aos3<<<jc_blocks(n, 256), 256, 0, ctx->stream>>>(stage, local, (size_t)n, h->attr[c][3], h->attr[c][4],
+                                                                          h->attr[c][5], nullptr, 0);
+                ctx->launches++;
+            }
+        } else {
+            for (int q = 3; q < 6 && rc == JETCU_OK; ++q) rc = jc_zero(ctx, h->attr[c][q], keep);
+        }
+        for (int q = 6; q < h->nattr && rc == JETCU_OK; ++q) rc = jc_zero(ctx, h->attr[c][q], keep);
+        if (ids) {  // caller-supplied original indices (every particle kept: own_only is false on this path)
+            STEP(jc_alloc(ctx, &dids, n));
+            STEP(jc_h2d(ctx, dids, ids, n));
+            if (rc == JETCU_OK) {
+                k_u64_to_u32<<<jc_blocks(n, 256), 256, 0, ctx->stream>>>(dids, h->orig[c], (size_t)n);
+                ctx->launches++;
+            }
+        }
+    }
+    if (rc == JETCU_OK) { h->np = keep; h->nsorted = keep; rc = jc_sync(ctx); }
+#undef STEP
+    jc_free(ctx, stage); jc_free(ctx, local); jc_free(ctx, dids);
+    return rc;
+}
+
 int jetcu_hybrid_set_particles(jetcu_hybrid* h, uint64_t n, const double* positions, const double* velocities) {
     HYB_ENTER(h);
     JC_ARG(ctx, n == 0 || positions != nullptr);
     JC_ARG(ctx, n < (1ull << 32) - 1);
-    h->np = 0;
-    JC_TRY(hyb_reserve(h, n));
-    h->np = n;
-    h->binned = false;
-    if (n == 0) return JETCU_OK;
-    double* stage = nullptr;
-    JC_TRY(jc_alloc(ctx, &stage, 3 * n));
-    int rc = jc_h2d(ctx, stage, positions, 3 * n);
-    int c = h->cur;
-    if (rc == JETCU_OK) {
-        k_aos_to_soa3<<<jc_blocks(n, 256), 256, 0, ctx->stream>>>(stage, h->attr[c][0], h->attr[c][1], h->attr[c][2], n, 0);
-        ctx->launches++;
-    }
-    if (velocities) {
-        if (rc == JETCU_OK) rc = jc_h2d(ctx, stage, velocities, 3 * n);
-        if (rc == JETCU_OK) {
-            k_aos_to_soa3<<<jc_blocks(n, 256), 256, 0, ctx->stream>>>(stage, h->attr[c][3], h->attr[c][4], h->attr[c][5], n, 0);
-            ctx->launches++;
-        }
-    } else {
-        for (int q = 3; q < 6 && rc == JETCU_OK; ++q) rc = jc_zero(ctx, h->attr[c][q], n);
-    }
-    for (int q = 6; q < h->nattr && rc == JETCU_OK; ++q) rc = jc_zero(ctx, h->attr[c][q], n);
-    if (rc == JETCU_OK) {
-        k_iota_u32<<<jc_blocks(n, 256), 256, 0, ctx->stream>>>(h->orig[c], 0, n);
-        ctx->launches++;
-        rc = jc_sync(ctx);
-    }
-    jc_free(ctx, stage);
-    return rc;
+    JC_TRY(hyb_upload(h, n, positions, velocities, nullptr, h->world > 1));
+    h->nglobal = n;
+    return JETCU_OK;
+}
+
+int jetcu_hybrid_set_local_particles(jetcu_hybrid* h, uint64_t n_local, const uint64_t* ids, const double* positions,
+                                     const double* velocities, uint64_t n_global) {
+    HYB_ENTER(h);
+    JC_ARG(ctx, n_local == 0 || (positions != nullptr && ids != nullptr));
+    JC_ARG(ctx, n_global < (1ull << 32) - 1 && n_local <= n_global);
+    JC_TRY(hyb_upload(h, n_local, positions, velocities, ids, false));
+    h->nglobal = n_global;
+    return JETCU_OK;
 }
 
 int jetcu_hybrid_emit_box(jetcu_hybrid* h, const double lower[3], const double upper[3], double spacing,
@@ -1042,52 +1293,69 @@ int jetcu_hybrid_emit_box(jetcu_hybrid* h, const double lower[3], const double u
         cnt[a] = c;
     }
     uint64_t total = (uint64_t)cnt[0] * cnt[1] * cnt[2];
-    JC_ARG(ctx, h->np + total < (1ull << 32) - 2);
-    uint64_t old = h->np, accepted = 0;
+    JC_ARG(ctx, h->nglobal + total < (1ull << 32) - 2);
+    const bool slab = h->world > 1;
+    uint64_t accepted = 0, accepted_here = 0;
     if (total > 0) {
-        uint32_t* slot = nullptr;
+        uint32_t *slot = nullptr, *mine = nullptr;
         JC_TRY(jc_alloc(ctx, &slot, total + 1));
         int rc = JETCU_OK;
-        k_emit_flags<<<jc_blocks(total + 1, 256), 256, 0, ctx->stream>>>(slot, (size_t)total, cnt[0], cnt[1], spacing, lo[0], lo[1],
-                                                                          lo[2], bx);
-        ctx->launches++;
-        rc = scan_exclusive_u32(ctx, slot, slot, total + 1);
-        uint32_t n_acc = 0;
+        if (slab) rc = jc_alloc(ctx, &mine, total + 1);
+        if (rc == JETCU_OK) {
+            k_emit_flags<<<jc_blocks(total + 1, 256), 256, 0, ctx->stream>>>(slot, mine, (size_t)total, cnt[0], cnt[1], spacing, lo[0],
+                                                                              lo[1], lo[2], bx, g.oz, 1.0 / g.hz, h->nz, h->z0, h->z1);
+            ctx->launches++;
+            rc = scan_exclusive_u32(ctx, slot, slot, total + 1);
+        }
+        if (rc == JETCU_OK && slab) rc = scan_exclusive_u32(ctx, mine, mine, total + 1);
+        uint32_t n_acc = 0, n_mine = 0;
         if (rc == JETCU_OK) rc = jc_d2h(ctx, &n_acc, slot + total, 1);
+        if (rc == JETCU_OK && slab) rc = jc_d2h(ctx, &n_mine, mine + total, 1);
         if (rc == JETCU_OK) rc = jc_sync(ctx);
         accepted = n_acc;
-        if (rc == JETCU_OK) rc = hyb_reserve(h, old + accepted);
-        if (rc == JETCU_OK && accepted > 0) {
+        accepted_here = slab ? n_mine : n_acc;
+        if (rc == JETCU_OK) rc = hyb_reserve(h, h->base + h->np + accepted_here);
+        if (rc == JETCU_OK && accepted_here > 0) {
             int c = h->cur;
             double z0[3] = {0, 0, 0};
             const double* vv = v0 ? v0 : z0;
+            const size_t at = h->base + h->np;
             k_emit_lattice<<<jc_blocks(total, 256), 256, 0, ctx->stream>>>(
-                h->attr[c][0], h->attr[c][1], h->attr[c][2], h->attr[c][3], h->attr[c][4], h->attr[c][5], h->orig[c],
-                (size_t)old, slot, (size_t)total, cnt[0], cnt[1], spacing, lo[0], lo[1], lo[2], vv[0], vv[1], vv[2]);
+                h->attr[c][0], h->attr[c][1], h->attr[c][2], h->attr[c][3], h->attr[c][4], h->attr[c][5], h->orig[c], at,
+                (size_t)h->nglobal, slot, slab ? mine : slot, (size_t)total, cnt[0], cnt[1], spacing, lo[0], lo[1], lo[2], vv[0],
+                vv[1], vv[2]);
             ctx->launches++;
-            for (int q = 6; q < h->nattr && rc == JETCU_OK; ++q) rc = jc_zero(ctx, h->attr[c][q] + old, accepted);
+            for (int q = 6; q < h->nattr && rc == JETCU_OK; ++q) rc = jc_zero(ctx, h->attr[c][q] + at, accepted_here);
         }
-        jc_free(ctx, slot);
+        jc_free(ctx, slot); jc_free(ctx, mine);
         if (rc != JETCU_OK) return rc;
     }
-    h->np = old + accepted;
+    h->np += accepted_here;
+    h->nglobal += accepted;
+    h->nsorted = h->np;  // ghosts (if any) are stale now; the next binning rebuilds them
     h->binned = false;
     if (n_emitted) *n_emitted = accepted;
     return jc_sync(ctx);
 }
 
-uint64_t jetcu_hybrid_num_particles(const jetcu_hybrid* h) { return h ? h->np : 0; }
+uint64_t jetcu_hybrid_num_particles(const jetcu_hybrid* h) { return h ? h->nglobal : 0; }
+uint64_t jetcu_hybrid_num_local_particles(const jetcu_hybrid* h) { return h ? h->np : 0; }
 
 static int download_vec3(jetcu_hybrid* h, int a0, double* host) {
     jetcu_ctx* ctx = h->ctx;
-    if (!host || h->np == 0) return JETCU_OK;
+    if (!host || h->nglobal == 0) return JETCU_OK;
     double* stage = nullptr;
-    JC_TRY(jc_alloc(ctx, &stage, 3 * h->np));
+    JC_TRY(jc_alloc(ctx, &stage, 3 * h->nglobal));
+    // slab mode: entries of particles owned by other ranks stay zero, so summing the ranks' arrays gives the whole set
+    if (h->world > 1) JC_TRY(jc_zero(ctx, stage, 3 * h->nglobal));
     int c = h->cur;
-    k_soa_to_aos3_orig<<<jc_blocks(h->np, 256), 256, 0, ctx->stream>>>(h->attr[c][a0], h->attr[c][a0 + 1], h->attr[c][a0 + 2],
-                                                                      h->orig[c], stage, h->np);
-    ctx->launches++;
-    int rc = jc_d2h(ctx, host, stage, 3 * h->np);
+    if (h->np) {
+        k_soa_to_aos3_orig<<<jc_blocks(h->np, 256), 256, 0, ctx->stream>>>(h->attr[c][a0] + h->base, h->attr[c][a0 + 1] + h->base,
+                                                                          h->attr[c][a0 + 2] + h->base, h->orig[c] + h->base, stage,
+                                                                          h->np);
+        ctx->launches++;
+    }
+    int rc = jc_d2h(ctx, host, stage, 3 * h->nglobal);
     if (rc == JETCU_OK) rc = jc_sync(ctx);
     jc_free(ctx, stage);
     return rc;
@@ -1097,6 +1365,34 @@ int jetcu_hybrid_get_particles(jetcu_hybrid* h, double* positions, double* veloc
     HYB_ENTER(h);
     JC_TRY(download_vec3(h, 0, positions));
     return download_vec3(h, 3, velocities);
+}
+
+int jetcu_hybrid_get_local_particles(jetcu_hybrid* h, uint64_t* ids, double* positions, double* velocities) {
+    HYB_ENTER(h);
+    const size_t np = h->np;
+    if (np == 0) return JETCU_OK;
+    const int c = h->cur;
+    double* stage = nullptr;
+    JC_TRY(jc_alloc(ctx, &stage, 3 * np));
+    int rc = JETCU_OK;
+    for (int part = 0; part < 2 && rc == JETCU_OK; ++part) {
+        double* host = part == 0 ? positions : velocities;
+        if (!host) continue;
+        const int a0 = 3 * part;
+        k_soa_to_aos3<<<jc_blocks(np, 256), 256, 0, ctx->stream>>>(h->attr[c][a0] + h->base, h->attr[c][a0 + 1] + h->base,
+                                                                  h->attr[c][a0 + 2] + h->base, stage, np);
+        ctx->launches++;
+        rc = jc_d2h(ctx, host, stage, 3 * np);
+    }
+    if (rc == JETCU_OK && ids) {
+        uint64_t* wide = reinterpret_cast<uint64_t*>(stage);
+        k_u32_to_u64<<<jc_blocks(np, 256), 256, 0, ctx->stream>>>(h->orig[c] + h->base, wide, np);
+        ctx->launches++;
+        rc = jc_d2h(ctx, ids, wide, np);
+    }
+    if (rc == JETCU_OK) rc = jc_sync(ctx);
+    jc_free(ctx, stage);
+    return rc;
 }
 
 int jetcu_hybrid_get_affine(jetcu_hybrid* h, double* cx, double* cy, double* cz) {
@@ -1184,12 +1480,23 @@ int jetcu_hybrid_apply_boundary_condition(jetcu_hybrid* h) {
     return hyb_zero_walls(h);
 }
 
+// Slab mode: this rank's planes of a face field become valid on every rank.  Cell-plane-partitioned part by an
+// in-place all-gather; the w-type field has one more plane (k = nz), owned by the last rank and broadcast.
+static int hyb_gather_planes(jetcu_hybrid* h, void* field, size_t plane_bytes, bool extra_top_plane) {
+    jetcu_ctx* ctx = h->ctx;
+    if (h->world <= 1) return JETCU_OK;
+    JC_TRY(comm_allgather_inplace(ctx, field, (size_t)(h->z1 - h->z0) * plane_bytes));
+    if (extra_top_plane) JC_TRY(comm_bcast(ctx, static_cast<char*>(field) + (size_t)h->nz * plane_bytes, plane_bytes, h->world - 1));
+    return JETCU_OK;
+}
+
 int jetcu_hybrid_transfer_particles_to_grids(jetcu_hybrid* h) {
     HYB_ENTER(h);
     JC_TRY(hyb_bin(h));
     GridD g = gridd(h);
-    AttrPtrs a = attr_ptrs(h, h->cur);
+    AttrPtrs a = attr_ptrs(h, h->cur);  // whole sorted array: cell_start indexes it from 0 (ghosts included)
     const bool apic = h->P.mode == JETCU_APIC;
+    const bool slab = h->world > 1;
     int slot = jc_prof_begin(ctx, JETCU_PROF_P2G);
     // u, v, w double as the fixed-point value accumulators; weight sums and markers start from zero as well
     JC_TRY(jc_zero(ctx, h->u, h->nu)); JC_TRY(jc_zero(ctx, h->v, h->nv)); JC_TRY(jc_zero(ctx, h->w, h->nw));
@@ -1198,14 +1505,28 @@ int jetcu_hybrid_transfer_particles_to_grids(jetcu_hybrid* h) {
         JC_TRY(jc_zero(ctx, h->wsum[q], nf[q])); JC_TRY(jc_zero(ctx, h->wsum_lo[q], nf[q])); JC_TRY(jc_zero(ctx, h->sum_lo[q], nf[q]));
     }
     JC_TRY(jc_zero(ctx, h->um, h->nu)); JC_TRY(jc_zero(ctx, h->vm, h->nv)); JC_TRY(jc_zero(ctx, h->wm, h->nw));
-    if (h->np > 0) {
-        JC_LAUNCH(ctx, k_p2g_vmax_partial, 592, 256, 0, a, (size_t)h->np, apic ? 1 : 0, g.hx, g.hy, g.hz, ctx->d_partials);
-        JC_LAUNCH(ctx, k_p2g_scale_final, 1, 256, 0, ctx->d_partials, 592, h->p2g_scale);
+    const bool flip = h->P.mode == JETCU_FLIP;
+    // planes of each face field this rank finalises: all of them, or (slab mode) the ones it owns — their sums are
+    // complete because the ghost particles of the neighbouring planes were summed along (integer accumulators: the
+    // bits do not depend on which rank, tile or order added a contribution)
+    const size_t pu = (size_t)(h->nx + 1) * h->ny, pv = (size_t)h->nx * (h->ny + 1), pw = (size_t)h->nx * h->ny;
+    const size_t k0 = (size_t)h->z0, nk = (size_t)(h->z1 - h->z0);
+    const size_t nkw = nk + ((!slab || h->me == h->world - 1) ? 1 : 0);
+    if (h->nglobal > 0) {
+        JC_LAUNCH(ctx, k_p2g_vmax_partial, 592, 256, 0, a, (size_t)h->nsorted, apic ? 1 : 0, g.hx, g.hy, g.hz, ctx->d_partials);
+        if (slab) {  // the fixed-point scale must be the same on every rank
+            JC_LAUNCH(ctx, k_max_final, 1, CFL_BLOCK, 0, ctx->d_partials, 592, ctx->d_scalars + 8);
+            JC_TRY(comm_allreduce_max_f64(ctx, ctx->d_scalars + 8, 1));
+            JC_LAUNCH(ctx, k_p2g_scale_final, 1, 256, 0, ctx->d_scalars + 8, 1, h->p2g_scale);
+        } else {
+            JC_LAUNCH(ctx, k_p2g_scale_final, 1, 256, 0, ctx->d_partials, 592, h->p2g_scale);
+        }
         P2GAcc acc;
         acc.sum[0] = (unsigned long long*)h->u; acc.sum[1] = (unsigned long long*)h->v; acc.sum[2] = (unsigned long long*)h->w;
         for (int q = 0; q < 3; ++q) { acc.wsum[q] = h->wsum[q]; acc.wsum_lo[q] = h->wsum_lo[q]; acc.sum_lo[q] = h->sum_lo[q]; }
         acc.marker[0] = h->um; acc.marker[1] = h->vm; acc.marker[2] = h->wm;
-        dim3 grid((g.nx + TC - 1) / TC, (g.ny + TC - 1) / TC, (g.nz + TC - 1) / TC);
+        const int kb = slab ? max(h->z0 - SLAB_GHOST, 0) : 0, ke = slab ? min(h->z1 + SLAB_GHOST, h->nz) : h->nz;
+        dim3 grid((g.nx + TC - 1) / TC, (g.ny + TC - 1) / TC, (ke - kb + TC - 1) / TC);
         const size_t smem = (size_t)(TC + 1) * (TC + 2) * (TC + 2) * (24 * 4 + 3);
         static bool attr_set = false;
         if (!attr_set) {
@@ -1213,14 +1534,28 @@ int jetcu_hybrid_transfer_particles_to_grids(jetcu_hybrid* h) {
             JC_CUDA(ctx, cudaFuncSetAttribute(k_p2g_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
         }
-        if (apic) JC_LAUNCH(ctx, (k_p2g_scatter<true>), grid, P2G_THREADS, smem, g, h->cell_start, a, h->p2g_scale, acc);
-        else JC_LAUNCH(ctx, (k_p2g_scatter<false>), grid, P2G_THREADS, smem, g, h->cell_start, a, h->p2g_scale, acc);
-        const bool flip = h->P.mode == JETCU_FLIP;
-        JC_LAUNCH(ctx, k_p2g_normalise, jc_blocks(h->nu, 256), 256, 0, h->u, h->sum_lo[0], h->wsum[0], h->wsum_lo[0], h->p2g_scale, flip ? h->ud : nullptr, h->p2g_err, h->nu);
-        JC_LAUNCH(ctx, k_p2g_normalise, jc_blocks(h->nv, 256), 256, 0, h->v, h->sum_lo[1], h->wsum[1], h->wsum_lo[1], h->p2g_scale, flip ? h->vd : nullptr, h->p2g_err, h->nv);
-        JC_LAUNCH(ctx, k_p2g_normalise, jc_blocks(h->nw, 256), 256, 0, h->w, h->sum_lo[2], h->wsum[2], h->wsum_lo[2], h->p2g_scale, flip ? h->wd : nullptr, h->p2g_err, h->nw);
+        if (h->nsorted > 0) {
+            if (apic) JC_LAUNCH(ctx, (k_p2g_scatter<true>), grid, P2G_THREADS, smem, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
+            else JC_LAUNCH(ctx, (k_p2g_scatter<false>), grid, P2G_THREADS, smem, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
+        }
+        JC_LAUNCH(ctx, k_p2g_normalise, jc_blocks(nk * pu, 256), 256, 0, h->u + k0 * pu, h->sum_lo[0] + k0 * pu, h->wsum[0] + k0 * pu,
+                  h->wsum_lo[0] + k0 * pu, h->p2g_scale, flip ? h->ud + k0 * pu : nullptr, h->p2g_err, nk * pu);
+        JC_LAUNCH(ctx, k_p2g_normalise, jc_blocks(nk * pv, 256), 256, 0, h->v + k0 * pv, h->sum_lo[1] + k0 * pv, h->wsum[1] + k0 * pv,
+                  h->wsum_lo[1] + k0 * pv, h->p2g_scale, flip ? h->vd + k0 * pv : nullptr, h->p2g_err, nk * pv);
+        JC_LAUNCH(ctx, k_p2g_normalise, jc_blocks(nkw * pw, 256), 256, 0, h->w + k0 * pw, h->sum_lo[2] + k0 * pw, h->wsum[2] + k0 * pw,
+                  h->wsum_lo[2] + k0 * pw, h->p2g_scale, flip ? h->wd + k0 * pw : nullptr, h->p2g_err, nkw * pw);
     } else if (h->P.mode == JETCU_FLIP) {
         JC_TRY(jc_zero(ctx, h->ud, h->nu)); JC_TRY(jc_zero(ctx, h->vd, h->nv)); JC_TRY(jc_zero(ctx, h->wd, h->nw));
+    }
+    if (slab) {  // the grid stages that follow (extrapolation, boundary conditions, system build) run replicated
+        JC_TRY(hyb_gather_planes(h, h->u, pu * 8, false)); JC_TRY(hyb_gather_planes(h, h->v, pv * 8, false));
+        JC_TRY(hyb_gather_planes(h, h->w, pw * 8, true));
+        JC_TRY(hyb_gather_planes(h, h->um, pu, false)); JC_TRY(hyb_gather_planes(h, h->vm, pv, false));
+        JC_TRY(hyb_gather_planes(h, h->wm, pw, true));
+        if (flip) {
+            JC_TRY(hyb_gather_planes(h, h->ud, pu * 4, false)); JC_TRY(hyb_gather_planes(h, h->vd, pv * 4, false));
+            JC_TRY(hyb_gather_planes(h, h->wd, pw * 4, true));
+        }
     }
     jc_prof_end(ctx, slot, 6, h->np);
     return JETCU_OK;
@@ -1235,10 +1570,14 @@ int jetcu_hybrid_build_signed_distance_field(jetcu_hybrid* h) {
     double band = 2.0 * radius;
     // a particle in cell c+d lies at least (|d|-0.5)h from the centre of cell c along that axis
     int rx = (int)floor(band / g.hx + 0.5 + 1e-9), ry = (int)floor(band / g.hy + 0.5 + 1e-9), rz = (int)floor(band / g.hz + 0.5 + 1e-9);
-    dim3 grid((g.nx + 31) / 32, (g.ny + 3) / 4, g.nz);
+    if (h->world > 1 && rz > SLAB_GHOST)
+        return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED, "particle SDF band reaches %d planes; slab mode carries %d ghost planes", rz,
+                          SLAB_GHOST);
+    dim3 grid((g.nx + 31) / 32, (g.ny + 3) / 4, h->z1 - h->z0);  // this rank's planes (all of them on a single GPU)
     int c = h->cur;
     JC_LAUNCH(ctx, k_build_sdf, grid, dim3(32, 4), 0, g, h->cell_start, h->attr[c][0], h->attr[c][1], h->attr[c][2], radius,
-              band, rx, ry, rz, h->sdf);
+              band, rx, ry, rz, h->z0, h->sdf);
+    JC_TRY(hyb_gather_planes(h, h->sdf, (size_t)h->nx * h->ny * 8, false));
     // extrapolateIntoCollider (src/jet/grid_fluid_solver3.cpp:355-369) is the identity without a collider
     return JETCU_OK;
 }
@@ -1289,7 +1628,7 @@ int jetcu_hybrid_transfer_grids_to_particles(jetcu_hybrid* h) {
     HYB_ENTER(h);
     GridD g = gridd(h);
     size_t np = h->np;
-    AttrPtrs a = attr_ptrs(h, h->cur);
+    AttrPtrs a = owned_ptrs(h);
     if (h->P.mode == JETCU_FLIP) {
         JC_LAUNCH(ctx, k_flip_delta, jc_blocks(h->nu, 256), 256, 0, h->u, h->ud, h->nu);
         JC_LAUNCH(ctx, k_flip_delta, jc_blocks(h->nv, 256), 256, 0, h->v, h->vd, h->nv);
@@ -1311,7 +1650,8 @@ int jetcu_hybrid_move_particles(jetcu_hybrid* h, double dt) {
     double sub_dt = dt / nsub;
     if (h->np)
         JC_LAUNCH(ctx, k_move, jc_blocks(h->np, 128), 128, 0, g, h->u, h->v, h->w, sub_dt, nsub,
-                  h->P.closed_domain_boundary_flag, attr_ptrs(h, h->cur), (size_t)h->np);
+                  h->P.closed_domain_boundary_flag, owned_ptrs(h), (size_t)h->np);
+    h->nsorted = h->np;  // the ghost copies are stale from here on
     h->binned = false;
     return JETCU_OK;
 }

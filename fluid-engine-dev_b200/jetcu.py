@@ -279,6 +279,23 @@ class HybridApi:
         self._c("hybrid_get_particles", self.h, _p(pos), _p(vel))
         return pos, vel
 
+    def num_local_particles(self):
+        return int(self._c("hybrid_num_local_particles", self.h, raw=True))
+
+    def get_local_particles(self):
+        """This rank's own particles (slab mode; all of them on one GPU): ids, positions, velocities."""
+        n = self.num_local_particles()
+        ids = np.zeros(n, dtype=np.uint64)
+        pos = np.zeros((n, 3))
+        vel = np.zeros((n, 3))
+        self._c("hybrid_get_local_particles", self.h, _p(ids, PU64), _p(pos), _p(vel))
+        return ids, pos, vel
+
+    def set_local_particles(self, ids, pos, vel, n_global):
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        self._c("hybrid_set_local_particles", self.h, u64(ids.shape[0]), _p(ids, PU64), _p(c64(pos)), _p(c64(vel)),
+                u64(n_global))
+
     def get_affine(self):
         n = self.num_particles()
         cx, cy, cz = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3))
@@ -393,9 +410,10 @@ class Jetcu(LinearApi):
         self.lib.jetcu_stream.argtypes = [C.c_void_p]
         self.lib.jetcu_mg_num_levels.restype = u32
         self.lib.jetcu_mg_num_levels.argtypes = [u64, u64, u64, u32]
-        if hasattr(self.lib, "jetcu_hybrid_num_particles"):
-            self.lib.jetcu_hybrid_num_particles.restype = u64
-            self.lib.jetcu_hybrid_num_particles.argtypes = [C.c_void_p]
+        for name in ("jetcu_hybrid_num_particles", "jetcu_hybrid_num_local_particles"):
+            if hasattr(self.lib, name):
+                getattr(self.lib, name).restype = u64
+                getattr(self.lib, name).argtypes = [C.c_void_p]
         self.ctx = C.c_void_p()
         rc = self.lib.jetcu_ctx_create(int(device), C.byref(self.ctx))
         if rc != 0:
@@ -447,3 +465,39 @@ class Jetcu(LinearApi):
         h = C.c_void_p()
         self._call("hybrid_create", C.byref(params), C.byref(h))
         return HybridApi(self._call_raw, h, params)
+
+    # ------------------------------------------------------------------ z-slab communicator (include/jetcu.h)
+    def comm_unique_id(self):
+        """128-byte NCCL id; call on rank 0 and hand it to the other ranks (e.g. torch.distributed.broadcast)."""
+        buf = (C.c_uint8 * 128)()
+        self._call_raw("comm_unique_id", buf)
+        return bytes(buf)
+
+    def comm_init(self, world, rank, unique_id):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._call("comm_init", C.c_int(world), C.c_int(rank), buf)
+        self.world, self.rank = world, rank
+
+    def comm_init_torch(self):
+        """Joins the z-slab communicator of the running torch.distributed job (one rank per GPU)."""
+        import torch
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        if world == 1:
+            return
+        dev = torch.device("cuda", self.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(self.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        self.comm_init(world, rank, bytes(t.cpu().numpy().tobytes()))
+
+    def comm_stats(self):
+        m, b = u64(0), u64(0)
+        self._call("comm_stats", C.byref(m), C.byref(b))
+        return int(m.value), int(b.value)
+
+    def slab_range(self, nz, world, rank):
+        z0, z1 = u64(0), u64(0)
+        self._call_raw("slab_range", u64(nz), C.c_int(world), C.c_int(rank), C.byref(z0), C.byref(z1))
+        return int(z0.value), int(z1.value)

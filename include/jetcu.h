@@ -63,6 +63,35 @@ enum {
 int jetcu_profile_enable(jetcu_ctx* ctx, int on);   /* on != 0 also clears the accumulators */
 int jetcu_profile_get(jetcu_ctx* ctx, int kind, double* total_ms, uint64_t* launches, uint64_t* units);
 
+/* ------------------------------------------------------------------ multi-GPU (z-slabs over NCCL / NVLink)
+ * The reference has no domain decomposition (one process, one allocation: SURVEY.md §8e); this is the new part.
+ * One process per GPU, one ctx per process.  After jetcu_comm_init the SAME calls (jetcu_mgpcg_solve,
+ * jetcu_pressure_solve, jetcu_hybrid_*) run SPMD: every rank passes the same full-size grid arguments and receives
+ * the same full-size results, the MGPCG solve inside works on this rank's z-slab with one halo-plane exchange per
+ * smoother colour pass / matvec / transfer, slab-invariant dot products (every rank sees the same PCG scalars) and
+ * the coarse MG levels replicated; particles live on the rank that owns their cell plane and migrate each step.
+ * Results are bit-identical to the single-GPU run.  nz must be a multiple of 2*world with >= 4 planes per rank.
+ * The 128-byte NCCL id is created on rank 0 and handed to the other ranks out of band (torch.distributed, MPI ...). */
+#define JETCU_UNIQUE_ID_BYTES 128
+int jetcu_comm_unique_id(uint8_t id[JETCU_UNIQUE_ID_BYTES]);
+int jetcu_comm_init(jetcu_ctx* ctx, int world, int rank, const uint8_t id[JETCU_UNIQUE_ID_BYTES]);
+int jetcu_comm_destroy(jetcu_ctx* ctx);
+int jetcu_comm_world(const jetcu_ctx* ctx);
+int jetcu_comm_rank(const jetcu_ctx* ctx);
+/* messages / payload bytes this rank has sent since jetcu_comm_init (bench.py's halo accounting) */
+int jetcu_comm_stats(const jetcu_ctx* ctx, uint64_t* messages, uint64_t* bytes_sent);
+/* cell planes [z0, z1) of an nz-plane grid owned by `rank` (uniform slabs; nz % world must be 0) */
+int jetcu_slab_range(uint64_t nz, int world, int rank, uint64_t* z0, uint64_t* z1);
+/* Host-only views of the decomposition logic (no GPU needed; what the world_size-2 CPU tests drive):
+ * - the MG plan: levels [0, *dist_levels) are slab-distributed with this rank's planes [z0[l], z1[l]), coarser levels
+ *   are replicated (z0 = 0, z1 = nz >> l); fails if level 0 cannot be split (nz % (2*world) != 0 or < 4 planes/rank);
+ * - the particle routing rule: bit q set = a particle in `cell_plane` held by rank `me` is copied to rank q (q owns the
+ *   plane or keeps it as one of its JETCU_SLAB_GHOST_PLANES ghost planes). */
+#define JETCU_SLAB_GHOST_PLANES 2
+int jetcu_slab_plan(uint64_t nx, uint64_t ny, uint64_t nz, uint32_t levels, int world, int rank,
+                    uint32_t* dist_levels, uint64_t* z0, uint64_t* z1);
+uint64_t jetcu_slab_route_mask(int64_t cell_plane, uint64_t nz, int world, int me);
+
 /* ------------------------------------------------------------------ types */
 
 /* == jet::FdmMatrixRow3 (include/jet/fdm_linear_system3.h:18-30): 32-byte AoS row. */
@@ -234,9 +263,18 @@ int jetcu_hybrid_set_particles(jetcu_hybrid*, uint64_t n, const double* position
  * directly on the device, in the reference's k,j,i order.  Appends; returns the count via n_emitted. */
 int jetcu_hybrid_emit_box(jetcu_hybrid*, const double lower[3], const double upper[3], double spacing,
                           const double initial_velocity[3], uint64_t* n_emitted);
-uint64_t jetcu_hybrid_num_particles(const jetcu_hybrid*);
+uint64_t jetcu_hybrid_num_particles(const jetcu_hybrid*);        /* all ranks together in slab mode */
+uint64_t jetcu_hybrid_num_local_particles(const jetcu_hybrid*);  /* owned by this rank (== the above on one GPU) */
 /* Returned in the caller's ORIGINAL particle order (the device keeps particles cell-sorted). */
 int jetcu_hybrid_get_particles(jetcu_hybrid*, double* positions, double* velocities);
+/* Slab mode (jetcu_comm_init'ed ctx): jetcu_hybrid_set_particles takes the WHOLE particle set on every rank and keeps
+ * the particles whose cell plane the rank owns; jetcu_hybrid_get_particles fills the entries of the particles the rank
+ * owns and zeroes the others (summing the ranks' arrays gives the whole set).  The two calls below move only a rank's
+ * own particles: `ids` are the original indices (< n_global), positions / velocities AoS in the same order.  The
+ * particles handed to set_local may lie anywhere: the next step migrates them to the owner of their cell plane. */
+int jetcu_hybrid_get_local_particles(jetcu_hybrid*, uint64_t* ids, double* positions, double* velocities);
+int jetcu_hybrid_set_local_particles(jetcu_hybrid*, uint64_t n_local, const uint64_t* ids, const double* positions,
+                                     const double* velocities, uint64_t n_global);
 /* APIC affine vectors _cX,_cY,_cZ (src/jet/apic_solver3.h), original order; NULL entries skipped. */
 int jetcu_hybrid_get_affine(jetcu_hybrid*, double* cx, double* cy, double* cz);
 

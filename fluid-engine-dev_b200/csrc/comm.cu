@@ -77,25 +77,27 @@ struct JcComm {
 int jc_comm_world(const jetcu_ctx* ctx) { return (ctx && ctx->comm) ? ctx->comm->world : 1; }
 int jc_comm_rank(const jetcu_ctx* ctx) { return (ctx && ctx->comm) ? ctx->comm->rank : 0; }
 
-int comm_halo_planes(jetcu_ctx* ctx, void* base, size_t plane_bytes, int k0, int k1, int nz) {
+int comm_halo_planes(jetcu_ctx* ctx, void* base, size_t plane_bytes, int k0, int k1, int nz, int depth) {
     JcComm* c = ctx->comm;
     if (!c || c->world <= 1) return JETCU_OK;
+    JC_ARG(ctx, depth >= 1 && depth <= k1 - k0);
     NcclApi* api = nccl_api();
     char* p = static_cast<char*>(base);
     const bool down = k0 > 0 && c->rank > 0, up = k1 < nz && c->rank + 1 < c->world;
     if (!down && !up) return JETCU_OK;
+    const size_t bytes = (size_t)depth * plane_bytes;
     JC_NCCL(ctx, api->GroupStart());
     if (down) {
-        JC_NCCL(ctx, api->Send(p + (size_t)k0 * plane_bytes, plane_bytes, ncclInt8, c->rank - 1, c->comm, ctx->stream));
-        JC_NCCL(ctx, api->Recv(p + (size_t)(k0 - 1) * plane_bytes, plane_bytes, ncclInt8, c->rank - 1, c->comm, ctx->stream));
+        JC_NCCL(ctx, api->Send(p + (size_t)k0 * plane_bytes, bytes, ncclInt8, c->rank - 1, c->comm, ctx->stream));
+        JC_NCCL(ctx, api->Recv(p + (size_t)(k0 - depth) * plane_bytes, bytes, ncclInt8, c->rank - 1, c->comm, ctx->stream));
     }
     if (up) {
-        JC_NCCL(ctx, api->Send(p + (size_t)(k1 - 1) * plane_bytes, plane_bytes, ncclInt8, c->rank + 1, c->comm, ctx->stream));
-        JC_NCCL(ctx, api->Recv(p + (size_t)k1 * plane_bytes, plane_bytes, ncclInt8, c->rank + 1, c->comm, ctx->stream));
+        JC_NCCL(ctx, api->Send(p + (size_t)(k1 - depth) * plane_bytes, bytes, ncclInt8, c->rank + 1, c->comm, ctx->stream));
+        JC_NCCL(ctx, api->Recv(p + (size_t)k1 * plane_bytes, bytes, ncclInt8, c->rank + 1, c->comm, ctx->stream));
     }
     JC_NCCL(ctx, api->GroupEnd());
     c->messages += (down ? 1 : 0) + (up ? 1 : 0);
-    c->bytes_sent += ((down ? 1 : 0) + (up ? 1 : 0)) * plane_bytes;
+    c->bytes_sent += ((down ? 1 : 0) + (up ? 1 : 0)) * bytes;
     return JETCU_OK;
 }
 

@@ -42,9 +42,10 @@ struct jetcu_ctx {
 // ---- multi-GPU plumbing (comm.cu): NCCL over NVLink, one rank per GPU; all calls enqueue on ctx->stream ------------
 int jc_comm_world(const jetcu_ctx* ctx);
 int jc_comm_rank(const jetcu_ctx* ctx);
-// Arrays are full-size and globally indexed on every rank; this rank owns planes [k0, k1) of nz.  Sends plane k0 down /
-// plane k1-1 up and receives plane k0-1 / k1 from the neighbouring ranks (no-op at the domain ends).
-int comm_halo_planes(jetcu_ctx* ctx, void* base, size_t plane_bytes, int k0, int k1, int nz);
+// Arrays are full-size and globally indexed on every rank; this rank owns planes [k0, k1) of nz.  Sends its `depth`
+// lowest planes down / highest planes up and receives planes [k0-depth, k0) / [k1, k1+depth) from the neighbouring
+// ranks (no-op at the domain ends; depth must not exceed the slab thickness).
+int comm_halo_planes(jetcu_ctx* ctx, void* base, size_t plane_bytes, int k0, int k1, int nz, int depth = 1);
 // In-place all-gather: rank r contributes bytes [r*bytes_per_rank, (r+1)*bytes_per_rank) of `base`.
 int comm_allgather_inplace(jetcu_ctx* ctx, void* base, size_t bytes_per_rank);
 int comm_allreduce_max_f64(jetcu_ctx* ctx, double* d_values, size_t n);
@@ -183,6 +184,8 @@ struct Mat {
     const uint8_t* code = nullptr;  // packed form: per cell, 2 bits per +face (right | up << 2 | front << 4):
                                     // 0 no coupling, 1 weight == 1.0f, 2 fractional weight (read cr/cu/cf)
     double sx = 0, sy = 0, sz = 0;  // invH^2 per axis (packed form)
+    double c6 = 0;                  // packed form: the diagonal of a cell whose six faces are all fully open liquid-liquid
+                                    // couplings, ((((((0+sx)+sx)+sy)+sy)+sz)+sz) as buildSingleSystem accumulates it
     size_t stride_y = 0, stride_z = 0;  // nx, nx*ny (packed form; used on the rare fractional-weight path)
     bool packed = false;
 };

@@ -197,9 +197,12 @@ __global__ void __launch_bounds__(BX* BY) k_relax_colour_code(Mat A, const doubl
     const double xl = i > 0 ? x[c - 1] : 0.0, xr = i + 1 < nx ? x[c + 1] : 0.0;
     const double xd = j > 0 ? x[c - sy] : 0.0, xu = j + 1 < ny ? x[c + sy] : 0.0;
     const double xb = k > 0 ? x[c - sz] : 0.0, xf = k + 1 < nz ? x[c + sz] : 0.0;
-    double cl, cr, cd, cu, cb, cf;
-    if (six == 0x555u) {  // all six faces fully open: the bulk of the liquid
+    double cl, cr, cd, cu, cb, cf, center;
+    if (six == 0x555u) {  // all six faces fully open liquid-liquid couplings: the bulk of the liquid
         cl = cr = -A.sx; cd = cu = -A.sy; cb = cf = -A.sz;
+        // the diagonal of such a cell is a per-level constant (Mat::c6): not read, so that in the bulk whole sectors of
+        // the center plane (half of which belong to the other colour anyway) stay in DRAM
+        center = A.c6;
     } else if ((six & 0xaaau) == 0) {  // open / closed faces only
         cl = mask_coef(six, -A.sx); cr = mask_coef(six >> 2, -A.sx);
         cd = mask_coef(six >> 4, -A.sy); cu = mask_coef(six >> 6, -A.sy);
@@ -209,9 +212,10 @@ __global__ void __launch_bounds__(BX* BY) k_relax_colour_code(Mat A, const doubl
         cd = face_coef((six >> 4) & 3u, A.sy, A.cu, c - sy); cu = face_coef((six >> 6) & 3u, A.sy, A.cu, c);
         cb = face_coef((six >> 8) & 3u, A.sz, A.cf, c - sz); cf = face_coef((six >> 10) & 3u, A.sz, A.cf, c);
     }
+    if (six != 0x555u) center = __ldg(A.center + c);
     // absent neighbours carry coefficient 0.0 and value 0.0: the literal 0.0 terms of the reference
     const double r = cl * xl + cr * xr + cd * xd + cu * xu + cb * xb + cf * xf;
-    x[c] = (1.0 - w) * x[c] + w * (b[c] - r) / A.center[c];
+    x[c] = (1.0 - w) * x[c] + w * (b[c] - r) / center;
 }
 
 static inline dim3 grid3z(Dim3i d, ZRange z) { return dim3((d.nx + BX - 1) / BX, (d.ny + BY - 1) / BY, z.k1 - z.k0); }
@@ -252,9 +256,21 @@ static int launch_colour(jetcu_ctx* ctx, Dim3i d, ZRange z, Mat A, const double*
     return JETCU_OK;
 }
 
-// `halo` = slab-distributed level: the planes just outside `z` are refreshed from the neighbouring ranks before each
-// colour pass (a red cell reads black neighbours only and vice versa, so one exchange per pass keeps the sweep
-// bit-identical to the undivided one).
+// `halo` = slab-distributed level.  Communication-avoiding sweeps: instead of refreshing one plane before every colour
+// pass (2 messages per neighbour and sweep), a block of k sweeps starts with ONE exchange of 2k planes and then
+// recomputes the neighbour's cells inside that halo redundantly, on a window that shrinks by one plane per colour pass
+// (red of sweep s on slab +- (2(k-s)-1) planes, black on slab +- (2(k-s)-2)); the last black pass covers exactly the
+// slab.  Every cell still sees the same operands in the same order, so the result stays bit-identical to the
+// undivided sweep; the redundant work is ~k/T of a pass, k is chosen as T/8 (at most 8, at least 1).  The caller must
+// have made b valid on fdm_relax_rhs_halo(T) planes around the slab (b is read-only here: one exchange per V-cycle level).
+// sweeps per exchange on a slab of T planes
+static inline int relax_block_sweeps(int T) {
+    int k = T / 8;
+    return k < 1 ? 1 : (k > 8 ? 8 : k);
+}
+// planes of b (which the sweeps only read) that the redundant halo cells need next to a slab of T planes
+int fdm_relax_rhs_halo(int T) { return 2 * relax_block_sweeps(T) - 1; }
+
 template <bool P>
 static int launch_relax(jetcu_ctx* ctx, Dim3i d, ZRange z, bool halo, Mat A, const double* b, double sor,
                         unsigned iterations, double** x, double** xalt, uint64_t* launches) {
@@ -265,11 +281,19 @@ static int launch_relax(jetcu_ctx* ctx, Dim3i d, ZRange z, bool halo, Mat A, con
         return JETCU_OK;
     }
     const size_t plane = (size_t)d.nx * d.ny * sizeof(double);
-    for (unsigned it = 0; it < iterations; ++it) {
-        for (int colour = 0; colour < 2; ++colour) {
-            if (halo) JC_TRY(comm_halo_planes(ctx, *x, plane, z.k0, z.k1, d.nz));
-            JC_TRY(launch_colour<P>(ctx, d, z, A, b, sor, colour, *x));
+    const int kmax = relax_block_sweeps(z.k1 - z.k0);
+    unsigned it = 0;
+    while (it < iterations) {
+        const int k = halo ? (int)((iterations - it < (unsigned)kmax) ? iterations - it : (unsigned)kmax) : (int)(iterations - it);
+        if (halo) JC_TRY(comm_halo_planes(ctx, *x, plane, z.k0, z.k1, d.nz, 2 * k));
+        for (int s2 = 0; s2 < k; ++s2) {
+            for (int colour = 0; colour < 2; ++colour) {
+                const int ext = halo ? 2 * (k - s2) - 1 - colour : 0;
+                ZRange w{z.k0 - ext < 0 ? 0 : z.k0 - ext, z.k1 + ext > d.nz ? d.nz : z.k1 + ext};
+                JC_TRY(launch_colour<P>(ctx, d, w, A, b, sor, colour, *x));
+            }
         }
+        it += (unsigned)k;
     }
     *launches = 2ull * iterations;
     return JETCU_OK;
@@ -542,6 +566,9 @@ int mg_vcycle(jetcu_ctx* ctx, MgLevels* mg, const jetcu_mgpcg_params* p, int l) 
     const bool dist = l < pl.dist_levels;
     const ZRange z{pl.z0[l], pl.z1[l]};
     const size_t plane = (size_t)d.nx * d.ny * sizeof(double);
+    // the smoother's redundant halo cells read b next to the slab; b[l] does not change during this level's visit
+    if (dist && fdm_relax_rhs_halo(z.k1 - z.k0) > 0)
+        JC_TRY(comm_halo_planes(ctx, mg->b[l], plane, z.k0, z.k1, d.nz, fdm_relax_rhs_halo(z.k1 - z.k0)));
     JC_TRY(fdm_relax_rb(ctx, d, z, dist, mg->A[l], mg->b[l], p->sor_factor, p->n_restriction, &mg->x[l], &mg->xalt[l], l));
     if (l + 1 < mg->levels) {
         const Dim3i dc = mg->dims[l + 1];

@@ -11,6 +11,7 @@
 // Parity notes: everything except the P2G summation order (reference: global particle index order) replays
 // the reference's expressions; P2G agrees to rounding (documented tolerance 1e-12 relative in the tests).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "particles.cuh"
@@ -415,6 +416,184 @@ __global__ void __launch_bounds__(P2G_THREADS)
             unsigned long long vl = (unsigned long long)sV[ax][0][t] | ((unsigned long long)sV[ax][1][t] << 32);
             unsigned long long vh = (unsigned long long)sV[ax][2][t] | ((unsigned long long)sV[ax][3][t] << 32);
             vh = vh - wh - (vl < wl ? 1ull : 0ull); vl = vl - wl;  // remove the bias: exact 128-bit subtraction
+            acc128(acc.sum[ax] + f, acc.sum_lo[ax] + f, vh, vl);
+            acc128(acc.wsum[ax] + f, acc.wsum_lo[ax] + f, wh, wl);
+            acc.marker[ax][f] = 1;
+        }
+    }
+}
+
+// ---- P2G, per-cell form ------------------------------------------------------------------------------------------
+// All particles of one cell deposit into the same small window of faces: 2 along the component's own (node-aligned)
+// axis x 3 x 3 along the two cell-centred axes = 18 faces.  One thread owns a cell, sums its particles' contributions
+// to those 18 faces in REGISTERS (FP64, in the cell's fixed order: ascending original index), and only then converts
+// the 18 partial sums to fixed point and adds them to the tile's shared accumulators: 18 conversions + limb atomics per
+// cell and component instead of 8 per particle (x8 particles).  The cross-cell / cross-tile / cross-rank combination is
+// still integer addition, so the result is independent of tile order and of the slab decomposition (a ghost cell is
+// summed by the very same expression on every rank that holds it).
+// Slots outside a particle's actual 2x2x2 corners get weight 0 (val = +-0): adding them changes nothing.
+__host__ __device__ constexpr unsigned p2g_combo_mask(int ox, int oy, int oz) {
+    unsigned m = 0;
+    for (int c = oz; c <= oz + 1; ++c)
+        for (int b = oy; b <= oy + 1; ++b)
+            for (int a = ox; a <= ox + 1; ++a) m |= 1u << ((c * 3 + b) * 3 + a);
+    return m;
+}
+
+template <bool APIC, int AX>
+__device__ __forceinline__ void p2g_cell_component(const GridD& g, int ci, int cj, int ck, uint32_t s0, uint32_t e0,
+                                                   const AttrPtrs& a, double scale, int I0, int J0, int K0, unsigned* sV,
+                                                   unsigned* sW, unsigned char* sM, const P2GAcc& acc) {
+    constexpr int NF = (TC + 1) * (TC + 2) * (TC + 2);
+    constexpr int NX = AX == 0 ? 2 : 3, NY = AX == 1 ? 2 : 3, NZ = AX == 2 ? 2 : 3;
+    const int sx = g.nx + (AX == 0), sy = g.ny + (AX == 1), sz = g.nz + (AX == 2);
+    const double ox = g.ox + 0.5 * (AX == 0 ? 0.0 : g.hx), oy = g.oy + 0.5 * (AX == 1 ? 0.0 : g.hy),
+                 oz = g.oz + 0.5 * (AX == 2 ? 0.0 : g.hz);
+    const double ihx = 1.0 / g.hx, ihy = 1.0 / g.hy, ihz = 1.0 / g.hz;
+    const double wscale = 1125899906842624.0;  // 2^50
+    // window origin in face indices
+    const int bx0 = ci - (AX == 0 ? 0 : 1), by0 = cj - (AX == 1 ? 0 : 1), bz0 = ck - (AX == 2 ? 0 : 1);
+    double sv[NZ][NY][NX], sw[NZ][NY][NX];
+#pragma unroll
+    for (int c = 0; c < NZ; ++c)
+#pragma unroll
+        for (int b = 0; b < NY; ++b)
+#pragma unroll
+            for (int x = 0; x < NX; ++x) { sv[c][b][x] = 0.0; sw[c][b][x] = 0.0; }
+    unsigned touched = 0;  // bit ((c*3 + b)*3 + a): slot is a real corner of at least one particle (markers)
+    for (uint32_t q = s0; q < e0; ++q) {
+        double px = a.p[0][q], py = a.p[1][q], pz = a.p[2][q];
+        if (APIC) {  // tangential clamp to [lo + h/2, hi - h/2] (apic_solver3.cpp:76-84,94-102,112-120)
+            if (AX != 0) px = jc_clamp(px, g.ox + g.hx / 2.0, (g.ox + g.hx * (double)g.nx) - g.hx / 2.0);
+            if (AX != 1) py = jc_clamp(py, g.oy + g.hy / 2.0, (g.oy + g.hy * (double)g.ny) - g.hy / 2.0);
+            if (AX != 2) pz = jc_clamp(pz, g.oz + g.hz / 2.0, (g.oz + g.hz * (double)g.nz) - g.hz / 2.0);
+        }
+        const BaseFrac bf = jc_base_mul(sx, sy, sz, ihx, ihy, ihz, ox, oy, oz, px, py, pz);
+        const double pv = a.p[3 + AX][q];
+        double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+        if (APIC) { c0 = a.p[6 + 3 * AX][q]; c1 = a.p[7 + 3 * AX][q]; c2 = a.p[8 + 3 * AX][q]; }
+        const int dx = bf.i - bx0, dy = bf.j - by0, dz = bf.k - bz0;  // 0 on the node axis, 0 or 1 on the centred ones
+        const bool inwin = (unsigned)dx <= (AX == 0 ? 0u : 1u) && (unsigned)dy <= (AX == 1 ? 0u : 1u) &&
+                           (unsigned)dz <= (AX == 2 ? 0u : 1u);
+        if (!inwin) {  // cannot happen for a particle binned into this cell; kept so that nothing is ever dropped
+#pragma unroll
+            for (int cnr = 0; cnr < 8; ++cnr) {
+                const int fi = (cnr & 1) ? bf.ip1 : bf.i, fj = (cnr & 2) ? bf.jp1 : bf.j, fk = (cnr & 4) ? bf.kp1 : bf.k;
+                const double wgt = jc_corner_weight(bf, cnr);
+                double val = pv * wgt;
+                if (APIC) {
+                    const double gx = ox + g.hx * (double)fi, gy = oy + g.hy * (double)fj, gz = oz + g.hz * (double)fk;
+                    val = wgt * (pv + (c0 * (gx - px) + c1 * (gy - py) + c2 * (gz - pz)));
+                }
+                unsigned long long vh, vl, wh, wl;
+                to_fixed128(val * scale, &vh, &vl);
+                to_fixed128(wgt * wscale, &wh, &wl);
+                const size_t f = ((size_t)fk * sy + fj) * sx + fi;
+                acc128(acc.sum[AX] + f, acc.sum_lo[AX] + f, vh, vl);
+                acc128(acc.wsum[AX] + f, acc.wsum_lo[AX] + f, wh, wl);
+                acc.marker[AX][f] = 1;
+            }
+            continue;
+        }
+        // the two real weights per axis placed at offset d, zero elsewhere
+        double Wx[3], Wy[3], Wz[3];
+        Wx[0] = dx == 0 ? 1 - bf.fx : 0.0; Wx[1] = dx == 0 ? bf.fx : 1 - bf.fx; Wx[2] = dx == 0 ? 0.0 : bf.fx;
+        Wy[0] = dy == 0 ? 1 - bf.fy : 0.0; Wy[1] = dy == 0 ? bf.fy : 1 - bf.fy; Wy[2] = dy == 0 ? 0.0 : bf.fy;
+        Wz[0] = dz == 0 ? 1 - bf.fz : 0.0; Wz[1] = dz == 0 ? bf.fz : 1 - bf.fz; Wz[2] = dz == 0 ? 0.0 : bf.fz;
+#pragma unroll
+        for (int c = 0; c < NZ; ++c)
+#pragma unroll
+            for (int b = 0; b < NY; ++b)
+#pragma unroll
+                for (int x = 0; x < NX; ++x) {
+                    const double wgt = Wx[x] * Wy[b] * Wz[c];  // (wx*wy)*wz as in array_samplers3-inl.h:176-192
+                    double val;
+                    if (APIC) {
+                        const double gx = ox + g.hx * (double)(bx0 + x), gy = oy + g.hy * (double)(by0 + b),
+                                     gz = oz + g.hz * (double)(bz0 + c);
+                        val = wgt * (pv + (c0 * (gx - px) + c1 * (gy - py) + c2 * (gz - pz)));
+                    } else {
+                        val = pv * wgt;
+                    }
+                    sv[c][b][x] += val; sw[c][b][x] += wgt;
+                }
+        // dx/dy/dz in {0,1}: one of 8 corner-block positions inside the window
+        const int combo = dx + 2 * dy + 4 * dz;
+        touched |= combo == 0 ? p2g_combo_mask(0, 0, 0) : combo == 1 ? p2g_combo_mask(1, 0, 0) : combo == 2 ? p2g_combo_mask(0, 1, 0)
+                 : combo == 3 ? p2g_combo_mask(1, 1, 0) : combo == 4 ? p2g_combo_mask(0, 0, 1) : combo == 5 ? p2g_combo_mask(1, 0, 1)
+                 : combo == 6 ? p2g_combo_mask(0, 1, 1) : p2g_combo_mask(1, 1, 1);
+    }
+    if (!touched) return;
+    // tile frame of this component (tile + one ring on the centred axes)
+    const int lx0 = I0 - (AX == 0 ? 0 : 1), ly0 = J0 - (AX == 1 ? 0 : 1), lz0 = K0 - (AX == 2 ? 0 : 1);
+    constexpr int TDX = TC + (AX == 0 ? 1 : 2), TDY = TC + (AX == 1 ? 1 : 2);
+#pragma unroll
+    for (int c = 0; c < NZ; ++c)
+#pragma unroll
+        for (int b = 0; b < NY; ++b)
+#pragma unroll
+            for (int x = 0; x < NX; ++x) {
+                if (!(touched >> ((c * 3 + b) * 3 + x) & 1u)) continue;
+                unsigned long long vh, vl, wh, wl;
+                to_fixed128(sv[c][b][x] * scale, &vh, &vl);
+                to_fixed128(sw[c][b][x] * wscale, &wh, &wl);
+                // bias the value by TWICE the weight: |sum v*w| <= max|v| * sum w < 2^e * sum w up to the rounding of the
+                // FP64 partial sums, so value + 2 * 2^e * weight is safely non-negative
+                const unsigned long long w2l = wl << 1, w2h = (wh << 1) | (wl >> 63);
+                const unsigned long long bl = vl + w2l, bh = vh + w2h + (bl < vl ? 1ull : 0ull);
+                const int t = ((bz0 + c - lz0) * TDY + (by0 + b - ly0)) * TDX + (bx0 + x - lx0);
+                acc_limbs(sV + t, NF, bh, bl);
+                acc_limbs(sW + t, NF, wh, wl);
+                sM[t] = 1;
+            }
+}
+
+template <bool APIC>
+__global__ void __launch_bounds__(P2G_THREADS)
+    k_p2g_cells(GridD g, int kbase, int kend, const uint32_t* __restrict__ cell_start, AttrPtrs a,
+                const P2GScale* __restrict__ sc, P2GAcc acc) {
+    constexpr int NF = (TC + 1) * (TC + 2) * (TC + 2);
+    extern __shared__ __align__(16) unsigned p2g_smem[];
+    unsigned(*sV)[4][NF] = reinterpret_cast<unsigned(*)[4][NF]>(p2g_smem);             // [3][limb] value + 2 * weight
+    unsigned(*sW)[4][NF] = reinterpret_cast<unsigned(*)[4][NF]>(p2g_smem + 12 * NF);   // [3][limb] weight
+    unsigned char(*sM)[NF] = reinterpret_cast<unsigned char(*)[NF]>(p2g_smem + 24 * NF);  // [3] markers
+    __shared__ int any;
+    const int I0 = blockIdx.x * TC, J0 = blockIdx.y * TC, K0 = kbase + blockIdx.z * TC;
+    if (threadIdx.x == 0) any = 0;
+    for (int t = threadIdx.x; t < 24 * NF; t += P2G_THREADS) p2g_smem[t] = 0u;
+    for (int t = threadIdx.x; t < 3 * NF; t += P2G_THREADS) (&sM[0][0])[t] = 0;
+    __syncthreads();
+    const double scale = sc->scale;
+    int touched = 0;
+    for (int cl = threadIdx.x; cl < TC * TC * TC; cl += P2G_THREADS) {
+        const int ci = I0 + (cl % TC), cj = J0 + ((cl / TC) % TC), ck = K0 + (cl / (TC * TC));
+        if (ci >= g.nx || cj >= g.ny || ck >= kend) continue;
+        const size_t cell = ((size_t)ck * g.ny + cj) * g.nx + ci;
+        const uint32_t s0 = cell_start[cell], e0 = cell_start[cell + 1];
+        if (s0 == e0) continue;
+        touched = 1;
+        p2g_cell_component<APIC, 0>(g, ci, cj, ck, s0, e0, a, scale, I0, J0, K0, &sV[0][0][0], &sW[0][0][0], &sM[0][0], acc);
+        p2g_cell_component<APIC, 1>(g, ci, cj, ck, s0, e0, a, scale, I0, J0, K0, &sV[1][0][0], &sW[1][0][0], &sM[1][0], acc);
+        p2g_cell_component<APIC, 2>(g, ci, cj, ck, s0, e0, a, scale, I0, J0, K0, &sV[2][0][0], &sW[2][0][0], &sM[2][0], acc);
+    }
+    if (touched) any = 1;
+    __syncthreads();
+    if (!any) return;
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        const int sx = g.nx + (ax == 0), sy = g.ny + (ax == 1);
+        const int lx0 = I0 - (ax == 0 ? 0 : 1), ly0 = J0 - (ax == 1 ? 0 : 1), lz0 = K0 - (ax == 2 ? 0 : 1);
+        const int dx = TC + (ax == 0 ? 1 : 2), dy = TC + (ax == 1 ? 1 : 2), dz = TC + (ax == 2 ? 1 : 2);
+        for (int t = threadIdx.x; t < dx * dy * dz; t += P2G_THREADS) {
+            if (!sM[ax][t]) continue;
+            const int lx = t % dx, ly = (t / dx) % dy, lz = t / (dx * dy);
+            const size_t f = ((size_t)(lz0 + lz) * sy + (ly0 + ly)) * sx + (lx0 + lx);
+            const unsigned long long wl = (unsigned long long)sW[ax][0][t] | ((unsigned long long)sW[ax][1][t] << 32);
+            const unsigned long long wh = (unsigned long long)sW[ax][2][t] | ((unsigned long long)sW[ax][3][t] << 32);
+            unsigned long long vl = (unsigned long long)sV[ax][0][t] | ((unsigned long long)sV[ax][1][t] << 32);
+            unsigned long long vh = (unsigned long long)sV[ax][2][t] | ((unsigned long long)sV[ax][3][t] << 32);
+            const unsigned long long w2l = wl << 1, w2h = (wh << 1) | (wl >> 63);
+            vh = vh - w2h - (vl < w2l ? 1ull : 0ull); vl = vl - w2l;  // remove the bias: exact 128-bit subtraction
             acc128(acc.sum[ax] + f, acc.sum_lo[ax] + f, vh, vl);
             acc128(acc.wsum[ax] + f, acc.wsum_lo[ax] + f, wh, wl);
             acc.marker[ax][f] = 1;
@@ -1532,11 +1711,21 @@ int jetcu_hybrid_transfer_particles_to_grids(jetcu_hybrid* h) {
         if (!attr_set) {
             JC_CUDA(ctx, cudaFuncSetAttribute(k_p2g_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             JC_CUDA(ctx, cudaFuncSetAttribute(k_p2g_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            JC_CUDA(ctx, cudaFuncSetAttribute(k_p2g_cells<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            JC_CUDA(ctx, cudaFuncSetAttribute(k_p2g_cells<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
         }
+        // per-cell register accumulation needs every component grid to have >= 2 samples per axis (its 2-wide node
+        // window must exist); degenerate 1-cell-thick grids take the per-particle form
+        const bool per_cell = g.nx >= 2 && g.ny >= 2 && g.nz >= 2 && !getenv("JETCU_P2G_PER_PARTICLE");
         if (h->nsorted > 0) {
-            if (apic) JC_LAUNCH(ctx, (k_p2g_scatter<true>), grid, P2G_THREADS, smem, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
-            else JC_LAUNCH(ctx, (k_p2g_scatter<false>), grid, P2G_THREADS, smem, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
+            if (per_cell) {
+                if (apic) JC_LAUNCH(ctx, (k_p2g_cells<true>), grid, P2G_THREADS, smem, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
+                else JC_LAUNCH(ctx, (k_p2g_cells<false>), grid, P2G_THREADS, smem, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
+            } else {
+                if (apic) JC_LAUNCH(ctx, (k_p2g_scatter<true>), grid, P2G_THREADS, smem, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
+                else JC_LAUNCH(ctx, (k_p2g_scatter<false>), grid, P2G_THREADS, smem, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
+            }
         }
         JC_LAUNCH(ctx, k_p2g_normalise, jc_blocks(nk * pu, 256), 256, 0, h->u + k0 * pu, h->sum_lo[0] + k0 * pu, h->wsum[0] + k0 * pu,
                   h->wsum_lo[0] + k0 * pu, h->p2g_scale, flip ? h->ud + k0 * pu : nullptr, h->p2g_err, nk * pu);

@@ -301,6 +301,11 @@ int pressure_solve_device(jetcu_ctx* ctx, PressureSystem* ps, const double* u_in
         m.stride_y = (size_t)d.nx; m.stride_z = (size_t)d.nx * d.ny;
         // term = weight * invHSqr with invHSqr = invH * invH (…pressure_solver3.cpp:127-128)
         m.sx = (1.0 / hx) * (1.0 / hx); m.sy = (1.0 / hy) * (1.0 / hy); m.sz = (1.0 / hz) * (1.0 / hz);
+        {   // k_build_system's accumulation order for a bulk cell: +x, -x, +y, -y, +z, -z, every term = 1.0f * invH^2
+            volatile double c = 0.0;
+            c += m.sx; c += m.sx; c += m.sy; c += m.sy; c += m.sz; c += m.sz;
+            m.c6 = c;
+        }
         ps->mg.A[l] = m;
         hx *= 2.0; hy *= 2.0; hz *= 2.0;
     }

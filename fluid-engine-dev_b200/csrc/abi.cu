@@ -1,6 +1,7 @@
 // abi.cu — the extern "C" boundary (include/jetcu.h): context management, linear-system seam (1) and
 // pressure-projection seam (2).  Host buffers in, host buffers out; all compute on the ctx's stream.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -96,6 +97,7 @@ int jetcu_ctx_create(int device, jetcu_ctx** out) {
         return rc;
     }
     ctx->psys = new PressureSystem();
+    if (getenv("JETCU_NO_GRAPHS")) ctx->graphs_ok = false;
     *out = ctx;
     return JETCU_OK;
 }

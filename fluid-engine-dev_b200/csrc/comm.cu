@@ -160,6 +160,15 @@ int comm_exchange(jetcu_ctx* ctx, void* const* send_ptr, const size_t* send_byte
     return JETCU_OK;
 }
 
+void comm_counters(const jetcu_ctx* ctx, uint64_t* messages, uint64_t* bytes) {
+    *messages = ctx->comm ? ctx->comm->messages : 0;
+    *bytes = ctx->comm ? ctx->comm->bytes_sent : 0;
+}
+
+void comm_counters_add(jetcu_ctx* ctx, uint64_t messages, uint64_t bytes) {
+    if (ctx->comm) { ctx->comm->messages += messages; ctx->comm->bytes_sent += bytes; }
+}
+
 void comm_free(jetcu_ctx* ctx) {
     JcComm* c = ctx->comm;
     if (!c) return;
@@ -208,6 +217,28 @@ int jetcu_comm_init(jetcu_ctx* ctx, int world, int rank, const uint8_t id[JETCU_
         return jetcu_fail(ctx, JETCU_ERR_CUDA, "communicator staging allocation failed");
     }
     ctx->comm = c;
+    // NCCL connects peers / rings lazily at the first operation that needs them, and that set-up is not legal inside a
+    // stream capture.  The V-cycle is replayed from a CUDA graph whose capture may well be the first traffic on this
+    // communicator, so every pattern the graphs contain is exercised once, eagerly, right here: halo send/recv with both
+    // neighbours (small and halo-sized, so that all p2p channels come up), all-gather, all-reduce and broadcast.
+    {
+        const size_t big = (size_t)32 << 20;
+        char* w = nullptr;
+        if (cudaMalloc((void**)&w, 4 * big) != cudaSuccess) { comm_free(ctx); return jetcu_fail(ctx, JETCU_ERR_OOM, "communicator warm-up buffer"); }
+        cudaMemsetAsync(w, 0, 4 * big, ctx->stream);
+        int rc = JETCU_OK;
+        for (size_t bytes : {(size_t)4096, big}) {
+            // planes of `bytes` each: [0] ghost-lo, [1] own-lo, [2] own-hi, [3] ghost-hi  ->  k0 = 1, k1 = 3 of nz = 4
+            if (rc == JETCU_OK) rc = comm_halo_planes(ctx, w, bytes, rank > 0 ? 1 : 0, rank + 1 < world ? 3 : 4, 4, 1);
+            if (rc == JETCU_OK) rc = comm_allgather_inplace(ctx, w, bytes / (size_t)world);
+        }
+        if (rc == JETCU_OK) rc = comm_allreduce_max_f64(ctx, reinterpret_cast<double*>(w), 1);
+        if (rc == JETCU_OK) rc = comm_bcast(ctx, w, 4096, world - 1);
+        if (rc == JETCU_OK) rc = jc_sync(ctx);
+        cudaFree(w);
+        if (rc != JETCU_OK) { std::string keep = ctx->error; comm_free(ctx); ctx->error = keep; return rc; }
+        c->messages = 0; c->bytes_sent = 0;
+    }
     return JETCU_OK;
 }
 

@@ -27,6 +27,7 @@ struct jetcu_ctx {
     double* d_partials = nullptr;  // dot-product partial sums (JC_PARTIALS_CAP doubles)
     // z-slab communicator (comm.cu); null = single GPU
     struct JcComm* comm = nullptr;
+    bool graphs_ok = true;   // cleared (for good) the first time a V-cycle capture fails; JETCU_NO_GRAPHS=1 also clears it
     // optional per-kernel-family timing (jetcu_profile_*): CUDA event pairs on `stream`, resolved lazily
     bool profile = false;
     struct ProfPending { cudaEvent_t e0, e1; int kind; uint64_t launches, units; };
@@ -56,6 +57,9 @@ int comm_allgather_u64_host(jetcu_ctx* ctx, const uint64_t* mine, size_t count, 
 int comm_exchange(jetcu_ctx* ctx, void* const* send_ptr, const size_t* send_bytes, void* const* recv_ptr,
                   const size_t* recv_bytes);
 void comm_free(jetcu_ctx* ctx);
+// message / byte counters (a replayed CUDA graph adds what its capture counted)
+void comm_counters(const jetcu_ctx* ctx, uint64_t* messages, uint64_t* bytes);
+void comm_counters_add(jetcu_ctx* ctx, uint64_t messages, uint64_t bytes);
 
 // Slab routing rule shared by the device kernel (k_slab_route) and the host-side test hook (jetcu_slab_route_mask):
 // bit q is set for every rank q != me whose extended slab [q*T - ghost, (q+1)*T + ghost) contains cell plane ck.

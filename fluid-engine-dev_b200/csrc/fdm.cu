@@ -505,6 +505,11 @@ int mg_alloc_vectors(jetcu_ctx* ctx, MgLevels* mg) {
 }
 
 void mg_free(jetcu_ctx* ctx, MgLevels* mg) {
+    for (auto& g : mg->vgraph) {
+        if (g.exec) { cudaStreamSynchronize(ctx->stream); cudaGraphExecDestroy(g.exec); }
+        g = MgLevels::VGraph();
+    }
+    jc_free(ctx, mg->pcg_d); jc_free(ctx, mg->pcg_s);
     for (int l = 0; l < JC_MAX_LEVELS; ++l) {
         for (int q = 0; q < 4; ++q) jc_free(ctx, mg->own_vec[l][q]);
         mg->x[l] = mg->xalt[l] = mg->b[l] = mg->buf[l] = nullptr;
@@ -600,14 +605,91 @@ int mg_vcycle(jetcu_ctx* ctx, MgLevels* mg, const jetcu_mgpcg_params* p, int l) 
 // CURRENT content of the output vector.  We run the cycle directly on (b_in, *x_inout) as level 0's b and x, with
 // *scratch as the ping-pong partner; on return *x_inout names the buffer holding the result (the two pointers may
 // have been exchanged).
-static int precondition(jetcu_ctx* ctx, MgLevels* mg, const jetcu_mgpcg_params* p, double* b_in, double** x_inout,
-                        double** scratch) {
+static int precondition_eager(jetcu_ctx* ctx, MgLevels* mg, const jetcu_mgpcg_params* p, double* b_in, double** x_inout,
+                              double** scratch) {
     double *saved_x = mg->x[0], *saved_alt = mg->xalt[0], *saved_b = mg->b[0];
     mg->x[0] = *x_inout; mg->xalt[0] = *scratch; mg->b[0] = b_in;
     int rc = mg_vcycle(ctx, mg, p, 0);
     *x_inout = mg->x[0]; *scratch = mg->xalt[0];
     mg->x[0] = saved_x; mg->xalt[0] = saved_alt; mg->b[0] = saved_b;
     return rc;
+}
+
+// FNV-1a over everything a captured V-cycle bakes in besides (b, x): matrices (passed by value), vectors, sweeps, plan.
+static uint64_t vcycle_key(const MgLevels* mg, const jetcu_mgpcg_params* p) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&h](const void* d, size_t n) {
+        const unsigned char* c = static_cast<const unsigned char*>(d);
+        for (size_t i = 0; i < n; ++i) { h ^= c[i]; h *= 1099511628211ull; }
+    };
+    mix(&mg->levels, sizeof(int));
+    for (int l = 0; l < mg->levels; ++l) {
+        const Mat& A = mg->A[l];
+        const void* ptrs[] = {A.center, A.right, A.up, A.front, A.cr, A.cu, A.cf, A.code, mg->x[l], mg->b[l], mg->buf[l]};
+        mix(ptrs, sizeof(ptrs));
+        const double sc[] = {A.sx, A.sy, A.sz, A.c6};
+        mix(sc, sizeof(sc));
+        mix(&mg->dims[l], sizeof(Dim3i));
+        mix(&mg->plan.z0[l], sizeof(int)); mix(&mg->plan.z1[l], sizeof(int));
+    }
+    mix(&mg->plan.world, sizeof(int)); mix(&mg->plan.rank, sizeof(int)); mix(&mg->plan.dist_levels, sizeof(int));
+    const uint32_t it[] = {p->n_restriction, p->n_correction, p->n_coarsest, p->n_final};
+    mix(it, sizeof(it));
+    mix(&p->sor_factor, sizeof(double));
+    return h;
+}
+
+// Replays (or first captures) the V-cycle on (b_in, *x_inout) as a CUDA graph.  The smoother works in place, so the
+// pointers never change hands; NCCL halo exchanges are captured along with the kernels.  Falls back to eager launches
+// while kernel-family profiling is on (its event pairs cannot live inside a graph) or once a capture has failed.
+static int precondition(jetcu_ctx* ctx, MgLevels* mg, const jetcu_mgpcg_params* p, double* b_in, double** x_inout,
+                        double** scratch) {
+    if (!ctx->graphs_ok || ctx->profile) return precondition_eager(ctx, mg, p, b_in, x_inout, scratch);
+    // level 0's x / b slots are overridden per call, keep them out of the key
+    double *saved_x = mg->x[0], *saved_b = mg->b[0];
+    mg->x[0] = nullptr; mg->b[0] = nullptr;
+    const uint64_t key = vcycle_key(mg, p);
+    mg->x[0] = saved_x; mg->b[0] = saved_b;
+    MgLevels::VGraph* slot = nullptr;
+    for (auto& g : mg->vgraph)
+        if (g.exec && g.b == b_in && g.x == *x_inout && g.key == key) slot = &g;
+    if (!slot) {
+        slot = (mg->vgraph[0].stamp <= mg->vgraph[1].stamp) ? &mg->vgraph[0] : &mg->vgraph[1];
+        if (slot->exec) { cudaStreamSynchronize(ctx->stream); cudaGraphExecDestroy(slot->exec); }
+        *slot = MgLevels::VGraph();
+        uint64_t m0, b0, m1, b1;
+        comm_counters(ctx, &m0, &b0);
+        const uint64_t l0 = ctx->launches;
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            ctx->graphs_ok = false;
+            return precondition_eager(ctx, mg, p, b_in, x_inout, scratch);
+        }
+        double *x = *x_inout, *sc = *scratch;
+        int rc = precondition_eager(ctx, mg, p, b_in, &x, &sc);
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+        cudaGraphExec_t exec = nullptr;
+        if (rc == JETCU_OK && e == cudaSuccess && graph && x == *x_inout) e = cudaGraphInstantiate(&exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        comm_counters(ctx, &m1, &b1);
+        if (rc != JETCU_OK || e != cudaSuccess || !exec) {  // nothing ran: counters back, eager from now on
+            cudaGetLastError();
+            ctx->launches = l0;
+            comm_counters_add(ctx, m0 - m1, b0 - b1);
+            ctx->graphs_ok = false;
+            return precondition_eager(ctx, mg, p, b_in, x_inout, scratch);
+        }
+        slot->exec = exec; slot->b = b_in; slot->x = *x_inout; slot->key = key;
+        slot->launches = ctx->launches - l0; slot->messages = m1 - m0; slot->bytes = b1 - b0;
+        ctx->launches = l0;
+        comm_counters_add(ctx, m0 - m1, b0 - b1);  // the capture itself sent nothing
+    }
+    slot->stamp = ++mg->vgraph_clock;
+    JC_CUDA(ctx, cudaGraphLaunch(slot->exec, ctx->stream));
+    ctx->launches += slot->launches;
+    comm_counters_add(ctx, slot->messages, slot->bytes);
+    return JETCU_OK;
 }
 
 static int read_scalar(jetcu_ctx* ctx, const double* d, double* out) {
@@ -638,8 +720,10 @@ int mgpcg_solve_device(jetcu_ctx* ctx, MgLevels* mg, const double* b, double* x,
     const size_t plane = nxy * sizeof(double);
     // level 0's own x / xalt / b are idle during PCG (the V-cycle runs on the PCG vectors): reuse them as r, q and the
     // ping-pong scratch t; buf[0] stays the residual temporary of the V-cycle.
-    double *r = mg->own_vec[0][0], *q = mg->own_vec[0][1], *t = mg->own_vec[0][2], *dd = nullptr, *s = nullptr;
-    JC_TRY(jc_alloc(ctx, &dd, n)); JC_TRY(jc_alloc(ctx, &s, n));
+    double *r = mg->own_vec[0][0], *q = mg->own_vec[0][1], *t = mg->own_vec[0][2];
+    if (!mg->pcg_d) JC_TRY(jc_alloc(ctx, &mg->pcg_d, n));
+    if (!mg->pcg_s) JC_TRY(jc_alloc(ctx, &mg->pcg_s, n));
+    double *dd = mg->pcg_d, *s = mg->pcg_s;
     cudaEvent_t e0, e1;
     JC_CUDA(ctx, cudaEventCreate(&e0)); JC_CUDA(ctx, cudaEventCreate(&e1));
     JC_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
@@ -703,9 +787,8 @@ int mgpcg_solve_device(jetcu_ctx* ctx, MgLevels* mg, const double* b, double* x,
         JC_TRY(jc_sync(ctx));
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    // dd / s / t may have been exchanged by the ping-pong smoother: keep one as level 0's third vector, free two
-    mg->own_vec[0][2] = t;
+    // dd / s / t may have been exchanged by a ping-pong smoother (the current one works in place: they never are)
+    mg->own_vec[0][2] = t; mg->pcg_d = dd; mg->pcg_s = s;
     mg->x[0] = mg->own_vec[0][0]; mg->xalt[0] = mg->own_vec[0][1]; mg->b[0] = mg->own_vec[0][2];
-    jc_free(ctx, dd); jc_free(ctx, s);
     return JETCU_OK;
 }

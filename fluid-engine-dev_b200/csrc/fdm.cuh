@@ -29,6 +29,18 @@ struct MgLevels {
     double* buf[JC_MAX_LEVELS] = {};
     // allocations owned by this object (the Mat views may also point at caller-owned memory)
     double* own_vec[JC_MAX_LEVELS][4] = {};
+    // PCG's search direction d and preconditioned residual s: kept between solves so that their addresses stay put
+    double *pcg_d = nullptr, *pcg_s = nullptr;
+    // One V-cycle = ~150 small launches (+ ~50 NCCL groups on slabs): captured once per (rhs, x) pair into a CUDA
+    // graph and replayed — the solve is launch-bound on the coarse levels otherwise (and on 8 slabs everywhere).
+    struct VGraph {
+        cudaGraphExec_t exec = nullptr;
+        const double* b = nullptr;
+        double* x = nullptr;
+        uint64_t key = 0;          // hash of everything else the capture baked in (matrices, sweeps, plan)
+        uint64_t launches = 0, messages = 0, bytes = 0, stamp = 0;
+    } vgraph[2];
+    uint64_t vgraph_clock = 0;
 };
 
 int fdm_aos_to_soa(jetcu_ctx* ctx, const jetcu_matrix_row* d_aos, MatSoA A, size_t n);

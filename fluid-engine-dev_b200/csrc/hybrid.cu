@@ -779,40 +779,53 @@ __global__ void __launch_bounds__(CFL_BLOCK) k_max_final(const double* __restric
 }
 
 // ------------------------------------------------------------------------------------------------ G2P + advection
-__device__ __forceinline__ void sample_velocity(const GridD& g, const double* u, const double* v, const double* w,
-                                                double px, double py, double pz, double* ou, double* ov, double* ow) {
+// POW2: all three spacings are powers of two (GridD::ih* != 0), so (x - o) / h is evaluated as the exact product with
+// 1/h and the division path is not even compiled in.  I = index type: int when every component grid has < 2^31
+// samples (always, up to ~1280^3), else long long — 64-bit integer multiplies were a third of this kernel's instructions.
+template <bool POW2>
+__device__ __forceinline__ double norm_pos(double x, double o, double h, double ih) {
+    return POW2 ? (x - o) * ih : jc_norm(x, o, h, ih);
+}
+
+template <bool POW2, typename I>
+__device__ __forceinline__ void sample_velocity(const GridD& g, const double* __restrict__ u, const double* __restrict__ v,
+                                                const double* __restrict__ w, double px, double py, double pz, double* ou,
+                                                double* ov, double* ow) {
     // FaceCenteredGrid3::sample: three LinearArraySampler3::operator() calls (face_centered_grid3.cpp:447-467).
     // The three component grids share their per-axis normalisations pairwise (node-aligned along the component's own
     // axis, cell-centred along the other two), so 6 barycentric evaluations serve all 3 samplers instead of 9; each is
     // the same expression the per-grid sampler evaluates, so the results are bit-identical to three jc_sample calls.
     int inx, icx, jny, jcy, knz, kcz;
     double fnx, fcx, fny, fcy, fnz, fcz;
-    jc_barycentric(jc_norm(px, g.ox + 0.5 * 0.0, g.hx, g.ihx), g.nx, &inx, &fnx);            // u grid: nx + 1 nodes
-    jc_barycentric(jc_norm(px, g.ox + 0.5 * g.hx, g.hx, g.ihx), g.nx - 1, &icx, &fcx);      // v, w grids
-    jc_barycentric(jc_norm(py, g.oy + 0.5 * 0.0, g.hy, g.ihy), g.ny, &jny, &fny);            // v grid
-    jc_barycentric(jc_norm(py, g.oy + 0.5 * g.hy, g.hy, g.ihy), g.ny - 1, &jcy, &fcy);      // u, w grids
-    jc_barycentric(jc_norm(pz, g.oz + 0.5 * 0.0, g.hz, g.ihz), g.nz, &knz, &fnz);            // w grid
-    jc_barycentric(jc_norm(pz, g.oz + 0.5 * g.hz, g.hz, g.ihz), g.nz - 1, &kcz, &fcz);      // u, v grids
+    jc_barycentric(norm_pos<POW2>(px, g.ox + 0.5 * 0.0, g.hx, g.ihx), g.nx, &inx, &fnx);            // u grid: nx + 1 nodes
+    jc_barycentric(norm_pos<POW2>(px, g.ox + 0.5 * g.hx, g.hx, g.ihx), g.nx - 1, &icx, &fcx);      // v, w grids
+    jc_barycentric(norm_pos<POW2>(py, g.oy + 0.5 * 0.0, g.hy, g.ihy), g.ny, &jny, &fny);            // v grid
+    jc_barycentric(norm_pos<POW2>(py, g.oy + 0.5 * g.hy, g.hy, g.ihy), g.ny - 1, &jcy, &fcy);      // u, w grids
+    jc_barycentric(norm_pos<POW2>(pz, g.oz + 0.5 * 0.0, g.hz, g.ihz), g.nz, &knz, &fnz);            // w grid
+    jc_barycentric(norm_pos<POW2>(pz, g.oz + 0.5 * g.hz, g.hz, g.ihz), g.nz - 1, &kcz, &fcz);      // u, v grids
     const int inx1 = min(inx + 1, g.nx), icx1 = min(icx + 1, g.nx - 1);
     const int jny1 = min(jny + 1, g.ny), jcy1 = min(jcy + 1, g.ny - 1);
     const int knz1 = min(knz + 1, g.nz), kcz1 = min(kcz + 1, g.nz - 1);
     {
-        const size_t sy = (size_t)(g.nx + 1), sz = sy * g.ny;
-        const size_t r00 = kcz * sz + jcy * sy, r10 = kcz * sz + jcy1 * sy, r01 = kcz1 * sz + jcy * sy, r11 = kcz1 * sz + jcy1 * sy;
+        const I sy = (I)(g.nx + 1), sz = sy * (I)g.ny;
+        const I r00 = (I)kcz * sz + (I)jcy * sy, r10 = (I)kcz * sz + (I)jcy1 * sy, r01 = (I)kcz1 * sz + (I)jcy * sy,
+                r11 = (I)kcz1 * sz + (I)jcy1 * sy;
         const double a = jc_lerp(jc_lerp(u[r00 + inx], u[r00 + inx1], fnx), jc_lerp(u[r10 + inx], u[r10 + inx1], fnx), fcy);
         const double b = jc_lerp(jc_lerp(u[r01 + inx], u[r01 + inx1], fnx), jc_lerp(u[r11 + inx], u[r11 + inx1], fnx), fcy);
         *ou = jc_lerp(a, b, fcz);
     }
     {
-        const size_t sy = (size_t)g.nx, sz = sy * (g.ny + 1);
-        const size_t r00 = kcz * sz + jny * sy, r10 = kcz * sz + jny1 * sy, r01 = kcz1 * sz + jny * sy, r11 = kcz1 * sz + jny1 * sy;
+        const I sy = (I)g.nx, sz = sy * (I)(g.ny + 1);
+        const I r00 = (I)kcz * sz + (I)jny * sy, r10 = (I)kcz * sz + (I)jny1 * sy, r01 = (I)kcz1 * sz + (I)jny * sy,
+                r11 = (I)kcz1 * sz + (I)jny1 * sy;
         const double a = jc_lerp(jc_lerp(v[r00 + icx], v[r00 + icx1], fcx), jc_lerp(v[r10 + icx], v[r10 + icx1], fcx), fny);
         const double b = jc_lerp(jc_lerp(v[r01 + icx], v[r01 + icx1], fcx), jc_lerp(v[r11 + icx], v[r11 + icx1], fcx), fny);
         *ov = jc_lerp(a, b, fcz);
     }
     {
-        const size_t sy = (size_t)g.nx, sz = sy * g.ny;
-        const size_t r00 = knz * sz + jcy * sy, r10 = knz * sz + jcy1 * sy, r01 = knz1 * sz + jcy * sy, r11 = knz1 * sz + jcy1 * sy;
+        const I sy = (I)g.nx, sz = sy * (I)g.ny;
+        const I r00 = (I)knz * sz + (I)jcy * sy, r10 = (I)knz * sz + (I)jcy1 * sy, r01 = (I)knz1 * sz + (I)jcy * sy,
+                r11 = (I)knz1 * sz + (I)jcy1 * sy;
         const double a = jc_lerp(jc_lerp(w[r00 + icx], w[r00 + icx1], fcx), jc_lerp(w[r10 + icx], w[r10 + icx1], fcx), fcy);
         const double b = jc_lerp(jc_lerp(w[r01 + icx], w[r01 + icx1], fcx), jc_lerp(w[r11 + icx], w[r11 + icx1], fcx), fcy);
         *ow = jc_lerp(a, b, fnz);
@@ -820,12 +833,13 @@ __device__ __forceinline__ void sample_velocity(const GridD& g, const double* u,
 }
 
 // PicSolver3::transferFromGridsToParticles, src/jet/pic_solver3.cpp:195-204.
+template <bool POW2, typename I>
 __global__ void k_g2p_pic(GridD g, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
                           AttrPtrs a, size_t np) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= np) return;
     double ou, ov, ow;
-    sample_velocity(g, u, v, w, a.p[0][p], a.p[1][p], a.p[2][p], &ou, &ov, &ow);
+    sample_velocity<POW2, I>(g, u, v, w, a.p[0][p], a.p[1][p], a.p[2][p], &ou, &ov, &ow);
     a.p[3][p] = ou; a.p[4][p] = ov; a.p[5][p] = ow;
 }
 
@@ -889,13 +903,14 @@ __device__ __forceinline__ void apic_affine(const GridD& g, const double* __rest
     *c0 = r0; *c1 = r1; *c2 = r2;
 }
 
+template <bool POW2, typename I>
 __global__ void k_g2p_apic(GridD g, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
                            AttrPtrs a, size_t np) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= np) return;
     double px = a.p[0][p], py = a.p[1][p], pz = a.p[2][p];
     double ou, ov, ow;
-    sample_velocity(g, u, v, w, px, py, pz, &ou, &ov, &ow);
+    sample_velocity<POW2, I>(g, u, v, w, px, py, pz, &ou, &ov, &ow);
     a.p[3][p] = ou; a.p[4][p] = ov; a.p[5][p] = ow;
     double c0, c1, c2;
     apic_affine<0>(g, u, px, py, pz, &c0, &c1, &c2); a.p[6][p] = c0; a.p[7][p] = c1; a.p[8][p] = c2;
@@ -905,6 +920,7 @@ __global__ void k_g2p_apic(GridD g, const double* __restrict__ u, const double* 
 
 // PicSolver3::moveParticles, src/jet/pic_solver3.cpp:206-282: uint(max(maxCfl,1)) midpoint-rule sub-steps, then
 // clamp to the domain box and zero the velocity component on closed walls (<= / >= tests).
+template <bool POW2, typename I>
 __global__ void k_move(GridD g, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
                        double dt, unsigned nsub, int flag, AttrPtrs a, size_t np) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -913,9 +929,9 @@ __global__ void k_move(GridD g, const double* __restrict__ u, const double* __re
     double p1x = p0x, p1y = p0y, p1z = p0z;
     for (unsigned t = 0; t < nsub; ++t) {
         double v0x, v0y, v0z, mvx, mvy, mvz;
-        sample_velocity(g, u, v, w, p0x, p0y, p0z, &v0x, &v0y, &v0z);
+        sample_velocity<POW2, I>(g, u, v, w, p0x, p0y, p0z, &v0x, &v0y, &v0z);
         double mx = p0x + 0.5 * dt * v0x, my = p0y + 0.5 * dt * v0y, mz = p0z + 0.5 * dt * v0z;
-        sample_velocity(g, u, v, w, mx, my, mz, &mvx, &mvy, &mvz);
+        sample_velocity<POW2, I>(g, u, v, w, mx, my, mz, &mvx, &mvy, &mvz);
         p1x = p0x + dt * mvx; p1y = p0y + dt * mvy; p1z = p0z + dt * mvz;
         p0x = p1x; p0y = p1y; p0z = p1z;
     }
@@ -1198,22 +1214,31 @@ static int hyb_bin(jetcu_hybrid* h) {
     uint64_t ntot = h->np;
     if (slab) JC_TRY(hyb_slab_exchange(h, &ntot));
     const int e0 = slab ? max(h->z0 - SLAB_GHOST, 0) : 0, e1 = slab ? min(h->z1 + SLAB_GHOST, h->nz) : h->nz;
-    JC_TRY(jc_zero(ctx, h->cell_start, h->nc + 2));
+    // only the cells of the window [lo, hi) can receive particles (the rest go to the trash bin at index nc): count,
+    // scan and per-cell ordering touch that range only, so the binning cost follows the slab, not the whole grid
+    const size_t nxy = (size_t)h->nx * h->ny, lo = (size_t)e0 * nxy, hi = (size_t)e1 * nxy;
+    JC_TRY(jc_zero(ctx, h->cell_start + lo, hi - lo + 1));
+    JC_TRY(jc_zero(ctx, h->cell_start + h->nc, 2));
     if (ntot > 0) {
         AttrPtrs src = owned_ptrs(h);
         JC_LAUNCH(ctx, k_cell_count, jc_blocks(ntot, 256), 256, 0, src.p[0], src.p[1], src.p[2], (size_t)ntot, g, e0, e1,
                   h->cell_of, h->rank, h->cell_start);
     }
-    JC_TRY(scan_exclusive_u32(ctx, h->cell_start, h->cell_start, h->nc + 2));
+    if (hi == h->nc) {
+        JC_TRY(scan_exclusive_u32(ctx, h->cell_start + lo, h->cell_start + lo, hi - lo + 2));
+    } else {  // cell_start[hi] = end of the window = where the trash bin starts
+        JC_TRY(scan_exclusive_u32(ctx, h->cell_start + lo, h->cell_start + lo, hi - lo + 1));
+        JC_TRY(jc_d2d(ctx, h->cell_start + h->nc, h->cell_start + hi, 1));
+    }
     if (ntot > 0) {
         JC_LAUNCH(ctx, k_scatter_perm, jc_blocks(ntot, 256), 256, 0, h->cell_of, h->rank, h->cell_start, h->perm, (size_t)ntot);
-        JC_LAUNCH(ctx, k_sort_cells, jc_blocks(h->nc, 128), 128, 0, h->cell_start, h->orig[h->cur] + h->base, h->perm, h->nc);
+        JC_LAUNCH(ctx, k_sort_cells, jc_blocks(hi - lo, 128), 128, 0, h->cell_start + lo, h->orig[h->cur] + h->base, h->perm,
+                  hi - lo);
         JC_LAUNCH(ctx, k_gather_attrs, jc_blocks(ntot, 256), 256, 0, owned_ptrs(h), attr_ptrs(h, 1 - h->cur),
                   h->orig[h->cur] + h->base, h->orig[1 - h->cur], h->perm, h->nattr, (size_t)ntot);
         h->cur = 1 - h->cur;
     }
     if (slab) {
-        const size_t nxy = (size_t)h->nx * h->ny;
         uint32_t marks[3] = {0, 0, 0};
         JC_TRY(jc_d2h(ctx, &marks[0], h->cell_start + (size_t)h->z0 * nxy, 1));
         JC_TRY(jc_d2h(ctx, &marks[1], h->cell_start + (size_t)h->z1 * nxy, 1));
@@ -1249,6 +1274,18 @@ static int hyb_extrapolate_one(jetcu_hybrid* h, double* data, const char* marker
     }
     return JETCU_OK;
 }
+
+// picks the sampler instantiation: exact-reciprocal normalisation when every spacing is a power of two, 32-bit sample
+// indices when every component grid has fewer than 2^31 samples
+#define HYB_SAMPLER_LAUNCH(kernel, grid, block, ...)                                                              \
+    do {                                                                                                          \
+        const bool pow2_ = g.ihx != 0.0 && g.ihy != 0.0 && g.ihz != 0.0;                                          \
+        const bool i32_ = h->nu < (1ull << 31) && h->nv < (1ull << 31) && h->nw < (1ull << 31);                   \
+        if (pow2_ && i32_) JC_LAUNCH(ctx, (kernel<true, int>), grid, block, 0, __VA_ARGS__);                      \
+        else if (pow2_) JC_LAUNCH(ctx, (kernel<true, long long>), grid, block, 0, __VA_ARGS__);                   \
+        else if (i32_) JC_LAUNCH(ctx, (kernel<false, int>), grid, block, 0, __VA_ARGS__);                         \
+        else JC_LAUNCH(ctx, (kernel<false, long long>), grid, block, 0, __VA_ARGS__);                             \
+    } while (0)
 
 #define HYB_ENTER(h)                                                      \
     if (!(h)) return JETCU_ERR_INVALID_ARG;                               \
@@ -1677,13 +1714,6 @@ int jetcu_hybrid_transfer_particles_to_grids(jetcu_hybrid* h) {
     const bool apic = h->P.mode == JETCU_APIC;
     const bool slab = h->world > 1;
     int slot = jc_prof_begin(ctx, JETCU_PROF_P2G);
-    // u, v, w double as the fixed-point value accumulators; weight sums and markers start from zero as well
-    JC_TRY(jc_zero(ctx, h->u, h->nu)); JC_TRY(jc_zero(ctx, h->v, h->nv)); JC_TRY(jc_zero(ctx, h->w, h->nw));
-    const size_t nf[3] = {h->nu, h->nv, h->nw};
-    for (int q = 0; q < 3; ++q) {
-        JC_TRY(jc_zero(ctx, h->wsum[q], nf[q])); JC_TRY(jc_zero(ctx, h->wsum_lo[q], nf[q])); JC_TRY(jc_zero(ctx, h->sum_lo[q], nf[q]));
-    }
-    JC_TRY(jc_zero(ctx, h->um, h->nu)); JC_TRY(jc_zero(ctx, h->vm, h->nv)); JC_TRY(jc_zero(ctx, h->wm, h->nw));
     const bool flip = h->P.mode == JETCU_FLIP;
     // planes of each face field this rank finalises: all of them, or (slab mode) the ones it owns — their sums are
     // complete because the ghost particles of the neighbouring planes were summed along (integer accumulators: the
@@ -1691,6 +1721,21 @@ int jetcu_hybrid_transfer_particles_to_grids(jetcu_hybrid* h) {
     const size_t pu = (size_t)(h->nx + 1) * h->ny, pv = (size_t)h->nx * (h->ny + 1), pw = (size_t)h->nx * h->ny;
     const size_t k0 = (size_t)h->z0, nk = (size_t)(h->z1 - h->z0);
     const size_t nkw = nk + ((!slab || h->me == h->world - 1) ? 1 : 0);
+    {   // u, v, w double as the fixed-point value accumulators; weight sums and markers start from zero as well.  Only the
+        // planes the tiles of this rank can touch (its particle window + one ring) need it; the others are overwritten
+        // by the all-gather below
+        const int kb0 = slab ? max(h->z0 - SLAB_GHOST, 0) : 0, ke0 = slab ? min(h->z1 + SLAB_GHOST, h->nz) : h->nz;
+        const size_t zlo = (size_t)max(kb0 - 1, 0), zhi = (size_t)min(ke0 + 1, h->nz);
+        const size_t pl[3] = {pu, pv, pw};
+        double* val[3] = {h->u, h->v, h->w};
+        char* mk[3] = {h->um, h->vm, h->wm};
+        for (int q = 0; q < 3; ++q) {
+            const size_t o = zlo * pl[q], c = (zhi - zlo + (q == 2 ? 1 : 0)) * pl[q];
+            JC_TRY(jc_zero(ctx, val[q] + o, c)); JC_TRY(jc_zero(ctx, h->wsum[q] + o, c));
+            JC_TRY(jc_zero(ctx, h->wsum_lo[q] + o, c)); JC_TRY(jc_zero(ctx, h->sum_lo[q] + o, c));
+            JC_TRY(jc_zero(ctx, mk[q] + o, c));
+        }
+    }
     if (h->nglobal > 0) {
         JC_LAUNCH(ctx, k_p2g_vmax_partial, 592, 256, 0, a, (size_t)h->nsorted, apic ? 1 : 0, g.hx, g.hy, g.hz, ctx->d_partials);
         if (slab) {  // the fixed-point scale must be the same on every rank
@@ -1825,9 +1870,9 @@ int jetcu_hybrid_transfer_grids_to_particles(jetcu_hybrid* h) {
         if (np) JC_LAUNCH(ctx, k_g2p_flip, jc_blocks(np, 128), 128, 0, g, h->u, h->v, h->w, h->ud, h->vd, h->wd,
                           h->P.pic_blending_factor, a, np);
     } else if (h->P.mode == JETCU_APIC) {
-        if (np) JC_LAUNCH(ctx, k_g2p_apic, jc_blocks(np, 128), 128, 0, g, h->u, h->v, h->w, a, np);
+        if (np) HYB_SAMPLER_LAUNCH(k_g2p_apic, jc_blocks(np, 128), 128, g, h->u, h->v, h->w, a, np);
     } else {
-        if (np) JC_LAUNCH(ctx, k_g2p_pic, jc_blocks(np, 128), 128, 0, g, h->u, h->v, h->w, a, np);
+        if (np) HYB_SAMPLER_LAUNCH(k_g2p_pic, jc_blocks(np, 128), 128, g, h->u, h->v, h->w, a, np);
     }
     return JETCU_OK;
 }
@@ -1838,8 +1883,8 @@ int jetcu_hybrid_move_particles(jetcu_hybrid* h, double dt) {
     unsigned nsub = (unsigned)fmax(h->P.max_cfl, 1.0);
     double sub_dt = dt / nsub;
     if (h->np)
-        JC_LAUNCH(ctx, k_move, jc_blocks(h->np, 128), 128, 0, g, h->u, h->v, h->w, sub_dt, nsub,
-                  h->P.closed_domain_boundary_flag, owned_ptrs(h), (size_t)h->np);
+        HYB_SAMPLER_LAUNCH(k_move, jc_blocks(h->np, 128), 128, g, h->u, h->v, h->w, sub_dt, nsub,
+                           h->P.closed_domain_boundary_flag, owned_ptrs(h), (size_t)h->np);
     h->nsorted = h->np;  // the ghost copies are stale from here on
     h->binned = false;
     return JETCU_OK;

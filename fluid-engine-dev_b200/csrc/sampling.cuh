@@ -33,22 +33,22 @@ static inline double jc_pow2_inverse(double h) {
 
 // getBarycentric, include/jet/detail/math_utils-inl.h:146-174 (iLow == 0 on this path).
 __device__ __forceinline__ void jc_barycentric(double x, int iHigh, int* i, double* f) {
-    double s = floor(x);
-    // floor(x) may be far outside int range for wild inputs; clamp through the same branches the reference takes.
-    long long ii = (long long)s;
+    // s = floor(x) is integer-valued, so the reference's integer tests (i < 0, i > iHigh - 1 on a ssize_t) are decided
+    // on the double itself — the same branches for every finite x, without a 64-bit float-to-int conversion; wild
+    // inputs (|x| beyond the int range) land in the clamps instead of overflowing the conversion.
+    const double s = floor(x);
     if (iHigh == 0) { *i = 0; *f = 0.0; }
-    else if (ii < 0) { *i = 0; *f = 0.0; }
-    else if (ii > (long long)iHigh - 1) { *i = iHigh - 1; *f = 1.0; }
-    else { *i = (int)ii; *f = x - s; }
+    else if (s < 0.0) { *i = 0; *f = 0.0; }
+    else if (s > (double)(iHigh - 1)) { *i = iHigh - 1; *f = 1.0; }
+    else { *i = (int)s; *f = x - s; }
 }
 
 __device__ __forceinline__ void jc_barycentricf(float x, int iHigh, int* i, float* f) {
-    float s = floorf(x);
-    long long ii = (long long)s;
+    const float s = floorf(x);
     if (iHigh == 0) { *i = 0; *f = 0.0f; }
-    else if (ii < 0) { *i = 0; *f = 0.0f; }
-    else if (ii > (long long)iHigh - 1) { *i = iHigh - 1; *f = 1.0f; }
-    else { *i = (int)ii; *f = x - s; }
+    else if (s < 0.0f) { *i = 0; *f = 0.0f; }
+    else if (s > (float)(iHigh - 1)) { *i = iHigh - 1; *f = 1.0f; }
+    else { *i = (int)s; *f = x - s; }
 }
 
 __device__ __forceinline__ double jc_lerp(double a, double b, double f) { return (1 - f) * a + f * b; }

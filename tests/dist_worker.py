@@ -117,6 +117,10 @@ def main():
     msgs, sent = jd.comm_stats()
     out["comm"] = {"messages": msgs, "bytes_sent": sent}
     out["ok"] = ok
+    outdir = os.environ.get("JETCU_DIST_OUT")
+    if outdir:   # one file per rank: concurrent ranks interleave their stdout lines
+        with open(os.path.join(outdir, "rank%d.json" % rank), "w") as f:
+            json.dump(out, f)
     print(json.dumps(out), flush=True)
     dist.barrier()
     dist.destroy_process_group()

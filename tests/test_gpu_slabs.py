@@ -17,14 +17,25 @@ def _gpus():
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_slabs_match_single_gpu(world):
+def test_slabs_match_single_gpu(world, tmp_path):
     if _gpus() < world:
         pytest.skip("needs %d GPUs" % world)
     n = 64
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", str(29511 + world), os.path.join(ROOT, "tests", "dist_worker.py"), str(n), "3"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
-    lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
-    assert r.returncode == 0 and len(lines) == world, (r.stdout[-4000:], r.stderr[-4000:])
+    env = dict(os.environ, JETCU_DIST_OUT=str(tmp_path))
+    # own process group + a hard limit: a communication bug must fail this test, not hang the box
+    p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT, env=env, start_new_session=True)
+    try:
+        out, err = p.communicate(timeout=240)
+    except subprocess.TimeoutExpired:
+        import signal
+        os.killpg(p.pid, signal.SIGKILL)
+        out, err = p.communicate()
+        pytest.fail("distributed worker timed out at world size %d\n%s\n%s" % (world, out[-3000:], err[-3000:]))
+    r = subprocess.CompletedProcess(cmd, p.returncode, out, err)
+    files = [os.path.join(str(tmp_path), "rank%d.json" % q) for q in range(world)]
+    assert r.returncode == 0 and all(os.path.exists(f) for f in files), (r.stdout[-4000:], r.stderr[-4000:])
+    lines = [json.load(open(f)) for f in files]
     for l in lines:
         assert l["ok"], l

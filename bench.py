@@ -380,6 +380,7 @@ def run_jetcu(args):
     h.close()
 
     if rank != 0:
+        jc.close()
         if dist is not None:
             dist.destroy_process_group()
         return
@@ -391,6 +392,7 @@ def run_jetcu(args):
     roof = {"bound": "hbm", "kernel": "red-black SOR sweep, finest MG level (k_relax_*)",
             "achieved": relax_gbs, "peak": peak, "unit": "GB/s", "frac": (relax_gbs / peak) if relax_gbs else None,
             "peak_source": peak_src, "traffic": (traffic or {}).get("relax_l0_bytes_per_launch"),
+            "traffic_source": (traffic or {}).get("source"),
             "bytes_per_launch_algorithmic": (relax_units * RELAX_BYTES_PER_CELL_SWEEP / relax_launches) if relax_launches else None,
             "launches": relax_launches, "avg_launch_ms": (relax_ms / relax_launches) if relax_launches else None,
             "share_of_step": relax_ms * 1e-3 / prof_s if prof_s > 0 else None,
@@ -432,6 +434,7 @@ def run_jetcu(args):
                       "(%d/%d)^3 cell ratio" % (args.workload, n_s, np_s, times[0], n_s, n),
             "sample_pcg_iterations": iters}
     print(json.dumps(line), flush=True)
+    jc.close()
     if dist is not None:
         dist.destroy_process_group()
 

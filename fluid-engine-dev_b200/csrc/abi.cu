@@ -105,8 +105,9 @@ int jetcu_ctx_create(int device, jetcu_ctx** out) {
 int jetcu_ctx_destroy(jetcu_ctx* ctx) {
     if (!ctx) return JETCU_OK;
     cudaSetDevice(ctx->device);
+    // graphs first: a captured V-cycle pins the NCCL communicator, and ncclCommDestroy waits for such references
+    if (ctx->psys) { pressure_free(ctx, ctx->psys); delete ctx->psys; ctx->psys = nullptr; }
     comm_free(ctx);
-    if (ctx->psys) { pressure_free(ctx, ctx->psys); delete ctx->psys; }
     cudaStreamSynchronize(ctx->stream);
     jc_prof_resolve(ctx);
     for (cudaEvent_t e : ctx->prof_free) cudaEventDestroy(e);

@@ -22,6 +22,7 @@ struct NcclApi {
     decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
     decltype(&ncclCommInitRank) CommInitRank = nullptr;
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclCommAbort) CommAbort = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
     decltype(&ncclGroupStart) GroupStart = nullptr;
     decltype(&ncclGroupEnd) GroupEnd = nullptr;
@@ -47,7 +48,7 @@ NcclApi* nccl_api() {
 #define SYM(field, name)                                                              \
     api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.lib, name));          \
     if (!api.field) { api.error = std::string("NCCL symbol missing: ") + name; return; }
-        SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+        SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy") SYM(CommAbort, "ncclCommAbort")
         SYM(GetErrorString, "ncclGetErrorString") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd")
         SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(AllGather, "ncclAllGather") SYM(AllReduce, "ncclAllReduce")
         SYM(Broadcast, "ncclBroadcast")
@@ -173,7 +174,12 @@ void comm_free(jetcu_ctx* ctx) {
     JcComm* c = ctx->comm;
     if (!c) return;
     cudaStreamSynchronize(ctx->stream);
-    if (c->comm) nccl_api()->CommDestroy(c->comm);
+    // ncclCommDestroy blocks until every CUDA graph that captured operations of this communicator is gone; if the caller
+    // still holds solver objects with live V-cycle graphs, abort the communicator instead of hanging in teardown
+    if (c->comm) {
+        if (ctx->live_graphs > 0) nccl_api()->CommAbort(c->comm);
+        else nccl_api()->CommDestroy(c->comm);
+    }
     if (c->d_small) cudaFree(c->d_small);
     if (c->h_small) cudaFreeHost(c->h_small);
     delete c;

@@ -27,6 +27,7 @@ struct jetcu_ctx {
     double* d_partials = nullptr;  // dot-product partial sums (JC_PARTIALS_CAP doubles)
     // z-slab communicator (comm.cu); null = single GPU
     struct JcComm* comm = nullptr;
+    int live_graphs = 0;     // instantiated V-cycle graphs (they pin the NCCL communicator they captured)
     bool graphs_ok = true;   // cleared (for good) the first time a V-cycle capture fails; JETCU_NO_GRAPHS=1 also clears it
     // optional per-kernel-family timing (jetcu_profile_*): CUDA event pairs on `stream`, resolved lazily
     bool profile = false;

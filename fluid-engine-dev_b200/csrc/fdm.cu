@@ -506,7 +506,7 @@ int mg_alloc_vectors(jetcu_ctx* ctx, MgLevels* mg) {
 
 void mg_free(jetcu_ctx* ctx, MgLevels* mg) {
     for (auto& g : mg->vgraph) {
-        if (g.exec) { cudaStreamSynchronize(ctx->stream); cudaGraphExecDestroy(g.exec); }
+        if (g.exec) { cudaStreamSynchronize(ctx->stream); cudaGraphExecDestroy(g.exec); ctx->live_graphs--; }
         g = MgLevels::VGraph();
     }
     jc_free(ctx, mg->pcg_d); jc_free(ctx, mg->pcg_s);
@@ -655,7 +655,7 @@ static int precondition(jetcu_ctx* ctx, MgLevels* mg, const jetcu_mgpcg_params* 
         if (g.exec && g.b == b_in && g.x == *x_inout && g.key == key) slot = &g;
     if (!slot) {
         slot = (mg->vgraph[0].stamp <= mg->vgraph[1].stamp) ? &mg->vgraph[0] : &mg->vgraph[1];
-        if (slot->exec) { cudaStreamSynchronize(ctx->stream); cudaGraphExecDestroy(slot->exec); }
+        if (slot->exec) { cudaStreamSynchronize(ctx->stream); cudaGraphExecDestroy(slot->exec); ctx->live_graphs--; }
         *slot = MgLevels::VGraph();
         uint64_t m0, b0, m1, b1;
         comm_counters(ctx, &m0, &b0);
@@ -681,6 +681,7 @@ static int precondition(jetcu_ctx* ctx, MgLevels* mg, const jetcu_mgpcg_params* 
             return precondition_eager(ctx, mg, p, b_in, x_inout, scratch);
         }
         slot->exec = exec; slot->b = b_in; slot->x = *x_inout; slot->key = key;
+        ctx->live_graphs++;
         slot->launches = ctx->launches - l0; slot->messages = m1 - m0; slot->bytes = b1 - b0;
         ctx->launches = l0;
         comm_counters_add(ctx, m0 - m1, b0 - b1);  // the capture itself sent nothing

@@ -122,6 +122,7 @@ def main():
         with open(os.path.join(outdir, "rank%d.json" % rank), "w") as f:
             json.dump(out, f)
     print(json.dumps(out), flush=True)
+    jd.close(); js.close()   # contexts (graphs, then the NCCL communicator) go before torch's process group
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

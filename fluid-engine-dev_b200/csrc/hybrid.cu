@@ -440,7 +440,36 @@ __host__ __device__ constexpr unsigned p2g_combo_mask(int ox, int oy, int oz) {
     return m;
 }
 
-template <bool APIC, int AX>
+// Carry-free shared accumulator (experimental, JETCU_P2G_KERNEL=carryfree): the 128-bit non-negative integer is spread
+// over five 32-bit words holding 26 bits each, so an addition is five independent fire-and-forget adds (RED) with no
+// carry to propagate — acc_limbs chains up to four atomics through their return values.  A word overflows only after 64
+// additions; a face receives at most 18 per tile and component here.
+__device__ __forceinline__ void acc_limbs26(unsigned* L, int stride, unsigned long long hi, unsigned long long lo) {
+    const unsigned M = (1u << 26) - 1u;
+    const unsigned l0 = (unsigned)lo & M, l1 = (unsigned)(lo >> 26) & M;
+    const unsigned l2 = (unsigned)((lo >> 52) | (hi << 12)) & M, l3 = (unsigned)(hi >> 14) & M, l4 = (unsigned)(hi >> 40);
+    if (l0) atomicAdd(L, l0);
+    if (l1) atomicAdd(L + stride, l1);
+    if (l2) atomicAdd(L + 2 * stride, l2);
+    if (l3) atomicAdd(L + 3 * stride, l3);
+    if (l4) atomicAdd(L + 4 * stride, l4);
+}
+
+__device__ __forceinline__ void limbs26_to_u128(const unsigned* L, int stride, unsigned long long* hi, unsigned long long* lo) {
+    unsigned long long h = 0ull, l = 0ull;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const unsigned long long v = L[j * stride];
+        const int sh = 26 * j;
+        const unsigned long long plo = sh < 64 ? v << sh : 0ull;
+        const unsigned long long phi = sh == 0 ? 0ull : (sh < 64 ? v >> (64 - sh) : v << (sh - 64));
+        l += plo;
+        h += phi + (l < plo ? 1ull : 0ull);
+    }
+    *hi = h; *lo = l;
+}
+
+template <bool APIC, int AX, bool CF>
 __device__ __forceinline__ void p2g_cell_component(const GridD& g, int ci, int cj, int ck, uint32_t s0, uint32_t e0,
                                                    const AttrPtrs& a, double scale, int I0, int J0, int K0, unsigned* sV,
                                                    unsigned* sW, unsigned char* sM, const P2GAcc& acc) {
@@ -542,25 +571,26 @@ __device__ __forceinline__ void p2g_cell_component(const GridD& g, int ci, int c
                 const unsigned long long w2l = wl << 1, w2h = (wh << 1) | (wl >> 63);
                 const unsigned long long bl = vl + w2l, bh = vh + w2h + (bl < vl ? 1ull : 0ull);
                 const int t = ((bz0 + c - lz0) * TDY + (by0 + b - ly0)) * TDX + (bx0 + x - lx0);
-                acc_limbs(sV + t, NF, bh, bl);
-                acc_limbs(sW + t, NF, wh, wl);
+                if (CF) { acc_limbs26(sV + t, NF, bh, bl); acc_limbs26(sW + t, NF, wh, wl); }
+                else { acc_limbs(sV + t, NF, bh, bl); acc_limbs(sW + t, NF, wh, wl); }
                 sM[t] = 1;
             }
 }
 
-template <bool APIC>
+template <bool APIC, bool CF>
 __global__ void __launch_bounds__(P2G_THREADS)
     k_p2g_cells(GridD g, int kbase, int kend, const uint32_t* __restrict__ cell_start, AttrPtrs a,
                 const P2GScale* __restrict__ sc, P2GAcc acc) {
     constexpr int NF = (TC + 1) * (TC + 2) * (TC + 2);
+    constexpr int NL = CF ? 5 : 4;  // 32-bit words per shared accumulator
     extern __shared__ __align__(16) unsigned p2g_smem[];
-    unsigned(*sV)[4][NF] = reinterpret_cast<unsigned(*)[4][NF]>(p2g_smem);             // [3][limb] value + 2 * weight
-    unsigned(*sW)[4][NF] = reinterpret_cast<unsigned(*)[4][NF]>(p2g_smem + 12 * NF);   // [3][limb] weight
-    unsigned char(*sM)[NF] = reinterpret_cast<unsigned char(*)[NF]>(p2g_smem + 24 * NF);  // [3] markers
+    unsigned(*sV)[NL][NF] = reinterpret_cast<unsigned(*)[NL][NF]>(p2g_smem);                 // [3][limb] value + 2 * weight
+    unsigned(*sW)[NL][NF] = reinterpret_cast<unsigned(*)[NL][NF]>(p2g_smem + 3 * NL * NF);   // [3][limb] weight
+    unsigned char(*sM)[NF] = reinterpret_cast<unsigned char(*)[NF]>(p2g_smem + 6 * NL * NF);  // [3] markers
     __shared__ int any;
     const int I0 = blockIdx.x * TC, J0 = blockIdx.y * TC, K0 = kbase + blockIdx.z * TC;
     if (threadIdx.x == 0) any = 0;
-    for (int t = threadIdx.x; t < 24 * NF; t += P2G_THREADS) p2g_smem[t] = 0u;
+    for (int t = threadIdx.x; t < 6 * NL * NF; t += P2G_THREADS) p2g_smem[t] = 0u;
     for (int t = threadIdx.x; t < 3 * NF; t += P2G_THREADS) (&sM[0][0])[t] = 0;
     __syncthreads();
     const double scale = sc->scale;
@@ -572,9 +602,9 @@ __global__ void __launch_bounds__(P2G_THREADS)
         const uint32_t s0 = cell_start[cell], e0 = cell_start[cell + 1];
         if (s0 == e0) continue;
         touched = 1;
-        p2g_cell_component<APIC, 0>(g, ci, cj, ck, s0, e0, a, scale, I0, J0, K0, &sV[0][0][0], &sW[0][0][0], &sM[0][0], acc);
-        p2g_cell_component<APIC, 1>(g, ci, cj, ck, s0, e0, a, scale, I0, J0, K0, &sV[1][0][0], &sW[1][0][0], &sM[1][0], acc);
-        p2g_cell_component<APIC, 2>(g, ci, cj, ck, s0, e0, a, scale, I0, J0, K0, &sV[2][0][0], &sW[2][0][0], &sM[2][0], acc);
+        p2g_cell_component<APIC, 0, CF>(g, ci, cj, ck, s0, e0, a, scale, I0, J0, K0, &sV[0][0][0], &sW[0][0][0], &sM[0][0], acc);
+        p2g_cell_component<APIC, 1, CF>(g, ci, cj, ck, s0, e0, a, scale, I0, J0, K0, &sV[1][0][0], &sW[1][0][0], &sM[1][0], acc);
+        p2g_cell_component<APIC, 2, CF>(g, ci, cj, ck, s0, e0, a, scale, I0, J0, K0, &sV[2][0][0], &sW[2][0][0], &sM[2][0], acc);
     }
     if (touched) any = 1;
     __syncthreads();
@@ -588,10 +618,16 @@ __global__ void __launch_bounds__(P2G_THREADS)
             if (!sM[ax][t]) continue;
             const int lx = t % dx, ly = (t / dx) % dy, lz = t / (dx * dy);
             const size_t f = ((size_t)(lz0 + lz) * sy + (ly0 + ly)) * sx + (lx0 + lx);
-            const unsigned long long wl = (unsigned long long)sW[ax][0][t] | ((unsigned long long)sW[ax][1][t] << 32);
-            const unsigned long long wh = (unsigned long long)sW[ax][2][t] | ((unsigned long long)sW[ax][3][t] << 32);
-            unsigned long long vl = (unsigned long long)sV[ax][0][t] | ((unsigned long long)sV[ax][1][t] << 32);
-            unsigned long long vh = (unsigned long long)sV[ax][2][t] | ((unsigned long long)sV[ax][3][t] << 32);
+            unsigned long long wl, wh, vl, vh;
+            if (CF) {
+                limbs26_to_u128(&sW[ax][0][t], NF, &wh, &wl);
+                limbs26_to_u128(&sV[ax][0][t], NF, &vh, &vl);
+            } else {
+                wl = (unsigned long long)sW[ax][0][t] | ((unsigned long long)sW[ax][1][t] << 32);
+                wh = (unsigned long long)sW[ax][2][t] | ((unsigned long long)sW[ax][3][t] << 32);
+                vl = (unsigned long long)sV[ax][0][t] | ((unsigned long long)sV[ax][1][t] << 32);
+                vh = (unsigned long long)sV[ax][2][t] | ((unsigned long long)sV[ax][3][t] << 32);
+            }
             const unsigned long long w2l = wl << 1, w2h = (wh << 1) | (wl >> 63);
             vh = vh - w2h - (vl < w2l ? 1ull : 0ull); vl = vl - w2l;  // remove the bias: exact 128-bit subtraction
             acc128(acc.sum[ax] + f, acc.sum_lo[ax] + f, vh, vl);
@@ -1751,22 +1787,31 @@ int jetcu_hybrid_transfer_particles_to_grids(jetcu_hybrid* h) {
         acc.marker[0] = h->um; acc.marker[1] = h->vm; acc.marker[2] = h->wm;
         const int kb = slab ? max(h->z0 - SLAB_GHOST, 0) : 0, ke = slab ? min(h->z1 + SLAB_GHOST, h->nz) : h->nz;
         dim3 grid((g.nx + TC - 1) / TC, (g.ny + TC - 1) / TC, (ke - kb + TC - 1) / TC);
-        const size_t smem = (size_t)(TC + 1) * (TC + 2) * (TC + 2) * (24 * 4 + 3);
+        const size_t nface = (size_t)(TC + 1) * (TC + 2) * (TC + 2);
+        const size_t smem = nface * (24 * 4 + 3), smem_cf = nface * (30 * 4 + 3);
         static bool attr_set = false;
         if (!attr_set) {
             JC_CUDA(ctx, cudaFuncSetAttribute(k_p2g_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             JC_CUDA(ctx, cudaFuncSetAttribute(k_p2g_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            JC_CUDA(ctx, cudaFuncSetAttribute(k_p2g_cells<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            JC_CUDA(ctx, cudaFuncSetAttribute(k_p2g_cells<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            JC_CUDA(ctx, cudaFuncSetAttribute((k_p2g_cells<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            JC_CUDA(ctx, cudaFuncSetAttribute((k_p2g_cells<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            JC_CUDA(ctx, cudaFuncSetAttribute((k_p2g_cells<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cf));
+            JC_CUDA(ctx, cudaFuncSetAttribute((k_p2g_cells<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cf));
             attr_set = true;
         }
         // per-cell register accumulation needs every component grid to have >= 2 samples per axis (its 2-wide node
-        // window must exist); degenerate 1-cell-thick grids take the per-particle form
-        const bool per_cell = g.nx >= 2 && g.ny >= 2 && g.nz >= 2 && !getenv("JETCU_P2G_PER_PARTICLE");
+        // window must exist); degenerate 1-cell-thick grids take the per-particle form.  JETCU_P2G_KERNEL selects the
+        // experimental variants for A/B runs: "particle" (per-particle form), "carryfree" (26-bit redundant limbs)
+        const char* pk = getenv("JETCU_P2G_KERNEL");
+        const bool per_cell = g.nx >= 2 && g.ny >= 2 && g.nz >= 2 && !(pk && !strcmp(pk, "particle"));
+        const bool carry_free = per_cell && pk && !strcmp(pk, "carryfree");
         if (h->nsorted > 0) {
-            if (per_cell) {
-                if (apic) JC_LAUNCH(ctx, (k_p2g_cells<true>), grid, P2G_THREADS, smem, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
-                else JC_LAUNCH(ctx, (k_p2g_cells<false>), grid, P2G_THREADS, smem, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
+            if (carry_free) {
+                if (apic) JC_LAUNCH(ctx, (k_p2g_cells<true, true>), grid, P2G_THREADS, smem_cf, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
+                else JC_LAUNCH(ctx, (k_p2g_cells<false, true>), grid, P2G_THREADS, smem_cf, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
+            } else if (per_cell) {
+                if (apic) JC_LAUNCH(ctx, (k_p2g_cells<true, false>), grid, P2G_THREADS, smem, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
+                else JC_LAUNCH(ctx, (k_p2g_cells<false, false>), grid, P2G_THREADS, smem, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
             } else {
                 if (apic) JC_LAUNCH(ctx, (k_p2g_scatter<true>), grid, P2G_THREADS, smem, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
                 else JC_LAUNCH(ctx, (k_p2g_scatter<false>), grid, P2G_THREADS, smem, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);

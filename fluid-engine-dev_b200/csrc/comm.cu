@@ -22,7 +22,6 @@ struct NcclApi {
     decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
     decltype(&ncclCommInitRank) CommInitRank = nullptr;
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
-    decltype(&ncclCommAbort) CommAbort = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
     decltype(&ncclGroupStart) GroupStart = nullptr;
     decltype(&ncclGroupEnd) GroupEnd = nullptr;
@@ -48,7 +47,7 @@ NcclApi* nccl_api() {
 #define SYM(field, name)                                                              \
     api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.lib, name));          \
     if (!api.field) { api.error = std::string("NCCL symbol missing: ") + name; return; }
-        SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy") SYM(CommAbort, "ncclCommAbort")
+        SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
         SYM(GetErrorString, "ncclGetErrorString") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd")
         SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(AllGather, "ncclAllGather") SYM(AllReduce, "ncclAllReduce")
         SYM(Broadcast, "ncclBroadcast")
@@ -174,12 +173,10 @@ void comm_free(jetcu_ctx* ctx) {
     JcComm* c = ctx->comm;
     if (!c) return;
     cudaStreamSynchronize(ctx->stream);
-    // ncclCommDestroy blocks until every CUDA graph that captured operations of this communicator is gone; if the caller
-    // still holds solver objects with live V-cycle graphs, abort the communicator instead of hanging in teardown
-    if (c->comm) {
-        if (ctx->live_graphs > 0) nccl_api()->CommAbort(c->comm);
-        else nccl_api()->CommDestroy(c->comm);
-    }
+    // NCCL's teardown (destroy and abort alike) polls until every CUDA graph that captured operations of this
+    // communicator has been destroyed.  Contexts free their own graphs first (jetcu_ctx_destroy); if the caller still
+    // holds solver objects with live V-cycle graphs, the communicator is deliberately leaked instead of hanging here.
+    if (c->comm && ctx->live_graphs <= 0) nccl_api()->CommDestroy(c->comm);
     if (c->d_small) cudaFree(c->d_small);
     if (c->h_small) cudaFreeHost(c->h_small);
     delete c;

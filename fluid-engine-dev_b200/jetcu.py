@@ -302,6 +302,19 @@ class HybridApi:
         self._c("hybrid_get_affine", self.h, _p(cx), _p(cy), _p(cz))
         return cx, cy, cz
 
+    def set_collider_shape(self, kind, a, b=(0.0, 0.0, 0.0), linear_velocity=(0.0, 0.0, 0.0), angular_velocity=(0.0, 0.0, 0.0),
+                           friction=0.0):
+        """Analytic rigid collider: kind "box" (a = lower, b = upper corner) or "sphere" (a = centre, b[0] = radius);
+        None / "none" removes it.  Oracle only so far (the CUDA path rejects colliders: SURVEY §8f-1)."""
+        code = {None: 0, "none": 0, "box": 1, "sphere": 2}[kind]
+        self._c("hybrid_set_collider_shape", self.h, C.c_int(code), (f64 * 3)(*a), (f64 * 3)(*b), (f64 * 3)(*linear_velocity),
+                (f64 * 3)(*angular_velocity), f64(friction))
+
+    def get_collider_sdf(self):
+        s = np.zeros(size3(self.grid.res))
+        self._c("hybrid_get_collider_sdf", self.h, _p(s))
+        return s
+
     def set_velocity(self, u, v, w):
         self._c("hybrid_set_velocity", self.h, _p(c64(u)), _p(c64(v)), _p(c64(w)))
 

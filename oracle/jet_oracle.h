@@ -98,6 +98,12 @@ int jeto_hybrid_emit_box(jeto_hybrid*, const double lower[3], const double upper
 uint64_t jeto_hybrid_num_particles(const jeto_hybrid*);
 int jeto_hybrid_get_particles(jeto_hybrid*, double* positions, double* velocities);
 int jeto_hybrid_get_affine(jeto_hybrid*, double* cx, double* cy, double* cz);
+/* Analytic rigid collider (RigidBodyCollider3 over a Box3 or Sphere3, identity transform) for the hybrid solver:
+ * kind 0 none, 1 box (a = lower corner, b = upper corner), 2 sphere (a = centre, b[0] = radius). */
+int jeto_hybrid_set_collider_shape(jeto_hybrid*, int kind, const double a[3], const double b[3],
+                                   const double linear_velocity[3], const double angular_velocity[3], double friction);
+/* GridFractionalBoundaryConditionSolver3::_colliderSdf after the next constrainVelocity / as rasterised (cell-centred). */
+int jeto_hybrid_get_collider_sdf(jeto_hybrid*, double* sdf);
 int jeto_hybrid_set_velocity(jeto_hybrid*, const double* u, const double* v, const double* w);
 int jeto_hybrid_get_velocity(jeto_hybrid*, double* u, double* v, double* w);
 int jeto_hybrid_get_sdf(jeto_hybrid*, double* sdf);

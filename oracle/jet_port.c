@@ -772,4 +772,5 @@ int jeto_pressure_get_system(uint32_t level, jeto_row* A, double* b, float* flui
     return 0;
 }
 
+#include "jet_port_collider.inc"
 #include "jet_port_particles.inc"

@@ -357,6 +357,34 @@ int jeto_hybrid_create(const jeto_hybrid_params* p, jeto_hybrid** out) {
 
 int jeto_hybrid_destroy(jeto_hybrid* h) { delete h; return 0; }
 
+int jeto_hybrid_set_collider_shape(jeto_hybrid* h, int kind, const double a[3], const double b[3], const double lin[3],
+                                   const double ang[3], double friction) {
+    if (kind == 0) { h->solver->setCollider(nullptr); return 0; }
+    Surface3Ptr surface;
+    if (kind == 1) surface = std::make_shared<Box3>(Vector3D(a[0], a[1], a[2]), Vector3D(b[0], b[1], b[2]));
+    else if (kind == 2) surface = std::make_shared<Sphere3>(Vector3D(a[0], a[1], a[2]), b[0]);
+    else return 1;
+    auto col = std::make_shared<RigidBodyCollider3>(surface,
+                                                    lin ? Vector3D(lin[0], lin[1], lin[2]) : Vector3D(),
+                                                    ang ? Vector3D(ang[0], ang[1], ang[2]) : Vector3D());
+    col->setFrictionCoefficient(friction);
+    h->solver->setCollider(col);
+    // what GridFluidSolver3::beginAdvanceTimeStep does before anything reads the collider grid (:448-453)
+    auto grids = h->solver->gridSystemData();
+    h->solver->_boundaryConditionSolver->updateCollider(col, grids->resolution(), grids->gridSpacing(), grids->origin());
+    return 0;
+}
+
+int jeto_hybrid_get_collider_sdf(jeto_hybrid* h, double* sdf) {
+    auto field = h->solver->colliderSdf();
+    auto grid = std::dynamic_pointer_cast<CellCenteredScalarGrid3>(field);
+    auto res = h->solver->gridSystemData()->resolution();
+    size_t n = res.x * res.y * res.z;
+    if (!grid) { for (size_t i = 0; i < n; ++i) sdf[i] = kMaxD; return 0; }
+    std::memcpy(sdf, grid->constDataAccessor().data(), n * sizeof(double));
+    return 0;
+}
+
 int jeto_hybrid_set_particles(jeto_hybrid* h, uint64_t n, const double* pos, const double* vel) {
     auto ps = h->solver->particleSystemData();
     ps->resize(n);

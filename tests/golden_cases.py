@@ -157,3 +157,53 @@ def hybrid(make_hybrid, mode, exact_bits, tol_pos=1e-5, tol_grid=1e-9):
     else:
         assert np.abs(pos - g["pos5"]).max() <= tol_pos * domain
     h.close()
+
+
+# ---------------------------------------------------------------------------------------------- colliders
+# FLIP / APIC dam column running into an analytic rigid collider.  Oracle-only so far: the
+# CUDA path rejects colliders; these are the answers it will be checked against.
+COLLIDER_CASES = {
+    "flip_box": dict(mode=FLIP, shape=dict(kind="box", a=(0.55, 0.0, 0.3), b=(0.8, 0.35, 0.7), friction=0.2)),
+    "apic_sphere_moving": dict(mode=APIC, shape=dict(kind="sphere", a=(0.62, 0.2, 0.5), b=(0.17, 0.0, 0.0),
+                                                     linear_velocity=(-0.3, 0.0, 0.05), angular_velocity=(0.0, 0.4, 0.0),
+                                                     friction=0.1)),
+}
+
+
+def collider_run(make_hybrid, name, n=12, steps=3):
+    case = COLLIDER_CASES[name]
+    prm = HybridParams.make(Grid.cube(n), mode=case["mode"], mgpcg=MgpcgParams.make(max_iterations=60, max_levels=2))
+    h = make_hybrid(prm)
+    h.set_collider_shape(**case["shape"])
+    out = {"collider_sdf": h.get_collider_sdf()}
+    rng = np.random.default_rng(21)
+    u = rng.uniform(-1, 1, (n, n, n + 1)); v = rng.uniform(-1, 1, (n, n + 1, n)); w = rng.uniform(-1, 1, (n + 1, n, n))
+    h.set_velocity(u, v, w)
+    h.apply_boundary_condition()
+    out["u_bc"], out["v_bc"], out["w_bc"] = h.get_velocity()
+    h.emit_box((0.0, 0.0, 0.0), (0.7, 0.7, 1.0), 0.5 / n, (0.8, 0.0, 0.0))
+    iters = []
+    for _ in range(steps):
+        iters.append(h.step(1.0 / 60.0).pcg_iterations)
+    out["pos"], out["vel"] = h.get_particles()
+    out["u"], out["v"], out["w"] = h.get_velocity()
+    out["sdf"] = h.get_sdf()
+    out["pressure"] = h.get_pressure()
+    out["iterations"] = np.array(iters)
+    h.close()
+    return out
+
+
+def collider(make_hybrid, name, exact_bits):
+    g = load("hybrid_collider_%s.npz" % name)
+    out = collider_run(make_hybrid, name)
+    if exact_bits:
+        for k in g.files:
+            exact(out[k], g[k], "%s: %s" % (name, k))
+    else:
+        exact(out["collider_sdf"], g["collider_sdf"], "collider sdf")
+        vs = max(float(np.abs(g[k]).max()) for k in ("u_bc", "v_bc", "w_bc"))
+        for k in ("u_bc", "v_bc", "w_bc"):
+            close(out[k], g[k], 1e-12, k, vs)
+        assert np.abs(out["pos"] - g["pos"]).max() <= 1e-5
+        close(out["pressure"], g["pressure"], 1e-6, "pressure")

@@ -35,3 +35,8 @@ def test_bin_points(port):
 @pytest.mark.parametrize("mode", [PIC, FLIP, APIC])
 def test_hybrid(port, mode):
     gc.hybrid(port.hybrid, mode, exact_bits=True)
+
+
+@pytest.mark.parametrize("name", sorted(gc.COLLIDER_CASES))
+def test_hybrid_with_collider(port, name):
+    gc.collider(port.hybrid, name, exact_bits=True)

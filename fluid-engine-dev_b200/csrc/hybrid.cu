@@ -17,6 +17,7 @@
 #include "particles.cuh"
 #include "pressure.cuh"
 #include "sampling.cuh"
+#include "collider.cuh"
 
 #define NATTR 15  // px,py,pz, vx,vy,vz, cX(3), cY(3), cZ(3)
 
@@ -50,6 +51,12 @@ struct jetcu_hybrid {
     uint64_t base = 0;     // first owned particle inside attr[cur]
     uint64_t nsorted = 0;  // ghost-lo + owned + ghost-hi (the cell-sorted live range starts at 0)
     uint64_t nglobal = 0;  // particles on all ranks (== np on a single GPU)
+    // analytic rigid collider; col.kind == 0: none
+    ColliderD col;
+    double* col_sdf = nullptr;                          // GridFractionalBoundaryConditionSolver3::_colliderSdf
+    double *bnd_u = nullptr, *bnd_v = nullptr, *bnd_w = nullptr;  // collider velocity at the face positions (pressure rhs)
+    double *tmp_u = nullptr, *tmp_v = nullptr, *tmp_w = nullptr;  // uTemp / vTemp / wTemp of constrainVelocity
+    char *cm_u = nullptr, *cm_v = nullptr, *cm_w = nullptr;       // its uMarker / vMarker / wMarker
     PressureSystem ps;
     jetcu_mgpcg_result last{};
     cudaEvent_t ev[12] = {};
@@ -1124,6 +1131,125 @@ __global__ void k_u64_to_u32(const uint64_t* __restrict__ in, uint32_t* __restri
     if (i < n) out[i] = (uint32_t)in[i];
 }
 
+// ------------------------------------------------------------------------------------------------ collider
+// GridFractionalBoundaryConditionSolver3::onColliderUpdated — src/jet/grid_fractional_boundary_condition_solver3.cpp:244-280:
+// _colliderSdf(i,j,k) = SurfaceToImplicit3(surface).signedDistance(dataPosition(i,j,k)).
+__global__ void __launch_bounds__(256) k_collider_sdf(GridD g, ColliderD c, double* __restrict__ sdf) {
+    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+    if (i >= g.nx || j >= g.ny) return;
+    const double pt[3] = {(g.ox + 0.5 * g.hx) + g.hx * (double)i, (g.oy + 0.5 * g.hy) + g.hy * (double)j,
+                          (g.oz + 0.5 * g.hz) + g.hz * (double)k};
+    sdf[((size_t)k * g.ny + j) * g.nx + i] = cd_signed_distance(c, pt);
+}
+
+__device__ __forceinline__ GridView collider_view(const GridD& g, const double* sdf) {
+    GridView v;
+    v.data = sdf; v.nx = g.nx; v.ny = g.ny; v.nz = g.nz; v.hx = g.hx; v.hy = g.hy; v.hz = g.hz;
+    v.ox = g.ox + 0.5 * g.hx; v.oy = g.oy + 0.5 * g.hy; v.oz = g.oz + 0.5 * g.hz;
+    v.ihx = g.ihx; v.ihy = g.ihy; v.ihz = g.ihz;
+    return v;
+}
+
+// constrainVelocity, first pass (…boundary_condition_solver3.cpp:55-104): faces whose open fraction is 0 take the
+// collider's velocity and are marked invalid (0) for the extrapolation that follows.
+template <int AXIS>
+__global__ void __launch_bounds__(256) k_constrain_markers(GridD g, ColliderD c, const double* __restrict__ csdf,
+                                                           double* __restrict__ data, char* __restrict__ marker) {
+    const int sx = g.nx + (AXIS == 0), sy = g.ny + (AXIS == 1), sz = g.nz + (AXIS == 2);
+    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+    if (i >= sx || j >= sy || k >= sz) return;
+    const GridView cs = collider_view(g, csdf);
+    const double fox = g.ox + 0.5 * (AXIS == 0 ? 0.0 : g.hx), foy = g.oy + 0.5 * (AXIS == 1 ? 0.0 : g.hy),
+                 foz = g.oz + 0.5 * (AXIS == 2 ? 0.0 : g.hz);
+    const double pt[3] = {fox + g.hx * (double)i, foy + g.hy * (double)j, foz + g.hz * (double)k};
+    const double hx = AXIS == 0 ? 0.5 * g.hx : 0.0, hy = AXIS == 1 ? 0.5 * g.hy : 0.0, hz = AXIS == 2 ? 0.5 * g.hz : 0.0;
+    const double phi0 = jc_sample(cs, pt[0] - hx, pt[1] - hy, pt[2] - hz);
+    const double phi1 = jc_sample(cs, pt[0] + hx, pt[1] + hy, pt[2] + hz);
+    double frac = jc_frac_inside_sdf(phi0, phi1);
+    frac = 1.0 - jc_clamp(frac, 0.0, 1.0);
+    const size_t f = ((size_t)k * sy + j) * sx + i;
+    if (frac > 0.0) {
+        marker[f] = 1;
+    } else {
+        double cv[3];
+        cd_velocity_at(c, pt, cv);
+        data[f] = cv[AXIS];
+        marker[f] = 0;
+    }
+}
+
+// boundaryVelocity.sample(facePosition) component as the pressure solver reads it (…pressure_solver3.cpp:242-255):
+// the collider's velocity field is collider->velocityAt (…boundary_condition_solver3.cpp:265-270).
+template <int AXIS>
+__global__ void __launch_bounds__(256) k_boundary_velocity(GridD g, ColliderD c, double* __restrict__ bnd) {
+    const int sx = g.nx + (AXIS == 0), sy = g.ny + (AXIS == 1), sz = g.nz + (AXIS == 2);
+    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+    if (i >= sx || j >= sy || k >= sz) return;
+    const double fox = g.ox + 0.5 * (AXIS == 0 ? 0.0 : g.hx), foy = g.oy + 0.5 * (AXIS == 1 ? 0.0 : g.hy),
+                 foz = g.oz + 0.5 * (AXIS == 2 ? 0.0 : g.hz);
+    const double pt[3] = {fox + g.hx * (double)i, foy + g.hy * (double)j, foz + g.hz * (double)k};
+    double cv[3];
+    cd_velocity_at(c, pt, cv);
+    bnd[((size_t)k * sy + j) * sx + i] = cv[AXIS];
+}
+
+// constrainVelocity, no-flux pass (…:115-187): inside the collider the (extrapolated) fluid velocity keeps only its
+// tangential part relative to the collider, with friction; reads the whole field, writes the temporary.
+template <int AXIS>
+__global__ void __launch_bounds__(256) k_constrain_project(GridD g, ColliderD c, const double* __restrict__ csdf,
+                                                           const double* __restrict__ u, const double* __restrict__ v,
+                                                           const double* __restrict__ w, double* __restrict__ temp) {
+    const int sx = g.nx + (AXIS == 0), sy = g.ny + (AXIS == 1), sz = g.nz + (AXIS == 2);
+    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+    if (i >= sx || j >= sy || k >= sz) return;
+    const GridView cs = collider_view(g, csdf);
+    const double fox = g.ox + 0.5 * (AXIS == 0 ? 0.0 : g.hx), foy = g.oy + 0.5 * (AXIS == 1 ? 0.0 : g.hy),
+                 foz = g.oz + 0.5 * (AXIS == 2 ? 0.0 : g.hz);
+    const double pt[3] = {fox + g.hx * (double)i, foy + g.hy * (double)j, foz + g.hz * (double)k};
+    const size_t f = ((size_t)k * sy + j) * sx + i;
+    const double* self = AXIS == 0 ? u : (AXIS == 1 ? v : w);
+    if (jc_sample(cs, pt[0], pt[1], pt[2]) < 0) {  // isInsideSdf
+        double cv[3], gr[3], vel[3];
+        cd_velocity_at(c, pt, cv);
+        vel[0] = jc_sample(comp_view(g, 0, u), pt[0], pt[1], pt[2]);
+        vel[1] = jc_sample(comp_view(g, 1, v), pt[0], pt[1], pt[2]);
+        vel[2] = jc_sample(comp_view(g, 2, w), pt[0], pt[1], pt[2]);
+        cd_grid_gradient(cs, pt[0], pt[1], pt[2], gr);
+        if (cd_len2(gr) > 0.0) {
+            const double l = cd_len(gr);
+            const double n[3] = {gr[0] / l, gr[1] / l, gr[2] / l};
+            const double velr[3] = {vel[0] - cv[0], vel[1] - cv[1], vel[2] - cv[2]};
+            double velt[3];
+            cd_project_friction(velr, n, c.friction, velt);
+            temp[f] = velt[AXIS] + cv[AXIS];
+        } else {
+            temp[f] = cv[AXIS];
+        }
+    } else {
+        temp[f] = self[f];
+    }
+}
+
+// GridFluidSolver3::extrapolateIntoCollider(ScalarGrid3*) marker — src/jet/grid_fluid_solver3.cpp:355-369
+__global__ void __launch_bounds__(256) k_outside_collider_marker(GridD g, const double* __restrict__ csdf, char* __restrict__ marker) {
+    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+    if (i >= g.nx || j >= g.ny) return;
+    const GridView cs = collider_view(g, csdf);
+    const double px = (g.ox + 0.5 * g.hx) + g.hx * (double)i, py = (g.oy + 0.5 * g.hy) + g.hy * (double)j,
+                 pz = (g.oz + 0.5 * g.hz) + g.hz * (double)k;
+    marker[((size_t)k * g.ny + j) * g.nx + i] = (jc_sample(cs, px, py, pz) < 0) ? 0 : 1;
+}
+
+// col->resolveCollision(0.0, 0.0, &positions[i], &velocities[i]) — src/jet/pic_solver3.cpp:268-281
+__global__ void k_resolve_collision(ColliderD c, AttrPtrs a, size_t np) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    double pos[3] = {a.p[0][p], a.p[1][p], a.p[2][p]}, vel[3] = {a.p[3][p], a.p[4][p], a.p[5][p]};
+    cd_resolve_collision(c, pos, vel);
+    a.p[0][p] = pos[0]; a.p[1][p] = pos[1]; a.p[2][p] = pos[2];
+    a.p[3][p] = vel[0]; a.p[4][p] = vel[1]; a.p[5][p] = vel[2];
+}
+
 // ================================================================================================ host side
 static AttrPtrs attr_ptrs(jetcu_hybrid* h, int which, size_t offset = 0) {
     AttrPtrs a;
@@ -1288,8 +1414,35 @@ static int hyb_bin(jetcu_hybrid* h) {
     return JETCU_OK;
 }
 
+static int hyb_extrapolate_one(jetcu_hybrid* h, double* data, const char* marker, int sx, int sy, int sz, unsigned depth);
+
+static inline dim3 face_grid(int sx, int sy, int sz) { return dim3((sx + 63) / 64, (sy + 3) / 4, sz); }
+
+// The collider branch of GridFractionalBoundaryConditionSolver3::constrainVelocity
+// (src/jet/grid_fractional_boundary_condition_solver3.cpp:55-187); grid-only work, replicated in slab mode.
+static int hyb_constrain_collider(jetcu_hybrid* h) {
+    jetcu_ctx* ctx = h->ctx;
+    GridD g = gridd(h);
+    const unsigned depth = (unsigned)ceil(h->P.max_cfl);  // GridFluidSolver3::applyBoundaryCondition, grid_fluid_solver3.cpp:346-353
+    const dim3 blk(64, 4);
+    const int nx = h->nx, ny = h->ny, nz = h->nz;
+    JC_LAUNCH(ctx, k_constrain_markers<0>, face_grid(nx + 1, ny, nz), blk, 0, g, h->col, h->col_sdf, h->u, h->cm_u);
+    JC_LAUNCH(ctx, k_constrain_markers<1>, face_grid(nx, ny + 1, nz), blk, 0, g, h->col, h->col_sdf, h->v, h->cm_v);
+    JC_LAUNCH(ctx, k_constrain_markers<2>, face_grid(nx, ny, nz + 1), blk, 0, g, h->col, h->col_sdf, h->w, h->cm_w);
+    JC_TRY(hyb_extrapolate_one(h, h->u, h->cm_u, nx + 1, ny, nz, depth));
+    JC_TRY(hyb_extrapolate_one(h, h->v, h->cm_v, nx, ny + 1, nz, depth));
+    JC_TRY(hyb_extrapolate_one(h, h->w, h->cm_w, nx, ny, nz + 1, depth));
+    JC_LAUNCH(ctx, k_constrain_project<0>, face_grid(nx + 1, ny, nz), blk, 0, g, h->col, h->col_sdf, h->u, h->v, h->w, h->tmp_u);
+    JC_LAUNCH(ctx, k_constrain_project<1>, face_grid(nx, ny + 1, nz), blk, 0, g, h->col, h->col_sdf, h->u, h->v, h->w, h->tmp_v);
+    JC_LAUNCH(ctx, k_constrain_project<2>, face_grid(nx, ny, nz + 1), blk, 0, g, h->col, h->col_sdf, h->u, h->v, h->w, h->tmp_w);
+    JC_TRY(jc_d2d(ctx, h->u, h->tmp_u, h->nu)); JC_TRY(jc_d2d(ctx, h->v, h->tmp_v, h->nv)); JC_TRY(jc_d2d(ctx, h->w, h->tmp_w, h->nw));
+    return JETCU_OK;
+}
+
+// GridFluidSolver3::applyBoundaryCondition == constrainVelocity: the collider branch (if any), then the closed walls.
 static int hyb_zero_walls(jetcu_hybrid* h) {
     jetcu_ctx* ctx = h->ctx;
+    if (h->col.kind != 0) JC_TRY(hyb_constrain_collider(h));
     GridD g = gridd(h);
     size_t m = (size_t)g.ny * g.nz;
     if ((size_t)g.nx * g.nz > m) m = (size_t)g.nx * g.nz;
@@ -1423,6 +1576,9 @@ int jetcu_hybrid_destroy(jetcu_hybrid* h) {
     jc_free(ctx, h->ud); jc_free(ctx, h->vd); jc_free(ctx, h->wd);
     for (int q = 0; q < 3; ++q) { jc_free(ctx, h->wsum[q]); jc_free(ctx, h->wsum_lo[q]); jc_free(ctx, h->sum_lo[q]); }
     jc_free(ctx, h->p2g_scale); jc_free(ctx, h->p2g_err);
+    jc_free(ctx, h->col_sdf); jc_free(ctx, h->bnd_u); jc_free(ctx, h->bnd_v); jc_free(ctx, h->bnd_w);
+    jc_free(ctx, h->tmp_u); jc_free(ctx, h->tmp_v); jc_free(ctx, h->tmp_w);
+    jc_free(ctx, h->cm_u); jc_free(ctx, h->cm_v); jc_free(ctx, h->cm_w);
     for (int b = 0; b < 2; ++b) {
         for (int q = 0; q < NATTR; ++q) jc_free(ctx, h->attr[b][q]);
         jc_free(ctx, h->orig[b]);
@@ -1660,9 +1816,52 @@ int jetcu_hybrid_set_collider(jetcu_hybrid* h, const double* collider_sdf, const
     HYB_ENTER(h);
     if (collider_sdf)
         return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED,
-                          "colliders inside the device-resident hybrid solver are not implemented yet "
-                          "(SURVEY §8f-1); jetcu_pressure_solve accepts a collider SDF");
+                          "a collider given only as an SDF grid cannot resolve particle collisions (the reference "
+                          "queries the analytic surface): use jetcu_hybrid_set_collider_shape");
     return JETCU_OK;
+}
+
+int jetcu_hybrid_set_collider_shape(jetcu_hybrid* h, int kind, const double a[3], const double b[3],
+                                    const double linear_velocity[3], const double angular_velocity[3], double friction) {
+    HYB_ENTER(h);
+    JC_ARG(ctx, kind >= JETCU_COLLIDER_NONE && kind <= JETCU_COLLIDER_SPHERE);
+    h->col = ColliderD();
+    if (kind == JETCU_COLLIDER_NONE) return JETCU_OK;
+    JC_ARG(ctx, a != nullptr && b != nullptr);
+    if (kind == JETCU_COLLIDER_SPHERE) JC_ARG(ctx, b[0] > 0.0);
+    ColliderD c;
+    c.kind = kind;
+    for (int q = 0; q < 3; ++q) {
+        c.a[q] = a[q]; c.b[q] = b[q];
+        c.lin[q] = linear_velocity ? linear_velocity[q] : 0.0;
+        c.ang[q] = angular_velocity ? angular_velocity[q] : 0.0;
+    }
+    c.friction = friction > 0.0 ? friction : 0.0;  // Collider3::setFrictionCoefficient clamps at 0 (collider3.cpp:78-80)
+    if (!h->col_sdf) {
+        JC_TRY(jc_alloc(ctx, &h->col_sdf, h->nc));
+        JC_TRY(jc_alloc(ctx, &h->bnd_u, h->nu)); JC_TRY(jc_alloc(ctx, &h->bnd_v, h->nv)); JC_TRY(jc_alloc(ctx, &h->bnd_w, h->nw));
+        JC_TRY(jc_alloc(ctx, &h->tmp_u, h->nu)); JC_TRY(jc_alloc(ctx, &h->tmp_v, h->nv)); JC_TRY(jc_alloc(ctx, &h->tmp_w, h->nw));
+        JC_TRY(jc_alloc(ctx, &h->cm_u, h->nu)); JC_TRY(jc_alloc(ctx, &h->cm_v, h->nv)); JC_TRY(jc_alloc(ctx, &h->cm_w, h->nw));
+    }
+    GridD g = gridd(h);
+    const dim3 blk(64, 4);
+    // the reference re-rasterises the (static) shape at every beginAdvanceTimeStep (grid_fluid_solver3.cpp:448-453):
+    // a pure function of the shape, so once here
+    JC_LAUNCH(ctx, k_collider_sdf, face_grid(h->nx, h->ny, h->nz), blk, 0, g, c, h->col_sdf);
+    JC_LAUNCH(ctx, k_boundary_velocity<0>, face_grid(h->nx + 1, h->ny, h->nz), blk, 0, g, c, h->bnd_u);
+    JC_LAUNCH(ctx, k_boundary_velocity<1>, face_grid(h->nx, h->ny + 1, h->nz), blk, 0, g, c, h->bnd_v);
+    JC_LAUNCH(ctx, k_boundary_velocity<2>, face_grid(h->nx, h->ny, h->nz + 1), blk, 0, g, c, h->bnd_w);
+    JC_TRY(jc_sync(ctx));
+    h->col = c;
+    return JETCU_OK;
+}
+
+int jetcu_hybrid_get_collider_sdf(jetcu_hybrid* h, double* sdf) {
+    HYB_ENTER(h);
+    JC_ARG(ctx, sdf);
+    if (h->col.kind == 0) { for (size_t i = 0; i < h->nc; ++i) sdf[i] = DBL_MAX; return JETCU_OK; }  // fill(kMaxD), :272
+    JC_TRY(jc_d2h(ctx, sdf, h->col_sdf, h->nc));
+    return jc_sync(ctx);
 }
 
 int jetcu_hybrid_set_velocity(jetcu_hybrid* h, const double* u, const double* v, const double* w) {
@@ -1857,6 +2056,10 @@ int jetcu_hybrid_build_signed_distance_field(jetcu_hybrid* h) {
     JC_LAUNCH(ctx, k_build_sdf, grid, dim3(32, 4), 0, g, h->cell_start, h->attr[c][0], h->attr[c][1], h->attr[c][2], radius,
               band, rx, ry, rz, h->z0, h->sdf);
     JC_TRY(hyb_gather_planes(h, h->sdf, (size_t)h->nx * h->ny * 8, false));
+    if (h->col.kind != 0) {  // GridFluidSolver3::extrapolateIntoCollider(ScalarGrid3*), grid_fluid_solver3.cpp:355-369
+        JC_LAUNCH(ctx, k_outside_collider_marker, face_grid(h->nx, h->ny, h->nz), dim3(64, 4), 0, g, h->col_sdf, h->cm_u);
+        JC_TRY(hyb_extrapolate_one(h, h->sdf, h->cm_u, h->nx, h->ny, h->nz, (unsigned)ceil(h->P.max_cfl)));
+    }
     // extrapolateIntoCollider (src/jet/grid_fluid_solver3.cpp:355-369) is the identity without a collider
     return JETCU_OK;
 }
@@ -1897,8 +2100,10 @@ int jetcu_hybrid_compute_pressure(jetcu_hybrid* h, double dt, jetcu_mgpcg_result
     (void)dt;
     // GridFluidSolver3::computePressure (:243-253): input is a clone of the velocity; every face is read and written
     // by the same thread of k_apply_gradient, so solving in place is equivalent.
-    JC_TRY(pressure_solve_device(ctx, &h->ps, h->u, h->v, h->w, nullptr, nullptr, nullptr, nullptr, h->sdf, &h->P.mgpcg,
-                                 h->u, h->v, h->w, &h->last));
+    const bool col = h->col.kind != 0;
+    JC_TRY(pressure_solve_device(ctx, &h->ps, h->u, h->v, h->w, col ? h->col_sdf : nullptr, col ? h->bnd_u : nullptr,
+                                 col ? h->bnd_v : nullptr, col ? h->bnd_w : nullptr, h->sdf, &h->P.mgpcg, h->u, h->v, h->w,
+                                 &h->last));
     if (result) *result = h->last;
     return hyb_zero_walls(h);
 }
@@ -1930,6 +2135,8 @@ int jetcu_hybrid_move_particles(jetcu_hybrid* h, double dt) {
     if (h->np)
         HYB_SAMPLER_LAUNCH(k_move, jc_blocks(h->np, 128), 128, g, h->u, h->v, h->w, sub_dt, nsub,
                            h->P.closed_domain_boundary_flag, owned_ptrs(h), (size_t)h->np);
+    if (h->np && h->col.kind != 0)
+        JC_LAUNCH(ctx, k_resolve_collision, jc_blocks(h->np, 128), 128, 0, h->col, owned_ptrs(h), (size_t)h->np);
     h->nsorted = h->np;  // the ghost copies are stale from here on
     h->binned = false;
     return JETCU_OK;

@@ -285,6 +285,18 @@ int jetcu_hybrid_set_collider(jetcu_hybrid*, const double* collider_sdf, const d
                               const double angular_velocity[3], const double rotation_origin[3],
                               double friction_coefficient);
 
+/* Analytic rigid collider == RigidBodyCollider3 (src/jet/rigid_body_collider3.cpp) over a Box3 / Sphere3 with identity
+ * transform installed with GridFluidSolver3::setCollider: kind BOX (a = lower corner, b = upper corner) or SPHERE
+ * (a = centre, b[0] = radius); NONE removes it.  Drives the collider branch of
+ * GridFractionalBoundaryConditionSolver3::constrainVelocity (src/jet/grid_fractional_boundary_condition_solver3.cpp:26-280),
+ * extrapolateIntoCollider (src/jet/grid_fluid_solver3.cpp:355-369), the moving-boundary terms of the pressure system and
+ * Collider3::resolveCollision (src/jet/collider3.cpp:19-74) after moveParticles.  [First CUDA implementation written
+ * against the pinned oracle without GPU time left in round 1: tests/test_gpu_collider.py is its first run.] */
+enum { JETCU_COLLIDER_NONE = 0, JETCU_COLLIDER_BOX = 1, JETCU_COLLIDER_SPHERE = 2 };
+int jetcu_hybrid_set_collider_shape(jetcu_hybrid*, int kind, const double a[3], const double b[3],
+                                    const double linear_velocity[3], const double angular_velocity[3], double friction);
+/* GridFractionalBoundaryConditionSolver3::colliderSdf() (cell-centred); kMaxD everywhere without a collider. */
+int jetcu_hybrid_get_collider_sdf(jetcu_hybrid*, double* sdf);
 int jetcu_hybrid_set_velocity(jetcu_hybrid*, const double* u, const double* v, const double* w);
 int jetcu_hybrid_get_velocity(jetcu_hybrid*, double* u, double* v, double* w);
 int jetcu_hybrid_get_sdf(jetcu_hybrid*, double* sdf);              /* PicSolver3::signedDistanceField() */

@@ -1,0 +1,83 @@
+"""GPU parity for analytic rigid colliders inside the device-resident solver (SURVEY.md §8a-a9 collider branch, §8f-1).
+
+STATUS: the CUDA side (csrc/collider.cuh + the k_constrain_* / k_resolve_collision kernels) was written against the
+pinned oracle (tests/test_oracle_collider.py: port == unmodified reference, bit for bit) after round 1's GPU minutes
+had run out, so this file is its FIRST execution.  The tests are therefore non-strict xfail: a pass shows up as XPASS,
+a failure as XFAIL and never hides the established parity suite (the file also sorts last on purpose).  Round 2 removes
+the marker as its first step.
+
+Expected: collider SDF, constrained velocities, markers — bit-exact (no reductions); steps — positions <= 1e-5 L,
+pressure <= 1e-6 relative (P2G sums in integers, the reference in particle order)."""
+import numpy as np
+import pytest
+
+import golden_cases as gc
+from gpu_common import checker, jetcu_or_fail
+from oracle_api import APIC, FLIP, PIC, Grid, HybridParams, MgpcgParams
+from test_oracle_collider import COLLIDERS
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first GPU run of the collider kernels (see module docstring)")]
+
+
+@pytest.fixture(scope="module")
+def jc():
+    return jetcu_or_fail()
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return checker()
+
+
+def exact(a, b, what):
+    assert np.array_equal(a, b), "%s: max abs diff %g" % (what, float(np.abs(a - b).max()))
+
+
+@pytest.mark.parametrize("name", sorted(COLLIDERS))
+def test_collider_sdf_bit_exact(jc, oracle, name):
+    n = 12
+    prm = HybridParams.make(Grid.cube(n), mode=PIC, mgpcg=MgpcgParams.make(max_levels=2))
+    a, b = jc.hybrid(prm), oracle.hybrid(prm)
+    a.set_collider_shape(**COLLIDERS[name]); b.set_collider_shape(**COLLIDERS[name])
+    exact(a.get_collider_sdf(), b.get_collider_sdf(), "collider sdf")
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("name", sorted(COLLIDERS))
+def test_constrain_velocity_bit_exact(jc, oracle, name):
+    n = 12
+    prm = HybridParams.make(Grid.cube(n), mode=PIC, mgpcg=MgpcgParams.make(max_levels=2))
+    a, b = jc.hybrid(prm), oracle.hybrid(prm)
+    a.set_collider_shape(**COLLIDERS[name]); b.set_collider_shape(**COLLIDERS[name])
+    rng = np.random.default_rng(5)
+    u = rng.uniform(-1, 1, (n, n, n + 1)); v = rng.uniform(-1, 1, (n, n + 1, n)); w = rng.uniform(-1, 1, (n + 1, n, n))
+    a.set_velocity(u, v, w); b.set_velocity(u, v, w)
+    a.apply_boundary_condition(); b.apply_boundary_condition()
+    for x, y, what in zip(a.get_velocity(), b.get_velocity(), "uvw"):
+        exact(x, y, "constrained " + what)
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("mode", [PIC, FLIP, APIC])
+@pytest.mark.parametrize("name", ["box", "box_moving", "sphere"])
+def test_steps_with_collider(jc, oracle, mode, name):
+    n = 16
+    prm = HybridParams.make(Grid.cube(n), mode=mode, mgpcg=MgpcgParams.make(max_iterations=40, max_levels=3))
+    a, b = jc.hybrid(prm), oracle.hybrid(prm)
+    a.set_collider_shape(**COLLIDERS[name]); b.set_collider_shape(**COLLIDERS[name])
+    box = ((0.0, 0.0, 0.0), (0.7, 0.7, 1.0))
+    assert a.emit_box(box[0], box[1], 0.5 / n, (0.8, 0.0, 0.0)) == b.emit_box(box[0], box[1], 0.5 / n, (0.8, 0.0, 0.0))
+    for s in range(3):
+        sa, sb = a.step(1.0 / 60.0), b.step(1.0 / 60.0)
+        pa, va = a.get_particles(); pb, vb = b.get_particles()
+        assert np.abs(pa - pb).max() <= 1e-5, "positions step %d: %g" % (s, np.abs(pa - pb).max())
+        pr_a, pr_b = a.get_pressure(), b.get_pressure()
+        if sb.pcg_true_residual_l2 <= 1e-8 * max(sb.pcg_b_l2, 1e-300):   # only where the oracle's own solve converged
+            assert np.abs(pr_a - pr_b).max() <= 1e-6 * max(np.abs(pr_b).max(), 1e-300), "pressure step %d" % s
+        exact(a.get_sdf(), b.get_sdf(), "particle sdf (extrapolated into the collider) step %d" % s) if s == 0 else None
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("name", sorted(gc.COLLIDER_CASES))
+def test_golden_collider(jc, name):
+    gc.collider(jc.hybrid, name, exact_bits=False)

@@ -14,45 +14,45 @@ struct ColliderD {
     double friction = 0.0;             // Collider3::frictionCoefficient()
 };
 
-__device__ __forceinline__ double cd_dot(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
-__device__ __forceinline__ double cd_len2(const double* a) { return a[0] * a[0] + a[1] * a[1] + a[2] * a[2]; }
-__device__ __forceinline__ double cd_len(const double* a) { return sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); }
-__device__ __forceinline__ double cd_max(double a, double b) { return (a < b) ? b : a; }  // std::max
+__host__ __device__ __forceinline__ double cd_dot(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__host__ __device__ __forceinline__ double cd_len2(const double* a) { return a[0] * a[0] + a[1] * a[1] + a[2] * a[2]; }
+__host__ __device__ __forceinline__ double cd_len(const double* a) { return sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); }
+__host__ __device__ __forceinline__ double cd_max(double a, double b) { return (a < b) ? b : a; }  // std::max
 
 // Transform3 with identity orientation and zero translation, spelt out (include/jet/detail/transform3-inl.h:45-47,
 // 72-79 over Matrix3x3::mul, matrix3x3-inl.h:208-213): exact no-ops except that -0.0 becomes +0.0.
-__device__ __forceinline__ void cd_to_local(const double* p, double* out) {
+__host__ __device__ __forceinline__ void cd_to_local(const double* p, double* out) {
     const double t0 = p[0] - 0.0, t1 = p[1] - 0.0, t2 = p[2] - 0.0;
     out[0] = 1.0 * t0 + 0.0 * t1 + 0.0 * t2;
     out[1] = 0.0 * t0 + 1.0 * t1 + 0.0 * t2;
     out[2] = 0.0 * t0 + 0.0 * t1 + 1.0 * t2;
 }
-__device__ __forceinline__ void cd_to_world_dir(const double* d, double* out) {
+__host__ __device__ __forceinline__ void cd_to_world_dir(const double* d, double* out) {
     out[0] = 1.0 * d[0] + 0.0 * d[1] + 0.0 * d[2];
     out[1] = 0.0 * d[0] + 1.0 * d[1] + 0.0 * d[2];
     out[2] = 0.0 * d[0] + 0.0 * d[1] + 1.0 * d[2];
 }
-__device__ __forceinline__ void cd_to_world(const double* p, double* out) {
+__host__ __device__ __forceinline__ void cd_to_world(const double* p, double* out) {
     double t[3];
     cd_to_world_dir(p, t);
     out[0] = t[0] + 0.0; out[1] = t[1] + 0.0; out[2] = t[2] + 0.0;
 }
 
 // normal of box plane q: +x, +y, +z (through upperCorner), -x, -y, -z (through lowerCorner) — src/jet/box3.cpp:30-35
-__device__ __forceinline__ void cd_box_normal(int q, double* n) {
+__host__ __device__ __forceinline__ void cd_box_normal(int q, double* n) {
     n[0] = n[1] = n[2] = 0.0;
     n[q % 3] = q < 3 ? 1.0 : -1.0;
 }
 
 // Plane3::closestPointLocal — src/jet/plane3.cpp:35-38: r = p - point; r - normal.dot(r) * normal + point
-__device__ __forceinline__ void cd_plane_closest(const double* n, const double* pt, const double* p, double* out) {
+__host__ __device__ __forceinline__ void cd_plane_closest(const double* n, const double* pt, const double* p, double* out) {
     const double r[3] = {p[0] - pt[0], p[1] - pt[1], p[2] - pt[2]};
     const double d = cd_dot(n, r);
 #pragma unroll
     for (int a = 0; a < 3; ++a) out[a] = (r[a] - n[a] * d) + pt[a];
 }
 
-__device__ __forceinline__ bool cd_box_contains(const ColliderD& c, const double* p) {  // bounding_box3-inl.h:77-91
+__host__ __device__ __forceinline__ bool cd_box_contains(const ColliderD& c, const double* p) {  // bounding_box3-inl.h:77-91
 #pragma unroll
     for (int a = 0; a < 3; ++a)
         if (c.b[a] < p[a] || c.a[a] > p[a]) return false;
@@ -61,7 +61,7 @@ __device__ __forceinline__ bool cd_box_contains(const ColliderD& c, const double
 
 // Box3::closestPointLocal (src/jet/box3.cpp:28-55) and closestNormalLocal (:57-100) in one pass: both scan the six
 // planes with the same strict `<` on the squared distance, so they pick the same plane.
-__device__ __forceinline__ void cd_box_closest_local(const ColliderD& c, const double* p, double* point, double* normal) {
+__host__ __device__ __forceinline__ void cd_box_closest_local(const ColliderD& c, const double* p, double* point, double* normal) {
     if (cd_box_contains(c, p)) {
         double n[3], best[3];
         cd_box_normal(0, n);
@@ -99,7 +99,7 @@ __device__ __forceinline__ void cd_box_closest_local(const ColliderD& c, const d
 }
 
 // Sphere3::closestNormalLocal / closestPointLocal — src/jet/sphere3.cpp:25-39
-__device__ __forceinline__ void cd_sphere_closest_local(const ColliderD& c, const double* p, double* point, double* normal) {
+__host__ __device__ __forceinline__ void cd_sphere_closest_local(const ColliderD& c, const double* p, double* point, double* normal) {
     const double eps = 2.220446049250313e-16;  // Vector3::isSimilar's default epsilon
     if (fabs(c.a[0] - p[0]) < eps && fabs(c.a[1] - p[1]) < eps && fabs(c.a[2] - p[2]) < eps) {
         normal[0] = 1.0; normal[1] = 0.0; normal[2] = 0.0;
@@ -112,7 +112,7 @@ __device__ __forceinline__ void cd_sphere_closest_local(const ColliderD& c, cons
     for (int a = 0; a < 3; ++a) point[a] = normal[a] * c.b[0] + c.a[a];  // radius * normal + center
 }
 
-__device__ __forceinline__ void cd_shape_closest_local(const ColliderD& c, const double* p, double* point, double* normal) {
+__host__ __device__ __forceinline__ void cd_shape_closest_local(const ColliderD& c, const double* p, double* point, double* normal) {
     if (c.kind == 1) cd_box_closest_local(c, p, point, normal); else cd_sphere_closest_local(c, p, point, normal);
 }
 
@@ -123,7 +123,7 @@ struct ColliderQuery {
     bool inside;
 };
 
-__device__ __forceinline__ ColliderQuery cd_query(const ColliderD& c, const double* p) {
+__host__ __device__ __forceinline__ ColliderQuery cd_query(const ColliderD& c, const double* p) {
     ColliderQuery q;
     double l[3], cp[3], n[3];
     cd_to_local(p, l);
@@ -143,7 +143,7 @@ __device__ __forceinline__ ColliderQuery cd_query(const ColliderD& c, const doub
 }
 
 // SurfaceToImplicit3(surface)->signedDistance(pt) — implicit_surface3.cpp:26-29, surface_to_implicit3.cpp:67-72
-__device__ __forceinline__ double cd_signed_distance(const ColliderD& c, const double* pt) {
+__host__ __device__ __forceinline__ double cd_signed_distance(const ColliderD& c, const double* pt) {
     double l[3];
     cd_to_local(pt, l);  // the wrapper's own (identity) transform
     const ColliderQuery q = cd_query(c, l);
@@ -153,14 +153,14 @@ __device__ __forceinline__ double cd_signed_distance(const ColliderD& c, const d
 }
 
 // RigidBodyCollider3::velocityAt — src/jet/rigid_body_collider3.cpp:25-28: linear + angular x (p - translation)
-__device__ __forceinline__ void cd_velocity_at(const ColliderD& c, const double* p, double* out) {
+__host__ __device__ __forceinline__ void cd_velocity_at(const ColliderD& c, const double* p, double* out) {
     const double r[3] = {p[0] - 0.0, p[1] - 0.0, p[2] - 0.0};
     const double cr[3] = {c.ang[1] * r[2] - r[1] * c.ang[2], c.ang[2] * r[0] - r[2] * c.ang[0], c.ang[0] * r[1] - r[0] * c.ang[1]};
     out[0] = c.lin[0] + cr[0]; out[1] = c.lin[1] + cr[1]; out[2] = c.lin[2] + cr[2];
 }
 
 // projectAndApplyFriction — src/jet/physics_helpers.h:33-45
-__device__ __forceinline__ void cd_project_friction(const double* vel, const double* n, double friction, double* out) {
+__host__ __device__ __forceinline__ void cd_project_friction(const double* vel, const double* n, double friction, double* out) {
     const double d = cd_dot(vel, n);
     double velt[3] = {vel[0] - n[0] * d, vel[1] - n[1] * d, vel[2] - n[2] * d};  // vel.projected(normal)
     if (cd_len2(velt) > 0) {
@@ -173,7 +173,7 @@ __device__ __forceinline__ void cd_project_friction(const double* vel, const dou
 
 // ScalarGrid3::gradient(x) — src/jet/scalar_grid3.cpp:89-102: sum over the 8 corners of getCoordinatesAndWeights of
 // weight * gradient3 (src/jet/fdm_utils.cpp:49-67: 0.5 * (right-left, up-down, front-back) / gridSpacing, clamped).
-__device__ __forceinline__ void cd_grid_gradient(const GridView& g, double px, double py, double pz, double* out) {
+__host__ __device__ __forceinline__ void cd_grid_gradient(const GridView& g, double px, double py, double pz, double* out) {
     const BaseFrac bf = jc_base_mul(g.nx, g.ny, g.nz, 1.0 / g.hx, 1.0 / g.hy, 1.0 / g.hz, g.ox, g.oy, g.oz, px, py, pz);
     const size_t sy = (size_t)g.nx, sz = (size_t)g.nx * g.ny;
     out[0] = out[1] = out[2] = 0.0;
@@ -191,7 +191,7 @@ __device__ __forceinline__ void cd_grid_gradient(const GridView& g, double px, d
 }
 
 // Collider3::resolveCollision(radius = 0, restitution = 0, &pos, &vel) — src/jet/collider3.cpp:19-74
-__device__ __forceinline__ void cd_resolve_collision(const ColliderD& c, double* pos, double* vel) {
+__host__ __device__ __forceinline__ void cd_resolve_collision(const ColliderD& c, double* pos, double* vel) {
     const double radius = 0.0, restitution = 0.0;
     const ColliderQuery q = cd_query(c, pos);
     double cvel[3];

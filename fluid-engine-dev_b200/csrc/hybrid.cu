@@ -17,7 +17,7 @@
 #include "particles.cuh"
 #include "pressure.cuh"
 #include "sampling.cuh"
-#include "collider.cuh"
+#include "particle_ops.cuh"
 
 #define NATTR 15  // px,py,pz, vx,vy,vz, cX(3), cY(3), cZ(3)
 
@@ -62,37 +62,10 @@ struct jetcu_hybrid {
     cudaEvent_t ev[12] = {};
 };
 
-struct GridD {
-    int nx, ny, nz;
-    double hx, hy, hz, ox, oy, oz;
-    double ihx, ihy, ihz;  // exact 1/h for power-of-two spacings, else 0 (jc_norm)
-};
-
 static GridD gridd(const jetcu_hybrid* h) {
     const jetcu_grid& g = h->P.grid;
     return GridD{h->nx, h->ny, h->nz, g.hx, g.hy, g.hz, g.ox, g.oy, g.oz,
                  jc_pow2_inverse(g.hx), jc_pow2_inverse(g.hy), jc_pow2_inverse(g.hz)};
-}
-
-// Component grid (AXIS = 0/1/2 -> u/v/w): size and data origin (src/jet/face_centered_grid3.cpp:430-444).
-template <int AXIS>
-__device__ __forceinline__ void comp_grid(const GridD& g, int* sx, int* sy, int* sz, double* ox, double* oy, double* oz) {
-    *sx = g.nx + (AXIS == 0); *sy = g.ny + (AXIS == 1); *sz = g.nz + (AXIS == 2);
-    *ox = g.ox + 0.5 * (AXIS == 0 ? 0.0 : g.hx);
-    *oy = g.oy + 0.5 * (AXIS == 1 ? 0.0 : g.hy);
-    *oz = g.oz + 0.5 * (AXIS == 2 ? 0.0 : g.hz);
-}
-
-__device__ __forceinline__ GridView comp_view(const GridD& g, int axis, const double* data) {
-    GridView v;
-    v.data = data;
-    v.nx = g.nx + (axis == 0); v.ny = g.ny + (axis == 1); v.nz = g.nz + (axis == 2);
-    v.hx = g.hx; v.hy = g.hy; v.hz = g.hz;
-    v.ox = g.ox + 0.5 * (axis == 0 ? 0.0 : g.hx);
-    v.oy = g.oy + 0.5 * (axis == 1 ? 0.0 : g.hy);
-    v.oz = g.oz + 0.5 * (axis == 2 ? 0.0 : g.hz);
-    v.ihx = g.ihx; v.ihy = g.ihy; v.ihz = g.ihz;
-    return v;
 }
 
 // ------------------------------------------------------------------------------------------------ cell sort
@@ -733,19 +706,7 @@ __global__ void __launch_bounds__(256) k_extrapolate_sweep(double* data, const c
                                                            int nx, int ny, int nz) {
     int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
     if (i >= nx || j >= ny) return;
-    const size_t sy = (size_t)nx, sz = (size_t)nx * ny;
-    size_t c = (size_t)k * sz + (size_t)j * sy + i;
-    if (v0[c]) { v1[c] = 1; return; }
-    double sum = 0.0;
-    unsigned count = 0;
-    if (i + 1 < nx && v0[c + 1]) { sum += data[c + 1]; ++count; }
-    if (i > 0 && v0[c - 1]) { sum += data[c - 1]; ++count; }
-    if (j + 1 < ny && v0[c + sy]) { sum += data[c + sy]; ++count; }
-    if (j > 0 && v0[c - sy]) { sum += data[c - sy]; ++count; }
-    if (k + 1 < nz && v0[c + sz]) { sum += data[c + sz]; ++count; }
-    if (k > 0 && v0[c - sz]) { sum += data[c - sz]; ++count; }
-    if (count > 0) { data[c] = sum / (double)count; v1[c] = 1; }
-    else v1[c] = 0;
+    extrapolate_cell(data, v0, v1, nx, ny, nz, i, j, k);
 }
 
 // ------------------------------------------------------------------------------------------------ grid ops
@@ -753,24 +714,7 @@ __global__ void __launch_bounds__(256) k_extrapolate_sweep(double* data, const c
 // (src/jet/grid_fractional_boundary_condition_solver3.cpp:190-232).  Without a collider the rest of
 // constrainVelocity is the identity (all face markers 1, no cell inside the collider SDF = kMaxD).
 __global__ void k_zero_walls(GridD g, int flag, double* __restrict__ u, double* __restrict__ v, double* __restrict__ w) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t nyz = (size_t)g.ny * g.nz, nxz = (size_t)g.nx * g.nz, nxy = (size_t)g.nx * g.ny;
-    if (t < nyz) {
-        int j = (int)(t % g.ny), k = (int)(t / g.ny);
-        size_t rowu = ((size_t)k * g.ny + j) * (g.nx + 1);
-        if (flag & JETCU_DIR_LEFT) u[rowu] = 0;
-        if (flag & JETCU_DIR_RIGHT) u[rowu + g.nx] = 0;
-    }
-    if (t < nxz) {
-        int i = (int)(t % g.nx), k = (int)(t / g.nx);
-        size_t base = (size_t)k * (g.ny + 1) * g.nx + i;
-        if (flag & JETCU_DIR_DOWN) v[base] = 0;
-        if (flag & JETCU_DIR_UP) v[base + (size_t)g.ny * g.nx] = 0;
-    }
-    if (t < nxy) {
-        if (flag & JETCU_DIR_BACK) w[t] = 0;
-        if (flag & JETCU_DIR_FRONT) w[(size_t)g.nz * nxy + t] = 0;
-    }
+    zero_walls_elem(g, flag, u, v, w, (size_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 __global__ void k_add_scalar(double* __restrict__ a, double s, size_t n) {
@@ -822,60 +766,7 @@ __global__ void __launch_bounds__(CFL_BLOCK) k_max_final(const double* __restric
 }
 
 // ------------------------------------------------------------------------------------------------ G2P + advection
-// POW2: all three spacings are powers of two (GridD::ih* != 0), so (x - o) / h is evaluated as the exact product with
-// 1/h and the division path is not even compiled in.  I = index type: int when every component grid has < 2^31
-// samples (always, up to ~1280^3), else long long — 64-bit integer multiplies were a third of this kernel's instructions.
-template <bool POW2>
-__device__ __forceinline__ double norm_pos(double x, double o, double h, double ih) {
-    return POW2 ? (x - o) * ih : jc_norm(x, o, h, ih);
-}
-
-template <bool POW2, typename I>
-__device__ __forceinline__ void sample_velocity(const GridD& g, const double* __restrict__ u, const double* __restrict__ v,
-                                                const double* __restrict__ w, double px, double py, double pz, double* ou,
-                                                double* ov, double* ow) {
-    // FaceCenteredGrid3::sample: three LinearArraySampler3::operator() calls (face_centered_grid3.cpp:447-467).
-    // The three component grids share their per-axis normalisations pairwise (node-aligned along the component's own
-    // axis, cell-centred along the other two), so 6 barycentric evaluations serve all 3 samplers instead of 9; each is
-    // the same expression the per-grid sampler evaluates, so the results are bit-identical to three jc_sample calls.
-    int inx, icx, jny, jcy, knz, kcz;
-    double fnx, fcx, fny, fcy, fnz, fcz;
-    jc_barycentric(norm_pos<POW2>(px, g.ox + 0.5 * 0.0, g.hx, g.ihx), g.nx, &inx, &fnx);            // u grid: nx + 1 nodes
-    jc_barycentric(norm_pos<POW2>(px, g.ox + 0.5 * g.hx, g.hx, g.ihx), g.nx - 1, &icx, &fcx);      // v, w grids
-    jc_barycentric(norm_pos<POW2>(py, g.oy + 0.5 * 0.0, g.hy, g.ihy), g.ny, &jny, &fny);            // v grid
-    jc_barycentric(norm_pos<POW2>(py, g.oy + 0.5 * g.hy, g.hy, g.ihy), g.ny - 1, &jcy, &fcy);      // u, w grids
-    jc_barycentric(norm_pos<POW2>(pz, g.oz + 0.5 * 0.0, g.hz, g.ihz), g.nz, &knz, &fnz);            // w grid
-    jc_barycentric(norm_pos<POW2>(pz, g.oz + 0.5 * g.hz, g.hz, g.ihz), g.nz - 1, &kcz, &fcz);      // u, v grids
-    const int inx1 = min(inx + 1, g.nx), icx1 = min(icx + 1, g.nx - 1);
-    const int jny1 = min(jny + 1, g.ny), jcy1 = min(jcy + 1, g.ny - 1);
-    const int knz1 = min(knz + 1, g.nz), kcz1 = min(kcz + 1, g.nz - 1);
-    {
-        const I sy = (I)(g.nx + 1), sz = sy * (I)g.ny;
-        const I r00 = (I)kcz * sz + (I)jcy * sy, r10 = (I)kcz * sz + (I)jcy1 * sy, r01 = (I)kcz1 * sz + (I)jcy * sy,
-                r11 = (I)kcz1 * sz + (I)jcy1 * sy;
-        const double a = jc_lerp(jc_lerp(u[r00 + inx], u[r00 + inx1], fnx), jc_lerp(u[r10 + inx], u[r10 + inx1], fnx), fcy);
-        const double b = jc_lerp(jc_lerp(u[r01 + inx], u[r01 + inx1], fnx), jc_lerp(u[r11 + inx], u[r11 + inx1], fnx), fcy);
-        *ou = jc_lerp(a, b, fcz);
-    }
-    {
-        const I sy = (I)g.nx, sz = sy * (I)(g.ny + 1);
-        const I r00 = (I)kcz * sz + (I)jny * sy, r10 = (I)kcz * sz + (I)jny1 * sy, r01 = (I)kcz1 * sz + (I)jny * sy,
-                r11 = (I)kcz1 * sz + (I)jny1 * sy;
-        const double a = jc_lerp(jc_lerp(v[r00 + icx], v[r00 + icx1], fcx), jc_lerp(v[r10 + icx], v[r10 + icx1], fcx), fny);
-        const double b = jc_lerp(jc_lerp(v[r01 + icx], v[r01 + icx1], fcx), jc_lerp(v[r11 + icx], v[r11 + icx1], fcx), fny);
-        *ov = jc_lerp(a, b, fcz);
-    }
-    {
-        const I sy = (I)g.nx, sz = sy * (I)g.ny;
-        const I r00 = (I)knz * sz + (I)jcy * sy, r10 = (I)knz * sz + (I)jcy1 * sy, r01 = (I)knz1 * sz + (I)jcy * sy,
-                r11 = (I)knz1 * sz + (I)jcy1 * sy;
-        const double a = jc_lerp(jc_lerp(w[r00 + icx], w[r00 + icx1], fcx), jc_lerp(w[r10 + icx], w[r10 + icx1], fcx), fcy);
-        const double b = jc_lerp(jc_lerp(w[r01 + icx], w[r01 + icx1], fcx), jc_lerp(w[r11 + icx], w[r11 + icx1], fcx), fcy);
-        *ow = jc_lerp(a, b, fnz);
-    }
-}
-
-// PicSolver3::transferFromGridsToParticles, src/jet/pic_solver3.cpp:195-204.
+// PicSolver3::transferFromGridsToParticles, src/jet/pic_solver3.cpp:195-204.  (Per-particle bodies: particle_ops.cuh.)
 template <bool POW2, typename I>
 __global__ void k_g2p_pic(GridD g, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
                           AttrPtrs a, size_t np) {
@@ -886,64 +777,15 @@ __global__ void k_g2p_pic(GridD g, const double* __restrict__ u, const double* _
     a.p[3][p] = ou; a.p[4][p] = ov; a.p[5][p] = ow;
 }
 
-// FlipSolver3::transferFromGridsToParticles, src/jet/flip_solver3.cpp:50-99: v += sampleF32(delta)(float(x)),
-// optional lerp towards the PIC sample.
 __global__ void k_g2p_flip(GridD g, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
                            const float* __restrict__ ud, const float* __restrict__ vd, const float* __restrict__ wd,
                            double blend, AttrPtrs a, size_t np) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= np) return;
-    double px = a.p[0][p], py = a.p[1][p], pz = a.p[2][p];
-    float xf = (float)px, yf = (float)py, zf = (float)pz;
-    float fhx = (float)g.hx, fhy = (float)g.hy, fhz = (float)g.hz;
-    GridView vu = comp_view(g, 0, u), vv = comp_view(g, 1, v), vw = comp_view(g, 2, w);
-    // float(h) of a power-of-two h is the same power of two, so the exact-reciprocal shortcut carries over
-    const float fix = (float)g.ihx, fiy = (float)g.ihy, fiz = (float)g.ihz;
-    double du = jc_samplef(ud, vu.nx, vu.ny, vu.nz, fhx, fhy, fhz, (float)vu.ox, (float)vu.oy, (float)vu.oz, xf, yf, zf, fix, fiy, fiz);
-    double dv = jc_samplef(vd, vv.nx, vv.ny, vv.nz, fhx, fhy, fhz, (float)vv.ox, (float)vv.oy, (float)vv.oz, xf, yf, zf, fix, fiy, fiz);
-    double dw = jc_samplef(wd, vw.nx, vw.ny, vw.nz, fhx, fhy, fhz, (float)vw.ox, (float)vw.oy, (float)vw.oz, xf, yf, zf, fix, fiy, fiz);
-    double f0 = a.p[3][p] + du, f1 = a.p[4][p] + dv, f2 = a.p[5][p] + dw;
-    if (blend > 0.0) {
-        double pu = jc_sample(vu, px, py, pz), pv = jc_sample(vv, px, py, pz), pw = jc_sample(vw, px, py, pz);
-        f0 = (1 - blend) * f0 + blend * pu;
-        f1 = (1 - blend) * f1 + blend * pv;
-        f2 = (1 - blend) * f2 + blend * pw;
-    }
-    a.p[3][p] = f0; a.p[4][p] = f1; a.p[5][p] = f2;
-}
-
-// ApicSolver3::transferFromGridsToParticles, src/jet/apic_solver3.cpp:148-229: PIC sample + c = sum gradW * value
-// with getCoordinatesAndGradientWeights (array_samplers3-inl.h:195-261) at the tangentially clamped position.
-template <int AXIS>
-__device__ __forceinline__ void apic_affine(const GridD& g, const double* __restrict__ data, double px, double py,
-                                            double pz, double* c0, double* c1, double* c2) {
-    int sx, sy, sz;
-    double ox, oy, oz;
-    comp_grid<AXIS>(g, &sx, &sy, &sz, &ox, &oy, &oz);
-    const double hix = g.ox + g.hx * (double)g.nx, hiy = g.oy + g.hy * (double)g.ny, hiz = g.oz + g.hz * (double)g.nz;
-    if (AXIS != 0) px = jc_clamp(px, g.ox + g.hx / 2.0, hix - g.hx / 2.0);
-    if (AXIS != 1) py = jc_clamp(py, g.oy + g.hy / 2.0, hiy - g.hy / 2.0);
-    if (AXIS != 2) pz = jc_clamp(pz, g.oz + g.hz / 2.0, hiz - g.hz / 2.0);
-    BaseFrac b = jc_base_div(sx, sy, sz, g.hx, g.hy, g.hz, ox, oy, oz, px, py, pz, g.ihx, g.ihy, g.ihz);
-    const double ix = 1.0 / g.hx, iy = 1.0 / g.hy, iz = 1.0 / g.hz;
-    const double fx = b.fx, fy = b.fy, fz = b.fz, ax = 1 - b.fx, ay = 1 - b.fy, az = 1 - b.fz;
-    double gw[8][3];
-    gw[0][0] = -ix * ay * az;    gw[0][1] = -iy * ax * az;    gw[0][2] = -iz * ax * ay;
-    gw[1][0] = ix * ay * az;     gw[1][1] = fx * (-iy) * az;  gw[1][2] = fx * ay * (-iz);
-    gw[2][0] = (-ix) * fy * az;  gw[2][1] = ax * iy * az;     gw[2][2] = ax * fy * (-iz);
-    gw[3][0] = ix * fy * az;     gw[3][1] = fx * iy * az;     gw[3][2] = fx * fy * (-iz);
-    gw[4][0] = (-ix) * ay * fz;  gw[4][1] = ax * (-iy) * fz;  gw[4][2] = ax * ay * iz;
-    gw[5][0] = ix * ay * fz;     gw[5][1] = fx * (-iy) * fz;  gw[5][2] = fx * ay * iz;
-    gw[6][0] = (-ix) * fy * fz;  gw[6][1] = ax * iy * fz;     gw[6][2] = ax * fy * iz;
-    gw[7][0] = ix * fy * fz;     gw[7][1] = fx * iy * fz;     gw[7][2] = fx * fy * iz;
-    double r0 = 0.0, r1 = 0.0, r2 = 0.0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        int ii = (q & 1) ? b.ip1 : b.i, jj = (q & 2) ? b.jp1 : b.j, kk = (q & 4) ? b.kp1 : b.k;
-        double val = data[((size_t)kk * sy + jj) * sx + ii];
-        r0 += gw[q][0] * val; r1 += gw[q][1] * val; r2 += gw[q][2] * val;
-    }
-    *c0 = r0; *c1 = r1; *c2 = r2;
+    const double pos[3] = {a.p[0][p], a.p[1][p], a.p[2][p]};
+    double vel[3] = {a.p[3][p], a.p[4][p], a.p[5][p]};
+    g2p_flip_particle(g, u, v, w, ud, vd, wd, blend, pos, vel);
+    a.p[3][p] = vel[0]; a.p[4][p] = vel[1]; a.p[5][p] = vel[2];
 }
 
 template <bool POW2, typename I>
@@ -961,33 +803,15 @@ __global__ void k_g2p_apic(GridD g, const double* __restrict__ u, const double* 
     apic_affine<2>(g, w, px, py, pz, &c0, &c1, &c2); a.p[12][p] = c0; a.p[13][p] = c1; a.p[14][p] = c2;
 }
 
-// PicSolver3::moveParticles, src/jet/pic_solver3.cpp:206-282: uint(max(maxCfl,1)) midpoint-rule sub-steps, then
-// clamp to the domain box and zero the velocity component on closed walls (<= / >= tests).
 template <bool POW2, typename I>
 __global__ void k_move(GridD g, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
                        double dt, unsigned nsub, int flag, AttrPtrs a, size_t np) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= np) return;
-    double p0x = a.p[0][p], p0y = a.p[1][p], p0z = a.p[2][p];
-    double p1x = p0x, p1y = p0y, p1z = p0z;
-    for (unsigned t = 0; t < nsub; ++t) {
-        double v0x, v0y, v0z, mvx, mvy, mvz;
-        sample_velocity<POW2, I>(g, u, v, w, p0x, p0y, p0z, &v0x, &v0y, &v0z);
-        double mx = p0x + 0.5 * dt * v0x, my = p0y + 0.5 * dt * v0y, mz = p0z + 0.5 * dt * v0z;
-        sample_velocity<POW2, I>(g, u, v, w, mx, my, mz, &mvx, &mvy, &mvz);
-        p1x = p0x + dt * mvx; p1y = p0y + dt * mvy; p1z = p0z + dt * mvz;
-        p0x = p1x; p0y = p1y; p0z = p1z;
-    }
-    const double hix = g.ox + g.hx * (double)g.nx, hiy = g.oy + g.hy * (double)g.ny, hiz = g.oz + g.hz * (double)g.nz;
-    double vx = a.p[3][p], vy = a.p[4][p], vz = a.p[5][p];
-    if ((flag & JETCU_DIR_LEFT) && p1x <= g.ox) { p1x = g.ox; vx = 0.0; }
-    if ((flag & JETCU_DIR_RIGHT) && p1x >= hix) { p1x = hix; vx = 0.0; }
-    if ((flag & JETCU_DIR_DOWN) && p1y <= g.oy) { p1y = g.oy; vy = 0.0; }
-    if ((flag & JETCU_DIR_UP) && p1y >= hiy) { p1y = hiy; vy = 0.0; }
-    if ((flag & JETCU_DIR_BACK) && p1z <= g.oz) { p1z = g.oz; vz = 0.0; }
-    if ((flag & JETCU_DIR_FRONT) && p1z >= hiz) { p1z = hiz; vz = 0.0; }
-    a.p[0][p] = p1x; a.p[1][p] = p1y; a.p[2][p] = p1z;
-    a.p[3][p] = vx; a.p[4][p] = vy; a.p[5][p] = vz;
+    double pos[3] = {a.p[0][p], a.p[1][p], a.p[2][p]}, vel[3] = {a.p[3][p], a.p[4][p], a.p[5][p]};
+    move_particle<POW2, I>(g, u, v, w, dt, nsub, flag, pos, vel);
+    a.p[0][p] = pos[0]; a.p[1][p] = pos[1]; a.p[2][p] = pos[2];
+    a.p[3][p] = vel[0]; a.p[4][p] = vel[1]; a.p[5][p] = vel[2];
 }
 
 // ------------------------------------------------------------------------------------------------ particle I/O
@@ -1132,112 +956,42 @@ __global__ void k_u64_to_u32(const uint64_t* __restrict__ in, uint32_t* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ collider
-// GridFractionalBoundaryConditionSolver3::onColliderUpdated — src/jet/grid_fractional_boundary_condition_solver3.cpp:244-280:
-// _colliderSdf(i,j,k) = SurfaceToImplicit3(surface).signedDistance(dataPosition(i,j,k)).
+// Thin launch wrappers: the per-cell / per-face / per-particle bodies live in collider_ops.cuh as __host__ __device__
+// functions, so that tests/hostcheck can run the very same source on the CPU against the oracle.
 __global__ void __launch_bounds__(256) k_collider_sdf(GridD g, ColliderD c, double* __restrict__ sdf) {
     int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
     if (i >= g.nx || j >= g.ny) return;
-    const double pt[3] = {(g.ox + 0.5 * g.hx) + g.hx * (double)i, (g.oy + 0.5 * g.hy) + g.hy * (double)j,
-                          (g.oz + 0.5 * g.hz) + g.hz * (double)k};
-    sdf[((size_t)k * g.ny + j) * g.nx + i] = cd_signed_distance(c, pt);
+    sdf[((size_t)k * g.ny + j) * g.nx + i] = collider_sdf_cell(g, c, i, j, k);
 }
 
-__device__ __forceinline__ GridView collider_view(const GridD& g, const double* sdf) {
-    GridView v;
-    v.data = sdf; v.nx = g.nx; v.ny = g.ny; v.nz = g.nz; v.hx = g.hx; v.hy = g.hy; v.hz = g.hz;
-    v.ox = g.ox + 0.5 * g.hx; v.oy = g.oy + 0.5 * g.hy; v.oz = g.oz + 0.5 * g.hz;
-    v.ihx = g.ihx; v.ihy = g.ihy; v.ihz = g.ihz;
-    return v;
-}
-
-// constrainVelocity, first pass (…boundary_condition_solver3.cpp:55-104): faces whose open fraction is 0 take the
-// collider's velocity and are marked invalid (0) for the extrapolation that follows.
 template <int AXIS>
 __global__ void __launch_bounds__(256) k_constrain_markers(GridD g, ColliderD c, const double* __restrict__ csdf,
                                                            double* __restrict__ data, char* __restrict__ marker) {
-    const int sx = g.nx + (AXIS == 0), sy = g.ny + (AXIS == 1), sz = g.nz + (AXIS == 2);
     int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
-    if (i >= sx || j >= sy || k >= sz) return;
-    const GridView cs = collider_view(g, csdf);
-    const double fox = g.ox + 0.5 * (AXIS == 0 ? 0.0 : g.hx), foy = g.oy + 0.5 * (AXIS == 1 ? 0.0 : g.hy),
-                 foz = g.oz + 0.5 * (AXIS == 2 ? 0.0 : g.hz);
-    const double pt[3] = {fox + g.hx * (double)i, foy + g.hy * (double)j, foz + g.hz * (double)k};
-    const double hx = AXIS == 0 ? 0.5 * g.hx : 0.0, hy = AXIS == 1 ? 0.5 * g.hy : 0.0, hz = AXIS == 2 ? 0.5 * g.hz : 0.0;
-    const double phi0 = jc_sample(cs, pt[0] - hx, pt[1] - hy, pt[2] - hz);
-    const double phi1 = jc_sample(cs, pt[0] + hx, pt[1] + hy, pt[2] + hz);
-    double frac = jc_frac_inside_sdf(phi0, phi1);
-    frac = 1.0 - jc_clamp(frac, 0.0, 1.0);
-    const size_t f = ((size_t)k * sy + j) * sx + i;
-    if (frac > 0.0) {
-        marker[f] = 1;
-    } else {
-        double cv[3];
-        cd_velocity_at(c, pt, cv);
-        data[f] = cv[AXIS];
-        marker[f] = 0;
-    }
+    if (i >= g.nx + (AXIS == 0) || j >= g.ny + (AXIS == 1) || k >= g.nz + (AXIS == 2)) return;
+    constrain_marker_face<AXIS>(g, c, csdf, data, marker, i, j, k);
 }
 
-// boundaryVelocity.sample(facePosition) component as the pressure solver reads it (…pressure_solver3.cpp:242-255):
-// the collider's velocity field is collider->velocityAt (…boundary_condition_solver3.cpp:265-270).
 template <int AXIS>
 __global__ void __launch_bounds__(256) k_boundary_velocity(GridD g, ColliderD c, double* __restrict__ bnd) {
-    const int sx = g.nx + (AXIS == 0), sy = g.ny + (AXIS == 1), sz = g.nz + (AXIS == 2);
     int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
-    if (i >= sx || j >= sy || k >= sz) return;
-    const double fox = g.ox + 0.5 * (AXIS == 0 ? 0.0 : g.hx), foy = g.oy + 0.5 * (AXIS == 1 ? 0.0 : g.hy),
-                 foz = g.oz + 0.5 * (AXIS == 2 ? 0.0 : g.hz);
-    const double pt[3] = {fox + g.hx * (double)i, foy + g.hy * (double)j, foz + g.hz * (double)k};
-    double cv[3];
-    cd_velocity_at(c, pt, cv);
-    bnd[((size_t)k * sy + j) * sx + i] = cv[AXIS];
+    if (i >= g.nx + (AXIS == 0) || j >= g.ny + (AXIS == 1) || k >= g.nz + (AXIS == 2)) return;
+    boundary_velocity_face<AXIS>(g, c, bnd, i, j, k);
 }
 
-// constrainVelocity, no-flux pass (…:115-187): inside the collider the (extrapolated) fluid velocity keeps only its
-// tangential part relative to the collider, with friction; reads the whole field, writes the temporary.
 template <int AXIS>
 __global__ void __launch_bounds__(256) k_constrain_project(GridD g, ColliderD c, const double* __restrict__ csdf,
                                                            const double* __restrict__ u, const double* __restrict__ v,
                                                            const double* __restrict__ w, double* __restrict__ temp) {
-    const int sx = g.nx + (AXIS == 0), sy = g.ny + (AXIS == 1), sz = g.nz + (AXIS == 2);
     int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
-    if (i >= sx || j >= sy || k >= sz) return;
-    const GridView cs = collider_view(g, csdf);
-    const double fox = g.ox + 0.5 * (AXIS == 0 ? 0.0 : g.hx), foy = g.oy + 0.5 * (AXIS == 1 ? 0.0 : g.hy),
-                 foz = g.oz + 0.5 * (AXIS == 2 ? 0.0 : g.hz);
-    const double pt[3] = {fox + g.hx * (double)i, foy + g.hy * (double)j, foz + g.hz * (double)k};
-    const size_t f = ((size_t)k * sy + j) * sx + i;
-    const double* self = AXIS == 0 ? u : (AXIS == 1 ? v : w);
-    if (jc_sample(cs, pt[0], pt[1], pt[2]) < 0) {  // isInsideSdf
-        double cv[3], gr[3], vel[3];
-        cd_velocity_at(c, pt, cv);
-        vel[0] = jc_sample(comp_view(g, 0, u), pt[0], pt[1], pt[2]);
-        vel[1] = jc_sample(comp_view(g, 1, v), pt[0], pt[1], pt[2]);
-        vel[2] = jc_sample(comp_view(g, 2, w), pt[0], pt[1], pt[2]);
-        cd_grid_gradient(cs, pt[0], pt[1], pt[2], gr);
-        if (cd_len2(gr) > 0.0) {
-            const double l = cd_len(gr);
-            const double n[3] = {gr[0] / l, gr[1] / l, gr[2] / l};
-            const double velr[3] = {vel[0] - cv[0], vel[1] - cv[1], vel[2] - cv[2]};
-            double velt[3];
-            cd_project_friction(velr, n, c.friction, velt);
-            temp[f] = velt[AXIS] + cv[AXIS];
-        } else {
-            temp[f] = cv[AXIS];
-        }
-    } else {
-        temp[f] = self[f];
-    }
+    if (i >= g.nx + (AXIS == 0) || j >= g.ny + (AXIS == 1) || k >= g.nz + (AXIS == 2)) return;
+    constrain_project_face<AXIS>(g, c, csdf, u, v, w, temp, i, j, k);
 }
 
-// GridFluidSolver3::extrapolateIntoCollider(ScalarGrid3*) marker — src/jet/grid_fluid_solver3.cpp:355-369
 __global__ void __launch_bounds__(256) k_outside_collider_marker(GridD g, const double* __restrict__ csdf, char* __restrict__ marker) {
     int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
     if (i >= g.nx || j >= g.ny) return;
-    const GridView cs = collider_view(g, csdf);
-    const double px = (g.ox + 0.5 * g.hx) + g.hx * (double)i, py = (g.oy + 0.5 * g.hy) + g.hy * (double)j,
-                 pz = (g.oz + 0.5 * g.hz) + g.hz * (double)k;
-    marker[((size_t)k * g.ny + j) * g.nx + i] = (jc_sample(cs, px, py, pz) < 0) ? 0 : 1;
+    marker[((size_t)k * g.ny + j) * g.nx + i] = outside_collider_cell(g, csdf, i, j, k);
 }
 
 // col->resolveCollision(0.0, 0.0, &positions[i], &velocities[i]) — src/jet/pic_solver3.cpp:268-281

@@ -18,10 +18,10 @@ struct GridView {
 // power of two is an exact scaling, so it equals the multiplication by the (exact) reciprocal bit for bit; the host
 // passes ih = 1/h only when h is a power of two (ih == 0 selects the literal division).  FP64 division costs ~30
 // instructions and the advection kernel needs 90 of them per particle, so this matters on 2^-k grids.
-__device__ __forceinline__ double jc_norm(double x, double o, double h, double ih) {
+__host__ __device__ __forceinline__ double jc_norm(double x, double o, double h, double ih) {
     return ih != 0.0 ? (x - o) * ih : (x - o) / h;
 }
-__device__ __forceinline__ float jc_normf(float x, float o, float h, float ih) {
+__host__ __device__ __forceinline__ float jc_normf(float x, float o, float h, float ih) {
     return ih != 0.0f ? (x - o) * ih : (x - o) / h;
 }
 
@@ -32,7 +32,7 @@ static inline double jc_pow2_inverse(double h) {
 }
 
 // getBarycentric, include/jet/detail/math_utils-inl.h:146-174 (iLow == 0 on this path).
-__device__ __forceinline__ void jc_barycentric(double x, int iHigh, int* i, double* f) {
+__host__ __device__ __forceinline__ void jc_barycentric(double x, int iHigh, int* i, double* f) {
     // s = floor(x) is integer-valued, so the reference's integer tests (i < 0, i > iHigh - 1 on a ssize_t) are decided
     // on the double itself — the same branches for every finite x, without a 64-bit float-to-int conversion; wild
     // inputs (|x| beyond the int range) land in the clamps instead of overflowing the conversion.
@@ -43,7 +43,7 @@ __device__ __forceinline__ void jc_barycentric(double x, int iHigh, int* i, doub
     else { *i = (int)s; *f = x - s; }
 }
 
-__device__ __forceinline__ void jc_barycentricf(float x, int iHigh, int* i, float* f) {
+__host__ __device__ __forceinline__ void jc_barycentricf(float x, int iHigh, int* i, float* f) {
     const float s = floorf(x);
     if (iHigh == 0) { *i = 0; *f = 0.0f; }
     else if (s < 0.0f) { *i = 0; *f = 0.0f; }
@@ -51,12 +51,12 @@ __device__ __forceinline__ void jc_barycentricf(float x, int iHigh, int* i, floa
     else { *i = (int)s; *f = x - s; }
 }
 
-__device__ __forceinline__ double jc_lerp(double a, double b, double f) { return (1 - f) * a + f * b; }
-__device__ __forceinline__ float jc_lerpf(float a, float b, float f) { return (1 - f) * a + f * b; }
+__host__ __device__ __forceinline__ double jc_lerp(double a, double b, double f) { return (1 - f) * a + f * b; }
+__host__ __device__ __forceinline__ float jc_lerpf(float a, float b, float f) { return (1 - f) * a + f * b; }
 
 // LinearArraySampler3<double,double>::operator(), include/jet/detail/array_samplers3-inl.h:115-149:
 // normalise with a DIVISION by h; nested lerp x -> y -> z (math_utils-inl.h:176-211).
-__device__ __forceinline__ double jc_sample(const GridView& g, double px, double py, double pz) {
+__host__ __device__ __forceinline__ double jc_sample(const GridView& g, double px, double py, double pz) {
     int i, j, k;
     double fx, fy, fz;
     jc_barycentric(jc_norm(px, g.ox, g.hx, g.ihx), g.nx - 1, &i, &fx);
@@ -73,7 +73,7 @@ __device__ __forceinline__ double jc_sample(const GridView& g, double px, double
 }
 
 // LinearArraySampler3<float,float>::operator() as FlipSolver3's delta sampler uses it (src/jet/flip_solver3.cpp:72-88).
-__device__ __forceinline__ float jc_samplef(const float* d, int nx, int ny, int nz, float hx, float hy, float hz,
+__host__ __device__ __forceinline__ float jc_samplef(const float* d, int nx, int ny, int nz, float hx, float hy, float hz,
                                             float ox, float oy, float oz, float px, float py, float pz,
                                             float ihx = 0.f, float ihy = 0.f, float ihz = 0.f) {
     int i, j, k;
@@ -97,7 +97,7 @@ struct BaseFrac {
     double fx, fy, fz;
 };
 
-__device__ __forceinline__ BaseFrac jc_base_mul(int nx, int ny, int nz, double ihx, double ihy, double ihz, double ox,
+__host__ __device__ __forceinline__ BaseFrac jc_base_mul(int nx, int ny, int nz, double ihx, double ihy, double ihz, double ox,
                                                 double oy, double oz, double px, double py, double pz) {
     BaseFrac b;
     jc_barycentric((px - ox) * ihx, nx - 1, &b.i, &b.fx);
@@ -108,7 +108,7 @@ __device__ __forceinline__ BaseFrac jc_base_mul(int nx, int ny, int nz, double i
 }
 
 // Same with the division form used by operator() and getCoordinatesAndGradientWeights (:195-261).
-__device__ __forceinline__ BaseFrac jc_base_div(int nx, int ny, int nz, double hx, double hy, double hz, double ox,
+__host__ __device__ __forceinline__ BaseFrac jc_base_div(int nx, int ny, int nz, double hx, double hy, double hz, double ox,
                                                 double oy, double oz, double px, double py, double pz,
                                                 double ihx = 0.0, double ihy = 0.0, double ihz = 0.0) {
     BaseFrac b;
@@ -120,7 +120,7 @@ __device__ __forceinline__ BaseFrac jc_base_div(int nx, int ny, int nz, double h
 }
 
 // Corner q (0..7) weight in the reference's corner order (i,j,k),(i+1,j,k),(i,j+1,k),(i+1,j+1,k),(i,j,k+1)...
-__device__ __forceinline__ double jc_corner_weight(const BaseFrac& b, int q) {
+__host__ __device__ __forceinline__ double jc_corner_weight(const BaseFrac& b, int q) {
     double wx = (q & 1) ? b.fx : (1 - b.fx);
     double wy = (q & 2) ? b.fy : (1 - b.fy);
     double wz = (q & 4) ? b.fz : (1 - b.fz);
@@ -128,7 +128,7 @@ __device__ __forceinline__ double jc_corner_weight(const BaseFrac& b, int q) {
 }
 
 // fractionInsideSdf, include/jet/detail/level_set_utils-inl.h:52-63.
-__device__ __forceinline__ double jc_frac_inside_sdf(double p0, double p1) {
+__host__ __device__ __forceinline__ double jc_frac_inside_sdf(double p0, double p1) {
     if (p0 < 0 && p1 < 0) return 1;
     if (p0 < 0 && !(p1 < 0)) return p0 / (p0 - p1);
     if (!(p0 < 0) && p1 < 0) return p1 / (p1 - p0);
@@ -136,7 +136,7 @@ __device__ __forceinline__ double jc_frac_inside_sdf(double p0, double p1) {
 }
 
 // fractionInside (marching-squares covered area), level_set_utils-inl.h:72-136.
-__device__ __forceinline__ double jc_frac_inside4(double bl, double br, double tl, double tr) {
+__host__ __device__ __forceinline__ double jc_frac_inside4(double bl, double br, double tl, double tr) {
     int cnt = (bl < 0) + (tl < 0) + (br < 0) + (tr < 0);
     double l0 = bl, l1 = br, l2 = tr, l3 = tl;
 #define JC_CYCLE() { double t = l0; l0 = l1; l1 = l2; l2 = l3; l3 = t; }
@@ -185,4 +185,4 @@ __device__ __forceinline__ double jc_frac_inside4(double bl, double br, double t
     return 0;
 }
 
-__device__ __forceinline__ double jc_clamp(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__host__ __device__ __forceinline__ double jc_clamp(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }

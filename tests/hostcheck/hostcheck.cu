@@ -1,0 +1,193 @@
+// hostcheck.cu — TEST INFRASTRUCTURE.  Runs the product's own __host__ __device__ kernel bodies
+// (fluid-engine-dev_b200/csrc/collider.cuh, collider_ops.cuh, sampling.cuh) on the CPU, with plain loops in place of
+// the kernel launches, so that `-m "not gpu"` tests can compare the CUDA source bit-for-bit with the oracle where no
+// GPU exists.  Built by tests/hostcheck/build.py with nvcc (host code only; no device is touched).
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../fluid-engine-dev_b200/csrc/particle_ops.cuh"
+
+static GridD make_grid(const jetcu_grid* g) {
+    return GridD{(int)g->nx, (int)g->ny, (int)g->nz, g->hx, g->hy, g->hz, g->ox, g->oy, g->oz,
+                 jc_pow2_inverse(g->hx), jc_pow2_inverse(g->hy), jc_pow2_inverse(g->hz)};
+}
+
+static ColliderD make_collider(int kind, const double* a, const double* b, const double* lin, const double* ang, double friction) {
+    ColliderD c;
+    c.kind = kind;
+    for (int q = 0; q < 3; ++q) { c.a[q] = a[q]; c.b[q] = b[q]; c.lin[q] = lin[q]; c.ang[q] = ang[q]; }
+    c.friction = friction > 0.0 ? friction : 0.0;
+    return c;
+}
+
+// what hyb_extrapolate_one does: `depth` sweeps of k_extrapolate_sweep with ping-pong validity maps
+static void extrapolate(double* data, const char* marker, int sx, int sy, int sz, unsigned depth) {
+    size_t n = (size_t)sx * sy * sz;
+    std::vector<char> v0(marker, marker + n), v1(n, 0);
+    for (unsigned it = 0; it < depth; ++it) {
+        for (int k = 0; k < sz; ++k)
+            for (int j = 0; j < sy; ++j)
+                for (int i = 0; i < sx; ++i) extrapolate_cell(data, v0.data(), v1.data(), sx, sy, sz, i, j, k);
+        v0.swap(v1);
+    }
+}
+
+template <int AXIS>
+static void markers(const GridD& g, const ColliderD& c, const double* csdf, double* data, char* marker) {
+    for (int k = 0; k < g.nz + (AXIS == 2); ++k)
+        for (int j = 0; j < g.ny + (AXIS == 1); ++j)
+            for (int i = 0; i < g.nx + (AXIS == 0); ++i) constrain_marker_face<AXIS>(g, c, csdf, data, marker, i, j, k);
+}
+
+template <int AXIS>
+static void project(const GridD& g, const ColliderD& c, const double* csdf, const double* u, const double* v, const double* w,
+                    double* temp) {
+    for (int k = 0; k < g.nz + (AXIS == 2); ++k)
+        for (int j = 0; j < g.ny + (AXIS == 1); ++j)
+            for (int i = 0; i < g.nx + (AXIS == 0); ++i) constrain_project_face<AXIS>(g, c, csdf, u, v, w, temp, i, j, k);
+}
+
+// ---- G2P and advection: the bodies of k_g2p_pic / k_g2p_flip / k_g2p_apic / k_move over n AoS particles.
+// variant: bit 0 = POW2 (exact-reciprocal normalisation; only legal for power-of-two spacings), bit 1 = 64-bit indices.
+template <bool POW2, typename I>
+static void g2p_pic_t(const GridD& g, const double* u, const double* v, const double* w, uint64_t n, const double* pos, double* vel) {
+    for (uint64_t p = 0; p < n; ++p)
+        sample_velocity<POW2, I>(g, u, v, w, pos[3 * p], pos[3 * p + 1], pos[3 * p + 2], vel + 3 * p, vel + 3 * p + 1, vel + 3 * p + 2);
+}
+template <bool POW2, typename I>
+static void move_t(const GridD& g, const double* u, const double* v, const double* w, double dt, unsigned nsub, int flag,
+                   uint64_t n, double* pos, double* vel) {
+    for (uint64_t p = 0; p < n; ++p) move_particle<POW2, I>(g, u, v, w, dt, nsub, flag, pos + 3 * p, vel + 3 * p);
+}
+
+extern "C" {
+
+// k_collider_sdf over the whole grid
+int hc_collider_sdf(const jetcu_grid* grid, int kind, const double* a, const double* b, const double* lin, const double* ang,
+                    double friction, double* sdf) {
+    GridD g = make_grid(grid);
+    ColliderD c = make_collider(kind, a, b, lin, ang, friction);
+    for (int k = 0; k < g.nz; ++k)
+        for (int j = 0; j < g.ny; ++j)
+            for (int i = 0; i < g.nx; ++i) sdf[((size_t)k * g.ny + j) * g.nx + i] = collider_sdf_cell(g, c, i, j, k);
+    return 0;
+}
+
+// hyb_zero_walls() of hybrid.cu == GridFluidSolver3::applyBoundaryCondition: hyb_constrain_collider, then the walls
+int hc_apply_boundary_condition(const jetcu_grid* grid, int kind, const double* a, const double* b, const double* lin,
+                                const double* ang, double friction, double max_cfl, int wall_flag, double* u, double* v,
+                                double* w) {
+    GridD g = make_grid(grid);
+    const size_t nu = (size_t)(g.nx + 1) * g.ny * g.nz, nv = (size_t)g.nx * (g.ny + 1) * g.nz, nw = (size_t)g.nx * g.ny * (g.nz + 1);
+    if (kind != 0) {
+        ColliderD c = make_collider(kind, a, b, lin, ang, friction);
+        std::vector<double> csdf((size_t)g.nx * g.ny * g.nz), tu(nu), tv(nv), tw(nw);
+        hc_collider_sdf(grid, kind, a, b, lin, ang, friction, csdf.data());
+        std::vector<char> mu(nu), mv(nv), mw(nw);
+        const unsigned depth = (unsigned)ceil(max_cfl);
+        markers<0>(g, c, csdf.data(), u, mu.data());
+        markers<1>(g, c, csdf.data(), v, mv.data());
+        markers<2>(g, c, csdf.data(), w, mw.data());
+        extrapolate(u, mu.data(), g.nx + 1, g.ny, g.nz, depth);
+        extrapolate(v, mv.data(), g.nx, g.ny + 1, g.nz, depth);
+        extrapolate(w, mw.data(), g.nx, g.ny, g.nz + 1, depth);
+        project<0>(g, c, csdf.data(), u, v, w, tu.data());
+        project<1>(g, c, csdf.data(), u, v, w, tv.data());
+        project<2>(g, c, csdf.data(), u, v, w, tw.data());
+        memcpy(u, tu.data(), nu * 8); memcpy(v, tv.data(), nv * 8); memcpy(w, tw.data(), nw * 8);
+    }
+    size_t m = (size_t)g.ny * g.nz;
+    if ((size_t)g.nx * g.nz > m) m = (size_t)g.nx * g.nz;
+    if ((size_t)g.nx * g.ny > m) m = (size_t)g.nx * g.ny;
+    for (size_t t = 0; t < m; ++t) zero_walls_elem(g, wall_flag, u, v, w, t);
+    return 0;
+}
+
+// boundary velocity samples handed to the pressure solver (k_boundary_velocity<AXIS>)
+int hc_boundary_velocity(const jetcu_grid* grid, int kind, const double* a, const double* b, const double* lin, const double* ang,
+                         double friction, double* bu, double* bv, double* bw) {
+    GridD g = make_grid(grid);
+    ColliderD c = make_collider(kind, a, b, lin, ang, friction);
+    for (int k = 0; k < g.nz; ++k) for (int j = 0; j < g.ny; ++j) for (int i = 0; i < g.nx + 1; ++i) boundary_velocity_face<0>(g, c, bu, i, j, k);
+    for (int k = 0; k < g.nz; ++k) for (int j = 0; j < g.ny + 1; ++j) for (int i = 0; i < g.nx; ++i) boundary_velocity_face<1>(g, c, bv, i, j, k);
+    for (int k = 0; k < g.nz + 1; ++k) for (int j = 0; j < g.ny; ++j) for (int i = 0; i < g.nx; ++i) boundary_velocity_face<2>(g, c, bw, i, j, k);
+    return 0;
+}
+
+// the extrapolateIntoCollider tail of jetcu_hybrid_build_signed_distance_field: k_outside_collider_marker + sweeps
+int hc_extrapolate_into_collider(const jetcu_grid* grid, int kind, const double* a, const double* b, const double* lin,
+                                 const double* ang, double friction, double max_cfl, double* sdf) {
+    GridD g = make_grid(grid);
+    std::vector<double> csdf((size_t)g.nx * g.ny * g.nz);
+    hc_collider_sdf(grid, kind, a, b, lin, ang, friction, csdf.data());
+    std::vector<char> marker(csdf.size());
+    for (int k = 0; k < g.nz; ++k)
+        for (int j = 0; j < g.ny; ++j)
+            for (int i = 0; i < g.nx; ++i) marker[((size_t)k * g.ny + j) * g.nx + i] = outside_collider_cell(g, csdf.data(), i, j, k);
+    extrapolate(sdf, marker.data(), g.nx, g.ny, g.nz, (unsigned)ceil(max_cfl));
+    return 0;
+}
+
+// k_resolve_collision over n AoS particles
+int hc_resolve_collision(int kind, const double* a, const double* b, const double* lin, const double* ang, double friction,
+                         uint64_t n, double* pos, double* vel) {
+    ColliderD c = make_collider(kind, a, b, lin, ang, friction);
+    for (uint64_t p = 0; p < n; ++p) cd_resolve_collision(c, pos + 3 * p, vel + 3 * p);
+    return 0;
+}
+
+// ---- G2P and advection entry points (templates above)
+int hc_g2p_pic(const jetcu_grid* grid, const double* u, const double* v, const double* w, int variant, uint64_t n,
+               const double* pos, double* vel) {
+    GridD g = make_grid(grid);
+    if ((variant & 1) && !(g.ihx != 0.0 && g.ihy != 0.0 && g.ihz != 0.0)) return 1;
+    switch (variant & 3) {
+        case 0: g2p_pic_t<false, int>(g, u, v, w, n, pos, vel); break;
+        case 1: g2p_pic_t<true, int>(g, u, v, w, n, pos, vel); break;
+        case 2: g2p_pic_t<false, long long>(g, u, v, w, n, pos, vel); break;
+        default: g2p_pic_t<true, long long>(g, u, v, w, n, pos, vel); break;
+    }
+    return 0;
+}
+
+int hc_g2p_flip(const jetcu_grid* grid, const double* u, const double* v, const double* w, const float* ud, const float* vd,
+                const float* wd, double blend, uint64_t n, const double* pos, double* vel) {
+    GridD g = make_grid(grid);
+    for (uint64_t p = 0; p < n; ++p) g2p_flip_particle(g, u, v, w, ud, vd, wd, blend, pos + 3 * p, vel + 3 * p);
+    return 0;
+}
+
+int hc_g2p_apic(const jetcu_grid* grid, const double* u, const double* v, const double* w, uint64_t n, const double* pos,
+                double* vel, double* cx, double* cy, double* cz) {
+    GridD g = make_grid(grid);
+    const bool pow2 = g.ihx != 0.0 && g.ihy != 0.0 && g.ihz != 0.0;
+    for (uint64_t p = 0; p < n; ++p) {
+        const double px = pos[3 * p], py = pos[3 * p + 1], pz = pos[3 * p + 2];
+        if (pow2) sample_velocity<true, int>(g, u, v, w, px, py, pz, vel + 3 * p, vel + 3 * p + 1, vel + 3 * p + 2);
+        else sample_velocity<false, int>(g, u, v, w, px, py, pz, vel + 3 * p, vel + 3 * p + 1, vel + 3 * p + 2);
+        apic_affine<0>(g, u, px, py, pz, cx + 3 * p, cx + 3 * p + 1, cx + 3 * p + 2);
+        apic_affine<1>(g, v, px, py, pz, cy + 3 * p, cy + 3 * p + 1, cy + 3 * p + 2);
+        apic_affine<2>(g, w, px, py, pz, cz + 3 * p, cz + 3 * p + 1, cz + 3 * p + 2);
+    }
+    return 0;
+}
+
+int hc_move_particles(const jetcu_grid* grid, const double* u, const double* v, const double* w, double dt_frame, double max_cfl,
+                      int flag, int variant, uint64_t n, double* pos, double* vel) {
+    GridD g = make_grid(grid);
+    if ((variant & 1) && !(g.ihx != 0.0 && g.ihy != 0.0 && g.ihz != 0.0)) return 1;
+    const unsigned nsub = (unsigned)fmax(max_cfl, 1.0);   // jetcu_hybrid_move_particles
+    const double dt = dt_frame / nsub;
+    switch (variant & 3) {
+        case 0: move_t<false, int>(g, u, v, w, dt, nsub, flag, n, pos, vel); break;
+        case 1: move_t<true, int>(g, u, v, w, dt, nsub, flag, n, pos, vel); break;
+        case 2: move_t<false, long long>(g, u, v, w, dt, nsub, flag, n, pos, vel); break;
+        default: move_t<true, long long>(g, u, v, w, dt, nsub, flag, n, pos, vel); break;
+    }
+    return 0;
+}
+
+}  // extern "C"

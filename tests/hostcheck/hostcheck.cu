@@ -8,7 +8,10 @@
 
 #include <vector>
 
-#include "../../fluid-engine-dev_b200/csrc/particle_ops.cuh"
+#include <algorithm>
+#include <numeric>
+
+#include "../../fluid-engine-dev_b200/csrc/p2g_ops.cuh"
 
 static GridD make_grid(const jetcu_grid* g) {
     return GridD{(int)g->nx, (int)g->ny, (int)g->nz, g->hx, g->hy, g->hz, g->ox, g->oy, g->oz,
@@ -63,7 +66,103 @@ static void move_t(const GridD& g, const double* u, const double* v, const doubl
     for (uint64_t p = 0; p < n; ++p) move_particle<POW2, I>(g, u, v, w, dt, nsub, flag, pos + 3 * p, vel + 3 * p);
 }
 
+// ---- P2G: jetcu_hybrid_transfer_particles_to_grids with the per-cell kernel (k_p2g_cells<APIC, CF>), tiles and
+// "threads" run one after the other, shared memory is a plain buffer, atomics plain additions.
+template <bool APIC, bool CF>
+static void p2g_tiles(const GridD& g, const std::vector<uint32_t>& cell_start, const AttrPtrs& a, double scale, const P2GAcc& acc) {
+    constexpr int NF = (TC + 1) * (TC + 2) * (TC + 2);
+    constexpr int NL = CF ? 5 : 4;
+    std::vector<unsigned> smem(6 * NL * NF);
+    std::vector<unsigned char> mark(3 * NF);
+    for (int K0 = 0; K0 < g.nz; K0 += TC)
+        for (int J0 = 0; J0 < g.ny; J0 += TC)
+            for (int I0 = 0; I0 < g.nx; I0 += TC) {
+                std::fill(smem.begin(), smem.end(), 0u);
+                std::fill(mark.begin(), mark.end(), (unsigned char)0);
+                unsigned* sV = smem.data();
+                unsigned* sW = smem.data() + 3 * NL * NF;
+                bool any = false;
+                for (int cl = 0; cl < TC * TC * TC; ++cl) {
+                    const int ci = I0 + (cl % TC), cj = J0 + ((cl / TC) % TC), ck = K0 + (cl / (TC * TC));
+                    if (ci >= g.nx || cj >= g.ny || ck >= g.nz) continue;
+                    const size_t cell = ((size_t)ck * g.ny + cj) * g.nx + ci;
+                    const uint32_t s0 = cell_start[cell], e0 = cell_start[cell + 1];
+                    if (s0 == e0) continue;
+                    any = true;
+                    p2g_cell_component<APIC, 0, CF>(g, ci, cj, ck, s0, e0, a, scale, I0, J0, K0, sV, sW, mark.data(), acc);
+                    p2g_cell_component<APIC, 1, CF>(g, ci, cj, ck, s0, e0, a, scale, I0, J0, K0, sV + NL * NF, sW + NL * NF, mark.data() + NF, acc);
+                    p2g_cell_component<APIC, 2, CF>(g, ci, cj, ck, s0, e0, a, scale, I0, J0, K0, sV + 2 * NL * NF, sW + 2 * NL * NF, mark.data() + 2 * NF, acc);
+                }
+                if (!any) continue;
+                for (int ax = 0; ax < 3; ++ax) {
+                    const int dx = TC + (ax == 0 ? 1 : 2), dy = TC + (ax == 1 ? 1 : 2), dz = TC + (ax == 2 ? 1 : 2);
+                    for (int t = 0; t < dx * dy * dz; ++t)
+                        p2g_tile_flush_face<CF>(g, I0, J0, K0, ax, t, sV + ax * NL * NF, sW + ax * NL * NF, mark.data() + ax * NF, acc);
+                }
+            }
+}
+
 extern "C" {
+
+// PIC / FLIP (apic = 0) or APIC (apic = 1) transferFromParticlesToGrids through the per-cell kernel's source;
+// carry_free selects the 26-bit redundant-limb shared accumulators.  AoS inputs in the caller's order.
+int hc_p2g(const jetcu_grid* grid, int apic, int carry_free, uint64_t n, const double* pos, const double* vel, const double* cx,
+           const double* cy, const double* cz, double* u, double* v, double* w, char* um, char* vm, char* wm, int* err) {
+    GridD g = make_grid(grid);
+    const size_t nc = (size_t)g.nx * g.ny * g.nz;
+    const size_t nf[3] = {(size_t)(g.nx + 1) * g.ny * g.nz, (size_t)g.nx * (g.ny + 1) * g.nz, (size_t)g.nx * g.ny * (g.nz + 1)};
+    // cell sort: by owning cell, ascending original index inside a cell (k_cell_count .. k_sort_cells .. k_gather_attrs)
+    std::vector<uint32_t> cell(n), order(n);
+    for (uint64_t p = 0; p < n; ++p) {
+        const int ci = cell_coord(pos[3 * p], g.ox, 1.0 / g.hx, g.nx), cj = cell_coord(pos[3 * p + 1], g.oy, 1.0 / g.hy, g.ny),
+                  ck = cell_coord(pos[3 * p + 2], g.oz, 1.0 / g.hz, g.nz);
+        cell[p] = (uint32_t)(((size_t)ck * g.ny + cj) * g.nx + ci);
+    }
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return cell[x] < cell[y]; });
+    std::vector<uint32_t> cell_start(nc + 1, 0);
+    for (uint64_t p = 0; p < n; ++p) cell_start[cell[p] + 1]++;
+    for (size_t c = 0; c < nc; ++c) cell_start[c + 1] += cell_start[c];
+    std::vector<std::vector<double>> soa(NATTR, std::vector<double>(n ? n : 1, 0.0));
+    for (uint64_t s = 0; s < n; ++s) {
+        const uint32_t p = order[s];
+        for (int q = 0; q < 3; ++q) {
+            soa[q][s] = pos[3 * p + q]; soa[3 + q][s] = vel[3 * p + q];
+            if (apic) { soa[6 + q][s] = cx[3 * p + q]; soa[9 + q][s] = cy[3 * p + q]; soa[12 + q][s] = cz[3 * p + q]; }
+        }
+    }
+    AttrPtrs a;
+    for (int q = 0; q < NATTR; ++q) a.p[q] = soa[q].data();
+    // fixed-point scale (k_p2g_vmax_partial + k_p2g_scale_final)
+    double vmax = 0.0;
+    for (uint64_t s = 0; s < n; ++s)
+        for (int ax = 0; ax < 3; ++ax) {
+            double val = fabs(a.p[3 + ax][s]);
+            if (apic) val += g.hx * fabs(a.p[6 + 3 * ax][s]) + g.hy * fabs(a.p[7 + 3 * ax][s]) + g.hz * fabs(a.p[8 + 3 * ax][s]);
+            vmax = fmax(vmax, val);
+        }
+    const P2GScale sc = p2g_scale_from_vmax(vmax);
+    // accumulators: the high words of the value sums live in u, v, w themselves (as in the product)
+    double* val[3] = {u, v, w};
+    char* mk[3] = {um, vm, wm};
+    std::vector<unsigned long long> sum_lo[3], wsum[3], wsum_lo[3];
+    P2GAcc acc;
+    for (int q = 0; q < 3; ++q) {
+        memset(val[q], 0, nf[q] * 8); memset(mk[q], 0, nf[q]);
+        sum_lo[q].assign(nf[q], 0ull); wsum[q].assign(nf[q], 0ull); wsum_lo[q].assign(nf[q], 0ull);
+        acc.sum[q] = reinterpret_cast<unsigned long long*>(val[q]); acc.sum_lo[q] = sum_lo[q].data();
+        acc.wsum[q] = wsum[q].data(); acc.wsum_lo[q] = wsum_lo[q].data(); acc.marker[q] = mk[q];
+    }
+    if (n > 0) {
+        if (apic) { if (carry_free) p2g_tiles<true, true>(g, cell_start, a, sc.scale, acc); else p2g_tiles<true, false>(g, cell_start, a, sc.scale, acc); }
+        else { if (carry_free) p2g_tiles<false, true>(g, cell_start, a, sc.scale, acc); else p2g_tiles<false, false>(g, cell_start, a, sc.scale, acc); }
+    }
+    *err = 0;
+    for (int q = 0; q < 3; ++q)
+        for (size_t f = 0; f < nf[q]; ++f)
+            p2g_normalise_face(val[q], sum_lo[q].data(), wsum[q].data(), wsum_lo[q].data(), sc.inv_scale, nullptr, err, f);
+    return 0;
+}
 
 // k_collider_sdf over the whole grid
 int hc_collider_sdf(const jetcu_grid* grid, int kind, const double* a, const double* b, const double* lin, const double* ang,

@@ -102,6 +102,79 @@ class StepStats(C.Structure):
 PIC, FLIP, APIC = 0, 1, 2
 
 
+class SmokeParams(C.Structure):
+    """== the knobs of jet::GridSmokeSolver3 (include/jet/grid_smoke_solver3.h:170-175) + GridFluidSolver3's."""
+    _fields_ = [("grid", Grid), ("closed_domain_boundary_flag", C.c_int32), ("reserved", C.c_int32), ("gravity", f64 * 3),
+                ("max_cfl", f64), ("buoyancy_density_factor", f64), ("buoyancy_temperature_factor", f64),
+                ("density_decay", f64), ("temperature_decay", f64), ("mgpcg", MgpcgParams)]
+
+    @classmethod
+    def make(cls, grid, mgpcg=None, gravity=(0.0, -9.8, 0.0), max_cfl=5.0, closed_domain_boundary_flag=63,
+             buoyancy_density_factor=-0.000625, buoyancy_temperature_factor=5.0, density_decay=0.001, temperature_decay=0.001):
+        p = cls()
+        p.grid = grid
+        p.closed_domain_boundary_flag = closed_domain_boundary_flag
+        p.gravity = (f64 * 3)(*gravity)
+        p.max_cfl = max_cfl
+        p.buoyancy_density_factor = buoyancy_density_factor
+        p.buoyancy_temperature_factor = buoyancy_temperature_factor
+        p.density_decay = density_decay
+        p.temperature_decay = temperature_decay
+        p.mgpcg = mgpcg if mgpcg is not None else MgpcgParams.make()
+        return p
+
+
+class SmokeApi:
+    """Wrapper over a jeto_smoke* / jetcu_smoke* handle (GridSmokeSolver3); `lib_call(name, *args)` raises on error."""
+
+    def __init__(self, lib_call, handle, params):
+        self._c = lib_call
+        self.h = handle
+        self.params = params
+        self.grid = params.grid
+
+    def close(self):
+        if self.h is not None:
+            self._c("smoke_destroy", self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_fields(self, density=None, temperature=None, u=None, v=None, w=None):
+        self._c("smoke_set_fields", self.h, _p(c64(density)), _p(c64(temperature)), _p(c64(u)), _p(c64(v)), _p(c64(w)))
+
+    def get_fields(self):
+        g = self.grid
+        out = dict(density=np.zeros(size3(g.res)), temperature=np.zeros(size3(g.res)), u=np.zeros(size3(g.usize)),
+                   v=np.zeros(size3(g.vsize)), w=np.zeros(size3(g.wsize)), pressure=np.zeros(size3(g.res)))
+        self._c("smoke_get_fields", self.h, _p(out["density"]), _p(out["temperature"]), _p(out["u"]), _p(out["v"]), _p(out["w"]),
+                _p(out["pressure"]))
+        return out
+
+    def step(self, dt):
+        r = MgpcgResult()
+        self._c("smoke_step", self.h, f64(dt), C.byref(r))
+        return r
+
+    def compute_external_forces(self, dt):
+        self._c("smoke_compute_external_forces", self.h, f64(dt))
+
+    def compute_pressure(self, dt):
+        r = MgpcgResult()
+        self._c("smoke_compute_pressure", self.h, f64(dt), C.byref(r))
+        return r
+
+    def compute_advection(self, dt):
+        self._c("smoke_compute_advection", self.h, f64(dt))
+
+    def end_advance_time_step(self, dt):
+        self._c("smoke_end_advance_time_step", self.h, f64(dt))
+
+
 def size3(shape_xyz):
     """numpy arrays holding Jet Array3 data are indexed [k, j, i] (x fastest)."""
     nx, ny, nz = shape_xyz

@@ -124,6 +124,33 @@ int jeto_hybrid_transfer_grids_to_particles(jeto_hybrid*);
 int jeto_hybrid_move_particles(jeto_hybrid*, double dt);
 int jeto_hybrid_compute_advection(jeto_hybrid*, double dt);
 
+/* ---------------------------------------------------------------- GridSmokeSolver3 (BASELINE config 5)
+ * GridSmokeSolver3 (src/jet/grid_smoke_solver3.cpp) on GridFluidSolver3::onAdvanceTimeStep
+ * (src/jet/grid_fluid_solver3.cpp:179-210): buoyancy, fractional pressure projection with MGPCG on an all-liquid domain
+ * (fluidSdf = -kMaxD, no collider), cubic semi-Lagrangian advection (CubicSemiLagrangian3, the solver's default) of
+ * density / temperature / velocity, decay.  No emitter, no collider, diffusion and viscosity coefficients 0 (defaults). */
+typedef struct jeto_smoke_params {
+    jeto_grid grid;
+    int32_t closed_domain_boundary_flag, reserved;
+    double gravity[3];
+    double max_cfl;
+    double buoyancy_density_factor, buoyancy_temperature_factor;   /* defaults -0.000625, 5.0 */
+    double density_decay, temperature_decay;                       /* defaults 0.001, 0.001 */
+    jeto_mgpcg_params mgpcg;
+} jeto_smoke_params;
+typedef struct jeto_smoke jeto_smoke;
+int jeto_smoke_create(const jeto_smoke_params* params, jeto_smoke** out);
+int jeto_smoke_destroy(jeto_smoke*);
+/* any pointer may be NULL (field left as it is / not returned); cell-centred density & temperature, face-centred u, v, w */
+int jeto_smoke_set_fields(jeto_smoke*, const double* density, const double* temperature, const double* u, const double* v,
+                          const double* w);
+int jeto_smoke_get_fields(jeto_smoke*, double* density, double* temperature, double* u, double* v, double* w, double* pressure);
+int jeto_smoke_step(jeto_smoke*, double dt, jeto_mgpcg_result* result);            /* onAdvanceTimeStep */
+int jeto_smoke_compute_external_forces(jeto_smoke*, double dt);                    /* computeBuoyancyForce + BC */
+int jeto_smoke_compute_pressure(jeto_smoke*, double dt, jeto_mgpcg_result* result);
+int jeto_smoke_compute_advection(jeto_smoke*, double dt);
+int jeto_smoke_end_advance_time_step(jeto_smoke*, double dt);                      /* computeDiffusion: decay */
+
 #ifdef __cplusplus
 }
 #endif

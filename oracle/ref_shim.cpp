@@ -540,4 +540,91 @@ int jeto_hybrid_transfer_grids_to_particles(jeto_hybrid* h) { h->solver->transfe
 int jeto_hybrid_move_particles(jeto_hybrid* h, double dt) { h->solver->moveParticles(dt); return 0; }
 int jeto_hybrid_compute_advection(jeto_hybrid* h, double dt) { h->solver->computeAdvection(dt); return 0; }
 
+// ------------------------------------------------------------------ smoke solver
+struct jeto_smoke {
+    std::shared_ptr<GridSmokeSolver3> solver;
+    std::shared_ptr<FdmMgpcgSolver3> lin;
+    std::shared_ptr<GridFractionalSinglePhasePressureSolver3> pressure;
+};
+
+int jeto_smoke_create(const jeto_smoke_params* p, jeto_smoke** out) {
+    auto* h = new jeto_smoke();
+    Size3 res(p->grid.nx, p->grid.ny, p->grid.nz);
+    Vector3D hh(p->grid.hx, p->grid.hy, p->grid.hz), o(p->grid.ox, p->grid.oy, p->grid.oz);
+    h->solver = std::make_shared<GridSmokeSolver3>(res, hh, o);
+    h->lin = makeMgpcg(&p->mgpcg);
+    h->pressure = std::make_shared<GridFractionalSinglePhasePressureSolver3>();
+    h->pressure->setLinearSystemSolver(h->lin);
+    h->solver->setPressureSolver(h->pressure);
+    h->solver->setGravity(Vector3D(p->gravity[0], p->gravity[1], p->gravity[2]));
+    h->solver->setMaxCfl(p->max_cfl);
+    h->solver->setClosedDomainBoundaryFlag(p->closed_domain_boundary_flag);
+    h->solver->setUseCompressedLinearSystem(false);
+    h->solver->setBuoyancySmokeDensityFactor(p->buoyancy_density_factor);
+    h->solver->setBuoyancyTemperatureFactor(p->buoyancy_temperature_factor);
+    h->solver->setSmokeDecayFactor(p->density_decay);
+    h->solver->setTemperatureDecayFactor(p->temperature_decay);
+    *out = h;
+    return 0;
+}
+
+int jeto_smoke_destroy(jeto_smoke* h) { delete h; return 0; }
+
+int jeto_smoke_set_fields(jeto_smoke* h, const double* den, const double* temp, const double* u, const double* v, const double* w) {
+    auto grids = h->solver->gridSystemData();
+    auto res = grids->resolution();
+    size_t nc = res.x * res.y * res.z;
+    if (den) std::memcpy(h->solver->smokeDensity()->dataAccessor().data(), den, nc * 8);
+    if (temp) std::memcpy(h->solver->temperature()->dataAccessor().data(), temp, nc * 8);
+    auto vel = grids->velocity();
+    if (u) std::memcpy(vel->uAccessor().data(), u, (res.x + 1) * res.y * res.z * 8);
+    if (v) std::memcpy(vel->vAccessor().data(), v, res.x * (res.y + 1) * res.z * 8);
+    if (w) std::memcpy(vel->wAccessor().data(), w, res.x * res.y * (res.z + 1) * 8);
+    return 0;
+}
+
+int jeto_smoke_get_fields(jeto_smoke* h, double* den, double* temp, double* u, double* v, double* w, double* pr) {
+    auto grids = h->solver->gridSystemData();
+    auto res = grids->resolution();
+    size_t nc = res.x * res.y * res.z;
+    if (den) std::memcpy(den, h->solver->smokeDensity()->constDataAccessor().data(), nc * 8);
+    if (temp) std::memcpy(temp, h->solver->temperature()->constDataAccessor().data(), nc * 8);
+    auto vel = grids->velocity();
+    if (u) std::memcpy(u, vel->uConstAccessor().data(), (res.x + 1) * res.y * res.z * 8);
+    if (v) std::memcpy(v, vel->vConstAccessor().data(), res.x * (res.y + 1) * res.z * 8);
+    if (w) std::memcpy(w, vel->wConstAccessor().data(), res.x * res.y * (res.z + 1) * 8);
+    if (pr) {
+        const auto& x = h->pressure->pressure();
+        if (x.size().x * x.size().y * x.size().z == nc) std::memcpy(pr, x.data(), nc * 8); else std::memset(pr, 0, nc * 8);
+    }
+    return 0;
+}
+
+static void smokeResult(jeto_smoke* h, jeto_mgpcg_result* r) {
+    if (!r) return;
+    std::memset(r, 0, sizeof(*r));
+    r->iterations = h->lin->lastNumberOfIterations();
+    r->last_residual = h->lin->lastResidual();
+    r->returned = 1;
+    const auto& sys = h->pressure->_mgSystem;
+    if (!sys.A.levels.empty()) {
+        r->true_residual_l2 = trueResidual(sys.A.levels.front(), sys.x.levels.front(), sys.b.levels.front());
+        r->b_l2 = FdmBlas3::l2Norm(sys.b.levels.front());
+    }
+}
+
+int jeto_smoke_step(jeto_smoke* h, double dt, jeto_mgpcg_result* r) {
+    h->solver->onAdvanceTimeStep(dt);
+    smokeResult(h, r);
+    return 0;
+}
+int jeto_smoke_compute_external_forces(jeto_smoke* h, double dt) { h->solver->computeExternalForces(dt); return 0; }
+int jeto_smoke_compute_pressure(jeto_smoke* h, double dt, jeto_mgpcg_result* r) {
+    h->solver->computePressure(dt);
+    smokeResult(h, r);
+    return 0;
+}
+int jeto_smoke_compute_advection(jeto_smoke* h, double dt) { h->solver->computeAdvection(dt); return 0; }
+int jeto_smoke_end_advance_time_step(jeto_smoke* h, double dt) { h->solver->endAdvanceTimeStep(dt); return 0; }
+
 }  // extern "C"

@@ -18,8 +18,8 @@ from jetcu_loader import load_package
 
 _pkg = load_package()
 from fluid_engine_dev_b200.jetcu import (APIC, FLIP, PIC, PD, PF, PU64, ROW_DTYPE, Grid, HybridApi, HybridParams,  # noqa: E402,F401
-                                          LinearApi, MgpcgParams, MgpcgResult, Row, StepStats, _p, c64, f64,
-                                          level_dims, size3, u32, u64)
+                                          LinearApi, MgpcgParams, MgpcgResult, Row, SmokeApi, SmokeParams, StepStats, _p, c64,
+                                          f64, level_dims, size3, u32, u64)
 
 
 class Oracle(LinearApi):
@@ -65,6 +65,11 @@ class Oracle(LinearApi):
         h = C.c_void_p()
         self._call("hybrid_create", C.byref(params), C.byref(h))
         return HybridApi(self._call, h, params)
+
+    def smoke(self, params):
+        h = C.c_void_p()
+        self._call("smoke_create", C.byref(params), C.byref(h))
+        return SmokeApi(self._call, h, params)
 
 
 def load_port():

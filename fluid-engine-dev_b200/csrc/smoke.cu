@@ -1,0 +1,277 @@
+// smoke.cu — device-resident GridSmokeSolver3 (BASELINE config 5) behind include/jetcu.h.
+//
+// Mirrors GridFluidSolver3::onAdvanceTimeStep (src/jet/grid_fluid_solver3.cpp:179-210) with GridSmokeSolver3's overrides
+// (src/jet/grid_smoke_solver3.cpp): boundary condition -> buoyancy -> pressure projection (the same
+// GridFractionalSinglePhasePressureSolver3 + MGPCG path as the liquid solver, on an all-liquid domain) -> cubic
+// semi-Lagrangian advection of density, temperature and velocity -> decay.  No emitter, no collider, zero diffusion /
+// viscosity coefficients (the solver's defaults).  Kernel bodies live in smoke_ops.cuh (__host__ __device__; checked on the
+// CPU by tests/hostcheck); this file holds the launch wrappers, the ambient-temperature reduction and the host side.
+// [Written after round 1's GPU minutes ran out: tests/test_gpu_zz_smoke.py is its first GPU run.]
+#include <math.h>
+#include <string.h>
+
+#include "pressure.cuh"
+#include "smoke_ops.cuh"
+
+struct jetcu_smoke {
+    jetcu_ctx* ctx = nullptr;
+    jetcu_smoke_params P{};
+    int nx = 0, ny = 0, nz = 0;
+    size_t nu = 0, nv = 0, nw = 0, nc = 0;
+    double *u = nullptr, *v = nullptr, *w = nullptr;        // velocity
+    double *u0 = nullptr, *v0 = nullptr, *w0 = nullptr;     // the clone the advection reads
+    double *den = nullptr, *temp = nullptr, *scratch = nullptr;
+    PressureSystem ps;
+    jetcu_mgpcg_result last{};
+};
+
+static GridD smoke_grid(const jetcu_smoke* h) {
+    const jetcu_grid& g = h->P.grid;
+    return GridD{h->nx, h->ny, h->nz, g.hx, g.hy, g.hz, g.ox, g.oy, g.oz,
+                 jc_pow2_inverse(g.hx), jc_pow2_inverse(g.hy), jc_pow2_inverse(g.hz)};
+}
+
+static inline dim3 sgrid(int sx, int sy, int sz) { return dim3((sx + 63) / 64, (sy + 3) / 4, sz); }
+
+__global__ void k_smoke_zero_walls(GridD g, int flag, double* __restrict__ u, double* __restrict__ v, double* __restrict__ w) {
+    zero_walls_elem(g, flag, u, v, w, (size_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+template <int AXIS>
+__global__ void __launch_bounds__(256) k_smoke_buoyancy(GridD g, const double* __restrict__ den, const double* __restrict__ temp,
+                                                        double fd, double ft, const double* __restrict__ t_sum, double inv_n,
+                                                        double dt, double up_a, double* __restrict__ comp) {
+    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+    if (i >= g.nx + (AXIS == 0) || j >= g.ny + (AXIS == 1) || k >= g.nz + (AXIS == 2)) return;
+    // tAmb = sum / N  (grid_smoke_solver3.cpp:147-151; inv_n is passed as N itself: the reference DIVIDES)
+    sm_buoyancy_face<AXIS>(g, den, temp, fd, ft, t_sum[0] / inv_n, dt, up_a, comp, i, j, k);
+}
+
+__global__ void __launch_bounds__(256) k_smoke_advect_cell(GridD g, const double* __restrict__ in, const double* __restrict__ u,
+                                                           const double* __restrict__ v, const double* __restrict__ w, double dt,
+                                                           double hmin, double* __restrict__ out) {
+    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+    if (i >= g.nx || j >= g.ny) return;
+    out[((size_t)k * g.ny + j) * g.nx + i] = sm_advect_cell(g, in, u, v, w, dt, hmin, i, j, k);
+}
+
+template <int AXIS>
+__global__ void __launch_bounds__(256) k_smoke_advect_face(GridD g, const double* __restrict__ u0, const double* __restrict__ v0,
+                                                           const double* __restrict__ w0, double dt, double hmin,
+                                                           double* __restrict__ out) {
+    const int sx = g.nx + (AXIS == 0), sy = g.ny + (AXIS == 1), sz = g.nz + (AXIS == 2);
+    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+    if (i >= sx || j >= sy || k >= sz) return;
+    out[((size_t)k * sy + j) * sx + i] = sm_advect_face<AXIS>(g, u0, v0, w0, dt, hmin, i, j, k);
+}
+
+__global__ void k_smoke_scale(double* __restrict__ a, double s, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] *= s;
+}
+
+// Sum of the temperature field for tAmb.  The reference adds the cells serially (k, j, i order); here a fixed two-stage
+// tree (592 CTAs, then one) — deterministic, differs from the serial sum by rounding only.
+#define SMOKE_SUM_GRID 592
+__global__ void __launch_bounds__(256) k_smoke_sum_partial(const double* __restrict__ a, size_t n, double* __restrict__ partials) {
+    __shared__ double sm[256];
+    double acc = 0.0;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)SMOKE_SUM_GRID * 256) acc += a[i];
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = sm[0];
+}
+__global__ void __launch_bounds__(256) k_smoke_sum_final(const double* __restrict__ partials, int n, double* __restrict__ out) {
+    __shared__ double sm[256];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) acc += partials[i];
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sm[0];
+}
+
+#define SMK_ENTER(h)                                                      \
+    if (!(h)) return JETCU_ERR_INVALID_ARG;                               \
+    jetcu_ctx* ctx = (h)->ctx;                                            \
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return jetcu_fail(ctx, JETCU_ERR_CUDA, "cudaSetDevice failed");
+
+static int smoke_apply_bc(jetcu_smoke* h) {
+    jetcu_ctx* ctx = h->ctx;
+    GridD g = smoke_grid(h);
+    size_t m = (size_t)g.ny * g.nz;
+    if ((size_t)g.nx * g.nz > m) m = (size_t)g.nx * g.nz;
+    if ((size_t)g.nx * g.ny > m) m = (size_t)g.nx * g.ny;
+    JC_LAUNCH(ctx, k_smoke_zero_walls, jc_blocks(m, 256), 256, 0, g, h->P.closed_domain_boundary_flag, h->u, h->v, h->w);
+    return JETCU_OK;
+}
+
+extern "C" {
+
+void jetcu_smoke_default_params(jetcu_smoke_params* p) {
+    memset(p, 0, sizeof(*p));
+    p->grid.nx = p->grid.ny = p->grid.nz = 1;
+    p->grid.hx = p->grid.hy = p->grid.hz = 1.0;
+    p->closed_domain_boundary_flag = JETCU_DIR_ALL;
+    p->gravity[1] = -9.8;
+    p->max_cfl = 5.0;
+    p->buoyancy_density_factor = -0.000625; p->buoyancy_temperature_factor = 5.0;   // include/jet/grid_smoke_solver3.h:172-175
+    p->density_decay = 0.001; p->temperature_decay = 0.001;
+    p->mgpcg.max_iterations = 100; p->mgpcg.max_levels = 5; p->mgpcg.n_restriction = 5; p->mgpcg.n_correction = 5;
+    p->mgpcg.n_coarsest = 20; p->mgpcg.n_final = 20; p->mgpcg.tolerance = 1e-9; p->mgpcg.sor_factor = 1.5;
+    p->mgpcg.use_red_black = 1;
+}
+
+int jetcu_smoke_destroy(jetcu_smoke* h) {
+    if (!h) return JETCU_OK;
+    jetcu_ctx* ctx = h->ctx;
+    cudaSetDevice(ctx->device);
+    jc_free(ctx, h->u); jc_free(ctx, h->v); jc_free(ctx, h->w); jc_free(ctx, h->u0); jc_free(ctx, h->v0); jc_free(ctx, h->w0);
+    jc_free(ctx, h->den); jc_free(ctx, h->temp); jc_free(ctx, h->scratch);
+    pressure_free(ctx, &h->ps);
+    cudaStreamSynchronize(ctx->stream);
+    delete h;
+    return JETCU_OK;
+}
+
+int jetcu_smoke_create(jetcu_ctx* ctx, const jetcu_smoke_params* p, jetcu_smoke** out) {
+    if (!ctx) return JETCU_ERR_INVALID_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return jetcu_fail(ctx, JETCU_ERR_CUDA, "cudaSetDevice failed");
+    JC_ARG(ctx, p && out);
+    JC_ARG(ctx, p->grid.nx > 0 && p->grid.ny > 0 && p->grid.nz > 0 && p->grid.nx < 32768 && p->grid.ny < 32768 && p->grid.nz < 32768);
+    JC_ARG(ctx, p->grid.hx > 0 && p->grid.hy > 0 && p->grid.hz > 0);
+    if (!p->mgpcg.use_red_black)
+        return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED, "lexicographic Gauss-Seidel is not available on the GPU path");
+    if (jetcu_mg_num_levels(p->grid.nx, p->grid.ny, p->grid.nz, p->mgpcg.max_levels) > 1) JC_ARG(ctx, p->grid.ny == p->grid.nz);
+    jetcu_smoke* h = new jetcu_smoke();
+    h->ctx = ctx;
+    h->P = *p;
+    h->nx = (int)p->grid.nx; h->ny = (int)p->grid.ny; h->nz = (int)p->grid.nz;
+    h->nu = (size_t)(h->nx + 1) * h->ny * h->nz; h->nv = (size_t)h->nx * (h->ny + 1) * h->nz;
+    h->nw = (size_t)h->nx * h->ny * (h->nz + 1); h->nc = (size_t)h->nx * h->ny * h->nz;
+    int rc = JETCU_OK;
+#define STEP(x) if (rc == JETCU_OK) rc = (x)
+    STEP(jc_alloc(ctx, &h->u, h->nu)); STEP(jc_alloc(ctx, &h->v, h->nv)); STEP(jc_alloc(ctx, &h->w, h->nw));
+    STEP(jc_alloc(ctx, &h->u0, h->nu)); STEP(jc_alloc(ctx, &h->v0, h->nv)); STEP(jc_alloc(ctx, &h->w0, h->nw));
+    STEP(jc_alloc(ctx, &h->den, h->nc)); STEP(jc_alloc(ctx, &h->temp, h->nc)); STEP(jc_alloc(ctx, &h->scratch, h->nc));
+    STEP(jc_zero(ctx, h->u, h->nu)); STEP(jc_zero(ctx, h->v, h->nv)); STEP(jc_zero(ctx, h->w, h->nw));
+    STEP(jc_zero(ctx, h->den, h->nc)); STEP(jc_zero(ctx, h->temp, h->nc));
+    STEP(pressure_prepare(ctx, &h->ps, &p->grid, p->mgpcg.max_levels));
+    STEP(jc_zero(ctx, h->ps.x0, h->nc));
+    STEP(jc_sync(ctx));
+#undef STEP
+    if (rc != JETCU_OK) { jetcu_smoke_destroy(h); return rc; }
+    *out = h;
+    return JETCU_OK;
+}
+
+int jetcu_smoke_set_fields(jetcu_smoke* h, const double* den, const double* temp, const double* u, const double* v, const double* w) {
+    SMK_ENTER(h);
+    if (den) JC_TRY(jc_h2d(ctx, h->den, den, h->nc));
+    if (temp) JC_TRY(jc_h2d(ctx, h->temp, temp, h->nc));
+    if (u) JC_TRY(jc_h2d(ctx, h->u, u, h->nu));
+    if (v) JC_TRY(jc_h2d(ctx, h->v, v, h->nv));
+    if (w) JC_TRY(jc_h2d(ctx, h->w, w, h->nw));
+    return jc_sync(ctx);
+}
+
+int jetcu_smoke_get_fields(jetcu_smoke* h, double* den, double* temp, double* u, double* v, double* w, double* pr) {
+    SMK_ENTER(h);
+    if (den) JC_TRY(jc_d2h(ctx, den, h->den, h->nc));
+    if (temp) JC_TRY(jc_d2h(ctx, temp, h->temp, h->nc));
+    if (u) JC_TRY(jc_d2h(ctx, u, h->u, h->nu));
+    if (v) JC_TRY(jc_d2h(ctx, v, h->v, h->nv));
+    if (w) JC_TRY(jc_d2h(ctx, w, h->w, h->nw));
+    if (pr) JC_TRY(jc_d2h(ctx, pr, h->ps.x0, h->nc));
+    return jc_sync(ctx);
+}
+
+// GridSmokeSolver3::computeExternalForces -> computeBuoyancyForce (src/jet/grid_smoke_solver3.cpp:91-93,131-187)
+int jetcu_smoke_compute_external_forces(jetcu_smoke* h, double dt) {
+    SMK_ENTER(h);
+    GridD g = smoke_grid(h);
+    const double* gr = h->P.gravity;
+    double up[3] = {0, 1, 0};
+    if (gr[0] * gr[0] + gr[1] * gr[1] + gr[2] * gr[2] > DBL_EPSILON) {
+        const double l = sqrt(gr[0] * gr[0] + gr[1] * gr[1] + gr[2] * gr[2]);
+        up[0] = -(gr[0] / l); up[1] = -(gr[1] / l); up[2] = -(gr[2] / l);
+    }
+    const double fd = h->P.buoyancy_density_factor, ft = h->P.buoyancy_temperature_factor;
+    if (fabs(fd) > DBL_EPSILON || fabs(ft) > DBL_EPSILON) {
+        JC_LAUNCH(ctx, k_smoke_sum_partial, SMOKE_SUM_GRID, 256, 0, h->temp, h->nc, ctx->d_partials);
+        JC_LAUNCH(ctx, k_smoke_sum_final, 1, 256, 0, ctx->d_partials, SMOKE_SUM_GRID, ctx->d_scalars + 16);
+        const double ncells = (double)h->nc;
+        const dim3 blk(64, 4);
+        if (fabs(up[0]) > DBL_EPSILON)
+            JC_LAUNCH(ctx, k_smoke_buoyancy<0>, sgrid(h->nx + 1, h->ny, h->nz), blk, 0, g, h->den, h->temp, fd, ft, ctx->d_scalars + 16,
+                      ncells, dt, up[0], h->u);
+        if (fabs(up[1]) > DBL_EPSILON)
+            JC_LAUNCH(ctx, k_smoke_buoyancy<1>, sgrid(h->nx, h->ny + 1, h->nz), blk, 0, g, h->den, h->temp, fd, ft, ctx->d_scalars + 16,
+                      ncells, dt, up[1], h->v);
+        if (fabs(up[2]) > DBL_EPSILON)
+            JC_LAUNCH(ctx, k_smoke_buoyancy<2>, sgrid(h->nx, h->ny, h->nz + 1), blk, 0, g, h->den, h->temp, fd, ft, ctx->d_scalars + 16,
+                      ncells, dt, up[2], h->w);
+        JC_TRY(smoke_apply_bc(h));
+    }
+    return JETCU_OK;
+}
+
+// GridFluidSolver3::computePressure (grid_fluid_solver3.cpp:243-253): fluidSdf = -kMaxD (:313-315), collider grid = kMaxD
+int jetcu_smoke_compute_pressure(jetcu_smoke* h, double dt, jetcu_mgpcg_result* result) {
+    SMK_ENTER(h);
+    (void)dt;
+    JC_TRY(pressure_solve_device(ctx, &h->ps, h->u, h->v, h->w, nullptr, nullptr, nullptr, nullptr, nullptr, &h->P.mgpcg, h->u,
+                                 h->v, h->w, &h->last));
+    if (result) *result = h->last;
+    return smoke_apply_bc(h);
+}
+
+// GridFluidSolver3::computeAdvection (grid_fluid_solver3.cpp:255-311) with CubicSemiLagrangian3
+int jetcu_smoke_compute_advection(jetcu_smoke* h, double dt) {
+    SMK_ENTER(h);
+    GridD g = smoke_grid(h);
+    const double hmin = fmin(fmin(g.hx, g.hy), g.hz);
+    const dim3 blk(64, 4);
+    // advectable scalars in registration order (density, temperature): input = clone, flow = the current velocity
+    double* fields[2] = {h->den, h->temp};
+    for (double* f : fields) {
+        JC_TRY(jc_d2d(ctx, h->scratch, f, h->nc));
+        JC_LAUNCH(ctx, k_smoke_advect_cell, sgrid(h->nx, h->ny, h->nz), blk, 0, g, h->scratch, h->u, h->v, h->w, dt, hmin, f);
+        // extrapolateIntoCollider: identity without a collider (every marker is 1)
+    }
+    // velocity: input = flow = the clone
+    JC_TRY(jc_d2d(ctx, h->u0, h->u, h->nu)); JC_TRY(jc_d2d(ctx, h->v0, h->v, h->nv)); JC_TRY(jc_d2d(ctx, h->w0, h->w, h->nw));
+    JC_LAUNCH(ctx, k_smoke_advect_face<0>, sgrid(h->nx + 1, h->ny, h->nz), blk, 0, g, h->u0, h->v0, h->w0, dt, hmin, h->u);
+    JC_LAUNCH(ctx, k_smoke_advect_face<1>, sgrid(h->nx, h->ny + 1, h->nz), blk, 0, g, h->u0, h->v0, h->w0, dt, hmin, h->v);
+    JC_LAUNCH(ctx, k_smoke_advect_face<2>, sgrid(h->nx, h->ny, h->nz + 1), blk, 0, g, h->u0, h->v0, h->w0, dt, hmin, h->w);
+    return smoke_apply_bc(h);
+}
+
+// GridSmokeSolver3::onEndAdvanceTimeStep -> computeDiffusion with zero diffusion coefficients: the decays (:118-128)
+int jetcu_smoke_end_advance_time_step(jetcu_smoke* h, double dt) {
+    SMK_ENTER(h);
+    (void)dt;
+    JC_LAUNCH(ctx, k_smoke_scale, jc_blocks(h->nc, 256), 256, 0, h->den, 1.0 - h->P.density_decay, h->nc);
+    JC_LAUNCH(ctx, k_smoke_scale, jc_blocks(h->nc, 256), 256, 0, h->temp, 1.0 - h->P.temperature_decay, h->nc);
+    return JETCU_OK;
+}
+
+// GridFluidSolver3::onAdvanceTimeStep (grid_fluid_solver3.cpp:179-210); viscosity 0 -> computeViscosity skipped (:231-241)
+int jetcu_smoke_step(jetcu_smoke* h, double dt, jetcu_mgpcg_result* result) {
+    SMK_ENTER(h);
+    JC_TRY(smoke_apply_bc(h));  // beginAdvanceTimeStep: applyBoundaryCondition (:455-456)
+    JC_TRY(jetcu_smoke_compute_external_forces(h, dt));
+    JC_TRY(jetcu_smoke_compute_pressure(h, dt, result));
+    JC_TRY(jetcu_smoke_compute_advection(h, dt));
+    JC_TRY(jetcu_smoke_end_advance_time_step(h, dt));
+    return jc_sync(ctx);
+}
+
+}  // extern "C"

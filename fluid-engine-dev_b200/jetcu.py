@@ -552,6 +552,11 @@ class Jetcu(LinearApi):
         self._call("hybrid_create", C.byref(params), C.byref(h))
         return HybridApi(self._call_raw, h, params)
 
+    def smoke(self, params):
+        h = C.c_void_p()
+        self._call("smoke_create", C.byref(params), C.byref(h))
+        return SmokeApi(self._call_raw, h, params)
+
     # ------------------------------------------------------------------ z-slab communicator (include/jetcu.h)
     def comm_unique_id(self):
         """128-byte NCCL id; call on rank 0 and hand it to the other ranks (e.g. torch.distributed.broadcast)."""

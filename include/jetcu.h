@@ -325,6 +325,39 @@ int jetcu_hybrid_transfer_grids_to_particles(jetcu_hybrid*);         /* transfer
 int jetcu_hybrid_move_particles(jetcu_hybrid*, double dt);           /* PicSolver3::moveParticles */
 int jetcu_hybrid_compute_advection(jetcu_hybrid*, double dt);        /* PicSolver3::computeAdvection */
 
+/* ------------------------------------------------ device-resident smoke solver (BASELINE config 5)
+ * Mirrors GridSmokeSolver3 (src/jet/grid_smoke_solver3.cpp) on GridFluidSolver3::onAdvanceTimeStep
+ * (src/jet/grid_fluid_solver3.cpp:179-210): buoyancy, fractional pressure projection with MGPCG on the all-liquid domain,
+ * cubic semi-Lagrangian advection (CubicSemiLagrangian3, the solver's default) of density / temperature / velocity,
+ * decay.  No emitter, no collider, zero diffusion and viscosity coefficients (the defaults).  Fields stay in HBM between
+ * calls.  [First CUDA implementation written against the pinned oracle after round 1's GPU minutes had run out; its
+ * kernel bodies are checked on the CPU by tests/hostcheck, tests/test_gpu_zz_smoke.py is the first GPU run.] */
+typedef struct jetcu_smoke jetcu_smoke;
+typedef struct jetcu_smoke_params {
+    jetcu_grid grid;
+    int32_t closed_domain_boundary_flag;   /* GridFluidSolver3::closedDomainBoundaryFlag (default JETCU_DIR_ALL) */
+    int32_t reserved;
+    double gravity[3];                     /* default (0,-9.8,0): only its direction matters (buoyancy "up") */
+    double max_cfl;                        /* default 5 */
+    double buoyancy_density_factor;        /* GridSmokeSolver3::buoyancySmokeDensityFactor (default -0.000625) */
+    double buoyancy_temperature_factor;    /* ::buoyancyTemperatureFactor (default 5.0) */
+    double density_decay;                  /* ::smokeDecayFactor (default 0.001) */
+    double temperature_decay;              /* ::temperatureDecayFactor (default 0.001) */
+    jetcu_mgpcg_params mgpcg;
+} jetcu_smoke_params;
+void jetcu_smoke_default_params(jetcu_smoke_params* p);
+int jetcu_smoke_create(jetcu_ctx*, const jetcu_smoke_params* params, jetcu_smoke** out);
+int jetcu_smoke_destroy(jetcu_smoke*);
+/* smokeDensity() / temperature() (cell-centred) and velocity() (face-centred); NULL = leave / skip */
+int jetcu_smoke_set_fields(jetcu_smoke*, const double* density, const double* temperature, const double* u, const double* v,
+                           const double* w);
+int jetcu_smoke_get_fields(jetcu_smoke*, double* density, double* temperature, double* u, double* v, double* w, double* pressure);
+int jetcu_smoke_step(jetcu_smoke*, double dt, jetcu_mgpcg_result* result);                 /* onAdvanceTimeStep */
+int jetcu_smoke_compute_external_forces(jetcu_smoke*, double dt);                          /* computeBuoyancyForce + BC */
+int jetcu_smoke_compute_pressure(jetcu_smoke*, double dt, jetcu_mgpcg_result* result);     /* computePressure + BC */
+int jetcu_smoke_compute_advection(jetcu_smoke*, double dt);                                /* computeAdvection */
+int jetcu_smoke_end_advance_time_step(jetcu_smoke*, double dt);                            /* computeDiffusion (decay) */
+
 #ifdef __cplusplus
 }
 #endif

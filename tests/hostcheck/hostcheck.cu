@@ -12,6 +12,7 @@
 #include <numeric>
 
 #include "../../fluid-engine-dev_b200/csrc/p2g_ops.cuh"
+#include "../../fluid-engine-dev_b200/csrc/smoke_ops.cuh"
 
 static GridD make_grid(const jetcu_grid* g) {
     return GridD{(int)g->nx, (int)g->ny, (int)g->nz, g->hx, g->hy, g->hz, g->ox, g->oy, g->oz,
@@ -286,6 +287,62 @@ int hc_move_particles(const jetcu_grid* grid, const double* u, const double* v, 
         case 2: move_t<false, long long>(g, u, v, w, dt, nsub, flag, n, pos, vel); break;
         default: move_t<true, long long>(g, u, v, w, dt, nsub, flag, n, pos, vel); break;
     }
+    return 0;
+}
+
+// ---- GridSmokeSolver3 stages: the bodies of smoke.cu's kernels behind plain loops (host code of smoke.cu replayed)
+static void smoke_walls(const GridD& g, int flag, double* u, double* v, double* w) {
+    size_t m = (size_t)g.ny * g.nz;
+    if ((size_t)g.nx * g.nz > m) m = (size_t)g.nx * g.nz;
+    if ((size_t)g.nx * g.ny > m) m = (size_t)g.nx * g.ny;
+    for (size_t t = 0; t < m; ++t) zero_walls_elem(g, flag, u, v, w, t);
+}
+
+// jetcu_smoke_compute_external_forces with the ambient temperature SUM supplied by the caller (the GPU reduces it with
+// a tree, the reference serially; the per-face arithmetic is what is checked here)
+int hc_smoke_buoyancy(const jetcu_grid* grid, const double* den, const double* temp, double fd, double ft, double t_sum,
+                      const double* gravity, double dt, int wall_flag, double* u, double* v, double* w) {
+    GridD g = make_grid(grid);
+    double up[3] = {0, 1, 0};
+    if (gravity[0] * gravity[0] + gravity[1] * gravity[1] + gravity[2] * gravity[2] > DBL_EPSILON) {
+        const double l = sqrt(gravity[0] * gravity[0] + gravity[1] * gravity[1] + gravity[2] * gravity[2]);
+        up[0] = -(gravity[0] / l); up[1] = -(gravity[1] / l); up[2] = -(gravity[2] / l);
+    }
+    if (!(fabs(fd) > DBL_EPSILON || fabs(ft) > DBL_EPSILON)) return 0;
+    const double t_amb = t_sum / (double)((size_t)g.nx * g.ny * g.nz);
+    if (fabs(up[0]) > DBL_EPSILON)
+        for (int k = 0; k < g.nz; ++k) for (int j = 0; j < g.ny; ++j) for (int i = 0; i < g.nx + 1; ++i)
+            sm_buoyancy_face<0>(g, den, temp, fd, ft, t_amb, dt, up[0], u, i, j, k);
+    if (fabs(up[1]) > DBL_EPSILON)
+        for (int k = 0; k < g.nz; ++k) for (int j = 0; j < g.ny + 1; ++j) for (int i = 0; i < g.nx; ++i)
+            sm_buoyancy_face<1>(g, den, temp, fd, ft, t_amb, dt, up[1], v, i, j, k);
+    if (fabs(up[2]) > DBL_EPSILON)
+        for (int k = 0; k < g.nz + 1; ++k) for (int j = 0; j < g.ny; ++j) for (int i = 0; i < g.nx; ++i)
+            sm_buoyancy_face<2>(g, den, temp, fd, ft, t_amb, dt, up[2], w, i, j, k);
+    smoke_walls(g, wall_flag, u, v, w);
+    return 0;
+}
+
+// jetcu_smoke_compute_advection
+int hc_smoke_advect(const jetcu_grid* grid, double dt, int wall_flag, double* den, double* temp, double* u, double* v, double* w) {
+    GridD g = make_grid(grid);
+    const size_t nc = (size_t)g.nx * g.ny * g.nz;
+    const size_t nu = (size_t)(g.nx + 1) * g.ny * g.nz, nv = (size_t)g.nx * (g.ny + 1) * g.nz, nw = (size_t)g.nx * g.ny * (g.nz + 1);
+    const double hmin = fmin(fmin(g.hx, g.hy), g.hz);
+    double* fields[2] = {den, temp};
+    for (double* f : fields) {
+        std::vector<double> in(f, f + nc);
+        for (int k = 0; k < g.nz; ++k) for (int j = 0; j < g.ny; ++j) for (int i = 0; i < g.nx; ++i)
+            f[((size_t)k * g.ny + j) * g.nx + i] = sm_advect_cell(g, in.data(), u, v, w, dt, hmin, i, j, k);
+    }
+    std::vector<double> u0(u, u + nu), v0(v, v + nv), w0(w, w + nw);
+    for (int k = 0; k < g.nz; ++k) for (int j = 0; j < g.ny; ++j) for (int i = 0; i < g.nx + 1; ++i)
+        u[((size_t)k * g.ny + j) * (g.nx + 1) + i] = sm_advect_face<0>(g, u0.data(), v0.data(), w0.data(), dt, hmin, i, j, k);
+    for (int k = 0; k < g.nz; ++k) for (int j = 0; j < g.ny + 1; ++j) for (int i = 0; i < g.nx; ++i)
+        v[((size_t)k * (g.ny + 1) + j) * g.nx + i] = sm_advect_face<1>(g, u0.data(), v0.data(), w0.data(), dt, hmin, i, j, k);
+    for (int k = 0; k < g.nz + 1; ++k) for (int j = 0; j < g.ny; ++j) for (int i = 0; i < g.nx; ++i)
+        w[((size_t)k * g.ny + j) * g.nx + i] = sm_advect_face<2>(g, u0.data(), v0.data(), w0.data(), dt, hmin, i, j, k);
+    smoke_walls(g, wall_flag, u, v, w);
     return 0;
 }
 

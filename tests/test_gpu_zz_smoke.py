@@ -1,0 +1,87 @@
+"""GPU parity for the device-resident GridSmokeSolver3 (BASELINE config 5).
+
+STATUS: csrc/smoke.cu was written against the pinned oracle (tests/test_oracle_smoke.py: port == unmodified reference)
+after round 1's GPU minutes had run out; its kernel bodies are verified on the CPU (tests/test_hostcheck_smoke.py), this
+file is the FIRST GPU execution.  Non-strict xfail, sorted last, so it cannot hide the established parity suite; round 2
+removes the marker first thing.
+
+Expected: advection bit-exact on identical inputs (per-cell arithmetic); buoyancy within 1e-12 (the ambient temperature
+is a tree sum on the GPU, a serial sum in the reference); pressure <= 1e-6 relative where the oracle converged; fields
+after 5 steps within 1e-9 of the field scale."""
+import numpy as np
+import pytest
+
+from gpu_common import checker, jetcu_or_fail
+from oracle_api import Grid, MgpcgParams, SmokeParams
+from test_oracle_smoke import plume
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first GPU run of the smoke kernels (see module docstring)")]
+
+
+@pytest.fixture(scope="module")
+def jc():
+    return jetcu_or_fail()
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return checker()
+
+
+def close(a, b, tol, what):
+    scale = max(float(np.abs(b).max()), 1e-300)
+    err = float(np.abs(a - b).max()) / scale
+    assert err <= tol, "%s: relative L-inf error %.3e > %.1e" % (what, err, tol)
+
+
+@pytest.mark.parametrize("n,domain,levels,gravity", [(16, 1.0, 3, (0.0, -9.8, 0.0)), (12, 0.9, 2, (3.0, -4.0, 1.0)), (32, 1.0, 4, (0.0, -9.8, 0.0))])
+def test_smoke_stages(jc, oracle, n, domain, levels, gravity):
+    prm = SmokeParams.make(Grid.cube(n, domain), mgpcg=MgpcgParams.make(max_iterations=60, max_levels=levels), gravity=gravity)
+    a, b = jc.smoke(prm), oracle.smoke(prm)
+    den, temp, u, v, w = plume(n, domain, seed=3)
+    b.set_fields(den, temp, 0 * u, 0 * v, 0 * w)
+    for _ in range(3):
+        b.step(1.0 / 30.0)            # a developed plume from the oracle: identical inputs for every stage below
+    dt = 1.0 / 30.0
+    f = b.get_fields()
+    sync = lambda: a.set_fields(*(b.get_fields()[k] for k in ("density", "temperature", "u", "v", "w")))
+    sync()
+    a.compute_external_forces(dt); b.compute_external_forces(dt)
+    fa, fb = a.get_fields(), b.get_fields()
+    vs = max(float(np.abs(fb[k]).max()) for k in "uvw")
+    for k in "uvw":
+        assert np.abs(fa[k] - fb[k]).max() <= 1e-12 * vs, "buoyancy " + k
+    sync()
+    ra, rb = a.compute_pressure(dt), b.compute_pressure(dt)
+    fa, fb = a.get_fields(), b.get_fields()
+    if rb.true_residual_l2 <= 1e-8 * max(rb.b_l2, 1e-300):
+        close(fa["pressure"], fb["pressure"], 1e-6, "pressure")
+        for k in "uvw":
+            assert np.abs(fa[k] - fb[k]).max() <= 1e-6 * vs, "projected " + k
+    sync()
+    a.compute_advection(dt); b.compute_advection(dt)
+    fa, fb = a.get_fields(), b.get_fields()
+    for k in ("density", "temperature", "u", "v", "w"):
+        assert np.array_equal(fa[k], fb[k]), "advected %s: max abs diff %g" % (k, np.abs(fa[k] - fb[k]).max())
+    sync()
+    a.end_advance_time_step(dt); b.end_advance_time_step(dt)
+    fa, fb = a.get_fields(), b.get_fields()
+    assert np.array_equal(fa["density"], fb["density"]) and np.array_equal(fa["temperature"], fb["temperature"])
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("n,levels", [(16, 3), (32, 4)])
+def test_smoke_steps(jc, oracle, n, levels):
+    prm = SmokeParams.make(Grid.cube(n), mgpcg=MgpcgParams.make(max_iterations=60, max_levels=levels))
+    a, b = jc.smoke(prm), oracle.smoke(prm)
+    den, temp, u, v, w = plume(n, seed=3)
+    a.set_fields(den, temp, 0 * u, 0 * v, 0 * w); b.set_fields(den, temp, 0 * u, 0 * v, 0 * w)
+    for s in range(5):
+        ra, rb = a.step(1.0 / 30.0), b.step(1.0 / 30.0)
+    fa, fb = a.get_fields(), b.get_fields()
+    vs = max(float(np.abs(fb[k]).max()) for k in "uvw")
+    for k in "uvw":
+        assert np.abs(fa[k] - fb[k]).max() <= 1e-9 * vs, "%s after 5 steps: %g" % (k, np.abs(fa[k] - fb[k]).max() / vs)
+    close(fa["density"], fb["density"], 1e-9, "density after 5 steps")
+    close(fa["temperature"], fb["temperature"], 1e-9, "temperature after 5 steps")
+    a.close(); b.close()

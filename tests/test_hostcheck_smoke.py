@@ -1,0 +1,73 @@
+"""The smoke kernels' bodies (csrc/smoke_ops.cuh: monotonic Catmull-Rom, the cubic sampler, the adaptive mid-point
+back-trace, scalar / face advection, buoyancy) executed on the CPU through tests/hostcheck, against the C oracle
+(bit-identical to the unmodified reference: tests/test_oracle_smoke.py) — bit for bit."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle_api import Grid, MgpcgParams, SmokeParams, have_port, load_port
+from test_hostcheck_collider import _load_hostcheck, dp, exact
+from test_oracle_smoke import plume
+
+pytestmark = pytest.mark.skipif(not have_port(), reason="oracle/libjetport.so not built")
+
+
+@pytest.fixture(scope="module")
+def hc():
+    lib = _load_hostcheck()
+    if lib is None:
+        pytest.skip("nvcc not available to build tests/hostcheck")
+    return lib
+
+
+@pytest.fixture(scope="module")
+def port():
+    o = load_port()
+    o.set_num_threads(0)
+    return o
+
+
+def developed(port, n, domain, levels, gravity, steps=3):
+    prm = SmokeParams.make(Grid.cube(n, domain), mgpcg=MgpcgParams.make(max_iterations=60, max_levels=levels), gravity=gravity)
+    s = port.smoke(prm)
+    den, temp, u, v, w = plume(n, domain, seed=3)
+    s.set_fields(den, temp, 0 * u, 0 * v, 0 * w)
+    for _ in range(steps):
+        s.step(1.0 / 30.0)
+    return prm, s
+
+
+@pytest.mark.parametrize("n,domain,levels,gravity", [(16, 1.0, 3, (0.0, -9.8, 0.0)), (12, 0.9, 2, (3.0, -4.0, 1.0))])
+def test_buoyancy(hc, port, n, domain, levels, gravity):
+    prm, s = developed(port, n, domain, levels, gravity)
+    f = s.get_fields()
+    dt = 1.0 / 60.0
+    s.compute_external_forces(dt)
+    want = s.get_fields()
+    t_sum = 0.0
+    for x in f["temperature"].ravel():      # the reference's serial k, j, i sum
+        t_sum += float(x)
+    u, v, w = f["u"].copy(), f["v"].copy(), f["w"].copy()
+    assert hc.hc_smoke_buoyancy(C.byref(prm.grid), dp(f["density"]), dp(f["temperature"]), C.c_double(prm.buoyancy_density_factor),
+                                C.c_double(prm.buoyancy_temperature_factor), C.c_double(t_sum), (C.c_double * 3)(*gravity),
+                                C.c_double(dt), C.c_int(prm.closed_domain_boundary_flag), dp(u), dp(v), dp(w)) == 0
+    for a, k in zip((u, v, w), "uvw"):
+        exact(a, want[k], "buoyancy " + k)
+    assert not np.array_equal(want["v"], f["v"])
+    s.close()
+
+
+@pytest.mark.parametrize("n,domain,levels,gravity,dt", [(16, 1.0, 3, (0.0, -9.8, 0.0), 1.0 / 30.0), (12, 0.9, 2, (3.0, -4.0, 1.0), 1.0 / 15.0)])
+def test_advection(hc, port, n, domain, levels, gravity, dt):
+    prm, s = developed(port, n, domain, levels, gravity, steps=5)
+    f = s.get_fields()
+    s.compute_advection(dt)
+    want = s.get_fields()
+    g = {k: f[k].copy() for k in ("density", "temperature", "u", "v", "w")}
+    assert hc.hc_smoke_advect(C.byref(prm.grid), C.c_double(dt), C.c_int(prm.closed_domain_boundary_flag), dp(g["density"]),
+                              dp(g["temperature"]), dp(g["u"]), dp(g["v"]), dp(g["w"])) == 0
+    for k in g:
+        exact(g[k], want[k], "advected " + k)
+    assert np.abs(want["density"] - f["density"]).max() > 1e-3   # the plume really moved
+    s.close()

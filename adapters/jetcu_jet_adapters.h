@@ -321,10 +321,8 @@ class CudaHybridSolver3 : public Base {
     void onAdvanceTimeStep(double timeIntervalInSeconds) override {
         auto grids = this->gridSystemData();
         if (grids->resolution().x == 0 || grids->resolution().y == 0 || grids->resolution().z == 0) return;
-        if (this->collider() != nullptr)
-            throw std::runtime_error("jetcu: colliders inside the device-resident hybrid solver are not supported yet; "
-                                     "use seam 2 (CudaGridFractionalSinglePhasePressureSolver3) with the stock solver");
         ensureDevice();
+        syncCollider();
         // PicSolver3::onBeginAdvanceTimeStep -> updateParticleEmitter (src/jet/pic_solver3.cpp:63-75)
         auto particles = this->particleSystemData();
         if (this->particleEmitter() != nullptr)
@@ -347,6 +345,7 @@ class CudaHybridSolver3 : public Base {
         _h = nullptr;
         _deviceCount = 0;
         _hostDirty = true;
+        _hasCollider = false;
     }
 
     void ensureDevice() {
@@ -403,6 +402,49 @@ class CudaHybridSolver3 : public Base {
         }
     }
 
+    //! Collider -> jetcu_hybrid_set_collider_shape.  The device path evaluates closed forms, so only what has one is
+    //! accepted: a RigidBodyCollider3 over a Box3 or Sphere3 with identity transform and unflipped normal (what the
+    //! hybrid_liquid_sim examples build, src/examples/hybrid_liquid_sim/main.cpp); anything else is an error, never a
+    //! silent fallback.  Re-sent every step: linear / angular velocity may be changed by the application between steps.
+    void syncCollider() {
+        const jet::Collider3Ptr col = this->collider();
+        if (col == nullptr) {
+            if (_hasCollider) _ctx->check(jetcu_hybrid_set_collider_shape(_h, JETCU_COLLIDER_NONE, nullptr, nullptr, nullptr, nullptr, 0.0));
+            _hasCollider = false;
+            return;
+        }
+        auto rigid = std::dynamic_pointer_cast<jet::RigidBodyCollider3>(col);
+        if (!rigid) throw std::runtime_error("jetcu: only RigidBodyCollider3 colliders run on the device");
+        const jet::Surface3Ptr surface = rigid->surface();
+        const jet::Transform3& t = surface->transform;
+        const jet::QuaternionD q = t.orientation();
+        if (surface->isNormalFlipped || t.translation().lengthSquared() != 0.0 || q.w != 1.0 || q.x != 0.0 || q.y != 0.0 || q.z != 0.0)
+            throw std::runtime_error("jetcu: device colliders need an identity transform and unflipped normals");
+        double a[3], b[3] = {0.0, 0.0, 0.0};
+        int kind;
+        if (auto box = std::dynamic_pointer_cast<jet::Box3>(surface)) {
+            kind = JETCU_COLLIDER_BOX;
+            a[0] = box->bound.lowerCorner.x; a[1] = box->bound.lowerCorner.y; a[2] = box->bound.lowerCorner.z;
+            b[0] = box->bound.upperCorner.x; b[1] = box->bound.upperCorner.y; b[2] = box->bound.upperCorner.z;
+        } else if (auto sphere = std::dynamic_pointer_cast<jet::Sphere3>(surface)) {
+            kind = JETCU_COLLIDER_SPHERE;
+            a[0] = sphere->center.x; a[1] = sphere->center.y; a[2] = sphere->center.z;
+            b[0] = sphere->radius;
+        } else {
+            throw std::runtime_error("jetcu: device colliders are Box3 or Sphere3 (closed forms); got another Surface3");
+        }
+        const double lin[3] = {rigid->linearVelocity.x, rigid->linearVelocity.y, rigid->linearVelocity.z};
+        const double ang[3] = {rigid->angularVelocity.x, rigid->angularVelocity.y, rigid->angularVelocity.z};
+        const double key[13] = {double(kind), a[0], a[1], a[2], b[0], b[1], b[2], lin[0], lin[1], lin[2], ang[0], ang[1], ang[2]};
+        const double fr = col->frictionCoefficient();
+        if (!_hasCollider || std::memcmp(key, _colliderKey, sizeof(key)) != 0 || fr != _colliderFriction) {
+            _ctx->check(jetcu_hybrid_set_collider_shape(_h, kind, a, b, lin, ang, fr));
+            std::memcpy(_colliderKey, key, sizeof(key));
+            _colliderFriction = fr;
+            _hasCollider = true;
+        }
+    }
+
     static double picBlend(jet::FlipSolver3* s) { return s->picBlendingFactor(); }
     static double picBlend(jet::PicSolver3*) { return 0.0; }
 
@@ -413,7 +455,88 @@ class CudaHybridSolver3 : public Base {
     bool _hostDirty = true;
     HostMirror _mirror = HostMirror::kEveryStep;
     jetcu_step_stats _stats = jetcu_step_stats();
+    bool _hasCollider = false;
+    double _colliderKey[13] = {};
+    double _colliderFriction = 0.0;
 };
+
+// ------------------------------------------------------------------------------------------------ smoke (config 5)
+//! GridSmokeSolver3 with the sub-step on the device: GridFluidSolver3::onAdvanceTimeStep
+//! (src/jet/grid_fluid_solver3.cpp:179-210) runs as jetcu_smoke_step.  Strict drop-in: emitters (VolumeGridEmitter3 ...)
+//! keep running on the host inside beginAdvanceTimeStep, so the fields go up before and come back after every sub-step.
+//! Supported configuration = what the device path implements: no collider, zero viscosity / diffusion coefficients, the
+//! default CubicSemiLagrangian3 advection; anything else throws instead of silently computing something different.
+class CudaGridSmokeSolver3 : public jet::GridSmokeSolver3 {
+ public:
+    CudaGridSmokeSolver3(const jet::Size3& resolution, const jet::Vector3D& gridSpacing, const jet::Vector3D& gridOrigin,
+                         const jetcu_mgpcg_params& mgpcg = makeMgpcgParams(100, 6, 5, 5, 20, 20, 1e-9, 1.5, true),
+                         ContextPtr ctx = ContextPtr())
+        : jet::GridSmokeSolver3(resolution, gridSpacing, gridOrigin), _ctx(ctx ? ctx : Context::shared()), _mgpcg(mgpcg) {}
+
+    ~CudaGridSmokeSolver3() override {
+        if (_h) jetcu_smoke_destroy(_h);
+    }
+
+    const jetcu_mgpcg_result& lastResult() const { return _last; }
+
+ protected:
+    void onAdvanceTimeStep(double timeIntervalInSeconds) override {
+        auto grids = gridSystemData();
+        const jet::Size3 res = grids->resolution();
+        if (res.x == 0 || res.y == 0 || res.z == 0) return;
+        if (collider() != nullptr) throw std::runtime_error("jetcu: the device smoke solver has no collider support yet");
+        if (viscosityCoefficient() > jet::kEpsilonD || smokeDiffusionCoefficient() > jet::kEpsilonD ||
+            temperatureDiffusionCoefficient() > jet::kEpsilonD)
+            throw std::runtime_error("jetcu: the device smoke solver implements zero viscosity / diffusion only");
+        if (std::dynamic_pointer_cast<jet::CubicSemiLagrangian3>(advectionSolver()) == nullptr)
+            throw std::runtime_error("jetcu: the device smoke solver implements CubicSemiLagrangian3 advection");
+        ensureDevice();
+        // the host part of beginAdvanceTimeStep: emitters write into the host grids (src/jet/grid_fluid_solver3.cpp:437-447)
+        if (emitter() != nullptr) emitter()->update(currentTimeInSeconds(), timeIntervalInSeconds);
+        auto vel = grids->velocity();
+        _ctx->check(jetcu_smoke_set_fields(_h, smokeDensity()->constDataAccessor().data(), temperature()->constDataAccessor().data(),
+                                           vel->uConstAccessor().data(), vel->vConstAccessor().data(), vel->wConstAccessor().data()));
+        _ctx->check(jetcu_smoke_step(_h, timeIntervalInSeconds, &_last));
+        _ctx->check(jetcu_smoke_get_fields(_h, smokeDensity()->dataAccessor().data(), temperature()->dataAccessor().data(),
+                                           vel->uAccessor().data(), vel->vAccessor().data(), vel->wAccessor().data(), nullptr));
+    }
+
+ private:
+    void ensureDevice() {
+        jetcu_smoke_params p;
+        jetcu_smoke_default_params(&p);
+        auto grids = gridSystemData();
+        const jet::Size3 res = grids->resolution();
+        const jet::Vector3D h = grids->gridSpacing(), o = grids->origin();
+        p.grid.nx = res.x; p.grid.ny = res.y; p.grid.nz = res.z;
+        p.grid.hx = h.x; p.grid.hy = h.y; p.grid.hz = h.z;
+        p.grid.ox = o.x; p.grid.oy = o.y; p.grid.oz = o.z;
+        p.closed_domain_boundary_flag = closedDomainBoundaryFlag();
+        const jet::Vector3D g = gravity();
+        p.gravity[0] = g.x; p.gravity[1] = g.y; p.gravity[2] = g.z;
+        p.max_cfl = maxCfl();
+        p.buoyancy_density_factor = buoyancySmokeDensityFactor();
+        p.buoyancy_temperature_factor = buoyancyTemperatureFactor();
+        p.density_decay = smokeDecayFactor();
+        p.temperature_decay = smokeTemperatureDecayFactor();
+        jetcu_mgpcg_params fromJet;
+        auto frac = std::dynamic_pointer_cast<jet::GridFractionalSinglePhasePressureSolver3>(pressureSolver());
+        if (frac && detail::mgpcgParamsOf(frac->linearSystemSolver(), &fromJet)) _mgpcg = fromJet;
+        p.mgpcg = _mgpcg;
+        if (_h && std::memcmp(&p, &_params, sizeof(p)) == 0) return;   // knobs unchanged since the last step
+        if (_h) jetcu_smoke_destroy(_h);
+        _h = nullptr;
+        _ctx->check(jetcu_smoke_create(_ctx->get(), &p, &_h));
+        _params = p;
+    }
+
+    ContextPtr _ctx;
+    jetcu_mgpcg_params _mgpcg;
+    jetcu_smoke* _h = nullptr;
+    jetcu_smoke_params _params = jetcu_smoke_params();
+    jetcu_mgpcg_result _last = jetcu_mgpcg_result();
+};
+typedef std::shared_ptr<CudaGridSmokeSolver3> CudaGridSmokeSolver3Ptr;
 
 typedef CudaHybridSolver3<jet::PicSolver3, JETCU_PIC> CudaPicSolver3;
 typedef CudaHybridSolver3<jet::FlipSolver3, JETCU_FLIP> CudaFlipSolver3;

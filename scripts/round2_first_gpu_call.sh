@@ -1,0 +1,29 @@
+#!/bin/bash
+# First GPU call of round 2 (one B200): everything round 1 could not run after its GPU minutes were gone.
+#   gpurun --timeout 1500 -- 'bash scripts/round2_first_gpu_call.sh'
+# Every step has its own timeout; results land in gpurun_out/r2_first/.
+set -u
+OUT=gpurun_out/r2_first
+mkdir -p $OUT
+run() { local name=$1; shift; echo "== $name"; timeout "$@" > $OUT/$name.log 2>&1; echo "rc=$? $(tail -2 $OUT/$name.log | tr '\n' ' ' | cut -c1-300)"; }
+
+# 1. the established parity suite + the two first-run files (non-strict xfail: XPASS = the new CUDA paths work)
+run pytest_gpu 600 python -m pytest tests -m gpu -q -rxX
+# 2. contract bench (graphs on) and the smoke probe
+run bench 400 python bench.py --steps 5 --warmup 3
+run bench_smoke 300 python scripts/bench_smoke.py 256 5 3
+# 3. P2G variants A/B: stage timers of the same 5 steps (ms_p2g in stages_ms)
+for k in default carryfree particle; do
+  JETCU_P2G_KERNEL=$k run bench_p2g_$k 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-projection
+done
+# 4. ncu: launch list of one sub-step and full captures of the kernels the step spends its time in
+run ncu_launches 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches.csv \
+    python scripts/ncu_step.py 256 2
+for k in k_relax_colour_code k_p2g_cells k_move k_gather_attrs k_mvm; do
+  run ncu_$k 300 ncu --set full --clock-control none --import-source on -k regex:$k -c 2 -f -o $OUT/$k python scripts/ncu_step.py 256 1
+done
+python scripts/ncu_summary.py launches $OUT/launches.csv > $OUT/launches_summary.txt 2>&1
+for k in k_relax_colour_code k_p2g_cells k_move k_gather_attrs k_mvm; do
+  python scripts/ncu_summary.py rep $OUT/$k.ncu-rep > $OUT/${k}_summary.txt 2>&1
+done
+ls -la $OUT

@@ -368,6 +368,57 @@ __global__ void __launch_bounds__(P2G_THREADS)
     }
 }
 
+// Component-serial form (experimental, JETCU_P2G_KERNEL=serial): the tile's u, v and w faces are accumulated one
+// component after the other through ONE set of shared accumulators (carry-free limbs), so a CTA needs a third of the
+// shared memory, and with 128 threads a third of the registers per CTA: 3 CTAs (12 warps) fit on an SM instead of 1 (8
+// warps) — the per-cell form is bound by the latency of its dependent shared-memory updates, not by bandwidth.  The
+// particles of a cell are read three times (L1 / L2 hits).  Same integer sums, hence the same bits as the other forms.
+#define P2G_SERIAL_THREADS 128
+template <bool APIC, int AX>
+__device__ __forceinline__ void p2g_component_pass(const GridD& g, int I0, int J0, int K0, int kend,
+                                                   const uint32_t* __restrict__ cell_start, const AttrPtrs& a, double scale,
+                                                   const P2GAcc& acc, unsigned* sV, unsigned* sW, unsigned char* sM, int* any) {
+    constexpr int NF = (TC + 1) * (TC + 2) * (TC + 2);
+    for (int t = threadIdx.x; t < 10 * NF; t += P2G_SERIAL_THREADS) sV[t] = 0u;   // sV and sW are contiguous: 2 x 5 limbs
+    for (int t = threadIdx.x; t < NF; t += P2G_SERIAL_THREADS) sM[t] = 0;
+    if (threadIdx.x == 0) *any = 0;
+    __syncthreads();
+    int touched = 0;
+    for (int cl = threadIdx.x; cl < TC * TC * TC; cl += P2G_SERIAL_THREADS) {
+        const int ci = I0 + (cl % TC), cj = J0 + ((cl / TC) % TC), ck = K0 + (cl / (TC * TC));
+        if (ci >= g.nx || cj >= g.ny || ck >= kend) continue;
+        const size_t cell = ((size_t)ck * g.ny + cj) * g.nx + ci;
+        const uint32_t s0 = cell_start[cell], e0 = cell_start[cell + 1];
+        if (s0 == e0) continue;
+        touched = 1;
+        p2g_cell_component<APIC, AX, true>(g, ci, cj, ck, s0, e0, a, scale, I0, J0, K0, sV, sW, sM, acc);
+    }
+    if (touched) *any = 1;
+    __syncthreads();
+    if (*any) {
+        constexpr int dx = TC + (AX == 0 ? 1 : 2), dy = TC + (AX == 1 ? 1 : 2), dz = TC + (AX == 2 ? 1 : 2);
+        for (int t = threadIdx.x; t < dx * dy * dz; t += P2G_SERIAL_THREADS) p2g_tile_flush_face<true>(g, I0, J0, K0, AX, t, sV, sW, sM, acc);
+    }
+    __syncthreads();
+}
+
+template <bool APIC>
+__global__ void __launch_bounds__(P2G_SERIAL_THREADS)
+    k_p2g_cells_serial(GridD g, int kbase, int kend, const uint32_t* __restrict__ cell_start, AttrPtrs a,
+                       const P2GScale* __restrict__ sc, P2GAcc acc) {
+    constexpr int NF = (TC + 1) * (TC + 2) * (TC + 2);
+    extern __shared__ __align__(16) unsigned p2g_smem[];
+    unsigned* sV = p2g_smem;            // [5][NF] value + 2 * weight
+    unsigned* sW = p2g_smem + 5 * NF;   // [5][NF] weight
+    unsigned char* sM = reinterpret_cast<unsigned char*>(p2g_smem + 10 * NF);
+    __shared__ int any;
+    const int I0 = blockIdx.x * TC, J0 = blockIdx.y * TC, K0 = kbase + blockIdx.z * TC;
+    const double scale = sc->scale;
+    p2g_component_pass<APIC, 0>(g, I0, J0, K0, kend, cell_start, a, scale, acc, sV, sW, sM, &any);
+    p2g_component_pass<APIC, 1>(g, I0, J0, K0, kend, cell_start, a, scale, acc, sV, sW, sM, &any);
+    p2g_component_pass<APIC, 2>(g, I0, J0, K0, kend, cell_start, a, scale, acc, sV, sW, sM, &any);
+}
+
 // u = sum / wsum where wsum > 0 (pic_solver3.cpp:178-192), back in double; FLIP's float snapshot
 // (src/jet/flip_solver3.cpp:39-47) is taken in the same pass.  err[0] is raised if a weight sum left the
 // fixed-point headroom (more than 2^HEADROOM particles' worth of weight on one face).
@@ -1496,12 +1547,24 @@ int jetcu_hybrid_transfer_particles_to_grids(jetcu_hybrid* h) {
         }
         // per-cell register accumulation needs every component grid to have >= 2 samples per axis (its 2-wide node
         // window must exist); degenerate 1-cell-thick grids take the per-particle form.  JETCU_P2G_KERNEL selects the
-        // experimental variants for A/B runs: "particle" (per-particle form), "carryfree" (26-bit redundant limbs)
+        // experimental variants for A/B runs: "particle" (per-particle form), "carryfree" (26-bit redundant limbs),
+        // "serial" (component-serial carry-free form, 128-thread CTAs)
         const char* pk = getenv("JETCU_P2G_KERNEL");
         const bool per_cell = g.nx >= 2 && g.ny >= 2 && g.nz >= 2 && !(pk && !strcmp(pk, "particle"));
         const bool carry_free = per_cell && pk && !strcmp(pk, "carryfree");
+        const bool serial = per_cell && pk && !strcmp(pk, "serial");
         if (h->nsorted > 0) {
-            if (carry_free) {
+            if (serial) {
+                const size_t smem_s = nface * (10 * 4 + 1);
+                static bool serial_attr = false;
+                if (!serial_attr) {
+                    JC_CUDA(ctx, cudaFuncSetAttribute(k_p2g_cells_serial<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+                    JC_CUDA(ctx, cudaFuncSetAttribute(k_p2g_cells_serial<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+                    serial_attr = true;
+                }
+                if (apic) JC_LAUNCH(ctx, (k_p2g_cells_serial<true>), grid, P2G_SERIAL_THREADS, smem_s, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
+                else JC_LAUNCH(ctx, (k_p2g_cells_serial<false>), grid, P2G_SERIAL_THREADS, smem_s, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
+            } else if (carry_free) {
                 if (apic) JC_LAUNCH(ctx, (k_p2g_cells<true, true>), grid, P2G_THREADS, smem_cf, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
                 else JC_LAUNCH(ctx, (k_p2g_cells<false, true>), grid, P2G_THREADS, smem_cf, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
             } else if (per_cell) {

@@ -13,7 +13,7 @@ run pytest_gpu 600 python -m pytest tests -m gpu -q -rxX
 run bench 400 python bench.py --steps 5 --warmup 3
 run bench_smoke 300 python scripts/bench_smoke.py 256 5 3
 # 3. P2G variants A/B: stage timers of the same 5 steps (ms_p2g in stages_ms)
-for k in default carryfree particle; do
+for k in default carryfree serial particle; do
   JETCU_P2G_KERNEL=$k run bench_p2g_$k 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-projection
 done
 # 4. ncu: launch list of one sub-step and full captures of the kernels the step spends its time in

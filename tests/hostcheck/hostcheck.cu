@@ -11,6 +11,8 @@
 #include <algorithm>
 #include <numeric>
 
+#include "../../fluid-engine-dev_b200/csrc/fdm_ops.cuh"
+#include "../../fluid-engine-dev_b200/csrc/pressure_ops.cuh"
 #include "../../fluid-engine-dev_b200/csrc/p2g_ops.cuh"
 #include "../../fluid-engine-dev_b200/csrc/smoke_ops.cuh"
 
@@ -343,6 +345,172 @@ int hc_smoke_advect(const jetcu_grid* grid, double dt, int wall_flag, double* de
     for (int k = 0; k < g.nz + 1; ++k) for (int j = 0; j < g.ny; ++j) for (int i = 0; i < g.nx; ++i)
         w[((size_t)k * g.ny + j) * g.nx + i] = sm_advect_face<2>(g, u0.data(), v0.data(), w0.data(), dt, hmin, i, j, k);
     smoke_walls(g, wall_flag, u, v, w);
+    return 0;
+}
+
+// ---- linear-system kernels (fdm_ops.cuh) and the pressure system (pressure_ops.cuh)
+}  // extern "C" (templates and state below)
+
+namespace {
+struct HostLevel {
+    int nx, ny, nz;
+    std::vector<float> sdf, uw, vw, ww, cr, cu, cf;
+    std::vector<double> center;
+    std::vector<uint8_t> code;
+    Mat m;
+};
+struct HostSystem {
+    jetcu_grid grid{};
+    std::vector<HostLevel> lv;
+    std::vector<double> b0;
+} g_sys;
+
+struct SoAMat {
+    std::vector<double> c, r, u, f;
+    Mat m;
+    SoAMat(const jetcu_matrix_row* A, size_t n) : c(n), r(n), u(n), f(n) {
+        for (size_t i = 0; i < n; ++i) { c[i] = A[i].center; r[i] = A[i].right; u[i] = A[i].up; f[i] = A[i].front; }
+        m.center = c.data(); m.right = r.data(); m.up = u.data(); m.front = f.data();
+    }
+};
+
+template <bool P>
+void relax_sweeps(const Mat& A, const double* b, double* x, double w, unsigned iterations, int nx, int ny, int nz, bool code) {
+    for (unsigned it = 0; it < iterations; ++it)
+        for (int colour = 0; colour < 2; ++colour)   // launch_colour<P>: red = (i+j+k) even, then black
+            for (int k = 0; k < nz; ++k)
+                for (int j = 0; j < ny; ++j)
+                    for (int i = (j + k + colour) & 1; i < nx; i += 2) {
+                        if (code) relax_cell_code(A, b, x, w, i, j, k, nx, ny, nz);
+                        else relax_cell<P>(A, b, x, w, i, j, k, nx, ny, nz);
+                    }
+}
+}  // namespace
+
+extern "C" {
+
+int hc_mvm(int nx, int ny, int nz, const jetcu_matrix_row* A, const double* v, double* out) {
+    SoAMat M(A, (size_t)nx * ny * nz);
+    for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) mvm_cell<false>(M.m, v, out, i, j, k, nx, ny, nz);
+    return 0;
+}
+int hc_residual(int nx, int ny, int nz, const jetcu_matrix_row* A, const double* x, const double* b, double* out) {
+    SoAMat M(A, (size_t)nx * ny * nz);
+    for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) residual_cell<false>(M.m, x, b, out, i, j, k, nx, ny, nz);
+    return 0;
+}
+int hc_relax(int nx, int ny, int nz, const jetcu_matrix_row* A, const double* b, double sor, unsigned iterations, double* x) {
+    SoAMat M(A, (size_t)nx * ny * nz);
+    relax_sweeps<false>(M.m, b, x, sor, iterations, nx, ny, nz, false);
+    return 0;
+}
+int hc_restrict(int nx, int ny, int nz, const double* finer, double* coarser) {   // (nx, ny, nz) = finer size
+    const int cx = nx / 2, cy = ny / 2, cz = nz / 2;
+    for (int k = 0; k < cz; ++k) for (int j = 0; j < cy; ++j) for (int i = 0; i < cx; ++i) restrict_cell(finer, coarser, i, j, k, cx, cy, cz);
+    return 0;
+}
+int hc_correct(int nx, int ny, int nz, const double* coarser, double* finer) {
+    for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) correct_cell(coarser, finer, i, j, k, nx, ny, nz);
+    return 0;
+}
+
+// pressure_solve_device's system build (buildWeights, restrict, buildSystem) with the packed matrix, on the host
+int hc_pressure_build(const jetcu_grid* grid, uint32_t max_levels, const double* fluid_sdf, const double* collider_sdf,
+                      const double* u, const double* v, const double* w, const double* bu, const double* bv, const double* bw) {
+    g_sys = HostSystem();
+    g_sys.grid = *grid;
+    GridP g{(int)grid->nx, (int)grid->ny, (int)grid->nz, grid->hx, grid->hy, grid->hz, grid->ox, grid->oy, grid->oz};
+    uint32_t levels = 1;
+    {
+        uint64_t nx = grid->nx, ny = grid->ny, nz = grid->nz;
+        for (; levels < max_levels; ++levels) {
+            if (nx % 2 == 0 && ny % 2 == 0 && nz % 2 == 0) { nx >>= 1; ny >>= 1; nz >>= 1; } else break;
+        }
+    }
+    g_sys.lv.resize(levels);
+    for (uint32_t l = 0; l < levels; ++l) {
+        HostLevel& L = g_sys.lv[l];
+        L.nx = g.nx >> l; L.ny = g.ny >> l; L.nz = g.nz >> l;
+        const size_t n = (size_t)L.nx * L.ny * L.nz;
+        L.sdf.assign(n, 0.f); L.uw.assign((size_t)(L.nx + 1) * L.ny * L.nz, 0.f); L.vw.assign((size_t)L.nx * (L.ny + 1) * L.nz, 0.f);
+        L.ww.assign((size_t)L.nx * L.ny * (L.nz + 1), 0.f);
+        L.center.assign(n, 0.0); L.cr.assign(n, 0.f); L.cu.assign(n, 0.f); L.cf.assign(n, 0.f); L.code.assign(n + 16, 0);
+    }
+    HostLevel& L0 = g_sys.lv[0];
+    for (int k = 0; k < g.nz; ++k) for (int j = 0; j < g.ny; ++j) for (int i = 0; i < g.nx; ++i) fluid_sdf0_cell(g, fluid_sdf, L0.sdf.data(), i, j, k);
+    for (int k = 0; k < g.nz; ++k) for (int j = 0; j < g.ny; ++j) for (int i = 0; i < g.nx + 1; ++i) face_weight0_face<0>(g, collider_sdf, L0.uw.data(), i, j, k);
+    for (int k = 0; k < g.nz; ++k) for (int j = 0; j < g.ny + 1; ++j) for (int i = 0; i < g.nx; ++i) face_weight0_face<1>(g, collider_sdf, L0.vw.data(), i, j, k);
+    for (int k = 0; k < g.nz + 1; ++k) for (int j = 0; j < g.ny; ++j) for (int i = 0; i < g.nx; ++i) face_weight0_face<2>(g, collider_sdf, L0.ww.data(), i, j, k);
+    auto restrict_all = [](const std::vector<float>& f, int fx, int fy, int fz, std::vector<float>& c, int cx, int cy, int cz) {
+        for (int k = 0; k < cz; ++k) for (int j = 0; j < cy; ++j) for (int i = 0; i < cx; ++i)
+            restrict_f32_cell(f.data(), fx, fy, fz, c.data(), cx, cy, cz, i, j, k);
+    };
+    for (uint32_t l = 1; l < levels; ++l) {
+        HostLevel &F = g_sys.lv[l - 1], &C = g_sys.lv[l];
+        restrict_all(F.sdf, F.nx, F.ny, F.nz, C.sdf, C.nx, C.ny, C.nz);
+        restrict_all(F.uw, F.nx + 1, F.ny, F.nz, C.uw, C.nx + 1, C.ny, C.nz);
+        restrict_all(F.vw, F.nx, F.ny + 1, F.nz, C.vw, C.nx, C.ny + 1, C.nz);
+        restrict_all(F.ww, F.nx, F.ny, F.nz + 1, C.ww, C.nx, C.ny, C.nz + 1);
+    }
+    g_sys.b0.assign((size_t)g.nx * g.ny * g.nz, 0.0);
+    double hx = g.hx, hy = g.hy, hz = g.hz;
+    for (uint32_t l = 0; l < levels; ++l) {
+        HostLevel& L = g_sys.lv[l];
+        for (int k = 0; k < L.nz; ++k) for (int j = 0; j < L.ny; ++j) for (int i = 0; i < L.nx; ++i)
+            build_system_cell(L.nx, L.ny, L.nz, hx, hy, hz, L.sdf.data(), L.uw.data(), L.vw.data(), L.ww.data(), l == 0 ? u : nullptr,
+                              l == 0 ? v : nullptr, l == 0 ? w : nullptr, l == 0 ? bu : nullptr, l == 0 ? bv : nullptr,
+                              l == 0 ? bw : nullptr, L.center.data(), L.cr.data(), L.cu.data(), L.cf.data(), L.code.data(),
+                              l == 0 ? g_sys.b0.data() : nullptr, i, j, k);
+        Mat m;
+        m.packed = true;
+        m.center = L.center.data(); m.cr = L.cr.data(); m.cu = L.cu.data(); m.cf = L.cf.data(); m.code = L.code.data();
+        m.stride_y = (size_t)L.nx; m.stride_z = (size_t)L.nx * L.ny;
+        m.sx = (1.0 / hx) * (1.0 / hx); m.sy = (1.0 / hy) * (1.0 / hy); m.sz = (1.0 / hz) * (1.0 / hz);
+        {
+            volatile double c = 0.0;
+            c += m.sx; c += m.sx; c += m.sy; c += m.sy; c += m.sz; c += m.sz;
+            m.c6 = c;
+        }
+        L.m = m;
+        hx *= 2.0; hy *= 2.0; hz *= 2.0;
+    }
+    return (int)levels;
+}
+
+// k_mat_to_aos<true> + b0
+int hc_pressure_get_rows(uint32_t level, jetcu_matrix_row* A, double* b) {
+    if (level >= g_sys.lv.size()) return 1;
+    const HostLevel& L = g_sys.lv[level];
+    const size_t n = (size_t)L.nx * L.ny * L.nz;
+    for (size_t i = 0; i < n; ++i) {
+        A[i].center = L.m.center[i]; A[i].right = m_right<true>(L.m, i); A[i].up = m_up<true>(L.m, i); A[i].front = m_front<true>(L.m, i);
+    }
+    if (b && level == 0) memcpy(b, g_sys.b0.data(), n * 8);
+    return 0;
+}
+int hc_packed_mvm(uint32_t level, const double* v, double* out) {
+    const HostLevel& L = g_sys.lv[level];
+    for (int k = 0; k < L.nz; ++k) for (int j = 0; j < L.ny; ++j) for (int i = 0; i < L.nx; ++i) mvm_cell<true>(L.m, v, out, i, j, k, L.nx, L.ny, L.nz);
+    return 0;
+}
+int hc_packed_residual(uint32_t level, const double* x, const double* b, double* out) {
+    const HostLevel& L = g_sys.lv[level];
+    for (int k = 0; k < L.nz; ++k) for (int j = 0; j < L.ny; ++j) for (int i = 0; i < L.nx; ++i) residual_cell<true>(L.m, x, b, out, i, j, k, L.nx, L.ny, L.nz);
+    return 0;
+}
+// use_codes = 1: k_relax_colour_code (what the solver launches); 0: k_relax_colour<true> (float weights, no codes)
+int hc_packed_relax(uint32_t level, const double* b, double sor, unsigned iterations, int use_codes, double* x) {
+    const HostLevel& L = g_sys.lv[level];
+    relax_sweeps<true>(L.m, b, x, sor, iterations, L.nx, L.ny, L.nz, use_codes != 0);
+    return 0;
+}
+// k_apply_gradient on level 0 of the last build
+int hc_apply_gradient(const double* x, const double* u_in, const double* v_in, const double* w_in, double* u_out, double* v_out, double* w_out) {
+    const HostLevel& L = g_sys.lv[0];
+    const jetcu_grid& g = g_sys.grid;
+    for (int k = 0; k < L.nz; ++k) for (int j = 0; j < L.ny; ++j) for (int i = 0; i < L.nx; ++i)
+        apply_gradient_cell(L.nx, L.ny, L.nz, g.hx, g.hy, g.hz, L.sdf.data(), L.uw.data(), L.vw.data(), L.ww.data(), x, u_in, v_in, w_in,
+                            u_out, v_out, w_out, i, j, k);
     return 0;
 }
 

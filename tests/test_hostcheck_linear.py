@@ -1,0 +1,103 @@
+"""The linear-system and pressure-system kernels' bodies (csrc/fdm_ops.cuh, pressure_ops.cuh) executed on the CPU through
+tests/hostcheck, against the C oracle — bit for bit:
+  * FdmBlas3 mvm / residual, red-black SOR, MG restrict / correct on host-supplied matrices (the SoA form);
+  * the pressure system build (weights, f32 restriction, 7-point matrix, rhs) in the PACKED form the solver runs on
+    (diagonal + face weights + one code byte per cell), expanded back to Jet's rows on every MG level;
+  * mvm / residual / SOR on the packed matrix in both smoother forms (float weights, face codes with the bulk-diagonal
+    shortcut) — i.e. the arithmetic of k_relax_colour_code, the kernel a FLIP step spends a third of its time in;
+  * applyPressureGradient."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import scenes
+from oracle_api import ROW_DTYPE, MgpcgParams, Row, have_port, load_port
+from test_hostcheck_collider import _load_hostcheck, dp, exact
+
+pytestmark = pytest.mark.skipif(not have_port(), reason="oracle/libjetport.so not built")
+PR = C.POINTER(Row)
+
+
+@pytest.fixture(scope="module")
+def hc():
+    lib = _load_hostcheck()
+    if lib is None:
+        pytest.skip("nvcc not available to build tests/hostcheck")
+    return lib
+
+
+@pytest.fixture(scope="module")
+def port():
+    o = load_port()
+    o.set_num_threads(0)
+    return o
+
+
+def rp(a):
+    return a.ctypes.data_as(PR)
+
+
+@pytest.mark.parametrize("shape", [(12, 10, 10), (7, 5, 5), (1, 1, 1), (16, 16, 16)])
+@pytest.mark.parametrize("spd", [True, False])
+def test_blas_and_relax(hc, port, shape, spd):
+    nx, ny, nz = shape
+    A, x, b = scenes.random_system(nx, ny, nz, seed=sum(shape), spd=spd)
+    out = np.zeros_like(x)
+    hc.hc_mvm(nx, ny, nz, rp(A), dp(x), dp(out)); exact(out, port.mvm(A, x), "mvm")
+    hc.hc_residual(nx, ny, nz, rp(A), dp(x), dp(b), dp(out)); exact(out, port.residual(A, x, b), "residual")
+    for sor, it in ((1.5, 3), (1.0, 1)):
+        xs = x.copy()
+        hc.hc_relax(nx, ny, nz, rp(A), dp(b), C.c_double(sor), C.c_uint(it), dp(xs))
+        exact(xs, port.relax_red_black(A, b, x, sor, it), "relax sor=%g" % sor)
+
+
+@pytest.mark.parametrize("fine", [(16, 12, 12), (2, 2, 2), (8, 6, 6)])
+def test_restrict_correct(hc, port, fine):
+    nx, ny, nz = fine
+    rng = np.random.default_rng(nx)
+    f = rng.uniform(-1, 1, (nz, ny, nx)); c = rng.uniform(-1, 1, (nz // 2, ny // 2, nx // 2))
+    got = np.zeros_like(c)
+    hc.hc_restrict(nx, ny, nz, dp(f), dp(got)); exact(got, port.restrict(f), "restrict")
+    got = f.copy()
+    hc.hc_correct(nx, ny, nz, dp(c), dp(got)); exact(got, port.correct(c, f), "correct")
+
+
+@pytest.mark.parametrize("n,kind,collider,domain", [(32, "slab", True, 1.0), (32, "column", True, 1.0), (24, "column", False, 0.9),
+                                                    (16, "slab", True, 1.0)])
+def test_packed_pressure_system(hc, port, n, kind, collider, domain):
+    sc = scenes.projection_scene(n, kind, collider)
+    grid = sc["grid"]
+    if domain != 1.0:
+        grid.hx = grid.hy = grid.hz = domain / n
+    max_levels = 4
+    prm = MgpcgParams.make(max_iterations=40, max_levels=max_levels)
+    uo, vo, wo, p, res = port.pressure_solve(grid, sc["u"], sc["v"], sc["w"], prm, collider_sdf=sc["collider_sdf"], fluid_sdf=sc["fluid_sdf"])
+    none = C.POINTER(C.c_double)()
+    csdf = dp(np.ascontiguousarray(sc["collider_sdf"])) if sc["collider_sdf"] is not None else none
+    levels = hc.hc_pressure_build(C.byref(grid), C.c_uint32(max_levels), dp(sc["fluid_sdf"]), csdf, dp(sc["u"]), dp(sc["v"]), dp(sc["w"]),
+                                  none, none, none)
+    assert levels == port.mg_num_levels(n, n, n, max_levels)
+    rng = np.random.default_rng(n)
+    for l in range(levels):
+        want = port.pressure_get_system(grid, l)
+        m = n >> l
+        A = np.zeros((m, m, m), dtype=ROW_DTYPE); b = np.zeros((m, m, m))
+        assert hc.hc_pressure_get_rows(C.c_uint32(l), rp(A), dp(b)) == 0
+        for fld in ("center", "right", "up", "front"):
+            exact(A[fld], want["A"][fld], "level %d A.%s" % (l, fld))
+        if l == 0:
+            exact(b, want["b"], "rhs")
+        # the packed kernels against the oracle's kernels on the SAME matrix
+        x = rng.uniform(-1, 1, (m, m, m)); rhs = rng.uniform(-1, 1, (m, m, m)); out = np.zeros_like(x)
+        hc.hc_packed_mvm(C.c_uint32(l), dp(x), dp(out)); exact(out, port.mvm(want["A"], x), "packed mvm level %d" % l)
+        hc.hc_packed_residual(C.c_uint32(l), dp(x), dp(rhs), dp(out)); exact(out, port.residual(want["A"], x, rhs), "packed residual level %d" % l)
+        ref = port.relax_red_black(want["A"], rhs, x, 1.5, 3)
+        for codes in (0, 1):
+            xs = x.copy()
+            hc.hc_packed_relax(C.c_uint32(l), dp(rhs), C.c_double(1.5), C.c_uint(3), C.c_int(codes), dp(xs))
+            exact(xs, ref, "packed SOR level %d (%s)" % (l, "face codes + bulk diagonal" if codes else "float weights"))
+    # applyPressureGradient with the oracle's pressure
+    gu, gv, gw = sc["u"].copy(), sc["v"].copy(), sc["w"].copy()
+    hc.hc_apply_gradient(dp(p), dp(sc["u"]), dp(sc["v"]), dp(sc["w"]), dp(gu), dp(gv), dp(gw))
+    exact(gu, uo, "projected u"); exact(gv, vo, "projected v"); exact(gw, wo, "projected w")

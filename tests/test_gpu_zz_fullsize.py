@@ -1,0 +1,65 @@
+"""Full-size (BASELINE.json sizes) checks through size-independent properties — the oracle cannot run 256^3 in test time:
+conservation, domain containment, original-order round trip, bit-reproducibility of two independent runs, solver
+convergence on the config-2 projection.  FLIP 256^3 tank = bench.py's workload (126 584 289 particles).
+
+Sorted last and non-strict xfail like the other first-run files: written after round 1's GPU minutes were gone (the
+code paths are the established ones, the risk is this test's own host-memory appetite: ~15 GB of numpy arrays)."""
+import numpy as np
+import pytest
+
+import scenes
+from gpu_common import jetcu_or_fail
+from oracle_api import FLIP, Grid, HybridParams, MgpcgParams
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first run of the full-size property checks")]
+
+N = 256
+
+
+@pytest.fixture(scope="module")
+def jc():
+    return jetcu_or_fail()
+
+
+def run_tank(jc, steps):
+    prm = HybridParams.make(Grid.cube(N), mode=FLIP, mgpcg=MgpcgParams.make(max_iterations=100, max_levels=6))
+    h = jc.hybrid(prm)
+    n = h.emit_box((0.0, 0.0, 0.0), (1.0, 0.9375, 1.0), 0.5 / N, (0.5, 0.0, 0.0))
+    stats = [h.step(1.0 / 240.0) for _ in range(steps)]
+    pos, vel = h.get_particles()
+    count = h.num_particles()
+    h.close()
+    return n, count, pos, vel, stats
+
+
+def test_flip_256_properties(jc):
+    n, count, pos, vel, stats = run_tank(jc, 2)
+    # the reference lattice: i * spacing <= width, inclusive (src/jet/grid_point_generator3.cpp:22-36)
+    assert n == 513 * 481 * 513 == count
+    assert pos.shape == (n, 3) and np.isfinite(pos).all() and np.isfinite(vel).all()
+    assert pos.min() >= 0.0 and pos.max() <= 1.0                      # moveParticles clamps to the closed domain
+    # original order: particle i started at lattice point i (k-major, j, i-minor) and moved less than 5 cells in 2 steps
+    idx = np.array([0, 1, 513, 513 * 481, n // 2, n - 1])
+    start = np.stack([(idx % 513) * (0.5 / N), ((idx // 513) % 481) * (0.5 / N), (idx // (513 * 481)) * (0.5 / N)], axis=1)
+    assert np.abs(pos[idx] - start).max() < 5.0 / N
+    for s in stats:
+        assert s.pcg_iterations >= 1 and np.isfinite(s.pcg_last_residual)
+    # bit-reproducibility: a second, independent run gives the same bits (integer P2G sums, fixed reduction trees)
+    n2, count2, pos2, vel2, stats2 = run_tank(jc, 2)
+    assert n2 == n and [s.pcg_iterations for s in stats2] == [s.pcg_iterations for s in stats]
+    assert np.array_equal(pos, pos2) and np.array_equal(vel, vel2)
+
+
+def test_projection_256_converges(jc):
+    sc = scenes.projection_scene(N, "slab", True)
+    prm = MgpcgParams.make(max_iterations=100, max_levels=7)
+    u, v, w, p, res = jc.pressure_solve(sc["grid"], sc["u"], sc["v"], sc["w"], prm, collider_sdf=sc["collider_sdf"],
+                                        fluid_sdf=sc["fluid_sdf"])
+    # the unmodified reference needs 72 iterations on this input; same control flow => same count
+    assert res.iterations == 72 and res.last_residual <= 1e-9
+    assert res.true_residual_l2 <= 1e-8 * res.b_l2
+    assert np.isfinite(p).all() and np.isfinite(u).all()
+    # faces the reference does not touch keep their incoming value: solid interior of the collider stays at +1
+    u2, v2, w2, p2, res2 = jc.pressure_solve(sc["grid"], sc["u"], sc["v"], sc["w"], prm, collider_sdf=sc["collider_sdf"],
+                                             fluid_sdf=sc["fluid_sdf"])
+    assert np.array_equal(p, p2) and np.array_equal(v, v2)            # idempotent / deterministic

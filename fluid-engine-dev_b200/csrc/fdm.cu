@@ -175,6 +175,54 @@ static inline int relax_block_sweeps(int T) {
 // planes of b (which the sweeps only read) that the redundant halo cells need next to a slab of T planes
 int fdm_relax_rhs_halo(int T) { return 2 * relax_block_sweeps(T) - 1; }
 
+// L2-resident sweep (experimental, JETCU_RELAX_CHUNK = planes per chunk, 0 = off): the red and the black pass of one
+// sweep are issued as an alternating sequence of z-chunks — red on planes up to c1 (one plane ahead), black on the chunk
+// [c0, c1), red on the next chunk ... — instead of two passes over the whole level.  Every red cell still reads only
+// black values from before the sweep (a black chunk is launched after the red launch that needed its planes, and the
+// next red launch starts one plane beyond it), every black cell reads red values of this sweep: the same operands in
+// the same order, bit-identical to the two full passes.  What changes is the traffic: the b / x / code sectors a red
+// launch pulled in (half of each sector belongs to the other colour) are still in the 126 MB L2 when the black launch
+// of the same chunk needs the other half, and x is written back once — ~25 B/cell/sweep from DRAM instead of ~47.
+static int relax_chunk_planes() {
+    static int c = -1;
+    if (c < 0) {
+        const char* e = getenv("JETCU_RELAX_CHUNK");
+        c = e ? atoi(e) : 0;
+        if (c < 0) c = 0;
+    }
+    return c;
+}
+
+// one sweep: red on the planes `rw`, black on the planes `bw` (bw inside rw; rw reaches one plane beyond bw wherever the
+// level continues), as whole passes (chunk == 0) or chunk-interleaved
+template <bool P>
+static int launch_sweep(jetcu_ctx* ctx, Dim3i d, ZRange rw, ZRange bw, int chunk, Mat A, const double* b, double sor, double* x,
+                        uint64_t* launches) {
+    if (chunk <= 0 || bw.k1 - bw.k0 <= chunk) {
+        JC_TRY(launch_colour<P>(ctx, d, rw, A, b, sor, 0, x));
+        JC_TRY(launch_colour<P>(ctx, d, bw, A, b, sor, 1, x));
+        *launches += 2;
+        return JETCU_OK;
+    }
+    int red_done = rw.k0;
+    for (int c0 = bw.k0; c0 < bw.k1; c0 += chunk) {
+        const int c1 = c0 + chunk < bw.k1 ? c0 + chunk : bw.k1;
+        const int need = c1 + 1 < rw.k1 ? c1 + 1 : rw.k1;   // black on [c0, c1) reads red up to plane c1
+        if (need > red_done) {
+            JC_TRY(launch_colour<P>(ctx, d, ZRange{red_done, need}, A, b, sor, 0, x));
+            red_done = need;
+            *launches += 1;
+        }
+        JC_TRY(launch_colour<P>(ctx, d, ZRange{c0, c1}, A, b, sor, 1, x));
+        *launches += 1;
+    }
+    if (red_done < rw.k1) {
+        JC_TRY(launch_colour<P>(ctx, d, ZRange{red_done, rw.k1}, A, b, sor, 0, x));
+        *launches += 1;
+    }
+    return JETCU_OK;
+}
+
 template <bool P>
 static int launch_relax(jetcu_ctx* ctx, Dim3i d, ZRange z, bool halo, Mat A, const double* b, double sor,
                         unsigned iterations, double** x, double** xalt, uint64_t* launches) {
@@ -186,20 +234,21 @@ static int launch_relax(jetcu_ctx* ctx, Dim3i d, ZRange z, bool halo, Mat A, con
     }
     const size_t plane = (size_t)d.nx * d.ny * sizeof(double);
     const int kmax = relax_block_sweeps(z.k1 - z.k0);
+    // chunking only pays where the level does not fit the L2 anyway (>= 64^3-ish: 25 B x 2M cells)
+    const int chunk = d.n() >= (size_t)(1 << 21) ? relax_chunk_planes() : 0;
+    *launches = 0;
     unsigned it = 0;
     while (it < iterations) {
         const int k = halo ? (int)((iterations - it < (unsigned)kmax) ? iterations - it : (unsigned)kmax) : (int)(iterations - it);
         if (halo) JC_TRY(comm_halo_planes(ctx, *x, plane, z.k0, z.k1, d.nz, 2 * k));
         for (int s2 = 0; s2 < k; ++s2) {
-            for (int colour = 0; colour < 2; ++colour) {
-                const int ext = halo ? 2 * (k - s2) - 1 - colour : 0;
-                ZRange w{z.k0 - ext < 0 ? 0 : z.k0 - ext, z.k1 + ext > d.nz ? d.nz : z.k1 + ext};
-                JC_TRY(launch_colour<P>(ctx, d, w, A, b, sor, colour, *x));
-            }
+            const int er = halo ? 2 * (k - s2) - 1 : 0, eb = halo ? 2 * (k - s2) - 2 : 0;
+            const ZRange rw{z.k0 - er < 0 ? 0 : z.k0 - er, z.k1 + er > d.nz ? d.nz : z.k1 + er};
+            const ZRange bw{z.k0 - eb < 0 ? 0 : z.k0 - eb, z.k1 + eb > d.nz ? d.nz : z.k1 + eb};
+            JC_TRY(launch_sweep<P>(ctx, d, rw, bw, chunk, A, b, sor, *x, launches));
         }
         it += (unsigned)k;
     }
-    *launches = 2ull * iterations;
     return JETCU_OK;
 }
 

@@ -16,6 +16,12 @@ run bench_smoke 300 python scripts/bench_smoke.py 256 5 3
 for k in default carryfree serial particle; do
   JETCU_P2G_KERNEL=$k run bench_p2g_$k 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-projection
 done
+# 3b. L2-resident chunk-interleaved SOR sweep A/B (bit-identical by construction and by tests/test_hostcheck_linear.py):
+#     mgpcg_solve_ms / stages_ms.ms_pressure and projection.mgpcg_solve_ms of the same bench
+for c in 16 32 64; do
+  JETCU_RELAX_CHUNK=$c run bench_relax_chunk_$c 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline
+done
+JETCU_RELAX_CHUNK=32 run pytest_gpu_chunk32 400 python -m pytest tests/test_gpu_pressure.py tests/test_gpu_linear.py -m gpu -q
 # 4. ncu: launch list of one sub-step and full captures of the kernels the step spends its time in
 run ncu_launches 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches.csv \
     python scripts/ncu_step.py 256 2

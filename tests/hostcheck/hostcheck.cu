@@ -504,6 +504,31 @@ int hc_packed_relax(uint32_t level, const double* b, double sor, unsigned iterat
     relax_sweeps<true>(L.m, b, x, sor, iterations, L.nx, L.ny, L.nz, use_codes != 0);
     return 0;
 }
+// launch_sweep<true> of fdm.cu with JETCU_RELAX_CHUNK = chunk: the red / black z-chunk interleaving, replayed with the
+// same loop structure (a "launch" = one colour over a plane range)
+int hc_packed_relax_chunked(uint32_t level, const double* b, double sor, unsigned iterations, int chunk, double* x) {
+    const HostLevel& L = g_sys.lv[level];
+    const int nx = L.nx, ny = L.ny, nz = L.nz;
+    auto colour_range = [&](int colour, int k0, int k1) {
+        for (int k = k0; k < k1; ++k)
+            for (int j = 0; j < ny; ++j)
+                for (int i = (j + k + colour) & 1; i < nx; i += 2) relax_cell_code(L.m, b, x, sor, i, j, k, nx, ny, nz);
+    };
+    for (unsigned it = 0; it < iterations; ++it) {
+        const int rw0 = 0, rw1 = nz, bw0 = 0, bw1 = nz;
+        if (chunk <= 0 || bw1 - bw0 <= chunk) { colour_range(0, rw0, rw1); colour_range(1, bw0, bw1); continue; }
+        int red_done = rw0;
+        for (int c0 = bw0; c0 < bw1; c0 += chunk) {
+            const int c1 = c0 + chunk < bw1 ? c0 + chunk : bw1;
+            const int need = c1 + 1 < rw1 ? c1 + 1 : rw1;
+            if (need > red_done) { colour_range(0, red_done, need); red_done = need; }
+            colour_range(1, c0, c1);
+        }
+        if (red_done < rw1) colour_range(0, red_done, rw1);
+    }
+    return 0;
+}
+
 // k_apply_gradient on level 0 of the last build
 int hc_apply_gradient(const double* x, const double* u_in, const double* v_in, const double* w_in, double* u_out, double* v_out, double* w_out) {
     const HostLevel& L = g_sys.lv[0];

@@ -97,6 +97,11 @@ def test_packed_pressure_system(hc, port, n, kind, collider, domain):
             xs = x.copy()
             hc.hc_packed_relax(C.c_uint32(l), dp(rhs), C.c_double(1.5), C.c_uint(3), C.c_int(codes), dp(xs))
             exact(xs, ref, "packed SOR level %d (%s)" % (l, "face codes + bulk diagonal" if codes else "float weights"))
+        # the L2-resident chunk-interleaved sweep order (JETCU_RELAX_CHUNK) must give the bits of the two full passes
+        for chunk in (1, 3, 5, m):
+            xs = x.copy()
+            hc.hc_packed_relax_chunked(C.c_uint32(l), dp(rhs), C.c_double(1.5), C.c_uint(3), C.c_int(chunk), dp(xs))
+            exact(xs, ref, "chunk-interleaved SOR level %d chunk %d" % (l, chunk))
     # applyPressureGradient with the oracle's pressure
     gu, gv, gw = sc["u"].copy(), sc["v"].copy(), sc["w"].copy()
     hc.hc_apply_gradient(dp(p), dp(sc["u"]), dp(sc["v"]), dp(sc["w"]), dp(gu), dp(gv), dp(gw))

@@ -405,13 +405,27 @@ def run_jetcu(args):
                                    "ms_g2p", "ms_move")}
     stages["pcg_iterations"] = [int(s["pcg_iterations"]) for s in stats]
     stages["pcg_true_rel_residual"] = [s["pcg_true_residual_l2"] / max(s["pcg_b_l2"], 1e-300) for s in stats]
+    # per-stage achieved bandwidth on SURVEY §8d's algorithmic bytes (P = particles, N = cells; FLIP): what the stage must
+    # move at the very least, divided by its measured time — the distance of every stage from the HBM roofline, not only
+    # the dominant kernel's.  At N > 1 the times are rank 0's and the bytes the whole domain's divided by the ranks.
+    P_, N_ = float(npart) / world, float(ncell) / world
+    mean_iters = sum(stages["pcg_iterations"]) / max(len(stages["pcg_iterations"]), 1)
+    stage_bytes = {"ms_bin": (40.0 + 96.0) * P_, "ms_p2g": 48.0 * P_ + 51.0 * N_, "ms_sdf": 24.0 * P_ + 8.0 * N_,
+                   "ms_g2p": 72.0 * P_ + 36.0 * N_, "ms_move": 96.0 * P_ + 24.0 * N_,
+                   "ms_pressure": N_ * ((56.0 + 1647.0 + 16.0) + mean_iters * 1799.0)}
+    stage_roofline = {}
+    for k, bts in stage_bytes.items():
+        if stages.get(k, 0) > 0:
+            gbs = bts / (stages[k] * 1e-3) / 1e9
+            stage_roofline[k[3:]] = {"algorithmic_gb": bts / 1e9, "gbs": gbs, "frac_of_hbm_peak": gbs / peak}
     line = {
         "metric": METRIC, "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, npart),
         "mcell_per_s": steps_per_s * ncell / 1e6, "particles_per_s": steps_per_s * npart,
-        "mgpcg_solve_ms": stages["ms_pressure"], "stages_ms": stages, "wall_s_timed_region": wall,
+        "mgpcg_solve_ms": stages["ms_pressure"], "stages_ms": stages, "stage_roofline": stage_roofline,
+        "wall_s_timed_region": wall,
         "gpu_launches": int(launches), "clocks": clk,
         "e2e": {"value": e2e_rate, "unit": "steps/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out,
                 "steps": k_e2e, "note": e2e_note},

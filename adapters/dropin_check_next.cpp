@@ -1,0 +1,150 @@
+// dropin_check_next.cpp — Jet-side check (public Jet API only) of the two adapter paths added after the three seams:
+//     collider   jet::FlipSolver3 + RigidBodyCollider3(Box3) through Animation::update  vs  jetcu::CudaFlipSolver3 with the
+//                same collider object (adapter forwards it as jetcu_hybrid_set_collider_shape)
+//     smoke      jet::GridSmokeSolver3 (plume from rest in a closed box)               vs  jetcu::CudaGridSmokeSolver3
+// Prints one JSON line with the deviations from the stock run.  Built by adapters/Makefile next to dropin_check;
+// tests/test_gpu_zz_dropin_next.py runs it (first GPU run pending, see that file).
+//
+//     dropin_check_next [--n 16] [--frames 3] [--levels 3] [--what collider|smoke]
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "jetcu_jet_adapters.h"
+
+using namespace jet;
+
+namespace {
+
+struct Options {
+    size_t n = 16;
+    int frames = 3;
+    size_t levels = 3;
+    std::string what = "collider";
+};
+
+template <class Solver>
+void setupLiquid(const std::shared_ptr<Solver>& solver, const Options& opt) {
+    const double h = 1.0 / static_cast<double>(opt.n);
+    auto box = std::make_shared<Box3>(Vector3D(0, 0, 0), Vector3D(0.5, 0.7, 1.0));
+    auto emitter = VolumeParticleEmitter3::builder()
+                       .withSurface(box)
+                       .withMaxRegion(solver->gridSystemData()->boundingBox())
+                       .withSpacing(0.5 * h)
+                       .withIsOneShot(true)
+                       .withJitter(0.0)
+                       .makeShared();
+    emitter->setPointGenerator(std::make_shared<GridPointGenerator3>());
+    solver->setParticleEmitter(emitter);
+    solver->setUseCompressedLinearSystem(false);
+    auto obstacle = std::make_shared<Box3>(Vector3D(0.6, 0.0, 0.3), Vector3D(0.85, 0.35, 0.7));
+    auto collider = std::make_shared<RigidBodyCollider3>(obstacle);
+    collider->setFrictionCoefficient(0.2);
+    solver->setCollider(collider);
+}
+
+int runCollider(const Options& opt) {
+    const double h = 1.0 / static_cast<double>(opt.n);
+    auto stock = std::make_shared<FlipSolver3>(Size3(opt.n, opt.n, opt.n), Vector3D(h, h, h), Vector3D());
+    {
+        auto pressure = std::make_shared<GridFractionalSinglePhasePressureSolver3>();
+        pressure->setLinearSystemSolver(std::make_shared<FdmMgpcgSolver3>(100, opt.levels, 5, 5, 20, 20, 1e-9, 1.5, true));
+        stock->setPressureSolver(pressure);
+    }
+    setupLiquid(stock, opt);
+    auto cuda = std::make_shared<jetcu::CudaFlipSolver3>(Size3(opt.n, opt.n, opt.n), Vector3D(h, h, h), Vector3D(),
+                                                         jetcu::makeMgpcgParams(100, opt.levels, 5, 5, 20, 20, 1e-9, 1.5, true));
+    setupLiquid(cuda, opt);
+    for (Frame frame(0, 1.0 / 60.0); frame.index < opt.frames; ++frame) {
+        stock->update(frame);
+        cuda->update(frame);
+    }
+    auto ps = stock->particleSystemData();
+    auto pc = cuda->particleSystemData();
+    double maxDx = 0.0;
+    const size_t n = ps->numberOfParticles();
+    if (pc->numberOfParticles() != n) { std::fprintf(stderr, "particle counts differ\n"); return 1; }
+    for (size_t i = 0; i < n; ++i) {
+        const Vector3D d = ps->positions()[i] - pc->positions()[i];
+        maxDx = std::max(maxDx, std::max(std::fabs(d.x), std::max(std::fabs(d.y), std::fabs(d.z))));
+    }
+    std::printf("{\"what\": \"collider\", \"n\": %zu, \"frames\": %d, \"particles\": %zu, \"max_dx\": %.3e}\n", opt.n, opt.frames, n, maxDx);
+    return 0;
+}
+
+template <class Solver>
+void setupSmoke(const std::shared_ptr<Solver>& solver, const Options& opt) {
+    solver->setUseCompressedLinearSystem(false);
+    auto pressure = std::make_shared<GridFractionalSinglePhasePressureSolver3>();
+    pressure->setLinearSystemSolver(std::make_shared<FdmMgpcgSolver3>(100, opt.levels, 5, 5, 20, 20, 1e-9, 1.5, true));
+    solver->setPressureSolver(pressure);
+    auto den = solver->smokeDensity();
+    auto temp = solver->temperature();
+    auto pos = den->dataPosition();
+    den->forEachDataPointIndex([&](size_t i, size_t j, size_t k) {
+        const Vector3D p = pos(i, j, k);
+        const double r = (p - Vector3D(0.5, 0.25, 0.45)).length();
+        const double v = clamp(1.0 - r / 0.2, 0.0, 1.0);
+        (*den)(i, j, k) = v;
+        (*temp)(i, j, k) = 2.0 * v + 0.1;
+    });
+}
+
+double fieldDiff(const ConstArrayAccessor3<double>& a, const ConstArrayAccessor3<double>& b, double* scale) {
+    double d = 0.0, s = 0.0;
+    const size_t n = a.size().x * a.size().y * a.size().z;
+    for (size_t i = 0; i < n; ++i) { d = std::max(d, std::fabs(a.data()[i] - b.data()[i])); s = std::max(s, std::fabs(a.data()[i])); }
+    *scale = std::max(*scale, s);
+    return d;
+}
+
+int runSmoke(const Options& opt) {
+    const double h = 1.0 / static_cast<double>(opt.n);
+    auto stock = std::make_shared<GridSmokeSolver3>(Size3(opt.n, opt.n, opt.n), Vector3D(h, h, h), Vector3D());
+    auto cuda = std::make_shared<jetcu::CudaGridSmokeSolver3>(Size3(opt.n, opt.n, opt.n), Vector3D(h, h, h), Vector3D());
+    setupSmoke(stock, opt);
+    setupSmoke(cuda, opt);
+    for (Frame frame(0, 1.0 / 30.0); frame.index < opt.frames; ++frame) {
+        stock->update(frame);
+        cuda->update(frame);
+    }
+    double vs = 0.0, ds = 0.0;
+    auto sv = stock->velocity();
+    auto cv = cuda->velocity();
+    double dv = fieldDiff(sv->uConstAccessor(), cv->uConstAccessor(), &vs);
+    dv = std::max(dv, fieldDiff(sv->vConstAccessor(), cv->vConstAccessor(), &vs));
+    dv = std::max(dv, fieldDiff(sv->wConstAccessor(), cv->wConstAccessor(), &vs));
+    const double dd = fieldDiff(stock->smokeDensity()->constDataAccessor(), cuda->smokeDensity()->constDataAccessor(), &ds);
+    std::printf("{\"what\": \"smoke\", \"n\": %zu, \"frames\": %d, \"velocity_rel\": %.3e, \"density_rel\": %.3e, \"velocity_scale\": %.3e}\n",
+                opt.n, opt.frames, dv / std::max(vs, 1e-300), dd / std::max(ds, 1e-300), vs);
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    Options opt;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        auto next = [&]() -> const char* { return (i + 1 < argc) ? argv[++i] : "0"; };
+        if (a == "--n") opt.n = std::strtoul(next(), nullptr, 10);
+        else if (a == "--frames") opt.frames = std::atoi(next());
+        else if (a == "--levels") opt.levels = std::strtoul(next(), nullptr, 10);
+        else if (a == "--what") opt.what = next();
+        else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
+    }
+    Logging::mute();
+    try {
+        if (opt.what == "collider") return runCollider(opt);
+        if (opt.what == "smoke") return runSmoke(opt);
+        std::fprintf(stderr, "unknown check %s\n", opt.what.c_str());
+        return 2;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "dropin_check_next: %s\n", e.what());
+        return 1;
+    }
+}

@@ -1,0 +1,34 @@
+"""Jet-side drop-in check of the adapter paths added after the three seams (adapters/dropin_check_next.cpp, public Jet API
+only): a FLIP dam break onto a RigidBodyCollider3(Box3) through jetcu::CudaFlipSolver3, and jet::GridSmokeSolver3 vs
+jetcu::CudaGridSmokeSolver3, each compared with the stock CPU solver in the same process.
+
+First GPU run pending (written after round 1's GPU minutes were gone): non-strict xfail, sorted last."""
+import json
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "adapters", "_build", "dropin_check_next")
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first GPU run of the collider / smoke adapters")]
+
+
+def run(*args):
+    if not os.path.exists(BIN):
+        pytest.fail("adapters/_build/dropin_check_next missing: run `make -C adapters` where /root/reference exists")
+    r = subprocess.run([BIN] + [str(a) for a in args], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def test_collider_scene_matches_stock_jet():
+    out = run("--what", "collider", "--n", 32, "--frames", 3, "--levels", 4)
+    assert out["particles"] > 10000
+    assert out["max_dx"] <= 1e-5, out          # BASELINE tolerance: 1e-5 of the domain size (= 1)
+
+
+def test_smoke_matches_stock_jet():
+    out = run("--what", "smoke", "--n", 32, "--frames", 5, "--levels", 4)
+    assert out["velocity_scale"] > 0.05        # the plume really rose
+    assert out["velocity_rel"] <= 1e-9 and out["density_rel"] <= 1e-9, out

@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 import scenes
-from oracle_api import APIC, FLIP, PIC, Grid, HybridParams, MgpcgParams
+from oracle_api import APIC, FLIP, PIC, Grid, HybridParams, MgpcgParams, SmokeParams
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -207,3 +207,33 @@ def collider(make_hybrid, name, exact_bits):
             close(out[k], g[k], 1e-12, k, vs)
         assert np.abs(out["pos"] - g["pos"]).max() <= 1e-5
         close(out["pressure"], g["pressure"], 1e-6, "pressure")
+
+
+# ---------------------------------------------------------------------------------------------- smoke (config 5)
+def smoke_run(make_smoke, n=16, levels=3, steps=5):
+    """Plume rising from rest in a closed box: GridSmokeSolver3 defaults, MGPCG(60, `levels`)."""
+    prm = SmokeParams.make(Grid.cube(n), mgpcg=MgpcgParams.make(max_iterations=60, max_levels=levels))
+    s = make_smoke(prm)
+    c = (np.arange(n) + 0.5) / n
+    Z, Y, X = np.meshgrid(c, c, c, indexing="ij")
+    den = np.ascontiguousarray(np.clip(1.0 - np.sqrt((X - 0.5) ** 2 + (Y - 0.25) ** 2 + (Z - 0.45) ** 2) / 0.2, 0.0, 1.0))
+    s.set_fields(den, 2.0 * den + 0.1)
+    iters = [int(s.step(1.0 / 30.0).iterations) for _ in range(steps)]
+    out = s.get_fields()
+    out["iterations"] = np.array(iters)
+    s.close()
+    return out
+
+
+def smoke(make_smoke, exact_bits):
+    g = load("smoke_16.npz")
+    out = smoke_run(make_smoke)
+    if exact_bits:
+        for k in g.files:
+            exact(out[k], g[k], "smoke: " + k)
+    else:
+        vs = max(float(np.abs(g[k]).max()) for k in "uvw")
+        for k in "uvw":
+            close(out[k], g[k], 1e-9, "smoke " + k, vs)
+        close(out["density"], g["density"], 1e-9, "smoke density")
+        close(out["temperature"], g["temperature"], 1e-9, "smoke temperature")

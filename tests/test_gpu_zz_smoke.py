@@ -11,6 +11,7 @@ after 5 steps within 1e-9 of the field scale."""
 import numpy as np
 import pytest
 
+import golden_cases as gc
 from gpu_common import checker, jetcu_or_fail
 from oracle_api import Grid, MgpcgParams, SmokeParams
 from test_oracle_smoke import plume
@@ -85,3 +86,7 @@ def test_smoke_steps(jc, oracle, n, levels):
     close(fa["density"], fb["density"], 1e-9, "density after 5 steps")
     close(fa["temperature"], fb["temperature"], 1e-9, "temperature after 5 steps")
     a.close(); b.close()
+
+
+def test_golden_smoke(jc):
+    gc.smoke(jc.smoke, exact_bits=False)

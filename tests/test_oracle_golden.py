@@ -40,3 +40,7 @@ def test_hybrid(port, mode):
 @pytest.mark.parametrize("name", sorted(gc.COLLIDER_CASES))
 def test_hybrid_with_collider(port, name):
     gc.collider(port.hybrid, name, exact_bits=True)
+
+
+def test_smoke(port):
+    gc.smoke(port.smoke, exact_bits=True)

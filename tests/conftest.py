@@ -19,4 +19,6 @@ def pytest_collection_modifyitems(config, items):
         return
     for item in items:
         if item.get_closest_marker("timeout") is None:
-            item.add_marker(pytest.mark.timeout(900))
+            # method="thread": a test stuck inside a native call (a CUDA sync that never returns) cannot be interrupted by
+            # a signal handler; the watchdog thread ends the run instead of letting it hang for good
+            item.add_marker(pytest.mark.timeout(900, method="thread"))

@@ -6,7 +6,7 @@
 // semi-Lagrangian advection of density, temperature and velocity -> decay.  No emitter, no collider, zero diffusion /
 // viscosity coefficients (the solver's defaults).  Kernel bodies live in smoke_ops.cuh (__host__ __device__; checked on the
 // CPU by tests/hostcheck); this file holds the launch wrappers, the ambient-temperature reduction and the host side.
-// [Written after round 1's GPU minutes ran out: tests/test_gpu_zz_smoke.py is its first GPU run.]
+// [Written after round 1's GPU minutes ran out: tests/firstrun/zz_smoke.py is its first GPU run.]
 #include <math.h>
 #include <string.h>
 

@@ -331,7 +331,7 @@ int jetcu_hybrid_compute_advection(jetcu_hybrid*, double dt);        /* PicSolve
  * cubic semi-Lagrangian advection (CubicSemiLagrangian3, the solver's default) of density / temperature / velocity,
  * decay.  No emitter, no collider, zero diffusion and viscosity coefficients (the defaults).  Fields stay in HBM between
  * calls.  [First CUDA implementation written against the pinned oracle after round 1's GPU minutes had run out; its
- * kernel bodies are checked on the CPU by tests/hostcheck, tests/test_gpu_zz_smoke.py is the first GPU run.] */
+ * kernel bodies are checked on the CPU by tests/hostcheck, tests/firstrun/zz_smoke.py is the first GPU run.] */
 typedef struct jetcu_smoke jetcu_smoke;
 typedef struct jetcu_smoke_params {
     jetcu_grid grid;

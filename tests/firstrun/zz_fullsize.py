@@ -2,8 +2,9 @@
 conservation, domain containment, original-order round trip, bit-reproducibility of two independent runs, solver
 convergence on the config-2 projection.  FLIP 256^3 tank = bench.py's workload (126 584 289 particles).
 
-Sorted last and non-strict xfail like the other first-run files: written after round 1's GPU minutes were gone (the
-code paths are the established ones, the risk is this test's own host-memory appetite: ~15 GB of numpy arrays)."""
+Run in a child process by tests/test_gpu_zz_firstrun.py like the other first-run files: written after round 1's GPU
+minutes were gone (the code paths are the established ones, the risk is this test's own host-memory appetite: ~15 GB of
+numpy arrays)."""
 import numpy as np
 import pytest
 
@@ -11,7 +12,7 @@ import scenes
 from gpu_common import jetcu_or_fail
 from oracle_api import FLIP, Grid, HybridParams, MgpcgParams
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first run of the full-size property checks")]
+pytestmark = pytest.mark.gpu
 
 N = 256
 

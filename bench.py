@@ -380,9 +380,7 @@ def run_jetcu(args):
     h.close()
 
     if rank != 0:
-        jc.close()
-        if dist is not None:
-            dist.destroy_process_group()
+        teardown(jc, dist)
         return
 
     peak, peak_src = read_peaks()
@@ -450,9 +448,22 @@ def run_jetcu(args):
                                                                          sum(times), n_s, n),
             "sample_pcg_iterations": iters}
     print(json.dumps(line), flush=True)
+    teardown(jc, dist)
+
+
+def teardown(jc, dist):
+    """Release the solver (graphs first, then the NCCL communicator) and the process group.  Every measurement is done and
+    rank 0's line is out by now, so a communicator that refuses to die must not cost the run: a watchdog ends the process
+    with status 0 if the orderly teardown has not finished in 60 s (ncclCommDestroy waits for peers and for captured
+    graphs; it has no timeout of its own)."""
+    import threading
+    t = threading.Timer(60.0, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
     jc.close()
     if dist is not None:
         dist.destroy_process_group()
+    t.cancel()
 
 
 def main():

@@ -72,6 +72,11 @@ class Grid(C.Structure):
         return (int(self.nx), int(self.ny), int(self.nz) + 1)
 
 
+class ColliderShape(C.Structure):
+    """jetcu_collider_shape / jeto_collider_shape (include/jetcu.h)."""
+    _fields_ = [("kind", C.c_int32), ("flipped", C.c_int32), ("a", f64 * 3), ("b", f64 * 3)]
+
+
 class HybridParams(C.Structure):
     _fields_ = [("grid", Grid), ("mode", C.c_int32), ("closed_domain_boundary_flag", C.c_int32),
                 ("pic_blending_factor", f64), ("gravity", f64 * 3), ("max_cfl", f64), ("mgpcg", MgpcgParams)]
@@ -375,13 +380,29 @@ class HybridApi:
         self._c("hybrid_get_affine", self.h, _p(cx), _p(cy), _p(cz))
         return cx, cy, cz
 
-    def set_collider_shape(self, kind, a, b=(0.0, 0.0, 0.0), linear_velocity=(0.0, 0.0, 0.0), angular_velocity=(0.0, 0.0, 0.0),
-                           friction=0.0):
-        """Analytic rigid collider: kind "box" (a = lower, b = upper corner) or "sphere" (a = centre, b[0] = radius);
-        None / "none" removes it.  Oracle only so far (the CUDA path rejects colliders: SURVEY §8f-1)."""
-        code = {None: 0, "none": 0, "box": 1, "sphere": 2}[kind]
-        self._c("hybrid_set_collider_shape", self.h, C.c_int(code), (f64 * 3)(*a), (f64 * 3)(*b), (f64 * 3)(*linear_velocity),
-                (f64 * 3)(*angular_velocity), f64(friction))
+    SHAPE_KINDS = {"box": 1, "sphere": 2, "cylinder": 3, "plane": 4}
+
+    def set_collider_shapes(self, shapes, as_set=True, linear_velocity=(0.0, 0.0, 0.0), angular_velocity=(0.0, 0.0, 0.0),
+                            friction=0.0):
+        """RigidBodyCollider3 over analytic surfaces with identity transforms.  `shapes`: dicts with
+        kind "box" (a = lower, b = upper corner) | "sphere" (a = centre, b[0] = radius) | "cylinder" (a = centre,
+        b[0] = radius, b[1] = height, axis y) | "plane" (a = point, b = unit normal), optional flipped=True
+        (Surface3::isNormalFlipped).  as_set: the collider's surface is an ImplicitSurfaceSet3 of them (required for more
+        than one); otherwise the single surface itself.  An empty list removes the collider."""
+        arr = (ColliderShape * max(len(shapes), 1))()
+        for i, sh in enumerate(shapes):
+            arr[i].kind = self.SHAPE_KINDS[sh["kind"]]
+            arr[i].flipped = 1 if sh.get("flipped", False) else 0
+            arr[i].a = (f64 * 3)(*sh["a"])
+            arr[i].b = (f64 * 3)(*sh.get("b", (0.0, 0.0, 0.0)))
+        self._c("hybrid_set_collider_shapes", self.h, arr, u32(len(shapes)), C.c_int(1 if as_set else 0),
+                (f64 * 3)(*linear_velocity), (f64 * 3)(*angular_velocity), f64(friction))
+
+    def set_collider_shape(self, kind, a=(0.0, 0.0, 0.0), b=(0.0, 0.0, 0.0), linear_velocity=(0.0, 0.0, 0.0),
+                           angular_velocity=(0.0, 0.0, 0.0), friction=0.0, flipped=False):
+        """One analytic surface as the collider (see set_collider_shapes); None / "none" removes it."""
+        shapes = [] if kind in (None, "none") else [dict(kind=kind, a=a, b=b, flipped=flipped)]
+        self.set_collider_shapes(shapes, False, linear_velocity, angular_velocity, friction)
 
     def get_collider_sdf(self):
         s = np.zeros(size3(self.grid.res))

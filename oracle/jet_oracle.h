@@ -98,8 +98,18 @@ int jeto_hybrid_emit_box(jeto_hybrid*, const double lower[3], const double upper
 uint64_t jeto_hybrid_num_particles(const jeto_hybrid*);
 int jeto_hybrid_get_particles(jeto_hybrid*, double* positions, double* velocities);
 int jeto_hybrid_get_affine(jeto_hybrid*, double* cx, double* cy, double* cz);
-/* Analytic rigid collider (RigidBodyCollider3 over a Box3 or Sphere3, identity transform) for the hybrid solver:
- * kind 0 none, 1 box (a = lower corner, b = upper corner), 2 sphere (a = centre, b[0] = radius). */
+/* Analytic rigid collider (RigidBodyCollider3, identity transforms) for the hybrid solver.  One explicit surface, or an
+ * ImplicitSurfaceSet3 of explicit surfaces (as_set != 0; needed for n > 1):
+ *   kind 1 Box3 (a = lower corner, b = upper corner), 2 Sphere3 (a = centre, b[0] = radius),
+ *        3 Cylinder3 (a = centre, b[0] = radius, b[1] = height), 4 Plane3 (a = point, b = unit normal);
+ *   flipped = Surface3::isNormalFlipped.  n == 0 removes the collider.  Same layout as jetcu_collider_shape. */
+typedef struct jeto_collider_shape {
+    int32_t kind, flipped;
+    double a[3], b[3];
+} jeto_collider_shape;
+int jeto_hybrid_set_collider_shapes(jeto_hybrid*, const jeto_collider_shape* shapes, uint32_t n, int as_set,
+                                    const double linear_velocity[3], const double angular_velocity[3], double friction);
+/* shorthand for one un-flipped box (kind 1) or sphere (kind 2); kind 0 removes the collider */
 int jeto_hybrid_set_collider_shape(jeto_hybrid*, int kind, const double a[3], const double b[3],
                                    const double linear_velocity[3], const double angular_velocity[3], double friction);
 /* GridFractionalBoundaryConditionSolver3::_colliderSdf after the next constrainVelocity / as rasterised (cell-centred). */

@@ -357,13 +357,35 @@ int jeto_hybrid_create(const jeto_hybrid_params* p, jeto_hybrid** out) {
 
 int jeto_hybrid_destroy(jeto_hybrid* h) { delete h; return 0; }
 
-int jeto_hybrid_set_collider_shape(jeto_hybrid* h, int kind, const double a[3], const double b[3], const double lin[3],
-                                   const double ang[3], double friction) {
-    if (kind == 0) { h->solver->setCollider(nullptr); return 0; }
+static Surface3Ptr makeShape(const jeto_collider_shape& s) {
+    const Vector3D a(s.a[0], s.a[1], s.a[2]), b(s.b[0], s.b[1], s.b[2]);
+    const bool flipped = s.flipped != 0;
+    switch (s.kind) {
+        case 1: return std::make_shared<Box3>(a, b, Transform3(), flipped);
+        case 2: return std::make_shared<Sphere3>(a, s.b[0], Transform3(), flipped);
+        case 3: return std::make_shared<Cylinder3>(a, s.b[0], s.b[1], Transform3(), flipped);
+        case 4: return std::make_shared<Plane3>(b, a, Transform3(), flipped);   // (normal, point)
+        default: return nullptr;
+    }
+}
+
+int jeto_hybrid_set_collider_shapes(jeto_hybrid* h, const jeto_collider_shape* shapes, uint32_t n, int as_set, const double lin[3],
+                                    const double ang[3], double friction) {
+    if (n == 0) { h->solver->setCollider(nullptr); return 0; }
+    if (n != 1 && !as_set) return 1;
     Surface3Ptr surface;
-    if (kind == 1) surface = std::make_shared<Box3>(Vector3D(a[0], a[1], a[2]), Vector3D(b[0], b[1], b[2]));
-    else if (kind == 2) surface = std::make_shared<Sphere3>(Vector3D(a[0], a[1], a[2]), b[0]);
-    else return 1;
+    if (as_set) {
+        std::vector<Surface3Ptr> members;
+        for (uint32_t i = 0; i < n; ++i) {
+            auto m = makeShape(shapes[i]);
+            if (!m) return 1;
+            members.push_back(m);
+        }
+        surface = std::make_shared<ImplicitSurfaceSet3>(members);   // addExplicitSurface each: SurfaceToImplicit3 wrappers
+    } else {
+        surface = makeShape(shapes[0]);
+        if (!surface) return 1;
+    }
     auto col = std::make_shared<RigidBodyCollider3>(surface,
                                                     lin ? Vector3D(lin[0], lin[1], lin[2]) : Vector3D(),
                                                     ang ? Vector3D(ang[0], ang[1], ang[2]) : Vector3D());
@@ -373,6 +395,16 @@ int jeto_hybrid_set_collider_shape(jeto_hybrid* h, int kind, const double a[3], 
     auto grids = h->solver->gridSystemData();
     h->solver->_boundaryConditionSolver->updateCollider(col, grids->resolution(), grids->gridSpacing(), grids->origin());
     return 0;
+}
+
+int jeto_hybrid_set_collider_shape(jeto_hybrid* h, int kind, const double a[3], const double b[3], const double lin[3],
+                                   const double ang[3], double friction) {
+    if (kind < 0 || kind > 2) return 1;
+    if (kind == 0) return jeto_hybrid_set_collider_shapes(h, nullptr, 0, 0, lin, ang, friction);
+    jeto_collider_shape s{};
+    s.kind = kind;
+    for (int q = 0; q < 3; ++q) { s.a[q] = a[q]; s.b[q] = b ? b[q] : 0.0; }
+    return jeto_hybrid_set_collider_shapes(h, &s, 1, 0, lin, ang, friction);
 }
 
 int jeto_hybrid_get_collider_sdf(jeto_hybrid* h, double* sdf) {

@@ -1,15 +1,41 @@
 // collider.cuh — analytic rigid collider of the hybrid solver on the device (SURVEY.md §8a-a9 with a collider, §8f-1):
-// RigidBodyCollider3 (src/jet/rigid_body_collider3.cpp) over a Box3 (src/jet/box3.cpp) or Sphere3 (src/jet/sphere3.cpp)
-// with identity transforms.  Closed forms replace the reference's per-point virtual Surface3 calls; every expression
-// keeps the reference's operand order (Vector3: include/jet/detail/vector3-inl.h) and the TU is built with -fmad=false,
-// so the collider SDF, the constrained velocities and the resolved particles are meant to be BIT-IDENTICAL to the CPU
-// path (checked against oracle/jet_port_collider.inc, which is pinned to the unmodified reference).
+// RigidBodyCollider3 (src/jet/rigid_body_collider3.cpp) over ONE explicit surface — Box3 (src/jet/box3.cpp), Sphere3
+// (sphere3.cpp), Cylinder3 (cylinder3.cpp), Plane3 (plane3.cpp), optionally normal-flipped — or over an
+// ImplicitSurfaceSet3 (implicit_surface_set3.cpp) of up to 8 of them, with identity transforms.  Closed forms replace the
+// reference's per-point virtual Surface3 calls; the set's Bvh3 (include/jet/detail/bvh3-inl.h) is built on the host with
+// the reference's split rule and walked on the device in the reference's order, so that ties between members resolve the
+// same way.  Every expression keeps the reference's operand order (Vector3: include/jet/detail/vector3-inl.h) and the
+// TU is built with -fmad=false, so the collider SDF, the constrained velocities and the resolved particles are
+// BIT-IDENTICAL to the CPU path for boxes, spheres and planes; Cylinder3 calls atan2 / cos / sin, where the device's libm
+// may differ from glibc in the last bit (checked against oracle/jet_port_collider.inc, which is pinned to the
+// unmodified reference; on the CPU — tests/hostcheck — every kind is bit-identical).
 #pragma once
 #include "sampling.cuh"
 
-struct ColliderD {
-    int kind = 0;        // 0 none, 1 Box3 (a = lowerCorner, b = upperCorner), 2 Sphere3 (a = center, b[0] = radius)
+#define JC_COLLIDER_MAX_SHAPES 8
+#define JC_SHAPE_BOX 1       // a = lowerCorner, b = upperCorner
+#define JC_SHAPE_SPHERE 2    // a = center, b[0] = radius
+#define JC_SHAPE_CYLINDER 3  // a = center, b[0] = radius, b[1] = height (axis y)
+#define JC_SHAPE_PLANE 4     // a = point, b = normal
+
+struct ShapeD {
+    int kind = 0, flipped = 0;  // flipped: Surface3::isNormalFlipped
     double a[3] = {}, b[3] = {};
+};
+
+struct BvhNodeD {  // Bvh3<T>::Node — bvh3-inl.h:17-45
+    double lo[3], hi[3];
+    int leaf, item, child, pad;
+};
+
+struct ColliderD {
+    int kind = 0;            // 0: no collider
+    int n = 0, is_set = 0;   // is_set: the surface is ImplicitSurfaceSet3(s[0..n)); else it is s[0] itself
+    int nnodes = 0, nitems = 0, nunb = 0;
+    ShapeD s[JC_COLLIDER_MAX_SHAPES];
+    BvhNodeD nodes[2 * JC_COLLIDER_MAX_SHAPES];
+    int items[JC_COLLIDER_MAX_SHAPES] = {};  // Bvh3::_items: the bounded members in insertion order
+    int unb[JC_COLLIDER_MAX_SHAPES] = {};    // ImplicitSurfaceSet3::_unboundedSurfaces
     double lin[3] = {}, ang[3] = {};   // RigidBodyCollider3::linearVelocity / angularVelocity
     double friction = 0.0;             // Collider3::frictionCoefficient()
 };
@@ -18,9 +44,14 @@ __host__ __device__ __forceinline__ double cd_dot(const double* a, const double*
 __host__ __device__ __forceinline__ double cd_len2(const double* a) { return a[0] * a[0] + a[1] * a[1] + a[2] * a[2]; }
 __host__ __device__ __forceinline__ double cd_len(const double* a) { return sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); }
 __host__ __device__ __forceinline__ double cd_max(double a, double b) { return (a < b) ? b : a; }  // std::max
+__host__ __device__ __forceinline__ double cd_min(double a, double b) { return (b < a) ? b : a; }  // std::min
+__host__ __device__ __forceinline__ double cd_dist(const double* a, const double* b) {            // a.distanceTo(b)
+    const double r[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
+    return cd_len(r);
+}
 
 // Transform3 with identity orientation and zero translation, spelt out (include/jet/detail/transform3-inl.h:45-47,
-// 72-79 over Matrix3x3::mul, matrix3x3-inl.h:208-213): exact no-ops except that -0.0 becomes +0.0.
+// 72-79 over Matrix3x3::mul, matrix3x3-inl.h:208-213): exact no-ops except that -0.0 may become +0.0.
 __host__ __device__ __forceinline__ void cd_to_local(const double* p, double* out) {
     const double t0 = p[0] - 0.0, t1 = p[1] - 0.0, t2 = p[2] - 0.0;
     out[0] = 1.0 * t0 + 0.0 * t1 + 0.0 * t2;
@@ -37,6 +68,23 @@ __host__ __device__ __forceinline__ void cd_to_world(const double* p, double* ou
     cd_to_world_dir(p, t);
     out[0] = t[0] + 0.0; out[1] = t[1] + 0.0; out[2] = t[2] + 0.0;
 }
+// Transform2 with orientation 0 (cos 1, sin 0) and zero translation — include/jet/detail/transform2-inl.h:48-54, 85-99
+__host__ __device__ __forceinline__ void cd2_to_local(const double* p, double* out) {
+    const double cs = 1.0, sn = 0.0;
+    const double x = p[0] - 0.0, y = p[1] - 0.0;
+    out[0] = cs * x + sn * y;
+    out[1] = -sn * x + cs * y;
+}
+__host__ __device__ __forceinline__ void cd2_to_world(const double* p, double* out) {
+    const double cs = 1.0, sn = 0.0;
+    out[0] = cs * p[0] - sn * p[1] + 0.0;
+    out[1] = sn * p[0] + cs * p[1] + 0.0;
+}
+__host__ __device__ __forceinline__ void cd2_to_world_dir(const double* d, double* out) {
+    const double cs = 1.0, sn = 0.0;
+    out[0] = cs * d[0] - sn * d[1];
+    out[1] = sn * d[0] + cs * d[1];
+}
 
 // normal of box plane q: +x, +y, +z (through upperCorner), -x, -y, -z (through lowerCorner) — src/jet/box3.cpp:30-35
 __host__ __device__ __forceinline__ void cd_box_normal(int q, double* n) {
@@ -52,7 +100,7 @@ __host__ __device__ __forceinline__ void cd_plane_closest(const double* n, const
     for (int a = 0; a < 3; ++a) out[a] = (r[a] - n[a] * d) + pt[a];
 }
 
-__host__ __device__ __forceinline__ bool cd_box_contains(const ColliderD& c, const double* p) {  // bounding_box3-inl.h:77-91
+__host__ __device__ __forceinline__ bool cd_box_contains(const ShapeD& c, const double* p) {  // bounding_box3-inl.h:77-91
 #pragma unroll
     for (int a = 0; a < 3; ++a)
         if (c.b[a] < p[a] || c.a[a] > p[a]) return false;
@@ -61,7 +109,7 @@ __host__ __device__ __forceinline__ bool cd_box_contains(const ColliderD& c, con
 
 // Box3::closestPointLocal (src/jet/box3.cpp:28-55) and closestNormalLocal (:57-100) in one pass: both scan the six
 // planes with the same strict `<` on the squared distance, so they pick the same plane.
-__host__ __device__ __forceinline__ void cd_box_closest_local(const ColliderD& c, const double* p, double* point, double* normal) {
+__host__ __device__ __forceinline__ void cd_box_closest_local(const ShapeD& c, const double* p, double* point, double* normal) {
     if (cd_box_contains(c, p)) {
         double n[3], best[3];
         cd_box_normal(0, n);
@@ -99,7 +147,7 @@ __host__ __device__ __forceinline__ void cd_box_closest_local(const ColliderD& c
 }
 
 // Sphere3::closestNormalLocal / closestPointLocal — src/jet/sphere3.cpp:25-39
-__host__ __device__ __forceinline__ void cd_sphere_closest_local(const ColliderD& c, const double* p, double* point, double* normal) {
+__host__ __device__ __forceinline__ void cd_sphere_closest_local(const ShapeD& c, const double* p, double* point, double* normal) {
     const double eps = 2.220446049250313e-16;  // Vector3::isSimilar's default epsilon
     if (fabs(c.a[0] - p[0]) < eps && fabs(c.a[1] - p[1]) < eps && fabs(c.a[2] - p[2]) < eps) {
         normal[0] = 1.0; normal[1] = 0.0; normal[2] = 0.0;
@@ -112,44 +160,361 @@ __host__ __device__ __forceinline__ void cd_sphere_closest_local(const ColliderD
     for (int a = 0; a < 3; ++a) point[a] = normal[a] * c.b[0] + c.a[a];  // radius * normal + center
 }
 
-__host__ __device__ __forceinline__ void cd_shape_closest_local(const ColliderD& c, const double* p, double* point, double* normal) {
-    if (c.kind == 1) cd_box_closest_local(c, p, point, normal); else cd_sphere_closest_local(c, p, point, normal);
+// ---- Box2 (src/jet/box2.cpp:28-96) over Plane2 (plane2.cpp:28-36) behind Surface2's public functions
+// (surface2.cpp:23-79): the 2-D profile Cylinder3 queries.  lo / hi = bound.lowerCorner / upperCorner. -----------------
+__host__ __device__ __forceinline__ void cd_box2_normal(int q, double* n) {  // (1,0) (0,1) through hi, (-1,0) (0,-1) through lo
+    n[0] = n[1] = 0.0;
+    n[q & 1] = q < 2 ? 1.0 : -1.0;
+}
+__host__ __device__ __forceinline__ void cd_plane2_closest(const double* n, const double* pt, const double* p, double* out) {
+    double l[2], q[2];
+    cd2_to_local(p, l);
+    const double r[2] = {l[0] - pt[0], l[1] - pt[1]};
+    const double d = n[0] * r[0] + n[1] * r[1];
+    q[0] = (r[0] - n[0] * d) + pt[0]; q[1] = (r[1] - n[1] * d) + pt[1];
+    cd2_to_world(q, out);
+}
+__host__ __device__ __forceinline__ bool cd_box2_contains(const double* lo, const double* hi, const double* p) {
+    if (hi[0] < p[0] || lo[0] > p[0]) return false;
+    if (hi[1] < p[1] || lo[1] > p[1]) return false;
+    return true;
+}
+__host__ __device__ __forceinline__ double cd2_dist2(const double* a, const double* b) {
+    const double x = a[0] - b[0], y = a[1] - b[1];
+    return x * x + y * y;
+}
+// Box2::closestPointLocal and closestNormalLocal in one pass (same plane scan, same strict comparisons)
+__host__ __device__ __forceinline__ void cd_box2_closest_local(const double* lo, const double* hi, const double* p, double* point,
+                                                               double* normal) {
+    if (cd_box2_contains(lo, hi, p)) {
+        double n[2], best[2];
+        cd_box2_normal(0, n);
+        cd_plane2_closest(n, hi, p, best);
+        double best2 = cd2_dist2(best, p);
+        int bq = 0;
+#pragma unroll
+        for (int q = 1; q < 4; ++q) {
+            double cand[2];
+            cd_box2_normal(q, n);
+            cd_plane2_closest(n, q < 2 ? hi : lo, p, cand);
+            const double e2 = cd2_dist2(cand, p);
+            if (e2 < best2) { best[0] = cand[0]; best[1] = cand[1]; best2 = e2; bq = q; }
+        }
+        point[0] = best[0]; point[1] = best[1];
+        cd_box2_normal(bq, normal);
+    } else {
+        point[0] = jc_clamp(p[0], lo[0], hi[0]); point[1] = jc_clamp(p[1], lo[1], hi[1]);
+        const double r[2] = {p[0] - point[0], p[1] - point[1]};
+        double n[2];
+        cd_box2_normal(0, n);
+        double bestcos = n[0] * r[0] + n[1] * r[1];
+        int bq = 0;
+#pragma unroll
+        for (int q = 1; q < 4; ++q) {
+            cd_box2_normal(q, n);
+            const double cs = n[0] * r[0] + n[1] * r[1];
+            if (cs > bestcos) { bq = q; bestcos = cs; }
+        }
+        cd_box2_normal(bq, normal);
+    }
 }
 
-// One query of the surface at world point p — Surface3::closestPoint / closestNormal / closestDistance / isInside
-// (src/jet/surface3.cpp:22-79, isNormalFlipped = false).
+// ---- Cylinder3 — src/jet/cylinder3.cpp:32-68 ------------------------------------------------------------------------
+struct CylProfile {
+    double r[3], rr[2], lo[2], hi[2];
+};
+__host__ __device__ __forceinline__ CylProfile cd_cyl_profile(const ShapeD& c, const double* p) {
+    CylProfile f;
+    f.r[0] = p[0] - c.a[0]; f.r[1] = p[1] - c.a[1]; f.r[2] = p[2] - c.a[2];
+    f.rr[0] = sqrt(f.r[0] * f.r[0] + f.r[2] * f.r[2]); f.rr[1] = f.r[1];
+    // Box2(Vector2D(-radius, -0.5 * height), Vector2D(radius, 0.5 * height)) -> BoundingBox2D(point1, point2): min / max
+    const double p1[2] = {-c.b[0], -0.5 * c.b[1]}, p2[2] = {c.b[0], 0.5 * c.b[1]};
+    f.lo[0] = cd_min(p1[0], p2[0]); f.lo[1] = cd_min(p1[1], p2[1]);
+    f.hi[0] = cd_max(p1[0], p2[0]); f.hi[1] = cd_max(p1[1], p2[1]);
+    return f;
+}
+// closestPointLocal (:32-42) and closestNormalLocal (:52-68): box.closestPoint(rr) / box.closestNormal(rr) are Surface2's
+// public functions (identity Transform2 around the *Local ones)
+__host__ __device__ __forceinline__ void cd_cyl_closest_local(const ShapeD& c, const double* p, double* point, double* normal) {
+    const CylProfile f = cd_cyl_profile(c, p);
+    double l[2], q[2], n2[2], cp[2], cn[2];
+    cd2_to_local(f.rr, l);
+    cd_box2_closest_local(f.lo, f.hi, l, q, n2);
+    cd2_to_world(q, cp);
+    cd2_to_world_dir(n2, cn);
+    cn[0] *= 1.0; cn[1] *= 1.0;
+    const double angle = atan2(f.r[2], f.r[0]);
+    point[0] = cp[0] * cos(angle) + c.a[0]; point[1] = cp[1] + c.a[1]; point[2] = cp[0] * sin(angle) + c.a[2];
+    if (cn[1] > 0) { normal[0] = 0.0; normal[1] = 1.0; normal[2] = 0.0; }
+    else if (cn[1] < 0) { normal[0] = 0.0; normal[1] = -1.0; normal[2] = 0.0; }
+    else {  // Vector3D(r.x, 0, r.z).normalized()
+        const double v[3] = {f.r[0], 0.0, f.r[2]};
+        const double len = cd_len(v);
+        normal[0] = v[0] / len; normal[1] = v[1] / len; normal[2] = v[2] / len;
+    }
+}
+// closestDistanceLocal (:44-50): box.closestDistance(rr) = Surface2::closestDistanceLocal on toLocal(rr)
+__host__ __device__ __forceinline__ double cd_cyl_closest_distance_local(const ShapeD& c, const double* p) {
+    const CylProfile f = cd_cyl_profile(c, p);
+    double l[2], q[2], n2[2];
+    cd2_to_local(f.rr, l);
+    cd_box2_closest_local(f.lo, f.hi, l, q, n2);
+    return sqrt(cd2_dist2(l, q));
+}
+
+// ---- one explicit surface: closestPointLocal + closestNormalLocal by kind, then Surface3's public functions
+// (src/jet/surface3.cpp:22-79) in one query ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void cd_shape_closest_local(const ShapeD& c, const double* p, double* point, double* normal) {
+    if (c.kind == JC_SHAPE_BOX) cd_box_closest_local(c, p, point, normal);
+    else if (c.kind == JC_SHAPE_SPHERE) cd_sphere_closest_local(c, p, point, normal);
+    else if (c.kind == JC_SHAPE_CYLINDER) cd_cyl_closest_local(c, p, point, normal);
+    else {  // Plane3: plane3.cpp:35-43
+        cd_plane_closest(c.b, c.a, p, point);
+        normal[0] = c.b[0]; normal[1] = c.b[1]; normal[2] = c.b[2];
+    }
+}
+
 struct ColliderQuery {
     double point[3], normal[3], distance;
     bool inside;
 };
 
-__host__ __device__ __forceinline__ ColliderQuery cd_query(const ColliderD& c, const double* p) {
+// closestPoint / closestNormal / closestDistance / isInside of shape `c` at world point p
+__host__ __device__ __forceinline__ ColliderQuery cd_surf_query(const ShapeD& c, const double* p) {
     ColliderQuery q;
     double l[3], cp[3], n[3];
     cd_to_local(p, l);
     cd_shape_closest_local(c, l, cp, n);
     cd_to_world(cp, q.point);
     cd_to_world_dir(n, q.normal);
-    q.normal[0] *= 1.0; q.normal[1] *= 1.0; q.normal[2] *= 1.0;  // result *= isNormalFlipped ? -1 : 1
+    const double f = c.flipped ? -1.0 : 1.0;  // result *= isNormalFlipped ? -1 : 1
+    q.normal[0] *= f; q.normal[1] *= f; q.normal[2] *= f;
     const double r[3] = {l[0] - cp[0], l[1] - cp[1], l[2] - cp[2]};
-    q.inside = cd_dot(r, n) < 0.0;  // Surface3::isInsideLocal
-    if (c.kind == 2) {              // Sphere3::closestDistanceLocal: |center.distanceTo(p) - radius|
-        const double s[3] = {c.a[0] - l[0], c.a[1] - l[1], c.a[2] - l[2]};
-        q.distance = fabs(cd_len(s) - c.b[0]);
-    } else {                        // Surface3::closestDistanceLocal: p.distanceTo(closestPointLocal(p))
-        q.distance = cd_len(r);
+    const bool in = cd_dot(r, n) < 0.0;       // Surface3::isInsideLocal
+    q.inside = (c.flipped != 0) == !in;       // isNormalFlipped == !isInsideLocal(...)
+    if (c.kind == JC_SHAPE_SPHERE) q.distance = fabs(cd_dist(c.a, l) - c.b[0]);   // Sphere3::closestDistanceLocal
+    else if (c.kind == JC_SHAPE_CYLINDER) q.distance = cd_cyl_closest_distance_local(c, l);
+    else q.distance = cd_len(r);              // Surface3::closestDistanceLocal: p.distanceTo(closestPointLocal(p))
+    return q;
+}
+__host__ __device__ __forceinline__ double cd_surf_closest_distance(const ShapeD& c, const double* p) {
+    double l[3];
+    cd_to_local(p, l);
+    if (c.kind == JC_SHAPE_SPHERE) return fabs(cd_dist(c.a, l) - c.b[0]);
+    if (c.kind == JC_SHAPE_CYLINDER) return cd_cyl_closest_distance_local(c, l);
+    double cp[3], n[3];
+    cd_shape_closest_local(c, l, cp, n);
+    return cd_dist(l, cp);
+}
+
+// ---- SurfaceToImplicit3(shape) with its own identity transform (surface_to_implicit3.cpp:41-76) ----------------------
+__host__ __device__ __forceinline__ ColliderQuery cd_wrap_query(const ShapeD& c, const double* p) {
+    double l[3];
+    cd_to_local(p, l);
+    const ColliderQuery s = cd_surf_query(c, l);
+    ColliderQuery q;
+    cd_to_world(s.point, q.point);
+    cd_to_world_dir(s.normal, q.normal);
+    q.normal[0] *= 1.0; q.normal[1] *= 1.0; q.normal[2] *= 1.0;
+    q.distance = s.distance;
+    q.inside = s.inside;
+    return q;
+}
+__host__ __device__ __forceinline__ double cd_wrap_closest_distance(const ShapeD& c, const double* p) {
+    double l[3];
+    cd_to_local(p, l);
+    return cd_surf_closest_distance(c, l);
+}
+// ImplicitSurface3::signedDistance (implicit_surface3.cpp:26-29) over SurfaceToImplicit3::signedDistanceLocal (:67-72)
+__host__ __device__ __forceinline__ double cd_wrap_signed_distance(const ShapeD& c, const double* pt) {
+    double l[3];
+    cd_to_local(pt, l);  // the wrapper's own (identity) transform
+    const ColliderQuery q = cd_surf_query(c, l);
+    const double d = cd_dist(q.point, l);  // x.distanceTo(otherPoint)
+    return q.inside ? -d : d;
+}
+
+// ---- Bvh3::nearest (bvh3-inl.h:80-165) with distanceFunc = member->closestDistance(pt) ----------------------------------
+struct BvhNearest {
+    int item;  // index into ColliderD::s, -1 = nullptr
+    double distance;
+};
+__host__ __device__ __forceinline__ BvhNearest cd_bvh_nearest(const ColliderD& c, const double* pt) {
+    BvhNearest best;
+    best.item = -1;
+    best.distance = DBL_MAX;
+    if (c.nnodes == 0) return best;
+    int todo[JC_COLLIDER_MAX_SHAPES], todoPos = 0, node = 0;
+    for (;;) {
+        const BvhNodeD& nd = c.nodes[node];
+        if (nd.leaf) {
+            const int m = c.items[nd.item];
+            const double dist = cd_wrap_closest_distance(c.s[m], pt);
+            if (dist < best.distance) { best.distance = dist; best.item = m; }
+            if (todoPos > 0) node = todo[--todoPos]; else break;
+        } else {
+            const double bestDistSqr = best.distance * best.distance;
+            const int left = node + 1, right = nd.child;
+            double dl[3], dr[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                dl[a] = jc_clamp(pt[a], c.nodes[left].lo[a], c.nodes[left].hi[a]) - pt[a];
+                dr[a] = jc_clamp(pt[a], c.nodes[right].lo[a], c.nodes[right].hi[a]) - pt[a];
+            }
+            const double dlsq = cd_len2(dl), drsq = cd_len2(dr);
+            const bool visitLeft = dlsq < bestDistSqr, visitRight = drsq < bestDistSqr;
+            if (visitLeft && visitRight) {
+                int first, second;
+                if (dlsq < drsq) { first = left; second = right; } else { first = right; second = left; }
+                todo[todoPos++] = second;
+                node = first;
+            } else if (visitLeft) node = left;
+            else if (visitRight) node = right;
+            else if (todoPos > 0) node = todo[--todoPos];
+            else break;
+        }
+    }
+    return best;
+}
+
+// ---- ImplicitSurfaceSet3::closestPointLocal / closestNormalLocal / closestDistanceLocal / isInsideLocal
+// (implicit_surface_set3.cpp:94-161, 206-214) in one query at the set-local point p ---------------------------------------
+__host__ __device__ __forceinline__ ColliderQuery cd_set_query_local(const ColliderD& c, const double* p) {
+    ColliderQuery q;
+    q.point[0] = q.point[1] = q.point[2] = DBL_MAX;
+    q.normal[0] = 1.0; q.normal[1] = 0.0; q.normal[2] = 0.0;
+    const BvhNearest nn = cd_bvh_nearest(c, p);
+    if (nn.item >= 0) {
+        const ColliderQuery w = cd_wrap_query(c.s[nn.item], p);
+        q.point[0] = w.point[0]; q.point[1] = w.point[1]; q.point[2] = w.point[2];
+        q.normal[0] = w.normal[0]; q.normal[1] = w.normal[1]; q.normal[2] = w.normal[2];
+    }
+    double minDist = nn.distance;
+    for (int u = 0; u < c.nunb; ++u) {
+        const ColliderQuery w = cd_wrap_query(c.s[c.unb[u]], p);
+        const double dist = cd_dist(w.point, p);  // pt.distanceTo(otherPoint)
+        if (dist < minDist) {
+            minDist = dist;
+            q.point[0] = w.point[0]; q.point[1] = w.point[1]; q.point[2] = w.point[2];
+            q.normal[0] = w.normal[0]; q.normal[1] = w.normal[1]; q.normal[2] = w.normal[2];
+        }
+    }
+    q.distance = minDist;
+    q.inside = false;
+    for (int i = 0; i < c.n; ++i) {
+        double l[3];
+        cd_to_local(p, l);  // the member wrapper's transform, then the shape's own inside cd_surf_query
+        if (cd_surf_query(c.s[i], l).inside) { q.inside = true; break; }
     }
     return q;
 }
 
-// SurfaceToImplicit3(surface)->signedDistance(pt) — implicit_surface3.cpp:26-29, surface_to_implicit3.cpp:67-72
-__host__ __device__ __forceinline__ double cd_signed_distance(const ColliderD& c, const double* pt) {
+// One query of the collider's surface (Collider3::surface()) at world point p through Surface3's public functions
+__host__ __device__ __forceinline__ ColliderQuery cd_query(const ColliderD& c, const double* p) {
+    if (!c.is_set) return cd_surf_query(c.s[0], p);
     double l[3];
-    cd_to_local(pt, l);  // the wrapper's own (identity) transform
-    const ColliderQuery q = cd_query(c, l);
-    const double r[3] = {q.point[0] - l[0], q.point[1] - l[1], q.point[2] - l[2]};
-    const double d = cd_len(r);  // x.distanceTo(otherPoint)
-    return q.inside ? -d : d;
+    cd_to_local(p, l);
+    const ColliderQuery s = cd_set_query_local(c, l);
+    ColliderQuery q;
+    cd_to_world(s.point, q.point);
+    cd_to_world_dir(s.normal, q.normal);
+    q.normal[0] *= 1.0; q.normal[1] *= 1.0; q.normal[2] *= 1.0;
+    q.distance = s.distance;
+    q.inside = s.inside;
+    return q;
+}
+
+// onColliderUpdated's implicitSurface->signedDistance(pt) (…boundary_condition_solver3.cpp:255-264): the set itself (min
+// over the members, implicit_surface_set3.cpp:216-224) or SurfaceToImplicit3(surface) around an explicit surface
+__host__ __device__ __forceinline__ double cd_signed_distance(const ColliderD& c, const double* pt) {
+    if (!c.is_set) return cd_wrap_signed_distance(c.s[0], pt);
+    double l[3];
+    cd_to_local(pt, l);
+    double sdf = DBL_MAX;
+    for (int i = 0; i < c.n; ++i) sdf = cd_min(sdf, cd_wrap_signed_distance(c.s[i], l));
+    return sdf;
+}
+
+// ---- host side: Surface3::boundingBox() of the members and Bvh3::build (bvh3-inl.h:49-69, 522-581) ----------------------
+inline void cd_shape_bounding_box(const ShapeD& c, double* lo, double* hi) {
+    double p1[3], p2[3], l0[3], h0[3], l1[3], h1[3];
+    for (int a = 0; a < 3; ++a) {
+        if (c.kind == JC_SHAPE_BOX) { p1[a] = c.a[a]; p2[a] = c.b[a]; }
+        else if (c.kind == JC_SHAPE_SPHERE) { p1[a] = c.a[a] - c.b[0]; p2[a] = c.a[a] + c.b[0]; }            // sphere3.cpp:96-99
+        else { const double e = (a == 1) ? 0.5 * c.b[1] : c.b[0]; p1[a] = c.a[a] - e; p2[a] = c.a[a] + e; }  // cylinder3.cpp:223-226
+        l0[a] = cd_min(p1[a], p2[a]); h0[a] = cd_max(p1[a], p2[a]);
+    }
+    cd_to_world(l0, l1); cd_to_world(h0, h1);  // the shape's transform, then the SurfaceToImplicit3 wrapper's
+    cd_to_world(l1, lo); cd_to_world(h1, hi);
+}
+inline int cd_bvh_qsplit(int* idx, int n, double pivot, int axis, const double (*blo)[3], const double (*bhi)[3]) {
+    int ret = 0;
+    for (int i = 0; i < n; ++i) {
+        const double centroid = 0.5f * (blo[idx[i]][axis] + bhi[idx[i]][axis]);
+        if (centroid < pivot) {
+            const int t = idx[i]; idx[i] = idx[ret]; idx[ret] = t;
+            ret++;
+        }
+    }
+    if (ret == 0 || ret == n) ret = n >> 1;
+    return ret;
+}
+inline void cd_bvh_build(ColliderD& c, int node, int* idx, int n, const double (*blo)[3], const double (*bhi)[3]) {
+    c.nnodes++;  // _nodes.push_back(Node()): `node` is its index
+    BvhNodeD& nd = c.nodes[node];
+    nd.pad = 0;
+    if (n == 1) {
+        nd.leaf = 1; nd.item = idx[0]; nd.child = -1;
+        for (int a = 0; a < 3; ++a) { nd.lo[a] = blo[idx[0]][a]; nd.hi[a] = bhi[idx[0]][a]; }
+        return;
+    }
+    double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    for (int i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a) { lo[a] = cd_min(lo[a], blo[idx[i]][a]); hi[a] = cd_max(hi[a], bhi[idx[i]][a]); }
+    const double d[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
+    int axis;
+    if (d[0] > d[1] && d[0] > d[2]) axis = 0; else axis = (d[1] > d[2]) ? 1 : 2;
+    const double pivot = 0.5 * (hi[axis] + lo[axis]);
+    const int mid = cd_bvh_qsplit(idx, n, pivot, axis, blo, bhi);
+    cd_bvh_build(c, node + 1, idx, mid, blo, bhi);
+    nd.leaf = 0; nd.item = -1; nd.child = c.nnodes;
+    for (int a = 0; a < 3; ++a) { nd.lo[a] = lo[a]; nd.hi[a] = hi[a]; }
+    cd_bvh_build(c, nd.child, idx + mid, n - mid, blo, bhi);
+}
+// ImplicitSurfaceSet3::buildBvh (implicit_surface_set3.cpp:233-246) + the _unboundedSurfaces list (:86-91)
+inline void cd_build_set(ColliderD& c) {
+    double blo[JC_COLLIDER_MAX_SHAPES][3], bhi[JC_COLLIDER_MAX_SHAPES][3];
+    c.nnodes = c.nitems = c.nunb = 0;
+    for (int i = 0; i < c.n; ++i) {
+        if (c.s[i].kind == JC_SHAPE_PLANE) { c.unb[c.nunb++] = i; continue; }  // Plane3::isBounded() == false
+        cd_shape_bounding_box(c.s[i], blo[c.nitems], bhi[c.nitems]);
+        c.items[c.nitems++] = i;
+    }
+    if (c.nitems == 0) return;
+    int idx[JC_COLLIDER_MAX_SHAPES];
+    for (int i = 0; i < c.nitems; ++i) idx[i] = i;
+    cd_bvh_build(c, 0, idx, c.nitems, blo, bhi);
+}
+
+// The ColliderD of jetcu_hybrid_set_collider_shapes' arguments (already validated): members, rigid-body velocity, friction
+// clamped at 0 as Collider3::setFrictionCoefficient does (collider3.cpp:78-80), and — for a set — the Bvh3, built once:
+// Collider3::update -> updateQueryEngine -> buildBvh gives the same tree at every step for a static set.
+inline ColliderD cd_make_collider(const jetcu_collider_shape* shapes, uint32_t n, int as_set, const double* lin, const double* ang,
+                                  double friction) {
+    ColliderD c;
+    if (n == 0) return c;
+    c.kind = 1;
+    c.n = (int)n;
+    c.is_set = as_set ? 1 : 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        c.s[i].kind = shapes[i].kind;
+        c.s[i].flipped = shapes[i].flipped ? 1 : 0;
+        for (int q = 0; q < 3; ++q) { c.s[i].a[q] = shapes[i].a[q]; c.s[i].b[q] = shapes[i].b[q]; }
+    }
+    for (int q = 0; q < 3; ++q) { c.lin[q] = lin ? lin[q] : 0.0; c.ang[q] = ang ? ang[q] : 0.0; }
+    c.friction = friction > 0.0 ? friction : 0.0;
+    if (c.is_set) cd_build_set(c);
+    return c;
 }
 
 // RigidBodyCollider3::velocityAt — src/jet/rigid_body_collider3.cpp:25-28: linear + angular x (p - translation)

@@ -1368,22 +1368,18 @@ int jetcu_hybrid_set_collider(jetcu_hybrid* h, const double* collider_sdf, const
     return JETCU_OK;
 }
 
-int jetcu_hybrid_set_collider_shape(jetcu_hybrid* h, int kind, const double a[3], const double b[3],
-                                    const double linear_velocity[3], const double angular_velocity[3], double friction) {
+int jetcu_hybrid_set_collider_shapes(jetcu_hybrid* h, const jetcu_collider_shape* shapes, uint32_t n, int as_set,
+                                     const double linear_velocity[3], const double angular_velocity[3], double friction) {
     HYB_ENTER(h);
-    JC_ARG(ctx, kind >= JETCU_COLLIDER_NONE && kind <= JETCU_COLLIDER_SPHERE);
-    h->col = ColliderD();
-    if (kind == JETCU_COLLIDER_NONE) return JETCU_OK;
-    JC_ARG(ctx, a != nullptr && b != nullptr);
-    if (kind == JETCU_COLLIDER_SPHERE) JC_ARG(ctx, b[0] > 0.0);
-    ColliderD c;
-    c.kind = kind;
-    for (int q = 0; q < 3; ++q) {
-        c.a[q] = a[q]; c.b[q] = b[q];
-        c.lin[q] = linear_velocity ? linear_velocity[q] : 0.0;
-        c.ang[q] = angular_velocity ? angular_velocity[q] : 0.0;
+    JC_ARG(ctx, n <= JC_COLLIDER_MAX_SHAPES && (n == 0 || shapes != nullptr));
+    JC_ARG(ctx, n <= 1 || as_set);  // several surfaces exist in Jet only as members of an ImplicitSurfaceSet3
+    for (uint32_t i = 0; i < n; ++i) {
+        JC_ARG(ctx, shapes[i].kind >= JETCU_COLLIDER_BOX && shapes[i].kind <= JETCU_COLLIDER_PLANE);
+        if (shapes[i].kind == JETCU_COLLIDER_SPHERE || shapes[i].kind == JETCU_COLLIDER_CYLINDER) JC_ARG(ctx, shapes[i].b[0] > 0.0);
     }
-    c.friction = friction > 0.0 ? friction : 0.0;  // Collider3::setFrictionCoefficient clamps at 0 (collider3.cpp:78-80)
+    h->col = ColliderD();
+    if (n == 0) return JETCU_OK;
+    const ColliderD c = cd_make_collider(shapes, n, as_set, linear_velocity, angular_velocity, friction);
     if (!h->col_sdf) {
         JC_TRY(jc_alloc(ctx, &h->col_sdf, h->nc));
         JC_TRY(jc_alloc(ctx, &h->bnd_u, h->nu)); JC_TRY(jc_alloc(ctx, &h->bnd_v, h->nv)); JC_TRY(jc_alloc(ctx, &h->bnd_w, h->nw));
@@ -1401,6 +1397,19 @@ int jetcu_hybrid_set_collider_shape(jetcu_hybrid* h, int kind, const double a[3]
     JC_TRY(jc_sync(ctx));
     h->col = c;
     return JETCU_OK;
+}
+
+int jetcu_hybrid_set_collider_shape(jetcu_hybrid* h, int kind, const double a[3], const double b[3],
+                                    const double linear_velocity[3], const double angular_velocity[3], double friction) {
+    HYB_ENTER(h);
+    JC_ARG(ctx, kind >= JETCU_COLLIDER_NONE && kind <= JETCU_COLLIDER_PLANE);
+    if (kind == JETCU_COLLIDER_NONE) return jetcu_hybrid_set_collider_shapes(h, nullptr, 0, 0, nullptr, nullptr, 0.0);
+    JC_ARG(ctx, a != nullptr && b != nullptr);
+    jetcu_collider_shape s;
+    memset(&s, 0, sizeof(s));
+    s.kind = kind;
+    for (int q = 0; q < 3; ++q) { s.a[q] = a[q]; s.b[q] = b[q]; }
+    return jetcu_hybrid_set_collider_shapes(h, &s, 1, 0, linear_velocity, angular_velocity, friction);
 }
 
 int jetcu_hybrid_get_collider_sdf(jetcu_hybrid* h, double* sdf) {

@@ -285,14 +285,33 @@ int jetcu_hybrid_set_collider(jetcu_hybrid*, const double* collider_sdf, const d
                               const double angular_velocity[3], const double rotation_origin[3],
                               double friction_coefficient);
 
-/* Analytic rigid collider == RigidBodyCollider3 (src/jet/rigid_body_collider3.cpp) over a Box3 / Sphere3 with identity
- * transform installed with GridFluidSolver3::setCollider: kind BOX (a = lower corner, b = upper corner) or SPHERE
- * (a = centre, b[0] = radius); NONE removes it.  Drives the collider branch of
- * GridFractionalBoundaryConditionSolver3::constrainVelocity (src/jet/grid_fractional_boundary_condition_solver3.cpp:26-280),
- * extrapolateIntoCollider (src/jet/grid_fluid_solver3.cpp:355-369), the moving-boundary terms of the pressure system and
- * Collider3::resolveCollision (src/jet/collider3.cpp:19-74) after moveParticles.  [First CUDA implementation written
- * against the pinned oracle without GPU time left in round 1: tests/test_gpu_collider.py is its first run.] */
-enum { JETCU_COLLIDER_NONE = 0, JETCU_COLLIDER_BOX = 1, JETCU_COLLIDER_SPHERE = 2 };
+/* Analytic rigid collider == RigidBodyCollider3 (src/jet/rigid_body_collider3.cpp) installed with
+ * GridFluidSolver3::setCollider, identity transforms.  Its surface is ONE explicit surface (as_set == 0, n == 1) or an
+ * ImplicitSurfaceSet3 of up to JETCU_COLLIDER_MAX_SHAPES explicit surfaces (as_set != 0; src/jet/implicit_surface_set3.cpp,
+ * members wrapped in SurfaceToImplicit3 as addExplicitSurface does, queried through the set's Bvh3 in the reference's
+ * traversal order):
+ *   BOX      Box3      (src/jet/box3.cpp)       a = lower corner, b = upper corner
+ *   SPHERE   Sphere3   (src/jet/sphere3.cpp)    a = centre, b[0] = radius
+ *   CYLINDER Cylinder3 (src/jet/cylinder3.cpp)  a = centre, b[0] = radius, b[1] = height (axis y)
+ *   PLANE    Plane3    (src/jet/plane3.cpp)     a = point, b = unit normal
+ * flipped = Surface3::isNormalFlipped (the spherical tank of src/examples/hybrid_liquid_sim/main.cpp:454-463); n == 0
+ * removes the collider.  Drives the collider branch of GridFractionalBoundaryConditionSolver3::constrainVelocity
+ * (src/jet/grid_fractional_boundary_condition_solver3.cpp:26-280), extrapolateIntoCollider
+ * (src/jet/grid_fluid_solver3.cpp:355-369), the moving-boundary terms of the pressure system and
+ * Collider3::resolveCollision (src/jet/collider3.cpp:19-74) after moveParticles.  [Written against the pinned oracle after
+ * round 1's GPU minutes were spent: bit-identical to it on the CPU (tests/test_hostcheck_collider.py);
+ * tests/firstrun/zz_collider.py is the first GPU run.] */
+enum { JETCU_COLLIDER_NONE = 0, JETCU_COLLIDER_BOX = 1, JETCU_COLLIDER_SPHERE = 2, JETCU_COLLIDER_CYLINDER = 3,
+       JETCU_COLLIDER_PLANE = 4 };
+#define JETCU_COLLIDER_MAX_SHAPES 8
+typedef struct jetcu_collider_shape {
+    int32_t kind;     /* JETCU_COLLIDER_BOX .. JETCU_COLLIDER_PLANE */
+    int32_t flipped;  /* Surface3::isNormalFlipped */
+    double a[3], b[3];
+} jetcu_collider_shape;
+int jetcu_hybrid_set_collider_shapes(jetcu_hybrid*, const jetcu_collider_shape* shapes, uint32_t n, int as_set,
+                                     const double linear_velocity[3], const double angular_velocity[3], double friction);
+/* shorthand for one un-flipped surface of `kind`; JETCU_COLLIDER_NONE removes the collider */
 int jetcu_hybrid_set_collider_shape(jetcu_hybrid*, int kind, const double a[3], const double b[3],
                                     const double linear_velocity[3], const double angular_velocity[3], double friction);
 /* GridFractionalBoundaryConditionSolver3::colliderSdf() (cell-centred); kMaxD everywhere without a collider. */

@@ -6,7 +6,8 @@ had run out, so this file is its FIRST execution.  It is run by tests/test_gpu_z
 (a device fault here cannot take the established parity suite down with it); the parent reports the child as a
 non-strict xfail.  Round 2 moves the file back under tests/ as its first step.
 
-Expected: collider SDF, constrained velocities, markers — bit-exact (no reductions); steps — positions <= 1e-5 L,
+Expected: collider SDF, constrained velocities, markers — bit-exact (no reductions) for boxes, spheres and planes, within
+1e-14 / 1e-12 where a Cylinder3 is involved (atan2 / cos / sin: device libm vs glibc); steps — positions <= 1e-5 L,
 pressure <= 1e-6 relative (P2G sums in integers, the reference in particle order)."""
 import numpy as np
 import pytest
@@ -14,7 +15,7 @@ import pytest
 import golden_cases as gc
 from gpu_common import checker, jetcu_or_fail
 from oracle_api import APIC, FLIP, PIC, Grid, HybridParams, MgpcgParams
-from test_oracle_collider import COLLIDERS
+from test_oracle_collider import ALL, COLLIDERS, SETS, STEP_CASES, install
 
 pytestmark = pytest.mark.gpu
 
@@ -33,38 +34,50 @@ def exact(a, b, what):
     assert np.array_equal(a, b), "%s: max abs diff %g" % (what, float(np.abs(a - b).max()))
 
 
-@pytest.mark.parametrize("name", sorted(COLLIDERS))
+def has_cylinder(name):
+    members = [COLLIDERS[name]] if name in COLLIDERS else SETS[name][0]
+    return any(m["kind"] == "cylinder" for m in members)
+
+
+def same(a, b, what, name, tol):
+    if has_cylinder(name):
+        assert np.abs(a - b).max() <= tol, "%s: max abs diff %g" % (what, float(np.abs(a - b).max()))
+    else:
+        exact(a, b, what)
+
+
+@pytest.mark.parametrize("name", ALL)
 def test_collider_sdf_bit_exact(jc, oracle, name):
     n = 12
     prm = HybridParams.make(Grid.cube(n), mode=PIC, mgpcg=MgpcgParams.make(max_levels=2))
     a, b = jc.hybrid(prm), oracle.hybrid(prm)
-    a.set_collider_shape(**COLLIDERS[name]); b.set_collider_shape(**COLLIDERS[name])
-    exact(a.get_collider_sdf(), b.get_collider_sdf(), "collider sdf")
+    install(a, name); install(b, name)
+    same(a.get_collider_sdf(), b.get_collider_sdf(), "collider sdf", name, 1e-14)
     a.close(); b.close()
 
 
-@pytest.mark.parametrize("name", sorted(COLLIDERS))
+@pytest.mark.parametrize("name", ALL)
 def test_constrain_velocity_bit_exact(jc, oracle, name):
     n = 12
     prm = HybridParams.make(Grid.cube(n), mode=PIC, mgpcg=MgpcgParams.make(max_levels=2))
     a, b = jc.hybrid(prm), oracle.hybrid(prm)
-    a.set_collider_shape(**COLLIDERS[name]); b.set_collider_shape(**COLLIDERS[name])
+    install(a, name); install(b, name)
     rng = np.random.default_rng(5)
     u = rng.uniform(-1, 1, (n, n, n + 1)); v = rng.uniform(-1, 1, (n, n + 1, n)); w = rng.uniform(-1, 1, (n + 1, n, n))
     a.set_velocity(u, v, w); b.set_velocity(u, v, w)
     a.apply_boundary_condition(); b.apply_boundary_condition()
     for x, y, what in zip(a.get_velocity(), b.get_velocity(), "uvw"):
-        exact(x, y, "constrained " + what)
+        same(x, y, "constrained " + what, name, 1e-12)
     a.close(); b.close()
 
 
 @pytest.mark.parametrize("mode", [PIC, FLIP, APIC])
-@pytest.mark.parametrize("name", ["box", "box_moving", "sphere"])
+@pytest.mark.parametrize("name", STEP_CASES)
 def test_steps_with_collider(jc, oracle, mode, name):
     n = 16
     prm = HybridParams.make(Grid.cube(n), mode=mode, mgpcg=MgpcgParams.make(max_iterations=40, max_levels=3))
     a, b = jc.hybrid(prm), oracle.hybrid(prm)
-    a.set_collider_shape(**COLLIDERS[name]); b.set_collider_shape(**COLLIDERS[name])
+    install(a, name); install(b, name)
     box = ((0.0, 0.0, 0.0), (0.7, 0.7, 1.0))
     assert a.emit_box(box[0], box[1], 0.5 / n, (0.8, 0.0, 0.0)) == b.emit_box(box[0], box[1], 0.5 / n, (0.8, 0.0, 0.0))
     for s in range(3):
@@ -74,7 +87,8 @@ def test_steps_with_collider(jc, oracle, mode, name):
         pr_a, pr_b = a.get_pressure(), b.get_pressure()
         if sb.pcg_true_residual_l2 <= 1e-8 * max(sb.pcg_b_l2, 1e-300):   # only where the oracle's own solve converged
             assert np.abs(pr_a - pr_b).max() <= 1e-6 * max(np.abs(pr_b).max(), 1e-300), "pressure step %d" % s
-        exact(a.get_sdf(), b.get_sdf(), "particle sdf (extrapolated into the collider) step %d" % s) if s == 0 else None
+        if s == 0:
+            same(a.get_sdf(), b.get_sdf(), "particle sdf (extrapolated into the collider) step 0", name, 1e-12)
     a.close(); b.close()
 
 

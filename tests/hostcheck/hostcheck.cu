@@ -21,14 +21,6 @@ static GridD make_grid(const jetcu_grid* g) {
                  jc_pow2_inverse(g->hx), jc_pow2_inverse(g->hy), jc_pow2_inverse(g->hz)};
 }
 
-static ColliderD make_collider(int kind, const double* a, const double* b, const double* lin, const double* ang, double friction) {
-    ColliderD c;
-    c.kind = kind;
-    for (int q = 0; q < 3; ++q) { c.a[q] = a[q]; c.b[q] = b[q]; c.lin[q] = lin[q]; c.ang[q] = ang[q]; }
-    c.friction = friction > 0.0 ? friction : 0.0;
-    return c;
-}
-
 // what hyb_extrapolate_one does: `depth` sweeps of k_extrapolate_sweep with ping-pong validity maps
 static void extrapolate(double* data, const char* marker, int sx, int sy, int sz, unsigned depth) {
     size_t n = (size_t)sx * sy * sz;
@@ -168,10 +160,10 @@ int hc_p2g(const jetcu_grid* grid, int apic, int carry_free, uint64_t n, const d
 }
 
 // k_collider_sdf over the whole grid
-int hc_collider_sdf(const jetcu_grid* grid, int kind, const double* a, const double* b, const double* lin, const double* ang,
+int hc_collider_sdf(const jetcu_grid* grid, const jetcu_collider_shape* shapes, uint32_t ns, int as_set, const double* lin, const double* ang,
                     double friction, double* sdf) {
     GridD g = make_grid(grid);
-    ColliderD c = make_collider(kind, a, b, lin, ang, friction);
+    ColliderD c = cd_make_collider(shapes, ns, as_set, lin, ang, friction);
     for (int k = 0; k < g.nz; ++k)
         for (int j = 0; j < g.ny; ++j)
             for (int i = 0; i < g.nx; ++i) sdf[((size_t)k * g.ny + j) * g.nx + i] = collider_sdf_cell(g, c, i, j, k);
@@ -179,15 +171,15 @@ int hc_collider_sdf(const jetcu_grid* grid, int kind, const double* a, const dou
 }
 
 // hyb_zero_walls() of hybrid.cu == GridFluidSolver3::applyBoundaryCondition: hyb_constrain_collider, then the walls
-int hc_apply_boundary_condition(const jetcu_grid* grid, int kind, const double* a, const double* b, const double* lin,
+int hc_apply_boundary_condition(const jetcu_grid* grid, const jetcu_collider_shape* shapes, uint32_t ns, int as_set, const double* lin,
                                 const double* ang, double friction, double max_cfl, int wall_flag, double* u, double* v,
                                 double* w) {
     GridD g = make_grid(grid);
     const size_t nu = (size_t)(g.nx + 1) * g.ny * g.nz, nv = (size_t)g.nx * (g.ny + 1) * g.nz, nw = (size_t)g.nx * g.ny * (g.nz + 1);
-    if (kind != 0) {
-        ColliderD c = make_collider(kind, a, b, lin, ang, friction);
+    if (ns != 0) {
+        ColliderD c = cd_make_collider(shapes, ns, as_set, lin, ang, friction);
         std::vector<double> csdf((size_t)g.nx * g.ny * g.nz), tu(nu), tv(nv), tw(nw);
-        hc_collider_sdf(grid, kind, a, b, lin, ang, friction, csdf.data());
+        hc_collider_sdf(grid, shapes, ns, as_set, lin, ang, friction, csdf.data());
         std::vector<char> mu(nu), mv(nv), mw(nw);
         const unsigned depth = (unsigned)ceil(max_cfl);
         markers<0>(g, c, csdf.data(), u, mu.data());
@@ -209,10 +201,10 @@ int hc_apply_boundary_condition(const jetcu_grid* grid, int kind, const double* 
 }
 
 // boundary velocity samples handed to the pressure solver (k_boundary_velocity<AXIS>)
-int hc_boundary_velocity(const jetcu_grid* grid, int kind, const double* a, const double* b, const double* lin, const double* ang,
+int hc_boundary_velocity(const jetcu_grid* grid, const jetcu_collider_shape* shapes, uint32_t ns, int as_set, const double* lin, const double* ang,
                          double friction, double* bu, double* bv, double* bw) {
     GridD g = make_grid(grid);
-    ColliderD c = make_collider(kind, a, b, lin, ang, friction);
+    ColliderD c = cd_make_collider(shapes, ns, as_set, lin, ang, friction);
     for (int k = 0; k < g.nz; ++k) for (int j = 0; j < g.ny; ++j) for (int i = 0; i < g.nx + 1; ++i) boundary_velocity_face<0>(g, c, bu, i, j, k);
     for (int k = 0; k < g.nz; ++k) for (int j = 0; j < g.ny + 1; ++j) for (int i = 0; i < g.nx; ++i) boundary_velocity_face<1>(g, c, bv, i, j, k);
     for (int k = 0; k < g.nz + 1; ++k) for (int j = 0; j < g.ny; ++j) for (int i = 0; i < g.nx; ++i) boundary_velocity_face<2>(g, c, bw, i, j, k);
@@ -220,11 +212,11 @@ int hc_boundary_velocity(const jetcu_grid* grid, int kind, const double* a, cons
 }
 
 // the extrapolateIntoCollider tail of jetcu_hybrid_build_signed_distance_field: k_outside_collider_marker + sweeps
-int hc_extrapolate_into_collider(const jetcu_grid* grid, int kind, const double* a, const double* b, const double* lin,
+int hc_extrapolate_into_collider(const jetcu_grid* grid, const jetcu_collider_shape* shapes, uint32_t ns, int as_set, const double* lin,
                                  const double* ang, double friction, double max_cfl, double* sdf) {
     GridD g = make_grid(grid);
     std::vector<double> csdf((size_t)g.nx * g.ny * g.nz);
-    hc_collider_sdf(grid, kind, a, b, lin, ang, friction, csdf.data());
+    hc_collider_sdf(grid, shapes, ns, as_set, lin, ang, friction, csdf.data());
     std::vector<char> marker(csdf.size());
     for (int k = 0; k < g.nz; ++k)
         for (int j = 0; j < g.ny; ++j)
@@ -234,9 +226,9 @@ int hc_extrapolate_into_collider(const jetcu_grid* grid, int kind, const double*
 }
 
 // k_resolve_collision over n AoS particles
-int hc_resolve_collision(int kind, const double* a, const double* b, const double* lin, const double* ang, double friction,
+int hc_resolve_collision(const jetcu_collider_shape* shapes, uint32_t ns, int as_set, const double* lin, const double* ang, double friction,
                          uint64_t n, double* pos, double* vel) {
-    ColliderD c = make_collider(kind, a, b, lin, ang, friction);
+    ColliderD c = cd_make_collider(shapes, ns, as_set, lin, ang, friction);
     for (uint64_t p = 0; p < n; ++p) cd_resolve_collision(c, pos + 3 * p, vel + 3 * p);
     return 0;
 }

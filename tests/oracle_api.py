@@ -17,7 +17,7 @@ REF_PATH = os.path.join(ROOT, "oracle", "_ref", "libjetref.so")
 from jetcu_loader import load_package
 
 _pkg = load_package()
-from fluid_engine_dev_b200.jetcu import (APIC, FLIP, PIC, PD, PF, PU64, ROW_DTYPE, Grid, HybridApi, HybridParams,  # noqa: E402,F401
+from fluid_engine_dev_b200.jetcu import (APIC, FLIP, PIC, PD, PF, PU64, ROW_DTYPE, ColliderShape, Grid, HybridApi, HybridParams,  # noqa: E402,F401
                                           LinearApi, MgpcgParams, MgpcgResult, Row, SmokeApi, SmokeParams, StepStats, _p, c64,
                                           f64, level_dims, size3, u32, u64)
 

@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 
 from oracle_api import FLIP, PIC, Grid, HybridParams, MgpcgParams, have_port, load_port
-from test_oracle_collider import COLLIDERS
+from oracle_api import ColliderShape
+from test_oracle_collider import ALL, COLLIDERS, SETS, install
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -42,10 +43,27 @@ def port():
     return o
 
 
-def shape_args(c):
-    kind = {"box": 1, "sphere": 2}[c["kind"]]
-    v3 = lambda k: (C.c_double * 3)(*c.get(k, (0.0, 0.0, 0.0)))
-    return [C.c_int(kind), v3("a"), v3("b"), v3("linear_velocity"), v3("angular_velocity"), C.c_double(c.get("friction", 0.0))]
+KINDS = {"box": 1, "sphere": 2, "cylinder": 3, "plane": 4}
+
+
+def shape_args(name):
+    """(shapes*, n, as_set, lin, ang, friction) of hostcheck's collider entry points for a COLLIDERS / SETS entry."""
+    if name in COLLIDERS:
+        c = COLLIDERS[name]
+        shapes, kw, as_set = [c], c, 0
+    else:
+        shapes, kw = SETS[name]
+        as_set = 1
+    arr = (ColliderShape * len(shapes))()
+    for i, sh in enumerate(shapes):
+        arr[i].kind = KINDS[sh["kind"]]
+        arr[i].flipped = 1 if sh.get("flipped", False) else 0
+        arr[i].a = (C.c_double * 3)(*sh["a"])
+        b = tuple(sh.get("b", (0.0, 0.0, 0.0))) + (0.0, 0.0, 0.0)
+        arr[i].b = (C.c_double * 3)(*b[:3])
+    v3 = lambda k: (C.c_double * 3)(*kw.get(k, (0.0, 0.0, 0.0)))
+    return [arr, C.c_uint32(len(shapes)), C.c_int(as_set), v3("linear_velocity"), v3("angular_velocity"),
+            C.c_double(kw.get("friction", 0.0))]
 
 
 def dp(a):
@@ -57,33 +75,33 @@ def exact(a, b, what):
     assert np.array_equal(a, b), "%s: max abs diff %g" % (what, float(np.abs(a - b).max()))
 
 
-@pytest.mark.parametrize("name", sorted(COLLIDERS))
+@pytest.mark.parametrize("name", ALL)
 @pytest.mark.parametrize("n,domain", [(12, 1.0), (10, 0.9)])   # power-of-two-free spacings: the division path of jc_norm
 def test_collider_sdf(hc, port, name, n, domain):
     grid = Grid.cube(n, domain)
     h = port.hybrid(HybridParams.make(grid, mode=PIC, mgpcg=MgpcgParams.make(max_levels=2)))
-    h.set_collider_shape(**COLLIDERS[name])
+    install(h, name)
     want = h.get_collider_sdf()
     got = np.zeros_like(want)
-    assert hc.hc_collider_sdf(C.byref(grid), *shape_args(COLLIDERS[name]), dp(got)) == 0
+    assert hc.hc_collider_sdf(C.byref(grid), *shape_args(name), dp(got)) == 0
     exact(got, want, "collider sdf")
     h.close()
 
 
-@pytest.mark.parametrize("name", sorted(COLLIDERS))
+@pytest.mark.parametrize("name", ALL)
 @pytest.mark.parametrize("n,domain", [(12, 1.0), (16, 1.0), (10, 0.9)])   # 16: power-of-two spacing -> exact-reciprocal path
 def test_apply_boundary_condition(hc, port, name, n, domain):
     grid = Grid.cube(n, domain)
     prm = HybridParams.make(grid, mode=PIC, mgpcg=MgpcgParams.make(max_levels=2))
     h = port.hybrid(prm)
-    h.set_collider_shape(**COLLIDERS[name])
+    install(h, name)
     rng = np.random.default_rng(n)
     u = rng.uniform(-1, 1, (n, n, n + 1)); v = rng.uniform(-1, 1, (n, n + 1, n)); w = rng.uniform(-1, 1, (n + 1, n, n))
     h.set_velocity(u, v, w)
     h.apply_boundary_condition()
     want = h.get_velocity()
     gu, gv, gw = u.copy(), v.copy(), w.copy()
-    assert hc.hc_apply_boundary_condition(C.byref(grid), *shape_args(COLLIDERS[name]), C.c_double(prm.max_cfl),
+    assert hc.hc_apply_boundary_condition(C.byref(grid), *shape_args(name), C.c_double(prm.max_cfl),
                                           C.c_int(prm.closed_domain_boundary_flag), dp(gu), dp(gv), dp(gw)) == 0
     for a, b, what in zip((gu, gv, gw), want, "uvw"):
         exact(a, b, "constrained " + what)
@@ -101,57 +119,68 @@ def test_walls_only(hc, port):
     h.apply_boundary_condition()
     z = (C.c_double * 3)(0, 0, 0)
     gu, gv, gw = u.copy(), v.copy(), w.copy()
-    hc.hc_apply_boundary_condition(C.byref(grid), C.c_int(0), z, z, z, z, C.c_double(0.0), C.c_double(5.0),
+    hc.hc_apply_boundary_condition(C.byref(grid), None, C.c_uint32(0), C.c_int(0), z, z, C.c_double(0.0), C.c_double(5.0),
                                    C.c_int(0b101011), dp(gu), dp(gv), dp(gw))
     for a, b, what in zip((gu, gv, gw), h.get_velocity(), "uvw"):
         exact(a, b, "walls " + what)
     h.close()
 
 
-@pytest.mark.parametrize("name", ["box", "box_moving", "sphere", "box_offgrid"])
+@pytest.mark.parametrize("name", ALL)
 def test_resolve_collision(hc, port, name):
     """Collider3::resolveCollision through PicSolver3::moveParticles with dt = 0 (positions stay, collisions resolve)."""
     n = 8
     grid = Grid.cube(n)
     h = port.hybrid(HybridParams.make(grid, mode=PIC, mgpcg=MgpcgParams.make(max_levels=2)))
-    h.set_collider_shape(**COLLIDERS[name])
+    install(h, name)
     rng = np.random.default_rng(3)
     pos = rng.uniform(0.02, 0.98, (20000, 3))
-    # plenty of particles exactly on faces / edges / the centre of the shape
-    c = COLLIDERS[name]
-    if c["kind"] == "box":
-        lo, hi = np.array(c["a"]), np.array(c["b"])
-        pos[:200] = np.clip(pos[:200], lo, hi)
-        pos[200:400, 0] = hi[0]; pos[400:600, 1] = np.clip(lo[1], 0.02, 0.98); pos[600] = np.clip((lo + hi) / 2, 0.02, 0.98)
-    else:
-        pos[0] = c["a"]; pos[1:300] = np.array(c["a"]) + rng.normal(size=(299, 3)) * 0.05
+    # plenty of particles exactly on faces / edges / axes / centres of the members
+    members = [COLLIDERS[name]] if name in COLLIDERS else SETS[name][0]
+    at = 0
+    for c in members:
+        a = np.array(c["a"], dtype=np.float64)
+        if c["kind"] == "box":
+            lo, hi = a, np.array(c["b"])
+            pos[at:at + 200] = np.clip(pos[at:at + 200], lo, hi)
+            pos[at + 200:at + 400, 0] = hi[0]; pos[at + 400:at + 600, 1] = lo[1]; pos[at + 600] = (lo + hi) / 2
+        elif c["kind"] == "plane":
+            nrm = np.array(c["b"])
+            q = pos[at:at + 300]
+            pos[at:at + 300] = q - np.outer((q - a) @ nrm, nrm)             # on the plane (up to rounding)
+            pos[at + 300:at + 600] -= 0.05 * nrm                             # and some well behind it
+        else:   # sphere / cylinder: the centre itself, a cloud around it, points on the axis
+            pos[at] = a
+            pos[at + 1:at + 300] = a + rng.normal(size=(299, 3)) * 0.05
+            pos[at + 300:at + 400, 0] = a[0]; pos[at + 300:at + 400, 2] = a[2]
+        at += 700
     pos = np.ascontiguousarray(np.clip(pos, 0.02, 0.98))
     vel = rng.uniform(-2, 2, pos.shape)
     h.set_particles(pos, vel)
     h.move_particles(0.0)
     want_p, want_v = h.get_particles()
     gp, gv = pos.copy(), vel.copy()
-    assert hc.hc_resolve_collision(*shape_args(c), C.c_uint64(len(gp)), dp(gp), dp(gv)) == 0
+    assert hc.hc_resolve_collision(*shape_args(name), C.c_uint64(len(gp)), dp(gp), dp(gv)) == 0
     moved = int((np.abs(want_p - pos).max(axis=1) > 0).sum())
     assert moved > 100, moved
     exact(gp, want_p, "resolved positions"); exact(gv, want_v, "resolved velocities")
     h.close()
 
 
-@pytest.mark.parametrize("name", ["box", "sphere"])
+@pytest.mark.parametrize("name", ["box", "sphere", "cylinder", "tank", "cylinders", "mixed"])
 def test_extrapolate_sdf_into_collider(hc, port, name):
     """The tail of buildSignedDistanceField: raw particle SDF (solver without collider) -> extrapolated (with collider)."""
     n = 12
     grid = Grid.cube(n)
     prm = HybridParams.make(grid, mode=FLIP, mgpcg=MgpcgParams.make(max_levels=2))
     raw_h, col_h = port.hybrid(prm), port.hybrid(prm)
-    col_h.set_collider_shape(**COLLIDERS[name])
+    install(col_h, name)
     for h in (raw_h, col_h):
         h.emit_box((0.0, 0.0, 0.0), (0.7, 0.7, 1.0), 0.5 / n)
         h.build_signed_distance_field()
     raw, want = raw_h.get_sdf(), col_h.get_sdf()
     assert not np.array_equal(raw, want)
     got = raw.copy()
-    assert hc.hc_extrapolate_into_collider(C.byref(grid), *shape_args(COLLIDERS[name]), C.c_double(prm.max_cfl), dp(got)) == 0
+    assert hc.hc_extrapolate_into_collider(C.byref(grid), *shape_args(name), C.c_double(prm.max_cfl), dp(got)) == 0
     exact(got, want, "sdf extrapolated into the collider")
     raw_h.close(); col_h.close()

@@ -1,11 +1,13 @@
 // dropin_check_next.cpp — Jet-side check (public Jet API only) of the two adapter paths added after the three seams:
 //     collider   jet::FlipSolver3 + RigidBodyCollider3(Box3) through Animation::update  vs  jetcu::CudaFlipSolver3 with the
-//                same collider object (adapter forwards it as jetcu_hybrid_set_collider_shape)
+//                same collider object (adapter forwards it as jetcu_hybrid_set_collider_shapes)
+//     pillars    the same with the collider of hybrid_liquid_sim example 3: an ImplicitSurfaceSet3 of three Cylinder3
+//     tank       the same inside a normal-flipped Sphere3 (example 6)
 //     smoke      jet::GridSmokeSolver3 (plume from rest in a closed box)               vs  jetcu::CudaGridSmokeSolver3
 // Prints one JSON line with the deviations from the stock run.  Built by adapters/Makefile next to dropin_check;
 // tests/test_gpu_zz_dropin_next.py runs it (first GPU run pending, see that file).
 //
-//     dropin_check_next [--n 16] [--frames 3] [--levels 3] [--what collider|smoke]
+//     dropin_check_next [--n 16] [--frames 3] [--levels 3] [--what collider|pillars|tank|smoke]
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -41,7 +43,18 @@ void setupLiquid(const std::shared_ptr<Solver>& solver, const Options& opt) {
     emitter->setPointGenerator(std::make_shared<GridPointGenerator3>());
     solver->setParticleEmitter(emitter);
     solver->setUseCompressedLinearSystem(false);
-    auto obstacle = std::make_shared<Box3>(Vector3D(0.6, 0.0, 0.3), Vector3D(0.85, 0.35, 0.7));
+    Surface3Ptr obstacle;
+    if (opt.what == "pillars") {
+        obstacle = ImplicitSurfaceSet3::builder()
+                       .withExplicitSurfaces({std::make_shared<Cylinder3>(Vector3D(0.65, 0.25, 0.2), 0.08, 0.5),
+                                              std::make_shared<Cylinder3>(Vector3D(0.7, 0.25, 0.5), 0.08, 0.5),
+                                              std::make_shared<Cylinder3>(Vector3D(0.65, 0.25, 0.8), 0.08, 0.5)})
+                       .makeShared();
+    } else if (opt.what == "tank") {
+        obstacle = Sphere3::builder().withCenter({0.5, 0.5, 0.5}).withRadius(0.48).withIsNormalFlipped(true).makeShared();
+    } else {
+        obstacle = std::make_shared<Box3>(Vector3D(0.6, 0.0, 0.3), Vector3D(0.85, 0.35, 0.7));
+    }
     auto collider = std::make_shared<RigidBodyCollider3>(obstacle);
     collider->setFrictionCoefficient(0.2);
     solver->setCollider(collider);
@@ -72,7 +85,7 @@ int runCollider(const Options& opt) {
         const Vector3D d = ps->positions()[i] - pc->positions()[i];
         maxDx = std::max(maxDx, std::max(std::fabs(d.x), std::max(std::fabs(d.y), std::fabs(d.z))));
     }
-    std::printf("{\"what\": \"collider\", \"n\": %zu, \"frames\": %d, \"particles\": %zu, \"max_dx\": %.3e}\n", opt.n, opt.frames, n, maxDx);
+    std::printf("{\"what\": \"%s\", \"n\": %zu, \"frames\": %d, \"particles\": %zu, \"max_dx\": %.3e}\n", opt.what.c_str(), opt.n, opt.frames, n, maxDx);
     return 0;
 }
 
@@ -139,7 +152,7 @@ int main(int argc, char** argv) {
     }
     Logging::mute();
     try {
-        if (opt.what == "collider") return runCollider(opt);
+        if (opt.what == "collider" || opt.what == "pillars" || opt.what == "tank") return runCollider(opt);
         if (opt.what == "smoke") return runSmoke(opt);
         std::fprintf(stderr, "unknown check %s\n", opt.what.c_str());
         return 2;

@@ -402,45 +402,84 @@ class CudaHybridSolver3 : public Base {
         }
     }
 
-    //! Collider -> jetcu_hybrid_set_collider_shape.  The device path evaluates closed forms, so only what has one is
-    //! accepted: a RigidBodyCollider3 over a Box3 or Sphere3 with identity transform and unflipped normal (what the
-    //! hybrid_liquid_sim examples build, src/examples/hybrid_liquid_sim/main.cpp); anything else is an error, never a
-    //! silent fallback.  Re-sent every step: linear / angular velocity may be changed by the application between steps.
+    //! Forwards the Jet collider to the device.  Accepted: a RigidBodyCollider3 whose surface is a Box3, Sphere3,
+    //! Cylinder3 or Plane3 (normal-flipped or not), or an ImplicitSurfaceSet3 of up to JETCU_COLLIDER_MAX_SHAPES such
+    //! surfaces added with addExplicitSurface — what the hybrid_liquid_sim examples build
+    //! (src/examples/hybrid_liquid_sim/main.cpp:253-278, 454-463) — all with identity transforms; anything else is an
+    //! error, never a silent fallback.  Re-sent when anything changed: the application may alter the linear / angular
+    //! velocity between steps.
+    static bool identityTransform(const jet::Transform3& t) {
+        const jet::QuaternionD q = t.orientation();
+        return t.translation().lengthSquared() == 0.0 && q.w == 1.0 && q.x == 0.0 && q.y == 0.0 && q.z == 0.0;
+    }
+
+    static jetcu_collider_shape shapeOf(const jet::Surface3Ptr& surface) {
+        if (!identityTransform(surface->transform))
+            throw std::runtime_error("jetcu: device colliders need identity transforms");
+        jetcu_collider_shape s;
+        std::memset(&s, 0, sizeof(s));
+        s.flipped = surface->isNormalFlipped ? 1 : 0;
+        if (auto box = std::dynamic_pointer_cast<jet::Box3>(surface)) {
+            s.kind = JETCU_COLLIDER_BOX;
+            s.a[0] = box->bound.lowerCorner.x; s.a[1] = box->bound.lowerCorner.y; s.a[2] = box->bound.lowerCorner.z;
+            s.b[0] = box->bound.upperCorner.x; s.b[1] = box->bound.upperCorner.y; s.b[2] = box->bound.upperCorner.z;
+        } else if (auto sphere = std::dynamic_pointer_cast<jet::Sphere3>(surface)) {
+            s.kind = JETCU_COLLIDER_SPHERE;
+            s.a[0] = sphere->center.x; s.a[1] = sphere->center.y; s.a[2] = sphere->center.z;
+            s.b[0] = sphere->radius;
+        } else if (auto cyl = std::dynamic_pointer_cast<jet::Cylinder3>(surface)) {
+            s.kind = JETCU_COLLIDER_CYLINDER;
+            s.a[0] = cyl->center.x; s.a[1] = cyl->center.y; s.a[2] = cyl->center.z;
+            s.b[0] = cyl->radius; s.b[1] = cyl->height;
+        } else if (auto plane = std::dynamic_pointer_cast<jet::Plane3>(surface)) {
+            s.kind = JETCU_COLLIDER_PLANE;
+            s.a[0] = plane->point.x; s.a[1] = plane->point.y; s.a[2] = plane->point.z;
+            s.b[0] = plane->normal.x; s.b[1] = plane->normal.y; s.b[2] = plane->normal.z;
+        } else {
+            throw std::runtime_error("jetcu: device colliders are Box3 / Sphere3 / Cylinder3 / Plane3 (closed forms) or an "
+                                     "ImplicitSurfaceSet3 of them; got another Surface3");
+        }
+        return s;
+    }
+
     void syncCollider() {
         const jet::Collider3Ptr col = this->collider();
         if (col == nullptr) {
-            if (_hasCollider) _ctx->check(jetcu_hybrid_set_collider_shape(_h, JETCU_COLLIDER_NONE, nullptr, nullptr, nullptr, nullptr, 0.0));
+            if (_hasCollider) _ctx->check(jetcu_hybrid_set_collider_shapes(_h, nullptr, 0, 0, nullptr, nullptr, 0.0));
             _hasCollider = false;
             return;
         }
         auto rigid = std::dynamic_pointer_cast<jet::RigidBodyCollider3>(col);
         if (!rigid) throw std::runtime_error("jetcu: only RigidBodyCollider3 colliders run on the device");
         const jet::Surface3Ptr surface = rigid->surface();
-        const jet::Transform3& t = surface->transform;
-        const jet::QuaternionD q = t.orientation();
-        if (surface->isNormalFlipped || t.translation().lengthSquared() != 0.0 || q.w != 1.0 || q.x != 0.0 || q.y != 0.0 || q.z != 0.0)
-            throw std::runtime_error("jetcu: device colliders need an identity transform and unflipped normals");
-        double a[3], b[3] = {0.0, 0.0, 0.0};
-        int kind;
-        if (auto box = std::dynamic_pointer_cast<jet::Box3>(surface)) {
-            kind = JETCU_COLLIDER_BOX;
-            a[0] = box->bound.lowerCorner.x; a[1] = box->bound.lowerCorner.y; a[2] = box->bound.lowerCorner.z;
-            b[0] = box->bound.upperCorner.x; b[1] = box->bound.upperCorner.y; b[2] = box->bound.upperCorner.z;
-        } else if (auto sphere = std::dynamic_pointer_cast<jet::Sphere3>(surface)) {
-            kind = JETCU_COLLIDER_SPHERE;
-            a[0] = sphere->center.x; a[1] = sphere->center.y; a[2] = sphere->center.z;
-            b[0] = sphere->radius;
+        std::vector<jetcu_collider_shape> shapes;
+        int asSet = 0;
+        if (auto set = std::dynamic_pointer_cast<jet::ImplicitSurfaceSet3>(surface)) {
+            if (set->isNormalFlipped || !identityTransform(set->transform))
+                throw std::runtime_error("jetcu: a device collider set needs an identity transform and unflipped normals");
+            if (set->numberOfSurfaces() == 0 || set->numberOfSurfaces() > JETCU_COLLIDER_MAX_SHAPES)
+                throw std::runtime_error("jetcu: a device collider set holds 1.." + std::to_string(JETCU_COLLIDER_MAX_SHAPES) + " surfaces");
+            for (size_t i = 0; i < set->numberOfSurfaces(); ++i) {
+                auto wrap = std::dynamic_pointer_cast<jet::SurfaceToImplicit3>(set->surfaceAt(i));
+                if (!wrap || wrap->isNormalFlipped || !identityTransform(wrap->transform))
+                    throw std::runtime_error("jetcu: collider set members must be explicit surfaces (addExplicitSurface)");
+                shapes.push_back(shapeOf(wrap->surface()));
+            }
+            asSet = 1;
         } else {
-            throw std::runtime_error("jetcu: device colliders are Box3 or Sphere3 (closed forms); got another Surface3");
+            shapes.push_back(shapeOf(surface));
         }
         const double lin[3] = {rigid->linearVelocity.x, rigid->linearVelocity.y, rigid->linearVelocity.z};
         const double ang[3] = {rigid->angularVelocity.x, rigid->angularVelocity.y, rigid->angularVelocity.z};
-        const double key[13] = {double(kind), a[0], a[1], a[2], b[0], b[1], b[2], lin[0], lin[1], lin[2], ang[0], ang[1], ang[2]};
         const double fr = col->frictionCoefficient();
-        if (!_hasCollider || std::memcmp(key, _colliderKey, sizeof(key)) != 0 || fr != _colliderFriction) {
-            _ctx->check(jetcu_hybrid_set_collider_shape(_h, kind, a, b, lin, ang, fr));
-            std::memcpy(_colliderKey, key, sizeof(key));
-            _colliderFriction = fr;
+        std::vector<double> key = {double(asSet), lin[0], lin[1], lin[2], ang[0], ang[1], ang[2], fr};
+        for (const auto& s : shapes) {
+            const double part[8] = {double(s.kind), double(s.flipped), s.a[0], s.a[1], s.a[2], s.b[0], s.b[1], s.b[2]};
+            key.insert(key.end(), part, part + 8);
+        }
+        if (!_hasCollider || key != _colliderKey) {
+            _ctx->check(jetcu_hybrid_set_collider_shapes(_h, shapes.data(), (uint32_t)shapes.size(), asSet, lin, ang, fr));
+            _colliderKey = key;
             _hasCollider = true;
         }
     }
@@ -456,8 +495,7 @@ class CudaHybridSolver3 : public Base {
     HostMirror _mirror = HostMirror::kEveryStep;
     jetcu_step_stats _stats = jetcu_step_stats();
     bool _hasCollider = false;
-    double _colliderKey[13] = {};
-    double _colliderFriction = 0.0;
+    std::vector<double> _colliderKey;
 };
 
 // ------------------------------------------------------------------------------------------------ smoke (config 5)

@@ -28,6 +28,14 @@ def test_collider_scene_matches_stock_jet():
     assert out["max_dx"] <= 1e-5, out          # BASELINE tolerance: 1e-5 of the domain size (= 1)
 
 
+@pytest.mark.parametrize("what", ["pillars", "tank"])
+def test_example_colliders_match_stock_jet(what):
+    """The colliders of hybrid_liquid_sim examples 3 / 6 (ImplicitSurfaceSet3 of Cylinder3; normal-flipped Sphere3)."""
+    out = run("--what", what, "--n", 32, "--frames", 3, "--levels", 4)
+    assert out["particles"] > 10000
+    assert out["max_dx"] <= 1e-5, out
+
+
 def test_smoke_matches_stock_jet():
     out = run("--what", "smoke", "--n", 32, "--frames", 5, "--levels", 4)
     assert out["velocity_scale"] > 0.05        # the plume really rose

@@ -436,16 +436,33 @@ __host__ __device__ __forceinline__ double cd_signed_distance(const ColliderD& c
 }
 
 // ---- host side: Surface3::boundingBox() of the members and Bvh3::build (bvh3-inl.h:49-69, 522-581) ----------------------
+// Transform3::toWorld(BoundingBox3D) with the identity transform (transform3-inl.h:87-98): the box of the eight transformed
+// corners, where corner(i) = (width, height, depth) * (-+1/2) + midPoint (bounding_box3-inl.h:150-152, 201-208) is NOT
+// exactly the stored corner — the round trip can move a bound by an ulp, and the BVH is built from the moved bounds.
+inline void cd_bbox_to_world(const double* l, const double* u, double* lo, double* hi) {
+    const double size[3] = {u[0] - l[0], u[1] - l[1], u[2] - l[2]};
+    const double mid[3] = {(u[0] + l[0]) / 2.0, (u[1] + l[1]) / 2.0, (u[2] + l[2]) / 2.0};
+    for (int a = 0; a < 3; ++a) { lo[a] = DBL_MAX; hi[a] = -DBL_MAX; }
+    for (int i = 0; i < 8; ++i) {
+        const double off[3] = {(i & 1) ? 0.5 : -0.5, (i & 2) ? 0.5 : -0.5, (i & 4) ? 0.5 : -0.5};
+        const double corner[3] = {size[0] * off[0] + mid[0], size[1] * off[1] + mid[1], size[2] * off[2] + mid[2]};
+        double w[3];
+        cd_to_world(corner, w);
+        for (int a = 0; a < 3; ++a) { lo[a] = cd_min(lo[a], w[a]); hi[a] = cd_max(hi[a], w[a]); }
+    }
+}
+// ImplicitSurface3::boundingBox() of SurfaceToImplicit3(shape): the shape's boundingBoxLocal through the shape's and the
+// wrapper's (identity) transforms
 inline void cd_shape_bounding_box(const ShapeD& c, double* lo, double* hi) {
     double p1[3], p2[3], l0[3], h0[3], l1[3], h1[3];
     for (int a = 0; a < 3; ++a) {
         if (c.kind == JC_SHAPE_BOX) { p1[a] = c.a[a]; p2[a] = c.b[a]; }
         else if (c.kind == JC_SHAPE_SPHERE) { p1[a] = c.a[a] - c.b[0]; p2[a] = c.a[a] + c.b[0]; }            // sphere3.cpp:96-99
         else { const double e = (a == 1) ? 0.5 * c.b[1] : c.b[0]; p1[a] = c.a[a] - e; p2[a] = c.a[a] + e; }  // cylinder3.cpp:223-226
-        l0[a] = cd_min(p1[a], p2[a]); h0[a] = cd_max(p1[a], p2[a]);
+        l0[a] = cd_min(p1[a], p2[a]); h0[a] = cd_max(p1[a], p2[a]);                                          // BoundingBox3D(p1, p2)
     }
-    cd_to_world(l0, l1); cd_to_world(h0, h1);  // the shape's transform, then the SurfaceToImplicit3 wrapper's
-    cd_to_world(l1, lo); cd_to_world(h1, hi);
+    cd_bbox_to_world(l0, h0, l1, h1);
+    cd_bbox_to_world(l1, h1, lo, hi);
 }
 inline int cd_bvh_qsplit(int* idx, int n, double pivot, int axis, const double (*blo)[3], const double (*bhi)[3]) {
     int ret = 0;

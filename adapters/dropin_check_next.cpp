@@ -3,11 +3,13 @@
 //                same collider object (adapter forwards it as jetcu_hybrid_set_collider_shapes)
 //     pillars    the same with the collider of hybrid_liquid_sim example 3: an ImplicitSurfaceSet3 of three Cylinder3
 //     tank       the same inside a normal-flipped Sphere3 (example 6)
+//     emit       the water drop of examples 1 / 2 (half-space + sphere): stock VolumeParticleEmitter3 set on the host  vs
+//                CudaFlipSolver3::emitOnDevice (lattice generated and tested on the GPU), then the same frames
 //     smoke      jet::GridSmokeSolver3 (plume from rest in a closed box)               vs  jetcu::CudaGridSmokeSolver3
 // Prints one JSON line with the deviations from the stock run.  Built by adapters/Makefile next to dropin_check;
 // tests/test_gpu_zz_dropin_next.py runs it (first GPU run pending, see that file).
 //
-//     dropin_check_next [--n 16] [--frames 3] [--levels 3] [--what collider|pillars|tank|smoke]
+//     dropin_check_next [--n 16] [--frames 3] [--levels 3] [--what collider|pillars|tank|emit|smoke]
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -89,6 +91,43 @@ int runCollider(const Options& opt) {
     return 0;
 }
 
+int runEmit(const Options& opt) {
+    const double h = 1.0 / static_cast<double>(opt.n);
+    auto stock = std::make_shared<FlipSolver3>(Size3(opt.n, opt.n, opt.n), Vector3D(h, h, h), Vector3D());
+    {
+        auto pressure = std::make_shared<GridFractionalSinglePhasePressureSolver3>();
+        pressure->setLinearSystemSolver(std::make_shared<FdmMgpcgSolver3>(100, opt.levels, 5, 5, 20, 20, 1e-9, 1.5, true));
+        stock->setPressureSolver(pressure);
+    }
+    stock->setUseCompressedLinearSystem(false);
+    auto cuda = std::make_shared<jetcu::CudaFlipSolver3>(Size3(opt.n, opt.n, opt.n), Vector3D(h, h, h), Vector3D(),
+                                                         jetcu::makeMgpcgParams(100, opt.levels, 5, 5, 20, 20, 1e-9, 1.5, true));
+    const BoundingBox3D domain = stock->gridSystemData()->boundingBox();
+    auto plane = Plane3::builder().withNormal({0, 1, 0}).withPoint({0, 0.25 * domain.height(), 0}).makeShared();
+    auto sphere = Sphere3::builder().withCenter(domain.midPoint()).withRadius(0.15 * domain.width()).makeShared();
+    auto e1 = VolumeParticleEmitter3::builder().withSurface(plane).withSpacing(0.5 * h).withMaxRegion(domain).withIsOneShot(true).makeShared();
+    e1->setPointGenerator(std::make_shared<GridPointGenerator3>());
+    auto e2 = VolumeParticleEmitter3::builder().withSurface(sphere).withSpacing(0.5 * h).withMaxRegion(domain).withIsOneShot(true).makeShared();
+    e2->setPointGenerator(std::make_shared<GridPointGenerator3>());
+    stock->setParticleEmitter(ParticleEmitterSet3::builder().withEmitters({e1, e2}).makeShared());
+    const size_t emitted = cuda->emitOnDevice(plane, 0.5 * h) + cuda->emitOnDevice(sphere, 0.5 * h);
+    for (Frame frame(0, 1.0 / 60.0); frame.index < opt.frames; ++frame) {
+        stock->update(frame);
+        cuda->update(frame);
+    }
+    auto ps = stock->particleSystemData();
+    auto pc = cuda->particleSystemData();
+    const size_t n = ps->numberOfParticles();
+    if (pc->numberOfParticles() != n || emitted != n) { std::fprintf(stderr, "particle counts differ: %zu %zu %zu\n", n, pc->numberOfParticles(), emitted); return 1; }
+    double maxDx = 0.0;
+    for (size_t i = 0; i < n; ++i) {
+        const Vector3D d = ps->positions()[i] - pc->positions()[i];
+        maxDx = std::max(maxDx, std::max(std::fabs(d.x), std::max(std::fabs(d.y), std::fabs(d.z))));
+    }
+    std::printf("{\"what\": \"emit\", \"n\": %zu, \"frames\": %d, \"particles\": %zu, \"max_dx\": %.3e}\n", opt.n, opt.frames, n, maxDx);
+    return 0;
+}
+
 template <class Solver>
 void setupSmoke(const std::shared_ptr<Solver>& solver, const Options& opt) {
     solver->setUseCompressedLinearSystem(false);
@@ -153,6 +192,7 @@ int main(int argc, char** argv) {
     Logging::mute();
     try {
         if (opt.what == "collider" || opt.what == "pillars" || opt.what == "tank") return runCollider(opt);
+        if (opt.what == "emit") return runEmit(opt);
         if (opt.what == "smoke") return runSmoke(opt);
         std::fprintf(stderr, "unknown check %s\n", opt.what.c_str());
         return 2;

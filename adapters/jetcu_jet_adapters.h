@@ -317,6 +317,27 @@ class CudaHybridSolver3 : public Base {
 
     const jetcu_step_stats& lastStepStats() const { return _stats; }
 
+    //! Device-side equivalent of attaching a one-shot jet::VolumeParticleEmitter3 (GridPointGenerator3, jitter 0, maxRegion =
+    //! the domain, as src/examples/hybrid_liquid_sim sets its emitters up) over `surface` and letting it fire: the lattice is
+    //! generated, tested against the surface and appended on the GPU in the reference's emission order
+    //! (jetcu_hybrid_emit_shapes) — no host lattice, no upload.  `surface`: Box3 / Sphere3 / Cylinder3 / Plane3 or an
+    //! ImplicitSurfaceSet3 of them.  Returns the number of particles emitted.  kEveryStep refreshes the host mirror;
+    //! kOnDemand only resizes it (values arrive with syncToHost()).
+    size_t emitOnDevice(const jet::Surface3Ptr& surface, double spacing, const jet::Vector3D& initialVelocity = jet::Vector3D()) {
+        ensureDevice();
+        uploadIfNeeded();
+        std::vector<jetcu_collider_shape> shapes;
+        int asSet = 0;
+        collectShapes(surface, &shapes, &asSet);
+        const double v0[3] = {initialVelocity.x, initialVelocity.y, initialVelocity.z};
+        uint64_t n = 0;
+        _ctx->check(jetcu_hybrid_emit_shapes(_h, shapes.data(), (uint32_t)shapes.size(), asSet, spacing, v0, &n));
+        _deviceCount += n;
+        if (_mirror == HostMirror::kEveryStep) syncToHost();
+        else this->particleSystemData()->resize(_deviceCount);
+        return (size_t)n;
+    }
+
  protected:
     void onAdvanceTimeStep(double timeIntervalInSeconds) override {
         auto grids = this->gridSystemData();
@@ -442,6 +463,27 @@ class CudaHybridSolver3 : public Base {
         return s;
     }
 
+    //! One explicit surface, or the members of an ImplicitSurfaceSet3 (asSet = 1), as jetcu_collider_shape records.
+    static void collectShapes(const jet::Surface3Ptr& surface, std::vector<jetcu_collider_shape>* shapes, int* asSet) {
+        shapes->clear();
+        *asSet = 0;
+        if (auto set = std::dynamic_pointer_cast<jet::ImplicitSurfaceSet3>(surface)) {
+            if (set->isNormalFlipped || !identityTransform(set->transform))
+                throw std::runtime_error("jetcu: a device surface set needs an identity transform and unflipped normals");
+            if (set->numberOfSurfaces() == 0 || set->numberOfSurfaces() > JETCU_COLLIDER_MAX_SHAPES)
+                throw std::runtime_error("jetcu: a device surface set holds 1.." + std::to_string(JETCU_COLLIDER_MAX_SHAPES) + " surfaces");
+            for (size_t i = 0; i < set->numberOfSurfaces(); ++i) {
+                auto wrap = std::dynamic_pointer_cast<jet::SurfaceToImplicit3>(set->surfaceAt(i));
+                if (!wrap || wrap->isNormalFlipped || !identityTransform(wrap->transform))
+                    throw std::runtime_error("jetcu: surface set members must be explicit surfaces (addExplicitSurface)");
+                shapes->push_back(shapeOf(wrap->surface()));
+            }
+            *asSet = 1;
+        } else {
+            shapes->push_back(shapeOf(surface));
+        }
+    }
+
     void syncCollider() {
         const jet::Collider3Ptr col = this->collider();
         if (col == nullptr) {
@@ -451,24 +493,9 @@ class CudaHybridSolver3 : public Base {
         }
         auto rigid = std::dynamic_pointer_cast<jet::RigidBodyCollider3>(col);
         if (!rigid) throw std::runtime_error("jetcu: only RigidBodyCollider3 colliders run on the device");
-        const jet::Surface3Ptr surface = rigid->surface();
         std::vector<jetcu_collider_shape> shapes;
         int asSet = 0;
-        if (auto set = std::dynamic_pointer_cast<jet::ImplicitSurfaceSet3>(surface)) {
-            if (set->isNormalFlipped || !identityTransform(set->transform))
-                throw std::runtime_error("jetcu: a device collider set needs an identity transform and unflipped normals");
-            if (set->numberOfSurfaces() == 0 || set->numberOfSurfaces() > JETCU_COLLIDER_MAX_SHAPES)
-                throw std::runtime_error("jetcu: a device collider set holds 1.." + std::to_string(JETCU_COLLIDER_MAX_SHAPES) + " surfaces");
-            for (size_t i = 0; i < set->numberOfSurfaces(); ++i) {
-                auto wrap = std::dynamic_pointer_cast<jet::SurfaceToImplicit3>(set->surfaceAt(i));
-                if (!wrap || wrap->isNormalFlipped || !identityTransform(wrap->transform))
-                    throw std::runtime_error("jetcu: collider set members must be explicit surfaces (addExplicitSurface)");
-                shapes.push_back(shapeOf(wrap->surface()));
-            }
-            asSet = 1;
-        } else {
-            shapes.push_back(shapeOf(surface));
-        }
+        collectShapes(rigid->surface(), &shapes, &asSet);
         const double lin[3] = {rigid->linearVelocity.x, rigid->linearVelocity.y, rigid->linearVelocity.z};
         const double ang[3] = {rigid->angularVelocity.x, rigid->angularVelocity.y, rigid->angularVelocity.z};
         const double fr = col->frictionCoefficient();

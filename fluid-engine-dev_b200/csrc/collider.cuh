@@ -513,6 +513,29 @@ inline void cd_build_set(ColliderD& c) {
     cd_bvh_build(c, 0, idx, c.nitems, blo, bhi);
 }
 
+// VolumeParticleEmitter3::emit's region (src/jet/volume_particle_emitter3.cpp:74-79): maxRegion [lo, hi] ∩ the implicit
+// surface's boundingBox() when the surface is bounded (no Plane3 member).  The surface is SurfaceToImplicit3(shape) for one
+// explicit surface, the set itself otherwise: Surface3::boundingBox() = toWorld(_bvh.boundingBox()), the merge of the members.
+inline void cd_emit_region(const ColliderD& e, double* lo, double* hi) {
+    for (int i = 0; i < e.n; ++i)
+        if (e.s[i].kind == JC_SHAPE_PLANE) return;
+    double sl[3], sh[3];
+    if (e.is_set) {
+        double ml[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mh[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+        for (int i = 0; i < e.n; ++i) {
+            double bl[3], bh[3];
+            cd_shape_bounding_box(e.s[i], bl, bh);
+            for (int a = 0; a < 3; ++a) { ml[a] = cd_min(ml[a], bl[a]); mh[a] = cd_max(mh[a], bh[a]); }
+        }
+        cd_bbox_to_world(ml, mh, sl, sh);
+    } else {
+        cd_shape_bounding_box(e.s[0], sl, sh);
+    }
+    for (int a = 0; a < 3; ++a) { lo[a] = cd_max(lo[a], sl[a]); hi[a] = cd_min(hi[a], sh[a]); }
+}
+// ... and its acceptance test at lattice point p (jitter 0): _implicitSurface->signedDistance(p) <= 0 (:93)
+__host__ __device__ __forceinline__ bool cd_emit_accept(const ColliderD& e, const double* p) { return cd_signed_distance(e, p) <= 0.0; }
+
 // The ColliderD of jetcu_hybrid_set_collider_shapes' arguments (already validated): members, rigid-body velocity, friction
 // clamped at 0 as Collider3::setFrictionCoefficient does (collider3.cpp:78-80), and — for a set — the Bvh3, built once:
 // Collider3::update -> updateQueryEngine -> buildBvh gives the same tree at every step for a static set.

@@ -692,6 +692,23 @@ __global__ void k_emit_flags(uint32_t* __restrict__ flags, uint32_t* __restrict_
     }
 }
 
+// the same for an analytic implicit surface (one explicit surface or an ImplicitSurfaceSet3): signedDistance(p) <= 0
+__global__ void k_emit_flags_shapes(uint32_t* __restrict__ flags, uint32_t* __restrict__ mine, size_t total, unsigned cx, unsigned cy,
+                                    double spacing, double lx, double ly, double lz, ColliderD e, double oz, double ihz, int nz,
+                                    int z0, int z1) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > total) return;
+    if (t == total) { flags[t] = 0; if (mine) mine[t] = 0; return; }
+    double p[3];
+    lattice_point(t, cx, cy, spacing, lx, ly, lz, p);
+    const bool acc = cd_emit_accept(e, p);
+    flags[t] = acc ? 1u : 0u;
+    if (mine) {
+        const int ck = cell_coord(p[2], oz, ihz, nz);
+        mine[t] = (acc && ck >= z0 && ck < z1) ? 1u : 0u;
+    }
+}
+
 // slot = exclusive scan of flags (position in the reference's emission order = the particle's original index),
 // local = exclusive scan of mine (position among this rank's particles; == slot on a single GPU)
 __global__ void k_emit_lattice(double* __restrict__ x, double* __restrict__ y, double* __restrict__ z, double* __restrict__ vx,
@@ -1217,29 +1234,12 @@ int jetcu_hybrid_set_local_particles(jetcu_hybrid* h, uint64_t n_local, const ui
     return JETCU_OK;
 }
 
-int jetcu_hybrid_emit_box(jetcu_hybrid* h, const double lower[3], const double upper[3], double spacing,
-                          const double v0[3], uint64_t* n_emitted) {
-    HYB_ENTER(h);
-    JC_ARG(ctx, lower && upper && spacing > 0);
+// Emission over the lattice of region [lo, hi] (GridPointGenerator3::forEachPoint, src/jet/grid_point_generator3.cpp:15-38):
+// flag kernel (box fast path or analytic surface) -> exclusive scan = the reference's emission order -> compaction.
+static int hyb_emit_lattice(jetcu_hybrid* h, const double lo[3], const double hi[3], double spacing, const double v0[3],
+                            uint64_t* n_emitted, const Box3d* box, const ColliderD* surf) {
+    jetcu_ctx* ctx = h->ctx;
     const jetcu_grid& g = h->P.grid;
-    // region = box ∩ domain bounding box (VolumeParticleEmitter3::emit, src/jet/volume_particle_emitter3.cpp:74-79)
-    double dlo[3] = {g.ox, g.oy, g.oz};
-    double dhi[3] = {g.ox + g.hx * (double)g.nx, g.oy + g.hy * (double)g.ny, g.oz + g.hz * (double)g.nz};
-    double lo[3], hi[3];
-    Box3d bx;
-    for (int a = 0; a < 3; ++a) {
-        // ImplicitSurface3::boundingBox() = Transform3::toWorld applied twice (Box3's and SurfaceToImplicit3's identity
-        // transforms: src/jet/surface3.cpp:27-29, surface_to_implicit3.cpp:63-65); each pass rebuilds the corners as
-        // size * (-+1/2) + midPoint (include/jet/detail/bounding_box3-inl.h:150-152,201-208), which is not exact.
-        double l = lower[a], u = upper[a];
-        for (int pass = 0; pass < 2; ++pass) {
-            double w = u - l, mid = (u + l) / 2.0;
-            double c0 = w * -0.5 + mid, c1 = w * 0.5 + mid;
-            l = fmin(c0, c1); u = fmax(c0, c1);
-        }
-        lo[a] = fmax(dlo[a], l); hi[a] = fmin(dhi[a], u);
-        bx.lo[a] = lower[a]; bx.hi[a] = upper[a];
-    }
     unsigned cnt[3];
     for (int a = 0; a < 3; ++a) {
         double width = hi[a] - lo[a];
@@ -1257,8 +1257,14 @@ int jetcu_hybrid_emit_box(jetcu_hybrid* h, const double lower[3], const double u
         int rc = JETCU_OK;
         if (slab) rc = jc_alloc(ctx, &mine, total + 1);
         if (rc == JETCU_OK) {
-            k_emit_flags<<<jc_blocks(total + 1, 256), 256, 0, ctx->stream>>>(slot, mine, (size_t)total, cnt[0], cnt[1], spacing, lo[0],
-                                                                              lo[1], lo[2], bx, g.oz, 1.0 / g.hz, h->nz, h->z0, h->z1);
+            if (box)
+                k_emit_flags<<<jc_blocks(total + 1, 256), 256, 0, ctx->stream>>>(slot, mine, (size_t)total, cnt[0], cnt[1], spacing,
+                                                                                  lo[0], lo[1], lo[2], *box, g.oz, 1.0 / g.hz, h->nz,
+                                                                                  h->z0, h->z1);
+            else
+                k_emit_flags_shapes<<<jc_blocks(total + 1, 256), 256, 0, ctx->stream>>>(slot, mine, (size_t)total, cnt[0], cnt[1],
+                                                                                         spacing, lo[0], lo[1], lo[2], *surf, g.oz,
+                                                                                         1.0 / g.hz, h->nz, h->z0, h->z1);
             ctx->launches++;
             rc = scan_exclusive_u32(ctx, slot, slot, total + 1);
         }
@@ -1291,6 +1297,50 @@ int jetcu_hybrid_emit_box(jetcu_hybrid* h, const double lower[3], const double u
     h->binned = false;
     if (n_emitted) *n_emitted = accepted;
     return jc_sync(ctx);
+}
+
+int jetcu_hybrid_emit_box(jetcu_hybrid* h, const double lower[3], const double upper[3], double spacing,
+                          const double v0[3], uint64_t* n_emitted) {
+    HYB_ENTER(h);
+    JC_ARG(ctx, lower && upper && spacing > 0);
+    const jetcu_grid& g = h->P.grid;
+    // region = box ∩ domain bounding box (VolumeParticleEmitter3::emit, src/jet/volume_particle_emitter3.cpp:74-79)
+    double dlo[3] = {g.ox, g.oy, g.oz};
+    double dhi[3] = {g.ox + g.hx * (double)g.nx, g.oy + g.hy * (double)g.ny, g.oz + g.hz * (double)g.nz};
+    double lo[3], hi[3];
+    Box3d bx;
+    for (int a = 0; a < 3; ++a) {
+        // ImplicitSurface3::boundingBox() = Transform3::toWorld applied twice (Box3's and SurfaceToImplicit3's identity
+        // transforms: src/jet/surface3.cpp:27-29, surface_to_implicit3.cpp:63-65); each pass rebuilds the corners as
+        // size * (-+1/2) + midPoint (include/jet/detail/bounding_box3-inl.h:150-152,201-208), which is not exact.
+        double l = lower[a], u = upper[a];
+        for (int pass = 0; pass < 2; ++pass) {
+            double w = u - l, mid = (u + l) / 2.0;
+            double c0 = w * -0.5 + mid, c1 = w * 0.5 + mid;
+            l = fmin(c0, c1); u = fmax(c0, c1);
+        }
+        lo[a] = fmax(dlo[a], l); hi[a] = fmin(dhi[a], u);
+        bx.lo[a] = lower[a]; bx.hi[a] = upper[a];
+    }
+    return hyb_emit_lattice(h, lo, hi, spacing, v0, n_emitted, &bx, nullptr);
+}
+
+// VolumeParticleEmitter3 over an analytic implicit surface: the emitters of the hybrid_liquid_sim examples —
+// half-space + sphere (main.cpp:110-141), a set of two boxes (:220-246) — on the device, in the reference's order.
+int jetcu_hybrid_emit_shapes(jetcu_hybrid* h, const jetcu_collider_shape* shapes, uint32_t n, int as_set, double spacing,
+                             const double v0[3], uint64_t* n_emitted) {
+    HYB_ENTER(h);
+    JC_ARG(ctx, shapes && n >= 1 && n <= JC_COLLIDER_MAX_SHAPES && spacing > 0 && (n == 1 || as_set));
+    for (uint32_t i = 0; i < n; ++i) {
+        JC_ARG(ctx, shapes[i].kind >= JETCU_COLLIDER_BOX && shapes[i].kind <= JETCU_COLLIDER_PLANE);
+        if (shapes[i].kind == JETCU_COLLIDER_SPHERE || shapes[i].kind == JETCU_COLLIDER_CYLINDER) JC_ARG(ctx, shapes[i].b[0] > 0.0);
+    }
+    const ColliderD e = cd_make_collider(shapes, n, as_set, nullptr, nullptr, 0.0);
+    const jetcu_grid& g = h->P.grid;
+    double lo[3] = {g.ox, g.oy, g.oz};
+    double hi[3] = {g.ox + g.hx * (double)g.nx, g.oy + g.hy * (double)g.ny, g.oz + g.hz * (double)g.nz};
+    cd_emit_region(e, lo, hi);
+    return hyb_emit_lattice(h, lo, hi, spacing, v0, n_emitted, nullptr, &e);
 }
 
 uint64_t jetcu_hybrid_num_particles(const jetcu_hybrid* h) { return h ? h->nglobal : 0; }

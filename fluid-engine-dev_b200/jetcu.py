@@ -382,6 +382,26 @@ class HybridApi:
 
     SHAPE_KINDS = {"box": 1, "sphere": 2, "cylinder": 3, "plane": 4}
 
+    def _shape_array(self, shapes):
+        arr = (ColliderShape * max(len(shapes), 1))()
+        for i, sh in enumerate(shapes):
+            arr[i].kind = self.SHAPE_KINDS[sh["kind"]]
+            arr[i].flipped = 1 if sh.get("flipped", False) else 0
+            arr[i].a = (f64 * 3)(*sh["a"])
+            b = tuple(sh.get("b", (0.0, 0.0, 0.0))) + (0.0, 0.0, 0.0)
+            arr[i].b = (f64 * 3)(*b[:3])
+        return arr
+
+    def emit_shapes(self, shapes, spacing, initial_velocity=(0.0, 0.0, 0.0), as_set=None):
+        """VolumeParticleEmitter3 (one shot, jitter 0, GridPointGenerator3, maxRegion = the domain) over one analytic surface
+        or an ImplicitSurfaceSet3 of them (dicts as for set_collider_shapes); returns the number of particles emitted."""
+        if as_set is None:
+            as_set = len(shapes) != 1
+        n = u64(0)
+        self._c("hybrid_emit_shapes", self.h, self._shape_array(shapes), u32(len(shapes)), C.c_int(1 if as_set else 0),
+                f64(spacing), (f64 * 3)(*initial_velocity), C.byref(n))
+        return int(n.value)
+
     def set_collider_shapes(self, shapes, as_set=True, linear_velocity=(0.0, 0.0, 0.0), angular_velocity=(0.0, 0.0, 0.0),
                             friction=0.0):
         """RigidBodyCollider3 over analytic surfaces with identity transforms.  `shapes`: dicts with
@@ -389,13 +409,7 @@ class HybridApi:
         b[0] = radius, b[1] = height, axis y) | "plane" (a = point, b = unit normal), optional flipped=True
         (Surface3::isNormalFlipped).  as_set: the collider's surface is an ImplicitSurfaceSet3 of them (required for more
         than one); otherwise the single surface itself.  An empty list removes the collider."""
-        arr = (ColliderShape * max(len(shapes), 1))()
-        for i, sh in enumerate(shapes):
-            arr[i].kind = self.SHAPE_KINDS[sh["kind"]]
-            arr[i].flipped = 1 if sh.get("flipped", False) else 0
-            arr[i].a = (f64 * 3)(*sh["a"])
-            arr[i].b = (f64 * 3)(*sh.get("b", (0.0, 0.0, 0.0)))
-        self._c("hybrid_set_collider_shapes", self.h, arr, u32(len(shapes)), C.c_int(1 if as_set else 0),
+        self._c("hybrid_set_collider_shapes", self.h, self._shape_array(shapes), u32(len(shapes)), C.c_int(1 if as_set else 0),
                 (f64 * 3)(*linear_velocity), (f64 * 3)(*angular_velocity), f64(friction))
 
     def set_collider_shape(self, kind, a=(0.0, 0.0, 0.0), b=(0.0, 0.0, 0.0), linear_velocity=(0.0, 0.0, 0.0),

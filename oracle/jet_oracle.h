@@ -95,9 +95,6 @@ int jeto_hybrid_destroy(jeto_hybrid*);
 int jeto_hybrid_set_particles(jeto_hybrid*, uint64_t n, const double* positions, const double* velocities);
 int jeto_hybrid_emit_box(jeto_hybrid*, const double lower[3], const double upper[3], double spacing,
                          const double initial_velocity[3], uint64_t* n_emitted);
-uint64_t jeto_hybrid_num_particles(const jeto_hybrid*);
-int jeto_hybrid_get_particles(jeto_hybrid*, double* positions, double* velocities);
-int jeto_hybrid_get_affine(jeto_hybrid*, double* cx, double* cy, double* cz);
 /* Analytic rigid collider (RigidBodyCollider3, identity transforms) for the hybrid solver.  One explicit surface, or an
  * ImplicitSurfaceSet3 of explicit surfaces (as_set != 0; needed for n > 1):
  *   kind 1 Box3 (a = lower corner, b = upper corner), 2 Sphere3 (a = centre, b[0] = radius),
@@ -107,6 +104,13 @@ typedef struct jeto_collider_shape {
     int32_t kind, flipped;
     double a[3], b[3];
 } jeto_collider_shape;
+/* VolumeParticleEmitter3 (one shot, jitter 0, GridPointGenerator3, maxRegion = domain) over one explicit surface or an
+ * ImplicitSurfaceSet3 of them (shapes as for jeto_hybrid_set_collider_shapes). */
+int jeto_hybrid_emit_shapes(jeto_hybrid*, const jeto_collider_shape* shapes, uint32_t n, int as_set, double spacing,
+                            const double initial_velocity[3], uint64_t* n_emitted);
+uint64_t jeto_hybrid_num_particles(const jeto_hybrid*);
+int jeto_hybrid_get_particles(jeto_hybrid*, double* positions, double* velocities);
+int jeto_hybrid_get_affine(jeto_hybrid*, double* cx, double* cy, double* cz);
 int jeto_hybrid_set_collider_shapes(jeto_hybrid*, const jeto_collider_shape* shapes, uint32_t n, int as_set,
                                     const double linear_velocity[3], const double angular_velocity[3], double friction);
 /* shorthand for one un-flipped box (kind 1) or sphere (kind 2); kind 0 removes the collider */

@@ -407,6 +407,39 @@ int jeto_hybrid_set_collider_shape(jeto_hybrid* h, int kind, const double a[3], 
     return jeto_hybrid_set_collider_shapes(h, &s, 1, 0, lin, ang, friction);
 }
 
+int jeto_hybrid_emit_shapes(jeto_hybrid* h, const jeto_collider_shape* shapes, uint32_t n, int as_set, double spacing,
+                            const double v0[3], uint64_t* n_emitted) {
+    if (n == 0 || (n != 1 && !as_set)) return 1;
+    auto ps = h->solver->particleSystemData();
+    size_t before = ps->numberOfParticles();
+    Surface3Ptr surface;
+    if (as_set) {
+        std::vector<Surface3Ptr> members;
+        for (uint32_t i = 0; i < n; ++i) {
+            auto m = makeShape(shapes[i]);
+            if (!m) return 1;
+            members.push_back(m);
+        }
+        surface = ImplicitSurfaceSet3::builder().withExplicitSurfaces(members).makeShared();   // as main.cpp:236-238
+    } else {
+        surface = makeShape(shapes[0]);
+        if (!surface) return 1;
+    }
+    auto emitter = VolumeParticleEmitter3::builder()
+                       .withSurface(surface)
+                       .withMaxRegion(h->solver->gridSystemData()->boundingBox())
+                       .withSpacing(spacing)
+                       .withInitialVelocity(v0 ? Vector3D(v0[0], v0[1], v0[2]) : Vector3D())
+                       .withIsOneShot(true)
+                       .withJitter(0.0)
+                       .makeShared();
+    emitter->setPointGenerator(std::make_shared<GridPointGenerator3>());
+    emitter->setTarget(ps);
+    emitter->update(0.0, 0.0);
+    if (n_emitted) *n_emitted = ps->numberOfParticles() - before;
+    return 0;
+}
+
 int jeto_hybrid_get_collider_sdf(jeto_hybrid* h, double* sdf) {
     auto field = h->solver->colliderSdf();
     auto grid = std::dynamic_pointer_cast<CellCenteredScalarGrid3>(field);

@@ -15,7 +15,7 @@ import pytest
 import golden_cases as gc
 from gpu_common import checker, jetcu_or_fail
 from oracle_api import APIC, FLIP, PIC, Grid, HybridParams, MgpcgParams
-from test_oracle_collider import ALL, COLLIDERS, SETS, STEP_CASES, install
+from test_oracle_collider import ALL, COLLIDERS, EMITTERS, SETS, STEP_CASES, install
 
 pytestmark = pytest.mark.gpu
 
@@ -95,3 +95,19 @@ def test_steps_with_collider(jc, oracle, mode, name):
 @pytest.mark.parametrize("name", sorted(gc.COLLIDER_CASES))
 def test_golden_collider(jc, name):
     gc.collider(jc.hybrid, name, exact_bits=False)
+
+
+@pytest.mark.parametrize("name", sorted(EMITTERS))
+def test_emit_shapes(jc, oracle, name):
+    """Device-side VolumeParticleEmitter3 over analytic surfaces (jetcu_hybrid_emit_shapes): same points, same order."""
+    n = 16
+    prm = HybridParams.make(Grid.cube(n), mode=PIC, mgpcg=MgpcgParams.make(max_levels=2))
+    a, b = jc.hybrid(prm), oracle.hybrid(prm)
+    na, nb = a.emit_shapes(EMITTERS[name], 0.5 / n, (0.1, 0.0, -0.2)), b.emit_shapes(EMITTERS[name], 0.5 / n, (0.1, 0.0, -0.2))
+    (pa, va), (pb, vb) = a.get_particles(), b.get_particles()
+    if any(m["kind"] == "cylinder" for m in EMITTERS[name]):   # atan2 / cos / sin: a point exactly on the surface may flip
+        assert abs(na - nb) <= 2
+    else:
+        assert na == nb
+        exact(pa, pb, "emitted positions"); exact(va, vb, "emitted velocities")
+    a.close(); b.close()

@@ -225,6 +225,34 @@ int hc_extrapolate_into_collider(const jetcu_grid* grid, const jetcu_collider_sh
     return 0;
 }
 
+// jetcu_hybrid_emit_shapes: cd_emit_region + the lattice loop of hyb_emit_lattice with k_emit_flags_shapes' acceptance test.
+// Call with pos == NULL to count; returns the number of accepted points through *n_out.
+int hc_emit_shapes(const jetcu_grid* g, const jetcu_collider_shape* shapes, uint32_t ns, int as_set, double spacing, double* pos,
+                   uint64_t* n_out) {
+    const ColliderD e = cd_make_collider(shapes, ns, as_set, nullptr, nullptr, 0.0);
+    double lo[3] = {g->ox, g->oy, g->oz};
+    double hi[3] = {g->ox + g->hx * (double)g->nx, g->oy + g->hy * (double)g->ny, g->oz + g->hz * (double)g->nz};
+    cd_emit_region(e, lo, hi);
+    unsigned cnt[3];
+    for (int a = 0; a < 3; ++a) {
+        double width = hi[a] - lo[a];
+        unsigned c = 0;
+        for (int i = 0; i * spacing <= width; ++i) ++c;
+        cnt[a] = c;
+    }
+    const size_t total = (size_t)cnt[0] * cnt[1] * cnt[2];
+    uint64_t o = 0;
+    for (size_t t = 0; t < total; ++t) {
+        const int i = (int)(t % cnt[0]), j = (int)((t / cnt[0]) % cnt[1]), k = (int)(t / ((size_t)cnt[0] * cnt[1]));
+        const double p[3] = {i * spacing + lo[0], j * spacing + lo[1], k * spacing + lo[2]};   // lattice_point() of hybrid.cu
+        if (!cd_emit_accept(e, p)) continue;
+        if (pos) { pos[3 * o] = p[0]; pos[3 * o + 1] = p[1]; pos[3 * o + 2] = p[2]; }
+        ++o;
+    }
+    *n_out = o;
+    return 0;
+}
+
 // k_resolve_collision over n AoS particles
 int hc_resolve_collision(const jetcu_collider_shape* shapes, uint32_t ns, int as_set, const double* lin, const double* ang, double friction,
                          uint64_t n, double* pos, double* vel) {

@@ -36,6 +36,13 @@ def test_example_colliders_match_stock_jet(what):
     assert out["max_dx"] <= 1e-5, out
 
 
+def test_device_emission_matches_host_emitters():
+    """Example 1 / 2's emitter set (half-space + sphere) on the host vs CudaFlipSolver3::emitOnDevice, then 3 frames."""
+    out = run("--what", "emit", "--n", 32, "--frames", 3, "--levels", 4)
+    assert out["particles"] > 10000
+    assert out["max_dx"] <= 1e-5, out
+
+
 def test_smoke_matches_stock_jet():
     out = run("--what", "smoke", "--n", 32, "--frames", 5, "--levels", 4)
     assert out["velocity_scale"] > 0.05        # the plume really rose

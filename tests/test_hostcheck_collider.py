@@ -11,7 +11,7 @@ import pytest
 
 from oracle_api import FLIP, PIC, Grid, HybridParams, MgpcgParams, have_port, load_port
 from oracle_api import ColliderShape
-from test_oracle_collider import ALL, COLLIDERS, SETS, install
+from test_oracle_collider import ALL, COLLIDERS, EMITTERS, SETS, install
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -184,3 +184,31 @@ def test_extrapolate_sdf_into_collider(hc, port, name):
     assert hc.hc_extrapolate_into_collider(C.byref(grid), *shape_args(name), C.c_double(prm.max_cfl), dp(got)) == 0
     exact(got, want, "sdf extrapolated into the collider")
     raw_h.close(); col_h.close()
+
+
+@pytest.mark.parametrize("name", sorted(EMITTERS))
+@pytest.mark.parametrize("n,domain", [(16, 1.0), (10, 0.9)])
+def test_emit_shapes(hc, port, name, n, domain):
+    """Device emission (region, lattice, acceptance) == VolumeParticleEmitter3 as restated by the oracle, point for point."""
+    grid = Grid.cube(n, domain)
+    h = port.hybrid(HybridParams.make(grid, mode=PIC, mgpcg=MgpcgParams.make(max_levels=2)))
+    shapes = EMITTERS[name]
+    spacing = 0.5 * domain / n
+    count = h.emit_shapes(shapes, spacing)
+    want, _ = h.get_particles()
+    assert count == len(want) and count > 100
+    arr = (ColliderShape * len(shapes))()
+    for i, sh in enumerate(shapes):
+        arr[i].kind = KINDS[sh["kind"]]; arr[i].flipped = 1 if sh.get("flipped", False) else 0
+        arr[i].a = (C.c_double * 3)(*sh["a"])
+        b = tuple(sh.get("b", (0.0, 0.0, 0.0))) + (0.0, 0.0, 0.0)
+        arr[i].b = (C.c_double * 3)(*b[:3])
+    got = np.zeros_like(want)
+    n_out = C.c_uint64(0)
+    assert hc.hc_emit_shapes(C.byref(grid), arr, C.c_uint32(len(shapes)), C.c_int(int(len(shapes) != 1)), C.c_double(spacing), None,
+                             C.byref(n_out)) == 0
+    assert n_out.value == count
+    assert hc.hc_emit_shapes(C.byref(grid), arr, C.c_uint32(len(shapes)), C.c_int(int(len(shapes) != 1)), C.c_double(spacing),
+                             dp(got), C.byref(n_out)) == 0
+    exact(got, want, "emitted positions")
+    h.close()

@@ -162,3 +162,35 @@ def test_stage_order_with_collider(libs, name):
     pa, va = a.get_particles(); pb, vb = b.get_particles()
     same(pa, pb, "positions"); same(va, vb, "velocities")
     a.close(); b.close()
+
+
+EMITTERS = {   # the emitters of src/examples/hybrid_liquid_sim (half-space + sphere; two boxes) and every other kind
+    "sphere": [dict(kind="sphere", a=(0.5, 0.5, 0.5), b=(0.3, 0.0, 0.0))],
+    "half_space": [dict(kind="plane", a=(0.0, 0.25, 0.0), b=(0.0, 1.0, 0.0))],
+    "cylinder": [dict(kind="cylinder", a=(0.4, 0.3, 0.6), b=(0.2, 0.5))],
+    "box": [dict(kind="box", a=(0.0, 0.0, 0.0), b=(0.5, 0.9375, 1.0))],
+    "two_boxes": [dict(kind="box", a=(0.0, 0.0, 0.0), b=(0.17 + 0.001, 0.25 + 0.001, 0.375 + 0.001)),
+                  dict(kind="box", a=(0.83 - 0.001, 0.0, 0.125 - 0.001), b=(1.17 + 0.001, 0.25 + 0.001, 0.75 + 0.001))],
+    "mixed": [dict(kind="sphere", a=(0.5, 0.5, 0.5), b=(0.2, 0.0, 0.0)), dict(kind="plane", a=(0.0, 0.25, 0.0), b=(0.0, 1.0, 0.0)),
+              dict(kind="cylinder", a=(0.8, 0.5, 0.2), b=(0.1, 0.6))],
+    "outside_of_sphere": [dict(kind="sphere", a=(0.5, 0.5, 0.5), b=(0.3, 0.0, 0.0), flipped=True)],
+}
+
+
+@pytest.mark.parametrize("name", sorted(EMITTERS))
+@pytest.mark.parametrize("n,domain", [(16, 1.0), (10, 0.9)])
+def test_emit_shapes_bit_exact(libs, name, n, domain):
+    """VolumeParticleEmitter3 (one shot, jitter 0, GridPointGenerator3, maxRegion = domain) over analytic surfaces: the
+    restatement emits the same points in the same order as the unmodified reference."""
+    ref, port = libs
+    prm = HybridParams.make(Grid.cube(n, domain), mode=PIC, mgpcg=MgpcgParams.make(max_levels=2))
+    a, b = ref.hybrid(prm), port.hybrid(prm)
+    spacing = 0.5 * domain / n
+    na, nb = a.emit_shapes(EMITTERS[name], spacing, (0.1, 0.0, -0.2)), b.emit_shapes(EMITTERS[name], spacing, (0.1, 0.0, -0.2))
+    assert na == nb and na > 100
+    (pa, va), (pb, vb) = a.get_particles(), b.get_particles()
+    same(pa, pb, "emitted positions"); same(va, vb, "emitted velocities")
+    # a second emitter appends (ParticleEmitterSet3: one after the other)
+    assert a.emit_shapes(EMITTERS["sphere"], spacing) == b.emit_shapes(EMITTERS["sphere"], spacing)
+    same(a.get_particles()[0], b.get_particles()[0], "positions after the second emitter")
+    a.close(); b.close()

@@ -317,6 +317,15 @@ class CudaHybridSolver3 : public Base {
 
     const jetcu_step_stats& lastStepStats() const { return _stats; }
 
+    //! saveParticleAsPos / saveParticleAsXyz of src/examples/hybrid_liquid_sim/main.cpp:29-63 (format JETCU_FRAME_POS /
+    //! JETCU_FRAME_XYZ), byte-identical files, written from the device-resident particle set without refreshing the
+    //! host mirror.
+    void saveParticles(const std::string& path, int format) {
+        ensureDevice();
+        uploadIfNeeded();
+        _ctx->check(jetcu_hybrid_save_positions(_h, path.c_str(), format));
+    }
+
     //! Device-side equivalent of attaching a one-shot jet::VolumeParticleEmitter3 (GridPointGenerator3, jitter 0, maxRegion =
     //! the domain, as src/examples/hybrid_liquid_sim sets its emitters up) over `surface` and letting it fire: the lattice is
     //! generated, tested against the surface and appended on the GPU in the reference's emission order

@@ -357,6 +357,11 @@ class HybridApi:
         self._c("hybrid_get_particles", self.h, _p(pos), _p(vel))
         return pos, vel
 
+    def save_positions(self, path, fmt="pos"):
+        """saveParticleAsPos / saveParticleAsXyz of the reference's examples (src/examples/hybrid_liquid_sim/main.cpp:29-63),
+        from the device-resident particle set; jetcu only (the oracles have no file output)."""
+        self._c("hybrid_save_positions", self.h, C.c_char_p(os.fsencode(path)), C.c_int({"pos": 0, "xyz": 1}[fmt]))
+
     def num_local_particles(self):
         return int(self._c("hybrid_num_local_particles", self.h, raw=True))
 

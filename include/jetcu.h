@@ -314,6 +314,21 @@ int jetcu_hybrid_set_collider_shapes(jetcu_hybrid*, const jetcu_collider_shape* 
 /* shorthand for one un-flipped surface of `kind`; JETCU_COLLIDER_NONE removes the collider */
 int jetcu_hybrid_set_collider_shape(jetcu_hybrid*, int kind, const double a[3], const double b[3],
                                     const double linear_velocity[3], const double angular_velocity[3], double friction);
+/* The particle frame files of the reference's examples (saveParticleAsPos / saveParticleAsXyz,
+ * src/examples/hybrid_liquid_sim/main.cpp:29-63), byte-identical to what they write for the same positions:
+ *   POS  jet::serialize(const uint8_t*, size_t, ...) (src/jet/serialization.cpp:25-38): a FlatBuffers `FlatData` table — a
+ *        fixed 24-byte frame (root offset, vtable, table, u32 length), the raw Vector3D array, zero padding to 4 bytes;
+ *   XYZ  one "x y z\n" line per particle, doubles as operator<< prints them by default ("%g").
+ * jetcu_hybrid_save_positions takes the positions from the device in the original particle order.  The remaining entry points
+ * are host-only and usable without a GPU. */
+enum { JETCU_FRAME_POS = 0, JETCU_FRAME_XYZ = 1 };
+int jetcu_hybrid_save_positions(jetcu_hybrid*, const char* path, int format);
+uint64_t jetcu_pos_frame_size(uint64_t payload_bytes);
+int jetcu_pos_frame_header(uint64_t payload_bytes, uint8_t header[24]);
+int jetcu_format_xyz(const double* positions, uint64_t n, char* out, uint64_t cap, uint64_t* out_size);
+int jetcu_write_pos_file(const char* path, const double* positions, uint64_t n);
+int jetcu_write_xyz_file(const char* path, const double* positions, uint64_t n);
+
 /* VolumeParticleEmitter3 (src/jet/volume_particle_emitter3.cpp:65-142; one shot, jitter 0, GridPointGenerator3, maxRegion =
  * the domain) over an analytic implicit surface, on the device: one explicit surface (Builder::withSurface wraps it in
  * SurfaceToImplicit3) or an ImplicitSurfaceSet3 of explicit surfaces — the emitters of src/examples/hybrid_liquid_sim

@@ -440,6 +440,28 @@ int jeto_hybrid_emit_shapes(jeto_hybrid* h, const jeto_collider_shape* shapes, u
     return 0;
 }
 
+// jet::serialize(const uint8_t*, size_t, std::vector<uint8_t>*) — src/jet/serialization.cpp:25-38 (the framing of the
+// examples' .pos files: saveParticleAsPos, src/examples/hybrid_liquid_sim/main.cpp:29-45)
+int jeto_serialize_bytes(const uint8_t* data, uint64_t size, uint8_t* out, uint64_t cap, uint64_t* out_size) {
+    std::vector<uint8_t> buffer;
+    jet::serialize(data, (size_t)size, &buffer);
+    *out_size = buffer.size();
+    if (buffer.size() > cap) return 1;
+    std::memcpy(out, buffer.data(), buffer.size());
+    return 0;
+}
+
+// what saveParticleAsXyz streams per particle (main.cpp:47-63): operator<< on doubles with the default format
+int jeto_format_xyz(const double* pos, uint64_t n, char* out, uint64_t cap, uint64_t* out_size) {
+    std::ostringstream os;
+    for (uint64_t i = 0; i < n; ++i) os << pos[3 * i] << ' ' << pos[3 * i + 1] << ' ' << pos[3 * i + 2] << std::endl;
+    const std::string s = os.str();
+    *out_size = s.size();
+    if (s.size() > cap) return 1;
+    std::memcpy(out, s.data(), s.size());
+    return 0;
+}
+
 int jeto_hybrid_get_collider_sdf(jeto_hybrid* h, double* sdf) {
     auto field = h->solver->colliderSdf();
     auto grid = std::dynamic_pointer_cast<CellCenteredScalarGrid3>(field);

@@ -111,3 +111,20 @@ def test_emit_shapes(jc, oracle, name):
         assert na == nb
         exact(pa, pb, "emitted positions"); exact(va, vb, "emitted velocities")
     a.close(); b.close()
+
+
+def test_save_positions(jc, tmp_path):
+    """.pos / .xyz frames from the device-resident set == the frame of the positions get_particles returns."""
+    n = 16
+    h = jc.hybrid(HybridParams.make(Grid.cube(n), mode=FLIP, mgpcg=MgpcgParams.make(max_levels=3)))
+    h.emit_shapes(EMITTERS["sphere"], 0.5 / n)
+    h.step(1.0 / 60.0)
+    pos, _ = h.get_particles()
+    h.save_positions(str(tmp_path / "f.pos"), "pos")
+    h.save_positions(str(tmp_path / "f.xyz"), "xyz")
+    raw = (tmp_path / "f.pos").read_bytes()
+    assert raw[:20].hex() == "0c00000000000600080004000600000004000000"
+    assert int.from_bytes(raw[20:24], "little") == pos.size * 8 and raw[24:] == pos.tobytes()
+    text = (tmp_path / "f.xyz").read_text().splitlines()
+    assert len(text) == len(pos) and text[0] == "%g %g %g" % tuple(pos[0]) and text[-1] == "%g %g %g" % tuple(pos[-1])
+    h.close()

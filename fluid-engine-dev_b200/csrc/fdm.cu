@@ -434,6 +434,19 @@ void mg_free(jetcu_ctx* ctx, MgLevels* mg) {
 // rank keeps an even number (>= 4) of planes and the level is too big for the single-CTA smoother; all coarser levels
 // are REPLICATED: their right-hand side is all-gathered once on the way down and every rank relaxes the whole (tiny)
 // level redundantly, which costs no further messages and keeps the arithmetic identical to one GPU.
+// Coarser levels than this many cells are replicated rather than slab-distributed (every result is bit-identical either
+// way; the trade is redundant smoothing on a small grid against ~10 latency-bound neighbour exchanges per level visit).
+// JETCU_SLAB_MIN_CELLS overrides the default for A/B runs.
+static size_t slab_min_cells() {
+    static long long v = -1;
+    if (v < 0) {
+        const char* e = getenv("JETCU_SLAB_MIN_CELLS");
+        v = e ? atoll(e) : (long long)SMALL_MAX_CELLS;
+        if (v < (long long)SMALL_MAX_CELLS) v = (long long)SMALL_MAX_CELLS;
+    }
+    return (size_t)v;
+}
+
 int slab_plan_compute(const Dim3i* dims, int levels, int world, int rank, SlabPlan* out) {
     SlabPlan& pl = *out;
     pl = SlabPlan();
@@ -443,7 +456,7 @@ int slab_plan_compute(const Dim3i* dims, int levels, int world, int rank, SlabPl
     int l = 0;
     for (; l < levels; ++l) {
         const int nz = dims[l].nz;
-        if (nz % (2 * world) != 0 || nz / world < 4 || dims[l].n() <= SMALL_MAX_CELLS) break;
+        if (nz % (2 * world) != 0 || nz / world < 4 || dims[l].n() <= (l == 0 ? (size_t)SMALL_MAX_CELLS : slab_min_cells())) break;
         pl.z0[l] = rank * (nz / world); pl.z1[l] = (rank + 1) * (nz / world);
     }
     pl.dist_levels = l;

@@ -7,8 +7,9 @@ OUT=gpurun_out/r2_first
 mkdir -p $OUT
 run() { local name=$1; shift; echo "== $name"; timeout "$@" > $OUT/$name.log 2>&1; echo "rc=$? $(tail -2 $OUT/$name.log | tr '\n' ' ' | cut -c1-300)"; }
 
-# 1. the established parity suite + the two first-run files (non-strict xfail: XPASS = the new CUDA paths work)
-run pytest_gpu 600 python -m pytest tests -m gpu -q -rxX
+# 1. the established parity suite + the first-run files in child processes (tests/test_gpu_zz_firstrun.py: XPASS = the new
+#    CUDA paths work; their logs land in gpurun_out/firstrun/)
+run pytest_gpu 1500 python -m pytest tests -m gpu -q -rxX
 # 2. contract bench (graphs on) and the smoke probe
 run bench 400 python bench.py --steps 5 --warmup 3
 run bench_smoke 300 python scripts/bench_smoke.py 256 5 3
@@ -33,3 +34,7 @@ for k in k_relax_colour_code k_p2g_cells k_move k_gather_attrs k_mvm; do
   python scripts/ncu_summary.py rep $OUT/$k.ncu-rep > $OUT/${k}_summary.txt 2>&1
 done
 ls -la $OUT
+
+# 5. (separate call, --gpus 8) fewer slab-distributed MG levels: replicate everything below ~1 M cells and compare ms_per_step
+#    JETCU_SLAB_MIN_CELLS=1000000 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+#        --master-port 29511 bench.py --gpus 8 --steps 5 --warmup 3

@@ -431,7 +431,8 @@ def run_jetcu(args):
     }
     if world > 1:
         line["comm"] = {"rank0_messages_per_step": (m1 - m0) / args.steps, "rank0_bytes_sent_per_step": (b1 - b0) / args.steps,
-                        "backend": "NCCL send/recv + all-gather on the solver stream"}
+                        "backend": ("peer-memory mailbox kernels over NVLink (CUDA IPC) for halo planes, NCCL all-gather"
+                                    if jc.comm_p2p_enabled() else "NCCL send/recv + all-gather on the solver stream")}
     # the two legs below are reported next to the measurement, they are not part of it: a failure in one of them is recorded
     # in its own key and must not cost the line
     if world == 1 and not args.no_projection:

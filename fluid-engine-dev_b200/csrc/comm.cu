@@ -12,6 +12,10 @@
 #include <string.h>
 
 #include <mutex>
+#include <string>
+#include <vector>
+#include <stddef.h>
+#include <stdio.h>
 
 #include "common.cuh"
 
@@ -64,7 +68,124 @@ struct JcComm {
     uint64_t* d_small = nullptr;  // staging for comm_allgather_u64_host (world * 64 values)
     uint64_t* h_small = nullptr;
     uint64_t messages = 0, bytes_sent = 0;
+    // peer-memory halo path (JETCU_P2P_HALO=1): a mailbox per rank, mapped into both neighbours through CUDA IPC
+    bool p2p = false;
+    char* box = nullptr;               // [P2P_HEADER | from-below slot 0, 1 | from-above slot 0, 1]
+    char* peer_box[2] = {nullptr, nullptr};  // the mailboxes of rank - 1 and rank + 1 in this process's address space
+    size_t slot_bytes = 0;
+    uint64_t p2p_exchanges = 0;
 };
+
+// ---- peer-memory halo exchange -------------------------------------------------------------------------------------------
+// NCCL's send/recv pair costs ~27 us per exchange at these sizes and a V-cycle on 8 slabs has ~54 of them:
+// latency, not bandwidth.  Here a rank PUSHES its boundary planes straight into the neighbour's mailbox over NVLink
+// (plain stores through a CUDA-IPC mapping), publishes a message number behind a system-scope fence, and PULLS its own
+// halo out of its mailbox once the neighbours' numbers have arrived: two small kernels, no host involvement, capturable
+// in the V-cycle graph (all protocol state lives in device memory).
+//   * Two slots per direction, message m uses slot m & 1.  No credit traffic is needed: rank r can only be pushing message
+//     m after its pull of m - 1 completed, i.e. after the neighbour pushed m - 1, which (stream order) the neighbour did
+//     after finishing its own pull of m - 2 — the previous user of slot m & 1.
+//   * Every rank performs the same sequence of exchanges (SPMD), so the per-rank counters agree without negotiation.
+//   * Waits are bounded (~2 s of clock64): on expiry a sticky error flag is raised and every later wait returns at once;
+//     the solver reads the flag at its next host synchronisation and fails loudly.  Nothing here can hang the GPU.
+struct P2PFlags {
+    unsigned long long data[2];  // last message number published by the rank below [0] / above [1] — written by the PEER
+    unsigned long long seq;      // exchanges completed on this rank
+    unsigned long long err;      // sticky: a wait timed out
+    unsigned int pushed, pulled; // CTA completion counters of the running kernel
+};
+#define P2P_HEADER 256
+#define P2P_THREADS 512
+#define P2P_TIMEOUT_CYCLES 4000000000ll
+
+__device__ __forceinline__ void p2p_publish(unsigned long long* flag, unsigned long long v) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(flag) = v;
+}
+__device__ __forceinline__ unsigned long long p2p_peek(const unsigned long long* flag) {
+    const unsigned long long v = *reinterpret_cast<const volatile unsigned long long*>(flag);
+    __threadfence_system();
+    return v;
+}
+
+// push: my boundary planes -> the neighbours' mailboxes; the last CTA to finish publishes the message number
+__global__ void __launch_bounds__(P2P_THREADS) k_p2p_push(P2PFlags* me, const uint4* __restrict__ src_dn, uint4* __restrict__ box_dn,
+                                                          unsigned long long* flag_dn, const uint4* __restrict__ src_up,
+                                                          uint4* __restrict__ box_up, unsigned long long* flag_up, size_t n16,
+                                                          size_t slot16) {
+    const unsigned long long seq = me->seq + 1;
+    const size_t off = (size_t)(seq & 1) * slot16;
+    for (size_t i = (size_t)blockIdx.x * P2P_THREADS + threadIdx.x; i < n16; i += (size_t)gridDim.x * P2P_THREADS) {
+        if (src_dn) box_dn[off + i] = src_dn[i];
+        if (src_up) box_up[off + i] = src_up[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(&me->pushed, 1u);
+        if (prev == gridDim.x - 1) {
+            me->pushed = 0;
+            if (flag_dn) p2p_publish(flag_dn, seq);
+            if (flag_up) p2p_publish(flag_up, seq);
+        }
+    }
+}
+
+// pull: wait for the neighbours' message numbers, copy my halo planes out of my mailbox; the last CTA advances seq
+__global__ void __launch_bounds__(P2P_THREADS) k_p2p_pull(P2PFlags* me, const uint4* __restrict__ box_dn, uint4* __restrict__ dst_dn,
+                                                          const uint4* __restrict__ box_up, uint4* __restrict__ dst_up, size_t n16,
+                                                          size_t slot16) {
+    const unsigned long long seq = me->seq + 1;
+    const size_t off = (size_t)(seq & 1) * slot16;
+    if (threadIdx.x == 0 && p2p_peek(&me->err) == 0) {
+        const long long t0 = clock64();
+        for (;;) {
+            const bool dn_ok = !dst_dn || p2p_peek(&me->data[0]) >= seq;
+            const bool up_ok = !dst_up || p2p_peek(&me->data[1]) >= seq;
+            if (dn_ok && up_ok) break;
+            if (clock64() - t0 > P2P_TIMEOUT_CYCLES) { me->err = 1; break; }
+        }
+    }
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * P2P_THREADS + threadIdx.x; i < n16; i += (size_t)gridDim.x * P2P_THREADS) {
+        if (dst_dn) dst_dn[i] = __ldcg(box_dn + off + i);
+        if (dst_up) dst_up[i] = __ldcg(box_up + off + i);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned prev = atomicAdd(&me->pulled, 1u);
+        if (prev == gridDim.x - 1) {  // every CTA has read seq (at its start) and finished: safe to advance
+            me->pulled = 0;
+            me->seq = seq;
+        }
+    }
+}
+
+static int comm_halo_p2p(jetcu_ctx* ctx, char* p, size_t plane_bytes, int k0, int k1, int depth, bool down, bool up) {
+    JcComm* c = ctx->comm;
+    const size_t bytes = (size_t)depth * plane_bytes, n16 = bytes / 16, slot16 = c->slot_bytes / 16;
+    P2PFlags* me = reinterpret_cast<P2PFlags*>(c->box);
+    // mailbox sides: [0] = written by the rank below, [1] = by the rank above
+    auto side = [&](char* box, int s) { return reinterpret_cast<uint4*>(box + P2P_HEADER + (size_t)s * 2 * c->slot_bytes); };
+    auto flag = [&](char* box, int s) { return &reinterpret_cast<P2PFlags*>(box)->data[s]; };
+    unsigned grid = (unsigned)((n16 + (size_t)P2P_THREADS * 4 - 1) / ((size_t)P2P_THREADS * 4));
+    if (grid < 1) grid = 1;
+    if (grid > 296) grid = 296;
+    k_p2p_push<<<grid, P2P_THREADS, 0, ctx->stream>>>(
+        me, down ? reinterpret_cast<const uint4*>(p + (size_t)k0 * plane_bytes) : nullptr, down ? side(c->peer_box[0], 1) : nullptr,
+        down ? flag(c->peer_box[0], 1) : nullptr, up ? reinterpret_cast<const uint4*>(p + (size_t)(k1 - depth) * plane_bytes) : nullptr,
+        up ? side(c->peer_box[1], 0) : nullptr, up ? flag(c->peer_box[1], 0) : nullptr, n16, slot16);
+    k_p2p_pull<<<grid, P2P_THREADS, 0, ctx->stream>>>(
+        me, down ? side(c->box, 0) : nullptr, down ? reinterpret_cast<uint4*>(p + (size_t)(k0 - depth) * plane_bytes) : nullptr,
+        up ? side(c->box, 1) : nullptr, up ? reinterpret_cast<uint4*>(p + (size_t)k1 * plane_bytes) : nullptr, n16, slot16);
+    ctx->launches += 2;
+    JC_CUDA(ctx, cudaGetLastError());
+    c->p2p_exchanges += 1;
+    c->messages += (down ? 1 : 0) + (up ? 1 : 0);
+    c->bytes_sent += ((down ? 1 : 0) + (up ? 1 : 0)) * bytes;
+    return JETCU_OK;
+}
 
 #define JC_NCCL(ctx, expr)                                                                                    \
     do {                                                                                                      \
@@ -86,6 +207,10 @@ int comm_halo_planes(jetcu_ctx* ctx, void* base, size_t plane_bytes, int k0, int
     const bool down = k0 > 0 && c->rank > 0, up = k1 < nz && c->rank + 1 < c->world;
     if (!down && !up) return JETCU_OK;
     const size_t bytes = (size_t)depth * plane_bytes;
+    // the same decision on every rank: sizes and alignment are properties of the level, not of the rank.  The un-owned end
+    // ranks (no neighbour on one side) still run both kernels so that their message counters stay in step.
+    if (c->p2p && bytes <= c->slot_bytes && bytes % 16 == 0 && plane_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0)
+        return comm_halo_p2p(ctx, p, plane_bytes, k0, k1, depth, down, up);
     JC_NCCL(ctx, api->GroupStart());
     if (down) {
         JC_NCCL(ctx, api->Send(p + (size_t)k0 * plane_bytes, bytes, ncclInt8, c->rank - 1, c->comm, ctx->stream));
@@ -177,10 +302,105 @@ void comm_free(jetcu_ctx* ctx) {
     // communicator has been destroyed.  Contexts free their own graphs first (jetcu_ctx_destroy); if the caller still
     // holds solver objects with live V-cycle graphs, the communicator is deliberately leaked instead of hanging here.
     if (c->comm && ctx->live_graphs <= 0) nccl_api()->CommDestroy(c->comm);
+    for (char*& pb : c->peer_box)
+        if (pb) { cudaIpcCloseMemHandle(pb); pb = nullptr; }
+    if (c->box) cudaFree(c->box);
     if (c->d_small) cudaFree(c->d_small);
     if (c->h_small) cudaFreeHost(c->h_small);
     delete c;
     ctx->comm = nullptr;
+}
+
+// Sticky time-out flag of the peer-memory path (see P2PFlags): read where the solver synchronises with the host anyway.
+int comm_p2p_check(jetcu_ctx* ctx) {
+    JcComm* c = ctx->comm;
+    if (!c || !c->p2p) return JETCU_OK;
+    unsigned long long err = 0;
+    JC_CUDA(ctx, cudaMemcpyAsync(&err, c->box + offsetof(P2PFlags, err), sizeof(err), cudaMemcpyDeviceToHost, ctx->stream));
+    JC_TRY(jc_sync(ctx));
+    if (err) return jetcu_fail(ctx, JETCU_ERR_NCCL, "peer-memory halo exchange: a neighbour's planes did not arrive within the "
+                                                    "time-out (rank %d of %d)", c->rank, c->world);
+    return JETCU_OK;
+}
+
+// JETCU_P2P_HALO=1: allocate the mailbox, swap CUDA-IPC handles through the NCCL communicator, map both neighbours, prove the
+// path with one self-checking exchange.  The path is switched on only if EVERY rank got through (an all-reduce decides), so
+// the ranks can never disagree about the protocol; otherwise a line on stderr and NCCL send/recv stays in charge.
+static int comm_p2p_setup(jetcu_ctx* ctx) {
+    JcComm* c = ctx->comm;
+    const char* want = getenv("JETCU_P2P_HALO");
+    if (!want || atoi(want) == 0) return JETCU_OK;
+    const char* mb = getenv("JETCU_P2P_SLOT_MB");
+    c->slot_bytes = (size_t)((mb && atoi(mb) > 0) ? atoi(mb) : 16) << 20;
+    double fail = 0.0;
+    cudaIpcMemHandle_t* d_handles = nullptr;
+    std::vector<cudaIpcMemHandle_t> handles((size_t)c->world);
+    if (cudaMalloc((void**)&c->box, P2P_HEADER + 4 * c->slot_bytes) != cudaSuccess) { c->box = nullptr; fail = 1.0; }
+    if (cudaMalloc((void**)&d_handles, (size_t)c->world * sizeof(cudaIpcMemHandle_t)) != cudaSuccess) { d_handles = nullptr; fail = 1.0; }
+    if (fail == 0.0) {
+        cudaMemsetAsync(c->box, 0, P2P_HEADER, ctx->stream);
+        cudaMemsetAsync(d_handles, 0, (size_t)c->world * sizeof(cudaIpcMemHandle_t), ctx->stream);
+        cudaIpcMemHandle_t mine;
+        if (cudaIpcGetMemHandle(&mine, c->box) != cudaSuccess) fail = 1.0;
+        else cudaMemcpyAsync(d_handles + c->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream);
+    }
+    // every rank takes part in the collectives below whatever happened above
+    if (d_handles) {
+        if (comm_allgather_inplace(ctx, d_handles, sizeof(cudaIpcMemHandle_t)) != JETCU_OK) fail = 1.0;
+        if (cudaMemcpyAsync(handles.data(), d_handles, handles.size() * sizeof(cudaIpcMemHandle_t), cudaMemcpyDeviceToHost,
+                            ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) fail = 1.0;
+    }
+    if (fail == 0.0) {
+        if (c->rank > 0 && cudaIpcOpenMemHandle((void**)&c->peer_box[0], handles[(size_t)c->rank - 1],
+                                                cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { c->peer_box[0] = nullptr; fail = 1.0; }
+        if (c->rank + 1 < c->world && cudaIpcOpenMemHandle((void**)&c->peer_box[1], handles[(size_t)c->rank + 1],
+                                                           cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { c->peer_box[1] = nullptr; fail = 1.0; }
+    }
+    cudaGetLastError();  // a failed attempt must not poison later launches
+    // agreement no. 1: mailboxes mapped everywhere?
+    double* d_flag = reinterpret_cast<double*>(c->d_small);
+    cudaMemcpyAsync(d_flag, &fail, sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    JC_TRY(comm_allreduce_max_f64(ctx, d_flag, 1));
+    cudaMemcpyAsync(&fail, d_flag, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    JC_TRY(jc_sync(ctx));
+    if (fail == 0.0) {
+        // self-check: 4 planes of 4 KiB per rank, plane value = 16 * rank + plane; three exchanges (both slots and a reuse)
+        const size_t plane = 4096;
+        std::vector<unsigned char> h(4 * plane);
+        unsigned char* w = nullptr;
+        if (cudaMalloc((void**)&w, 4 * plane) != cudaSuccess) fail = 1.0;
+        c->p2p = true;
+        for (int round = 0; round < 3 && fail == 0.0; ++round) {
+            for (int q = 0; q < 4; ++q) memset(h.data() + (size_t)q * plane, 16 * c->rank + q + 64 * round, plane);
+            cudaMemcpyAsync(w, h.data(), 4 * plane, cudaMemcpyHostToDevice, ctx->stream);
+            if (comm_halo_planes(ctx, w, plane, c->rank > 0 ? 1 : 0, c->rank + 1 < c->world ? 3 : 4, 4, 1) != JETCU_OK) fail = 1.0;
+            cudaMemcpyAsync(h.data(), w, 4 * plane, cudaMemcpyDeviceToHost, ctx->stream);
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) fail = 1.0;
+            // my ghost-lo plane [0] must hold the lower neighbour's own-hi plane (its plane 2), my ghost-hi [3] the upper one's plane 1
+            if (c->rank > 0 && (h[0] != (unsigned char)(16 * (c->rank - 1) + 2 + 64 * round) || h[plane - 1] != h[0])) fail = 1.0;
+            if (c->rank + 1 < c->world && (h[3 * plane] != (unsigned char)(16 * (c->rank + 1) + 1 + 64 * round) || h[4 * plane - 1] != h[3 * plane])) fail = 1.0;
+        }
+        if (comm_p2p_check(ctx) != JETCU_OK) fail = 1.0;
+        if (w) cudaFree(w);
+        cudaGetLastError();
+        // agreement no. 2: did the data arrive everywhere?
+        cudaMemcpyAsync(d_flag, &fail, sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        c->p2p = false;  // the vote itself goes through NCCL
+        JC_TRY(comm_allreduce_max_f64(ctx, d_flag, 1));
+        cudaMemcpyAsync(&fail, d_flag, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        JC_TRY(jc_sync(ctx));
+    }
+    if (d_handles) cudaFree(d_handles);
+    c->p2p = fail == 0.0;
+    if (!c->p2p) {
+        fprintf(stderr, "jetcu: JETCU_P2P_HALO requested but the peer-memory path is unavailable on rank %d; using NCCL send/recv\n", c->rank);
+        for (char*& pb : c->peer_box)
+            if (pb) { cudaIpcCloseMemHandle(pb); pb = nullptr; }
+        if (c->box) { cudaFree(c->box); c->box = nullptr; }
+        cudaGetLastError();
+        ctx->error.clear();
+    }
+    return JETCU_OK;
 }
 
 extern "C" {
@@ -242,8 +462,15 @@ int jetcu_comm_init(jetcu_ctx* ctx, int world, int rank, const uint8_t id[JETCU_
         if (rc != JETCU_OK) { std::string keep = ctx->error; comm_free(ctx); ctx->error = keep; return rc; }
         c->messages = 0; c->bytes_sent = 0;
     }
+    {
+        const int rc = comm_p2p_setup(ctx);
+        if (rc != JETCU_OK) { std::string keep = ctx->error; comm_free(ctx); ctx->error = keep; return rc; }
+        c->messages = 0; c->bytes_sent = 0; c->p2p_exchanges = 0;
+    }
     return JETCU_OK;
 }
+
+int jetcu_comm_p2p_enabled(const jetcu_ctx* ctx) { return (ctx && ctx->comm && ctx->comm->p2p) ? 1 : 0; }
 
 int jetcu_comm_destroy(jetcu_ctx* ctx) {
     if (!ctx) return JETCU_ERR_INVALID_ARG;

@@ -48,6 +48,9 @@ int jc_comm_rank(const jetcu_ctx* ctx);
 // lowest planes down / highest planes up and receives planes [k0-depth, k0) / [k1, k1+depth) from the neighbouring
 // ranks (no-op at the domain ends; depth must not exceed the slab thickness).
 int comm_halo_planes(jetcu_ctx* ctx, void* base, size_t plane_bytes, int k0, int k1, int nz, int depth = 1);
+// Peer-memory variant of the same exchange (JETCU_P2P_HALO=1, comm.cu): its bounded waits raise a sticky flag instead of
+// hanging; comm_p2p_check reads it (one host sync) and turns it into an error.
+int comm_p2p_check(jetcu_ctx* ctx);
 // In-place all-gather: rank r contributes bytes [r*bytes_per_rank, (r+1)*bytes_per_rank) of `base`.
 int comm_allgather_inplace(jetcu_ctx* ctx, void* base, size_t bytes_per_rank);
 int comm_allreduce_max_f64(jetcu_ctx* ctx, double* d_values, size_t n);

@@ -692,6 +692,7 @@ int mgpcg_solve_device(jetcu_ctx* ctx, MgLevels* mg, const double* b, double* x,
         ++iter;
     }
     if (dist) JC_TRY(comm_allgather_inplace(ctx, x, cnt * sizeof(double)));  // pressure complete on every rank
+    if (dist) JC_TRY(comm_p2p_check(ctx));
     JC_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
 
     if (result) {

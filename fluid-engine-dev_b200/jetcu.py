@@ -628,6 +628,10 @@ class Jetcu(LinearApi):
         self._call("comm_stats", C.byref(m), C.byref(b))
         return int(m.value), int(b.value)
 
+    def comm_p2p_enabled(self):
+        """True when halo planes travel through peer memory (JETCU_P2P_HALO=1) instead of NCCL send/recv."""
+        return bool(self._call("comm_p2p_enabled", raw=True))
+
     def slab_range(self, nz, world, rank):
         z0, z1 = u64(0), u64(0)
         self._call_raw("slab_range", u64(nz), C.c_int(world), C.c_int(rank), C.byref(z0), C.byref(z1))

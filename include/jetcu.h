@@ -80,6 +80,11 @@ int jetcu_comm_world(const jetcu_ctx* ctx);
 int jetcu_comm_rank(const jetcu_ctx* ctx);
 /* messages / payload bytes this rank has sent since jetcu_comm_init (bench.py's halo accounting) */
 int jetcu_comm_stats(const jetcu_ctx* ctx, uint64_t* messages, uint64_t* bytes_sent);
+/* 1 when halo planes travel through peer memory (JETCU_P2P_HALO=1 at jetcu_comm_init: a CUDA-IPC mailbox per rank, written by
+ * the neighbours' kernels over NVLink, two kernels per exchange and no host involvement) instead of NCCL send/recv; the switch
+ * is taken by all ranks together after a self-checking exchange, and never silently: it falls back with a line on stderr.
+ * Results are bit-identical either way. */
+int jetcu_comm_p2p_enabled(const jetcu_ctx*);
 /* cell planes [z0, z1) of an nz-plane grid owned by `rank` (uniform slabs; nz % world must be 0) */
 int jetcu_slab_range(uint64_t nz, int world, int rank, uint64_t* z0, uint64_t* z1);
 /* Host-only views of the decomposition logic (no GPU needed; what the world_size-2 CPU tests drive):

@@ -38,3 +38,7 @@ ls -la $OUT
 # 5. (separate call, --gpus 8) fewer slab-distributed MG levels: replicate everything below ~1 M cells and compare ms_per_step
 #    JETCU_SLAB_MIN_CELLS=1000000 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
 #        --master-port 29511 bench.py --gpus 8 --steps 5 --warmup 3
+#    and the peer-memory halo path (first run; bit-identity + timing), on 2 GPUs first:
+#    gpurun --gpus 2 --timeout 900 -- 'timeout 600 python -m pytest tests/test_gpu_slabs.py -m gpu -q -rxX; for p in 0 1; do
+#        JETCU_P2P_HALO=$p timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+#        --master-port 2952$p bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_2gpu_p2p$p.json; done'

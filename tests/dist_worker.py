@@ -115,7 +115,7 @@ def main():
             check(name + "_set_local_roundtrip_bits", np.array_equal(p2, hs.get_particles()[0]))
         hd.close(); hs.close()
     msgs, sent = jd.comm_stats()
-    out["comm"] = {"messages": msgs, "bytes_sent": sent}
+    out["comm"] = {"messages": msgs, "bytes_sent": sent, "p2p": jd.comm_p2p_enabled()}
     out["ok"] = ok
     outdir = os.environ.get("JETCU_DIST_OUT")
     if outdir:   # one file per rank: concurrent ranks interleave their stdout lines

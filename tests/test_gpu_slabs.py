@@ -16,14 +16,21 @@ def _gpus():
     return torch.cuda.device_count()
 
 
+FIRST_RUN = pytest.mark.xfail(strict=False, reason="first GPU run of the peer-memory halo path (written after round 1's GPU "
+                                                       "minutes were spent; every wait in it is bounded, the worker has a hard limit)")
+
+
+@pytest.mark.parametrize("halo", ["nccl", pytest.param("p2p", marks=FIRST_RUN)])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_slabs_match_single_gpu(world, tmp_path):
+def test_slabs_match_single_gpu(world, halo, tmp_path):
+    """halo = "p2p": the same checks with JETCU_P2P_HALO=1 — halo planes pushed into the neighbours' CUDA-IPC mailboxes by
+    kernels instead of NCCL send/recv; the result must not change by a bit and the path must really be the one in use."""
     if _gpus() < world:
         pytest.skip("needs %d GPUs" % world)
     n = 64
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
-           "127.0.0.1", "--master-port", str(29511 + world), os.path.join(ROOT, "tests", "dist_worker.py"), str(n), "3"]
-    env = dict(os.environ, JETCU_DIST_OUT=str(tmp_path))
+           "127.0.0.1", "--master-port", str(29511 + world + (10 if halo == "p2p" else 0)), os.path.join(ROOT, "tests", "dist_worker.py"), str(n), "3"]
+    env = dict(os.environ, JETCU_DIST_OUT=str(tmp_path), JETCU_P2P_HALO="1" if halo == "p2p" else "0")
     # own process group + a hard limit: a communication bug must fail this test, not hang the box
     p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT, env=env, start_new_session=True)
     try:
@@ -39,3 +46,4 @@ def test_slabs_match_single_gpu(world, tmp_path):
     lines = [json.load(open(f)) for f in files]
     for l in lines:
         assert l["ok"], l
+        assert l["comm"]["p2p"] == (halo == "p2p"), l["comm"]

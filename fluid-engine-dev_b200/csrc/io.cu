@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -59,8 +60,7 @@ int jetcu_write_pos_file(const char* path, const double* positions, uint64_t n) 
     return ok ? JETCU_OK : JETCU_ERR_INVALID_ARG;
 }
 
-int jetcu_write_xyz_file(const char* path, const double* positions, uint64_t n) {
-    if (!path || (n && !positions)) return JETCU_ERR_INVALID_ARG;
+static int write_xyz_file(const char* path, const double* positions, uint64_t n) {
     FILE* f = fopen(path, "w");
     if (!f) return JETCU_ERR_INVALID_ARG;
     // formatting is the cost (~100 ns per number): blocks of particles are formatted by a few threads, written in order
@@ -95,16 +95,35 @@ int jetcu_write_xyz_file(const char* path, const double* positions, uint64_t n) 
     return ok ? JETCU_OK : JETCU_ERR_INVALID_ARG;
 }
 
+// no C++ exception may cross the C boundary: allocation (text blocks, the host copy of the positions) and thread creation
+// failures become status codes
+int jetcu_write_xyz_file(const char* path, const double* positions, uint64_t n) {
+    if (!path || (n && !positions)) return JETCU_ERR_INVALID_ARG;
+    try {
+        return write_xyz_file(path, positions, n);
+    } catch (const std::bad_alloc&) {
+        return JETCU_ERR_OOM;
+    } catch (...) {
+        return JETCU_ERR_INVALID_ARG;
+    }
+}
+
 // saveParticleAsPos / saveParticleAsXyz for the device-resident particle set (original particle order)
 int jetcu_hybrid_save_positions(jetcu_hybrid* h, const char* path, int format) {
     if (!h || !path || (format != JETCU_FRAME_POS && format != JETCU_FRAME_XYZ)) return JETCU_ERR_INVALID_ARG;
-    const uint64_t n = jetcu_hybrid_num_particles(h);
-    std::vector<double> pos((size_t)n * 3);
-    if (n) {
-        const int rc = jetcu_hybrid_get_particles(h, pos.data(), nullptr);
-        if (rc != JETCU_OK) return rc;
+    try {
+        const uint64_t n = jetcu_hybrid_num_particles(h);
+        std::vector<double> pos((size_t)n * 3);
+        if (n) {
+            const int rc = jetcu_hybrid_get_particles(h, pos.data(), nullptr);
+            if (rc != JETCU_OK) return rc;
+        }
+        return format == JETCU_FRAME_POS ? jetcu_write_pos_file(path, pos.data(), n) : jetcu_write_xyz_file(path, pos.data(), n);
+    } catch (const std::bad_alloc&) {
+        return JETCU_ERR_OOM;
+    } catch (...) {
+        return JETCU_ERR_INVALID_ARG;
     }
-    return format == JETCU_FRAME_POS ? jetcu_write_pos_file(path, pos.data(), n) : jetcu_write_xyz_file(path, pos.data(), n);
 }
 
 }  // extern "C"

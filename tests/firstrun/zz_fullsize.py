@@ -10,7 +10,7 @@ import pytest
 
 import scenes
 from gpu_common import jetcu_or_fail
-from oracle_api import FLIP, Grid, HybridParams, MgpcgParams
+from oracle_api import APIC, FLIP, Grid, HybridParams, MgpcgParams
 
 pytestmark = pytest.mark.gpu
 
@@ -22,8 +22,8 @@ def jc():
     return jetcu_or_fail()
 
 
-def run_tank(jc, steps):
-    prm = HybridParams.make(Grid.cube(N), mode=FLIP, mgpcg=MgpcgParams.make(max_iterations=100, max_levels=6))
+def run_tank(jc, steps, mode=FLIP):
+    prm = HybridParams.make(Grid.cube(N), mode=mode, mgpcg=MgpcgParams.make(max_iterations=100, max_levels=6))
     h = jc.hybrid(prm)
     n = h.emit_box((0.0, 0.0, 0.0), (1.0, 0.9375, 1.0), 0.5 / N, (0.5, 0.0, 0.0))
     stats = [h.step(1.0 / 240.0) for _ in range(steps)]
@@ -49,6 +49,20 @@ def test_flip_256_properties(jc):
     n2, count2, pos2, vel2, stats2 = run_tank(jc, 2)
     assert n2 == n and [s.pcg_iterations for s in stats2] == [s.pcg_iterations for s in stats]
     assert np.array_equal(pos, pos2) and np.array_equal(vel, vel2)
+
+
+def test_apic_256_properties(jc):
+    """BASELINE configs[2]: APIC at 256^3 (126.6 M particles, 120 B of state each) — one device, same invariants."""
+    n, count, pos, vel, stats = run_tank(jc, 2, APIC)
+    assert n == 513 * 481 * 513 == count
+    assert np.isfinite(pos).all() and np.isfinite(vel).all() and pos.min() >= 0.0 and pos.max() <= 1.0
+    for s in stats:
+        assert s.pcg_iterations >= 1 and np.isfinite(s.pcg_last_residual)
+    h0 = hash(pos.tobytes()), hash(vel.tobytes())
+    del pos, vel
+    n2, count2, pos2, vel2, stats2 = run_tank(jc, 2, APIC)
+    assert (hash(pos2.tobytes()), hash(vel2.tobytes())) == h0          # bit-reproducible
+    assert [s.pcg_iterations for s in stats2] == [s.pcg_iterations for s in stats]
 
 
 def test_projection_256_converges(jc):

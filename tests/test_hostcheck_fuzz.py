@@ -160,3 +160,41 @@ def test_collider_boundary_condition_random_grid(hc, port, seed):
     for a, b, what in zip((gu, gv, gw), want, "uvw"):
         exact(a, b, "constrained " + what)
     h.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_smoke_stages_random_grid(hc, port, seed):
+    """Buoyancy and cubic semi-Lagrangian advection (csrc/smoke_ops.cuh) on random fields over a random grid."""
+    from oracle_api import SmokeParams
+    rng = np.random.default_rng(5000 + seed)
+    grid = random_grid(rng)
+    gravity = [(0.0, -9.8, 0.0), (3.0, -4.0, 1.0), (0.0, 0.0, -5.0)][seed % 3]
+    prm = SmokeParams.make(grid, mgpcg=MgpcgParams.make(max_iterations=30, max_levels=1), gravity=gravity)
+    s = port.smoke(prm)
+    nx, ny, nz = grid.res
+    den = rng.uniform(0.0, 1.0, (nz, ny, nx)); temp = rng.uniform(0.0, 5.0, (nz, ny, nx))
+    hmin = min(grid.hx, grid.hy, grid.hz)
+    u = rng.uniform(-1, 1, (nz, ny, nx + 1)) * 3 * hmin * 30; v = rng.uniform(-1, 1, (nz, ny + 1, nx)) * 3 * hmin * 30
+    w = rng.uniform(-1, 1, (nz + 1, ny, nx)) * 3 * hmin * 30       # up to ~3 cells per step: several back-trace sub-steps
+    s.set_fields(den, temp, u, v, w)
+    dt = 1.0 / 30.0
+    f = s.get_fields()
+    s.compute_external_forces(dt)
+    want = s.get_fields()
+    t_sum = 0.0
+    for x in f["temperature"].ravel():
+        t_sum += float(x)
+    gu, gv, gw = f["u"].copy(), f["v"].copy(), f["w"].copy()
+    assert hc.hc_smoke_buoyancy(C.byref(prm.grid), dp(f["density"]), dp(f["temperature"]), C.c_double(prm.buoyancy_density_factor),
+                                C.c_double(prm.buoyancy_temperature_factor), C.c_double(t_sum), (C.c_double * 3)(*gravity),
+                                C.c_double(dt), C.c_int(prm.closed_domain_boundary_flag), dp(gu), dp(gv), dp(gw)) == 0
+    for a, k in zip((gu, gv, gw), "uvw"):
+        exact(a, want[k], "buoyancy " + k)
+    s.compute_advection(dt)
+    adv = s.get_fields()
+    g = {k: want[k].copy() for k in ("density", "temperature", "u", "v", "w")}
+    assert hc.hc_smoke_advect(C.byref(prm.grid), C.c_double(dt), C.c_int(prm.closed_domain_boundary_flag), dp(g["density"]),
+                              dp(g["temperature"]), dp(g["u"]), dp(g["v"]), dp(g["w"])) == 0
+    for k in g:
+        exact(g[k], adv[k], "advected " + k)
+    s.close()

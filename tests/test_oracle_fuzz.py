@@ -67,3 +67,31 @@ def test_random_configuration_bit_exact(libs, seed):
         for what, x, y in fields:
             assert np.array_equal(x, y), "step %d %s: max abs diff %g" % (step, what, float(np.nanmax(np.abs(x - y))))
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_smoke_configuration_bit_exact(libs, seed):
+    """GridSmokeSolver3: three steps from random density / temperature fields at rest on a random grid."""
+    from oracle_api import SmokeParams
+    ref, port = libs
+    rng = np.random.default_rng(6000 + seed)
+    nyz = int(rng.choice([6, 8, 10, 12]))
+    nx = int(rng.choice([nyz, nyz + 2, nyz + 3, 2 * nyz]))
+    h = float(rng.choice([1.0 / nyz, 0.07, 0.125, 0.1]))
+    aniso = rng.random() < 0.4
+    grid = Grid(nx, nyz, nyz, h, h * (1.25 if aniso else 1.0), h * (0.8 if aniso else 1.0),
+                *(float(x) for x in rng.choice([0.0, 0.3, -0.45, 1.5], 3)))
+    levels = int(rng.choice([1, 2])) if nx % 2 == 0 else 1
+    gravity = [(0.0, -9.8, 0.0), (3.0, -4.0, 1.0), (0.0, 0.0, -5.0)][seed % 3]
+    prm = SmokeParams.make(grid, mgpcg=MgpcgParams.make(max_iterations=40, max_levels=levels), gravity=gravity)
+    a, b = ref.smoke(prm), port.smoke(prm)
+    den = rng.uniform(0.0, 1.0, (nyz, nyz, nx)); temp = rng.uniform(0.0, 5.0, (nyz, nyz, nx))
+    for s in (a, b):
+        s.set_fields(den, temp, np.zeros((nyz, nyz, nx + 1)), np.zeros((nyz, nyz + 1, nx)), np.zeros((nyz + 1, nyz, nx)))
+    for step in range(3):
+        a.step(1.0 / 30.0); b.step(1.0 / 30.0)
+        fa, fb = a.get_fields(), b.get_fields()
+        for k in fa:
+            assert np.array_equal(fa[k], fb[k]), "step %d %s: %g" % (step, k, float(np.nanmax(np.abs(fa[k] - fb[k]))))
+    assert float(np.abs(fb["v"]).max()) > 0.05
+    a.close(); b.close()

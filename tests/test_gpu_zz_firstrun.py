@@ -15,7 +15,7 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-FILES = {"collider": 900, "smoke": 900, "fullsize": 1500}           # name -> child time limit, seconds
+FILES = {"collider": 900, "smoke": 900, "fuzz": 900, "fullsize": 1500}           # name -> child time limit, seconds
 
 pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first GPU run (see module docstring)")]
 

@@ -472,6 +472,36 @@ int jetcu_comm_init(jetcu_ctx* ctx, int world, int rank, const uint8_t id[JETCU_
 
 int jetcu_comm_p2p_enabled(const jetcu_ctx* ctx) { return (ctx && ctx->comm && ctx->comm->p2p) ? 1 : 0; }
 
+// Diagnostic: `iters` back-to-back halo exchanges of `depth` planes of `plane_bytes` on a scratch slab, timed with CUDA events
+// on the solver stream — the per-exchange latency that bounds the distributed V-cycle, for whichever transport
+// is active (NCCL send/recv or the peer-memory mailboxes).
+int jetcu_comm_halo_benchmark(jetcu_ctx* ctx, uint64_t plane_bytes, int depth, int iters, double* ms_per_exchange) {
+    if (!ctx) return JETCU_ERR_INVALID_ARG;
+    JC_ARG(ctx, ctx->comm != nullptr && plane_bytes >= 16 && depth >= 1 && depth <= 64 && iters >= 1 && ms_per_exchange != nullptr);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return jetcu_fail(ctx, JETCU_ERR_CUDA, "cudaSetDevice failed");
+    JcComm* c = ctx->comm;
+    const int nzl = 4 * depth;                          // [ghost-lo | own (2 * depth planes) | ghost-hi]
+    char* w = nullptr;
+    JC_CUDA(ctx, cudaMalloc((void**)&w, (size_t)nzl * plane_bytes));
+    cudaMemsetAsync(w, 0, (size_t)nzl * plane_bytes, ctx->stream);
+    const int k0 = c->rank > 0 ? depth : 0, k1 = c->rank + 1 < c->world ? 3 * depth : nzl;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int rc = JETCU_OK;
+    for (int i = 0; i < 5 && rc == JETCU_OK; ++i) rc = comm_halo_planes(ctx, w, (size_t)plane_bytes, k0, k1, nzl, depth);
+    cudaEventRecord(e0, ctx->stream);
+    for (int i = 0; i < iters && rc == JETCU_OK; ++i) rc = comm_halo_planes(ctx, w, (size_t)plane_bytes, k0, k1, nzl, depth);
+    cudaEventRecord(e1, ctx->stream);
+    if (rc == JETCU_OK) rc = jc_sync(ctx);
+    if (rc == JETCU_OK) rc = comm_p2p_check(ctx);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(w);
+    *ms_per_exchange = (double)ms / (double)iters;
+    return rc;
+}
+
 int jetcu_comm_destroy(jetcu_ctx* ctx) {
     if (!ctx) return JETCU_ERR_INVALID_ARG;
     cudaSetDevice(ctx->device);

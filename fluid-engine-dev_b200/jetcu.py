@@ -632,6 +632,12 @@ class Jetcu(LinearApi):
         """True when halo planes travel through peer memory (JETCU_P2P_HALO=1) instead of NCCL send/recv."""
         return bool(self._call("comm_p2p_enabled", raw=True))
 
+    def comm_halo_benchmark(self, plane_bytes, depth=1, iters=200):
+        """Average device milliseconds per halo exchange (both neighbours) for the active transport."""
+        ms = f64(0.0)
+        self._call("comm_halo_benchmark", u64(plane_bytes), C.c_int(depth), C.c_int(iters), C.byref(ms))
+        return float(ms.value)
+
     def slab_range(self, nz, world, rank):
         z0, z1 = u64(0), u64(0)
         self._call_raw("slab_range", u64(nz), C.c_int(world), C.c_int(rank), C.byref(z0), C.byref(z1))

@@ -85,6 +85,9 @@ int jetcu_comm_stats(const jetcu_ctx* ctx, uint64_t* messages, uint64_t* bytes_s
  * is taken by all ranks together after a self-checking exchange, and never silently: it falls back with a line on stderr.
  * Results are bit-identical either way. */
 int jetcu_comm_p2p_enabled(const jetcu_ctx*);
+/* Diagnostic: average device time (ms) of one halo exchange of `depth` planes of `plane_bytes` with both neighbours, over
+ * `iters` back-to-back exchanges on a scratch slab — the latency that bounds the slab-distributed V-cycle. */
+int jetcu_comm_halo_benchmark(jetcu_ctx*, uint64_t plane_bytes, int depth, int iters, double* ms_per_exchange);
 /* cell planes [z0, z1) of an nz-plane grid owned by `rank` (uniform slabs; nz % world must be 0) */
 int jetcu_slab_range(uint64_t nz, int world, int rank, uint64_t* z0, uint64_t* z1);
 /* Host-only views of the decomposition logic (no GPU needed; what the world_size-2 CPU tests drive):

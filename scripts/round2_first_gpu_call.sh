@@ -42,3 +42,6 @@ ls -la $OUT
 #    gpurun --gpus 2 --timeout 900 -- 'timeout 600 python -m pytest tests/test_gpu_slabs.py -m gpu -q -rxX; for p in 0 1; do
 #        JETCU_P2P_HALO=$p timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
 #        --master-port 2952$p bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_2gpu_p2p$p.json; done'
+#    per-exchange latency of both transports (profiles evidence for DESIGN.md §4):
+#    for p in 0 1; do JETCU_P2P_HALO=$p timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+#        --master-port 2953$p scripts/halo_latency.py > gpurun_out/halo_latency_p2p$p.json; done

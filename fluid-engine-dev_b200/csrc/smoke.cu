@@ -65,6 +65,12 @@ __global__ void __launch_bounds__(256) k_smoke_advect_face(GridD g, const double
     out[((size_t)k * sy + j) * sx + i] = sm_advect_face<AXIS>(g, u0, v0, w0, dt, hmin, i, j, k);
 }
 
+__global__ void __launch_bounds__(256) k_smoke_emit_step(GridD g, ColliderD e, double width, double lo, double hi, double* __restrict__ field) {
+    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+    if (i >= g.nx || j >= g.ny) return;
+    sm_emit_step_cell(g, e, width, lo, hi, field, i, j, k);
+}
+
 __global__ void k_smoke_scale(double* __restrict__ a, double s, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] *= s;
@@ -190,6 +196,24 @@ int jetcu_smoke_get_fields(jetcu_smoke* h, double* den, double* temp, double* u,
     if (v) JC_TRY(jc_d2h(ctx, v, h->v, h->nv));
     if (w) JC_TRY(jc_d2h(ctx, w, h->w, h->nw));
     if (pr) JC_TRY(jc_d2h(ctx, pr, h->ps.x0, h->nc));
+    return jc_sync(ctx);
+}
+
+// VolumeGridEmitter3 (step-function targets on smoke density and temperature) fired once on the device
+int jetcu_smoke_emit_step(jetcu_smoke* h, const jetcu_collider_shape* shapes, uint32_t n, int as_set, double density_min,
+                          double density_max, double temperature_min, double temperature_max) {
+    SMK_ENTER(h);
+    JC_ARG(ctx, shapes && n >= 1 && n <= JC_COLLIDER_MAX_SHAPES && (n == 1 || as_set));
+    for (uint32_t i = 0; i < n; ++i) {
+        JC_ARG(ctx, shapes[i].kind >= JETCU_COLLIDER_BOX && shapes[i].kind <= JETCU_COLLIDER_PLANE);
+        if (shapes[i].kind == JETCU_COLLIDER_SPHERE || shapes[i].kind == JETCU_COLLIDER_CYLINDER) JC_ARG(ctx, shapes[i].b[0] > 0.0);
+    }
+    const ColliderD e = cd_make_collider(shapes, n, as_set, nullptr, nullptr, 0.0);
+    GridD g = smoke_grid(h);
+    const double width = cd_min(cd_min(g.hx, g.hy), g.hz);   // scalarGridTarget->gridSpacing().min()
+    const dim3 blk(64, 4);
+    JC_LAUNCH(ctx, k_smoke_emit_step, sgrid(h->nx, h->ny, h->nz), blk, 0, g, e, width, density_min, density_max, h->den);
+    JC_LAUNCH(ctx, k_smoke_emit_step, sgrid(h->nx, h->ny, h->nz), blk, 0, g, e, width, temperature_min, temperature_max, h->temp);
     return jc_sync(ctx);
 }
 

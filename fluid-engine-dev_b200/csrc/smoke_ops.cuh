@@ -131,3 +131,19 @@ __host__ __device__ __forceinline__ void sm_buoyancy_face(const GridD& g, const 
                          ft * (jc_sample(sm_cell_view(g, temp), pt[0], pt[1], pt[2]) - t_amb);
     comp[((size_t)k * sy + j) * sx + i] += dt * fBuoy * up_a;
 }
+
+// VolumeGridEmitter3 with a step-function target (src/jet/volume_grid_emitter3.cpp:33-42, 83-99), one cell: the source of
+// src/examples/smoke_sim.  smearedHeavisideSdf — include/jet/detail/level_set_utils-inl.h:29-40 (float literals 0.5f as there).
+__host__ __device__ __forceinline__ double sm_smeared_heaviside_sdf(double phi) {
+    if (phi > 1.5) return 1;
+    if (phi < -1.5) return 0;
+    return 0.5f + phi / 3.0 + 0.5f * (1.0 / 3.14159265358979323846264338327950288) * sin(3.14159265358979323846264338327950288 * phi / 1.5);
+}
+__host__ __device__ __forceinline__ void sm_emit_step_cell(const GridD& g, const ColliderD& e, double width, double lo, double hi,
+                                                           double* field, int i, int j, int k) {
+    const double sdf = collider_sdf_cell(g, e, i, j, k);   // sourceRegion()->signedDistance(dataPosition(i, j, k))
+    const double step = 1.0 - sm_smeared_heaviside_sdf(sdf / width);
+    double* cell = field + ((size_t)k * g.ny + j) * g.nx + i;
+    *cell = cd_max(*cell, (hi - lo) * step + lo);
+}
+

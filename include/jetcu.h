@@ -402,6 +402,14 @@ int jetcu_smoke_destroy(jetcu_smoke*);
 int jetcu_smoke_set_fields(jetcu_smoke*, const double* density, const double* temperature, const double* u, const double* v,
                            const double* w);
 int jetcu_smoke_get_fields(jetcu_smoke*, double* density, double* temperature, double* u, double* v, double* w, double* pressure);
+/* VolumeGridEmitter3 with addStepFunctionTarget(smokeDensity, density_min, density_max) and
+ * addStepFunctionTarget(temperature, temperature_min, temperature_max) (src/jet/volume_grid_emitter3.cpp:33-42, 83-99), fired
+ * once on the device: value = max(old, (max - min) * (1 - smearedHeavisideSdf(sdf / min h)) + min) at every cell centre — the
+ * smoke source of src/examples/smoke_sim/main.cpp:203-216.  Source region: shapes as for jetcu_hybrid_set_collider_shapes
+ * (Builder::withSourceRegion wraps one explicit surface in SurfaceToImplicit3, a set stays an ImplicitSurfaceSet3).  A
+ * continuous emitter (isOneShot = false) is this call before every step. */
+int jetcu_smoke_emit_step(jetcu_smoke*, const jetcu_collider_shape* shapes, uint32_t n, int as_set, double density_min,
+                          double density_max, double temperature_min, double temperature_max);
 int jetcu_smoke_step(jetcu_smoke*, double dt, jetcu_mgpcg_result* result);                 /* onAdvanceTimeStep */
 int jetcu_smoke_compute_external_forces(jetcu_smoke*, double dt);                          /* computeBuoyancyForce + BC */
 int jetcu_smoke_compute_pressure(jetcu_smoke*, double dt, jetcu_mgpcg_result* result);     /* computePressure + BC */

@@ -159,6 +159,10 @@ int jeto_smoke_destroy(jeto_smoke*);
 int jeto_smoke_set_fields(jeto_smoke*, const double* density, const double* temperature, const double* u, const double* v,
                           const double* w);
 int jeto_smoke_get_fields(jeto_smoke*, double* density, double* temperature, double* u, double* v, double* w, double* pressure);
+/* VolumeGridEmitter3 with step-function targets on smoke density [dmin, dmax] and temperature [tmin, tmax], fired once (shapes
+ * as for jeto_hybrid_set_collider_shapes): the smoke source of src/examples/smoke_sim. */
+int jeto_smoke_emit_step(jeto_smoke*, const jeto_collider_shape* shapes, uint32_t n, int as_set, double dmin, double dmax,
+                         double tmin, double tmax);
 int jeto_smoke_step(jeto_smoke*, double dt, jeto_mgpcg_result* result);            /* onAdvanceTimeStep */
 int jeto_smoke_compute_external_forces(jeto_smoke*, double dt);                    /* computeBuoyancyForce + BC */
 int jeto_smoke_compute_pressure(jeto_smoke*, double dt, jeto_mgpcg_result* result);

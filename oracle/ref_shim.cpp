@@ -632,6 +632,7 @@ struct jeto_smoke {
     std::shared_ptr<GridSmokeSolver3> solver;
     std::shared_ptr<FdmMgpcgSolver3> lin;
     std::shared_ptr<GridFractionalSinglePhasePressureSolver3> pressure;
+    bool solved = false;   // pressure() dereferences an empty MG hierarchy before the first solve
 };
 
 int jeto_smoke_create(const jeto_smoke_params* p, jeto_smoke** out) {
@@ -681,8 +682,11 @@ int jeto_smoke_get_fields(jeto_smoke* h, double* den, double* temp, double* u, d
     if (v) std::memcpy(v, vel->vConstAccessor().data(), res.x * (res.y + 1) * res.z * 8);
     if (w) std::memcpy(w, vel->wConstAccessor().data(), res.x * res.y * (res.z + 1) * 8);
     if (pr) {
-        const auto& x = h->pressure->pressure();
-        if (x.size().x * x.size().y * x.size().z == nc) std::memcpy(pr, x.data(), nc * 8); else std::memset(pr, 0, nc * 8);
+        std::memset(pr, 0, nc * 8);
+        if (h->solved) {
+            const auto& x = h->pressure->pressure();
+            if (x.size().x * x.size().y * x.size().z == nc) std::memcpy(pr, x.data(), nc * 8);
+        }
     }
     return 0;
 }
@@ -702,16 +706,41 @@ static void smokeResult(jeto_smoke* h, jeto_mgpcg_result* r) {
 
 int jeto_smoke_step(jeto_smoke* h, double dt, jeto_mgpcg_result* r) {
     h->solver->onAdvanceTimeStep(dt);
+    h->solved = true;
     smokeResult(h, r);
     return 0;
 }
 int jeto_smoke_compute_external_forces(jeto_smoke* h, double dt) { h->solver->computeExternalForces(dt); return 0; }
 int jeto_smoke_compute_pressure(jeto_smoke* h, double dt, jeto_mgpcg_result* r) {
     h->solver->computePressure(dt);
+    h->solved = true;
     smokeResult(h, r);
     return 0;
 }
 int jeto_smoke_compute_advection(jeto_smoke* h, double dt) { h->solver->computeAdvection(dt); return 0; }
 int jeto_smoke_end_advance_time_step(jeto_smoke* h, double dt) { h->solver->endAdvanceTimeStep(dt); return 0; }
+
+int jeto_smoke_emit_step(jeto_smoke* h, const jeto_collider_shape* shapes, uint32_t n, int as_set, double dmin, double dmax,
+                         double tmin, double tmax) {
+    if (n == 0 || (n != 1 && !as_set)) return 1;
+    Surface3Ptr surface;
+    if (as_set) {
+        std::vector<Surface3Ptr> members;
+        for (uint32_t i = 0; i < n; ++i) {
+            auto m = makeShape(shapes[i]);
+            if (!m) return 1;
+            members.push_back(m);
+        }
+        surface = ImplicitSurfaceSet3::builder().withExplicitSurfaces(members).makeShared();
+    } else {
+        surface = makeShape(shapes[0]);
+        if (!surface) return 1;
+    }
+    auto emitter = VolumeGridEmitter3::builder().withSourceRegion(surface).withIsOneShot(true).makeShared();   // smoke_sim/main.cpp:209-216
+    emitter->addStepFunctionTarget(h->solver->smokeDensity(), dmin, dmax);
+    emitter->addStepFunctionTarget(h->solver->temperature(), tmin, tmax);
+    emitter->update(0.0, 0.0);
+    return 0;
+}
 
 }  // extern "C"

@@ -346,6 +346,18 @@ int hc_smoke_buoyancy(const jetcu_grid* grid, const double* den, const double* t
 }
 
 // jetcu_smoke_compute_advection
+// k_smoke_emit_step over the whole grid (jetcu_smoke_emit_step applies it to density and temperature)
+int hc_smoke_emit_step(const jetcu_grid* grid, const jetcu_collider_shape* shapes, uint32_t ns, int as_set, double lo, double hi,
+                       double* field) {
+    GridD g = make_grid(grid);
+    const ColliderD e = cd_make_collider(shapes, ns, as_set, nullptr, nullptr, 0.0);
+    const double width = cd_min(cd_min(g.hx, g.hy), g.hz);
+    for (int k = 0; k < g.nz; ++k)
+        for (int j = 0; j < g.ny; ++j)
+            for (int i = 0; i < g.nx; ++i) sm_emit_step_cell(g, e, width, lo, hi, field, i, j, k);
+    return 0;
+}
+
 int hc_smoke_advect(const jetcu_grid* grid, double dt, int wall_flag, double* den, double* temp, double* u, double* v, double* w) {
     GridD g = make_grid(grid);
     const size_t nc = (size_t)g.nx * g.ny * g.nz;

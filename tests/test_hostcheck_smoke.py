@@ -8,7 +8,7 @@ import pytest
 
 from oracle_api import Grid, MgpcgParams, SmokeParams, have_port, load_port
 from test_hostcheck_collider import _load_hostcheck, dp, exact
-from test_oracle_smoke import plume
+from test_oracle_smoke import EMIT_GRIDS, plume, source_shapes
 
 pytestmark = pytest.mark.skipif(not have_port(), reason="oracle/libjetport.so not built")
 
@@ -71,3 +71,32 @@ def test_advection(hc, port, n, domain, levels, gravity, dt):
         exact(g[k], want[k], "advected " + k)
     assert np.abs(want["density"] - f["density"]).max() > 1e-3   # the plume really moved
     s.close()
+
+
+@pytest.mark.parametrize("which", range(4))
+@pytest.mark.parametrize("gi", range(len(EMIT_GRIDS)))
+def test_emit_step(hc, port, gi, which):
+    from oracle_api import ColliderShape
+    grid = EMIT_GRIDS[gi]
+    prm = SmokeParams.make(grid, mgpcg=MgpcgParams.make(max_iterations=40, max_levels=1))
+    s = port.smoke(prm)
+    rng = np.random.default_rng(10 * gi + which)
+    nx, ny, nz = grid.res
+    den0, t0 = rng.uniform(0, 0.5, (nz, ny, nx)), rng.uniform(0, 0.5, (nz, ny, nx))
+    s.set_fields(den0, t0, np.zeros((nz, ny, nx + 1)), np.zeros((nz, ny + 1, nx)), np.zeros((nz + 1, ny, nx)))
+    shapes = source_shapes(grid, which)
+    s.emit_step(shapes, (0.0, 1.0), (0.25, 2.0))
+    want = s.get_fields()
+    arr = (ColliderShape * len(shapes))()
+    for i, sh in enumerate(shapes):
+        arr[i].kind = {"box": 1, "sphere": 2, "cylinder": 3, "plane": 4}[sh["kind"]]
+        arr[i].a = (C.c_double * 3)(*sh["a"])
+        b = tuple(sh.get("b", (0.0, 0.0, 0.0))) + (0.0, 0.0, 0.0)
+        arr[i].b = (C.c_double * 3)(*b[:3])
+    den, temp = den0.copy(), t0.copy()
+    args = [C.byref(grid), arr, C.c_uint32(len(shapes)), C.c_int(int(len(shapes) != 1))]
+    assert hc.hc_smoke_emit_step(*args, C.c_double(0.0), C.c_double(1.0), dp(den)) == 0
+    assert hc.hc_smoke_emit_step(*args, C.c_double(0.25), C.c_double(2.0), dp(temp)) == 0
+    exact(den, want["density"], "emitted density"); exact(temp, want["temperature"], "emitted temperature")
+    s.close()
+

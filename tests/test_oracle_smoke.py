@@ -78,3 +78,43 @@ def test_smoke_steps_bit_exact(libs, n, levels, gravity):
     vmax = max(np.abs(fb[k]).max() for k in "uvw")
     assert 0.05 < vmax < 10.0 and fb["density"].max() > 0.1
     a.close(); b.close()
+
+
+def source_shapes(grid, which):
+    lo = np.array([grid.ox, grid.oy, grid.oz]); size = np.array([grid.nx * grid.hx, grid.ny * grid.hy, grid.nz * grid.hz])
+    c = lo + np.array([0.5, 0.05, 0.5]) * size
+    return [[dict(kind="box", a=tuple(c - np.array([0.05, 1.0, 0.05]) * size), b=tuple(c + np.array([0.05, 0.0, 0.05]) * size))],   # smoke_sim ex. 1
+            [dict(kind="sphere", a=tuple(lo + 0.4 * size), b=(0.2 * size.min(), 0.0, 0.0))],
+            [dict(kind="cylinder", a=tuple(lo + 0.5 * size), b=(0.15 * size.min(), 0.4 * size[1]))],
+            [dict(kind="sphere", a=tuple(lo + 0.3 * size), b=(0.15 * size.min(), 0.0, 0.0)),
+             dict(kind="box", a=tuple(lo + 0.5 * size), b=tuple(lo + 0.7 * size))]][which]
+
+
+EMIT_GRIDS = [Grid.cube(16), Grid(11, 8, 8, 0.125, 0.125, 0.125, 0.3, -0.45, 1.5), Grid(14, 12, 12, 0.1, 0.125, 0.08, 0.0, 0.3, 0.3),
+              Grid(20, 10, 10, 0.07, 0.07, 0.07, 1.5, 0.0, -0.45)]
+
+
+@pytest.mark.parametrize("which", range(4))
+@pytest.mark.parametrize("gi", range(len(EMIT_GRIDS)))
+def test_emit_step_bit_exact(libs, gi, which):
+    """VolumeGridEmitter3 with step-function targets on density and temperature (the source of src/examples/smoke_sim)."""
+    ref, port = libs
+    grid = EMIT_GRIDS[gi]
+    prm = SmokeParams.make(grid, mgpcg=MgpcgParams.make(max_iterations=40, max_levels=1))
+    a, b = ref.smoke(prm), port.smoke(prm)
+    rng = np.random.default_rng(10 * gi + which)
+    nx, ny, nz = grid.res
+    den0, t0 = rng.uniform(0, 0.5, (nz, ny, nx)), rng.uniform(0, 0.5, (nz, ny, nx))
+    for s in (a, b):
+        s.set_fields(den0, t0, np.zeros((nz, ny, nx + 1)), np.zeros((nz, ny + 1, nx)), np.zeros((nz + 1, ny, nx)))
+        s.emit_step(source_shapes(grid, which), (0.0, 1.0), (0.25, 2.0))
+    fa, fb = a.get_fields(), b.get_fields()
+    same(fa, fb, "after the emission")
+    assert (fb["density"] > den0).sum() >= 1 and fb["temperature"].max() > 0.5
+    # a continuous emitter re-fires before every step: emit -> step -> emit stays identical
+    for s in (a, b):
+        s.step(1.0 / 30.0)
+        s.emit_step(source_shapes(grid, which), (0.0, 1.0), (0.25, 2.0))
+    same(a.get_fields(), b.get_fields(), "after a step and a second emission")
+    a.close(); b.close()
+

@@ -174,3 +174,12 @@ __host__ __device__ __forceinline__ char outside_collider_cell(const GridD& g, c
                  pz = (g.oz + 0.5 * g.hz) + g.hz * (double)k;
     return (jc_sample(cs, px, py, pz) < 0) ? 0 : 1;
 }
+
+// GridPointGenerator3::forEachPoint, point t of the (cx, cy, .) lattice in the generator's k, j, i order
+// (src/jet/grid_point_generator3.cpp:24-33): position = index * spacing + lowerCorner
+__host__ __device__ __forceinline__ void lattice_point(size_t t, unsigned cx, unsigned cy, double spacing, double lx, double ly,
+                                                       double lz, double p[3]) {
+    int i = (int)(t % cx), j = (int)((t / cx) % cy), k = (int)(t / ((size_t)cx * cy));
+    p[0] = i * spacing + lx; p[1] = j * spacing + ly; p[2] = k * spacing + lz;
+}
+

@@ -669,11 +669,6 @@ __device__ __forceinline__ bool box_emit_accept(const double p[3], const Box3d& 
     return inside || best_d2 == 0.0;
 }
 
-__device__ __forceinline__ void lattice_point(size_t t, unsigned cx, unsigned cy, double spacing, double lx, double ly,
-                                              double lz, double p[3]) {
-    int i = (int)(t % cx), j = (int)((t / cx) % cy), k = (int)(t / ((size_t)cx * cy));
-    p[0] = i * spacing + lx; p[1] = j * spacing + ly; p[2] = k * spacing + lz;
-}
 
 // flags[t] = lattice point t is emitted; mine[t] (slab mode, else null) = ... and its cell plane belongs to this rank
 __global__ void k_emit_flags(uint32_t* __restrict__ flags, uint32_t* __restrict__ mine, size_t total, unsigned cx, unsigned cy,

@@ -243,8 +243,8 @@ int hc_emit_shapes(const jetcu_grid* g, const jetcu_collider_shape* shapes, uint
     const size_t total = (size_t)cnt[0] * cnt[1] * cnt[2];
     uint64_t o = 0;
     for (size_t t = 0; t < total; ++t) {
-        const int i = (int)(t % cnt[0]), j = (int)((t / cnt[0]) % cnt[1]), k = (int)(t / ((size_t)cnt[0] * cnt[1]));
-        const double p[3] = {i * spacing + lo[0], j * spacing + lo[1], k * spacing + lo[2]};   // lattice_point() of hybrid.cu
+        double p[3];
+        lattice_point(t, cnt[0], cnt[1], spacing, lo[0], lo[1], lo[2], p);
         if (!cd_emit_accept(e, p)) continue;
         if (pos) { pos[3 * o] = p[0]; pos[3 * o + 1] = p[1]; pos[3 * o + 2] = p[2]; }
         ++o;

@@ -47,3 +47,25 @@ def test_smoke_matches_stock_jet():
     out = run("--what", "smoke", "--n", 32, "--frames", 5, "--levels", 4)
     assert out["velocity_scale"] > 0.05        # the plume really rose
     assert out["velocity_rel"] <= 1e-9 and out["density_rel"] <= 1e-9, out
+
+
+APP = os.path.join(ROOT, "adapters", "_build", "hybrid_liquid_sim_cuda")
+
+
+@pytest.mark.parametrize("example", [1, 3, 6])
+def test_example_application_next_to_stock_jet(example, tmp_path):
+    """adapters/hybrid_liquid_sim_cuda: the scenes of Jet's hybrid_liquid_sim example on jetcu's solver classes — device
+    emission, device collider, frames written from the device — stepped next to a stock Jet solver (--compare)."""
+    if not os.path.exists(APP):
+        pytest.fail("adapters/_build/hybrid_liquid_sim_cuda missing: run `make -C adapters` where /root/reference exists")
+    r = subprocess.run([APP, "-e", str(example), "-r", "32", "-f", "3", "-o", str(tmp_path), "-m", "pos", "--compare"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    frames = [l for l in r.stdout.splitlines() if l.startswith("frame ")]
+    assert len(frames) == 3, r.stdout
+    for l in frames:
+        dx = float(l.rsplit(" ", 1)[1])
+        assert 0.0 <= dx <= 1e-5, l                     # -1 = particle counts differ
+    first = (tmp_path / "frame_000000.pos").read_bytes()
+    assert first[:20].hex() == "0c00000000000600080004000600000004000000" and (len(first) - 24) % 24 == 0 and len(first) > 24 * 1000
+

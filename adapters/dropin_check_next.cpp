@@ -3,13 +3,15 @@
 //                same collider object (adapter forwards it as jetcu_hybrid_set_collider_shapes)
 //     pillars    the same with the collider of hybrid_liquid_sim example 3: an ImplicitSurfaceSet3 of three Cylinder3
 //     tank       the same inside a normal-flipped Sphere3 (example 6)
+//     compressed stock Jet only, no GPU: FlipSolver3 + MGPCG with setUseCompressedLinearSystem(true) vs (false) — with a
+//                multigrid solver installed the reference ignores the flag, which is why the adapters may accept it
 //     emit       the water drop of examples 1 / 2 (half-space + sphere): stock VolumeParticleEmitter3 set on the host  vs
 //                CudaFlipSolver3::emitOnDevice (lattice generated and tested on the GPU), then the same frames
 //     smoke      jet::GridSmokeSolver3 (plume from rest in a closed box)               vs  jetcu::CudaGridSmokeSolver3
 // Prints one JSON line with the deviations from the stock run.  Built by adapters/Makefile next to dropin_check;
 // tests/test_gpu_zz_dropin_next.py runs it (first GPU run pending, see that file).
 //
-//     dropin_check_next [--n 16] [--frames 3] [--levels 3] [--what collider|pillars|tank|emit|smoke]
+//     dropin_check_next [--n 16] [--frames 3] [--levels 3] [--what collider|pillars|tank|emit|compressed|smoke]
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -88,6 +90,33 @@ int runCollider(const Options& opt) {
         maxDx = std::max(maxDx, std::max(std::fabs(d.x), std::max(std::fabs(d.y), std::fabs(d.z))));
     }
     std::printf("{\"what\": \"%s\", \"n\": %zu, \"frames\": %d, \"particles\": %zu, \"max_dx\": %.3e}\n", opt.what.c_str(), opt.n, opt.frames, n, maxDx);
+    return 0;
+}
+
+int runCompressed(const Options& opt) {
+    const double h = 1.0 / static_cast<double>(opt.n);
+    std::shared_ptr<FlipSolver3> solvers[2];
+    for (int q = 0; q < 2; ++q) {
+        solvers[q] = std::make_shared<FlipSolver3>(Size3(opt.n, opt.n, opt.n), Vector3D(h, h, h), Vector3D());
+        auto pressure = std::make_shared<GridFractionalSinglePhasePressureSolver3>();
+        pressure->setLinearSystemSolver(std::make_shared<FdmMgpcgSolver3>(100, opt.levels, 5, 5, 20, 20, 1e-9, 1.5, true));
+        solvers[q]->setPressureSolver(pressure);
+        Options scene = opt;
+        scene.what = "collider";
+        setupLiquid(solvers[q], scene);                       // sets the flag to false ...
+        solvers[q]->setUseCompressedLinearSystem(q == 1);     // ... and here it is switched on for the second solver
+    }
+    for (Frame frame(0, 1.0 / 60.0); frame.index < opt.frames; ++frame)
+        for (auto& s : solvers) s->update(frame);
+    auto p0 = solvers[0]->particleSystemData();
+    auto p1 = solvers[1]->particleSystemData();
+    const size_t n = p0->numberOfParticles();
+    if (p1->numberOfParticles() != n) { std::fprintf(stderr, "particle counts differ\n"); return 1; }
+    size_t different = 0;
+    for (size_t i = 0; i < n; ++i)
+        if (std::memcmp(&p0->positions()[i], &p1->positions()[i], sizeof(Vector3D)) != 0 ||
+            std::memcmp(&p0->velocities()[i], &p1->velocities()[i], sizeof(Vector3D)) != 0) ++different;
+    std::printf("{\"what\": \"compressed\", \"n\": %zu, \"frames\": %d, \"particles\": %zu, \"different\": %zu}\n", opt.n, opt.frames, n, different);
     return 0;
 }
 
@@ -192,6 +221,7 @@ int main(int argc, char** argv) {
     Logging::mute();
     try {
         if (opt.what == "collider" || opt.what == "pillars" || opt.what == "tank") return runCollider(opt);
+        if (opt.what == "compressed") return runCompressed(opt);
         if (opt.what == "emit") return runEmit(opt);
         if (opt.what == "smoke") return runSmoke(opt);
         std::fprintf(stderr, "unknown check %s\n", opt.what.c_str());

@@ -199,8 +199,12 @@ class CudaGridFractionalSinglePhasePressureSolver3 final : public jet::GridPress
                const jet::ScalarField3& fluidSdf = jet::ConstantScalarField3(-jet::kMaxD),
                bool useCompressed = false) override {
         (void)timeIntervalInSeconds;
-        if (useCompressed)
-            throw std::runtime_error("jetcu: the compressed linear system is not on the GPU path (SURVEY §8f-4)");
+        // With a multigrid linear-system solver installed — and this path IS FdmMgpcgSolver3 — the reference neither builds nor
+        // solves the compressed system: buildSystem fills _mgSystem whatever the flag says and solve calls
+        // _mgSystemSolver->solve(&_mgSystem) (src/jet/grid_fractional_single_phase_pressure_solver3.cpp:465-481, 651-690).
+        // So setUseCompressedLinearSystem(true), as Jet's examples do, changes nothing here either (checked on the CPU by
+        // `dropin_check_next --what compressed`: stock Jet with MGPCG, flag on vs off, bit-identical particles).
+        (void)useCompressed;
         const jet::Size3 res = input.resolution();
         JET_THROW_INVALID_ARG_IF(output->resolution() != res);
         const jet::Vector3D h = input.gridSpacing(), o = input.origin();

@@ -1,8 +1,9 @@
 // hybrid_liquid_sim_cuda.cpp — what switching a Jet application over looks like: the scenes of Jet's own hybrid_liquid_sim
 // example (src/examples/hybrid_liquid_sim/main.cpp) with jetcu's solver classes in place of Jet's.  Public Jet API plus
 // adapters/jetcu_jet_adapters.h only; nothing of the example's source is reused — the scenes are re-described here on CUBIC
-// grids, because a multi-level MGPCG needs ny == nz (the reference's own FdmMgUtils3::correct clamps k against n.y,
-// src/jet/fdm_mg_linear_system3.cpp:159, which is why Jet's example falls back to ICCG on its 1 x 2 x 1 domains).
+// grids so that --compare has a well-defined stock run next to it: on ny != nz the reference's own multi-level V-cycle reads
+// out of bounds (FdmMgUtils3::correct clamps k against n.y, src/jet/fdm_mg_linear_system3.cpp:159), which is why Jet's example
+// falls back to ICCG on its 1 x 2 x 1 domains.  (jetcu itself accepts such shapes, clamping against n.z.)
 //
 //     hybrid_liquid_sim_cuda [-e 1|3|6] [-r 64] [-f 10] [-o out_dir] [-m pos|xyz|none] [--host-emit] [--compare]
 //

@@ -217,8 +217,6 @@ int setup_levels(jetcu_ctx* ctx, MgLevels* mg, std::vector<DevMat*>& mats, uint6
         JC_TRY(m->upload(A[l], mg->dims[l].n()));
         mg->A[l] = mat_of(m->A);
     }
-    // FdmMgUtils3::correct's clamp is only well defined for ny == nz (src/jet/fdm_mg_linear_system3.cpp:159)
-    if (levels > 1) JC_ARG(ctx, ny == nz);
     return mg_alloc_vectors(ctx, mg);
 }
 
@@ -289,7 +287,6 @@ int jetcu_fdm_correct(jetcu_ctx* ctx, uint64_t nx, uint64_t ny, uint64_t nz, con
     JC_TRY(check_dims(ctx, nx, ny, nz));
     JC_ARG(ctx, finer && coarser);
     JC_ARG(ctx, nx % 2 == 0 && ny % 2 == 0 && nz % 2 == 0);
-    JC_ARG(ctx, ny == nz);
     size_t n = nx * ny * nz;
     DevVec f(ctx), c(ctx);
     JC_TRY(f.upload(finer, n)); JC_TRY(c.upload(coarser, n / 8));
@@ -373,7 +370,6 @@ int jetcu_pressure_solve(jetcu_ctx* ctx, const jetcu_grid* g, const double* u_in
     JC_TRY(check_dims(ctx, g->nx, g->ny, g->nz));
     JC_ARG(ctx, g->hx > 0 && g->hy > 0 && g->hz > 0);
     uint32_t levels = jetcu_mg_num_levels(g->nx, g->ny, g->nz, p->max_levels);
-    if (levels > 1) JC_ARG(ctx, g->ny == g->nz);  // see jetcu_fdm_correct
     size_t nc = g->nx * g->ny * g->nz;
     size_t nu = (g->nx + 1) * g->ny * g->nz, nv = g->nx * (g->ny + 1) * g->nz, nw = g->nx * g->ny * (g->nz + 1);
     JC_TRY(pressure_prepare(ctx, ctx->psys, g, p->max_levels));

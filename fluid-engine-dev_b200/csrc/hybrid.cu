@@ -1065,7 +1065,6 @@ int jetcu_hybrid_create(jetcu_ctx* ctx, const jetcu_hybrid_params* p, jetcu_hybr
     JC_ARG(ctx, (uint64_t)p->grid.nx * p->grid.ny * p->grid.nz < (1ull << 32) - 2);
     if (!p->mgpcg.use_red_black)
         return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED, "lexicographic Gauss-Seidel is not available on the GPU path");
-    if (jetcu_mg_num_levels(p->grid.nx, p->grid.ny, p->grid.nz, p->mgpcg.max_levels) > 1) JC_ARG(ctx, p->grid.ny == p->grid.nz);
     jetcu_hybrid* h = new jetcu_hybrid();
     h->ctx = ctx;
     h->P = *p;

@@ -155,7 +155,6 @@ int jetcu_smoke_create(jetcu_ctx* ctx, const jetcu_smoke_params* p, jetcu_smoke*
     JC_ARG(ctx, p->grid.hx > 0 && p->grid.hy > 0 && p->grid.hz > 0);
     if (!p->mgpcg.use_red_black)
         return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED, "lexicographic Gauss-Seidel is not available on the GPU path");
-    if (jetcu_mg_num_levels(p->grid.nx, p->grid.ny, p->grid.nz, p->mgpcg.max_levels) > 1) JC_ARG(ctx, p->grid.ny == p->grid.nz);
     jetcu_smoke* h = new jetcu_smoke();
     h->ctx = ctx;
     h->P = *p;

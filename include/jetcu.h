@@ -156,8 +156,10 @@ int jetcu_fdm_relax_red_black(jetcu_ctx*, uint64_t nx, uint64_t ny, uint64_t nz,
 int jetcu_fdm_restrict(jetcu_ctx*, uint64_t nx, uint64_t ny, uint64_t nz,
                        const double* finer, double* coarser);
 /* FdmMgUtils3::correct (src/jet/fdm_mg_linear_system3.cpp:100-179): finer += P coarser.
- * The reference's k-clamp tests n.y instead of n.z (:159); we implement the intended n.z test, which is
- * identical whenever ny == nz (the only case in which the reference does not read out of bounds). */
+ * The reference's k-clamp tests n.y instead of n.z (:159); we implement the intended n.z test, which is identical whenever
+ * ny == nz — the shapes on which the reference is well defined (for ny > nz it reads a coarse plane beyond the array) and on
+ * which every parity claim of this library is made.  ny != nz is accepted as an EXTENSION with the n.z clamp: a multi-level
+ * V-cycle on the 1 x 2 x 1 / 3 x 2 x 1.5 domains of Jet's examples, where Jet itself can only run ICCG. */
 int jetcu_fdm_correct(jetcu_ctx*, uint64_t nx, uint64_t ny, uint64_t nz,
                       const double* coarser, double* finer);
 /* FdmBlas3::dot (src/jet/fdm_linear_system3.cpp:49-65). Deterministic two-stage tree (not the serial order). */

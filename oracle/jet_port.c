@@ -162,11 +162,13 @@ int jeto_fdm_restrict(uint64_t fnx, uint64_t fny, uint64_t fnz, const double* fi
 }
 
 /* FdmMgUtils3::correct — src/jet/fdm_mg_linear_system3.cpp:100-179: finer += trilinear (1/4,3/4) prolongation.
- * The reference clamps k against n.y (:159); identical to n.z whenever ny == nz, which callers must ensure. */
+ * The reference clamps k against n.y (:159): identical to clamping against n.z whenever ny == nz — the only shapes on which
+ * the reference is well defined (for ny > nz it reads one coarse plane beyond the array, for ny < nz it clamps too early) and
+ * the only shapes on which this function is compared with it.  For ny != nz the clamp is against n.z, the evident intent:
+ * there is no reference answer to match there, only the requirement that the V-cycle stays a valid preconditioner. */
 int jeto_fdm_correct(uint64_t fnx, uint64_t fny, uint64_t fnz, const double* coarser, double* finer) {
     ssz nx = (ssz)fnx, ny = (ssz)fny, nz = (ssz)fnz;
     ssz cnx = nx / 2, cny = ny / 2;
-    if (fny != fnz) return 1;
 #pragma omp parallel for schedule(static)
     for (ssz k = 0; k < nz; ++k)
         for (ssz j = 0; j < ny; ++j)

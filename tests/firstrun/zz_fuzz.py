@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 
 from gpu_common import checker, jetcu_or_fail
-from test_oracle_fuzz import random_case
+from oracle_api import FLIP, Grid, HybridParams, MgpcgParams
+from test_oracle_fuzz import NONCUBIC, random_case
 
 pytestmark = pytest.mark.gpu
 
@@ -46,3 +47,24 @@ def test_random_configuration(jc, oracle, seed):
             for x, y, nm in zip(a.get_markers(), b.get_markers(), "uvw"):
                 assert np.array_equal(x, y), "marker " + nm
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("shape", NONCUBIC)
+def test_noncubic_multilevel_extension(jc, oracle, shape):
+    """ny != nz with three MG levels (no reference answer: see tests/test_oracle_fuzz.py): CUDA vs the C oracle, which clamp
+    the prolongation against n.z alike — the usual tolerances."""
+    nx, ny, nz = shape
+    h = 1.0 / nx
+    prm = HybridParams.make(Grid(nx, ny, nz, h, h, h, 0.0, 0.0, 0.0), mode=FLIP, mgpcg=MgpcgParams.make(max_iterations=100, max_levels=3))
+    from oracle_api import load_port
+    port = load_port(); port.set_num_threads(0)          # the reference library itself is undefined on these shapes
+    a, b = jc.hybrid(prm), port.hybrid(prm)
+    for s in (a, b):
+        s.emit_box((0.0, 0.0, 0.0), (0.4 * nx * h, 0.6 * ny * h, nz * h), 0.5 * h, (0.5, 0.0, 0.0))
+    for step in range(2):
+        sa, sb = a.step(1.0 / 60.0), b.step(1.0 / 60.0)
+        assert sa.pcg_iterations == sb.pcg_iterations
+        pa, pb = a.get_particles()[0], b.get_particles()[0]
+        assert np.abs(pa - pb).max() <= 1e-5 * max(nx, ny, nz) * h
+    a.close(); b.close()
+

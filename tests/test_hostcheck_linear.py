@@ -52,7 +52,7 @@ def test_blas_and_relax(hc, port, shape, spd):
         exact(xs, port.relax_red_black(A, b, x, sor, it), "relax sor=%g" % sor)
 
 
-@pytest.mark.parametrize("fine", [(16, 12, 12), (2, 2, 2), (8, 6, 6)])
+@pytest.mark.parametrize("fine", [(16, 12, 12), (2, 2, 2), (8, 6, 6), (8, 16, 8), (12, 8, 6), (6, 4, 10)])   # the last three: ny != nz (extension)
 def test_restrict_correct(hc, port, fine):
     nx, ny, nz = fine
     rng = np.random.default_rng(nx)

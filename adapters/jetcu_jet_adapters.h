@@ -26,6 +26,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <typeinfo>
 #include <vector>
 
 #include "../include/jetcu.h"
@@ -542,8 +543,9 @@ class CudaHybridSolver3 : public Base {
 //! GridSmokeSolver3 with the sub-step on the device: GridFluidSolver3::onAdvanceTimeStep
 //! (src/jet/grid_fluid_solver3.cpp:179-210) runs as jetcu_smoke_step.  Strict drop-in: emitters (VolumeGridEmitter3 ...)
 //! keep running on the host inside beginAdvanceTimeStep, so the fields go up before and come back after every sub-step.
-//! Supported configuration = what the device path implements: no collider, zero viscosity / diffusion coefficients, the
-//! default CubicSemiLagrangian3 advection; anything else throws instead of silently computing something different.
+//! Supported configuration = what the device path implements: no collider, zero viscosity / diffusion coefficients,
+//! CubicSemiLagrangian3 (the default) or SemiLagrangian3 advection; anything else throws instead of silently computing
+//! something different.
 class CudaGridSmokeSolver3 : public jet::GridSmokeSolver3 {
  public:
     CudaGridSmokeSolver3(const jet::Size3& resolution, const jet::Vector3D& gridSpacing, const jet::Vector3D& gridOrigin,
@@ -566,8 +568,10 @@ class CudaGridSmokeSolver3 : public jet::GridSmokeSolver3 {
         if (viscosityCoefficient() > jet::kEpsilonD || smokeDiffusionCoefficient() > jet::kEpsilonD ||
             temperatureDiffusionCoefficient() > jet::kEpsilonD)
             throw std::runtime_error("jetcu: the device smoke solver implements zero viscosity / diffusion only");
-        if (std::dynamic_pointer_cast<jet::CubicSemiLagrangian3>(advectionSolver()) == nullptr)
-            throw std::runtime_error("jetcu: the device smoke solver implements CubicSemiLagrangian3 advection");
+        // exactly CubicSemiLagrangian3 or exactly SemiLagrangian3 (its base class); any other subclass samples differently
+        if (advectionSolver() == nullptr || (typeid(*advectionSolver()) != typeid(jet::CubicSemiLagrangian3) &&
+                                             typeid(*advectionSolver()) != typeid(jet::SemiLagrangian3)))
+            throw std::runtime_error("jetcu: the device smoke solver implements SemiLagrangian3 / CubicSemiLagrangian3 advection");
         ensureDevice();
         // the host part of beginAdvanceTimeStep: emitters write into the host grids (src/jet/grid_fluid_solver3.cpp:437-447)
         if (emitter() != nullptr) emitter()->update(currentTimeInSeconds(), timeIntervalInSeconds);
@@ -597,6 +601,7 @@ class CudaGridSmokeSolver3 : public jet::GridSmokeSolver3 {
         p.buoyancy_temperature_factor = buoyancyTemperatureFactor();
         p.density_decay = smokeDecayFactor();
         p.temperature_decay = smokeTemperatureDecayFactor();
+        p.advection = typeid(*advectionSolver()) == typeid(jet::SemiLagrangian3) ? JETCU_ADVECT_LINEAR : JETCU_ADVECT_CUBIC;
         jetcu_mgpcg_params fromJet;
         auto frac = std::dynamic_pointer_cast<jet::GridFractionalSinglePhasePressureSolver3>(pressureSolver());
         if (frac && detail::mgpcgParamsOf(frac->linearSystemSolver(), &fromJet)) _mgpcg = fromJet;

@@ -49,20 +49,20 @@ __global__ void __launch_bounds__(256) k_smoke_buoyancy(GridD g, const double* _
 
 __global__ void __launch_bounds__(256) k_smoke_advect_cell(GridD g, const double* __restrict__ in, const double* __restrict__ u,
                                                            const double* __restrict__ v, const double* __restrict__ w, double dt,
-                                                           double hmin, double* __restrict__ out) {
+                                                           double hmin, bool linear, double* __restrict__ out) {
     int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
     if (i >= g.nx || j >= g.ny) return;
-    out[((size_t)k * g.ny + j) * g.nx + i] = sm_advect_cell(g, in, u, v, w, dt, hmin, i, j, k);
+    out[((size_t)k * g.ny + j) * g.nx + i] = sm_advect_cell(g, in, u, v, w, dt, hmin, i, j, k, linear);
 }
 
 template <int AXIS>
 __global__ void __launch_bounds__(256) k_smoke_advect_face(GridD g, const double* __restrict__ u0, const double* __restrict__ v0,
-                                                           const double* __restrict__ w0, double dt, double hmin,
+                                                           const double* __restrict__ w0, double dt, double hmin, bool linear,
                                                            double* __restrict__ out) {
     const int sx = g.nx + (AXIS == 0), sy = g.ny + (AXIS == 1), sz = g.nz + (AXIS == 2);
     int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
     if (i >= sx || j >= sy || k >= sz) return;
-    out[((size_t)k * sy + j) * sx + i] = sm_advect_face<AXIS>(g, u0, v0, w0, dt, hmin, i, j, k);
+    out[((size_t)k * sy + j) * sx + i] = sm_advect_face<AXIS>(g, u0, v0, w0, dt, hmin, i, j, k, linear);
 }
 
 __global__ void __launch_bounds__(256) k_smoke_emit_step(GridD g, ColliderD e, double width, double lo, double hi, double* __restrict__ field) {
@@ -155,6 +155,7 @@ int jetcu_smoke_create(jetcu_ctx* ctx, const jetcu_smoke_params* p, jetcu_smoke*
     JC_ARG(ctx, p->grid.hx > 0 && p->grid.hy > 0 && p->grid.hz > 0);
     if (!p->mgpcg.use_red_black)
         return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED, "lexicographic Gauss-Seidel is not available on the GPU path");
+    JC_ARG(ctx, p->advection == JETCU_ADVECT_CUBIC || p->advection == JETCU_ADVECT_LINEAR);
     jetcu_smoke* h = new jetcu_smoke();
     h->ctx = ctx;
     h->P = *p;
@@ -261,19 +262,20 @@ int jetcu_smoke_compute_advection(jetcu_smoke* h, double dt) {
     SMK_ENTER(h);
     GridD g = smoke_grid(h);
     const double hmin = fmin(fmin(g.hx, g.hy), g.hz);
+    const bool linear = h->P.advection == JETCU_ADVECT_LINEAR;
     const dim3 blk(64, 4);
     // advectable scalars in registration order (density, temperature): input = clone, flow = the current velocity
     double* fields[2] = {h->den, h->temp};
     for (double* f : fields) {
         JC_TRY(jc_d2d(ctx, h->scratch, f, h->nc));
-        JC_LAUNCH(ctx, k_smoke_advect_cell, sgrid(h->nx, h->ny, h->nz), blk, 0, g, h->scratch, h->u, h->v, h->w, dt, hmin, f);
+        JC_LAUNCH(ctx, k_smoke_advect_cell, sgrid(h->nx, h->ny, h->nz), blk, 0, g, h->scratch, h->u, h->v, h->w, dt, hmin, linear, f);
         // extrapolateIntoCollider: identity without a collider (every marker is 1)
     }
     // velocity: input = flow = the clone
     JC_TRY(jc_d2d(ctx, h->u0, h->u, h->nu)); JC_TRY(jc_d2d(ctx, h->v0, h->v, h->nv)); JC_TRY(jc_d2d(ctx, h->w0, h->w, h->nw));
-    JC_LAUNCH(ctx, k_smoke_advect_face<0>, sgrid(h->nx + 1, h->ny, h->nz), blk, 0, g, h->u0, h->v0, h->w0, dt, hmin, h->u);
-    JC_LAUNCH(ctx, k_smoke_advect_face<1>, sgrid(h->nx, h->ny + 1, h->nz), blk, 0, g, h->u0, h->v0, h->w0, dt, hmin, h->v);
-    JC_LAUNCH(ctx, k_smoke_advect_face<2>, sgrid(h->nx, h->ny, h->nz + 1), blk, 0, g, h->u0, h->v0, h->w0, dt, hmin, h->w);
+    JC_LAUNCH(ctx, k_smoke_advect_face<0>, sgrid(h->nx + 1, h->ny, h->nz), blk, 0, g, h->u0, h->v0, h->w0, dt, hmin, linear, h->u);
+    JC_LAUNCH(ctx, k_smoke_advect_face<1>, sgrid(h->nx, h->ny + 1, h->nz), blk, 0, g, h->u0, h->v0, h->w0, dt, hmin, linear, h->v);
+    JC_LAUNCH(ctx, k_smoke_advect_face<2>, sgrid(h->nx, h->ny, h->nz + 1), blk, 0, g, h->u0, h->v0, h->w0, dt, hmin, linear, h->w);
     return smoke_apply_bc(h);
 }
 

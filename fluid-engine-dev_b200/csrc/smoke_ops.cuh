@@ -100,24 +100,27 @@ __host__ __device__ __forceinline__ GridView sm_cell_view(const GridD& g, const 
 }
 
 // SemiLagrangian3::advect(ScalarGrid3): one cell of a cell-centred field (in = the clone, flow = current velocity)
+// `linear`: SemiLagrangian3 itself (input.sampler(), the trilinear LinearArraySampler3 — semi_lagrangian3.cpp:162-176) instead of
+// CubicSemiLagrangian3's overrides (cubic_semi_lagrangian3.cpp:15-55)
 __host__ __device__ __forceinline__ double sm_advect_cell(const GridD& g, const double* in, const double* u, const double* v,
-                                                          const double* w, double dt, double hmin, int i, int j, int k) {
+                                                          const double* w, double dt, double hmin, int i, int j, int k,
+                                                          bool linear = false) {
     const GridView si = sm_cell_view(g, in);
     const double start[3] = {si.ox + g.hx * (double)i, si.oy + g.hy * (double)j, si.oz + g.hz * (double)k};
     double pt[3];
     sm_back_trace(g, u, v, w, dt, hmin, start, pt);
-    return sm_sample_cubic(si, pt[0], pt[1], pt[2]);
+    return linear ? jc_sample(si, pt[0], pt[1], pt[2]) : sm_sample_cubic(si, pt[0], pt[1], pt[2]);
 }
 
 // SemiLagrangian3::advect(FaceCenteredGrid3): one face of component AXIS (input = flow = the velocity clone u0, v0, w0)
 template <int AXIS>
 __host__ __device__ __forceinline__ double sm_advect_face(const GridD& g, const double* u0, const double* v0, const double* w0,
-                                                          double dt, double hmin, int i, int j, int k) {
+                                                          double dt, double hmin, int i, int j, int k, bool linear = false) {
     const GridView sc = comp_view(g, AXIS, AXIS == 0 ? u0 : (AXIS == 1 ? v0 : w0));
     const double start[3] = {sc.ox + g.hx * (double)i, sc.oy + g.hy * (double)j, sc.oz + g.hz * (double)k};
     double pt[3];
     sm_back_trace(g, u0, v0, w0, dt, hmin, start, pt);
-    return sm_sample_cubic(sc, pt[0], pt[1], pt[2]);
+    return linear ? jc_sample(sc, pt[0], pt[1], pt[2]) : sm_sample_cubic(sc, pt[0], pt[1], pt[2]);
 }
 
 // computeBuoyancyForce: one face of component AXIS; up_a = component AXIS of -gravity.normalized(), t_amb = mean temperature

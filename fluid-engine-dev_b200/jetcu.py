@@ -109,15 +109,17 @@ PIC, FLIP, APIC = 0, 1, 2
 
 class SmokeParams(C.Structure):
     """== the knobs of jet::GridSmokeSolver3 (include/jet/grid_smoke_solver3.h:170-175) + GridFluidSolver3's."""
-    _fields_ = [("grid", Grid), ("closed_domain_boundary_flag", C.c_int32), ("reserved", C.c_int32), ("gravity", f64 * 3),
+    _fields_ = [("grid", Grid), ("closed_domain_boundary_flag", C.c_int32), ("advection", C.c_int32), ("gravity", f64 * 3),
                 ("max_cfl", f64), ("buoyancy_density_factor", f64), ("buoyancy_temperature_factor", f64),
                 ("density_decay", f64), ("temperature_decay", f64), ("mgpcg", MgpcgParams)]
 
     @classmethod
     def make(cls, grid, mgpcg=None, gravity=(0.0, -9.8, 0.0), max_cfl=5.0, closed_domain_boundary_flag=63,
-             buoyancy_density_factor=-0.000625, buoyancy_temperature_factor=5.0, density_decay=0.001, temperature_decay=0.001):
+             buoyancy_density_factor=-0.000625, buoyancy_temperature_factor=5.0, density_decay=0.001, temperature_decay=0.001,
+             advection="cubic"):
         p = cls()
         p.grid = grid
+        p.advection = {"cubic": 0, "linear": 1}[advection]   # CubicSemiLagrangian3 (Jet's default) / SemiLagrangian3
         p.closed_domain_boundary_flag = closed_domain_boundary_flag
         p.gravity = (f64 * 3)(*gravity)
         p.max_cfl = max_cfl

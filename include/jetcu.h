@@ -385,10 +385,12 @@ int jetcu_hybrid_compute_advection(jetcu_hybrid*, double dt);        /* PicSolve
  * calls.  [First CUDA implementation written against the pinned oracle after round 1's GPU minutes had run out; its
  * kernel bodies are checked on the CPU by tests/hostcheck, tests/firstrun/zz_smoke.py is the first GPU run.] */
 typedef struct jetcu_smoke jetcu_smoke;
+enum { JETCU_ADVECT_CUBIC = 0, JETCU_ADVECT_LINEAR = 1 };
 typedef struct jetcu_smoke_params {
     jetcu_grid grid;
     int32_t closed_domain_boundary_flag;   /* GridFluidSolver3::closedDomainBoundaryFlag (default JETCU_DIR_ALL) */
-    int32_t reserved;
+    int32_t advection;                     /* GridFluidSolver3::advectionSolver(): JETCU_ADVECT_CUBIC = CubicSemiLagrangian3 (Jet's
+                                              default), JETCU_ADVECT_LINEAR = SemiLagrangian3 (src/examples/smoke_sim example 2) */
     double gravity[3];                     /* default (0,-9.8,0): only its direction matters (buoyancy "up") */
     double max_cfl;                        /* default 5 */
     double buoyancy_density_factor;        /* GridSmokeSolver3::buoyancySmokeDensityFactor (default -0.000625) */

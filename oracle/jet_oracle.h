@@ -145,7 +145,8 @@ int jeto_hybrid_compute_advection(jeto_hybrid*, double dt);
  * density / temperature / velocity, decay.  No emitter, no collider, diffusion and viscosity coefficients 0 (defaults). */
 typedef struct jeto_smoke_params {
     jeto_grid grid;
-    int32_t closed_domain_boundary_flag, reserved;
+    int32_t closed_domain_boundary_flag;
+    int32_t advection;   /* 0: CubicSemiLagrangian3 (the solver's default), 1: SemiLagrangian3 (linear sampler) */
     double gravity[3];
     double max_cfl;
     double buoyancy_density_factor, buoyancy_temperature_factor;   /* defaults -0.000625, 5.0 */

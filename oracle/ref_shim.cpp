@@ -652,6 +652,7 @@ int jeto_smoke_create(const jeto_smoke_params* p, jeto_smoke** out) {
     h->solver->setBuoyancyTemperatureFactor(p->buoyancy_temperature_factor);
     h->solver->setSmokeDecayFactor(p->density_decay);
     h->solver->setTemperatureDecayFactor(p->temperature_decay);
+    if (p->advection == 1) h->solver->setAdvectionSolver(std::make_shared<SemiLagrangian3>());   // else the default: CubicSemiLagrangian3
     *out = h;
     return 0;
 }

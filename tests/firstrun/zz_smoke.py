@@ -35,9 +35,11 @@ def close(a, b, tol, what):
     assert err <= tol, "%s: relative L-inf error %.3e > %.1e" % (what, err, tol)
 
 
+@pytest.mark.parametrize("advection", ["cubic", "linear"])     # CubicSemiLagrangian3 (Jet's default) / SemiLagrangian3
 @pytest.mark.parametrize("n,domain,levels,gravity", [(16, 1.0, 3, (0.0, -9.8, 0.0)), (12, 0.9, 2, (3.0, -4.0, 1.0)), (32, 1.0, 4, (0.0, -9.8, 0.0))])
-def test_smoke_stages(jc, oracle, n, domain, levels, gravity):
-    prm = SmokeParams.make(Grid.cube(n, domain), mgpcg=MgpcgParams.make(max_iterations=60, max_levels=levels), gravity=gravity)
+def test_smoke_stages(jc, oracle, n, domain, levels, gravity, advection):
+    prm = SmokeParams.make(Grid.cube(n, domain), mgpcg=MgpcgParams.make(max_iterations=60, max_levels=levels), gravity=gravity,
+                           advection=advection)
     a, b = jc.smoke(prm), oracle.smoke(prm)
     den, temp, u, v, w = plume(n, domain, seed=3)
     b.set_fields(den, temp, 0 * u, 0 * v, 0 * w)

@@ -358,7 +358,8 @@ int hc_smoke_emit_step(const jetcu_grid* grid, const jetcu_collider_shape* shape
     return 0;
 }
 
-int hc_smoke_advect(const jetcu_grid* grid, double dt, int wall_flag, double* den, double* temp, double* u, double* v, double* w) {
+int hc_smoke_advect(const jetcu_grid* grid, double dt, int wall_flag, int linear_i, double* den, double* temp, double* u, double* v, double* w) {
+    const bool linear = linear_i != 0;
     GridD g = make_grid(grid);
     const size_t nc = (size_t)g.nx * g.ny * g.nz;
     const size_t nu = (size_t)(g.nx + 1) * g.ny * g.nz, nv = (size_t)g.nx * (g.ny + 1) * g.nz, nw = (size_t)g.nx * g.ny * (g.nz + 1);
@@ -367,15 +368,15 @@ int hc_smoke_advect(const jetcu_grid* grid, double dt, int wall_flag, double* de
     for (double* f : fields) {
         std::vector<double> in(f, f + nc);
         for (int k = 0; k < g.nz; ++k) for (int j = 0; j < g.ny; ++j) for (int i = 0; i < g.nx; ++i)
-            f[((size_t)k * g.ny + j) * g.nx + i] = sm_advect_cell(g, in.data(), u, v, w, dt, hmin, i, j, k);
+            f[((size_t)k * g.ny + j) * g.nx + i] = sm_advect_cell(g, in.data(), u, v, w, dt, hmin, i, j, k, linear);
     }
     std::vector<double> u0(u, u + nu), v0(v, v + nv), w0(w, w + nw);
     for (int k = 0; k < g.nz; ++k) for (int j = 0; j < g.ny; ++j) for (int i = 0; i < g.nx + 1; ++i)
-        u[((size_t)k * g.ny + j) * (g.nx + 1) + i] = sm_advect_face<0>(g, u0.data(), v0.data(), w0.data(), dt, hmin, i, j, k);
+        u[((size_t)k * g.ny + j) * (g.nx + 1) + i] = sm_advect_face<0>(g, u0.data(), v0.data(), w0.data(), dt, hmin, i, j, k, linear);
     for (int k = 0; k < g.nz; ++k) for (int j = 0; j < g.ny + 1; ++j) for (int i = 0; i < g.nx; ++i)
-        v[((size_t)k * (g.ny + 1) + j) * g.nx + i] = sm_advect_face<1>(g, u0.data(), v0.data(), w0.data(), dt, hmin, i, j, k);
+        v[((size_t)k * (g.ny + 1) + j) * g.nx + i] = sm_advect_face<1>(g, u0.data(), v0.data(), w0.data(), dt, hmin, i, j, k, linear);
     for (int k = 0; k < g.nz + 1; ++k) for (int j = 0; j < g.ny; ++j) for (int i = 0; i < g.nx; ++i)
-        w[((size_t)k * g.ny + j) * g.nx + i] = sm_advect_face<2>(g, u0.data(), v0.data(), w0.data(), dt, hmin, i, j, k);
+        w[((size_t)k * g.ny + j) * g.nx + i] = sm_advect_face<2>(g, u0.data(), v0.data(), w0.data(), dt, hmin, i, j, k, linear);
     smoke_walls(g, wall_flag, u, v, w);
     return 0;
 }

@@ -169,7 +169,8 @@ def test_smoke_stages_random_grid(hc, port, seed):
     rng = np.random.default_rng(5000 + seed)
     grid = random_grid(rng)
     gravity = [(0.0, -9.8, 0.0), (3.0, -4.0, 1.0), (0.0, 0.0, -5.0)][seed % 3]
-    prm = SmokeParams.make(grid, mgpcg=MgpcgParams.make(max_iterations=30, max_levels=1), gravity=gravity)
+    prm = SmokeParams.make(grid, mgpcg=MgpcgParams.make(max_iterations=30, max_levels=1), gravity=gravity,
+                           advection="linear" if seed % 2 else "cubic")
     s = port.smoke(prm)
     nx, ny, nz = grid.res
     den = rng.uniform(0.0, 1.0, (nz, ny, nx)); temp = rng.uniform(0.0, 5.0, (nz, ny, nx))
@@ -193,7 +194,7 @@ def test_smoke_stages_random_grid(hc, port, seed):
     s.compute_advection(dt)
     adv = s.get_fields()
     g = {k: want[k].copy() for k in ("density", "temperature", "u", "v", "w")}
-    assert hc.hc_smoke_advect(C.byref(prm.grid), C.c_double(dt), C.c_int(prm.closed_domain_boundary_flag), dp(g["density"]),
+    assert hc.hc_smoke_advect(C.byref(prm.grid), C.c_double(dt), C.c_int(prm.closed_domain_boundary_flag), C.c_int(prm.advection), dp(g["density"]),
                               dp(g["temperature"]), dp(g["u"]), dp(g["v"]), dp(g["w"])) == 0
     for k in g:
         exact(g[k], adv[k], "advected " + k)

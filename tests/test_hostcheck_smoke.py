@@ -28,8 +28,9 @@ def port():
     return o
 
 
-def developed(port, n, domain, levels, gravity, steps=3):
-    prm = SmokeParams.make(Grid.cube(n, domain), mgpcg=MgpcgParams.make(max_iterations=60, max_levels=levels), gravity=gravity)
+def developed(port, n, domain, levels, gravity, steps=3, advection="cubic"):
+    prm = SmokeParams.make(Grid.cube(n, domain), mgpcg=MgpcgParams.make(max_iterations=60, max_levels=levels), gravity=gravity,
+                           advection=advection)
     s = port.smoke(prm)
     den, temp, u, v, w = plume(n, domain, seed=3)
     s.set_fields(den, temp, 0 * u, 0 * v, 0 * w)
@@ -58,14 +59,15 @@ def test_buoyancy(hc, port, n, domain, levels, gravity):
     s.close()
 
 
+@pytest.mark.parametrize("advection", ["cubic", "linear"])
 @pytest.mark.parametrize("n,domain,levels,gravity,dt", [(16, 1.0, 3, (0.0, -9.8, 0.0), 1.0 / 30.0), (12, 0.9, 2, (3.0, -4.0, 1.0), 1.0 / 15.0)])
-def test_advection(hc, port, n, domain, levels, gravity, dt):
-    prm, s = developed(port, n, domain, levels, gravity, steps=5)
+def test_advection(hc, port, n, domain, levels, gravity, dt, advection):
+    prm, s = developed(port, n, domain, levels, gravity, steps=5, advection=advection)
     f = s.get_fields()
     s.compute_advection(dt)
     want = s.get_fields()
     g = {k: f[k].copy() for k in ("density", "temperature", "u", "v", "w")}
-    assert hc.hc_smoke_advect(C.byref(prm.grid), C.c_double(dt), C.c_int(prm.closed_domain_boundary_flag), dp(g["density"]),
+    assert hc.hc_smoke_advect(C.byref(prm.grid), C.c_double(dt), C.c_int(prm.closed_domain_boundary_flag), C.c_int(prm.advection), dp(g["density"]),
                               dp(g["temperature"]), dp(g["u"]), dp(g["v"]), dp(g["w"])) == 0
     for k in g:
         exact(g[k], want[k], "advected " + k)

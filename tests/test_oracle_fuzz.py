@@ -83,7 +83,8 @@ def test_random_smoke_configuration_bit_exact(libs, seed):
                 *(float(x) for x in rng.choice([0.0, 0.3, -0.45, 1.5], 3)))
     levels = int(rng.choice([1, 2])) if nx % 2 == 0 else 1
     gravity = [(0.0, -9.8, 0.0), (3.0, -4.0, 1.0), (0.0, 0.0, -5.0)][seed % 3]
-    prm = SmokeParams.make(grid, mgpcg=MgpcgParams.make(max_iterations=40, max_levels=levels), gravity=gravity)
+    prm = SmokeParams.make(grid, mgpcg=MgpcgParams.make(max_iterations=40, max_levels=levels), gravity=gravity,
+                           advection="linear" if seed % 2 else "cubic")     # SemiLagrangian3 / CubicSemiLagrangian3
     a, b = ref.smoke(prm), port.smoke(prm)
     den = rng.uniform(0.0, 1.0, (nyz, nyz, nx)); temp = rng.uniform(0.0, 5.0, (nyz, nyz, nx))
     for s in (a, b):

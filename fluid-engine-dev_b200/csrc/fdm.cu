@@ -435,13 +435,16 @@ void mg_free(jetcu_ctx* ctx, MgLevels* mg) {
 // are REPLICATED: their right-hand side is all-gathered once on the way down and every rank relaxes the whole (tiny)
 // level redundantly, which costs no further messages and keeps the arithmetic identical to one GPU.
 // Coarser levels than this many cells are replicated rather than slab-distributed (every result is bit-identical either
-// way; the trade is redundant smoothing on a small grid against ~10 latency-bound neighbour exchanges per level visit).
-// JETCU_SLAB_MIN_CELLS overrides the default for A/B runs.
+// way).  Default 300 000 = "64^3 and below": at those sizes a colour pass is launch-latency-bound whether it covers the
+// whole level or an eighth of it (a few microseconds), while a distributed level visit costs 10-14 dependent neighbour
+// exchanges of ~27 us each (measured) — at 8 slabs of 256^3 that removes 28 of the ~54 exchanges of a
+// V-cycle.  128^3 (2.1 M cells) stays distributed: its sweeps are bandwidth-bound, so splitting them still pays.
+// JETCU_SLAB_MIN_CELLS overrides the threshold for A/B runs (8192 = the round-1 plan: distribute down to 4 planes per rank).
 static size_t slab_min_cells() {
     static long long v = -1;
     if (v < 0) {
         const char* e = getenv("JETCU_SLAB_MIN_CELLS");
-        v = e ? atoll(e) : (long long)SMALL_MAX_CELLS;
+        v = e ? atoll(e) : 300000ll;
         if (v < (long long)SMALL_MAX_CELLS) v = (long long)SMALL_MAX_CELLS;
     }
     return (size_t)v;

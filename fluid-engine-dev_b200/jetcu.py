@@ -167,6 +167,21 @@ class SmokeApi:
         self._c("smoke_emit_step", self.h, arr, u32(len(shapes)), C.c_int(1 if as_set else 0), f64(density[0]), f64(density[1]),
                 f64(temperature[0]), f64(temperature[1]))
 
+    def set_collider_shapes(self, shapes, as_set=None, linear_velocity=(0.0, 0.0, 0.0), angular_velocity=(0.0, 0.0, 0.0), friction=0.0):
+        """GridFluidSolver3::setCollider(RigidBodyCollider3 over analytic surfaces); shapes as for HybridApi.set_collider_shapes,
+        an empty list removes the collider."""
+        if as_set is None:
+            as_set = len(shapes) > 1
+        arr = (ColliderShape * max(len(shapes), 1))()
+        for i, sh in enumerate(shapes):
+            arr[i].kind = HybridApi.SHAPE_KINDS[sh["kind"]]
+            arr[i].flipped = 1 if sh.get("flipped", False) else 0
+            arr[i].a = (f64 * 3)(*sh["a"])
+            b = tuple(sh.get("b", (0.0, 0.0, 0.0))) + (0.0, 0.0, 0.0)
+            arr[i].b = (f64 * 3)(*b[:3])
+        self._c("smoke_set_collider_shapes", self.h, arr, u32(len(shapes)), C.c_int(1 if as_set else 0), (f64 * 3)(*linear_velocity),
+                (f64 * 3)(*angular_velocity), f64(friction))
+
     def set_fields(self, density=None, temperature=None, u=None, v=None, w=None):
         self._c("smoke_set_fields", self.h, _p(c64(density)), _p(c64(temperature)), _p(c64(u)), _p(c64(v)), _p(c64(w)))
 

@@ -164,6 +164,11 @@ int jeto_smoke_get_fields(jeto_smoke*, double* density, double* temperature, dou
  * as for jeto_hybrid_set_collider_shapes): the smoke source of src/examples/smoke_sim. */
 int jeto_smoke_emit_step(jeto_smoke*, const jeto_collider_shape* shapes, uint32_t n, int as_set, double dmin, double dmax,
                          double tmin, double tmax);
+/* GridFluidSolver3::setCollider(RigidBodyCollider3 over analytic surfaces) on the smoke solver (src/examples/smoke_sim uses a
+ * sphere): constrainVelocity's collider branch, the collider SDF in the pressure system, SemiLagrangian3's boundary handling
+ * (cells inside the collider are not advected, back-traces stop at the surface) and extrapolateIntoCollider of the scalars. */
+int jeto_smoke_set_collider_shapes(jeto_smoke*, const jeto_collider_shape* shapes, uint32_t n, int as_set,
+                                   const double linear_velocity[3], const double angular_velocity[3], double friction);
 int jeto_smoke_step(jeto_smoke*, double dt, jeto_mgpcg_result* result);            /* onAdvanceTimeStep */
 int jeto_smoke_compute_external_forces(jeto_smoke*, double dt);                    /* computeBuoyancyForce + BC */
 int jeto_smoke_compute_pressure(jeto_smoke*, double dt, jeto_mgpcg_result* result);

@@ -744,4 +744,31 @@ int jeto_smoke_emit_step(jeto_smoke* h, const jeto_collider_shape* shapes, uint3
     return 0;
 }
 
+int jeto_smoke_set_collider_shapes(jeto_smoke* h, const jeto_collider_shape* shapes, uint32_t n, int as_set, const double lin[3],
+                                   const double ang[3], double friction) {
+    if (n == 0) { h->solver->setCollider(nullptr); return 0; }
+    if (n != 1 && !as_set) return 1;
+    Surface3Ptr surface;
+    if (as_set) {
+        std::vector<Surface3Ptr> members;
+        for (uint32_t i = 0; i < n; ++i) {
+            auto m = makeShape(shapes[i]);
+            if (!m) return 1;
+            members.push_back(m);
+        }
+        surface = std::make_shared<ImplicitSurfaceSet3>(members);
+    } else {
+        surface = makeShape(shapes[0]);
+        if (!surface) return 1;
+    }
+    auto col = std::make_shared<RigidBodyCollider3>(surface, lin ? Vector3D(lin[0], lin[1], lin[2]) : Vector3D(),
+                                                    ang ? Vector3D(ang[0], ang[1], ang[2]) : Vector3D());
+    col->setFrictionCoefficient(friction);
+    h->solver->setCollider(col);
+    // what GridFluidSolver3::beginAdvanceTimeStep does before anything reads the collider grid (:448-453)
+    auto grids = h->solver->gridSystemData();
+    h->solver->_boundaryConditionSolver->updateCollider(col, grids->resolution(), grids->gridSpacing(), grids->origin());
+    return 0;
+}
+
 }  // extern "C"

@@ -8,10 +8,11 @@
 //     emit       the water drop of examples 1 / 2 (half-space + sphere): stock VolumeParticleEmitter3 set on the host  vs
 //                CudaFlipSolver3::emitOnDevice (lattice generated and tested on the GPU), then the same frames
 //     smoke      jet::GridSmokeSolver3 (plume from rest in a closed box)               vs  jetcu::CudaGridSmokeSolver3
+//     smoke_collider  the same with smoke_sim example 1's continuous box source and sphere collider
 // Prints one JSON line with the deviations from the stock run.  Built by adapters/Makefile next to dropin_check;
 // tests/test_gpu_zz_dropin_next.py runs it (first GPU run pending, see that file).
 //
-//     dropin_check_next [--n 16] [--frames 3] [--levels 3] [--what collider|pillars|tank|emit|compressed|smoke]
+//     dropin_check_next [--n 16] [--frames 3] [--levels 3] [--what collider|pillars|tank|emit|compressed|smoke|smoke_collider]
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -173,6 +174,15 @@ void setupSmoke(const std::shared_ptr<Solver>& solver, const Options& opt) {
         (*den)(i, j, k) = v;
         (*temp)(i, j, k) = 2.0 * v + 0.1;
     });
+    if (opt.what == "smoke_collider") {   // src/examples/smoke_sim example 1: a continuous box source under a sphere
+        auto source = Box3::builder().withLowerCorner({0.45, -1, 0.45}).withUpperCorner({0.55, 0.05, 0.55}).makeShared();
+        auto emitter = VolumeGridEmitter3::builder().withSourceRegion(source).withIsOneShot(false).makeShared();
+        solver->setEmitter(emitter);
+        emitter->addStepFunctionTarget(solver->smokeDensity(), 0, 1);
+        emitter->addStepFunctionTarget(solver->temperature(), 0, 1);
+        auto sphere = Sphere3::builder().withCenter({0.5, 0.3, 0.5}).withRadius(0.075).makeShared();
+        solver->setCollider(RigidBodyCollider3::builder().withSurface(sphere).makeShared());
+    }
 }
 
 double fieldDiff(const ConstArrayAccessor3<double>& a, const ConstArrayAccessor3<double>& b, double* scale) {
@@ -223,7 +233,7 @@ int main(int argc, char** argv) {
         if (opt.what == "collider" || opt.what == "pillars" || opt.what == "tank") return runCollider(opt);
         if (opt.what == "compressed") return runCompressed(opt);
         if (opt.what == "emit") return runEmit(opt);
-        if (opt.what == "smoke") return runSmoke(opt);
+        if (opt.what == "smoke" || opt.what == "smoke_collider") return runSmoke(opt);
         std::fprintf(stderr, "unknown check %s\n", opt.what.c_str());
         return 2;
     } catch (const std::exception& e) {

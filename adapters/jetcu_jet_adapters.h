@@ -181,6 +181,63 @@ inline const double* cellSamples(const jet::ScalarField3& f, const jet::Size3& r
     return out;
 }
 
+// ---- analytic surfaces (colliders, emitters): Jet objects -> jetcu_collider_shape records
+inline bool identityTransform(const jet::Transform3& t) {
+    const jet::QuaternionD q = t.orientation();
+    return t.translation().lengthSquared() == 0.0 && q.w == 1.0 && q.x == 0.0 && q.y == 0.0 && q.z == 0.0;
+}
+
+inline jetcu_collider_shape shapeOf(const jet::Surface3Ptr& surface) {
+    if (!identityTransform(surface->transform))
+        throw std::runtime_error("jetcu: device colliders need identity transforms");
+    jetcu_collider_shape s;
+    std::memset(&s, 0, sizeof(s));
+    s.flipped = surface->isNormalFlipped ? 1 : 0;
+    if (auto box = std::dynamic_pointer_cast<jet::Box3>(surface)) {
+        s.kind = JETCU_COLLIDER_BOX;
+        s.a[0] = box->bound.lowerCorner.x; s.a[1] = box->bound.lowerCorner.y; s.a[2] = box->bound.lowerCorner.z;
+        s.b[0] = box->bound.upperCorner.x; s.b[1] = box->bound.upperCorner.y; s.b[2] = box->bound.upperCorner.z;
+    } else if (auto sphere = std::dynamic_pointer_cast<jet::Sphere3>(surface)) {
+        s.kind = JETCU_COLLIDER_SPHERE;
+        s.a[0] = sphere->center.x; s.a[1] = sphere->center.y; s.a[2] = sphere->center.z;
+        s.b[0] = sphere->radius;
+    } else if (auto cyl = std::dynamic_pointer_cast<jet::Cylinder3>(surface)) {
+        s.kind = JETCU_COLLIDER_CYLINDER;
+        s.a[0] = cyl->center.x; s.a[1] = cyl->center.y; s.a[2] = cyl->center.z;
+        s.b[0] = cyl->radius; s.b[1] = cyl->height;
+    } else if (auto plane = std::dynamic_pointer_cast<jet::Plane3>(surface)) {
+        s.kind = JETCU_COLLIDER_PLANE;
+        s.a[0] = plane->point.x; s.a[1] = plane->point.y; s.a[2] = plane->point.z;
+        s.b[0] = plane->normal.x; s.b[1] = plane->normal.y; s.b[2] = plane->normal.z;
+    } else {
+        throw std::runtime_error("jetcu: device colliders are Box3 / Sphere3 / Cylinder3 / Plane3 (closed forms) or an "
+                                 "ImplicitSurfaceSet3 of them; got another Surface3");
+    }
+    return s;
+}
+
+//! One explicit surface, or the members of an ImplicitSurfaceSet3 (asSet = 1), as jetcu_collider_shape records.
+inline void collectShapes(const jet::Surface3Ptr& surface, std::vector<jetcu_collider_shape>* shapes, int* asSet) {
+    shapes->clear();
+    *asSet = 0;
+    if (auto set = std::dynamic_pointer_cast<jet::ImplicitSurfaceSet3>(surface)) {
+        if (set->isNormalFlipped || !identityTransform(set->transform))
+            throw std::runtime_error("jetcu: a device surface set needs an identity transform and unflipped normals");
+        if (set->numberOfSurfaces() == 0 || set->numberOfSurfaces() > JETCU_COLLIDER_MAX_SHAPES)
+            throw std::runtime_error("jetcu: a device surface set holds 1.." + std::to_string(JETCU_COLLIDER_MAX_SHAPES) + " surfaces");
+        for (size_t i = 0; i < set->numberOfSurfaces(); ++i) {
+            auto wrap = std::dynamic_pointer_cast<jet::SurfaceToImplicit3>(set->surfaceAt(i));
+            if (!wrap || wrap->isNormalFlipped || !identityTransform(wrap->transform))
+                throw std::runtime_error("jetcu: surface set members must be explicit surfaces (addExplicitSurface)");
+            shapes->push_back(shapeOf(wrap->surface()));
+        }
+        *asSet = 1;
+    } else {
+        shapes->push_back(shapeOf(surface));
+    }
+}
+
+
 }  // namespace detail
 
 // ------------------------------------------------------------------------------------------------ seam 2
@@ -342,7 +399,7 @@ class CudaHybridSolver3 : public Base {
         uploadIfNeeded();
         std::vector<jetcu_collider_shape> shapes;
         int asSet = 0;
-        collectShapes(surface, &shapes, &asSet);
+        detail::collectShapes(surface, &shapes, &asSet);
         const double v0[3] = {initialVelocity.x, initialVelocity.y, initialVelocity.z};
         uint64_t n = 0;
         _ctx->check(jetcu_hybrid_emit_shapes(_h, shapes.data(), (uint32_t)shapes.size(), asSet, spacing, v0, &n));
@@ -443,61 +500,6 @@ class CudaHybridSolver3 : public Base {
     //! (src/examples/hybrid_liquid_sim/main.cpp:253-278, 454-463) — all with identity transforms; anything else is an
     //! error, never a silent fallback.  Re-sent when anything changed: the application may alter the linear / angular
     //! velocity between steps.
-    static bool identityTransform(const jet::Transform3& t) {
-        const jet::QuaternionD q = t.orientation();
-        return t.translation().lengthSquared() == 0.0 && q.w == 1.0 && q.x == 0.0 && q.y == 0.0 && q.z == 0.0;
-    }
-
-    static jetcu_collider_shape shapeOf(const jet::Surface3Ptr& surface) {
-        if (!identityTransform(surface->transform))
-            throw std::runtime_error("jetcu: device colliders need identity transforms");
-        jetcu_collider_shape s;
-        std::memset(&s, 0, sizeof(s));
-        s.flipped = surface->isNormalFlipped ? 1 : 0;
-        if (auto box = std::dynamic_pointer_cast<jet::Box3>(surface)) {
-            s.kind = JETCU_COLLIDER_BOX;
-            s.a[0] = box->bound.lowerCorner.x; s.a[1] = box->bound.lowerCorner.y; s.a[2] = box->bound.lowerCorner.z;
-            s.b[0] = box->bound.upperCorner.x; s.b[1] = box->bound.upperCorner.y; s.b[2] = box->bound.upperCorner.z;
-        } else if (auto sphere = std::dynamic_pointer_cast<jet::Sphere3>(surface)) {
-            s.kind = JETCU_COLLIDER_SPHERE;
-            s.a[0] = sphere->center.x; s.a[1] = sphere->center.y; s.a[2] = sphere->center.z;
-            s.b[0] = sphere->radius;
-        } else if (auto cyl = std::dynamic_pointer_cast<jet::Cylinder3>(surface)) {
-            s.kind = JETCU_COLLIDER_CYLINDER;
-            s.a[0] = cyl->center.x; s.a[1] = cyl->center.y; s.a[2] = cyl->center.z;
-            s.b[0] = cyl->radius; s.b[1] = cyl->height;
-        } else if (auto plane = std::dynamic_pointer_cast<jet::Plane3>(surface)) {
-            s.kind = JETCU_COLLIDER_PLANE;
-            s.a[0] = plane->point.x; s.a[1] = plane->point.y; s.a[2] = plane->point.z;
-            s.b[0] = plane->normal.x; s.b[1] = plane->normal.y; s.b[2] = plane->normal.z;
-        } else {
-            throw std::runtime_error("jetcu: device colliders are Box3 / Sphere3 / Cylinder3 / Plane3 (closed forms) or an "
-                                     "ImplicitSurfaceSet3 of them; got another Surface3");
-        }
-        return s;
-    }
-
-    //! One explicit surface, or the members of an ImplicitSurfaceSet3 (asSet = 1), as jetcu_collider_shape records.
-    static void collectShapes(const jet::Surface3Ptr& surface, std::vector<jetcu_collider_shape>* shapes, int* asSet) {
-        shapes->clear();
-        *asSet = 0;
-        if (auto set = std::dynamic_pointer_cast<jet::ImplicitSurfaceSet3>(surface)) {
-            if (set->isNormalFlipped || !identityTransform(set->transform))
-                throw std::runtime_error("jetcu: a device surface set needs an identity transform and unflipped normals");
-            if (set->numberOfSurfaces() == 0 || set->numberOfSurfaces() > JETCU_COLLIDER_MAX_SHAPES)
-                throw std::runtime_error("jetcu: a device surface set holds 1.." + std::to_string(JETCU_COLLIDER_MAX_SHAPES) + " surfaces");
-            for (size_t i = 0; i < set->numberOfSurfaces(); ++i) {
-                auto wrap = std::dynamic_pointer_cast<jet::SurfaceToImplicit3>(set->surfaceAt(i));
-                if (!wrap || wrap->isNormalFlipped || !identityTransform(wrap->transform))
-                    throw std::runtime_error("jetcu: surface set members must be explicit surfaces (addExplicitSurface)");
-                shapes->push_back(shapeOf(wrap->surface()));
-            }
-            *asSet = 1;
-        } else {
-            shapes->push_back(shapeOf(surface));
-        }
-    }
-
     void syncCollider() {
         const jet::Collider3Ptr col = this->collider();
         if (col == nullptr) {
@@ -509,7 +511,7 @@ class CudaHybridSolver3 : public Base {
         if (!rigid) throw std::runtime_error("jetcu: only RigidBodyCollider3 colliders run on the device");
         std::vector<jetcu_collider_shape> shapes;
         int asSet = 0;
-        collectShapes(rigid->surface(), &shapes, &asSet);
+        detail::collectShapes(rigid->surface(), &shapes, &asSet);
         const double lin[3] = {rigid->linearVelocity.x, rigid->linearVelocity.y, rigid->linearVelocity.z};
         const double ang[3] = {rigid->angularVelocity.x, rigid->angularVelocity.y, rigid->angularVelocity.z};
         const double fr = col->frictionCoefficient();
@@ -543,7 +545,7 @@ class CudaHybridSolver3 : public Base {
 //! GridSmokeSolver3 with the sub-step on the device: GridFluidSolver3::onAdvanceTimeStep
 //! (src/jet/grid_fluid_solver3.cpp:179-210) runs as jetcu_smoke_step.  Strict drop-in: emitters (VolumeGridEmitter3 ...)
 //! keep running on the host inside beginAdvanceTimeStep, so the fields go up before and come back after every sub-step.
-//! Supported configuration = what the device path implements: no collider, zero viscosity / diffusion coefficients,
+//! Supported configuration = what the device path implements: analytic rigid colliders, zero viscosity / diffusion coefficients,
 //! CubicSemiLagrangian3 (the default) or SemiLagrangian3 advection; anything else throws instead of silently computing
 //! something different.
 class CudaGridSmokeSolver3 : public jet::GridSmokeSolver3 {
@@ -564,7 +566,6 @@ class CudaGridSmokeSolver3 : public jet::GridSmokeSolver3 {
         auto grids = gridSystemData();
         const jet::Size3 res = grids->resolution();
         if (res.x == 0 || res.y == 0 || res.z == 0) return;
-        if (collider() != nullptr) throw std::runtime_error("jetcu: the device smoke solver has no collider support yet");
         if (viscosityCoefficient() > jet::kEpsilonD || smokeDiffusionCoefficient() > jet::kEpsilonD ||
             temperatureDiffusionCoefficient() > jet::kEpsilonD)
             throw std::runtime_error("jetcu: the device smoke solver implements zero viscosity / diffusion only");
@@ -573,6 +574,7 @@ class CudaGridSmokeSolver3 : public jet::GridSmokeSolver3 {
                                              typeid(*advectionSolver()) != typeid(jet::SemiLagrangian3)))
             throw std::runtime_error("jetcu: the device smoke solver implements SemiLagrangian3 / CubicSemiLagrangian3 advection");
         ensureDevice();
+        syncCollider();
         // the host part of beginAdvanceTimeStep: emitters write into the host grids (src/jet/grid_fluid_solver3.cpp:437-447)
         if (emitter() != nullptr) emitter()->update(currentTimeInSeconds(), timeIntervalInSeconds);
         auto vel = grids->velocity();
@@ -613,9 +615,39 @@ class CudaGridSmokeSolver3 : public jet::GridSmokeSolver3 {
         _params = p;
     }
 
+    //! RigidBodyCollider3 over Box3 / Sphere3 / Cylinder3 / Plane3 or an ImplicitSurfaceSet3 of them (identity transforms), as in
+    //! the liquid adapter; re-sent when anything about it changed.
+    void syncCollider() {
+        const jet::Collider3Ptr col = collider();
+        std::vector<double> key;
+        std::vector<jetcu_collider_shape> shapes;
+        int asSet = 0;
+        double lin[3] = {0, 0, 0}, ang[3] = {0, 0, 0}, fr = 0.0;
+        if (col != nullptr) {
+            auto rigid = std::dynamic_pointer_cast<jet::RigidBodyCollider3>(col);
+            if (!rigid) throw std::runtime_error("jetcu: only RigidBodyCollider3 colliders run on the device");
+            detail::collectShapes(rigid->surface(), &shapes, &asSet);
+            lin[0] = rigid->linearVelocity.x; lin[1] = rigid->linearVelocity.y; lin[2] = rigid->linearVelocity.z;
+            ang[0] = rigid->angularVelocity.x; ang[1] = rigid->angularVelocity.y; ang[2] = rigid->angularVelocity.z;
+            fr = col->frictionCoefficient();
+            key = {double(asSet), lin[0], lin[1], lin[2], ang[0], ang[1], ang[2], fr};
+            for (const auto& s : shapes) {
+                const double part[8] = {double(s.kind), double(s.flipped), s.a[0], s.a[1], s.a[2], s.b[0], s.b[1], s.b[2]};
+                key.insert(key.end(), part, part + 8);
+            }
+        }
+        if (key != _colliderKey || _colliderHandle != _h) {
+            _ctx->check(jetcu_smoke_set_collider_shapes(_h, shapes.data(), (uint32_t)shapes.size(), asSet, lin, ang, fr));
+            _colliderKey = key;
+            _colliderHandle = _h;
+        }
+    }
+
     ContextPtr _ctx;
     jetcu_mgpcg_params _mgpcg;
     jetcu_smoke* _h = nullptr;
+    std::vector<double> _colliderKey;
+    jetcu_smoke* _colliderHandle = nullptr;   // the device solver the key was sent to (ensureDevice may recreate it)
     jetcu_smoke_params _params = jetcu_smoke_params();
     jetcu_mgpcg_result _last = jetcu_mgpcg_result();
 };

@@ -21,6 +21,13 @@ struct jetcu_smoke {
     double *u = nullptr, *v = nullptr, *w = nullptr;        // velocity
     double *u0 = nullptr, *v0 = nullptr, *w0 = nullptr;     // the clone the advection reads
     double *den = nullptr, *temp = nullptr, *scratch = nullptr;
+    // rigid collider (GridFluidSolver3::setCollider), col.kind == 0: none — the same pieces as in the hybrid solver
+    ColliderD col;
+    double* col_sdf = nullptr;                                    // GridFractionalBoundaryConditionSolver3::_colliderSdf
+    double *bnd_u = nullptr, *bnd_v = nullptr, *bnd_w = nullptr;  // collider velocity at the face positions (pressure rhs)
+    double *tmp_u = nullptr, *tmp_v = nullptr, *tmp_w = nullptr;  // uTemp / vTemp / wTemp of constrainVelocity
+    char *cm_u = nullptr, *cm_v = nullptr, *cm_w = nullptr;       // its markers; cm_u doubles as the scalar extrapolation marker
+    char *valid0 = nullptr, *valid1 = nullptr;                    // ping-pong validity maps of extrapolateToRegion
     PressureSystem ps;
     jetcu_mgpcg_result last{};
 };
@@ -49,20 +56,21 @@ __global__ void __launch_bounds__(256) k_smoke_buoyancy(GridD g, const double* _
 
 __global__ void __launch_bounds__(256) k_smoke_advect_cell(GridD g, const double* __restrict__ in, const double* __restrict__ u,
                                                            const double* __restrict__ v, const double* __restrict__ w, double dt,
-                                                           double hmin, bool linear, double* __restrict__ out) {
+                                                           double hmin, bool linear, const double* __restrict__ csdf,
+                                                           double* __restrict__ out) {
     int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
     if (i >= g.nx || j >= g.ny) return;
-    out[((size_t)k * g.ny + j) * g.nx + i] = sm_advect_cell(g, in, u, v, w, dt, hmin, i, j, k, linear);
+    out[((size_t)k * g.ny + j) * g.nx + i] = sm_advect_cell(g, in, u, v, w, dt, hmin, i, j, k, linear, csdf);
 }
 
 template <int AXIS>
 __global__ void __launch_bounds__(256) k_smoke_advect_face(GridD g, const double* __restrict__ u0, const double* __restrict__ v0,
                                                            const double* __restrict__ w0, double dt, double hmin, bool linear,
-                                                           double* __restrict__ out) {
+                                                           const double* __restrict__ csdf, double* __restrict__ out) {
     const int sx = g.nx + (AXIS == 0), sy = g.ny + (AXIS == 1), sz = g.nz + (AXIS == 2);
     int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
     if (i >= sx || j >= sy || k >= sz) return;
-    out[((size_t)k * sy + j) * sx + i] = sm_advect_face<AXIS>(g, u0, v0, w0, dt, hmin, i, j, k, linear);
+    out[((size_t)k * sy + j) * sx + i] = sm_advect_face<AXIS>(g, u0, v0, w0, dt, hmin, i, j, k, linear, csdf);
 }
 
 __global__ void __launch_bounds__(256) k_smoke_emit_step(GridD g, ColliderD e, double width, double lo, double hi, double* __restrict__ field) {
@@ -104,14 +112,83 @@ __global__ void __launch_bounds__(256) k_smoke_sum_final(const double* __restric
     if (threadIdx.x == 0) out[0] = sm[0];
 }
 
+// Collider pieces: thin launch wrappers around collider_ops.cuh (the bodies hybrid.cu's kernels wrap too; checked on the CPU by
+// tests/hostcheck).  Kept local to this TU so that the liquid solver's translation unit is not touched.
+__global__ void __launch_bounds__(256) k_smk_collider_sdf(GridD g, ColliderD c, double* __restrict__ sdf) {
+    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+    if (i >= g.nx || j >= g.ny) return;
+    sdf[((size_t)k * g.ny + j) * g.nx + i] = collider_sdf_cell(g, c, i, j, k);
+}
+template <int AXIS>
+__global__ void __launch_bounds__(256) k_smk_boundary_velocity(GridD g, ColliderD c, double* __restrict__ bnd) {
+    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+    if (i >= g.nx + (AXIS == 0) || j >= g.ny + (AXIS == 1) || k >= g.nz + (AXIS == 2)) return;
+    boundary_velocity_face<AXIS>(g, c, bnd, i, j, k);
+}
+template <int AXIS>
+__global__ void __launch_bounds__(256) k_smk_constrain_markers(GridD g, ColliderD c, const double* __restrict__ csdf,
+                                                               double* __restrict__ data, char* __restrict__ marker) {
+    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+    if (i >= g.nx + (AXIS == 0) || j >= g.ny + (AXIS == 1) || k >= g.nz + (AXIS == 2)) return;
+    constrain_marker_face<AXIS>(g, c, csdf, data, marker, i, j, k);
+}
+template <int AXIS>
+__global__ void __launch_bounds__(256) k_smk_constrain_project(GridD g, ColliderD c, const double* __restrict__ csdf,
+                                                               const double* __restrict__ u, const double* __restrict__ v,
+                                                               const double* __restrict__ w, double* __restrict__ temp) {
+    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+    if (i >= g.nx + (AXIS == 0) || j >= g.ny + (AXIS == 1) || k >= g.nz + (AXIS == 2)) return;
+    constrain_project_face<AXIS>(g, c, csdf, u, v, w, temp, i, j, k);
+}
+__global__ void __launch_bounds__(256) k_smk_outside_marker(GridD g, const double* __restrict__ csdf, char* __restrict__ marker) {
+    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+    if (i >= g.nx || j >= g.ny) return;
+    marker[((size_t)k * g.ny + j) * g.nx + i] = outside_collider_cell(g, csdf, i, j, k);
+}
+__global__ void __launch_bounds__(256) k_smk_extrapolate_sweep(double* data, const char* __restrict__ v0, char* __restrict__ v1, int nx,
+                                                               int ny, int nz) {
+    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+    if (i >= nx || j >= ny) return;
+    extrapolate_cell(data, v0, v1, nx, ny, nz, i, j, k);
+}
+
 #define SMK_ENTER(h)                                                      \
     if (!(h)) return JETCU_ERR_INVALID_ARG;                               \
     jetcu_ctx* ctx = (h)->ctx;                                            \
     if (cudaSetDevice(ctx->device) != cudaSuccess) return jetcu_fail(ctx, JETCU_ERR_CUDA, "cudaSetDevice failed");
 
+// extrapolateToRegion (include/jet/detail/array_utils-inl.h:191-239), `depth` sweeps from the validity map `marker`
+static int smoke_extrapolate(jetcu_smoke* h, double* data, const char* marker, int sx, int sy, int sz, unsigned depth) {
+    jetcu_ctx* ctx = h->ctx;
+    JC_TRY(jc_d2d(ctx, h->valid0, marker, (size_t)sx * sy * sz));
+    char *v0 = h->valid0, *v1 = h->valid1;
+    for (unsigned it = 0; it < depth; ++it) {
+        JC_LAUNCH(ctx, k_smk_extrapolate_sweep, sgrid(sx, sy, sz), dim3(64, 4), 0, data, v0, v1, sx, sy, sz);
+        char* t = v0; v0 = v1; v1 = t;
+    }
+    return JETCU_OK;
+}
+
+// GridFluidSolver3::applyBoundaryCondition == constrainVelocity: the collider branch (…boundary_condition_solver3.cpp:55-187),
+// then the closed walls (:190-232)
 static int smoke_apply_bc(jetcu_smoke* h) {
     jetcu_ctx* ctx = h->ctx;
     GridD g = smoke_grid(h);
+    if (h->col.kind != 0) {
+        const unsigned depth = (unsigned)ceil(h->P.max_cfl);  // grid_fluid_solver3.cpp:346-353
+        const dim3 blk(64, 4);
+        const int nx = h->nx, ny = h->ny, nz = h->nz;
+        JC_LAUNCH(ctx, k_smk_constrain_markers<0>, sgrid(nx + 1, ny, nz), blk, 0, g, h->col, h->col_sdf, h->u, h->cm_u);
+        JC_LAUNCH(ctx, k_smk_constrain_markers<1>, sgrid(nx, ny + 1, nz), blk, 0, g, h->col, h->col_sdf, h->v, h->cm_v);
+        JC_LAUNCH(ctx, k_smk_constrain_markers<2>, sgrid(nx, ny, nz + 1), blk, 0, g, h->col, h->col_sdf, h->w, h->cm_w);
+        JC_TRY(smoke_extrapolate(h, h->u, h->cm_u, nx + 1, ny, nz, depth));
+        JC_TRY(smoke_extrapolate(h, h->v, h->cm_v, nx, ny + 1, nz, depth));
+        JC_TRY(smoke_extrapolate(h, h->w, h->cm_w, nx, ny, nz + 1, depth));
+        JC_LAUNCH(ctx, k_smk_constrain_project<0>, sgrid(nx + 1, ny, nz), blk, 0, g, h->col, h->col_sdf, h->u, h->v, h->w, h->tmp_u);
+        JC_LAUNCH(ctx, k_smk_constrain_project<1>, sgrid(nx, ny + 1, nz), blk, 0, g, h->col, h->col_sdf, h->u, h->v, h->w, h->tmp_v);
+        JC_LAUNCH(ctx, k_smk_constrain_project<2>, sgrid(nx, ny, nz + 1), blk, 0, g, h->col, h->col_sdf, h->u, h->v, h->w, h->tmp_w);
+        JC_TRY(jc_d2d(ctx, h->u, h->tmp_u, h->nu)); JC_TRY(jc_d2d(ctx, h->v, h->tmp_v, h->nv)); JC_TRY(jc_d2d(ctx, h->w, h->tmp_w, h->nw));
+    }
     size_t m = (size_t)g.ny * g.nz;
     if ((size_t)g.nx * g.nz > m) m = (size_t)g.nx * g.nz;
     if ((size_t)g.nx * g.ny > m) m = (size_t)g.nx * g.ny;
@@ -141,6 +218,9 @@ int jetcu_smoke_destroy(jetcu_smoke* h) {
     cudaSetDevice(ctx->device);
     jc_free(ctx, h->u); jc_free(ctx, h->v); jc_free(ctx, h->w); jc_free(ctx, h->u0); jc_free(ctx, h->v0); jc_free(ctx, h->w0);
     jc_free(ctx, h->den); jc_free(ctx, h->temp); jc_free(ctx, h->scratch);
+    jc_free(ctx, h->col_sdf); jc_free(ctx, h->bnd_u); jc_free(ctx, h->bnd_v); jc_free(ctx, h->bnd_w);
+    jc_free(ctx, h->tmp_u); jc_free(ctx, h->tmp_v); jc_free(ctx, h->tmp_w);
+    jc_free(ctx, h->cm_u); jc_free(ctx, h->cm_v); jc_free(ctx, h->cm_w); jc_free(ctx, h->valid0); jc_free(ctx, h->valid1);
     pressure_free(ctx, &h->ps);
     cudaStreamSynchronize(ctx->stream);
     delete h;
@@ -199,6 +279,40 @@ int jetcu_smoke_get_fields(jetcu_smoke* h, double* den, double* temp, double* u,
     return jc_sync(ctx);
 }
 
+// GridFluidSolver3::setCollider(RigidBodyCollider3 over analytic surfaces) on the smoke solver
+int jetcu_smoke_set_collider_shapes(jetcu_smoke* h, const jetcu_collider_shape* shapes, uint32_t n, int as_set,
+                                    const double linear_velocity[3], const double angular_velocity[3], double friction) {
+    SMK_ENTER(h);
+    JC_ARG(ctx, n <= JC_COLLIDER_MAX_SHAPES && (n == 0 || shapes != nullptr) && (n <= 1 || as_set));
+    for (uint32_t i = 0; i < n; ++i) {
+        JC_ARG(ctx, shapes[i].kind >= JETCU_COLLIDER_BOX && shapes[i].kind <= JETCU_COLLIDER_PLANE);
+        if (shapes[i].kind == JETCU_COLLIDER_SPHERE || shapes[i].kind == JETCU_COLLIDER_CYLINDER) JC_ARG(ctx, shapes[i].b[0] > 0.0);
+    }
+    h->col = ColliderD();
+    if (n == 0) return JETCU_OK;
+    const ColliderD c = cd_make_collider(shapes, n, as_set, linear_velocity, angular_velocity, friction);
+    if (!h->col_sdf) {
+        JC_TRY(jc_alloc(ctx, &h->col_sdf, h->nc));
+        JC_TRY(jc_alloc(ctx, &h->bnd_u, h->nu)); JC_TRY(jc_alloc(ctx, &h->bnd_v, h->nv)); JC_TRY(jc_alloc(ctx, &h->bnd_w, h->nw));
+        JC_TRY(jc_alloc(ctx, &h->tmp_u, h->nu)); JC_TRY(jc_alloc(ctx, &h->tmp_v, h->nv)); JC_TRY(jc_alloc(ctx, &h->tmp_w, h->nw));
+        JC_TRY(jc_alloc(ctx, &h->cm_u, h->nu)); JC_TRY(jc_alloc(ctx, &h->cm_v, h->nv)); JC_TRY(jc_alloc(ctx, &h->cm_w, h->nw));
+        size_t m = h->nu > h->nv ? h->nu : h->nv;
+        if (h->nw > m) m = h->nw;
+        JC_TRY(jc_alloc(ctx, &h->valid0, m)); JC_TRY(jc_alloc(ctx, &h->valid1, m));
+    }
+    GridD g = smoke_grid(h);
+    const dim3 blk(64, 4);
+    // re-rasterised by the reference at every beginAdvanceTimeStep (grid_fluid_solver3.cpp:448-453): a pure function of the
+    // (static) shape, so once here
+    JC_LAUNCH(ctx, k_smk_collider_sdf, sgrid(h->nx, h->ny, h->nz), blk, 0, g, c, h->col_sdf);
+    JC_LAUNCH(ctx, k_smk_boundary_velocity<0>, sgrid(h->nx + 1, h->ny, h->nz), blk, 0, g, c, h->bnd_u);
+    JC_LAUNCH(ctx, k_smk_boundary_velocity<1>, sgrid(h->nx, h->ny + 1, h->nz), blk, 0, g, c, h->bnd_v);
+    JC_LAUNCH(ctx, k_smk_boundary_velocity<2>, sgrid(h->nx, h->ny, h->nz + 1), blk, 0, g, c, h->bnd_w);
+    JC_TRY(jc_sync(ctx));
+    h->col = c;
+    return JETCU_OK;
+}
+
 // VolumeGridEmitter3 (step-function targets on smoke density and temperature) fired once on the device
 int jetcu_smoke_emit_step(jetcu_smoke* h, const jetcu_collider_shape* shapes, uint32_t n, int as_set, double density_min,
                           double density_max, double temperature_min, double temperature_max) {
@@ -251,8 +365,9 @@ int jetcu_smoke_compute_external_forces(jetcu_smoke* h, double dt) {
 int jetcu_smoke_compute_pressure(jetcu_smoke* h, double dt, jetcu_mgpcg_result* result) {
     SMK_ENTER(h);
     (void)dt;
-    JC_TRY(pressure_solve_device(ctx, &h->ps, h->u, h->v, h->w, nullptr, nullptr, nullptr, nullptr, nullptr, &h->P.mgpcg, h->u,
-                                 h->v, h->w, &h->last));
+    const bool col = h->col.kind != 0;
+    JC_TRY(pressure_solve_device(ctx, &h->ps, h->u, h->v, h->w, col ? h->col_sdf : nullptr, col ? h->bnd_u : nullptr,
+                                 col ? h->bnd_v : nullptr, col ? h->bnd_w : nullptr, nullptr, &h->P.mgpcg, h->u, h->v, h->w, &h->last));
     if (result) *result = h->last;
     return smoke_apply_bc(h);
 }
@@ -263,19 +378,23 @@ int jetcu_smoke_compute_advection(jetcu_smoke* h, double dt) {
     GridD g = smoke_grid(h);
     const double hmin = fmin(fmin(g.hx, g.hy), g.hz);
     const bool linear = h->P.advection == JETCU_ADVECT_LINEAR;
+    const double* csdf = h->col.kind != 0 ? h->col_sdf : nullptr;   // boundarySdf = *colliderSdf() (kMaxD grid without collider)
     const dim3 blk(64, 4);
     // advectable scalars in registration order (density, temperature): input = clone, flow = the current velocity
     double* fields[2] = {h->den, h->temp};
     for (double* f : fields) {
         JC_TRY(jc_d2d(ctx, h->scratch, f, h->nc));
-        JC_LAUNCH(ctx, k_smoke_advect_cell, sgrid(h->nx, h->ny, h->nz), blk, 0, g, h->scratch, h->u, h->v, h->w, dt, hmin, linear, f);
-        // extrapolateIntoCollider: identity without a collider (every marker is 1)
+        JC_LAUNCH(ctx, k_smoke_advect_cell, sgrid(h->nx, h->ny, h->nz), blk, 0, g, h->scratch, h->u, h->v, h->w, dt, hmin, linear, csdf, f);
+        if (csdf) {  // GridFluidSolver3::extrapolateIntoCollider(ScalarGrid3*), grid_fluid_solver3.cpp:355-369
+            JC_LAUNCH(ctx, k_smk_outside_marker, sgrid(h->nx, h->ny, h->nz), blk, 0, g, csdf, h->cm_u);
+            JC_TRY(smoke_extrapolate(h, f, h->cm_u, h->nx, h->ny, h->nz, (unsigned)ceil(h->P.max_cfl)));
+        }
     }
     // velocity: input = flow = the clone
     JC_TRY(jc_d2d(ctx, h->u0, h->u, h->nu)); JC_TRY(jc_d2d(ctx, h->v0, h->v, h->nv)); JC_TRY(jc_d2d(ctx, h->w0, h->w, h->nw));
-    JC_LAUNCH(ctx, k_smoke_advect_face<0>, sgrid(h->nx + 1, h->ny, h->nz), blk, 0, g, h->u0, h->v0, h->w0, dt, hmin, linear, h->u);
-    JC_LAUNCH(ctx, k_smoke_advect_face<1>, sgrid(h->nx, h->ny + 1, h->nz), blk, 0, g, h->u0, h->v0, h->w0, dt, hmin, linear, h->v);
-    JC_LAUNCH(ctx, k_smoke_advect_face<2>, sgrid(h->nx, h->ny, h->nz + 1), blk, 0, g, h->u0, h->v0, h->w0, dt, hmin, linear, h->w);
+    JC_LAUNCH(ctx, k_smoke_advect_face<0>, sgrid(h->nx + 1, h->ny, h->nz), blk, 0, g, h->u0, h->v0, h->w0, dt, hmin, linear, csdf, h->u);
+    JC_LAUNCH(ctx, k_smoke_advect_face<1>, sgrid(h->nx, h->ny + 1, h->nz), blk, 0, g, h->u0, h->v0, h->w0, dt, hmin, linear, csdf, h->v);
+    JC_LAUNCH(ctx, k_smoke_advect_face<2>, sgrid(h->nx, h->ny, h->nz + 1), blk, 0, g, h->u0, h->v0, h->w0, dt, hmin, linear, csdf, h->w);
     return smoke_apply_bc(h);
 }
 

@@ -65,8 +65,11 @@ __host__ __device__ __forceinline__ void sm_flow(const GridD& g, const double* u
 }
 
 // SemiLagrangian3::backTrace — src/jet/semi_lagrangian3.cpp:117-160 (adaptive mid-point sub-steps)
+// `csdf` = the collider SDF grid (boundarySdf = *colliderSdf(), sampled linearly), nullptr for a solver without collider: its
+// grid holds kMaxD, phi0 * phi1 is +inf and the boundary branch cannot trigger.
+__host__ __device__ __forceinline__ GridView sm_cell_view(const GridD& g, const double* data);
 __host__ __device__ __forceinline__ void sm_back_trace(const GridD& g, const double* u, const double* v, const double* w, double dt,
-                                                       double h, const double* start, double* out) {
+                                                       double h, const double* start, double* out, const double* csdf = nullptr) {
     double remaining = dt;
     double pt0[3] = {start[0], start[1], start[2]}, pt1[3] = {start[0], start[1], start[2]};
     // The reference loops until the time is used up; the number of sub-steps is ~ |v| dt / h, i.e. a handful in any sane
@@ -85,6 +88,17 @@ __host__ __device__ __forceinline__ void sm_back_trace(const GridD& g, const dou
         sm_flow(g, u, v, w, mid, mv);
 #pragma unroll
         for (int a = 0; a < 3; ++a) pt1[a] = pt0[a] - mv[a] * dt;
+        if (csdf) {  // boundary handling (:146-153): stop at the collider surface
+            const GridView bs = sm_cell_view(g, csdf);
+            const double phi0 = jc_sample(bs, pt0[0], pt0[1], pt0[2]);
+            const double phi1 = jc_sample(bs, pt1[0], pt1[1], pt1[2]);
+            if (phi0 * phi1 < 0.0) {
+                const double wgt = fabs(phi1) / (fabs(phi0) + fabs(phi1));
+#pragma unroll
+                for (int a = 0; a < 3; ++a) pt1[a] = pt0[a] * wgt + pt1[a] * (1.0 - wgt);  // w * pt0 + (1.0 - w) * pt1
+                break;
+            }
+        }
         remaining -= dt;
         pt0[0] = pt1[0]; pt0[1] = pt1[1]; pt0[2] = pt1[2];
     }
@@ -104,22 +118,27 @@ __host__ __device__ __forceinline__ GridView sm_cell_view(const GridD& g, const 
 // CubicSemiLagrangian3's overrides (cubic_semi_lagrangian3.cpp:15-55)
 __host__ __device__ __forceinline__ double sm_advect_cell(const GridD& g, const double* in, const double* u, const double* v,
                                                           const double* w, double dt, double hmin, int i, int j, int k,
-                                                          bool linear = false) {
+                                                          bool linear = false, const double* csdf = nullptr) {
     const GridView si = sm_cell_view(g, in);
     const double start[3] = {si.ox + g.hx * (double)i, si.oy + g.hy * (double)j, si.oz + g.hz * (double)k};
+    // inside the collider the output grid is not written (semi_lagrangian3.cpp:36-40): it keeps its value, which `in` cloned
+    if (csdf && !(jc_sample(sm_cell_view(g, csdf), start[0], start[1], start[2]) > 0.0)) return in[((size_t)k * g.ny + j) * g.nx + i];
     double pt[3];
-    sm_back_trace(g, u, v, w, dt, hmin, start, pt);
+    sm_back_trace(g, u, v, w, dt, hmin, start, pt, csdf);
     return linear ? jc_sample(si, pt[0], pt[1], pt[2]) : sm_sample_cubic(si, pt[0], pt[1], pt[2]);
 }
 
 // SemiLagrangian3::advect(FaceCenteredGrid3): one face of component AXIS (input = flow = the velocity clone u0, v0, w0)
 template <int AXIS>
 __host__ __device__ __forceinline__ double sm_advect_face(const GridD& g, const double* u0, const double* v0, const double* w0,
-                                                          double dt, double hmin, int i, int j, int k, bool linear = false) {
+                                                          double dt, double hmin, int i, int j, int k, bool linear = false,
+                                                          const double* csdf = nullptr) {
     const GridView sc = comp_view(g, AXIS, AXIS == 0 ? u0 : (AXIS == 1 ? v0 : w0));
     const double start[3] = {sc.ox + g.hx * (double)i, sc.oy + g.hy * (double)j, sc.oz + g.hz * (double)k};
+    if (csdf && !(jc_sample(sm_cell_view(g, csdf), start[0], start[1], start[2]) > 0.0))   // :88-118, per component
+        return sc.data[((size_t)k * (g.ny + (AXIS == 1)) + j) * (g.nx + (AXIS == 0)) + i];
     double pt[3];
-    sm_back_trace(g, u0, v0, w0, dt, hmin, start, pt);
+    sm_back_trace(g, u0, v0, w0, dt, hmin, start, pt, csdf);
     return linear ? jc_sample(sc, pt[0], pt[1], pt[2]) : sm_sample_cubic(sc, pt[0], pt[1], pt[2]);
 }
 

@@ -414,6 +414,13 @@ int jetcu_smoke_get_fields(jetcu_smoke*, double* density, double* temperature, d
  * continuous emitter (isOneShot = false) is this call before every step. */
 int jetcu_smoke_emit_step(jetcu_smoke*, const jetcu_collider_shape* shapes, uint32_t n, int as_set, double density_min,
                           double density_max, double temperature_min, double temperature_max);
+/* GridFluidSolver3::setCollider(RigidBodyCollider3 over analytic surfaces) on the smoke solver (src/examples/smoke_sim puts a
+ * sphere in the plume): the collider branch of constrainVelocity, the collider SDF and velocity in the pressure system,
+ * SemiLagrangian3's boundary handling (cells inside the collider are not advected, back-traces stop at the surface —
+ * src/jet/semi_lagrangian3.cpp:36-40, 146-153) and extrapolateIntoCollider of density and temperature
+ * (src/jet/grid_fluid_solver3.cpp:355-369).  Shapes as for jetcu_hybrid_set_collider_shapes; n == 0 removes the collider. */
+int jetcu_smoke_set_collider_shapes(jetcu_smoke*, const jetcu_collider_shape* shapes, uint32_t n, int as_set,
+                                    const double linear_velocity[3], const double angular_velocity[3], double friction);
 int jetcu_smoke_step(jetcu_smoke*, double dt, jetcu_mgpcg_result* result);                 /* onAdvanceTimeStep */
 int jetcu_smoke_compute_external_forces(jetcu_smoke*, double dt);                          /* computeBuoyancyForce + BC */
 int jetcu_smoke_compute_pressure(jetcu_smoke*, double dt, jetcu_mgpcg_result* result);     /* computePressure + BC */

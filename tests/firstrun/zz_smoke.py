@@ -14,7 +14,7 @@ import pytest
 import golden_cases as gc
 from gpu_common import checker, jetcu_or_fail
 from oracle_api import Grid, MgpcgParams, SmokeParams
-from test_oracle_smoke import EMIT_GRIDS, plume, source_shapes
+from test_oracle_smoke import EMIT_GRIDS, SMOKE_COLLIDERS, plume, smoke_collider_run, source_shapes
 
 pytestmark = pytest.mark.gpu
 
@@ -111,4 +111,13 @@ def test_emit_step(jc, oracle, gi, which):
     for k in ("density", "temperature"):
         assert np.abs(fa[k] - fb[k]).max() <= 1e-14, k
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("ci", range(len(SMOKE_COLLIDERS)))
+def test_smoke_with_collider(jc, oracle, ci):
+    """Rising smoke hitting a rigid collider (src/examples/smoke_sim example 1), 10 steps with a continuous emitter: within 1e-9
+    of the field scale (the ambient temperature is a tree sum on the GPU; sin / atan2 are device libm)."""
+    fa, fb = smoke_collider_run(jc, SMOKE_COLLIDERS[ci], 10), smoke_collider_run(oracle, SMOKE_COLLIDERS[ci], 10)
+    for k in ("density", "temperature", "u", "v", "w"):
+        close(fa[-1][k], fb[-1][k], 1e-9 if k in ("density", "temperature") else 1e-7, "after 10 steps: " + k)
 

@@ -358,27 +358,49 @@ int hc_smoke_emit_step(const jetcu_grid* grid, const jetcu_collider_shape* shape
     return 0;
 }
 
-int hc_smoke_advect(const jetcu_grid* grid, double dt, int wall_flag, int linear_i, double* den, double* temp, double* u, double* v, double* w) {
+// jetcu_smoke_compute_advection; ns > 0: with a rigid collider (boundary handling in the back-trace, cells inside the collider not
+// advected, extrapolateIntoCollider of the scalars, the collider branch of the boundary condition afterwards)
+int hc_smoke_advect_collider(const jetcu_grid* grid, double dt, int wall_flag, int linear_i, const jetcu_collider_shape* shapes,
+                             uint32_t ns, int as_set, const double* lin, const double* ang, double friction, double max_cfl, double* den,
+                             double* temp, double* u, double* v, double* w) {
     const bool linear = linear_i != 0;
     GridD g = make_grid(grid);
     const size_t nc = (size_t)g.nx * g.ny * g.nz;
     const size_t nu = (size_t)(g.nx + 1) * g.ny * g.nz, nv = (size_t)g.nx * (g.ny + 1) * g.nz, nw = (size_t)g.nx * g.ny * (g.nz + 1);
     const double hmin = fmin(fmin(g.hx, g.hy), g.hz);
+    std::vector<double> sdf_store;
+    const double* csdf = nullptr;
+    if (ns > 0) {
+        sdf_store.resize(nc);
+        hc_collider_sdf(grid, shapes, ns, as_set, lin, ang, friction, sdf_store.data());
+        csdf = sdf_store.data();
+    }
     double* fields[2] = {den, temp};
     for (double* f : fields) {
         std::vector<double> in(f, f + nc);
         for (int k = 0; k < g.nz; ++k) for (int j = 0; j < g.ny; ++j) for (int i = 0; i < g.nx; ++i)
-            f[((size_t)k * g.ny + j) * g.nx + i] = sm_advect_cell(g, in.data(), u, v, w, dt, hmin, i, j, k, linear);
+            f[((size_t)k * g.ny + j) * g.nx + i] = sm_advect_cell(g, in.data(), u, v, w, dt, hmin, i, j, k, linear, csdf);
+        if (csdf) {
+            std::vector<char> marker(nc);
+            for (int k = 0; k < g.nz; ++k) for (int j = 0; j < g.ny; ++j) for (int i = 0; i < g.nx; ++i)
+                marker[((size_t)k * g.ny + j) * g.nx + i] = outside_collider_cell(g, csdf, i, j, k);
+            extrapolate(f, marker.data(), g.nx, g.ny, g.nz, (unsigned)ceil(max_cfl));
+        }
     }
     std::vector<double> u0(u, u + nu), v0(v, v + nv), w0(w, w + nw);
     for (int k = 0; k < g.nz; ++k) for (int j = 0; j < g.ny; ++j) for (int i = 0; i < g.nx + 1; ++i)
-        u[((size_t)k * g.ny + j) * (g.nx + 1) + i] = sm_advect_face<0>(g, u0.data(), v0.data(), w0.data(), dt, hmin, i, j, k, linear);
+        u[((size_t)k * g.ny + j) * (g.nx + 1) + i] = sm_advect_face<0>(g, u0.data(), v0.data(), w0.data(), dt, hmin, i, j, k, linear, csdf);
     for (int k = 0; k < g.nz; ++k) for (int j = 0; j < g.ny + 1; ++j) for (int i = 0; i < g.nx; ++i)
-        v[((size_t)k * (g.ny + 1) + j) * g.nx + i] = sm_advect_face<1>(g, u0.data(), v0.data(), w0.data(), dt, hmin, i, j, k, linear);
+        v[((size_t)k * (g.ny + 1) + j) * g.nx + i] = sm_advect_face<1>(g, u0.data(), v0.data(), w0.data(), dt, hmin, i, j, k, linear, csdf);
     for (int k = 0; k < g.nz + 1; ++k) for (int j = 0; j < g.ny; ++j) for (int i = 0; i < g.nx; ++i)
-        w[((size_t)k * g.ny + j) * g.nx + i] = sm_advect_face<2>(g, u0.data(), v0.data(), w0.data(), dt, hmin, i, j, k, linear);
+        w[((size_t)k * g.ny + j) * g.nx + i] = sm_advect_face<2>(g, u0.data(), v0.data(), w0.data(), dt, hmin, i, j, k, linear, csdf);
+    if (ns > 0) return hc_apply_boundary_condition(grid, shapes, ns, as_set, lin, ang, friction, max_cfl, wall_flag, u, v, w);
     smoke_walls(g, wall_flag, u, v, w);
     return 0;
+}
+
+int hc_smoke_advect(const jetcu_grid* grid, double dt, int wall_flag, int linear_i, double* den, double* temp, double* u, double* v, double* w) {
+    return hc_smoke_advect_collider(grid, dt, wall_flag, linear_i, nullptr, 0, 0, nullptr, nullptr, 0.0, 5.0, den, temp, u, v, w);
 }
 
 // ---- linear-system kernels (fdm_ops.cuh) and the pressure system (pressure_ops.cuh)

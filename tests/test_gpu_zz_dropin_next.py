@@ -43,8 +43,9 @@ def test_device_emission_matches_host_emitters():
     assert out["max_dx"] <= 1e-5, out
 
 
-def test_smoke_matches_stock_jet():
-    out = run("--what", "smoke", "--n", 32, "--frames", 5, "--levels", 4)
+@pytest.mark.parametrize("what", ["smoke", "smoke_collider"])
+def test_smoke_matches_stock_jet(what):
+    out = run("--what", what, "--n", 32, "--frames", 5, "--levels", 4)
     assert out["velocity_scale"] > 0.05        # the plume really rose
     assert out["velocity_rel"] <= 1e-9 and out["density_rel"] <= 1e-9, out
 

@@ -8,7 +8,7 @@ import pytest
 
 from oracle_api import Grid, MgpcgParams, SmokeParams, have_port, load_port
 from test_hostcheck_collider import _load_hostcheck, dp, exact
-from test_oracle_smoke import EMIT_GRIDS, plume, source_shapes
+from test_oracle_smoke import EMIT_GRIDS, SMOKE_COLLIDERS, plume, source_shapes
 
 pytestmark = pytest.mark.skipif(not have_port(), reason="oracle/libjetport.so not built")
 
@@ -100,5 +100,41 @@ def test_emit_step(hc, port, gi, which):
     assert hc.hc_smoke_emit_step(*args, C.c_double(0.0), C.c_double(1.0), dp(den)) == 0
     assert hc.hc_smoke_emit_step(*args, C.c_double(0.25), C.c_double(2.0), dp(temp)) == 0
     exact(den, want["density"], "emitted density"); exact(temp, want["temperature"], "emitted temperature")
+    s.close()
+
+
+@pytest.mark.parametrize("ci", range(len(SMOKE_COLLIDERS)))
+def test_advection_with_collider(hc, port, ci):
+    """computeAdvection with a rigid collider on a developed plume: boundary handling in the back-trace, untouched cells inside the
+    collider, extrapolateIntoCollider of the scalars, the collider boundary condition on the advected velocity."""
+    from oracle_api import ColliderShape
+    grid, levels, shapes, kw, advection = SMOKE_COLLIDERS[ci]
+    prm = SmokeParams.make(grid, mgpcg=MgpcgParams.make(max_iterations=60, max_levels=levels), advection=advection)
+    s = port.smoke(prm)
+    nx, ny, nz = grid.res
+    lo = np.array([grid.ox, grid.oy, grid.oz]); size = np.array([nx * grid.hx, ny * grid.hy, nz * grid.hz])
+    source = [dict(kind="box", a=tuple(lo + np.array([0.35, -1.0, 0.35]) * size), b=tuple(lo + np.array([0.65, 0.15, 0.65]) * size))]
+    s.set_collider_shapes(shapes, **kw)
+    for _ in range(8):
+        s.emit_step(source, (0.0, 1.0), (0.0, 1.0))
+        s.step(1.0 / 30.0)
+    f = s.get_fields()
+    dt = 1.0 / 20.0
+    s.compute_advection(dt)
+    want = s.get_fields()
+    arr = (ColliderShape * len(shapes))()
+    for i, sh in enumerate(shapes):
+        arr[i].kind = {"box": 1, "sphere": 2, "cylinder": 3, "plane": 4}[sh["kind"]]
+        arr[i].a = (C.c_double * 3)(*sh["a"])
+        b = tuple(sh.get("b", (0.0, 0.0, 0.0))) + (0.0, 0.0, 0.0)
+        arr[i].b = (C.c_double * 3)(*b[:3])
+    v3 = lambda k: (C.c_double * 3)(*kw.get(k, (0.0, 0.0, 0.0)))
+    g = {k: f[k].copy() for k in ("density", "temperature", "u", "v", "w")}
+    assert hc.hc_smoke_advect_collider(C.byref(prm.grid), C.c_double(dt), C.c_int(prm.closed_domain_boundary_flag), C.c_int(prm.advection),
+                                       arr, C.c_uint32(len(shapes)), C.c_int(int(len(shapes) > 1)), v3("linear_velocity"),
+                                       v3("angular_velocity"), C.c_double(kw.get("friction", 0.0)), C.c_double(prm.max_cfl),
+                                       dp(g["density"]), dp(g["temperature"]), dp(g["u"]), dp(g["v"]), dp(g["w"])) == 0
+    for k in g:
+        exact(g[k], want[k], "advected " + k)
     s.close()
 

@@ -394,7 +394,8 @@ class CudaHybridSolver3 : public Base {
     //! (jetcu_hybrid_emit_shapes) — no host lattice, no upload.  `surface`: Box3 / Sphere3 / Cylinder3 / Plane3 or an
     //! ImplicitSurfaceSet3 of them.  Returns the number of particles emitted.  kEveryStep refreshes the host mirror;
     //! kOnDemand only resizes it (values arrive with syncToHost()).
-    size_t emitOnDevice(const jet::Surface3Ptr& surface, double spacing, const jet::Vector3D& initialVelocity = jet::Vector3D()) {
+    size_t emitOnDevice(const jet::Surface3Ptr& surface, double spacing, const jet::Vector3D& initialVelocity = jet::Vector3D(),
+                        int lattice = JETCU_LATTICE_GRID /* JETCU_LATTICE_BCC = VolumeParticleEmitter3's default generator */) {
         ensureDevice();
         uploadIfNeeded();
         std::vector<jetcu_collider_shape> shapes;
@@ -402,7 +403,7 @@ class CudaHybridSolver3 : public Base {
         detail::collectShapes(surface, &shapes, &asSet);
         const double v0[3] = {initialVelocity.x, initialVelocity.y, initialVelocity.z};
         uint64_t n = 0;
-        _ctx->check(jetcu_hybrid_emit_shapes(_h, shapes.data(), (uint32_t)shapes.size(), asSet, spacing, v0, &n));
+        _ctx->check(jetcu_hybrid_emit_shapes(_h, shapes.data(), (uint32_t)shapes.size(), asSet, lattice, spacing, v0, &n));
         _deviceCount += n;
         if (_mirror == HostMirror::kEveryStep) syncToHost();
         else this->particleSystemData()->resize(_deviceCount);

@@ -183,3 +183,43 @@ __host__ __device__ __forceinline__ void lattice_point(size_t t, unsigned cx, un
     p[0] = i * spacing + lx; p[1] = j * spacing + ly; p[2] = k * spacing + lz;
 }
 
+// The emitters' point sequences.  bcc = 0: GridPointGenerator3 (above); bcc = 1: BccLatticePointGenerator, VolumeParticleEmitter3's
+// default (src/jet/bcc_lattice_point_generator.cpp:12-45): layers half a spacing apart in z, every other layer shifted by half a
+// spacing in x and y, so even layers hold cx0 * cy0 points and odd layers cx1 * cy1.
+struct LatticeD {
+    int bcc;
+    unsigned cx0, cy0, cx1, cy1, cz;
+    double spacing, half, lx, ly, lz;
+};
+// counts with the generators' own loop tests (`i * spacing + offset <= width`), total number of points
+inline size_t cd_lattice_make(const double lo[3], const double hi[3], double spacing, int bcc, LatticeD* L) {
+    L->bcc = bcc; L->spacing = spacing; L->half = spacing / 2.0; L->lx = lo[0]; L->ly = lo[1]; L->lz = lo[2];
+    const double w = hi[0] - lo[0], hgt = hi[1] - lo[1], d = hi[2] - lo[2];
+    auto count = [](double step, double offset, double width) { unsigned c = 0; for (int i = 0; i * step + offset <= width; ++i) ++c; return c; };
+    if (!bcc) {
+        L->cx0 = L->cx1 = 0; L->cy0 = L->cy1 = 0; L->cz = 0;
+        for (int i = 0; i * spacing <= w; ++i) ++L->cx0;      // literally GridPointGenerator3's tests (no "+ 0.0")
+        for (int j = 0; j * spacing <= hgt; ++j) ++L->cy0;
+        for (int k = 0; k * spacing <= d; ++k) ++L->cz;
+        L->cx1 = L->cx0; L->cy1 = L->cy0;
+        return (size_t)L->cx0 * L->cy0 * L->cz;
+    }
+    L->cx0 = count(spacing, 0.0, w); L->cx1 = count(spacing, L->half, w);
+    L->cy0 = count(spacing, 0.0, hgt); L->cy1 = count(spacing, L->half, hgt);
+    L->cz = 0;
+    for (int k = 0; k * L->half <= d; ++k) ++L->cz;
+    const size_t n0 = (size_t)L->cx0 * L->cy0, n1 = (size_t)L->cx1 * L->cy1;
+    return (size_t)(L->cz / 2) * (n0 + n1) + (size_t)(L->cz & 1u) * n0;
+}
+__host__ __device__ __forceinline__ void lattice_point_l(const LatticeD& L, size_t t, double p[3]) {
+    if (!L.bcc) { lattice_point(t, L.cx0, L.cy0, L.spacing, L.lx, L.ly, L.lz, p); return; }
+    const size_t n0 = (size_t)L.cx0 * L.cy0, n1 = (size_t)L.cx1 * L.cy1, pair = n0 + n1;
+    const size_t q = t / pair, r = t % pair;
+    const bool odd = r >= n0;
+    const size_t idx = odd ? r - n0 : r;
+    const unsigned cx = odd ? L.cx1 : L.cx0;
+    const double offset = odd ? L.half : 0.0;
+    const int i = (int)(idx % cx), j = (int)(idx / cx), k = (int)(2 * q + (odd ? 1 : 0));
+    p[0] = i * L.spacing + offset + L.lx; p[1] = j * L.spacing + offset + L.ly; p[2] = k * L.half + L.lz;
+}
+

@@ -688,14 +688,13 @@ __global__ void k_emit_flags(uint32_t* __restrict__ flags, uint32_t* __restrict_
 }
 
 // the same for an analytic implicit surface (one explicit surface or an ImplicitSurfaceSet3): signedDistance(p) <= 0
-__global__ void k_emit_flags_shapes(uint32_t* __restrict__ flags, uint32_t* __restrict__ mine, size_t total, unsigned cx, unsigned cy,
-                                    double spacing, double lx, double ly, double lz, ColliderD e, double oz, double ihz, int nz,
-                                    int z0, int z1) {
+__global__ void k_emit_flags_shapes(uint32_t* __restrict__ flags, uint32_t* __restrict__ mine, size_t total, LatticeD L, ColliderD e,
+                                    double oz, double ihz, int nz, int z0, int z1) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t > total) return;
     if (t == total) { flags[t] = 0; if (mine) mine[t] = 0; return; }
     double p[3];
-    lattice_point(t, cx, cy, spacing, lx, ly, lz, p);
+    lattice_point_l(L, t, p);
     const bool acc = cd_emit_accept(e, p);
     flags[t] = acc ? 1u : 0u;
     if (mine) {
@@ -716,6 +715,22 @@ __global__ void k_emit_lattice(double* __restrict__ x, double* __restrict__ y, d
     if (local[t + 1] == local[t]) return;  // rejected lattice point (or another rank's)
     double p[3];
     lattice_point(t, cx, cy, spacing, lx, ly, lz, p);
+    size_t o = offset + local[t];
+    x[o] = p[0]; y[o] = p[1]; z[o] = p[2];
+    vx[o] = v0x; vy[o] = v0y; vz[o] = v0z;
+    orig[o] = (uint32_t)(orig_base + slot[t]);
+}
+
+// the same for either point generator (LatticeD), used by the analytic-surface emitters
+__global__ void k_emit_lattice_l(double* __restrict__ x, double* __restrict__ y, double* __restrict__ z, double* __restrict__ vx,
+                                 double* __restrict__ vy, double* __restrict__ vz, uint32_t* __restrict__ orig, size_t offset,
+                                 size_t orig_base, const uint32_t* __restrict__ slot, const uint32_t* __restrict__ local,
+                                 size_t total, LatticeD L, double v0x, double v0y, double v0z) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    if (local[t + 1] == local[t]) return;
+    double p[3];
+    lattice_point_l(L, t, p);
     size_t o = offset + local[t];
     x[o] = p[0]; y[o] = p[1]; z[o] = p[2];
     vx[o] = v0x; vy[o] = v0y; vz[o] = v0z;
@@ -1231,17 +1246,12 @@ int jetcu_hybrid_set_local_particles(jetcu_hybrid* h, uint64_t n_local, const ui
 // Emission over the lattice of region [lo, hi] (GridPointGenerator3::forEachPoint, src/jet/grid_point_generator3.cpp:15-38):
 // flag kernel (box fast path or analytic surface) -> exclusive scan = the reference's emission order -> compaction.
 static int hyb_emit_lattice(jetcu_hybrid* h, const double lo[3], const double hi[3], double spacing, const double v0[3],
-                            uint64_t* n_emitted, const Box3d* box, const ColliderD* surf) {
+                            uint64_t* n_emitted, const Box3d* box, const ColliderD* surf, int bcc = 0) {
     jetcu_ctx* ctx = h->ctx;
     const jetcu_grid& g = h->P.grid;
-    unsigned cnt[3];
-    for (int a = 0; a < 3; ++a) {
-        double width = hi[a] - lo[a];
-        unsigned c = 0;
-        for (int i = 0; i * spacing <= width; ++i) ++c;  // same loop test as GridPointGenerator3::forEachPoint
-        cnt[a] = c;
-    }
-    uint64_t total = (uint64_t)cnt[0] * cnt[1] * cnt[2];
+    LatticeD L;
+    const uint64_t total = cd_lattice_make(lo, hi, spacing, bcc, &L);   // the generators' own loop tests
+    const unsigned cnt[3] = {L.cx0, L.cy0, L.cz};                       // the grid lattice of the Box3 fast path
     JC_ARG(ctx, h->nglobal + total < (1ull << 32) - 2);
     const bool slab = h->world > 1;
     uint64_t accepted = 0, accepted_here = 0;
@@ -1256,8 +1266,7 @@ static int hyb_emit_lattice(jetcu_hybrid* h, const double lo[3], const double hi
                                                                                   lo[0], lo[1], lo[2], *box, g.oz, 1.0 / g.hz, h->nz,
                                                                                   h->z0, h->z1);
             else
-                k_emit_flags_shapes<<<jc_blocks(total + 1, 256), 256, 0, ctx->stream>>>(slot, mine, (size_t)total, cnt[0], cnt[1],
-                                                                                         spacing, lo[0], lo[1], lo[2], *surf, g.oz,
+                k_emit_flags_shapes<<<jc_blocks(total + 1, 256), 256, 0, ctx->stream>>>(slot, mine, (size_t)total, L, *surf, g.oz,
                                                                                          1.0 / g.hz, h->nz, h->z0, h->z1);
             ctx->launches++;
             rc = scan_exclusive_u32(ctx, slot, slot, total + 1);
@@ -1275,10 +1284,15 @@ static int hyb_emit_lattice(jetcu_hybrid* h, const double lo[3], const double hi
             double z0[3] = {0, 0, 0};
             const double* vv = v0 ? v0 : z0;
             const size_t at = h->base + h->np;
-            k_emit_lattice<<<jc_blocks(total, 256), 256, 0, ctx->stream>>>(
-                h->attr[c][0], h->attr[c][1], h->attr[c][2], h->attr[c][3], h->attr[c][4], h->attr[c][5], h->orig[c], at,
-                (size_t)h->nglobal, slot, slab ? mine : slot, (size_t)total, cnt[0], cnt[1], spacing, lo[0], lo[1], lo[2], vv[0],
-                vv[1], vv[2]);
+            if (box)
+                k_emit_lattice<<<jc_blocks(total, 256), 256, 0, ctx->stream>>>(
+                    h->attr[c][0], h->attr[c][1], h->attr[c][2], h->attr[c][3], h->attr[c][4], h->attr[c][5], h->orig[c], at,
+                    (size_t)h->nglobal, slot, slab ? mine : slot, (size_t)total, cnt[0], cnt[1], spacing, lo[0], lo[1], lo[2], vv[0],
+                    vv[1], vv[2]);
+            else
+                k_emit_lattice_l<<<jc_blocks(total, 256), 256, 0, ctx->stream>>>(
+                    h->attr[c][0], h->attr[c][1], h->attr[c][2], h->attr[c][3], h->attr[c][4], h->attr[c][5], h->orig[c], at,
+                    (size_t)h->nglobal, slot, slab ? mine : slot, (size_t)total, L, vv[0], vv[1], vv[2]);
             ctx->launches++;
             for (int q = 6; q < h->nattr && rc == JETCU_OK; ++q) rc = jc_zero(ctx, h->attr[c][q] + at, accepted_here);
         }
@@ -1321,10 +1335,11 @@ int jetcu_hybrid_emit_box(jetcu_hybrid* h, const double lower[3], const double u
 
 // VolumeParticleEmitter3 over an analytic implicit surface: the emitters of the hybrid_liquid_sim examples —
 // half-space + sphere (main.cpp:110-141), a set of two boxes (:220-246) — on the device, in the reference's order.
-int jetcu_hybrid_emit_shapes(jetcu_hybrid* h, const jetcu_collider_shape* shapes, uint32_t n, int as_set, double spacing,
+int jetcu_hybrid_emit_shapes(jetcu_hybrid* h, const jetcu_collider_shape* shapes, uint32_t n, int as_set, int lattice, double spacing,
                              const double v0[3], uint64_t* n_emitted) {
     HYB_ENTER(h);
     JC_ARG(ctx, shapes && n >= 1 && n <= JC_COLLIDER_MAX_SHAPES && spacing > 0 && (n == 1 || as_set));
+    JC_ARG(ctx, lattice == JETCU_LATTICE_GRID || lattice == JETCU_LATTICE_BCC);
     for (uint32_t i = 0; i < n; ++i) {
         JC_ARG(ctx, shapes[i].kind >= JETCU_COLLIDER_BOX && shapes[i].kind <= JETCU_COLLIDER_PLANE);
         if (shapes[i].kind == JETCU_COLLIDER_SPHERE || shapes[i].kind == JETCU_COLLIDER_CYLINDER) JC_ARG(ctx, shapes[i].b[0] > 0.0);
@@ -1334,7 +1349,7 @@ int jetcu_hybrid_emit_shapes(jetcu_hybrid* h, const jetcu_collider_shape* shapes
     double lo[3] = {g.ox, g.oy, g.oz};
     double hi[3] = {g.ox + g.hx * (double)g.nx, g.oy + g.hy * (double)g.ny, g.oz + g.hz * (double)g.nz};
     cd_emit_region(e, lo, hi);
-    return hyb_emit_lattice(h, lo, hi, spacing, v0, n_emitted, nullptr, &e);
+    return hyb_emit_lattice(h, lo, hi, spacing, v0, n_emitted, nullptr, &e, lattice == JETCU_LATTICE_BCC ? 1 : 0);
 }
 
 uint64_t jetcu_hybrid_num_particles(const jetcu_hybrid* h) { return h ? h->nglobal : 0; }

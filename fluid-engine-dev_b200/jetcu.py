@@ -430,14 +430,15 @@ class HybridApi:
             arr[i].b = (f64 * 3)(*b[:3])
         return arr
 
-    def emit_shapes(self, shapes, spacing, initial_velocity=(0.0, 0.0, 0.0), as_set=None):
+    def emit_shapes(self, shapes, spacing, initial_velocity=(0.0, 0.0, 0.0), as_set=None, lattice="grid"):
         """VolumeParticleEmitter3 (one shot, jitter 0, GridPointGenerator3, maxRegion = the domain) over one analytic surface
         or an ImplicitSurfaceSet3 of them (dicts as for set_collider_shapes); returns the number of particles emitted."""
         if as_set is None:
             as_set = len(shapes) != 1
         n = u64(0)
+        # lattice: "grid" = GridPointGenerator3 (what hybrid_liquid_sim installs), "bcc" = BccLatticePointGenerator (the default)
         self._c("hybrid_emit_shapes", self.h, self._shape_array(shapes), u32(len(shapes)), C.c_int(1 if as_set else 0),
-                f64(spacing), (f64 * 3)(*initial_velocity), C.byref(n))
+                C.c_int({"grid": 0, "bcc": 1}[lattice]), f64(spacing), (f64 * 3)(*initial_velocity), C.byref(n))
         return int(n.value)
 
     def set_collider_shapes(self, shapes, as_set=True, linear_velocity=(0.0, 0.0, 0.0), angular_velocity=(0.0, 0.0, 0.0),

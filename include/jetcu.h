@@ -341,11 +341,14 @@ int jetcu_write_xyz_file(const char* path, const double* positions, uint64_t n);
 
 /* VolumeParticleEmitter3 (src/jet/volume_particle_emitter3.cpp:65-142; one shot, jitter 0, GridPointGenerator3, maxRegion =
  * the domain) over an analytic implicit surface, on the device: one explicit surface (Builder::withSurface wraps it in
- * SurfaceToImplicit3) or an ImplicitSurfaceSet3 of explicit surfaces — the emitters of src/examples/hybrid_liquid_sim
+ * SurfaceToImplicit3) or an ImplicitSurfaceSet3 of explicit surfaces, on either of Jet's point generators — the emitters of
+ * src/examples/hybrid_liquid_sim
  * (half-space + sphere, main.cpp:110-141; two boxes, :220-246).  Region = domain ∩ surface bounding box when bounded; every
  * lattice point with signedDistance <= 0 is appended in the generator's k, j, i order with velocity `initial_velocity`.
  * Shapes as for jetcu_hybrid_set_collider_shapes.  jetcu_hybrid_emit_box is the single-Box3 form. */
-int jetcu_hybrid_emit_shapes(jetcu_hybrid*, const jetcu_collider_shape* shapes, uint32_t n, int as_set, double spacing,
+enum { JETCU_LATTICE_GRID = 0,   /* GridPointGenerator3 (src/jet/grid_point_generator3.cpp:15-38): what hybrid_liquid_sim installs */
+       JETCU_LATTICE_BCC = 1 }; /* BccLatticePointGenerator (src/jet/bcc_lattice_point_generator.cpp:12-45): the emitter's default */
+int jetcu_hybrid_emit_shapes(jetcu_hybrid*, const jetcu_collider_shape* shapes, uint32_t n, int as_set, int lattice, double spacing,
                              const double initial_velocity[3], uint64_t* n_emitted);
 /* GridFractionalBoundaryConditionSolver3::colliderSdf() (cell-centred); kMaxD everywhere without a collider. */
 int jetcu_hybrid_get_collider_sdf(jetcu_hybrid*, double* sdf);

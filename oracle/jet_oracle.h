@@ -106,7 +106,8 @@ typedef struct jeto_collider_shape {
 } jeto_collider_shape;
 /* VolumeParticleEmitter3 (one shot, jitter 0, GridPointGenerator3, maxRegion = domain) over one explicit surface or an
  * ImplicitSurfaceSet3 of them (shapes as for jeto_hybrid_set_collider_shapes). */
-int jeto_hybrid_emit_shapes(jeto_hybrid*, const jeto_collider_shape* shapes, uint32_t n, int as_set, double spacing,
+int jeto_hybrid_emit_shapes(jeto_hybrid*, const jeto_collider_shape* shapes, uint32_t n, int as_set,
+                            int lattice /* 0 GridPointGenerator3, 1 BccLatticePointGenerator (the emitter's default) */, double spacing,
                             const double initial_velocity[3], uint64_t* n_emitted);
 uint64_t jeto_hybrid_num_particles(const jeto_hybrid*);
 int jeto_hybrid_get_particles(jeto_hybrid*, double* positions, double* velocities);

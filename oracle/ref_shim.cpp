@@ -407,7 +407,7 @@ int jeto_hybrid_set_collider_shape(jeto_hybrid* h, int kind, const double a[3], 
     return jeto_hybrid_set_collider_shapes(h, &s, 1, 0, lin, ang, friction);
 }
 
-int jeto_hybrid_emit_shapes(jeto_hybrid* h, const jeto_collider_shape* shapes, uint32_t n, int as_set, double spacing,
+int jeto_hybrid_emit_shapes(jeto_hybrid* h, const jeto_collider_shape* shapes, uint32_t n, int as_set, int lattice, double spacing,
                             const double v0[3], uint64_t* n_emitted) {
     if (n == 0 || (n != 1 && !as_set)) return 1;
     auto ps = h->solver->particleSystemData();
@@ -433,7 +433,7 @@ int jeto_hybrid_emit_shapes(jeto_hybrid* h, const jeto_collider_shape* shapes, u
                        .withIsOneShot(true)
                        .withJitter(0.0)
                        .makeShared();
-    emitter->setPointGenerator(std::make_shared<GridPointGenerator3>());
+    if (lattice == 0) emitter->setPointGenerator(std::make_shared<GridPointGenerator3>());   // else the default: BccLatticePointGenerator
     emitter->setTarget(ps);
     emitter->update(0.0, 0.0);
     if (n_emitted) *n_emitted = ps->numberOfParticles() - before;

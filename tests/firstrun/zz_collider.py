@@ -97,13 +97,14 @@ def test_golden_collider(jc, name):
     gc.collider(jc.hybrid, name, exact_bits=False)
 
 
+@pytest.mark.parametrize("lattice", ["grid", "bcc"])
 @pytest.mark.parametrize("name", sorted(EMITTERS))
-def test_emit_shapes(jc, oracle, name):
+def test_emit_shapes(jc, oracle, name, lattice):
     """Device-side VolumeParticleEmitter3 over analytic surfaces (jetcu_hybrid_emit_shapes): same points, same order."""
     n = 16
     prm = HybridParams.make(Grid.cube(n), mode=PIC, mgpcg=MgpcgParams.make(max_levels=2))
     a, b = jc.hybrid(prm), oracle.hybrid(prm)
-    na, nb = a.emit_shapes(EMITTERS[name], 0.5 / n, (0.1, 0.0, -0.2)), b.emit_shapes(EMITTERS[name], 0.5 / n, (0.1, 0.0, -0.2))
+    na, nb = (s.emit_shapes(EMITTERS[name], 0.5 / n, (0.1, 0.0, -0.2), lattice=lattice) for s in (a, b))
     (pa, va), (pb, vb) = a.get_particles(), b.get_particles()
     if any(m["kind"] == "cylinder" for m in EMITTERS[name]):   # atan2 / cos / sin: a point exactly on the surface may flip
         assert abs(na - nb) <= 2

@@ -227,24 +227,18 @@ int hc_extrapolate_into_collider(const jetcu_grid* grid, const jetcu_collider_sh
 
 // jetcu_hybrid_emit_shapes: cd_emit_region + the lattice loop of hyb_emit_lattice with k_emit_flags_shapes' acceptance test.
 // Call with pos == NULL to count; returns the number of accepted points through *n_out.
-int hc_emit_shapes(const jetcu_grid* g, const jetcu_collider_shape* shapes, uint32_t ns, int as_set, double spacing, double* pos,
+int hc_emit_shapes(const jetcu_grid* g, const jetcu_collider_shape* shapes, uint32_t ns, int as_set, int bcc, double spacing, double* pos,
                    uint64_t* n_out) {
     const ColliderD e = cd_make_collider(shapes, ns, as_set, nullptr, nullptr, 0.0);
     double lo[3] = {g->ox, g->oy, g->oz};
     double hi[3] = {g->ox + g->hx * (double)g->nx, g->oy + g->hy * (double)g->ny, g->oz + g->hz * (double)g->nz};
     cd_emit_region(e, lo, hi);
-    unsigned cnt[3];
-    for (int a = 0; a < 3; ++a) {
-        double width = hi[a] - lo[a];
-        unsigned c = 0;
-        for (int i = 0; i * spacing <= width; ++i) ++c;
-        cnt[a] = c;
-    }
-    const size_t total = (size_t)cnt[0] * cnt[1] * cnt[2];
+    LatticeD L;
+    const size_t total = cd_lattice_make(lo, hi, spacing, bcc, &L);
     uint64_t o = 0;
     for (size_t t = 0; t < total; ++t) {
         double p[3];
-        lattice_point(t, cnt[0], cnt[1], spacing, lo[0], lo[1], lo[2], p);
+        lattice_point_l(L, t, p);
         if (!cd_emit_accept(e, p)) continue;
         if (pos) { pos[3 * o] = p[0]; pos[3 * o + 1] = p[1]; pos[3 * o + 2] = p[2]; }
         ++o;

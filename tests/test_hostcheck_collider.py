@@ -186,15 +186,17 @@ def test_extrapolate_sdf_into_collider(hc, port, name):
     raw_h.close(); col_h.close()
 
 
+@pytest.mark.parametrize("lattice", ["grid", "bcc"])      # GridPointGenerator3 / BccLatticePointGenerator
 @pytest.mark.parametrize("name", sorted(EMITTERS))
 @pytest.mark.parametrize("n,domain", [(16, 1.0), (10, 0.9)])
-def test_emit_shapes(hc, port, name, n, domain):
+def test_emit_shapes(hc, port, name, n, domain, lattice):
     """Device emission (region, lattice, acceptance) == VolumeParticleEmitter3 as restated by the oracle, point for point."""
     grid = Grid.cube(n, domain)
     h = port.hybrid(HybridParams.make(grid, mode=PIC, mgpcg=MgpcgParams.make(max_levels=2)))
     shapes = EMITTERS[name]
     spacing = 0.5 * domain / n
-    count = h.emit_shapes(shapes, spacing)
+    count = h.emit_shapes(shapes, spacing, lattice=lattice)
+    bcc = C.c_int(int(lattice == "bcc"))
     want, _ = h.get_particles()
     assert count == len(want) and count > 100
     arr = (ColliderShape * len(shapes))()
@@ -205,10 +207,10 @@ def test_emit_shapes(hc, port, name, n, domain):
         arr[i].b = (C.c_double * 3)(*b[:3])
     got = np.zeros_like(want)
     n_out = C.c_uint64(0)
-    assert hc.hc_emit_shapes(C.byref(grid), arr, C.c_uint32(len(shapes)), C.c_int(int(len(shapes) != 1)), C.c_double(spacing), None,
+    assert hc.hc_emit_shapes(C.byref(grid), arr, C.c_uint32(len(shapes)), C.c_int(int(len(shapes) != 1)), bcc, C.c_double(spacing), None,
                              C.byref(n_out)) == 0
     assert n_out.value == count
-    assert hc.hc_emit_shapes(C.byref(grid), arr, C.c_uint32(len(shapes)), C.c_int(int(len(shapes) != 1)), C.c_double(spacing),
+    assert hc.hc_emit_shapes(C.byref(grid), arr, C.c_uint32(len(shapes)), C.c_int(int(len(shapes) != 1)), bcc, C.c_double(spacing),
                              dp(got), C.byref(n_out)) == 0
     exact(got, want, "emitted positions")
     h.close()

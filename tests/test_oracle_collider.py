@@ -177,20 +177,21 @@ EMITTERS = {   # the emitters of src/examples/hybrid_liquid_sim (half-space + sp
 }
 
 
+@pytest.mark.parametrize("lattice", ["grid", "bcc"])      # GridPointGenerator3 / BccLatticePointGenerator (the default)
 @pytest.mark.parametrize("name", sorted(EMITTERS))
 @pytest.mark.parametrize("n,domain", [(16, 1.0), (10, 0.9)])
-def test_emit_shapes_bit_exact(libs, name, n, domain):
+def test_emit_shapes_bit_exact(libs, name, n, domain, lattice):
     """VolumeParticleEmitter3 (one shot, jitter 0, GridPointGenerator3, maxRegion = domain) over analytic surfaces: the
     restatement emits the same points in the same order as the unmodified reference."""
     ref, port = libs
     prm = HybridParams.make(Grid.cube(n, domain), mode=PIC, mgpcg=MgpcgParams.make(max_levels=2))
     a, b = ref.hybrid(prm), port.hybrid(prm)
     spacing = 0.5 * domain / n
-    na, nb = a.emit_shapes(EMITTERS[name], spacing, (0.1, 0.0, -0.2)), b.emit_shapes(EMITTERS[name], spacing, (0.1, 0.0, -0.2))
+    na, nb = (s.emit_shapes(EMITTERS[name], spacing, (0.1, 0.0, -0.2), lattice=lattice) for s in (a, b))
     assert na == nb and na > 100
     (pa, va), (pb, vb) = a.get_particles(), b.get_particles()
     same(pa, pb, "emitted positions"); same(va, vb, "emitted velocities")
     # a second emitter appends (ParticleEmitterSet3: one after the other)
-    assert a.emit_shapes(EMITTERS["sphere"], spacing) == b.emit_shapes(EMITTERS["sphere"], spacing)
+    assert a.emit_shapes(EMITTERS["sphere"], spacing, lattice=lattice) == b.emit_shapes(EMITTERS["sphere"], spacing, lattice=lattice)
     same(a.get_particles()[0], b.get_particles()[0], "positions after the second emitter")
     a.close(); b.close()

@@ -18,6 +18,7 @@
 #include <stdio.h>
 
 #include "common.cuh"
+#include "p2p_ops.cuh"
 
 namespace {
 
@@ -88,13 +89,6 @@ struct JcComm {
 //   * Every rank performs the same sequence of exchanges (SPMD), so the per-rank counters agree without negotiation.
 //   * Waits are bounded (~2 s of clock64): on expiry a sticky error flag is raised and every later wait returns at once;
 //     the solver reads the flag at its next host synchronisation and fails loudly.  Nothing here can hang the GPU.
-struct P2PFlags {
-    unsigned long long data[2];  // last message number published by the rank below [0] / above [1] — written by the PEER
-    unsigned long long seq;      // exchanges completed on this rank
-    unsigned long long err;      // sticky: a wait timed out
-    unsigned int pushed, pulled; // CTA completion counters of the running kernel
-};
-#define P2P_HEADER 256
 #define P2P_THREADS 512
 #define P2P_TIMEOUT_CYCLES 4000000000ll
 
@@ -109,76 +103,61 @@ __device__ __forceinline__ unsigned long long p2p_peek(const unsigned long long*
 }
 
 // push: my boundary planes -> the neighbours' mailboxes; the last CTA to finish publishes the message number
-__global__ void __launch_bounds__(P2P_THREADS) k_p2p_push(P2PFlags* me, const uint4* __restrict__ src_dn, uint4* __restrict__ box_dn,
-                                                          unsigned long long* flag_dn, const uint4* __restrict__ src_up,
-                                                          uint4* __restrict__ box_up, unsigned long long* flag_up, size_t n16,
-                                                          size_t slot16) {
-    const unsigned long long seq = me->seq + 1;
-    const size_t off = (size_t)(seq & 1) * slot16;
-    for (size_t i = (size_t)blockIdx.x * P2P_THREADS + threadIdx.x; i < n16; i += (size_t)gridDim.x * P2P_THREADS) {
-        if (src_dn) box_dn[off + i] = src_dn[i];
-        if (src_up) box_up[off + i] = src_up[i];
+__global__ void __launch_bounds__(P2P_THREADS) k_p2p_push(P2PExchange e) {
+    const unsigned long long seq = e.me->seq + 1;
+    const size_t off = p2p_slot_offset(e, seq);
+    for (size_t i = (size_t)blockIdx.x * P2P_THREADS + threadIdx.x; i < e.n16; i += (size_t)gridDim.x * P2P_THREADS) {
+        if (e.src_dn) e.box_dn[off + i] = e.src_dn[i];
+        if (e.src_up) e.box_up[off + i] = e.src_up[i];
     }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned prev = atomicAdd(&me->pushed, 1u);
+        const unsigned prev = atomicAdd(&e.me->pushed, 1u);
         if (prev == gridDim.x - 1) {
-            me->pushed = 0;
-            if (flag_dn) p2p_publish(flag_dn, seq);
-            if (flag_up) p2p_publish(flag_up, seq);
+            e.me->pushed = 0;
+            if (e.flag_dn) p2p_publish(e.flag_dn, seq);
+            if (e.flag_up) p2p_publish(e.flag_up, seq);
         }
     }
 }
 
 // pull: wait for the neighbours' message numbers, copy my halo planes out of my mailbox; the last CTA advances seq
-__global__ void __launch_bounds__(P2P_THREADS) k_p2p_pull(P2PFlags* me, const uint4* __restrict__ box_dn, uint4* __restrict__ dst_dn,
-                                                          const uint4* __restrict__ box_up, uint4* __restrict__ dst_up, size_t n16,
-                                                          size_t slot16) {
-    const unsigned long long seq = me->seq + 1;
-    const size_t off = (size_t)(seq & 1) * slot16;
-    if (threadIdx.x == 0 && p2p_peek(&me->err) == 0) {
+__global__ void __launch_bounds__(P2P_THREADS) k_p2p_pull(P2PExchange e) {
+    const unsigned long long seq = e.me->seq + 1;
+    const size_t off = p2p_slot_offset(e, seq);
+    if (threadIdx.x == 0 && p2p_peek(&e.me->err) == 0) {
         const long long t0 = clock64();
         for (;;) {
-            const bool dn_ok = !dst_dn || p2p_peek(&me->data[0]) >= seq;
-            const bool up_ok = !dst_up || p2p_peek(&me->data[1]) >= seq;
-            if (dn_ok && up_ok) break;
-            if (clock64() - t0 > P2P_TIMEOUT_CYCLES) { me->err = 1; break; }
+            if (p2p_arrived(e, p2p_peek(&e.me->data[0]), p2p_peek(&e.me->data[1]), seq)) break;
+            if (clock64() - t0 > P2P_TIMEOUT_CYCLES) { e.me->err = 1; break; }
         }
     }
     __syncthreads();
-    for (size_t i = (size_t)blockIdx.x * P2P_THREADS + threadIdx.x; i < n16; i += (size_t)gridDim.x * P2P_THREADS) {
-        if (dst_dn) dst_dn[i] = __ldcg(box_dn + off + i);
-        if (dst_up) dst_up[i] = __ldcg(box_up + off + i);
+    for (size_t i = (size_t)blockIdx.x * P2P_THREADS + threadIdx.x; i < e.n16; i += (size_t)gridDim.x * P2P_THREADS) {
+        if (e.dst_dn) e.dst_dn[i] = __ldcg(e.in_dn + off + i);
+        if (e.dst_up) e.dst_up[i] = __ldcg(e.in_up + off + i);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        const unsigned prev = atomicAdd(&me->pulled, 1u);
+        const unsigned prev = atomicAdd(&e.me->pulled, 1u);
         if (prev == gridDim.x - 1) {  // every CTA has read seq (at its start) and finished: safe to advance
-            me->pulled = 0;
-            me->seq = seq;
+            e.me->pulled = 0;
+            e.me->seq = seq;
         }
     }
 }
 
 static int comm_halo_p2p(jetcu_ctx* ctx, char* p, size_t plane_bytes, int k0, int k1, int depth, bool down, bool up) {
     JcComm* c = ctx->comm;
-    const size_t bytes = (size_t)depth * plane_bytes, n16 = bytes / 16, slot16 = c->slot_bytes / 16;
-    P2PFlags* me = reinterpret_cast<P2PFlags*>(c->box);
-    // mailbox sides: [0] = written by the rank below, [1] = by the rank above
-    auto side = [&](char* box, int s) { return reinterpret_cast<uint4*>(box + P2P_HEADER + (size_t)s * 2 * c->slot_bytes); };
-    auto flag = [&](char* box, int s) { return &reinterpret_cast<P2PFlags*>(box)->data[s]; };
-    unsigned grid = (unsigned)((n16 + (size_t)P2P_THREADS * 4 - 1) / ((size_t)P2P_THREADS * 4));
+    const size_t bytes = (size_t)depth * plane_bytes;
+    const P2PExchange e = p2p_exchange(c->box, c->peer_box[0], c->peer_box[1], c->slot_bytes, p, plane_bytes, k0, k1, depth, down, up);
+    unsigned grid = (unsigned)((e.n16 + (size_t)P2P_THREADS * 4 - 1) / ((size_t)P2P_THREADS * 4));
     if (grid < 1) grid = 1;
     if (grid > 296) grid = 296;
-    k_p2p_push<<<grid, P2P_THREADS, 0, ctx->stream>>>(
-        me, down ? reinterpret_cast<const uint4*>(p + (size_t)k0 * plane_bytes) : nullptr, down ? side(c->peer_box[0], 1) : nullptr,
-        down ? flag(c->peer_box[0], 1) : nullptr, up ? reinterpret_cast<const uint4*>(p + (size_t)(k1 - depth) * plane_bytes) : nullptr,
-        up ? side(c->peer_box[1], 0) : nullptr, up ? flag(c->peer_box[1], 0) : nullptr, n16, slot16);
-    k_p2p_pull<<<grid, P2P_THREADS, 0, ctx->stream>>>(
-        me, down ? side(c->box, 0) : nullptr, down ? reinterpret_cast<uint4*>(p + (size_t)(k0 - depth) * plane_bytes) : nullptr,
-        up ? side(c->box, 1) : nullptr, up ? reinterpret_cast<uint4*>(p + (size_t)k1 * plane_bytes) : nullptr, n16, slot16);
+    k_p2p_push<<<grid, P2P_THREADS, 0, ctx->stream>>>(e);
+    k_p2p_pull<<<grid, P2P_THREADS, 0, ctx->stream>>>(e);
     ctx->launches += 2;
     JC_CUDA(ctx, cudaGetLastError());
     c->p2p_exchanges += 1;

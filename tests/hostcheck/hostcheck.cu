@@ -15,6 +15,7 @@
 #include "../../fluid-engine-dev_b200/csrc/pressure_ops.cuh"
 #include "../../fluid-engine-dev_b200/csrc/p2g_ops.cuh"
 #include "../../fluid-engine-dev_b200/csrc/smoke_ops.cuh"
+#include "../../fluid-engine-dev_b200/csrc/p2p_ops.cuh"
 
 static GridD make_grid(const jetcu_grid* g) {
     return GridD{(int)g->nx, (int)g->ny, (int)g->nz, g->hx, g->hy, g->hz, g->ox, g->oy, g->oz,
@@ -395,6 +396,66 @@ int hc_smoke_advect_collider(const jetcu_grid* grid, double dt, int wall_flag, i
 
 int hc_smoke_advect(const jetcu_grid* grid, double dt, int wall_flag, int linear_i, double* den, double* temp, double* u, double* v, double* w) {
     return hc_smoke_advect_collider(grid, dt, wall_flag, linear_i, nullptr, 0, 0, nullptr, nullptr, 0.0, 5.0, den, temp, u, v, w);
+}
+
+// ---- peer-memory halo exchange (p2p_ops.cuh): a chain of `world` ranks in host memory, each with its full-size globally indexed
+// array (planes of `plane_bytes`, `T` owned planes per rank) and its mailbox; `exchanges` rounds of push (all ranks, in the order
+// given by `reverse`) then pull, with the very addressing comm.cu's kernels use.  Owned planes carry a (rank, plane, round) pattern,
+// everything else is poisoned before each round.  Returns the number of halo bytes that do not hold the owner's pattern (0 = pass),
+// or -1 if a pull would have had to wait (message numbers out of step).
+long long hc_p2p_chain(int world, int T, uint64_t plane_bytes, int depth, int exchanges, uint64_t slot_bytes, int reverse) {
+    const int nz = world * T;
+    std::vector<std::vector<unsigned char>> arr(world, std::vector<unsigned char>((size_t)nz * plane_bytes));
+    std::vector<std::vector<unsigned char>> box(world, std::vector<unsigned char>(P2P_HEADER + 4 * slot_bytes, 0));
+    auto pattern = [&](int plane, int round, size_t byte) { return (unsigned char)(plane * 7 + round * 31 + (byte % 13) + 1); };
+    long long bad = 0;
+    for (int round = 0; round < exchanges; ++round) {
+        std::vector<P2PExchange> ex(world);
+        for (int r = 0; r < world; ++r) {
+            std::fill(arr[r].begin(), arr[r].end(), (unsigned char)0xEE);
+            for (int k = r * T; k < (r + 1) * T; ++k)
+                for (size_t b = 0; b < plane_bytes; ++b) arr[r][(size_t)k * plane_bytes + b] = pattern(k, round, b);
+            const bool down = r > 0, up = r + 1 < world;
+            ex[r] = p2p_exchange(reinterpret_cast<char*>(box[r].data()), down ? reinterpret_cast<char*>(box[r - 1].data()) : nullptr,
+                                 up ? reinterpret_cast<char*>(box[r + 1].data()) : nullptr, slot_bytes, reinterpret_cast<char*>(arr[r].data()),
+                                 plane_bytes, r * T, (r + 1) * T, depth, down, up);
+        }
+        for (int q = 0; q < world; ++q) {   // push (k_p2p_push)
+            const int r = reverse ? world - 1 - q : q;
+            const P2PExchange& e = ex[r];
+            const unsigned long long seq = e.me->seq + 1;
+            const size_t off = p2p_slot_offset(e, seq);
+            for (size_t i = 0; i < e.n16; ++i) {
+                if (e.src_dn) e.box_dn[off + i] = e.src_dn[i];
+                if (e.src_up) e.box_up[off + i] = e.src_up[i];
+            }
+            if (e.flag_dn) *e.flag_dn = seq;
+            if (e.flag_up) *e.flag_up = seq;
+        }
+        for (int r = 0; r < world; ++r) {   // pull (k_p2p_pull)
+            const P2PExchange& e = ex[r];
+            const unsigned long long seq = e.me->seq + 1;
+            if (!p2p_arrived(e, e.me->data[0], e.me->data[1], seq)) return -1;
+            const size_t off = p2p_slot_offset(e, seq);
+            for (size_t i = 0; i < e.n16; ++i) {
+                if (e.dst_dn) e.dst_dn[i] = e.in_dn[off + i];
+                if (e.dst_up) e.dst_up[i] = e.in_up[off + i];
+            }
+            e.me->seq = seq;
+        }
+        for (int r = 0; r < world; ++r) {   // every halo plane must hold its owner's pattern of this round, nothing else changed
+            for (int k = 0; k < nz; ++k) {
+                const bool owned = k >= r * T && k < (r + 1) * T;
+                const bool halo = (r > 0 && k >= r * T - depth && k < r * T) || (r + 1 < world && k >= (r + 1) * T && k < (r + 1) * T + depth);
+                for (size_t b = 0; b < plane_bytes; ++b) {
+                    const unsigned char got = arr[r][(size_t)k * plane_bytes + b];
+                    const unsigned char want = (owned || halo) ? pattern(k, round, b) : (unsigned char)0xEE;
+                    if (got != want) ++bad;
+                }
+            }
+        }
+    }
+    return bad;
 }
 
 // ---- linear-system kernels (fdm_ops.cuh) and the pressure system (pressure_ops.cuh)

@@ -35,14 +35,5 @@ for k in k_relax_colour_code k_p2g_cells k_move k_gather_attrs k_mvm; do
 done
 ls -la $OUT
 
-# 5. (separate call, --gpus 8) the slab plan: the default replicates MG levels of 64^3 and below (session 9, from the measured
-#    exchange latency); A/B it against the round-1 plan (JETCU_SLAB_MIN_CELLS=8192) and against replicating 128^3 too (3000000)
-#    JETCU_SLAB_MIN_CELLS=8192 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
-#        --master-port 29511 bench.py --gpus 8 --steps 5 --warmup 3
-#    and the peer-memory halo path (first run; bit-identity + timing), on 2 GPUs first:
-#    gpurun --gpus 2 --timeout 900 -- 'timeout 600 python -m pytest tests/test_gpu_slabs.py -m gpu -q -rxX; for p in 0 1; do
-#        JETCU_P2P_HALO=$p timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-#        --master-port 2952$p bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_2gpu_p2p$p.json; done'
-#    per-exchange latency of both transports (profiles evidence for DESIGN.md §4):
-#    for p in 0 1; do JETCU_P2P_HALO=$p timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-#        --master-port 2953$p scripts/halo_latency.py > gpurun_out/halo_latency_p2p$p.json; done
+# 5. multi-GPU (separate calls, --gpus 2 then 8): scripts/round2_multi_gpu_call.sh — slab parity with both halo transports, halo
+#    latency, the slab-plan and peer-memory A/B benches.

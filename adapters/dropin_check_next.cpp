@@ -9,10 +9,11 @@
 //                CudaFlipSolver3::emitOnDevice (lattice generated and tested on the GPU), then the same frames
 //     smoke      jet::GridSmokeSolver3 (plume from rest in a closed box)               vs  jetcu::CudaGridSmokeSolver3
 //     smoke_collider  the same with smoke_sim example 1's continuous box source and sphere collider
+//     smoke_device    ... with the source as a device-side emitter and the fields resident on the device (kOnDemand)
 // Prints one JSON line with the deviations from the stock run.  Built by adapters/Makefile next to dropin_check;
 // tests/test_gpu_zz_dropin_next.py runs it (first GPU run pending, see that file).
 //
-//     dropin_check_next [--n 16] [--frames 3] [--levels 3] [--what collider|pillars|tank|emit|compressed|smoke|smoke_collider]
+//     dropin_check_next [--n 16] [--frames 3] [--levels 3] [--what collider|pillars|tank|emit|compressed|smoke|smoke_collider|smoke_device]
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -158,6 +159,15 @@ int runEmit(const Options& opt) {
     return 0;
 }
 
+// smoke_device: the jetcu solver gets the source as a device-side emitter and keeps its fields on the device between sub-steps
+inline bool attachDeviceEmitter(const std::shared_ptr<GridSmokeSolver3>&, const Surface3Ptr&, const Options&) { return false; }
+inline bool attachDeviceEmitter(const std::shared_ptr<jetcu::CudaGridSmokeSolver3>& solver, const Surface3Ptr& source, const Options& opt) {
+    if (opt.what != "smoke_device") return false;
+    solver->addDeviceStepEmitter(source, 0, 1, 0, 1);
+    solver->setHostMirror(jetcu::HostMirror::kOnDemand);
+    return true;
+}
+
 template <class Solver>
 void setupSmoke(const std::shared_ptr<Solver>& solver, const Options& opt) {
     solver->setUseCompressedLinearSystem(false);
@@ -174,12 +184,14 @@ void setupSmoke(const std::shared_ptr<Solver>& solver, const Options& opt) {
         (*den)(i, j, k) = v;
         (*temp)(i, j, k) = 2.0 * v + 0.1;
     });
-    if (opt.what == "smoke_collider") {   // src/examples/smoke_sim example 1: a continuous box source under a sphere
+    if (opt.what == "smoke_collider" || opt.what == "smoke_device") {   // src/examples/smoke_sim example 1: a continuous box source under a sphere
         auto source = Box3::builder().withLowerCorner({0.45, -1, 0.45}).withUpperCorner({0.55, 0.05, 0.55}).makeShared();
-        auto emitter = VolumeGridEmitter3::builder().withSourceRegion(source).withIsOneShot(false).makeShared();
-        solver->setEmitter(emitter);
-        emitter->addStepFunctionTarget(solver->smokeDensity(), 0, 1);
-        emitter->addStepFunctionTarget(solver->temperature(), 0, 1);
+        if (!attachDeviceEmitter(solver, source, opt)) {
+            auto emitter = VolumeGridEmitter3::builder().withSourceRegion(source).withIsOneShot(false).makeShared();
+            solver->setEmitter(emitter);
+            emitter->addStepFunctionTarget(solver->smokeDensity(), 0, 1);
+            emitter->addStepFunctionTarget(solver->temperature(), 0, 1);
+        }
         auto sphere = Sphere3::builder().withCenter({0.5, 0.3, 0.5}).withRadius(0.075).makeShared();
         solver->setCollider(RigidBodyCollider3::builder().withSurface(sphere).makeShared());
     }
@@ -203,6 +215,7 @@ int runSmoke(const Options& opt) {
         stock->update(frame);
         cuda->update(frame);
     }
+    cuda->syncToHost();   // kOnDemand (smoke_device): the fields lived on the device until now
     double vs = 0.0, ds = 0.0;
     auto sv = stock->velocity();
     auto cv = cuda->velocity();
@@ -233,7 +246,7 @@ int main(int argc, char** argv) {
         if (opt.what == "collider" || opt.what == "pillars" || opt.what == "tank") return runCollider(opt);
         if (opt.what == "compressed") return runCompressed(opt);
         if (opt.what == "emit") return runEmit(opt);
-        if (opt.what == "smoke" || opt.what == "smoke_collider") return runSmoke(opt);
+        if (opt.what == "smoke" || opt.what == "smoke_collider" || opt.what == "smoke_device") return runSmoke(opt);
         std::fprintf(stderr, "unknown check %s\n", opt.what.c_str());
         return 2;
     } catch (const std::exception& e) {

@@ -562,6 +562,30 @@ class CudaGridSmokeSolver3 : public jet::GridSmokeSolver3 {
 
     const jetcu_mgpcg_result& lastResult() const { return _last; }
 
+    //! kEveryStep (default): strict drop-in, the fields go up before and come back after every sub-step.  kOnDemand: the
+    //! fields stay on the device between sub-steps as long as no host-side Jet emitter is attached; syncToHost() fetches
+    //! them, markHostDirty() announces host-side edits.
+    void setHostMirror(HostMirror m) { _mirror = m; }
+    void markHostDirty() { _hostDirty = true; }
+    void syncToHost() {
+        if (!_h) return;
+        auto vel = gridSystemData()->velocity();
+        _ctx->check(jetcu_smoke_get_fields(_h, smokeDensity()->dataAccessor().data(), temperature()->dataAccessor().data(),
+                                           vel->uAccessor().data(), vel->vAccessor().data(), vel->wAccessor().data(), nullptr));
+    }
+
+    //! Device-side smoke source: the equivalent of a continuous jet::VolumeGridEmitter3 over `surface` with
+    //! addStepFunctionTarget(smokeDensity(), dMin, dMax) and addStepFunctionTarget(temperature(), tMin, tMax) — what
+    //! src/examples/smoke_sim attaches — fired on the GPU before every sub-step (jetcu_smoke_emit_step).  The mapper of a Jet
+    //! emitter target is an opaque lambda, so this cannot be read off a Jet emitter object; a Jet emitter set with setEmitter()
+    //! keeps running on the host.
+    void addDeviceStepEmitter(const jet::Surface3Ptr& surface, double dMin, double dMax, double tMin, double tMax) {
+        DeviceEmitter e;
+        detail::collectShapes(surface, &e.shapes, &e.asSet);
+        e.v[0] = dMin; e.v[1] = dMax; e.v[2] = tMin; e.v[3] = tMax;
+        _deviceEmitters.push_back(e);
+    }
+
  protected:
     void onAdvanceTimeStep(double timeIntervalInSeconds) override {
         auto grids = gridSystemData();
@@ -576,14 +600,24 @@ class CudaGridSmokeSolver3 : public jet::GridSmokeSolver3 {
             throw std::runtime_error("jetcu: the device smoke solver implements SemiLagrangian3 / CubicSemiLagrangian3 advection");
         ensureDevice();
         syncCollider();
-        // the host part of beginAdvanceTimeStep: emitters write into the host grids (src/jet/grid_fluid_solver3.cpp:437-447)
-        if (emitter() != nullptr) emitter()->update(currentTimeInSeconds(), timeIntervalInSeconds);
-        auto vel = grids->velocity();
-        _ctx->check(jetcu_smoke_set_fields(_h, smokeDensity()->constDataAccessor().data(), temperature()->constDataAccessor().data(),
-                                           vel->uConstAccessor().data(), vel->vConstAccessor().data(), vel->wConstAccessor().data()));
+        // the host part of beginAdvanceTimeStep: Jet emitters write into the host grids (src/jet/grid_fluid_solver3.cpp:437-447)
+        const bool hostEmitter = emitter() != nullptr;
+        const bool resident = _mirror == HostMirror::kOnDemand && !hostEmitter;
+        if (hostEmitter) {
+            if (_mirror == HostMirror::kOnDemand && !_hostDirty && _uploadedOnce) syncToHost();   // the emitter reads the current fields
+            emitter()->update(currentTimeInSeconds(), timeIntervalInSeconds);
+        }
+        if (!resident || _hostDirty || !_uploadedOnce) {
+            auto vel = grids->velocity();
+            _ctx->check(jetcu_smoke_set_fields(_h, smokeDensity()->constDataAccessor().data(), temperature()->constDataAccessor().data(),
+                                               vel->uConstAccessor().data(), vel->vConstAccessor().data(), vel->wConstAccessor().data()));
+            _hostDirty = false;
+            _uploadedOnce = true;
+        }
+        for (const DeviceEmitter& e : _deviceEmitters)
+            _ctx->check(jetcu_smoke_emit_step(_h, e.shapes.data(), (uint32_t)e.shapes.size(), e.asSet, e.v[0], e.v[1], e.v[2], e.v[3]));
         _ctx->check(jetcu_smoke_step(_h, timeIntervalInSeconds, &_last));
-        _ctx->check(jetcu_smoke_get_fields(_h, smokeDensity()->dataAccessor().data(), temperature()->dataAccessor().data(),
-                                           vel->uAccessor().data(), vel->vAccessor().data(), vel->wAccessor().data(), nullptr));
+        if (_mirror == HostMirror::kEveryStep) syncToHost();
     }
 
  private:
@@ -610,8 +644,12 @@ class CudaGridSmokeSolver3 : public jet::GridSmokeSolver3 {
         if (frac && detail::mgpcgParamsOf(frac->linearSystemSolver(), &fromJet)) _mgpcg = fromJet;
         p.mgpcg = _mgpcg;
         if (_h && std::memcmp(&p, &_params, sizeof(p)) == 0) return;   // knobs unchanged since the last step
-        if (_h) jetcu_smoke_destroy(_h);
+        if (_h) {   // knobs changed: the live fields move to the new device solver through the host
+            if (_uploadedOnce && !_hostDirty) syncToHost();
+            jetcu_smoke_destroy(_h);
+        }
         _h = nullptr;
+        _uploadedOnce = false;
         _ctx->check(jetcu_smoke_create(_ctx->get(), &p, &_h));
         _params = p;
     }
@@ -644,9 +682,18 @@ class CudaGridSmokeSolver3 : public jet::GridSmokeSolver3 {
         }
     }
 
+    struct DeviceEmitter {
+        std::vector<jetcu_collider_shape> shapes;
+        int asSet = 0;
+        double v[4] = {0, 1, 0, 1};
+    };
+
     ContextPtr _ctx;
     jetcu_mgpcg_params _mgpcg;
     jetcu_smoke* _h = nullptr;
+    HostMirror _mirror = HostMirror::kEveryStep;
+    bool _hostDirty = true, _uploadedOnce = false;
+    std::vector<DeviceEmitter> _deviceEmitters;
     std::vector<double> _colliderKey;
     jetcu_smoke* _colliderHandle = nullptr;   // the device solver the key was sent to (ensureDevice may recreate it)
     jetcu_smoke_params _params = jetcu_smoke_params();

@@ -43,7 +43,7 @@ def test_device_emission_matches_host_emitters():
     assert out["max_dx"] <= 1e-5, out
 
 
-@pytest.mark.parametrize("what", ["smoke", "smoke_collider"])
+@pytest.mark.parametrize("what", ["smoke", "smoke_collider", "smoke_device"])
 def test_smoke_matches_stock_jet(what):
     out = run("--what", what, "--n", 32, "--frames", 5, "--levels", 4)
     assert out["velocity_scale"] > 0.05        # the plume really rose

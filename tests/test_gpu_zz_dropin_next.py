@@ -70,3 +70,18 @@ def test_example_application_next_to_stock_jet(example, tmp_path):
     first = (tmp_path / "frame_000000.pos").read_bytes()
     assert first[:20].hex() == "0c00000000000600080004000600000004000000" and (len(first) - 24) % 24 == 0 and len(first) > 24 * 1000
 
+
+@pytest.mark.parametrize("flags", [[], ["--linear"]])
+def test_smoke_application_next_to_stock_jet(flags):
+    """adapters/smoke_sim_cuda: smoke_sim example 1 (continuous box source under a sphere) with the source on the device, stepped
+    next to a stock GridSmokeSolver3 with Jet's own VolumeGridEmitter3."""
+    app = os.path.join(ROOT, "adapters", "_build", "smoke_sim_cuda")
+    if not os.path.exists(app):
+        pytest.fail("adapters/_build/smoke_sim_cuda missing: run `make -C adapters` where /root/reference exists")
+    r = subprocess.run([app, "-r", "32", "-f", "6", "--compare"] + flags, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    frames = [l for l in r.stdout.splitlines() if l.startswith("frame ")]
+    assert len(frames) == 6, r.stdout
+    for l in frames:
+        assert float(l.rsplit(" ", 1)[1]) <= 1e-8, l
+

@@ -620,6 +620,16 @@ class CudaGridSmokeSolver3 : public jet::GridSmokeSolver3 {
         if (_mirror == HostMirror::kEveryStep) syncToHost();
     }
 
+    //! GridFluidSolver3::numberOfSubTimeSteps (src/jet/grid_fluid_solver3.cpp:212-217) on the device-resident velocity: in
+    //! kOnDemand mode the host grid is stale, and the CFL number must come from the live field.
+    unsigned int numberOfSubTimeSteps(double timeIntervalInSeconds) const override {
+        if (!_h || !_uploadedOnce || _hostDirty || _mirror == HostMirror::kEveryStep)
+            return jet::GridSmokeSolver3::numberOfSubTimeSteps(timeIntervalInSeconds);
+        uint32_t n = 1;
+        _ctx->check(jetcu_smoke_num_sub_steps(_h, timeIntervalInSeconds, &n));
+        return n;
+    }
+
  private:
     void ensureDevice() {
         jetcu_smoke_params p;

@@ -112,6 +112,36 @@ __global__ void __launch_bounds__(256) k_smoke_sum_final(const double* __restric
     if (threadIdx.x == 0) out[0] = sm[0];
 }
 
+// GridFluidSolver3::cfl, src/jet/grid_fluid_solver3.cpp:57-72: max over cells of the SIGNED components of valueAtCellCenter + dt*g,
+// starting from 0 (max is exact: any reduction order gives the same bits) — the liquid solver's k_cfl_partial, local to this TU
+__global__ void __launch_bounds__(256) k_smoke_cfl_partial(GridD g, const double* __restrict__ u, const double* __restrict__ v,
+                                                           const double* __restrict__ w, double dtgx, double dtgy, double dtgz,
+                                                           double* __restrict__ partials) {
+    __shared__ double sm[256];
+    double m = 0.0;
+    const size_t nc = (size_t)g.nx * g.ny * g.nz;
+    for (size_t c = (size_t)blockIdx.x * 256 + threadIdx.x; c < nc; c += (size_t)SMOKE_SUM_GRID * 256) m = fmax(m, sm_cfl_cell(g, u, v, w, dtgx, dtgy, dtgz, c));
+    sm[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = sm[0];
+}
+__global__ void __launch_bounds__(256) k_smoke_max_final(const double* __restrict__ partials, int n, double* __restrict__ out) {
+    __shared__ double sm[256];
+    double m = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) m = fmax(m, partials[i]);
+    sm[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sm[0];
+}
+
 // Collider pieces: thin launch wrappers around collider_ops.cuh (the bodies hybrid.cu's kernels wrap too; checked on the CPU by
 // tests/hostcheck).  Kept local to this TU so that the liquid solver's translation unit is not touched.
 __global__ void __launch_bounds__(256) k_smk_collider_sdf(GridD g, ColliderD c, double* __restrict__ sdf) {
@@ -277,6 +307,28 @@ int jetcu_smoke_get_fields(jetcu_smoke* h, double* den, double* temp, double* u,
     if (w) JC_TRY(jc_d2h(ctx, w, h->w, h->nw));
     if (pr) JC_TRY(jc_d2h(ctx, pr, h->ps.x0, h->nc));
     return jc_sync(ctx);
+}
+
+// GridFluidSolver3::cfl / numberOfSubTimeSteps (src/jet/grid_fluid_solver3.cpp:57-72, 212-217) on the device-resident velocity
+int jetcu_smoke_cfl(jetcu_smoke* h, double dt, double* cfl) {
+    SMK_ENTER(h);
+    JC_ARG(ctx, cfl);
+    GridD g = smoke_grid(h);
+    const double* gr = h->P.gravity;
+    JC_LAUNCH(ctx, k_smoke_cfl_partial, SMOKE_SUM_GRID, 256, 0, g, h->u, h->v, h->w, dt * gr[0], dt * gr[1], dt * gr[2], ctx->d_partials);
+    JC_LAUNCH(ctx, k_smoke_max_final, 1, 256, 0, ctx->d_partials, SMOKE_SUM_GRID, ctx->d_scalars + 17);
+    JC_TRY(jc_d2h(ctx, ctx->h_scalars, ctx->d_scalars + 17, 1));
+    JC_TRY(jc_sync(ctx));
+    *cfl = ctx->h_scalars[0] * dt / fmin(fmin(g.hx, g.hy), g.hz);
+    return JETCU_OK;
+}
+int jetcu_smoke_num_sub_steps(jetcu_smoke* h, double dt, uint32_t* n) {
+    SMK_ENTER(h);
+    JC_ARG(ctx, n);
+    double c;
+    JC_TRY(jetcu_smoke_cfl(h, dt, &c));
+    *n = (uint32_t)fmax(ceil(c / h->P.max_cfl), 1.0);
+    return JETCU_OK;
 }
 
 // GridFluidSolver3::setCollider(RigidBodyCollider3 over analytic surfaces) on the smoke solver

@@ -169,3 +169,20 @@ __host__ __device__ __forceinline__ void sm_emit_step_cell(const GridD& g, const
     *cell = cd_max(*cell, (hi - lo) * step + lo);
 }
 
+// GridFluidSolver3::cfl, one cell (linear index c): the largest SIGNED component of valueAtCellCenter + dt * gravity
+// (src/jet/grid_fluid_solver3.cpp:60-66, face_centered_grid3.cpp:128-135); dtg = dt * gravity
+__host__ __device__ __forceinline__ double sm_cfl_cell(const GridD& g, const double* u, const double* v, const double* w, double dtgx,
+                                                       double dtgy, double dtgz, size_t c) {
+    const int i = (int)(c % g.nx);
+    const size_t t = c / g.nx;
+    const int j = (int)(t % g.ny), k = (int)(t / g.ny);
+    const size_t iu = ((size_t)k * g.ny + j) * (g.nx + 1) + i;
+    const size_t iv = ((size_t)k * (g.ny + 1) + j) * g.nx + i;
+    const double vx = 0.5 * (u[iu] + u[iu + 1]) + dtgx;
+    const double vy = 0.5 * (v[iv] + v[iv + g.nx]) + dtgy;
+    const double vz = 0.5 * (w[c] + w[c + (size_t)g.nx * g.ny]) + dtgz;
+    double m = 0.0;
+    m = fmax(m, vx); m = fmax(m, vy); m = fmax(m, vz);
+    return m;
+}
+

@@ -198,6 +198,16 @@ class SmokeApi:
         self._c("smoke_step", self.h, f64(dt), C.byref(r))
         return r
 
+    def cfl(self, dt):
+        c = f64(0.0)
+        self._c("smoke_cfl", self.h, f64(dt), C.byref(c))
+        return float(c.value)
+
+    def num_sub_steps(self, dt):
+        n = u32(0)
+        self._c("smoke_num_sub_steps", self.h, f64(dt), C.byref(n))
+        return int(n.value)
+
     def compute_external_forces(self, dt):
         self._c("smoke_compute_external_forces", self.h, f64(dt))
 

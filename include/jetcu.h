@@ -424,6 +424,10 @@ int jetcu_smoke_emit_step(jetcu_smoke*, const jetcu_collider_shape* shapes, uint
  * (src/jet/grid_fluid_solver3.cpp:355-369).  Shapes as for jetcu_hybrid_set_collider_shapes; n == 0 removes the collider. */
 int jetcu_smoke_set_collider_shapes(jetcu_smoke*, const jetcu_collider_shape* shapes, uint32_t n, int as_set,
                                     const double linear_velocity[3], const double angular_velocity[3], double friction);
+/* GridFluidSolver3::cfl / numberOfSubTimeSteps (src/jet/grid_fluid_solver3.cpp:57-72, 212-217) evaluated on the device-resident
+ * velocity, so that adaptive sub-stepping does not need the fields on the host. */
+int jetcu_smoke_cfl(jetcu_smoke*, double dt, double* cfl);
+int jetcu_smoke_num_sub_steps(jetcu_smoke*, double dt, uint32_t* n);
 int jetcu_smoke_step(jetcu_smoke*, double dt, jetcu_mgpcg_result* result);                 /* onAdvanceTimeStep */
 int jetcu_smoke_compute_external_forces(jetcu_smoke*, double dt);                          /* computeBuoyancyForce + BC */
 int jetcu_smoke_compute_pressure(jetcu_smoke*, double dt, jetcu_mgpcg_result* result);     /* computePressure + BC */

@@ -170,6 +170,8 @@ int jeto_smoke_emit_step(jeto_smoke*, const jeto_collider_shape* shapes, uint32_
  * (cells inside the collider are not advected, back-traces stop at the surface) and extrapolateIntoCollider of the scalars. */
 int jeto_smoke_set_collider_shapes(jeto_smoke*, const jeto_collider_shape* shapes, uint32_t n, int as_set,
                                    const double linear_velocity[3], const double angular_velocity[3], double friction);
+int jeto_smoke_cfl(jeto_smoke*, double dt, double* cfl);                               /* GridFluidSolver3::cfl */
+int jeto_smoke_num_sub_steps(jeto_smoke*, double dt, uint32_t* n);                   /* ::numberOfSubTimeSteps */
 int jeto_smoke_step(jeto_smoke*, double dt, jeto_mgpcg_result* result);            /* onAdvanceTimeStep */
 int jeto_smoke_compute_external_forces(jeto_smoke*, double dt);                    /* computeBuoyancyForce + BC */
 int jeto_smoke_compute_pressure(jeto_smoke*, double dt, jeto_mgpcg_result* result);

@@ -771,4 +771,7 @@ int jeto_smoke_set_collider_shapes(jeto_smoke* h, const jeto_collider_shape* sha
     return 0;
 }
 
+int jeto_smoke_cfl(jeto_smoke* h, double dt, double* cfl) { *cfl = h->solver->cfl(dt); return 0; }
+int jeto_smoke_num_sub_steps(jeto_smoke* h, double dt, uint32_t* n) { *n = h->solver->numberOfSubTimeSteps(dt); return 0; }
+
 }  // extern "C"

@@ -121,3 +121,15 @@ def test_smoke_with_collider(jc, oracle, ci):
     for k in ("density", "temperature", "u", "v", "w"):
         close(fa[-1][k], fb[-1][k], 1e-9 if k in ("density", "temperature") else 1e-7, "after 10 steps: " + k)
 
+
+def test_cfl_and_sub_steps(jc, oracle):
+    """GridFluidSolver3::cfl / numberOfSubTimeSteps from the device-resident velocity (max is exact: bit-identical)."""
+    prm = SmokeParams.make(Grid.cube(16), mgpcg=MgpcgParams.make(max_iterations=60, max_levels=3), max_cfl=0.5)
+    a, b = jc.smoke(prm), oracle.smoke(prm)
+    den, temp, u, v, w = plume(16, 1.0, seed=3)
+    for s in (a, b):
+        s.set_fields(den, temp, u, v, w)
+    for dt in (1.0 / 60.0, 0.25, 2.0):
+        assert a.cfl(dt) == b.cfl(dt) and a.num_sub_steps(dt) == b.num_sub_steps(dt)
+    a.close(); b.close()
+

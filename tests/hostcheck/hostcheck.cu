@@ -353,6 +353,16 @@ int hc_smoke_emit_step(const jetcu_grid* grid, const jetcu_collider_shape* shape
     return 0;
 }
 
+// jetcu_smoke_cfl: k_smoke_cfl_partial's body over all cells
+int hc_smoke_cfl(const jetcu_grid* grid, const double* u, const double* v, const double* w, const double* gravity, double dt, double* cfl) {
+    GridD g = make_grid(grid);
+    double m = 0.0;
+    const size_t nc = (size_t)g.nx * g.ny * g.nz;
+    for (size_t c = 0; c < nc; ++c) m = fmax(m, sm_cfl_cell(g, u, v, w, dt * gravity[0], dt * gravity[1], dt * gravity[2], c));
+    *cfl = m * dt / fmin(fmin(g.hx, g.hy), g.hz);
+    return 0;
+}
+
 // jetcu_smoke_compute_advection; ns > 0: with a rigid collider (boundary handling in the back-trace, cells inside the collider not
 // advected, extrapolateIntoCollider of the scalars, the collider branch of the boundary condition afterwards)
 int hc_smoke_advect_collider(const jetcu_grid* grid, double dt, int wall_flag, int linear_i, const jetcu_collider_shape* shapes,

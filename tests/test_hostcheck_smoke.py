@@ -138,3 +138,14 @@ def test_advection_with_collider(hc, port, ci):
         exact(g[k], want[k], "advected " + k)
     s.close()
 
+
+def test_cfl(hc, port):
+    prm, s = developed(port, 16, 1.0, 3, (3.0, -4.0, 1.0), steps=6)
+    f = s.get_fields()
+    for dt in (1.0 / 60.0, 0.25, 2.0):
+        got = C.c_double(0.0)
+        assert hc.hc_smoke_cfl(C.byref(prm.grid), dp(f["u"]), dp(f["v"]), dp(f["w"]), (C.c_double * 3)(3.0, -4.0, 1.0), C.c_double(dt),
+                               C.byref(got)) == 0
+        assert got.value == s.cfl(dt)
+    s.close()
+

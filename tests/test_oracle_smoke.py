@@ -158,3 +158,23 @@ def test_smoke_with_collider_bit_exact(libs, ci):
         same(a, b, "step %d" % step)
     assert float(np.abs(fb[-1]["v"]).max()) > 0.2
 
+
+@pytest.mark.parametrize("ci", range(len(SMOKE_COLLIDERS)))
+def test_cfl_and_sub_steps_bit_exact(libs, ci):
+    """GridFluidSolver3::cfl / numberOfSubTimeSteps on a developed plume (adaptive sub-stepping decides on them)."""
+    ref, port = libs
+    grid, levels, shapes, kw, advection = SMOKE_COLLIDERS[ci]
+    prm = SmokeParams.make(grid, mgpcg=MgpcgParams.make(max_iterations=60, max_levels=levels), advection=advection, max_cfl=0.5)
+    out = []
+    for lib in (ref, port):
+        s = lib.smoke(prm)
+        nx, ny, nz = grid.res
+        lo = np.array([grid.ox, grid.oy, grid.oz]); size = np.array([nx * grid.hx, ny * grid.hy, nz * grid.hz])
+        s.emit_step([dict(kind="box", a=tuple(lo + np.array([0.35, -1.0, 0.35]) * size), b=tuple(lo + np.array([0.65, 0.15, 0.65]) * size))])
+        for _ in range(6):
+            s.step(1.0 / 30.0)
+        out.append([(s.cfl(dt), s.num_sub_steps(dt)) for dt in (1.0 / 60.0, 1.0 / 10.0, 1.0)])
+        s.close()
+    assert out[0] == out[1], out
+    assert out[1][-1][1] > 1          # the long frame really needs sub-steps
+

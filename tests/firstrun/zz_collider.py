@@ -129,3 +129,8 @@ def test_save_positions(jc, tmp_path):
     text = (tmp_path / "f.xyz").read_text().splitlines()
     assert len(text) == len(pos) and text[0] == "%g %g %g" % tuple(pos[0]) and text[-1] == "%g %g %g" % tuple(pos[-1])
     h.close()
+
+
+def test_golden_emission(jc):
+    gc.emission(jc.hybrid, exact_bits=False)
+

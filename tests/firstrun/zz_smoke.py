@@ -133,3 +133,8 @@ def test_cfl_and_sub_steps(jc, oracle):
         assert a.cfl(dt) == b.cfl(dt) and a.num_sub_steps(dt) == b.num_sub_steps(dt)
     a.close(); b.close()
 
+
+@pytest.mark.parametrize("advection", ["cubic", "linear"])
+def test_golden_smoke_example1(jc, advection):
+    gc.smoke_example1(jc.smoke, exact_bits=False, advection=advection)
+

@@ -44,3 +44,13 @@ def test_hybrid_with_collider(port, name):
 
 def test_smoke(port):
     gc.smoke(port.smoke, exact_bits=True)
+
+
+@pytest.mark.parametrize("advection", ["cubic", "linear"])
+def test_smoke_example1(port, advection):
+    gc.smoke_example1(port.smoke, exact_bits=True, advection=advection)
+
+
+def test_emission(port):
+    gc.emission(port.hybrid)
+

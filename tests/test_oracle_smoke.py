@@ -119,21 +119,24 @@ def test_emit_step_bit_exact(libs, gi, which):
     a.close(); b.close()
 
 
+# Two MG levels: with more the reference's own MGPCG stagnates near 1e-7 next to a collider that vanishes on the coarse levels and
+# runs into the iteration limit — bit-identity between port and reference holds either way, but a converged solve is the fairer
+# target for the CUDA path (tests/firstrun/zz_smoke.py).
 SMOKE_COLLIDERS = [   # (grid, MG levels, collider shapes, collider kwargs, advection)
-    (Grid.cube(16), 3, [dict(kind="sphere", a=(0.5, 0.3, 0.5), b=(0.12, 0.0, 0.0))], dict(), "cubic"),                 # smoke_sim example 1
-    (Grid.cube(16), 3, [dict(kind="sphere", a=(0.5, 0.3, 0.5), b=(0.12, 0.0, 0.0))],
+    (Grid.cube(16), 2, [dict(kind="sphere", a=(0.5, 0.3, 0.5), b=(0.12, 0.0, 0.0))], dict(), "cubic"),                 # smoke_sim example 1
+    (Grid.cube(16), 2, [dict(kind="sphere", a=(0.5, 0.3, 0.5), b=(0.12, 0.0, 0.0))],
      dict(linear_velocity=(0.2, 0.0, -0.1), friction=0.3), "linear"),
     (Grid.cube(12, 0.9), 2, [dict(kind="box", a=(0.3, 0.2, 0.3), b=(0.6, 0.35, 0.6))], dict(friction=0.2), "cubic"),
-    (Grid(14, 12, 12, 0.1, 0.125, 0.08, 0.0, 0.3, 0.3), 1, [dict(kind="cylinder", a=(0.7, 0.9, 0.8), b=(0.15, 0.5))],
+    (Grid(14, 12, 12, 0.1, 0.125, 0.08, 0.0, 0.3, 0.3), 2, [dict(kind="cylinder", a=(0.7, 0.9, 0.8), b=(0.15, 0.5))],
      dict(angular_velocity=(0.0, 0.5, 0.0)), "cubic"),
-    (Grid.cube(16), 3, [dict(kind="sphere", a=(0.35, 0.35, 0.5), b=(0.1, 0.0, 0.0)),
+    (Grid.cube(16), 2, [dict(kind="sphere", a=(0.35, 0.35, 0.5), b=(0.1, 0.0, 0.0)),
                         dict(kind="box", a=(0.6, 0.3, 0.4), b=(0.75, 0.5, 0.6))], dict(), "linear"),
 ]
 
 
 def smoke_collider_run(lib, case, steps):
     grid, levels, shapes, kw, advection = case
-    prm = SmokeParams.make(grid, mgpcg=MgpcgParams.make(max_iterations=60, max_levels=levels), advection=advection)
+    prm = SmokeParams.make(grid, mgpcg=MgpcgParams.make(max_iterations=100, max_levels=levels), advection=advection)
     s = lib.smoke(prm)
     nx, ny, nz = grid.res
     lo = np.array([grid.ox, grid.oy, grid.oz]); size = np.array([nx * grid.hx, ny * grid.hy, nz * grid.hz])

@@ -109,6 +109,7 @@ int run(const Options& opt) {
         attachCollider(stock, scene);
         attachHostEmitters(stock, scene, 0.5 * h);
     }
+    Logging::mute();  // stock Jet logs every stage at INFO level to stdout; this program's frame lines are its output
     std::printf("example %d at %zu^3, %zu MG levels, %s emission%s\n", opt.example, opt.r, levels, opt.hostEmit ? "host" : "device",
                 opt.hostEmit ? "" : (" (" + std::to_string(emitted) + " particles)").c_str());
     for (Frame frame(0, 1.0 / opt.fps); frame.index < opt.frames; ++frame) {

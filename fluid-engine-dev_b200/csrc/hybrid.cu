@@ -31,11 +31,8 @@ struct jetcu_hybrid {
     char *valid0 = nullptr, *valid1 = nullptr;
     double* sdf = nullptr;
     float *ud = nullptr, *vd = nullptr, *wd = nullptr;
-    unsigned long long* wsum[3] = {};      // P2G fixed-point weight sums (u, v, w faces), high words
-    unsigned long long* wsum_lo[3] = {};   // ... low words
-    unsigned long long* sum_lo[3] = {};    // low words of the value sums (high words live in u, v, w)
-    struct P2GScale* p2g_scale = nullptr;  // device: 2^k / 2^-k of the current step's value accumulators
-    int* p2g_err = nullptr;                // device flag: fixed-point headroom exceeded
+    double* wsum[3] = {};                  // P2G weight sums (u, v, w faces); the value sums live in u, v, w themselves
+    int* p2g_err = nullptr;                // device flag: a particle outside its cell's face window (cannot happen)
     // particles
     uint64_t np = 0, cap = 0;
     int nattr = 6;
@@ -112,13 +109,22 @@ __global__ void k_sort_cells(const uint32_t* __restrict__ cell_start, const uint
     }
 }
 
-__global__ void k_gather_attrs(AttrPtrs src, AttrPtrs dst, const uint32_t* __restrict__ orig_src,
-                               uint32_t* __restrict__ orig_dst, const uint32_t* __restrict__ perm, int nattr, size_t np) {
+// NA is a template parameter so that the attribute loop unrolls into compile-time indices of the kernel-parameter
+// arrays: a run-time `nattr` makes the compiler copy both AttrPtrs to local memory (240 B of stack per thread — at
+// 126.6 M particles ncu showed 31 GB of DRAM writes for 6.6 GB of payload, profiles/r02_c1_particle_kernels.md).
+template <int NA>
+__global__ void __launch_bounds__(256) k_gather_attrs(AttrPtrs src, AttrPtrs dst, const uint32_t* __restrict__ orig_src,
+                                                      uint32_t* __restrict__ orig_dst, const uint32_t* __restrict__ perm, size_t np) {
     size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= np) return;
-    uint32_t from = perm[s];
-    for (int a = 0; a < nattr; ++a) dst.p[a][s] = src.p[a][from];
-    orig_dst[s] = orig_src[from];
+    const uint32_t from = perm[s];
+    double v[NA];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) v[a] = src.p[a][from];
+    const uint32_t o = orig_src[from];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) dst.p[a][s] = v[a];
+    orig_dst[s] = o;
 }
 
 // ------------------------------------------------------------------------------------------------ z-slab routing
@@ -145,289 +151,97 @@ __global__ void k_slab_route(const double* __restrict__ pz, size_t np, double oz
 }
 
 // message to one rank: (nattr + 1) blocks of `cnt` doubles (attributes, then the original index as a double)
-__global__ void k_slab_pack(AttrPtrs src, const uint32_t* __restrict__ orig, const uint32_t* __restrict__ list, int nattr,
+template <int NA>
+__global__ void k_slab_pack(AttrPtrs src, const uint32_t* __restrict__ orig, const uint32_t* __restrict__ list,
                             size_t cnt, double* __restrict__ msg) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cnt) return;
     const uint32_t p = list[i];
-    for (int a = 0; a < nattr; ++a) msg[(size_t)a * cnt + i] = src.p[a][p];
-    msg[(size_t)nattr * cnt + i] = (double)orig[p];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) msg[(size_t)a * cnt + i] = src.p[a][p];
+    msg[(size_t)NA * cnt + i] = (double)orig[p];
 }
 
-__global__ void k_slab_unpack(const double* __restrict__ msg, int nattr, size_t cnt, AttrPtrs dst, uint32_t* __restrict__ orig,
+template <int NA>
+__global__ void k_slab_unpack(const double* __restrict__ msg, size_t cnt, AttrPtrs dst, uint32_t* __restrict__ orig,
                               size_t at) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cnt) return;
-    for (int a = 0; a < nattr; ++a) dst.p[a][at + i] = msg[(size_t)a * cnt + i];
-    orig[at + i] = (uint32_t)msg[(size_t)nattr * cnt + i];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) dst.p[a][at + i] = msg[(size_t)a * cnt + i];
+    orig[at + i] = (uint32_t)msg[(size_t)NA * cnt + i];
 }
 
 // ------------------------------------------------------------------------------------------------ P2G
 // transferFromParticlesToGrids: PIC src/jet/pic_solver3.cpp:118-193, APIC src/jet/apic_solver3.cpp:26-146.
-//
-// The reference accumulates `u += v*w; wsum += w` over particles in a serial loop, so any parallel version has to
-// choose its own summation order.  Here the sums are carried in 128-bit FIXED POINT (two 64-bit words, carry
-// propagated by hand): every contribution is converted once to a multiple of 2^-(k+64) (k chosen per step from
-// max|value| so that nothing can overflow) and added as an integer.  Integer addition is associative, so the result
-// does not depend on the order of the particles, of the tiles, or — on several GPUs — of the slabs: bit-reproducible
-// by construction.  With 114 fractional bits a contribution keeps all 53 bits of its double down to 2^-61 of
-// max|value| (weights down to 2^-61), so faces at the liquid fringe that only see tiny weights are as accurate as
-// in the reference's double sum.
-//
-// Structure: particles are cell-sorted; a CTA owns a tile of TC^3 cells, walks the particles of its 64 cell rows
-// (contiguous ranges, coalesced SoA reads), accumulates into shared-memory tiles of the u/v/w faces the tile can
-// reach (tile + one ring), and finally adds the tile into the global accumulators.  Markers are plain stores of 1.
-// max over particles of the largest value a particle can deposit: |v_a| (+ h * (|c_a0|+|c_a1|+|c_a2|) for APIC)
-__global__ void __launch_bounds__(256) k_p2g_vmax_partial(AttrPtrs a, size_t np, int apic, double hx, double hy, double hz,
-                                                          double* __restrict__ partials) {
-    __shared__ double sm[256];
-    double m = 0.0;
-    for (size_t p = (size_t)blockIdx.x * 256 + threadIdx.x; p < np; p += (size_t)gridDim.x * 256) {
+// Design and summation order: p2g_ops.cuh.  One CTA = one tile of P2G_TX x P2G_TY x TZ cells, one thread per cell;
+// launched once per tile colour (parity of the tile index per axis), so a CTA owns every face its window reaches for
+// the duration of the launch and adds into the global arrays without atomics.
+template <bool APIC, int AX, int TZ>
+__device__ __forceinline__ void p2g_tile_component(const GridD& g, int I0, int J0, int K0, int ci, int cj, int ck, uint32_t s0,
+                                                   uint32_t e0, const AttrPtrs& a, double* ex, unsigned* tm,
+                                                   double* __restrict__ U, double* __restrict__ W, char* __restrict__ M, int* err) {
+    constexpr int NT = P2G_TX * P2G_TY * TZ;
+    constexpr int WX = P2G_TX + (AX == 0 ? 1 : 2), WY = P2G_TY + (AX == 1 ? 1 : 2), WZ = TZ + (AX == 2 ? 1 : 2);
+    const int tid = threadIdx.x;
+    unsigned touched = 0;
+    if (e0 > s0) {
+        double sv[P2G_SLOTS], sw[P2G_SLOTS];
+        touched = p2g_cell_partial<APIC, AX>(g, ci, cj, ck, s0, e0, a, sv, sw, err);
 #pragma unroll
-        for (int ax = 0; ax < 3; ++ax) {
-            double v = fabs(a.p[3 + ax][p]);
-            if (apic) v += hx * fabs(a.p[6 + 3 * ax][p]) + hy * fabs(a.p[7 + 3 * ax][p]) + hz * fabs(a.p[8 + 3 * ax][p]);
-            m = fmax(m, v);
+        for (int s = 0; s < P2G_SLOTS; ++s) { ex[s * NT + tid] = sv[s]; ex[(P2G_SLOTS + s) * NT + tid] = sw[s]; }
+    }
+    tm[tid] = touched;
+    __syncthreads();
+    const int sx = g.nx + (AX == 0), sy = g.ny + (AX == 1), sz = g.nz + (AX == 2);
+    const int fx0 = I0 - (AX == 0 ? 0 : 1), fy0 = J0 - (AX == 1 ? 0 : 1), fz0 = K0 - (AX == 2 ? 0 : 1);
+    for (int f = tid; f < WX * WY * WZ; f += NT) {
+        const int lx = f % WX, ly = (f / WX) % WY, lz = f / (WX * WY);
+        const int fi = fx0 + lx, fj = fy0 + ly, fk = fz0 + lz;
+        if ((unsigned)fi >= (unsigned)sx || (unsigned)fj >= (unsigned)sy || (unsigned)fk >= (unsigned)sz) continue;
+        double v, w;
+        if (p2g_face_gather<AX, TZ>(ex, tm, lx, ly, lz, &v, &w)) {
+            const size_t idx = ((size_t)fk * sy + fj) * sx + fi;
+            U[idx] += v; W[idx] += w; M[idx] = 1;
         }
     }
-    sm[threadIdx.x] = m;
     __syncthreads();
-    for (int s2 = 128; s2 > 0; s2 >>= 1) {
-        if (threadIdx.x < s2) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + s2]);
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) partials[blockIdx.x] = sm[0];
 }
 
-__global__ void __launch_bounds__(256) k_p2g_scale_final(const double* __restrict__ partials, int n, P2GScale* out) {
-    __shared__ double sm[256];
-    double m = 0.0;
-    for (int i = threadIdx.x; i < n; i += 256) m = fmax(m, partials[i]);
-    sm[threadIdx.x] = m;
-    __syncthreads();
-    for (int s2 = 128; s2 > 0; s2 >>= 1) {
-        if (threadIdx.x < s2) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + s2]);
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        *out = p2g_scale_from_vmax(sm[0]);
-    }
-}
+struct P2GOut {
+    double* val[3];   // u, v, w: value sums (normalised in place afterwards)
+    double* wsum[3];  // weight sums
+    char* marker[3];
+};
 
-template <bool APIC>
-__global__ void __launch_bounds__(P2G_THREADS)
-    k_p2g_scatter(GridD g, int kbase, int kend, const uint32_t* __restrict__ cell_start, AttrPtrs a,
-                  const P2GScale* __restrict__ sc, P2GAcc acc) {
-    // per component: tile of faces reachable from the TC^3 cells: the component's own axis spans TC+1, the others TC+2
-    constexpr int NF = (TC + 1) * (TC + 2) * (TC + 2);
-    // Shared accumulators: 128-bit integers as four 32-bit limbs (32-bit shared atomics are native; 64-bit ones
-    // compile to compare-and-swap spin loops).  The value accumulator holds value + 2^e * weight, which is never
-    // negative (|value| < 2^e * weight), so small contributions leave the high limbs untouched; the bias equals the
-    // weight accumulator bit for bit and is removed exactly when the tile is flushed.
-    extern __shared__ __align__(16) unsigned p2g_smem[];
-    unsigned(*sV)[4][NF] = reinterpret_cast<unsigned(*)[4][NF]>(p2g_smem);             // [3][limb] value + bias
-    unsigned(*sW)[4][NF] = reinterpret_cast<unsigned(*)[4][NF]>(p2g_smem + 12 * NF);   // [3][limb] weight
-    unsigned char(*sM)[NF] = reinterpret_cast<unsigned char(*)[NF]>(p2g_smem + 24 * NF);  // [3] markers
-    __shared__ int any;
-    // cell planes [kbase, kend): the whole grid, or (slab mode) this rank's slab plus its ghost planes
-    const int I0 = blockIdx.x * TC, J0 = blockIdx.y * TC, K0 = kbase + blockIdx.z * TC;
-    if (threadIdx.x == 0) any = 0;
-    for (int t = threadIdx.x; t < 24 * NF; t += P2G_THREADS) p2g_smem[t] = 0u;
-    for (int t = threadIdx.x; t < 3 * NF; t += P2G_THREADS) (&sM[0][0])[t] = 0;
-    __syncthreads();
-    const double scale = sc->scale;
-    const double wscale = 1125899906842624.0;  // 2^50
-    const double ihx = 1.0 / g.hx, ihy = 1.0 / g.hy, ihz = 1.0 / g.hz;
-    const double lox = g.ox + g.hx / 2.0, hix = (g.ox + g.hx * (double)g.nx) - g.hx / 2.0;
-    const double loy = g.oy + g.hy / 2.0, hiy = (g.oy + g.hy * (double)g.ny) - g.hy / 2.0;
-    const double loz = g.oz + g.hz / 2.0, hiz = (g.oz + g.hz * (double)g.nz) - g.hz / 2.0;
-    int touched = 0;
-    // one thread per cell, walking the cell's particles: the lanes of a warp then work on 32 DIFFERENT cells, so that
-    // concurrent atomics rarely hit the same face (the particles of one cell all hit the same few faces)
-    for (int cl = threadIdx.x; cl < TC * TC * TC; cl += P2G_THREADS) {
-        const int ci = I0 + (cl % TC), cj = J0 + ((cl / TC) % TC), ck = K0 + (cl / (TC * TC));
-        if (ci >= g.nx || cj >= g.ny || ck >= kend) continue;
+template <bool APIC, int TZ>
+__global__ void __launch_bounds__(P2G_TX * P2G_TY * TZ)
+    k_p2g_tile(GridD g, int par_x, int par_y, int tz_first, int kb, int ke, const uint32_t* __restrict__ cell_start, AttrPtrs a,
+               P2GOut out, int* __restrict__ err) {
+    constexpr int NT = P2G_TX * P2G_TY * TZ;
+    extern __shared__ __align__(16) double p2g_ex[];  // [2][P2G_SLOTS][NT]
+    __shared__ unsigned tm[NT];
+    const int tid = threadIdx.x;
+    const int I0 = (2 * blockIdx.x + par_x) * P2G_TX, J0 = (2 * blockIdx.y + par_y) * P2G_TY, K0 = (tz_first + 2 * blockIdx.z) * TZ;
+    const int ci = I0 + tid % P2G_TX, cj = J0 + (tid / P2G_TX) % P2G_TY, ck = K0 + tid / (P2G_TX * P2G_TY);
+    uint32_t s0 = 0, e0 = 0;
+    // cell planes [kb, ke): the whole grid, or (slab mode) this rank's slab plus its ghost planes
+    if (ci < g.nx && cj < g.ny && ck >= kb && ck < ke) {
         const size_t cell = ((size_t)ck * g.ny + cj) * g.nx + ci;
-        const uint32_t s0 = cell_start[cell], e0 = cell_start[cell + 1];
-        for (uint32_t q = s0; q < e0; ++q) {
-            touched = 1;
-            const double px0 = a.p[0][q], py0 = a.p[1][q], pz0 = a.p[2][q];
-#pragma unroll
-            for (int ax = 0; ax < 3; ++ax) {
-                const int sx = g.nx + (ax == 0), sy = g.ny + (ax == 1), sz = g.nz + (ax == 2);
-                const double ox = g.ox + 0.5 * (ax == 0 ? 0.0 : g.hx), oy = g.oy + 0.5 * (ax == 1 ? 0.0 : g.hy),
-                             oz = g.oz + 0.5 * (ax == 2 ? 0.0 : g.hz);
-                double px = px0, py = py0, pz = pz0;
-                if (APIC) {  // tangential clamp to [lo + h/2, hi - h/2] (apic_solver3.cpp:76-84,94-102,112-120)
-                    if (ax != 0) px = jc_clamp(px, lox, hix);
-                    if (ax != 1) py = jc_clamp(py, loy, hiy);
-                    if (ax != 2) pz = jc_clamp(pz, loz, hiz);
-                }
-                const BaseFrac bf = jc_base_mul(sx, sy, sz, ihx, ihy, ihz, ox, oy, oz, px, py, pz);
-                const double pv = a.p[3 + ax][q];
-                double c0 = 0.0, c1 = 0.0, c2 = 0.0;
-                if (APIC) { c0 = a.p[6 + 3 * ax][q]; c1 = a.p[7 + 3 * ax][q]; c2 = a.p[8 + 3 * ax][q]; }
-                // local tile frame of this component
-                const int lx0 = I0 - (ax == 0 ? 0 : 1), ly0 = J0 - (ax == 1 ? 0 : 1), lz0 = K0 - (ax == 2 ? 0 : 1);
-                const int dx = TC + (ax == 0 ? 1 : 2), dy = TC + (ax == 1 ? 1 : 2), dz = TC + (ax == 2 ? 1 : 2);
-#pragma unroll
-                for (int cnr = 0; cnr < 8; ++cnr) {  // the reference's corner order
-                    const int fi = (cnr & 1) ? bf.ip1 : bf.i, fj = (cnr & 2) ? bf.jp1 : bf.j, fk = (cnr & 4) ? bf.kp1 : bf.k;
-                    const double wgt = jc_corner_weight(bf, cnr);
-                    double val;
-                    if (APIC) {
-                        // apicTerm = c . (facePosition - clampedPosition); facePosition = faceOrigin + h*(i,j,k)
-                        const double gx = ox + g.hx * (double)fi, gy = oy + g.hy * (double)fj, gz = oz + g.hz * (double)fk;
-                        const double term = c0 * (gx - px) + c1 * (gy - py) + c2 * (gz - pz);
-                        val = wgt * (pv + term);
-                    } else {
-                        val = pv * wgt;
-                    }
-                    unsigned long long vh, vl, wh, wl;
-                    to_fixed128(val * scale, &vh, &vl);
-                    to_fixed128(wgt * wscale, &wh, &wl);
-                    const int lx = fi - lx0, ly = fj - ly0, lz = fk - lz0;
-                    if ((unsigned)lx < (unsigned)dx && (unsigned)ly < (unsigned)dy && (unsigned)lz < (unsigned)dz) {
-                        const int t = (lz * dy + ly) * dx + lx;
-                        unsigned long long bl = vl + wl, bh = vh + wh + (bl < vl ? 1ull : 0ull);  // value + bias >= 0
-                        acc_limbs(&sV[ax][0][t], NF, bh, bl);
-                        acc_limbs(&sW[ax][0][t], NF, wh, wl);
-                        sM[ax][t] = 1;
-                    } else {  // cannot happen for in-domain particles; kept so that a wild position is still summed
-                        const size_t f = ((size_t)fk * sy + fj) * sx + fi;
-                        acc128(acc.sum[ax] + f, acc.sum_lo[ax] + f, vh, vl);
-                        acc128(acc.wsum[ax] + f, acc.wsum_lo[ax] + f, wh, wl);
-                        acc.marker[ax][f] = 1;
-                    }
-                }
-            }
-        }
+        s0 = cell_start[cell]; e0 = cell_start[cell + 1];
     }
-    if (touched) any = 1;
-    __syncthreads();
-    if (!any) return;
-    // add the tile into the global accumulators (integer adds: order-independent)
-#pragma unroll
-    for (int ax = 0; ax < 3; ++ax) {
-        const int sx = g.nx + (ax == 0), sy = g.ny + (ax == 1);
-        const int lx0 = I0 - (ax == 0 ? 0 : 1), ly0 = J0 - (ax == 1 ? 0 : 1), lz0 = K0 - (ax == 2 ? 0 : 1);
-        const int dx = TC + (ax == 0 ? 1 : 2), dy = TC + (ax == 1 ? 1 : 2), dz = TC + (ax == 2 ? 1 : 2);
-        for (int t = threadIdx.x; t < dx * dy * dz; t += P2G_THREADS) {
-            if (!sM[ax][t]) continue;
-            const int lx = t % dx, ly = (t / dx) % dy, lz = t / (dx * dy);
-            const size_t f = ((size_t)(lz0 + lz) * sy + (ly0 + ly)) * sx + (lx0 + lx);
-            const unsigned long long wl = (unsigned long long)sW[ax][0][t] | ((unsigned long long)sW[ax][1][t] << 32);
-            const unsigned long long wh = (unsigned long long)sW[ax][2][t] | ((unsigned long long)sW[ax][3][t] << 32);
-            unsigned long long vl = (unsigned long long)sV[ax][0][t] | ((unsigned long long)sV[ax][1][t] << 32);
-            unsigned long long vh = (unsigned long long)sV[ax][2][t] | ((unsigned long long)sV[ax][3][t] << 32);
-            vh = vh - wh - (vl < wl ? 1ull : 0ull); vl = vl - wl;  // remove the bias: exact 128-bit subtraction
-            acc128(acc.sum[ax] + f, acc.sum_lo[ax] + f, vh, vl);
-            acc128(acc.wsum[ax] + f, acc.wsum_lo[ax] + f, wh, wl);
-            acc.marker[ax][f] = 1;
-        }
-    }
+    if (!__syncthreads_or(e0 > s0)) return;
+    p2g_tile_component<APIC, 0, TZ>(g, I0, J0, K0, ci, cj, ck, s0, e0, a, p2g_ex, tm, out.val[0], out.wsum[0], out.marker[0], err);
+    p2g_tile_component<APIC, 1, TZ>(g, I0, J0, K0, ci, cj, ck, s0, e0, a, p2g_ex, tm, out.val[1], out.wsum[1], out.marker[1], err);
+    p2g_tile_component<APIC, 2, TZ>(g, I0, J0, K0, ci, cj, ck, s0, e0, a, p2g_ex, tm, out.val[2], out.wsum[2], out.marker[2], err);
 }
 
-template <bool APIC, bool CF>
-__global__ void __launch_bounds__(P2G_THREADS)
-    k_p2g_cells(GridD g, int kbase, int kend, const uint32_t* __restrict__ cell_start, AttrPtrs a,
-                const P2GScale* __restrict__ sc, P2GAcc acc) {
-    constexpr int NF = (TC + 1) * (TC + 2) * (TC + 2);
-    constexpr int NL = CF ? 5 : 4;  // 32-bit words per shared accumulator
-    extern __shared__ __align__(16) unsigned p2g_smem[];
-    unsigned(*sV)[NL][NF] = reinterpret_cast<unsigned(*)[NL][NF]>(p2g_smem);                 // [3][limb] value + 2 * weight
-    unsigned(*sW)[NL][NF] = reinterpret_cast<unsigned(*)[NL][NF]>(p2g_smem + 3 * NL * NF);   // [3][limb] weight
-    unsigned char(*sM)[NF] = reinterpret_cast<unsigned char(*)[NF]>(p2g_smem + 6 * NL * NF);  // [3] markers
-    __shared__ int any;
-    const int I0 = blockIdx.x * TC, J0 = blockIdx.y * TC, K0 = kbase + blockIdx.z * TC;
-    if (threadIdx.x == 0) any = 0;
-    for (int t = threadIdx.x; t < 6 * NL * NF; t += P2G_THREADS) p2g_smem[t] = 0u;
-    for (int t = threadIdx.x; t < 3 * NF; t += P2G_THREADS) (&sM[0][0])[t] = 0;
-    __syncthreads();
-    const double scale = sc->scale;
-    int touched = 0;
-    for (int cl = threadIdx.x; cl < TC * TC * TC; cl += P2G_THREADS) {
-        const int ci = I0 + (cl % TC), cj = J0 + ((cl / TC) % TC), ck = K0 + (cl / (TC * TC));
-        if (ci >= g.nx || cj >= g.ny || ck >= kend) continue;
-        const size_t cell = ((size_t)ck * g.ny + cj) * g.nx + ci;
-        const uint32_t s0 = cell_start[cell], e0 = cell_start[cell + 1];
-        if (s0 == e0) continue;
-        touched = 1;
-        p2g_cell_component<APIC, 0, CF>(g, ci, cj, ck, s0, e0, a, scale, I0, J0, K0, &sV[0][0][0], &sW[0][0][0], &sM[0][0], acc);
-        p2g_cell_component<APIC, 1, CF>(g, ci, cj, ck, s0, e0, a, scale, I0, J0, K0, &sV[1][0][0], &sW[1][0][0], &sM[1][0], acc);
-        p2g_cell_component<APIC, 2, CF>(g, ci, cj, ck, s0, e0, a, scale, I0, J0, K0, &sV[2][0][0], &sW[2][0][0], &sM[2][0], acc);
-    }
-    if (touched) any = 1;
-    __syncthreads();
-    if (!any) return;
-#pragma unroll
-    for (int ax = 0; ax < 3; ++ax) {
-        const int dx = TC + (ax == 0 ? 1 : 2), dy = TC + (ax == 1 ? 1 : 2), dz = TC + (ax == 2 ? 1 : 2);
-        for (int t = threadIdx.x; t < dx * dy * dz; t += P2G_THREADS)
-            p2g_tile_flush_face<CF>(g, I0, J0, K0, ax, t, &sV[ax][0][0], &sW[ax][0][0], &sM[ax][0], acc);
-    }
-}
-
-// Component-serial form (experimental, JETCU_P2G_KERNEL=serial): the tile's u, v and w faces are accumulated one
-// component after the other through ONE set of shared accumulators (carry-free limbs), so a CTA needs a third of the
-// shared memory, and with 128 threads a third of the registers per CTA: 3 CTAs (12 warps) fit on an SM instead of 1 (8
-// warps) — the per-cell form is bound by the latency of its dependent shared-memory updates, not by bandwidth.  The
-// particles of a cell are read three times (L1 / L2 hits).  Same integer sums, hence the same bits as the other forms.
-#define P2G_SERIAL_THREADS 128
-template <bool APIC, int AX>
-__device__ __forceinline__ void p2g_component_pass(const GridD& g, int I0, int J0, int K0, int kend,
-                                                   const uint32_t* __restrict__ cell_start, const AttrPtrs& a, double scale,
-                                                   const P2GAcc& acc, unsigned* sV, unsigned* sW, unsigned char* sM, int* any) {
-    constexpr int NF = (TC + 1) * (TC + 2) * (TC + 2);
-    for (int t = threadIdx.x; t < 10 * NF; t += P2G_SERIAL_THREADS) sV[t] = 0u;   // sV and sW are contiguous: 2 x 5 limbs
-    for (int t = threadIdx.x; t < NF; t += P2G_SERIAL_THREADS) sM[t] = 0;
-    if (threadIdx.x == 0) *any = 0;
-    __syncthreads();
-    int touched = 0;
-    for (int cl = threadIdx.x; cl < TC * TC * TC; cl += P2G_SERIAL_THREADS) {
-        const int ci = I0 + (cl % TC), cj = J0 + ((cl / TC) % TC), ck = K0 + (cl / (TC * TC));
-        if (ci >= g.nx || cj >= g.ny || ck >= kend) continue;
-        const size_t cell = ((size_t)ck * g.ny + cj) * g.nx + ci;
-        const uint32_t s0 = cell_start[cell], e0 = cell_start[cell + 1];
-        if (s0 == e0) continue;
-        touched = 1;
-        p2g_cell_component<APIC, AX, true>(g, ci, cj, ck, s0, e0, a, scale, I0, J0, K0, sV, sW, sM, acc);
-    }
-    if (touched) *any = 1;
-    __syncthreads();
-    if (*any) {
-        constexpr int dx = TC + (AX == 0 ? 1 : 2), dy = TC + (AX == 1 ? 1 : 2), dz = TC + (AX == 2 ? 1 : 2);
-        for (int t = threadIdx.x; t < dx * dy * dz; t += P2G_SERIAL_THREADS) p2g_tile_flush_face<true>(g, I0, J0, K0, AX, t, sV, sW, sM, acc);
-    }
-    __syncthreads();
-}
-
-template <bool APIC>
-__global__ void __launch_bounds__(P2G_SERIAL_THREADS)
-    k_p2g_cells_serial(GridD g, int kbase, int kend, const uint32_t* __restrict__ cell_start, AttrPtrs a,
-                       const P2GScale* __restrict__ sc, P2GAcc acc) {
-    constexpr int NF = (TC + 1) * (TC + 2) * (TC + 2);
-    extern __shared__ __align__(16) unsigned p2g_smem[];
-    unsigned* sV = p2g_smem;            // [5][NF] value + 2 * weight
-    unsigned* sW = p2g_smem + 5 * NF;   // [5][NF] weight
-    unsigned char* sM = reinterpret_cast<unsigned char*>(p2g_smem + 10 * NF);
-    __shared__ int any;
-    const int I0 = blockIdx.x * TC, J0 = blockIdx.y * TC, K0 = kbase + blockIdx.z * TC;
-    const double scale = sc->scale;
-    p2g_component_pass<APIC, 0>(g, I0, J0, K0, kend, cell_start, a, scale, acc, sV, sW, sM, &any);
-    p2g_component_pass<APIC, 1>(g, I0, J0, K0, kend, cell_start, a, scale, acc, sV, sW, sM, &any);
-    p2g_component_pass<APIC, 2>(g, I0, J0, K0, kend, cell_start, a, scale, acc, sV, sW, sM, &any);
-}
-
-// u = sum / wsum where wsum > 0 (pic_solver3.cpp:178-192), back in double; FLIP's float snapshot
-// (src/jet/flip_solver3.cpp:39-47) is taken in the same pass.  err[0] is raised if a weight sum left the
-// fixed-point headroom (more than 2^HEADROOM particles' worth of weight on one face).
-__global__ void k_p2g_normalise(double* __restrict__ u, const unsigned long long* __restrict__ sum_lo,
-                                const unsigned long long* __restrict__ wsum, const unsigned long long* __restrict__ wsum_lo,
-                                const P2GScale* __restrict__ sc, float* __restrict__ snapshot, int* __restrict__ err, size_t n) {
+// u = sum / wsum where wsum > 0 (pic_solver3.cpp:178-192); FLIP's float snapshot (src/jet/flip_solver3.cpp:39-47) is
+// taken in the same pass.
+__global__ void k_p2g_normalise(double* __restrict__ u, const double* __restrict__ wsum, float* __restrict__ snapshot, size_t n) {
     size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n) return;
-    p2g_normalise_face(u, sum_lo, wsum, wsum_lo, sc->inv_scale, snapshot, err, f);
+    p2g_normalise_face(u, wsum, snapshot, f);
 }
 
 __global__ void k_flip_delta(const double* __restrict__ in, float* __restrict__ d, size_t n) {
@@ -910,8 +724,12 @@ static int hyb_slab_exchange(jetcu_hybrid* h, uint64_t* ntot) {
         }
         for (int q = 0; q < G && rc == JETCU_OK; ++q) {
             if (!mine[q]) continue;
-            k_slab_pack<<<jc_blocks(mine[q], 256), 256, 0, ctx->stream>>>(own, orig, d_list + send_off[q], h->nattr, (size_t)mine[q],
-                                                                         sendbuf + send_off[q] * rec);
+            if (h->nattr == 6)
+                k_slab_pack<6><<<jc_blocks(mine[q], 256), 256, 0, ctx->stream>>>(own, orig, d_list + send_off[q], (size_t)mine[q],
+                                                                                sendbuf + send_off[q] * rec);
+            else
+                k_slab_pack<NATTR><<<jc_blocks(mine[q], 256), 256, 0, ctx->stream>>>(own, orig, d_list + send_off[q], (size_t)mine[q],
+                                                                                    sendbuf + send_off[q] * rec);
             ctx->launches++;
         }
     }
@@ -929,8 +747,10 @@ static int hyb_slab_exchange(jetcu_hybrid* h, uint64_t* ntot) {
         for (int q = 0; q < G; ++q) {
             const size_t c = recv_off[q + 1] - recv_off[q];
             if (!c) continue;
-            k_slab_unpack<<<jc_blocks(c, 256), 256, 0, ctx->stream>>>(recvbuf + recv_off[q] * rec, h->nattr, c, dst, dorig,
-                                                                     np + recv_off[q]);
+            if (h->nattr == 6)
+                k_slab_unpack<6><<<jc_blocks(c, 256), 256, 0, ctx->stream>>>(recvbuf + recv_off[q] * rec, c, dst, dorig, np + recv_off[q]);
+            else
+                k_slab_unpack<NATTR><<<jc_blocks(c, 256), 256, 0, ctx->stream>>>(recvbuf + recv_off[q] * rec, c, dst, dorig, np + recv_off[q]);
             ctx->launches++;
         }
     }
@@ -970,8 +790,12 @@ static int hyb_bin(jetcu_hybrid* h) {
         JC_LAUNCH(ctx, k_scatter_perm, jc_blocks(ntot, 256), 256, 0, h->cell_of, h->rank, h->cell_start, h->perm, (size_t)ntot);
         JC_LAUNCH(ctx, k_sort_cells, jc_blocks(hi - lo, 128), 128, 0, h->cell_start + lo, h->orig[h->cur] + h->base, h->perm,
                   hi - lo);
-        JC_LAUNCH(ctx, k_gather_attrs, jc_blocks(ntot, 256), 256, 0, owned_ptrs(h), attr_ptrs(h, 1 - h->cur),
-                  h->orig[h->cur] + h->base, h->orig[1 - h->cur], h->perm, h->nattr, (size_t)ntot);
+        if (h->nattr == 6)
+            JC_LAUNCH(ctx, k_gather_attrs<6>, jc_blocks(ntot, 256), 256, 0, owned_ptrs(h), attr_ptrs(h, 1 - h->cur),
+                      h->orig[h->cur] + h->base, h->orig[1 - h->cur], h->perm, (size_t)ntot);
+        else
+            JC_LAUNCH(ctx, k_gather_attrs<NATTR>, jc_blocks(ntot, 256), 256, 0, owned_ptrs(h), attr_ptrs(h, 1 - h->cur),
+                      h->orig[h->cur] + h->base, h->orig[1 - h->cur], h->perm, (size_t)ntot);
         h->cur = 1 - h->cur;
     }
     if (slab) {
@@ -1112,10 +936,10 @@ int jetcu_hybrid_create(jetcu_ctx* ctx, const jetcu_hybrid_params* p, jetcu_hybr
     {
         const size_t nf[3] = {h->nu, h->nv, h->nw};
         for (int q = 0; q < 3; ++q) {
-            STEP(jc_alloc(ctx, &h->wsum[q], nf[q])); STEP(jc_alloc(ctx, &h->wsum_lo[q], nf[q])); STEP(jc_alloc(ctx, &h->sum_lo[q], nf[q]));
+            STEP(jc_alloc(ctx, &h->wsum[q], nf[q]));
         }
     }
-    STEP(jc_alloc(ctx, &h->p2g_scale, 1)); STEP(jc_alloc(ctx, &h->p2g_err, 1)); STEP(jc_zero(ctx, h->p2g_err, 1));
+    STEP(jc_alloc(ctx, &h->p2g_err, 1)); STEP(jc_zero(ctx, h->p2g_err, 1));
     STEP(jc_alloc(ctx, &h->sdf, h->nc));
     if (p->mode == JETCU_FLIP) {
         STEP(jc_alloc(ctx, &h->ud, h->nu)); STEP(jc_alloc(ctx, &h->vd, h->nv)); STEP(jc_alloc(ctx, &h->wd, h->nw));
@@ -1147,8 +971,8 @@ int jetcu_hybrid_destroy(jetcu_hybrid* h) {
     jc_free(ctx, h->um); jc_free(ctx, h->vm); jc_free(ctx, h->wm);
     jc_free(ctx, h->valid0); jc_free(ctx, h->valid1); jc_free(ctx, h->sdf);
     jc_free(ctx, h->ud); jc_free(ctx, h->vd); jc_free(ctx, h->wd);
-    for (int q = 0; q < 3; ++q) { jc_free(ctx, h->wsum[q]); jc_free(ctx, h->wsum_lo[q]); jc_free(ctx, h->sum_lo[q]); }
-    jc_free(ctx, h->p2g_scale); jc_free(ctx, h->p2g_err);
+    for (int q = 0; q < 3; ++q) jc_free(ctx, h->wsum[q]);
+    jc_free(ctx, h->p2g_err);
     jc_free(ctx, h->col_sdf); jc_free(ctx, h->bnd_u); jc_free(ctx, h->bnd_v); jc_free(ctx, h->bnd_w);
     jc_free(ctx, h->tmp_u); jc_free(ctx, h->tmp_v); jc_free(ctx, h->tmp_w);
     jc_free(ctx, h->cm_u); jc_free(ctx, h->cm_v); jc_free(ctx, h->cm_w);
@@ -1566,89 +1390,57 @@ int jetcu_hybrid_transfer_particles_to_grids(jetcu_hybrid* h) {
     int slot = jc_prof_begin(ctx, JETCU_PROF_P2G);
     const bool flip = h->P.mode == JETCU_FLIP;
     // planes of each face field this rank finalises: all of them, or (slab mode) the ones it owns — their sums are
-    // complete because the ghost particles of the neighbouring planes were summed along (integer accumulators: the
-    // bits do not depend on which rank, tile or order added a contribution)
+    // complete because the ghost particles of the neighbouring planes were summed along, cell by cell and tile by tile in
+    // the same order as on a single GPU (p2g_ops.cuh)
     const size_t pu = (size_t)(h->nx + 1) * h->ny, pv = (size_t)h->nx * (h->ny + 1), pw = (size_t)h->nx * h->ny;
     const size_t k0 = (size_t)h->z0, nk = (size_t)(h->z1 - h->z0);
     const size_t nkw = nk + ((!slab || h->me == h->world - 1) ? 1 : 0);
-    {   // u, v, w double as the fixed-point value accumulators; weight sums and markers start from zero as well.  Only the
-        // planes the tiles of this rank can touch (its particle window + one ring) need it; the others are overwritten
-        // by the all-gather below
-        const int kb0 = slab ? max(h->z0 - SLAB_GHOST, 0) : 0, ke0 = slab ? min(h->z1 + SLAB_GHOST, h->nz) : h->nz;
-        const size_t zlo = (size_t)max(kb0 - 1, 0), zhi = (size_t)min(ke0 + 1, h->nz);
+    const int kb = slab ? max(h->z0 - SLAB_GHOST, 0) : 0, ke = slab ? min(h->z1 + SLAB_GHOST, h->nz) : h->nz;
+    {   // u, v, w double as the value sums; weight sums and markers start from zero as well.  Only the planes the cells of
+        // this rank can reach (its particle window + one ring) need it; the others are overwritten by the all-gather below
+        const size_t zlo = (size_t)max(kb - 1, 0), zhi = (size_t)min(ke + 1, h->nz);
         const size_t pl[3] = {pu, pv, pw};
         double* val[3] = {h->u, h->v, h->w};
         char* mk[3] = {h->um, h->vm, h->wm};
         for (int q = 0; q < 3; ++q) {
             const size_t o = zlo * pl[q], c = (zhi - zlo + (q == 2 ? 1 : 0)) * pl[q];
-            JC_TRY(jc_zero(ctx, val[q] + o, c)); JC_TRY(jc_zero(ctx, h->wsum[q] + o, c));
-            JC_TRY(jc_zero(ctx, h->wsum_lo[q] + o, c)); JC_TRY(jc_zero(ctx, h->sum_lo[q] + o, c));
-            JC_TRY(jc_zero(ctx, mk[q] + o, c));
+            JC_TRY(jc_zero(ctx, val[q] + o, c)); JC_TRY(jc_zero(ctx, h->wsum[q] + o, c)); JC_TRY(jc_zero(ctx, mk[q] + o, c));
         }
     }
     if (h->nglobal > 0) {
-        JC_LAUNCH(ctx, k_p2g_vmax_partial, 592, 256, 0, a, (size_t)h->nsorted, apic ? 1 : 0, g.hx, g.hy, g.hz, ctx->d_partials);
-        if (slab) {  // the fixed-point scale must be the same on every rank
-            JC_LAUNCH(ctx, k_max_final, 1, CFL_BLOCK, 0, ctx->d_partials, 592, ctx->d_scalars + 8);
-            JC_TRY(comm_allreduce_max_f64(ctx, ctx->d_scalars + 8, 1));
-            JC_LAUNCH(ctx, k_p2g_scale_final, 1, 256, 0, ctx->d_scalars + 8, 1, h->p2g_scale);
-        } else {
-            JC_LAUNCH(ctx, k_p2g_scale_final, 1, 256, 0, ctx->d_partials, 592, h->p2g_scale);
-        }
-        P2GAcc acc;
-        acc.sum[0] = (unsigned long long*)h->u; acc.sum[1] = (unsigned long long*)h->v; acc.sum[2] = (unsigned long long*)h->w;
-        for (int q = 0; q < 3; ++q) { acc.wsum[q] = h->wsum[q]; acc.wsum_lo[q] = h->wsum_lo[q]; acc.sum_lo[q] = h->sum_lo[q]; }
-        acc.marker[0] = h->um; acc.marker[1] = h->vm; acc.marker[2] = h->wm;
-        const int kb = slab ? max(h->z0 - SLAB_GHOST, 0) : 0, ke = slab ? min(h->z1 + SLAB_GHOST, h->nz) : h->nz;
-        dim3 grid((g.nx + TC - 1) / TC, (g.ny + TC - 1) / TC, (ke - kb + TC - 1) / TC);
-        const size_t nface = (size_t)(TC + 1) * (TC + 2) * (TC + 2);
-        const size_t smem = nface * (24 * 4 + 3), smem_cf = nface * (30 * 4 + 3);
-        static bool attr_set = false;
-        if (!attr_set) {
-            JC_CUDA(ctx, cudaFuncSetAttribute(k_p2g_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            JC_CUDA(ctx, cudaFuncSetAttribute(k_p2g_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            JC_CUDA(ctx, cudaFuncSetAttribute((k_p2g_cells<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            JC_CUDA(ctx, cudaFuncSetAttribute((k_p2g_cells<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            JC_CUDA(ctx, cudaFuncSetAttribute((k_p2g_cells<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cf));
-            JC_CUDA(ctx, cudaFuncSetAttribute((k_p2g_cells<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cf));
-            attr_set = true;
-        }
-        // per-cell register accumulation needs every component grid to have >= 2 samples per axis (its 2-wide node
-        // window must exist); degenerate 1-cell-thick grids take the per-particle form.  JETCU_P2G_KERNEL selects the
-        // experimental variants for A/B runs: "particle" (per-particle form), "carryfree" (26-bit redundant limbs),
-        // "serial" (component-serial carry-free form, 128-thread CTAs)
-        const char* pk = getenv("JETCU_P2G_KERNEL");
-        const bool per_cell = g.nx >= 2 && g.ny >= 2 && g.nz >= 2 && !(pk && !strcmp(pk, "particle"));
-        const bool carry_free = per_cell && pk && !strcmp(pk, "carryfree");
-        const bool serial = per_cell && pk && !strcmp(pk, "serial");
         if (h->nsorted > 0) {
-            if (serial) {
-                const size_t smem_s = nface * (10 * 4 + 1);
-                static bool serial_attr = false;
-                if (!serial_attr) {
-                    JC_CUDA(ctx, cudaFuncSetAttribute(k_p2g_cells_serial<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-                    JC_CUDA(ctx, cudaFuncSetAttribute(k_p2g_cells_serial<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-                    serial_attr = true;
-                }
-                if (apic) JC_LAUNCH(ctx, (k_p2g_cells_serial<true>), grid, P2G_SERIAL_THREADS, smem_s, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
-                else JC_LAUNCH(ctx, (k_p2g_cells_serial<false>), grid, P2G_SERIAL_THREADS, smem_s, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
-            } else if (carry_free) {
-                if (apic) JC_LAUNCH(ctx, (k_p2g_cells<true, true>), grid, P2G_THREADS, smem_cf, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
-                else JC_LAUNCH(ctx, (k_p2g_cells<false, true>), grid, P2G_THREADS, smem_cf, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
-            } else if (per_cell) {
-                if (apic) JC_LAUNCH(ctx, (k_p2g_cells<true, false>), grid, P2G_THREADS, smem, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
-                else JC_LAUNCH(ctx, (k_p2g_cells<false, false>), grid, P2G_THREADS, smem, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
-            } else {
-                if (apic) JC_LAUNCH(ctx, (k_p2g_scatter<true>), grid, P2G_THREADS, smem, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
-                else JC_LAUNCH(ctx, (k_p2g_scatter<false>), grid, P2G_THREADS, smem, g, kb, ke, h->cell_start, a, h->p2g_scale, acc);
+            P2GOut out;
+            out.val[0] = h->u; out.val[1] = h->v; out.val[2] = h->w;
+            for (int q = 0; q < 3; ++q) out.wsum[q] = h->wsum[q];
+            out.marker[0] = h->um; out.marker[1] = h->vm; out.marker[2] = h->wm;
+            // tiles are aligned to the GLOBAL cell lattice (not to the slab), so that every rank forms the same tile sums.
+            // APIC carries 3 more attributes per component through the cell loop: 256-thread tiles keep it in registers
+            const int TZ = apic ? P2G_TZ_APIC : P2G_TZ;
+            const int ntx = (g.nx + P2G_TX - 1) / P2G_TX, nty = (g.ny + P2G_TY - 1) / P2G_TY;
+            const int tzlo = kb / TZ, tzhi = (ke - 1) / TZ;  // inclusive
+            const size_t smem = (size_t)2 * P2G_SLOTS * P2G_TX * P2G_TY * TZ * sizeof(double);
+            // per device, cheap: set on every call (the attribute belongs to the current device's copy of the function)
+            if (apic) JC_CUDA(ctx, cudaFuncSetAttribute((k_p2g_tile<true, P2G_TZ_APIC>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else JC_CUDA(ctx, cudaFuncSetAttribute((k_p2g_tile<false, P2G_TZ>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            for (int colour = 0; colour < 8; ++colour) {  // fixed colour order = the order in which a rim face receives its tiles
+                const int par_x = colour & 1, par_y = (colour >> 1) & 1, par_z = colour >> 2;
+                const int cx = (ntx - par_x + 1) / 2, cy = (nty - par_y + 1) / 2;
+                const int tz_first = tzlo + ((tzlo & 1) != par_z ? 1 : 0);
+                const int cz = tz_first > tzhi ? 0 : (tzhi - tz_first) / 2 + 1;
+                if (cx <= 0 || cy <= 0 || cz <= 0) continue;
+                dim3 grid(cx, cy, cz);
+                if (apic) JC_LAUNCH(ctx, (k_p2g_tile<true, P2G_TZ_APIC>), grid, P2G_TX * P2G_TY * P2G_TZ_APIC, smem, g, par_x, par_y,
+                                    tz_first, kb, ke, h->cell_start, a, out, h->p2g_err);
+                else JC_LAUNCH(ctx, (k_p2g_tile<false, P2G_TZ>), grid, P2G_TX * P2G_TY * P2G_TZ, smem, g, par_x, par_y, tz_first, kb, ke,
+                               h->cell_start, a, out, h->p2g_err);
             }
         }
-        JC_LAUNCH(ctx, k_p2g_normalise, jc_blocks(nk * pu, 256), 256, 0, h->u + k0 * pu, h->sum_lo[0] + k0 * pu, h->wsum[0] + k0 * pu,
-                  h->wsum_lo[0] + k0 * pu, h->p2g_scale, flip ? h->ud + k0 * pu : nullptr, h->p2g_err, nk * pu);
-        JC_LAUNCH(ctx, k_p2g_normalise, jc_blocks(nk * pv, 256), 256, 0, h->v + k0 * pv, h->sum_lo[1] + k0 * pv, h->wsum[1] + k0 * pv,
-                  h->wsum_lo[1] + k0 * pv, h->p2g_scale, flip ? h->vd + k0 * pv : nullptr, h->p2g_err, nk * pv);
-        JC_LAUNCH(ctx, k_p2g_normalise, jc_blocks(nkw * pw, 256), 256, 0, h->w + k0 * pw, h->sum_lo[2] + k0 * pw, h->wsum[2] + k0 * pw,
-                  h->wsum_lo[2] + k0 * pw, h->p2g_scale, flip ? h->wd + k0 * pw : nullptr, h->p2g_err, nkw * pw);
+        JC_LAUNCH(ctx, k_p2g_normalise, jc_blocks(nk * pu, 256), 256, 0, h->u + k0 * pu, h->wsum[0] + k0 * pu,
+                  flip ? h->ud + k0 * pu : nullptr, nk * pu);
+        JC_LAUNCH(ctx, k_p2g_normalise, jc_blocks(nk * pv, 256), 256, 0, h->v + k0 * pv, h->wsum[1] + k0 * pv,
+                  flip ? h->vd + k0 * pv : nullptr, nk * pv);
+        JC_LAUNCH(ctx, k_p2g_normalise, jc_blocks(nkw * pw, 256), 256, 0, h->w + k0 * pw, h->wsum[2] + k0 * pw,
+                  flip ? h->wd + k0 * pw : nullptr, nkw * pw);
     } else if (h->P.mode == JETCU_FLIP) {
         JC_TRY(jc_zero(ctx, h->ud, h->nu)); JC_TRY(jc_zero(ctx, h->vd, h->nv)); JC_TRY(jc_zero(ctx, h->wd, h->nw));
     }
@@ -1810,8 +1602,8 @@ int jetcu_hybrid_step(jetcu_hybrid* h, double dt, jetcu_step_stats* st) {
     JC_TRY(jc_sync(ctx));
     if (p2g_err) {
         jc_zero(ctx, h->p2g_err, 1);
-        return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED,
-                          "P2G fixed-point headroom exceeded: more than 4096 particles' worth of weight on one face");
+        return jetcu_fail(ctx, JETCU_ERR_CUDA,
+                          "P2G: a particle lies outside the face window of the cell it was binned into");
     }
     if (st) {
         memset(st, 0, sizeof(*st));

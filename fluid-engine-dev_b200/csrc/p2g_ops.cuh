@@ -1,7 +1,7 @@
-// p2g_ops.cuh — arithmetic of the particle-to-grid transfer as __host__ __device__ functions: 128-bit fixed-point
-// conversion and accumulation, the per-cell register accumulation, the tile flush and the normalisation.  hybrid.cu's
-// kernels are wrappers (shared memory, thread loops, __syncthreads around them); tests/hostcheck runs the same source on
-// the CPU — atomics become plain additions there — against exact integer arithmetic and the oracle.
+// p2g_ops.cuh — arithmetic of the particle-to-grid transfer as __host__ __device__ functions: the per-cell register
+// accumulation, the per-face gather of a tile's partial sums and the normalisation.  hybrid.cu's kernel is a wrapper
+// (shared memory, thread loops, __syncthreads around them); tests/hostcheck runs the same source on the CPU against the
+// oracle.
 #pragma once
 #include <math.h>
 #include "particle_ops.cuh"
@@ -21,164 +21,57 @@ struct AttrPtrs {
 };
 
 
-#define TC 8
-#define P2G_THREADS 256
-#define P2G_KW 50          // weight sums: fixed point with 50 fractional bits (sum of weights per face < 4096)
-#define P2G_HEADROOM 12    // value sums: max|value| * 2^HEADROOM * 2^k < 2^62
-
-struct P2GScale {
-    double scale, inv_scale;  // 2^k, 2^-k
-};
-
-
-// atomics of the accumulation: real atomics on the device, plain read-modify-write in the single-threaded host check
-template <typename T>
-__host__ __device__ __forceinline__ T jc_atomic_add(T* p, T v) {
-#ifdef __CUDA_ARCH__
-    return atomicAdd(p, v);
-#else
-    const T old = *p;
-    *p = old + v;
-    return old;
+// ---- P2G: per-cell partial sums, exchanged through shared memory, gathered per face -----------------------------------
+// transferFromParticlesToGrids: PIC src/jet/pic_solver3.cpp:118-193, APIC src/jet/apic_solver3.cpp:26-146.
+//
+// The reference accumulates `u += v*w; wsum += w` over the particles in one serial loop, so a parallel version has to choose
+// its own summation order; ours is fixed by the GRID, never by scheduling (no atomics anywhere):
+//   1. particles are cell-sorted (ascending original index inside a cell).  All particles of one cell deposit into the
+//      same window of faces per component: 2 along the component's own (node-aligned) axis x 3 x 3 along the two
+//      cell-centred axes = 18 faces.  One thread owns a cell and sums its particles' contributions to those 18 faces in
+//      REGISTERS, in the cell's particle order (p2g_cell_partial);
+//   2. the 18 (value, weight) partial sums of every cell of a tile go to shared memory, and one thread per FACE of the
+//      tile's window adds up the partial sums of the <= 18 cells of the tile that reach it, in a fixed slot order
+//      (p2g_face_gather);
+//   3. faces on a tile's rim also receive from neighbouring tiles.  Tiles are launched in 8 colour passes (parity of the
+//      tile index per axis); the windows of two tiles of one colour never overlap, so a tile adds its face sums into the
+//      global arrays with a plain read-modify-write, and a rim face receives its <= 8 tile sums in colour order.
+// Every face therefore sees one fixed sequence of FP64 additions that depends only on the particle set and on the
+// globally aligned tile lattice — bit-reproducible run to run and across z-slab decompositions (a rank holds every cell
+// within two planes of its slab, i.e. every cell that reaches one of its faces).  Versus the reference only the summation
+// order differs (documented tolerance 1e-12 relative).
+#define P2G_TX 8
+#define P2G_TY 8
+#define P2G_SLOTS 18
+#ifndef P2G_TZ
+#define P2G_TZ 8   // cells per tile along z (threads per CTA = P2G_TX * P2G_TY * P2G_TZ)
 #endif
-}
-__host__ __device__ __forceinline__ unsigned long long jc_double2ull_rd(double x) {  // x >= 0: round down == truncate
-#ifdef __CUDA_ARCH__
-    return __double2ull_rd(x);
-#else
-    return (unsigned long long)x;
+#ifndef P2G_TZ_APIC
+#define P2G_TZ_APIC 4
 #endif
+
+// slot of window position (x, b, c) for component AX: the node axis has 2 positions, the centred axes 3
+template <int AX>
+__host__ __device__ constexpr int p2g_slot(int x, int b, int c) {
+    return (c * (AX == 1 ? 2 : 3) + b) * (AX == 0 ? 2 : 3) + x;
 }
 
-// fixed-point scale of one step from the largest value a particle can deposit
-__host__ __device__ __forceinline__ P2GScale p2g_scale_from_vmax(double vmax) {
-    int e = (vmax > 0.0 && isfinite(vmax)) ? ilogb(vmax) + 1 : 0;  // vmax < 2^e
-    int k = 62 - P2G_HEADROOM - e;
-    P2GScale s;
-    s.scale = ldexp(1.0, k);
-    s.inv_scale = ldexp(1.0, -k);
-    return s;
-}
-
-struct P2GAcc {  // global accumulators; the high words of the value sums live in the velocity arrays themselves
-    unsigned long long* sum[3];     // value sum, high word
-    unsigned long long* sum_lo[3];  // value sum, low word
-    unsigned long long* wsum[3];    // weight sum, high word
-    unsigned long long* wsum_lo[3]; // weight sum, low word
-    char* marker[3];
-};
-
-// |t| < 2^63 -> signed 128-bit fixed point with 64 fractional bits (two's complement in hi:lo)
-__host__ __device__ __forceinline__ void to_fixed128(double t, unsigned long long* hi, unsigned long long* lo) {
-    const double a = fabs(t), fl = floor(a);
-    unsigned long long h = (unsigned long long)fl;
-    unsigned long long l = jc_double2ull_rd((a - fl) * 18446744073709551616.0);  // exact difference, < 2^64
-    if (t < 0.0) { l = 0ull - l; h = ~h + (l == 0ull ? 1ull : 0ull); }
-    *hi = h; *lo = l;
-}
-
-// (HI:LO) += (hi:lo) with two 64-bit atomics; the number of carries out of LO is fixed by the final sum, so the
-// result is independent of the order in which contributions arrive.
-__host__ __device__ __forceinline__ void acc128(unsigned long long* HI, unsigned long long* LO, unsigned long long hi,
-                                       unsigned long long lo) {
-    if (lo) {
-        const unsigned long long old = jc_atomic_add(LO, lo);
-        hi += (old > ~lo) ? 1ull : 0ull;
-    }
-    if (hi) jc_atomic_add(HI, hi);
-}
-
-// The same on a shared-memory accumulator stored as four 32-bit limbs `stride` words apart (non-negative addend).
-__host__ __device__ __forceinline__ void acc_limbs(unsigned* L, int stride, unsigned long long hi, unsigned long long lo) {
-    const unsigned x[4] = {(unsigned)lo, (unsigned)(lo >> 32), (unsigned)hi, (unsigned)(hi >> 32)};
-    unsigned carry = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const unsigned long long add = (unsigned long long)x[j] + carry;
-        const unsigned a32 = (unsigned)add;
-        carry = (unsigned)(add >> 32);
-        if (a32) {
-            const unsigned old = jc_atomic_add(L + j * stride, a32);
-            carry += (old > ~a32) ? 1u : 0u;
-        }
-    }
-}
-
-__host__ __device__ __forceinline__ double from_fixed128(unsigned long long hi, unsigned long long lo) {  // value * 2^64
-    const bool neg = (long long)hi < 0;
-    if (neg) { lo = 0ull - lo; hi = ~hi + (lo == 0ull ? 1ull : 0ull); }
-    const double v = (double)hi * 18446744073709551616.0 + (double)lo;
-    return neg ? -v : v;
-}
-
-
-// ---- P2G, per-cell form ------------------------------------------------------------------------------------------
-// All particles of one cell deposit into the same small window of faces: 2 along the component's own (node-aligned)
-// axis x 3 x 3 along the two cell-centred axes = 18 faces.  One thread owns a cell, sums its particles' contributions
-// to those 18 faces in REGISTERS (FP64, in the cell's fixed order: ascending original index), and only then converts
-// the 18 partial sums to fixed point and adds them to the tile's shared accumulators: 18 conversions + limb atomics per
-// cell and component instead of 8 per particle (x8 particles).  The cross-cell / cross-tile / cross-rank combination is
-// still integer addition, so the result is independent of tile order and of the slab decomposition (a ghost cell is
-// summed by the very same expression on every rank that holds it).
-// Slots outside a particle's actual 2x2x2 corners get weight 0 (val = +-0): adding them changes nothing.
-__host__ __device__ constexpr unsigned p2g_combo_mask(int ox, int oy, int oz) {
-    unsigned m = 0;
-    for (int c = oz; c <= oz + 1; ++c)
-        for (int b = oy; b <= oy + 1; ++b)
-            for (int a = ox; a <= ox + 1; ++a) m |= 1u << ((c * 3 + b) * 3 + a);
-    return m;
-}
-
-// Carry-free shared accumulator (experimental, JETCU_P2G_KERNEL=carryfree): the 128-bit non-negative integer is spread
-// over five 32-bit words holding 26 bits each, so an addition is five independent fire-and-forget adds (RED) with no
-// carry to propagate — acc_limbs chains up to four atomics through their return values.  A word overflows only after 64
-// additions; a face receives at most 18 per tile and component here.
-__host__ __device__ __forceinline__ void acc_limbs26(unsigned* L, int stride, unsigned long long hi, unsigned long long lo) {
-    const unsigned M = (1u << 26) - 1u;
-    const unsigned l0 = (unsigned)lo & M, l1 = (unsigned)(lo >> 26) & M;
-    const unsigned l2 = (unsigned)((lo >> 52) | (hi << 12)) & M, l3 = (unsigned)(hi >> 14) & M, l4 = (unsigned)(hi >> 40);
-    if (l0) jc_atomic_add(L, l0);
-    if (l1) jc_atomic_add(L + stride, l1);
-    if (l2) jc_atomic_add(L + 2 * stride, l2);
-    if (l3) jc_atomic_add(L + 3 * stride, l3);
-    if (l4) jc_atomic_add(L + 4 * stride, l4);
-}
-
-__host__ __device__ __forceinline__ void limbs26_to_u128(const unsigned* L, int stride, unsigned long long* hi, unsigned long long* lo) {
-    unsigned long long h = 0ull, l = 0ull;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-        const unsigned long long v = L[j * stride];
-        const int sh = 26 * j;
-        const unsigned long long plo = sh < 64 ? v << sh : 0ull;
-        const unsigned long long phi = sh == 0 ? 0ull : (sh < 64 ? v >> (64 - sh) : v << (sh - 64));
-        l += plo;
-        h += phi + (l < plo ? 1ull : 0ull);
-    }
-    *hi = h; *lo = l;
-}
-
-template <bool APIC, int AX, bool CF>
-__host__ __device__ __forceinline__ void p2g_cell_component(const GridD& g, int ci, int cj, int ck, uint32_t s0, uint32_t e0,
-                                                   const AttrPtrs& a, double scale, int I0, int J0, int K0, unsigned* sV,
-                                                   unsigned* sW, unsigned char* sM, const P2GAcc& acc) {
-    constexpr int NF = (TC + 1) * (TC + 2) * (TC + 2);
+// Partial sums of one cell for component AX.  sv / sw: P2G_SLOTS accumulators (value, weight); returns the mask of slots
+// that are a real corner of at least one particle (the reference marks all 8 corners of a particle, also those that get
+// weight 0).  Slots outside a particle's actual 2x2x2 corners receive weight 0 (val = +-0): adding them changes nothing.
+template <bool APIC, int AX>
+__host__ __device__ __forceinline__ unsigned p2g_cell_partial(const GridD& g, int ci, int cj, int ck, uint32_t s0, uint32_t e0,
+                                                              const AttrPtrs& a, double* sv, double* sw, int* err) {
     constexpr int NX = AX == 0 ? 2 : 3, NY = AX == 1 ? 2 : 3, NZ = AX == 2 ? 2 : 3;
     const int sx = g.nx + (AX == 0), sy = g.ny + (AX == 1), sz = g.nz + (AX == 2);
     const double ox = g.ox + 0.5 * (AX == 0 ? 0.0 : g.hx), oy = g.oy + 0.5 * (AX == 1 ? 0.0 : g.hy),
                  oz = g.oz + 0.5 * (AX == 2 ? 0.0 : g.hz);
     const double ihx = 1.0 / g.hx, ihy = 1.0 / g.hy, ihz = 1.0 / g.hz;
-    const double wscale = 1125899906842624.0;  // 2^50
     // window origin in face indices
     const int bx0 = ci - (AX == 0 ? 0 : 1), by0 = cj - (AX == 1 ? 0 : 1), bz0 = ck - (AX == 2 ? 0 : 1);
-    double sv[NZ][NY][NX], sw[NZ][NY][NX];
 #pragma unroll
-    for (int c = 0; c < NZ; ++c)
-#pragma unroll
-        for (int b = 0; b < NY; ++b)
-#pragma unroll
-            for (int x = 0; x < NX; ++x) { sv[c][b][x] = 0.0; sw[c][b][x] = 0.0; }
-    unsigned touched = 0;  // bit ((c*3 + b)*3 + a): slot is a real corner of at least one particle (markers)
+    for (int s = 0; s < P2G_SLOTS; ++s) { sv[s] = 0.0; sw[s] = 0.0; }
+    unsigned touched = 0;
     for (uint32_t q = s0; q < e0; ++q) {
         double px = a.p[0][q], py = a.p[1][q], pz = a.p[2][q];
         if (APIC) {  // tangential clamp to [lo + h/2, hi - h/2] (apic_solver3.cpp:76-84,94-102,112-120)
@@ -193,24 +86,8 @@ __host__ __device__ __forceinline__ void p2g_cell_component(const GridD& g, int 
         const int dx = bf.i - bx0, dy = bf.j - by0, dz = bf.k - bz0;  // 0 on the node axis, 0 or 1 on the centred ones
         const bool inwin = (unsigned)dx <= (AX == 0 ? 0u : 1u) && (unsigned)dy <= (AX == 1 ? 0u : 1u) &&
                            (unsigned)dz <= (AX == 2 ? 0u : 1u);
-        if (!inwin) {  // cannot happen for a particle binned into this cell; kept so that nothing is ever dropped
-#pragma unroll
-            for (int cnr = 0; cnr < 8; ++cnr) {
-                const int fi = (cnr & 1) ? bf.ip1 : bf.i, fj = (cnr & 2) ? bf.jp1 : bf.j, fk = (cnr & 4) ? bf.kp1 : bf.k;
-                const double wgt = jc_corner_weight(bf, cnr);
-                double val = pv * wgt;
-                if (APIC) {
-                    const double gx = ox + g.hx * (double)fi, gy = oy + g.hy * (double)fj, gz = oz + g.hz * (double)fk;
-                    val = wgt * (pv + (c0 * (gx - px) + c1 * (gy - py) + c2 * (gz - pz)));
-                }
-                unsigned long long vh, vl, wh, wl;
-                to_fixed128(val * scale, &vh, &vl);
-                to_fixed128(wgt * wscale, &wh, &wl);
-                const size_t f = ((size_t)fk * sy + fj) * sx + fi;
-                acc128(acc.sum[AX] + f, acc.sum_lo[AX] + f, vh, vl);
-                acc128(acc.wsum[AX] + f, acc.wsum_lo[AX] + f, wh, wl);
-                acc.marker[AX][f] = 1;
-            }
+        if (!inwin) {  // cannot happen for a particle binned into this cell by cell_coord (same expressions); never silent
+            *err = 1;
             continue;
         }
         // the two real weights per axis placed at offset d, zero elsewhere
@@ -233,84 +110,58 @@ __host__ __device__ __forceinline__ void p2g_cell_component(const GridD& g, int 
                     } else {
                         val = pv * wgt;
                     }
-                    sv[c][b][x] += val; sw[c][b][x] += wgt;
+                    sv[p2g_slot<AX>(x, b, c)] += val; sw[p2g_slot<AX>(x, b, c)] += wgt;
                 }
-        // dx/dy/dz in {0,1}: one of 8 corner-block positions inside the window
-        const int combo = dx + 2 * dy + 4 * dz;
-        touched |= combo == 0 ? p2g_combo_mask(0, 0, 0) : combo == 1 ? p2g_combo_mask(1, 0, 0) : combo == 2 ? p2g_combo_mask(0, 1, 0)
-                 : combo == 3 ? p2g_combo_mask(1, 1, 0) : combo == 4 ? p2g_combo_mask(0, 0, 1) : combo == 5 ? p2g_combo_mask(1, 0, 1)
-                 : combo == 6 ? p2g_combo_mask(0, 1, 1) : p2g_combo_mask(1, 1, 1);
+        // the particle's 2x2x2 corner block inside the window: the block at (0,0,0) shifted to (dx,dy,dz)
+        constexpr unsigned block = 1u | (1u << 1) | (1u << NX) | (1u << (NX + 1)) | (1u << (NX * NY)) | (1u << (NX * NY + 1)) |
+                                   (1u << (NX * NY + NX)) | (1u << (NX * NY + NX + 1));
+        touched |= block << ((dz * NY + dy) * NX + dx);
     }
-    if (!touched) return;
-    // tile frame of this component (tile + one ring on the centred axes)
-    const int lx0 = I0 - (AX == 0 ? 0 : 1), ly0 = J0 - (AX == 1 ? 0 : 1), lz0 = K0 - (AX == 2 ? 0 : 1);
-    constexpr int TDX = TC + (AX == 0 ? 1 : 2), TDY = TC + (AX == 1 ? 1 : 2);
+    return touched;
+}
+
+// One face of component AX's window of a tile of TX x TY x TZ cells (window = tile + one ring on the centred axes, + 1
+// on the node axis): local face coordinates (lx, ly, lz).  ex = exchange buffer [2][P2G_SLOTS][ncell] (values, then
+// weights), tm = touched masks per cell.  Adds up the partial sums of the tile's cells that reach the face, fixed order.
+template <int AX, int TZ>
+__host__ __device__ __forceinline__ bool p2g_face_gather(const double* ex, const unsigned* tm, int lx, int ly, int lz, double* v,
+                                                         double* w) {
+    constexpr int NX = AX == 0 ? 2 : 3, NY = AX == 1 ? 2 : 3, NZ = AX == 2 ? 2 : 3;
+    constexpr int NCELL = P2G_TX * P2G_TY * TZ;
+    double sv = 0.0, sw = 0.0;
+    bool any = false;
 #pragma unroll
-    for (int c = 0; c < NZ; ++c)
+    for (int c = 0; c < NZ; ++c) {
+        const int cz = lz - c;
+        if (cz < 0 || cz >= TZ) continue;
 #pragma unroll
-        for (int b = 0; b < NY; ++b)
+        for (int b = 0; b < NY; ++b) {
+            const int cy = ly - b;
+            if (cy < 0 || cy >= P2G_TY) continue;
 #pragma unroll
             for (int x = 0; x < NX; ++x) {
-                if (!(touched >> ((c * 3 + b) * 3 + x) & 1u)) continue;
-                unsigned long long vh, vl, wh, wl;
-                to_fixed128(sv[c][b][x] * scale, &vh, &vl);
-                to_fixed128(sw[c][b][x] * wscale, &wh, &wl);
-                // bias the value by TWICE the weight: |sum v*w| <= max|v| * sum w < 2^e * sum w up to the rounding of the
-                // FP64 partial sums, so value + 2 * 2^e * weight is safely non-negative
-                const unsigned long long w2l = wl << 1, w2h = (wh << 1) | (wl >> 63);
-                const unsigned long long bl = vl + w2l, bh = vh + w2h + (bl < vl ? 1ull : 0ull);
-                const int t = ((bz0 + c - lz0) * TDY + (by0 + b - ly0)) * TDX + (bx0 + x - lx0);
-                if (CF) { acc_limbs26(sV + t, NF, bh, bl); acc_limbs26(sW + t, NF, wh, wl); }
-                else { acc_limbs(sV + t, NF, bh, bl); acc_limbs(sW + t, NF, wh, wl); }
-                sM[t] = 1;
+                const int cx = lx - x;
+                if (cx < 0 || cx >= P2G_TX) continue;
+                const int cell = (cz * P2G_TY + cy) * P2G_TX + cx;
+                const int s = p2g_slot<AX>(x, b, c);
+                if ((tm[cell] >> s) & 1u) {
+                    any = true;
+                    sv += ex[s * NCELL + cell];
+                    sw += ex[(P2G_SLOTS + s) * NCELL + cell];
+                }
             }
+        }
+    }
+    *v = sv; *w = sw;
+    return any;
 }
 
-
-// One face of a tile: the shared accumulators (value + 2 * weight bias, weight) are rebuilt as 128-bit integers, the bias
-// is removed exactly and the face is added to the global accumulators.  t = index inside component ax's tile frame.
-template <bool CF>
-__host__ __device__ __forceinline__ void p2g_tile_flush_face(const GridD& g, int I0, int J0, int K0, int ax, int t,
-                                                             const unsigned* sV, const unsigned* sW, const unsigned char* sM,
-                                                             const P2GAcc& acc) {
-    constexpr int NF = (TC + 1) * (TC + 2) * (TC + 2);
-    if (!sM[t]) return;
-    const int sx = g.nx + (ax == 0), sy = g.ny + (ax == 1);
-    const int lx0 = I0 - (ax == 0 ? 0 : 1), ly0 = J0 - (ax == 1 ? 0 : 1), lz0 = K0 - (ax == 2 ? 0 : 1);
-    const int dx = TC + (ax == 0 ? 1 : 2), dy = TC + (ax == 1 ? 1 : 2);
-    const int lx = t % dx, ly = (t / dx) % dy, lz = t / (dx * dy);
-    const size_t f = ((size_t)(lz0 + lz) * sy + (ly0 + ly)) * sx + (lx0 + lx);
-    unsigned long long wl, wh, vl, vh;
-    if (CF) {
-        limbs26_to_u128(sW + t, NF, &wh, &wl);
-        limbs26_to_u128(sV + t, NF, &vh, &vl);
-    } else {
-        wl = (unsigned long long)sW[t] | ((unsigned long long)sW[NF + t] << 32);
-        wh = (unsigned long long)sW[2 * NF + t] | ((unsigned long long)sW[3 * NF + t] << 32);
-        vl = (unsigned long long)sV[t] | ((unsigned long long)sV[NF + t] << 32);
-        vh = (unsigned long long)sV[2 * NF + t] | ((unsigned long long)sV[3 * NF + t] << 32);
-    }
-    const unsigned long long w2l = wl << 1, w2h = (wh << 1) | (wl >> 63);
-    vh = vh - w2h - (vl < w2l ? 1ull : 0ull); vl = vl - w2l;  // remove the bias: exact 128-bit subtraction
-    acc128(acc.sum[ax] + f, acc.sum_lo[ax] + f, vh, vl);
-    acc128(acc.wsum[ax] + f, acc.wsum_lo[ax] + f, wh, wl);
-    acc.marker[ax][f] = 1;
-}
-
-// u = sum / wsum where wsum > 0 (pic_solver3.cpp:178-192), back in double; FLIP's float snapshot
-// (src/jet/flip_solver3.cpp:39-47) is taken in the same pass.  err[0] is raised if a weight sum left the
-// fixed-point headroom (more than 2^HEADROOM particles' worth of weight on one face).
-__host__ __device__ __forceinline__ void p2g_normalise_face(double* u, const unsigned long long* sum_lo, const unsigned long long* wsum,
-                                                            const unsigned long long* wsum_lo, double inv_scale, float* snapshot,
-                                                            int* err, size_t f) {
-    const double S = from_fixed128(reinterpret_cast<const unsigned long long*>(u)[f], sum_lo[f]);  // value * 2^(k+64)
-    const unsigned long long Wh = wsum[f], Wl = wsum_lo[f];
-    double val = S * 5.421010862427522e-20 * inv_scale;  // * 2^-64 * 2^-k (exact scalings)
-    if (Wh | Wl) {
-        const double wd = from_fixed128(Wh, Wl) * 5.421010862427522e-20 * 8.8817841970012523e-16;  // * 2^-64 * 2^-50
-        val = val / wd;
-        if (wd > (double)(1 << P2G_HEADROOM)) err[0] = 1;
-    }
+// u = sum / wsum where wsum > 0 (pic_solver3.cpp:178-192); FLIP's float snapshot (src/jet/flip_solver3.cpp:39-47) is
+// taken in the same pass.
+__host__ __device__ __forceinline__ void p2g_normalise_face(double* u, const double* wsum, float* snapshot, size_t f) {
+    const double w = wsum[f];
+    double val = u[f];
+    if (w > 0.0) val = val / w;
     u[f] = val;
     if (snapshot) snapshot[f] = (float)val;
 }

@@ -306,6 +306,35 @@ EMISSION_CASES = {   # name -> (shapes, lattice): hybrid_liquid_sim's emitters (
 }
 
 
+def cylinder_surface_distance(points, shape):
+    """|distance| of points to the surface of a Cylinder3 (a = centre, b = (radius, height), axis y): the Box2 profile in
+    (rho, y) of src/jet/cylinder3.cpp:44-50."""
+    c, (radius, height) = np.asarray(shape["a"], dtype=np.float64), shape["b"][:2]
+    r = points - c
+    rho, dy = np.sqrt(r[:, 0] ** 2 + r[:, 2] ** 2), np.abs(r[:, 1])
+    ex, ey = rho - radius, dy - 0.5 * height
+    outside = np.sqrt(np.maximum(ex, 0.0) ** 2 + np.maximum(ey, 0.0) ** 2)
+    inside = np.minimum(-ex, -ey)
+    return np.where((ex > 0) | (ey > 0), outside, inside)
+
+
+def same_points_up_to_cylinder_surface(a, b, shapes, tol=1e-12):
+    """Emission over a Cylinder3: SurfaceToImplicit3::signedDistanceLocal measures the distance to closestPointLocal, which
+    Cylinder3 rebuilds through atan2 / cos / sin (src/jet/cylinder3.cpp:32-42).  For a lattice point exactly ON the surface that
+    distance is 0 or a few 1e-17 depending on the last bit of libm, and with it `signedDistance <= 0`: the device's libm and
+    glibc may disagree on exactly those points and on no others.  Both sets are sub-sequences of the same lattice in the same
+    order, so: every point emitted by one side only lies on a cylinder's surface (<= tol), everything else is bit-identical."""
+    sa, sb = {tuple(p) for p in a.tolist()}, {tuple(p) for p in b.tolist()}
+    odd = np.array(sorted(sa ^ sb), dtype=np.float64).reshape(-1, 3)
+    if len(odd):
+        cyl = [s for s in shapes if s["kind"] == "cylinder"]
+        d = np.min(np.stack([np.abs(cylinder_surface_distance(odd, s)) for s in cyl]), axis=0)
+        assert d.max() <= tol, "%d points differ, farthest from a cylinder surface: %g" % (len(odd), d.max())
+    common_a = np.array([p for p in a.tolist() if tuple(p) in sb], dtype=np.float64)
+    common_b = np.array([p for p in b.tolist() if tuple(p) in sa], dtype=np.float64)
+    assert np.array_equal(common_a, common_b), "common points are not in the same order"
+
+
 def emission_run(make_hybrid, n=16):
     out = {}
     for name, (shapes, lattice) in EMISSION_CASES.items():
@@ -322,6 +351,6 @@ def emission(make_hybrid, exact_bits=True):
     for name in EMISSION_CASES:
         if exact_bits or "cylinder" not in name:
             exact(out[name], g[name], "emission " + name)
-        else:   # atan2 / cos / sin on the device: a lattice point exactly on the surface may flip
-            assert abs(len(out[name]) - len(g[name])) <= 2
+        else:
+            same_points_up_to_cylinder_surface(out[name], g[name], EMISSION_CASES[name][0])
 

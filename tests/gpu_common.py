@@ -7,15 +7,7 @@ from oracle_api import have_port, have_ref, load_port, load_ref
 
 
 def jetcu_or_fail():
-    """The CUDA library must load on a GPU box — a missing extension is a hard failure, never a skip.
-
-    JETCU_TEST_DRYRUN=port is a development aid for boxes WITHOUT a GPU: the C oracle stands in for the CUDA library so that the
-    bodies of the -m gpu tests themselves (fixtures, shapes, tolerances) can be exercised; it proves nothing about the product
-    and is never set by the test suite."""
-    if os.environ.get("JETCU_TEST_DRYRUN", "") == "port":
-        o = load_port()
-        o.set_num_threads(0)
-        return o
+    """The CUDA library must load on a GPU box — a missing extension is a hard failure, never a skip."""
     from fluid_engine_dev_b200 import Jetcu
     return Jetcu(0)
 

@@ -62,101 +62,132 @@ static void move_t(const GridD& g, const double* u, const double* v, const doubl
     for (uint64_t p = 0; p < n; ++p) move_particle<POW2, I>(g, u, v, w, dt, nsub, flag, pos + 3 * p, vel + 3 * p);
 }
 
-// ---- P2G: jetcu_hybrid_transfer_particles_to_grids with the per-cell kernel (k_p2g_cells<APIC, CF>), tiles and
-// "threads" run one after the other, shared memory is a plain buffer, atomics plain additions.
-template <bool APIC, bool CF>
-static void p2g_tiles(const GridD& g, const std::vector<uint32_t>& cell_start, const AttrPtrs& a, double scale, const P2GAcc& acc) {
-    constexpr int NF = (TC + 1) * (TC + 2) * (TC + 2);
-    constexpr int NL = CF ? 5 : 4;
-    std::vector<unsigned> smem(6 * NL * NF);
-    std::vector<unsigned char> mark(3 * NF);
-    for (int K0 = 0; K0 < g.nz; K0 += TC)
-        for (int J0 = 0; J0 < g.ny; J0 += TC)
-            for (int I0 = 0; I0 < g.nx; I0 += TC) {
-                std::fill(smem.begin(), smem.end(), 0u);
-                std::fill(mark.begin(), mark.end(), (unsigned char)0);
-                unsigned* sV = smem.data();
-                unsigned* sW = smem.data() + 3 * NL * NF;
-                bool any = false;
-                for (int cl = 0; cl < TC * TC * TC; ++cl) {
-                    const int ci = I0 + (cl % TC), cj = J0 + ((cl / TC) % TC), ck = K0 + (cl / (TC * TC));
-                    if (ci >= g.nx || cj >= g.ny || ck >= g.nz) continue;
-                    const size_t cell = ((size_t)ck * g.ny + cj) * g.nx + ci;
-                    const uint32_t s0 = cell_start[cell], e0 = cell_start[cell + 1];
-                    if (s0 == e0) continue;
-                    any = true;
-                    p2g_cell_component<APIC, 0, CF>(g, ci, cj, ck, s0, e0, a, scale, I0, J0, K0, sV, sW, mark.data(), acc);
-                    p2g_cell_component<APIC, 1, CF>(g, ci, cj, ck, s0, e0, a, scale, I0, J0, K0, sV + NL * NF, sW + NL * NF, mark.data() + NF, acc);
-                    p2g_cell_component<APIC, 2, CF>(g, ci, cj, ck, s0, e0, a, scale, I0, J0, K0, sV + 2 * NL * NF, sW + 2 * NL * NF, mark.data() + 2 * NF, acc);
+// ---- P2G: jetcu_hybrid_transfer_particles_to_grids with k_p2g_tile<APIC, TZ>: the 8 colour passes, the tiles of a pass
+// and the "threads" of a tile run one after the other, shared memory is a plain buffer.  Cell planes [kb, ke) carry
+// particles (slab mode: the rank's slab + ghost planes), exactly as in the kernel.
+template <bool APIC, int AX, int TZ>
+static void p2g_tile_component_host(const GridD& g, int I0, int J0, int K0, int kb, int ke, const std::vector<uint32_t>& cell_start,
+                                    const AttrPtrs& a, std::vector<double>& ex, std::vector<unsigned>& tm, double* U, double* W,
+                                    char* M, int* err) {
+    constexpr int NT = P2G_TX * P2G_TY * TZ;
+    constexpr int WX = P2G_TX + (AX == 0 ? 1 : 2), WY = P2G_TY + (AX == 1 ? 1 : 2), WZ = TZ + (AX == 2 ? 1 : 2);
+    for (int tid = 0; tid < NT; ++tid) {
+        const int ci = I0 + tid % P2G_TX, cj = J0 + (tid / P2G_TX) % P2G_TY, ck = K0 + tid / (P2G_TX * P2G_TY);
+        uint32_t s0 = 0, e0 = 0;
+        if (ci < g.nx && cj < g.ny && ck >= kb && ck < ke) {
+            const size_t cell = ((size_t)ck * g.ny + cj) * g.nx + ci;
+            s0 = cell_start[cell]; e0 = cell_start[cell + 1];
+        }
+        unsigned touched = 0;
+        if (e0 > s0) {
+            double sv[P2G_SLOTS], sw[P2G_SLOTS];
+            touched = p2g_cell_partial<APIC, AX>(g, ci, cj, ck, s0, e0, a, sv, sw, err);
+            for (int q = 0; q < P2G_SLOTS; ++q) { ex[q * NT + tid] = sv[q]; ex[(P2G_SLOTS + q) * NT + tid] = sw[q]; }
+        }
+        tm[tid] = touched;
+    }
+    const int sx = g.nx + (AX == 0), sy = g.ny + (AX == 1), sz = g.nz + (AX == 2);
+    const int fx0 = I0 - (AX == 0 ? 0 : 1), fy0 = J0 - (AX == 1 ? 0 : 1), fz0 = K0 - (AX == 2 ? 0 : 1);
+    for (int f = 0; f < WX * WY * WZ; ++f) {
+        const int lx = f % WX, ly = (f / WX) % WY, lz = f / (WX * WY);
+        const int fi = fx0 + lx, fj = fy0 + ly, fk = fz0 + lz;
+        if ((unsigned)fi >= (unsigned)sx || (unsigned)fj >= (unsigned)sy || (unsigned)fk >= (unsigned)sz) continue;
+        double v, w;
+        if (p2g_face_gather<AX, TZ>(ex.data(), tm.data(), lx, ly, lz, &v, &w)) {
+            const size_t idx = ((size_t)fk * sy + fj) * sx + fi;
+            U[idx] += v; W[idx] += w; M[idx] = 1;
+        }
+    }
+}
+
+template <bool APIC, int TZ>
+static void p2g_tiles(const GridD& g, int kb, int ke, const std::vector<uint32_t>& cell_start, const AttrPtrs& a, double* val[3],
+                      double* wsum[3], char* mk[3], int* err) {
+    constexpr int NT = P2G_TX * P2G_TY * TZ;
+    std::vector<double> ex((size_t)2 * P2G_SLOTS * NT, 0.0);
+    std::vector<unsigned> tm(NT, 0u);
+    const int ntx = (g.nx + P2G_TX - 1) / P2G_TX, nty = (g.ny + P2G_TY - 1) / P2G_TY, tzlo = kb / TZ, tzhi = (ke - 1) / TZ;
+    for (int colour = 0; colour < 8; ++colour) {
+        const int par_x = colour & 1, par_y = (colour >> 1) & 1, par_z = colour >> 2;
+        for (int tz = tzlo + ((tzlo & 1) != par_z ? 1 : 0); tz <= tzhi; tz += 2)
+            for (int ty = par_y; ty < nty; ty += 2)
+                for (int tx = par_x; tx < ntx; tx += 2) {
+                    const int I0 = tx * P2G_TX, J0 = ty * P2G_TY, K0 = tz * TZ;
+                    p2g_tile_component_host<APIC, 0, TZ>(g, I0, J0, K0, kb, ke, cell_start, a, ex, tm, val[0], wsum[0], mk[0], err);
+                    p2g_tile_component_host<APIC, 1, TZ>(g, I0, J0, K0, kb, ke, cell_start, a, ex, tm, val[1], wsum[1], mk[1], err);
+                    p2g_tile_component_host<APIC, 2, TZ>(g, I0, J0, K0, kb, ke, cell_start, a, ex, tm, val[2], wsum[2], mk[2], err);
                 }
-                if (!any) continue;
-                for (int ax = 0; ax < 3; ++ax) {
-                    const int dx = TC + (ax == 0 ? 1 : 2), dy = TC + (ax == 1 ? 1 : 2), dz = TC + (ax == 2 ? 1 : 2);
-                    for (int t = 0; t < dx * dy * dz; ++t)
-                        p2g_tile_flush_face<CF>(g, I0, J0, K0, ax, t, sV + ax * NL * NF, sW + ax * NL * NF, mark.data() + ax * NF, acc);
-                }
-            }
+    }
 }
 
 extern "C" {
 
-// PIC / FLIP (apic = 0) or APIC (apic = 1) transferFromParticlesToGrids through the per-cell kernel's source;
-// carry_free selects the 26-bit redundant-limb shared accumulators.  AoS inputs in the caller's order.
-int hc_p2g(const jetcu_grid* grid, int apic, int carry_free, uint64_t n, const double* pos, const double* vel, const double* cx,
+// PIC / FLIP (apic = 0) or APIC (apic = 1) transferFromParticlesToGrids through the tile kernel's source with tiles of tz
+// (4 or 8) cell planes.  slabs > 1 replays the z-slab mode: every "rank" sees only the particles of its slab + 2 ghost
+// planes and finalises the face planes it owns — the result must not depend on slabs.  AoS inputs in the caller's order.
+int hc_p2g(const jetcu_grid* grid, int apic, int tz, int slabs, uint64_t n, const double* pos, const double* vel, const double* cx,
            const double* cy, const double* cz, double* u, double* v, double* w, char* um, char* vm, char* wm, int* err) {
     GridD g = make_grid(grid);
     const size_t nc = (size_t)g.nx * g.ny * g.nz;
-    const size_t nf[3] = {(size_t)(g.nx + 1) * g.ny * g.nz, (size_t)g.nx * (g.ny + 1) * g.nz, (size_t)g.nx * g.ny * (g.nz + 1)};
+    const size_t pl[3] = {(size_t)(g.nx + 1) * g.ny, (size_t)g.nx * (g.ny + 1), (size_t)g.nx * g.ny};
+    const size_t nf[3] = {pl[0] * g.nz, pl[1] * g.nz, pl[2] * (g.nz + 1)};
+    if (slabs < 1 || g.nz % slabs != 0 || (tz != 4 && tz != 8)) return 1;
     // cell sort: by owning cell, ascending original index inside a cell (k_cell_count .. k_sort_cells .. k_gather_attrs)
     std::vector<uint32_t> cell(n), order(n);
+    std::vector<int> plane(n);
     for (uint64_t p = 0; p < n; ++p) {
         const int ci = cell_coord(pos[3 * p], g.ox, 1.0 / g.hx, g.nx), cj = cell_coord(pos[3 * p + 1], g.oy, 1.0 / g.hy, g.ny),
                   ck = cell_coord(pos[3 * p + 2], g.oz, 1.0 / g.hz, g.nz);
         cell[p] = (uint32_t)(((size_t)ck * g.ny + cj) * g.nx + ci);
+        plane[p] = ck;
     }
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return cell[x] < cell[y]; });
-    std::vector<uint32_t> cell_start(nc + 1, 0);
-    for (uint64_t p = 0; p < n; ++p) cell_start[cell[p] + 1]++;
-    for (size_t c = 0; c < nc; ++c) cell_start[c + 1] += cell_start[c];
-    std::vector<std::vector<double>> soa(NATTR, std::vector<double>(n ? n : 1, 0.0));
-    for (uint64_t s = 0; s < n; ++s) {
-        const uint32_t p = order[s];
-        for (int q = 0; q < 3; ++q) {
-            soa[q][s] = pos[3 * p + q]; soa[3 + q][s] = vel[3 * p + q];
-            if (apic) { soa[6 + q][s] = cx[3 * p + q]; soa[9 + q][s] = cy[3 * p + q]; soa[12 + q][s] = cz[3 * p + q]; }
-        }
-    }
-    AttrPtrs a;
-    for (int q = 0; q < NATTR; ++q) a.p[q] = soa[q].data();
-    // fixed-point scale (k_p2g_vmax_partial + k_p2g_scale_final)
-    double vmax = 0.0;
-    for (uint64_t s = 0; s < n; ++s)
-        for (int ax = 0; ax < 3; ++ax) {
-            double val = fabs(a.p[3 + ax][s]);
-            if (apic) val += g.hx * fabs(a.p[6 + 3 * ax][s]) + g.hy * fabs(a.p[7 + 3 * ax][s]) + g.hz * fabs(a.p[8 + 3 * ax][s]);
-            vmax = fmax(vmax, val);
-        }
-    const P2GScale sc = p2g_scale_from_vmax(vmax);
-    // accumulators: the high words of the value sums live in u, v, w themselves (as in the product)
-    double* val[3] = {u, v, w};
-    char* mk[3] = {um, vm, wm};
-    std::vector<unsigned long long> sum_lo[3], wsum[3], wsum_lo[3];
-    P2GAcc acc;
-    for (int q = 0; q < 3; ++q) {
-        memset(val[q], 0, nf[q] * 8); memset(mk[q], 0, nf[q]);
-        sum_lo[q].assign(nf[q], 0ull); wsum[q].assign(nf[q], 0ull); wsum_lo[q].assign(nf[q], 0ull);
-        acc.sum[q] = reinterpret_cast<unsigned long long*>(val[q]); acc.sum_lo[q] = sum_lo[q].data();
-        acc.wsum[q] = wsum[q].data(); acc.wsum_lo[q] = wsum_lo[q].data(); acc.marker[q] = mk[q];
-    }
-    if (n > 0) {
-        if (apic) { if (carry_free) p2g_tiles<true, true>(g, cell_start, a, sc.scale, acc); else p2g_tiles<true, false>(g, cell_start, a, sc.scale, acc); }
-        else { if (carry_free) p2g_tiles<false, true>(g, cell_start, a, sc.scale, acc); else p2g_tiles<false, false>(g, cell_start, a, sc.scale, acc); }
-    }
+    double* out[3] = {u, v, w};
+    char* outm[3] = {um, vm, wm};
     *err = 0;
-    for (int q = 0; q < 3; ++q)
-        for (size_t f = 0; f < nf[q]; ++f)
-            p2g_normalise_face(val[q], sum_lo[q].data(), wsum[q].data(), wsum_lo[q].data(), sc.inv_scale, nullptr, err, f);
+    const int T = g.nz / slabs;
+    for (int rank = 0; rank < slabs; ++rank) {
+        const int z0 = rank * T, z1 = z0 + T;
+        const int kb = slabs > 1 ? std::max(z0 - 2, 0) : 0, ke = slabs > 1 ? std::min(z1 + 2, g.nz) : g.nz;
+        // this rank's sorted particle array: the particles of the planes [kb, ke) only
+        std::vector<uint32_t> mine;
+        for (uint64_t s = 0; s < n; ++s) if (plane[order[s]] >= kb && plane[order[s]] < ke) mine.push_back(order[s]);
+        const size_t m = mine.size();
+        std::vector<uint32_t> cell_start(nc + 1, 0);
+        for (size_t s = 0; s < m; ++s) cell_start[cell[mine[s]] + 1]++;
+        for (size_t c = 0; c < nc; ++c) cell_start[c + 1] += cell_start[c];
+        std::vector<std::vector<double>> soa(NATTR, std::vector<double>(m ? m : 1, 0.0));
+        for (size_t s = 0; s < m; ++s) {
+            const uint32_t p = mine[s];
+            for (int q = 0; q < 3; ++q) {
+                soa[q][s] = pos[3 * p + q]; soa[3 + q][s] = vel[3 * p + q];
+                if (apic) { soa[6 + q][s] = cx[3 * p + q]; soa[9 + q][s] = cy[3 * p + q]; soa[12 + q][s] = cz[3 * p + q]; }
+            }
+        }
+        AttrPtrs a;
+        for (int q = 0; q < NATTR; ++q) a.p[q] = soa[q].data();
+        std::vector<double> valv[3], wsv[3];
+        std::vector<char> mkv[3];
+        double *val[3], *ws[3];
+        char* mk[3];
+        for (int q = 0; q < 3; ++q) {
+            valv[q].assign(nf[q], 0.0); wsv[q].assign(nf[q], 0.0); mkv[q].assign(nf[q], 0);
+            val[q] = valv[q].data(); ws[q] = wsv[q].data(); mk[q] = mkv[q].data();
+        }
+        if (m > 0) {
+            if (apic) { if (tz == 4) p2g_tiles<true, 4>(g, kb, ke, cell_start, a, val, ws, mk, err); else p2g_tiles<true, 8>(g, kb, ke, cell_start, a, val, ws, mk, err); }
+            else { if (tz == 4) p2g_tiles<false, 4>(g, kb, ke, cell_start, a, val, ws, mk, err); else p2g_tiles<false, 8>(g, kb, ke, cell_start, a, val, ws, mk, err); }
+        }
+        // the planes this rank owns (the last rank also owns the top w plane)
+        for (int q = 0; q < 3; ++q) {
+            const size_t f0 = (size_t)z0 * pl[q], f1 = ((size_t)z1 + ((q == 2 && rank == slabs - 1) ? 1 : 0)) * pl[q];
+            for (size_t f = f0; f < f1; ++f) {
+                p2g_normalise_face(val[q], ws[q], nullptr, f);
+                out[q][f] = val[q][f]; outm[q][f] = mk[q][f];
+            }
+        }
+    }
     return 0;
 }
 

@@ -1,8 +1,7 @@
 """Jet-side drop-in check of the adapter paths added after the three seams (adapters/dropin_check_next.cpp, public Jet API
 only): a FLIP dam break onto a RigidBodyCollider3(Box3) through jetcu::CudaFlipSolver3, and jet::GridSmokeSolver3 vs
 jetcu::CudaGridSmokeSolver3, each compared with the stock CPU solver in the same process.
-
-First GPU run pending (written after round 1's GPU minutes were gone): non-strict xfail, sorted last."""
+"""
 import json
 import os
 import subprocess
@@ -11,7 +10,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "adapters", "_build", "dropin_check_next")
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first GPU run of the collider / smoke adapters")]
+pytestmark = pytest.mark.gpu
 
 
 def run(*args):

@@ -1,11 +1,9 @@
-"""The particle-to-grid transfer's arithmetic (csrc/p2g_ops.cuh: per-cell register accumulation, 128-bit fixed-point
-conversion, shared-limb accumulation in BOTH representations, tile flush, normalisation) executed on the CPU through
-tests/hostcheck:
+"""The particle-to-grid transfer's arithmetic (csrc/p2g_ops.cuh: per-cell register accumulation, per-face gather of a tile's
+partial sums, colour-ordered tile passes, normalisation) executed on the CPU through tests/hostcheck:
   * against the C oracle (the reference's serial particle-order sum): markers bit-exact, velocities within the
     documented 1e-12 relative (only the summation order differs);
-  * carry-free (26-bit redundant limbs) against the default (32-bit limbs with carry chains): BIT-IDENTICAL — both add the
-    same per-cell partial sums as exact integers, only the shared-memory representation differs.  This is the check the
-    experimental JETCU_P2G_KERNEL=carryfree variant needs before its first GPU run."""
+  * z-slab decompositions (2 and 4 "ranks", each with its slab + 2 ghost planes of particles) against the undivided
+    domain: BIT-IDENTICAL — the summation order is fixed by the cell and tile lattice, not by who holds the particles."""
 import ctypes as C
 
 import numpy as np
@@ -33,7 +31,7 @@ def port():
     return o
 
 
-def run_hc(hc, grid, apic, cf, pos, vel, aff):
+def run_hc(hc, grid, apic, tz, slabs, pos, vel, aff):
     nx, ny, nz = grid.res
     u = np.zeros((nz, ny, nx + 1)); v = np.zeros((nz, ny + 1, nx)); w = np.zeros((nz + 1, ny, nx))
     um = np.zeros(u.shape, dtype=np.int8); vm = np.zeros(v.shape, dtype=np.int8); wm = np.zeros(w.shape, dtype=np.int8)
@@ -41,7 +39,7 @@ def run_hc(hc, grid, apic, cf, pos, vel, aff):
     cp = lambda a: a.ctypes.data_as(PC)
     z = np.zeros_like(pos)
     cx, cy, cz = aff if aff is not None else (z, z, z)
-    rc = hc.hc_p2g(C.byref(grid), C.c_int(1 if apic else 0), C.c_int(1 if cf else 0), C.c_uint64(len(pos)), dp(pos), dp(vel),
+    rc = hc.hc_p2g(C.byref(grid), C.c_int(1 if apic else 0), C.c_int(tz), C.c_int(slabs), C.c_uint64(len(pos)), dp(pos), dp(vel),
                    dp(cx), dp(cy), dp(cz), dp(u), dp(v), dp(w), cp(um), cp(vm), cp(wm), C.byref(err))
     assert rc == 0 and err.value == 0
     return (u, v, w), (um, vm, wm)
@@ -49,7 +47,7 @@ def run_hc(hc, grid, apic, cf, pos, vel, aff):
 
 @pytest.mark.parametrize("mode", [PIC, APIC])
 @pytest.mark.parametrize("n,domain,jitter", [(16, 1.0, 0.0), (12, 0.9, 0.37), (20, 1.0, 0.49)])
-def test_p2g_against_oracle_and_between_variants(hc, port, mode, n, domain, jitter):
+def test_p2g_against_oracle_and_between_decompositions(hc, port, mode, n, domain, jitter):
     grid = Grid.cube(n, domain)
     prm = HybridParams.make(grid, mode=mode, mgpcg=MgpcgParams.make(max_iterations=20, max_levels=2))
     h = port.hybrid(prm)
@@ -70,24 +68,15 @@ def test_p2g_against_oracle_and_between_variants(hc, port, mode, n, domain, jitt
     h.transfer_particles_to_grids()
     want = h.get_velocity()
     want_m = h.get_markers()
-    got, got_m = run_hc(hc, grid, mode == APIC, False, pos, vel, aff)
-    got_cf, got_m_cf = run_hc(hc, grid, mode == APIC, True, pos, vel, aff)
+    tz = 4 if mode == APIC else 8          # the tile heights the product launches (P2G_TZ_APIC / P2G_TZ)
+    got, got_m = run_hc(hc, grid, mode == APIC, tz, 1, pos, vel, aff)
     scale = max(float(np.abs(a).max()) for a in want)
     for a, b, am, bm, nm in zip(got, want, got_m, want_m, "uvw"):
         exact(am, bm, "marker " + nm)
         assert np.abs(a - b).max() <= 1e-12 * scale, "%s: %g" % (nm, np.abs(a - b).max() / scale)
-    for a, b, am, bm, nm in zip(got_cf, got, got_m_cf, got_m, "uvw"):
-        exact(a, b, "carry-free vs default " + nm)
-        exact(am, bm, "carry-free marker " + nm)
-    h.close()
-
-
-def test_p2g_empty_and_single_particle(hc, port):
-    grid = Grid.cube(8)
-    (u, v, w), (um, vm, wm) = run_hc(hc, grid, False, False, np.zeros((0, 3)), np.zeros((0, 3)), None)
-    assert not u.any() and not um.any()
-    pos = np.array([[0.31, 0.52, 0.77]]); vel = np.array([[1.0, -2.0, 0.5]])
-    (u, v, w), (um, vm, wm) = run_hc(hc, grid, False, True, pos, vel, None)
-    # a single particle: every touched face carries exactly the particle's velocity component (sum / weight)
-    assert um.sum() == 8 and vm.sum() == 8 and wm.sum() == 8
-    assert np.allclose(u[um == 1], 1.0, rtol=1e-15) and np.allclose(v[vm == 1], -2.0, rtol=1e-15) and np.allclose(w[wm == 1], 0.5, rtol=1e-15)
+    # z-slab decompositions: every rank sums the ghost cells along, tile by tile in the same order -> the same bits
+    for slabs in (2, 4):
+        if n % slabs == 0 and n // slabs >= 4:
+            got_s, got_m_s = run_hc(hc, grid, mode == APIC, tz, slabs, pos, vel, aff)
+            for a, b, am, bm, nm in zip(got_s, got, got_m_s, got_m, "uvw"):
+                exact(a, b, "%d slabs vs one domain: %s" % (slabs, nm)); exact(am, bm, "%d slabs: marker %s" % (slabs, nm))

@@ -347,7 +347,16 @@ class CudaHybridSolver3 : public Base {
     CudaHybridSolver3(const jet::Size3& resolution, const jet::Vector3D& gridSpacing, const jet::Vector3D& gridOrigin,
                       const jetcu_mgpcg_params& mgpcg = makeMgpcgParams(100, 6, 5, 5, 20, 20, 1e-9, 1.5, true),
                       ContextPtr ctx = ContextPtr())
-        : Base(resolution, gridSpacing, gridOrigin), _ctx(ctx ? ctx : Context::shared()), _mgpcg(mgpcg) {}
+        : Base(resolution, gridSpacing, gridOrigin), _ctx(ctx ? ctx : Context::shared()), _mgpcg(mgpcg) {
+        // what runs on the device is what the Jet object shows: a fractional pressure solver carrying an FdmMgpcgSolver3 with
+        // these parameters replaces the default-constructed one (whose linear solver is FdmIccgSolver3).  Callers may
+        // install their own afterwards (setPressureSolver); ensureDevice() re-reads it every step.
+        auto pressure = std::make_shared<jet::GridFractionalSinglePhasePressureSolver3>();
+        pressure->setLinearSystemSolver(std::make_shared<jet::FdmMgpcgSolver3>(
+            mgpcg.max_iterations, mgpcg.max_levels, mgpcg.n_restriction, mgpcg.n_correction, mgpcg.n_coarsest, mgpcg.n_final,
+            mgpcg.tolerance, mgpcg.sor_factor, mgpcg.use_red_black != 0));
+        this->setPressureSolver(pressure);
+    }
 
     ~CudaHybridSolver3() override {
         if (_h) jetcu_hybrid_destroy(_h);
@@ -355,7 +364,11 @@ class CudaHybridSolver3 : public Base {
 
     void setHostMirror(HostMirror m) { _mirror = m; }
     HostMirror hostMirror() const { return _mirror; }
-    void setCudaMgpcgParams(const jetcu_mgpcg_params& p) { _mgpcg = p; releaseDevice(); }
+    void setCudaMgpcgParams(const jetcu_mgpcg_params& p) { _mgpcg = p; }
+    //! Opt in to running MGPCG (the constructor's parameters) although the Jet-side pressure solver carries another linear
+    //! system solver (FdmIccgSolver3 by default).  Off by default: a different solver than the one configured is an error.
+    void setAllowSolverSubstitution(bool allow) { _allowSolverSubstitution = allow; }
+    bool allowSolverSubstitution() const { return _allowSolverSubstitution; }
 
     //! Tell the adapter that host-side particles or the velocity grid were edited by the caller since the last step.
     void markHostDirty() { _hostDirty = true; }
@@ -414,10 +427,15 @@ class CudaHybridSolver3 : public Base {
     void onAdvanceTimeStep(double timeIntervalInSeconds) override {
         auto grids = this->gridSystemData();
         if (grids->resolution().x == 0 || grids->resolution().y == 0 || grids->resolution().z == 0) return;
+        // GridFluidSolver3::computeViscosity (grid_fluid_solver3.cpp:221-231) has no device counterpart: never skip it silently
+        if (this->viscosityCoefficient() > jet::kEpsilonD)
+            throw std::runtime_error("jetcu: the device hybrid solver implements zero viscosity only (viscosityCoefficient() > 0)");
         ensureDevice();
+        // GridFluidSolver3::beginAdvanceTimeStep -> updateCollider (grid_fluid_solver3.cpp:255-275, 371-375): animated
+        // colliders move in their onBeginUpdate callbacks, so it has to run before the collider is forwarded
+        if (this->collider() != nullptr) this->collider()->update(this->currentTimeInSeconds(), timeIntervalInSeconds);
         syncCollider();
         // PicSolver3::onBeginAdvanceTimeStep -> updateParticleEmitter (src/jet/pic_solver3.cpp:63-75)
-        auto particles = this->particleSystemData();
         if (this->particleEmitter() != nullptr)
             this->particleEmitter()->update(this->currentTimeInSeconds(), timeIntervalInSeconds);
         uploadIfNeeded();
@@ -441,8 +459,13 @@ class CudaHybridSolver3 : public Base {
         _hasCollider = false;
     }
 
+    //! Reads the solver's knobs from the Jet object EVERY step (setGravity / setMaxCfl / setClosedDomainBoundaryFlag /
+    //! setPicBlendingFactor / a re-configured linear solver between steps are honoured like in GridFluidSolver3) and creates
+    //! the device solver on first use.  The pressure solve on the device is MGPCG; a Jet-side linear system solver that is
+    //! not an FdmMgpcgSolver3 / CudaFdmMgpcgSolver3 (e.g. the FdmIccgSolver3 a default-constructed
+    //! GridFractionalSinglePhasePressureSolver3 carries) is an error unless the caller opted in with
+    //! setAllowSolverSubstitution(true), in which case the constructor's MGPCG parameters are used.
     void ensureDevice() {
-        if (_h) return;
         jetcu_hybrid_params p;
         jetcu_hybrid_default_params(&p);
         auto grids = this->gridSystemData();
@@ -457,34 +480,47 @@ class CudaHybridSolver3 : public Base {
         const jet::Vector3D g = this->gravity();
         p.gravity[0] = g.x; p.gravity[1] = g.y; p.gravity[2] = g.z;
         p.max_cfl = this->maxCfl();
-        // honour an MGPCG configured on the Jet pressure solver; otherwise the ctor's parameters
-        jetcu_mgpcg_params fromJet;
-        auto frac = std::dynamic_pointer_cast<jet::GridFractionalSinglePhasePressureSolver3>(this->pressureSolver());
-        if (frac && detail::mgpcgParamsOf(frac->linearSystemSolver(), &fromJet)) _mgpcg = fromJet;
+        jetcu_mgpcg_params mg = _mgpcg;
         auto cu = std::dynamic_pointer_cast<CudaGridFractionalSinglePhasePressureSolver3>(this->pressureSolver());
-        if (cu) _mgpcg = cu->cudaParams();
-        p.mgpcg = _mgpcg;
+        auto frac = std::dynamic_pointer_cast<jet::GridFractionalSinglePhasePressureSolver3>(this->pressureSolver());
+        jetcu_mgpcg_params fromJet;
+        if (cu) mg = cu->cudaParams();
+        else if (frac && detail::mgpcgParamsOf(frac->linearSystemSolver(), &fromJet)) mg = fromJet;
+        else if (!_allowSolverSubstitution)
+            throw std::runtime_error(
+                "jetcu: the pressure solver installed on this solver does not carry an MGPCG linear system solver (Jet's "
+                "default is FdmIccgSolver3); the device path solves with MGPCG only. Install FdmMgpcgSolver3 / "
+                "CudaFdmMgpcgSolver3, or call setAllowSolverSubstitution(true) to use the constructor's MGPCG parameters");
+        p.mgpcg = mg;
+        if (_h && std::memcmp(&p, &_params, sizeof(p)) == 0) return;
+        if (_h && std::memcmp(&p.grid, &_params.grid, sizeof(p.grid)) == 0) {
+            _ctx->check(jetcu_hybrid_update_params(_h, &p));   // knobs changed between steps: device state stays
+            _params = p;
+            return;
+        }
+        if (_h) {   // the grid itself changed (resizeGrid): the live particles move to the new device solver through the host
+            if (!_hostDirty) syncToHost();
+            releaseDevice();
+        }
         _ctx->check(jetcu_hybrid_create(_ctx->get(), &p, &_h));
+        _params = p;
         _hostDirty = true;
     }
 
     void uploadIfNeeded() {
         auto particles = this->particleSystemData();
         const size_t n = particles->numberOfParticles();
+        if (!_hostDirty && n > _deviceCount && _deviceCount > 0) {
+            // a host emitter appended particles (ParticleSystemData3::addParticles) while the device holds the live copy of
+            // the old ones: only the tail goes up, the device-resident state (APIC affine vectors included) stays
+            _ctx->check(jetcu_hybrid_append_particles(
+                _h, n - _deviceCount, reinterpret_cast<const double*>(particles->positions().data() + _deviceCount),
+                reinterpret_cast<const double*>(particles->velocities().data() + _deviceCount)));
+            _deviceCount = n;
+            return;
+        }
         if (_hostDirty || n != _deviceCount) {
             // host state is authoritative: (re)upload everything, including the velocity grid
-            if (_mirror == HostMirror::kOnDemand && !_hostDirty && n > _deviceCount && _deviceCount > 0) {
-                // emitter appended particles while the device holds the live copy of the old ones: fetch those first
-                std::vector<jet::Vector3D> newPos(particles->positions().data() + _deviceCount,
-                                                  particles->positions().data() + n);
-                std::vector<jet::Vector3D> newVel(particles->velocities().data() + _deviceCount,
-                                                  particles->velocities().data() + n);
-                const size_t old = _deviceCount;
-                syncToHost();
-                particles->resize(n);
-                std::copy(newPos.begin(), newPos.end(), particles->positions().data() + old);
-                std::copy(newVel.begin(), newVel.end(), particles->velocities().data() + old);
-            }
             _ctx->check(jetcu_hybrid_set_particles(_h, n, reinterpret_cast<const double*>(particles->positions().data()),
                                                    reinterpret_cast<const double*>(particles->velocities().data())));
             auto vel = this->velocity();
@@ -533,6 +569,8 @@ class CudaHybridSolver3 : public Base {
 
     ContextPtr _ctx;
     jetcu_mgpcg_params _mgpcg;
+    jetcu_hybrid_params _params = jetcu_hybrid_params();
+    bool _allowSolverSubstitution = false;
     jetcu_hybrid* _h = nullptr;
     size_t _deviceCount = 0;
     bool _hostDirty = true;

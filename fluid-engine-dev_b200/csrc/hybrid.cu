@@ -31,6 +31,7 @@ struct jetcu_hybrid {
     char *valid0 = nullptr, *valid1 = nullptr;
     double* sdf = nullptr;
     float *ud = nullptr, *vd = nullptr, *wd = nullptr;
+    double* pair[3] = {};                  // pair arrays of u, v, w for the advection samples (particle_ops.cuh: jc_load_x2)
     double* wsum[3] = {};                  // P2G weight sums (u, v, w faces); the value sums live in u, v, w themselves
     int* p2g_err = nullptr;                // device flag: a particle outside its cell's face window (cannot happen)
     // particles
@@ -42,6 +43,7 @@ struct jetcu_hybrid {
     uint32_t *cell_of = nullptr, *rank = nullptr, *perm = nullptr;
     uint32_t* cell_start = nullptr;  // nc + 1
     bool binned = false;
+    bool counted = false;  // cell_of / rank / per-cell counts already produced by the advection kernel of the last step
     // z-slab mode (the ctx had a multi-rank communicator when the solver was created): this rank owns the cell planes
     // [z0, z1); after binning attr[cur] holds [ghost-lo | owned | ghost-hi | dead], the owned block starts at `base`.
     int world = 1, me = 0, z0 = 0, z1 = 0;
@@ -183,27 +185,43 @@ __device__ __forceinline__ void p2g_tile_component(const GridD& g, int I0, int J
                                                    double* __restrict__ U, double* __restrict__ W, char* __restrict__ M, int* err) {
     constexpr int NT = P2G_TX * P2G_TY * TZ;
     constexpr int WX = P2G_TX + (AX == 0 ? 1 : 2), WY = P2G_TY + (AX == 1 ? 1 : 2), WZ = TZ + (AX == 2 ? 1 : 2);
+    constexpr int NW = WX * WY * WZ, PER = (NW + NT - 1) / NT;   // window faces, faces per thread
     const int tid = threadIdx.x;
     unsigned touched = 0;
+    double sv[P2G_SLOTS], sw[P2G_SLOTS];
     if (e0 > s0) {
-        double sv[P2G_SLOTS], sw[P2G_SLOTS];
         touched = p2g_cell_partial<APIC, AX>(g, ci, cj, ck, s0, e0, a, sv, sw, err);
 #pragma unroll
-        for (int s = 0; s < P2G_SLOTS; ++s) { ex[s * NT + tid] = sv[s]; ex[(P2G_SLOTS + s) * NT + tid] = sw[s]; }
+        for (int s = 0; s < P2G_SLOTS; ++s) ex[s * NT + tid] = sv[s];
     }
     tm[tid] = touched;
     __syncthreads();
+    double fv[PER], fw[PER];
+    bool hit[PER];
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+        const int f = tid + r * NT;
+        hit[r] = false; fv[r] = 0.0;
+        if (f < NW) hit[r] = p2g_face_gather<AX, TZ>(ex, tm, f % WX, (f / WX) % WY, f / (WX * WY), &fv[r]);
+    }
+    __syncthreads();
+    if (e0 > s0) {
+#pragma unroll
+        for (int s = 0; s < P2G_SLOTS; ++s) ex[s * NT + tid] = sw[s];
+    }
+    __syncthreads();
     const int sx = g.nx + (AX == 0), sy = g.ny + (AX == 1), sz = g.nz + (AX == 2);
     const int fx0 = I0 - (AX == 0 ? 0 : 1), fy0 = J0 - (AX == 1 ? 0 : 1), fz0 = K0 - (AX == 2 ? 0 : 1);
-    for (int f = tid; f < WX * WY * WZ; f += NT) {
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+        if (!hit[r]) continue;
+        const int f = tid + r * NT;
         const int lx = f % WX, ly = (f / WX) % WY, lz = f / (WX * WY);
+        p2g_face_gather<AX, TZ>(ex, tm, lx, ly, lz, &fw[r]);
         const int fi = fx0 + lx, fj = fy0 + ly, fk = fz0 + lz;
         if ((unsigned)fi >= (unsigned)sx || (unsigned)fj >= (unsigned)sy || (unsigned)fk >= (unsigned)sz) continue;
-        double v, w;
-        if (p2g_face_gather<AX, TZ>(ex, tm, lx, ly, lz, &v, &w)) {
-            const size_t idx = ((size_t)fk * sy + fj) * sx + fi;
-            U[idx] += v; W[idx] += w; M[idx] = 1;
-        }
+        const size_t idx = ((size_t)fk * sy + fj) * sx + fi;
+        U[idx] += fv[r]; W[idx] += fw[r]; M[idx] = 1;
     }
     __syncthreads();
 }
@@ -219,7 +237,7 @@ __global__ void __launch_bounds__(P2G_TX * P2G_TY * TZ)
     k_p2g_tile(GridD g, int par_x, int par_y, int tz_first, int kb, int ke, const uint32_t* __restrict__ cell_start, AttrPtrs a,
                P2GOut out, int* __restrict__ err) {
     constexpr int NT = P2G_TX * P2G_TY * TZ;
-    extern __shared__ __align__(16) double p2g_ex[];  // [2][P2G_SLOTS][NT]
+    extern __shared__ __align__(16) double p2g_ex[];  // [P2G_SLOTS][NT]: value partials, then weight partials
     __shared__ unsigned tm[NT];
     const int tid = threadIdx.x;
     const int I0 = (2 * blockIdx.x + par_x) * P2G_TX, J0 = (2 * blockIdx.y + par_y) * P2G_TY, K0 = (tz_first + 2 * blockIdx.z) * TZ;
@@ -410,15 +428,76 @@ __global__ void k_g2p_apic(GridD g, const double* __restrict__ u, const double* 
     apic_affine<2>(g, w, px, py, pz, &c0, &c1, &c2); a.p[12][p] = c0; a.p[13][p] = c1; a.p[14][p] = c2;
 }
 
+// Tail of the advection kernels on a single GPU without a collider: the particle's NEW cell, its slot inside the cell and
+// the per-cell counts — k_cell_count's work for the next step's binning — while the final position is still in registers
+// (the next step then skips k_cell_count and its 24 B/particle re-read of the positions).
+__device__ __forceinline__ void count_cell(const GridD& g, const double* pos, size_t p, uint32_t* __restrict__ cell_of,
+                                           uint32_t* __restrict__ rank, uint32_t* __restrict__ count) {
+    if (!count) return;
+    const int ci = cell_coord(pos[0], g.ox, 1.0 / g.hx, g.nx);
+    const int cj = cell_coord(pos[1], g.oy, 1.0 / g.hy, g.ny);
+    const int ck = cell_coord(pos[2], g.oz, 1.0 / g.hz, g.nz);
+    const uint32_t cell = (uint32_t)(((size_t)ck * g.ny + cj) * g.nx + ci);
+    cell_of[p] = cell;
+    rank[p] = atomicAdd(&count[cell], 1u);
+}
+
 template <bool POW2, typename I>
 __global__ void k_move(GridD g, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
-                       double dt, unsigned nsub, int flag, AttrPtrs a, size_t np) {
+                       double dt, unsigned nsub, int flag, AttrPtrs a, size_t np, uint32_t* __restrict__ cell_of,
+                       uint32_t* __restrict__ rank, uint32_t* __restrict__ count) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= np) return;
     double pos[3] = {a.p[0][p], a.p[1][p], a.p[2][p]}, vel[3] = {a.p[3][p], a.p[4][p], a.p[5][p]};
-    move_particle<POW2, I>(g, u, v, w, dt, nsub, flag, pos, vel);
+    move_particle<POW2, I, true>(g, u, v, w, dt, nsub, flag, pos, vel);   // u, v, w: PAIR arrays (k_pack_pairs)
     a.p[0][p] = pos[0]; a.p[1][p] = pos[1]; a.p[2][p] = pos[2];
+    count_cell(g, pos, p, cell_of, rank, count);
     a.p[3][p] = vel[0]; a.p[4][p] = vel[1]; a.p[5][p] = vel[2];
+}
+
+// Fused transferFromGridsToParticles + moveParticles of one sub-step (PicSolver3::computeAdvection runs them back to back,
+// src/jet/pic_solver3.cpp:95-112): the particle arrays are read and written once instead of twice.
+//   PIC : the grid velocity sampled at the particle is its new velocity AND the first sample of the first midpoint
+//         sub-step (same expression, same point), so one of the 11 samples disappears as well;
+//   FLIP: velocity += float delta sample (pic blending factor 0; a non-zero factor takes the two-kernel path).
+// u, v, w are pair arrays.
+template <bool POW2, typename I>
+__global__ void k_pic_move(GridD g, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
+                       double dt, unsigned nsub, int flag, AttrPtrs a, size_t np, uint32_t* __restrict__ cell_of,
+                       uint32_t* __restrict__ rank, uint32_t* __restrict__ count) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    double pos[3] = {a.p[0][p], a.p[1][p], a.p[2][p]}, vel[3];
+    sample_velocity<POW2, I, true>(g, u, v, w, pos[0], pos[1], pos[2], &vel[0], &vel[1], &vel[2]);
+    const double first[3] = {vel[0], vel[1], vel[2]};
+    move_particle<POW2, I, true>(g, u, v, w, dt, nsub, flag, pos, vel, first);
+    a.p[0][p] = pos[0]; a.p[1][p] = pos[1]; a.p[2][p] = pos[2];
+    count_cell(g, pos, p, cell_of, rank, count);
+    a.p[3][p] = vel[0]; a.p[4][p] = vel[1]; a.p[5][p] = vel[2];
+}
+
+template <bool POW2, typename I>
+__global__ void k_flip_move(GridD g, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
+                            const float* __restrict__ ud, const float* __restrict__ vd, const float* __restrict__ wd, double dt,
+                            unsigned nsub, int flag, AttrPtrs a, size_t np, uint32_t* __restrict__ cell_of,
+                            uint32_t* __restrict__ rank, uint32_t* __restrict__ count) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    double pos[3] = {a.p[0][p], a.p[1][p], a.p[2][p]}, vel[3] = {a.p[3][p], a.p[4][p], a.p[5][p]};
+    g2p_flip_particle(g, nullptr, nullptr, nullptr, ud, vd, wd, 0.0, pos, vel);
+    move_particle<POW2, I, true>(g, u, v, w, dt, nsub, flag, pos, vel);
+    a.p[0][p] = pos[0]; a.p[1][p] = pos[1]; a.p[2][p] = pos[2];
+    count_cell(g, pos, p, cell_of, rank, count);
+    a.p[3][p] = vel[0]; a.p[4][p] = vel[1]; a.p[5][p] = vel[2];
+}
+
+// pair array of one component (particle_ops.cuh: jc_load_x2); with d != nullptr also FLIP's delta = float(u) - snapshot
+// (src/jet/flip_solver3.cpp:57-70) in the same pass over the field
+__global__ void k_pack_pairs(const double* __restrict__ in, double* __restrict__ pairs, float* __restrict__ d, int sx, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    pack_pair(in, pairs, i, sx);
+    if (d) d[i] = (float)in[i] - d[i];
 }
 
 // ------------------------------------------------------------------------------------------------ particle I/O
@@ -676,7 +755,7 @@ static int hyb_reserve(jetcu_hybrid* h, uint64_t need) {
     h->cap = cap;
     h->base = 0;
     h->nsorted = h->np;
-    h->binned = false;
+    h->binned = false; h->counted = false;
     return JETCU_OK;
 }
 
@@ -773,13 +852,16 @@ static int hyb_bin(jetcu_hybrid* h) {
     // only the cells of the window [lo, hi) can receive particles (the rest go to the trash bin at index nc): count,
     // scan and per-cell ordering touch that range only, so the binning cost follows the slab, not the whole grid
     const size_t nxy = (size_t)h->nx * h->ny, lo = (size_t)e0 * nxy, hi = (size_t)e1 * nxy;
-    JC_TRY(jc_zero(ctx, h->cell_start + lo, hi - lo + 1));
-    JC_TRY(jc_zero(ctx, h->cell_start + h->nc, 2));
-    if (ntot > 0) {
-        AttrPtrs src = owned_ptrs(h);
-        JC_LAUNCH(ctx, k_cell_count, jc_blocks(ntot, 256), 256, 0, src.p[0], src.p[1], src.p[2], (size_t)ntot, g, e0, e1,
-                  h->cell_of, h->rank, h->cell_start);
+    if (!(h->counted && !slab)) {   // else: the last step's advection kernel already counted (count_cell)
+        JC_TRY(jc_zero(ctx, h->cell_start + lo, hi - lo + 1));
+        JC_TRY(jc_zero(ctx, h->cell_start + h->nc, 2));
+        if (ntot > 0) {
+            AttrPtrs src = owned_ptrs(h);
+            JC_LAUNCH(ctx, k_cell_count, jc_blocks(ntot, 256), 256, 0, src.p[0], src.p[1], src.p[2], (size_t)ntot, g, e0, e1,
+                      h->cell_of, h->rank, h->cell_start);
+        }
     }
+    h->counted = false;
     if (hi == h->nc) {
         JC_TRY(scan_exclusive_u32(ctx, h->cell_start + lo, h->cell_start + lo, hi - lo + 2));
     } else {  // cell_start[hi] = end of the window = where the trash bin starts
@@ -936,7 +1018,7 @@ int jetcu_hybrid_create(jetcu_ctx* ctx, const jetcu_hybrid_params* p, jetcu_hybr
     {
         const size_t nf[3] = {h->nu, h->nv, h->nw};
         for (int q = 0; q < 3; ++q) {
-            STEP(jc_alloc(ctx, &h->wsum[q], nf[q]));
+            STEP(jc_alloc(ctx, &h->wsum[q], nf[q])); STEP(jc_alloc(ctx, &h->pair[q], 2 * nf[q]));
         }
     }
     STEP(jc_alloc(ctx, &h->p2g_err, 1)); STEP(jc_zero(ctx, h->p2g_err, 1));
@@ -963,6 +1045,16 @@ int jetcu_hybrid_create(jetcu_ctx* ctx, const jetcu_hybrid_params* p, jetcu_hybr
     return JETCU_OK;
 }
 
+int jetcu_hybrid_update_params(jetcu_hybrid* h, const jetcu_hybrid_params* p) {
+    HYB_ENTER(h);
+    JC_ARG(ctx, p != nullptr);
+    if (memcmp(&p->grid, &h->P.grid, sizeof(p->grid)) != 0 || p->mode != h->P.mode)
+        return jetcu_fail(ctx, JETCU_ERR_INVALID_ARG, "jetcu_hybrid_update_params: grid and mode are fixed at creation");
+    JC_ARG(ctx, p->max_cfl > 0.0);
+    h->P = *p;   // gravity, maxCfl, picBlendingFactor, closedDomainBoundaryFlag, MGPCG parameters: read at every stage call
+    return JETCU_OK;
+}
+
 int jetcu_hybrid_destroy(jetcu_hybrid* h) {
     if (!h) return JETCU_OK;
     jetcu_ctx* ctx = h->ctx;
@@ -971,7 +1063,7 @@ int jetcu_hybrid_destroy(jetcu_hybrid* h) {
     jc_free(ctx, h->um); jc_free(ctx, h->vm); jc_free(ctx, h->wm);
     jc_free(ctx, h->valid0); jc_free(ctx, h->valid1); jc_free(ctx, h->sdf);
     jc_free(ctx, h->ud); jc_free(ctx, h->vd); jc_free(ctx, h->wd);
-    for (int q = 0; q < 3; ++q) jc_free(ctx, h->wsum[q]);
+    for (int q = 0; q < 3; ++q) { jc_free(ctx, h->wsum[q]); jc_free(ctx, h->pair[q]); }
     jc_free(ctx, h->p2g_err);
     jc_free(ctx, h->col_sdf); jc_free(ctx, h->bnd_u); jc_free(ctx, h->bnd_v); jc_free(ctx, h->bnd_w);
     jc_free(ctx, h->tmp_u); jc_free(ctx, h->tmp_v); jc_free(ctx, h->tmp_w);
@@ -990,12 +1082,14 @@ int jetcu_hybrid_destroy(jetcu_hybrid* h) {
 
 // Uploads n AoS particles; on a single GPU all of them, in slab mode (own_only) those whose cell plane this rank owns.
 // ids == nullptr: original index = position in the caller's array (+ id_base).
+// append: the uploaded particles join the device-resident set (which keeps its state, APIC affine vectors included) as
+// original indices nglobal .. nglobal + n - 1; otherwise they replace it.
 static int hyb_upload(jetcu_hybrid* h, uint64_t n, const double* positions, const double* velocities, const uint64_t* ids,
-                      bool own_only) {
+                      bool own_only, bool append = false) {
     jetcu_ctx* ctx = h->ctx;
     const jetcu_grid& gg = h->P.grid;
-    h->np = 0; h->base = 0; h->nsorted = 0;
-    h->binned = false;
+    if (!append) { h->np = 0; h->base = 0; h->nsorted = 0; }
+    h->binned = false; h->counted = false;
     if (n == 0) return JETCU_OK;
     double* stage = nullptr;
     uint32_t* local = nullptr;
@@ -1016,33 +1110,36 @@ static int hyb_upload(jetcu_hybrid* h, uint64_t n, const double* positions, cons
         STEP(jc_sync(ctx));
         keep = k32;
     }
-    STEP(hyb_reserve(h, keep));
+    STEP(hyb_reserve(h, (append ? h->base + h->np : 0) + keep));
     const int c = h->cur;
+    const size_t at = append ? h->base + h->np : 0;   // after hyb_reserve: growing moves the owned block to offset 0
     if (rc == JETCU_OK && keep > 0) {
-        k_compact_aos3<<<jc_blocks(n, 256), 256, 0, ctx->stream>>>(stage, local, (size_t)n, h->attr[c][0], h->attr[c][1],
-                                                                  h->attr[c][2], ids ? nullptr : h->orig[c], 0);
+        k_compact_aos3<<<jc_blocks(n, 256), 256, 0, ctx->stream>>>(stage, local, (size_t)n, h->attr[c][0] + at, h->attr[c][1] + at,
+                                                                  h->attr[c][2] + at, ids ? nullptr : h->orig[c] + at,
+                                                                  append ? (size_t)h->nglobal : 0);
         ctx->launches++;
         if (velocities) {
             STEP(jc_h2d(ctx, stage, velocities, 3 * n));
             if (rc == JETCU_OK) {
-                k_compact_aos3<<<jc_blocks(n, 256), 256, 0, ctx->stream>>>(stage, local, (size_t)n, h->attr[c][3], h->attr[c][4],
-                                                                          h->attr[c][5], nullptr, 0);
+                k_compact_aos3<<<jc_blocks(n, 256), 256, 0, ctx->stream>>>(stage, local, (size_t)n, h->attr[c][3] + at,
+                                                                          h->attr[c][4] + at, h->attr[c][5] + at, nullptr, 0);
                 ctx->launches++;
             }
         } else {
-            for (int q = 3; q < 6 && rc == JETCU_OK; ++q) rc = jc_zero(ctx, h->attr[c][q], keep);
+            for (int q = 3; q < 6 && rc == JETCU_OK; ++q) rc = jc_zero(ctx, h->attr[c][q] + at, keep);
         }
-        for (int q = 6; q < h->nattr && rc == JETCU_OK; ++q) rc = jc_zero(ctx, h->attr[c][q], keep);
+        // new particles start with zero affine vectors: _cX.resize(n) value-initialises the tail (apic_solver3.cpp:36-38)
+        for (int q = 6; q < h->nattr && rc == JETCU_OK; ++q) rc = jc_zero(ctx, h->attr[c][q] + at, keep);
         if (ids) {  // caller-supplied original indices (every particle kept: own_only is false on this path)
             STEP(jc_alloc(ctx, &dids, n));
             STEP(jc_h2d(ctx, dids, ids, n));
             if (rc == JETCU_OK) {
-                k_u64_to_u32<<<jc_blocks(n, 256), 256, 0, ctx->stream>>>(dids, h->orig[c], (size_t)n);
+                k_u64_to_u32<<<jc_blocks(n, 256), 256, 0, ctx->stream>>>(dids, h->orig[c] + at, (size_t)n);
                 ctx->launches++;
             }
         }
     }
-    if (rc == JETCU_OK) { h->np = keep; h->nsorted = keep; rc = jc_sync(ctx); }
+    if (rc == JETCU_OK) { h->np = (append ? h->np : 0) + keep; h->nsorted = h->np; rc = jc_sync(ctx); }
 #undef STEP
     jc_free(ctx, stage); jc_free(ctx, local); jc_free(ctx, dids);
     return rc;
@@ -1054,6 +1151,15 @@ int jetcu_hybrid_set_particles(jetcu_hybrid* h, uint64_t n, const double* positi
     JC_ARG(ctx, n < (1ull << 32) - 1);
     JC_TRY(hyb_upload(h, n, positions, velocities, nullptr, h->world > 1));
     h->nglobal = n;
+    return JETCU_OK;
+}
+
+int jetcu_hybrid_append_particles(jetcu_hybrid* h, uint64_t n_new, const double* positions, const double* velocities) {
+    HYB_ENTER(h);
+    JC_ARG(ctx, n_new == 0 || positions != nullptr);
+    JC_ARG(ctx, h->nglobal + n_new < (1ull << 32) - 1);
+    JC_TRY(hyb_upload(h, n_new, positions, velocities, nullptr, h->world > 1, true));
+    h->nglobal += n_new;
     return JETCU_OK;
 }
 
@@ -1126,7 +1232,7 @@ static int hyb_emit_lattice(jetcu_hybrid* h, const double lo[3], const double hi
     h->np += accepted_here;
     h->nglobal += accepted;
     h->nsorted = h->np;  // ghosts (if any) are stale now; the next binning rebuilds them
-    h->binned = false;
+    h->binned = false; h->counted = false;
     if (n_emitted) *n_emitted = accepted;
     return jc_sync(ctx);
 }
@@ -1418,7 +1524,7 @@ int jetcu_hybrid_transfer_particles_to_grids(jetcu_hybrid* h) {
             const int TZ = apic ? P2G_TZ_APIC : P2G_TZ;
             const int ntx = (g.nx + P2G_TX - 1) / P2G_TX, nty = (g.ny + P2G_TY - 1) / P2G_TY;
             const int tzlo = kb / TZ, tzhi = (ke - 1) / TZ;  // inclusive
-            const size_t smem = (size_t)2 * P2G_SLOTS * P2G_TX * P2G_TY * TZ * sizeof(double);
+            const size_t smem = (size_t)P2G_SLOTS * P2G_TX * P2G_TY * TZ * sizeof(double);
             // per device, cheap: set on every call (the attribute belongs to the current device's copy of the function)
             if (apic) JC_CUDA(ctx, cudaFuncSetAttribute((k_p2g_tile<true, P2G_TZ_APIC>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             else JC_CUDA(ctx, cudaFuncSetAttribute((k_p2g_tile<false, P2G_TZ>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1546,19 +1652,78 @@ int jetcu_hybrid_transfer_grids_to_particles(jetcu_hybrid* h) {
     return JETCU_OK;
 }
 
+// pair arrays of the current velocity field; flip_delta: also turn FLIP's snapshot into the delta field (one pass per field)
+static int hyb_pack_pairs(jetcu_hybrid* h, bool flip_delta) {
+    jetcu_ctx* ctx = h->ctx;
+    JC_LAUNCH(ctx, k_pack_pairs, jc_blocks(h->nu, 256), 256, 0, h->u, h->pair[0], flip_delta ? h->ud : nullptr, h->nx + 1, h->nu);
+    JC_LAUNCH(ctx, k_pack_pairs, jc_blocks(h->nv, 256), 256, 0, h->v, h->pair[1], flip_delta ? h->vd : nullptr, h->nx, h->nv);
+    JC_LAUNCH(ctx, k_pack_pairs, jc_blocks(h->nw, 256), 256, 0, h->w, h->pair[2], flip_delta ? h->wd : nullptr, h->nx, h->nw);
+    return JETCU_OK;
+}
+
+// whether the advection kernel of this step also does the next binning's counting pass: one GPU (slab mode routes and
+// exchanges particles first), no collider (resolveCollision moves particles after the advection kernel)
+static bool hyb_count_in_move(const jetcu_hybrid* h) {
+    return h->world == 1 && h->col.kind == 0 && h->np > 0 && !getenv("JETCU_NO_FUSED_COUNT");
+}
+
+static int hyb_before_move(jetcu_hybrid* h, bool count) {
+    if (!count) return JETCU_OK;
+    return jc_zero(h->ctx, h->cell_start, h->nc + 2);
+}
+
+static int hyb_after_move(jetcu_hybrid* h, bool counted) {
+    jetcu_ctx* ctx = h->ctx;
+    if (h->np && h->col.kind != 0)
+        JC_LAUNCH(ctx, k_resolve_collision, jc_blocks(h->np, 128), 128, 0, h->col, owned_ptrs(h), (size_t)h->np);
+    h->nsorted = h->np;  // the ghost copies are stale from here on
+    h->binned = false;
+    h->counted = counted;
+    return JETCU_OK;
+}
+
 int jetcu_hybrid_move_particles(jetcu_hybrid* h, double dt) {
     HYB_ENTER(h);
     GridD g = gridd(h);
     unsigned nsub = (unsigned)fmax(h->P.max_cfl, 1.0);
     double sub_dt = dt / nsub;
-    if (h->np)
-        HYB_SAMPLER_LAUNCH(k_move, jc_blocks(h->np, 128), 128, g, h->u, h->v, h->w, sub_dt, nsub,
-                           h->P.closed_domain_boundary_flag, owned_ptrs(h), (size_t)h->np);
-    if (h->np && h->col.kind != 0)
-        JC_LAUNCH(ctx, k_resolve_collision, jc_blocks(h->np, 128), 128, 0, h->col, owned_ptrs(h), (size_t)h->np);
-    h->nsorted = h->np;  // the ghost copies are stale from here on
-    h->binned = false;
-    return JETCU_OK;
+    const bool count = hyb_count_in_move(h);
+    JC_TRY(hyb_before_move(h, count));
+    if (h->np) {
+        JC_TRY(hyb_pack_pairs(h, false));
+        HYB_SAMPLER_LAUNCH(k_move, jc_blocks(h->np, 128), 128, g, h->pair[0], h->pair[1], h->pair[2], sub_dt, nsub,
+                           h->P.closed_domain_boundary_flag, owned_ptrs(h), (size_t)h->np, h->cell_of, h->rank,
+                           count ? h->cell_start : nullptr);
+    }
+    return hyb_after_move(h, count);
+}
+
+// transferFromGridsToParticles + moveParticles of one sub-step; PIC and FLIP (blending factor 0) in one fused kernel
+static int hyb_g2p_move(jetcu_hybrid* h, double dt) {
+    jetcu_ctx* ctx = h->ctx;
+    const bool fused = h->P.mode == JETCU_PIC || (h->P.mode == JETCU_FLIP && !(h->P.pic_blending_factor > 0.0));
+    if (!fused || getenv("JETCU_UNFUSED_ADVECTION")) {
+        JC_TRY(jetcu_hybrid_transfer_grids_to_particles(h));
+        return jetcu_hybrid_move_particles(h, dt);
+    }
+    GridD g = gridd(h);
+    const unsigned nsub = (unsigned)fmax(h->P.max_cfl, 1.0);
+    const double sub_dt = dt / nsub;
+    const bool flip = h->P.mode == JETCU_FLIP;
+    JC_TRY(hyb_pack_pairs(h, flip));
+    const bool count = hyb_count_in_move(h);
+    JC_TRY(hyb_before_move(h, count));
+    if (h->np) {
+        if (flip)
+            HYB_SAMPLER_LAUNCH(k_flip_move, jc_blocks(h->np, 128), 128, g, h->pair[0], h->pair[1], h->pair[2], h->ud, h->vd, h->wd,
+                               sub_dt, nsub, h->P.closed_domain_boundary_flag, owned_ptrs(h), (size_t)h->np, h->cell_of, h->rank,
+                               count ? h->cell_start : nullptr);
+        else
+            HYB_SAMPLER_LAUNCH(k_pic_move, jc_blocks(h->np, 128), 128, g, h->pair[0], h->pair[1], h->pair[2], sub_dt, nsub,
+                               h->P.closed_domain_boundary_flag, owned_ptrs(h), (size_t)h->np, h->cell_of, h->rank,
+                               count ? h->cell_start : nullptr);
+    }
+    return hyb_after_move(h, count);
 }
 
 int jetcu_hybrid_compute_advection(jetcu_hybrid* h, double dt) {
@@ -1566,8 +1731,7 @@ int jetcu_hybrid_compute_advection(jetcu_hybrid* h, double dt) {
     // PicSolver3::computeAdvection, src/jet/pic_solver3.cpp:95-112
     JC_TRY(jetcu_hybrid_extrapolate_velocity_to_air(h));
     JC_TRY(hyb_zero_walls(h));
-    JC_TRY(jetcu_hybrid_transfer_grids_to_particles(h));
-    return jetcu_hybrid_move_particles(h, dt);
+    return hyb_g2p_move(h, dt);
 }
 
 int jetcu_hybrid_step(jetcu_hybrid* h, double dt, jetcu_step_stats* st) {
@@ -1592,9 +1756,8 @@ int jetcu_hybrid_step(jetcu_hybrid* h, double dt, jetcu_step_stats* st) {
     JC_TRY(jetcu_hybrid_extrapolate_velocity_to_air(h));
     JC_TRY(hyb_zero_walls(h));
     MARK(7);
-    JC_TRY(jetcu_hybrid_transfer_grids_to_particles(h));
-    MARK(8);
-    JC_TRY(jetcu_hybrid_move_particles(h, dt));
+    MARK(8);   // G2P and advection run fused (hyb_g2p_move): ms_g2p is reported as 0, ms_move covers both
+    JC_TRY(hyb_g2p_move(h, dt));
     MARK(9);
 #undef MARK
     int p2g_err = 0;
@@ -1621,6 +1784,7 @@ int jetcu_hybrid_step(jetcu_hybrid* h, double dt, jetcu_step_stats* st) {
         st->ms_pressure = el(5, 6);
         st->ms_g2p = el(7, 8);
         st->ms_move = el(8, 9);
+        st->ms_mgpcg_solve = h->last.solve_ms;
     }
     return JETCU_OK;
 }

@@ -30,7 +30,8 @@ struct AttrPtrs {
 //      same window of faces per component: 2 along the component's own (node-aligned) axis x 3 x 3 along the two
 //      cell-centred axes = 18 faces.  One thread owns a cell and sums its particles' contributions to those 18 faces in
 //      REGISTERS, in the cell's particle order (p2g_cell_partial);
-//   2. the 18 (value, weight) partial sums of every cell of a tile go to shared memory, and one thread per FACE of the
+//   2. the 18 partial sums of every cell of a tile go to shared memory (values first, then weights: half the buffer,
+//      which leaves the L1 big enough to keep the particle sectors the cell loop walks), and one thread per FACE of the
 //      tile's window adds up the partial sums of the <= 18 cells of the tile that reach it, in a fixed slot order
 //      (p2g_face_gather);
 //   3. faces on a tile's rim also receive from neighbouring tiles.  Tiles are launched in 8 colour passes (parity of the
@@ -121,14 +122,14 @@ __host__ __device__ __forceinline__ unsigned p2g_cell_partial(const GridD& g, in
 }
 
 // One face of component AX's window of a tile of TX x TY x TZ cells (window = tile + one ring on the centred axes, + 1
-// on the node axis): local face coordinates (lx, ly, lz).  ex = exchange buffer [2][P2G_SLOTS][ncell] (values, then
-// weights), tm = touched masks per cell.  Adds up the partial sums of the tile's cells that reach the face, fixed order.
+// on the node axis): local face coordinates (lx, ly, lz).  ex = exchange buffer [P2G_SLOTS][ncell] holding one kind of
+// partial sum (values or weights), tm = touched masks per cell.  Adds up the partial sums of the tile's cells that reach
+// the face, in a fixed order; returns whether any cell touched the face.
 template <int AX, int TZ>
-__host__ __device__ __forceinline__ bool p2g_face_gather(const double* ex, const unsigned* tm, int lx, int ly, int lz, double* v,
-                                                         double* w) {
+__host__ __device__ __forceinline__ bool p2g_face_gather(const double* ex, const unsigned* tm, int lx, int ly, int lz, double* out) {
     constexpr int NX = AX == 0 ? 2 : 3, NY = AX == 1 ? 2 : 3, NZ = AX == 2 ? 2 : 3;
     constexpr int NCELL = P2G_TX * P2G_TY * TZ;
-    double sv = 0.0, sw = 0.0;
+    double sum = 0.0;
     bool any = false;
 #pragma unroll
     for (int c = 0; c < NZ; ++c) {
@@ -146,13 +147,12 @@ __host__ __device__ __forceinline__ bool p2g_face_gather(const double* ex, const
                 const int s = p2g_slot<AX>(x, b, c);
                 if ((tm[cell] >> s) & 1u) {
                     any = true;
-                    sv += ex[s * NCELL + cell];
-                    sw += ex[(P2G_SLOTS + s) * NCELL + cell];
+                    sum += ex[s * NCELL + cell];
                 }
             }
         }
     }
-    *v = sv; *w = sw;
+    *out = sum;
     return any;
 }
 

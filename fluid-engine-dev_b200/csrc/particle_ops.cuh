@@ -12,7 +12,34 @@ __host__ __device__ __forceinline__ double norm_pos(double x, double o, double h
     return POW2 ? (x - o) * ih : jc_norm(x, o, h, ih);
 }
 
-template <bool POW2, typename I>
+// PAIRS: the component arrays are "pair arrays" — entry i holds (d[i], d[min(i + 1, sx - 1)]) as a 16-byte double2
+// (k_pack_pairs), so the two x-neighbours of a trilinear sample arrive in ONE 128-bit load.  The advection kernel is bound
+// by the number of L1 load wavefronts (ncu: l1tex data-pipe 90 % busy, FP64 43 %), not by DRAM; pairs halve them.  The
+// values are the same doubles, so the results are bit-identical to the plain-array form.
+template <bool PAIRS>
+__host__ __device__ __forceinline__ void jc_load_x2(const double* __restrict__ d, size_t lo, size_t hi, double* a, double* b) {
+    if (PAIRS) {
+        const double2 q = reinterpret_cast<const double2*>(d)[lo];
+        *a = q.x; *b = q.y;
+    } else {
+        *a = d[lo]; *b = d[hi];
+    }
+}
+
+template <bool PAIRS, typename I>
+__host__ __device__ __forceinline__ double sample_rows(const double* __restrict__ d, I r00, I r10, I r01, I r11, int i, int i1, double fx,
+                                              double fy, double fz) {
+    double a0, a1, b0, b1, c0, c1, d0, d1;
+    jc_load_x2<PAIRS>(d, (size_t)(r00 + i), (size_t)(r00 + i1), &a0, &a1);
+    jc_load_x2<PAIRS>(d, (size_t)(r10 + i), (size_t)(r10 + i1), &b0, &b1);
+    jc_load_x2<PAIRS>(d, (size_t)(r01 + i), (size_t)(r01 + i1), &c0, &c1);
+    jc_load_x2<PAIRS>(d, (size_t)(r11 + i), (size_t)(r11 + i1), &d0, &d1);
+    const double a = jc_lerp(jc_lerp(a0, a1, fx), jc_lerp(b0, b1, fx), fy);
+    const double b = jc_lerp(jc_lerp(c0, c1, fx), jc_lerp(d0, d1, fx), fy);
+    return jc_lerp(a, b, fz);
+}
+
+template <bool POW2, typename I, bool PAIRS = false>
 __host__ __device__ __forceinline__ void sample_velocity(const GridD& g, const double* __restrict__ u, const double* __restrict__ v,
                                                 const double* __restrict__ w, double px, double py, double pz, double* ou,
                                                 double* ov, double* ow) {
@@ -33,28 +60,26 @@ __host__ __device__ __forceinline__ void sample_velocity(const GridD& g, const d
     const int knz1 = min(knz + 1, g.nz), kcz1 = min(kcz + 1, g.nz - 1);
     {
         const I sy = (I)(g.nx + 1), sz = sy * (I)g.ny;
-        const I r00 = (I)kcz * sz + (I)jcy * sy, r10 = (I)kcz * sz + (I)jcy1 * sy, r01 = (I)kcz1 * sz + (I)jcy * sy,
-                r11 = (I)kcz1 * sz + (I)jcy1 * sy;
-        const double a = jc_lerp(jc_lerp(u[r00 + inx], u[r00 + inx1], fnx), jc_lerp(u[r10 + inx], u[r10 + inx1], fnx), fcy);
-        const double b = jc_lerp(jc_lerp(u[r01 + inx], u[r01 + inx1], fnx), jc_lerp(u[r11 + inx], u[r11 + inx1], fnx), fcy);
-        *ou = jc_lerp(a, b, fcz);
+        *ou = sample_rows<PAIRS, I>(u, (I)kcz * sz + (I)jcy * sy, (I)kcz * sz + (I)jcy1 * sy, (I)kcz1 * sz + (I)jcy * sy,
+                                    (I)kcz1 * sz + (I)jcy1 * sy, inx, inx1, fnx, fcy, fcz);
     }
     {
         const I sy = (I)g.nx, sz = sy * (I)(g.ny + 1);
-        const I r00 = (I)kcz * sz + (I)jny * sy, r10 = (I)kcz * sz + (I)jny1 * sy, r01 = (I)kcz1 * sz + (I)jny * sy,
-                r11 = (I)kcz1 * sz + (I)jny1 * sy;
-        const double a = jc_lerp(jc_lerp(v[r00 + icx], v[r00 + icx1], fcx), jc_lerp(v[r10 + icx], v[r10 + icx1], fcx), fny);
-        const double b = jc_lerp(jc_lerp(v[r01 + icx], v[r01 + icx1], fcx), jc_lerp(v[r11 + icx], v[r11 + icx1], fcx), fny);
-        *ov = jc_lerp(a, b, fcz);
+        *ov = sample_rows<PAIRS, I>(v, (I)kcz * sz + (I)jny * sy, (I)kcz * sz + (I)jny1 * sy, (I)kcz1 * sz + (I)jny * sy,
+                                    (I)kcz1 * sz + (I)jny1 * sy, icx, icx1, fcx, fny, fcz);
     }
     {
         const I sy = (I)g.nx, sz = sy * (I)g.ny;
-        const I r00 = (I)knz * sz + (I)jcy * sy, r10 = (I)knz * sz + (I)jcy1 * sy, r01 = (I)knz1 * sz + (I)jcy * sy,
-                r11 = (I)knz1 * sz + (I)jcy1 * sy;
-        const double a = jc_lerp(jc_lerp(w[r00 + icx], w[r00 + icx1], fcx), jc_lerp(w[r10 + icx], w[r10 + icx1], fcx), fcy);
-        const double b = jc_lerp(jc_lerp(w[r01 + icx], w[r01 + icx1], fcx), jc_lerp(w[r11 + icx], w[r11 + icx1], fcx), fcy);
-        *ow = jc_lerp(a, b, fnz);
+        *ow = sample_rows<PAIRS, I>(w, (I)knz * sz + (I)jcy * sy, (I)knz * sz + (I)jcy1 * sy, (I)knz1 * sz + (I)jcy * sy,
+                                    (I)knz1 * sz + (I)jcy1 * sy, icx, icx1, fcx, fcy, fnz);
     }
+}
+
+// One entry of a pair array (see jc_load_x2): i = linear index into an array whose x extent is sx.
+__host__ __device__ __forceinline__ void pack_pair(const double* __restrict__ d, double* __restrict__ out, size_t i, int sx) {
+    const double a = d[i];
+    const double b = ((int)(i % (size_t)sx) + 1 < sx) ? d[i + 1] : a;
+    out[2 * i] = a; out[2 * i + 1] = b;
 }
 
 
@@ -119,16 +144,19 @@ __host__ __device__ __forceinline__ void apic_affine(const GridD& g, const doubl
 
 // PicSolver3::moveParticles, src/jet/pic_solver3.cpp:206-282: uint(max(maxCfl,1)) midpoint-rule sub-steps, then
 // clamp to the domain box and zero the velocity component on closed walls (<= / >= tests).  pos, vel: in/out.
-template <bool POW2, typename I>
+// first != nullptr: the grid velocity at the starting position is already known (a PIC transfer just sampled it there: the
+// fused G2P + advection kernel) and replaces the first sample of the first sub-step — the same expression at the same point.
+template <bool POW2, typename I, bool PAIRS = false>
 __host__ __device__ __forceinline__ void move_particle(const GridD& g, const double* u, const double* v, const double* w, double dt,
-                                                       unsigned nsub, int flag, double* pos, double* vel) {
+                                                       unsigned nsub, int flag, double* pos, double* vel, const double* first = nullptr) {
     double p0x = pos[0], p0y = pos[1], p0z = pos[2];
     double p1x = p0x, p1y = p0y, p1z = p0z;
     for (unsigned t = 0; t < nsub; ++t) {
         double v0x, v0y, v0z, mvx, mvy, mvz;
-        sample_velocity<POW2, I>(g, u, v, w, p0x, p0y, p0z, &v0x, &v0y, &v0z);
+        if (t == 0 && first) { v0x = first[0]; v0y = first[1]; v0z = first[2]; }
+        else sample_velocity<POW2, I, PAIRS>(g, u, v, w, p0x, p0y, p0z, &v0x, &v0y, &v0z);
         double mx = p0x + 0.5 * dt * v0x, my = p0y + 0.5 * dt * v0y, mz = p0z + 0.5 * dt * v0z;
-        sample_velocity<POW2, I>(g, u, v, w, mx, my, mz, &mvx, &mvy, &mvz);
+        sample_velocity<POW2, I, PAIRS>(g, u, v, w, mx, my, mz, &mvx, &mvy, &mvz);
         p1x = p0x + dt * mvx; p1y = p0y + dt * mvy; p1z = p0z + dt * mvz;
         p0x = p1x; p0y = p1y; p0z = p1z;
     }

@@ -98,7 +98,8 @@ class HybridParams(C.Structure):
 class StepStats(C.Structure):
     _fields_ = [("pcg_iterations", u32), ("pcg_last_residual", f64), ("pcg_true_residual_l2", f64),
                 ("pcg_b_l2", f64), ("ms_total", f64), ("ms_bin", f64), ("ms_p2g", f64), ("ms_sdf", f64),
-                ("ms_extrapolate", f64), ("ms_bc", f64), ("ms_pressure", f64), ("ms_g2p", f64), ("ms_move", f64)]
+                ("ms_extrapolate", f64), ("ms_bc", f64), ("ms_pressure", f64), ("ms_g2p", f64), ("ms_move", f64),
+                ("ms_mgpcg_solve", f64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -383,6 +384,11 @@ class HybridApi:
         pos = c64(pos)
         vel = c64(vel) if vel is not None else np.zeros_like(pos)
         self._c("hybrid_set_particles", self.h, u64(pos.shape[0]), _p(pos), _p(vel))
+
+    def append_particles(self, pos, vel=None):
+        pos = c64(pos)
+        vel = c64(vel) if vel is not None else None
+        self._c("hybrid_append_particles", self.h, u64(pos.shape[0]), _p(pos), _p(vel) if vel is not None else None)
 
     def emit_box(self, lower, upper, spacing, v0=(0.0, 0.0, 0.0)):
         n = u64(0)

@@ -260,14 +260,24 @@ typedef struct jetcu_step_stats {
     double pcg_true_residual_l2;
     double pcg_b_l2;
     double ms_total, ms_bin, ms_p2g, ms_sdf, ms_extrapolate, ms_bc, ms_pressure, ms_g2p, ms_move;
+    double ms_mgpcg_solve;      /* device time of the MGPCG solve alone (ms_pressure also holds the system build and the gradient) */
 } jetcu_step_stats;
 
 void jetcu_hybrid_default_params(jetcu_hybrid_params* p);
 int jetcu_hybrid_create(jetcu_ctx*, const jetcu_hybrid_params* params, jetcu_hybrid** out);
 int jetcu_hybrid_destroy(jetcu_hybrid*);
+/* GridFluidSolver3's setters between steps (setGravity, setMaxCfl, setClosedDomainBoundaryFlag,
+ * FlipSolver3::setPicBlendingFactor, a re-configured linear solver): everything in `params` except grid and mode, which are
+ * fixed at creation (JETCU_ERR_INVALID_ARG if they differ).  The device-resident state is untouched. */
+int jetcu_hybrid_update_params(jetcu_hybrid*, const jetcu_hybrid_params* params);
 
 /* ParticleSystemData3::positions()/velocities() (AoS xyz doubles). set replaces all particles. */
 int jetcu_hybrid_set_particles(jetcu_hybrid*, uint64_t n, const double* positions, const double* velocities);
+/* ParticleSystemData3::addParticles (src/jet/particle_system_data3.cpp:158-197) as a host emitter uses it between steps:
+ * appends n_new particles (original indices num_particles() ...) to the device-resident set, which keeps its state —
+ * in particular ApicSolver3's affine vectors, which `_cX.resize(n)` (src/jet/apic_solver3.cpp:36-38) preserves for the old
+ * particles and zero-initialises for the new ones.  velocities may be NULL (zero). */
+int jetcu_hybrid_append_particles(jetcu_hybrid*, uint64_t n_new, const double* positions, const double* velocities);
 /* Emits the lattice VolumeParticleEmitter3 + GridPointGenerator3 produce for an axis-aligned box
  * (src/jet/volume_particle_emitter3.cpp:65-140, src/jet/grid_point_generator3.cpp:12-37; jitter 0, one shot),
  * directly on the device, in the reference's k,j,i order.  Appends; returns the count via n_emitted. */

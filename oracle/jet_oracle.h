@@ -54,6 +54,7 @@ typedef struct jeto_step_stats {
     uint32_t pcg_iterations;
     double pcg_last_residual, pcg_true_residual_l2, pcg_b_l2;
     double ms_total, ms_bin, ms_p2g, ms_sdf, ms_extrapolate, ms_bc, ms_pressure, ms_g2p, ms_move;
+    double ms_mgpcg_solve;   /* layout of jetcu_step_stats; the oracles leave it 0 */
 } jeto_step_stats;
 
 const char* jeto_kind(void);          /* "port" or "reference" */
@@ -93,6 +94,7 @@ typedef struct jeto_hybrid jeto_hybrid;
 int jeto_hybrid_create(const jeto_hybrid_params* params, jeto_hybrid** out);
 int jeto_hybrid_destroy(jeto_hybrid*);
 int jeto_hybrid_set_particles(jeto_hybrid*, uint64_t n, const double* positions, const double* velocities);
+int jeto_hybrid_append_particles(jeto_hybrid*, uint64_t n, const double* positions, const double* velocities);
 int jeto_hybrid_emit_box(jeto_hybrid*, const double lower[3], const double upper[3], double spacing,
                          const double initial_velocity[3], uint64_t* n_emitted);
 /* Analytic rigid collider (RigidBodyCollider3, identity transforms) for the hybrid solver.  One explicit surface, or an

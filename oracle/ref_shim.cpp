@@ -483,6 +483,17 @@ int jeto_hybrid_set_particles(jeto_hybrid* h, uint64_t n, const double* pos, con
     return 0;
 }
 
+// ParticleSystemData3::addParticles (src/jet/particle_system_data3.cpp:158-197): what a host emitter does between steps
+int jeto_hybrid_append_particles(jeto_hybrid* h, uint64_t n, const double* pos, const double* vel) {
+    Array1<Vector3D> P(n), V(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        P[i] = Vector3D(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+        V[i] = vel ? Vector3D(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2]) : Vector3D();
+    }
+    h->solver->particleSystemData()->addParticles(P.constAccessor(), V.constAccessor());
+    return 0;
+}
+
 int jeto_hybrid_emit_box(jeto_hybrid* h, const double lower[3], const double upper[3], double spacing,
                          const double v0[3], uint64_t* n_emitted) {
     auto ps = h->solver->particleSystemData();

@@ -1,7 +1,7 @@
-"""Golden for the BENCHMARK-SIZE workload: bench.py's FLIP 256^3 sloshing tank (126 584 289 particles) stepped by the
+"""Golden for the BENCHMARK-SIZE workload: bench.py's FLIP 256^3 tank (126 584 289 particles, at rest) stepped by the
 UNMODIFIED reference (oracle/_ref/libjetref.so) for the first K sub-steps.  Run here (the container with /root/reference):
 
-    make -C oracle ref && python tests/golden/make_golden_256.py [K=3] [mode=flip|apic]
+    make -C oracle ref && python tests/golden/make_golden_256.py [K=3] [mode=flip|apic] [v0x=0.0]
 
 A 256^3 step of the reference costs minutes and 30+ GB of host memory, so the GPU box never runs it inside a test: the
 committed fixture carries, per sub-step, the PCG iteration count and residuals, every 65 521-th particle (position and
@@ -28,16 +28,17 @@ def main():
     k = int(sys.argv[1]) if len(sys.argv) > 1 else 3
     mode_name = sys.argv[2] if len(sys.argv) > 2 else "flip"
     mode = APIC if mode_name == "apic" else FLIP
+    v0x = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0
     ref = load_ref()
     assert ref.kind == "reference"
     ref.set_num_threads(0)
     prm = HybridParams.make(Grid.cube(N), mode=mode, mgpcg=MgpcgParams.make(max_iterations=100, max_levels=6))
     h = ref.hybrid(prm)
     t0 = time.perf_counter()
-    n = h.emit_box((0.0, 0.0, 0.0), (1.0, 0.9375, 1.0), 0.5 / N, (0.5, 0.0, 0.0))
+    n = h.emit_box((0.0, 0.0, 0.0), (1.0, 0.9375, 1.0), 0.5 / N, (v0x, 0.0, 0.0))
     print("emitted %d particles in %.1f s" % (n, time.perf_counter() - t0), flush=True)
     idx = np.arange(0, n, STRIDE)
-    out = dict(n=np.array(n), idx=idx, dt=np.array(1.0 / 240.0), threads=np.array(ref.num_threads()))
+    out = dict(n=np.array(n), idx=idx, dt=np.array(1.0 / 240.0), threads=np.array(ref.num_threads()), v0x=np.array(v0x))
     log = []
     for s in range(k):
         t0 = time.perf_counter()
@@ -59,7 +60,7 @@ def main():
         log.append(dict(step=s, seconds=sec, **{kk: (float(v) if isinstance(v, float) else int(v)) for kk, v in d.items()}))
         print(json.dumps(log[-1]), flush=True)
         del pos, vel, pr
-        np.savez_compressed(os.path.join(HERE, "fullsize_%s_256.npz" % mode_name), steps=np.array(s + 1), **out)
+        np.savez_compressed(os.path.join(HERE, "fullsize_%s_256%s.npz" % (mode_name, "" if v0x == 0.0 else "_slosh")), steps=np.array(s + 1), **out)
     h.close()
 
 

@@ -56,10 +56,28 @@ static void g2p_pic_t(const GridD& g, const double* u, const double* v, const do
     for (uint64_t p = 0; p < n; ++p)
         sample_velocity<POW2, I>(g, u, v, w, pos[3 * p], pos[3 * p + 1], pos[3 * p + 2], vel + 3 * p, vel + 3 * p + 1, vel + 3 * p + 2);
 }
+// as k_move runs it: on PAIR arrays built by k_pack_pairs' body.  variant bit 2: the fused PIC kernel's form (k_pic_move) —
+// the grid velocity at the particle becomes its velocity and stands in for the first sample of the first sub-step.
 template <bool POW2, typename I>
 static void move_t(const GridD& g, const double* u, const double* v, const double* w, double dt, unsigned nsub, int flag,
-                   uint64_t n, double* pos, double* vel) {
-    for (uint64_t p = 0; p < n; ++p) move_particle<POW2, I>(g, u, v, w, dt, nsub, flag, pos + 3 * p, vel + 3 * p);
+                   uint64_t n, double* pos, double* vel, bool pic_fused) {
+    const size_t nf[3] = {(size_t)(g.nx + 1) * g.ny * g.nz, (size_t)g.nx * (g.ny + 1) * g.nz, (size_t)g.nx * g.ny * (g.nz + 1)};
+    const double* in[3] = {u, v, w};
+    std::vector<double> pr[3];
+    for (int q = 0; q < 3; ++q) {
+        pr[q].resize(2 * nf[q]);
+        for (size_t i = 0; i < nf[q]; ++i) pack_pair(in[q], pr[q].data(), i, g.nx + (q == 0));
+    }
+    for (uint64_t p = 0; p < n; ++p) {
+        if (pic_fused) {
+            double* vp = vel + 3 * p;
+            sample_velocity<POW2, I, true>(g, pr[0].data(), pr[1].data(), pr[2].data(), pos[3 * p], pos[3 * p + 1], pos[3 * p + 2], vp, vp + 1, vp + 2);
+            const double first[3] = {vp[0], vp[1], vp[2]};
+            move_particle<POW2, I, true>(g, pr[0].data(), pr[1].data(), pr[2].data(), dt, nsub, flag, pos + 3 * p, vp, first);
+        } else {
+            move_particle<POW2, I, true>(g, pr[0].data(), pr[1].data(), pr[2].data(), dt, nsub, flag, pos + 3 * p, vel + 3 * p);
+        }
+    }
 }
 
 // ---- P2G: jetcu_hybrid_transfer_particles_to_grids with k_p2g_tile<APIC, TZ>: the 8 colour passes, the tiles of a pass
@@ -67,8 +85,8 @@ static void move_t(const GridD& g, const double* u, const double* v, const doubl
 // particles (slab mode: the rank's slab + ghost planes), exactly as in the kernel.
 template <bool APIC, int AX, int TZ>
 static void p2g_tile_component_host(const GridD& g, int I0, int J0, int K0, int kb, int ke, const std::vector<uint32_t>& cell_start,
-                                    const AttrPtrs& a, std::vector<double>& ex, std::vector<unsigned>& tm, double* U, double* W,
-                                    char* M, int* err) {
+                                    const AttrPtrs& a, std::vector<double>& ex, std::vector<double>& exw, std::vector<unsigned>& tm,
+                                    double* U, double* W, char* M, int* err) {
     constexpr int NT = P2G_TX * P2G_TY * TZ;
     constexpr int WX = P2G_TX + (AX == 0 ? 1 : 2), WY = P2G_TY + (AX == 1 ? 1 : 2), WZ = TZ + (AX == 2 ? 1 : 2);
     for (int tid = 0; tid < NT; ++tid) {
@@ -82,7 +100,7 @@ static void p2g_tile_component_host(const GridD& g, int I0, int J0, int K0, int 
         if (e0 > s0) {
             double sv[P2G_SLOTS], sw[P2G_SLOTS];
             touched = p2g_cell_partial<APIC, AX>(g, ci, cj, ck, s0, e0, a, sv, sw, err);
-            for (int q = 0; q < P2G_SLOTS; ++q) { ex[q * NT + tid] = sv[q]; ex[(P2G_SLOTS + q) * NT + tid] = sw[q]; }
+            for (int q = 0; q < P2G_SLOTS; ++q) { ex[q * NT + tid] = sv[q]; exw[q * NT + tid] = sw[q]; }
         }
         tm[tid] = touched;
     }
@@ -93,7 +111,8 @@ static void p2g_tile_component_host(const GridD& g, int I0, int J0, int K0, int 
         const int fi = fx0 + lx, fj = fy0 + ly, fk = fz0 + lz;
         if ((unsigned)fi >= (unsigned)sx || (unsigned)fj >= (unsigned)sy || (unsigned)fk >= (unsigned)sz) continue;
         double v, w;
-        if (p2g_face_gather<AX, TZ>(ex.data(), tm.data(), lx, ly, lz, &v, &w)) {
+        if (p2g_face_gather<AX, TZ>(ex.data(), tm.data(), lx, ly, lz, &v)) {
+            p2g_face_gather<AX, TZ>(exw.data(), tm.data(), lx, ly, lz, &w);
             const size_t idx = ((size_t)fk * sy + fj) * sx + fi;
             U[idx] += v; W[idx] += w; M[idx] = 1;
         }
@@ -104,7 +123,7 @@ template <bool APIC, int TZ>
 static void p2g_tiles(const GridD& g, int kb, int ke, const std::vector<uint32_t>& cell_start, const AttrPtrs& a, double* val[3],
                       double* wsum[3], char* mk[3], int* err) {
     constexpr int NT = P2G_TX * P2G_TY * TZ;
-    std::vector<double> ex((size_t)2 * P2G_SLOTS * NT, 0.0);
+    std::vector<double> ex((size_t)P2G_SLOTS * NT, 0.0), exw((size_t)P2G_SLOTS * NT, 0.0);  // the kernel reuses one buffer
     std::vector<unsigned> tm(NT, 0u);
     const int ntx = (g.nx + P2G_TX - 1) / P2G_TX, nty = (g.ny + P2G_TY - 1) / P2G_TY, tzlo = kb / TZ, tzhi = (ke - 1) / TZ;
     for (int colour = 0; colour < 8; ++colour) {
@@ -113,9 +132,9 @@ static void p2g_tiles(const GridD& g, int kb, int ke, const std::vector<uint32_t
             for (int ty = par_y; ty < nty; ty += 2)
                 for (int tx = par_x; tx < ntx; tx += 2) {
                     const int I0 = tx * P2G_TX, J0 = ty * P2G_TY, K0 = tz * TZ;
-                    p2g_tile_component_host<APIC, 0, TZ>(g, I0, J0, K0, kb, ke, cell_start, a, ex, tm, val[0], wsum[0], mk[0], err);
-                    p2g_tile_component_host<APIC, 1, TZ>(g, I0, J0, K0, kb, ke, cell_start, a, ex, tm, val[1], wsum[1], mk[1], err);
-                    p2g_tile_component_host<APIC, 2, TZ>(g, I0, J0, K0, kb, ke, cell_start, a, ex, tm, val[2], wsum[2], mk[2], err);
+                    p2g_tile_component_host<APIC, 0, TZ>(g, I0, J0, K0, kb, ke, cell_start, a, ex, exw, tm, val[0], wsum[0], mk[0], err);
+                    p2g_tile_component_host<APIC, 1, TZ>(g, I0, J0, K0, kb, ke, cell_start, a, ex, exw, tm, val[1], wsum[1], mk[1], err);
+                    p2g_tile_component_host<APIC, 2, TZ>(g, I0, J0, K0, kb, ke, cell_start, a, ex, exw, tm, val[2], wsum[2], mk[2], err);
                 }
     }
 }
@@ -330,10 +349,10 @@ int hc_move_particles(const jetcu_grid* grid, const double* u, const double* v, 
     const unsigned nsub = (unsigned)fmax(max_cfl, 1.0);   // jetcu_hybrid_move_particles
     const double dt = dt_frame / nsub;
     switch (variant & 3) {
-        case 0: move_t<false, int>(g, u, v, w, dt, nsub, flag, n, pos, vel); break;
-        case 1: move_t<true, int>(g, u, v, w, dt, nsub, flag, n, pos, vel); break;
-        case 2: move_t<false, long long>(g, u, v, w, dt, nsub, flag, n, pos, vel); break;
-        default: move_t<true, long long>(g, u, v, w, dt, nsub, flag, n, pos, vel); break;
+        case 0: move_t<false, int>(g, u, v, w, dt, nsub, flag, n, pos, vel, (variant & 4) != 0); break;
+        case 1: move_t<true, int>(g, u, v, w, dt, nsub, flag, n, pos, vel, (variant & 4) != 0); break;
+        case 2: move_t<false, long long>(g, u, v, w, dt, nsub, flag, n, pos, vel, (variant & 4) != 0); break;
+        default: move_t<true, long long>(g, u, v, w, dt, nsub, flag, n, pos, vel, (variant & 4) != 0); break;
     }
     return 0;
 }

@@ -128,6 +128,33 @@ def test_hybrid_stages_vs_oracle(jc, oracle, mode, n, levels):
         assert np.abs(va - vb).max() <= 1e-4 * max(np.abs(vb).max(), 1.0)
 
 
+@pytest.mark.parametrize("mode", [APIC, FLIP])
+def test_append_particles_keeps_device_state(jc, oracle, mode):
+    """A continuous emitter between steps (ParticleSystemData3::addParticles): jetcu_hybrid_append_particles uploads the
+    tail only; the old particles keep their state — for APIC the affine vectors, which `_cX.resize(n)` preserves
+    (src/jet/apic_solver3.cpp:36-38) — and the new ones start from zero affine vectors."""
+    n = 16
+    prm = HybridParams.make(Grid.cube(n), mode=mode, mgpcg=MgpcgParams.make(max_iterations=100, max_levels=3))
+    a, b = jc.hybrid(prm), oracle.hybrid(prm)
+    assert a.emit_box((0, 0, 0), (0.4, 0.6, 1.0), 0.5 / n) == b.emit_box((0, 0, 0), (0.4, 0.6, 1.0), 0.5 / n)
+    dt = 1 / 60.0
+    rng = np.random.default_rng(9)
+    for step in range(4):
+        a.step(dt); b.step(dt)
+        new_p = np.ascontiguousarray(rng.uniform((0.6, 0.5, 0.2), (0.8, 0.7, 0.8), (300, 3)))
+        new_v = np.ascontiguousarray(np.tile((0.0, -1.0, 0.0), (300, 1)))
+        a.append_particles(new_p, new_v); b.append_particles(new_p, new_v)
+        assert a.num_particles() == b.num_particles()
+        if mode == APIC:
+            for x, y in zip(a.get_affine(), b.get_affine()):
+                assert np.abs(x - y).max() <= 1e-6 * max(np.abs(y).max(), 1.0)
+                assert not x[-300:].any() and np.abs(x[:-300]).max() > 0.0
+    a.step(dt); b.step(dt)
+    (pa, va), (pb, vb) = a.get_particles(), b.get_particles()
+    assert np.abs(pa - pb).max() <= 1e-5 and np.abs(va - vb).max() <= 1e-4 * max(np.abs(vb).max(), 1.0)
+    a.close(); b.close()
+
+
 def test_particle_order_round_trip(jc):
     n = 16
     prm = HybridParams.make(Grid.cube(n), mode=FLIP, mgpcg=MgpcgParams.make(max_levels=3))

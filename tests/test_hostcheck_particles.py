@@ -59,6 +59,16 @@ def test_move_particles(hc, port, n, domain):
         assert hc.hc_move_particles(C.byref(grid), dp(u), dp(v), dp(w), C.c_double(dt), C.c_double(prm.max_cfl),
                                     C.c_int(prm.closed_domain_boundary_flag), C.c_int(var), C.c_uint64(len(gp)), dp(gp), dp(gv)) == 0
         exact(gp, want_p, "moved positions (variant %d)" % var); exact(gv, want_v, "velocities after wall clamp (variant %d)" % var)
+    # the fused PIC form (k_pic_move): transferFromGridsToParticles + moveParticles in one pass over the particles
+    h.set_particles(pos, vel)
+    h.transfer_grids_to_particles()
+    h.move_particles(dt)
+    want_p, want_v = h.get_particles()
+    for var in variants(domain):
+        gp, gv = pos.copy(), vel.copy()
+        assert hc.hc_move_particles(C.byref(grid), dp(u), dp(v), dp(w), C.c_double(dt), C.c_double(prm.max_cfl),
+                                    C.c_int(prm.closed_domain_boundary_flag), C.c_int(var | 4), C.c_uint64(len(gp)), dp(gp), dp(gv)) == 0
+        exact(gp, want_p, "fused G2P + move positions (variant %d)" % var); exact(gv, want_v, "fused G2P + move velocities (variant %d)" % var)
     h.close()
 
 

@@ -24,7 +24,7 @@ while levels < 6 and m % 2 == 0 and m > 4:
     m //= 2
     levels += 1
 h = jc.hybrid(HybridParams.make(Grid.cube(n), mode=mode, mgpcg=MgpcgParams.make(max_iterations=100, max_levels=levels)))
-npart = h.emit_box((0.0, 0.0, 0.0), (1.0, 0.9375, 1.0), 0.5 / n, (0.5, 0.0, 0.0))
+npart = h.emit_box((0.0, 0.0, 0.0), (1.0, 0.9375, 1.0), 0.5 / n, (0.0, 0.0, 0.0))
 for s in range(steps):
     st = h.step(1.0 / 240.0)
     print(npart, st.as_dict())

@@ -2,9 +2,11 @@
 conservation, domain containment, original-order round trip, bit-reproducibility of two independent runs, solver
 convergence on the config-2 projection.  FLIP 256^3 tank = bench.py's workload (126 584 289 particles).
 
-Run in a child process by tests/test_gpu_zz_firstrun.py like the other first-run files: written after round 1's GPU
-minutes were gone (the code paths are the established ones, the risk is this test's own host-memory appetite: ~15 GB of
-numpy arrays)."""
+test_flip_256_matches_reference_golden compares the first sub-steps of that very workload with the UNMODIFIED reference:
+tests/golden/fullsize_flip_256*.npz were produced by tests/golden/make_golden_256.py from oracle/_ref (minutes per step on the
+CPU, which is why the fixture carries samples: every 65 521-th particle, a 16^3 sub-lattice of the pressure, the PCG iteration
+counts and residuals).  Host memory appetite of this file: ~15 GB of numpy arrays."""
+import os
 import numpy as np
 import pytest
 
@@ -20,6 +22,38 @@ N = 256
 @pytest.fixture(scope="module")
 def jc():
     return jetcu_or_fail()
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", ["fullsize_flip_256", "fullsize_flip_256_slosh"])
+def test_flip_256_matches_reference_golden(jc, name):
+    """bench.py's workload at its full size against the unmodified reference, sub-step by sub-step: PCG iteration counts equal,
+    lastResidual / ||b|| / true residual of every solve to 1e-6 relative (they are sums over 16.7 M cells of a solve that is
+    replayed operation by operation), sampled particle positions within 1e-5 of the domain size (BASELINE tolerance; observed
+    ~1e-13), sampled pressure within 1e-6 of max |p| — also where the reference's own solve stops early or diverges (the
+    `_slosh` fixture's first solve runs into the 100-iteration cap with a residual of 8e11 on both sides)."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    steps, n_ref, idx, v0x = int(g["steps"]), int(g["n"]), g["idx"], float(g["v0x"]) if "v0x" in g else 0.5
+    prm = HybridParams.make(Grid.cube(N), mode=FLIP, mgpcg=MgpcgParams.make(max_iterations=100, max_levels=6))
+    h = jc.hybrid(prm)
+    assert h.emit_box((0.0, 0.0, 0.0), (1.0, 0.9375, 1.0), 0.5 / N, (v0x, 0.0, 0.0)) == n_ref
+    for s in range(steps):
+        st = h.step(float(g["dt"]))
+        assert st.pcg_iterations == int(g["iters%d" % s]), "step %d: %d iterations, reference %d" % (s, st.pcg_iterations, int(g["iters%d" % s]))
+        for mine, ref in ((st.pcg_last_residual, g["last_residual%d" % s]), (st.pcg_b_l2, g["b_l2%d" % s]),
+                          (st.pcg_true_residual_l2, g["true_residual%d" % s])):
+            assert abs(mine - float(ref)) <= 1e-6 * abs(float(ref)), "step %d: %r vs reference %r" % (s, mine, float(ref))
+        pos, vel = h.get_particles()
+        assert np.abs(pos[idx] - g["pos%d" % s]).max() <= 1e-5, "step %d positions: %g" % (s, np.abs(pos[idx] - g["pos%d" % s]).max())
+        vs = max(float(np.abs(g["vel%d" % s]).max()), 1.0)
+        assert np.abs(vel[idx] - g["vel%d" % s]).max() <= 1e-4 * vs
+        assert np.abs(pos.sum(axis=0, dtype=np.float64) - g["possum%d" % s]).max() <= 1e-5 * n_ref * 1e-3   # mean position to 1e-8
+        del pos, vel
+        pr = h.get_pressure()[8::16, 8::16, 8::16]
+        assert np.abs(pr - g["pressure%d" % s]).max() <= 1e-6 * float(g["pmax%d" % s]), "step %d pressure" % s
+    h.close()
 
 
 def run_tank(jc, steps, mode=FLIP):

@@ -16,11 +16,7 @@ def _gpus():
     return torch.cuda.device_count()
 
 
-FIRST_RUN = pytest.mark.xfail(strict=False, reason="first GPU run of the peer-memory halo path (written after round 1's GPU "
-                                                       "minutes were spent; every wait in it is bounded, the worker has a hard limit)")
-
-
-@pytest.mark.parametrize("halo", ["nccl", pytest.param("p2p", marks=FIRST_RUN)])
+@pytest.mark.parametrize("halo", ["nccl", "p2p"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_slabs_match_single_gpu(world, halo, tmp_path):
     """halo = "p2p": the same checks with JETCU_P2P_HALO=1 — halo planes pushed into the neighbours' CUDA-IPC mailboxes by

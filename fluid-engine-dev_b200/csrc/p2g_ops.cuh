@@ -57,12 +57,40 @@ __host__ __device__ constexpr int p2g_slot(int x, int b, int c) {
     return (c * (AX == 1 ? 2 : 3) + b) * (AX == 0 ? 2 : 3) + x;
 }
 
+// Where the cell loop reads a particle's attributes from.  Logical attribute ids: 0..2 position, 3 the velocity component
+// of the pass, 4..6 that component's APIC affine vector.
+#define P2G_A_VEL 3
+#define P2G_A_C0 4
+template <int AX>
+struct P2GGlobalSrc {   // straight from the SoA arrays in HBM
+    const AttrPtrs* a;
+    __host__ __device__ __forceinline__ double get(int attr, uint32_t q) const {
+        return a->p[attr < 3 ? attr : (attr == P2G_A_VEL ? 3 + AX : 6 + 3 * AX + (attr - P2G_A_C0))][q];
+    }
+};
+// padded slot of the tile-relative particle index i in the staging arrays: one spare slot per 8 particles, so that the
+// lanes of a warp (one cell each, ~8 particles apart) fall into different shared-memory banks
+__host__ __device__ __forceinline__ int p2g_pad(int i) { return i + (i >> 3); }
+template <int AX>
+struct P2GStagedSrc {   // from the CTA's shared-memory copy of its tile's particles (k_p2g_tile); the overflow of an
+    const double* sh;   // unusually dense tile falls back to HBM
+    int stride;         // doubles per staged attribute
+    int cap;            // particles staged
+    uint32_t q0;        // global index of the cell's first particle ...
+    int i0;             // ... and its tile-relative index
+    P2GGlobalSrc<AX> g;
+    __host__ __device__ __forceinline__ double get(int attr, uint32_t q) const {
+        const int i = i0 + (int)(q - q0);
+        return i < cap ? sh[attr * stride + p2g_pad(i)] : g.get(attr, q);
+    }
+};
+
 // Partial sums of one cell for component AX.  sv / sw: P2G_SLOTS accumulators (value, weight); returns the mask of slots
 // that are a real corner of at least one particle (the reference marks all 8 corners of a particle, also those that get
 // weight 0).  Slots outside a particle's actual 2x2x2 corners receive weight 0 (val = +-0): adding them changes nothing.
-template <bool APIC, int AX>
+template <bool APIC, int AX, class Src>
 __host__ __device__ __forceinline__ unsigned p2g_cell_partial(const GridD& g, int ci, int cj, int ck, uint32_t s0, uint32_t e0,
-                                                              const AttrPtrs& a, double* sv, double* sw, int* err) {
+                                                              const Src& a, double* sv, double* sw, int* err) {
     constexpr int NX = AX == 0 ? 2 : 3, NY = AX == 1 ? 2 : 3, NZ = AX == 2 ? 2 : 3;
     const int sx = g.nx + (AX == 0), sy = g.ny + (AX == 1), sz = g.nz + (AX == 2);
     const double ox = g.ox + 0.5 * (AX == 0 ? 0.0 : g.hx), oy = g.oy + 0.5 * (AX == 1 ? 0.0 : g.hy),
@@ -74,16 +102,16 @@ __host__ __device__ __forceinline__ unsigned p2g_cell_partial(const GridD& g, in
     for (int s = 0; s < P2G_SLOTS; ++s) { sv[s] = 0.0; sw[s] = 0.0; }
     unsigned touched = 0;
     for (uint32_t q = s0; q < e0; ++q) {
-        double px = a.p[0][q], py = a.p[1][q], pz = a.p[2][q];
+        double px = a.get(0, q), py = a.get(1, q), pz = a.get(2, q);
         if (APIC) {  // tangential clamp to [lo + h/2, hi - h/2] (apic_solver3.cpp:76-84,94-102,112-120)
             if (AX != 0) px = jc_clamp(px, g.ox + g.hx / 2.0, (g.ox + g.hx * (double)g.nx) - g.hx / 2.0);
             if (AX != 1) py = jc_clamp(py, g.oy + g.hy / 2.0, (g.oy + g.hy * (double)g.ny) - g.hy / 2.0);
             if (AX != 2) pz = jc_clamp(pz, g.oz + g.hz / 2.0, (g.oz + g.hz * (double)g.nz) - g.hz / 2.0);
         }
         const BaseFrac bf = jc_base_mul(sx, sy, sz, ihx, ihy, ihz, ox, oy, oz, px, py, pz);
-        const double pv = a.p[3 + AX][q];
+        const double pv = a.get(P2G_A_VEL, q);
         double c0 = 0.0, c1 = 0.0, c2 = 0.0;
-        if (APIC) { c0 = a.p[6 + 3 * AX][q]; c1 = a.p[7 + 3 * AX][q]; c2 = a.p[8 + 3 * AX][q]; }
+        if (APIC) { c0 = a.get(P2G_A_C0, q); c1 = a.get(P2G_A_C0 + 1, q); c2 = a.get(P2G_A_C0 + 2, q); }
         const int dx = bf.i - bx0, dy = bf.j - by0, dz = bf.k - bz0;  // 0 on the node axis, 0 or 1 on the centred ones
         const bool inwin = (unsigned)dx <= (AX == 0 ? 0u : 1u) && (unsigned)dy <= (AX == 1 ? 0u : 1u) &&
                            (unsigned)dz <= (AX == 2 ? 0u : 1u);

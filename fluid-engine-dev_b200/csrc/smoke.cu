@@ -30,6 +30,8 @@ struct jetcu_smoke {
     char *valid0 = nullptr, *valid1 = nullptr;                    // ping-pong validity maps of extrapolateToRegion
     PressureSystem ps;
     jetcu_mgpcg_result last{};
+    cudaEvent_t ev[5] = {};
+    double ms_forces = 0, ms_pressure = 0, ms_advection = 0, ms_decay = 0;
 };
 
 static GridD smoke_grid(const jetcu_smoke* h) {
@@ -54,11 +56,12 @@ __global__ void __launch_bounds__(256) k_smoke_buoyancy(GridD g, const double* _
     sm_buoyancy_face<AXIS>(g, den, temp, fd, ft, t_sum[0] / inv_n, dt, up_a, comp, i, j, k);
 }
 
+// k0: first plane of this launch (z-slab mode: a rank advects the planes it owns, the fields are all-gathered afterwards)
 __global__ void __launch_bounds__(256) k_smoke_advect_cell(GridD g, const double* __restrict__ in, const double* __restrict__ u,
                                                            const double* __restrict__ v, const double* __restrict__ w, double dt,
                                                            double hmin, bool linear, const double* __restrict__ csdf,
-                                                           double* __restrict__ out) {
-    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+                                                           double* __restrict__ out, int k0) {
+    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = k0 + blockIdx.z;
     if (i >= g.nx || j >= g.ny) return;
     out[((size_t)k * g.ny + j) * g.nx + i] = sm_advect_cell(g, in, u, v, w, dt, hmin, i, j, k, linear, csdf);
 }
@@ -66,9 +69,9 @@ __global__ void __launch_bounds__(256) k_smoke_advect_cell(GridD g, const double
 template <int AXIS>
 __global__ void __launch_bounds__(256) k_smoke_advect_face(GridD g, const double* __restrict__ u0, const double* __restrict__ v0,
                                                            const double* __restrict__ w0, double dt, double hmin, bool linear,
-                                                           const double* __restrict__ csdf, double* __restrict__ out) {
+                                                           const double* __restrict__ csdf, double* __restrict__ out, int k0) {
     const int sx = g.nx + (AXIS == 0), sy = g.ny + (AXIS == 1), sz = g.nz + (AXIS == 2);
-    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = k0 + blockIdx.z;
     if (i >= sx || j >= sy || k >= sz) return;
     out[((size_t)k * sy + j) * sx + i] = sm_advect_face<AXIS>(g, u0, v0, w0, dt, hmin, i, j, k, linear, csdf);
 }
@@ -253,6 +256,7 @@ int jetcu_smoke_destroy(jetcu_smoke* h) {
     jc_free(ctx, h->cm_u); jc_free(ctx, h->cm_v); jc_free(ctx, h->cm_w); jc_free(ctx, h->valid0); jc_free(ctx, h->valid1);
     pressure_free(ctx, &h->ps);
     cudaStreamSynchronize(ctx->stream);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     delete h;
     return JETCU_OK;
 }
@@ -424,6 +428,22 @@ int jetcu_smoke_compute_pressure(jetcu_smoke* h, double dt, jetcu_mgpcg_result* 
     return smoke_apply_bc(h);
 }
 
+// z-slab mode: the planes [z0, z1) this rank advects.  Storage stays replicated (full-size, globally indexed arrays on
+// every rank, like the liquid solver's grids): the semi-Lagrangian back-trace reads up to maxCfl + 2 planes away, which a
+// replicated input serves without a halo protocol; only the OUTPUT planes are exchanged (one all-gather per field).
+static void smoke_slab(const jetcu_smoke* h, int* z0, int* z1, int* world, int* rank) {
+    *world = jc_comm_world(h->ctx); *rank = jc_comm_rank(h->ctx);
+    if (*world > 1 && h->nz % *world == 0) { const int T = h->nz / *world; *z0 = *rank * T; *z1 = *z0 + T; }
+    else { *z0 = 0; *z1 = h->nz; *world = 1; *rank = 0; }
+}
+
+static int smoke_gather_planes(jetcu_smoke* h, int world, int z0, int z1, void* field, size_t plane_bytes, bool extra_top_plane) {
+    if (world <= 1) return JETCU_OK;
+    JC_TRY(comm_allgather_inplace(h->ctx, field, (size_t)(z1 - z0) * plane_bytes));
+    if (extra_top_plane) JC_TRY(comm_bcast(h->ctx, static_cast<char*>(field) + (size_t)h->nz * plane_bytes, plane_bytes, world - 1));
+    return JETCU_OK;
+}
+
 // GridFluidSolver3::computeAdvection (grid_fluid_solver3.cpp:255-311) with CubicSemiLagrangian3
 int jetcu_smoke_compute_advection(jetcu_smoke* h, double dt) {
     SMK_ENTER(h);
@@ -432,11 +452,16 @@ int jetcu_smoke_compute_advection(jetcu_smoke* h, double dt) {
     const bool linear = h->P.advection == JETCU_ADVECT_LINEAR;
     const double* csdf = h->col.kind != 0 ? h->col_sdf : nullptr;   // boundarySdf = *colliderSdf() (kMaxD grid without collider)
     const dim3 blk(64, 4);
+    int z0, z1, world, rank;
+    smoke_slab(h, &z0, &z1, &world, &rank);
+    const int nk = z1 - z0, nkw = nk + (rank == world - 1 ? 1 : 0);   // the last rank also owns the top w plane
+    const size_t pc = (size_t)h->nx * h->ny * 8, pu = (size_t)(h->nx + 1) * h->ny * 8, pv = (size_t)h->nx * (h->ny + 1) * 8;
     // advectable scalars in registration order (density, temperature): input = clone, flow = the current velocity
     double* fields[2] = {h->den, h->temp};
     for (double* f : fields) {
         JC_TRY(jc_d2d(ctx, h->scratch, f, h->nc));
-        JC_LAUNCH(ctx, k_smoke_advect_cell, sgrid(h->nx, h->ny, h->nz), blk, 0, g, h->scratch, h->u, h->v, h->w, dt, hmin, linear, csdf, f);
+        JC_LAUNCH(ctx, k_smoke_advect_cell, sgrid(h->nx, h->ny, nk), blk, 0, g, h->scratch, h->u, h->v, h->w, dt, hmin, linear, csdf, f, z0);
+        JC_TRY(smoke_gather_planes(h, world, z0, z1, f, pc, false));
         if (csdf) {  // GridFluidSolver3::extrapolateIntoCollider(ScalarGrid3*), grid_fluid_solver3.cpp:355-369
             JC_LAUNCH(ctx, k_smk_outside_marker, sgrid(h->nx, h->ny, h->nz), blk, 0, g, csdf, h->cm_u);
             JC_TRY(smoke_extrapolate(h, f, h->cm_u, h->nx, h->ny, h->nz, (unsigned)ceil(h->P.max_cfl)));
@@ -444,9 +469,12 @@ int jetcu_smoke_compute_advection(jetcu_smoke* h, double dt) {
     }
     // velocity: input = flow = the clone
     JC_TRY(jc_d2d(ctx, h->u0, h->u, h->nu)); JC_TRY(jc_d2d(ctx, h->v0, h->v, h->nv)); JC_TRY(jc_d2d(ctx, h->w0, h->w, h->nw));
-    JC_LAUNCH(ctx, k_smoke_advect_face<0>, sgrid(h->nx + 1, h->ny, h->nz), blk, 0, g, h->u0, h->v0, h->w0, dt, hmin, linear, csdf, h->u);
-    JC_LAUNCH(ctx, k_smoke_advect_face<1>, sgrid(h->nx, h->ny + 1, h->nz), blk, 0, g, h->u0, h->v0, h->w0, dt, hmin, linear, csdf, h->v);
-    JC_LAUNCH(ctx, k_smoke_advect_face<2>, sgrid(h->nx, h->ny, h->nz + 1), blk, 0, g, h->u0, h->v0, h->w0, dt, hmin, linear, csdf, h->w);
+    JC_LAUNCH(ctx, k_smoke_advect_face<0>, sgrid(h->nx + 1, h->ny, nk), blk, 0, g, h->u0, h->v0, h->w0, dt, hmin, linear, csdf, h->u, z0);
+    JC_LAUNCH(ctx, k_smoke_advect_face<1>, sgrid(h->nx, h->ny + 1, nk), blk, 0, g, h->u0, h->v0, h->w0, dt, hmin, linear, csdf, h->v, z0);
+    JC_LAUNCH(ctx, k_smoke_advect_face<2>, sgrid(h->nx, h->ny, nkw), blk, 0, g, h->u0, h->v0, h->w0, dt, hmin, linear, csdf, h->w, z0);
+    JC_TRY(smoke_gather_planes(h, world, z0, z1, h->u, pu, false));
+    JC_TRY(smoke_gather_planes(h, world, z0, z1, h->v, pv, false));
+    JC_TRY(smoke_gather_planes(h, world, z0, z1, h->w, pc, true));
     return smoke_apply_bc(h);
 }
 
@@ -462,12 +490,34 @@ int jetcu_smoke_end_advance_time_step(jetcu_smoke* h, double dt) {
 // GridFluidSolver3::onAdvanceTimeStep (grid_fluid_solver3.cpp:179-210); viscosity 0 -> computeViscosity skipped (:231-241)
 int jetcu_smoke_step(jetcu_smoke* h, double dt, jetcu_mgpcg_result* result) {
     SMK_ENTER(h);
+    if (!h->ev[0]) for (auto& e : h->ev) JC_CUDA(ctx, cudaEventCreate(&e));
+    cudaStream_t st = ctx->stream;
+    cudaEventRecord(h->ev[0], st);
     JC_TRY(smoke_apply_bc(h));  // beginAdvanceTimeStep: applyBoundaryCondition (:455-456)
     JC_TRY(jetcu_smoke_compute_external_forces(h, dt));
+    cudaEventRecord(h->ev[1], st);
     JC_TRY(jetcu_smoke_compute_pressure(h, dt, result));
+    cudaEventRecord(h->ev[2], st);
     JC_TRY(jetcu_smoke_compute_advection(h, dt));
+    cudaEventRecord(h->ev[3], st);
     JC_TRY(jetcu_smoke_end_advance_time_step(h, dt));
-    return jc_sync(ctx);
+    cudaEventRecord(h->ev[4], st);
+    JC_TRY(jc_sync(ctx));
+    float ms[4] = {0, 0, 0, 0};
+    for (int q = 0; q < 4; ++q) cudaEventElapsedTime(&ms[q], h->ev[q], h->ev[q + 1]);
+    h->ms_forces = ms[0]; h->ms_pressure = ms[1]; h->ms_advection = ms[2]; h->ms_decay = ms[3];
+    return JETCU_OK;
+}
+
+// device time of the stages of the last jetcu_smoke_step (CUDA events on the library's stream), milliseconds:
+// buoyancy + boundary condition, pressure projection, advection (all five fields), decay
+int jetcu_smoke_last_step_ms(jetcu_smoke* h, double* forces, double* pressure, double* advection, double* decay) {
+    SMK_ENTER(h);
+    if (forces) *forces = h->ms_forces;
+    if (pressure) *pressure = h->ms_pressure;
+    if (advection) *advection = h->ms_advection;
+    if (decay) *decay = h->ms_decay;
+    return JETCU_OK;
 }
 
 }  // extern "C"

@@ -199,6 +199,11 @@ class SmokeApi:
         self._c("smoke_step", self.h, f64(dt), C.byref(r))
         return r
 
+    def last_step_ms(self):
+        f, p, a, d = f64(0), f64(0), f64(0), f64(0)
+        self._c("smoke_last_step_ms", self.h, C.byref(f), C.byref(p), C.byref(a), C.byref(d))
+        return {"ms_forces": f.value, "ms_pressure": p.value, "ms_advection": a.value, "ms_decay": d.value}
+
     def cfl(self, dt):
         c = f64(0.0)
         self._c("smoke_cfl", self.h, f64(dt), C.byref(c))

@@ -436,6 +436,9 @@ int jetcu_smoke_set_collider_shapes(jetcu_smoke*, const jetcu_collider_shape* sh
                                     const double linear_velocity[3], const double angular_velocity[3], double friction);
 /* GridFluidSolver3::cfl / numberOfSubTimeSteps (src/jet/grid_fluid_solver3.cpp:57-72, 212-217) evaluated on the device-resident
  * velocity, so that adaptive sub-stepping does not need the fields on the host. */
+/* Device time (ms, CUDA events) of the stages of the last jetcu_smoke_step: buoyancy + boundary condition, pressure projection,
+ * advection of all five fields, decay.  Any pointer may be NULL. */
+int jetcu_smoke_last_step_ms(jetcu_smoke*, double* forces, double* pressure, double* advection, double* decay);
 int jetcu_smoke_cfl(jetcu_smoke*, double dt, double* cfl);
 int jetcu_smoke_num_sub_steps(jetcu_smoke*, double dt, uint32_t* n);
 int jetcu_smoke_step(jetcu_smoke*, double dt, jetcu_mgpcg_result* result);                 /* onAdvanceTimeStep */

@@ -114,6 +114,23 @@ def main():
         if mode == FLIP:   # APIC's affine vectors are not part of the local set call: positions only agree for PIC/FLIP
             check(name + "_set_local_roundtrip_bits", np.array_equal(p2, hs.get_particles()[0]))
         hd.close(); hs.close()
+    # ---- BASELINE config 5: GridSmokeSolver3 on slabs (MGPCG distributed, advection of the owned planes + all-gather)
+    from fluid_engine_dev_b200.jetcu import SmokeParams
+    sp = SmokeParams.make(Grid.cube(n), mgpcg=MgpcgParams.make(max_iterations=100, max_levels=5))
+    sd_, ss_ = jd.smoke(sp), js.smoke(sp)
+    c = (np.arange(n) + 0.5) / n
+    Z, Y, X = np.meshgrid(c, c, c, indexing="ij")
+    den = np.ascontiguousarray(np.clip(1.0 - np.sqrt((X - 0.5) ** 2 + (Y - 0.25) ** 2 + (Z - 0.45) ** 2) / 0.2, 0.0, 1.0))
+    for q in (sd_, ss_):
+        q.set_fields(den, 2.0 * den + 0.1)
+    for s in range(steps):
+        r1_, r2_ = sd_.step(1.0 / 60.0), ss_.step(1.0 / 60.0)
+        check("smoke_step%d_pcg" % s, r1_.iterations == r2_.iterations and r1_.last_residual == r2_.last_residual,
+              [int(r1_.iterations), int(r2_.iterations)])
+    fd_, fs_ = sd_.get_fields(), ss_.get_fields()
+    check("smoke_fields_bits", all(np.array_equal(fd_[k], fs_[k]) for k in fs_))
+    check("smoke_moved", float(np.abs(fs_["v"]).max()) > 1e-3)
+    sd_.close(); ss_.close()
     msgs, sent = jd.comm_stats()
     out["comm"] = {"messages": msgs, "bytes_sent": sent, "p2p": jd.comm_p2p_enabled()}
     out["ok"] = ok

@@ -99,7 +99,8 @@ static void p2g_tile_component_host(const GridD& g, int I0, int J0, int K0, int 
         unsigned touched = 0;
         if (e0 > s0) {
             double sv[P2G_SLOTS], sw[P2G_SLOTS];
-            touched = p2g_cell_partial<APIC, AX>(g, ci, cj, ck, s0, e0, a, sv, sw, err);
+            const P2GGlobalSrc<AX> src{&a};
+            touched = p2g_cell_partial<APIC, AX>(g, ci, cj, ck, s0, e0, src, sv, sw, err);
             for (int q = 0; q < P2G_SLOTS; ++q) { ex[q * NT + tid] = sv[q]; exw[q * NT + tid] = sw[q]; }
         }
         tm[tid] = touched;

@@ -223,6 +223,45 @@ static int launch_sweep(jetcu_ctx* ctx, Dim3i d, ZRange rw, ZRange bw, int chunk
     return JETCU_OK;
 }
 
+// L2-resident sweeps, several at a time (JETCU_RELAX_SKEW = sweeps per group, needs JETCU_RELAX_CHUNK > 0): the 2S colour
+// passes of S consecutive sweeps are issued as a skewed wavefront over z-chunks — for chunk c = 0, 1, ...: for pass
+// p = 0 .. 2S-1: colour p & 1 on the planes [c*C - p, (c+1)*C - p).  Pass p reaches plane k only after pass p - 1 covered
+// k - 1 .. k + 1 (it is one plane ahead in every chunk), and pass p + 1 has not yet touched k - 1 .. k + 1 (it trails by
+// one plane), so every cell update reads exactly the operands of the S full sweeps run one after the other: bit-identical.
+// The working set between the first and the last touch of a plane is (C + 2S) planes of x / b / centre / code, which the
+// 126 MB L2 holds, so DRAM sees each plane once per GROUP instead of twice per sweep.
+static int relax_skew_sweeps() {
+    static int c = -1;
+    if (c < 0) {
+        const char* e = getenv("JETCU_RELAX_SKEW");
+        c = e ? atoi(e) : 0;
+        if (c < 0) c = 0;
+    }
+    return c;
+}
+
+template <bool P>
+static int launch_sweeps_skewed(jetcu_ctx* ctx, Dim3i d, ZRange z, int chunk, int sweeps, Mat A, const double* b, double sor,
+                                double* x, uint64_t* launches) {
+    const int passes = 2 * sweeps;
+    for (int c0 = z.k0;; c0 += chunk) {
+        bool any = false;
+        for (int p = 0; p < passes; ++p) {
+            int lo = c0 - p, hi = c0 + chunk - p;
+            if (lo < z.k0) lo = z.k0;
+            if (hi > z.k1) hi = z.k1;
+            if (c0 - p >= z.k1) continue;      // this pass is done with the level
+            any = true;
+            if (lo < hi) {
+                JC_TRY(launch_colour<P>(ctx, d, ZRange{lo, hi}, A, b, sor, p & 1, x));
+                *launches += 1;
+            }
+        }
+        if (!any) break;
+    }
+    return JETCU_OK;
+}
+
 template <bool P>
 static int launch_relax(jetcu_ctx* ctx, Dim3i d, ZRange z, bool halo, Mat A, const double* b, double sor,
                         unsigned iterations, double** x, double** xalt, uint64_t* launches) {
@@ -238,6 +277,15 @@ static int launch_relax(jetcu_ctx* ctx, Dim3i d, ZRange z, bool halo, Mat A, con
     const int chunk = d.n() >= (size_t)(1 << 21) ? relax_chunk_planes() : 0;
     *launches = 0;
     unsigned it = 0;
+    const int skew = relax_skew_sweeps();
+    if (!halo && chunk > 0 && skew > 1 && z.k1 - z.k0 > chunk) {   // undivided level: groups of `skew` sweeps as one wavefront
+        while (it < iterations) {
+            const int s2 = (int)((iterations - it < (unsigned)skew) ? iterations - it : (unsigned)skew);
+            JC_TRY(launch_sweeps_skewed<P>(ctx, d, z, chunk, s2, A, b, sor, *x, launches));
+            it += (unsigned)s2;
+        }
+        return JETCU_OK;
+    }
     while (it < iterations) {
         const int k = halo ? (int)((iterations - it < (unsigned)kmax) ? iterations - it : (unsigned)kmax) : (int)(iterations - it);
         if (halo) JC_TRY(comm_halo_planes(ctx, *x, plane, z.k0, z.k1, d.nz, 2 * k));

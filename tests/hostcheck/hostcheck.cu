@@ -700,6 +700,37 @@ int hc_packed_relax_chunked(uint32_t level, const double* b, double sor, unsigne
     return 0;
 }
 
+// launch_sweeps_skewed<true> of fdm.cu (JETCU_RELAX_SKEW = skew sweeps per group, JETCU_RELAX_CHUNK = chunk planes): the
+// skewed wavefront of 2 * skew colour passes over z-chunks, replayed with the same loop structure
+int hc_packed_relax_skewed(uint32_t level, const double* b, double sor, unsigned iterations, int chunk, int skew, double* x) {
+    const HostLevel& L = g_sys.lv[level];
+    const int nx = L.nx, ny = L.ny, nz = L.nz;
+    auto colour_range = [&](int colour, int k0, int k1) {
+        for (int k = k0; k < k1; ++k)
+            for (int j = 0; j < ny; ++j)
+                for (int i = (j + k + colour) & 1; i < nx; i += 2) relax_cell_code(L.m, b, x, sor, i, j, k, nx, ny, nz);
+    };
+    unsigned it = 0;
+    while (it < iterations) {
+        const int s2 = (int)((iterations - it < (unsigned)skew) ? iterations - it : (unsigned)skew);
+        const int passes = 2 * s2;
+        for (int c0 = 0;; c0 += chunk) {
+            bool any = false;
+            for (int p = 0; p < passes; ++p) {
+                int lo = c0 - p, hi = c0 + chunk - p;
+                if (lo < 0) lo = 0;
+                if (hi > nz) hi = nz;
+                if (c0 - p >= nz) continue;
+                any = true;
+                if (lo < hi) colour_range(p & 1, lo, hi);
+            }
+            if (!any) break;
+        }
+        it += (unsigned)s2;
+    }
+    return 0;
+}
+
 // k_apply_gradient on level 0 of the last build
 int hc_apply_gradient(const double* x, const double* u_in, const double* v_in, const double* w_in, double* u_out, double* v_out, double* w_out) {
     const HostLevel& L = g_sys.lv[0];

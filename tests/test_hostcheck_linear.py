@@ -102,6 +102,12 @@ def test_packed_pressure_system(hc, port, n, kind, collider, domain):
             xs = x.copy()
             hc.hc_packed_relax_chunked(C.c_uint32(l), dp(rhs), C.c_double(1.5), C.c_uint(3), C.c_int(chunk), dp(xs))
             exact(xs, ref, "chunk-interleaved SOR level %d chunk %d" % (l, chunk))
+        # several sweeps as one skewed wavefront over z-chunks (JETCU_RELAX_SKEW): still the bits of the full passes
+        ref5 = port.relax_red_black(want["A"], rhs, x, 1.5, 5)
+        for chunk, skew in ((1, 2), (2, 5), (3, 3), (4, 2), (m, 5)):
+            xs = x.copy()
+            hc.hc_packed_relax_skewed(C.c_uint32(l), dp(rhs), C.c_double(1.5), C.c_uint(5), C.c_int(chunk), C.c_int(skew), dp(xs))
+            exact(xs, ref5, "skewed SOR wavefront level %d chunk %d skew %d" % (l, chunk, skew))
     # applyPressureGradient with the oracle's pressure
     gu, gv, gw = sc["u"].copy(), sc["v"].copy(), sc["w"].copy()
     hc.hc_apply_gradient(dp(p), dp(sc["u"]), dp(sc["v"]), dp(sc["w"]), dp(gu), dp(gv), dp(gw))

@@ -179,70 +179,38 @@ __global__ void k_slab_unpack(const double* __restrict__ msg, size_t cnt, AttrPt
 // Design and summation order: p2g_ops.cuh.  One CTA = one tile of P2G_TX x P2G_TY x TZ cells, one thread per cell;
 // launched once per tile colour (parity of the tile index per axis), so a CTA owns every face its window reaches for
 // the duration of the launch and adds into the global arrays without atomics.
-// Shared memory of k_p2g_tile: [staging: NA attributes x `stride` doubles][exchange: P2G_SLOTS x NT doubles].
-//   staging  — the tile's particles, copied from HBM with coalesced loads (a tile's x-rows are contiguous particle ranges):
-//              positions once, the velocity component (+ affine vector) of each pass before that pass.  The cell loop (one
-//              thread per cell, lane stride ~8 particles) then reads shared memory instead of walking HBM with 32 half-used
-//              sectors per warp load (ncu, round 2: long-scoreboard stalls at 16 warps/SM dominated the un-staged kernel);
-//   exchange — per-cell partial sums on their way to the per-face gather.
-template <int TZ, bool APIC>
-struct P2GTileCfg {
-    static constexpr int NT = P2G_TX * P2G_TY * TZ;
-    static constexpr int NA = APIC ? 7 : 4;                 // staged attributes: x, y, z, v_AX (, c_AX[0..2])
-    // particles staged per tile: what fits next to the exchange buffer in ~223 KB of shared memory (the lattice fill is 8
-    // per cell; PIC/FLIP: 8.25 per cell of a 512-cell tile, APIC: 10.9 per cell of a 256-cell tile); the rest reads HBM
-    static constexpr int CAP = ((223 * 1024 / 8 - P2G_SLOTS * NT) / NA) * 8 / 9 - 8;
-    static constexpr int STRIDE = CAP + CAP / 8 + 8;        // padded (p2g_pad)
-    static constexpr int ROWS = P2G_TY * TZ;
-    static constexpr size_t SMEM = ((size_t)NA * STRIDE + (size_t)P2G_SLOTS * NT) * sizeof(double);
-};
-
+// Measured alternatives (round 2, profiles/r02_p2g_variants.md): exchanging values and weights in two rounds through half
+// the buffer (L1 hit rate 10 % -> 51 %, but two more barriers per component: 11.5 ms instead of 9.8 ms for the 8 launches)
+// and staging the tile's particles in shared memory with coalesced row copies (14 ms) were both slower than this form.
 template <bool APIC, int AX, int TZ>
 __device__ __forceinline__ void p2g_tile_component(const GridD& g, int I0, int J0, int K0, int ci, int cj, int ck, uint32_t s0,
-                                                   uint32_t e0, const AttrPtrs& a, const double* stage, int i0, double* ex,
-                                                   unsigned* tm, double* __restrict__ U, double* __restrict__ W,
-                                                   char* __restrict__ M, int* err) {
-    using Cfg = P2GTileCfg<TZ, APIC>;
-    constexpr int NT = Cfg::NT;
+                                                   uint32_t e0, const AttrPtrs& a, double* ex, unsigned* tm,
+                                                   double* __restrict__ U, double* __restrict__ W, char* __restrict__ M, int* err) {
+    constexpr int NT = P2G_TX * P2G_TY * TZ;
     constexpr int WX = P2G_TX + (AX == 0 ? 1 : 2), WY = P2G_TY + (AX == 1 ? 1 : 2), WZ = TZ + (AX == 2 ? 1 : 2);
-    constexpr int NW = WX * WY * WZ, PER = (NW + NT - 1) / NT;   // window faces, faces per thread
     const int tid = threadIdx.x;
     unsigned touched = 0;
-    double sv[P2G_SLOTS], sw[P2G_SLOTS];
     if (e0 > s0) {
-        const P2GStagedSrc<AX> src{stage, Cfg::STRIDE, Cfg::CAP, s0, i0, P2GGlobalSrc<AX>{&a}};
+        double sv[P2G_SLOTS], sw[P2G_SLOTS];
+        const P2GGlobalSrc<AX> src{&a};
         touched = p2g_cell_partial<APIC, AX>(g, ci, cj, ck, s0, e0, src, sv, sw, err);
 #pragma unroll
-        for (int s = 0; s < P2G_SLOTS; ++s) ex[s * NT + tid] = sv[s];
+        for (int s = 0; s < P2G_SLOTS; ++s) { ex[s * NT + tid] = sv[s]; ex[(P2G_SLOTS + s) * NT + tid] = sw[s]; }
     }
     tm[tid] = touched;
     __syncthreads();
-    double fv[PER], fw[PER];
-    bool hit[PER];
-#pragma unroll
-    for (int r = 0; r < PER; ++r) {
-        const int f = tid + r * NT;
-        hit[r] = false; fv[r] = 0.0;
-        if (f < NW) hit[r] = p2g_face_gather<AX, TZ>(ex, tm, f % WX, (f / WX) % WY, f / (WX * WY), &fv[r]);
-    }
-    __syncthreads();
-    if (e0 > s0) {
-#pragma unroll
-        for (int s = 0; s < P2G_SLOTS; ++s) ex[s * NT + tid] = sw[s];
-    }
-    __syncthreads();
     const int sx = g.nx + (AX == 0), sy = g.ny + (AX == 1), sz = g.nz + (AX == 2);
     const int fx0 = I0 - (AX == 0 ? 0 : 1), fy0 = J0 - (AX == 1 ? 0 : 1), fz0 = K0 - (AX == 2 ? 0 : 1);
-#pragma unroll
-    for (int r = 0; r < PER; ++r) {
-        if (!hit[r]) continue;
-        const int f = tid + r * NT;
+    for (int f = tid; f < WX * WY * WZ; f += NT) {
         const int lx = f % WX, ly = (f / WX) % WY, lz = f / (WX * WY);
-        p2g_face_gather<AX, TZ>(ex, tm, lx, ly, lz, &fw[r]);
         const int fi = fx0 + lx, fj = fy0 + ly, fk = fz0 + lz;
         if ((unsigned)fi >= (unsigned)sx || (unsigned)fj >= (unsigned)sy || (unsigned)fk >= (unsigned)sz) continue;
-        const size_t idx = ((size_t)fk * sy + fj) * sx + fi;
-        U[idx] += fv[r]; W[idx] += fw[r]; M[idx] = 1;
+        double v, w;
+        if (p2g_face_gather<AX, TZ>(ex, tm, lx, ly, lz, &v)) {
+            p2g_face_gather<AX, TZ>(ex + P2G_SLOTS * NT, tm, lx, ly, lz, &w);
+            const size_t idx = ((size_t)fk * sy + fj) * sx + fi;
+            U[idx] += v; W[idx] += w; M[idx] = 1;
+        }
     }
     __syncthreads();
 }
@@ -253,86 +221,26 @@ struct P2GOut {
     char* marker[3];
 };
 
-// copies attribute `src` of the tile's particles into staging slot `slot`: warp w takes the x-rows w, w + nwarps, ...
-template <int TZ, bool APIC>
-__device__ __forceinline__ void p2g_stage_attr(double* stage, int slot, const double* __restrict__ src, const uint32_t* row_s,
-                                               const uint32_t* row_off) {
-    using Cfg = P2GTileCfg<TZ, APIC>;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* dst = stage + (size_t)slot * Cfg::STRIDE;
-    for (int row = warp; row < Cfg::ROWS; row += Cfg::NT / 32) {
-        const uint32_t rs = row_s[row], off = row_off[row], cnt = row_off[row + 1] - off;
-        for (uint32_t i = lane; i < cnt; i += 32) {
-            const int t = (int)(off + i);
-            if (t < Cfg::CAP) dst[p2g_pad(t)] = src[rs + i];
-        }
-    }
-}
-
 template <bool APIC, int TZ>
 __global__ void __launch_bounds__(P2G_TX * P2G_TY * TZ)
     k_p2g_tile(GridD g, int par_x, int par_y, int tz_first, int kb, int ke, const uint32_t* __restrict__ cell_start, AttrPtrs a,
                P2GOut out, int* __restrict__ err) {
-    using Cfg = P2GTileCfg<TZ, APIC>;
-    constexpr int NT = Cfg::NT, ROWS = Cfg::ROWS;
-    extern __shared__ __align__(16) double p2g_smem[];
-    double* stage = p2g_smem;                                   // [NA][STRIDE]
-    double* ex = p2g_smem + (size_t)Cfg::NA * Cfg::STRIDE;      // [P2G_SLOTS][NT]: value partials, then weight partials
+    constexpr int NT = P2G_TX * P2G_TY * TZ;
+    extern __shared__ __align__(16) double p2g_ex[];  // [2][P2G_SLOTS][NT]: value partials, weight partials
     __shared__ unsigned tm[NT];
-    __shared__ uint32_t row_s[ROWS], row_off[ROWS + 1];
     const int tid = threadIdx.x;
     const int I0 = (2 * blockIdx.x + par_x) * P2G_TX, J0 = (2 * blockIdx.y + par_y) * P2G_TY, K0 = (tz_first + 2 * blockIdx.z) * TZ;
-    const int cx = tid % P2G_TX, row = tid / P2G_TX;            // row = cy + P2G_TY * cz
-    const int ci = I0 + cx, cj = J0 + row % P2G_TY, ck = K0 + row / P2G_TY;
+    const int ci = I0 + tid % P2G_TX, cj = J0 + (tid / P2G_TX) % P2G_TY, ck = K0 + tid / (P2G_TX * P2G_TY);
     uint32_t s0 = 0, e0 = 0;
     // cell planes [kb, ke): the whole grid, or (slab mode) this rank's slab plus its ghost planes
-    const bool row_ok = cj < g.ny && ck >= kb && ck < ke;
-    if (ci < g.nx && row_ok) {
+    if (ci < g.nx && cj < g.ny && ck >= kb && ck < ke) {
         const size_t cell = ((size_t)ck * g.ny + cj) * g.nx + ci;
         s0 = cell_start[cell]; e0 = cell_start[cell + 1];
     }
     if (!__syncthreads_or(e0 > s0)) return;
-    // the tile's x-rows are contiguous particle ranges [row_s, row_s + count); their tile-relative offsets by a prefix sum
-    if (cx == 0) {
-        uint32_t rs = 0, re = 0;
-        if (row_ok) {
-            const size_t c0 = ((size_t)ck * g.ny + cj) * g.nx + I0;
-            const int w = min(P2G_TX, g.nx - I0);
-            rs = cell_start[c0]; re = cell_start[c0 + w];
-        }
-        row_s[row] = rs; row_off[row + 1] = re - rs;
-    }
-    __syncthreads();
-    if (tid < 32) {   // inclusive scan of ROWS (<= 64) counts by one warp
-        uint32_t v0 = tid < ROWS ? row_off[tid + 1] : 0u, v1 = tid + 32 < ROWS ? row_off[tid + 33] : 0u;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t0 = __shfl_up_sync(0xffffffffu, v0, d), t1 = __shfl_up_sync(0xffffffffu, v1, d);
-            if (tid >= d) { v0 += t0; v1 += t1; }
-        }
-        v1 += __shfl_sync(0xffffffffu, v0, 31);
-        if (tid == 0) row_off[0] = 0;
-        if (tid < ROWS) row_off[tid + 1] = v0;
-        if (tid + 32 < ROWS) row_off[tid + 33] = v1;
-    }
-    __syncthreads();
-    const int i0 = (int)(row_off[row] + (s0 - row_s[row]));    // tile-relative index of this cell's first particle
-    p2g_stage_attr<TZ, APIC>(stage, 0, a.p[0], row_s, row_off);
-    p2g_stage_attr<TZ, APIC>(stage, 1, a.p[1], row_s, row_off);
-    p2g_stage_attr<TZ, APIC>(stage, 2, a.p[2], row_s, row_off);
-#pragma unroll
-    for (int ax = 0; ax < 3; ++ax) {
-        p2g_stage_attr<TZ, APIC>(stage, P2G_A_VEL, a.p[3 + ax], row_s, row_off);
-        if (APIC) {
-            p2g_stage_attr<TZ, APIC>(stage, P2G_A_C0, a.p[6 + 3 * ax], row_s, row_off);
-            p2g_stage_attr<TZ, APIC>(stage, P2G_A_C0 + 1, a.p[7 + 3 * ax], row_s, row_off);
-            p2g_stage_attr<TZ, APIC>(stage, P2G_A_C0 + 2, a.p[8 + 3 * ax], row_s, row_off);
-        }
-        __syncthreads();
-        if (ax == 0) p2g_tile_component<APIC, 0, TZ>(g, I0, J0, K0, ci, cj, ck, s0, e0, a, stage, i0, ex, tm, out.val[0], out.wsum[0], out.marker[0], err);
-        if (ax == 1) p2g_tile_component<APIC, 1, TZ>(g, I0, J0, K0, ci, cj, ck, s0, e0, a, stage, i0, ex, tm, out.val[1], out.wsum[1], out.marker[1], err);
-        if (ax == 2) p2g_tile_component<APIC, 2, TZ>(g, I0, J0, K0, ci, cj, ck, s0, e0, a, stage, i0, ex, tm, out.val[2], out.wsum[2], out.marker[2], err);
-    }
+    p2g_tile_component<APIC, 0, TZ>(g, I0, J0, K0, ci, cj, ck, s0, e0, a, p2g_ex, tm, out.val[0], out.wsum[0], out.marker[0], err);
+    p2g_tile_component<APIC, 1, TZ>(g, I0, J0, K0, ci, cj, ck, s0, e0, a, p2g_ex, tm, out.val[1], out.wsum[1], out.marker[1], err);
+    p2g_tile_component<APIC, 2, TZ>(g, I0, J0, K0, ci, cj, ck, s0, e0, a, p2g_ex, tm, out.val[2], out.wsum[2], out.marker[2], err);
 }
 
 // u = sum / wsum where wsum > 0 (pic_solver3.cpp:178-192); FLIP's float snapshot (src/jet/flip_solver3.cpp:39-47) is
@@ -1605,7 +1513,7 @@ int jetcu_hybrid_transfer_particles_to_grids(jetcu_hybrid* h) {
             const int TZ = apic ? P2G_TZ_APIC : P2G_TZ;
             const int ntx = (g.nx + P2G_TX - 1) / P2G_TX, nty = (g.ny + P2G_TY - 1) / P2G_TY;
             const int tzlo = kb / TZ, tzhi = (ke - 1) / TZ;  // inclusive
-            const size_t smem = apic ? P2GTileCfg<P2G_TZ_APIC, true>::SMEM : P2GTileCfg<P2G_TZ, false>::SMEM;
+            const size_t smem = (size_t)2 * P2G_SLOTS * P2G_TX * P2G_TY * TZ * sizeof(double);
             // per device, cheap: set on every call (the attribute belongs to the current device's copy of the function)
             if (apic) JC_CUDA(ctx, cudaFuncSetAttribute((k_p2g_tile<true, P2G_TZ_APIC>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             else JC_CUDA(ctx, cudaFuncSetAttribute((k_p2g_tile<false, P2G_TZ>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -30,8 +30,7 @@ struct AttrPtrs {
 //      same window of faces per component: 2 along the component's own (node-aligned) axis x 3 x 3 along the two
 //      cell-centred axes = 18 faces.  One thread owns a cell and sums its particles' contributions to those 18 faces in
 //      REGISTERS, in the cell's particle order (p2g_cell_partial);
-//   2. the 18 partial sums of every cell of a tile go to shared memory (values first, then weights: half the buffer,
-//      which leaves the L1 big enough to keep the particle sectors the cell loop walks), and one thread per FACE of the
+//   2. the 18 (value, weight) partial sums of every cell of a tile go to shared memory, and one thread per FACE of the
 //      tile's window adds up the partial sums of the <= 18 cells of the tile that reach it, in a fixed slot order
 //      (p2g_face_gather);
 //   3. faces on a tile's rim also receive from neighbouring tiles.  Tiles are launched in 8 colour passes (parity of the
@@ -68,23 +67,6 @@ struct P2GGlobalSrc {   // straight from the SoA arrays in HBM
         return a->p[attr < 3 ? attr : (attr == P2G_A_VEL ? 3 + AX : 6 + 3 * AX + (attr - P2G_A_C0))][q];
     }
 };
-// padded slot of the tile-relative particle index i in the staging arrays: one spare slot per 8 particles, so that the
-// lanes of a warp (one cell each, ~8 particles apart) fall into different shared-memory banks
-__host__ __device__ __forceinline__ int p2g_pad(int i) { return i + (i >> 3); }
-template <int AX>
-struct P2GStagedSrc {   // from the CTA's shared-memory copy of its tile's particles (k_p2g_tile); the overflow of an
-    const double* sh;   // unusually dense tile falls back to HBM
-    int stride;         // doubles per staged attribute
-    int cap;            // particles staged
-    uint32_t q0;        // global index of the cell's first particle ...
-    int i0;             // ... and its tile-relative index
-    P2GGlobalSrc<AX> g;
-    __host__ __device__ __forceinline__ double get(int attr, uint32_t q) const {
-        const int i = i0 + (int)(q - q0);
-        return i < cap ? sh[attr * stride + p2g_pad(i)] : g.get(attr, q);
-    }
-};
-
 // Partial sums of one cell for component AX.  sv / sw: P2G_SLOTS accumulators (value, weight); returns the mask of slots
 // that are a real corner of at least one particle (the reference marks all 8 corners of a particle, also those that get
 // weight 0).  Slots outside a particle's actual 2x2x2 corners receive weight 0 (val = +-0): adding them changes nothing.

@@ -169,13 +169,17 @@ static int launch_colour(jetcu_ctx* ctx, Dim3i d, ZRange z, Mat A, const double*
 // have made b valid on fdm_relax_rhs_halo(T) planes around the slab (b is read-only here: one exchange per V-cycle level).
 // sweeps per exchange on a slab of T planes
 static inline int relax_block_sweeps(int T) {
-    int k = T / 8;
+    // JETCU_RELAX_BLOCK_DIV (default 8): sweeps per halo exchange = T / div, at most 8.  A smaller divisor trades redundant
+    // halo work (2k / T of a pass) for fewer dependent exchanges — worth it where a pass is launch-latency-bound anyway
+    static int div = 0;
+    if (div == 0) { const char* e = getenv("JETCU_RELAX_BLOCK_DIV"); div = e ? atoi(e) : 8; if (div < 2) div = 2; }
+    int k = T / div;
     return k < 1 ? 1 : (k > 8 ? 8 : k);
 }
 // planes of b (which the sweeps only read) that the redundant halo cells need next to a slab of T planes
 int fdm_relax_rhs_halo(int T) { return 2 * relax_block_sweeps(T) - 1; }
 
-// L2-resident sweep (experimental, JETCU_RELAX_CHUNK = planes per chunk, 0 = off): the red and the black pass of one
+// L2-resident sweep (JETCU_RELAX_CHUNK = planes per chunk, default by launch size, 0 = off): the red and the black pass of one
 // sweep are issued as an alternating sequence of z-chunks — red on planes up to c1 (one plane ahead), black on the chunk
 // [c0, c1), red on the next chunk ... — instead of two passes over the whole level.  Every red cell still reads only
 // black values from before the sweep (a black chunk is launched after the red launch that needed its planes, and the
@@ -183,14 +187,21 @@ int fdm_relax_rhs_halo(int T) { return 2 * relax_block_sweeps(T) - 1; }
 // the same order, bit-identical to the two full passes.  What changes is the traffic: the b / x / code sectors a red
 // launch pulled in (half of each sector belongs to the other colour) are still in the 126 MB L2 when the black launch
 // of the same chunk needs the other half, and x is written back once — ~25 B/cell/sweep from DRAM instead of ~47.
-static int relax_chunk_planes() {
-    static int c = -1;
-    if (c < 0) {
+// planes per chunk for a level with `plane_cells` cells per plane: JETCU_RELAX_CHUNK (planes) if set, else the number of
+// planes that makes a launch ~3.5 M cells (JETCU_RELAX_CHUNK_CELLS) — 48-64 planes at 256^2, 13 at 512^2, 6 at 768^2: the
+// measured optimum at 256^3 (profiles/r02_sor_wavefront.md) carried over by launch size.  0 = whole-level passes.
+static int relax_chunk_planes(size_t plane_cells) {
+    static long long planes = -2, cells = -1;
+    if (planes == -2) {
         const char* e = getenv("JETCU_RELAX_CHUNK");
-        c = e ? atoi(e) : 0;
-        if (c < 0) c = 0;
+        planes = e ? atoll(e) : -1;
+        const char* c = getenv("JETCU_RELAX_CHUNK_CELLS");
+        cells = c ? atoll(c) : 3500000ll;
     }
-    return c;
+    if (planes >= 0) return (int)planes;
+    if (cells <= 0) return 0;
+    const long long p = cells / (long long)(plane_cells ? plane_cells : 1);
+    return p < 1 ? 1 : (p > (1 << 20) ? (1 << 20) : (int)p);
 }
 
 // one sweep: red on the planes `rw`, black on the planes `bw` (bw inside rw; rw reaches one plane beyond bw wherever the
@@ -223,7 +234,7 @@ static int launch_sweep(jetcu_ctx* ctx, Dim3i d, ZRange rw, ZRange bw, int chunk
     return JETCU_OK;
 }
 
-// L2-resident sweeps, several at a time (JETCU_RELAX_SKEW = sweeps per group, needs JETCU_RELAX_CHUNK > 0): the 2S colour
+// L2-resident sweeps, several at a time (JETCU_RELAX_SKEW = sweeps per group, default 20, needs a chunk size > 0): the 2S colour
 // passes of S consecutive sweeps are issued as a skewed wavefront over z-chunks — for chunk c = 0, 1, ...: for pass
 // p = 0 .. 2S-1: colour p & 1 on the planes [c*C - p, (c+1)*C - p).  Pass p reaches plane k only after pass p - 1 covered
 // k - 1 .. k + 1 (it is one plane ahead in every chunk), and pass p + 1 has not yet touched k - 1 .. k + 1 (it trails by
@@ -234,24 +245,23 @@ static int relax_skew_sweeps() {
     static int c = -1;
     if (c < 0) {
         const char* e = getenv("JETCU_RELAX_SKEW");
-        c = e ? atoi(e) : 0;
+        c = e ? atoi(e) : 20;   // measured (profiles/r02_sor_wavefront.md); <= 1 = one sweep at a time
         if (c < 0) c = 0;
     }
     return c;
 }
 
+// w0[p] / w1[p] = the plane window of pass p (all equal on an undivided level; on a slab the redundant-halo windows that
+// shrink by one plane per pass, see launch_relax).
 template <bool P>
-static int launch_sweeps_skewed(jetcu_ctx* ctx, Dim3i d, ZRange z, int chunk, int sweeps, Mat A, const double* b, double sor,
-                                double* x, uint64_t* launches) {
-    const int passes = 2 * sweeps;
-    for (int c0 = z.k0;; c0 += chunk) {
+static int launch_sweeps_skewed(jetcu_ctx* ctx, Dim3i d, const int* w0, const int* w1, int passes, int chunk, Mat A, const double* b,
+                                double sor, double* x, uint64_t* launches) {
+    for (int c0 = w0[0];; c0 += chunk) {
         bool any = false;
         for (int p = 0; p < passes; ++p) {
-            int lo = c0 - p, hi = c0 + chunk - p;
-            if (lo < z.k0) lo = z.k0;
-            if (hi > z.k1) hi = z.k1;
-            if (c0 - p >= z.k1) continue;      // this pass is done with the level
+            if (c0 - p >= w1[p]) continue;      // this pass is done with the level
             any = true;
+            const int lo = c0 - p > w0[p] ? c0 - p : w0[p], hi = c0 + chunk - p < w1[p] ? c0 + chunk - p : w1[p];
             if (lo < hi) {
                 JC_TRY(launch_colour<P>(ctx, d, ZRange{lo, hi}, A, b, sor, p & 1, x));
                 *launches += 1;
@@ -274,14 +284,17 @@ static int launch_relax(jetcu_ctx* ctx, Dim3i d, ZRange z, bool halo, Mat A, con
     const size_t plane = (size_t)d.nx * d.ny * sizeof(double);
     const int kmax = relax_block_sweeps(z.k1 - z.k0);
     // chunking only pays where the level does not fit the L2 anyway (>= 64^3-ish: 25 B x 2M cells)
-    const int chunk = d.n() >= (size_t)(1 << 21) ? relax_chunk_planes() : 0;
+    const int chunk = d.n() >= (size_t)(1 << 21) ? relax_chunk_planes((size_t)d.nx * d.ny) : 0;
     *launches = 0;
     unsigned it = 0;
     const int skew = relax_skew_sweeps();
+    int w0[64], w1[64];
     if (!halo && chunk > 0 && skew > 1 && z.k1 - z.k0 > chunk) {   // undivided level: groups of `skew` sweeps as one wavefront
         while (it < iterations) {
-            const int s2 = (int)((iterations - it < (unsigned)skew) ? iterations - it : (unsigned)skew);
-            JC_TRY(launch_sweeps_skewed<P>(ctx, d, z, chunk, s2, A, b, sor, *x, launches));
+            int s2 = (int)((iterations - it < (unsigned)skew) ? iterations - it : (unsigned)skew);
+            if (s2 > 32) s2 = 32;
+            for (int p = 0; p < 2 * s2; ++p) { w0[p] = z.k0; w1[p] = z.k1; }
+            JC_TRY(launch_sweeps_skewed<P>(ctx, d, w0, w1, 2 * s2, chunk, A, b, sor, *x, launches));
             it += (unsigned)s2;
         }
         return JETCU_OK;
@@ -289,6 +302,16 @@ static int launch_relax(jetcu_ctx* ctx, Dim3i d, ZRange z, bool halo, Mat A, con
     while (it < iterations) {
         const int k = halo ? (int)((iterations - it < (unsigned)kmax) ? iterations - it : (unsigned)kmax) : (int)(iterations - it);
         if (halo) JC_TRY(comm_halo_planes(ctx, *x, plane, z.k0, z.k1, d.nz, 2 * k));
+        if (halo && chunk > 0 && skew > 1 && z.k1 - z.k0 > chunk && k <= 32) {
+            // a slab's block of k sweeps between two exchanges as ONE wavefront: pass p works on the slab +- (2k - 1 - p) planes
+            for (int p = 0; p < 2 * k; ++p) {
+                const int e = 2 * k - 1 - p;
+                w0[p] = z.k0 - e < 0 ? 0 : z.k0 - e; w1[p] = z.k1 + e > d.nz ? d.nz : z.k1 + e;
+            }
+            JC_TRY(launch_sweeps_skewed<P>(ctx, d, w0, w1, 2 * k, chunk, A, b, sor, *x, launches));
+            it += (unsigned)k;
+            continue;
+        }
         for (int s2 = 0; s2 < k; ++s2) {
             const int er = halo ? 2 * (k - s2) - 1 : 0, eb = halo ? 2 * (k - s2) - 2 : 0;
             const ZRange rw{z.k0 - er < 0 ? 0 : z.k0 - er, z.k1 + er > d.nz ? d.nz : z.k1 + er};

@@ -1509,14 +1509,19 @@ int jetcu_hybrid_transfer_particles_to_grids(jetcu_hybrid* h) {
             for (int q = 0; q < 3; ++q) out.wsum[q] = h->wsum[q];
             out.marker[0] = h->um; out.marker[1] = h->vm; out.marker[2] = h->wm;
             // tiles are aligned to the GLOBAL cell lattice (not to the slab), so that every rank forms the same tile sums.
-            // APIC carries 3 more attributes per component through the cell loop: 256-thread tiles keep it in registers
-            const int TZ = apic ? P2G_TZ_APIC : P2G_TZ;
+            // Tile height: 8 cell planes (512 threads, one CTA per SM) for PIC / FLIP, 4 (256 threads) for APIC, which carries
+            // 3 more attributes per component through the cell loop and would spill at 128 registers; JETCU_P2G_TZ=4 selects
+            // the small tile for PIC / FLIP as well (two independent CTAs per SM instead of one).
+            static const int tz_env = getenv("JETCU_P2G_TZ") ? atoi(getenv("JETCU_P2G_TZ")) : 0;
+            const int TZ = (apic || tz_env == P2G_TZ_APIC) ? P2G_TZ_APIC : P2G_TZ;
             const int ntx = (g.nx + P2G_TX - 1) / P2G_TX, nty = (g.ny + P2G_TY - 1) / P2G_TY;
             const int tzlo = kb / TZ, tzhi = (ke - 1) / TZ;  // inclusive
             const size_t smem = (size_t)2 * P2G_SLOTS * P2G_TX * P2G_TY * TZ * sizeof(double);
+            const int threads = P2G_TX * P2G_TY * TZ;
             // per device, cheap: set on every call (the attribute belongs to the current device's copy of the function)
-            if (apic) JC_CUDA(ctx, cudaFuncSetAttribute((k_p2g_tile<true, P2G_TZ_APIC>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            else JC_CUDA(ctx, cudaFuncSetAttribute((k_p2g_tile<false, P2G_TZ>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            void (*kern)(GridD, int, int, int, int, int, const uint32_t*, AttrPtrs, P2GOut, int*) =
+                apic ? k_p2g_tile<true, P2G_TZ_APIC> : (TZ == P2G_TZ ? k_p2g_tile<false, P2G_TZ> : k_p2g_tile<false, P2G_TZ_APIC>);
+            JC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             for (int colour = 0; colour < 8; ++colour) {  // fixed colour order = the order in which a rim face receives its tiles
                 const int par_x = colour & 1, par_y = (colour >> 1) & 1, par_z = colour >> 2;
                 const int cx = (ntx - par_x + 1) / 2, cy = (nty - par_y + 1) / 2;
@@ -1524,10 +1529,7 @@ int jetcu_hybrid_transfer_particles_to_grids(jetcu_hybrid* h) {
                 const int cz = tz_first > tzhi ? 0 : (tzhi - tz_first) / 2 + 1;
                 if (cx <= 0 || cy <= 0 || cz <= 0) continue;
                 dim3 grid(cx, cy, cz);
-                if (apic) JC_LAUNCH(ctx, (k_p2g_tile<true, P2G_TZ_APIC>), grid, P2G_TX * P2G_TY * P2G_TZ_APIC, smem, g, par_x, par_y,
-                                    tz_first, kb, ke, h->cell_start, a, out, h->p2g_err);
-                else JC_LAUNCH(ctx, (k_p2g_tile<false, P2G_TZ>), grid, P2G_TX * P2G_TY * P2G_TZ, smem, g, par_x, par_y, tz_first, kb, ke,
-                               h->cell_start, a, out, h->p2g_err);
+                JC_LAUNCH(ctx, kern, grid, threads, smem, g, par_x, par_y, tz_first, kb, ke, h->cell_start, a, out, h->p2g_err);
             }
         }
         JC_LAUNCH(ctx, k_p2g_normalise, jc_blocks(nk * pu, 256), 256, 0, h->u + k0 * pu, h->wsum[0] + k0 * pu,

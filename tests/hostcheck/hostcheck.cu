@@ -731,6 +731,36 @@ int hc_packed_relax_skewed(uint32_t level, const double* b, double sor, unsigned
     return 0;
 }
 
+// launch_relax<true>'s slab branch with the wavefront on: one block of k sweeps on the slab [z0, z1) whose 2k halo planes
+// are valid in x (here: the whole array is), pass p on the slab +- (2k - 1 - p) planes, skewed over z-chunks.  Only the
+// planes [z0, z1) of the result are meaningful.
+int hc_packed_relax_skewed_slab(uint32_t level, const double* b, double sor, int k, int chunk, int z0, int z1, double* x) {
+    const HostLevel& L = g_sys.lv[level];
+    const int nx = L.nx, ny = L.ny, nz = L.nz;
+    auto colour_range = [&](int colour, int k0, int k1) {
+        for (int kk = k0; kk < k1; ++kk)
+            for (int j = 0; j < ny; ++j)
+                for (int i = (j + kk + colour) & 1; i < nx; i += 2) relax_cell_code(L.m, b, x, sor, i, j, kk, nx, ny, nz);
+    };
+    const int passes = 2 * k;
+    std::vector<int> w0(passes), w1(passes);
+    for (int p = 0; p < passes; ++p) {
+        const int e = 2 * k - 1 - p;
+        w0[p] = z0 - e < 0 ? 0 : z0 - e; w1[p] = z1 + e > nz ? nz : z1 + e;
+    }
+    for (int c0 = w0[0];; c0 += chunk) {
+        bool any = false;
+        for (int p = 0; p < passes; ++p) {
+            if (c0 - p >= w1[p]) continue;
+            any = true;
+            const int lo = c0 - p > w0[p] ? c0 - p : w0[p], hi = c0 + chunk - p < w1[p] ? c0 + chunk - p : w1[p];
+            if (lo < hi) colour_range(p & 1, lo, hi);
+        }
+        if (!any) break;
+    }
+    return 0;
+}
+
 // k_apply_gradient on level 0 of the last build
 int hc_apply_gradient(const double* x, const double* u_in, const double* v_in, const double* w_in, double* u_out, double* v_out, double* w_out) {
     const HostLevel& L = g_sys.lv[0];

@@ -108,6 +108,14 @@ def test_packed_pressure_system(hc, port, n, kind, collider, domain):
             xs = x.copy()
             hc.hc_packed_relax_skewed(C.c_uint32(l), dp(rhs), C.c_double(1.5), C.c_uint(5), C.c_int(chunk), C.c_int(skew), dp(xs))
             exact(xs, ref5, "skewed SOR wavefront level %d chunk %d skew %d" % (l, chunk, skew))
+        # a slab's communication-avoiding block of k sweeps (redundant halo windows shrinking by a plane per pass) as one
+        # wavefront: the owned planes carry the bits of k undivided sweeps
+        if m >= 8:
+            for k, chunk, (z0, z1) in ((2, 2, (0, m // 2)), (2, 3, (m // 2, m)), (1, 1, (m // 4, m // 2)), (3, 2, (m // 4, 3 * m // 4))):
+                refk = port.relax_red_black(want["A"], rhs, x, 1.5, k)
+                xs = x.copy()
+                hc.hc_packed_relax_skewed_slab(C.c_uint32(l), dp(rhs), C.c_double(1.5), C.c_int(k), C.c_int(chunk), C.c_int(z0), C.c_int(z1), dp(xs))
+                exact(xs[z0:z1], refk[z0:z1], "slab block wavefront level %d k %d chunk %d planes %d..%d" % (l, k, chunk, z0, z1))
     # applyPressureGradient with the oracle's pressure
     gu, gv, gw = sc["u"].copy(), sc["v"].copy(), sc["w"].copy()
     hc.hc_apply_gradient(dp(p), dp(sc["u"]), dp(sc["v"]), dp(sc["w"]), dp(gu), dp(gv), dp(gw))

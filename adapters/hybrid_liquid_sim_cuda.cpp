@@ -35,6 +35,7 @@ struct Options {
     std::string out = ".";
     std::string format = "none";
     bool hostEmit = false, compare = false;
+    bool iccg = false;   // the examples' own solver configuration: default FdmIccgSolver3 + setUseCompressedLinearSystem(true)
     double fps = 60.0;
 };
 
@@ -94,6 +95,10 @@ int run(const Options& opt) {
     size_t levels = 1;
     for (size_t n = opt.r; n % 2 == 0 && n > 8 && levels < 6; n /= 2) ++levels;
     auto cuda = std::make_shared<Cuda>(res, Vector3D(h, h, h), Vector3D(), jetcu::makeMgpcgParams(100, levels, 5, 5, 20, 20, 1e-9, 1.5, true));
+    if (opt.iccg) {   // src/examples/hybrid_liquid_sim/main.cpp:219: a default-constructed pressure solver (ICCG) + compressed system
+        cuda->setPressureSolver(std::make_shared<GridFractionalSinglePhasePressureSolver3>());
+        cuda->setUseCompressedLinearSystem(true);
+    }
     cuda->setHostMirror(opt.compare ? jetcu::HostMirror::kEveryStep : jetcu::HostMirror::kOnDemand);
     attachCollider(cuda, scene);
     size_t emitted = 0;
@@ -103,9 +108,9 @@ int run(const Options& opt) {
     if (opt.compare) {
         stock = std::make_shared<Stock>(res, Vector3D(h, h, h), Vector3D());
         auto pressure = std::make_shared<GridFractionalSinglePhasePressureSolver3>();
-        pressure->setLinearSystemSolver(std::make_shared<FdmMgpcgSolver3>(100, levels, 5, 5, 20, 20, 1e-9, 1.5, true));
+        if (!opt.iccg) pressure->setLinearSystemSolver(std::make_shared<FdmMgpcgSolver3>(100, levels, 5, 5, 20, 20, 1e-9, 1.5, true));
         stock->setPressureSolver(pressure);
-        stock->setUseCompressedLinearSystem(false);
+        stock->setUseCompressedLinearSystem(opt.iccg);
         attachCollider(stock, scene);
         attachHostEmitters(stock, scene, 0.5 * h);
     }
@@ -155,7 +160,8 @@ int main(int argc, char** argv) {
         else if (a == "-m") opt.format = next();
         else if (a == "--host-emit") opt.hostEmit = true;
         else if (a == "--compare") opt.compare = true;
-        else { std::fprintf(stderr, "usage: %s [-e 1|3|6] [-r N] [-f frames] [-o dir] [-m pos|xyz|none] [--host-emit] [--compare]\n", argv[0]); return 2; }
+        else if (a == "--iccg") opt.iccg = true;
+        else { std::fprintf(stderr, "usage: %s [-e 1|3|6] [-r N] [-f frames] [-o dir] [-m pos|xyz|none] [--host-emit] [--compare] [--iccg]\n", argv[0]); return 2; }
     }
     if (opt.format != "pos" && opt.format != "xyz" && opt.format != "none") { std::fprintf(stderr, "unknown format %s\n", opt.format.c_str()); return 2; }
     try {

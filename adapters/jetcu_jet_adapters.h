@@ -69,6 +69,14 @@ class Context {
 };
 typedef std::shared_ptr<Context> ContextPtr;
 
+inline jetcu_mgpcg_params makeMgpcgParams(unsigned int, size_t, unsigned int, unsigned int, unsigned int, unsigned int, double, double, bool);
+//! == constructor arguments of jet::FdmIccgSolver3 (Jet's default linear solver: 100 iterations, 1e-6)
+inline jetcu_mgpcg_params makeIccgParams(unsigned int maxNumberOfIterations = 100, double tolerance = 1e-6) {
+    jetcu_mgpcg_params p = makeMgpcgParams(maxNumberOfIterations, 1, 0, 0, 0, 0, tolerance, 1.0, true);
+    p.linear_solver = JETCU_SOLVER_ICCG;
+    return p;
+}
+
 inline jetcu_mgpcg_params makeMgpcgParams(unsigned int numberOfCgIter, size_t maxNumberOfLevels,
                                           unsigned int numberOfRestrictionIter, unsigned int numberOfCorrectionIter,
                                           unsigned int numberOfCoarsestIter, unsigned int numberOfFinalIter,
@@ -139,6 +147,44 @@ class CudaFdmMgpcgSolver3 final : public jet::FdmMgSolver3 {
 };
 typedef std::shared_ptr<CudaFdmMgpcgSolver3> CudaFdmMgpcgSolver3Ptr;
 
+//! Drop-in for jet::FdmIccgSolver3 (`final`, include/jet/fdm_iccg_solver3.h:18), the default linear solver of Jet's pressure and
+//! diffusion solvers: same constructor arguments, same accessors.  solve(FdmLinearSystem3*) runs on the device
+//! (jetcu_iccg_solve: incomplete-Cholesky substitutions as tile-hyperplane sweeps).  solveCompressed is NOT taken over — the
+//! base class's `return false` stays, which makes GridFractionalSinglePhasePressureSolver3 report failure rather than use
+//! another code path; install it with setUseCompressedLinearSystem(false), or use the seam-2 / seam-3 classes, which accept the
+//! compressed flag and solve the equivalent uncompressed system on the device.
+class CudaFdmIccgSolver3 final : public jet::FdmLinearSystemSolver3 {
+ public:
+    CudaFdmIccgSolver3(unsigned int maxNumberOfIterations, double tolerance, ContextPtr ctx = ContextPtr())
+        : _ctx(ctx ? ctx : Context::shared()), _maxIter(maxNumberOfIterations), _tol(tolerance) {
+        std::memset(&_last, 0, sizeof(_last));
+    }
+
+    bool solve(jet::FdmLinearSystem3* system) override {
+        const jet::Size3 n = system->A.size();
+        JET_THROW_INVALID_ARG_IF(system->b.size() != n);
+        JET_THROW_INVALID_ARG_IF(system->x.size() != n);
+        if (n.x * n.y * n.z == 0) return true;
+        static_assert(sizeof(jet::FdmMatrixRow3) == sizeof(jetcu_matrix_row), "FdmMatrixRow3 must be 4 doubles");
+        _ctx->check(jetcu_iccg_solve(_ctx->get(), n.x, n.y, n.z, reinterpret_cast<const jetcu_matrix_row*>(system->A.data()),
+                                     system->b.data(), system->x.data(), _maxIter, _tol, &_last));
+        return _last.returned != 0;
+    }
+
+    unsigned int maxNumberOfIterations() const { return _maxIter; }
+    unsigned int lastNumberOfIterations() const { return _last.iterations; }
+    double tolerance() const { return _tol; }
+    double lastResidual() const { return _last.last_residual; }
+    double lastSolveMilliseconds() const { return _last.solve_ms; }
+
+ private:
+    ContextPtr _ctx;
+    unsigned int _maxIter;
+    double _tol;
+    jetcu_mgpcg_result _last;
+};
+typedef std::shared_ptr<CudaFdmIccgSolver3> CudaFdmIccgSolver3Ptr;
+
 namespace detail {
 
 //! MGPCG parameters of whatever linear solver a Jet pressure solver carries (FdmMgpcgSolver3 or our seam-1 class).
@@ -155,6 +201,18 @@ inline bool mgpcgParamsOf(const jet::FdmLinearSystemSolver3Ptr& lin, jetcu_mgpcg
         return true;
     }
     return false;
+}
+
+//! Parameters of an ICCG linear solver (Jet's FdmIccgSolver3 or our CudaFdmIccgSolver3) as jetcu parameters.
+inline bool iccgParamsOf(const jet::FdmLinearSystemSolver3Ptr& lin, jetcu_mgpcg_params* out) {
+    unsigned int it = 0;
+    double tol = 0.0;
+    if (auto s = std::dynamic_pointer_cast<jet::FdmIccgSolver3>(lin)) { it = s->maxNumberOfIterations(); tol = s->tolerance(); }
+    else if (auto c = std::dynamic_pointer_cast<CudaFdmIccgSolver3>(lin)) { it = c->maxNumberOfIterations(); tol = c->tolerance(); }
+    else return false;
+    *out = makeMgpcgParams(it, 1, 0, 0, 0, 0, tol, 1.0, true);
+    out->linear_solver = JETCU_SOLVER_ICCG;
+    return true;
 }
 
 //! Cell-centred samples of a ScalarField3 for grid (res, h, origin): the raw array when the field already is a
@@ -262,7 +320,10 @@ class CudaGridFractionalSinglePhasePressureSolver3 final : public jet::GridPress
         // _mgSystemSolver->solve(&_mgSystem) (src/jet/grid_fractional_single_phase_pressure_solver3.cpp:465-481, 651-690).
         // So setUseCompressedLinearSystem(true), as Jet's examples do, changes nothing here either (checked on the CPU by
         // `dropin_check_next --what compressed`: stock Jet with MGPCG, flag on vs off, bit-identical particles).
-        (void)useCompressed;
+        // With ICCG parameters (params.linear_solver = JETCU_SOLVER_ICCG, e.g. from makeIccgParams) the flag is forwarded: the
+        // device then solves the reference's compressed system in its equivalent uncompressed form.
+        jetcu_mgpcg_params prm = _p;
+        if ((prm.linear_solver & JETCU_SOLVER_ICCG) && useCompressed) prm.linear_solver |= JETCU_SOLVER_COMPRESSED;
         const jet::Size3 res = input.resolution();
         JET_THROW_INVALID_ARG_IF(output->resolution() != res);
         const jet::Vector3D h = input.gridSpacing(), o = input.origin();
@@ -305,7 +366,7 @@ class CudaGridFractionalSinglePhasePressureSolver3 final : public jet::GridPress
 
         _pressure.resize(res);
         _ctx->check(jetcu_pressure_solve(_ctx->get(), &g, input.uConstAccessor().data(), input.vConstAccessor().data(),
-                                         input.wConstAccessor().data(), csdf, bu, bv, bw, fsdf, &_p,
+                                         input.wConstAccessor().data(), csdf, bu, bv, bw, fsdf, &prm,
                                          output->uAccessor().data(), output->vAccessor().data(),
                                          output->wAccessor().data(), _pressure.data(), &_last));
     }
@@ -461,10 +522,9 @@ class CudaHybridSolver3 : public Base {
 
     //! Reads the solver's knobs from the Jet object EVERY step (setGravity / setMaxCfl / setClosedDomainBoundaryFlag /
     //! setPicBlendingFactor / a re-configured linear solver between steps are honoured like in GridFluidSolver3) and creates
-    //! the device solver on first use.  The pressure solve on the device is MGPCG; a Jet-side linear system solver that is
-    //! not an FdmMgpcgSolver3 / CudaFdmMgpcgSolver3 (e.g. the FdmIccgSolver3 a default-constructed
-    //! GridFractionalSinglePhasePressureSolver3 carries) is an error unless the caller opted in with
-    //! setAllowSolverSubstitution(true), in which case the constructor's MGPCG parameters are used.
+    //! the device solver on first use.  The pressure solve on the device is MGPCG or ICCG, whichever the Jet-side pressure
+    //! solver carries (FdmMgpcgSolver3 / FdmIccgSolver3 or their Cuda* counterparts); any other linear system solver is an
+    //! error unless the caller opted in with setAllowSolverSubstitution(true) (then: the constructor's MGPCG parameters).
     void ensureDevice() {
         jetcu_hybrid_params p;
         jetcu_hybrid_default_params(&p);
@@ -486,11 +546,16 @@ class CudaHybridSolver3 : public Base {
         jetcu_mgpcg_params fromJet;
         if (cu) mg = cu->cudaParams();
         else if (frac && detail::mgpcgParamsOf(frac->linearSystemSolver(), &fromJet)) mg = fromJet;
-        else if (!_allowSolverSubstitution)
+        else if (frac && detail::iccgParamsOf(frac->linearSystemSolver(), &fromJet)) {
+            // Jet's default solver (what src/examples/hybrid_liquid_sim runs): ICCG on the device; the compressed-system flag
+            // selects the same linear system without its identity rows in the reference and is solved uncompressed here
+            mg = fromJet;
+            if (this->useCompressedLinearSystem()) mg.linear_solver |= JETCU_SOLVER_COMPRESSED;
+        } else if (!_allowSolverSubstitution)
             throw std::runtime_error(
-                "jetcu: the pressure solver installed on this solver does not carry an MGPCG linear system solver (Jet's "
-                "default is FdmIccgSolver3); the device path solves with MGPCG only. Install FdmMgpcgSolver3 / "
-                "CudaFdmMgpcgSolver3, or call setAllowSolverSubstitution(true) to use the constructor's MGPCG parameters");
+                "jetcu: the pressure solver installed on this solver carries neither an MGPCG nor an ICCG linear system solver; "
+                "the device path implements FdmMgpcgSolver3 and FdmIccgSolver3. Install one of them (or their Cuda* "
+                "counterparts), or call setAllowSolverSubstitution(true) to use the constructor's MGPCG parameters");
         p.mgpcg = mg;
         if (_h && std::memcmp(&p, &_params, sizeof(p)) == 0) return;
         if (_h && std::memcmp(&p.grid, &_params.grid, sizeof(p.grid)) == 0) {

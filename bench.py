@@ -632,7 +632,8 @@ def main():
     ap.add_argument("--mode", default="flip", choices=["flip", "apic", "pic"])
     ap.add_argument("--ref-budget-s", type=float, default=float(os.environ.get("JETCU_REF_BUDGET_S", "420")),
                     help="--impl reference: wall budget for the real-size CPU run")
-    ap.add_argument("--n", type=int, default=256)
+    ap.add_argument("--n", "--grid", dest="n", type=int, default=256,
+                    help="grid size n^3 (use --grid under torchrun: its own parser finds --n ambiguous)")
     ap.add_argument("--dt", type=float, default=1.0 / 240.0)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--sample-n", type=int, default=0, help="grid size of the CPU sample (0 = automatic)")

@@ -360,6 +360,38 @@ int jetcu_mgpcg_solve(jetcu_ctx* ctx, uint64_t nx, uint64_t ny, uint64_t nz, uin
     return rc;
 }
 
+int jetcu_iccg_solve(jetcu_ctx* ctx, uint64_t nx, uint64_t ny, uint64_t nz, const jetcu_matrix_row* A, const double* b, double* x,
+                     uint32_t max_iterations, double tolerance, jetcu_mgpcg_result* result) {
+    JC_ENTER(ctx);
+    JC_TRY(check_dims(ctx, nx, ny, nz));
+    JC_ARG(ctx, A && b && x);
+    const size_t n = nx * ny * nz;
+    DevMat m(ctx);
+    DevVec db(ctx), dx(ctx);
+    JC_TRY(m.upload(A, n)); JC_TRY(db.upload(b, n)); JC_TRY(dx.upload(nullptr, n));
+    JC_TRY(iccg_solve_device(ctx, Dim3i{(int)nx, (int)ny, (int)nz}, mat_of(m.A), db.p, dx.p, max_iterations, tolerance, result));
+    JC_TRY(jc_d2h(ctx, x, dx.p, n));
+    return jc_sync(ctx);
+}
+
+int jetcu_iccg_precondition(jetcu_ctx* ctx, uint64_t nx, uint64_t ny, uint64_t nz, const jetcu_matrix_row* A, const double* b,
+                            double* d, double* y, double* x) {
+    JC_ENTER(ctx);
+    JC_TRY(check_dims(ctx, nx, ny, nz));
+    JC_ARG(ctx, A && b && y && x);
+    const size_t n = nx * ny * nz;
+    const Dim3i dim{(int)nx, (int)ny, (int)nz};
+    DevMat m(ctx);
+    DevVec db(ctx), dd(ctx), dy(ctx), dx(ctx);
+    JC_TRY(m.upload(A, n)); JC_TRY(db.upload(b, n)); JC_TRY(dd.upload(nullptr, n)); JC_TRY(dy.upload(nullptr, n));
+    JC_TRY(dx.upload(nullptr, n));
+    JC_TRY(iccg_build(ctx, dim, mat_of(m.A), dd.p));
+    JC_TRY(iccg_precondition(ctx, dim, mat_of(m.A), dd.p, db.p, dy.p, dx.p));
+    if (d) JC_TRY(jc_d2h(ctx, d, dd.p, n));
+    JC_TRY(jc_d2h(ctx, y, dy.p, n)); JC_TRY(jc_d2h(ctx, x, dx.p, n));
+    return jc_sync(ctx);
+}
+
 // ---------------------------------------------------------------------------------------------- seam 2
 int jetcu_pressure_solve(jetcu_ctx* ctx, const jetcu_grid* g, const double* u_in, const double* v_in,
                          const double* w_in, const double* collider_sdf, const double* bnd_u, const double* bnd_v,

@@ -81,3 +81,9 @@ int mg_vcycle(jetcu_ctx* ctx, MgLevels* mg, const jetcu_mgpcg_params* p, int lev
 // Solves A[0] x = b with MG-preconditioned CG exactly as FdmMgpcgSolver3 does. b, x: device, level-0 size.
 int mgpcg_solve_device(jetcu_ctx* ctx, MgLevels* mg, const double* b, double* x, const jetcu_mgpcg_params* p,
                        jetcu_mgpcg_result* result);
+
+// FdmIccgSolver3 (iccg.cu): incomplete-Cholesky preconditioned CG on one level, tile-hyperplane substitutions
+int iccg_build(jetcu_ctx* ctx, Dim3i d, Mat A, double* dinv);
+int iccg_precondition(jetcu_ctx* ctx, Dim3i d, Mat A, const double* dinv, const double* b, double* y, double* x);
+int iccg_solve_device(jetcu_ctx* ctx, Dim3i d, Mat A, const double* b, double* x, uint32_t max_iterations, double tolerance,
+                      jetcu_mgpcg_result* result);

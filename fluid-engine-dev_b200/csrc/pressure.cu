@@ -138,7 +138,14 @@ int pressure_solve_device(jetcu_ctx* ctx, PressureSystem* ps, const double* u_in
         ps->mg.A[l] = m;
         hx *= 2.0; hy *= 2.0; hz *= 2.0;
     }
-    JC_TRY(mgpcg_solve_device(ctx, &ps->mg, ps->b0, ps->x0, p, result));
+    // FdmIccgSolver3 (Jet's default) works on the single level-0 system — buildSingleSystem is the same function in both paths
+    // (…pressure_solver3.cpp:651-713) — and so does the device.  useCompressedLinearSystem(true) (JETCU_SOLVER_COMPRESSED)
+    // asks the reference to drop the air rows (buildCompressedSystem, :269-444); they are identity rows with b = 0 that no
+    // liquid row couples to, so the liquid-cell solution is the same and the device keeps the uncompressed layout.
+    if (p->linear_solver & JETCU_SOLVER_ICCG)
+        JC_TRY(iccg_solve_device(ctx, ps->dims[0], ps->mg.A[0], ps->b0, ps->x0, p->max_iterations, p->tolerance, result));
+    else
+        JC_TRY(mgpcg_solve_device(ctx, &ps->mg, ps->b0, ps->x0, p, result));
     JC_LAUNCH(ctx, k_apply_gradient, pgrid(g.nx, g.ny, g.nz), blk, 0, g.nx, g.ny, g.nz, g.hx, g.hy, g.hz, ps->sdf[0],
               ps->uw[0], ps->vw[0], ps->ww[0], ps->x0, u_in, v_in, w_in, u_out, v_out, w_out);
     return JETCU_OK;

@@ -29,13 +29,19 @@ ROW_DTYPE = np.dtype([("center", "<f8"), ("right", "<f8"), ("up", "<f8"), ("fron
 class MgpcgParams(C.Structure):
     _fields_ = [("max_iterations", u32), ("max_levels", u32), ("n_restriction", u32), ("n_correction", u32),
                 ("n_coarsest", u32), ("n_final", u32), ("tolerance", f64), ("sor_factor", f64),
-                ("use_red_black", C.c_int32), ("reserved", C.c_int32)]
+                ("use_red_black", C.c_int32), ("linear_solver", C.c_int32)]
 
     @classmethod
     def make(cls, max_iterations=100, max_levels=5, n_restriction=5, n_correction=5, n_coarsest=20, n_final=20,
              tolerance=1e-9, sor_factor=1.5, use_red_black=True):
         return cls(max_iterations, max_levels, n_restriction, n_correction, n_coarsest, n_final, tolerance,
                    sor_factor, 1 if use_red_black else 0, 0)
+
+    @classmethod
+    def iccg(cls, max_iterations=100, tolerance=1e-6, compressed=False):
+        """FdmIccgSolver3(maxNumberOfIterations, tolerance) — Jet's default linear solver — as the pressure solve's solver;
+        compressed = GridFluidSolver3::setUseCompressedLinearSystem(true) (the device solves the same system uncompressed)."""
+        return cls(max_iterations, 1, 0, 0, 0, 0, tolerance, 1.0, 1, 1 | (2 if compressed else 0))
 
 
 class MgpcgResult(C.Structure):
@@ -320,6 +326,22 @@ class LinearApi:
         self._call("mgpcg_solve", u64(nx), u64(ny), u64(nz), u32(len(A_levels)), self._level_ptrs(A_levels), _p(b),
                    _p(x), C.byref(params), C.byref(res))
         return x, res
+
+    def iccg_solve(self, A, b, max_iterations=100, tolerance=1e-6):
+        nz, ny, nx = b.shape
+        x = np.zeros_like(b)
+        res = MgpcgResult()
+        A = np.ascontiguousarray(A)
+        self._call("iccg_solve", u64(nx), u64(ny), u64(nz), A.ctypes.data_as(C.POINTER(Row)), _p(b), _p(x), u32(max_iterations),
+                   f64(tolerance), C.byref(res))
+        return x, res
+
+    def iccg_precondition(self, A, b):
+        nz, ny, nx = b.shape
+        d, y, x = np.zeros_like(b), np.zeros_like(b), np.zeros_like(b)
+        A = np.ascontiguousarray(A)
+        self._call("iccg_precondition", u64(nx), u64(ny), u64(nz), A.ctypes.data_as(C.POINTER(Row)), _p(b), _p(d), _p(y), _p(x))
+        return d, y, x
 
     def pressure_solve(self, grid, u, v, w, params, collider_sdf=None, bnd=(None, None, None), fluid_sdf=None,
                        out=None, want_pressure=True):

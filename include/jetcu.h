@@ -118,8 +118,11 @@ typedef struct jetcu_mgpcg_params {
     double tolerance;           /* maxTolerance */
     double sor_factor;          /* sorFactor */
     int32_t use_red_black;      /* useRedBlackOrdering; 0 -> JETCU_ERR_UNSUPPORTED */
-    int32_t reserved;
+    int32_t linear_solver;      /* which FdmLinearSystemSolver3 the pressure solve runs: JETCU_SOLVER_MGPCG (0, all fields
+                                   above apply) or JETCU_SOLVER_ICCG (FdmIccgSolver3: max_iterations and tolerance apply,
+                                   one level), optionally | JETCU_SOLVER_COMPRESSED (see jetcu_pressure_solve) */
 } jetcu_mgpcg_params;
+enum { JETCU_SOLVER_MGPCG = 0, JETCU_SOLVER_ICCG = 1, JETCU_SOLVER_COMPRESSED = 2 };
 
 typedef struct jetcu_mgpcg_result {
     uint32_t iterations;        /* FdmMgpcgSolver3::lastNumberOfIterations() */
@@ -179,6 +182,17 @@ int jetcu_fdm_vcycle(jetcu_ctx*, uint64_t nx, uint64_t ny, uint64_t nz, uint32_t
 int jetcu_mgpcg_solve(jetcu_ctx*, uint64_t nx, uint64_t ny, uint64_t nz, uint32_t levels,
                       const jetcu_matrix_row* const* A, const double* b, double* x,
                       const jetcu_mgpcg_params* params, jetcu_mgpcg_result* result);
+
+/* == jet::FdmIccgSolver3::solve(FdmLinearSystem3*) (src/jet/fdm_iccg_solver3.cpp:152-188): incomplete-Cholesky preconditioned
+ * CG, x = 0 initial guess, exit on sigma <= tolerance^2 or max_iterations; the preconditioner's lexicographic recurrences
+ * (:14-70) run as tile-hyperplane sweeps with the reference's per-cell arithmetic.  The default linear solver of Jet's
+ * pressure solvers (100 iterations, 1e-6).  Single GPU. */
+int jetcu_iccg_solve(jetcu_ctx*, uint64_t nx, uint64_t ny, uint64_t nz, const jetcu_matrix_row* A, const double* b, double* x,
+                     uint32_t max_iterations, double tolerance, jetcu_mgpcg_result* result);
+/* Preconditioner::build + Preconditioner::solve on their own (parity tests): d (optional), y and x receive the incomplete-
+ * Cholesky diagonal, the forward and the backward substitution of b. */
+int jetcu_iccg_precondition(jetcu_ctx*, uint64_t nx, uint64_t ny, uint64_t nz, const jetcu_matrix_row* A, const double* b,
+                            double* d, double* y, double* x);
 
 /* Number of MG levels Jet builds for a finest resolution (FdmMgUtils3::resizeArrayWithFinest,
  * include/jet/detail/fdm_mg_linear_system3-inl.h:34-50). */

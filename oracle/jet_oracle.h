@@ -27,7 +27,7 @@ typedef struct jeto_row { double center, right, up, front; } jeto_row;
 typedef struct jeto_mgpcg_params {
     uint32_t max_iterations, max_levels, n_restriction, n_correction, n_coarsest, n_final;
     double tolerance, sor_factor;
-    int32_t use_red_black, reserved;
+    int32_t use_red_black, linear_solver;   /* linear_solver: 0 MGPCG, 1 ICCG, | 2 = useCompressedLinearSystem */
 } jeto_mgpcg_params;
 
 typedef struct jeto_mgpcg_result {
@@ -73,6 +73,11 @@ int jeto_fdm_vcycle(uint64_t nx, uint64_t ny, uint64_t nz, uint32_t levels, cons
                     const double* b, double* x, const jeto_mgpcg_params* params);
 int jeto_mgpcg_solve(uint64_t nx, uint64_t ny, uint64_t nz, uint32_t levels, const jeto_row* const* A,
                      const double* b, double* x, const jeto_mgpcg_params* params, jeto_mgpcg_result* result);
+/* FdmIccgSolver3::solve(FdmLinearSystem3*) and its Preconditioner::build / solve (src/jet/fdm_iccg_solver3.cpp:14-70,152-188) */
+int jeto_iccg_solve(uint64_t nx, uint64_t ny, uint64_t nz, const jeto_row* A, const double* b, double* x,
+                    uint32_t max_iterations, double tolerance, jeto_mgpcg_result* result);
+int jeto_iccg_precondition(uint64_t nx, uint64_t ny, uint64_t nz, const jeto_row* A, const double* b, double* d, double* y,
+                           double* x);
 uint32_t jeto_mg_num_levels(uint64_t nx, uint64_t ny, uint64_t nz, uint32_t max_levels);
 
 int jeto_pressure_solve(const jeto_grid* grid, const double* u_in, const double* v_in, const double* w_in,

@@ -340,6 +340,104 @@ int jeto_mgpcg_solve(uint64_t nx, uint64_t ny, uint64_t nz, uint32_t levels, con
     return mgpcg_core(nx, ny, nz, levels, A, b, x, p, result);
 }
 
+/* ====================================================================== ICCG */
+/* FdmIccgSolver3::Preconditioner::build — src/jet/fdm_iccg_solver3.cpp:14-36 (lexicographic recurrence). */
+static void ic_build(ssz nx, ssz ny, ssz nz, const jeto_row* A, double* d) {
+    for (ssz k = 0; k < nz; ++k)
+        for (ssz j = 0; j < ny; ++j)
+            for (ssz i = 0; i < nx; ++i) {
+                size_t c = IDX(i, j, k, nx, ny);
+                double denom = A[c].center - ((i > 0) ? (A[c - 1].right * A[c - 1].right) * d[c - 1] : 0.0) -
+                               ((j > 0) ? (A[c - nx].up * A[c - nx].up) * d[c - nx] : 0.0) -
+                               ((k > 0) ? (A[c - nx * ny].front * A[c - nx * ny].front) * d[c - nx * ny] : 0.0);
+                d[c] = (fabs(denom) > 0.0) ? 1.0 / denom : 0.0;
+            }
+}
+
+/* FdmIccgSolver3::Preconditioner::solve — :38-70: forward substitution into y, backward into x. */
+static void ic_solve(ssz nx, ssz ny, ssz nz, const jeto_row* A, const double* d, const double* b, double* y, double* x) {
+    for (ssz k = 0; k < nz; ++k)
+        for (ssz j = 0; j < ny; ++j)
+            for (ssz i = 0; i < nx; ++i) {
+                size_t c = IDX(i, j, k, nx, ny);
+                y[c] = (b[c] - ((i > 0) ? A[c - 1].right * y[c - 1] : 0.0) - ((j > 0) ? A[c - nx].up * y[c - nx] : 0.0) -
+                        ((k > 0) ? A[c - nx * ny].front * y[c - nx * ny] : 0.0)) * d[c];
+            }
+    for (ssz k = nz - 1; k >= 0; --k)
+        for (ssz j = ny - 1; j >= 0; --j)
+            for (ssz i = nx - 1; i >= 0; --i) {
+                size_t c = IDX(i, j, k, nx, ny);
+                x[c] = (y[c] - ((i + 1 < nx) ? A[c].right * x[c + 1] : 0.0) - ((j + 1 < ny) ? A[c].up * x[c + nx] : 0.0) -
+                        ((k + 1 < nz) ? A[c].front * x[c + nx * ny] : 0.0)) * d[c];
+            }
+}
+
+int jeto_iccg_precondition(uint64_t nx, uint64_t ny, uint64_t nz, const jeto_row* A, const double* b, double* d, double* y,
+                           double* x) {
+    size_t n = (size_t)nx * ny * nz;
+    double* dd = d ? d : (double*)calloc(n, sizeof(double));
+    ic_build((ssz)nx, (ssz)ny, (ssz)nz, A, dd);
+    ic_solve((ssz)nx, (ssz)ny, (ssz)nz, A, dd, b, y, x);
+    if (!d) free(dd);
+    return 0;
+}
+
+/* FdmIccgSolver3::solve(FdmLinearSystem3*) — :152-188 = pcg<FdmBlas3, Preconditioner> (cg-inl.h:18-94) with x = 0. */
+int jeto_iccg_solve(uint64_t nx, uint64_t ny, uint64_t nz, const jeto_row* A, const double* b, double* x,
+                    uint32_t max_iterations, double tolerance, jeto_mgpcg_result* result) {
+    size_t n = (size_t)nx * ny * nz;
+    double* r = (double*)calloc(n, sizeof(double));
+    double* d = (double*)calloc(n, sizeof(double));
+    double* q = (double*)calloc(n, sizeof(double));
+    double* s = (double*)calloc(n, sizeof(double));
+    double* dinv = (double*)calloc(n, sizeof(double));
+    double* y = (double*)calloc(n, sizeof(double));
+    double t0 = now_ms();
+    memset(x, 0, n * sizeof(double));
+    ic_build((ssz)nx, (ssz)ny, (ssz)nz, A, dinv);
+    jeto_fdm_residual(nx, ny, nz, A, x, b, r);
+    ic_solve((ssz)nx, (ssz)ny, (ssz)nz, A, dinv, r, y, d);
+    double sigmaNew;
+    jeto_fdm_dot(n, r, d, &sigmaNew);
+    uint32_t iter = 0;
+    int trigger = 0;
+    while (sigmaNew > tolerance * tolerance && iter < max_iterations) {
+        jeto_fdm_mvm(nx, ny, nz, A, d, q);
+        double dq;
+        jeto_fdm_dot(n, d, q, &dq);
+        double alpha = sigmaNew / dq;
+        jeto_fdm_axpy(n, alpha, d, x, x);
+        if (trigger || (iter % 50 == 0 && iter > 0)) {
+            jeto_fdm_residual(nx, ny, nz, A, x, b, r);
+            trigger = 0;
+        } else {
+            jeto_fdm_axpy(n, -alpha, q, r, r);
+        }
+        ic_solve((ssz)nx, (ssz)ny, (ssz)nz, A, dinv, r, y, s);
+        double sigmaOld = sigmaNew;
+        jeto_fdm_dot(n, r, s, &sigmaNew);
+        if (sigmaNew > sigmaOld) trigger = 1;
+        double beta = sigmaNew / sigmaOld;
+        jeto_fdm_axpy(n, beta, d, s, d);
+        ++iter;
+    }
+    double t1 = now_ms();
+    if (result) {
+        result->iterations = iter;
+        result->last_residual = sqrt(fabs(sigmaNew));
+        result->returned = (result->last_residual <= tolerance || iter < max_iterations) ? 1 : 0;
+        jeto_fdm_residual(nx, ny, nz, A, x, b, r);
+        double rr, bb;
+        jeto_fdm_dot(n, r, r, &rr);
+        jeto_fdm_dot(n, b, b, &bb);
+        result->true_residual_l2 = sqrt(rr);
+        result->b_l2 = sqrt(bb);
+        result->solve_ms = t1 - t0;
+    }
+    free(r); free(d); free(q); free(s); free(dinv); free(y);
+    return 0;
+}
+
 /* ====================================================================== samplers */
 
 /* getBarycentric — include/jet/detail/math_utils-inl.h:146-174 (iLow is always 0 on this path). */
@@ -710,7 +808,11 @@ static int pressure_core(const jeto_grid* g, const double* u_in, const double* v
     }
     const jeto_row* Ac[16];
     for (uint32_t l = 0; l < S->levels; ++l) Ac[l] = S->A[l];
-    int rc = mgpcg_core(nx, ny, nz, S->levels, Ac, S->b0, S->x0, p, result);
+    /* FdmIccgSolver3 works on the level-0 system alone; with useCompressedLinearSystem the reference drops the air rows
+     * (identity rows, b = 0, uncoupled): the port solves the uncompressed system in both cases (same solution on the liquid
+     * cells to rounding; the unmodified reference covers the compressed arithmetic itself). */
+    int rc = (p->linear_solver & 1) ? jeto_iccg_solve(nx, ny, nz, S->A[0], S->b0, S->x0, p->max_iterations, p->tolerance, result)
+                                    : mgpcg_core(nx, ny, nz, S->levels, Ac, S->b0, S->x0, p, result);
     if (rc) return rc;
 
     /* applyPressureGradient — :715-765 */

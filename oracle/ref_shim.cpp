@@ -192,6 +192,47 @@ int jeto_mgpcg_solve(uint64_t nx, uint64_t ny, uint64_t nz, uint32_t levels, con
     return 0;
 }
 
+// FdmIccgSolver3::solve(FdmLinearSystem3*) — the reference's own object on a caller-supplied system
+int jeto_iccg_solve(uint64_t nx, uint64_t ny, uint64_t nz, const jeto_row* A, const double* b, double* x,
+                    uint32_t max_iterations, double tolerance, jeto_mgpcg_result* result) {
+    FdmLinearSystem3 sys;
+    const Size3 size(nx, ny, nz);
+    sys.A.resize(size); sys.b.resize(size); sys.x.resize(size);
+    fillMatrix(&sys.A, A, size);
+    fillVector(&sys.b, b, size);
+    FdmIccgSolver3 solver(max_iterations, tolerance);
+    double t0 = nowMs();
+    bool ret = solver.solve(&sys);
+    double t1 = nowMs();
+    copyOut(x, sys.x);
+    if (result) {
+        result->iterations = solver.lastNumberOfIterations();
+        result->returned = ret ? 1 : 0;
+        result->last_residual = solver.lastResidual();
+        result->true_residual_l2 = trueResidual(sys.A, sys.x, sys.b);
+        result->b_l2 = FdmBlas3::l2Norm(sys.b);
+        result->solve_ms = t1 - t0;
+    }
+    return 0;
+}
+
+// FdmIccgSolver3::Preconditioner::build / solve on their own
+int jeto_iccg_precondition(uint64_t nx, uint64_t ny, uint64_t nz, const jeto_row* A, const double* b, double* d, double* y,
+                           double* x) {
+    const Size3 size(nx, ny, nz);
+    FdmMatrix3 m(size);
+    FdmVector3 rhs(size), out(size);
+    fillMatrix(&m, A, size);
+    fillVector(&rhs, b, size);
+    FdmIccgSolver3::Preconditioner pre;
+    pre.build(m);
+    pre.solve(rhs, &out);
+    if (d) copyOut(d, pre.d);
+    copyOut(y, pre.y);
+    copyOut(x, out);
+    return 0;
+}
+
 int jeto_pressure_solve(const jeto_grid* g, const double* u_in, const double* v_in, const double* w_in,
                         const double* collider_sdf, const double* bnd_u, const double* bnd_v, const double* bnd_w,
                         const double* fluid_sdf, const jeto_mgpcg_params* p, double* u_out, double* v_out,
@@ -250,6 +291,37 @@ int jeto_pressure_solve(const jeto_grid* g, const double* u_in, const double* v_
     }
 
     g_lastPressureSolver.reset(new GridFractionalSinglePhasePressureSolver3());
+    if (p->linear_solver & 1) {   // FdmIccgSolver3, optionally on the compressed (liquid cells only) system
+        auto iccg = std::make_shared<FdmIccgSolver3>(p->max_iterations, p->tolerance);
+        g_lastPressureSolver->setLinearSystemSolver(iccg);
+        const bool compressed = (p->linear_solver & 2) != 0;
+        double t0 = nowMs();
+        g_lastPressureSolver->solve(input, 0.0, &output, *bsdf, *bvel, *fsdf, compressed);
+        double t1 = nowMs();
+        std::memcpy(u_out, output.uAccessor().data(), nu * sizeof(double));
+        std::memcpy(v_out, output.vAccessor().data(), nv * sizeof(double));
+        std::memcpy(w_out, output.wAccessor().data(), nw * sizeof(double));
+        if (pressure_out) copyOut(pressure_out, g_lastPressureSolver->pressure());
+        if (result) {
+            result->iterations = iccg->lastNumberOfIterations();
+            result->last_residual = iccg->lastResidual();
+            result->returned = (iccg->lastResidual() <= iccg->tolerance() ||
+                                iccg->lastNumberOfIterations() < iccg->maxNumberOfIterations()) ? 1 : 0;
+            if (compressed) {
+                const auto& cs = g_lastPressureSolver->_compSystem;
+                VectorND r(cs.b.size());
+                FdmCompressedBlas3::residual(cs.A, cs.x, cs.b, &r);
+                result->true_residual_l2 = FdmCompressedBlas3::l2Norm(r);
+                result->b_l2 = FdmCompressedBlas3::l2Norm(cs.b);
+            } else {
+                const auto& sys = g_lastPressureSolver->_system;
+                result->true_residual_l2 = trueResidual(sys.A, sys.x, sys.b);
+                result->b_l2 = FdmBlas3::l2Norm(sys.b);
+            }
+            result->solve_ms = t1 - t0;
+        }
+        return 0;
+    }
     auto lin = makeMgpcg(p);
     g_lastPressureSolver->setLinearSystemSolver(lin);
     double t0 = nowMs();
@@ -325,6 +397,7 @@ int jeto_bin_points_serial(uint64_t n, const double* positions, uint64_t rx, uin
 struct jeto_hybrid {
     std::shared_ptr<PicSolver3> solver;
     std::shared_ptr<FdmMgpcgSolver3> lin;
+    std::shared_ptr<FdmIccgSolver3> iccg;   // when params.mgpcg.linear_solver & 1
     std::shared_ptr<GridFractionalSinglePhasePressureSolver3> pressure;
     int mode;
 };
@@ -343,14 +416,19 @@ int jeto_hybrid_create(const jeto_hybrid_params* p, jeto_hybrid** out) {
     } else {
         h->solver = std::make_shared<ApicSolver3>(res, hh, o);
     }
-    h->lin = makeMgpcg(&p->mgpcg);
     h->pressure = std::make_shared<GridFractionalSinglePhasePressureSolver3>();
-    h->pressure->setLinearSystemSolver(h->lin);
+    if (p->mgpcg.linear_solver & 1) {   // Jet's default solver, as the hybrid_liquid_sim examples run it
+        h->iccg = std::make_shared<FdmIccgSolver3>(p->mgpcg.max_iterations, p->mgpcg.tolerance);
+        h->pressure->setLinearSystemSolver(h->iccg);
+    } else {
+        h->lin = makeMgpcg(&p->mgpcg);
+        h->pressure->setLinearSystemSolver(h->lin);
+    }
     h->solver->setPressureSolver(h->pressure);
     h->solver->setGravity(Vector3D(p->gravity[0], p->gravity[1], p->gravity[2]));
     h->solver->setMaxCfl(p->max_cfl);
     h->solver->setClosedDomainBoundaryFlag(p->closed_domain_boundary_flag);
-    h->solver->setUseCompressedLinearSystem(false);
+    h->solver->setUseCompressedLinearSystem((p->mgpcg.linear_solver & 2) != 0);
     *out = h;
     return 0;
 }
@@ -584,6 +662,25 @@ int jeto_hybrid_num_sub_steps(jeto_hybrid* h, double dt, uint32_t* n) { *n = h->
 static void fillStats(jeto_hybrid* h, jeto_step_stats* st, double ms) {
     if (!st) return;
     std::memset(st, 0, sizeof(*st));
+    if (h->iccg) {
+        st->pcg_iterations = h->iccg->lastNumberOfIterations();
+        st->pcg_last_residual = h->iccg->lastResidual();
+        if (h->solver->useCompressedLinearSystem()) {
+            const auto& cs = h->pressure->_compSystem;
+            if (cs.b.size() > 0) {
+                VectorND r(cs.b.size());
+                FdmCompressedBlas3::residual(cs.A, cs.x, cs.b, &r);
+                st->pcg_true_residual_l2 = FdmCompressedBlas3::l2Norm(r);
+                st->pcg_b_l2 = FdmCompressedBlas3::l2Norm(cs.b);
+            }
+        } else {
+            const auto& sys = h->pressure->_system;
+            st->pcg_true_residual_l2 = trueResidual(sys.A, sys.x, sys.b);
+            st->pcg_b_l2 = FdmBlas3::l2Norm(sys.b);
+        }
+        st->ms_total = ms;
+        return;
+    }
     st->pcg_iterations = h->lin->lastNumberOfIterations();
     st->pcg_last_residual = h->lin->lastResidual();
     const auto& sys = h->pressure->_mgSystem;

@@ -15,13 +15,17 @@ parity)
 latency)
   for p in 0 1; do JETCU_P2P_HALO=$p run halo_latency_p2p$p 200 $TR --master-port 2953$p scripts/halo_latency.py; done ;;
 bench256)
-  JETCU_P2P_HALO=0 run bench256_nccl 400 $TR --master-port 29541 bench.py --gpus $N --steps 10 --warmup 3
-  JETCU_P2P_HALO=1 run bench256_p2p 400 $TR --master-port 29542 bench.py --gpus $N --steps 10 --warmup 3 ;;
+  run bench256 200 $TR --master-port 29541 bench.py --gpus $N --steps 10 --warmup 3 ;;
+bench256_p2p)
+  JETCU_P2P_HALO=1 run bench256_p2p 200 $TR --master-port 29542 bench.py --gpus $N --steps 10 --warmup 3 ;;
+knobs)
+  JETCU_SLAB_MIN_CELLS=3000000 run bench256_replicate128 200 $TR --master-port 29543 bench.py --gpus $N --steps 10 --warmup 3 --e2e-steps 0
+  JETCU_RELAX_BLOCK_DIV=4 run bench256_blockdiv4 200 $TR --master-port 29544 bench.py --gpus $N --steps 10 --warmup 3 --e2e-steps 0 ;;
 bench512)
-  run bench512 900 $TR --master-port 29545 bench.py --gpus $N --n 512 --steps 5 --warmup 2 --e2e-steps 1 ;;
+  run bench512 420 $TR --master-port 29545 bench.py --gpus $N --grid 512 --steps 5 --warmup 2 --e2e-steps ${E2E512:-1} ;;
 smoke)
   S=${SMOKE_N:-768}
-  run smoke$S 900 $TR --master-port 29546 scripts/bench_smoke.py $S 5 2 ;;
+  run smoke$S 420 $TR --master-port 29546 scripts/bench_smoke.py $S 4 2 ;;
 esac; done
 python - $OUT <<'PY'
 import json, sys, glob, os

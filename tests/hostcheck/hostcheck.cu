@@ -14,6 +14,7 @@
 #include "../../fluid-engine-dev_b200/csrc/fdm_ops.cuh"
 #include "../../fluid-engine-dev_b200/csrc/pressure_ops.cuh"
 #include "../../fluid-engine-dev_b200/csrc/p2g_ops.cuh"
+#include "../../fluid-engine-dev_b200/csrc/iccg_ops.cuh"
 #include "../../fluid-engine-dev_b200/csrc/smoke_ops.cuh"
 #include "../../fluid-engine-dev_b200/csrc/p2p_ops.cuh"
 
@@ -575,6 +576,35 @@ int hc_relax(int nx, int ny, int nz, const jetcu_matrix_row* A, const double* b,
     relax_sweeps<false>(M.m, b, x, sor, iterations, nx, ny, nz, false);
     return 0;
 }
+// k_ic_tiles<false, OP> of iccg.cu in its launch order: tile hyperplanes one after the other (backward: descending), the
+// tiles of a hyperplane in any order (here: ascending), inside a tile the cell hyperplanes one after the other.  FdmIccgSolver3's
+// Preconditioner::build (d) and ::solve (y forward, x backward).
+int hc_iccg_precondition(int nx, int ny, int nz, const jetcu_matrix_row* A, const double* b, double* d, double* y, double* x) {
+    SoAMat M(A, (size_t)nx * ny * nz);
+    const int T = 8, ntx = (nx + T - 1) / T, nty = (ny + T - 1) / T, ntz = (nz + T - 1) / T, last = ntx + nty + ntz - 3;
+    for (int op = 0; op < 3; ++op)
+        for (int s = 0; s <= last; ++s) {
+            const int S = op == 2 ? last - s : s;
+            for (int tj = 0; tj < nty; ++tj)
+                for (int ti = 0; ti < ntx; ++ti) {
+                    const int tk = S - ti - tj;
+                    if (tk < 0 || tk >= ntz) continue;
+                    for (int step = 0; step <= 3 * T - 3; ++step)
+                        for (int t = 0; t < T * T * T; ++t) {
+                            const int cx = t % T, cy = (t / T) % T, cz = t / (T * T);
+                            const int i = ti * T + cx, j = tj * T + cy, k = tk * T + cz;
+                            const int mine = op == 2 ? (3 * T - 3) - (cx + cy + cz) : cx + cy + cz;
+                            if (i >= nx || j >= ny || k >= nz || mine != step) continue;
+                            const size_t c = ((size_t)k * ny + j) * nx + i;
+                            if (op == 0) d[c] = ic_build_cell<false>(M.m, d, i, j, k, nx, ny);
+                            else if (op == 1) y[c] = ic_forward_cell<false>(M.m, b, y, d, i, j, k, nx, ny);
+                            else x[c] = ic_backward_cell<false>(M.m, y, x, d, i, j, k, nx, ny, nz);
+                        }
+                }
+        }
+    return 0;
+}
+
 int hc_restrict(int nx, int ny, int nz, const double* finer, double* coarser) {   // (nx, ny, nz) = finer size
     const int cx = nx / 2, cy = ny / 2, cz = nz / 2;
     for (int k = 0; k < cz; ++k) for (int j = 0; j < cy; ++j) for (int i = 0; i < cx; ++i) restrict_cell(finer, coarser, i, j, k, cx, cy, cz);

@@ -70,6 +70,19 @@ def test_example_application_next_to_stock_jet(example, tmp_path):
     assert first[:20].hex() == "0c00000000000600080004000600000004000000" and (len(first) - 24) % 24 == 0 and len(first) > 24 * 1000
 
 
+def test_example_application_with_its_own_solver_configuration(tmp_path):
+    """hybrid_liquid_sim example 3 exactly as Jet ships it (main.cpp:219): a default-constructed pressure solver, i.e.
+    FdmIccgSolver3(100, 1e-6), and setUseCompressedLinearSystem(true) on both sides — stock Jet builds the compressed CSR system,
+    the adapter forwards ICCG + the flag to the device."""
+    r = subprocess.run([APP, "-e", "3", "-r", "32", "-f", "3", "-o", str(tmp_path), "-m", "none", "--compare", "--iccg"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    frames = [l for l in r.stdout.splitlines() if l.startswith("frame ")]
+    assert len(frames) == 3, r.stdout
+    for l in frames:
+        assert 0.0 <= float(l.rsplit(" ", 1)[1]) <= 1e-5, l
+
+
 @pytest.mark.parametrize("flags", [[], ["--linear"]])
 def test_smoke_application_next_to_stock_jet(flags):
     """adapters/smoke_sim_cuda: smoke_sim example 1 (continuous box source under a sphere) with the source on the device, stepped

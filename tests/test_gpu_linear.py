@@ -102,6 +102,33 @@ def test_mgpcg_vs_oracle(jc, oracle, n, levels, shift):
         assert abs(r0.true_residual_l2 - r1.true_residual_l2) <= 1e-3 * r1.true_residual_l2
 
 
+@pytest.mark.parametrize("shape,spd", [((1, 1, 1), True), ((9, 3, 26), False), ((20, 17, 9), True), ((33, 17, 40), True), ((64, 64, 64), True)])
+def test_iccg_preconditioner_bit_exact(jc, oracle, shape, spd):
+    """FdmIccgSolver3::Preconditioner (src/jet/fdm_iccg_solver3.cpp:14-70): the reference's lexicographic recurrences, run on the
+    device as tile-hyperplane sweeps (csrc/iccg.cu) — the same per-cell arithmetic, hence the same bits (no reduction)."""
+    nx, ny, nz = shape
+    A, _, b = scenes.random_system(nx, ny, nz, seed=40 + sum(shape), spd=spd)
+    for got, want, what in zip(jc.iccg_precondition(A, b), oracle.iccg_precondition(A, b), ("IC diagonal", "forward", "backward")):
+        same(got, want, what)
+
+
+@pytest.mark.parametrize("n", [16, 40])
+def test_iccg_vs_oracle(jc, oracle, n):
+    """FdmIccgSolver3::solve (:152-188): same iteration count (dot products are a fixed tree here, serial sums in the reference:
+    +-1 at the tolerance threshold), solution to 1e-9 of its scale."""
+    A = scenes.poisson_levels(n, 1)[0]
+    A["center"] += 0.05
+    b = np.random.default_rng(n).uniform(-1, 1, (n, n, n))
+    (xg, rg), (xo, ro) = jc.iccg_solve(A, b, 200, 1e-9), oracle.iccg_solve(A, b, 200, 1e-9)
+    assert abs(int(rg.iterations) - int(ro.iterations)) <= 1 and rg.returned == ro.returned == 1
+    assert ro.true_residual_l2 <= 1e-8 * ro.b_l2
+    assert np.abs(xg - xo).max() <= 1e-9 * np.abs(xo).max()
+    # the iteration cap as the exit (Jet's default is 100 iterations: large systems leave through it)
+    (xg, rg), (xo, ro) = jc.iccg_solve(A, b, 5, 1e-12), oracle.iccg_solve(A, b, 5, 1e-12)
+    assert rg.iterations == ro.iterations == 5 and rg.returned == ro.returned == 0
+    assert np.abs(xg - xo).max() <= 1e-12 * np.abs(xo).max() and abs(rg.last_residual - ro.last_residual) <= 1e-10 * ro.last_residual
+
+
 def test_errors(jc):
     from fluid_engine_dev_b200 import JetcuError
     A, x, b = scenes.random_system(4, 4, 4)

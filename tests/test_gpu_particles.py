@@ -155,6 +155,22 @@ def test_append_particles_keeps_device_state(jc, oracle, mode):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("mode", [FLIP, APIC])
+def test_steps_with_default_iccg_compressed(jc, oracle, mode):
+    """hybrid_liquid_sim's own solver configuration (src/examples/hybrid_liquid_sim/main.cpp:219): the default FdmIccgSolver3 and
+    setUseCompressedLinearSystem(true).  Five sub-steps of a dam break: positions within 1e-5 of the domain size."""
+    n = 24
+    prm = HybridParams.make(Grid.cube(n), mode=mode, mgpcg=MgpcgParams.iccg(100, 1e-6, compressed=True))
+    a, b = jc.hybrid(prm), oracle.hybrid(prm)
+    assert a.emit_box((0, 0, 0), (0.4, 0.6, 1.0), 0.5 / n) == b.emit_box((0, 0, 0), (0.4, 0.6, 1.0), 0.5 / n)
+    for step in range(5):
+        sa, sb = a.step(1 / 60.0), b.step(1 / 60.0)
+        assert abs(int(sa.pcg_iterations) - int(sb.pcg_iterations)) <= 1
+        pa, _ = a.get_particles(); pb, _ = b.get_particles()
+        assert np.abs(pa - pb).max() <= 1e-5, "step %d: %g" % (step, np.abs(pa - pb).max())
+    a.close(); b.close()
+
+
 def test_particle_order_round_trip(jc):
     n = 16
     prm = HybridParams.make(Grid.cube(n), mode=FLIP, mgpcg=MgpcgParams.make(max_levels=3))

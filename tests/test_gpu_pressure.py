@@ -23,6 +23,18 @@ def oracle():
     return checker()
 
 
+def test_reference_known_answer_default_iccg(jc):
+    """GridFractionalSinglePhasePressureSolver3.SolveFreeSurface / SolveFreeSurfaceCompressed as the reference runs them: the
+    default FdmIccgSolver3(100, 1e-6) -> velocity 0, pressure 1.5 - j."""
+    from test_oracle_known_answers import free_surface_case
+    grid, u, v, w, sdf = free_surface_case()
+    for compressed in (False, True):
+        uo, vo, wo, pr, res = jc.pressure_solve(grid, u, v, w, MgpcgParams.iccg(100, 1e-6, compressed=compressed), fluid_sdf=sdf)
+        assert np.abs(uo).max() < 1e-6 and np.abs(vo).max() < 1e-6 and np.abs(wo).max() < 1e-6
+        for j in range(2):
+            assert np.abs(pr[:, j, :] - (1.5 - j)).max() < 1e-6
+
+
 def test_reference_known_answers(jc):
     check_free_surface(jc)       # pressure = 1.5 - j, velocity -> 0
     check_relax_decreases(jc)
@@ -86,6 +98,25 @@ def test_pressure_moving_boundary_and_defaults(jc, oracle):
                 assert np.abs(r0[3] - r1[3]).max() <= 1e-6 * max(np.abs(r1[3]).max(), 1e-30)
             else:
                 assert np.abs(r0[3]).max() > 1e5
+
+
+@pytest.mark.parametrize("compressed", [False, True])
+@pytest.mark.parametrize("n,kind,collider", [(16, "column", True), (32, "slab", True), (24, "column", False)])
+def test_pressure_default_iccg_solver(jc, oracle, n, kind, collider, compressed):
+    """The configuration a default-constructed Jet solver (and every hybrid_liquid_sim example) runs: FdmIccgSolver3, optionally
+    with setUseCompressedLinearSystem(true).  The oracle is the unmodified reference where available, which then
+    really builds the compressed CSR system (…pressure_solver3.cpp:269-444); the device solves the same system uncompressed.
+    north_star's bound: pressure within 1e-6 relative L-inf at equal solver tolerance."""
+    sc = scenes.projection_scene(n, kind, collider)
+    prm = MgpcgParams.iccg(400, 1e-9, compressed=compressed)
+    args = (sc["grid"], sc["u"], sc["v"], sc["w"], prm)
+    kw = dict(collider_sdf=sc["collider_sdf"], fluid_sdf=sc["fluid_sdf"])
+    ug, vg, wg, pg, rg = jc.pressure_solve(*args, **kw)
+    uo, vo, wo, po, ro = oracle.pressure_solve(*args, **kw)
+    assert ro.true_residual_l2 <= 1e-7 * ro.b_l2 and abs(int(rg.iterations) - int(ro.iterations)) <= 1
+    assert np.abs(pg - po).max() <= 1e-6 * np.abs(po).max()
+    for a, b in ((ug, uo), (vg, vo), (wg, wo)):
+        assert np.abs(a - b).max() <= 1e-6
 
 
 def test_pressure_output_keeps_untouched_faces(jc, oracle):

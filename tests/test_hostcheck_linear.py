@@ -52,6 +52,20 @@ def test_blas_and_relax(hc, port, shape, spd):
         exact(xs, port.relax_red_black(A, b, x, sor, it), "relax sor=%g" % sor)
 
 
+@pytest.mark.parametrize("shape", [(20, 17, 9), (8, 8, 8), (1, 1, 1), (9, 3, 26), (16, 16, 16)])
+@pytest.mark.parametrize("spd", [True, False])
+def test_iccg_preconditioner_tile_hyperplanes(hc, port, shape, spd):
+    """FdmIccgSolver3::Preconditioner (src/jet/fdm_iccg_solver3.cpp:14-70) is three lexicographic recurrences; iccg.cu sweeps
+    8^3 tiles in tile-hyperplane order and the cells of a tile in cell-hyperplane order.  The traversal, replayed on the CPU
+    with the kernel's cell bodies, gives the bits of the serial loops (oracle port == unmodified reference)."""
+    nx, ny, nz = shape
+    A, _, b = scenes.random_system(nx, ny, nz, seed=7 + sum(shape), spd=spd)
+    d, y, x = np.zeros_like(b), np.zeros_like(b), np.zeros_like(b)
+    assert hc.hc_iccg_precondition(nx, ny, nz, rp(A), dp(b), dp(d), dp(y), dp(x)) == 0
+    wd, wy, wx = port.iccg_precondition(A, b)
+    exact(d, wd, "IC diagonal"); exact(y, wy, "forward substitution"); exact(x, wx, "backward substitution")
+
+
 @pytest.mark.parametrize("fine", [(16, 12, 12), (2, 2, 2), (8, 6, 6), (8, 16, 8), (12, 8, 6), (6, 4, 10)])   # the last three: ny != nz (extension)
 def test_restrict_correct(hc, port, fine):
     nx, ny, nz = fine

@@ -46,6 +46,17 @@ def test_solve_free_surface(oracle):
     check_free_surface(oracle)
 
 
+def test_solve_free_surface_default_iccg(oracle):
+    """The reference's test as written: a default-constructed solver, i.e. FdmIccgSolver3(100, 1e-6) (…pressure_solver3.cpp:450),
+    with and without the compressed system (…solver3_tests.cpp:17-74 and :76-133)."""
+    grid, u, v, w, sdf = free_surface_case()
+    for compressed in (False, True):
+        uo, vo, wo, pr, res = oracle.pressure_solve(grid, u, v, w, MgpcgParams.iccg(100, 1e-6, compressed=compressed), fluid_sdf=sdf)
+        assert np.abs(uo).max() < 1e-6 and np.abs(vo).max() < 1e-6 and np.abs(wo).max() < 1e-6
+        for j in range(2):
+            assert np.abs(pr[:, j, :] - (1.5 - j)).max() < 1e-6
+
+
 def check_relax_decreases(api):
     """FdmGaussSeidelSolver3.RelaxRedBlack (src/tests/unit_tests/fdm_gauss_seidel_solver3_tests.cpp:64-84):
     the residual norm decreases monotonically over red-black sweeps on a Poisson system."""

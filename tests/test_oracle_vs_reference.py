@@ -97,6 +97,47 @@ def test_pressure_solve_bit_exact(libs, n, kind, collider, levels):
     same(s0[0]["b"], s1[0]["b"])
 
 
+@pytest.mark.parametrize("shape,spd", [((12, 10, 7), True), ((9, 9, 9), False), ((1, 1, 1), True), ((16, 16, 16), True)])
+def test_iccg_bit_exact(libs, shape, spd):
+    """FdmIccgSolver3 (src/jet/fdm_iccg_solver3.cpp:14-70, 152-188), Jet's default linear solver: the restatement equals the
+    unmodified reference bit for bit — incomplete-Cholesky diagonal, both substitutions, solution, iteration count, residual."""
+    ref, port = libs
+    nx, ny, nz = shape
+    A, _, b = scenes.random_system(nx, ny, nz, seed=100 + sum(shape), spd=spd)
+    for x, y in zip(ref.iccg_precondition(A, b), port.iccg_precondition(A, b)):
+        same(x, y)
+    if spd:
+        (xr, rr), (xp, rp) = ref.iccg_solve(A, b, 60, 1e-10), port.iccg_solve(A, b, 60, 1e-10)
+        same(xr, xp)
+        assert rr.iterations == rp.iterations and rr.last_residual == rp.last_residual and rr.returned == rp.returned
+
+
+@pytest.mark.parametrize("n,kind,collider", [(16, "column", True), (24, "slab", False), (20, "column", False)])
+def test_pressure_solve_iccg_and_compressed(libs, n, kind, collider):
+    """GridFractionalSinglePhasePressureSolver3 with its default FdmIccgSolver3: uncompressed, port == reference bit for bit;
+    with useCompressedLinearSystem(true) (what hybrid_liquid_sim sets, main.cpp:219) the reference solves the liquid cells only
+    (buildCompressedSystem, …pressure_solver3.cpp:269-444) — the same system without its uncoupled identity rows — and the
+    uncompressed restatement agrees with it to rounding: pressure 1e-9 relative (north_star's bound: 1e-6), iterations equal."""
+    ref, port = libs
+    sc = scenes.projection_scene(n, kind, collider)
+    args = (sc["grid"], sc["u"], sc["v"], sc["w"])
+    kw = dict(collider_sdf=sc["collider_sdf"], fluid_sdf=sc["fluid_sdf"])
+    r0 = ref.pressure_solve(*args, MgpcgParams.iccg(300, 1e-9), **kw)
+    p0 = port.pressure_solve(*args, MgpcgParams.iccg(300, 1e-9), **kw)
+    for a, b in zip(r0[:4], p0[:4]):
+        same(a, b)
+    assert r0[4].iterations == p0[4].iterations and r0[4].last_residual == p0[4].last_residual
+    assert r0[4].true_residual_l2 <= 1e-7 * r0[4].b_l2          # the case really converges
+    rc = ref.pressure_solve(*args, MgpcgParams.iccg(300, 1e-9, compressed=True), **kw)
+    pc = port.pressure_solve(*args, MgpcgParams.iccg(300, 1e-9, compressed=True), **kw)
+    scale = np.abs(rc[3]).max()
+    assert np.abs(rc[3] - pc[3]).max() <= 1e-9 * scale
+    vscale = max(float(np.abs(a).max()) for a in args[1:])     # the two solves stop at 1e-9: velocities agree to that level
+    for a, b in zip(rc[:3], pc[:3]):
+        assert np.abs(a - b).max() <= 1e-7 * vscale
+    assert abs(int(rc[4].iterations) - int(pc[4].iterations)) <= 1
+
+
 def test_pressure_defaults_and_moving_boundary(libs):
     """NULL fluid SDF (all liquid), NULL collider, and a non-zero boundary velocity."""
     ref, port = libs

@@ -452,7 +452,10 @@ def run_jetcu(args):
     traffic = read_traffic()
     roof = {"bound": "hbm", "kernel": "red-black SOR sweep, finest MG level (k_relax_*)",
             "achieved": relax_gbs, "peak": peak, "unit": "GB/s", "frac": (relax_gbs / peak) if relax_gbs else None,
-            "peak_source": peak_src, "traffic": (traffic or {}).get("relax_l0_bytes_per_launch"),
+            "peak_source": peak_src,
+            # DRAM bytes per launch from the committed ncu capture: bytes per cell and colour pass x the cells one launch covers
+            "traffic": ((traffic or {}).get("relax_l0_dram_bytes_per_cell_pass", 0.0) * relax_units * 2.0 / relax_launches)
+            if (traffic and relax_launches) else None,
             "traffic_source": (traffic or {}).get("source"),
             "bytes_per_launch_algorithmic": (relax_units * RELAX_BYTES_PER_CELL_SWEEP / relax_launches) if relax_launches else None,
             "launches": relax_launches, "avg_launch_ms": (relax_ms / relax_launches) if relax_launches else None,

@@ -168,25 +168,28 @@ static int launch_colour(jetcu_ctx* ctx, Dim3i d, ZRange z, Mat A, const double*
 // undivided sweep; the redundant work is ~k/T of a pass, k is chosen as T/8 (at most 8, at least 1).  The caller must
 // have made b valid on fdm_relax_rhs_halo(T) planes around the slab (b is read-only here: one exchange per V-cycle level).
 // sweeps per exchange on a slab of T planes
-static inline int relax_block_sweeps(int T) {
-    // JETCU_RELAX_BLOCK_DIV (default 8): sweeps per halo exchange = T / div, at most 8.  A smaller divisor trades redundant
-    // halo work (2k / T of a pass) for fewer dependent exchanges — worth it where a pass is launch-latency-bound anyway
-    static int div = 0;
-    if (div == 0) { const char* e = getenv("JETCU_RELAX_BLOCK_DIV"); div = e ? atoi(e) : 8; if (div < 2) div = 2; }
-    int k = T / div;
+// sweeps per exchange on a slab of T planes with `plane_cells` cells per plane.  One exchange costs a latency L (~25 us for
+// a dependent NCCL send/recv pair, profiles/r02_multi) whatever its depth — the BYTES per sweep are 2 planes per neighbour
+// either way — while the redundant halo work of a block of k sweeps is ~4 k planes per sweep: k* = sqrt(L / (4 t_plane)),
+// t_plane = plane_cells x 23.6 B / HBM rate (ncu: 23.6 B per cell and colour pass).  256^2 planes: 5; 512^2: 3; 128^2: 8.
+// At most 8 and at most T / 4 (the halo of 2 k planes must come out of the neighbour's own slab).
+// JETCU_RELAX_BLOCK_DIV = d forces the round-1 rule k = T / d.
+static inline int relax_block_sweeps(int T, size_t plane_cells) {
+    static int div = -1;
+    if (div < 0) { const char* e = getenv("JETCU_RELAX_BLOCK_DIV"); div = e ? atoi(e) : 0; if (div < 0) div = 0; }
+    int k;
+    if (div >= 2) {
+        k = T / div;
+    } else {
+        const double t_plane = (double)plane_cells * 23.6 / 6.5e12;
+        k = (int)(sqrt(25e-6 / (4.0 * t_plane)) + 0.5);
+        if (k > T / 4) k = T / 4;
+    }
     return k < 1 ? 1 : (k > 8 ? 8 : k);
 }
 // planes of b (which the sweeps only read) that the redundant halo cells need next to a slab of T planes
-int fdm_relax_rhs_halo(int T) { return 2 * relax_block_sweeps(T) - 1; }
+int fdm_relax_rhs_halo(int T, size_t plane_cells) { return 2 * relax_block_sweeps(T, plane_cells) - 1; }
 
-// L2-resident sweep (JETCU_RELAX_CHUNK = planes per chunk, default by launch size, 0 = off): the red and the black pass of one
-// sweep are issued as an alternating sequence of z-chunks — red on planes up to c1 (one plane ahead), black on the chunk
-// [c0, c1), red on the next chunk ... — instead of two passes over the whole level.  Every red cell still reads only
-// black values from before the sweep (a black chunk is launched after the red launch that needed its planes, and the
-// next red launch starts one plane beyond it), every black cell reads red values of this sweep: the same operands in
-// the same order, bit-identical to the two full passes.  What changes is the traffic: the b / x / code sectors a red
-// launch pulled in (half of each sector belongs to the other colour) are still in the 126 MB L2 when the black launch
-// of the same chunk needs the other half, and x is written back once — ~25 B/cell/sweep from DRAM instead of ~47.
 // planes per chunk for a level with `plane_cells` cells per plane: JETCU_RELAX_CHUNK (planes) if set, else the number of
 // planes that makes a launch ~3.5 M cells (JETCU_RELAX_CHUNK_CELLS) — 48-64 planes at 256^2, 13 at 512^2, 6 at 768^2: the
 // measured optimum at 256^3 (profiles/r02_sor_wavefront.md) carried over by launch size.  0 = whole-level passes.
@@ -282,7 +285,7 @@ static int launch_relax(jetcu_ctx* ctx, Dim3i d, ZRange z, bool halo, Mat A, con
         return JETCU_OK;
     }
     const size_t plane = (size_t)d.nx * d.ny * sizeof(double);
-    const int kmax = relax_block_sweeps(z.k1 - z.k0);
+    const int kmax = relax_block_sweeps(z.k1 - z.k0, (size_t)d.nx * d.ny);
     // chunking only pays where the level does not fit the L2 anyway (>= 64^3-ish: 25 B x 2M cells)
     const int chunk = d.n() >= (size_t)(1 << 21) ? relax_chunk_planes((size_t)d.nx * d.ny) : 0;
     *launches = 0;
@@ -572,8 +575,8 @@ int mg_vcycle(jetcu_ctx* ctx, MgLevels* mg, const jetcu_mgpcg_params* p, int l) 
     const ZRange z{pl.z0[l], pl.z1[l]};
     const size_t plane = (size_t)d.nx * d.ny * sizeof(double);
     // the smoother's redundant halo cells read b next to the slab; b[l] does not change during this level's visit
-    if (dist && fdm_relax_rhs_halo(z.k1 - z.k0) > 0)
-        JC_TRY(comm_halo_planes(ctx, mg->b[l], plane, z.k0, z.k1, d.nz, fdm_relax_rhs_halo(z.k1 - z.k0)));
+    if (dist && fdm_relax_rhs_halo(z.k1 - z.k0, (size_t)d.nx * d.ny) > 0)
+        JC_TRY(comm_halo_planes(ctx, mg->b[l], plane, z.k0, z.k1, d.nz, fdm_relax_rhs_halo(z.k1 - z.k0, (size_t)d.nx * d.ny)));
     JC_TRY(fdm_relax_rb(ctx, d, z, dist, mg->A[l], mg->b[l], p->sor_factor, p->n_restriction, &mg->x[l], &mg->xalt[l], l));
     if (l + 1 < mg->levels) {
         const Dim3i dc = mg->dims[l + 1];

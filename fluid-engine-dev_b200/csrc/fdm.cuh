@@ -59,7 +59,7 @@ int fdm_relax_rb(jetcu_ctx* ctx, Dim3i d, Mat A, const double* b, double sor, un
 // slab form: planes `z` only; `halo` = refresh the planes around `z` from the neighbouring ranks before each colour pass
 int fdm_relax_rb(jetcu_ctx* ctx, Dim3i d, ZRange z, bool halo, Mat A, const double* b, double sor, unsigned iterations,
                  double** x, double** xalt, int level = -1);
-int fdm_relax_rhs_halo(int slab_planes);  // planes of b the slab smoother reads outside the slab
+int fdm_relax_rhs_halo(int slab_planes, size_t plane_cells);  // planes of b the slab smoother reads outside the slab
 int fdm_restrict(jetcu_ctx* ctx, Dim3i fine, const double* finer, double* coarser);
 int fdm_restrict(jetcu_ctx* ctx, Dim3i fine, ZRange coarse_planes, const double* finer, double* coarser);
 int fdm_correct(jetcu_ctx* ctx, Dim3i fine, const double* coarser, double* finer);

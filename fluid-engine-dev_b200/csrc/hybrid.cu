@@ -251,6 +251,11 @@ __global__ void k_p2g_normalise(double* __restrict__ u, const double* __restrict
     p2g_normalise_face(u, wsum, snapshot, f);
 }
 
+__global__ void k_snapshot_f32(const double* __restrict__ in, float* __restrict__ d, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = (float)in[i];
+}
+
 __global__ void k_flip_delta(const double* __restrict__ in, float* __restrict__ d, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) d[i] = (float)in[i] - d[i];  // src/jet/flip_solver3.cpp:57-70
@@ -1533,11 +1538,11 @@ int jetcu_hybrid_transfer_particles_to_grids(jetcu_hybrid* h) {
             }
         }
         JC_LAUNCH(ctx, k_p2g_normalise, jc_blocks(nk * pu, 256), 256, 0, h->u + k0 * pu, h->wsum[0] + k0 * pu,
-                  flip ? h->ud + k0 * pu : nullptr, nk * pu);
+                  (flip && !slab) ? h->ud + k0 * pu : nullptr, nk * pu);
         JC_LAUNCH(ctx, k_p2g_normalise, jc_blocks(nk * pv, 256), 256, 0, h->v + k0 * pv, h->wsum[1] + k0 * pv,
-                  flip ? h->vd + k0 * pv : nullptr, nk * pv);
+                  (flip && !slab) ? h->vd + k0 * pv : nullptr, nk * pv);
         JC_LAUNCH(ctx, k_p2g_normalise, jc_blocks(nkw * pw, 256), 256, 0, h->w + k0 * pw, h->wsum[2] + k0 * pw,
-                  flip ? h->wd + k0 * pw : nullptr, nkw * pw);
+                  (flip && !slab) ? h->wd + k0 * pw : nullptr, nkw * pw);
     } else if (h->P.mode == JETCU_FLIP) {
         JC_TRY(jc_zero(ctx, h->ud, h->nu)); JC_TRY(jc_zero(ctx, h->vd, h->nv)); JC_TRY(jc_zero(ctx, h->wd, h->nw));
     }
@@ -1546,9 +1551,11 @@ int jetcu_hybrid_transfer_particles_to_grids(jetcu_hybrid* h) {
         JC_TRY(hyb_gather_planes(h, h->w, pw * 8, true));
         JC_TRY(hyb_gather_planes(h, h->um, pu, false)); JC_TRY(hyb_gather_planes(h, h->vm, pv, false));
         JC_TRY(hyb_gather_planes(h, h->wm, pw, true));
-        if (flip) {
-            JC_TRY(hyb_gather_planes(h, h->ud, pu * 4, false)); JC_TRY(hyb_gather_planes(h, h->vd, pv * 4, false));
-            JC_TRY(hyb_gather_planes(h, h->wd, pw * 4, true));
+        if (flip) {   // FlipSolver3's float snapshot of the transferred velocity (flip_solver3.cpp:39-47): float(u) of the
+                      // gathered field, instead of all-gathering a second (float) copy of every plane
+            JC_LAUNCH(ctx, k_snapshot_f32, jc_blocks(h->nu, 256), 256, 0, h->u, h->ud, h->nu);
+            JC_LAUNCH(ctx, k_snapshot_f32, jc_blocks(h->nv, 256), 256, 0, h->v, h->vd, h->nv);
+            JC_LAUNCH(ctx, k_snapshot_f32, jc_blocks(h->nw, 256), 256, 0, h->w, h->wd, h->nw);
         }
     }
     jc_prof_end(ctx, slot, 6, h->np);

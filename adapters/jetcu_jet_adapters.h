@@ -488,10 +488,17 @@ class CudaHybridSolver3 : public Base {
     void onAdvanceTimeStep(double timeIntervalInSeconds) override {
         auto grids = this->gridSystemData();
         if (grids->resolution().x == 0 || grids->resolution().y == 0 || grids->resolution().z == 0) return;
-        // GridFluidSolver3::computeViscosity (grid_fluid_solver3.cpp:221-231) has no device counterpart: never skip it silently
-        if (this->viscosityCoefficient() > jet::kEpsilonD)
-            throw std::runtime_error("jetcu: the device hybrid solver implements zero viscosity only (viscosityCoefficient() > 0)");
+        // GridFluidSolver3::computeViscosity (grid_fluid_solver3.cpp:231-241) runs on the device with what a default-
+        // constructed solver carries: GridBackwardEulerDiffusionSolver3 (Neumann) over FdmIccgSolver3(100, kEpsilonD).
+        // Any other diffusion solver installed on the Jet object is refused, never replaced silently.
+        if (this->viscosityCoefficient() > jet::kEpsilonD) {
+            auto diff = std::dynamic_pointer_cast<jet::GridBackwardEulerDiffusionSolver3>(this->diffusionSolver());
+            if (!diff)
+                throw std::runtime_error("jetcu: computeViscosity on the device needs Jet's GridBackwardEulerDiffusionSolver3 "
+                                         "(the solver's default); another GridDiffusionSolver3 is installed");
+        }
         ensureDevice();
+        _ctx->check(jetcu_hybrid_set_viscosity(_h, this->viscosityCoefficient() > jet::kEpsilonD ? this->viscosityCoefficient() : 0.0));
         // GridFluidSolver3::beginAdvanceTimeStep -> updateCollider (grid_fluid_solver3.cpp:255-275, 371-375): animated
         // colliders move in their onBeginUpdate callbacks, so it has to run before the collider is forwarded
         if (this->collider() != nullptr) this->collider()->update(this->currentTimeInSeconds(), timeIntervalInSeconds);
@@ -649,7 +656,7 @@ class CudaHybridSolver3 : public Base {
 //! GridSmokeSolver3 with the sub-step on the device: GridFluidSolver3::onAdvanceTimeStep
 //! (src/jet/grid_fluid_solver3.cpp:179-210) runs as jetcu_smoke_step.  Strict drop-in: emitters (VolumeGridEmitter3 ...)
 //! keep running on the host inside beginAdvanceTimeStep, so the fields go up before and come back after every sub-step.
-//! Supported configuration = what the device path implements: analytic rigid colliders, zero viscosity / diffusion coefficients,
+//! Supported configuration = what the device path implements: analytic rigid colliders, viscosity / diffusion through Jet's default diffusion solver,
 //! CubicSemiLagrangian3 (the default) or SemiLagrangian3 advection; anything else throws instead of silently computing
 //! something different.
 class CudaGridSmokeSolver3 : public jet::GridSmokeSolver3 {
@@ -694,14 +701,20 @@ class CudaGridSmokeSolver3 : public jet::GridSmokeSolver3 {
         auto grids = gridSystemData();
         const jet::Size3 res = grids->resolution();
         if (res.x == 0 || res.y == 0 || res.z == 0) return;
-        if (viscosityCoefficient() > jet::kEpsilonD || smokeDiffusionCoefficient() > jet::kEpsilonD ||
-            temperatureDiffusionCoefficient() > jet::kEpsilonD)
-            throw std::runtime_error("jetcu: the device smoke solver implements zero viscosity / diffusion only");
+        // computeViscosity / computeDiffusion run on the device with what a default-constructed solver carries
+        // (GridBackwardEulerDiffusionSolver3, Neumann, FdmIccgSolver3(100, kEpsilonD)); another diffusion solver is refused
+        const bool diffusive = viscosityCoefficient() > jet::kEpsilonD || smokeDiffusionCoefficient() > jet::kEpsilonD ||
+                               temperatureDiffusionCoefficient() > jet::kEpsilonD;
+        if (diffusive && !std::dynamic_pointer_cast<jet::GridBackwardEulerDiffusionSolver3>(diffusionSolver()))
+            throw std::runtime_error("jetcu: viscosity / diffusion on the device need Jet's GridBackwardEulerDiffusionSolver3 "
+                                     "(the solver's default); another GridDiffusionSolver3 is installed");
         // exactly CubicSemiLagrangian3 or exactly SemiLagrangian3 (its base class); any other subclass samples differently
         if (advectionSolver() == nullptr || (typeid(*advectionSolver()) != typeid(jet::CubicSemiLagrangian3) &&
                                              typeid(*advectionSolver()) != typeid(jet::SemiLagrangian3)))
             throw std::runtime_error("jetcu: the device smoke solver implements SemiLagrangian3 / CubicSemiLagrangian3 advection");
         ensureDevice();
+        _ctx->check(jetcu_smoke_set_diffusion(_h, std::max(viscosityCoefficient(), 0.0), std::max(smokeDiffusionCoefficient(), 0.0),
+                                              std::max(temperatureDiffusionCoefficient(), 0.0)));
         syncCollider();
         // the host part of beginAdvanceTimeStep: Jet emitters write into the host grids (src/jet/grid_fluid_solver3.cpp:437-447)
         const bool hostEmitter = emitter() != nullptr;

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjetcu.so")
-SOURCES = ["abi.cu", "fdm.cu", "iccg.cu", "pressure.cu", "particles.cu", "hybrid.cu", "smoke.cu", "comm.cu", "io.cu"]
+SOURCES = ["abi.cu", "fdm.cu", "iccg.cu", "pressure.cu", "particles.cu", "hybrid.cu", "smoke.cu", "diffusion.cu", "comm.cu", "io.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",   # B200 only
     "-lineinfo", "-O3", "-std=c++17",

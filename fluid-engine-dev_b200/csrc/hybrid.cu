@@ -19,6 +19,7 @@
 #include "sampling.cuh"
 #include "particle_ops.cuh"
 #include "p2g_ops.cuh"
+#include "diffusion.cuh"
 
 
 struct jetcu_hybrid {
@@ -58,6 +59,7 @@ struct jetcu_hybrid {
     char *cm_u = nullptr, *cm_v = nullptr, *cm_w = nullptr;       // its uMarker / vMarker / wMarker
     PressureSystem ps;
     jetcu_mgpcg_result last{};
+    double viscosity = 0.0;   // GridFluidSolver3::viscosityCoefficient(): > kEpsilonD switches computeViscosity on
     cudaEvent_t ev[12] = {};
 };
 
@@ -182,7 +184,7 @@ __global__ void k_slab_unpack(const double* __restrict__ msg, size_t cnt, AttrPt
 // Measured alternatives (round 2, profiles/r02_p2g_variants.md): exchanging values and weights in two rounds through half
 // the buffer (L1 hit rate 10 % -> 51 %, but two more barriers per component: 11.5 ms instead of 9.8 ms for the 8 launches)
 // and staging the tile's particles in shared memory with coalesced row copies (14 ms) were both slower than this form.
-template <bool APIC, int AX, int TZ>
+template <bool APIC, int AX, int TZ, bool PF>
 __device__ __forceinline__ void p2g_tile_component(const GridD& g, int I0, int J0, int K0, int ci, int cj, int ck, uint32_t s0,
                                                    uint32_t e0, const AttrPtrs& a, double* ex, unsigned* tm,
                                                    double* __restrict__ U, double* __restrict__ W, char* __restrict__ M, int* err) {
@@ -193,7 +195,7 @@ __device__ __forceinline__ void p2g_tile_component(const GridD& g, int I0, int J
     if (e0 > s0) {
         double sv[P2G_SLOTS], sw[P2G_SLOTS];
         const P2GGlobalSrc<AX> src{&a};
-        touched = p2g_cell_partial<APIC, AX>(g, ci, cj, ck, s0, e0, src, sv, sw, err);
+        touched = p2g_cell_partial<APIC, AX, P2GGlobalSrc<AX>, PF>(g, ci, cj, ck, s0, e0, src, sv, sw, err);
 #pragma unroll
         for (int s = 0; s < P2G_SLOTS; ++s) { ex[s * NT + tid] = sv[s]; ex[(P2G_SLOTS + s) * NT + tid] = sw[s]; }
     }
@@ -221,8 +223,15 @@ struct P2GOut {
     char* marker[3];
 };
 
-template <bool APIC, int TZ>
-__global__ void __launch_bounds__(P2G_TX * P2G_TY * TZ)
+#ifndef P2G_PF_DEFAULT
+#define P2G_PF_DEFAULT 1
+#endif
+// MINB: CTAs per SM the register allocation is held to.  A 256-thread tile (TZ = 4) compiled without it takes 146 (APIC: 196)
+// registers and ONE such CTA fits an SM — 8 warps; with MINB = 2 it is held to 128 and two tiles share an SM, so one tile's
+// exchange / gather / read-modify-write phases overlap the other's particle loop.
+// PF: software-pipelined particle loads in the cell loop (p2g_ops.cuh).
+template <bool APIC, int TZ, int MINB, bool PF>
+__global__ void __launch_bounds__(P2G_TX * P2G_TY * TZ, MINB)
     k_p2g_tile(GridD g, int par_x, int par_y, int tz_first, int kb, int ke, const uint32_t* __restrict__ cell_start, AttrPtrs a,
                P2GOut out, int* __restrict__ err) {
     constexpr int NT = P2G_TX * P2G_TY * TZ;
@@ -238,9 +247,9 @@ __global__ void __launch_bounds__(P2G_TX * P2G_TY * TZ)
         s0 = cell_start[cell]; e0 = cell_start[cell + 1];
     }
     if (!__syncthreads_or(e0 > s0)) return;
-    p2g_tile_component<APIC, 0, TZ>(g, I0, J0, K0, ci, cj, ck, s0, e0, a, p2g_ex, tm, out.val[0], out.wsum[0], out.marker[0], err);
-    p2g_tile_component<APIC, 1, TZ>(g, I0, J0, K0, ci, cj, ck, s0, e0, a, p2g_ex, tm, out.val[1], out.wsum[1], out.marker[1], err);
-    p2g_tile_component<APIC, 2, TZ>(g, I0, J0, K0, ci, cj, ck, s0, e0, a, p2g_ex, tm, out.val[2], out.wsum[2], out.marker[2], err);
+    p2g_tile_component<APIC, 0, TZ, PF>(g, I0, J0, K0, ci, cj, ck, s0, e0, a, p2g_ex, tm, out.val[0], out.wsum[0], out.marker[0], err);
+    p2g_tile_component<APIC, 1, TZ, PF>(g, I0, J0, K0, ci, cj, ck, s0, e0, a, p2g_ex, tm, out.val[1], out.wsum[1], out.marker[1], err);
+    p2g_tile_component<APIC, 2, TZ, PF>(g, I0, J0, K0, ci, cj, ck, s0, e0, a, p2g_ex, tm, out.val[2], out.wsum[2], out.marker[2], err);
 }
 
 // u = sum / wsum where wsum > 0 (pic_solver3.cpp:178-192); FLIP's float snapshot (src/jet/flip_solver3.cpp:39-47) is
@@ -436,14 +445,21 @@ __device__ __forceinline__ void count_cell(const GridD& g, const double* pos, si
     rank[p] = atomicAdd(&count[cell], 1u);
 }
 
-template <bool POW2, typename I>
-__global__ void k_move(GridD g, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
+// CC: keep the 8 corner values per component of the last sample in registers (particle_ops.cuh: CornerCache)
+// CC = 0: no cache (86 registers); 1: cache, 4 CTAs of 128 threads per SM (<= 128 registers, no spills);
+// 2: cache, 5 CTAs per SM (96 registers, 48 bytes of spills).  JETCU_MOVE_CACHE selects; default 2 (GPU call 8, 256^3:
+// FLIP 18.5 ms without, 18.8 ms with 4 CTAs, 17.7 ms with 5 CTAs; PIC 16.6 -> 14.6 ms).
+#define MOVE_MIN_BLOCKS(CC) ((CC) == 1 ? 4 : 5)
+template <bool POW2, typename I, int CC>
+__global__ void __launch_bounds__(128, MOVE_MIN_BLOCKS(CC))
+    k_move(GridD g, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
                        double dt, unsigned nsub, int flag, AttrPtrs a, size_t np, uint32_t* __restrict__ cell_of,
                        uint32_t* __restrict__ rank, uint32_t* __restrict__ count) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= np) return;
     double pos[3] = {a.p[0][p], a.p[1][p], a.p[2][p]}, vel[3] = {a.p[3][p], a.p[4][p], a.p[5][p]};
-    move_particle<POW2, I, true>(g, u, v, w, dt, nsub, flag, pos, vel);   // u, v, w: PAIR arrays (k_pack_pairs)
+    CornerCache<I> cc;
+    move_particle<POW2, I, true>(g, u, v, w, dt, nsub, flag, pos, vel, nullptr, CC ? &cc : nullptr);   // u, v, w: PAIR arrays (k_pack_pairs)
     a.p[0][p] = pos[0]; a.p[1][p] = pos[1]; a.p[2][p] = pos[2];
     count_cell(g, pos, p, cell_of, rank, count);
     a.p[3][p] = vel[0]; a.p[4][p] = vel[1]; a.p[5][p] = vel[2];
@@ -455,23 +471,26 @@ __global__ void k_move(GridD g, const double* __restrict__ u, const double* __re
 //         sub-step (same expression, same point), so one of the 11 samples disappears as well;
 //   FLIP: velocity += float delta sample (pic blending factor 0; a non-zero factor takes the two-kernel path).
 // u, v, w are pair arrays.
-template <bool POW2, typename I>
-__global__ void k_pic_move(GridD g, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
+template <bool POW2, typename I, int CC>
+__global__ void __launch_bounds__(128, MOVE_MIN_BLOCKS(CC))
+    k_pic_move(GridD g, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
                        double dt, unsigned nsub, int flag, AttrPtrs a, size_t np, uint32_t* __restrict__ cell_of,
                        uint32_t* __restrict__ rank, uint32_t* __restrict__ count) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= np) return;
     double pos[3] = {a.p[0][p], a.p[1][p], a.p[2][p]}, vel[3];
-    sample_velocity<POW2, I, true>(g, u, v, w, pos[0], pos[1], pos[2], &vel[0], &vel[1], &vel[2]);
+    CornerCache<I> cc;
+    sample_velocity<POW2, I, true>(g, u, v, w, pos[0], pos[1], pos[2], &vel[0], &vel[1], &vel[2], CC ? &cc : nullptr);
     const double first[3] = {vel[0], vel[1], vel[2]};
-    move_particle<POW2, I, true>(g, u, v, w, dt, nsub, flag, pos, vel, first);
+    move_particle<POW2, I, true>(g, u, v, w, dt, nsub, flag, pos, vel, first, CC ? &cc : nullptr);
     a.p[0][p] = pos[0]; a.p[1][p] = pos[1]; a.p[2][p] = pos[2];
     count_cell(g, pos, p, cell_of, rank, count);
     a.p[3][p] = vel[0]; a.p[4][p] = vel[1]; a.p[5][p] = vel[2];
 }
 
-template <bool POW2, typename I>
-__global__ void k_flip_move(GridD g, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
+template <bool POW2, typename I, int CC>
+__global__ void __launch_bounds__(128, MOVE_MIN_BLOCKS(CC))
+    k_flip_move(GridD g, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
                             const float* __restrict__ ud, const float* __restrict__ vd, const float* __restrict__ wd, double dt,
                             unsigned nsub, int flag, AttrPtrs a, size_t np, uint32_t* __restrict__ cell_of,
                             uint32_t* __restrict__ rank, uint32_t* __restrict__ count) {
@@ -479,7 +498,8 @@ __global__ void k_flip_move(GridD g, const double* __restrict__ u, const double*
     if (p >= np) return;
     double pos[3] = {a.p[0][p], a.p[1][p], a.p[2][p]}, vel[3] = {a.p[3][p], a.p[4][p], a.p[5][p]};
     g2p_flip_particle(g, nullptr, nullptr, nullptr, ud, vd, wd, 0.0, pos, vel);
-    move_particle<POW2, I, true>(g, u, v, w, dt, nsub, flag, pos, vel);
+    CornerCache<I> cc;
+    move_particle<POW2, I, true>(g, u, v, w, dt, nsub, flag, pos, vel, nullptr, CC ? &cc : nullptr);
     a.p[0][p] = pos[0]; a.p[1][p] = pos[1]; a.p[2][p] = pos[2];
     count_cell(g, pos, p, cell_of, rank, count);
     a.p[3][p] = vel[0]; a.p[4][p] = vel[1]; a.p[5][p] = vel[2];
@@ -948,6 +968,28 @@ static int hyb_extrapolate_one(jetcu_hybrid* h, double* data, const char* marker
         else if (pow2_) JC_LAUNCH(ctx, (kernel<true, long long>), grid, block, 0, __VA_ARGS__);                   \
         else if (i32_) JC_LAUNCH(ctx, (kernel<false, int>), grid, block, 0, __VA_ARGS__);                         \
         else JC_LAUNCH(ctx, (kernel<false, long long>), grid, block, 0, __VA_ARGS__);                             \
+    } while (0)
+
+// advection kernels: <POW2, I, CC>; JETCU_MOVE_CACHE=0 selects the uncached form (A/B; results are bit-identical)
+static inline int hyb_move_cache() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("JETCU_MOVE_CACHE"); on = e ? atoi(e) : 2; if (on < 0 || on > 2) on = 2; }
+    return on;
+}
+#define HYB_MOVE_LAUNCH_(kernel, CC_, grid, block, ...)                                                           \
+    do {                                                                                                          \
+        const bool pow2_ = g.ihx != 0.0 && g.ihy != 0.0 && g.ihz != 0.0;                                          \
+        const bool i32_ = h->nu < (1ull << 31) && h->nv < (1ull << 31) && h->nw < (1ull << 31);                   \
+        if (pow2_ && i32_) JC_LAUNCH(ctx, (kernel<true, int, CC_>), grid, block, 0, __VA_ARGS__);                 \
+        else if (pow2_) JC_LAUNCH(ctx, (kernel<true, long long, CC_>), grid, block, 0, __VA_ARGS__);              \
+        else if (i32_) JC_LAUNCH(ctx, (kernel<false, int, CC_>), grid, block, 0, __VA_ARGS__);                    \
+        else JC_LAUNCH(ctx, (kernel<false, long long, CC_>), grid, block, 0, __VA_ARGS__);                        \
+    } while (0)
+#define HYB_MOVE_LAUNCH(kernel, grid, block, ...)                                                                 \
+    do {                                                                                                          \
+        if (hyb_move_cache() == 1) HYB_MOVE_LAUNCH_(kernel, 1, grid, block, __VA_ARGS__);                         \
+        else if (hyb_move_cache() == 2) HYB_MOVE_LAUNCH_(kernel, 2, grid, block, __VA_ARGS__);                    \
+        else HYB_MOVE_LAUNCH_(kernel, 0, grid, block, __VA_ARGS__);                                               \
     } while (0)
 
 #define HYB_ENTER(h)                                                      \
@@ -1514,18 +1556,25 @@ int jetcu_hybrid_transfer_particles_to_grids(jetcu_hybrid* h) {
             for (int q = 0; q < 3; ++q) out.wsum[q] = h->wsum[q];
             out.marker[0] = h->um; out.marker[1] = h->vm; out.marker[2] = h->wm;
             // tiles are aligned to the GLOBAL cell lattice (not to the slab), so that every rank forms the same tile sums.
-            // Tile height: 8 cell planes (512 threads, one CTA per SM) for PIC / FLIP, 4 (256 threads) for APIC, which carries
-            // 3 more attributes per component through the cell loop and would spill at 128 registers; JETCU_P2G_TZ=4 selects
-            // the small tile for PIC / FLIP as well (two independent CTAs per SM instead of one).
+            // Tile height: 4 cell planes (256 threads) held to 128 registers, so that two CTAs share an SM and one tile's
+            // exchange / gather / read-modify-write phases overlap the other's particle loop, with software-pipelined particle
+            // loads (GPU call 8, 256^3 FLIP: 12.24 ms for the 8-plane tile without either -> 11.16 ms).  APIC carries 3 more
+            // attributes per component through the cell loop and spills at 128 registers: one 256-thread CTA per SM at 227
+            // registers, pipelined loads (23.8 -> 19.5 ms).  JETCU_P2G_TZ=8 / JETCU_P2G_PF=0 / JETCU_P2G_MINB select the others.
             static const int tz_env = getenv("JETCU_P2G_TZ") ? atoi(getenv("JETCU_P2G_TZ")) : 0;
-            const int TZ = (apic || tz_env == P2G_TZ_APIC) ? P2G_TZ_APIC : P2G_TZ;
+            static const int minb_env = getenv("JETCU_P2G_MINB") ? atoi(getenv("JETCU_P2G_MINB")) : 0;
+            static const int pf_env = getenv("JETCU_P2G_PF") ? atoi(getenv("JETCU_P2G_PF")) : P2G_PF_DEFAULT;
+            const int TZ = (apic || tz_env != P2G_TZ) ? P2G_TZ_APIC : P2G_TZ;   // default since GPU call 8: the 4-plane tile
             const int ntx = (g.nx + P2G_TX - 1) / P2G_TX, nty = (g.ny + P2G_TY - 1) / P2G_TY;
             const int tzlo = kb / TZ, tzhi = (ke - 1) / TZ;  // inclusive
             const size_t smem = (size_t)2 * P2G_SLOTS * P2G_TX * P2G_TY * TZ * sizeof(double);
             const int threads = P2G_TX * P2G_TY * TZ;
             // per device, cheap: set on every call (the attribute belongs to the current device's copy of the function)
             void (*kern)(GridD, int, int, int, int, int, const uint32_t*, AttrPtrs, P2GOut, int*) =
-                apic ? k_p2g_tile<true, P2G_TZ_APIC> : (TZ == P2G_TZ ? k_p2g_tile<false, P2G_TZ> : k_p2g_tile<false, P2G_TZ_APIC>);
+                apic ? (minb_env == 2 ? k_p2g_tile<true, P2G_TZ_APIC, 2, true>
+                                      : (pf_env ? k_p2g_tile<true, P2G_TZ_APIC, 0, true> : k_p2g_tile<true, P2G_TZ_APIC, 0, false>))
+                     : (TZ == P2G_TZ ? (pf_env ? k_p2g_tile<false, P2G_TZ, 0, true> : k_p2g_tile<false, P2G_TZ, 0, false>)
+                                     : (pf_env ? k_p2g_tile<false, P2G_TZ_APIC, 2, true> : k_p2g_tile<false, P2G_TZ_APIC, 2, false>));
             JC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             for (int colour = 0; colour < 8; ++colour) {  // fixed colour order = the order in which a rim face receives its tiles
                 const int par_x = colour & 1, par_y = (colour >> 1) & 1, par_z = colour >> 2;
@@ -1618,6 +1667,35 @@ int jetcu_hybrid_compute_external_forces(jetcu_hybrid* h, double dt) {
     return JETCU_OK;
 }
 
+// GridFluidSolver3::setViscosityCoefficient / computeViscosity (src/jet/grid_fluid_solver3.cpp:231-241): the solver's own
+// GridBackwardEulerDiffusionSolver3 (default boundary type Neumann, ICCG(100, kEpsilonD)) on a clone of the velocity,
+// boundarySdf = colliderSdf(), fluidSdf = the particle SDF; then applyBoundaryCondition.
+int jetcu_hybrid_set_viscosity(jetcu_hybrid* h, double coefficient) {
+    if (!h) return JETCU_ERR_INVALID_ARG;
+    if (!(coefficient >= 0.0)) return jetcu_fail(h->ctx, JETCU_ERR_INVALID_ARG, "viscosity coefficient %g", coefficient);
+    h->viscosity = coefficient;
+    return JETCU_OK;
+}
+
+int jetcu_hybrid_compute_viscosity(jetcu_hybrid* h, double dt, jetcu_mgpcg_result results[3]) {
+    HYB_ENTER(h);
+    if (results) memset(results, 0, 3 * sizeof(jetcu_mgpcg_result));
+    if (!(h->viscosity > DBL_EPSILON)) return JETCU_OK;
+    if (h->world > 1)
+        return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED, "computeViscosity (ICCG) is not slab-distributed: one GPU only");
+    double *u0 = nullptr, *v0 = nullptr, *w0 = nullptr;
+    int rc = JETCU_OK;
+#define STEP(e) if (rc == JETCU_OK) rc = (e)
+    STEP(jc_alloc(ctx, &u0, h->nu)); STEP(jc_alloc(ctx, &v0, h->nv)); STEP(jc_alloc(ctx, &w0, h->nw));
+    STEP(jc_d2d(ctx, u0, h->u, h->nu)); STEP(jc_d2d(ctx, v0, h->v, h->nv)); STEP(jc_d2d(ctx, w0, h->w, h->nw));
+    STEP(diffusion_solve_faces(ctx, gridd(h), u0, v0, w0, h->viscosity, dt, 1, h->col.kind != 0 ? h->col_sdf : nullptr, h->sdf, 100,
+                               DBL_EPSILON, h->u, h->v, h->w, results));
+#undef STEP
+    jc_free(ctx, u0); jc_free(ctx, v0); jc_free(ctx, w0);
+    if (rc != JETCU_OK) return rc;
+    return jetcu_hybrid_apply_boundary_condition(h);
+}
+
 int jetcu_hybrid_compute_pressure(jetcu_hybrid* h, double dt, jetcu_mgpcg_result* result) {
     HYB_ENTER(h);
     (void)dt;
@@ -1689,7 +1767,7 @@ int jetcu_hybrid_move_particles(jetcu_hybrid* h, double dt) {
     JC_TRY(hyb_before_move(h, count));
     if (h->np) {
         JC_TRY(hyb_pack_pairs(h, false));
-        HYB_SAMPLER_LAUNCH(k_move, jc_blocks(h->np, 128), 128, g, h->pair[0], h->pair[1], h->pair[2], sub_dt, nsub,
+        HYB_MOVE_LAUNCH(k_move, jc_blocks(h->np, 128), 128, g, h->pair[0], h->pair[1], h->pair[2], sub_dt, nsub,
                            h->P.closed_domain_boundary_flag, owned_ptrs(h), (size_t)h->np, h->cell_of, h->rank,
                            count ? h->cell_start : nullptr);
     }
@@ -1713,11 +1791,11 @@ static int hyb_g2p_move(jetcu_hybrid* h, double dt) {
     JC_TRY(hyb_before_move(h, count));
     if (h->np) {
         if (flip)
-            HYB_SAMPLER_LAUNCH(k_flip_move, jc_blocks(h->np, 128), 128, g, h->pair[0], h->pair[1], h->pair[2], h->ud, h->vd, h->wd,
+            HYB_MOVE_LAUNCH(k_flip_move, jc_blocks(h->np, 128), 128, g, h->pair[0], h->pair[1], h->pair[2], h->ud, h->vd, h->wd,
                                sub_dt, nsub, h->P.closed_domain_boundary_flag, owned_ptrs(h), (size_t)h->np, h->cell_of, h->rank,
                                count ? h->cell_start : nullptr);
         else
-            HYB_SAMPLER_LAUNCH(k_pic_move, jc_blocks(h->np, 128), 128, g, h->pair[0], h->pair[1], h->pair[2], sub_dt, nsub,
+            HYB_MOVE_LAUNCH(k_pic_move, jc_blocks(h->np, 128), 128, g, h->pair[0], h->pair[1], h->pair[2], sub_dt, nsub,
                                h->P.closed_domain_boundary_flag, owned_ptrs(h), (size_t)h->np, h->cell_of, h->rank,
                                count ? h->cell_start : nullptr);
     }
@@ -1748,6 +1826,7 @@ int jetcu_hybrid_step(jetcu_hybrid* h, double dt, jetcu_step_stats* st) {
     MARK(4);
     JC_TRY(hyb_zero_walls(h));
     JC_TRY(jetcu_hybrid_compute_external_forces(h, dt));
+    JC_TRY(jetcu_hybrid_compute_viscosity(h, dt, nullptr));   // no-op unless set_viscosity(> kEpsilonD); counted under ms_bc
     MARK(5);
     JC_TRY(jetcu_hybrid_compute_pressure(h, dt, nullptr));
     MARK(6);

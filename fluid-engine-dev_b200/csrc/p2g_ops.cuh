@@ -70,7 +70,7 @@ struct P2GGlobalSrc {   // straight from the SoA arrays in HBM
 // Partial sums of one cell for component AX.  sv / sw: P2G_SLOTS accumulators (value, weight); returns the mask of slots
 // that are a real corner of at least one particle (the reference marks all 8 corners of a particle, also those that get
 // weight 0).  Slots outside a particle's actual 2x2x2 corners receive weight 0 (val = +-0): adding them changes nothing.
-template <bool APIC, int AX, class Src>
+template <bool APIC, int AX, class Src, bool PF = true>
 __host__ __device__ __forceinline__ unsigned p2g_cell_partial(const GridD& g, int ci, int cj, int ck, uint32_t s0, uint32_t e0,
                                                               const Src& a, double* sv, double* sw, int* err) {
     constexpr int NX = AX == 0 ? 2 : 3, NY = AX == 1 ? 2 : 3, NZ = AX == 2 ? 2 : 3;
@@ -83,17 +83,34 @@ __host__ __device__ __forceinline__ unsigned p2g_cell_partial(const GridD& g, in
 #pragma unroll
     for (int s = 0; s < P2G_SLOTS; ++s) { sv[s] = 0.0; sw[s] = 0.0; }
     unsigned touched = 0;
+    // software pipeline: the next particle's attributes are requested before the current one is accumulated, so the
+    // ~250-instruction dependent chain of a particle hides the L2 latency of the next loads (ncu, profiles/r02_p2g_variants.md:
+    // long-scoreboard stalls were 43 % of the cycles between two issues with 16 resident warps per SM)
+    double npx = 0.0, npy = 0.0, npz = 0.0, npv = 0.0, nc0 = 0.0, nc1 = 0.0, nc2 = 0.0;
+    if (PF && s0 < e0) {
+        npx = a.get(0, s0); npy = a.get(1, s0); npz = a.get(2, s0); npv = a.get(P2G_A_VEL, s0);
+        if (APIC) { nc0 = a.get(P2G_A_C0, s0); nc1 = a.get(P2G_A_C0 + 1, s0); nc2 = a.get(P2G_A_C0 + 2, s0); }
+    }
     for (uint32_t q = s0; q < e0; ++q) {
-        double px = a.get(0, q), py = a.get(1, q), pz = a.get(2, q);
+        double px = npx, py = npy, pz = npz;
+        double pv = npv;
+        double c0 = nc0, c1 = nc1, c2 = nc2;
+        if (!PF) {   // plain form: load, then accumulate
+            px = a.get(0, q); py = a.get(1, q); pz = a.get(2, q);
+        } else if (q + 1 < e0) {
+            npx = a.get(0, q + 1); npy = a.get(1, q + 1); npz = a.get(2, q + 1); npv = a.get(P2G_A_VEL, q + 1);
+            if (APIC) { nc0 = a.get(P2G_A_C0, q + 1); nc1 = a.get(P2G_A_C0 + 1, q + 1); nc2 = a.get(P2G_A_C0 + 2, q + 1); }
+        }
         if (APIC) {  // tangential clamp to [lo + h/2, hi - h/2] (apic_solver3.cpp:76-84,94-102,112-120)
             if (AX != 0) px = jc_clamp(px, g.ox + g.hx / 2.0, (g.ox + g.hx * (double)g.nx) - g.hx / 2.0);
             if (AX != 1) py = jc_clamp(py, g.oy + g.hy / 2.0, (g.oy + g.hy * (double)g.ny) - g.hy / 2.0);
             if (AX != 2) pz = jc_clamp(pz, g.oz + g.hz / 2.0, (g.oz + g.hz * (double)g.nz) - g.hz / 2.0);
         }
         const BaseFrac bf = jc_base_mul(sx, sy, sz, ihx, ihy, ihz, ox, oy, oz, px, py, pz);
-        const double pv = a.get(P2G_A_VEL, q);
-        double c0 = 0.0, c1 = 0.0, c2 = 0.0;
-        if (APIC) { c0 = a.get(P2G_A_C0, q); c1 = a.get(P2G_A_C0 + 1, q); c2 = a.get(P2G_A_C0 + 2, q); }
+        if (!PF) {
+            pv = a.get(P2G_A_VEL, q);
+            if (APIC) { c0 = a.get(P2G_A_C0, q); c1 = a.get(P2G_A_C0 + 1, q); c2 = a.get(P2G_A_C0 + 2, q); }
+        }
         const int dx = bf.i - bx0, dy = bf.j - by0, dz = bf.k - bz0;  // 0 on the node axis, 0 or 1 on the centred ones
         const bool inwin = (unsigned)dx <= (AX == 0 ? 0u : 1u) && (unsigned)dy <= (AX == 1 ? 0u : 1u) &&
                            (unsigned)dz <= (AX == 2 ? 0u : 1u);

@@ -39,10 +39,39 @@ __host__ __device__ __forceinline__ double sample_rows(const double* __restrict_
     return jc_lerp(a, b, fz);
 }
 
+// Corner cache of the advection kernel.  The 10 samples of one particle's midpoint sub-steps (pic_solver3.cpp:206-282) lie
+// within a fraction of a cell of each other, so consecutive samples of a component mostly interpolate between the SAME 8
+// corner values.  ncu (profiles/r02_c7_move.md) shows the kernel bound by L1 data-stage wavefronts — 120 128-bit loads per
+// particle, 86 % of the LSU data pipe, FP64 pipe 40 % — so the corners of the last sample stay in registers, keyed by the
+// linear index of the base corner, and are reloaded only when the base changes.  Same doubles, same expressions:
+// bit-identical to the uncached form (tests/hostcheck runs this very source against the oracle).
+template <typename I>
+struct CornerCache {
+    I key[3];
+    double c[3][8];
+    __host__ __device__ __forceinline__ CornerCache() { key[0] = key[1] = key[2] = (I)-1; }
+};
+
+template <typename I>
+__host__ __device__ __forceinline__ double sample_rows_cached(const double* __restrict__ d, I r00, I r10, I r01, I r11, int i,
+                                                              double fx, double fy, double fz, I* key, double* c) {
+    const I k0 = r00 + (I)i;
+    if (k0 != *key) {
+        jc_load_x2<true>(d, (size_t)(r00 + i), 0, &c[0], &c[1]);
+        jc_load_x2<true>(d, (size_t)(r10 + i), 0, &c[2], &c[3]);
+        jc_load_x2<true>(d, (size_t)(r01 + i), 0, &c[4], &c[5]);
+        jc_load_x2<true>(d, (size_t)(r11 + i), 0, &c[6], &c[7]);
+        *key = k0;
+    }
+    const double a = jc_lerp(jc_lerp(c[0], c[1], fx), jc_lerp(c[2], c[3], fx), fy);
+    const double b = jc_lerp(jc_lerp(c[4], c[5], fx), jc_lerp(c[6], c[7], fx), fy);
+    return jc_lerp(a, b, fz);
+}
+
 template <bool POW2, typename I, bool PAIRS = false>
 __host__ __device__ __forceinline__ void sample_velocity(const GridD& g, const double* __restrict__ u, const double* __restrict__ v,
                                                 const double* __restrict__ w, double px, double py, double pz, double* ou,
-                                                double* ov, double* ow) {
+                                                double* ov, double* ow, CornerCache<I>* cc = nullptr) {
     // FaceCenteredGrid3::sample: three LinearArraySampler3::operator() calls (face_centered_grid3.cpp:447-467).
     // The three component grids share their per-axis normalisations pairwise (node-aligned along the component's own
     // axis, cell-centred along the other two), so 6 barycentric evaluations serve all 3 samplers instead of 9; each is
@@ -58,6 +87,24 @@ __host__ __device__ __forceinline__ void sample_velocity(const GridD& g, const d
     const int inx1 = min(inx + 1, g.nx), icx1 = min(icx + 1, g.nx - 1);
     const int jny1 = min(jny + 1, g.ny), jcy1 = min(jcy + 1, g.ny - 1);
     const int knz1 = min(knz + 1, g.nz), kcz1 = min(kcz + 1, g.nz - 1);
+    if (PAIRS && cc) {   // the pair entry at i already holds the value at min(i + 1, sx - 1): i1 is not needed
+        {
+            const I sy = (I)(g.nx + 1), sz = sy * (I)g.ny;
+            *ou = sample_rows_cached<I>(u, (I)kcz * sz + (I)jcy * sy, (I)kcz * sz + (I)jcy1 * sy, (I)kcz1 * sz + (I)jcy * sy,
+                                        (I)kcz1 * sz + (I)jcy1 * sy, inx, fnx, fcy, fcz, &cc->key[0], cc->c[0]);
+        }
+        {
+            const I sy = (I)g.nx, sz = sy * (I)(g.ny + 1);
+            *ov = sample_rows_cached<I>(v, (I)kcz * sz + (I)jny * sy, (I)kcz * sz + (I)jny1 * sy, (I)kcz1 * sz + (I)jny * sy,
+                                        (I)kcz1 * sz + (I)jny1 * sy, icx, fcx, fny, fcz, &cc->key[1], cc->c[1]);
+        }
+        {
+            const I sy = (I)g.nx, sz = sy * (I)g.ny;
+            *ow = sample_rows_cached<I>(w, (I)knz * sz + (I)jcy * sy, (I)knz * sz + (I)jcy1 * sy, (I)knz1 * sz + (I)jcy * sy,
+                                        (I)knz1 * sz + (I)jcy1 * sy, icx, fcx, fcy, fnz, &cc->key[2], cc->c[2]);
+        }
+        return;
+    }
     {
         const I sy = (I)(g.nx + 1), sz = sy * (I)g.ny;
         *ou = sample_rows<PAIRS, I>(u, (I)kcz * sz + (I)jcy * sy, (I)kcz * sz + (I)jcy1 * sy, (I)kcz1 * sz + (I)jcy * sy,
@@ -148,15 +195,16 @@ __host__ __device__ __forceinline__ void apic_affine(const GridD& g, const doubl
 // fused G2P + advection kernel) and replaces the first sample of the first sub-step — the same expression at the same point.
 template <bool POW2, typename I, bool PAIRS = false>
 __host__ __device__ __forceinline__ void move_particle(const GridD& g, const double* u, const double* v, const double* w, double dt,
-                                                       unsigned nsub, int flag, double* pos, double* vel, const double* first = nullptr) {
+                                                       unsigned nsub, int flag, double* pos, double* vel, const double* first = nullptr,
+                                                       CornerCache<I>* cc = nullptr) {
     double p0x = pos[0], p0y = pos[1], p0z = pos[2];
     double p1x = p0x, p1y = p0y, p1z = p0z;
     for (unsigned t = 0; t < nsub; ++t) {
         double v0x, v0y, v0z, mvx, mvy, mvz;
         if (t == 0 && first) { v0x = first[0]; v0y = first[1]; v0z = first[2]; }
-        else sample_velocity<POW2, I, PAIRS>(g, u, v, w, p0x, p0y, p0z, &v0x, &v0y, &v0z);
+        else sample_velocity<POW2, I, PAIRS>(g, u, v, w, p0x, p0y, p0z, &v0x, &v0y, &v0z, cc);
         double mx = p0x + 0.5 * dt * v0x, my = p0y + 0.5 * dt * v0y, mz = p0z + 0.5 * dt * v0z;
-        sample_velocity<POW2, I, PAIRS>(g, u, v, w, mx, my, mz, &mvx, &mvy, &mvz);
+        sample_velocity<POW2, I, PAIRS>(g, u, v, w, mx, my, mz, &mvx, &mvy, &mvz, cc);
         p1x = p0x + dt * mvx; p1y = p0y + dt * mvy; p1z = p0z + dt * mvz;
         p0x = p1x; p0y = p1y; p0z = p1z;
     }

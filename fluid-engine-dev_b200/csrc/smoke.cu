@@ -12,6 +12,7 @@
 
 #include "pressure.cuh"
 #include "smoke_ops.cuh"
+#include "diffusion.cuh"
 
 struct jetcu_smoke {
     jetcu_ctx* ctx = nullptr;
@@ -32,6 +33,8 @@ struct jetcu_smoke {
     jetcu_mgpcg_result last{};
     cudaEvent_t ev[5] = {};
     double ms_forces = 0, ms_pressure = 0, ms_advection = 0, ms_decay = 0;
+    // GridFluidSolver3::viscosityCoefficient, GridSmokeSolver3::smokeDiffusionCoefficient / temperatureDiffusionCoefficient
+    double viscosity = 0.0, smoke_diffusion = 0.0, temperature_diffusion = 0.0;
 };
 
 static GridD smoke_grid(const jetcu_smoke* h) {
@@ -478,16 +481,52 @@ int jetcu_smoke_compute_advection(jetcu_smoke* h, double dt) {
     return smoke_apply_bc(h);
 }
 
-// GridSmokeSolver3::onEndAdvanceTimeStep -> computeDiffusion with zero diffusion coefficients: the decays (:118-128)
+// setViscosityCoefficient / setSmokeDiffusionCoefficient / setTemperatureDiffusionCoefficient
+int jetcu_smoke_set_diffusion(jetcu_smoke* h, double viscosity, double smoke_diffusion, double temperature_diffusion) {
+    if (!h) return JETCU_ERR_INVALID_ARG;
+    if (!(viscosity >= 0.0 && smoke_diffusion >= 0.0 && temperature_diffusion >= 0.0))
+        return jetcu_fail(h->ctx, JETCU_ERR_INVALID_ARG, "negative diffusion coefficient");
+    h->viscosity = viscosity; h->smoke_diffusion = smoke_diffusion; h->temperature_diffusion = temperature_diffusion;
+    return JETCU_OK;
+}
+
+// GridFluidSolver3::computeViscosity (grid_fluid_solver3.cpp:231-241): fluidSdf() of a grid fluid solver is
+// ConstantScalarField3(-kMaxD), so every sample outside the collider is fluid.  Single GPU (ICCG).
+int jetcu_smoke_compute_viscosity(jetcu_smoke* h, double dt) {
+    SMK_ENTER(h);
+    if (!(h->viscosity > DBL_EPSILON)) return JETCU_OK;
+    JC_TRY(jc_d2d(ctx, h->u0, h->u, h->nu)); JC_TRY(jc_d2d(ctx, h->v0, h->v, h->nv)); JC_TRY(jc_d2d(ctx, h->w0, h->w, h->nw));
+    JC_TRY(diffusion_solve_faces(ctx, smoke_grid(h), h->u0, h->v0, h->w0, h->viscosity, dt, 1, h->col.kind != 0 ? h->col_sdf : nullptr,
+                                 nullptr, 100, DBL_EPSILON, h->u, h->v, h->w, nullptr));
+    return smoke_apply_bc(h);
+}
+
+// one scalar of GridSmokeSolver3::computeDiffusion (grid_smoke_solver3.cpp:91-117): solve on a clone, extrapolateIntoCollider
+static int smoke_diffuse_scalar(jetcu_smoke* h, double* field, double coefficient, double dt) {
+    jetcu_ctx* ctx = h->ctx;
+    const GridD g = smoke_grid(h);
+    const double* csdf = h->col.kind != 0 ? h->col_sdf : nullptr;
+    JC_TRY(jc_d2d(ctx, h->scratch, field, h->nc));
+    JC_TRY(diffusion_solve_array(ctx, g, 0, h->scratch, coefficient, dt, 1, csdf, nullptr, 100, DBL_EPSILON, field, nullptr, nullptr));
+    if (csdf) {
+        JC_LAUNCH(ctx, k_smk_outside_marker, sgrid(h->nx, h->ny, h->nz), dim3(64, 4), 0, g, csdf, h->cm_u);
+        JC_TRY(smoke_extrapolate(h, field, h->cm_u, h->nx, h->ny, h->nz, (unsigned)ceil(h->P.max_cfl)));
+    }
+    return JETCU_OK;
+}
+
+// GridSmokeSolver3::onEndAdvanceTimeStep -> computeDiffusion (:85-128): the scalar diffusion solves where their coefficients are
+// > kEpsilonD, then the decays
 int jetcu_smoke_end_advance_time_step(jetcu_smoke* h, double dt) {
     SMK_ENTER(h);
-    (void)dt;
+    if (h->smoke_diffusion > DBL_EPSILON) JC_TRY(smoke_diffuse_scalar(h, h->den, h->smoke_diffusion, dt));
+    if (h->temperature_diffusion > DBL_EPSILON) JC_TRY(smoke_diffuse_scalar(h, h->temp, h->temperature_diffusion, dt));
     JC_LAUNCH(ctx, k_smoke_scale, jc_blocks(h->nc, 256), 256, 0, h->den, 1.0 - h->P.density_decay, h->nc);
     JC_LAUNCH(ctx, k_smoke_scale, jc_blocks(h->nc, 256), 256, 0, h->temp, 1.0 - h->P.temperature_decay, h->nc);
     return JETCU_OK;
 }
 
-// GridFluidSolver3::onAdvanceTimeStep (grid_fluid_solver3.cpp:179-210); viscosity 0 -> computeViscosity skipped (:231-241)
+// GridFluidSolver3::onAdvanceTimeStep (grid_fluid_solver3.cpp:179-210)
 int jetcu_smoke_step(jetcu_smoke* h, double dt, jetcu_mgpcg_result* result) {
     SMK_ENTER(h);
     if (!h->ev[0]) for (auto& e : h->ev) JC_CUDA(ctx, cudaEventCreate(&e));
@@ -495,6 +534,7 @@ int jetcu_smoke_step(jetcu_smoke* h, double dt, jetcu_mgpcg_result* result) {
     cudaEventRecord(h->ev[0], st);
     JC_TRY(smoke_apply_bc(h));  // beginAdvanceTimeStep: applyBoundaryCondition (:455-456)
     JC_TRY(jetcu_smoke_compute_external_forces(h, dt));
+    JC_TRY(jetcu_smoke_compute_viscosity(h, dt));   // no-op unless set_diffusion(viscosity > kEpsilonD)
     cudaEventRecord(h->ev[1], st);
     JC_TRY(jetcu_smoke_compute_pressure(h, dt, result));
     cudaEventRecord(h->ev[2], st);

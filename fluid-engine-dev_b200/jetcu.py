@@ -234,6 +234,14 @@ class SmokeApi:
     def end_advance_time_step(self, dt):
         self._c("smoke_end_advance_time_step", self.h, f64(dt))
 
+    def set_diffusion(self, viscosity=0.0, smoke_diffusion=0.0, temperature_diffusion=0.0):
+        """GridFluidSolver3::setViscosityCoefficient, GridSmokeSolver3::setSmokeDiffusionCoefficient /
+        setTemperatureDiffusionCoefficient (> kEpsilonD switches the GridBackwardEulerDiffusionSolver3 solves on)."""
+        self._c("smoke_set_diffusion", self.h, f64(viscosity), f64(smoke_diffusion), f64(temperature_diffusion))
+
+    def compute_viscosity(self, dt):
+        self._c("smoke_compute_viscosity", self.h, f64(dt))
+
 
 def size3(shape_xyz):
     """numpy arrays holding Jet Array3 data are indexed [k, j, i] (x fastest)."""
@@ -355,6 +363,28 @@ class LinearApi:
                    _p(c64(bnd[1])), _p(c64(bnd[2])), _p(c64(fluid_sdf)), C.byref(params), _p(uo), _p(vo), _p(wo),
                    _p(p), C.byref(res))
         return uo, vo, wo, p, res
+
+    def diffusion_solve_faces(self, grid, u, v, w, coefficient, dt, boundary_type=1, collider_sdf=None, fluid_sdf=None,
+                              max_iterations=100, tolerance=2.220446049250313e-16):
+        """GridBackwardEulerDiffusionSolver3::solve(FaceCenteredGrid3) — boundary_type 0 Dirichlet, 1 Neumann (Jet's default);
+        ICCG(100, kEpsilonD) unless told otherwise.  Returns u, v, w and the three solves' results."""
+        uo, vo, wo = np.zeros_like(u), np.zeros_like(v), np.zeros_like(w)
+        res = (MgpcgResult * 3)()
+        self._call("diffusion_solve_faces", C.byref(grid), _p(c64(u)), _p(c64(v)), _p(c64(w)), f64(coefficient), f64(dt),
+                   C.c_int(boundary_type), _p(c64(collider_sdf)), _p(c64(fluid_sdf)), u32(max_iterations), f64(tolerance),
+                   _p(uo), _p(vo), _p(wo), res)
+        return uo, vo, wo, list(res)
+
+    def diffusion_solve_cells(self, grid, source, coefficient, dt, boundary_type=1, collider_sdf=None, fluid_sdf=None,
+                              max_iterations=100, tolerance=2.220446049250313e-16, want_markers=False):
+        """GridBackwardEulerDiffusionSolver3::solve(ScalarGrid3) on a cell-centred grid."""
+        dest = np.zeros_like(source)
+        markers = np.zeros(source.shape, dtype=np.int8) if want_markers else None
+        res = MgpcgResult()
+        self._call("diffusion_solve_cells", C.byref(grid), _p(c64(source)), f64(coefficient), f64(dt), C.c_int(boundary_type),
+                   _p(c64(collider_sdf)), _p(c64(fluid_sdf)), u32(max_iterations), f64(tolerance), _p(dest),
+                   markers.ctypes.data_as(C.c_void_p) if want_markers else None, C.byref(res))
+        return (dest, res, markers) if want_markers else (dest, res)
 
     def pressure_get_system(self, grid, level):
         nx, ny, nz = (int(grid.nx) >> level, int(grid.ny) >> level, int(grid.nz) >> level)
@@ -578,6 +608,15 @@ class HybridApi:
         r = MgpcgResult()
         self._c("hybrid_compute_pressure", self.h, f64(dt), C.byref(r))
         return r
+
+    def set_viscosity(self, coefficient):
+        """GridFluidSolver3::setViscosityCoefficient: > kEpsilonD switches computeViscosity on in step()."""
+        self._c("hybrid_set_viscosity", self.h, f64(coefficient))
+
+    def compute_viscosity(self, dt):
+        r = (MgpcgResult * 3)()
+        self._c("hybrid_compute_viscosity", self.h, f64(dt), r)
+        return list(r)
 
     def transfer_grids_to_particles(self):
         self._c("hybrid_transfer_grids_to_particles", self.h)

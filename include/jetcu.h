@@ -194,6 +194,21 @@ int jetcu_iccg_solve(jetcu_ctx*, uint64_t nx, uint64_t ny, uint64_t nz, const je
 int jetcu_iccg_precondition(jetcu_ctx*, uint64_t nx, uint64_t ny, uint64_t nz, const jetcu_matrix_row* A, const double* b,
                             double* d, double* y, double* x);
 
+/* == jet::GridBackwardEulerDiffusionSolver3::solve (src/jet/grid_backward_euler_diffusion_solver3.cpp), SURVEY §8f-4: the
+ * FaceCenteredGrid3 overload (:108-160: u, v, w one after the other, each with its own markers) and the ScalarGrid3 overload
+ * (:22-50) on a CellCenteredScalarGrid3.  Host buffers, x-fastest.  boundary_type 0 = Dirichlet, 1 = Neumann (the class
+ * default, header :38).  collider_sdf / fluid_sdf: cell-centred SDF arrays sampled linearly at the data positions, or NULL
+ * for the constant fields the fluid solvers pass when there is none (collider grid filled with kMaxD; ConstantScalarField3(
+ * -kMaxD)).  Linear solver: FdmIccgSolver3(max_iterations, tolerance) — the class default is (100, kEpsilonD), :20-23.
+ * markers (optional): kFluid 0 / kAir 1 / kBoundary 2 per sample (:16-18).  Single GPU. */
+int jetcu_diffusion_solve_faces(jetcu_ctx*, const jetcu_grid* grid, const double* u, const double* v, const double* w,
+                                double coefficient, double dt, int boundary_type, const double* collider_sdf,
+                                const double* fluid_sdf, uint32_t max_iterations, double tolerance, double* u_out, double* v_out,
+                                double* w_out, jetcu_mgpcg_result results[3]);
+int jetcu_diffusion_solve_cells(jetcu_ctx*, const jetcu_grid* grid, const double* source, double coefficient, double dt,
+                                int boundary_type, const double* collider_sdf, const double* fluid_sdf, uint32_t max_iterations,
+                                double tolerance, double* dest, char* markers, jetcu_mgpcg_result* result);
+
 /* Number of MG levels Jet builds for a finest resolution (FdmMgUtils3::resizeArrayWithFinest,
  * include/jet/detail/fdm_mg_linear_system3-inl.h:34-50). */
 uint32_t jetcu_mg_num_levels(uint64_t nx, uint64_t ny, uint64_t nz, uint32_t max_levels);
@@ -400,6 +415,13 @@ int jetcu_hybrid_extrapolate_velocity_to_air(jetcu_hybrid*);         /* PicSolve
 int jetcu_hybrid_begin_advance_time_step(jetcu_hybrid*, double dt);  /* beginAdvanceTimeStep incl. PicSolver3::onBeginAdvanceTimeStep */
 int jetcu_hybrid_compute_external_forces(jetcu_hybrid*, double dt);  /* computeGravity + BC */
 int jetcu_hybrid_compute_pressure(jetcu_hybrid*, double dt, jetcu_mgpcg_result* result); /* computePressure + BC */
+/* == GridFluidSolver3::setViscosityCoefficient / computeViscosity (src/jet/grid_fluid_solver3.cpp:231-241).  A coefficient
+ * > kEpsilonD makes jetcu_hybrid_step run computeViscosity between the external forces and the pressure projection: the three
+ * face grids through GridBackwardEulerDiffusionSolver3 (its default boundary type, Neumann; ICCG(100, kEpsilonD)) with
+ * boundarySdf = the collider SDF and fluidSdf = the particle SDF, then applyBoundaryCondition.  results (optional): the u, v, w
+ * ICCG solves.  Single GPU (ICCG is not slab-distributed: JETCU_ERR_UNSUPPORTED under a communicator). */
+int jetcu_hybrid_set_viscosity(jetcu_hybrid*, double coefficient);
+int jetcu_hybrid_compute_viscosity(jetcu_hybrid*, double dt, jetcu_mgpcg_result results[3]);
 int jetcu_hybrid_transfer_grids_to_particles(jetcu_hybrid*);         /* transferFromGridsToParticles */
 int jetcu_hybrid_move_particles(jetcu_hybrid*, double dt);           /* PicSolver3::moveParticles */
 int jetcu_hybrid_compute_advection(jetcu_hybrid*, double dt);        /* PicSolver3::computeAdvection */
@@ -459,7 +481,13 @@ int jetcu_smoke_step(jetcu_smoke*, double dt, jetcu_mgpcg_result* result);      
 int jetcu_smoke_compute_external_forces(jetcu_smoke*, double dt);                          /* computeBuoyancyForce + BC */
 int jetcu_smoke_compute_pressure(jetcu_smoke*, double dt, jetcu_mgpcg_result* result);     /* computePressure + BC */
 int jetcu_smoke_compute_advection(jetcu_smoke*, double dt);                                /* computeAdvection */
-int jetcu_smoke_end_advance_time_step(jetcu_smoke*, double dt);                            /* computeDiffusion (decay) */
+int jetcu_smoke_end_advance_time_step(jetcu_smoke*, double dt);                            /* computeDiffusion (diffusion + decay) */
+/* == GridFluidSolver3::setViscosityCoefficient, GridSmokeSolver3::setSmokeDiffusionCoefficient / setTemperatureDiffusionCoefficient.
+ * Coefficients > kEpsilonD switch on computeViscosity in jetcu_smoke_step (src/jet/grid_fluid_solver3.cpp:231-241) and the scalar
+ * solves of computeDiffusion in jetcu_smoke_end_advance_time_step (src/jet/grid_smoke_solver3.cpp:85-117), each through
+ * GridBackwardEulerDiffusionSolver3 (Neumann, ICCG(100, kEpsilonD)) with the collider SDF as boundary.  Single GPU. */
+int jetcu_smoke_set_diffusion(jetcu_smoke*, double viscosity, double smoke_diffusion, double temperature_diffusion);
+int jetcu_smoke_compute_viscosity(jetcu_smoke*, double dt);
 
 #ifdef __cplusplus
 }

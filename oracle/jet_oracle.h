@@ -145,6 +145,25 @@ int jeto_hybrid_compute_pressure(jeto_hybrid*, double dt, jeto_mgpcg_result* res
 int jeto_hybrid_transfer_grids_to_particles(jeto_hybrid*);
 int jeto_hybrid_move_particles(jeto_hybrid*, double dt);
 int jeto_hybrid_compute_advection(jeto_hybrid*, double dt);
+/* GridFluidSolver3::setViscosityCoefficient / computeViscosity (src/jet/grid_fluid_solver3.cpp:231-241): when > kEpsilonD the
+ * step solves the three face grids with the solver's GridBackwardEulerDiffusionSolver3 (default boundary type, ICCG(100,
+ * kEpsilonD)) between the external forces and the pressure projection.  results: the u, v, w ICCG solves (port) / the w solve
+ * in all three slots (reference shim: the class exposes its last solve only). */
+int jeto_hybrid_set_viscosity(jeto_hybrid*, double coefficient);
+int jeto_hybrid_compute_viscosity(jeto_hybrid*, double dt, jeto_mgpcg_result results[3]);
+
+/* ---------------------------------------------------------------- GridBackwardEulerDiffusionSolver3
+ * solve(FaceCenteredGrid3) / solve(ScalarGrid3 = CellCenteredScalarGrid3) of src/jet/grid_backward_euler_diffusion_solver3.cpp
+ * with FdmIccgSolver3(max_iterations, tolerance) (the class default is (100, kEpsilonD), :20-23).  boundary_type 0 = Dirichlet,
+ * 1 = Neumann (header default).  collider_sdf / fluid_sdf: cell-centred SDF arrays (CellCenteredScalarGrid3, sampled linearly at
+ * the data positions) or NULL for the constant fields the fluid solvers pass when there is none (+kMaxD / -kMaxD). */
+int jeto_diffusion_solve_faces(const jeto_grid* grid, const double* u, const double* v, const double* w, double coefficient, double dt,
+                               int boundary_type, const double* collider_sdf, const double* fluid_sdf, uint32_t max_iterations,
+                               double tolerance, double* u_out, double* v_out, double* w_out, jeto_mgpcg_result results[3]);
+int jeto_diffusion_solve_cells(const jeto_grid* grid, const double* source, double coefficient, double dt, int boundary_type,
+                               const double* collider_sdf, const double* fluid_sdf, uint32_t max_iterations, double tolerance,
+                               double* dest, char* markers /* optional: kFluid 0 / kAir 1 / kBoundary 2 (port only) */,
+                               jeto_mgpcg_result* result);
 
 /* ---------------------------------------------------------------- GridSmokeSolver3 (BASELINE config 5)
  * GridSmokeSolver3 (src/jet/grid_smoke_solver3.cpp) on GridFluidSolver3::onAdvanceTimeStep
@@ -183,7 +202,11 @@ int jeto_smoke_step(jeto_smoke*, double dt, jeto_mgpcg_result* result);         
 int jeto_smoke_compute_external_forces(jeto_smoke*, double dt);                    /* computeBuoyancyForce + BC */
 int jeto_smoke_compute_pressure(jeto_smoke*, double dt, jeto_mgpcg_result* result);
 int jeto_smoke_compute_advection(jeto_smoke*, double dt);
-int jeto_smoke_end_advance_time_step(jeto_smoke*, double dt);                      /* computeDiffusion: decay */
+int jeto_smoke_end_advance_time_step(jeto_smoke*, double dt);                      /* computeDiffusion: diffusion + decay */
+/* GridFluidSolver3::setViscosityCoefficient, GridSmokeSolver3::setSmokeDiffusionCoefficient / setTemperatureDiffusionCoefficient:
+ * coefficients > kEpsilonD switch computeViscosity (step) / the scalar diffusion solves (end_advance_time_step) on. */
+int jeto_smoke_set_diffusion(jeto_smoke*, double viscosity, double smoke_diffusion, double temperature_diffusion);
+int jeto_smoke_compute_viscosity(jeto_smoke*, double dt);
 
 #ifdef __cplusplus
 }

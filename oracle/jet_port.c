@@ -878,4 +878,5 @@ int jeto_pressure_get_system(uint32_t level, jeto_row* A, double* b, float* flui
 
 #include "jet_port_collider.inc"
 #include "jet_port_particles.inc"
+#include "jet_port_diffusion.inc"
 #include "jet_port_smoke.inc"

@@ -735,6 +735,86 @@ int jeto_hybrid_transfer_grids_to_particles(jeto_hybrid* h) { h->solver->transfe
 int jeto_hybrid_move_particles(jeto_hybrid* h, double dt) { h->solver->moveParticles(dt); return 0; }
 int jeto_hybrid_compute_advection(jeto_hybrid* h, double dt) { h->solver->computeAdvection(dt); return 0; }
 
+// ------------------------------------------------------------------ GridBackwardEulerDiffusionSolver3
+int jeto_hybrid_set_viscosity(jeto_hybrid* h, double coefficient) { h->solver->setViscosityCoefficient(coefficient); return 0; }
+
+static void fillIccgResult(const std::shared_ptr<FdmIccgSolver3>& iccg, jeto_mgpcg_result* r) {
+    std::memset(r, 0, sizeof(*r));
+    r->iterations = iccg->lastNumberOfIterations();
+    r->last_residual = iccg->lastResidual();
+    r->returned = (iccg->lastResidual() <= iccg->tolerance() || iccg->lastNumberOfIterations() < iccg->maxNumberOfIterations()) ? 1 : 0;
+}
+
+int jeto_hybrid_compute_viscosity(jeto_hybrid* h, double dt, jeto_mgpcg_result results[3]) {
+    h->solver->computeViscosity(dt);
+    if (results) {
+        auto diff = std::dynamic_pointer_cast<GridBackwardEulerDiffusionSolver3>(h->solver->diffusionSolver());
+        auto iccg = diff ? std::dynamic_pointer_cast<FdmIccgSolver3>(diff->_systemSolver) : nullptr;
+        for (int q = 0; q < 3; ++q) {
+            std::memset(&results[q], 0, sizeof(results[q]));
+            if (iccg && h->solver->viscosityCoefficient() > kEpsilonD) fillIccgResult(iccg, &results[q]);
+        }
+    }
+    return 0;
+}
+
+static ScalarField3Ptr cellField(const jeto_grid* g, const double* data, double constant) {
+    if (!data) return std::make_shared<ConstantScalarField3>(constant);
+    auto grid = std::make_shared<CellCenteredScalarGrid3>(Size3(g->nx, g->ny, g->nz), Vector3D(g->hx, g->hy, g->hz),
+                                                          Vector3D(g->ox, g->oy, g->oz));
+    std::memcpy(grid->dataAccessor().data(), data, sizeof(double) * g->nx * g->ny * g->nz);
+    return grid;
+}
+
+int jeto_diffusion_solve_faces(const jeto_grid* g, const double* u, const double* v, const double* w, double coefficient, double dt,
+                               int boundary_type, const double* collider_sdf, const double* fluid_sdf, uint32_t max_iterations,
+                               double tolerance, double* ou, double* ov, double* ow, jeto_mgpcg_result results[3]) {
+    const Size3 res(g->nx, g->ny, g->nz);
+    const Vector3D hh(g->hx, g->hy, g->hz), o(g->ox, g->oy, g->oz);
+    FaceCenteredGrid3 src(res, hh, o), dst(res, hh, o);
+    std::memcpy(src.uAccessor().data(), u, sizeof(double) * (g->nx + 1) * g->ny * g->nz);
+    std::memcpy(src.vAccessor().data(), v, sizeof(double) * g->nx * (g->ny + 1) * g->nz);
+    std::memcpy(src.wAccessor().data(), w, sizeof(double) * g->nx * g->ny * (g->nz + 1));
+    // the collider SDF the fluid solvers pass is always a grid (kMaxD-filled when there is no collider)
+    std::vector<double> none;
+    if (!collider_sdf) { none.assign((size_t)g->nx * g->ny * g->nz, kMaxD); collider_sdf = none.data(); }
+    auto boundary = cellField(g, collider_sdf, kMaxD);
+    auto fluid = cellField(g, fluid_sdf, -kMaxD);
+    GridBackwardEulerDiffusionSolver3 solver(boundary_type == 0 ? GridBackwardEulerDiffusionSolver3::Dirichlet
+                                                                : GridBackwardEulerDiffusionSolver3::Neumann);
+    auto iccg = std::make_shared<FdmIccgSolver3>(max_iterations, tolerance);
+    solver.setLinearSystemSolver(iccg);
+    solver.solve(src, coefficient, dt, &dst, *boundary, *fluid);
+    std::memcpy(ou, dst.uAccessor().data(), sizeof(double) * (g->nx + 1) * g->ny * g->nz);
+    std::memcpy(ov, dst.vAccessor().data(), sizeof(double) * g->nx * (g->ny + 1) * g->nz);
+    std::memcpy(ow, dst.wAccessor().data(), sizeof(double) * g->nx * g->ny * (g->nz + 1));
+    if (results) for (int q = 0; q < 3; ++q) fillIccgResult(iccg, &results[q]);   // the w solve (the class keeps its last only)
+    return 0;
+}
+
+int jeto_diffusion_solve_cells(const jeto_grid* g, const double* source, double coefficient, double dt, int boundary_type,
+                               const double* collider_sdf, const double* fluid_sdf, uint32_t max_iterations, double tolerance,
+                               double* dest, char* markers, jeto_mgpcg_result* result) {
+    const Size3 res(g->nx, g->ny, g->nz);
+    const Vector3D hh(g->hx, g->hy, g->hz), o(g->ox, g->oy, g->oz);
+    CellCenteredScalarGrid3 src(res, hh, o), dst(res, hh, o);
+    const size_t n = (size_t)g->nx * g->ny * g->nz;
+    std::memcpy(src.dataAccessor().data(), source, sizeof(double) * n);
+    std::vector<double> none;
+    if (!collider_sdf) { none.assign(n, kMaxD); collider_sdf = none.data(); }
+    auto boundary = cellField(g, collider_sdf, kMaxD);
+    auto fluid = cellField(g, fluid_sdf, -kMaxD);
+    GridBackwardEulerDiffusionSolver3 solver(boundary_type == 0 ? GridBackwardEulerDiffusionSolver3::Dirichlet
+                                                                : GridBackwardEulerDiffusionSolver3::Neumann);
+    auto iccg = std::make_shared<FdmIccgSolver3>(max_iterations, tolerance);
+    solver.setLinearSystemSolver(iccg);
+    solver.solve(src, coefficient, dt, &dst, *boundary, *fluid);
+    std::memcpy(dest, dst.dataAccessor().data(), sizeof(double) * n);
+    if (markers) for (size_t i = 0; i < n; ++i) markers[i] = solver._markers.data()[i];
+    if (result) fillIccgResult(iccg, result);
+    return 0;
+}
+
 // ------------------------------------------------------------------ smoke solver
 struct jeto_smoke {
     std::shared_ptr<GridSmokeSolver3> solver;
@@ -828,6 +908,13 @@ int jeto_smoke_compute_pressure(jeto_smoke* h, double dt, jeto_mgpcg_result* r) 
 }
 int jeto_smoke_compute_advection(jeto_smoke* h, double dt) { h->solver->computeAdvection(dt); return 0; }
 int jeto_smoke_end_advance_time_step(jeto_smoke* h, double dt) { h->solver->endAdvanceTimeStep(dt); return 0; }
+int jeto_smoke_set_diffusion(jeto_smoke* h, double viscosity, double smokeDiffusion, double temperatureDiffusion) {
+    h->solver->setViscosityCoefficient(viscosity);
+    h->solver->setSmokeDiffusionCoefficient(smokeDiffusion);
+    h->solver->setTemperatureDiffusionCoefficient(temperatureDiffusion);
+    return 0;
+}
+int jeto_smoke_compute_viscosity(jeto_smoke* h, double dt) { h->solver->computeViscosity(dt); return 0; }
 
 int jeto_smoke_emit_step(jeto_smoke* h, const jeto_collider_shape* shapes, uint32_t n, int as_set, double dmin, double dmax,
                          double tmin, double tmax) {

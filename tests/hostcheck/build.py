@@ -18,7 +18,7 @@ def nvcc_path():
 
 
 def build():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("collider.cuh", "collider_ops.cuh", "particle_ops.cuh", "p2g_ops.cuh", "smoke_ops.cuh", "fdm_ops.cuh", "pressure_ops.cuh", "common.cuh", "sampling.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("collider.cuh", "collider_ops.cuh", "particle_ops.cuh", "p2g_ops.cuh", "smoke_ops.cuh", "fdm_ops.cuh", "pressure_ops.cuh", "common.cuh", "sampling.cuh", "diffusion_ops.cuh", "iccg_ops.cuh", "p2p_ops.cuh")]
     if os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     nvcc = nvcc_path()

@@ -17,6 +17,7 @@
 #include "../../fluid-engine-dev_b200/csrc/iccg_ops.cuh"
 #include "../../fluid-engine-dev_b200/csrc/smoke_ops.cuh"
 #include "../../fluid-engine-dev_b200/csrc/p2p_ops.cuh"
+#include "../../fluid-engine-dev_b200/csrc/diffusion_ops.cuh"
 
 static GridD make_grid(const jetcu_grid* g) {
     return GridD{(int)g->nx, (int)g->ny, (int)g->nz, g->hx, g->hy, g->hz, g->ox, g->oy, g->oz,
@@ -69,14 +70,17 @@ static void move_t(const GridD& g, const double* u, const double* v, const doubl
         pr[q].resize(2 * nf[q]);
         for (size_t i = 0; i < nf[q]; ++i) pack_pair(in[q], pr[q].data(), i, g.nx + (q == 0));
     }
+    // even particles through the corner cache (the kernels' default, CornerCache in particle_ops.cuh), odd ones without
     for (uint64_t p = 0; p < n; ++p) {
+        CornerCache<I> cache;
+        CornerCache<I>* cc = (p & 1) ? nullptr : &cache;
         if (pic_fused) {
             double* vp = vel + 3 * p;
-            sample_velocity<POW2, I, true>(g, pr[0].data(), pr[1].data(), pr[2].data(), pos[3 * p], pos[3 * p + 1], pos[3 * p + 2], vp, vp + 1, vp + 2);
+            sample_velocity<POW2, I, true>(g, pr[0].data(), pr[1].data(), pr[2].data(), pos[3 * p], pos[3 * p + 1], pos[3 * p + 2], vp, vp + 1, vp + 2, cc);
             const double first[3] = {vp[0], vp[1], vp[2]};
-            move_particle<POW2, I, true>(g, pr[0].data(), pr[1].data(), pr[2].data(), dt, nsub, flag, pos + 3 * p, vp, first);
+            move_particle<POW2, I, true>(g, pr[0].data(), pr[1].data(), pr[2].data(), dt, nsub, flag, pos + 3 * p, vp, first, cc);
         } else {
-            move_particle<POW2, I, true>(g, pr[0].data(), pr[1].data(), pr[2].data(), dt, nsub, flag, pos + 3 * p, vel + 3 * p);
+            move_particle<POW2, I, true>(g, pr[0].data(), pr[1].data(), pr[2].data(), dt, nsub, flag, pos + 3 * p, vel + 3 * p, nullptr, cc);
         }
     }
 }
@@ -101,7 +105,9 @@ static void p2g_tile_component_host(const GridD& g, int I0, int J0, int K0, int 
         if (e0 > s0) {
             double sv[P2G_SLOTS], sw[P2G_SLOTS];
             const P2GGlobalSrc<AX> src{&a};
-            touched = p2g_cell_partial<APIC, AX>(g, ci, cj, ck, s0, e0, src, sv, sw, err);
+            // both forms of the cell loop (software-pipelined loads / plain), alternating by cell
+            touched = (tid & 1) ? p2g_cell_partial<APIC, AX, decltype(src), true>(g, ci, cj, ck, s0, e0, src, sv, sw, err)
+                                : p2g_cell_partial<APIC, AX, decltype(src), false>(g, ci, cj, ck, s0, e0, src, sv, sw, err);
             for (int q = 0; q < P2G_SLOTS; ++q) { ex[q * NT + tid] = sv[q]; exw[q * NT + tid] = sw[q]; }
         }
         tm[tid] = touched;
@@ -798,6 +804,24 @@ int hc_apply_gradient(const double* x, const double* u_in, const double* v_in, c
     for (int k = 0; k < L.nz; ++k) for (int j = 0; j < L.ny; ++j) for (int i = 0; i < L.nx; ++i)
         apply_gradient_cell(L.nx, L.ny, L.nz, g.hx, g.hy, g.hz, L.sdf.data(), L.uw.data(), L.vw.data(), L.ww.data(), x, u_in, v_in, w_in,
                             u_out, v_out, w_out, i, j, k);
+    return 0;
+}
+
+// diffusion.cu's k_diff_markers + k_diff_system behind plain loops: markers, matrix rows and right-hand side of one array of
+// GridBackwardEulerDiffusionSolver3::solve (kind 0 = cell-centred, 1/2/3 = u/v/w), as diffusion_solve_array launches them
+int hc_diffusion_system(const jetcu_grid* grid, int kind, const double* f, double coefficient, double dt, int boundary_type,
+                        const double* csdf, const double* fsdf, char* markers, jetcu_matrix_row* A, double* b) {
+    GridD g = make_grid(grid);
+    const DiffArray a = diff_array(g, kind);
+    const double tc = dt * coefficient;
+    const double cx = tc / (g.hx * g.hx), cy = tc / (g.hy * g.hy), cz = tc / (g.hz * g.hz);
+    for (int k = 0; k < a.sz; ++k) for (int j = 0; j < a.sy; ++j) for (int i = 0; i < a.sx; ++i)
+        markers[((size_t)k * a.sy + j) * a.sx + i] = diff_marker(g, a, csdf, fsdf, i, j, k);
+    for (int k = 0; k < a.sz; ++k) for (int j = 0; j < a.sy; ++j) for (int i = 0; i < a.sx; ++i) {
+        const size_t c = ((size_t)k * a.sy + j) * a.sx + i;
+        diff_matrix_row(markers, a.sx, a.sy, a.sz, i, j, k, cx, cy, cz, boundary_type == 0, &A[c].center, &A[c].right, &A[c].up, &A[c].front);
+        b[c] = diff_rhs(markers, f, a.sx, a.sy, a.sz, i, j, k, cx, cy, cz, boundary_type == 0);
+    }
     return 0;
 }
 

@@ -113,7 +113,11 @@ def test_pressure_default_iccg_solver(jc, oracle, n, kind, collider, compressed)
     kw = dict(collider_sdf=sc["collider_sdf"], fluid_sdf=sc["fluid_sdf"])
     ug, vg, wg, pg, rg = jc.pressure_solve(*args, **kw)
     uo, vo, wo, po, ro = oracle.pressure_solve(*args, **kw)
-    assert ro.true_residual_l2 <= 1e-7 * ro.b_l2 and abs(int(rg.iterations) - int(ro.iterations)) <= 1
+    # CG's iteration count depends on the rounding of its dot products once it runs for hundreds of iterations (the device
+    # reduces with a fixed tree, the reference serially: first B200 run, 32^3 slab, 229 vs 234 iterations at the same
+    # tolerance); what must agree is the converged state — both below the tolerance, pressure within north_star's 1e-6
+    assert ro.true_residual_l2 <= 1e-7 * ro.b_l2 and rg.true_residual_l2 <= 1e-7 * rg.b_l2
+    assert abs(int(rg.iterations) - int(ro.iterations)) <= max(1, int(ro.iterations) // 20)
     assert np.abs(pg - po).max() <= 1e-6 * np.abs(po).max()
     for a, b in ((ug, uo), (vg, vo), (wg, wo)):
         assert np.abs(a - b).max() <= 1e-6

@@ -134,10 +134,12 @@ SMOKE_COLLIDERS = [   # (grid, MG levels, collider shapes, collider kwargs, adve
 ]
 
 
-def smoke_collider_run(lib, case, steps):
+def smoke_collider_run(lib, case, steps, diffusion=None):
     grid, levels, shapes, kw, advection = case
     prm = SmokeParams.make(grid, mgpcg=MgpcgParams.make(max_iterations=100, max_levels=levels), advection=advection)
     s = lib.smoke(prm)
+    if diffusion:
+        s.set_diffusion(*diffusion)
     nx, ny, nz = grid.res
     lo = np.array([grid.ox, grid.oy, grid.oz]); size = np.array([nx * grid.hx, ny * grid.hy, nz * grid.hz])
     source = [dict(kind="box", a=tuple(lo + np.array([0.35, -1.0, 0.35]) * size), b=tuple(lo + np.array([0.65, 0.15, 0.65]) * size))]
@@ -160,6 +162,19 @@ def test_smoke_with_collider_bit_exact(libs, ci):
     for step, (a, b) in enumerate(zip(fa, fb)):
         same(a, b, "step %d" % step)
     assert float(np.abs(fb[-1]["v"]).max()) > 0.2
+
+
+@pytest.mark.parametrize("ci,diffusion", [(0, (0.02, 0.001, 0.003)), (2, (0.0, 0.002, 0.0)), (4, (0.05, 0.0, 0.004))])
+def test_smoke_with_viscosity_and_diffusion_bit_exact(libs, ci, diffusion):
+    """SURVEY §8f-4: GridFluidSolver3::computeViscosity (grid_fluid_solver3.cpp:231-241) and GridSmokeSolver3::computeDiffusion's
+    scalar solves (grid_smoke_solver3.cpp:85-117) through GridBackwardEulerDiffusionSolver3 + ICCG, next to a collider."""
+    ref, port = libs
+    fa = smoke_collider_run(ref, SMOKE_COLLIDERS[ci], 4, diffusion)
+    fb = smoke_collider_run(port, SMOKE_COLLIDERS[ci], 4, diffusion)
+    for step, (a, b) in enumerate(zip(fa, fb)):
+        same(a, b, "step %d" % step)
+    plain = smoke_collider_run(port, SMOKE_COLLIDERS[ci], 4)
+    assert float(np.abs(plain[-1]["density"] - fb[-1]["density"]).max()) > 1e-6   # the solves really change the fields
 
 
 @pytest.mark.parametrize("ci", range(len(SMOKE_COLLIDERS)))

@@ -13,6 +13,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "particles.cuh"
 #include "pressure.cuh"
@@ -217,6 +218,25 @@ __device__ __forceinline__ void p2g_tile_component(const GridD& g, int I0, int J
     __syncthreads();
 }
 
+// prefetch.global.L2 of the window faces thread tid will add into (same face <-> thread mapping as the gather loop)
+template <int AX, int TZ>
+__device__ __forceinline__ void p2g_prefetch_faces(const GridD& g, int I0, int J0, int K0, const double* __restrict__ U,
+                                                   const double* __restrict__ W) {
+    constexpr int NT = P2G_TX * P2G_TY * TZ;
+    constexpr int WX = P2G_TX + (AX == 0 ? 1 : 2), WY = P2G_TY + (AX == 1 ? 1 : 2), WZ = TZ + (AX == 2 ? 1 : 2);
+    const int sx = g.nx + (AX == 0), sy = g.ny + (AX == 1), sz = g.nz + (AX == 2);
+    const int fx0 = I0 - (AX == 0 ? 0 : 1), fy0 = J0 - (AX == 1 ? 0 : 1), fz0 = K0 - (AX == 2 ? 0 : 1);
+    for (int f = threadIdx.x; f < WX * WY * WZ; f += NT) {
+        const int lx = f % WX, ly = (f / WX) % WY, lz = f / (WX * WY);
+        const int fi = fx0 + lx, fj = fy0 + ly, fk = fz0 + lz;
+        if ((unsigned)fi >= (unsigned)sx || (unsigned)fj >= (unsigned)sy || (unsigned)fk >= (unsigned)sz) continue;
+        if (lx != 0 && (fi & 3) != 0) continue;   // one request per 32-byte sector of a face row is enough
+        const size_t idx = ((size_t)fk * sy + fj) * sx + fi;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(U + idx));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(W + idx));
+    }
+}
+
 struct P2GOut {
     double* val[3];   // u, v, w: value sums (normalised in place afterwards)
     double* wsum[3];  // weight sums
@@ -247,6 +267,11 @@ __global__ void __launch_bounds__(P2G_TX * P2G_TY * TZ, MINB)
         s0 = cell_start[cell]; e0 = cell_start[cell + 1];
     }
     if (!__syncthreads_or(e0 > s0)) return;
+    if (PF) {   // the face sums are read-modify-written at the end of each component: start pulling them into L2 now
+        p2g_prefetch_faces<0, TZ>(g, I0, J0, K0, out.val[0], out.wsum[0]);
+        p2g_prefetch_faces<1, TZ>(g, I0, J0, K0, out.val[1], out.wsum[1]);
+        p2g_prefetch_faces<2, TZ>(g, I0, J0, K0, out.val[2], out.wsum[2]);
+    }
     p2g_tile_component<APIC, 0, TZ, PF>(g, I0, J0, K0, ci, cj, ck, s0, e0, a, p2g_ex, tm, out.val[0], out.wsum[0], out.marker[0], err);
     p2g_tile_component<APIC, 1, TZ, PF>(g, I0, J0, K0, ci, cj, ck, s0, e0, a, p2g_ex, tm, out.val[1], out.wsum[1], out.marker[1], err);
     p2g_tile_component<APIC, 2, TZ, PF>(g, I0, J0, K0, ci, cj, ck, s0, e0, a, p2g_ex, tm, out.val[2], out.wsum[2], out.marker[2], err);
@@ -446,10 +471,13 @@ __device__ __forceinline__ void count_cell(const GridD& g, const double* pos, si
 }
 
 // CC: keep the 8 corner values per component of the last sample in registers (particle_ops.cuh: CornerCache)
-// CC = 0: no cache (86 registers); 1: cache, 4 CTAs of 128 threads per SM (<= 128 registers, no spills);
-// 2: cache, 5 CTAs per SM (96 registers, 48 bytes of spills).  JETCU_MOVE_CACHE selects; default 2 (GPU call 8, 256^3:
-// FLIP 18.5 ms without, 18.8 ms with 4 CTAs, 17.7 ms with 5 CTAs; PIC 16.6 -> 14.6 ms).
-#define MOVE_MIN_BLOCKS(CC) ((CC) == 1 ? 4 : 5)
+// CC = 0: no cache, 5 CTAs of 128 threads per SM (96 registers); 1: cache, 4 CTAs (128 registers); 2: cache, 5 CTAs (96
+// registers, 48 B of spills); 3 / 4: no cache, 6 / 8 CTAs (80 / 64 registers); 5: cache, 6 CTAs (80 registers, 172 B of spills).
+// JETCU_MOVE_CACHE selects one for all three kernels; default: the fastest measured per kernel at 256^3 (GPU call 10:
+// FLIP 18.5 / - / 17.7 / 17.8 / 17.8 / 16.9 ms for 0..5, PIC 16.6 / - / 14.7 / 16.1 / 15.9 / 15.7 ms).  Occupancy alone does
+// nothing (variants 3, 4): the kernel is bound by its FP64 instruction count (profiles/r02_move_variants.md).
+#define MOVE_MIN_BLOCKS(CC) ((CC) == 1 ? 4 : ((CC) == 3 || (CC) == 5) ? 6 : ((CC) == 4 ? 8 : 5))
+#define MOVE_CACHED(CC) ((CC) == 1 || (CC) == 2 || (CC) == 5)
 template <bool POW2, typename I, int CC>
 __global__ void __launch_bounds__(128, MOVE_MIN_BLOCKS(CC))
     k_move(GridD g, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
@@ -459,7 +487,7 @@ __global__ void __launch_bounds__(128, MOVE_MIN_BLOCKS(CC))
     if (p >= np) return;
     double pos[3] = {a.p[0][p], a.p[1][p], a.p[2][p]}, vel[3] = {a.p[3][p], a.p[4][p], a.p[5][p]};
     CornerCache<I> cc;
-    move_particle<POW2, I, true>(g, u, v, w, dt, nsub, flag, pos, vel, nullptr, CC ? &cc : nullptr);   // u, v, w: PAIR arrays (k_pack_pairs)
+    move_particle<POW2, I, true>(g, u, v, w, dt, nsub, flag, pos, vel, nullptr, MOVE_CACHED(CC) ? &cc : nullptr);   // u, v, w: PAIR arrays (k_pack_pairs)
     a.p[0][p] = pos[0]; a.p[1][p] = pos[1]; a.p[2][p] = pos[2];
     count_cell(g, pos, p, cell_of, rank, count);
     a.p[3][p] = vel[0]; a.p[4][p] = vel[1]; a.p[5][p] = vel[2];
@@ -480,9 +508,9 @@ __global__ void __launch_bounds__(128, MOVE_MIN_BLOCKS(CC))
     if (p >= np) return;
     double pos[3] = {a.p[0][p], a.p[1][p], a.p[2][p]}, vel[3];
     CornerCache<I> cc;
-    sample_velocity<POW2, I, true>(g, u, v, w, pos[0], pos[1], pos[2], &vel[0], &vel[1], &vel[2], CC ? &cc : nullptr);
+    sample_velocity<POW2, I, true>(g, u, v, w, pos[0], pos[1], pos[2], &vel[0], &vel[1], &vel[2], MOVE_CACHED(CC) ? &cc : nullptr);
     const double first[3] = {vel[0], vel[1], vel[2]};
-    move_particle<POW2, I, true>(g, u, v, w, dt, nsub, flag, pos, vel, first, CC ? &cc : nullptr);
+    move_particle<POW2, I, true>(g, u, v, w, dt, nsub, flag, pos, vel, first, MOVE_CACHED(CC) ? &cc : nullptr);
     a.p[0][p] = pos[0]; a.p[1][p] = pos[1]; a.p[2][p] = pos[2];
     count_cell(g, pos, p, cell_of, rank, count);
     a.p[3][p] = vel[0]; a.p[4][p] = vel[1]; a.p[5][p] = vel[2];
@@ -499,7 +527,7 @@ __global__ void __launch_bounds__(128, MOVE_MIN_BLOCKS(CC))
     double pos[3] = {a.p[0][p], a.p[1][p], a.p[2][p]}, vel[3] = {a.p[3][p], a.p[4][p], a.p[5][p]};
     g2p_flip_particle(g, nullptr, nullptr, nullptr, ud, vd, wd, 0.0, pos, vel);
     CornerCache<I> cc;
-    move_particle<POW2, I, true>(g, u, v, w, dt, nsub, flag, pos, vel, nullptr, CC ? &cc : nullptr);
+    move_particle<POW2, I, true>(g, u, v, w, dt, nsub, flag, pos, vel, nullptr, MOVE_CACHED(CC) ? &cc : nullptr);
     a.p[0][p] = pos[0]; a.p[1][p] = pos[1]; a.p[2][p] = pos[2];
     count_cell(g, pos, p, cell_of, rank, count);
     a.p[3][p] = vel[0]; a.p[4][p] = vel[1]; a.p[5][p] = vel[2];
@@ -773,6 +801,31 @@ static int hyb_reserve(jetcu_hybrid* h, uint64_t need) {
     return JETCU_OK;
 }
 
+// JETCU_BIN_TRACE=1: wall-clock of the binning's sub-stages with a stream synchronisation after each (diagnosis only: the
+// synchronisations perturb the step), printed by every rank to stderr.
+struct BinTrace {
+    bool on;
+    jetcu_ctx* ctx;
+    double t0;
+    char buf[512];
+    int len = 0;
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    explicit BinTrace(jetcu_ctx* c) : ctx(c) {
+        static int env = -1;
+        if (env < 0) { const char* e = getenv("JETCU_BIN_TRACE"); env = (e && atoi(e)) ? 1 : 0; }
+        on = env != 0;
+        if (on) { cudaStreamSynchronize(ctx->stream); t0 = now(); }
+    }
+    void mark(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(ctx->stream);
+        const double t = now();
+        len += snprintf(buf + len, sizeof(buf) - len, " %s %.3f", what, t - t0);
+        t0 = t;
+    }
+    void flush(int rank) { if (on && len) fprintf(stderr, "[bin trace rank %d]%s\n", rank, buf); len = 0; }
+};
+
 // Slab mode, first half of the binning: copies every owned particle to the other ranks whose extended slab holds its
 // (new) cell plane — migration and ghost refresh in one exchange — and appends what the other ranks sent to the owned
 // block.  *ntot = owned + received.
@@ -786,14 +839,17 @@ static int hyb_slab_exchange(jetcu_hybrid* h, uint64_t* ntot) {
     JC_TRY(jc_zero(ctx, d_cnt, 3 * (size_t)G));
     AttrPtrs own = owned_ptrs(h);
     uint32_t* orig = h->orig[h->cur] + h->base;
+    BinTrace tr(ctx);
     if (np) JC_LAUNCH(ctx, k_slab_route<false>, jc_blocks(np, 256), 256, 0, own.p[2], np, gg.oz, 1.0 / gg.hz, h->nz, T, G, h->me,
                       d_cnt, nullptr, nullptr);
     uint32_t cnt32[64] = {};
     JC_TRY(jc_d2h(ctx, cnt32, d_cnt, (size_t)G));
     JC_TRY(jc_sync(ctx));
+    tr.mark("route-count");
     uint64_t mine[64] = {}, all[64 * 64];
     for (int q = 0; q < G; ++q) mine[q] = cnt32[q];
     JC_TRY(comm_allgather_u64_host(ctx, mine, (size_t)G, all));
+    tr.mark("allgather-counts");
     size_t send_off[65] = {}, recv_off[65] = {};
     uint32_t off32[64] = {};
     for (int q = 0; q < G; ++q) {
@@ -832,8 +888,11 @@ static int hyb_slab_exchange(jetcu_hybrid* h, uint64_t* ntot) {
         sp[q] = sendbuf + send_off[q] * rec; sb[q] = (size_t)mine[q] * rec * sizeof(double);
         rp[q] = recvbuf + recv_off[q] * rec; rb[q] = (size_t)(recv_off[q + 1] - recv_off[q]) * rec * sizeof(double);
     }
+    tr.mark("pack");
     STEP(comm_exchange(ctx, sp, sb, rp, rb));
+    tr.mark("exchange");
     STEP(hyb_reserve(h, h->base + np + nrecv));  // may move the owned block to offset 0
+    tr.mark("reserve");
     if (rc == JETCU_OK) {
         AttrPtrs dst = owned_ptrs(h);
         uint32_t* dorig = h->orig[h->cur] + h->base;
@@ -849,6 +908,9 @@ static int hyb_slab_exchange(jetcu_hybrid* h, uint64_t* ntot) {
     }
 #undef STEP
     jc_free(ctx, d_list); jc_free(ctx, sendbuf); jc_free(ctx, recvbuf); jc_free(ctx, d_cnt);
+    tr.mark("unpack");
+    if (tr.on) { tr.len += snprintf(tr.buf + tr.len, sizeof(tr.buf) - tr.len, " | owned %zu sent %zu received %zu", np, nsend, nrecv); }
+    tr.flush(h->me);
     *ntot = np + nrecv;
     return rc;
 }
@@ -862,6 +924,7 @@ static int hyb_bin(jetcu_hybrid* h) {
     const bool slab = h->world > 1;
     uint64_t ntot = h->np;
     if (slab) JC_TRY(hyb_slab_exchange(h, &ntot));
+    BinTrace tr(ctx);
     const int e0 = slab ? max(h->z0 - SLAB_GHOST, 0) : 0, e1 = slab ? min(h->z1 + SLAB_GHOST, h->nz) : h->nz;
     // only the cells of the window [lo, hi) can receive particles (the rest go to the trash bin at index nc): count,
     // scan and per-cell ordering touch that range only, so the binning cost follows the slab, not the whole grid
@@ -876,12 +939,14 @@ static int hyb_bin(jetcu_hybrid* h) {
         }
     }
     h->counted = false;
+    tr.mark("count");
     if (hi == h->nc) {
         JC_TRY(scan_exclusive_u32(ctx, h->cell_start + lo, h->cell_start + lo, hi - lo + 2));
     } else {  // cell_start[hi] = end of the window = where the trash bin starts
         JC_TRY(scan_exclusive_u32(ctx, h->cell_start + lo, h->cell_start + lo, hi - lo + 1));
         JC_TRY(jc_d2d(ctx, h->cell_start + h->nc, h->cell_start + hi, 1));
     }
+    tr.mark("scan");
     if (ntot > 0) {
         JC_LAUNCH(ctx, k_scatter_perm, jc_blocks(ntot, 256), 256, 0, h->cell_of, h->rank, h->cell_start, h->perm, (size_t)ntot);
         JC_LAUNCH(ctx, k_sort_cells, jc_blocks(hi - lo, 128), 128, 0, h->cell_start + lo, h->orig[h->cur] + h->base, h->perm,
@@ -894,6 +959,7 @@ static int hyb_bin(jetcu_hybrid* h) {
                       h->orig[h->cur] + h->base, h->orig[1 - h->cur], h->perm, (size_t)ntot);
         h->cur = 1 - h->cur;
     }
+    tr.mark("perm-sort-gather");
     if (slab) {
         uint32_t marks[3] = {0, 0, 0};
         JC_TRY(jc_d2h(ctx, &marks[0], h->cell_start + (size_t)h->z0 * nxy, 1));
@@ -901,6 +967,9 @@ static int hyb_bin(jetcu_hybrid* h) {
         JC_TRY(jc_d2h(ctx, &marks[2], h->cell_start + h->nc, 1));
         JC_TRY(jc_sync(ctx));
         h->base = marks[0]; h->np = marks[1] - marks[0]; h->nsorted = marks[2];
+        tr.mark("marks");
+        if (tr.on) tr.len += snprintf(tr.buf + tr.len, sizeof(tr.buf) - tr.len, " | ntot %llu window cells %zu", (unsigned long long)ntot, hi - lo);
+        tr.flush(h->me);
     } else {
         h->base = 0; h->nsorted = h->np;
     }
@@ -971,10 +1040,10 @@ static int hyb_extrapolate_one(jetcu_hybrid* h, double* data, const char* marker
     } while (0)
 
 // advection kernels: <POW2, I, CC>; JETCU_MOVE_CACHE=0 selects the uncached form (A/B; results are bit-identical)
-static inline int hyb_move_cache() {
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("JETCU_MOVE_CACHE"); on = e ? atoi(e) : 2; if (on < 0 || on > 2) on = 2; }
-    return on;
+static inline int hyb_move_cache(int dflt) {
+    static int on = -2;
+    if (on == -2) { const char* e = getenv("JETCU_MOVE_CACHE"); on = e ? atoi(e) : -1; if (on < -1 || on > 5) on = -1; }
+    return on < 0 ? dflt : on;
 }
 #define HYB_MOVE_LAUNCH_(kernel, CC_, grid, block, ...)                                                           \
     do {                                                                                                          \
@@ -985,10 +1054,15 @@ static inline int hyb_move_cache() {
         else if (i32_) JC_LAUNCH(ctx, (kernel<false, int, CC_>), grid, block, 0, __VA_ARGS__);                    \
         else JC_LAUNCH(ctx, (kernel<false, long long, CC_>), grid, block, 0, __VA_ARGS__);                        \
     } while (0)
-#define HYB_MOVE_LAUNCH(kernel, grid, block, ...)                                                                 \
+// DFLT: the variant measured fastest for that kernel at 256^3 (GPU call 10, profiles/r02_move_variants.md)
+#define HYB_MOVE_LAUNCH(kernel, DFLT, grid, block, ...)                                                           \
     do {                                                                                                          \
-        if (hyb_move_cache() == 1) HYB_MOVE_LAUNCH_(kernel, 1, grid, block, __VA_ARGS__);                         \
-        else if (hyb_move_cache() == 2) HYB_MOVE_LAUNCH_(kernel, 2, grid, block, __VA_ARGS__);                    \
+        const int cc_ = hyb_move_cache(DFLT);                                                                     \
+        if (cc_ == 1) HYB_MOVE_LAUNCH_(kernel, 1, grid, block, __VA_ARGS__);                                      \
+        else if (cc_ == 2) HYB_MOVE_LAUNCH_(kernel, 2, grid, block, __VA_ARGS__);                                 \
+        else if (cc_ == 3) HYB_MOVE_LAUNCH_(kernel, 3, grid, block, __VA_ARGS__);                                 \
+        else if (cc_ == 4) HYB_MOVE_LAUNCH_(kernel, 4, grid, block, __VA_ARGS__);                                 \
+        else if (cc_ == 5) HYB_MOVE_LAUNCH_(kernel, 5, grid, block, __VA_ARGS__);                                 \
         else HYB_MOVE_LAUNCH_(kernel, 0, grid, block, __VA_ARGS__);                                               \
     } while (0)
 
@@ -1767,7 +1841,7 @@ int jetcu_hybrid_move_particles(jetcu_hybrid* h, double dt) {
     JC_TRY(hyb_before_move(h, count));
     if (h->np) {
         JC_TRY(hyb_pack_pairs(h, false));
-        HYB_MOVE_LAUNCH(k_move, jc_blocks(h->np, 128), 128, g, h->pair[0], h->pair[1], h->pair[2], sub_dt, nsub,
+        HYB_MOVE_LAUNCH(k_move, 2, jc_blocks(h->np, 128), 128, g, h->pair[0], h->pair[1], h->pair[2], sub_dt, nsub,
                            h->P.closed_domain_boundary_flag, owned_ptrs(h), (size_t)h->np, h->cell_of, h->rank,
                            count ? h->cell_start : nullptr);
     }
@@ -1791,11 +1865,11 @@ static int hyb_g2p_move(jetcu_hybrid* h, double dt) {
     JC_TRY(hyb_before_move(h, count));
     if (h->np) {
         if (flip)
-            HYB_MOVE_LAUNCH(k_flip_move, jc_blocks(h->np, 128), 128, g, h->pair[0], h->pair[1], h->pair[2], h->ud, h->vd, h->wd,
+            HYB_MOVE_LAUNCH(k_flip_move, 5, jc_blocks(h->np, 128), 128, g, h->pair[0], h->pair[1], h->pair[2], h->ud, h->vd, h->wd,
                                sub_dt, nsub, h->P.closed_domain_boundary_flag, owned_ptrs(h), (size_t)h->np, h->cell_of, h->rank,
                                count ? h->cell_start : nullptr);
         else
-            HYB_MOVE_LAUNCH(k_pic_move, jc_blocks(h->np, 128), 128, g, h->pair[0], h->pair[1], h->pair[2], sub_dt, nsub,
+            HYB_MOVE_LAUNCH(k_pic_move, 2, jc_blocks(h->np, 128), 128, g, h->pair[0], h->pair[1], h->pair[2], sub_dt, nsub,
                                h->P.closed_domain_boundary_flag, owned_ptrs(h), (size_t)h->np, h->cell_of, h->rank,
                                count ? h->cell_start : nullptr);
     }

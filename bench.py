@@ -483,7 +483,8 @@ def run_jetcu(args):
     stage_bytes = {"ms_bin": (40.0 + 2.0 * attr) * P_, "ms_p2g": attr * P_ + 51.0 * N_, "ms_sdf": 24.0 * P_ + 8.0 * N_,
                    "ms_g2p": g2p_p * P_ + g2p_c * N_, "ms_move": 96.0 * P_ + 24.0 * N_,
                    "ms_pressure": N_ * ((56.0 + 1647.0 + 16.0) + mean_iters * 1799.0)}
-    fused_adv = stages.get("ms_g2p", 0) < 1e-3   # PIC / FLIP: G2P and advection are one kernel (hybrid.cu: hyb_g2p_move)
+    # PIC / FLIP: G2P and advection are one kernel (hybrid.cu: hyb_g2p_move) — ms_g2p is then the gap between two event records
+    fused_adv = stages.get("ms_g2p", 0) < 0.05
     if fused_adv:   # one pass over the particles: G2P's velocity write and the advection's re-read disappear
         stage_bytes["ms_move"] = (48.0 + 48.0) * P_ + (g2p_c + 24.0) * N_
         del stage_bytes["ms_g2p"]
@@ -493,11 +494,12 @@ def run_jetcu(args):
             gbs = bts / (stages[k] * 1e-3) / 1e9
             stage_roofline[k[3:]] = {"algorithmic_gb": bts / 1e9, "gbs": gbs, "frac_of_hbm_peak": gbs / peak}
     if "move" in stage_roofline:
-        # ncu (profiles/r02_c1_particle_kernels.md): the advection kernel is bound by L1 load wavefronts and FP64 issue (10
-        # trilinear FP64 samples of 3 components per particle replayed operation by operation: ~1 050 FP64 instructions per
-        # particle, floor = P * 1050 / (148 SMs * 64 lanes * clock)), not by DRAM
-        fp64_floor_ms = P_ * 1050.0 / (148 * 64 * 1.9e9) * 1e3
-        stage_roofline["move"].update({"bound": "fp64 issue + L1 load wavefronts (not HBM)", "fp64_floor_ms": fp64_floor_ms,
+        # ncu (profiles/r02_move_variants.md): the advection kernel follows its FP64 instruction count — 10 trilinear FP64 samples
+        # of 3 components per particle replayed operation by operation (no FMA contraction: bit-identical positions) are
+        # ~1 100 FP64 instructions per particle; neither occupancy nor ten times fewer loads (corner cache) move it.
+        # floor = P * 1100 / (148 SMs * 64 FP64 lanes * clock)
+        fp64_floor_ms = P_ * 1100.0 / (148 * 64 * 1.9e9) * 1e3
+        stage_roofline["move"].update({"bound": "fp64 issue (not HBM)", "fp64_floor_ms": fp64_floor_ms,
                                        "frac_of_fp64_floor": fp64_floor_ms / stages["ms_move"],
                                        "fused_with_g2p": bool(fused_adv)})
     # fixed-work numbers (independent of how many iterations a step's solve happens to take): one PCG iteration = one

@@ -140,18 +140,30 @@ __global__ void __launch_bounds__(256) k_gather_attrs(AttrPtrs src, AttrPtrs dst
 // locally iff it lies in this rank's extended slab.  The cell sort that follows puts [ghost-lo | owned | ghost-hi] in
 // order, so "owned" stays one contiguous range.  FILL = false only counts, FILL = true writes the index lists.
 #define SLAB_GHOST JETCU_SLAB_GHOST_PLANES
+// One atomicAdd per warp and destination (ballot + popc): a rank sends ~1 M particles to each neighbour per step and the
+// per-particle atomics on the two or three counters serialised in the L2 — 0.95 ms for the counting pass and as much again
+// for the fill at 2 GPUs, a cost that does not shrink with the rank count (JETCU_BIN_TRACE, profiles/r02_multi_b.md).
 template <bool FILL>
 __global__ void k_slab_route(const double* __restrict__ pz, size_t np, double oz, double ihz, int nz, int T, int world, int me,
                              uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets, uint32_t* __restrict__ lists) {
-    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= np) return;
-    const int ck = cell_coord(pz[p], oz, ihz, nz);
-    unsigned long long m = jc_slab_dest_mask(ck, T, world, me, SLAB_GHOST);
-    while (m) {
-        const int q = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        const uint32_t slot = atomicAdd(&counts[q], 1u);
-        if (FILL) lists[offsets[q] + slot] = (uint32_t)p;
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long m = 0;
+    if (p < np) m = jc_slab_dest_mask(cell_coord(pz[p], oz, ihz, nz), T, world, me, SLAB_GHOST);
+    const unsigned lane = threadIdx.x & 31u, full = 0xffffffffu;
+    for (;;) {   // blockDim is a multiple of 32: whole warps take every iteration together
+        const unsigned pending = __ballot_sync(full, m != 0ull);
+        if (!pending) break;
+        const int q = __shfl_sync(full, __ffsll((long long)m) - 1, __ffs((int)pending) - 1);   // a destination still pending
+        const bool has = (m >> q) & 1ull;
+        const unsigned b = __ballot_sync(full, has);
+        uint32_t base = 0;
+        const int leader = __ffs((int)b) - 1;
+        if ((int)lane == leader) base = atomicAdd(&counts[q], (uint32_t)__popc(b));
+        base = __shfl_sync(full, base, leader);
+        if (has) {
+            if (FILL) lists[offsets[q] + base + (uint32_t)__popc(b & ((1u << lane) - 1u))] = (uint32_t)p;
+            m &= ~(1ull << q);
+        }
     }
 }
 

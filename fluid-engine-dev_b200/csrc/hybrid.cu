@@ -43,7 +43,8 @@ struct jetcu_hybrid {
     uint32_t* orig[2] = {};
     int cur = 0;
     uint32_t *cell_of = nullptr, *rank = nullptr, *perm = nullptr;
-    uint32_t* cell_start = nullptr;  // nc + 1
+    uint32_t* cell_start = nullptr;  // nc + 2: first particle of every cell (compact copy of sub_start[8 * cell])
+    uint32_t* sub_start = nullptr;   // 8 * nc + 2: counts, then starts, of every (cell, octant) bin (p2g_ops.cuh: p2g_octant)
     bool binned = false;
     bool counted = false;  // cell_of / rank / per-cell counts already produced by the advection kernel of the last step
     // z-slab mode (the ctx had a multi-rank communicator when the solver was created): this rank owns the cell planes
@@ -71,20 +72,22 @@ static GridD gridd(const jetcu_hybrid* h) {
 }
 
 // ------------------------------------------------------------------------------------------------ cell sort
+// Bin of a particle = 8 * cell + octant (the half of the cell per axis: the staggered-lattice P2G walks octant ranges).
 // Particles whose cell plane lies outside [e0, e1) (slab mode: this rank's slab + ghost planes) go to the trash bin,
-// cell id nx*ny*nz, which sorts behind every real cell and is dropped.
+// 8 * nx*ny*nz, which sorts behind every real bin and is dropped.
 __global__ void k_cell_count(const double* __restrict__ px, const double* __restrict__ py, const double* __restrict__ pz,
                              size_t np, GridD g, int e0, int e1, uint32_t* __restrict__ cell_of,
                              uint32_t* __restrict__ rank, uint32_t* __restrict__ count) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= np) return;
-    int ci = cell_coord(px[p], g.ox, 1.0 / g.hx, g.nx);
-    int cj = cell_coord(py[p], g.oy, 1.0 / g.hy, g.ny);
-    int ck = cell_coord(pz[p], g.oz, 1.0 / g.hz, g.nz);
-    uint32_t cell = (uint32_t)(((size_t)ck * g.ny + cj) * g.nx + ci);
-    if (ck < e0 || ck >= e1) cell = (uint32_t)((size_t)g.nx * g.ny * g.nz);
-    cell_of[p] = cell;
-    rank[p] = atomicAdd(&count[cell], 1u);  // slot inside the cell; order fixed up by k_sort_cells
+    const double x = px[p], y = py[p], z = pz[p];
+    int ci = cell_coord(x, g.ox, 1.0 / g.hx, g.nx);
+    int cj = cell_coord(y, g.oy, 1.0 / g.hy, g.ny);
+    int ck = cell_coord(z, g.oz, 1.0 / g.hz, g.nz);
+    uint32_t bin = (uint32_t)((((size_t)ck * g.ny + cj) * g.nx + ci) * 8 + p2g_octant(g, x, y, z, ci, cj, ck));
+    if (ck < e0 || ck >= e1) bin = (uint32_t)((size_t)g.nx * g.ny * g.nz * 8);
+    cell_of[p] = bin;
+    rank[p] = atomicAdd(&count[bin], 1u);  // slot inside the bin; order fixed up by k_sort_cells
 }
 
 __global__ void k_scatter_perm(const uint32_t* __restrict__ cell_of, const uint32_t* __restrict__ rank,
@@ -94,12 +97,16 @@ __global__ void k_scatter_perm(const uint32_t* __restrict__ cell_of, const uint3
     perm[cell_start[cell_of[p]] + rank[p]] = (uint32_t)p;
 }
 
-// Make the order inside every cell deterministic: ascending ORIGINAL particle index (insertion sort; ~8 items).
-__global__ void k_sort_cells(const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ orig,
-                             uint32_t* __restrict__ perm, size_t nc) {
+// Make the order inside every bin deterministic: ascending ORIGINAL particle index (insertion sort; a bin holds about one
+// particle, a cell about eight).  The thread of a cell's octant 0 also writes the compact per-cell start.
+__global__ void k_sort_cells(const uint32_t* __restrict__ sub_start, const uint32_t* __restrict__ orig,
+                             uint32_t* __restrict__ perm, uint32_t* __restrict__ cell_start, size_t nbins) {
     size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nc) return;
-    uint32_t s = cell_start[c], e = cell_start[c + 1];
+    if (c > nbins) return;
+    uint32_t s = sub_start[c];
+    if ((c & 7) == 0) cell_start[c >> 3] = s;   // c == nbins: the end of the window
+    if (c == nbins) return;
+    uint32_t e = sub_start[c + 1];
     for (uint32_t a = s + 1; a < e; ++a) {
         uint32_t pa = perm[a];
         uint32_t ka = orig[pa];
@@ -287,6 +294,104 @@ __global__ void __launch_bounds__(P2G_TX * P2G_TY * TZ, MINB)
     p2g_tile_component<APIC, 0, TZ, PF>(g, I0, J0, K0, ci, cj, ck, s0, e0, a, p2g_ex, tm, out.val[0], out.wsum[0], out.marker[0], err);
     p2g_tile_component<APIC, 1, TZ, PF>(g, I0, J0, K0, ci, cj, ck, s0, e0, a, p2g_ex, tm, out.val[1], out.wsum[1], out.marker[1], err);
     p2g_tile_component<APIC, 2, TZ, PF>(g, I0, J0, K0, ci, cj, ck, s0, e0, a, p2g_ex, tm, out.val[2], out.wsum[2], out.marker[2], err);
+}
+
+// ---- P2G on the staggered lattice (default; the arithmetic and the summation order are described in p2g_ops.cuh) ------
+// One CTA owns a tile of 8 x 8 x TZ STAGGERED cells of each component in turn, one thread per staggered cell: it walks the
+// octant ranges that make up its staggered cell with 8 (value, weight) accumulator pairs in registers, the 16 partial sums go
+// through shared memory once, one thread per face of the tile's 9 x 9 x (TZ + 1) window adds the <= 8 of them that reach
+// it, and the tile's face sums are added into the global arrays by plain read-modify-write — tiles are launched in 8 colour
+// passes whose windows never overlap.  Against the 18-slot window kernel above (k_p2g_tile, JETCU_P2G_KERNEL=window): no
+// zero-weight slots (8 instead of 18 products per particle and component), 16 instead of 36 accumulators per thread (half
+// the registers: twice the resident warps), an 8-term instead of an 18-term face gather through 32 KB instead of 73 KB of
+// shared memory.
+template <bool APIC, int AX, int TZ>
+__device__ __forceinline__ void p2g_stag_component(const GridD& g, int I0, int J0, int K0, int kb, int ke,
+                                                   const uint32_t* __restrict__ sub_start, const AttrPtrs& a, double* ex,
+                                                   unsigned char* tm, double* __restrict__ U, double* __restrict__ W,
+                                                   char* __restrict__ M, int* err) {
+    constexpr int NT = P2G_TX * P2G_TY * TZ;
+    constexpr int WX = P2G_TX + 1, WY = P2G_TY + 1, WZ = TZ + 1;
+    const int tid = threadIdx.x;
+    const int I = I0 + tid % P2G_TX, J = J0 + (tid / P2G_TX) % P2G_TY, K = K0 + tid / (P2G_TX * P2G_TY);
+    const int NI = p2g_stag_count(g.nx, AX == 0), NJ = p2g_stag_count(g.ny, AX == 1), NK = p2g_stag_count(g.nz, AX == 2);
+    bool any = false;
+    if (I < NI && J < NJ && K < NK) {
+        double sv[8], sw[8];
+        const P2GGlobalSrc<AX> src{&a};
+        any = p2g_stag_partial<APIC, AX, P2GGlobalSrc<AX>>(g, I, J, K, kb, ke, sub_start, src, sv, sw, err);
+        if (any) {
+#pragma unroll
+            for (int s = 0; s < 8; ++s) { ex[s * NT + tid] = sv[s]; ex[(8 + s) * NT + tid] = sw[s]; }
+        }
+    }
+    tm[tid] = any ? 1 : 0;
+    if (__syncthreads_or(any)) {
+        const int sx = g.nx + (AX == 0), sy = g.ny + (AX == 1), sz = g.nz + (AX == 2);
+        for (int f = tid; f < WX * WY * WZ; f += NT) {
+            const int lx = f % WX, ly = (f / WX) % WY, lz = f / (WX * WY);
+            const int fi = I0 + lx, fj = J0 + ly, fk = K0 + lz;
+            if (fi >= sx || fj >= sy || fk >= sz) continue;
+            double v, w;
+            if (p2g_stag_gather<TZ>(ex, tm, lx, ly, lz, &v)) {
+                p2g_stag_gather<TZ>(ex + 8 * NT, tm, lx, ly, lz, &w);
+                const size_t idx = ((size_t)fk * sy + fj) * sx + fi;
+                U[idx] += v; W[idx] += w; M[idx] = 1;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+template <int AX, int TZ>
+__device__ __forceinline__ void p2g_stag_prefetch(const GridD& g, int I0, int J0, int K0, const double* __restrict__ U,
+                                                  const double* __restrict__ W) {
+    constexpr int NT = P2G_TX * P2G_TY * TZ;
+    constexpr int WX = P2G_TX + 1, WY = P2G_TY + 1, WZ = TZ + 1;
+    const int sx = g.nx + (AX == 0), sy = g.ny + (AX == 1), sz = g.nz + (AX == 2);
+    for (int f = threadIdx.x; f < WX * WY * WZ; f += NT) {
+        const int lx = f % WX, ly = (f / WX) % WY, lz = f / (WX * WY);
+        const int fi = I0 + lx, fj = J0 + ly, fk = K0 + lz;
+        if (fi >= sx || fj >= sy || fk >= sz) continue;
+        if (lx != 0 && (fi & 3) != 0) continue;   // one request per 32-byte sector of a face row is enough
+        const size_t idx = ((size_t)fk * sy + fj) * sx + fi;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(U + idx));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(W + idx));
+    }
+}
+
+// MINB: CTAs per SM the register allocation is held to (3: 85 registers, 4: 64)
+template <bool APIC, int TZ, int MINB>
+__global__ void __launch_bounds__(P2G_TX * P2G_TY * TZ, MINB)
+    k_p2g_stag(GridD g, int par_x, int par_y, int tz_first, int kb, int ke, const uint32_t* __restrict__ cell_start,
+               const uint32_t* __restrict__ sub_start, AttrPtrs a, P2GOut out, int* __restrict__ err) {
+    constexpr int NT = P2G_TX * P2G_TY * TZ;
+    __shared__ double ex[16 * NT];   // [2][8][NT]: value partials, weight partials
+    __shared__ unsigned char tm[NT];
+    const int tid = threadIdx.x;
+    const int I0 = (2 * blockIdx.x + par_x) * P2G_TX, J0 = (2 * blockIdx.y + par_y) * P2G_TY, K0 = (tz_first + 2 * blockIdx.z) * TZ;
+    {   // a tile whose cells [I0, I0 + 8] x [J0, J0 + 8] x [K0, K0 + TZ] hold no particle deposits nothing: each thread looks
+        // at the two x-neighbours of its cell in the 2 x 2 rows above it (compact per-cell starts, coalesced)
+        const int ci = I0 + tid % P2G_TX, cj = J0 + (tid / P2G_TX) % P2G_TY, ck = K0 + tid / (P2G_TX * P2G_TY);
+        bool have = false;
+        if (ci < g.nx) {
+            const int i1 = min(ci + 2, g.nx);
+            for (int dz = 0; dz < 2; ++dz)
+                for (int dy = 0; dy < 2; ++dy) {
+                    const int j = cj + dy, k = ck + dz;
+                    if (j >= g.ny || k < kb || k >= ke) continue;
+                    const size_t row = ((size_t)k * g.ny + j) * g.nx;
+                    have |= cell_start[row + i1] > cell_start[row + ci];
+                }
+        }
+        if (!__syncthreads_or(have)) return;
+    }
+    p2g_stag_prefetch<0, TZ>(g, I0, J0, K0, out.val[0], out.wsum[0]);
+    p2g_stag_prefetch<1, TZ>(g, I0, J0, K0, out.val[1], out.wsum[1]);
+    p2g_stag_prefetch<2, TZ>(g, I0, J0, K0, out.val[2], out.wsum[2]);
+    p2g_stag_component<APIC, 0, TZ>(g, I0, J0, K0, kb, ke, sub_start, a, ex, tm, out.val[0], out.wsum[0], out.marker[0], err);
+    p2g_stag_component<APIC, 1, TZ>(g, I0, J0, K0, kb, ke, sub_start, a, ex, tm, out.val[1], out.wsum[1], out.marker[1], err);
+    p2g_stag_component<APIC, 2, TZ>(g, I0, J0, K0, kb, ke, sub_start, a, ex, tm, out.val[2], out.wsum[2], out.marker[2], err);
 }
 
 // u = sum / wsum where wsum > 0 (pic_solver3.cpp:178-192); FLIP's float snapshot (src/jet/flip_solver3.cpp:39-47) is
@@ -477,9 +582,9 @@ __device__ __forceinline__ void count_cell(const GridD& g, const double* pos, si
     const int ci = cell_coord(pos[0], g.ox, 1.0 / g.hx, g.nx);
     const int cj = cell_coord(pos[1], g.oy, 1.0 / g.hy, g.ny);
     const int ck = cell_coord(pos[2], g.oz, 1.0 / g.hz, g.nz);
-    const uint32_t cell = (uint32_t)(((size_t)ck * g.ny + cj) * g.nx + ci);
-    cell_of[p] = cell;
-    rank[p] = atomicAdd(&count[cell], 1u);
+    const uint32_t bin = (uint32_t)((((size_t)ck * g.ny + cj) * g.nx + ci) * 8 + p2g_octant(g, pos[0], pos[1], pos[2], ci, cj, ck));
+    cell_of[p] = bin;
+    rank[p] = atomicAdd(&count[bin], 1u);
 }
 
 // CC: keep the 8 corner values per component of the last sample in registers (particle_ops.cuh: CornerCache)
@@ -941,28 +1046,32 @@ static int hyb_bin(jetcu_hybrid* h) {
     // only the cells of the window [lo, hi) can receive particles (the rest go to the trash bin at index nc): count,
     // scan and per-cell ordering touch that range only, so the binning cost follows the slab, not the whole grid
     const size_t nxy = (size_t)h->nx * h->ny, lo = (size_t)e0 * nxy, hi = (size_t)e1 * nxy;
+    // bins = (cell, octant) pairs, 8 per cell (k_cell_count); the trash bin sits behind the last real one
+    const size_t blo = 8 * lo, bhi = 8 * hi, btrash = 8 * h->nc;
     if (!(h->counted && !slab)) {   // else: the last step's advection kernel already counted (count_cell)
-        JC_TRY(jc_zero(ctx, h->cell_start + lo, hi - lo + 1));
-        JC_TRY(jc_zero(ctx, h->cell_start + h->nc, 2));
+        JC_TRY(jc_zero(ctx, h->sub_start + blo, bhi - blo + 1));
+        JC_TRY(jc_zero(ctx, h->sub_start + btrash, 2));
         if (ntot > 0) {
             AttrPtrs src = owned_ptrs(h);
             JC_LAUNCH(ctx, k_cell_count, jc_blocks(ntot, 256), 256, 0, src.p[0], src.p[1], src.p[2], (size_t)ntot, g, e0, e1,
-                      h->cell_of, h->rank, h->cell_start);
+                      h->cell_of, h->rank, h->sub_start);
         }
     }
     h->counted = false;
     tr.mark("count");
     if (hi == h->nc) {
-        JC_TRY(scan_exclusive_u32(ctx, h->cell_start + lo, h->cell_start + lo, hi - lo + 2));
-    } else {  // cell_start[hi] = end of the window = where the trash bin starts
-        JC_TRY(scan_exclusive_u32(ctx, h->cell_start + lo, h->cell_start + lo, hi - lo + 1));
-        JC_TRY(jc_d2d(ctx, h->cell_start + h->nc, h->cell_start + hi, 1));
+        JC_TRY(scan_exclusive_u32(ctx, h->sub_start + blo, h->sub_start + blo, bhi - blo + 2));
+    } else {  // sub_start[bhi] = end of the window = where the trash bin starts
+        JC_TRY(scan_exclusive_u32(ctx, h->sub_start + blo, h->sub_start + blo, bhi - blo + 1));
+        JC_TRY(jc_d2d(ctx, h->sub_start + btrash, h->sub_start + bhi, 1));
     }
     tr.mark("scan");
+    if (ntot > 0) JC_LAUNCH(ctx, k_scatter_perm, jc_blocks(ntot, 256), 256, 0, h->cell_of, h->rank, h->sub_start, h->perm, (size_t)ntot);
+    // per-bin order by original index + the compact per-cell starts cell_start[lo .. hi]
+    JC_LAUNCH(ctx, k_sort_cells, jc_blocks(bhi - blo + 1, 128), 128, 0, h->sub_start + blo, h->orig[h->cur] + h->base, h->perm,
+              h->cell_start + lo, bhi - blo);
+    JC_TRY(jc_d2d(ctx, h->cell_start + h->nc, h->sub_start + btrash, 2));
     if (ntot > 0) {
-        JC_LAUNCH(ctx, k_scatter_perm, jc_blocks(ntot, 256), 256, 0, h->cell_of, h->rank, h->cell_start, h->perm, (size_t)ntot);
-        JC_LAUNCH(ctx, k_sort_cells, jc_blocks(hi - lo, 128), 128, 0, h->cell_start + lo, h->orig[h->cur] + h->base, h->perm,
-                  hi - lo);
         if (h->nattr == 6)
             JC_LAUNCH(ctx, k_gather_attrs<6>, jc_blocks(ntot, 256), 256, 0, owned_ptrs(h), attr_ptrs(h, 1 - h->cur),
                       h->orig[h->cur] + h->base, h->orig[1 - h->cur], h->perm, (size_t)ntot);
@@ -1105,7 +1214,9 @@ int jetcu_hybrid_create(jetcu_ctx* ctx, const jetcu_hybrid_params* p, jetcu_hybr
     JC_ARG(ctx, p->grid.nx > 0 && p->grid.ny > 0 && p->grid.nz > 0 && p->grid.nx < 32768 && p->grid.ny < 32768 && p->grid.nz < 32768);
     JC_ARG(ctx, p->grid.hx > 0 && p->grid.hy > 0 && p->grid.hz > 0);
     JC_ARG(ctx, p->mode >= JETCU_PIC && p->mode <= JETCU_APIC);
-    JC_ARG(ctx, (uint64_t)p->grid.nx * p->grid.ny * p->grid.nz < (1ull << 32) - 2);
+    // particle bins are (cell, octant) pairs held in 32-bit indices: up to 2^29 cells (812^3)
+    if ((uint64_t)p->grid.nx * p->grid.ny * p->grid.nz * 8 >= (1ull << 32) - 2)
+        return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED, "the hybrid solver bins particles in 32-bit (cell, octant) indices: at most 2^29 cells");
     if (!p->mgpcg.use_red_black)
         return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED, "lexicographic Gauss-Seidel is not available on the GPU path");
     jetcu_hybrid* h = new jetcu_hybrid();
@@ -1151,6 +1262,8 @@ int jetcu_hybrid_create(jetcu_ctx* ctx, const jetcu_hybrid_params* p, jetcu_hybr
     }
     STEP(jc_alloc(ctx, &h->cell_start, h->nc + 2));  // + the trash bin of slab mode + the end marker
     STEP(jc_zero(ctx, h->cell_start, h->nc + 2));
+    STEP(jc_alloc(ctx, &h->sub_start, 8 * h->nc + 2));
+    STEP(jc_zero(ctx, h->sub_start, 8 * h->nc + 2));
     if (rc == JETCU_OK) {
         // signedDistanceField is created with kMaxD (src/jet/pic_solver3.cpp:29-30)
         k_fill_f64<<<jc_blocks(h->nc, 256), 256, 0, ctx->stream>>>(h->sdf, DBL_MAX, h->nc);
@@ -1194,7 +1307,7 @@ int jetcu_hybrid_destroy(jetcu_hybrid* h) {
         for (int q = 0; q < NATTR; ++q) jc_free(ctx, h->attr[b][q]);
         jc_free(ctx, h->orig[b]);
     }
-    jc_free(ctx, h->cell_of); jc_free(ctx, h->rank); jc_free(ctx, h->perm); jc_free(ctx, h->cell_start);
+    jc_free(ctx, h->cell_of); jc_free(ctx, h->rank); jc_free(ctx, h->perm); jc_free(ctx, h->cell_start); jc_free(ctx, h->sub_start);
     pressure_free(ctx, &h->ps);
     for (int e = 0; e < 12; ++e) if (h->ev[e]) cudaEventDestroy(h->ev[e]);
     cudaStreamSynchronize(ctx->stream);
@@ -1641,7 +1754,28 @@ int jetcu_hybrid_transfer_particles_to_grids(jetcu_hybrid* h) {
             out.val[0] = h->u; out.val[1] = h->v; out.val[2] = h->w;
             for (int q = 0; q < 3; ++q) out.wsum[q] = h->wsum[q];
             out.marker[0] = h->um; out.marker[1] = h->vm; out.marker[2] = h->wm;
-            // tiles are aligned to the GLOBAL cell lattice (not to the slab), so that every rank forms the same tile sums.
+            // tiles are aligned to the GLOBAL lattice (not to the slab), so that every rank forms the same tile sums.
+            static const bool window_kernel = getenv("JETCU_P2G_KERNEL") && !strcmp(getenv("JETCU_P2G_KERNEL"), "window");
+            if (!window_kernel) {
+                // staggered-lattice kernel: tiles of 8 x 8 x 4 staggered cells, 256 threads
+                constexpr int TZ = 4;
+                const int ntx = (g.nx + P2G_TX - 1) / P2G_TX, nty = (g.ny + P2G_TY - 1) / P2G_TY;
+                const int tzlo = max(kb - 1, 0) / TZ, tzhi = (ke - 1) / TZ;  // staggered planes [kb - 1, ke - 1]
+                static const int minb = getenv("JETCU_P2G_MINB") ? atoi(getenv("JETCU_P2G_MINB")) : 0;
+                void (*kern)(GridD, int, int, int, int, int, const uint32_t*, const uint32_t*, AttrPtrs, P2GOut, int*) =
+                    apic ? (minb == 3 ? k_p2g_stag<true, TZ, 3> : k_p2g_stag<true, TZ, 2>)
+                         : (minb == 4 ? k_p2g_stag<false, TZ, 4> : (minb == 2 ? k_p2g_stag<false, TZ, 2> : k_p2g_stag<false, TZ, 3>));
+                for (int colour = 0; colour < 8; ++colour) {  // fixed colour order = the order in which a rim face receives its tiles
+                    const int par_x = colour & 1, par_y = (colour >> 1) & 1, par_z = colour >> 2;
+                    const int cx = (ntx - par_x + 1) / 2, cy = (nty - par_y + 1) / 2;
+                    const int tz_first = tzlo + ((tzlo & 1) != par_z ? 1 : 0);
+                    const int cz = tz_first > tzhi ? 0 : (tzhi - tz_first) / 2 + 1;
+                    if (cx <= 0 || cy <= 0 || cz <= 0) continue;
+                    JC_LAUNCH(ctx, kern, dim3(cx, cy, cz), P2G_TX * P2G_TY * TZ, 0, g, par_x, par_y, tz_first, kb, ke, h->cell_start,
+                              h->sub_start, a, out, h->p2g_err);
+                }
+            } else {
+            // 18-slot window kernel (round 2's first form, kept for A/B runs).
             // Tile height: 4 cell planes (256 threads) held to 128 registers, so that two CTAs share an SM and one tile's
             // exchange / gather / read-modify-write phases overlap the other's particle loop, with software-pipelined particle
             // loads (GPU call 8, 256^3 FLIP: 12.24 ms for the 8-plane tile without either -> 11.16 ms).  APIC carries 3 more
@@ -1670,6 +1804,7 @@ int jetcu_hybrid_transfer_particles_to_grids(jetcu_hybrid* h) {
                 if (cx <= 0 || cy <= 0 || cz <= 0) continue;
                 dim3 grid(cx, cy, cz);
                 JC_LAUNCH(ctx, kern, grid, threads, smem, g, par_x, par_y, tz_first, kb, ke, h->cell_start, a, out, h->p2g_err);
+            }
             }
         }
         JC_LAUNCH(ctx, k_p2g_normalise, jc_blocks(nk * pu, 256), 256, 0, h->u + k0 * pu, h->wsum[0] + k0 * pu,
@@ -1831,7 +1966,7 @@ static bool hyb_count_in_move(const jetcu_hybrid* h) {
 
 static int hyb_before_move(jetcu_hybrid* h, bool count) {
     if (!count) return JETCU_OK;
-    return jc_zero(h->ctx, h->cell_start, h->nc + 2);
+    return jc_zero(h->ctx, h->sub_start, 8 * h->nc + 2);
 }
 
 static int hyb_after_move(jetcu_hybrid* h, bool counted) {
@@ -1855,7 +1990,7 @@ int jetcu_hybrid_move_particles(jetcu_hybrid* h, double dt) {
         JC_TRY(hyb_pack_pairs(h, false));
         HYB_MOVE_LAUNCH(k_move, 2, jc_blocks(h->np, 128), 128, g, h->pair[0], h->pair[1], h->pair[2], sub_dt, nsub,
                            h->P.closed_domain_boundary_flag, owned_ptrs(h), (size_t)h->np, h->cell_of, h->rank,
-                           count ? h->cell_start : nullptr);
+                           count ? h->sub_start : nullptr);
     }
     return hyb_after_move(h, count);
 }
@@ -1879,11 +2014,11 @@ static int hyb_g2p_move(jetcu_hybrid* h, double dt) {
         if (flip)
             HYB_MOVE_LAUNCH(k_flip_move, 5, jc_blocks(h->np, 128), 128, g, h->pair[0], h->pair[1], h->pair[2], h->ud, h->vd, h->wd,
                                sub_dt, nsub, h->P.closed_domain_boundary_flag, owned_ptrs(h), (size_t)h->np, h->cell_of, h->rank,
-                               count ? h->cell_start : nullptr);
+                               count ? h->sub_start : nullptr);
         else
             HYB_MOVE_LAUNCH(k_pic_move, 2, jc_blocks(h->np, 128), 128, g, h->pair[0], h->pair[1], h->pair[2], sub_dt, nsub,
                                h->P.closed_domain_boundary_flag, owned_ptrs(h), (size_t)h->np, h->cell_of, h->rank,
-                               count ? h->cell_start : nullptr);
+                               count ? h->sub_start : nullptr);
     }
     return hyb_after_move(h, count);
 }

@@ -183,6 +183,204 @@ __host__ __device__ __forceinline__ bool p2g_face_gather(const double* ex, const
     return any;
 }
 
+// ---- P2G on the STAGGERED lattice: 8 accumulators per thread instead of 18 ---------------------------------------------
+// All particles whose sampler base index for component AX is (I, J, K) deposit into exactly the 8 faces (I..I+1, J..J+1,
+// K..K+1) with weights that are products of (1 - f, f) per axis — no window, no zero-weight slots, no conditional weights.
+// These particles are the "staggered cell" (I, J, K) of the component: on the component's node axis it coincides with the
+// owning cell, on the two cell-centred axes it spans the upper half of cell S and the lower half of cell S + 1 (clamped
+// bases at the walls add the outermost half cells).  The binning therefore sorts the particles by (cell, OCTANT) — the
+// half of the cell per axis, p2g_octant — and a thread owning a staggered cell walks the octant ranges of the <= 4 cells
+// that make it up, in a fixed order (cells: first centred axis fastest; octants ascending; original index inside an octant).
+// Summation order per face: the 8 staggered cells around it in (z, y, x) order inside a tile (p2g_stag_gather), tiles in
+// colour order — fixed by the lattice alone, hence bit-reproducible and independent of a z-slab decomposition.
+__host__ __device__ __forceinline__ int jc_ffs32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return __ffs((int)v);
+#else
+    return __builtin_ffs((int)v);
+#endif
+}
+
+// Half of its cell a particle lies in, per axis, as the sampler of a cell-centred axis sees it: 1 iff the base index of
+// that axis (floor of the position normalised against the data origin o + h/2, the expression of jc_base_mul) reaches the
+// cell index.  Octant = (zh * 2 + yh) * 2 + xh.
+__host__ __device__ __forceinline__ int p2g_octant(const GridD& g, double px, double py, double pz, int ci, int cj, int ck) {
+    const int xh = floor((px - (g.ox + 0.5 * g.hx)) * (1.0 / g.hx)) >= (double)ci ? 1 : 0;
+    const int yh = floor((py - (g.oy + 0.5 * g.hy)) * (1.0 / g.hy)) >= (double)cj ? 1 : 0;
+    const int zh = floor((pz - (g.oz + 0.5 * g.hz)) * (1.0 / g.hz)) >= (double)ck ? 1 : 0;
+    return (zh * 2 + yh) * 2 + xh;
+}
+
+// staggered cells along an axis of n cells: n on the component's node axis, n - 1 (at least 1) on a centred axis
+__host__ __device__ __forceinline__ int p2g_stag_count(int n, bool node_axis) { return node_axis ? n : (n > 1 ? n - 1 : 1); }
+
+// Accepted halves (bit 0: lower, bit 1: upper) of the cells S and S + 1 that make up staggered index S on a centred axis.
+__host__ __device__ __forceinline__ void p2g_stag_halves(int S, int n, unsigned* hA, unsigned* hB) {
+    *hA = 2u | (S == 0 ? 1u : 0u);                       // cell S: its upper half (+ the lower one at the low wall)
+    *hB = S + 1 < n ? (1u | (S + 1 == n - 1 ? 2u : 0u)) : 0u;   // cell S + 1: its lower half (+ the upper one at the high wall)
+    if (n == 1) *hA = 3u;
+}
+
+// Walks the particles of one staggered cell: the runs of accepted octants (bit 8 * c + o of `pend`) of its <= 4 cells, in
+// ascending (cell, octant) order.  sub_start: start of every (cell, octant) range in the sorted particle arrays, 8 * cell + octant.
+struct P2GWalker {
+    const uint32_t* sub_start;
+    size_t cell0, strideA, strideB;
+    uint32_t pend, q, e;
+    __host__ __device__ __forceinline__ uint32_t next() {   // index of the next particle; 0xffffffff when there is none
+        while (q == e) {   // next non-empty run of accepted octants of one cell
+            if (!pend) return 0xffffffffu;
+            const int lo = jc_ffs32(pend) - 1;
+            const uint32_t inv = ~(pend >> lo);
+            int run = inv ? jc_ffs32(inv) - 1 : 8;
+            if (run > 8 - (lo & 7)) run = 8 - (lo & 7);
+            pend &= ~(((1u << run) - 1u) << lo);
+            const int c = lo >> 3;
+            const size_t sb = 8 * (cell0 + (size_t)(c & 1) * strideA + (size_t)(c >> 1) * strideB) + (size_t)(lo & 7);
+            q = sub_start[sb]; e = sub_start[sb + run];
+        }
+        return q++;
+    }
+};
+
+// Fraction of jc_barycentric(x, iHigh) (sampling.cuh) for a particle whose base index is known to be S, without branches
+// and without the float-to-int conversion: with s = floor(x), the base is S iff s == S, or s < S at the low wall (S == 0:
+// jc_barycentric clamps to i = 0, f = 0), or s > S at the high wall (S == iHigh - 1: i = iHigh - 1, f = 1).  *ok is
+// cleared otherwise.  iHigh == 0 (a single face along the axis): i = 0, f = 0 whatever x is.
+struct P2GAxis {
+    double dS;
+    bool low_ok, high_ok, deg;
+    __host__ __device__ __forceinline__ void set(int S, int iHigh) {
+        dS = (double)S; deg = iHigh == 0; low_ok = S == 0 || deg; high_ok = S == iHigh - 1 || deg;
+    }
+    __host__ __device__ __forceinline__ double frac(double x, bool* ok) const {
+        const double s = floor(x);
+        const bool lt = s < dS, gt = s > dS;
+        double f = x - s;
+        f = lt ? 0.0 : f; f = gt ? 1.0 : f; f = deg ? 0.0 : f;
+        *ok &= !((lt && !low_ok) || (gt && !high_ok));
+        return f;
+    }
+};
+
+// Partial sums of staggered cell (I, J, K) of component AX: sv / sw = 8 accumulators (value, weight), slot (c * 2 + b) * 2 + x
+// for face (I + x, J + b, K + c).  Cell planes outside [kb, ke) hold no particles on this rank.  Returns whether the
+// staggered cell holds a particle (the reference marks all 8 corners of a particle, pic_solver3.cpp:160-176).  The next
+// particle's attributes are requested before the current one is accumulated (the loads are one sector per lane: latency).
+template <bool APIC, int AX, class Src>
+__host__ __device__ __forceinline__ bool p2g_stag_partial(const GridD& g, int I, int J, int K, int kb, int ke,
+                                                          const uint32_t* __restrict__ sub_start, const Src& a, double* sv, double* sw,
+                                                          int* err) {
+    const int sx = g.nx + (AX == 0), sy = g.ny + (AX == 1), sz = g.nz + (AX == 2);
+    const double ox = g.ox + 0.5 * (AX == 0 ? 0.0 : g.hx), oy = g.oy + 0.5 * (AX == 1 ? 0.0 : g.hy),
+                 oz = g.oz + 0.5 * (AX == 2 ? 0.0 : g.hz);
+    const double ihx = 1.0 / g.hx, ihy = 1.0 / g.hy, ihz = 1.0 / g.hz;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) { sv[s] = 0.0; sw[s] = 0.0; }
+    // the <= 4 cells: A = first centred axis (cell-index stride strideA), B = second; octant masks per cell
+    unsigned hx[2] = {3u, 0u}, hy[2] = {3u, 0u}, hz[2] = {3u, 0u};
+    if (AX != 0) p2g_stag_halves(I, g.nx, &hx[0], &hx[1]);
+    if (AX != 1) p2g_stag_halves(J, g.ny, &hy[0], &hy[1]);
+    if (AX != 2) p2g_stag_halves(K, g.nz, &hz[0], &hz[1]);
+    P2GWalker wk;
+    wk.pend = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int da = c & 1, db = c >> 1;
+        const int dx = AX == 0 ? 0 : da, dy = AX == 0 ? da : (AX == 1 ? 0 : db), dz = AX == 2 ? 0 : db;
+        const int ck = K + dz;
+        if (ck < kb || ck >= ke) continue;
+        const unsigned mx = hx[dx], my = hy[dy], mz = hz[dz];
+        const unsigned m8 = ((mx & 1u ? 0x55u : 0u) | (mx & 2u ? 0xAAu : 0u)) & ((my & 1u ? 0x33u : 0u) | (my & 2u ? 0xCCu : 0u)) &
+                            ((mz & 1u ? 0x0Fu : 0u) | (mz & 2u ? 0xF0u : 0u));
+        wk.pend |= m8 << (8 * c);
+    }
+    wk.sub_start = sub_start;
+    wk.strideA = AX == 0 ? (size_t)g.nx : 1; wk.strideB = AX == 2 ? (size_t)g.nx : (size_t)g.nx * g.ny;
+    wk.cell0 = ((size_t)K * g.ny + J) * g.nx + I;
+    wk.q = 0; wk.e = 0;
+    uint32_t cur = wk.next();
+    if (cur == 0xffffffffu) return false;
+    P2GAxis axx, axy, axz;
+    axx.set(I, sx - 1); axy.set(J, sy - 1); axz.set(K, sz - 1);
+    // face positions of the two corners per axis (APIC)
+    const double gx0 = ox + g.hx * (double)I, gx1 = ox + g.hx * (double)(I + 1), gy0 = oy + g.hy * (double)J,
+                 gy1 = oy + g.hy * (double)(J + 1), gz0 = oz + g.hz * (double)K, gz1 = oz + g.hz * (double)(K + 1);
+    double npx = a.get(0, cur), npy = a.get(1, cur), npz = a.get(2, cur), npv = a.get(P2G_A_VEL, cur);
+    double nc0 = 0.0, nc1 = 0.0, nc2 = 0.0;
+    if (APIC) { nc0 = a.get(P2G_A_C0, cur); nc1 = a.get(P2G_A_C0 + 1, cur); nc2 = a.get(P2G_A_C0 + 2, cur); }
+    bool ok = true;
+    do {
+        double px = npx, py = npy, pz = npz;
+        const double pv = npv, c0 = nc0, c1 = nc1, c2 = nc2;
+        cur = wk.next();
+        if (cur != 0xffffffffu) {
+            npx = a.get(0, cur); npy = a.get(1, cur); npz = a.get(2, cur); npv = a.get(P2G_A_VEL, cur);
+            if (APIC) { nc0 = a.get(P2G_A_C0, cur); nc1 = a.get(P2G_A_C0 + 1, cur); nc2 = a.get(P2G_A_C0 + 2, cur); }
+        }
+        if (APIC) {  // tangential clamp to [lo + h/2, hi - h/2] (apic_solver3.cpp:76-84,94-102,112-120)
+            if (AX != 0) px = jc_clamp(px, g.ox + g.hx / 2.0, (g.ox + g.hx * (double)g.nx) - g.hx / 2.0);
+            if (AX != 1) py = jc_clamp(py, g.oy + g.hy / 2.0, (g.oy + g.hy * (double)g.ny) - g.hy / 2.0);
+            if (AX != 2) pz = jc_clamp(pz, g.oz + g.hz / 2.0, (g.oz + g.hz * (double)g.nz) - g.hz / 2.0);
+        }
+        // base index + fractions of getCoordinatesAndWeights (array_samplers3-inl.h:151-193; jc_base_mul): the base is (I, J, K)
+        // for a particle binned by cell_coord / p2g_octant — checked, never silent
+        const double fx = axx.frac((px - ox) * ihx, &ok), fy = axy.frac((py - oy) * ihy, &ok), fz = axz.frac((pz - oz) * ihz, &ok);
+        const double wx[2] = {1 - fx, fx}, wy[2] = {1 - fy, fy}, wz[2] = {1 - fz, fz};
+        double ax[2], ay[2], az[2];
+        if (APIC) {
+            ax[0] = c0 * (gx0 - px); ax[1] = c0 * (gx1 - px);
+            ay[0] = c1 * (gy0 - py); ay[1] = c1 * (gy1 - py);
+            az[0] = c2 * (gz0 - pz); az[1] = c2 * (gz1 - pz);
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int x = 0; x < 2; ++x) {
+                    const double wgt = (wx[x] * wy[b]) * wz[c];  // (wx*wy)*wz as in array_samplers3-inl.h:176-192
+                    const double val = APIC ? pv + ((ax[x] + ay[b]) + az[c]) : pv;
+                    const int s = (c * 2 + b) * 2 + x;
+                    sv[s] = fma(val, wgt, sv[s]); sw[s] += wgt;
+                }
+    } while (cur != 0xffffffffu);
+    if (!ok) *err = 1;
+    return true;
+}
+
+// One face (lx, ly, lz) of the window of a tile of TX x TY x TZ staggered cells (window = tile + 1 on every axis): adds up
+// the partial sums of the tile's staggered cells around it in (z, y, x) order.  ex = [8][ncell] partial sums of one kind,
+// tm = "holds a particle" per staggered cell.  Returns whether any of them does.
+template <int TZ>
+__host__ __device__ __forceinline__ bool p2g_stag_gather(const double* ex, const unsigned char* tm, int lx, int ly, int lz, double* out) {
+    constexpr int NCELL = P2G_TX * P2G_TY * TZ;
+    double sum = 0.0;
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const int cz = lz - c;
+        if (cz < 0 || cz >= TZ) continue;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int cy = ly - b;
+            if (cy < 0 || cy >= P2G_TY) continue;
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+                const int cx = lx - x;
+                if (cx < 0 || cx >= P2G_TX) continue;
+                const int cell = (cz * P2G_TY + cy) * P2G_TX + cx;
+                if (tm[cell]) {
+                    any = true;
+                    sum += ex[((c * 2 + b) * 2 + x) * NCELL + cell];
+                }
+            }
+        }
+    }
+    *out = sum;
+    return any;
+}
+
 // u = sum / wsum where wsum > 0 (pic_solver3.cpp:178-192); FLIP's float snapshot (src/jet/flip_solver3.cpp:39-47) is
 // taken in the same pass.
 __host__ __device__ __forceinline__ void p2g_normalise_face(double* u, const double* wsum, float* snapshot, size_t f) {

@@ -147,29 +147,88 @@ static void p2g_tiles(const GridD& g, int kb, int ke, const std::vector<uint32_t
     }
 }
 
+// ---- the staggered-lattice kernel k_p2g_stag<APIC, TZ>: same replay (colour passes, tiles, "threads", plain buffers)
+template <bool APIC, int AX, int TZ>
+static void p2g_stag_component_host(const GridD& g, int I0, int J0, int K0, int kb, int ke, const std::vector<uint32_t>& sub_start,
+                                    const AttrPtrs& a, std::vector<double>& ex, std::vector<unsigned char>& tm, double* U, double* W,
+                                    char* M, int* err) {
+    constexpr int NT = P2G_TX * P2G_TY * TZ;
+    constexpr int WX = P2G_TX + 1, WY = P2G_TY + 1, WZ = TZ + 1;
+    const int NI = p2g_stag_count(g.nx, AX == 0), NJ = p2g_stag_count(g.ny, AX == 1), NK = p2g_stag_count(g.nz, AX == 2);
+    bool tile_any = false;
+    for (int tid = 0; tid < NT; ++tid) {
+        const int I = I0 + tid % P2G_TX, J = J0 + (tid / P2G_TX) % P2G_TY, K = K0 + tid / (P2G_TX * P2G_TY);
+        bool any = false;
+        if (I < NI && J < NJ && K < NK) {
+            double sv[8], sw[8];
+            const P2GGlobalSrc<AX> src{&a};
+            any = p2g_stag_partial<APIC, AX, P2GGlobalSrc<AX>>(g, I, J, K, kb, ke, sub_start.data(), src, sv, sw, err);
+            if (any) for (int q = 0; q < 8; ++q) { ex[q * NT + tid] = sv[q]; ex[(8 + q) * NT + tid] = sw[q]; }
+        }
+        tm[tid] = any ? 1 : 0;
+        tile_any |= any;
+    }
+    if (!tile_any) return;
+    const int sx = g.nx + (AX == 0), sy = g.ny + (AX == 1), sz = g.nz + (AX == 2);
+    for (int f = 0; f < WX * WY * WZ; ++f) {
+        const int lx = f % WX, ly = (f / WX) % WY, lz = f / (WX * WY);
+        const int fi = I0 + lx, fj = J0 + ly, fk = K0 + lz;
+        if (fi >= sx || fj >= sy || fk >= sz) continue;
+        double v, w;
+        if (p2g_stag_gather<TZ>(ex.data(), tm.data(), lx, ly, lz, &v)) {
+            p2g_stag_gather<TZ>(ex.data() + 8 * NT, tm.data(), lx, ly, lz, &w);
+            const size_t idx = ((size_t)fk * sy + fj) * sx + fi;
+            U[idx] += v; W[idx] += w; M[idx] = 1;
+        }
+    }
+}
+
+template <bool APIC, int TZ>
+static void p2g_stag_tiles(const GridD& g, int kb, int ke, const std::vector<uint32_t>& sub_start, const AttrPtrs& a, double* val[3],
+                           double* wsum[3], char* mk[3], int* err) {
+    constexpr int NT = P2G_TX * P2G_TY * TZ;
+    std::vector<double> ex((size_t)16 * NT, 0.0);
+    std::vector<unsigned char> tm(NT, 0);
+    const int ntx = (g.nx + P2G_TX - 1) / P2G_TX, nty = (g.ny + P2G_TY - 1) / P2G_TY;
+    const int tzlo = std::max(kb - 1, 0) / TZ, tzhi = (ke - 1) / TZ;
+    for (int colour = 0; colour < 8; ++colour) {
+        const int par_x = colour & 1, par_y = (colour >> 1) & 1, par_z = colour >> 2;
+        for (int tz = tzlo + ((tzlo & 1) != par_z ? 1 : 0); tz <= tzhi; tz += 2)
+            for (int ty = par_y; ty < nty; ty += 2)
+                for (int tx = par_x; tx < ntx; tx += 2) {
+                    const int I0 = tx * P2G_TX, J0 = ty * P2G_TY, K0 = tz * TZ;
+                    p2g_stag_component_host<APIC, 0, TZ>(g, I0, J0, K0, kb, ke, sub_start, a, ex, tm, val[0], wsum[0], mk[0], err);
+                    p2g_stag_component_host<APIC, 1, TZ>(g, I0, J0, K0, kb, ke, sub_start, a, ex, tm, val[1], wsum[1], mk[1], err);
+                    p2g_stag_component_host<APIC, 2, TZ>(g, I0, J0, K0, kb, ke, sub_start, a, ex, tm, val[2], wsum[2], mk[2], err);
+                }
+    }
+}
+
 extern "C" {
 
 // PIC / FLIP (apic = 0) or APIC (apic = 1) transferFromParticlesToGrids through the tile kernel's source with tiles of tz
 // (4 or 8) cell planes.  slabs > 1 replays the z-slab mode: every "rank" sees only the particles of its slab + 2 ghost
 // planes and finalises the face planes it owns — the result must not depend on slabs.  AoS inputs in the caller's order.
+// tz = 0 selects the staggered-lattice kernel (k_p2g_stag, the product's default), tz = 4 / 8 the 18-slot window kernel.
 int hc_p2g(const jetcu_grid* grid, int apic, int tz, int slabs, uint64_t n, const double* pos, const double* vel, const double* cx,
            const double* cy, const double* cz, double* u, double* v, double* w, char* um, char* vm, char* wm, int* err) {
     GridD g = make_grid(grid);
     const size_t nc = (size_t)g.nx * g.ny * g.nz;
     const size_t pl[3] = {(size_t)(g.nx + 1) * g.ny, (size_t)g.nx * (g.ny + 1), (size_t)g.nx * g.ny};
     const size_t nf[3] = {pl[0] * g.nz, pl[1] * g.nz, pl[2] * (g.nz + 1)};
-    if (slabs < 1 || g.nz % slabs != 0 || (tz != 4 && tz != 8)) return 1;
-    // cell sort: by owning cell, ascending original index inside a cell (k_cell_count .. k_sort_cells .. k_gather_attrs)
-    std::vector<uint32_t> cell(n), order(n);
+    if (slabs < 1 || g.nz % slabs != 0 || (tz != 0 && tz != 4 && tz != 8)) return 1;
+    // bin sort: by (owning cell, octant), ascending original index inside a bin (k_cell_count .. k_sort_cells .. k_gather_attrs)
+    std::vector<uint32_t> cell(n), order(n), bin(n);
     std::vector<int> plane(n);
     for (uint64_t p = 0; p < n; ++p) {
         const int ci = cell_coord(pos[3 * p], g.ox, 1.0 / g.hx, g.nx), cj = cell_coord(pos[3 * p + 1], g.oy, 1.0 / g.hy, g.ny),
                   ck = cell_coord(pos[3 * p + 2], g.oz, 1.0 / g.hz, g.nz);
         cell[p] = (uint32_t)(((size_t)ck * g.ny + cj) * g.nx + ci);
+        bin[p] = 8 * cell[p] + (uint32_t)p2g_octant(g, pos[3 * p], pos[3 * p + 1], pos[3 * p + 2], ci, cj, ck);
         plane[p] = ck;
     }
     std::iota(order.begin(), order.end(), 0u);
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return cell[x] < cell[y]; });
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return bin[x] < bin[y]; });
     double* out[3] = {u, v, w};
     char* outm[3] = {um, vm, wm};
     *err = 0;
@@ -184,6 +243,9 @@ int hc_p2g(const jetcu_grid* grid, int apic, int tz, int slabs, uint64_t n, cons
         std::vector<uint32_t> cell_start(nc + 1, 0);
         for (size_t s = 0; s < m; ++s) cell_start[cell[mine[s]] + 1]++;
         for (size_t c = 0; c < nc; ++c) cell_start[c + 1] += cell_start[c];
+        std::vector<uint32_t> sub_start(8 * nc + 1, 0);
+        for (size_t s = 0; s < m; ++s) sub_start[bin[mine[s]] + 1]++;
+        for (size_t c = 0; c < 8 * nc; ++c) sub_start[c + 1] += sub_start[c];
         std::vector<std::vector<double>> soa(NATTR, std::vector<double>(m ? m : 1, 0.0));
         for (size_t s = 0; s < m; ++s) {
             const uint32_t p = mine[s];
@@ -202,7 +264,10 @@ int hc_p2g(const jetcu_grid* grid, int apic, int tz, int slabs, uint64_t n, cons
             valv[q].assign(nf[q], 0.0); wsv[q].assign(nf[q], 0.0); mkv[q].assign(nf[q], 0);
             val[q] = valv[q].data(); ws[q] = wsv[q].data(); mk[q] = mkv[q].data();
         }
-        if (m > 0) {
+        if (m > 0 && tz == 0) {
+            if (apic) p2g_stag_tiles<true, 4>(g, kb, ke, sub_start, a, val, ws, mk, err);
+            else p2g_stag_tiles<false, 4>(g, kb, ke, sub_start, a, val, ws, mk, err);
+        } else if (m > 0) {
             if (apic) { if (tz == 4) p2g_tiles<true, 4>(g, kb, ke, cell_start, a, val, ws, mk, err); else p2g_tiles<true, 8>(g, kb, ke, cell_start, a, val, ws, mk, err); }
             else { if (tz == 4) p2g_tiles<false, 4>(g, kb, ke, cell_start, a, val, ws, mk, err); else p2g_tiles<false, 8>(g, kb, ke, cell_start, a, val, ws, mk, err); }
         }

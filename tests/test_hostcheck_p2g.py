@@ -45,9 +45,10 @@ def run_hc(hc, grid, apic, tz, slabs, pos, vel, aff):
     return (u, v, w), (um, vm, wm)
 
 
+@pytest.mark.parametrize("tz", [0, 4], ids=["staggered", "window"])   # 0: k_p2g_stag (the default), 4: k_p2g_tile (A/B kernel)
 @pytest.mark.parametrize("mode", [PIC, APIC])
 @pytest.mark.parametrize("n,domain,jitter", [(16, 1.0, 0.0), (12, 0.9, 0.37), (20, 1.0, 0.49)])
-def test_p2g_against_oracle_and_between_decompositions(hc, port, mode, n, domain, jitter):
+def test_p2g_against_oracle_and_between_decompositions(hc, port, mode, n, domain, jitter, tz):
     grid = Grid.cube(n, domain)
     prm = HybridParams.make(grid, mode=mode, mgpcg=MgpcgParams.make(max_iterations=20, max_levels=2))
     h = port.hybrid(prm)
@@ -68,7 +69,6 @@ def test_p2g_against_oracle_and_between_decompositions(hc, port, mode, n, domain
     h.transfer_particles_to_grids()
     want = h.get_velocity()
     want_m = h.get_markers()
-    tz = 4 if mode == APIC else 8          # the tile heights the product launches (P2G_TZ_APIC / P2G_TZ)
     got, got_m = run_hc(hc, grid, mode == APIC, tz, 1, pos, vel, aff)
     scale = max(float(np.abs(a).max()) for a in want)
     for a, b, am, bm, nm in zip(got, want, got_m, want_m, "uvw"):
@@ -80,3 +80,34 @@ def test_p2g_against_oracle_and_between_decompositions(hc, port, mode, n, domain
             got_s, got_m_s = run_hc(hc, grid, mode == APIC, tz, slabs, pos, vel, aff)
             for a, b, am, bm, nm in zip(got_s, got, got_m_s, got_m, "uvw"):
                 exact(a, b, "%d slabs vs one domain: %s" % (slabs, nm)); exact(am, bm, "%d slabs: marker %s" % (slabs, nm))
+
+
+@pytest.mark.parametrize("mode", [PIC, APIC])
+@pytest.mark.parametrize("res", [(2, 2, 2), (1, 5, 3), (3, 1, 4), (4, 3, 1), (1, 1, 1), (9, 2, 17), (17, 9, 5)])
+def test_p2g_staggered_degenerate_grids(hc, port, mode, res):
+    """Grids with one or two cells along an axis (a single staggered cell whose halves overlap, clamped bases on both walls
+    at once) and tile-straddling sizes; particles on the domain faces and corners included."""
+    rng = np.random.default_rng(sum(res) * 7 + mode)
+    grid = Grid(res[0], res[1], res[2], 0.25, 0.25, 0.25, 0.5, -1.0, 0.0)
+    prm = HybridParams.make(grid, mode=mode, mgpcg=MgpcgParams.make(max_iterations=5, max_levels=1))
+    h = port.hybrid(prm)
+    lo = np.array([grid.ox, grid.oy, grid.oz]); size = np.array(res) * 0.25
+    n = 40 * res[0] * res[1] * res[2] + 30
+    pos = lo + rng.uniform(0.0, 1.0, (n, 3)) * size
+    pos[:24] = lo + size * rng.choice([0.0, 0.5, 1.0], (24, 3))
+    vel = rng.uniform(-1.0, 1.0, (n, 3))
+    h.set_particles(np.ascontiguousarray(pos), vel)
+    aff = None
+    if mode == APIC:
+        h.step(1.0 / 240.0)           # gives the particles non-trivial affine vectors
+        aff = h.get_affine()
+    pos, vel = h.get_particles()
+    assert np.isfinite(pos).all() and np.isfinite(vel).all()
+    h.transfer_particles_to_grids()
+    want, want_m = h.get_velocity(), h.get_markers()
+    got, got_m = run_hc(hc, grid, mode == APIC, 0, 1, pos, vel, aff)
+    scale = max(float(np.abs(a).max()) for a in want)
+    for a, b, am, bm, nm in zip(got, want, got_m, want_m, "uvw"):
+        exact(am, bm, "marker " + nm)
+        assert np.abs(a - b).max() <= 1e-12 * scale, "%s: %g" % (nm, np.abs(a - b).max() / scale)
+    h.close()

@@ -33,12 +33,26 @@ def sources():
     return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
+STAMP = LIB + ".srchash"
+
+
+def source_hash():
+    """sha256 over the compiler flags and the CONTENT of every file the library is built from (not their mtimes)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(HERE, "..", "include", "jetcu.h")]
+    for d in deps:
+        if os.path.isfile(d):
+            h.update(os.path.basename(d).encode())
+            h.update(open(d, "rb").read())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(LIB):
+    """The in-tree library is reused only if it was built from exactly these sources (content hash recorded next to it)."""
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "jetcu.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return open(STAMP).read().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
@@ -66,6 +80,8 @@ def build(force=False, verbose=False):
     if r.returncode != 0:
         sys.stderr.write(" ".join(cmd) + "\n" + r.stdout)
         raise RuntimeError("link failed")
+    with open(STAMP, "w") as f:
+        f.write(source_hash() + "\n")
     return LIB
 
 

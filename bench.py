@@ -13,7 +13,7 @@
   scripts/bench_smoke.py = config 5 (its own metric, its own JSON line).
 * --impl reference: the reference's own CPU implementation (oracle/_ref/libjetref.so = unmodified Jet, OpenMP, all
   host threads; else the C port) stepping THE SAME scene at THE SAME size: the first k sub-steps that fit the wall budget
-  (--ref-budget-s, default 420 s; k <= --steps, no warm-up — every sub-step is minutes of deterministic CPU work).  The line
+  (--ref-budget-s, default 260 s; k <= --steps, no warm-up — every sub-step is minutes of deterministic CPU work).  The line
   carries the ms_per_step it observed, `steps` = k, and per-step PCG iterations / position samples for parity.
 
 A "step" is one GridFluidSolver3::onAdvanceTimeStep sub-step (SURVEY.md §3.2).  Synthetic, deterministic scene.
@@ -635,7 +635,7 @@ def main():
     ap.add_argument("--impl", default="jetcu", choices=["jetcu", "reference"])
     ap.add_argument("--workload", default="tank", choices=["tank", "slosh", "dam"])
     ap.add_argument("--mode", default="flip", choices=["flip", "apic", "pic"])
-    ap.add_argument("--ref-budget-s", type=float, default=float(os.environ.get("JETCU_REF_BUDGET_S", "420")),
+    ap.add_argument("--ref-budget-s", type=float, default=float(os.environ.get("JETCU_REF_BUDGET_S", "260")),
                     help="--impl reference: wall budget for the real-size CPU run")
     ap.add_argument("--n", "--grid", dest="n", type=int, default=256,
                     help="grid size n^3 (use --grid under torchrun: its own parser finds --n ambiguous)")

@@ -2,6 +2,9 @@
 // Target: sm_100a only (B200). Built with -fmad=false: the reference is compiled without FMA contraction and
 // every stencil here is HBM-bound, so exact IEEE replay of Jet's expressions costs nothing.
 #pragma once
+#ifndef JETCU_PDL_DEFAULT
+#define JETCU_PDL_DEFAULT 1
+#endif
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -104,6 +107,51 @@ int jetcu_fail(jetcu_ctx* ctx, int code, const char* fmt, ...);
 #define JC_ARG(ctx, cond)                                                                           \
     do {                                                                                            \
         if (!(cond)) return jetcu_fail((ctx), JETCU_ERR_INVALID_ARG, "invalid argument: %s", #cond); \
+    } while (0)
+
+// Programmatic dependent launch (sm_90+): a kernel launched through JC_LAUNCH_PDL may become resident while the previous
+// kernel of the stream is still draining — its CTAs call jc_pdl_prologue() first, which (1) lets the NEXT dependent
+// launch start as early as possible and (2) blocks until the previous grid has completed and its writes are visible.
+// Only the launch gap and the tail of the previous grid are overlapped, never the data: results are unchanged.  The
+// kernels that call the prologue behave exactly as before when launched without the attribute (the wait returns at once).
+// JETCU_PDL=0 switches the attribute off (plain stream order).
+__device__ __forceinline__ void jc_pdl_prologue() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+static inline bool jc_pdl_on() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("JETCU_PDL"); v = e ? (atoi(e) != 0) : JETCU_PDL_DEFAULT; }
+    return v != 0;
+}
+template <typename... KA, typename... CA>
+static inline cudaError_t jc_launch_pdl(void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, CA&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KA>(args)...);
+}
+// `pdl` = this launch directly follows another kernel launch of the same stream (not a copy, memset or collective)
+#define JC_LAUNCH_PDL(ctx, pdl, kernel, grid, block, smem, ...)                                     \
+    do {                                                                                            \
+        if ((pdl) && jc_pdl_on()) {                                                                 \
+            cudaError_t _l = jc_launch_pdl(kernel, (grid), (block), (smem), (ctx)->stream, __VA_ARGS__); \
+            if (_l != cudaSuccess)                                                                  \
+                return jetcu_fail((ctx), JETCU_ERR_CUDA, "dependent launch of %s failed: %s (%s:%d)", #kernel, \
+                                  cudaGetErrorString(_l), __FILE__, __LINE__);                      \
+        } else {                                                                                    \
+            kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                        \
+        }                                                                                           \
+        (ctx)->launches++;                                                                          \
+        cudaError_t _e = cudaPeekAtLastError();                                                     \
+        if (_e != cudaSuccess)                                                                      \
+            return jetcu_fail((ctx), JETCU_ERR_CUDA, "launch of %s failed: %s (%s:%d)", #kernel,    \
+                              cudaGetErrorString(_e), __FILE__, __LINE__);                          \
     } while (0)
 
 // Every kernel launch goes through this so that jetcu_launch_count() is an honest count.

@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_relax_small(Mat A, const doub
 template <bool P>
 __global__ void __launch_bounds__(BX* BY) k_relax_colour(Mat A, const double* __restrict__ b, double* __restrict__ x,
                                                          double w, int colour, int nx, int ny, int nz, int k0) {
+    jc_pdl_prologue();
     int j = blockIdx.y * BY + threadIdx.y, k = k0 + blockIdx.z;
     int i = 2 * (blockIdx.x * BX + threadIdx.x) + ((j + k + colour) & 1);
     if (i >= nx || j >= ny) return;
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(BX* BY) k_relax_colour(Mat A, const double* __
 //     2 fractional => weight fetched on demand), so a pass streams center 8 + b 8 + x 8 r + ~8 w + code 1 = 33 B/cell.
 __global__ void __launch_bounds__(BX* BY) k_relax_colour_code(Mat A, const double* __restrict__ b, double* __restrict__ x,
                                                               double w, int colour, int nx, int ny, int nz, int k0) {
+    jc_pdl_prologue();
     const int j = blockIdx.y * BY + threadIdx.y, k = k0 + blockIdx.z;
     const int i = 2 * (blockIdx.x * BX + threadIdx.x) + ((j + k + colour) & 1);
     if (i >= nx || j >= ny) return;
@@ -152,11 +154,16 @@ int fdm_residual(jetcu_ctx* ctx, Dim3i d, Mat A, const double* x, const double* 
 }
 
 // One colour pass over the planes of `z` (colour 0 = red = (i+j+k) even with GLOBAL k).
+// `after_pass` = the previous operation of the stream is another colour pass (launch_relax keeps track): the launch may then
+// be a programmatic dependent launch (common.cuh), which hides the launch gap between the ~50 dependent passes of a level visit.
 template <bool P>
-static int launch_colour(jetcu_ctx* ctx, Dim3i d, ZRange z, Mat A, const double* b, double sor, int colour, double* x) {
+static int launch_colour(jetcu_ctx* ctx, Dim3i d, ZRange z, Mat A, const double* b, double sor, int colour, double* x,
+                         bool after_pass = false) {
     dim3 grid(((d.nx + 1) / 2 + BX - 1) / BX, (d.ny + BY - 1) / BY, z.k1 - z.k0);
-    if (P && A.code != nullptr) JC_LAUNCH(ctx, k_relax_colour_code, grid, dim3(BX, BY), 0, A, b, x, sor, colour, d.nx, d.ny, d.nz, z.k0);
-    else JC_LAUNCH(ctx, k_relax_colour<P>, grid, dim3(BX, BY), 0, A, b, x, sor, colour, d.nx, d.ny, d.nz, z.k0);
+    if (P && A.code != nullptr)
+        JC_LAUNCH_PDL(ctx, after_pass, k_relax_colour_code, grid, dim3(BX, BY), 0, A, b, x, sor, colour, d.nx, d.ny, d.nz, z.k0);
+    else
+        JC_LAUNCH_PDL(ctx, after_pass, k_relax_colour<P>, grid, dim3(BX, BY), 0, A, b, x, sor, colour, d.nx, d.ny, d.nz, z.k0);
     return JETCU_OK;
 }
 
@@ -211,10 +218,10 @@ static int relax_chunk_planes(size_t plane_cells) {
 // level continues), as whole passes (chunk == 0) or chunk-interleaved
 template <bool P>
 static int launch_sweep(jetcu_ctx* ctx, Dim3i d, ZRange rw, ZRange bw, int chunk, Mat A, const double* b, double sor, double* x,
-                        uint64_t* launches) {
+                        uint64_t* launches, bool after_pass) {
     if (chunk <= 0 || bw.k1 - bw.k0 <= chunk) {
-        JC_TRY(launch_colour<P>(ctx, d, rw, A, b, sor, 0, x));
-        JC_TRY(launch_colour<P>(ctx, d, bw, A, b, sor, 1, x));
+        JC_TRY(launch_colour<P>(ctx, d, rw, A, b, sor, 0, x, after_pass));
+        JC_TRY(launch_colour<P>(ctx, d, bw, A, b, sor, 1, x, true));
         *launches += 2;
         return JETCU_OK;
     }
@@ -223,15 +230,17 @@ static int launch_sweep(jetcu_ctx* ctx, Dim3i d, ZRange rw, ZRange bw, int chunk
         const int c1 = c0 + chunk < bw.k1 ? c0 + chunk : bw.k1;
         const int need = c1 + 1 < rw.k1 ? c1 + 1 : rw.k1;   // black on [c0, c1) reads red up to plane c1
         if (need > red_done) {
-            JC_TRY(launch_colour<P>(ctx, d, ZRange{red_done, need}, A, b, sor, 0, x));
+            JC_TRY(launch_colour<P>(ctx, d, ZRange{red_done, need}, A, b, sor, 0, x, after_pass));
             red_done = need;
             *launches += 1;
+            after_pass = true;
         }
-        JC_TRY(launch_colour<P>(ctx, d, ZRange{c0, c1}, A, b, sor, 1, x));
+        JC_TRY(launch_colour<P>(ctx, d, ZRange{c0, c1}, A, b, sor, 1, x, after_pass));
         *launches += 1;
+        after_pass = true;
     }
     if (red_done < rw.k1) {
-        JC_TRY(launch_colour<P>(ctx, d, ZRange{red_done, rw.k1}, A, b, sor, 0, x));
+        JC_TRY(launch_colour<P>(ctx, d, ZRange{red_done, rw.k1}, A, b, sor, 0, x, after_pass));
         *launches += 1;
     }
     return JETCU_OK;
@@ -258,7 +267,7 @@ static int relax_skew_sweeps() {
 // shrink by one plane per pass, see launch_relax).
 template <bool P>
 static int launch_sweeps_skewed(jetcu_ctx* ctx, Dim3i d, const int* w0, const int* w1, int passes, int chunk, Mat A, const double* b,
-                                double sor, double* x, uint64_t* launches) {
+                                double sor, double* x, uint64_t* launches, bool after_pass) {
     for (int c0 = w0[0];; c0 += chunk) {
         bool any = false;
         for (int p = 0; p < passes; ++p) {
@@ -266,8 +275,9 @@ static int launch_sweeps_skewed(jetcu_ctx* ctx, Dim3i d, const int* w0, const in
             any = true;
             const int lo = c0 - p > w0[p] ? c0 - p : w0[p], hi = c0 + chunk - p < w1[p] ? c0 + chunk - p : w1[p];
             if (lo < hi) {
-                JC_TRY(launch_colour<P>(ctx, d, ZRange{lo, hi}, A, b, sor, p & 1, x));
+                JC_TRY(launch_colour<P>(ctx, d, ZRange{lo, hi}, A, b, sor, p & 1, x, after_pass));
                 *launches += 1;
+                after_pass = true;
             }
         }
         if (!any) break;
@@ -297,7 +307,7 @@ static int launch_relax(jetcu_ctx* ctx, Dim3i d, ZRange z, bool halo, Mat A, con
             int s2 = (int)((iterations - it < (unsigned)skew) ? iterations - it : (unsigned)skew);
             if (s2 > 32) s2 = 32;
             for (int p = 0; p < 2 * s2; ++p) { w0[p] = z.k0; w1[p] = z.k1; }
-            JC_TRY(launch_sweeps_skewed<P>(ctx, d, w0, w1, 2 * s2, chunk, A, b, sor, *x, launches));
+            JC_TRY(launch_sweeps_skewed<P>(ctx, d, w0, w1, 2 * s2, chunk, A, b, sor, *x, launches, it > 0));
             it += (unsigned)s2;
         }
         return JETCU_OK;
@@ -311,7 +321,7 @@ static int launch_relax(jetcu_ctx* ctx, Dim3i d, ZRange z, bool halo, Mat A, con
                 const int e = 2 * k - 1 - p;
                 w0[p] = z.k0 - e < 0 ? 0 : z.k0 - e; w1[p] = z.k1 + e > d.nz ? d.nz : z.k1 + e;
             }
-            JC_TRY(launch_sweeps_skewed<P>(ctx, d, w0, w1, 2 * k, chunk, A, b, sor, *x, launches));
+            JC_TRY(launch_sweeps_skewed<P>(ctx, d, w0, w1, 2 * k, chunk, A, b, sor, *x, launches, false));  // follows the exchange
             it += (unsigned)k;
             continue;
         }
@@ -319,7 +329,7 @@ static int launch_relax(jetcu_ctx* ctx, Dim3i d, ZRange z, bool halo, Mat A, con
             const int er = halo ? 2 * (k - s2) - 1 : 0, eb = halo ? 2 * (k - s2) - 2 : 0;
             const ZRange rw{z.k0 - er < 0 ? 0 : z.k0 - er, z.k1 + er > d.nz ? d.nz : z.k1 + er};
             const ZRange bw{z.k0 - eb < 0 ? 0 : z.k0 - eb, z.k1 + eb > d.nz ? d.nz : z.k1 + eb};
-            JC_TRY(launch_sweep<P>(ctx, d, rw, bw, chunk, A, b, sor, *x, launches));
+            JC_TRY(launch_sweep<P>(ctx, d, rw, bw, chunk, A, b, sor, *x, launches, halo ? s2 > 0 : (it > 0 || s2 > 0)));
         }
         it += (unsigned)k;
     }

@@ -8,7 +8,7 @@
 // with wall times and deviations from the stock run.  Built by adapters/Makefile against the unmodified reference
 // (oracle/_ref/libjet_ref.a) and libjetcu.so;  tests/test_gpu_dropin.py runs it on the GPU box.
 //
-//     dropin_check [--n 32] [--frames 3] [--fps 60] [--levels 4] [--mode flip|apic|pic] [--skip-seam12]
+//     dropin_check [--n 32] [--frames 3] [--fps 60] [--levels 4] [--mode flip|apic|pic] [--skip-seam12] [--natural-ordering]
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -29,6 +29,7 @@ struct Options {
     size_t levels = 4;
     std::string mode = "flip";
     bool skipSeam12 = false;
+    bool redBlack = true;
 };
 
 double nowS() {
@@ -96,7 +97,7 @@ double relLinf(const std::vector<double>& a, const std::vector<double>& b) {
 }
 
 std::shared_ptr<FdmMgpcgSolver3> stockMgpcg(const Options& opt) {
-    return std::make_shared<FdmMgpcgSolver3>(100, opt.levels, 5, 5, 20, 20, 1e-9, 1.5, true);
+    return std::make_shared<FdmMgpcgSolver3>(100, opt.levels, 5, 5, 20, 20, 1e-9, 1.5, opt.redBlack);
 }
 
 template <class Stock, class Cuda>
@@ -119,7 +120,7 @@ int runMode(const Options& opt) {
             auto solver = makeSolver<Stock>(opt);
             setupScene(solver, opt);
             auto pressure = std::make_shared<GridFractionalSinglePhasePressureSolver3>();
-            auto lin = std::make_shared<jetcu::CudaFdmMgpcgSolver3>(100, opt.levels, 5, 5, 20, 20, 1e-9, 1.5, true);
+            auto lin = std::make_shared<jetcu::CudaFdmMgpcgSolver3>(100, opt.levels, 5, 5, 20, 20, 1e-9, 1.5, opt.redBlack);
             pressure->setLinearSystemSolver(lin);
             solver->setPressureSolver(pressure);
             runFrames(solver, opt, &seam1);
@@ -130,7 +131,7 @@ int runMode(const Options& opt) {
             auto solver = makeSolver<Stock>(opt);
             setupScene(solver, opt);
             auto pressure = std::make_shared<jetcu::CudaGridFractionalSinglePhasePressureSolver3>(
-                jetcu::makeMgpcgParams(100, opt.levels, 5, 5, 20, 20, 1e-9, 1.5, true));
+                jetcu::makeMgpcgParams(100, opt.levels, 5, 5, 20, 20, 1e-9, 1.5, opt.redBlack));
             solver->setPressureSolver(pressure);
             runFrames(solver, opt, &seam2);
             seam2.pressure.assign(pressure->pressure().data(), pressure->pressure().data() + opt.n * opt.n * opt.n);
@@ -140,7 +141,7 @@ int runMode(const Options& opt) {
     {  // ---- seam 3: device-resident solver subclass
         const double h = 1.0 / static_cast<double>(opt.n);
         auto solver = std::make_shared<Cuda>(Size3(opt.n, opt.n, opt.n), Vector3D(h, h, h), Vector3D(),
-                                             jetcu::makeMgpcgParams(100, opt.levels, 5, 5, 20, 20, 1e-9, 1.5, true));
+                                             jetcu::makeMgpcgParams(100, opt.levels, 5, 5, 20, 20, 1e-9, 1.5, opt.redBlack));
         setupScene(solver, opt);
         runFrames(solver, opt, &seam3);
         seam3.lastIterations = solver->lastStepStats().pcg_iterations;
@@ -175,6 +176,7 @@ int main(int argc, char** argv) {
         else if (a == "--levels") opt.levels = std::strtoul(next(), nullptr, 10);
         else if (a == "--mode") opt.mode = next();
         else if (a == "--skip-seam12") opt.skipSeam12 = true;
+        else if (a == "--natural-ordering") opt.redBlack = false;   // FdmMgpcgSolver3's constructor default (useRedBlackOrdering = false)
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     Logging::mute();

@@ -269,6 +269,19 @@ int jetcu_fdm_relax_red_black(jetcu_ctx* ctx, uint64_t nx, uint64_t ny, uint64_t
     return jc_sync(ctx);
 }
 
+int jetcu_fdm_relax(jetcu_ctx* ctx, uint64_t nx, uint64_t ny, uint64_t nz, const jetcu_matrix_row* A, const double* b,
+                    double sor_factor, uint32_t iterations, double* x) {
+    JC_ENTER(ctx);
+    JC_TRY(check_dims(ctx, nx, ny, nz));
+    JC_ARG(ctx, A && x && b);
+    size_t n = nx * ny * nz;
+    DevMat m(ctx); DevVec dx(ctx), db(ctx);
+    JC_TRY(m.upload(A, n)); JC_TRY(dx.upload(x, n)); JC_TRY(db.upload(b, n));
+    JC_TRY(fdm_relax_lex(ctx, Dim3i{(int)nx, (int)ny, (int)nz}, mat_of(m.A), db.p, sor_factor, iterations, dx.p));
+    JC_TRY(jc_d2h(ctx, x, dx.p, n));
+    return jc_sync(ctx);
+}
+
 int jetcu_fdm_restrict(jetcu_ctx* ctx, uint64_t nx, uint64_t ny, uint64_t nz, const double* finer, double* coarser) {
     JC_ENTER(ctx);
     JC_TRY(check_dims(ctx, nx, ny, nz));
@@ -322,8 +335,6 @@ int jetcu_fdm_vcycle(jetcu_ctx* ctx, uint64_t nx, uint64_t ny, uint64_t nz, uint
     JC_ENTER(ctx);
     JC_TRY(check_dims(ctx, nx, ny, nz));
     JC_ARG(ctx, A && b && x && p);
-    if (!p->use_red_black)
-        return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED, "lexicographic Gauss-Seidel is not available on the GPU path");
     MgLevels mg;
     std::vector<DevMat*> mats;
     int rc = setup_levels(ctx, &mg, mats, nx, ny, nz, levels, A);
@@ -450,8 +461,6 @@ int jetcu_pressure_vcycle(jetcu_ctx* ctx, const double* b, double* x, const jetc
     JC_ENTER(ctx);
     PressureSystem* ps = ctx->psys;
     JC_ARG(ctx, ps && ps->levels > 0 && b && x && p);
-    if (!p->use_red_black)
-        return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED, "lexicographic Gauss-Seidel is not available on the GPU path");
     MgLevels* mg = &ps->mg;
     size_t n = ps->dims[0].n();
     JC_TRY(jc_h2d(ctx, mg->x[0], x, n));

@@ -124,6 +124,10 @@ __global__ void __launch_bounds__(BX* BY) k_relax_colour_code(Mat A, const doubl
     relax_cell_code(A, b, x, w, i, j, k, nx, ny, nz);
 }
 
+// A 3-D CTA tile (TX x-pairs x TY rows x TZ planes, so that the z-neighbours of the inner planes hit in the L1) was measured in
+// round 2 (GPU call 17, profiles/r02_sor_wavefront.md): eight shapes from 64x4x2 to 32x4x8, none faster than the plane tile
+// (25.28-35.9 ms per solve against 25.38) — the pass is bound by DRAM, not by L2 -> L1 traffic.  Removed again.
+
 static inline dim3 grid3z(Dim3i d, ZRange z) { return dim3((d.nx + BX - 1) / BX, (d.ny + BY - 1) / BY, z.k1 - z.k0); }
 static inline ZRange zfull(Dim3i d) { return ZRange{0, d.nz}; }
 
@@ -349,6 +353,102 @@ int fdm_relax_rb(jetcu_ctx* ctx, Dim3i d, ZRange z, bool halo, Mat A, const doub
 int fdm_relax_rb(jetcu_ctx* ctx, Dim3i d, Mat A, const double* b, double sor, unsigned iterations, double** x,
                  double** xalt, int level) {
     return fdm_relax_rb(ctx, d, zfull(d), false, A, b, sor, iterations, x, xalt, level);
+}
+
+// ---- FdmGaussSeidelSolver3::relax, src/jet/fdm_gauss_seidel_solver3.cpp:103-120: the natural (lexicographic) ordering ----------
+// The smoother FdmMgSolver3 / FdmMgpcgSolver3 install unless useRedBlackOrdering is set (src/jet/fdm_mg_solver3.cpp:26-49;
+// `false` is the constructors' default).  As written it is one serial loop, i fastest.  A cell reads the NEW values of its three
+// lower neighbours and the OLD values of its three upper ones, so the update order only has to respect the partial order
+// "lower neighbours first": every cell of a hyperplane i + j + k = h is independent of the others.  Two schedules, both with the
+// per-cell body of the red-black kernels (relax_cell / relax_cell_code: the reference's expression, fdm_ops.cuh):
+//  * k_relax_lex_tiles — GS_T^3 tiles, one CTA each; launch t runs, for every sweep s in flight, the tiles of tile hyperplane
+//    S = t - 2 s (inside a tile the 3 GS_T - 2 cell hyperplanes run one after the other between __syncthreads).  Sweep s + 1
+//    trails sweep s by two tile hyperplanes: the tiles it reads above itself (S + 1) were finished by sweep s in the previous
+//    launch and are not touched again before the next one, so no tile is written and read by different CTAs of one launch.
+//    n sweeps of a level with H tile hyperplanes take H + 2 (n - 1) launches instead of n H.
+//  * k_relax_lex_small — levels of at most SMALL_MAX_CELLS cells: one CTA, the same pipelining at cell granularity
+//    (cell hyperplane h of sweep s runs in step h + 2 s).
+// Bit-identical to the serial loop (tests/test_hostcheck_linear.py replays both schedules on the CPU against the oracle,
+// tests/test_gpu_linear.py compares the device with the oracle and the unmodified reference).
+#define GS_T 8
+template <bool P, bool CODE>
+__global__ void __launch_bounds__(GS_T* GS_T* GS_T)
+    k_relax_lex_tiles(Mat A, const double* __restrict__ b, double* x, double w, int nx, int ny, int nz, int t, int s_first) {
+    jc_pdl_prologue();
+    const int ti = blockIdx.x, tj = blockIdx.y, tk = t - 2 * (s_first + (int)blockIdx.z) - ti - tj;
+    const int ntz = (nz + GS_T - 1) / GS_T;
+    if (tk < 0 || tk >= ntz) return;
+    const int cx = threadIdx.x % GS_T, cy = (threadIdx.x / GS_T) % GS_T, cz = threadIdx.x / (GS_T * GS_T);
+    const int i = ti * GS_T + cx, j = tj * GS_T + cy, k = tk * GS_T + cz;
+    const bool live = i < nx && j < ny && k < nz;
+    const int mine = cx + cy + cz;
+    for (int step = 0; step <= 3 * GS_T - 3; ++step) {
+        if (live && mine == step) {
+            if (CODE) relax_cell_code(A, b, x, w, i, j, k, nx, ny, nz);
+            else relax_cell<P>(A, b, x, w, i, j, k, nx, ny, nz);
+        }
+        __syncthreads();   // orders this CTA's global stores before its next hyperplane's loads
+    }
+}
+
+template <bool P>
+__global__ void __launch_bounds__(SMALL_THREADS) k_relax_lex_small(Mat A, const double* __restrict__ b, double* x, double w,
+                                                                   int nx, int ny, int nz, unsigned iterations) {
+    const int n = nx * ny * nz;
+    const int steps = (nx + ny + nz - 2) + 2 * ((int)iterations - 1);
+    for (int step = 0; step < steps; ++step) {
+        for (int c = threadIdx.x; c < n; c += SMALL_THREADS) {
+            const int i = c % nx, j = (c / nx) % ny, k = c / (nx * ny);
+            const int lag = step - (i + j + k);   // = 2 x (the sweep this cell is in at this step)
+            if (lag < 0 || (lag & 1) || lag / 2 >= (int)iterations) continue;
+            relax_cell<P>(A, b, x, w, i, j, k, nx, ny, nz);
+        }
+        __syncthreads();
+    }
+}
+
+// sweeps in flight per group of launches (gridDim.z); a group of n sweeps costs H + 2 (n - 1) launches
+#define GS_MAX_INFLIGHT 32
+template <bool P>
+static int launch_relax_lex(jetcu_ctx* ctx, Dim3i d, Mat A, const double* b, double sor, unsigned iterations, double* x,
+                            uint64_t* launches) {
+    *launches = 0;
+    if (d.n() <= SMALL_MAX_CELLS) {
+        JC_LAUNCH(ctx, k_relax_lex_small<P>, 1, SMALL_THREADS, 0, A, b, x, sor, d.nx, d.ny, d.nz, iterations);
+        *launches = 1;
+        return JETCU_OK;
+    }
+    const int ntx = (d.nx + GS_T - 1) / GS_T, nty = (d.ny + GS_T - 1) / GS_T, ntz = (d.nz + GS_T - 1) / GS_T;
+    const int last = ntx + nty + ntz - 3;   // highest tile hyperplane
+    const bool code = P && A.code != nullptr;
+    for (unsigned done = 0; done < iterations;) {
+        const int n = (int)((iterations - done < GS_MAX_INFLIGHT) ? iterations - done : GS_MAX_INFLIGHT);
+        for (int t = 0; t <= last + 2 * (n - 1); ++t) {
+            // sweeps s with 0 <= t - 2 s <= last
+            int s_lo = t - last > 0 ? (t - last + 1) / 2 : 0, s_hi = t / 2 < n - 1 ? t / 2 : n - 1;
+            if (s_lo > s_hi) continue;
+            dim3 grid(ntx, nty, s_hi - s_lo + 1);
+            const bool after = t > 0;   // the previous operation of the stream is the previous launch of this group
+            if (code) JC_LAUNCH_PDL(ctx, after, (k_relax_lex_tiles<P, true>), grid, GS_T * GS_T * GS_T, 0, A, b, x, sor, d.nx, d.ny, d.nz, t, s_lo);
+            else JC_LAUNCH_PDL(ctx, after, (k_relax_lex_tiles<P, false>), grid, GS_T * GS_T * GS_T, 0, A, b, x, sor, d.nx, d.ny, d.nz, t, s_lo);
+            *launches += 1;
+        }
+        done += (unsigned)n;
+    }
+    return JETCU_OK;
+}
+
+int fdm_relax_lex(jetcu_ctx* ctx, Dim3i d, Mat A, const double* b, double sor, unsigned iterations, double* x, int level) {
+    if (iterations == 0 || d.n() == 0) return JETCU_OK;
+    if (jc_comm_world(ctx) > 1)
+        return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED, "lexicographic Gauss-Seidel (useRedBlackOrdering = false) is not slab-"
+                          "distributed: use useRedBlackOrdering = true on a multi-GPU communicator");
+    int slot = jc_prof_begin(ctx, level == 0 ? JETCU_PROF_RELAX_L0 : JETCU_PROF_RELAX_COARSE);
+    uint64_t launches = 0;
+    int rc = A.packed ? launch_relax_lex<true>(ctx, d, A, b, sor, iterations, x, &launches)
+                      : launch_relax_lex<false>(ctx, d, A, b, sor, iterations, x, &launches);
+    jc_prof_end(ctx, slot, launches, (uint64_t)d.n() * iterations);
+    return rc;
 }
 
 __global__ void __launch_bounds__(BX* BY) k_restrict(const double* __restrict__ finer, double* __restrict__ coarser,
@@ -578,6 +678,13 @@ extern "C" int jetcu_slab_plan(uint64_t nx, uint64_t ny, uint64_t nz, uint32_t l
 // mg->x[l] / mg->xalt[l] may be exchanged by the smoother; mg->x[l] always names the current iterate.
 // On a slab-distributed level every rank works on its planes [z0, z1) of the full-size (globally indexed) arrays and
 // refreshes the two planes around them from its neighbours before each stencil application.
+// the smoother FdmMgSolver3's constructor installs (src/jet/fdm_mg_solver3.cpp:26-49): relaxRedBlack or the natural relax
+static int vc_relax(jetcu_ctx* ctx, MgLevels* mg, const jetcu_mgpcg_params* p, int l, bool dist, ZRange z, unsigned iterations) {
+    if (p->use_red_black)
+        return fdm_relax_rb(ctx, mg->dims[l], z, dist, mg->A[l], mg->b[l], p->sor_factor, iterations, &mg->x[l], &mg->xalt[l], l);
+    return fdm_relax_lex(ctx, mg->dims[l], mg->A[l], mg->b[l], p->sor_factor, iterations, mg->x[l], l);
+}
+
 int mg_vcycle(jetcu_ctx* ctx, MgLevels* mg, const jetcu_mgpcg_params* p, int l) {
     const Dim3i d = mg->dims[l];
     const SlabPlan& pl = mg->plan;
@@ -587,7 +694,7 @@ int mg_vcycle(jetcu_ctx* ctx, MgLevels* mg, const jetcu_mgpcg_params* p, int l) 
     // the smoother's redundant halo cells read b next to the slab; b[l] does not change during this level's visit
     if (dist && fdm_relax_rhs_halo(z.k1 - z.k0, (size_t)d.nx * d.ny) > 0)
         JC_TRY(comm_halo_planes(ctx, mg->b[l], plane, z.k0, z.k1, d.nz, fdm_relax_rhs_halo(z.k1 - z.k0, (size_t)d.nx * d.ny)));
-    JC_TRY(fdm_relax_rb(ctx, d, z, dist, mg->A[l], mg->b[l], p->sor_factor, p->n_restriction, &mg->x[l], &mg->xalt[l], l));
+    JC_TRY(vc_relax(ctx, mg, p, l, dist, z, p->n_restriction));
     if (l + 1 < mg->levels) {
         const Dim3i dc = mg->dims[l + 1];
         const ZRange cz{z.k0 / 2, z.k1 / 2};
@@ -606,10 +713,9 @@ int mg_vcycle(jetcu_ctx* ctx, MgLevels* mg, const jetcu_mgpcg_params* p, int l) 
             JC_TRY(comm_halo_planes(ctx, mg->x[l + 1], (size_t)dc.nx * dc.ny * sizeof(double), pl.z0[l + 1], pl.z1[l + 1], dc.nz));
         JC_TRY(fdm_correct(ctx, d, z, mg->x[l + 1], mg->x[l]));
         jc_prof_end(ctx, slot, 1, (uint64_t)d.nx * d.ny * (z.k1 - z.k0));
-        JC_TRY(fdm_relax_rb(ctx, d, z, dist, mg->A[l], mg->b[l], p->sor_factor, l > 0 ? p->n_correction : p->n_final,
-                            &mg->x[l], &mg->xalt[l], l));
+        JC_TRY(vc_relax(ctx, mg, p, l, dist, z, l > 0 ? p->n_correction : p->n_final));
     } else {
-        JC_TRY(fdm_relax_rb(ctx, d, z, dist, mg->A[l], mg->b[l], p->sor_factor, p->n_coarsest, &mg->x[l], &mg->xalt[l], l));
+        JC_TRY(vc_relax(ctx, mg, p, l, dist, z, p->n_coarsest));
     }
     return JETCU_OK;
 }
@@ -646,7 +752,7 @@ static uint64_t vcycle_key(const MgLevels* mg, const jetcu_mgpcg_params* p) {
         mix(&mg->plan.z0[l], sizeof(int)); mix(&mg->plan.z1[l], sizeof(int));
     }
     mix(&mg->plan.world, sizeof(int)); mix(&mg->plan.rank, sizeof(int)); mix(&mg->plan.dist_levels, sizeof(int));
-    const uint32_t it[] = {p->n_restriction, p->n_correction, p->n_coarsest, p->n_final};
+    const uint32_t it[] = {p->n_restriction, p->n_correction, p->n_coarsest, p->n_final, (uint32_t)(p->use_red_black != 0)};
     mix(it, sizeof(it));
     mix(&p->sor_factor, sizeof(double));
     return h;
@@ -721,9 +827,9 @@ static int read_scalar(jetcu_ctx* ctx, const double* d, double* out) {
 // takes the same branches and produces the bits of the single-GPU solve.
 int mgpcg_solve_device(jetcu_ctx* ctx, MgLevels* mg, const double* b, double* x, const jetcu_mgpcg_params* p,
                        jetcu_mgpcg_result* result) {
-    if (!p->use_red_black)
-        return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED,
-                          "lexicographic Gauss-Seidel is inherently serial; use useRedBlackOrdering = true");
+    if (!p->use_red_black && jc_comm_world(ctx) > 1)
+        return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED, "lexicographic Gauss-Seidel (useRedBlackOrdering = false) is not slab-"
+                          "distributed: use useRedBlackOrdering = true on a multi-GPU communicator");
     JC_TRY(mg_make_plan(ctx, mg));
     const Dim3i d = mg->dims[0];
     const size_t n = d.n();

@@ -59,6 +59,8 @@ int fdm_relax_rb(jetcu_ctx* ctx, Dim3i d, Mat A, const double* b, double sor, un
 // slab form: planes `z` only; `halo` = refresh the planes around `z` from the neighbouring ranks before each colour pass
 int fdm_relax_rb(jetcu_ctx* ctx, Dim3i d, ZRange z, bool halo, Mat A, const double* b, double sor, unsigned iterations,
                  double** x, double** xalt, int level = -1);
+// `iterations` sweeps of the natural (lexicographic) Gauss-Seidel ordering, in place; single GPU (fdm.cu)
+int fdm_relax_lex(jetcu_ctx* ctx, Dim3i d, Mat A, const double* b, double sor, unsigned iterations, double* x, int level = -1);
 int fdm_relax_rhs_halo(int slab_planes, size_t plane_cells);  // planes of b the slab smoother reads outside the slab
 int fdm_restrict(jetcu_ctx* ctx, Dim3i fine, const double* finer, double* coarser);
 int fdm_restrict(jetcu_ctx* ctx, Dim3i fine, ZRange coarse_planes, const double* finer, double* coarser);

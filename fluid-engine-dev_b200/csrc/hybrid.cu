@@ -1217,8 +1217,9 @@ int jetcu_hybrid_create(jetcu_ctx* ctx, const jetcu_hybrid_params* p, jetcu_hybr
     // particle bins are (cell, octant) pairs held in 32-bit indices: up to 2^29 cells (812^3)
     if ((uint64_t)p->grid.nx * p->grid.ny * p->grid.nz * 8 >= (1ull << 32) - 2)
         return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED, "the hybrid solver bins particles in 32-bit (cell, octant) indices: at most 2^29 cells");
-    if (!p->mgpcg.use_red_black)
-        return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED, "lexicographic Gauss-Seidel is not available on the GPU path");
+    if (!p->mgpcg.use_red_black && jc_comm_world(ctx) > 1)
+        return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED, "lexicographic Gauss-Seidel (useRedBlackOrdering = false) is not slab-distributed: "
+                          "use useRedBlackOrdering = true on a multi-GPU communicator");
     jetcu_hybrid* h = new jetcu_hybrid();
     h->ctx = ctx;
     h->P = *p;

@@ -270,8 +270,9 @@ int jetcu_smoke_create(jetcu_ctx* ctx, const jetcu_smoke_params* p, jetcu_smoke*
     JC_ARG(ctx, p && out);
     JC_ARG(ctx, p->grid.nx > 0 && p->grid.ny > 0 && p->grid.nz > 0 && p->grid.nx < 32768 && p->grid.ny < 32768 && p->grid.nz < 32768);
     JC_ARG(ctx, p->grid.hx > 0 && p->grid.hy > 0 && p->grid.hz > 0);
-    if (!p->mgpcg.use_red_black)
-        return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED, "lexicographic Gauss-Seidel is not available on the GPU path");
+    if (!p->mgpcg.use_red_black && jc_comm_world(ctx) > 1)
+        return jetcu_fail(ctx, JETCU_ERR_UNSUPPORTED, "lexicographic Gauss-Seidel (useRedBlackOrdering = false) is not slab-distributed: "
+                          "use useRedBlackOrdering = true on a multi-GPU communicator");
     JC_ARG(ctx, p->advection == JETCU_ADVECT_CUBIC || p->advection == JETCU_ADVECT_LINEAR);
     jetcu_smoke* h = new jetcu_smoke();
     h->ctx = ctx;

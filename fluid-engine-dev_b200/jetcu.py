@@ -290,6 +290,13 @@ class LinearApi:
                    u32(iterations), _p(out))
         return out
 
+    def relax(self, A, b, x, sor=1.5, iterations=1):
+        """FdmGaussSeidelSolver3::relax, the natural (lexicographic) ordering (fdm_gauss_seidel_solver3.cpp:103-120)."""
+        nz, ny, nx = x.shape
+        out = np.array(x, dtype=np.float64, order="C", copy=True)
+        self._call("fdm_relax", u64(nx), u64(ny), u64(nz), _p(A, C.POINTER(Row)), _p(b), f64(sor), u32(iterations), _p(out))
+        return out
+
     def restrict(self, finer):
         nz, ny, nx = finer.shape
         out = np.empty((nz // 2, ny // 2, nx // 2), dtype=np.float64)

@@ -28,7 +28,7 @@ enum {
     JETCU_OK = 0,
     JETCU_ERR_INVALID_ARG = 1, /* mirrors std::invalid_argument from JET_THROW_INVALID_ARG_IF (include/jet/macros.h:37-41) */
     JETCU_ERR_CUDA = 2,        /* CUDA runtime error; text in jetcu_last_error() */
-    JETCU_ERR_UNSUPPORTED = 3, /* e.g. lexicographic Gauss-Seidel (inherently serial) */
+    JETCU_ERR_UNSUPPORTED = 3, /* e.g. ICCG or lexicographic Gauss-Seidel under a multi-GPU communicator */
     JETCU_ERR_OOM = 4,
     JETCU_ERR_NCCL = 5
 };
@@ -117,7 +117,9 @@ typedef struct jetcu_mgpcg_params {
     uint32_t n_final;           /* numberOfFinalIter (post-smoothing sweeps on level 0) */
     double tolerance;           /* maxTolerance */
     double sor_factor;          /* sorFactor */
-    int32_t use_red_black;      /* useRedBlackOrdering; 0 -> JETCU_ERR_UNSUPPORTED */
+    int32_t use_red_black;      /* useRedBlackOrdering; 0 = the natural (lexicographic) Gauss-Seidel ordering, the reference
+                                   constructors' default: tile-hyperplane wavefront on the device, single GPU only
+                                   (JETCU_ERR_UNSUPPORTED under a multi-rank communicator) */
     int32_t linear_solver;      /* which FdmLinearSystemSolver3 the pressure solve runs: JETCU_SOLVER_MGPCG (0, all fields
                                    above apply) or JETCU_SOLVER_ICCG (FdmIccgSolver3: max_iterations and tolerance apply,
                                    one level), optionally | JETCU_SOLVER_COMPRESSED (see jetcu_pressure_solve) */
@@ -155,6 +157,14 @@ int jetcu_fdm_residual(jetcu_ctx*, uint64_t nx, uint64_t ny, uint64_t nz,
 int jetcu_fdm_relax_red_black(jetcu_ctx*, uint64_t nx, uint64_t ny, uint64_t nz,
                               const jetcu_matrix_row* A, const double* b, double sor_factor,
                               uint32_t iterations, double* x);
+/* `iterations` x FdmGaussSeidelSolver3::relax (src/jet/fdm_gauss_seidel_solver3.cpp:103-120), the natural (lexicographic)
+ * ordering — what FdmMgSolver3 / FdmMgpcgSolver3 smooth with unless useRedBlackOrdering is set — in place on x.  The
+ * reference's loop is serial; a cell depends on its three lower neighbours' new and its three upper neighbours' old values,
+ * so the device sweeps 8^3 tiles in tile-hyperplane order, consecutive sweeps pipelined two hyperplanes apart: the same
+ * operands per cell, bit-identical to the serial loop. */
+int jetcu_fdm_relax(jetcu_ctx*, uint64_t nx, uint64_t ny, uint64_t nz,
+                    const jetcu_matrix_row* A, const double* b, double sor_factor,
+                    uint32_t iterations, double* x);
 /* FdmMgUtils3::restrict (src/jet/fdm_mg_linear_system3.cpp:43-98); (nx,ny,nz) = finer size, all even. */
 int jetcu_fdm_restrict(jetcu_ctx*, uint64_t nx, uint64_t ny, uint64_t nz,
                        const double* finer, double* coarser);

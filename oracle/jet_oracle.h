@@ -65,6 +65,8 @@ int jeto_fdm_mvm(uint64_t nx, uint64_t ny, uint64_t nz, const jeto_row* A, const
 int jeto_fdm_residual(uint64_t nx, uint64_t ny, uint64_t nz, const jeto_row* A, const double* x, const double* b, double* result);
 int jeto_fdm_relax_red_black(uint64_t nx, uint64_t ny, uint64_t nz, const jeto_row* A, const double* b,
                              double sor_factor, uint32_t iterations, double* x);
+int jeto_fdm_relax(uint64_t nx, uint64_t ny, uint64_t nz, const jeto_row* A, const double* b,
+                   double sor_factor, uint32_t iterations, double* x);   /* FdmGaussSeidelSolver3::relax (lexicographic) */
 int jeto_fdm_restrict(uint64_t nx, uint64_t ny, uint64_t nz, const double* finer, double* coarser);
 int jeto_fdm_correct(uint64_t nx, uint64_t ny, uint64_t nz, const double* coarser, double* finer);
 int jeto_fdm_dot(uint64_t n, const double* a, const double* b, double* result);

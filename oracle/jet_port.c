@@ -135,6 +135,35 @@ int jeto_fdm_relax_red_black(uint64_t nx, uint64_t ny, uint64_t nz, const jeto_r
     return 0;
 }
 
+/* FdmGaussSeidelSolver3::relax — src/jet/fdm_gauss_seidel_solver3.cpp:103-120: the natural (lexicographic) ordering,
+ * A.forEachIndex = i fastest, then j, then k, in place; the default ordering of FdmMgSolver3 / FdmMgpcgSolver3
+ * (useRedBlackOrdering = false, include/jet/fdm_mgpcg_solver3.h:41).  Serial by construction. */
+int jeto_fdm_relax(uint64_t unx, uint64_t uny, uint64_t unz, const jeto_row* A, const double* b, double w,
+                   uint32_t iterations, double* x) {
+    const ssz nx = (ssz)unx, ny = (ssz)uny, nz = (ssz)unz;
+    for (uint32_t it = 0; it < iterations; ++it)
+        for (ssz k = 0; k < nz; ++k)
+            for (ssz j = 0; j < ny; ++j)
+                for (ssz i = 0; i < nx; ++i) {
+                    const ssz c = (k * ny + j) * nx + i;
+                    double r = ((i > 0) ? A[c - 1].right * x[c - 1] : 0.0) +
+                               ((i + 1 < nx) ? A[c].right * x[c + 1] : 0.0) +
+                               ((j > 0) ? A[c - nx].up * x[c - nx] : 0.0) +
+                               ((j + 1 < ny) ? A[c].up * x[c + nx] : 0.0) +
+                               ((k > 0) ? A[c - nx * ny].front * x[c - nx * ny] : 0.0) +
+                               ((k + 1 < nz) ? A[c].front * x[c + nx * ny] : 0.0);
+                    x[c] = (1.0 - w) * x[c] + w * (b[c] - r) / A[c].center;
+                }
+    return 0;
+}
+
+/* the smoother FdmMgSolver3's constructor installs (src/jet/fdm_mg_solver3.cpp:26-49) */
+static void mg_relax(const jeto_mgpcg_params* p, uint64_t nx, uint64_t ny, uint64_t nz, const jeto_row* A, const double* b,
+                     uint32_t iterations, double* x) {
+    if (p->use_red_black) jeto_fdm_relax_red_black(nx, ny, nz, A, b, p->sor_factor, iterations, x);
+    else jeto_fdm_relax(nx, ny, nz, A, b, p->sor_factor, iterations, x);
+}
+
 /* FdmMgUtils3::restrict — src/jet/fdm_mg_linear_system3.cpp:43-98: (1,3,3,1)/8 tensor filter, edge-clamped,
  * accumulated z-outer / y / x-inner. (nx,ny,nz) is the FINER size. */
 int jeto_fdm_restrict(uint64_t fnx, uint64_t fny, uint64_t fnz, const double* finer, double* coarser) {
@@ -237,23 +266,22 @@ static void mg_free(mg_ws* w) {
  * level only produce MgResult.lastResidualNorm, which FdmMgpcgSolver3::Preconditioner discards; they do not
  * change x and are omitted (the finest-level norm is available through jeto_fdm_residual). */
 static void vcycle(mg_ws* w, const jeto_mgpcg_params* p, uint32_t l) {
-    jeto_fdm_relax_red_black(w->nx[l], w->ny[l], w->nz[l], w->A[l], w->b[l], p->sor_factor, p->n_restriction, w->x[l]);
+    mg_relax(p, w->nx[l], w->ny[l], w->nz[l], w->A[l], w->b[l], p->n_restriction, w->x[l]);
     if (l + 1 < w->levels) {
         jeto_fdm_residual(w->nx[l], w->ny[l], w->nz[l], w->A[l], w->x[l], w->b[l], w->buf[l]);
         jeto_fdm_restrict(w->nx[l], w->ny[l], w->nz[l], w->buf[l], w->b[l + 1]);
         memset(w->x[l + 1], 0, lvl_n(w, l + 1) * sizeof(double));
         vcycle(w, p, l + 1);
         jeto_fdm_correct(w->nx[l], w->ny[l], w->nz[l], w->x[l + 1], w->x[l]);
-        jeto_fdm_relax_red_black(w->nx[l], w->ny[l], w->nz[l], w->A[l], w->b[l], p->sor_factor,
-                                 l > 0 ? p->n_correction : p->n_final, w->x[l]);
+        mg_relax(p, w->nx[l], w->ny[l], w->nz[l], w->A[l], w->b[l], l > 0 ? p->n_correction : p->n_final, w->x[l]);
     } else {
-        jeto_fdm_relax_red_black(w->nx[l], w->ny[l], w->nz[l], w->A[l], w->b[l], p->sor_factor, p->n_coarsest, w->x[l]);
+        mg_relax(p, w->nx[l], w->ny[l], w->nz[l], w->A[l], w->b[l], p->n_coarsest, w->x[l]);
     }
 }
 
 int jeto_fdm_vcycle(uint64_t nx, uint64_t ny, uint64_t nz, uint32_t levels, const jeto_row* const* A,
                     const double* b, double* x, const jeto_mgpcg_params* p) {
-    if (!p->use_red_black || levels > 16) return 3;
+    if (levels > 16) return 3;
     mg_ws w;
     mg_alloc(&w, nx, ny, nz, levels, A);
     size_t n = lvl_n(&w, 0);
@@ -279,7 +307,7 @@ static void precond(mg_ws* w, const jeto_mgpcg_params* p, const double* b, doubl
  * FdmMgpcgSolver3::solve — src/jet/fdm_mgpcg_solver3.cpp:54-80 (x zeroed first). */
 static int mgpcg_core(uint64_t nx, uint64_t ny, uint64_t nz, uint32_t levels, const jeto_row* const* A,
                       const double* b, double* x, const jeto_mgpcg_params* p, jeto_mgpcg_result* result) {
-    if (!p->use_red_black || levels > 16) return 3;
+    if (levels > 16) return 3;
     mg_ws w;
     mg_alloc(&w, nx, ny, nz, levels, A);
     size_t n = lvl_n(&w, 0);

@@ -122,6 +122,16 @@ int jeto_fdm_relax_red_black(uint64_t nx, uint64_t ny, uint64_t nz, const jeto_r
     return 0;
 }
 
+int jeto_fdm_relax(uint64_t nx, uint64_t ny, uint64_t nz, const jeto_row* A, const double* b, double sor_factor,
+                   uint32_t iterations, double* x) {
+    Size3 s(nx, ny, nz);
+    FdmMatrix3 m; FdmVector3 xx, bb;
+    fillMatrix(&m, A, s); fillVector(&xx, x, s); fillVector(&bb, b, s);
+    for (uint32_t it = 0; it < iterations; ++it) FdmGaussSeidelSolver3::relax(m, bb, sor_factor, &xx);
+    copyOut(x, xx);
+    return 0;
+}
+
 int jeto_fdm_restrict(uint64_t nx, uint64_t ny, uint64_t nz, const double* finer, double* coarser) {
     FdmVector3 f, c(Size3(nx / 2, ny / 2, nz / 2));
     fillVector(&f, finer, Size3(nx, ny, nz));

@@ -628,6 +628,57 @@ void relax_sweeps(const Mat& A, const double* b, double* x, double w, unsigned i
                         else relax_cell<P>(A, b, x, w, i, j, k, nx, ny, nz);
                     }
 }
+
+// launch_relax_lex of fdm.cu (the natural Gauss-Seidel ordering, FdmGaussSeidelSolver3::relax) replayed with its loop structure.
+// Levels of at most 8192 cells: k_relax_lex_small's steps (cell hyperplane h of sweep s in step h + 2 s); larger ones: the
+// launches of k_relax_lex_tiles (tile hyperplane t - 2 s for every sweep s in flight, 32 at most), inside a tile the cell
+// hyperplanes in order.  CTAs of one launch / threads of one step run concurrently on the device, so the replay visits them
+// in ascending (order 0) or descending (order 1) order: both must give the serial loop's bits.
+template <bool P>
+void relax_lex_schedule(const Mat& A, const double* b, double* x, double w, unsigned iterations, int nx, int ny, int nz, bool code,
+                        int order) {
+    auto cell = [&](int i, int j, int k) {
+        if (code) relax_cell_code(A, b, x, w, i, j, k, nx, ny, nz);
+        else relax_cell<P>(A, b, x, w, i, j, k, nx, ny, nz);
+    };
+    const long long n = (long long)nx * ny * nz;
+    if (n <= 8192) {
+        const int steps = (nx + ny + nz - 2) + 2 * ((int)iterations - 1);
+        for (int step = 0; step < steps; ++step)
+            for (long long q = 0; q < n; ++q) {
+                const long long c = order ? n - 1 - q : q;
+                const int i = (int)(c % nx), j = (int)((c / nx) % ny), k = (int)(c / ((long long)nx * ny));
+                const int lag = step - (i + j + k);
+                if (lag < 0 || (lag & 1) || lag / 2 >= (int)iterations) continue;
+                relax_cell<P>(A, b, x, w, i, j, k, nx, ny, nz);   // the small kernel never uses the codes
+            }
+        return;
+    }
+    const int T = 8, ntx = (nx + T - 1) / T, nty = (ny + T - 1) / T, ntz = (nz + T - 1) / T, last = ntx + nty + ntz - 3;
+    for (unsigned done = 0; done < iterations;) {
+        const int ns = (int)((iterations - done < 32u) ? iterations - done : 32u);
+        for (int t = 0; t <= last + 2 * (ns - 1); ++t) {
+            const int s_lo = t - last > 0 ? (t - last + 1) / 2 : 0, s_hi = t / 2 < ns - 1 ? t / 2 : ns - 1;
+            const int nsl = s_hi - s_lo + 1;
+            if (nsl <= 0) continue;
+            const long long ctas = (long long)nsl * nty * ntx;
+            for (long long q = 0; q < ctas; ++q) {
+                const long long cta = order ? ctas - 1 - q : q;
+                const int ti = (int)(cta % ntx), tj = (int)((cta / ntx) % nty), bz = (int)(cta / ((long long)ntx * nty));
+                const int tk = t - 2 * (s_lo + bz) - ti - tj;
+                if (tk < 0 || tk >= ntz) continue;
+                for (int step = 0; step <= 3 * T - 3; ++step)
+                    for (int th = 0; th < T * T * T; ++th) {
+                        const int cx = th % T, cy = (th / T) % T, cz = th / (T * T);
+                        const int i = ti * T + cx, j = tj * T + cy, k = tk * T + cz;
+                        if (i >= nx || j >= ny || k >= nz || cx + cy + cz != step) continue;
+                        cell(i, j, k);
+                    }
+            }
+        }
+        done += (unsigned)ns;
+    }
+}
 }  // namespace
 
 extern "C" {
@@ -645,6 +696,11 @@ int hc_residual(int nx, int ny, int nz, const jetcu_matrix_row* A, const double*
 int hc_relax(int nx, int ny, int nz, const jetcu_matrix_row* A, const double* b, double sor, unsigned iterations, double* x) {
     SoAMat M(A, (size_t)nx * ny * nz);
     relax_sweeps<false>(M.m, b, x, sor, iterations, nx, ny, nz, false);
+    return 0;
+}
+int hc_relax_lex(int nx, int ny, int nz, const jetcu_matrix_row* A, const double* b, double sor, unsigned iterations, int order, double* x) {
+    SoAMat M(A, (size_t)nx * ny * nz);
+    relax_lex_schedule<false>(M.m, b, x, sor, iterations, nx, ny, nz, false, order);
     return 0;
 }
 // k_ic_tiles<false, OP> of iccg.cu in its launch order: tile hyperplanes one after the other (backward: descending), the
@@ -774,6 +830,12 @@ int hc_packed_residual(uint32_t level, const double* x, const double* b, double*
 int hc_packed_relax(uint32_t level, const double* b, double sor, unsigned iterations, int use_codes, double* x) {
     const HostLevel& L = g_sys.lv[level];
     relax_sweeps<true>(L.m, b, x, sor, iterations, L.nx, L.ny, L.nz, use_codes != 0);
+    return 0;
+}
+// the natural ordering on a packed level (k_relax_lex_tiles<true, true> / k_relax_lex_small<true>)
+int hc_packed_relax_lex(uint32_t level, const double* b, double sor, unsigned iterations, int order, double* x) {
+    const HostLevel& L = g_sys.lv[level];
+    relax_lex_schedule<true>(L.m, b, x, sor, iterations, L.nx, L.ny, L.nz, L.m.code != nullptr, order);
     return 0;
 }
 // launch_sweep<true> of fdm.cu with JETCU_RELAX_CHUNK = chunk: the red / black z-chunk interleaving, replayed with the

@@ -35,6 +35,18 @@ def test_three_seams_match_stock_jet(mode):
 
 
 @pytest.mark.gpu
+def test_three_seams_natural_ordering():
+    """FdmMgpcgSolver3's constructor default, useRedBlackOrdering = false (include/jet/fdm_mgpcg_solver3.h:41): the serial
+    FdmGaussSeidelSolver3::relax on the CPU, the tile-hyperplane wavefront on the device."""
+    out = run("--n", 32, "--frames", 2, "--levels", 4, "--mode", "flip", "--natural-ordering")
+    for seam in ("seam1", "seam2", "seam3"):
+        assert out[seam + "_max_dx"] <= 1e-5, out
+        assert out[seam + "_last_iterations"] == out["stock_last_iterations"], out
+    for seam in ("seam1", "seam2"):
+        assert out[seam + "_pressure_rel"] <= 1e-6, out
+
+
+@pytest.mark.gpu
 def test_flip_64_ten_frames_device_resident():
     out = run("--n", 64, "--frames", 10, "--levels", 5, "--mode", "flip", "--skip-seam12")
     assert out["particles"] == 516516   # SURVEY §8d config 1

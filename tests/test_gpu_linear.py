@@ -46,6 +46,12 @@ def test_stencils_bit_exact(jc, oracle, shape, spd):
     same(jc.residual(A, x, b), oracle.residual(A, x, b), "residual")
     same(jc.relax_red_black(A, b, x, 1.5, 3), oracle.relax_red_black(A, b, x, 1.5, 3), "relaxRedBlack x3")
     same(jc.relax_red_black(A, b, x, 1.0, 1), oracle.relax_red_black(A, b, x, 1.0, 1), "relaxRedBlack w=1")
+    # the natural (lexicographic) ordering, FdmGaussSeidelSolver3::relax: serial in the reference, a tile-hyperplane wavefront
+    # of pipelined sweeps on the device (fdm.cu) — the same operands per cell, hence the same bits
+    same(jc.relax(A, b, x, 1.5, 3), oracle.relax(A, b, x, 1.5, 3), "relax (natural ordering) x3")
+    same(jc.relax(A, b, x, 1.0, 1), oracle.relax(A, b, x, 1.0, 1), "relax (natural ordering) w=1")
+    if spd:
+        same(jc.relax(A, b, x, 1.3, 35), oracle.relax(A, b, x, 1.3, 35), "relax (natural ordering) x35: two launch groups")
     same(jc.axpy(0.3, x, b), oracle.axpy(0.3, x, b), "axpy")
     d0, d1 = jc.dot(x, b), oracle.dot(x, b)
     assert abs(d0 - d1) <= 1e-14 * np.abs(x * b).sum() + 1e-300
@@ -69,18 +75,20 @@ def test_dot_deterministic(jc):
     assert len(vals) == 1
 
 
+@pytest.mark.parametrize("red_black", [True, False])   # False: the reference constructors' default ordering
 @pytest.mark.parametrize("n,levels", [(16, 3), (32, 4), (64, 5)])
-def test_vcycle_bit_exact(jc, oracle, n, levels):
+def test_vcycle_bit_exact(jc, oracle, n, levels, red_black):
     Al = scenes.poisson_levels(n, levels)
     rng = np.random.default_rng(3)
     b = rng.uniform(-1, 1, (n, n, n)); b -= b.mean()
     x0 = rng.uniform(-1, 1, (n, n, n))
-    p = MgpcgParams.make(max_levels=levels)
+    p = MgpcgParams.make(max_levels=levels, use_red_black=red_black)
     same(jc.vcycle(Al, b, x0, p), oracle.vcycle(Al, b, x0, p), "V-cycle")
 
 
+@pytest.mark.parametrize("red_black", [True, False])
 @pytest.mark.parametrize("n,levels,shift", [(32, 4, 0.05), (32, 3, 0.5), (64, 5, 0.01)])
-def test_mgpcg_vs_oracle(jc, oracle, n, levels, shift):
+def test_mgpcg_vs_oracle(jc, oracle, n, levels, shift, red_black):
     """SPD (regularised) Poisson systems.  Where the oracle's TRUE residual is small (the reference's PCG can leave
     early on sigma <= tol^2) x must agree within 1e-6 relative L-inf; in every case the iteration
     count and the exit sigma must follow the oracle (same control flow)."""
@@ -89,7 +97,7 @@ def test_mgpcg_vs_oracle(jc, oracle, n, levels, shift):
         A["center"] += shift
     rng = np.random.default_rng(7)
     b = rng.uniform(-1, 1, (n, n, n))
-    p = MgpcgParams.make(max_iterations=100, max_levels=levels, tolerance=1e-9)
+    p = MgpcgParams.make(max_iterations=100, max_levels=levels, tolerance=1e-9, use_red_black=red_black)
     x0, r0 = jc.mgpcg_solve(Al, b, p)
     x1, r1 = oracle.mgpcg_solve(Al, b, p)
     assert abs(int(r0.iterations) - int(r1.iterations)) <= 1
@@ -132,10 +140,6 @@ def test_iccg_vs_oracle(jc, oracle, n):
 def test_errors(jc):
     from fluid_engine_dev_b200 import JetcuError
     A, x, b = scenes.random_system(4, 4, 4)
-    p = MgpcgParams.make(max_levels=1, use_red_black=False)
-    with pytest.raises(JetcuError) as e:
-        jc.mgpcg_solve([A], b, p)
-    assert e.value.rc == 3  # JETCU_ERR_UNSUPPORTED: lexicographic GS is serial
     with pytest.raises(JetcuError) as e:
         jc.restrict(np.zeros((3, 4, 4)))
     assert e.value.rc == 1  # JETCU_ERR_INVALID_ARG, like JET_ASSERT(finer == 2*coarser)

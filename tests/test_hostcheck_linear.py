@@ -66,6 +66,25 @@ def test_iccg_preconditioner_tile_hyperplanes(hc, port, shape, spd):
     exact(d, wd, "IC diagonal"); exact(y, wy, "forward substitution"); exact(x, wx, "backward substitution")
 
 
+@pytest.mark.parametrize("shape", [(20, 17, 9), (8, 8, 8), (1, 1, 1), (9, 3, 26), (16, 16, 16), (33, 32, 24), (40, 24, 24)])
+@pytest.mark.parametrize("spd", [True, False])
+def test_lexicographic_relax_schedules(hc, port, shape, spd):
+    """FdmGaussSeidelSolver3::relax (src/jet/fdm_gauss_seidel_solver3.cpp:103-120) is one serial loop; fdm.cu runs it as a
+    wavefront: cell hyperplanes of pipelined sweeps in one CTA on small levels (<= 8192 cells), tile hyperplanes of pipelined
+    sweeps (two apart) on large ones.  Replayed on the CPU with the kernel's cell body, visiting the concurrent CTAs / cells of
+    a launch / step in ascending and in descending order, both schedules give the bits of the serial loop."""
+    nx, ny, nz = shape
+    A, x, b = scenes.random_system(nx, ny, nz, seed=11 + sum(shape), spd=spd)
+    for sor, it in ((1.5, 1), (1.5, 5), (1.0, 2), (1.3, 35)):
+        if it > 5 and (not spd or (nx * ny * nz > 8192 and nx * ny * nz != 33 * 32 * 24)):
+            continue   # the > 32 sweeps case (two launch groups): convergent systems, one large and every small shape
+        want = port.relax(A, b, x, sor, it)
+        for order in (0, 1):
+            xs = x.copy()
+            assert hc.hc_relax_lex(nx, ny, nz, rp(A), dp(b), C.c_double(sor), C.c_uint(it), C.c_int(order), dp(xs)) == 0
+            exact(xs, want, "lexicographic relax sor=%g sweeps=%d order=%d" % (sor, it, order))
+
+
 @pytest.mark.parametrize("fine", [(16, 12, 12), (2, 2, 2), (8, 6, 6), (8, 16, 8), (12, 8, 6), (6, 4, 10)])   # the last three: ny != nz (extension)
 def test_restrict_correct(hc, port, fine):
     nx, ny, nz = fine
@@ -111,6 +130,12 @@ def test_packed_pressure_system(hc, port, n, kind, collider, domain):
             xs = x.copy()
             hc.hc_packed_relax(C.c_uint32(l), dp(rhs), C.c_double(1.5), C.c_uint(3), C.c_int(codes), dp(xs))
             exact(xs, ref, "packed SOR level %d (%s)" % (l, "face codes + bulk diagonal" if codes else "float weights"))
+        # the natural ordering on the packed level (k_relax_lex_tiles with face codes / k_relax_lex_small), both visiting orders
+        lex = port.relax(want["A"], rhs, x, 1.5, 3)
+        for order in (0, 1):
+            xs = x.copy()
+            hc.hc_packed_relax_lex(C.c_uint32(l), dp(rhs), C.c_double(1.5), C.c_uint(3), C.c_int(order), dp(xs))
+            exact(xs, lex, "packed lexicographic relax level %d order %d" % (l, order))
         # the L2-resident chunk-interleaved sweep order (JETCU_RELAX_CHUNK) must give the bits of the two full passes
         for chunk in (1, 3, 5, m):
             xs = x.copy()

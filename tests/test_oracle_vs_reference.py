@@ -33,6 +33,8 @@ def test_blas_and_relax_bit_exact(libs, shape, spd):
     same(ref.residual(A, x, b), port.residual(A, x, b))
     same(ref.relax_red_black(A, b, x, 1.5, 3), port.relax_red_black(A, b, x, 1.5, 3))
     same(ref.relax_red_black(A, b, x, 1.0, 1), port.relax_red_black(A, b, x, 1.0, 1))
+    same(ref.relax(A, b, x, 1.5, 3), port.relax(A, b, x, 1.5, 3))   # the natural ordering, FdmGaussSeidelSolver3::relax
+    same(ref.relax(A, b, x, 1.0, 1), port.relax(A, b, x, 1.0, 1))
     assert ref.dot(x, b) == port.dot(x, b)
     same(ref.axpy(0.3, x, b), port.axpy(0.3, x, b))
 
@@ -55,15 +57,16 @@ def test_mg_num_levels(libs):
             assert ref.mg_num_levels(*dims, ml) == port.mg_num_levels(*dims, ml)
 
 
+@pytest.mark.parametrize("red_black", [True, False])   # False = the natural ordering, the reference constructors' default
 @pytest.mark.parametrize("n,levels", [(16, 3), (32, 4)])
-def test_vcycle_and_mgpcg_bit_exact(libs, n, levels):
+def test_vcycle_and_mgpcg_bit_exact(libs, n, levels, red_black):
     ref, port = libs
     Al = scenes.poisson_levels(n, levels)
     rng = np.random.default_rng(3)
     b = rng.uniform(-1, 1, (n, n, n))
     b -= b.mean()
     x0 = rng.uniform(-1, 1, (n, n, n))
-    p = MgpcgParams.make(max_iterations=25, max_levels=levels, tolerance=1e-9)
+    p = MgpcgParams.make(max_iterations=25, max_levels=levels, tolerance=1e-9, use_red_black=red_black)
     same(ref.vcycle(Al, b, x0, p), port.vcycle(Al, b, x0, p))
     xr, rr = ref.mgpcg_solve(Al, b, p)
     xp, rp = port.mgpcg_solve(Al, b, p)
@@ -71,13 +74,14 @@ def test_vcycle_and_mgpcg_bit_exact(libs, n, levels):
     assert rr.iterations == rp.iterations and rr.last_residual == rp.last_residual and rr.returned == rp.returned
 
 
-@pytest.mark.parametrize("n,kind,collider,levels", [(16, "slab", False, 3), (16, "column", True, 3),
-                                                     (32, "column", True, 5), (32, "slab", True, 4),
-                                                     (24, "column", False, 9)])
-def test_pressure_solve_bit_exact(libs, n, kind, collider, levels):
+@pytest.mark.parametrize("n,kind,collider,levels,red_black", [(16, "slab", False, 3, True), (16, "column", True, 3, True),
+                                                               (32, "column", True, 5, True), (32, "slab", True, 4, True),
+                                                               (24, "column", False, 9, True), (16, "column", True, 3, False),
+                                                               (32, "slab", True, 4, False)])
+def test_pressure_solve_bit_exact(libs, n, kind, collider, levels, red_black):
     ref, port = libs
     sc = scenes.projection_scene(n, kind, collider)
-    p = MgpcgParams.make(max_iterations=200, max_levels=levels)
+    p = MgpcgParams.make(max_iterations=200, max_levels=levels, use_red_black=red_black)
     out = []
     for o in (ref, port):
         r = o.pressure_solve(sc["grid"], sc["u"], sc["v"], sc["w"], p, collider_sdf=sc["collider_sdf"],

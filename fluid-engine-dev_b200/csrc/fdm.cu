@@ -82,21 +82,33 @@ __global__ void __launch_bounds__(BX* BY) k_residual(Mat A, const double* __rest
 //     colour passes — the coarse MG levels are pure launch latency otherwise.
 #define SMALL_THREADS 1024
 #define SMALL_MAX_CELLS 8192
-template <bool P>
+//     SMEM: x lives in shared memory for the duration (levels of at most SMALL_SMEM_CELLS cells = 48 KB): a colour pass then
+//     costs a shared-memory round trip instead of a global one per __syncthreads (the same arithmetic on the same values).
+#define SMALL_SMEM_CELLS 6144
+template <bool P, bool SMEM>
 __global__ void __launch_bounds__(SMALL_THREADS) k_relax_small(Mat A, const double* __restrict__ b, double* x, double w,
                                                                int nx, int ny, int nz, unsigned iterations) {
+    __shared__ double xs[SMEM ? SMALL_SMEM_CELLS : 1];
     const int hx = (nx + 1) / 2;
     const int pairs = hx * ny * nz;
+    double* xw = x;
+    if (SMEM) {
+        for (int c = threadIdx.x; c < nx * ny * nz; c += SMALL_THREADS) xs[c] = x[c];
+        __syncthreads();
+        xw = xs;
+    }
     for (unsigned it = 0; it < 2 * iterations; ++it) {
         const int colour = it & 1;
         for (int t = threadIdx.x; t < pairs; t += SMALL_THREADS) {
             int ip = t % hx, j = (t / hx) % ny, k = t / (hx * ny);
             int i = 2 * ip + ((j + k + colour) & 1);
             if (i >= nx) continue;
-            relax_cell<P>(A, b, x, w, i, j, k, nx, ny, nz);
+            relax_cell<P>(A, b, xw, w, i, j, k, nx, ny, nz);
         }
         __syncthreads();
     }
+    if (SMEM)
+        for (int c = threadIdx.x; c < nx * ny * nz; c += SMALL_THREADS) x[c] = xs[c];
 }
 
 // (b) Any grid, any matrix form: one launch per colour, one thread per cell of that colour (x-pairs).  With 8-byte
@@ -294,7 +306,8 @@ static int launch_relax(jetcu_ctx* ctx, Dim3i d, ZRange z, bool halo, Mat A, con
                         unsigned iterations, double** x, double** xalt, uint64_t* launches) {
     (void)xalt;
     if (!halo && d.n() <= SMALL_MAX_CELLS) {
-        JC_LAUNCH(ctx, k_relax_small<P>, 1, SMALL_THREADS, 0, A, b, *x, sor, d.nx, d.ny, d.nz, iterations);
+        if (d.n() <= SMALL_SMEM_CELLS) JC_LAUNCH(ctx, (k_relax_small<P, true>), 1, SMALL_THREADS, 0, A, b, *x, sor, d.nx, d.ny, d.nz, iterations);
+        else JC_LAUNCH(ctx, (k_relax_small<P, false>), 1, SMALL_THREADS, 0, A, b, *x, sor, d.nx, d.ny, d.nz, iterations);
         *launches = 1;
         return JETCU_OK;
     }
@@ -371,40 +384,70 @@ int fdm_relax_rb(jetcu_ctx* ctx, Dim3i d, Mat A, const double* b, double sor, un
 // Bit-identical to the serial loop (tests/test_hostcheck_linear.py replays both schedules on the CPU against the oracle,
 // tests/test_gpu_linear.py compares the device with the oracle and the unmodified reference).
 #define GS_T 8
+#define GS_H (GS_T + 2)
+// The tile's x values and a one-cell halo around them live in shared memory for the tile's 3 GS_T - 2 steps, each thread's
+// coefficients, diagonal and right-hand side in registers (all global loads of a tile are issued at once, up front): a step is
+// a shared-memory round trip instead of a global one.  Halo cells outside the level hold 0.0 (see relax_update).  The halo is
+// read once at the start: the lower neighbour tiles carry this sweep's values from earlier launches, the upper ones the
+// previous sweep's, and neither is written during this launch.
 template <bool P, bool CODE>
 __global__ void __launch_bounds__(GS_T* GS_T* GS_T)
     k_relax_lex_tiles(Mat A, const double* __restrict__ b, double* x, double w, int nx, int ny, int nz, int t, int s_first) {
     jc_pdl_prologue();
+    __shared__ double xs[GS_H * GS_H * GS_H];
     const int ti = blockIdx.x, tj = blockIdx.y, tk = t - 2 * (s_first + (int)blockIdx.z) - ti - tj;
     const int ntz = (nz + GS_T - 1) / GS_T;
     if (tk < 0 || tk >= ntz) return;
+    const int i0 = ti * GS_T, j0 = tj * GS_T, k0 = tk * GS_T;
+    for (int e = threadIdx.x; e < GS_H * GS_H * GS_H; e += GS_T * GS_T * GS_T) {
+        const int gi = i0 + e % GS_H - 1, gj = j0 + (e / GS_H) % GS_H - 1, gk = k0 + e / (GS_H * GS_H) - 1;
+        const bool in = gi >= 0 && gi < nx && gj >= 0 && gj < ny && gk >= 0 && gk < nz;
+        xs[e] = in ? x[((size_t)gk * ny + gj) * nx + gi] : 0.0;
+    }
     const int cx = threadIdx.x % GS_T, cy = (threadIdx.x / GS_T) % GS_T, cz = threadIdx.x / (GS_T * GS_T);
-    const int i = ti * GS_T + cx, j = tj * GS_T + cy, k = tk * GS_T + cz;
+    const int i = i0 + cx, j = j0 + cy, k = k0 + cz;
     const bool live = i < nx && j < ny && k < nz;
     const int mine = cx + cy + cz;
-    for (int step = 0; step <= 3 * GS_T - 3; ++step) {
-        if (live && mine == step) {
-            if (CODE) relax_cell_code(A, b, x, w, i, j, k, nx, ny, nz);
-            else relax_cell<P>(A, b, x, w, i, j, k, nx, ny, nz);
-        }
-        __syncthreads();   // orders this CTA's global stores before its next hyperplane's loads
+    const int o = ((cz + 1) * GS_H + (cy + 1)) * GS_H + (cx + 1);
+    RelaxCoefs q;
+    double bb = 0.0;
+    if (live) {
+        q = CODE ? relax_coefs_code(A, i, j, k, nx, ny, nz) : relax_coefs<P>(A, i, j, k, nx, ny, nz);
+        bb = b[((size_t)k * ny + j) * nx + i];
     }
+    __syncthreads();
+    for (int step = 0; step <= 3 * GS_T - 3; ++step) {
+        if (live && mine == step)
+            xs[o] = relax_update(q, bb, w, xs[o], xs[o - 1], xs[o + 1], xs[o - GS_H], xs[o + GS_H], xs[o - GS_H * GS_H], xs[o + GS_H * GS_H]);
+        __syncthreads();
+    }
+    if (live) x[((size_t)k * ny + j) * nx + i] = xs[o];
 }
 
-template <bool P>
+// one CTA, whole level; SMEM: x in shared memory for the duration (as k_relax_small)
+template <bool P, bool SMEM>
 __global__ void __launch_bounds__(SMALL_THREADS) k_relax_lex_small(Mat A, const double* __restrict__ b, double* x, double w,
                                                                    int nx, int ny, int nz, unsigned iterations) {
+    __shared__ double xs[SMEM ? SMALL_SMEM_CELLS : 1];
     const int n = nx * ny * nz;
     const int steps = (nx + ny + nz - 2) + 2 * ((int)iterations - 1);
+    double* xw = x;
+    if (SMEM) {
+        for (int c = threadIdx.x; c < n; c += SMALL_THREADS) xs[c] = x[c];
+        __syncthreads();
+        xw = xs;
+    }
     for (int step = 0; step < steps; ++step) {
         for (int c = threadIdx.x; c < n; c += SMALL_THREADS) {
             const int i = c % nx, j = (c / nx) % ny, k = c / (nx * ny);
             const int lag = step - (i + j + k);   // = 2 x (the sweep this cell is in at this step)
             if (lag < 0 || (lag & 1) || lag / 2 >= (int)iterations) continue;
-            relax_cell<P>(A, b, x, w, i, j, k, nx, ny, nz);
+            relax_cell<P>(A, b, xw, w, i, j, k, nx, ny, nz);
         }
         __syncthreads();
     }
+    if (SMEM)
+        for (int c = threadIdx.x; c < n; c += SMALL_THREADS) x[c] = xs[c];
 }
 
 // sweeps in flight per group of launches (gridDim.z); a group of n sweeps costs H + 2 (n - 1) launches
@@ -414,7 +457,8 @@ static int launch_relax_lex(jetcu_ctx* ctx, Dim3i d, Mat A, const double* b, dou
                             uint64_t* launches) {
     *launches = 0;
     if (d.n() <= SMALL_MAX_CELLS) {
-        JC_LAUNCH(ctx, k_relax_lex_small<P>, 1, SMALL_THREADS, 0, A, b, x, sor, d.nx, d.ny, d.nz, iterations);
+        if (d.n() <= SMALL_SMEM_CELLS) JC_LAUNCH(ctx, (k_relax_lex_small<P, true>), 1, SMALL_THREADS, 0, A, b, x, sor, d.nx, d.ny, d.nz, iterations);
+        else JC_LAUNCH(ctx, (k_relax_lex_small<P, false>), 1, SMALL_THREADS, 0, A, b, x, sor, d.nx, d.ny, d.nz, iterations);
         *launches = 1;
         return JETCU_OK;
     }

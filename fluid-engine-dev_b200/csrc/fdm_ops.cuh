@@ -139,6 +139,74 @@ __host__ __device__ __forceinline__ void relax_cell_code(const Mat& A, const dou
     x[c] = (1.0 - w) * x[c] + w * (b[c] - r) / center;
 }
 
+// The SOR update split into "gather the cell's coefficients" and "combine them with the seven x values", for kernels that hold
+// x somewhere else than in the global array (k_relax_lex_tiles keeps its tile of x in shared memory).  Absent neighbours carry
+// coefficient 0.0 and must be given the value 0.0: 0.0 * 0.0 = +0.0 is the literal 0.0 term of the reference, so the sum r — and
+// with it the update — has the bits of relax_cell / relax_cell_code (the same products, added in the same order).
+struct RelaxCoefs {
+    double c[6];     // -i, +i, -j, +j, -k, +k
+    double center;
+};
+
+template <bool P>
+__host__ __device__ __forceinline__ RelaxCoefs relax_coefs(const Mat& A, int i, int j, int k, int nx, int ny, int nz) {
+    const size_t sy = (size_t)nx, sz = (size_t)nx * ny, c = ((size_t)k * ny + j) * nx + i;
+    RelaxCoefs q;
+    q.c[0] = (i > 0) ? m_right<P>(A, c - 1) : 0.0;
+    q.c[1] = (i + 1 < nx) ? m_right<P>(A, c) : 0.0;
+    q.c[2] = (j > 0) ? m_up<P>(A, c - sy) : 0.0;
+    q.c[3] = (j + 1 < ny) ? m_up<P>(A, c) : 0.0;
+    q.c[4] = (k > 0) ? m_front<P>(A, c - sz) : 0.0;
+    q.c[5] = (k + 1 < nz) ? m_front<P>(A, c) : 0.0;
+    q.center = A.center[c];
+    return q;
+}
+
+// the face-code form: the coefficients relax_cell_code uses (bulk-diagonal shortcut included)
+__host__ __device__ __forceinline__ RelaxCoefs relax_coefs_code(const Mat& A, int i, int j, int k, int nx, int ny, int nz) {
+    const size_t sy = (size_t)nx, sz = (size_t)nx * ny, c = ((size_t)k * ny + j) * nx + i;
+    (void)nz;
+    const unsigned own = jc_ldg(A.code + c);
+    const unsigned lft = i > 0 ? jc_ldg(A.code + c - 1) : 0u;
+    const unsigned dwn = j > 0 ? jc_ldg(A.code + c - sy) : 0u;
+    const unsigned bck = k > 0 ? jc_ldg(A.code + c - sz) : 0u;
+    const unsigned six = (lft & 3u) | ((own & 3u) << 2) | (((dwn >> 2) & 3u) << 4) | (((own >> 2) & 3u) << 6) |
+                         (((bck >> 4) & 3u) << 8) | (((own >> 4) & 3u) << 10);
+    RelaxCoefs q;
+    if (six == 0x555u) {
+        q.c[0] = q.c[1] = -A.sx; q.c[2] = q.c[3] = -A.sy; q.c[4] = q.c[5] = -A.sz;
+        q.center = A.c6;
+    } else if ((six & 0xaaau) == 0) {
+        q.c[0] = mask_coef(six, -A.sx); q.c[1] = mask_coef(six >> 2, -A.sx);
+        q.c[2] = mask_coef(six >> 4, -A.sy); q.c[3] = mask_coef(six >> 6, -A.sy);
+        q.c[4] = mask_coef(six >> 8, -A.sz); q.c[5] = mask_coef(six >> 10, -A.sz);
+    } else {
+        q.c[0] = face_coef(six & 3u, A.sx, A.cr, c - 1); q.c[1] = face_coef((six >> 2) & 3u, A.sx, A.cr, c);
+        q.c[2] = face_coef((six >> 4) & 3u, A.sy, A.cu, c - sy); q.c[3] = face_coef((six >> 6) & 3u, A.sy, A.cu, c);
+        q.c[4] = face_coef((six >> 8) & 3u, A.sz, A.cf, c - sz); q.c[5] = face_coef((six >> 10) & 3u, A.sz, A.cf, c);
+    }
+    if (six != 0x555u) q.center = jc_ldg(A.center + c);
+    return q;
+}
+
+// x_new = (1 - w) x + w (b - r) / center with r = the six products in the reference's order
+__host__ __device__ __forceinline__ double relax_update(const RelaxCoefs& q, double b, double w, double xc, double xl, double xr,
+                                                        double xd, double xu, double xb, double xf) {
+    const double r = q.c[0] * xl + q.c[1] * xr + q.c[2] * xd + q.c[3] * xu + q.c[4] * xb + q.c[5] * xf;
+    return (1.0 - w) * xc + w * (b - r) / q.center;
+}
+
+// the same update on the global array (what the shared-memory tile kernel computes, with absent neighbours read as 0.0):
+// tests/hostcheck replays k_relax_lex_tiles with this body
+template <bool P, bool CODE>
+__host__ __device__ __forceinline__ void relax_cell_split(const Mat& A, const double* __restrict__ b, double* x, double w, int i, int j,
+                                                          int k, int nx, int ny, int nz) {
+    const size_t sy = (size_t)nx, sz = (size_t)nx * ny, c = ((size_t)k * ny + j) * nx + i;
+    const RelaxCoefs q = CODE ? relax_coefs_code(A, i, j, k, nx, ny, nz) : relax_coefs<P>(A, i, j, k, nx, ny, nz);
+    x[c] = relax_update(q, b[c], w, x[c], i > 0 ? x[c - 1] : 0.0, i + 1 < nx ? x[c + 1] : 0.0, j > 0 ? x[c - sy] : 0.0,
+                        j + 1 < ny ? x[c + sy] : 0.0, k > 0 ? x[c - sz] : 0.0, k + 1 < nz ? x[c + sz] : 0.0);
+}
+
 // FdmMgUtils3::restrict, src/jet/fdm_mg_linear_system3.cpp:43-98: 4x4x4 (1,3,3,1)/8 tensor filter with edge clamp;
 // accumulation z-outer, y, x-inner; w = (kx*ky)*kz.  (i, j, k) = COARSE cell.
 __host__ __device__ __forceinline__ void restrict_cell(const double* __restrict__ finer, double* __restrict__ coarser, int i, int j,

@@ -13,6 +13,7 @@
 
 #include <new>
 #include <string>
+#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -72,22 +73,33 @@ static int write_xyz_file(const char* path, const double* positions, uint64_t n)
     for (uint64_t base = 0; base < n && ok; base += block * nt) {
         std::vector<std::string> text(nt);
         std::vector<std::thread> pool;
-        for (unsigned t = 0; t < nt; ++t) {
+        std::atomic<bool> failed(false);   // a worker ran out of memory: no exception may leave a thread (std::terminate)
+        bool spawn_failed = false;
+        for (unsigned t = 0; t < nt && !spawn_failed; ++t) {
             const uint64_t b0 = base + (uint64_t)t * block;
             if (b0 >= n) break;
             const uint64_t cnt = (n - b0 < block) ? n - b0 : block;
-            pool.emplace_back([&text, t, positions, b0, cnt]() {
-                std::string& s = text[t];
-                s.resize((size_t)cnt * 48);
-                uint64_t need = 0;
-                if (jetcu_format_xyz(positions + 3 * b0, cnt, &s[0], s.size(), &need) != JETCU_OK) {
-                    s.resize((size_t)need);
-                    jetcu_format_xyz(positions + 3 * b0, cnt, &s[0], s.size(), &need);
-                }
-                s.resize((size_t)need);
-            });
+            try {
+                pool.emplace_back([&text, &failed, t, positions, b0, cnt]() {
+                    try {
+                        std::string& s = text[t];
+                        s.resize((size_t)cnt * 48);
+                        uint64_t need = 0;
+                        if (jetcu_format_xyz(positions + 3 * b0, cnt, &s[0], s.size(), &need) != JETCU_OK) {
+                            s.resize((size_t)need);
+                            jetcu_format_xyz(positions + 3 * b0, cnt, &s[0], s.size(), &need);
+                        }
+                        s.resize((size_t)need);
+                    } catch (...) {
+                        failed = true;
+                    }
+                });
+            } catch (...) {   // thread creation failed: join what runs, then report
+                spawn_failed = true;
+            }
         }
         for (auto& th : pool) th.join();
+        if (spawn_failed || failed) { fclose(f); return JETCU_ERR_INVALID_ARG; }
         for (unsigned t = 0; t < nt && ok; ++t)
             if (!text[t].empty()) ok = fwrite(text[t].data(), 1, text[t].size(), f) == text[t].size();
     }

@@ -672,7 +672,9 @@ void relax_lex_schedule(const Mat& A, const double* b, double* x, double w, unsi
                         const int cx = th % T, cy = (th / T) % T, cz = th / (T * T);
                         const int i = ti * T + cx, j = tj * T + cy, k = tk * T + cz;
                         if (i >= nx || j >= ny || k >= nz || cx + cy + cz != step) continue;
-                        cell(i, j, k);
+                        // the tile kernel's arithmetic: coefficients gathered first, absent neighbours as 0.0 (fdm_ops.cuh)
+                        if (code) relax_cell_split<P, true>(A, b, x, w, i, j, k, nx, ny, nz);
+                        else relax_cell_split<P, false>(A, b, x, w, i, j, k, nx, ny, nz);
                     }
             }
         }

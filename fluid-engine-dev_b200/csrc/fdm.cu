@@ -623,6 +623,17 @@ __global__ void k_pcg_update(double alpha, const double* __restrict__ d, const d
     if (update_r) r[i] = -alpha * q[i] + r[i];
 }
 
+// the same update with alpha = sigma / (d . q) formed on the device from the two dot-product results (the IEEE division the host
+// would do: same bits), so that the solver does not have to wait for d . q on the host
+__global__ void k_pcg_update_dev(const double* __restrict__ sigma, const double* __restrict__ dq, const double* __restrict__ d,
+                                 const double* __restrict__ q, double* __restrict__ x, double* __restrict__ r, int update_r, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double alpha = *sigma / *dq;
+    x[i] = alpha * d[i] + x[i];
+    if (update_r) r[i] = -alpha * q[i] + r[i];
+}
+
 int fdm_axpy(jetcu_ctx* ctx, size_t n, double a, const double* x, const double* y, double* out) {
     JC_LAUNCH(ctx, k_axpy, jc_blocks(n, 256), 256, 0, a, x, y, out, n);
     return JETCU_OK;
@@ -908,12 +919,12 @@ int mgpcg_solve_device(jetcu_ctx* ctx, MgLevels* mg, const double* b, double* x,
             JC_TRY(fdm_mvm(ctx, d, z, mg->A[0], dd, q));
             jc_prof_end(ctx, slot, 1, cnt);
         }
-        double dq;
-        JC_TRY(fdm_dot_planes(ctx, d, z, dist, dd, q, ctx->d_scalars));
-        JC_TRY(read_scalar(ctx, ctx->d_scalars, &dq));
-        double alpha = sigmaNew / dq;
+        // alpha = sigmaNew / (d . q) is formed on the device (d_scalars[0] still holds sigmaNew, the last r . s): one host round
+        // trip per iteration (sigma, for the loop control) instead of two
+        JC_TRY(fdm_dot_planes(ctx, d, z, dist, dd, q, ctx->d_scalars + 1));
         bool recompute = trigger || (iter % 50 == 0 && iter > 0);
-        JC_TRY(fdm_pcg_update(ctx, cnt, alpha, dd + off, q + off, x + off, r + off, !recompute));
+        JC_LAUNCH(ctx, k_pcg_update_dev, jc_blocks(cnt, 256), 256, 0, ctx->d_scalars, ctx->d_scalars + 1, dd + off, q + off, x + off,
+                  r + off, recompute ? 0 : 1, cnt);
         if (recompute) {
             if (dist) JC_TRY(comm_halo_planes(ctx, x, plane, z.k0, z.k1, d.nz));
             JC_TRY(fdm_residual(ctx, d, z, mg->A[0], x, b, r));

@@ -14,25 +14,50 @@
 #define IC_T 8
 
 // op: 0 = build d, 1 = forward (out = y), 2 = backward (out = x).  Tile hyperplane S: tiles with ti + tj + tk == S.
+// The tile of `out` and the one-cell layer of neighbour values it depends on (below it for build / forward, above it for
+// backward: finished by earlier launches) live in shared memory, the cell's couplings, right-hand side and diagonal in registers,
+// all fetched up front: a cell hyperplane costs a shared-memory round trip instead of a global one (round 2, GPU call 21).
+#define IC_H (IC_T + 1)
 template <bool P, int OP>
 __global__ void __launch_bounds__(IC_T* IC_T* IC_T)
     k_ic_tiles(Mat A, const double* __restrict__ in, const double* __restrict__ dinv, double* out, int nx, int ny, int nz, int S) {
+    jc_pdl_prologue();
+    __shared__ double vs[IC_H * IC_H * IC_H];
     const int ti = blockIdx.x, tj = blockIdx.y, tk = S - ti - tj;
     const int ntz = (nz + IC_T - 1) / IC_T;
     if (tk < 0 || tk >= ntz) return;
+    const int i0 = ti * IC_T, j0 = tj * IC_T, k0 = tk * IC_T;
+    constexpr int LO = OP == 2 ? 0 : 1;   // local coordinate of the tile's first cell inside the (IC_T + 1)^3 block
+    for (int e = threadIdx.x; e < IC_H * IC_H * IC_H; e += IC_T * IC_T * IC_T) {
+        const int lx = e % IC_H - LO, ly = (e / IC_H) % IC_H - LO, lz = e / (IC_H * IC_H) - LO;
+        const bool halo = OP == 2 ? (lx == IC_T || ly == IC_T || lz == IC_T) : (lx < 0 || ly < 0 || lz < 0);
+        const int gi = i0 + lx, gj = j0 + ly, gk = k0 + lz;
+        const bool in_level = gi >= 0 && gi < nx && gj >= 0 && gj < ny && gk >= 0 && gk < nz;
+        vs[e] = (halo && in_level) ? out[((size_t)gk * ny + gj) * nx + gi] : 0.0;   // the tile's own cells are written before read
+    }
     const int cx = threadIdx.x % IC_T, cy = (threadIdx.x / IC_T) % IC_T, cz = threadIdx.x / (IC_T * IC_T);
-    const int i = ti * IC_T + cx, j = tj * IC_T + cy, k = tk * IC_T + cz;
+    const int i = i0 + cx, j = j0 + cy, k = k0 + cz;
     const bool live = i < nx && j < ny && k < nz;
     const int mine = OP == 2 ? (3 * IC_T - 3) - (cx + cy + cz) : cx + cy + cz;   // backward: highest local hyperplane first
     const size_t c = ((size_t)k * ny + j) * nx + i;
+    const int o = ((cz + LO) * IC_H + (cy + LO)) * IC_H + (cx + LO);
+    constexpr int DIR = OP == 2 ? 1 : -1;
+    IcCoefs q;
+    double rhs = 0.0, dg = 0.0;
+    if (live) {
+        q = OP == 2 ? ic_upper_coefs<P>(A, i, j, k, nx, ny, nz) : ic_lower_coefs<P>(A, i, j, k, nx, ny);
+        rhs = OP == 0 ? A.center[c] : in[c];
+        if (OP != 0) dg = dinv[c];
+    }
+    __syncthreads();
     for (int step = 0; step <= 3 * IC_T - 3; ++step) {
         if (live && mine == step) {
-            if (OP == 0) out[c] = ic_build_cell<P>(A, out, i, j, k, nx, ny);
-            else if (OP == 1) out[c] = ic_forward_cell<P>(A, in, out, dinv, i, j, k, nx, ny);
-            else out[c] = ic_backward_cell<P>(A, in, out, dinv, i, j, k, nx, ny, nz);
+            const double vx = vs[o + DIR], vy = vs[o + DIR * IC_H], vz = vs[o + DIR * IC_H * IC_H];
+            vs[o] = OP == 0 ? ic_build_update(q, rhs, vx, vy, vz) : ic_sub_update(q, rhs, vx, vy, vz, dg);
         }
-        __syncthreads();   // orders this CTA's global stores before its next hyperplane's loads
+        __syncthreads();
     }
+    if (live) out[c] = vs[o];
 }
 
 template <bool P, int OP>
@@ -42,7 +67,7 @@ static int ic_sweep(jetcu_ctx* ctx, Dim3i d, Mat A, const double* in, const doub
     dim3 grid(ntx, nty);
     for (int s = 0; s <= last; ++s) {
         const int S = OP == 2 ? last - s : s;
-        JC_LAUNCH(ctx, (k_ic_tiles<P, OP>), grid, IC_T * IC_T * IC_T, 0, A, in, dinv, out, d.nx, d.ny, d.nz, S);
+        JC_LAUNCH_PDL(ctx, s > 0, (k_ic_tiles<P, OP>), grid, IC_T * IC_T * IC_T, 0, A, in, dinv, out, d.nx, d.ny, d.nz, S);
     }
     return JETCU_OK;
 }

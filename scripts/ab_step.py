@@ -25,6 +25,7 @@ ap.add_argument("--steps", type=int, default=6)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--dt", type=float, default=1.0 / 240.0)
 ap.add_argument("--tag", default="")
+ap.add_argument("--iccg", action="store_true", help="FdmIccgSolver3(100, 1e-6) + compressed flag: what Jet's hybrid_liquid_sim examples run")
 ap.add_argument("--natural-ordering", action="store_true", help="useRedBlackOrdering = false (FdmMgpcgSolver3's constructor default)")
 a = ap.parse_args()
 scenes = {"tank": ((0.0, 0.0, 0.0), (1.0, 0.9375, 1.0), (0.0, 0.0, 0.0)),
@@ -37,7 +38,8 @@ while levels < 6 and m % 2 == 0 and m > 4:
     m //= 2
     levels += 1
 mode = {"flip": FLIP, "apic": APIC, "pic": PIC}[a.mode]
-h = jc.hybrid(HybridParams.make(Grid.cube(a.n), mode=mode, mgpcg=MgpcgParams.make(max_iterations=100, max_levels=levels, use_red_black=not a.natural_ordering)))
+solver = MgpcgParams.iccg(100, 1e-6, compressed=True) if a.iccg else MgpcgParams.make(max_iterations=100, max_levels=levels, use_red_black=not a.natural_ordering)
+h = jc.hybrid(HybridParams.make(Grid.cube(a.n), mode=mode, mgpcg=solver))
 npart = h.emit_box(lo, hi, 0.5 / a.n, v0)
 for _ in range(a.warmup):
     h.step(a.dt)

@@ -27,7 +27,7 @@ def jc():
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("name", ["fullsize_flip_256", "fullsize_flip_256_slosh"])
+@pytest.mark.parametrize("name", ["fullsize_flip_256", "fullsize_flip_256_slosh", "fullsize_apic_256"])
 def test_flip_256_matches_reference_golden(jc, name):
     """bench.py's workload at its full size against the unmodified reference, sub-step by sub-step: PCG iteration counts equal,
     lastResidual / ||b|| / true residual of every solve to 1e-6 relative (they are sums over 16.7 M cells of a solve that is
@@ -36,7 +36,8 @@ def test_flip_256_matches_reference_golden(jc, name):
     `_slosh` fixture's first solve runs into the 100-iteration cap with a residual of 8e11 on both sides)."""
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     steps, n_ref, idx, v0x = int(g["steps"]), int(g["n"]), g["idx"], float(g["v0x"]) if "v0x" in g else 0.5
-    prm = HybridParams.make(Grid.cube(N), mode=FLIP, mgpcg=MgpcgParams.make(max_iterations=100, max_levels=6))
+    # fullsize_apic_256 = BASELINE configs[2] (APIC 256^3 full step), the same tank scene through ApicSolver3
+    prm = HybridParams.make(Grid.cube(N), mode=APIC if "apic" in name else FLIP, mgpcg=MgpcgParams.make(max_iterations=100, max_levels=6))
     h = jc.hybrid(prm)
     assert h.emit_box((0.0, 0.0, 0.0), (1.0, 0.9375, 1.0), 0.5 / N, (v0x, 0.0, 0.0)) == n_ref
     for s in range(steps):

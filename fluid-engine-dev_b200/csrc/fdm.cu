@@ -424,6 +424,63 @@ __global__ void __launch_bounds__(GS_T* GS_T* GS_T)
     if (live) x[((size_t)k * ny + j) * nx + i] = xs[o];
 }
 
+// The face-code form of the tile kernel with ONE THREAD PER x-ROW of the tile (64 threads): at step s the thread of row (cy, cz)
+// updates the cell cx = s - cy - cz of its row, if there is one.  A tile hyperplane has at most 48 cells, so 512 threads per
+// tile left 90 % of the resident threads idle at every step and held the SM to 4 tiles; with 64 threads, the tile's x (+ halo),
+// right-hand side and code bytes in 13 KB of shared memory and the coefficients decoded from the code bytes at the step
+// (relax_coefs_of_six: the bulk cell needs no load at all), 16 tiles share an SM.  The same functions on the same values as
+// k_relax_lex_tiles<true, true>: bit-identical.
+#define GS_C (GS_T + 1)
+__global__ void __launch_bounds__(GS_T* GS_T, 16)
+    k_relax_lex_rows(Mat A, const double* __restrict__ b, double* x, double w, int nx, int ny, int nz, int t, int s_first) {
+    jc_pdl_prologue();
+    __shared__ double xs[GS_H * GS_H * GS_H];
+    __shared__ double bs[GS_T * GS_T * GS_T];
+    __shared__ unsigned char cs[GS_C * GS_C * GS_C];   // the tile's codes and the layer below it on every axis
+    const int ti = blockIdx.x, tj = blockIdx.y, tk = t - 2 * (s_first + (int)blockIdx.z) - ti - tj;
+    const int ntz = (nz + GS_T - 1) / GS_T;
+    if (tk < 0 || tk >= ntz) return;
+    const int i0 = ti * GS_T, j0 = tj * GS_T, k0 = tk * GS_T;
+    const size_t sy = (size_t)nx, sz = (size_t)nx * ny;
+    for (int e = threadIdx.x; e < GS_H * GS_H * GS_H; e += GS_T * GS_T) {
+        const int gi = i0 + e % GS_H - 1, gj = j0 + (e / GS_H) % GS_H - 1, gk = k0 + e / (GS_H * GS_H) - 1;
+        const bool in = gi >= 0 && gi < nx && gj >= 0 && gj < ny && gk >= 0 && gk < nz;
+        xs[e] = in ? x[(size_t)gk * sz + (size_t)gj * sy + gi] : 0.0;
+    }
+    for (int e = threadIdx.x; e < GS_T * GS_T * GS_T; e += GS_T * GS_T) {
+        const int gi = i0 + e % GS_T, gj = j0 + (e / GS_T) % GS_T, gk = k0 + e / (GS_T * GS_T);
+        bs[e] = (gi < nx && gj < ny && gk < nz) ? b[(size_t)gk * sz + (size_t)gj * sy + gi] : 0.0;
+    }
+    for (int e = threadIdx.x; e < GS_C * GS_C * GS_C; e += GS_T * GS_T) {
+        const int gi = i0 + e % GS_C - 1, gj = j0 + (e / GS_C) % GS_C - 1, gk = k0 + e / (GS_C * GS_C) - 1;
+        const bool in = gi >= 0 && gi < nx && gj >= 0 && gj < ny && gk >= 0 && gk < nz;
+        cs[e] = in ? jc_ldg(A.code + (size_t)gk * sz + (size_t)gj * sy + gi) : (unsigned char)0;
+    }
+    const int cy = threadIdx.x % GS_T, cz = threadIdx.x / GS_T;
+    const int j = j0 + cy, k = k0 + cz;
+    const bool row_live = j < ny && k < nz;
+    __syncthreads();
+    for (int step = 0; step <= 3 * GS_T - 3; ++step) {
+        const int cx = step - cy - cz;
+        if (row_live && cx >= 0 && cx < GS_T && i0 + cx < nx) {
+            const int o = ((cz + 1) * GS_H + (cy + 1)) * GS_H + (cx + 1);
+            const int oc = ((cz + 1) * GS_C + (cy + 1)) * GS_C + (cx + 1);
+            const unsigned six = relax_six(cs[oc], cs[oc - 1], cs[oc - GS_C], cs[oc - GS_C * GS_C]);
+            const RelaxCoefs q = relax_coefs_of_six(A, six, (size_t)k * sz + (size_t)j * sy + (size_t)(i0 + cx), sy, sz);
+            xs[o] = relax_update(q, bs[(cz * GS_T + cy) * GS_T + cx], w, xs[o], xs[o - 1], xs[o + 1], xs[o - GS_H], xs[o + GS_H],
+                                 xs[o - GS_H * GS_H], xs[o + GS_H * GS_H]);
+        }
+        __syncthreads();
+    }
+    if (row_live) {
+        double* dst = x + (size_t)k * sz + (size_t)j * sy + i0;
+        const int o = ((cz + 1) * GS_H + (cy + 1)) * GS_H + 1;
+#pragma unroll
+        for (int cx = 0; cx < GS_T; ++cx)
+            if (i0 + cx < nx) dst[cx] = xs[o + cx];
+    }
+}
+
 // one CTA, whole level; SMEM: x in shared memory for the duration (as k_relax_small)
 template <bool P, bool SMEM>
 __global__ void __launch_bounds__(SMALL_THREADS) k_relax_lex_small(Mat A, const double* __restrict__ b, double* x, double w,
@@ -473,7 +530,9 @@ static int launch_relax_lex(jetcu_ctx* ctx, Dim3i d, Mat A, const double* b, dou
             if (s_lo > s_hi) continue;
             dim3 grid(ntx, nty, s_hi - s_lo + 1);
             const bool after = t > 0;   // the previous operation of the stream is the previous launch of this group
-            if (code) JC_LAUNCH_PDL(ctx, after, (k_relax_lex_tiles<P, true>), grid, GS_T * GS_T * GS_T, 0, A, b, x, sor, d.nx, d.ny, d.nz, t, s_lo);
+            static const bool rows = !(getenv("JETCU_LEX_ROWS") && atoi(getenv("JETCU_LEX_ROWS")) == 0);
+            if (code && rows) JC_LAUNCH_PDL(ctx, after, k_relax_lex_rows, grid, GS_T * GS_T, 0, A, b, x, sor, d.nx, d.ny, d.nz, t, s_lo);
+            else if (code) JC_LAUNCH_PDL(ctx, after, (k_relax_lex_tiles<P, true>), grid, GS_T * GS_T * GS_T, 0, A, b, x, sor, d.nx, d.ny, d.nz, t, s_lo);
             else JC_LAUNCH_PDL(ctx, after, (k_relax_lex_tiles<P, false>), grid, GS_T * GS_T * GS_T, 0, A, b, x, sor, d.nx, d.ny, d.nz, t, s_lo);
             *launches += 1;
         }

@@ -162,16 +162,13 @@ __host__ __device__ __forceinline__ RelaxCoefs relax_coefs(const Mat& A, int i, 
     return q;
 }
 
-// the face-code form: the coefficients relax_cell_code uses (bulk-diagonal shortcut included)
-__host__ __device__ __forceinline__ RelaxCoefs relax_coefs_code(const Mat& A, int i, int j, int k, int nx, int ny, int nz) {
-    const size_t sy = (size_t)nx, sz = (size_t)nx * ny, c = ((size_t)k * ny + j) * nx + i;
-    (void)nz;
-    const unsigned own = jc_ldg(A.code + c);
-    const unsigned lft = i > 0 ? jc_ldg(A.code + c - 1) : 0u;
-    const unsigned dwn = j > 0 ? jc_ldg(A.code + c - sy) : 0u;
-    const unsigned bck = k > 0 ? jc_ldg(A.code + c - sz) : 0u;
-    const unsigned six = (lft & 3u) | ((own & 3u) << 2) | (((dwn >> 2) & 3u) << 4) | (((own >> 2) & 3u) << 6) |
-                         (((bck >> 4) & 3u) << 8) | (((own >> 4) & 3u) << 10);
+// the face-code form: the coefficients relax_cell_code uses (bulk-diagonal shortcut included).  `six` = the six 2-bit face
+// classes of cell c in the sum order -i,+i,-j,+j,-k,+k, from the cell's own code byte and those of its three lower neighbours.
+__host__ __device__ __forceinline__ unsigned relax_six(unsigned own, unsigned lft, unsigned dwn, unsigned bck) {
+    return (lft & 3u) | ((own & 3u) << 2) | (((dwn >> 2) & 3u) << 4) | (((own >> 2) & 3u) << 6) | (((bck >> 4) & 3u) << 8) |
+           (((own >> 4) & 3u) << 10);
+}
+__host__ __device__ __forceinline__ RelaxCoefs relax_coefs_of_six(const Mat& A, unsigned six, size_t c, size_t sy, size_t sz) {
     RelaxCoefs q;
     if (six == 0x555u) {
         q.c[0] = q.c[1] = -A.sx; q.c[2] = q.c[3] = -A.sy; q.c[4] = q.c[5] = -A.sz;
@@ -187,6 +184,15 @@ __host__ __device__ __forceinline__ RelaxCoefs relax_coefs_code(const Mat& A, in
     }
     if (six != 0x555u) q.center = jc_ldg(A.center + c);
     return q;
+}
+__host__ __device__ __forceinline__ RelaxCoefs relax_coefs_code(const Mat& A, int i, int j, int k, int nx, int ny, int nz) {
+    const size_t sy = (size_t)nx, sz = (size_t)nx * ny, c = ((size_t)k * ny + j) * nx + i;
+    (void)nz;
+    const unsigned own = jc_ldg(A.code + c);
+    const unsigned lft = i > 0 ? jc_ldg(A.code + c - 1) : 0u;
+    const unsigned dwn = j > 0 ? jc_ldg(A.code + c - sy) : 0u;
+    const unsigned bck = k > 0 ? jc_ldg(A.code + c - sz) : 0u;
+    return relax_coefs_of_six(A, relax_six(own, lft, dwn, bck), c, sy, sz);
 }
 
 // x_new = (1 - w) x + w (b - r) / center with r = the six products in the reference's order

@@ -530,7 +530,10 @@ static int launch_relax_lex(jetcu_ctx* ctx, Dim3i d, Mat A, const double* b, dou
             if (s_lo > s_hi) continue;
             dim3 grid(ntx, nty, s_hi - s_lo + 1);
             const bool after = t > 0;   // the previous operation of the stream is the previous launch of this group
-            static const bool rows = !(getenv("JETCU_LEX_ROWS") && atoi(getenv("JETCU_LEX_ROWS")) == 0);
+            // one thread per tile row pays where a launch has enough tiles to fill 16 per SM (GPU call 22: 256^3 80.7 -> 68.6 ms
+            // per solve, but 128^3 18.8 -> 27.7: few tiles per launch, and the 64-thread prologue is the longer one); 1 / 0 force it
+            static const int rows_env = getenv("JETCU_LEX_ROWS") ? atoi(getenv("JETCU_LEX_ROWS")) : -1;
+            const bool rows = rows_env >= 0 ? rows_env != 0 : (size_t)ntx * nty * ntz >= 16384;
             if (code && rows) JC_LAUNCH_PDL(ctx, after, k_relax_lex_rows, grid, GS_T * GS_T, 0, A, b, x, sor, d.nx, d.ny, d.nz, t, s_lo);
             else if (code) JC_LAUNCH_PDL(ctx, after, (k_relax_lex_tiles<P, true>), grid, GS_T * GS_T * GS_T, 0, A, b, x, sor, d.nx, d.ny, d.nz, t, s_lo);
             else JC_LAUNCH_PDL(ctx, after, (k_relax_lex_tiles<P, false>), grid, GS_T * GS_T * GS_T, 0, A, b, x, sor, d.nx, d.ny, d.nz, t, s_lo);

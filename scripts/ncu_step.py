@@ -18,12 +18,15 @@ from fluid_engine_dev_b200.jetcu import FLIP, APIC, Grid, HybridParams, MgpcgPar
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 mode = APIC if (len(sys.argv) > 3 and sys.argv[3] == "apic") else FLIP
+solver_kind = sys.argv[4] if len(sys.argv) > 4 else "mgpcg"   # mgpcg | natural (useRedBlackOrdering = false) | iccg
 jc = Jetcu(0)
 levels, m = 1, n
 while levels < 6 and m % 2 == 0 and m > 4:
     m //= 2
     levels += 1
-h = jc.hybrid(HybridParams.make(Grid.cube(n), mode=mode, mgpcg=MgpcgParams.make(max_iterations=100, max_levels=levels)))
+solver = (MgpcgParams.iccg(100, 1e-6, compressed=True) if solver_kind == "iccg"
+          else MgpcgParams.make(max_iterations=100, max_levels=levels, use_red_black=solver_kind != "natural"))
+h = jc.hybrid(HybridParams.make(Grid.cube(n), mode=mode, mgpcg=solver))
 npart = h.emit_box((0.0, 0.0, 0.0), (1.0, 0.9375, 1.0), 0.5 / n, (0.0, 0.0, 0.0))
 for s in range(steps):
     st = h.step(1.0 / 240.0)

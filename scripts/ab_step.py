@@ -50,5 +50,12 @@ out = {"tag": a.tag, "n": a.n, "mode": a.mode, "workload": a.workload, "particle
        "iters": [int(s["pcg_iterations"]) for s in st]}
 for k in keys:
     out[k] = round(sum(s[k] for s in st) / len(st), 3)
+if os.environ.get("AB_HASH"):   # bit-identity checks between builds / switches: digests of the final state
+    import hashlib
+    import numpy as np
+    pos, vel = h.get_particles()
+    out["sha_pos"] = hashlib.sha1(np.ascontiguousarray(pos).tobytes()).hexdigest()
+    out["sha_vel"] = hashlib.sha1(np.ascontiguousarray(vel).tobytes()).hexdigest()
+    out["sha_pressure"] = hashlib.sha1(np.ascontiguousarray(h.get_pressure()).tobytes()).hexdigest()
 print(json.dumps(out))
 h.close()

@@ -17,7 +17,7 @@ def libs():
     return ref, port
 
 
-def random_case(rng):
+def random_case(rng, natural=False):
     nyz = int(rng.choice([6, 8, 10, 12]))
     nx = int(rng.choice([nyz, nyz + 2, nyz + 4, 2 * nyz]))       # multi-level MG needs ny == nz (the reference's own limit)
     h = float(rng.choice([1.0 / nyz, 0.07, 0.125, 0.1]))
@@ -31,6 +31,8 @@ def random_case(rng):
                             max_cfl=float(rng.choice([5.0, 5.0, 2.5, 1.0])),
                             closed_domain_boundary_flag=int(rng.choice([63, 63, 0b101011, 0b111100, 0])),
                             pic_blending_factor=float(rng.choice([0.0, 0.05, 1.0])))
+    if natural:   # FdmMgpcgSolver3's constructor default: the natural (lexicographic) Gauss-Seidel ordering (no RNG draw: the
+        prm.mgpcg.use_red_black = 0   # cases of the other seeds stay what they were)
     lo, size = np.array(origin), np.array([nx * h, nyz * hy, nyz * hz])
     n = int(rng.integers(200, 3000))
     pos = lo + rng.uniform(0.02, 0.7, (n, 3)) * size
@@ -52,7 +54,7 @@ def random_case(rng):
 @pytest.mark.parametrize("seed", range(24))
 def test_random_configuration_bit_exact(libs, seed):
     ref, port = libs
-    prm, pos, vel, collider = random_case(np.random.default_rng(1000 + seed))
+    prm, pos, vel, collider = random_case(np.random.default_rng(1000 + seed), natural=seed % 4 == 3)
     a, b = ref.hybrid(prm), port.hybrid(prm)
     for h in (a, b):
         if collider:

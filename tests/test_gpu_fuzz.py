@@ -2,7 +2,8 @@
 unmodified reference bit for bit): non-zero origins, non-cubic and anisotropic grids, odd wall flags, tilted gravity, every
 transfer mode, one or two MG levels, random analytic colliders.  Two sub-steps; BASELINE tolerances: positions <= 1e-5 of the
 domain size, pressure <= 1e-6 relative where the oracle's own solve converged; particle SDF and markers bit-exact on step 0
-when no cylinder (device libm) is involved.  First GPU run: executed in a child process by tests/test_gpu_zz_firstrun.py."""
+when no cylinder (device libm) is involved.  Every fourth configuration smooths with the natural Gauss-Seidel ordering (the
+reference constructors' default)."""
 import numpy as np
 import pytest
 

@@ -1,9 +1,7 @@
 """GPU parity for the device-resident GridSmokeSolver3 (BASELINE config 5).
 
-STATUS: csrc/smoke.cu was written against the pinned oracle (tests/test_oracle_smoke.py: port == unmodified reference)
-after round 1's GPU minutes had run out; its kernel bodies are verified on the CPU (tests/test_hostcheck_smoke.py), this
-file is the FIRST GPU execution.  tests/test_gpu_zz_firstrun.py runs it in a child pytest process and reports it as a
-non-strict xfail, so it cannot hide (or crash) the established parity suite; round 2 moves it back under tests/.
+csrc/smoke.cu is checked against the pinned oracle (tests/test_oracle_smoke.py: port == unmodified reference); its kernel
+bodies are also verified on the CPU (tests/test_hostcheck_smoke.py).  Green on B200 since round 2's first GPU call.
 
 Expected: advection bit-exact on identical inputs (per-cell arithmetic); buoyancy within 1e-12 (the ambient temperature
 is a tree sum on the GPU, a serial sum in the reference); pressure <= 1e-6 relative where the oracle converged; fields

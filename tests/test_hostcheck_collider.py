@@ -1,7 +1,7 @@
 """The CUDA source of the collider path, executed on the CPU (tests/hostcheck: the __host__ __device__ kernel bodies of
 csrc/collider.cuh / collider_ops.cuh behind plain loops), against the C oracle — bit for bit.  This is what can be
 verified about those kernels without a GPU: every arithmetic expression and index computation of the per-cell /
-per-face / per-particle bodies; only the launch geometry is left to tests/firstrun/zz_collider.py."""
+per-face / per-particle bodies; only the launch geometry is left to tests/test_gpu_collider.py."""
 import ctypes as C
 import importlib.util
 import os

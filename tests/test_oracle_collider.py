@@ -4,7 +4,7 @@ Cylinder3 / Plane3 (plain or normal-flipped) or an ImplicitSurfaceSet3 of them (
 collider SDF rasterisation, constrainVelocity's collider branch, extrapolateIntoCollider, the pressure system with a
 moving boundary, and Collider3::resolveCollision.  Everything here is per-cell / per-particle arithmetic without
 reductions except P2G (serial in both), so the port must be BIT-IDENTICAL.  CPU only; this pins the oracle the CUDA
-path is checked against (tests/test_hostcheck_collider.py on the CPU, tests/firstrun/zz_collider.py on the GPU)."""
+path is checked against (tests/test_hostcheck_collider.py on the CPU, tests/test_gpu_collider.py on the GPU)."""
 import numpy as np
 import pytest
 

@@ -121,7 +121,7 @@ def test_emit_step_bit_exact(libs, gi, which):
 
 # Two MG levels: with more the reference's own MGPCG stagnates near 1e-7 next to a collider that vanishes on the coarse levels and
 # runs into the iteration limit — bit-identity between port and reference holds either way, but a converged solve is the fairer
-# target for the CUDA path (tests/firstrun/zz_smoke.py).
+# target for the CUDA path (tests/test_gpu_smoke.py).
 SMOKE_COLLIDERS = [   # (grid, MG levels, collider shapes, collider kwargs, advection)
     (Grid.cube(16), 2, [dict(kind="sphere", a=(0.5, 0.3, 0.5), b=(0.12, 0.0, 0.0))], dict(), "cubic"),                 # smoke_sim example 1
     (Grid.cube(16), 2, [dict(kind="sphere", a=(0.5, 0.3, 0.5), b=(0.12, 0.0, 0.0))],

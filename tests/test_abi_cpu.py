@@ -75,3 +75,43 @@ def test_no_cpu_fallback(lib):
     from fluid_engine_dev_b200 import Jetcu, JetcuError
     with pytest.raises(JetcuError):
         Jetcu(0)
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under the package, include/ or adapters/ may import, link, dlopen or name it
+    (bench.py may, in its CPU-baseline / reference legs only — checked by name below)."""
+    needles = ("jeto_", "libjetport", "libjetref", "oracle_api", "jet_port", "ref_shim")
+    roots = [os.path.join(ROOT, "fluid-engine-dev_b200"), os.path.join(ROOT, "include")]
+    hits = []
+    for root in roots:
+        for dirpath, dirnames, filenames in os.walk(root):
+            dirnames[:] = [d for d in dirnames if d not in ("build", "__pycache__")]
+            for f in filenames:
+                if not f.endswith((".cu", ".cuh", ".h", ".py", ".cpp")):
+                    continue
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                # comments and docstrings may say what a kernel is checked against; code may not reach it
+                if f.endswith(".py"):
+                    text = re.sub(r'''("""|\'\'\').*?\1''', "", text, flags=re.S)
+                    text = re.sub(r"#[^\n]*", "", text)
+                else:
+                    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+                    text = re.sub(r"//[^\n]*", "", text)
+                hits += ["%s: %s" % (os.path.join(dirpath, f), n) for n in needles if n in text]
+    assert not hits, hits
+    # the shared library has no dependency on an oracle library either
+    out = subprocess.run(["ldd", LIB], capture_output=True, text=True)
+    if out.returncode == 0:
+        assert "jetport" not in out.stdout and "jetref" not in out.stdout, out.stdout
+    # bench.py reaches the oracle only inside its two CPU legs (run_reference = `--impl reference`, cpu_baseline_leg) and the
+    # two helpers only they call
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+
+    def enclosing(pos):
+        fn = re.findall(r"^def (\w+)\(", bench[:pos], flags=re.M)
+        return fn[-1] if fn else None
+
+    for m in re.finditer(r"oracle_api", bench):
+        assert enclosing(m.start()) in ("load_oracle", "cpu_steps", "run_reference", "cpu_baseline_leg"), enclosing(m.start())
+    for m in re.finditer(r"(?<!def )\b(load_oracle|cpu_steps)\(", bench):
+        assert enclosing(m.start()) in ("run_reference", "cpu_baseline_leg"), (m.group(1), enclosing(m.start()))

@@ -662,8 +662,16 @@ void relax_lex_schedule(const Mat& A, const double* b, double* x, double w, unsi
             const int nsl = s_hi - s_lo + 1;
             if (nsl <= 0) continue;
             const long long ctas = (long long)nsl * nty * ntx;
+            // order >= 2: a pseudo-random permutation of the launch's CTAs (q -> (a q + b) mod ctas with gcd(a, ctas) = 1)
+            long long pa = 1, pb = 0;
+            if (order >= 2) {
+                pa = 2654435761ll % ctas; if (pa == 0) pa = 1;
+                auto gcd = [](long long u, long long v) { while (v) { const long long r = u % v; u = v; v = r; } return u; };
+                while (gcd(pa, ctas) != 1) ++pa;
+                pb = (long long)(40503u * (unsigned)(t + 7 * order)) % ctas;
+            }
             for (long long q = 0; q < ctas; ++q) {
-                const long long cta = order ? ctas - 1 - q : q;
+                const long long cta = order >= 2 ? (pa * q + pb) % ctas : (order ? ctas - 1 - q : q);
                 const int ti = (int)(cta % ntx), tj = (int)((cta / ntx) % nty), bz = (int)(cta / ((long long)ntx * nty));
                 const int tk = t - 2 * (s_lo + bz) - ti - tj;
                 if (tk < 0 || tk >= ntz) continue;

@@ -79,7 +79,7 @@ def test_lexicographic_relax_schedules(hc, port, shape, spd):
         if it > 5 and (not spd or (nx * ny * nz > 8192 and nx * ny * nz != 33 * 32 * 24)):
             continue   # the > 32 sweeps case (two launch groups): convergent systems, one large and every small shape
         want = port.relax(A, b, x, sor, it)
-        for order in (0, 1):
+        for order in (0, 1, 2, 3):   # ascending, descending, two pseudo-random permutations of a launch's CTAs
             xs = x.copy()
             assert hc.hc_relax_lex(nx, ny, nz, rp(A), dp(b), C.c_double(sor), C.c_uint(it), C.c_int(order), dp(xs)) == 0
             exact(xs, want, "lexicographic relax sor=%g sweeps=%d order=%d" % (sor, it, order))
